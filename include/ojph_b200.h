@@ -1,0 +1,130 @@
+/* ojph_b200.h -- C ABI of libojph_b200.so: the B200-native HTJ2K hot path behind OpenJPH's
+ * codestream interface.  Plain pointers and sizes only; every function returns 0 on success or
+ * a negative status (the message is available from ojb_last_error(), formatted like the
+ * reference's "ojph error 0x%08X" -- src/core/others/ojph_message.cpp:156-171).
+ *
+ * Each entry point names the reference interface it stands in for (paths are relative to the
+ * OpenJPH tree, v0.31.0).  INTEGRATION.md shows the binding a maintainer would add on the
+ * reference side.
+ */
+#ifndef OJPH_B200_H
+#define OJPH_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Codestream parameters: the union of what ojph_compress sets through param_siz / param_cod /
+ * param_qcd (src/core/openjph/ojph_params.h; setters used at
+ * src/apps/ojph_compress/ojph_compress.cpp:678-709). */
+typedef struct ojb_params {
+  uint32_t width, height;          /* image extent  (param_siz::set_image_extent) */
+  uint32_t off_x, off_y;           /* image offset  (set_image_offset) */
+  uint32_t tile_w, tile_h;         /* tile size; 0,0 = one tile (set_tile_size) */
+  uint32_t tile_off_x, tile_off_y; /* tile offset   (set_tile_offset) */
+  uint32_t num_comps;              /* set_num_components, <= 16 through this struct */
+  uint32_t bit_depth[16];          /* set_component(c, downsampling, bit_depth, is_signed) */
+  uint32_t is_signed[16];
+  uint32_t dx[16], dy[16];
+  uint32_t num_decomps;            /* param_cod::set_num_decomposition */
+  uint32_t block_w, block_h;       /* set_block_dims */
+  uint32_t num_precincts;          /* set_precinct_size; 0 = default (2^15) */
+  uint32_t precinct_w[33], precinct_h[33];
+  uint32_t reversible;             /* set_reversible */
+  uint32_t color_transform;        /* set_color_transform */
+  uint32_t prog_order;             /* 0 LRCP 1 RLCP 2 RPCL 3 PCRL 4 CPRL (set_progression_order) */
+  float    qstep;                  /* param_qcd::set_irrev_quant; <= 0 = library default */
+  uint32_t qfactor;                /* param_qcd::set_qfactor; 0 = unset */
+  uint32_t tlm;                    /* codestream::request_tlm_marker */
+  uint32_t tilepart_div;           /* codestream::set_tilepart_divisions: bit0 resolutions, bit1 components */
+  int32_t  planar;                 /* codestream::set_planar; -1 = not called */
+} ojb_params;
+
+typedef struct ojb_frame_info {
+  uint32_t width, height, off_x, off_y, num_comps;
+  uint32_t bit_depth[16], is_signed[16], dx[16], dy[16], comp_w[16], comp_h[16];
+  uint32_t num_decomps, reversible, color_transform, num_tiles;
+} ojb_frame_info;
+
+/* sample container of frame buffers */
+enum { OJB_U8 = 0, OJB_U16 = 1, OJB_I32 = 2 };
+
+typedef struct ojb_encoder ojb_encoder;
+typedef struct ojb_decoder ojb_decoder;
+
+const char* ojb_last_error(void);
+const char* ojb_version(void);
+int ojb_device_count(void);
+int ojb_set_device(int device);
+void ojb_params_default(ojb_params* p);      /* the reference's defaults: 5 levels, 64x64, RPCL */
+
+/* pinned host memory for frame / codestream buffers (optional; any host pointer works) */
+void* ojb_host_alloc(uint64_t bytes);
+void ojb_host_free(void* p);
+
+/* ---- encode: ojph::codestream write side (src/core/openjph/ojph_codestream.h:88-383) ---- */
+ojb_encoder* ojb_enc_create(void);                       /* codestream::codestream() */
+void ojb_enc_destroy(ojb_encoder* e);                    /* ~codestream / close() */
+/* access_siz/cod/qcd setters + write_headers(): validates, builds geometry and device arenas */
+int ojb_enc_configure(ojb_encoder* e, const ojb_params* p, uint32_t sample_type);
+/* codestream::exchange(line_buf*, ui32& next_comp): first call with line == NULL; returns the
+ * line to fill next (library owned, si32 samples), NULL after the last line */
+int32_t* ojb_enc_exchange(ojb_encoder* e, int32_t* line, uint32_t* next_comp);
+/* codestream::flush(): encodes the exchanged frame on the GPU into out */
+int ojb_enc_flush(ojb_encoder* e, uint8_t* out, uint64_t out_cap, uint64_t* out_len);
+/* frame-at-once fast path: component planes in the configured container, strides in samples
+ * (NULL = tight); host pointers (pinned or pageable) */
+int ojb_enc_encode_frame(ojb_encoder* e, const void* const* planes, const uint32_t* strides,
+                         uint8_t* out, uint64_t out_cap, uint64_t* out_len);
+/* device-resident variants: the frame lives in the encoder's image buffer */
+void* ojb_enc_device_plane(ojb_encoder* e, uint32_t comp);
+int ojb_enc_upload_frame(ojb_encoder* e, const void* const* planes, const uint32_t* strides);
+int ojb_enc_encode_resident(ojb_encoder* e, uint8_t* out, uint64_t out_cap, uint64_t* out_len,
+                            int out_on_device);
+uint32_t ojb_enc_kernel_launches(ojb_encoder* e);
+uint32_t ojb_enc_num_blocks(ojb_encoder* e);
+/* parity hook: copy one sub-band's quantised sign-magnitude plane (what the block coder reads)
+ * after an encode; out has band_w * band_h words */
+int ojb_enc_read_band(ojb_encoder* e, uint32_t tile, uint32_t comp, uint32_t res, uint32_t band,
+                      uint32_t* out, uint32_t* band_w, uint32_t* band_h);
+
+/* ---- decode: ojph::codestream read side ------------------------------------------------- */
+ojb_decoder* ojb_dec_create(void);
+void ojb_dec_destroy(ojb_decoder* d);
+int ojb_dec_enable_resilience(ojb_decoder* d);           /* codestream::enable_resilience() */
+/* codestream::read_headers(infile_base*): j2c must stay valid until the decode call returns */
+int ojb_dec_read_headers(ojb_decoder* d, const uint8_t* j2c, uint64_t len, uint32_t sample_type,
+                         ojb_frame_info* info);
+/* codestream::create() + the pull() loop: decodes every component into planes */
+int ojb_dec_decode_frame(ojb_decoder* d, void* const* planes, const uint32_t* strides);
+int ojb_dec_decode_resident(ojb_decoder* d);             /* result stays in the device image buffer */
+void* ojb_dec_device_plane(ojb_decoder* d, uint32_t comp);
+uint32_t ojb_dec_failed_blocks(ojb_decoder* d);
+uint32_t ojb_dec_kernel_launches(ojb_decoder* d);
+int ojb_dec_read_band(ojb_decoder* d, uint32_t tile, uint32_t comp, uint32_t res, uint32_t band,
+                      uint32_t* out, uint32_t* band_w, uint32_t* band_h);
+
+/* ---- kernel-level batch entry points (fine boundary: struct codeblock_fun,
+ *      src/core/codestream/ojph_codeblock_fun.h:93-120) ----------------------------------- */
+typedef struct ojb_block_desc {
+  uint64_t sample_off;     /* word offset of sample (0,0) in the samples array */
+  uint32_t stride, w, h;   /* stride in words */
+  uint32_t missing_msbs;   /* encode: K_max - 1; decode: from the packet header */
+  uint32_t num_passes;     /* decode only */
+  uint32_t len1, len2;     /* decode in: cleanup / refinement bytes; encode out: len1 = bytes */
+  uint64_t byte_off;       /* offset of the block's coded bytes in the bytes array */
+  uint32_t status;         /* out: 0 ok, 1 failed / not coded */
+  uint32_t causal;
+} ojb_block_desc;
+/* encode_cb32 for n blocks: samples = MSB-aligned sign-magnitude (host); coded bytes are packed
+ * into bytes (cap bytes_cap) and desc[i].byte_off / len1 are filled */
+int ojb_encode_blocks(const uint32_t* samples, uint64_t n_words, ojb_block_desc* desc, uint32_t n,
+                      uint8_t* bytes, uint64_t bytes_cap, uint64_t* bytes_used);
+/* decode_cb32 for n blocks: output sign-magnitude samples (out_mode 0) written to samples */
+int ojb_decode_blocks(const uint8_t* bytes, uint64_t n_bytes, ojb_block_desc* desc, uint32_t n,
+                      uint32_t* samples, uint64_t n_words);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OJPH_B200_H */

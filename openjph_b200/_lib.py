@@ -1,0 +1,105 @@
+"""ctypes binding of libojph_b200.so (the C-ABI in include/ojph_b200.h).
+
+The product path loads the nvcc-built library that sits next to this file and fails loudly
+when it is missing -- there is no CPU fallback.  (tests/ may hand `bind()` the SIMT-emulator
+build of the same sources to check kernel logic without a GPU; that never happens here.)
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libojph_b200.so")
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("width", C.c_uint32), ("height", C.c_uint32), ("off_x", C.c_uint32), ("off_y", C.c_uint32),
+        ("tile_w", C.c_uint32), ("tile_h", C.c_uint32), ("tile_off_x", C.c_uint32), ("tile_off_y", C.c_uint32),
+        ("num_comps", C.c_uint32), ("bit_depth", C.c_uint32 * 16), ("is_signed", C.c_uint32 * 16),
+        ("dx", C.c_uint32 * 16), ("dy", C.c_uint32 * 16),
+        ("num_decomps", C.c_uint32), ("block_w", C.c_uint32), ("block_h", C.c_uint32),
+        ("num_precincts", C.c_uint32), ("precinct_w", C.c_uint32 * 33), ("precinct_h", C.c_uint32 * 33),
+        ("reversible", C.c_uint32), ("color_transform", C.c_uint32), ("prog_order", C.c_uint32),
+        ("qstep", C.c_float), ("qfactor", C.c_uint32), ("tlm", C.c_uint32), ("tilepart_div", C.c_uint32),
+        ("planar", C.c_int32),
+    ]
+
+
+class FrameInfo(C.Structure):
+    _fields_ = [
+        ("width", C.c_uint32), ("height", C.c_uint32), ("off_x", C.c_uint32), ("off_y", C.c_uint32),
+        ("num_comps", C.c_uint32), ("bit_depth", C.c_uint32 * 16), ("is_signed", C.c_uint32 * 16),
+        ("dx", C.c_uint32 * 16), ("dy", C.c_uint32 * 16), ("comp_w", C.c_uint32 * 16), ("comp_h", C.c_uint32 * 16),
+        ("num_decomps", C.c_uint32), ("reversible", C.c_uint32), ("color_transform", C.c_uint32),
+        ("num_tiles", C.c_uint32),
+    ]
+
+
+class BlockDesc(C.Structure):
+    _fields_ = [
+        ("sample_off", C.c_uint64), ("stride", C.c_uint32), ("w", C.c_uint32), ("h", C.c_uint32),
+        ("missing_msbs", C.c_uint32), ("num_passes", C.c_uint32), ("len1", C.c_uint32), ("len2", C.c_uint32),
+        ("byte_off", C.c_uint64), ("status", C.c_uint32), ("causal", C.c_uint32),
+    ]
+
+
+# every symbol include/ojph_b200.h declares: name -> (restype, argtypes)
+_VP, _U32, _U64, _I = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
+SYMBOLS = {
+    "ojb_last_error": (C.c_char_p, []),
+    "ojb_version": (C.c_char_p, []),
+    "ojb_device_count": (_I, []),
+    "ojb_set_device": (_I, [_I]),
+    "ojb_params_default": (None, [C.POINTER(Params)]),
+    "ojb_host_alloc": (_VP, [_U64]),
+    "ojb_host_free": (None, [_VP]),
+    "ojb_enc_create": (_VP, []),
+    "ojb_enc_destroy": (None, [_VP]),
+    "ojb_enc_configure": (_I, [_VP, C.POINTER(Params), _U32]),
+    "ojb_enc_exchange": (_VP, [_VP, _VP, C.POINTER(_U32)]),
+    "ojb_enc_flush": (_I, [_VP, _VP, _U64, C.POINTER(_U64)]),
+    "ojb_enc_encode_frame": (_I, [_VP, C.POINTER(_VP), C.POINTER(_U32), _VP, _U64, C.POINTER(_U64)]),
+    "ojb_enc_device_plane": (_VP, [_VP, _U32]),
+    "ojb_enc_upload_frame": (_I, [_VP, C.POINTER(_VP), C.POINTER(_U32)]),
+    "ojb_enc_encode_resident": (_I, [_VP, _VP, _U64, C.POINTER(_U64), _I]),
+    "ojb_enc_kernel_launches": (_U32, [_VP]),
+    "ojb_enc_num_blocks": (_U32, [_VP]),
+    "ojb_enc_read_band": (_I, [_VP, _U32, _U32, _U32, _U32, _VP, C.POINTER(_U32), C.POINTER(_U32)]),
+    "ojb_dec_create": (_VP, []),
+    "ojb_dec_destroy": (None, [_VP]),
+    "ojb_dec_enable_resilience": (_I, [_VP]),
+    "ojb_dec_read_headers": (_I, [_VP, _VP, _U64, _U32, C.POINTER(FrameInfo)]),
+    "ojb_dec_decode_frame": (_I, [_VP, C.POINTER(_VP), C.POINTER(_U32)]),
+    "ojb_dec_decode_resident": (_I, [_VP]),
+    "ojb_dec_device_plane": (_VP, [_VP, _U32]),
+    "ojb_dec_failed_blocks": (_U32, [_VP]),
+    "ojb_dec_kernel_launches": (_U32, [_VP]),
+    "ojb_dec_read_band": (_I, [_VP, _U32, _U32, _U32, _U32, _VP, C.POINTER(_U32), C.POINTER(_U32)]),
+    "ojb_encode_blocks": (_I, [_VP, _U64, C.POINTER(BlockDesc), _U32, _VP, _U64, C.POINTER(_U64)]),
+    "ojb_decode_blocks": (_I, [_VP, _U64, C.POINTER(BlockDesc), _U32, _VP, _U64]),
+}
+
+
+def bind(path):
+    """Load a build of the C-ABI and attach prototypes to every declared symbol."""
+    lib = C.CDLL(path)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)      # AttributeError if the library does not export it
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+_lib = None
+
+
+def lib():
+    """The product library.  Raises if the CUDA build is absent -- never falls back."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  openjph_b200 has no CPU fallback.")
+        _lib = bind(LIB_PATH)
+    return _lib

@@ -1,0 +1,86 @@
+// assemble.cu -- codestream assembly on the device.
+//
+// After the block encoder has run, every code-block sits in its own slot as two pieces
+// (MagSgn+MEL at the slot start, VLC at the slot end).  The host computes, from the per-block
+// lengths, the packet headers (tag trees, ojb_layout.cpp) and the final byte offset of every
+// block; these kernels then place block bytes and header bytes at their final positions so a
+// single device->host copy delivers the finished codestream.  This replaces the reference's
+// precinct::write / tile::flush memcpy chain (src/core/codestream/ojph_precinct.cpp:281-324,
+// ojph_tile.cpp:584-772).
+#include "ojb_device.h"
+#include "ojb_kernels.h"
+
+namespace ojb {
+
+namespace {
+
+// warp-cooperative byte copy with 4-byte stores where the destination allows it
+__device__ __forceinline__ void warp_copy(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src,
+                                          uint32_t n, uint32_t lane) {
+  // head: bring dst to 4-byte alignment
+  uint32_t head = (uint32_t)((4 - ((size_t)dst & 3)) & 3);
+  if (head > n) head = n;
+  if (lane < head) dst[lane] = src[lane];
+  dst += head; src += head; n -= head;
+  uint32_t nw = n >> 2;
+  const uint32_t sh = (uint32_t)((size_t)src & 3) * 8;
+  if (sh == 0) {
+    const uint32_t* s4 = reinterpret_cast<const uint32_t*>(src);
+    uint32_t* d4 = reinterpret_cast<uint32_t*>(dst);
+    for (uint32_t i = lane; i < nw; i += 32) d4[i] = s4[i];
+  } else {
+    const uint32_t* s4 = reinterpret_cast<const uint32_t*>(src - (sh >> 3));
+    uint32_t* d4 = reinterpret_cast<uint32_t*>(dst);
+    for (uint32_t i = lane; i < nw; i += 32) d4[i] = __funnelshift_r(s4[i], s4[i + 1], sh);
+  }
+  uint32_t done = nw << 2;
+  uint32_t tail = n - done;
+  if (lane < tail) dst[done + lane] = src[done + lane];
+}
+
+__global__ void __launch_bounds__(128)
+gather_blocks_kernel(const EncBlock* __restrict__ blocks, const EncResult* __restrict__ results,
+                     const uint64_t* __restrict__ dst_off, uint32_t nblocks,
+                     const uint8_t* __restrict__ slots, uint8_t* __restrict__ out)
+{
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= nblocks) return;
+  const EncResult r = results[warp];
+  if (r.len_head + r.len_tail == 0) return;
+  const EncBlock b = blocks[warp];
+  uint8_t* d = out + dst_off[warp];
+  const uint8_t* slot = slots + b.slot_off;
+  warp_copy(d, slot, r.len_head, lane);
+  warp_copy(d + r.len_head, slot + b.slot_cap - r.len_tail, r.len_tail, lane);
+}
+
+__global__ void __launch_bounds__(128)
+assemble_kernel(const CopyPiece* __restrict__ pieces, uint32_t npieces, const uint8_t* __restrict__ slots,
+                const uint8_t* __restrict__ headers, uint8_t* __restrict__ out)
+{
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= npieces) return;
+  const CopyPiece p = pieces[warp];
+  const uint8_t* src = (p.src_sel ? headers : slots) + p.src_off;
+  warp_copy(out + p.dst_off, src, p.len, lane);
+}
+
+} // namespace
+
+void launch_gather_blocks(const EncBlock* blocks, const EncResult* results, const uint64_t* dst_off,
+                          uint32_t nblocks, const uint8_t* slots, uint8_t* out, cudaStream_t st)
+{
+  if (nblocks == 0) return;
+  dim3 grid((nblocks + 3) / 4), block(128);
+  OJB_LAUNCH(gather_blocks_kernel, grid, block, 0, st, blocks, results, dst_off, nblocks, slots, out);
+}
+
+void launch_assemble(const CopyPiece* pieces, uint32_t npieces, const uint8_t* slots,
+                     const uint8_t* headers, uint8_t* out, cudaStream_t st)
+{
+  if (npieces == 0) return;
+  dim3 grid((npieces + 3) / 4), block(128);
+  OJB_LAUNCH(assemble_kernel, grid, block, 0, st, pieces, npieces, slots, headers, out);
+}
+
+} // namespace ojb

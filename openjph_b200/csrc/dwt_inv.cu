@@ -1,0 +1,245 @@
+// dwt_inv.cu -- one inverse DWT level (5/3 int32 / 9/7 fp32) per launch, fused with what sits
+// either side of it on the reference's decode path:
+//   load    : LL + HL/LH/HH coefficient planes (already de-quantised by the block decoder's
+//             fused tx_from_cb32, src/core/codestream/ojph_codestream_gen.cpp:124-168)
+//   lifting : HORIZONTAL synthesis first, then vertical (resolution::pull_line,
+//             src/core/codestream/ojph_resolution.cpp:738-781 / :841-898; rev_horz_syn,
+//             rev_vert_step(synthesis), irv_* in src/core/transform/ojph_transform.cpp:514-849)
+//   top level: inverse RCT / ICT, level shift or float->int with rounding and clamping, store
+//             to the image in its container type (tile::pull, ojph_tile.cpp:425-516;
+//             rct_backward, ict_backward, rev_convert, irv_convert_to_integer in ojph_colour.cpp)
+// Same tiling as dwt_fwd.cu: a 128x32 output tile (+4 halo) per CTA in shared memory.
+#include "dwt_common.cuh"
+#include "ojb_kernels.h"
+
+namespace ojb {
+
+namespace {
+
+template <bool REV> struct PxI;
+template <> struct PxI<true>  { typedef int T; };
+template <> struct PxI<false> { typedef float T; };
+
+__device__ __forceinline__ void store_sample(void* img, uint32_t type, uint64_t byte_off, size_t idx, int v) {
+  unsigned char* base = reinterpret_cast<unsigned char*>(img) + byte_off;
+  if (type == SRC_U8) base[idx] = (unsigned char)min(max(v, 0), 255);
+  else if (type == SRC_U16) reinterpret_cast<unsigned short*>(base)[idx] = (unsigned short)min(max(v, 0), 65535);
+  else reinterpret_cast<int*>(base)[idx] = v;
+}
+
+// round half away from zero by truncation, as ojph_round does (ojph_arch.h:317-326)
+__device__ __forceinline__ int round_haz(float t) { return (int)(t + (t >= 0.0f ? 0.5f : -0.5f)); }
+
+template <bool REV>
+__global__ void __launch_bounds__(DW_THREADS)
+dwt_inv_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, void* __restrict__ image,
+               uint32_t* __restrict__ coef)
+{
+  typedef typename PxI<REV>::T T;
+  OJB_DYN_SMEM(T, smem);
+  __shared__ DwtJob sj;
+  {
+    uint32_t ji = find_job(jobs, njobs, blockIdx.x);
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(&jobs[ji]);
+    uint32_t* d = reinterpret_cast<uint32_t*>(&sj);
+    for (uint32_t i = threadIdx.x; i < sizeof(DwtJob) / 4; i += blockDim.x) d[i] = s[i];
+  }
+  __syncthreads();
+  const DwtJob& J = sj;
+  const uint32_t tid = threadIdx.x;
+  const uint32_t local = blockIdx.x - J.cta_base;
+  const uint32_t tx = local % J.tiles_x, ty = local / J.tiles_x;
+  const int x0 = (int)J.x0, y0 = (int)J.y0, x1 = x0 + (int)J.w, y1 = y0 + (int)J.h;
+  const int U0 = (x0 / DW_TW) * DW_TW + (int)tx * DW_TW;
+  const int V0 = (y0 / DW_TH) * DW_TH + (int)ty * DW_TH;
+  const uint32_t nc = J.ncomp;
+  const T* cf = reinterpret_cast<const T*>(coef);
+
+  // ---- load: interleave the four bands (mirrored coordinates at the borders)
+  for (uint32_t e = tid; e < DW_ROWS * DW_COLS; e += DW_THREADS) {
+    const uint32_t r = e / DW_COLS, c = e - r * DW_COLS;
+    const int u = reflect_coord(U0 - DW_H + (int)c, x0, x1 - 1);
+    const int v = reflect_coord(V0 - DW_H + (int)r, y0, y1 - 1);
+    for (uint32_t k = 0; k < nc; ++k) {
+      T val;
+      if (J.nodwt) {
+        val = cf[J.band_off[k][0] + (size_t)(v - y0) * J.band_stride[k][0] + (size_t)(u - x0)];
+      } else {
+        const int bh = u & 1, bv = v & 1, band = bh + 2 * bv;
+        const int bx = (u >> 1) - (bh ? (x0 >> 1) : ((x0 + 1) >> 1));
+        const int by = (v >> 1) - (bv ? (y0 >> 1) : ((y0 + 1) >> 1));
+        if (band == 0 && !J.last) val = cf[J.ll_off[k] + (size_t)by * J.ll_stride[k] + (size_t)bx];
+        else val = cf[J.band_off[k][band] + (size_t)by * J.band_stride[k][band] + (size_t)bx];
+      }
+      smem[k * DW_TILE_WORDS + r * DW_PITCH + c] = val;
+    }
+  }
+  __syncthreads();
+
+  if (!J.nodwt) {
+    const int NSTEPS = REV ? 2 : 4;
+    // ---- horizontal synthesis on every row (halo rows feed the vertical pass)
+    if (J.w > 1) {
+      if (!REV) {   // low * K, high * 1/K (irv_horz_syn, ojph_transform.cpp:797-809)
+        const float K = IRV_K, Kinv = 1.0f / IRV_K;
+        for (uint32_t k = 0; k < nc; ++k) {
+          T* t = smem + k * DW_TILE_WORDS;
+          for (uint32_t e = tid; e < DW_ROWS * DW_COLS; e += DW_THREADS) {
+            const uint32_t r = e / DW_COLS, c = e - r * DW_COLS;
+            t[r * DW_PITCH + c] = (T)__fmul_rn((float)t[r * DW_PITCH + c], (c & 1) ? Kinv : K);
+          }
+        }
+        __syncthreads();
+      }
+      for (int s = 1; s <= NSTEPS; ++s) {
+        // synthesis step s updates even positions for odd s, odd positions for even s
+        const int par = (s & 1) ? 0 : 1;
+        int cfirst = s; if ((cfirst & 1) != par) ++cfirst;
+        int clast = DW_COLS - 1 - s; if ((clast & 1) != par) --clast;
+        const int ncols = (clast - cfirst) / 2 + 1;
+        const int count = DW_ROWS * ncols;
+        for (uint32_t k = 0; k < nc; ++k) {
+          T* t = smem + k * DW_TILE_WORDS;
+          for (int e = (int)tid; e < count; e += DW_THREADS) {
+            const int r = e / ncols, j = e - r * ncols;
+            const int c = cfirst + 2 * j;
+            T d = t[r * DW_PITCH + c], a = t[r * DW_PITCH + c - 1], b = t[r * DW_PITCH + c + 1];
+            if (REV) {
+              if (s == 1) d = (T)((int)d - (((int)a + (int)b + 2) >> 2));
+              else d = (T)((int)d + (((int)a + (int)b) >> 1));
+            } else {
+              const float co = (s == 1) ? IRV_DELTA : (s == 2) ? IRV_GAMMA : (s == 3) ? IRV_BETA : IRV_ALPHA;
+              d = (T)__fadd_rn((float)d, __fmul_rn(-co, __fadd_rn((float)a, (float)b)));
+            }
+            t[r * DW_PITCH + c] = d;
+          }
+        }
+        __syncthreads();
+      }
+    } else if (x0 & 1) {   // single odd column: high-pass sample / 2
+      for (uint32_t k = 0; k < nc; ++k) {
+        T* t = smem + k * DW_TILE_WORDS;
+        for (uint32_t e = tid; e < DW_ROWS * DW_COLS; e += DW_THREADS) {
+          const uint32_t r = e / DW_COLS, c = e - r * DW_COLS;
+          t[r * DW_PITCH + c] = REV ? (T)((int)t[r * DW_PITCH + c] >> 1) : (T)__fmul_rn((float)t[r * DW_PITCH + c], 0.5f);
+        }
+      }
+      __syncthreads();
+    }
+    // ---- vertical synthesis on the columns this tile outputs
+    if (J.h > 1) {
+      if (!REV) {   // even rows * K, odd rows * 1/K (ojph_resolution.cpp:855-872)
+        const float K = IRV_K, Kinv = 1.0f / IRV_K;
+        for (uint32_t k = 0; k < nc; ++k) {
+          T* t = smem + k * DW_TILE_WORDS;
+          for (uint32_t e = tid; e < DW_ROWS * DW_TW; e += DW_THREADS) {
+            const uint32_t r = e / DW_TW, c = DW_H + (e - r * DW_TW);
+            t[r * DW_PITCH + c] = (T)__fmul_rn((float)t[r * DW_PITCH + c], (r & 1) ? Kinv : K);
+          }
+        }
+        __syncthreads();
+      }
+      for (int s = 1; s <= NSTEPS; ++s) {
+        const int par = (s & 1) ? 0 : 1;
+        int rfirst = s; if ((rfirst & 1) != par) ++rfirst;
+        int rlast = DW_ROWS - 1 - s; if ((rlast & 1) != par) --rlast;
+        const int count = ((rlast - rfirst) / 2 + 1) * DW_TW;
+        for (uint32_t k = 0; k < nc; ++k) {
+          T* t = smem + k * DW_TILE_WORDS;
+          for (int e = (int)tid; e < count; e += DW_THREADS) {
+            const int rr = e / DW_TW, c = DW_H + (e - rr * DW_TW);
+            const int r = rfirst + 2 * rr;
+            T d = t[r * DW_PITCH + c], a = t[(r - 1) * DW_PITCH + c], b = t[(r + 1) * DW_PITCH + c];
+            if (REV) {
+              if (s == 1) d = (T)((int)d - (((int)a + (int)b + 2) >> 2));
+              else d = (T)((int)d + (((int)a + (int)b) >> 1));
+            } else {
+              const float co = (s == 1) ? IRV_DELTA : (s == 2) ? IRV_GAMMA : (s == 3) ? IRV_BETA : IRV_ALPHA;
+              d = (T)__fadd_rn((float)d, __fmul_rn(-co, __fadd_rn((float)a, (float)b)));
+            }
+            t[r * DW_PITCH + c] = d;
+          }
+        }
+        __syncthreads();
+      }
+    } else if (y0 & 1) {   // single odd row: / 2 (ojph_resolution.cpp:814-827, :918-920)
+      for (uint32_t k = 0; k < nc; ++k) {
+        T* t = smem + k * DW_TILE_WORDS;
+        for (uint32_t e = tid; e < DW_ROWS * DW_COLS; e += DW_THREADS) {
+          const uint32_t r = e / DW_COLS, c = e - r * DW_COLS;
+          t[r * DW_PITCH + c] = REV ? (T)((int)t[r * DW_PITCH + c] >> 1) : (T)__fmul_rn((float)t[r * DW_PITCH + c], 0.5f);
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- store
+  for (uint32_t e = tid; e < DW_TH * DW_TW; e += DW_THREADS) {
+    const uint32_t rr = e / DW_TW, cc = e - rr * DW_TW;
+    const int r = DW_H + (int)rr, c = DW_H + (int)cc;
+    const int u = U0 + (int)cc, v = V0 + (int)rr;
+    if (u < x0 || u >= x1 || v < y0 || v >= y1) continue;
+    if (!J.first) {
+      reinterpret_cast<T*>(coef)[J.full_off[0] + (size_t)(v - y0) * J.full_stride[0] + (size_t)(u - x0)] =
+        smem[r * DW_PITCH + c];
+      continue;
+    }
+    int out[3];
+    if (REV) {
+      int a[3];
+      for (uint32_t k = 0; k < nc; ++k) a[k] = (int)smem[k * DW_TILE_WORDS + r * DW_PITCH + c];
+      if (nc == 3) {
+        int yy = a[0], cb = a[1], cr = a[2];
+        int gg = yy - ((cb + cr) >> 2);
+        a[0] = cr + gg; a[1] = gg; a[2] = cb + gg;
+      }
+      const int shift = J.is_signed ? 0 : (1 << (J.bit_depth - 1));
+      for (uint32_t k = 0; k < nc; ++k) out[k] = a[k] + shift;
+    } else {
+      float f[3];
+      for (uint32_t k = 0; k < nc; ++k) f[k] = (float)smem[k * DW_TILE_WORDS + r * DW_PITCH + c];
+      if (nc == 3) {
+        float yy = f[0], cb = f[1], cr = f[2];
+        f[1] = __fsub_rn(__fsub_rn(yy, __fmul_rn(ICT_GAMMA_CR2G, cr)), __fmul_rn(ICT_GAMMA_CB2G, cb));
+        f[0] = __fadd_rn(yy, __fmul_rn(ICT_GAMMA_CR2R, cr));
+        f[2] = __fadd_rn(yy, __fmul_rn(ICT_GAMMA_CB2B, cb));
+      }
+      // irv_convert_to_integer (ojph_colour.cpp:317-360): round, clamp to the B-bit range
+      const int B = (int)J.bit_depth;
+      const float mul = (float)(1ull << B);
+      const int lo = -(1 << (B - 1)), hi = (1 << (B - 1)) - 1;
+      const float flo = (float)lo, fhi = -(float)lo;
+      const int half = J.is_signed ? 0 : (1 << (B - 1));
+      for (uint32_t k = 0; k < nc; ++k) {
+        float t = __fmul_rn(f[k], mul);
+        int q = round_haz(t);
+        q = t >= flo ? q : lo;
+        q = t < fhi ? q : hi;
+        out[k] = q + half;
+      }
+    }
+    for (uint32_t k = 0; k < nc; ++k)
+      store_sample(image, J.src_type, J.full_off[k], (size_t)(v - y0) * J.full_stride[k] + (size_t)(u - x0), out[k]);
+  }
+}
+
+} // namespace
+
+void launch_dwt_inv(const DwtJob* jobs, uint32_t njobs, uint32_t total_ctas, bool reversible,
+                    uint32_t max_ncomp, void* image, uint32_t* coef, cudaStream_t st)
+{
+  if (total_ctas == 0) return;
+  size_t smem = (size_t)max_ncomp * DW_TILE_WORDS * 4;
+  if (reversible) {
+    auto k = dwt_inv_kernel<true>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    OJB_LAUNCH(k, dim3(total_ctas), dim3(DW_THREADS), smem, st, jobs, njobs, image, coef);
+  } else {
+    auto k = dwt_inv_kernel<false>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    OJB_LAUNCH(k, dim3(total_ctas), dim3(DW_THREADS), smem, st, jobs, njobs, image, coef);
+  }
+}
+
+} // namespace ojb

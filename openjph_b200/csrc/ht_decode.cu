@@ -1,0 +1,519 @@
+// ht_decode.cu -- HTJ2K block decoder for sm_100a: cleanup pass (+ SigProp + MagRef).
+//
+// Results are those of the reference's ojph_decode_codeblock32
+// (src/core/coding/ojph_block_decoder32.cpp:742-1612).  The work is split by its dependency
+// structure rather than by the reference's loop nest:
+//   step 1  MEL + VLC/U-VLC decoding is a strictly serial chain per code-block (each codeword's
+//           position and context depend on the previous one, :869-1089).  A warp cannot speed
+//           one chain up, so ONE THREAD decodes one code-block and a warp runs 32 chains at
+//           once; the per-quad records (rho, e_k, e_1, u) go to a scratch area.
+//   step 2  MagSgn decoding is parallel once bit positions are known: ONE WARP per code-block,
+//           lane i owns quad column i; the MagSgn segment is de-stuffed in parallel into a flat
+//           bit buffer (byte k contributes 7 bits iff byte k-1 is 0xFF), each quad-row does one
+//           warp scan of the per-quad bit counts and every lane extracts its own samples
+//           (:1091-1316).  Exponent prediction needs only the previous quad-row, kept in
+//           registers and exchanged with shuffles.
+//   SPP / MRP  (only present in streams from other encoders) run after step 2.
+// The de-quantisation the reference does line by line afterwards (tx_from_cb32,
+// src/core/codestream/ojph_codestream_gen.cpp:124-168) is fused into the final store.
+#include "ojb_device.h"
+#include "ojb_kernels.h"
+
+namespace ojb {
+
+#define FULL 0xFFFFFFFFu
+#define DEC_WARPS 4
+
+// block status bits
+#define DST_FAIL 1u
+
+namespace {
+
+struct DecTables {            // shared-memory copy
+  uint16_t vlc0[1024], vlc1[1024], uvlc0[320], uvlc1[256];
+};
+
+// ---- step 1 readers (thread-private) ------------------------------------------------------
+struct MelDec {
+  const uint8_t* p; int size; unsigned long long tmp; int bits; bool unstuff; int k;
+};
+__device__ __forceinline__ void mel_fill(MelDec& m) {       // keep >= 6 bits, MSB first
+  while (m.bits <= 56) {
+    uint32_t d = 0xFF;
+    if (m.size > 0) { d = *m.p++; if (m.size == 1) d |= 0xF; --m.size; }
+    int nb = 8 - (m.unstuff ? 1 : 0);
+    m.unstuff = (d == 0xFF);
+    d &= (1u << nb) - 1u;
+    m.tmp |= (unsigned long long)d << (64 - nb - m.bits);
+    m.bits += nb;
+  }
+}
+// one run: value 2*z+1 = z zero events then a one event; 2*z' (even) = z'+... see mel_decode
+// (:170-208): returns the reference's run code
+__device__ __forceinline__ int mel_next_run(MelDec& m) {
+  if (m.bits < 6) mel_fill(m);
+  const int eval = (int)((0x5433222111000ull >> (4 * m.k)) & 7ull);
+  int run;
+  if (m.tmp & (1ull << 63)) {
+    run = ((1 << eval) - 1) << 1;
+    m.k = m.k < 12 ? m.k + 1 : 12;
+    m.tmp <<= 1; m.bits -= 1;
+  } else {
+    run = (int)(m.tmp >> (63 - eval)) & ((1 << eval) - 1);
+    m.k = m.k > 0 ? m.k - 1 : 0;
+    m.tmp <<= eval + 1; m.bits -= eval + 1;
+    run = (run << 1) + 1;
+  }
+  return run;
+}
+
+struct RevDec {               // backward-growing stream (VLC)
+  const uint8_t* p; int size; unsigned long long tmp; uint32_t bits; bool unstuff;
+};
+__device__ __forceinline__ void rev_fill(RevDec& v) {       // keep >= 32 bits, LSB first
+  while (v.bits <= 56) {
+    uint32_t d = 0;
+    if (v.size > 0) { d = *v.p--; --v.size; }
+    uint32_t nb = 8 - ((v.unstuff && (d & 0x7F) == 0x7F) ? 1u : 0u);
+    v.unstuff = d > 0x8F;
+    d &= (1u << nb) - 1u;
+    v.tmp |= (unsigned long long)d << v.bits;
+    v.bits += nb;
+  }
+}
+
+__global__ void __launch_bounds__(128)
+ht_dec_step1_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
+                    const uint8_t* __restrict__ cs, uint32_t* __restrict__ scratch,
+                    const uint16_t* __restrict__ tables, uint32_t* __restrict__ block_status)
+{
+  __shared__ DecTables T;
+  {
+    uint16_t* d = reinterpret_cast<uint16_t*>(&T);
+    for (uint32_t i = threadIdx.x; i < sizeof(DecTables) / 2; i += blockDim.x) d[i] = tables[i];
+  }
+  __syncthreads();
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nblocks) return;
+  const DecBlock blk = blocks[b];
+  uint32_t np = blk.num_passes;
+  if (np == 0 || blk.len1 == 0) { block_status[b] = 0; return; }     // empty block: zero-filled later
+  // validity gates (:752-820)
+  if (np > 1 && blk.len2 == 0) np = 1;
+  bool ok = true;
+  if (np > 3 || blk.missing_msbs >= 30 || blk.len1 < 2) ok = false;
+  if (blk.missing_msbs == 29 && np > 1) np = 1;      // p == 1: refinement passes are skipped
+  const uint8_t* data = cs + blk.data_off;
+  int lcup = (int)blk.len1, scup = 0;
+  if (ok) {
+    scup = ((int)data[lcup - 1] << 4) + (data[lcup - 2] & 0xF);
+    if (scup < 2 || scup > lcup || scup > 4079) ok = false;
+  }
+  if (!ok || blk.w > 64) { block_status[b] = DST_FAIL; return; }
+
+  MelDec mel; mel.p = data + lcup - scup; mel.size = scup - 1; mel.tmp = 0; mel.bits = 0;
+  mel.unstuff = false; mel.k = 0;
+  RevDec vlc; vlc.p = data + lcup - 2; vlc.size = scup - 2;
+  {
+    uint32_t d = *vlc.p--;
+    vlc.tmp = d >> 4;
+    vlc.bits = 4 - (((vlc.tmp & 7) == 7) ? 1u : 0u);
+    vlc.unstuff = (d | 0xF) > 0x8F;
+  }
+  int run = mel_next_run(mel);
+
+  const uint32_t width = blk.w, height = blk.h;
+  const uint32_t nq = (width + 1) >> 1, qstride = (nq + 1) & ~1u;   // quads per row (even stride)
+  uint32_t* rec = scratch + blk.scratch_off;
+  uint32_t prev_bl = 0, prev_br = 0;      // bit q: bottom-left / bottom-right significance of the row above
+
+  for (uint32_t y = 0; y < height; y += 2) {
+    const uint16_t* vtab = y ? T.vlc1 : T.vlc0;
+    uint32_t cur_bl = 0, cur_br = 0, rho_left = 0;
+    uint32_t* rrow = rec + (size_t)(y >> 1) * qstride;
+    for (uint32_t q = 0; q < nq; q += 2) {
+      uint32_t t[2] = {0, 0};
+      #pragma unroll
+      for (uint32_t i = 0; i < 2; ++i) {
+        const uint32_t qq = q + i;
+        if (qq < nq) {
+          uint32_t c;
+          if (y == 0) c = (rho_left & 1) | (rho_left >> 1);
+          else {
+            const uint32_t a = (((prev_br << 1) >> qq) | (prev_bl >> qq)) & 1u;
+            const uint32_t l = ((rho_left >> 2) | (rho_left >> 3)) & 1u;
+            const uint32_t r = ((prev_br >> qq) | (qq < 31 ? (prev_bl >> (qq + 1)) : 0u)) & 1u;
+            c = a | (l << 1) | (r << 2);
+          }
+          rev_fill(vlc);
+          uint32_t e = vtab[(c << 7) | ((uint32_t)vlc.tmp & 0x7F)];
+          if (c == 0) {               // significance of an all-zero context comes from MEL
+            run -= 2;
+            if (run != -1) e = 0;
+            if (run < 0) run = mel_next_run(mel);
+          }
+          vlc.tmp >>= (e & 7); vlc.bits -= (e & 7);
+          t[i] = e;
+          rho_left = (e >> 4) & 15u;
+          cur_bl |= ((rho_left >> 1) & 1u) << qq;
+          cur_br |= ((rho_left >> 3) & 1u) << qq;
+        }
+      }
+      // U-VLC of the pair (:940-974 initial row, :1066-1085 others)
+      uint32_t mode = ((t[0] >> 3) & 1u) | (((t[1] >> 3) & 1u) << 1);
+      uint32_t ent;
+      rev_fill(vlc);
+      if (y == 0) {
+        if (mode == 3) {
+          run -= 2;
+          if (run == -1) mode = 4;
+          if (run < 0) run = mel_next_run(mel);
+        }
+        ent = T.uvlc0[(mode << 6) | ((uint32_t)vlc.tmp & 0x3F)];
+      } else
+        ent = T.uvlc1[(mode << 6) | ((uint32_t)vlc.tmp & 0x3F)];
+      vlc.tmp >>= (ent & 7); vlc.bits -= (ent & 7);
+      ent >>= 3;
+      uint32_t len = ent & 0xF;
+      uint32_t suf = (uint32_t)vlc.tmp & ((1u << len) - 1u);
+      vlc.tmp >>= len; vlc.bits -= len;
+      ent >>= 4;
+      len = ent & 7; ent >>= 3;
+      const uint32_t kap = (y == 0) ? 1u : 0u;
+      uint32_t u0 = kap + (ent & 7) + (suf & ~(0xFFu << len));
+      uint32_t u1 = kap + (ent >> 3) + (suf >> len);
+      rrow[q] = (t[0] & 0xFFFF) | (u0 << 16);
+      if (q + 1 < qstride) rrow[q + 1] = (t[1] & 0xFFFF) | (u1 << 16);
+    }
+    prev_bl = cur_bl; prev_br = cur_br;
+  }
+  block_status[b] = (np << 8);        // ok; effective number of passes for step 2
+}
+
+// ---- step 2 --------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t load_u32_unaligned(const uint8_t* p) {
+  const uint32_t* a = reinterpret_cast<const uint32_t*>((size_t)p & ~(size_t)3);
+  uint32_t sh = (uint32_t)((size_t)p & 3) * 8;
+  uint32_t lo = a[0];
+  if (sh == 0) return lo;
+  return __funnelshift_r(lo, a[1], sh);
+}
+
+// fetch 32 bits at bit position pos from a word buffer (words beyond nwords read as all ones)
+__device__ __forceinline__ uint32_t fetch_bits(const uint32_t* buf, uint32_t pos, uint32_t nwords) {
+  uint32_t wi = pos >> 5, sh = pos & 31;
+  uint32_t lo = wi < nwords ? buf[wi] : 0xFFFFFFFFu;
+  uint32_t hi = wi + 1 < nwords ? buf[wi + 1] : 0xFFFFFFFFu;
+  return __funnelshift_r(lo, hi, sh);
+}
+
+__device__ __forceinline__ uint32_t to_output(uint32_t sm, uint32_t mode, uint32_t shift, float delta) {
+  if (mode == DEC_OUT_SIGNMAG) return sm;
+  if (mode == DEC_OUT_INT) {
+    int v = (int)((sm & 0x7FFFFFFFu) >> shift);
+    return (uint32_t)((sm & 0x80000000u) ? -v : v);
+  }
+  float f = __fmul_rn((float)(sm & 0x7FFFFFFFu), delta);
+  return __float_as_uint(f) | (sm & 0x80000000u);
+}
+
+// simple byte-wise readers for the refinement passes (lane 0 only)
+struct FwdBits {              // SPP: forward, 0 fed when exhausted, 7-bit byte after 0xFF
+  const uint8_t* p; int size; unsigned long long tmp; uint32_t bits; bool unstuff;
+};
+__device__ __forceinline__ void fwd_fill(FwdBits& f) {
+  while (f.bits <= 56) {
+    uint32_t d = 0;
+    if (f.size > 0) { d = *f.p++; --f.size; }
+    uint32_t nb = 8 - (f.unstuff ? 1u : 0u);
+    f.unstuff = (d == 0xFF);
+    d &= (1u << nb) - 1u;
+    f.tmp |= (unsigned long long)d << f.bits; f.bits += nb;
+  }
+}
+__device__ __forceinline__ uint32_t fwd_get(FwdBits& f) {
+  if (f.bits == 0) fwd_fill(f);
+  uint32_t b = (uint32_t)f.tmp & 1u; f.tmp >>= 1; --f.bits; return b;
+}
+
+__device__ __forceinline__ uint32_t rec_rho(const uint32_t* rec, uint32_t qstride, uint32_t x, uint32_t y,
+                                            uint32_t width, uint32_t height) {
+  if (x >= width || y >= height) return 0;
+  uint32_t r = rec[(size_t)(y >> 1) * qstride + (x >> 1)];
+  return ((r >> 4) >> (2 * (x & 1) + (y & 1))) & 1u;
+}
+
+// SigProp + MagRef, serial restatement executed by one lane on the block's sign-magnitude
+// samples (ojph_block_decoder32.cpp:1318-1612)
+__device__ void refine_passes(const DecBlock& blk, uint32_t np, const uint8_t* data, uint32_t* dst,
+                              const uint32_t* rec, uint32_t qstride, uint32_t p)
+{
+  const uint32_t width = blk.w, height = blk.h, stride = blk.stride;
+  const bool causal = (blk.flags & 1) != 0;
+  // ---- significance propagation
+  {
+    FwdBits sp; sp.p = data + blk.len1; sp.size = (int)blk.len2; sp.tmp = 0; sp.bits = 0; sp.unstuff = false;
+    const uint32_t val = 3u << (p - 2);
+    for (uint32_t y0 = 0; y0 < height; y0 += 4) {
+      uint32_t prev_col = 0;    // final neighbourhood flags (rows 0..3) of the column left of the group
+      for (uint32_t x0 = 0; x0 < width; x0 += 4) {
+        // V(c, j): vertically integrated significance of column c at stripe row j, CUP-only
+        // for columns of this and the next group (plus row above: final, row below: CUP)
+        uint32_t V[6];           // columns x0-1 .. x0+4
+        uint32_t cs[4];
+        for (int ci = 0; ci < 5; ++ci) {
+          const uint32_t c = x0 + (uint32_t)ci;
+          uint32_t col = 0;
+          for (uint32_t j = 0; j < 4; ++j) col |= rec_rho(rec, qstride, c, y0 + j, width, height) << j;
+          if (ci < 4) cs[ci] = col;
+          uint32_t v = col | ((col & 7u) << 1) | ((col & 14u) >> 1);
+          if (c < width) {
+            if (y0 > 0 && dst[(size_t)(y0 - 1) * stride + c] != 0) v |= 1u;          // row above: final state
+            if (!causal && rec_rho(rec, qstride, c, y0 + 4, width, height)) v |= 8u;  // row below: CUP only
+          }
+          V[ci + 1] = v;
+        }
+        V[0] = prev_col;
+        uint32_t cand[4], newsig[4] = {0, 0, 0, 0};
+        uint32_t inside[4];
+        for (int i = 0; i < 4; ++i) {
+          uint32_t in = 0;
+          for (uint32_t j = 0; j < 4; ++j) if (x0 + i < width && y0 + j < height) in |= 1u << j;
+          inside[i] = in;
+          cand[i] = (V[i] | V[i + 1] | V[i + 2]) & in & ~cs[i];
+        }
+        uint32_t nnew = 0;
+        for (int i = 0; i < 4; ++i)
+          for (uint32_t j = 0; j < 4; ++j) {
+            if (!((cand[i] >> j) & 1u)) continue;
+            if (fwd_get(sp)) {
+              newsig[i] |= 1u << j; ++nnew;
+              // neighbours later in scan order become candidates (:1452-1492)
+              uint32_t own = (j < 3 ? (2u << j) : 0u);                         // sample below
+              uint32_t nxt = (1u << j) | (j ? (1u << (j - 1)) : 0u) | (j < 3 ? (2u << j) : 0u);
+              cand[i] |= own & inside[i] & ~cs[i];
+              if (i < 3) cand[i + 1] |= nxt & inside[i + 1] & ~cs[i + 1];
+            }
+          }
+        if (nnew)
+          for (int i = 0; i < 4; ++i)
+            for (uint32_t j = 0; j < 4; ++j)
+              if ((newsig[i] >> j) & 1u)
+                dst[(size_t)(y0 + j) * stride + x0 + i] = (fwd_get(sp) << 31) | val;
+        // state handed to the next group: last column, final significance, vertically integrated
+        {
+          uint32_t f = cs[3] | newsig[3];
+          uint32_t v = f | ((f & 7u) << 1) | ((f & 14u) >> 1);
+          v |= V[4] & 9u & ~0u;    // row-above / row-below contributions of that column
+          prev_col = v;
+        }
+      }
+    }
+  }
+  // ---- magnitude refinement
+  if (np > 2) {
+    RevDec mr; mr.p = data + blk.len1 + blk.len2 - 1; mr.size = (int)blk.len2; mr.tmp = 0; mr.bits = 0;
+    mr.unstuff = true;
+    const uint32_t half = 1u << (p - 2);
+    for (uint32_t y0 = 0; y0 < height; y0 += 4)
+      for (uint32_t x0 = 0; x0 < width; x0 += 8) {
+        for (uint32_t i = 0; i < 8; ++i)
+          for (uint32_t j = 0; j < 4; ++j) {
+            if (!rec_rho(rec, qstride, x0 + i, y0 + j, width, height)) continue;
+            if (mr.bits == 0) rev_fill(mr);
+            uint32_t sym = (uint32_t)mr.tmp & 1u; mr.tmp >>= 1; --mr.bits;
+            dst[(size_t)(y0 + j) * stride + x0 + i] ^= ((1u - sym) << (p - 1)) | half;
+          }
+      }
+  }
+}
+
+__global__ void __launch_bounds__(DEC_WARPS * 32)
+ht_dec_step2_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
+                    const uint8_t* __restrict__ cs, uint32_t* __restrict__ coef,
+                    uint32_t* __restrict__ scratch, uint32_t out_mode,
+                    uint32_t* __restrict__ block_status)
+{
+  __shared__ uint32_t s_stage[DEC_WARPS][40];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t b = blockIdx.x * DEC_WARPS + warp;
+  if (b >= nblocks) return;
+  const DecBlock blk = blocks[b];
+  const uint32_t width = blk.w, height = blk.h, stride = blk.stride;
+  uint32_t* dst = coef + blk.dst_off;
+  const uint32_t st = block_status[b];
+  const uint32_t np = st >> 8;
+  const uint32_t shift = 31u - blk.K_max;
+  const float delta = blk.delta;
+
+  bool fail = (st & DST_FAIL) != 0;
+  const bool empty = (np == 0) && !fail;
+  const uint32_t nq = (width + 1) >> 1, qstride = (nq + 1) & ~1u;
+  const uint32_t* rec = scratch + blk.scratch_off;
+  const uint32_t nqrows = (height + 1) >> 1;
+  uint32_t* msbuf = scratch + blk.scratch_off + (size_t)qstride * nqrows;   // de-stuffed MagSgn words
+  const uint32_t x = 2 * lane;
+  const bool has0 = x < width, has1 = x + 1 < width;
+  const uint32_t mmsbp2 = blk.missing_msbs + 2u;
+  const uint32_t p = 30u - blk.missing_msbs;
+
+  if (!fail && !empty) {
+    const uint8_t* data = cs + blk.data_off;
+    const int lcup = (int)blk.len1;
+    const int scup = ((int)data[lcup - 1] << 4) + (data[lcup - 2] & 0xF);
+    const uint32_t mslen = (uint32_t)(lcup - scup);
+    // ---- de-stuff the MagSgn segment: 128 raw bytes per step
+    uint32_t nbits_total = 0;           // bits written so far
+    uint32_t carry_word = 0;            // partial last word (bits nbits_total & 31)
+    bool prev_ff = false;
+    uint32_t* stage = s_stage[warp];
+    for (uint32_t base = 0; base < mslen; base += 128) {
+      const uint32_t off = base + 4 * lane;
+      uint32_t w = 0xFFFFFFFFu;
+      if (off < mslen) {
+        w = load_u32_unaligned(data + off);
+        if (off + 4 > mslen) w |= 0xFFFFFFFFu << (8 * (mslen - off));    // beyond the segment: 0xFF
+      }
+      const uint32_t lastb = w >> 24;
+      uint32_t pv = __shfl_up_sync(FULL, lastb, 1);
+      const bool pff = lane ? (pv == 0xFF) : prev_ff;
+      const uint32_t b0 = w & 0xFF, b1 = (w >> 8) & 0xFF, b2 = (w >> 16) & 0xFF, b3 = w >> 24;
+      const uint32_t n0 = 8 - (pff ? 1u : 0u), n1 = 8 - (b0 == 0xFF ? 1u : 0u),
+                     n2 = 8 - (b1 == 0xFF ? 1u : 0u), n3 = 8 - (b2 == 0xFF ? 1u : 0u);
+      uint32_t t = b0 & ((1u << n0) - 1u);
+      t |= (b1 & ((1u << n1) - 1u)) << n0;
+      t |= (b2 & ((1u << n2) - 1u)) << (n0 + n1);
+      t |= (b3 & ((1u << n3) - 1u)) << (n0 + n1 + n2);
+      uint32_t n = (off < mslen) ? (n0 + n1 + n2 + n3) : 0u;
+      if (off < mslen && off + 4 > mslen) {           // partial last word: count only real bytes
+        const uint32_t k = mslen - off;
+        n = n0 + (k > 1 ? n1 : 0) + (k > 2 ? n2 : 0);
+        t &= (n < 32) ? ((1u << n) - 1u) : 0xFFFFFFFFu;
+      }
+      uint32_t incl = n;
+      #pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(FULL, incl, d); if ((int)lane >= d) incl += o; }
+      const uint32_t tot = __shfl_sync(FULL, incl, 31);
+      const uint32_t cb = nbits_total & 31;
+      // stage: carry bits then this chunk's bits
+      for (uint32_t i = lane; i < 36; i += 32) stage[i] = 0;
+      __syncwarp();
+      if (lane == 0) stage[0] = carry_word;
+      __syncwarp();
+      if (n) {
+        const uint32_t o = cb + incl - n;
+        const unsigned long long v = (unsigned long long)t << (o & 31);
+        atomicOr(&stage[o >> 5], (uint32_t)v);
+        if ((uint32_t)(v >> 32)) atomicOr(&stage[(o >> 5) + 1], (uint32_t)(v >> 32));
+      }
+      __syncwarp();
+      const uint32_t nb = cb + tot, nw = nb >> 5;
+      uint32_t* o32 = msbuf + (nbits_total >> 5);
+      for (uint32_t i = lane; i < nw; i += 32) o32[i] = stage[i];
+      carry_word = stage[nw];
+      __syncwarp();
+      nbits_total += tot;
+      // last real byte of this chunk decides the stuffing of the next chunk's first byte
+      const uint32_t last_off = min(mslen, base + 128) - 1 - base;     // byte index within the chunk
+      const uint32_t wsrc = __shfl_sync(FULL, w, last_off >> 2);
+      prev_ff = ((wsrc >> (8 * (last_off & 3))) & 0xFF) == 0xFF;
+    }
+    // tail: remaining bits + ones (an exhausted MagSgn stream reads as 0xFF bytes)
+    const uint32_t ms_words = (nbits_total >> 5) + 1;
+    if (lane == 0) msbuf[nbits_total >> 5] = carry_word | ((nbits_total & 31) ? (0xFFFFFFFFu << (nbits_total & 31)) : 0xFFFFFFFFu);
+    __syncwarp();
+
+    // ---- quad rows
+    uint32_t pos = 0;                       // MagSgn bit position
+    uint32_t pv1 = 0, pv3 = 0;              // v_n of bottom-left / bottom-right sample of the row above
+    for (uint32_t y = 0; y < height; y += 2) {
+      const uint32_t r = (lane < nq) ? rec[(size_t)(y >> 1) * qstride + lane] : 0;
+      const uint32_t inf = r & 0xFFFF, uq = r >> 16;
+      const uint32_t rho = (inf >> 4) & 15u;
+      uint32_t Uq;
+      if (y == 0) Uq = uq;
+      else {
+        uint32_t l = __shfl_up_sync(FULL, pv3, 1); if (lane == 0) l = 0;
+        uint32_t rr = __shfl_down_sync(FULL, pv1, 1); if (lane == 31) rr = 0;
+        const uint32_t emax = 31u - (uint32_t)__clz((int)((l | pv1 | pv3 | rr) | 2u));
+        const uint32_t kappa = (rho & (rho - 1)) ? emax : 1u;
+        Uq = uq + kappa;
+      }
+      if (__any_sync(FULL, (lane < nq) && Uq > mmsbp2)) { fail = true; break; }
+      const uint32_t ek = inf >> 12, e1 = (inf >> 8) & 15u;
+      uint32_t m[4];
+      #pragma unroll
+      for (int i = 0; i < 4; ++i) m[i] = ((rho >> i) & 1u) ? Uq - ((ek >> i) & 1u) : 0u;
+      const uint32_t mine = (lane < nq) ? (m[0] + m[1] + m[2] + m[3]) : 0u;
+      uint32_t incl = mine;
+      #pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(FULL, incl, d); if ((int)lane >= d) incl += o; }
+      const uint32_t tot = __shfl_sync(FULL, incl, 31);
+      uint32_t bp = pos + incl - mine;
+      uint32_t out[4], vn[4];
+      #pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        out[i] = 0; vn[i] = 0;
+        if ((rho >> i) & 1u) {
+          const uint32_t ms = fetch_bits(msbuf, bp, ms_words);
+          bp += m[i];
+          uint32_t v = ms & ((1u << m[i]) - 1u);
+          v |= ((e1 >> i) & 1u) << m[i];
+          v |= 1u;
+          vn[i] = v;
+          out[i] = (ms << 31) | ((v + 2u) << (p - 1));
+        }
+      }
+      pos += tot;
+      pv1 = vn[1]; pv3 = vn[3];
+      const uint32_t om = (np > 1) ? (uint32_t)DEC_OUT_SIGNMAG : out_mode;
+      uint32_t* r0 = dst + (size_t)y * stride;
+      if (has0) r0[x] = to_output(out[0], om, shift, delta);
+      if (has1) r0[x + 1] = to_output(out[2], om, shift, delta);
+      if (y + 1 < height) {
+        uint32_t* r1 = r0 + stride;
+        if (has0) r1[x] = to_output(out[1], om, shift, delta);
+        if (has1) r1[x + 1] = to_output(out[3], om, shift, delta);
+      }
+    }
+
+    if (!fail && np > 1) {
+      __syncwarp();
+      __threadfence_block();
+      if (lane == 0) refine_passes(blk, np, data, dst, rec, qstride, p);
+      __syncwarp();
+      __threadfence_block();
+      if (out_mode != DEC_OUT_SIGNMAG)
+        for (uint32_t yy = 0; yy < height; ++yy)
+          for (uint32_t xx = lane; xx < width; xx += 32) {
+            uint32_t* q = dst + (size_t)yy * stride + xx;
+            *q = to_output(*q, out_mode, shift, delta);
+          }
+    }
+  }
+
+  if (fail || empty) {                      // not decodable / not included: a block of zeros
+    for (uint32_t yy = 0; yy < height; ++yy)
+      for (uint32_t xx = lane; xx < width; xx += 32) dst[(size_t)yy * stride + xx] = 0;
+    if (lane == 0) block_status[b] = fail ? DST_FAIL : 0u;
+  } else if (lane == 0) block_status[b] = 0;
+}
+
+} // namespace
+
+void launch_ht_decode(const DecBlock* blocks, uint32_t nblocks, const uint8_t* codestream,
+                      uint32_t* coef, uint32_t* scratch, const uint16_t* tables, uint32_t out_mode,
+                      uint32_t* block_status, cudaStream_t st)
+{
+  if (nblocks == 0) return;
+  {
+    dim3 grid((nblocks + 127) / 128), block(128);
+    OJB_LAUNCH(ht_dec_step1_kernel, grid, block, 0, st, blocks, nblocks, codestream, scratch, tables, block_status);
+  }
+  {
+    dim3 grid((nblocks + DEC_WARPS - 1) / DEC_WARPS), block(DEC_WARPS * 32);
+    OJB_LAUNCH(ht_dec_step2_kernel, grid, block, 0, st, blocks, nblocks, codestream, coef, scratch, out_mode, block_status);
+  }
+}
+
+} // namespace ojb

@@ -1,0 +1,321 @@
+// ojb_capi.cpp -- the extern "C" surface declared in include/ojph_b200.h.
+#include "../../include/ojph_b200.h"
+#include "ojb_codec.h"
+#include "ht_tables.h"
+#include <cstring>
+#include <new>
+
+using namespace ojb;
+
+struct ojb_encoder { Encoder enc; bool configured = false; };
+struct ojb_decoder { Decoder dec; bool have_headers = false; };
+
+static thread_local char g_err[1024] = "";
+
+template <typename F> static int guarded(F&& f) {
+  try { f(); return 0; }
+  catch (const Error& e) { snprintf(g_err, sizeof(g_err), "%s", e.what()); return -(int)((e.code >> 16) ? (e.code >> 16) : 1); }
+  catch (const std::bad_alloc&) { snprintf(g_err, sizeof(g_err), "ojph error: out of memory"); return -1000; }
+  catch (const std::exception& e) { snprintf(g_err, sizeof(g_err), "%s", e.what()); return -1001; }
+  catch (...) { snprintf(g_err, sizeof(g_err), "ojph error: unknown exception"); return -1002; }
+}
+
+static void to_params(const ojb_params* s, Params& P) {
+  if (s->num_comps == 0 || s->num_comps > 16) fail(0x00040005, "wrong number of components");
+  P = Params();
+  P.Xsiz = s->width; P.Ysiz = s->height; P.XOsiz = s->off_x; P.YOsiz = s->off_y;
+  P.XTsiz = s->tile_w; P.YTsiz = s->tile_h; P.XTOsiz = s->tile_off_x; P.YTOsiz = s->tile_off_y;
+  P.comps.resize(s->num_comps);
+  for (uint32_t c = 0; c < s->num_comps; ++c) {
+    if (s->bit_depth[c] == 0 || s->bit_depth[c] > 32) fail(0x00040006, "wrong bit depth");
+    if (s->dx[c] == 0 || s->dy[c] == 0 || s->dx[c] > 255 || s->dy[c] > 255) fail(0x00040007, "wrong component sub-sampling");
+    P.comps[c].bit_depth = (uint8_t)s->bit_depth[c]; P.comps[c].is_signed = s->is_signed[c] != 0;
+    P.comps[c].dx = (uint8_t)s->dx[c]; P.comps[c].dy = (uint8_t)s->dy[c];
+  }
+  if (s->num_decomps > 32) fail(0x00050001, "maximum number of decompositions cannot exceed 32");
+  P.num_decomps = (uint8_t)s->num_decomps;
+  P.set_block_dims(s->block_w, s->block_h);
+  if (s->num_precincts) P.set_precincts((int)s->num_precincts, s->precinct_w, s->precinct_h);
+  if (s->prog_order > 4) fail(0x00050031, "unknown progression order");
+  P.prog_order = (uint8_t)s->prog_order;
+  P.mc_trans = s->color_transform ? 1 : 0;
+  P.wavelet = s->reversible ? DWT_REV53 : DWT_IRV97;
+  if (!s->reversible) {
+    if (s->qstep > 0.0f) P.qcd.base_delta = s->qstep;
+    if (s->qfactor) {
+      if (s->qfactor > 100) fail(0x00050181, "Qfactor must be between 1 and 100, but was set to %i.", s->qfactor);
+      P.qcd.qfactor = (uint8_t)s->qfactor;
+    }
+  }
+  P.need_tlm = s->tlm != 0;
+  P.tilepart_div = s->tilepart_div & 3u;
+  P.planar = s->planar;
+}
+
+extern "C" {
+
+const char* ojb_last_error(void) { return g_err; }
+const char* ojb_version(void) { return "openjph_b200 0.1 (HTJ2K hot path of OpenJPH 0.31.0 on sm_100a)"; }
+
+int ojb_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
+int ojb_set_device(int device) { return guarded([&] { cuda_check(cudaSetDevice(device), "cudaSetDevice"); }); }
+
+void ojb_params_default(ojb_params* p) {
+  memset(p, 0, sizeof(*p));
+  p->num_comps = 1; p->bit_depth[0] = 8;
+  for (int c = 0; c < 16; ++c) { p->dx[c] = 1; p->dy[c] = 1; p->bit_depth[c] = 8; }
+  p->num_decomps = 5; p->block_w = 64; p->block_h = 64; p->prog_order = 2; p->planar = -1;
+  p->qstep = -1.0f;
+}
+
+void* ojb_host_alloc(uint64_t bytes) { void* p = nullptr; if (cudaMallocHost(&p, (size_t)bytes) != cudaSuccess) return nullptr; return p; }
+void ojb_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+ojb_encoder* ojb_enc_create(void) {
+  ojb_encoder* e = nullptr;
+  guarded([&] { e = new ojb_encoder(); });
+  return e;
+}
+void ojb_enc_destroy(ojb_encoder* e) { delete e; }
+
+int ojb_enc_configure(ojb_encoder* e, const ojb_params* p, uint32_t sample_type) {
+  return guarded([&] {
+    if (sample_type > 2) fail(0x000B0012, "unknown sample container");
+    Params P; to_params(p, P);
+    e->enc.configure(P, sample_type);
+    e->configured = true;
+  });
+}
+
+int32_t* ojb_enc_exchange(ojb_encoder* e, int32_t* line, uint32_t* next_comp) {
+  int32_t* r = nullptr;
+  guarded([&] {
+    if (!e->configured) fail(0x000B0013, "encoder is not configured");
+    uint32_t nc = 0; r = e->enc.exchange(line, nc); if (next_comp) *next_comp = nc;
+  });
+  return r;
+}
+
+int ojb_enc_flush(ojb_encoder* e, uint8_t* out, uint64_t out_cap, uint64_t* out_len) {
+  return guarded([&] {
+    if (!e->configured) fail(0x000B0013, "encoder is not configured");
+    Encoder& E = e->enc;
+    uint32_t nc = E.params.num_comps();
+    std::vector<const void*> pl(nc);
+    // exchanged lines are si32; convert by temporarily treating the frame as an I32 image
+    size_t o = 0;
+    std::vector<uint32_t> w(nc), h(nc);
+    for (uint32_t c = 0; c < nc; ++c) { w[c] = E.params.comp_width(c); h[c] = E.params.comp_height(c); }
+    if (E.img_type != ST_I32) fail(0x000B0016, "the line interface needs the 32-bit sample container (OJB_I32)");
+    for (uint32_t c = 0; c < nc; ++c) { pl[c] = E.h_frame.as<int32_t>() + o; o += (size_t)w[c] * h[c]; }
+    *out_len = E.encode(pl.data(), nullptr, false, out, (size_t)out_cap, false);
+  });
+}
+
+int ojb_enc_encode_frame(ojb_encoder* e, const void* const* planes, const uint32_t* strides,
+                         uint8_t* out, uint64_t out_cap, uint64_t* out_len) {
+  return guarded([&] {
+    if (!e->configured) fail(0x000B0013, "encoder is not configured");
+    *out_len = e->enc.encode(planes, strides, false, out, (size_t)out_cap, false);
+  });
+}
+
+} // extern "C"
+
+// device-side accessors
+namespace ojb {
+static void* img_plane(CodecBase& cb, uint32_t c) { return cb.d_image.as<uint8_t>() + cb.img_off[c]; }
+static void upload_frame(Encoder& E, const void* const* planes, const uint32_t* strides) {
+  uint32_t es = E.img_type == ST_U8 ? 1u : (E.img_type == ST_U16 ? 2u : 4u);
+  for (uint32_t c = 0; c < E.params.num_comps(); ++c) {
+    uint8_t* d = E.d_image.as<uint8_t>() + E.img_off[c];
+    uint32_t st = strides ? strides[c] : E.img_w[c];
+    if (st == E.img_w[c])
+      cuda_check(cudaMemcpyAsync(d, planes[c], (size_t)E.img_w[c] * E.img_h[c] * es, cudaMemcpyHostToDevice, E.stream), "upload");
+    else
+      for (uint32_t y = 0; y < E.img_h[c]; ++y)
+        cuda_check(cudaMemcpyAsync(d + (size_t)y * E.img_w[c] * es, (const uint8_t*)planes[c] + (size_t)y * st * es,
+                                   (size_t)E.img_w[c] * es, cudaMemcpyHostToDevice, E.stream), "upload");
+  }
+  cuda_check(cudaStreamSynchronize(E.stream), "upload sync");
+}
+static void read_band(CodecBase& cb, uint32_t tile, uint32_t comp, uint32_t res, uint32_t band, uint32_t* out,
+                      uint32_t* bw, uint32_t* bh) {
+  if (tile >= cb.layout.tiles.size() || comp >= cb.params.num_comps() || res > cb.params.num_decomps || band > 3)
+    fail(0x000B0014, "no such sub-band");
+  const BandGeom& bg = cb.layout.tiles[tile].comps[comp].res[res].bands[band];
+  *bw = bg.rect.w; *bh = bg.rect.h;
+  if (bg.empty || out == nullptr) return;
+  for (uint32_t y = 0; y < bg.rect.h; ++y)
+    cuda_check(cudaMemcpy(out + (size_t)y * bg.rect.w,
+                          cb.d_coef.as<uint32_t>() + bg.plane_off + bg.plane_pad_x + (size_t)y * bg.plane_stride,
+                          (size_t)bg.rect.w * 4, cudaMemcpyDeviceToHost), "read_band");
+}
+}
+
+extern "C" {
+
+void* ojb_enc_device_plane(ojb_encoder* e, uint32_t comp) {
+  if (!e->configured || comp >= e->enc.params.num_comps()) return nullptr;
+  return img_plane(e->enc, comp);
+}
+int ojb_enc_upload_frame(ojb_encoder* e, const void* const* planes, const uint32_t* strides) {
+  return guarded([&] {
+    if (!e->configured) fail(0x000B0013, "encoder is not configured");
+    upload_frame(e->enc, planes, strides);
+  });
+}
+int ojb_enc_encode_resident(ojb_encoder* e, uint8_t* out, uint64_t out_cap, uint64_t* out_len, int out_on_device) {
+  return guarded([&] {
+    if (!e->configured) fail(0x000B0013, "encoder is not configured");
+    *out_len = e->enc.encode(nullptr, nullptr, true, out, (size_t)out_cap, out_on_device != 0);
+  });
+}
+uint32_t ojb_enc_kernel_launches(ojb_encoder* e) { return e->enc.last_launches; }
+uint32_t ojb_enc_num_blocks(ojb_encoder* e) { return e->configured ? e->enc.layout.num_blocks : 0; }
+int ojb_enc_read_band(ojb_encoder* e, uint32_t tile, uint32_t comp, uint32_t res, uint32_t band,
+                      uint32_t* out, uint32_t* band_w, uint32_t* band_h) {
+  return guarded([&] {
+    if (!e->configured) fail(0x000B0013, "encoder is not configured");
+    read_band(e->enc, tile, comp, res, band, out, band_w, band_h);
+  });
+}
+
+ojb_decoder* ojb_dec_create(void) {
+  ojb_decoder* d = nullptr;
+  guarded([&] { d = new ojb_decoder(); });
+  return d;
+}
+void ojb_dec_destroy(ojb_decoder* d) { delete d; }
+int ojb_dec_enable_resilience(ojb_decoder* d) { d->dec.resilient = true; return 0; }
+
+int ojb_dec_read_headers(ojb_decoder* d, const uint8_t* j2c, uint64_t len, uint32_t sample_type,
+                         ojb_frame_info* info) {
+  return guarded([&] {
+    if (sample_type > 2) fail(0x000B0012, "unknown sample container");
+    d->dec.read_headers(j2c, (size_t)len, sample_type);
+    d->have_headers = true;
+    if (info) {
+      FrameInfo fi; d->dec.info(fi);
+      static_assert(sizeof(FrameInfo) == sizeof(ojb_frame_info), "frame info layout");
+      memcpy(info, &fi, sizeof(fi));
+    }
+  });
+}
+int ojb_dec_decode_frame(ojb_decoder* d, void* const* planes, const uint32_t* strides) {
+  return guarded([&] {
+    if (!d->have_headers) fail(0x000B0015, "read_headers has not been called");
+    d->dec.decode(planes, strides, false);
+  });
+}
+int ojb_dec_decode_resident(ojb_decoder* d) {
+  return guarded([&] {
+    if (!d->have_headers) fail(0x000B0015, "read_headers has not been called");
+    d->dec.decode(nullptr, nullptr, true);
+  });
+}
+void* ojb_dec_device_plane(ojb_decoder* d, uint32_t comp) {
+  if (!d->have_headers || comp >= d->dec.params.num_comps()) return nullptr;
+  return img_plane(d->dec, comp);
+}
+uint32_t ojb_dec_failed_blocks(ojb_decoder* d) { return d->dec.failed_blocks; }
+uint32_t ojb_dec_kernel_launches(ojb_decoder* d) { return d->dec.last_launches; }
+int ojb_dec_read_band(ojb_decoder* d, uint32_t tile, uint32_t comp, uint32_t res, uint32_t band,
+                      uint32_t* out, uint32_t* band_w, uint32_t* band_h) {
+  return guarded([&] {
+    if (!d->have_headers) fail(0x000B0015, "read_headers has not been called");
+    read_band(d->dec, tile, comp, res, band, out, band_w, band_h);
+  });
+}
+
+// ---- kernel-level batch entry points ------------------------------------------------------
+int ojb_encode_blocks(const uint32_t* samples, uint64_t n_words, ojb_block_desc* desc, uint32_t n,
+                      uint8_t* bytes, uint64_t bytes_cap, uint64_t* bytes_used) {
+  return guarded([&] {
+    const HtTables& t = ht_tables();
+    std::vector<uint16_t> tb(2 * 2048 + 36, 0);
+    memcpy(tb.data(), t.enc_vlc, sizeof(t.enc_vlc));
+    memcpy(tb.data() + 2 * 2048, t.enc_uvlc, sizeof(t.enc_uvlc));
+    DeviceBuf d_s, d_b, d_r, d_t, d_sl, d_st;
+    d_s.reserve((n_words + 64) * 4);
+    cuda_check(cudaMemcpy(d_s.p, samples, n_words * 4, cudaMemcpyHostToDevice), "samples");
+    d_t.reserve(tb.size() * 2);
+    cuda_check(cudaMemcpy(d_t.p, tb.data(), tb.size() * 2, cudaMemcpyHostToDevice), "tables");
+    std::vector<EncBlock> eb(n);
+    uint64_t slot = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+      if (desc[i].w == 0 || desc[i].h == 0 || desc[i].w > 64 || desc[i].w * desc[i].h > 4096 || desc[i].missing_msbs > 29)
+        fail(0x000B0021, "unsupported code-block geometry");
+      eb[i].src_off = desc[i].sample_off; eb[i].stride = desc[i].stride; eb[i].w = (uint16_t)desc[i].w; eb[i].h = (uint16_t)desc[i].h;
+      eb[i].p = (uint16_t)(30u - desc[i].missing_msbs);
+      uint64_t kmax = desc[i].missing_msbs + 1;
+      uint64_t ms = ((uint64_t)desc[i].w * desc[i].h * (kmax + 1) + 7) / 8; ms += ms / 15 + 8;
+      uint64_t nq = (uint64_t)((desc[i].w + 1) / 2) * ((desc[i].h + 1) / 2);
+      uint64_t vl = ((nq + 1) / 2 * 30 + 12 + 7) / 8; vl += vl / 7 + 8;
+      uint64_t cap = (ms + vl + 192 + 160 + 15) & ~(uint64_t)15;
+      eb[i].slot_off = slot; eb[i].slot_cap = (uint32_t)cap; slot += cap;
+    }
+    d_b.reserve(n * sizeof(EncBlock)); d_r.reserve(n * sizeof(EncResult)); d_sl.reserve(slot + 64); d_st.reserve(64);
+    cuda_check(cudaMemcpy(d_b.p, eb.data(), n * sizeof(EncBlock), cudaMemcpyHostToDevice), "blocks");
+    cuda_check(cudaMemset(d_st.p, 0, 16), "status");
+    launch_ht_encode(d_b.as<EncBlock>(), n, d_s.as<uint32_t>(), d_sl.as<uint8_t>(), d_r.as<EncResult>(),
+                     d_t.as<uint16_t>(), d_st.as<uint32_t>(), 0);
+    cuda_check(cudaDeviceSynchronize(), "ht_encode");
+    cuda_check(cudaGetLastError(), "ht_encode");
+    std::vector<EncResult> res(n);
+    cuda_check(cudaMemcpy(res.data(), d_r.p, n * sizeof(EncResult), cudaMemcpyDeviceToHost), "results");
+    std::vector<uint8_t> sl(slot);
+    cuda_check(cudaMemcpy(sl.data(), d_sl.p, slot, cudaMemcpyDeviceToHost), "slots");
+    uint64_t pos = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+      uint32_t len = res[i].len_head + res[i].len_tail;
+      desc[i].byte_off = pos; desc[i].len1 = len; desc[i].len2 = 0; desc[i].status = len ? 0 : 1;
+      if (pos + len > bytes_cap) fail(0x000B0030, "output buffer too small");
+      memcpy(bytes + pos, sl.data() + eb[i].slot_off, res[i].len_head);
+      memcpy(bytes + pos + res[i].len_head, sl.data() + eb[i].slot_off + eb[i].slot_cap - res[i].len_tail, res[i].len_tail);
+      pos += len;
+    }
+    *bytes_used = pos;
+  });
+}
+
+int ojb_decode_blocks(const uint8_t* bytes, uint64_t n_bytes, ojb_block_desc* desc, uint32_t n,
+                      uint32_t* samples, uint64_t n_words) {
+  return guarded([&] {
+    const HtTables& t = ht_tables();
+    std::vector<uint16_t> tb(1024 * 2 + 320 + 256);
+    memcpy(tb.data(), t.dec_vlc, sizeof(t.dec_vlc));
+    memcpy(tb.data() + 2048, t.dec_uvlc0, sizeof(t.dec_uvlc0));
+    memcpy(tb.data() + 2048 + 320, t.dec_uvlc1, sizeof(t.dec_uvlc1));
+    DeviceBuf d_cs, d_b, d_t, d_o, d_sc, d_st;
+    d_cs.reserve(n_bytes + 64);
+    cuda_check(cudaMemset(d_cs.p, 0, d_cs.cap), "cs");
+    cuda_check(cudaMemcpy(d_cs.p, bytes, n_bytes, cudaMemcpyHostToDevice), "cs");
+    d_t.reserve(tb.size() * 2);
+    cuda_check(cudaMemcpy(d_t.p, tb.data(), tb.size() * 2, cudaMemcpyHostToDevice), "tables");
+    std::vector<DecBlock> db(n);
+    size_t scratch = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+      DecBlock& d = db[i]; memset(&d, 0, sizeof(d));
+      d.data_off = desc[i].byte_off; d.dst_off = desc[i].sample_off; d.stride = desc[i].stride;
+      d.w = (uint16_t)desc[i].w; d.h = (uint16_t)desc[i].h; d.len1 = desc[i].len1; d.len2 = desc[i].len2;
+      d.missing_msbs = (uint8_t)desc[i].missing_msbs; d.num_passes = (uint8_t)desc[i].num_passes;
+      d.K_max = (uint8_t)(desc[i].missing_msbs + 1); d.flags = desc[i].causal ? 1 : 0;
+      uint32_t nq = (d.w + 1u) / 2, qs = (nq + 1) & ~1u, nqr = (d.h + 1u) / 2;
+      d.scratch_off = scratch; scratch += (size_t)qs * nqr + (d.len1 + 3) / 4 + 4;
+    }
+    d_b.reserve(n * sizeof(DecBlock)); d_o.reserve((n_words + 64) * 4); d_sc.reserve((scratch + 64) * 4); d_st.reserve(n * 4 + 16);
+    cuda_check(cudaMemcpy(d_b.p, db.data(), n * sizeof(DecBlock), cudaMemcpyHostToDevice), "blocks");
+    cuda_check(cudaMemcpy(d_o.p, samples, n_words * 4, cudaMemcpyHostToDevice), "out init");
+    launch_ht_decode(d_b.as<DecBlock>(), n, d_cs.as<uint8_t>(), d_o.as<uint32_t>(), d_sc.as<uint32_t>(),
+                     d_t.as<uint16_t>(), DEC_OUT_SIGNMAG, d_st.as<uint32_t>(), 0);
+    cuda_check(cudaDeviceSynchronize(), "ht_decode");
+    cuda_check(cudaGetLastError(), "ht_decode");
+    cuda_check(cudaMemcpy(samples, d_o.p, n_words * 4, cudaMemcpyDeviceToHost), "samples");
+    std::vector<uint32_t> st(n);
+    cuda_check(cudaMemcpy(st.data(), d_st.p, n * 4, cudaMemcpyDeviceToHost), "status");
+    for (uint32_t i = 0; i < n; ++i) desc[i].status = st[i] & 1u;
+  });
+}
+
+} // extern "C"

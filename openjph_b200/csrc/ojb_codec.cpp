@@ -1,0 +1,591 @@
+// ojb_codec.cpp -- host orchestration of the B200 HTJ2K path (see ojb_codec.h).
+#include "ojb_codec.h"
+#include "ht_tables.h"
+#include <algorithm>
+#include <cstring>
+
+namespace ojb {
+
+void cuda_check(cudaError_t e, const char* what) {
+  if (e != cudaSuccess) fail(0x000B00C0, "CUDA failure in %s: %s", what, cudaGetErrorString(e));
+}
+#define CK(x) cuda_check((x), #x)
+
+DeviceBuf::~DeviceBuf() { if (p) cudaFree(p); }
+void DeviceBuf::reserve(size_t n) {
+  if (n <= cap) return;
+  if (p) { cudaFree(p); p = nullptr; cap = 0; }
+  size_t want = (n + 255) & ~(size_t)255;
+  CK(cudaMalloc(&p, want));
+  cap = want;
+}
+PinnedBuf::~PinnedBuf() { if (p) cudaFreeHost(p); }
+void PinnedBuf::reserve(size_t n) {
+  if (n <= cap) return;
+  if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+  size_t want = (n + 4095) & ~(size_t)4095;
+  CK(cudaMallocHost(&p, want));
+  cap = want;
+}
+
+CodecBase::CodecBase() { CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)); }
+CodecBase::~CodecBase() { if (stream) cudaStreamDestroy(stream); }
+
+void CodecBase::upload_tables() {
+  const HtTables& t = ht_tables();
+  std::vector<uint16_t> e(2 * 2048 + 36, 0);
+  memcpy(e.data(), t.enc_vlc, sizeof(t.enc_vlc));
+  memcpy(e.data() + 2 * 2048, t.enc_uvlc, sizeof(t.enc_uvlc));
+  d_tables_enc.reserve(e.size() * 2);
+  CK(cudaMemcpy(d_tables_enc.p, e.data(), e.size() * 2, cudaMemcpyHostToDevice));
+  std::vector<uint16_t> d(1024 * 2 + 320 + 256);
+  memcpy(d.data(), t.dec_vlc, sizeof(t.dec_vlc));
+  memcpy(d.data() + 2048, t.dec_uvlc0, sizeof(t.dec_uvlc0));
+  memcpy(d.data() + 2048 + 320, t.dec_uvlc1, sizeof(t.dec_uvlc1));
+  d_tables_dec.reserve(d.size() * 2);
+  CK(cudaMemcpy(d_tables_dec.p, d.data(), d.size() * 2, cudaMemcpyHostToDevice));
+}
+
+static inline uint32_t esize_of(uint32_t st) { return st == ST_U8 ? 1u : (st == ST_U16 ? 2u : 4u); }
+
+void CodecBase::plan_image(uint32_t sample_type) {
+  img_type = sample_type;
+  uint32_t nc = params.num_comps();
+  img_off.assign(nc, 0); img_w.assign(nc, 0); img_h.assign(nc, 0);
+  size_t off = 0;
+  for (uint32_t c = 0; c < nc; ++c) {
+    if (sample_type == ST_U8 && params.comps[c].bit_depth > 8)
+      fail(0x000B0010, "8-bit sample container with %d-bit component", params.comps[c].bit_depth);
+    if (sample_type == ST_U16 && params.comps[c].bit_depth > 16)
+      fail(0x000B0010, "16-bit sample container with %d-bit component", params.comps[c].bit_depth);
+    if (sample_type != ST_I32 && params.comps[c].is_signed)
+      fail(0x000B0011, "signed components need the 32-bit sample container");
+    img_w[c] = params.comp_width(c); img_h[c] = params.comp_height(c);
+    img_off[c] = off;
+    off += (size_t)img_w[c] * img_h[c] * esize_of(sample_type);
+    off = (off + 255) & ~(size_t)255;
+  }
+  img_bytes = off + 256;
+  d_image.reserve(img_bytes);
+}
+
+void CodecBase::build_dwt_jobs(bool forward) {
+  const Params& P = params;
+  uint32_t D = P.num_decomps, nc = P.num_comps();
+  uint32_t nlev = D == 0 ? 1 : D;
+  jobs.assign(nlev, std::vector<DwtJob>());
+  job_ctas.assign(nlev, 0); job_maxc.assign(nlev, 1);
+  uint32_t es = esize_of(img_type);
+  for (uint32_t li = 0; li < nlev; ++li) {
+    uint32_t r = D == 0 ? 0 : D - li;          // resolution being split (or rebuilt)
+    uint32_t cta = 0;
+    for (const TileGeom& t : layout.tiles) {
+      for (uint32_t c = 0; c < nc; ) {
+        bool fused = (r == D) && P.color_transform() && c == 0;
+        uint32_t k = fused ? 3 : 1;
+        DwtJob j; memset(&j, 0, sizeof(j));
+        const ResGeom& rg = t.comps[c].res[r];
+        j.w = rg.rect.w; j.h = rg.rect.h; j.x0 = rg.rect.x0; j.y0 = rg.rect.y0;
+        j.ncomp = k; j.first = (r == D) ? 1u : 0u; j.last = (r <= 1) ? 1u : 0u; j.nodwt = (D == 0) ? 1u : 0u;
+        j.src_type = img_type; j.bit_depth = P.comps[c].bit_depth; j.is_signed = P.comps[c].is_signed ? 1u : 0u;
+        for (uint32_t i = 0; i < k; ++i) {
+          const TileCompGeom& tc = t.comps[c + i];
+          const ResGeom& rr = tc.res[r];
+          if (r == D) {
+            uint32_t cx0 = div_ceil(P.XOsiz, P.comps[c + i].dx), cy0 = div_ceil(P.YOsiz, P.comps[c + i].dy);
+            j.full_off[i] = img_off[c + i] + ((uint64_t)(tc.rect.y0 - cy0) * img_w[c + i] + (tc.rect.x0 - cx0)) * es;
+            j.full_stride[i] = img_w[c + i];
+          } else { j.full_off[i] = rr.plane_off; j.full_stride[i] = rr.plane_stride; }
+          if (r > 0) {
+            const ResGeom& lo = tc.res[r - 1];
+            j.ll_off[i] = lo.plane_off; j.ll_stride[i] = lo.plane_stride;
+            for (uint32_t b = 1; b < 4; ++b) {
+              const BandGeom& bg = rr.bands[b];
+              j.band_off[i][b] = bg.plane_off + bg.plane_pad_x; j.band_stride[i][b] = bg.plane_stride;
+              j.band_shift[i][b] = 31u - bg.K_max;
+              j.band_scale[i][b] = forward ? bg.delta_inv : bg.delta;
+            }
+            if (r == 1) {
+              const BandGeom& bg = lo.bands[0];
+              j.band_off[i][0] = bg.plane_off + bg.plane_pad_x; j.band_stride[i][0] = bg.plane_stride;
+              j.band_shift[i][0] = 31u - bg.K_max;
+              j.band_scale[i][0] = forward ? bg.delta_inv : bg.delta;
+            }
+          } else {   // zero decomposition levels
+            const BandGeom& bg = rr.bands[0];
+            j.band_off[i][0] = bg.plane_off + bg.plane_pad_x; j.band_stride[i][0] = bg.plane_stride;
+            j.band_shift[i][0] = 31u - bg.K_max;
+            j.band_scale[i][0] = forward ? bg.delta_inv : bg.delta;
+          }
+        }
+        dwt_tiling(j.x0, j.y0, j.w, j.h, j.tiles_x, j.tiles_y);
+        j.cta_base = cta;
+        uint32_t n = j.tiles_x * j.tiles_y;
+        if (n) { cta += n; jobs[li].push_back(j); job_maxc[li] = std::max(job_maxc[li], k); }
+        c += k;
+      }
+    }
+    job_ctas[li] = cta;
+  }
+  size_t total = 0;
+  job_dev_off.assign(nlev, 0);
+  for (uint32_t li = 0; li < nlev; ++li) { job_dev_off[li] = total; total += jobs[li].size(); }
+  d_jobs.reserve(std::max<size_t>(1, total) * sizeof(DwtJob));
+  for (uint32_t li = 0; li < nlev; ++li)
+    if (!jobs[li].empty())
+      CK(cudaMemcpy(d_jobs.as<DwtJob>() + job_dev_off[li], jobs[li].data(), jobs[li].size() * sizeof(DwtJob),
+                    cudaMemcpyHostToDevice));
+}
+
+static void check_block_widths(const Layout& L) {
+  for (const TileGeom& t : L.tiles)
+    for (const TileCompGeom& tc : t.comps)
+      for (const ResGeom& rg : tc.res)
+        for (uint32_t b = 0; b < 4; ++b)
+          if (!rg.bands[b].empty && (1u << rg.bands[b].xcb) > 64)
+            fail(0x000B0020, "code-block width %u: widths above 64 are not supported by the GPU "
+                 "block coder yet", 1u << rg.bands[b].xcb);
+}
+
+//------------------------------------------------------------------------------------------
+// Encoder
+//------------------------------------------------------------------------------------------
+void Encoder::configure(const Params& p, uint32_t sample_type) {
+  params = p;
+  params.finalize_for_encode();
+  layout.build(params);
+  check_block_widths(layout);
+  plan_image(sample_type);
+  upload_tables();
+  d_coef.reserve((layout.coef_words + 64) * 4);
+  CK(cudaMemset(d_coef.p, 0, d_coef.cap));
+  build_dwt_jobs(true);
+  // block descriptors and slots
+  h_blocks.assign(layout.num_blocks, EncBlock());
+  size_t slot = 0;
+  for (const TileGeom& t : layout.tiles)
+    for (const TileCompGeom& tc : t.comps)
+      for (const ResGeom& rg : tc.res)
+        for (uint32_t b = 0; b < 4; ++b) {
+          const BandGeom& bg = rg.bands[b];
+          if (bg.empty) continue;
+          for (uint32_t by = 0; by < bg.nbh; ++by)
+            for (uint32_t bx = 0; bx < bg.nbw; ++bx) {
+              Rect r = bg.block_rect(bx, by);
+              EncBlock& e = h_blocks[bg.block_base + by * bg.nbw + bx];
+              e.src_off = bg.plane_off + bg.plane_pad_x + (uint64_t)(r.y0 - bg.rect.y0) * bg.plane_stride + (r.x0 - bg.rect.x0);
+              e.stride = bg.plane_stride; e.w = (uint16_t)r.w; e.h = (uint16_t)r.h;
+              e.p = (uint16_t)(31u - bg.K_max);
+              // worst case: (K_max+1) MagSgn bits / sample (+1/15 stuffing), 30 VLC bits / quad pair
+              // (+1/7), 192 MEL bytes, working margin of the kernel
+              uint64_t ms = ((uint64_t)r.w * r.h * (bg.K_max + 1) + 7) / 8; ms += ms / 15 + 8;
+              uint64_t nq = (uint64_t)((r.w + 1) / 2) * ((r.h + 1) / 2);
+              uint64_t vl = ((nq + 1) / 2 * 30 + 12 + 7) / 8; vl += vl / 7 + 8;
+              uint64_t cap = ms + vl + 192 + 160;
+              cap = (cap + 15) & ~(uint64_t)15;
+              e.slot_off = slot; e.slot_cap = (uint32_t)cap;
+              slot += cap;
+            }
+        }
+  slot_bytes = slot + 64;
+  d_slots.reserve(slot_bytes);
+  d_blocks.reserve(std::max<size_t>(1, h_blocks.size()) * sizeof(EncBlock));
+  if (!h_blocks.empty())
+    CK(cudaMemcpy(d_blocks.p, h_blocks.data(), h_blocks.size() * sizeof(EncBlock), cudaMemcpyHostToDevice));
+  d_results.reserve(std::max<size_t>(1, h_blocks.size()) * sizeof(EncResult));
+  h_results.reserve(std::max<size_t>(1, h_blocks.size()) * sizeof(EncResult));
+  d_dst.reserve(std::max<size_t>(1, h_blocks.size()) * 8);
+  h_dst.reserve(std::max<size_t>(1, h_blocks.size()) * 8);
+  d_status.reserve(256); h_status.reserve(256);
+  coded.assign(layout.num_blocks, CodedBlock());
+  main_header.clear();
+  params.write_main_header(main_header, nullptr, nullptr, 0);
+  // line-based front end state
+  line_cur.assign(params.num_comps(), 0); cur_comp = 0; lines_done = false;
+}
+
+int32_t* Encoder::exchange(const int32_t* line_written, uint32_t& next_comp) {
+  // ojph::codestream::exchange (ojph_codestream_local.cpp:1176-1224): the caller fills the
+  // returned line; planar => all rows of comp 0 first, else row by row, comp by comp
+  uint32_t nc = params.num_comps();
+  if (h_frame.p == nullptr) {
+    size_t tot = 0; for (uint32_t c = 0; c < nc; ++c) tot += (size_t)img_w[c] * img_h[c];
+    h_frame.reserve(tot * 4);
+    uint32_t mw = 0; for (uint32_t c = 0; c < nc; ++c) mw = std::max(mw, img_w[c]);
+    line_buf.assign(mw, 0);
+  }
+  auto plane = [&](uint32_t c) { size_t o = 0; for (uint32_t i = 0; i < c; ++i) o += (size_t)img_w[i] * img_h[i]; return h_frame.as<int32_t>() + o; };
+  if (line_written) {
+    if (lines_done) { next_comp = 0; return nullptr; }
+    memcpy(plane(cur_comp) + (size_t)line_cur[cur_comp] * img_w[cur_comp], line_written, (size_t)img_w[cur_comp] * 4);
+    line_cur[cur_comp]++;
+    if (params.planar == 1) {
+      if (line_cur[cur_comp] >= img_h[cur_comp]) { if (++cur_comp >= nc) { lines_done = true; next_comp = 0; return nullptr; } }
+    } else {
+      // next component that still has rows, in round-robin order
+      uint32_t tries = 0;
+      do { cur_comp = (cur_comp + 1) % nc; ++tries; } while (line_cur[cur_comp] >= img_h[cur_comp] && tries <= nc);
+      if (tries > nc) { lines_done = true; next_comp = 0; return nullptr; }
+    }
+  }
+  next_comp = cur_comp;
+  return line_buf.data();
+}
+
+size_t Encoder::encode(const void* const* planes, const uint32_t* strides, bool planes_on_device,
+                       uint8_t* out, size_t out_cap, bool out_on_device)
+{
+  const Params& P = params;
+  uint32_t nc = P.num_comps(), es = esize_of(img_type);
+  last_launches = 0;
+  // 1. image planes -> device
+  if (planes) {
+    for (uint32_t c = 0; c < nc; ++c) {
+      uint8_t* d = d_image.as<uint8_t>() + img_off[c];
+      uint32_t st = strides ? strides[c] : img_w[c];
+      cudaMemcpyKind kind = planes_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+      if (st == img_w[c])
+        CK(cudaMemcpyAsync(d, planes[c], (size_t)img_w[c] * img_h[c] * es, kind, stream));
+      else
+        for (uint32_t y = 0; y < img_h[c]; ++y)
+          CK(cudaMemcpyAsync(d + (size_t)y * img_w[c] * es, (const uint8_t*)planes[c] + (size_t)y * st * es,
+                             (size_t)img_w[c] * es, kind, stream));
+    }
+  }
+  // 2. transform + block coding
+  CK(cudaMemsetAsync(d_status.p, 0, 16, stream));
+  for (size_t li = 0; li < jobs.size(); ++li) {
+    if (job_ctas[li] == 0) continue;
+    launch_dwt_fwd(d_jobs.as<DwtJob>() + job_dev_off[li], (uint32_t)jobs[li].size(), job_ctas[li], P.reversible(),
+                   job_maxc[li], d_image.p, d_coef.as<uint32_t>(), stream);
+    ++last_launches;
+  }
+  uint32_t nb = (uint32_t)h_blocks.size();
+  launch_ht_encode(d_blocks.as<EncBlock>(), nb, d_coef.as<uint32_t>(), d_slots.as<uint8_t>(),
+                   d_results.as<EncResult>(), d_tables_enc.as<uint16_t>(), d_status.as<uint32_t>(), stream);
+  ++last_launches;
+  if (nb) CK(cudaMemcpyAsync(h_results.p, d_results.p, (size_t)nb * sizeof(EncResult), cudaMemcpyDeviceToHost, stream));
+  CK(cudaMemcpyAsync(h_status.p, d_status.p, 16, cudaMemcpyDeviceToHost, stream));
+  CK(cudaStreamSynchronize(stream));
+  CK(cudaGetLastError());
+  status_flags = h_status.as<uint32_t>()[0];
+  if (status_flags & 2u) fail(0x00020001, "mel encoder's buffer is full");
+  if (status_flags & 1u) fail(0x00020005, "block encoder's output slot is full");
+
+  // 3. packet headers and final layout on the host
+  const EncResult* res = h_results.as<EncResult>();
+  for (uint32_t b = 0; b < nb; ++b) {
+    CodedBlock& cb = coded[b];
+    uint32_t len = res[b].len_head + res[b].len_tail;
+    cb.pass_len[0] = len; cb.pass_len[1] = 0;
+    cb.num_passes = len ? 1 : 0;
+    cb.missing_msbs = len ? (uint8_t)(30u - h_blocks[b].p) : 0;
+  }
+  struct Pkt { PacketRef ref; size_t hdr_off; uint32_t hdr_len, body; };
+  struct TilePart { uint32_t tile, first, count, tp_idx, tp_cnt; uint64_t bytes; };
+  std::vector<uint8_t> hdr;                // packet headers, in codestream order
+  std::vector<Pkt> pkts;
+  std::vector<TilePart> tps;
+  std::vector<PacketRef> seq; std::vector<uint32_t> tp_first;
+  for (uint32_t t = 0; t < (uint32_t)layout.tiles.size(); ++t) {
+    layout.packet_sequence(t, seq, tp_first);
+    size_t base = pkts.size();
+    for (const PacketRef& pr : seq) {
+      const ResGeom& rg = layout.res_of(pr);
+      Pkt k; k.ref = pr; k.hdr_off = hdr.size();
+      k.body = write_packet_header(rg, rg.precincts[pr.precinct], coded.data(), hdr);
+      k.hdr_len = (uint32_t)(hdr.size() - k.hdr_off);
+      pkts.push_back(k);
+    }
+    for (size_t i = 0; i < tp_first.size(); ++i) {
+      TilePart tp; tp.tile = t; tp.first = (uint32_t)(base + tp_first[i]);
+      uint32_t end = (i + 1 < tp_first.size()) ? tp_first[i + 1] : (uint32_t)seq.size();
+      tp.count = end - tp_first[i]; tp.tp_idx = (uint32_t)i; tp.tp_cnt = (uint32_t)tp_first.size();
+      tp.bytes = 0;
+      for (uint32_t q = 0; q < tp.count; ++q) tp.bytes += pkts[tp.first + q].hdr_len + pkts[tp.first + q].body;
+      tps.push_back(tp);
+    }
+  }
+  // marker bytes: main header [+ TLM], SOT+SOD per tile-part, EOC
+  std::vector<uint8_t> blob;               // everything that is not code-block data, in order
+  struct Piece { size_t src, dst; uint32_t len; };
+  std::vector<Piece> pieces;
+  uint64_t pos = 0;
+  auto add_piece = [&](size_t src, uint32_t len) {
+    if (!pieces.empty() && pieces.back().src + pieces.back().len == src && pieces.back().dst + pieces.back().len == pos)
+      pieces.back().len += len;
+    else pieces.push_back(Piece{ src, (size_t)pos, len });
+    pos += len;
+  };
+  blob = main_header;
+  if (P.need_tlm) {
+    if (4 + 6 * tps.size() > 65535) fail(0x000500B1, "too many tile-parts for one TLM marker segment");
+    put_u16(blob, M_TLM); put_u16(blob, (uint32_t)(4 + 6 * tps.size())); put_u8(blob, 0); put_u8(blob, 0x60);
+    for (const TilePart& tp : tps) { put_u16(blob, tp.tile); put_u32(blob, (uint32_t)(tp.bytes + 14)); }
+  }
+  add_piece(0, (uint32_t)blob.size());
+  uint64_t* dst = h_dst.as<uint64_t>();
+  for (const TilePart& tp : tps) {
+    size_t s = blob.size();
+    put_u16(blob, M_SOT); put_u16(blob, 10); put_u16(blob, tp.tile); put_u32(blob, (uint32_t)(tp.bytes + 14));
+    put_u8(blob, tp.tp_idx); put_u8(blob, tp.tp_cnt);
+    put_u16(blob, M_SOD);
+    add_piece(s, 14);
+    for (uint32_t q = 0; q < tp.count; ++q) {
+      const Pkt& k = pkts[tp.first + q];
+      size_t hs = blob.size();
+      blob.insert(blob.end(), hdr.begin() + (long)k.hdr_off, hdr.begin() + (long)(k.hdr_off + k.hdr_len));
+      add_piece(hs, k.hdr_len);
+      if (k.body == 0) continue;
+      const ResGeom& rg = layout.res_of(k.ref);
+      const PrecinctGeom& pc = rg.precincts[k.ref.precinct];
+      for (uint32_t sb = 0; sb < 4; ++sb) {
+        const BandGeom& bg = rg.bands[sb];
+        if (bg.empty) continue;
+        const Rect& ci = pc.cb_idx[sb];
+        for (uint32_t y = 0; y < ci.h; ++y)
+          for (uint32_t x = 0; x < ci.w; ++x) {
+            uint32_t bi = bg.block_base + (ci.y0 + y) * bg.nbw + ci.x0 + x;
+            dst[bi] = pos; pos += coded[bi].pass_len[0];
+          }
+      }
+    }
+  }
+  { size_t s = blob.size(); put_u16(blob, M_EOC); add_piece(s, 2); }
+  const size_t total = (size_t)pos;
+  if (total > out_cap) fail(0x000B0030, "output buffer too small: need %zu bytes, have %zu", total, out_cap);
+
+  // 4. assemble on the device, one copy out
+  uint8_t* dev_out;
+  if (out_on_device) dev_out = out; else { d_out.reserve(total + 64); dev_out = d_out.as<uint8_t>(); }
+  h_hdr.reserve(blob.size() + 64); memcpy(h_hdr.p, blob.data(), blob.size());
+  d_hdr.reserve(blob.size() + 64);
+  CK(cudaMemcpyAsync(d_hdr.p, h_hdr.p, blob.size(), cudaMemcpyHostToDevice, stream));
+  h_pieces.reserve(pieces.size() * sizeof(CopyPiece)); d_pieces.reserve(pieces.size() * sizeof(CopyPiece));
+  CopyPiece* cp = h_pieces.as<CopyPiece>();
+  for (size_t i = 0; i < pieces.size(); ++i) { cp[i].src_off = pieces[i].src; cp[i].dst_off = pieces[i].dst; cp[i].len = pieces[i].len; cp[i].src_sel = 1; }
+  CK(cudaMemcpyAsync(d_pieces.p, h_pieces.p, pieces.size() * sizeof(CopyPiece), cudaMemcpyHostToDevice, stream));
+  if (nb) CK(cudaMemcpyAsync(d_dst.p, h_dst.p, (size_t)nb * 8, cudaMemcpyHostToDevice, stream));
+  launch_gather_blocks(d_blocks.as<EncBlock>(), d_results.as<EncResult>(), d_dst.as<uint64_t>(), nb,
+                       d_slots.as<uint8_t>(), dev_out, stream);
+  launch_assemble(d_pieces.as<CopyPiece>(), (uint32_t)pieces.size(), d_slots.as<uint8_t>(), d_hdr.as<uint8_t>(), dev_out, stream);
+  last_launches += 2;
+  if (!out_on_device) CK(cudaMemcpyAsync(out, dev_out, total, cudaMemcpyDeviceToHost, stream));
+  CK(cudaStreamSynchronize(stream));
+  CK(cudaGetLastError());
+  // reset the line front end for the next frame
+  std::fill(line_cur.begin(), line_cur.end(), 0u); cur_comp = 0; lines_done = false;
+  return total;
+}
+
+//------------------------------------------------------------------------------------------
+// Decoder
+//------------------------------------------------------------------------------------------
+void Decoder::read_headers(const uint8_t* data, size_t len, uint32_t sample_type) {
+  Params np;
+  size_t sot = np.read_main_header(data, len);
+  j2c = data; j2c_len = len; first_sot = sot;
+  // geometry depends on SIZ/COD/QCD/QCC only; rebuild when any of those bytes changed
+  std::vector<uint8_t> sig;
+  {
+    // strip COM/TLM-like segments is unnecessary: compare everything up to the first SOT
+    sig.assign(data, data + sot);
+    sig.push_back((uint8_t)sample_type);
+  }
+  if (sig == header_sig && !layout.tiles.empty()) return;
+  header_sig = sig;
+  params = np;
+  // the decoder side derives the same planar default as the reference (read_headers :879)
+  params.planar = params.color_transform() ? 0 : 1;
+  for (uint32_t c = 0; c < params.num_comps(); ++c) {
+    uint32_t pr = params.precision(c);
+    if (pr > 32) fail(0x000B0001, "component %u needs %u-bit coefficients; only the 32-bit path is "
+                      "implemented on the GPU", c, pr);
+  }
+  layout.build(params);
+  check_block_widths(layout);
+  plan_image(sample_type);
+  upload_tables();
+  d_coef.reserve((layout.coef_words + 64) * 4);
+  build_dwt_jobs(false);
+  // geometry part of the block records
+  h_dec_proto.assign(layout.num_blocks, DecBlock());
+  size_t scratch = 0;
+  for (const TileGeom& t : layout.tiles)
+    for (const TileCompGeom& tc : t.comps)
+      for (const ResGeom& rg : tc.res)
+        for (uint32_t b = 0; b < 4; ++b) {
+          const BandGeom& bg = rg.bands[b];
+          if (bg.empty) continue;
+          for (uint32_t by = 0; by < bg.nbh; ++by)
+            for (uint32_t bx = 0; bx < bg.nbw; ++bx) {
+              Rect r = bg.block_rect(bx, by);
+              DecBlock& d = h_dec_proto[bg.block_base + by * bg.nbw + bx];
+              memset(&d, 0, sizeof(d));
+              d.dst_off = bg.plane_off + bg.plane_pad_x + (uint64_t)(r.y0 - bg.rect.y0) * bg.plane_stride + (r.x0 - bg.rect.x0);
+              d.stride = bg.plane_stride; d.w = (uint16_t)r.w; d.h = (uint16_t)r.h;
+              d.K_max = (uint8_t)bg.K_max; d.delta = bg.delta;
+              d.flags = params.stripe_causal() ? 1 : 0;
+              // quad records + de-stuffed MagSgn (a cleanup segment is < 65535 bytes; sized per frame)
+              uint32_t nq = (r.w + 1) / 2, qs = (nq + 1) & ~1u, nqr = (r.h + 1) / 2;
+              d.scratch_off = scratch;
+              scratch += (size_t)qs * nqr;      // MagSgn words are appended per frame
+            }
+        }
+  coded.assign(layout.num_blocks, CodedBlock());
+  d_dec.reserve(std::max<size_t>(1, h_dec_proto.size()) * sizeof(DecBlock));
+  h_dec.reserve(std::max<size_t>(1, h_dec_proto.size()) * sizeof(DecBlock));
+  d_bstatus.reserve(std::max<size_t>(1, h_dec_proto.size()) * 4);
+  h_bstatus.reserve(std::max<size_t>(1, h_dec_proto.size()) * 4);
+}
+
+void Decoder::info(FrameInfo& fi) const {
+  memset(&fi, 0, sizeof(fi));
+  fi.width = params.Xsiz; fi.height = params.Ysiz; fi.off_x = params.XOsiz; fi.off_y = params.YOsiz;
+  fi.num_comps = params.num_comps();
+  for (uint32_t c = 0; c < fi.num_comps && c < 16; ++c) {
+    fi.bit_depth[c] = params.comps[c].bit_depth; fi.is_signed[c] = params.comps[c].is_signed;
+    fi.dx[c] = params.comps[c].dx; fi.dy[c] = params.comps[c].dy;
+    fi.comp_w[c] = params.comp_width(c); fi.comp_h[c] = params.comp_height(c);
+  }
+  fi.num_decomps = params.num_decomps; fi.reversible = params.reversible(); fi.color_transform = params.color_transform();
+  fi.num_tiles = (uint32_t)layout.tiles.size();
+}
+
+void Decoder::parse_tiles() {
+  // tile-part loop of codestream::read (ojph_codestream_local.cpp:912-1115) and
+  // tile::parse_tile_header (ojph_tile.cpp:777-936)
+  for (CodedBlock& cb : coded) cb = CodedBlock();
+  size_t ntiles = layout.tiles.size();
+  std::vector<std::vector<PacketRef>> seqs(ntiles);
+  std::vector<uint32_t> next_pkt(ntiles, 0), next_tp(ntiles, 0);
+  std::vector<bool> have_seq(ntiles, false);
+  size_t pos = first_sot;
+  const uint8_t* d = j2c;
+  while (pos + 2 <= j2c_len) {
+    // find SOT or EOC
+    if (!(d[pos] == 0xFF && (d[pos + 1] == 0x90 || d[pos + 1] == 0xD9))) { ++pos; continue; }
+    if (d[pos + 1] == 0xD9) break;
+    if (pos + 12 > j2c_len) {
+      if (resilient) break;
+      fail(0x00050091, "error reading SOT marker");
+    }
+    uint32_t Lsot = ((uint32_t)d[pos + 2] << 8) | d[pos + 3];
+    uint32_t Isot = ((uint32_t)d[pos + 4] << 8) | d[pos + 5];
+    uint32_t Psot = ((uint32_t)d[pos + 6] << 24) | ((uint32_t)d[pos + 7] << 16) | ((uint32_t)d[pos + 8] << 8) | d[pos + 9];
+    uint32_t TPsot = d[pos + 10], TNsot = d[pos + 11];
+    (void)TNsot;
+    if (Lsot != 10) { if (resilient) { pos += 2; continue; } fail(0x00050092, "error in SOT length"); }
+    size_t tile_start = pos + 12;          // file position after the SOT segment
+    size_t tp_end = Psot ? pos + Psot : j2c_len;
+    if (tp_end > j2c_len) tp_end = j2c_len;
+    if (Isot >= ntiles) {
+      if (!resilient) fail(0x00030061, "wrong tile index");
+      pos = tp_end; continue;
+    }
+    // skip tile-part header segments up to SOD
+    size_t q = tile_start; bool sod = false;
+    while (q + 2 <= tp_end) {
+      if (d[q] != 0xFF) { ++q; continue; }
+      uint8_t m = d[q + 1];
+      if (m == 0x93) { sod = true; q += 2; break; }
+      bool seg = (m == 0x52 || m == 0x53 || m == 0x5C || m == 0x5D || m == 0x5E || m == 0x5F || m == 0x61 ||
+                  m == 0x58 || m == 0x64 || m == 0x76);
+      if (!seg) { ++q; continue; }
+      if (q + 4 > tp_end) break;
+      uint32_t L = ((uint32_t)d[q + 2] << 8) | d[q + 3];
+      q += 2 + L;
+    }
+    if (!sod) {
+      if (!resilient) fail(0x00030063, "File terminated early before start of data is found for tile "
+                           "indexed %d and tile part %d", Isot, TPsot);
+      pos = tp_end; continue;
+    }
+    if (TPsot != next_tp[Isot]) {
+      if (!resilient) fail(0x00030091, "wrong tile part index");
+    }
+    ++next_tp[Isot];
+    uint32_t payload = Psot ? Psot - 12 : (uint32_t)(j2c_len - tile_start);
+    uint32_t data_left = payload - (uint32_t)(q - tile_start);
+    if (q + data_left > j2c_len) data_left = (uint32_t)(j2c_len - q);
+    if (!have_seq[Isot]) { std::vector<uint32_t> tpf; layout.packet_sequence(Isot, seqs[Isot], tpf); have_seq[Isot] = true; }
+    try {
+      std::vector<PacketRef>& seq = seqs[Isot];
+      while (data_left > 0 && next_pkt[Isot] < seq.size()) {
+        const PacketRef& pr = seq[next_pkt[Isot]++];
+        const ResGeom& rg = layout.res_of(pr);
+        parse_packet(params, rg, rg.precincts[pr.precinct], coded.data(), d, q, data_left);
+      }
+    } catch (const Error& e) {
+      if (!resilient) throw;
+    }
+    pos = tp_end;
+  }
+}
+
+uint32_t Decoder::decode(void* const* planes, const uint32_t* strides, bool planes_on_device) {
+  const Params& P = params;
+  uint32_t nc = P.num_comps(), es = esize_of(img_type), D = P.num_decomps;
+  last_launches = 0;
+  // codestream to the device while the host parses packet headers
+  d_cs.reserve(j2c_len + 64);
+  CK(cudaMemcpyAsync(d_cs.p, j2c, j2c_len, cudaMemcpyHostToDevice, stream));
+  CK(cudaMemsetAsync(d_cs.as<uint8_t>() + j2c_len, 0, 32, stream));
+  parse_tiles();
+  uint32_t nb = (uint32_t)h_dec_proto.size();
+  DecBlock* hd = h_dec.as<DecBlock>();
+  size_t scratch_fixed = 0;
+  if (nb) { const DecBlock& l = h_dec_proto[nb - 1]; uint32_t nq = (l.w + 1u) / 2, qs = (nq + 1) & ~1u; scratch_fixed = l.scratch_off + (size_t)qs * ((l.h + 1u) / 2); }
+  size_t scratch = scratch_fixed;
+  // per-block scratch = quad records (fixed part, laid out per block) ... MagSgn words appended
+  // right after each block's records would move the records; keep records at proto offsets and put
+  // the MagSgn buffers in a second region addressed through scratch_off + records size.
+  // To keep one offset per block the records region of block b is re-based here.
+  for (uint32_t b = 0; b < nb; ++b) {
+    DecBlock d = h_dec_proto[b];
+    const CodedBlock& cb = coded[b];
+    d.len1 = cb.pass_len[0]; d.len2 = cb.pass_len[1];
+    d.num_passes = cb.num_passes; d.missing_msbs = cb.missing_msbs; d.data_off = cb.data_off;
+    uint32_t nq = (d.w + 1u) / 2, qs = (nq + 1) & ~1u, nqr = (d.h + 1u) / 2;
+    d.scratch_off = scratch;
+    scratch += (size_t)qs * nqr + (d.len1 + 3) / 4 + 4;
+    hd[b] = d;
+  }
+  d_scratch.reserve((scratch + 64) * 4);
+  if (nb) CK(cudaMemcpyAsync(d_dec.p, h_dec.p, (size_t)nb * sizeof(DecBlock), cudaMemcpyHostToDevice, stream));
+  launch_ht_decode(d_dec.as<DecBlock>(), nb, d_cs.as<uint8_t>(), d_coef.as<uint32_t>(), d_scratch.as<uint32_t>(),
+                   d_tables_dec.as<uint16_t>(), P.reversible() ? (uint32_t)DEC_OUT_INT : (uint32_t)DEC_OUT_FLOAT,
+                   d_bstatus.as<uint32_t>(), stream);
+  last_launches += 2;
+  if (nb) CK(cudaMemcpyAsync(h_bstatus.p, d_bstatus.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, stream));
+  // synthesis, coarsest level first
+  for (size_t li = jobs.size(); li-- > 0; ) {
+    if (job_ctas[li] == 0) continue;
+    launch_dwt_inv(d_jobs.as<DwtJob>() + job_dev_off[li], (uint32_t)jobs[li].size(), job_ctas[li], P.reversible(),
+                   job_maxc[li], d_image.p, d_coef.as<uint32_t>(), stream);
+    ++last_launches;
+  }
+  (void)D;
+  if (planes) {
+    for (uint32_t c = 0; c < nc; ++c) {
+      const uint8_t* s = d_image.as<uint8_t>() + img_off[c];
+      uint32_t st = strides ? strides[c] : img_w[c];
+      cudaMemcpyKind kind = planes_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+      if (st == img_w[c])
+        CK(cudaMemcpyAsync(planes[c], s, (size_t)img_w[c] * img_h[c] * es, kind, stream));
+      else
+        for (uint32_t y = 0; y < img_h[c]; ++y)
+          CK(cudaMemcpyAsync((uint8_t*)planes[c] + (size_t)y * st * es, s + (size_t)y * img_w[c] * es,
+                             (size_t)img_w[c] * es, kind, stream));
+    }
+  }
+  CK(cudaStreamSynchronize(stream));
+  CK(cudaGetLastError());
+  failed_blocks = 0;
+  const uint32_t* bs = h_bstatus.as<uint32_t>();
+  for (uint32_t b = 0; b < nb; ++b) if (bs[b] & 1u) ++failed_blocks;
+  if (failed_blocks && !resilient) fail(0x000300A1, "Error decoding a codeblock.");
+  return failed_blocks;
+}
+
+} // namespace ojb

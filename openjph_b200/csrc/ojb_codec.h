@@ -1,0 +1,107 @@
+// ojb_codec.h -- encoder / decoder objects: the B200 counterparts of the reference's
+// local::codestream (src/core/codestream/ojph_codestream_local.h:63-169).  exchange()/pull()
+// only move lines in and out of a pinned frame buffer; all GPU work happens in flush() (encode)
+// and create() (decode) -- SURVEY §8(b).
+#pragma once
+#include "ojb_layout.h"
+#include "ojb_kernels.h"
+#include <memory>
+
+namespace ojb {
+
+void cuda_check(cudaError_t e, const char* what);
+
+struct DeviceBuf {
+  void* p = nullptr; size_t cap = 0;
+  ~DeviceBuf();
+  void reserve(size_t n);
+  template <typename T> T* as() { return reinterpret_cast<T*>(p); }
+};
+struct PinnedBuf {
+  void* p = nullptr; size_t cap = 0;
+  ~PinnedBuf();
+  void reserve(size_t n);
+  template <typename T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+struct Timings { float h2d_ms = 0, kernels_ms = 0, host_ms = 0, d2h_ms = 0; };
+
+// sample container of the image buffers handed to / returned by the frame calls
+enum SampleType : uint32_t { ST_U8 = 0, ST_U16 = 1, ST_I32 = 2 };
+
+class CodecBase {
+public:
+  CodecBase();
+  virtual ~CodecBase();
+  Params params;
+  Layout layout;
+  cudaStream_t stream = nullptr;
+  uint32_t last_launches = 0;          // kernels launched by the last frame call
+  void upload_tables();
+  DeviceBuf d_tables_enc, d_tables_dec;
+  // image planes on the device: component c at byte offset img_off[c], tight rows
+  DeviceBuf d_image;
+  std::vector<uint64_t> img_off;
+  std::vector<uint32_t> img_w, img_h;
+  uint32_t img_type = ST_I32;
+  size_t img_bytes = 0;
+  void plan_image(uint32_t sample_type);
+  DeviceBuf d_coef;                    // coefficient arena (32-bit words)
+  // DWT jobs per level (index 0: full resolution level D, ...), uploaded once
+  std::vector<std::vector<DwtJob>> jobs;
+  std::vector<uint32_t> job_ctas, job_maxc;
+  DeviceBuf d_jobs;
+  std::vector<size_t> job_dev_off;
+  void build_dwt_jobs(bool forward);
+};
+
+class Encoder : public CodecBase {
+public:
+  // finalises parameters, builds geometry and device arenas, produces the main header
+  void configure(const Params& p, uint32_t sample_type);
+  // encode one frame whose component planes are on the host (pinned or pageable) or on the
+  // device; planes[c] points at sample (0,0) of component c, stride in samples
+  size_t encode(const void* const* planes, const uint32_t* strides, bool planes_on_device,
+                uint8_t* out, size_t out_cap, bool out_on_device);
+  uint32_t status_flags = 0;
+  // line-based front end (ojph::codestream::exchange): lines go to a pinned frame
+  PinnedBuf h_frame;
+  std::vector<uint32_t> line_cur;
+  uint32_t cur_comp = 0;
+  bool lines_done = false;
+  int32_t* exchange(const int32_t* line_written, uint32_t& next_comp);
+  std::vector<int32_t> line_buf;
+  std::vector<uint8_t> main_header;
+  std::vector<EncBlock> h_blocks;
+  DeviceBuf d_blocks, d_results, d_status, d_slots, d_dst, d_hdr, d_pieces, d_out;
+  PinnedBuf h_results, h_dst, h_hdr, h_pieces, h_status;
+  std::vector<CodedBlock> coded;
+  size_t slot_bytes = 0;
+  size_t out_cap_dev = 0;
+};
+
+struct FrameInfo {
+  uint32_t width, height, off_x, off_y, num_comps;
+  uint32_t bit_depth[16], is_signed[16], dx[16], dy[16], comp_w[16], comp_h[16];
+  uint32_t num_decomps, reversible, color_transform, num_tiles;
+};
+
+class Decoder : public CodecBase {
+public:
+  bool resilient = false;
+  // parse main header; (re)builds geometry when parameters changed
+  void read_headers(const uint8_t* j2c, size_t len, uint32_t sample_type);
+  void info(FrameInfo& fi) const;
+  // decode into planes (host or device); returns number of code-blocks that failed to decode
+  uint32_t decode(void* const* planes, const uint32_t* strides, bool planes_on_device);
+  uint32_t failed_blocks = 0;
+  const uint8_t* j2c = nullptr; size_t j2c_len = 0; size_t first_sot = 0;
+  std::vector<uint8_t> header_sig;     // bytes of the main header the geometry was built for
+  std::vector<CodedBlock> coded;
+  std::vector<DecBlock> h_dec_proto;   // geometry part of DecBlock, per block
+  DeviceBuf d_cs, d_dec, d_scratch, d_bstatus;
+  PinnedBuf h_dec, h_bstatus;
+  void parse_tiles();
+};
+
+} // namespace ojb

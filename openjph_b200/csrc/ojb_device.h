@@ -1,0 +1,87 @@
+// ojb_device.h -- descriptors shared by host orchestration and the CUDA kernels, plus the
+// launch shim that lets the same .cu sources run under tests/emu (CPU, tests only).
+#pragma once
+#include <cstdint>
+#include <cstddef>
+
+#ifdef OJB_EMU_BUILD
+  #include "cuda_emu.h"
+  #define OJB_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    ojb_emu::launch((grid), (block), (smem), [=]() { kernel(__VA_ARGS__); })
+  #define OJB_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(ojb_emu::dyn_smem())
+#else
+  #include <cuda_runtime.h>
+  #define OJB_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+  #define OJB_DYN_SMEM(type, name) extern __shared__ __align__(16) unsigned char name##_raw[]; \
+    type* name = reinterpret_cast<type*>(name##_raw)
+#endif
+
+namespace ojb {
+
+// ---- HT block encoder -------------------------------------------------------------------
+// One record per code-block; the kernel reads sign-magnitude samples (bit 31 sign, magnitude
+// MSB-aligned: |v| << (31 - K_max)), same convention as the reference's code-block buffers
+// (ojph_codestream_gen.cpp:59-78, ojph_codeblock.cpp:115-139).
+struct EncBlock {
+  uint64_t src_off;     // word offset of sample (0,0) in the coefficient arena
+  uint64_t slot_off;    // byte offset of the output slot in the slot arena (16-byte aligned)
+  uint32_t stride;      // words between rows
+  uint32_t slot_cap;    // slot size in bytes (multiple of 16)
+  uint16_t w, h;
+  uint16_t p;           // 30 - missing_msbs = 31 - K_max
+  uint16_t pad;
+};
+// result per block: [0] bytes at slot start (MagSgn + MEL), [1] bytes at slot end (VLC);
+// both 0 for a block with no significant sample (not included in the packet).
+struct EncResult { uint32_t len_head, len_tail; };
+
+// ---- HT block decoder -------------------------------------------------------------------
+struct DecBlock {
+  uint64_t data_off;    // byte offset of the coded bytes in the codestream buffer
+  uint64_t dst_off;     // word offset of sample (0,0) in the coefficient arena
+  uint64_t scratch_off; // word offset of this block's scratch (quad records, destuffed MagSgn)
+  uint32_t len1, len2;  // cleanup bytes, SPP+MRP bytes
+  uint32_t stride;      // words between rows of dst
+  uint16_t w, h;
+  uint8_t missing_msbs, num_passes, K_max, flags;   // flags bit0: stripe-causal
+  float delta;          // irreversible: step (already / 2^(31-K_max)); reversible: unused
+};
+enum : uint32_t {       // DecBlock output modes
+  DEC_OUT_SIGNMAG = 0,  // raw sign-magnitude (kernel-level parity with ojph_decode_codeblock32)
+  DEC_OUT_INT = 1,      // reversible: signed integers (tx_from_cb32 fused)
+  DEC_OUT_FLOAT = 2     // irreversible: float coefficient (tx_from_cb32 fused)
+};
+
+// ---- DWT --------------------------------------------------------------------------------
+enum : uint32_t { SRC_U8 = 0, SRC_U16 = 1, SRC_I32 = 2, SRC_COEF = 3 };
+
+// one analysis (or synthesis) level of one tile-component (or of 3 colour components at once
+// for the first level when the colour transform is used)
+struct DwtJob {
+  // geometry of the resolution being split
+  uint32_t w, h;          // size
+  uint32_t x0, y0;        // origin (only parity and band-origin arithmetic matter)
+  // source / destination of the full-resolution samples
+  uint64_t full_off[3];   // word offset in arena (SRC_COEF) or byte offset in image buffer
+  uint32_t full_stride[3];// in samples
+  // LL output (next level input) -- arena word offsets
+  uint64_t ll_off[3];
+  uint32_t ll_stride[3];
+  // detail bands HL, LH, HH (+ LL as band 0 when this is the last level): sign-magnitude planes
+  uint64_t band_off[3][4];
+  uint32_t band_stride[3][4];
+  uint32_t band_shift[3][4];   // reversible: 31 - K_max
+  float band_scale[3][4];      // irreversible: delta_inv (forward) / delta (inverse)
+  uint32_t ncomp;         // 1, or 3 when the colour transform is fused (level 1 only)
+  uint32_t first;         // 1: full-resolution side is the image (level shift / colour transform)
+  uint32_t last;          // 1: LL is a final band (quantise it to band 0), else raw to ll_off
+  uint32_t nodwt;         // 1: zero decomposition levels: convert/quantise only
+  uint32_t src_type;      // SRC_* of the image buffer when first
+  uint32_t bit_depth;     // for level shift / float conversion when first
+  uint32_t is_signed;
+  uint32_t tiles_x, tiles_y;   // CTA tiling of this job
+  uint32_t cta_base;      // first CTA index of this job in the launch
+};
+
+} // namespace ojb

@@ -1,0 +1,36 @@
+// ojb_kernels.h -- host-callable launchers of the CUDA kernels (one translation unit each).
+#pragma once
+#include "ojb_device.h"
+
+namespace ojb {
+
+// HT cleanup encoder, one warp per code-block (ht_encode.cu)
+// tables: uint16 enc_vlc[2][2048] followed by enc_uvlc[33] in device memory
+void launch_ht_encode(const EncBlock* blocks, uint32_t nblocks, const uint32_t* coef, uint8_t* slots,
+                      EncResult* results, const uint16_t* tables, uint32_t* status, cudaStream_t st);
+
+// HT decoder (ht_decode.cu): step 1 = MEL/VLC chain, one THREAD per code-block; step 2 =
+// MagSgn (+SPP +MRP) one WARP per code-block.
+// tables: uint16 dec_vlc[2][1024], dec_uvlc0[320], dec_uvlc1[256]
+void launch_ht_decode(const DecBlock* blocks, uint32_t nblocks, const uint8_t* codestream,
+                      uint32_t* coef, uint32_t* scratch, const uint16_t* tables, uint32_t out_mode,
+                      uint32_t* block_status, cudaStream_t st);
+
+// forward / inverse DWT levels (dwt_fwd.cu / dwt_inv.cu).  jobs live in device memory.
+void launch_dwt_fwd(const DwtJob* jobs, uint32_t njobs, uint32_t total_ctas, bool reversible,
+                    uint32_t max_ncomp, const void* image, uint32_t* coef, cudaStream_t st);
+void launch_dwt_inv(const DwtJob* jobs, uint32_t njobs, uint32_t total_ctas, bool reversible,
+                    uint32_t max_ncomp, void* image, uint32_t* coef, cudaStream_t st);
+// CTA tiling of a w x h resolution at origin (x0,y0): number of tiles across / down
+void dwt_tiling(uint32_t x0, uint32_t y0, uint32_t w, uint32_t h, uint32_t& tx, uint32_t& ty);
+
+// codestream assembly (assemble.cu): copy pieces (block heads/tails, header bytes) to their
+// final offsets
+struct CopyPiece { uint64_t src_off; uint64_t dst_off; uint32_t len; uint32_t src_sel; };  // src_sel 0: slots, 1: headers
+void launch_assemble(const CopyPiece* pieces, uint32_t npieces, const uint8_t* slots,
+                     const uint8_t* headers, uint8_t* out, cudaStream_t st);
+// block pieces computed on the device from per-block results + destination offsets
+void launch_gather_blocks(const EncBlock* blocks, const EncResult* results, const uint64_t* dst_off,
+                          uint32_t nblocks, const uint8_t* slots, uint8_t* out, cudaStream_t st);
+
+} // namespace ojb

@@ -1,0 +1,537 @@
+// ojb_layout.cpp -- geometry, packet sequencing, packet headers (see ojb_layout.h).
+#include "ojb_layout.h"
+#include <algorithm>
+#include <climits>
+#include <cstring>
+
+namespace ojb {
+
+//------------------------------------------------------------------------------------------
+// geometry
+//------------------------------------------------------------------------------------------
+Rect BandGeom::block_rect(uint32_t bx, uint32_t by) const {
+  // code-block grid is anchored at multiples of the nominal size in band coordinates
+  // (ojph_subband.cpp:186-203, :313-333)
+  uint32_t nw = 1u << xcb, nh = 1u << ycb;
+  uint32_t gx = (rect.x0 >> xcb) << xcb, gy = (rect.y0 >> ycb) << ycb;
+  uint32_t x0 = std::max(rect.x0, gx + bx * nw), x1 = std::min(rect.x1(), gx + (bx + 1) * nw);
+  uint32_t y0 = std::max(rect.y0, gy + by * nh), y1 = std::min(rect.y1(), gy + (by + 1) * nh);
+  Rect r; r.x0 = x0; r.y0 = y0; r.w = x1 - x0; r.h = y1 - y0;
+  return r;
+}
+
+static void build_band(const Params& p, uint32_t comp, ResGeom& rg, uint32_t b, const Rect& br,
+                       uint32_t& block_counter, uint64_t& arena) {
+  BandGeom& bg = rg.bands[b];
+  bg.rect = br; bg.band_num = b;
+  const QuantSet& q = p.quant_for(comp);
+  bg.K_max = q.kmax(rg.res_num, b);
+  if (!p.reversible()) {
+    float d = q.irrev_delta(rg.res_num, b);
+    d /= (float)(1u << (31 - bg.K_max));
+    bg.delta = d; bg.delta_inv = 1.0f / d;
+  }
+  bg.empty = br.empty();
+  if (bg.empty) return;
+  uint32_t off = rg.res_num > 0 ? 1u : 0u;
+  bg.xcb = std::min(p.log_cb_w(), rg.log_ppx - off);
+  bg.ycb = std::min(p.log_cb_h(), rg.log_ppy - off);
+  bg.nbw = ((br.x1() + (1u << bg.xcb) - 1) >> bg.xcb) - (br.x0 >> bg.xcb);
+  bg.nbh = ((br.y1() + (1u << bg.ycb) - 1) >> bg.ycb) - (br.y0 >> bg.ycb);
+  bg.block_base = block_counter;
+  block_counter += bg.nbw * bg.nbh;
+  bg.plane_pad_x = br.x0 & 3u;
+  bg.plane_stride = (bg.plane_pad_x + br.w + 15u) & ~15u;     // 64-byte rows
+  bg.plane_off = arena;
+  arena += (uint64_t)bg.plane_stride * br.h + 16;            // slack for vector tails
+  arena = (arena + 31) & ~(uint64_t)31;
+}
+
+static void build_precincts(const Params& p, const TileGeom& tile, const TileCompGeom& tc,
+                            ResGeom& rg) {
+  const Rect& rr = rg.rect;
+  rg.npw = rg.nph = 0;
+  if (rr.empty()) return;
+  uint32_t D = p.num_decomps;
+  rg.npw = ((rr.x1() + (1u << rg.log_ppx) - 1) >> rg.log_ppx) - (rr.x0 >> rg.log_ppx);
+  rg.nph = ((rr.y1() + (1u << rg.log_ppy) - 1) >> rg.log_ppy) - (rr.y0 >> rg.log_ppy);
+  rg.precincts.assign((size_t)rg.npw * rg.nph, PrecinctGeom());
+  uint32_t xlb = (rr.x0 >> rg.log_ppx) << rg.log_ppx, ylb = (rr.y0 >> rg.log_ppy) << rg.log_ppy;
+  // resolution down-sampling relative to the canvas, including component sub-sampling
+  // (tile_comp::finalize_alloc passes comp_downsamp as the initial res_downsamp)
+  uint64_t dsx = (uint64_t)p.comps[tc.comp].dx << (D - rg.res_num);
+  uint64_t dsy = (uint64_t)p.comps[tc.comp].dy << (D - rg.res_num);
+  for (uint32_t y = 0; y < rg.nph; ++y)
+    for (uint32_t x = 0; x < rg.npw; ++x) {
+      PrecinctGeom& pc = rg.precincts[(size_t)y * rg.npw + x];
+      uint32_t tx = (uint32_t)(dsx * (xlb + (x << rg.log_ppx)));
+      uint32_t ty = (uint32_t)(dsy * (ylb + (y << rg.log_ppy)));
+      pc.img_x = std::max(tx, tile.rect.x0);
+      pc.img_y = std::max(ty, tile.rect.y0);
+    }
+  // code-block index rectangles (subband::get_cb_indices)
+  uint32_t shift = rg.res_num > 0 ? 1u : 0u;
+  for (uint32_t b = (rg.res_num ? 1 : 0); b < (rg.res_num ? 4u : 1u); ++b) {
+    const BandGeom& bg = rg.bands[b];
+    if (bg.empty) continue;
+    uint32_t coly = 0;
+    for (uint32_t y = 0; y < rg.nph; ++y) {
+      uint32_t pcy0 = std::max(rr.y0, ylb + (y << rg.log_ppy));
+      uint32_t pcy1 = std::min(rr.y1(), ylb + ((y + 1) << rg.log_ppy));
+      pcy0 = (pcy0 - (b >> 1) + (1u << shift) - 1) >> shift;
+      pcy1 = (pcy1 - (b >> 1) + (1u << shift) - 1) >> shift;
+      uint32_t yb = ((pcy1 + (1u << bg.ycb) - 1) >> bg.ycb) - (pcy0 >> bg.ycb);
+      uint32_t colx = 0;
+      for (uint32_t x = 0; x < rg.npw; ++x) {
+        uint32_t pcx0 = std::max(rr.x0, xlb + (x << rg.log_ppx));
+        uint32_t pcx1 = std::min(rr.x1(), xlb + ((x + 1) << rg.log_ppx));
+        pcx0 = (pcx0 - (b & 1) + (1u << shift) - 1) >> shift;
+        pcx1 = (pcx1 - (b & 1) + (1u << shift) - 1) >> shift;
+        uint32_t xb = ((pcx1 + (1u << bg.xcb) - 1) >> bg.xcb) - (pcx0 >> bg.xcb);
+        Rect& r = rg.precincts[(size_t)y * rg.npw + x].cb_idx[b];
+        r.x0 = colx; r.y0 = coly; r.w = xb; r.h = yb;
+        colx += xb;
+      }
+      coly += yb;
+    }
+  }
+}
+
+void Layout::build(const Params& params) {
+  p = &params;
+  const Params& P = params;
+  uint32_t nc = P.num_comps(), D = P.num_decomps;
+  ntw = div_ceil(P.Xsiz - P.XTOsiz, P.XTsiz);
+  nth = div_ceil(P.Ysiz - P.YTOsiz, P.YTsiz);
+  if ((uint64_t)ntw * nth > 65535) fail(0x00030011, "the number of tiles cannot exceed 65535");
+  if ((uint64_t)ntw * nth == 0) fail(0x00030012, "the number of tiles cannot be 0");
+  tiles.assign((size_t)ntw * nth, TileGeom());
+  num_blocks = 0;
+  uint64_t arena = 0;
+  for (uint32_t ty = 0; ty < nth; ++ty)
+    for (uint32_t tx = 0; tx < ntw; ++tx) {
+      TileGeom& t = tiles[(size_t)ty * ntw + tx];
+      t.idx = ty * ntw + tx;
+      uint32_t x0 = P.XTOsiz + tx * P.XTsiz, x1 = x0 + P.XTsiz;
+      uint32_t y0 = P.YTOsiz + ty * P.YTsiz, y1 = y0 + P.YTsiz;
+      t.rect.x0 = std::max(x0, P.XOsiz); t.rect.w = std::min(x1, P.Xsiz) - t.rect.x0;
+      t.rect.y0 = std::max(y0, P.YOsiz); t.rect.h = std::min(y1, P.Ysiz) - t.rect.y0;
+      t.comps.assign(nc, TileCompGeom());
+      for (uint32_t c = 0; c < nc; ++c) {
+        TileCompGeom& tc = t.comps[c];
+        tc.comp = c;
+        uint32_t dx = P.comps[c].dx, dy = P.comps[c].dy;
+        tc.rect.x0 = div_ceil(t.rect.x0, dx); tc.rect.w = div_ceil(t.rect.x1(), dx) - tc.rect.x0;
+        tc.rect.y0 = div_ceil(t.rect.y0, dy); tc.rect.h = div_ceil(t.rect.y1(), dy) - tc.rect.y0;
+        tc.res.assign(D + 1, ResGeom());
+        Rect rr = tc.rect;
+        for (int r = (int)D; r >= 0; --r) {
+          ResGeom& rg = tc.res[r];
+          rg.rect = rr; rg.res_num = (uint32_t)r;
+          rg.log_ppx = P.log_pp_w((uint32_t)r); rg.log_ppy = P.log_pp_h((uint32_t)r);
+          // sample plane of this resolution (input of the level-r analysis / output of synthesis)
+          rg.plane_stride = (rr.w + 15u) & ~15u;
+          rg.plane_off = arena;
+          if (r != (int)D || true) {   // top level planes are used by the decoder as well
+            arena += (uint64_t)rg.plane_stride * rr.h + 16;
+            arena = (arena + 31) & ~(uint64_t)31;
+          }
+          uint32_t trx0 = rr.x0, trx1 = rr.x1(), try0 = rr.y0, try1 = rr.y1();
+          if (r > 0) {
+            for (uint32_t i = 1; i < 4; ++i) {
+              Rect br;
+              br.x0 = (trx0 - (i & 1) + 1) >> 1; br.w = ((trx1 - (i & 1) + 1) >> 1) - br.x0;
+              br.y0 = (try0 - (i >> 1) + 1) >> 1; br.h = ((try1 - (i >> 1) + 1) >> 1) - br.y0;
+              build_band(P, c, rg, i, br, num_blocks, arena);
+            }
+            Rect ll;
+            ll.x0 = (trx0 + 1) >> 1; ll.w = ((trx1 + 1) >> 1) - ll.x0;
+            ll.y0 = (try0 + 1) >> 1; ll.h = ((try1 + 1) >> 1) - ll.y0;
+            rr = ll;
+          } else
+            build_band(P, c, rg, 0, rr, num_blocks, arena);
+        }
+        for (uint32_t r = 0; r <= D; ++r) build_precincts(P, t, tc, tc.res[r]);
+      }
+    }
+  coef_words = arena;
+}
+
+//------------------------------------------------------------------------------------------
+// packet sequencing
+//------------------------------------------------------------------------------------------
+void Layout::packet_sequence(uint32_t tile, std::vector<PacketRef>& seq,
+                             std::vector<uint32_t>& tp_first) const {
+  const TileGeom& t = tiles[tile];
+  const Params& P = *p;
+  uint32_t nc = P.num_comps(), D = P.num_decomps;
+  seq.clear(); tp_first.clear();
+  // per (comp,res) cursor over precincts in raster order
+  std::vector<uint32_t> cur((size_t)nc * (D + 1), 0);
+  auto npre = [&](uint32_t c, uint32_t r) { return (uint32_t)t.comps[c].res[r].precincts.size(); };
+  auto emit_all = [&](uint32_t c, uint32_t r) {
+    for (uint32_t i = 0; i < npre(c, r); ++i) seq.push_back(PacketRef{ tile, c, r, i });
+  };
+  auto emit_one = [&](uint32_t c, uint32_t r) {
+    seq.push_back(PacketRef{ tile, c, r, cur[(size_t)c * (D + 1) + r]++ });
+  };
+  auto top_left = [&](uint32_t c, uint32_t r, uint32_t& x, uint32_t& y) {
+    uint32_t i = cur[(size_t)c * (D + 1) + r];
+    if (i >= npre(c, r)) return false;
+    x = t.comps[c].res[r].precincts[i].img_x; y = t.comps[c].res[r].precincts[i].img_y;
+    return true;
+  };
+  uint32_t div = P.tilepart_div;
+  if (div == TP_NONE) tp_first.push_back(0);
+  if (P.prog_order == PO_LRCP || P.prog_order == PO_RLCP) {
+    for (uint32_t r = 0; r <= D; ++r) {
+      if (div == TP_RES) tp_first.push_back((uint32_t)seq.size());
+      for (uint32_t c = 0; c < nc; ++c) {
+        if (div & TP_COMP) tp_first.push_back((uint32_t)seq.size());
+        emit_all(c, r);
+      }
+    }
+  } else if (P.prog_order == PO_RPCL) {
+    for (uint32_t r = 0; r <= D; ++r) {
+      if (div == TP_RES) tp_first.push_back((uint32_t)seq.size());
+      for (;;) {
+        bool found = false; uint32_t best_c = 0, bx = INT_MAX, by = INT_MAX, x, y;
+        for (uint32_t c = 0; c < nc; ++c) {
+          if (!top_left(c, r, x, y)) continue;
+          found = true;
+          if (y < by || (y == by && x < bx)) { bx = x; by = y; best_c = c; }
+        }
+        if (!found) break;
+        emit_one(best_c, r);
+      }
+    }
+  } else if (P.prog_order == PO_PCRL) {
+    for (;;) {
+      bool found = false; uint32_t bc = 0, br = 0, bx = INT_MAX, by = INT_MAX, x, y;
+      for (uint32_t c = 0; c < nc; ++c)
+        for (uint32_t r = 0; r <= D; ++r) {
+          if (!top_left(c, r, x, y)) continue;
+          found = true;
+          if (y < by || (y == by && x < bx) || (y == by && x == bx && c < bc) ||
+              (y == by && x == bx && c == bc && r < br)) { bx = x; by = y; bc = c; br = r; }
+        }
+      if (!found) break;
+      emit_one(bc, br);
+    }
+  } else {  // CPRL
+    for (uint32_t c = 0; c < nc; ++c) {
+      if (div == TP_COMP) tp_first.push_back((uint32_t)seq.size());
+      for (;;) {
+        bool found = false; uint32_t br = 0, bx = INT_MAX, by = INT_MAX, x, y;
+        for (uint32_t r = 0; r <= D; ++r) {
+          if (!top_left(c, r, x, y)) continue;
+          found = true;
+          if (y < by || (y == by && x < bx)) { bx = x; by = y; br = r; }
+        }
+        if (!found) break;
+        emit_one(c, br);
+      }
+    }
+  }
+  if (tp_first.empty()) tp_first.push_back(0);
+}
+
+//------------------------------------------------------------------------------------------
+// packet headers
+//------------------------------------------------------------------------------------------
+namespace {
+
+inline uint32_t log2ceil(uint32_t x) {
+  uint32_t t = 31u - (uint32_t)__builtin_clz(x);
+  return t + ((x & (x - 1)) ? 1u : 0u);
+}
+
+// Tag tree with the reference's storage behaviour: level i is a linear array of
+// 4^(num_levels-1-i) entries pre-filled with init; an entry is addressed as
+// x + y * ceil(w / 2^i).  When a level's width is odd, the "right child" of the last
+// column aliases the first entry of the next row -- the reference computes its minima
+// that way (ojph_precinct.cpp:57-87,142-165), so byte-identical headers need the same.
+struct TagTree {
+  uint32_t w, h, nl;
+  std::vector<std::vector<uint8_t>> lev;
+  void init(uint32_t nlev, uint32_t ww, uint32_t hh, uint8_t v) {
+    w = ww; h = hh; nl = nlev;
+    lev.resize(nl + 1);
+    for (uint32_t i = 0; i < nl; ++i) lev[i].assign((size_t)1 << ((nl - 1 - i) << 1), v);
+    lev[nl].assign(1, 0);
+  }
+  uint8_t& at(uint32_t x, uint32_t y, uint32_t l) {
+    return lev[l][x + (size_t)y * ((w + (1u << l) - 1) >> l)];
+  }
+};
+
+struct BitWriter {   // MSB first; a byte after 0xFF carries 7 bits (ojph_bitbuffer_write.h:85-143)
+  std::vector<uint8_t>& o; int avail = 8; uint32_t tmp = 0;
+  explicit BitWriter(std::vector<uint8_t>& out) : o(out) {}
+  void bit(uint32_t b) {
+    --avail; tmp |= (b & 1u) << avail;
+    if (avail <= 0) { o.push_back((uint8_t)tmp); avail = 8 - (tmp != 0xFF ? 0 : 1); tmp = 0; }
+  }
+  void bits(uint32_t v, int n) { for (int i = n - 1; i >= 0; --i) bit(v >> i); }
+  void finish() { if (avail < 8) o.push_back((uint8_t)tmp); }
+};
+
+struct BitReader {   // ojph_bitbuffer_read.h:73-130
+  const uint8_t* d; size_t& pos; uint32_t& left; uint32_t tmp = 0; int avail = 0; bool unstuff = false;
+  BitReader(const uint8_t* data, size_t& p, uint32_t& l) : d(data), pos(p), left(l) {}
+  bool fill() {
+    if (left > 0) { uint8_t t = d[pos++]; tmp = t; avail = 8 - (unstuff ? 1 : 0); unstuff = (t == 0xFF); --left; return true; }
+    tmp = 0; avail = 8 - (unstuff ? 1 : 0); unstuff = false; return false;
+  }
+  bool bit(uint32_t& b) { bool r = true; if (avail == 0) r = fill(); b = (tmp >> --avail) & 1u; return r; }
+  bool bits(int n, uint32_t& v) {
+    v = 0; bool r = true;
+    while (n) {
+      if (avail == 0) r = fill();
+      int t = std::min(avail, n);
+      v <<= t; avail -= t; n -= t;
+      v |= (tmp >> avail) & ((1u << t) - 1);
+    }
+    return r;
+  }
+  bool finish() { bool r = true; if (unstuff) r = fill(); tmp = 0; avail = 0; return r; }
+};
+
+} // namespace
+
+uint32_t write_packet_header(const ResGeom& res, const PrecinctGeom& pc,
+                             const CodedBlock* blocks, std::vector<uint8_t>& out) {
+  size_t start = out.size();
+  BitWriter bw(out);
+  bool coded = false;
+  int skipped_bands = 0;
+  uint32_t body = 0;
+  for (uint32_t s = 0; s < 4; ++s) {
+    const BandGeom& bg = res.bands[s];
+    if (bg.empty) continue;
+    const Rect& ci = pc.cb_idx[s];
+    if (ci.w == 0 || ci.h == 0) continue;
+    uint32_t nl = 1 + std::max(log2ceil(ci.w), log2ceil(ci.h));
+    TagTree inc, incf, mm, mmf;
+    inc.init(nl, ci.w, ci.h, 255); incf.init(nl, ci.w, ci.h, 0);
+    mm.init(nl, ci.w, ci.h, 255); mmf.init(nl, ci.w, ci.h, 0);
+    const CodedBlock* base = blocks + bg.block_base;
+    for (uint32_t y = 0; y < ci.h; ++y)
+      for (uint32_t x = 0; x < ci.w; ++x) {
+        const CodedBlock& cb = base[(size_t)(ci.y0 + y) * bg.nbw + ci.x0 + x];
+        inc.at(x, y, 0) = cb.num_passes == 0 ? 1 : 0;
+        mm.at(x, y, 0) = cb.missing_msbs;
+      }
+    for (uint32_t l = 1; l < nl; ++l) {
+      uint32_t hh = (ci.h + (1u << l) - 1) >> l, ww = (ci.w + (1u << l) - 1) >> l;
+      for (uint32_t y = 0; y < hh; ++y)
+        for (uint32_t x = 0; x < ww; ++x) {
+          uint8_t a = std::min(inc.at(x << 1, y << 1, l - 1), inc.at((x << 1) + 1, y << 1, l - 1));
+          uint8_t b = std::min(inc.at(x << 1, (y << 1) + 1, l - 1), inc.at((x << 1) + 1, (y << 1) + 1, l - 1));
+          inc.at(x, y, l) = std::min(a, b); incf.at(x, y, l) = 0;
+          a = std::min(mm.at(x << 1, y << 1, l - 1), mm.at((x << 1) + 1, y << 1, l - 1));
+          b = std::min(mm.at(x << 1, (y << 1) + 1, l - 1), mm.at((x << 1) + 1, (y << 1) + 1, l - 1));
+          mm.at(x, y, l) = std::min(a, b); mmf.at(x, y, l) = 0;
+        }
+    }
+    if (inc.at(0, 0, nl - 1) != 0) {          // nothing included in this band
+      if (coded) bw.bit(0); else ++skipped_bands;
+      continue;
+    }
+    if (!coded) {
+      coded = true;
+      bw.bit(1);                               // non-empty packet
+      for (int i = 0; i < skipped_bands; ++i) bw.bit(0);
+      skipped_bands = 0;
+    }
+    for (uint32_t y = 0; y < ci.h; ++y)
+      for (uint32_t x = 0; x < ci.w; ++x) {
+        const CodedBlock& cb = base[(size_t)(ci.y0 + y) * bg.nbw + ci.x0 + x];
+        for (uint32_t cl = nl; cl > 0; --cl) {   // inclusion
+          uint32_t lm = cl - 1;
+          if (incf.at(x >> lm, y >> lm, lm) == 0) {
+            uint32_t skipped = inc.at(x >> lm, y >> lm, lm);
+            skipped -= inc.at(x >> cl, y >> cl, cl);
+            bw.bit(1 - skipped);
+            incf.at(x >> lm, y >> lm, lm) = 1;
+          }
+          if (inc.at(x >> lm, y >> lm, lm) > 0) break;
+        }
+        if (cb.num_passes == 0) continue;
+        for (uint32_t cl = nl; cl > 0; --cl) {   // missing msbs
+          uint32_t lm = cl - 1;
+          if (mmf.at(x >> lm, y >> lm, lm) == 0) {
+            int nz = mm.at(x >> lm, y >> lm, lm);
+            nz -= mm.at(x >> cl, y >> cl, cl);
+            for (int i = 0; i < nz; ++i) bw.bit(0);
+            bw.bit(1);
+            mmf.at(x >> lm, y >> lm, lm) = 1;
+          }
+        }
+        if (cb.num_passes == 3) bw.bits(12, 4);
+        else if (cb.num_passes == 2) bw.bits(2, 2);
+        else bw.bits(0, 1);
+        int bits1 = 32 - (cb.pass_len[0] ? __builtin_clz(cb.pass_len[0]) : 32);
+        int extra = cb.num_passes > 2 ? 1 : 0;
+        int bits2 = 0;
+        if (cb.num_passes > 1) bits2 = 32 - (cb.pass_len[1] ? __builtin_clz(cb.pass_len[1]) : 32);
+        int nb = std::max(std::max(bits1, bits2 - extra) - 3, 0);
+        bw.bits(0xFFFFFFFEu, nb + 1);
+        bw.bits(cb.pass_len[0], nb + 3);
+        if (cb.num_passes > 1) bw.bits(cb.pass_len[1], nb + 3 + extra);
+        body += cb.pass_len[0] + cb.pass_len[1];
+      }
+  }
+  if (coded) bw.finish();
+  else { out.resize(start); out.push_back(0); }   // empty packet: one zero byte
+  return body;
+}
+
+void parse_packet(const Params& P, const ResGeom& res, const PrecinctGeom& pc,
+                  CodedBlock* blocks, const uint8_t* data, size_t& pos, uint32_t& data_left) {
+  BitReader br(data, pos, data_left);
+  if (P.uses_sop() && data_left >= 2) {            // optional SOP marker segment
+    if (data[pos] == 0xFF && data[pos + 1] == 0x91) {
+      pos += 2; data_left -= 2;
+      if (data_left < 4) throw Error(0x00030092, "precinct truncated early");
+      uint32_t L = ((uint32_t)data[pos] << 8) | data[pos + 1];
+      if (L != 4) throw Error(0x00030092, "something is wrong with SOP length");
+      pos += 4; data_left -= 4;
+    }
+  }
+  bool empty_packet = true;
+  for (uint32_t s = 0; s < 4; ++s) {
+    const BandGeom& bg = res.bands[s];
+    if (bg.empty) continue;
+    const Rect& ci = pc.cb_idx[s];
+    if (ci.w == 0 || ci.h == 0) continue;
+    uint32_t bit;
+    if (empty_packet) {
+      br.bit(bit);
+      if (bit == 0) {                              // empty packet
+        br.finish();
+        if (P.uses_eph() && data_left >= 2) { pos += 2; data_left -= 2; }
+        return;
+      }
+      empty_packet = false;
+    }
+    uint32_t nl = 1 + std::max(log2ceil(ci.w), log2ceil(ci.h));
+    TagTree inc, incf, mm, mmf;
+    inc.init(nl, ci.w, ci.h, 0); incf.init(nl, ci.w, ci.h, 0);
+    mm.init(nl, ci.w, ci.h, 0); mmf.init(nl, ci.w, ci.h, 0);
+    CodedBlock* base = blocks + bg.block_base;
+    for (uint32_t y = 0; y < ci.h; ++y)
+      for (uint32_t x = 0; x < ci.w; ++x) {
+        CodedBlock& cb = base[(size_t)(ci.y0 + y) * bg.nbw + ci.x0 + x];
+        bool empty_cb = false;
+        for (uint32_t cl = nl; cl > 0; --cl) {
+          uint32_t l = cl - 1;
+          empty_cb = inc.at(x >> l, y >> l, l) == 1;
+          if (empty_cb) break;
+          if (incf.at(x >> l, y >> l, l) == 0) {
+            if (!br.bit(bit)) { data_left = 0; throw Error(0x00030092, "error reading from file p1"); }
+            empty_cb = (bit == 0);
+            inc.at(x >> l, y >> l, l) = (uint8_t)(1 - bit);
+            incf.at(x >> l, y >> l, l) = 1;
+          }
+          if (empty_cb) break;
+        }
+        if (empty_cb) continue;
+        uint32_t mmsbs = 0;
+        for (uint32_t lp = nl; lp > 0; --lp) {
+          uint32_t l = lp - 1;
+          mmsbs = mm.at(x >> lp, y >> lp, lp);
+          if (mmf.at(x >> l, y >> l, l) == 0) {
+            bit = 0;
+            while (bit == 0) {
+              if (!br.bit(bit)) { data_left = 0; throw Error(0x00030092, "error reading from file p2"); }
+              mmsbs += 1 - bit;
+            }
+            mm.at(x >> l, y >> l, l) = (uint8_t)mmsbs;
+            mmf.at(x >> l, y >> l, l) = 1;
+          }
+        }
+        if (mmsbs > bg.K_max)
+          throw Error(0x00030092, "error in parsing a tile header; missing msbs are larger or "
+                      "equal to Kmax. The most likely cause is a corruption in the bitstream.");
+        cb.missing_msbs = (uint8_t)mmsbs;
+        uint32_t np = 1;
+        if (!br.bit(bit)) { data_left = 0; throw Error(0x00030092, "error reading from file p3"); }
+        if (bit) {
+          np = 2;
+          if (!br.bit(bit)) { data_left = 0; throw Error(0x00030092, "error reading from file p4"); }
+          if (bit) {
+            if (!br.bits(2, bit)) { data_left = 0; throw Error(0x00030092, "error reading from file p5"); }
+            np = 3 + bit;
+            if (bit == 3) {
+              if (!br.bits(5, bit)) { data_left = 0; throw Error(0x00030092, "error reading from file p6"); }
+              np = 6 + bit;
+              if (bit == 31) {
+                if (!br.bits(7, bit)) { data_left = 0; throw Error(0x00030092, "error reading from file p7"); }
+                np = 37 + bit;
+              }
+            }
+          }
+        }
+        // placeholder passes: every group of 3 adds one missing msb (ojph_precinct.cpp:466-480)
+        uint32_t phld = (np - 1) / 3;
+        cb.missing_msbs = (uint8_t)(cb.missing_msbs + phld);
+        phld *= 3;
+        cb.num_passes = (uint8_t)(np - phld);
+        cb.pass_len[0] = cb.pass_len[1] = 0;
+        int Lblock = 3;
+        bit = 1;
+        while (bit) {
+          if (!br.bit(bit)) { data_left = 0; throw Error(0x00030092, "error reading from file p8"); }
+          Lblock += (int)bit;
+        }
+        int nb = Lblock + 31 - __builtin_clz(phld + 1);
+        if (!br.bits(nb, bit)) { data_left = 0; throw Error(0x00030092, "error reading from file p9"); }
+        if (bit < 2)
+          throw Error(0x00030092, "The cleanup segment of an HT codeblock cannot contain less than 2 bytes");
+        if (bit >= 65535)
+          throw Error(0x00030092, "The cleanup segment of an HT codeblock must contain less than 65535 bytes");
+        cb.pass_len[0] = bit;
+        if (cb.num_passes > 1) {
+          nb = Lblock + (cb.num_passes > 2 ? 1 : 0);
+          if (!br.bits(nb, bit)) { data_left = 0; throw Error(0x00030092, "error reading from file p10"); }
+          if (bit >= 2047)
+            throw Error(0x00030092, "The refinement segment (SigProp and MagRep passes) of an HT "
+                        "codeblock must contain less than 2047 bytes");
+          cb.pass_len[1] = bit;
+        }
+      }
+  }
+  if (empty_packet) { uint32_t bit = 0; br.bit(bit); }
+  br.finish();
+  if (P.uses_eph() && data_left >= 2) {
+    if (!(data[pos] == 0xFF && data[pos + 1] == 0x92))
+      throw Error(0x00030092, "should find EPH, but found something else");
+    pos += 2; data_left -= 2;
+  }
+  // code-block bodies follow in band / raster order
+  for (uint32_t s = 0; s < 4; ++s) {
+    const BandGeom& bg = res.bands[s];
+    if (bg.empty) continue;
+    const Rect& ci = pc.cb_idx[s];
+    CodedBlock* base = blocks + bg.block_base;
+    for (uint32_t y = 0; y < ci.h; ++y)
+      for (uint32_t x = 0; x < ci.w; ++x) {
+        CodedBlock& cb = base[(size_t)(ci.y0 + y) * bg.nbw + ci.x0 + x];
+        uint32_t nbytes = cb.pass_len[0] + cb.pass_len[1];
+        if (data_left) {
+          if (nbytes) {
+            if (nbytes > data_left) {              // truncated block: do not decode it
+              cb.pass_len[0] = cb.pass_len[1] = 0;
+              pos += data_left; data_left = 0;
+            } else {
+              cb.data_off = pos; pos += nbytes; data_left -= nbytes;
+            }
+          }
+        } else
+          cb.pass_len[0] = cb.pass_len[1] = 0;
+      }
+  }
+}
+
+} // namespace ojb

@@ -1,0 +1,540 @@
+// ojb_params.cpp -- see ojb_params.h for the reference file:line each piece mirrors.
+#include "ojb_params.h"
+#include <cmath>
+#include <cstring>
+#include <algorithm>
+
+namespace ojb {
+
+#include "ojb_gain_tables.inc"
+
+namespace {
+
+inline float energy_gain_l(uint32_t d, bool rev) { return rev ? kEnergy_5x3_l[d] : kEnergy_9x7_l[d]; }
+inline float energy_gain_h(uint32_t d, bool rev) { return rev ? kEnergy_5x3_h[d] : kEnergy_9x7_h[d]; }
+inline float bibo_gain_l(uint32_t d, bool rev) { return rev ? kBibo_5x3_l[d] : kBibo_9x7_l[d]; }
+inline float bibo_gain_h(uint32_t d, bool rev) { return rev ? kBibo_5x3_h[d] : kBibo_9x7_h[d]; }
+
+// Qfactor model (ojph_params.cpp:604-726): visual weight tables by chroma format and
+// component type, reference step from the quality factor.
+const float* visual_weights(uint32_t sx, uint32_t sy, int ctype, bool& ok) {
+  ok = true;
+  int fmt;  // 1: 420, 2: 422, 3: 444
+  if (sx == 2 && sy == 2) fmt = 1;
+  else if (sx == 2 && sy == 1) fmt = 2;
+  else if (sx == 1 && sy == 1) fmt = 3;
+  else { ok = false; return kVw_y; }
+  if (ctype == 0) return kVw_y;
+  if (ctype == 1) return fmt == 1 ? kVw_cb420 : (fmt == 2 ? kVw_cb422 : kVw_cb444);
+  return fmt == 1 ? kVw_cr420 : (fmt == 2 ? kVw_cr422 : kVw_cr444);
+}
+inline float vw_weight(const float* v, uint32_t level, uint32_t band) {
+  if (band == 0) return v[18];
+  level = std::min(level, 6u);
+  return v[(level - 1) * 3 + (3 - band)];
+}
+inline float vw_gain(int ctype) {
+  if (ctype == 0) return 1.0f;
+  if (ctype == 1) return 1.8051f / 1.7321f;
+  return 1.5734f / 1.7321f;
+}
+float vw_delta_ref(uint32_t qfactor, uint32_t bit_depth, float& power) {
+  constexpr uint8_t t0 = 65, t1 = 97;
+  constexpr float alpha_t0 = 0.04f, alpha_t1 = 0.10f;
+  constexpr float m_t0 = 2.0f * (1.0f - t0 / 100.0f);
+  constexpr float m_t1 = 2.0f * (1.0f - t1 / 100.0f);
+  float m_q = qfactor < 50 ? 50.0f / (float)qfactor : 2.0f * (1.0f - (float)qfactor / 100.0f);
+  float alpha_q;
+  if (qfactor <= t0) { power = 1.0f; alpha_q = alpha_t0; }
+  else if (qfactor < t1) {
+    power = std::log(m_q) - std::log(m_t1);
+    power /= std::log(m_t0) - std::log(m_t1);
+    alpha_q = alpha_t1 * std::pow(alpha_t0 / alpha_t1, power);
+  } else { power = 0.0f; alpha_q = alpha_t1; }
+  const float eps = std::sqrt(0.5f) * std::ldexp(1.0f, -(int)bit_depth);
+  return alpha_q * m_q + eps;
+}
+
+// exponent/mantissa packing of an irreversible step (encode_SPqcd, ojph_params.cpp:1602)
+uint16_t pack_step(float delta) {
+  int exp = 0;
+  while (delta < 1.0f) { exp++; delta *= 2.0f; }
+  int mantissa = (int)round(delta * (float)(1 << 11)) - (1 << 11);
+  mantissa = mantissa < (1 << 11) ? mantissa : 0x7FF;
+  return (uint16_t)((exp << 11) | mantissa);
+}
+
+} // namespace
+
+//------------------------------------------------------------------------------------------
+// QuantSet
+//------------------------------------------------------------------------------------------
+void QuantSet::set_rev_quant(uint32_t nd, uint32_t bd, bool color) {
+  uint32_t B = bd + (color ? 1u : 0u);          // one extra bit after the RCT
+  int s = 0;
+  double bl = bibo_gain_l(nd, true);
+  uint32_t X = (uint32_t)ceil(log(bl * bl) / M_LN2);
+  uint8_t tmp[97];
+  tmp[s++] = (uint8_t)(B + X);
+  uint32_t max_BX = B + X;
+  for (uint32_t d = nd; d > 0; --d) {
+    double l = bibo_gain_l(d, true), h = bibo_gain_h(d - 1, true);
+    X = (uint32_t)ceil(log(h * l) / M_LN2);
+    tmp[s++] = (uint8_t)(B + X); max_BX = std::max(max_BX, B + X);
+    tmp[s++] = (uint8_t)(B + X);
+    X = (uint32_t)ceil(log(h * h) / M_LN2);
+    tmp[s++] = (uint8_t)(B + X); max_BX = std::max(max_BX, B + X);
+  }
+  if (max_BX > 38)
+    fail(0x00050151, "The specified combination of bit_depth, colour transform, and type of "
+         "wavelet transform requires more than 38 bits; it requires %d bits.", max_BX);
+  int guard = std::max(1, (int)max_BX - 31);
+  Sqcd = (uint8_t)(guard << 5);
+  for (int i = 0; i < s; ++i) SP[i] = (uint16_t)(uint8_t)((uint8_t)(tmp[i] - guard) << 3);
+}
+
+void QuantSet::set_irrev_quant(uint32_t nd) {
+  Sqcd = (uint8_t)((1 << 5) | 0x2);             // one guard bit, scalar expounded
+  float g_c = 1.0f, delta_ref = base_delta, power = 1.0f;
+  const float* weights = kVw_no_weights;
+  if (qfactor != 0) {
+    bool ok;
+    weights = visual_weights(sx, sy, ctype, ok);
+    if (!ok)
+      fail(0x00050161, "Qfactor can only be used on components with 4:4:4, 4:2:2 or 4:2:0 sampling");
+    if (ctype == 0 && sx != 1 && sy != 1)
+      fail(0x00050162, "Qfactor can only be used for a Y or luminance component when it is "
+           "not downsampled.");
+    g_c = vw_gain(ctype);
+    delta_ref = vw_delta_ref(qfactor, bit_depth, power);
+  }
+  uint32_t b = 0;
+  float gl = energy_gain_l(nd, false);
+  float w_b = std::pow(vw_weight(weights, nd, 0), power);
+  SP[b++] = pack_step(delta_ref / (gl * gl * g_c * w_b));
+  for (uint32_t d = nd; d > 0; --d) {
+    float l = energy_gain_l(d, false), h = energy_gain_h(d - 1, false);
+    w_b = std::pow(vw_weight(weights, d, 1), power);
+    SP[b++] = pack_step(delta_ref / (h * l * g_c * w_b));
+    w_b = std::pow(vw_weight(weights, d, 2), power);
+    SP[b++] = pack_step(delta_ref / (l * h * g_c * w_b));
+    w_b = std::pow(vw_weight(weights, d, 3), power);
+    SP[b++] = pack_step(delta_ref / (h * h * g_c * w_b));
+  }
+}
+
+uint32_t QuantSet::kmax(uint32_t res, uint32_t band) const {
+  uint32_t idx = res ? (res - 1) * 3 + band : 0;
+  if (idx >= num_subbands) idx = num_subbands - 1;
+  uint32_t bits = 0;
+  if ((Sqcd & 0x1F) == 0) { bits = (uint32_t)(SP[idx] & 0xFF) >> 3; bits = bits ? bits - 1 : 0; }
+  else bits = (uint32_t)(SP[idx] >> 11) - 1;
+  return bits + guard_bits();
+}
+
+uint32_t QuantSet::largest_kmax() const {
+  uint32_t bits = 0;
+  for (uint32_t i = 0; i < num_subbands; ++i) {
+    uint32_t t;
+    if ((Sqcd & 0x1F) == 0) { t = (uint32_t)(SP[i] & 0xFF) >> 3; t = t ? t - 1 : 0; }
+    else t = (uint32_t)(SP[i] >> 11) - 1;
+    bits = std::max(bits, t);
+  }
+  return bits + guard_bits();
+}
+
+float QuantSet::irrev_delta(uint32_t res, uint32_t band) const {
+  static const float arr[4] = { 1.0f, 2.0f, 2.0f, 4.0f };
+  if ((Sqcd & 0x1F) != 2)
+    fail(0x00050101, "irreversible transform with reversible (no quantization) step sizes");
+  uint32_t idx = res ? (res - 1) * 3 + band : 0;
+  if (idx >= num_subbands) idx = num_subbands - 1;
+  int eps = SP[idx] >> 11;
+  float mantissa = (float)((SP[idx] & 0x7FF) | 0x800) * arr[band];
+  mantissa /= (float)(1 << 11);
+  mantissa /= (float)(1u << eps);
+  return mantissa;
+}
+
+//------------------------------------------------------------------------------------------
+// Params
+//------------------------------------------------------------------------------------------
+const QuantSet& Params::quant_for(uint32_t c) const {
+  for (const QuantSet& q : qcc) if (q.comp_idx == c) return q;
+  return qcd;
+}
+QuantSet* Params::find_qcc(uint32_t c) {
+  for (QuantSet& q : qcc) if (q.comp_idx == c) return &q;
+  return nullptr;
+}
+QuantSet& Params::add_qcc(uint32_t c) {
+  qcc.emplace_back();
+  QuantSet& q = qcc.back();
+  q.is_qcc = true; q.comp_idx = (uint16_t)c;
+  return q;
+}
+
+uint32_t Params::precision(uint32_t c) const {
+  uint32_t p = 0;
+  if (color_transform() && c < 3) {
+    for (uint32_t i = 0; i < 3; ++i) p = std::max(p, quant_for(i).largest_kmax());
+  } else
+    p = quant_for(c).largest_kmax();
+  return p + 2;   // + sign bit + one spare bit (ojph_params.cpp:1700-1706)
+}
+
+void Params::set_block_dims(uint32_t w, uint32_t h) {
+  uint32_t lw = w ? ilog2(w) : 0, lh = h ? ilog2(h) : 0;
+  if (w == 0 || w != (1u << lw) || h == 0 || h != (1u << lh) || lw < 2 || lh < 2 || lw + lh > 12)
+    fail(0x00050011, "incorrect code block dimensions");
+  cb_w_exp = (uint8_t)(lw - 2); cb_h_exp = (uint8_t)(lh - 2);
+}
+
+void Params::set_precincts(int n, const uint32_t* w, const uint32_t* h) {
+  if (n == 0 || w == nullptr || h == nullptr) { Scod &= 0xFE; return; }
+  Scod |= 1;
+  for (int i = 0; i <= num_decomps; ++i) {
+    uint32_t pw = w[i < n ? i : n - 1], ph = h[i < n ? i : n - 1];
+    if (pw == 0 || ph == 0) fail(0x00050021, "precinct width or height cannot be 0");
+    uint32_t PPx = ilog2(pw), PPy = ilog2(ph);
+    if (pw != (1u << PPx) || ph != (1u << PPy))
+      fail(0x00050022, "precinct width and height should be a power of 2");
+    if (PPx > 15 || PPy > 15) fail(0x00050023, "precinct size is too large");
+    if (i > 0 && (PPx == 0 || PPy == 0)) fail(0x00050024, "precinct size is too small");
+    precinct_size[i] = (uint8_t)(PPx | (PPy << 4));
+  }
+}
+
+static void make_quant_steps(QuantSet& q, uint32_t comp, const Params& p) {
+  if (q.is_init) fail(0x00040001, "Quantization step sizes already initialized.");
+  q.is_init = true;
+  q.num_decomps = p.num_decomps;
+  q.bit_depth = p.comps[comp].bit_depth;
+  q.is_signed = p.comps[comp].is_signed;
+  q.is_color_trans = p.color_transform();
+  q.wavelet = p.wavelet;
+  q.sx = p.comps[comp].dx; q.sy = p.comps[comp].dy;
+  q.num_subbands = 1 + 3 * q.num_decomps;
+  if (q.wavelet == DWT_REV53)
+    q.set_rev_quant(q.num_decomps, q.bit_depth, comp < 3 ? q.is_color_trans : false);
+  else {
+    if (q.base_delta == -1.0f) {
+      uint32_t t = std::min(16u, q.bit_depth);
+      q.base_delta = 1.0f / (float)(1 << t);
+    }
+    q.set_irrev_quant(q.num_decomps);
+  }
+}
+
+void Params::finalize_for_encode() {
+  // tile size 0x0 => one tile covering the image (ojph_codestream_local.cpp:562-570)
+  if (XTsiz == 0 && YTsiz == 0) { XTsiz = Xsiz + XOsiz; YTsiz = Ysiz + YOsiz; }
+  // SIZ validity (ojph_params_local.h:234-248)
+  if (Xsiz == 0 || Ysiz == 0 || XTsiz == 0 || YTsiz == 0)
+    fail(0x00040001, "Image extent and/or tile size cannot be zero");
+  if (XTOsiz > XOsiz || YTOsiz > YOsiz)
+    fail(0x00040002, "Tile offset has to be smaller than the image offset");
+  if (XTsiz + XTOsiz <= XOsiz || YTsiz + YTOsiz <= YOsiz)
+    fail(0x00040003, "The top left tile must intersect with the image");
+  if (Xsiz <= XOsiz || Ysiz <= YOsiz)
+    fail(0x00040004, "The image extent must be larger than the image offset");
+  uint32_t nc = num_comps();
+  if (nc == 0 || nc > 16384) fail(0x00040005, "wrong number of components");
+  // COD validity (ojph_params_local.h:450-513)
+  if (mc_trans == 1 && nc < 3)
+    fail(0x00040011, "color transform can only be employed when the image has 3 or more "
+         "color components");
+  if (mc_trans == 1) {
+    for (uint32_t i = 1; i < 3; ++i) {
+      if (comps[i].dx != comps[0].dx || comps[i].dy != comps[0].dy)
+        fail(0x00040012, "when color transform is used, the first 3 colour components must "
+             "have the same downsampling factor.");
+      if (comps[i].bit_depth != comps[0].bit_depth)
+        fail(0x00040014, "when color transform is used, the first 3 colour components must "
+             "have the same bit depth.");
+      if (comps[i].is_signed != comps[0].is_signed)
+        fail(0x00040015, "when color transform is used, the first 3 colour components must "
+             "have the same signedness (signed or unsigned).");
+    }
+  }
+  if (prog_order == PO_RPCL || prog_order == PO_PCRL)
+    for (uint32_t i = 0; i < nc; ++i)
+      if ((comps[i].dx & (comps[i].dx - 1)) || (comps[i].dy & (comps[i].dy - 1)))
+        fail(0x00040013, "For RPCL and PCRL progression orders,component downsampling "
+             "factors have to be powers of 2");
+
+  // QCD / QCC (param_qcd::check_validity, ojph_params.cpp:1359-1431)
+  for (QuantSet& q : qcc) q.enabled = q.comp_idx < nc;
+  uint32_t qcd_comp = 0;
+  for (uint32_t c = 0; c < nc; ++c) if (find_qcc(c) == nullptr) { qcd_comp = c; break; }
+  if (qcd.qfactor != 0) {
+    for (uint32_t i = 0; i < nc; ++i) {
+      if (find_qcc(i) == nullptr) {
+        QuantSet& q = add_qcc(i);
+        q.qfactor = qcd.qfactor;
+        q.ctype = (nc < 3) ? 0 : (int)(i < 3u ? i : 0u);
+      }
+    }
+  }
+  make_quant_steps(qcd, qcd_comp, *this);
+  for (uint32_t c = 0; c < nc; ++c) {
+    QuantSet* q = find_qcc(c);
+    if (q == nullptr) {
+      bool needed = qcd.num_decomps != num_decomps || qcd.bit_depth != comps[c].bit_depth ||
+                    qcd.is_signed != comps[c].is_signed ||
+                    qcd.is_color_trans != color_transform() || qcd.wavelet != wavelet;
+      if (!needed) continue;
+      QuantSet& nq = add_qcc(c);
+      nq.base_delta = qcd.base_delta;
+      q = &nq;
+    }
+    make_quant_steps(*q, c, *this);
+  }
+
+  // CAP (ojph_params_local.h:982-998); MAGB over QCD and every QCC (ojph_params.cpp:1615)
+  if (wavelet == DWT_REV53) Ccap0 &= 0xFFDF; else Ccap0 |= 0x0020;
+  Ccap0 &= 0xFFE0;
+  uint32_t B = 0;
+  auto magb = [&](const QuantSet& q) {
+    uint32_t nd = (q.num_subbands - 1) / 3;
+    for (uint32_t i = 0; i < q.num_subbands; ++i) {
+      uint32_t t;
+      if ((q.Sqcd & 0x1F) == 0) t = ((uint32_t)(q.SP[i] & 0xFF) >> 3) + q.guard_bits() - 1u;
+      else { uint32_t nb = nd - (i ? (i - 1) / 3 : 0); t = (uint32_t)(q.SP[i] >> 11) + q.guard_bits() - nb; }
+      B = std::max(B, t);
+    }
+  };
+  magb(qcd);
+  for (const QuantSet& q : qcc) magb(q);
+  uint32_t Bp = (B <= 8) ? 0 : (B < 28 ? B - 8 : 13 + (B >> 2));
+  Ccap0 = (uint16_t)(Ccap0 | (uint16_t)Bp);
+
+  // 32-bit coefficient path only (64-bit path is out of scope)
+  for (uint32_t c = 0; c < nc; ++c) {
+    uint32_t pr = quant_for(c).largest_kmax() + 2;
+    if (color_transform() && c < 3)
+      for (uint32_t i = 0; i < 3; ++i) pr = std::max(pr, quant_for(i).largest_kmax() + 2);
+    if (pr > 32)
+      fail(0x000B0001, "component %u needs %u-bit coefficients; only the 32-bit path is "
+           "implemented on the GPU", c, pr);
+  }
+
+  // tile-part division rules (ojph_codestream_local.cpp:583-621)
+  if ((prog_order == PO_LRCP || prog_order == PO_RLCP) && tilepart_div == TP_COMP)
+    tilepart_div |= TP_RES;
+  if (prog_order == PO_RPCL && (tilepart_div & TP_COMP)) tilepart_div &= ~(uint32_t)TP_COMP;
+  if (prog_order == PO_PCRL && tilepart_div != 0) tilepart_div = 0;
+  if (prog_order == PO_CPRL && (tilepart_div & TP_RES)) tilepart_div &= ~(uint32_t)TP_RES;
+  if (planar == -1) planar = color_transform() ? 1 : 0;
+  else if (planar == 1 && color_transform())
+    fail(0x00030021, "the planar interface option cannot be used when colour transform is "
+         "employed");
+}
+
+static void write_quant(std::vector<uint8_t>& o, const QuantSet& q, uint32_t nc) {
+  int irrev = q.Sqcd & 0x1F;
+  uint32_t L = q.is_qcc ? (4 + (nc < 257 ? 0 : 1)) : 3;
+  L += (irrev == 0 ? 1 : 2) * q.num_subbands;
+  put_u16(o, q.is_qcc ? M_QCC : M_QCD);
+  put_u16(o, L);
+  if (q.is_qcc) { if (nc < 257) put_u8(o, q.comp_idx); else put_u16(o, q.comp_idx); }
+  put_u8(o, q.Sqcd);
+  for (uint32_t i = 0; i < q.num_subbands; ++i)
+    if (irrev == 0) put_u8(o, q.SP[i] & 0xFF); else put_u16(o, q.SP[i]);
+}
+
+void Params::write_main_header(std::vector<uint8_t>& o, const char* const* comments,
+                               const uint32_t* comment_lens, uint32_t n_comments) const {
+  uint32_t nc = num_comps();
+  put_u16(o, M_SOC);
+  // SIZ
+  put_u16(o, M_SIZ); put_u16(o, 38 + 3 * nc); put_u16(o, Rsiz);
+  put_u32(o, Xsiz); put_u32(o, Ysiz); put_u32(o, XOsiz); put_u32(o, YOsiz);
+  put_u32(o, XTsiz); put_u32(o, YTsiz); put_u32(o, XTOsiz); put_u32(o, YTOsiz);
+  put_u16(o, nc);
+  for (uint32_t c = 0; c < nc; ++c) {
+    put_u8(o, (uint32_t)(comps[c].bit_depth - 1) + (comps[c].is_signed ? 0x80u : 0u));
+    put_u8(o, comps[c].dx); put_u8(o, comps[c].dy);
+  }
+  // CAP
+  put_u16(o, M_CAP); put_u16(o, 8); put_u32(o, Pcap); put_u16(o, Ccap0);
+  // COD
+  put_u16(o, M_COD);
+  put_u16(o, 12 + ((Scod & 1) ? 1 + num_decomps : 0));
+  put_u8(o, Scod); put_u8(o, prog_order); put_u16(o, num_layers); put_u8(o, mc_trans);
+  put_u8(o, num_decomps); put_u8(o, cb_w_exp); put_u8(o, cb_h_exp); put_u8(o, block_style);
+  put_u8(o, wavelet);
+  if (Scod & 1) for (int i = 0; i <= num_decomps; ++i) put_u8(o, precinct_size[i]);
+  // QCD, QCC
+  write_quant(o, qcd, nc);
+  for (const QuantSet& q : qcc) if (q.enabled) write_quant(o, q, nc);
+  // COM: library signature, needed for byte-identical output
+  // (ojph_codestream_local.cpp:668-686)
+  static const char sig[] = "OpenJPH Ver 0.31.0.";
+  put_u16(o, M_COM); put_u16(o, (uint32_t)strlen(sig) + 4); put_u16(o, 1);
+  o.insert(o.end(), sig, sig + strlen(sig));
+  for (uint32_t i = 0; i < n_comments; ++i) {
+    put_u16(o, M_COM); put_u16(o, comment_lens[i] + 4); put_u16(o, 1);
+    o.insert(o.end(), comments[i], comments[i] + comment_lens[i]);
+  }
+}
+
+//------------------------------------------------------------------------------------------
+// main-header parsing
+//------------------------------------------------------------------------------------------
+namespace {
+struct Reader {
+  const uint8_t* d; size_t n, pos;
+  bool has(size_t k) const { return pos + k <= n; }
+  uint32_t u8() { if (!has(1)) fail(0x00030051, "File ended before finding a tile segment"); return d[pos++]; }
+  uint32_t u16() { uint32_t a = u8(); return (a << 8) | u8(); }
+  uint32_t u32() { uint32_t a = u16(); return (a << 16) | u16(); }
+};
+
+void read_quant(Reader& r, QuantSet& q, bool is_qcc, uint32_t nc) {
+  uint32_t L = r.u16();
+  uint32_t hdr = 3;
+  q.is_qcc = is_qcc;
+  if (is_qcc) {
+    if (nc < 257) { q.comp_idx = (uint16_t)r.u8(); hdr = 4; }
+    else { q.comp_idx = (uint16_t)r.u16(); hdr = 5; }
+  }
+  q.Sqcd = (uint8_t)r.u8();
+  int style = q.Sqcd & 0x1F;
+  if (style == 0) {
+    q.num_subbands = L - hdr;
+    if (q.num_subbands == 0 || q.num_subbands > 97)
+      fail(0x00050083, "wrong Lqcd value of %d in QCD marker", L);
+    for (uint32_t i = 0; i < q.num_subbands; ++i) q.SP[i] = (uint16_t)r.u8();
+  } else if (style == 2) {
+    q.num_subbands = (L - hdr) / 2;
+    if (q.num_subbands == 0 || q.num_subbands > 97 || L != hdr + 2 * q.num_subbands)
+      fail(0x00050086, "wrong Lqcd value of %d in QCD marker", L);
+    for (uint32_t i = 0; i < q.num_subbands; ++i) q.SP[i] = (uint16_t)r.u16();
+  } else if (style == 1)
+    fail(0x00050089, "Scalar derived quantization is not supported yet in QCD marker");
+  else
+    fail(0x00050088, "wrong Sqcd value in QCD marker");
+  q.is_init = true;
+}
+} // namespace
+
+size_t Params::read_main_header(const uint8_t* data, size_t len) {
+  Reader r{ data, len, 0 };
+  // find SOC then SIZ (find_marker, ojph_codestream_local.cpp:717-741)
+  auto find = [&](uint16_t m) {
+    while (r.pos + 1 < r.n) {
+      if (r.d[r.pos] == 0xFF && r.d[r.pos + 1] == (m & 0xFF)) { r.pos += 2; return true; }
+      ++r.pos;
+    }
+    return false;
+  };
+  if (!find(M_SOC) || !find(M_SIZ)) fail(0x00030051, "File ended before finding a tile segment");
+  // SIZ
+  {
+    uint32_t L = r.u16();
+    int nc = ((int)L - 38) / 3;
+    if ((int)L != 38 + 3 * nc) fail(0x00050042, "error in SIZ marker length");
+    Rsiz = (uint16_t)r.u16();
+    if ((Rsiz & 0x4000) == 0) fail(0x00050044, "Rsiz bit 14 is not set (this is not a JPH file)");
+    Xsiz = r.u32(); Ysiz = r.u32(); XOsiz = r.u32(); YOsiz = r.u32();
+    XTsiz = r.u32(); YTsiz = r.u32(); XTOsiz = r.u32(); YTOsiz = r.u32();
+    uint32_t C = r.u16();
+    if ((int)C != nc) fail(0x0005004E, "Csiz does not match the SIZ marker size");
+    if (C == 0) fail(0x0005004F, "Wrong Csiz value of 0 in SIZ marker segment");
+    comps.resize(C);
+    for (uint32_t c = 0; c < C; ++c) {
+      uint32_t s = r.u8(), xr = r.u8(), yr = r.u8();
+      if ((s & 0x7F) > 37) fail(0x00050054, "Wrong SIZ-SSiz value of %d", s);
+      if (xr == 0) fail(0x00050055, "Wrong SIZ-XRsiz value of %d", xr);
+      if (yr == 0) fail(0x00050056, "Wrong SIZ-YRsiz value of %d", yr);
+      comps[c].bit_depth = (uint8_t)((s & 0x7F) + 1);
+      comps[c].is_signed = (s & 0x80) != 0;
+      comps[c].dx = (uint8_t)xr; comps[c].dy = (uint8_t)yr;
+    }
+    if (Xsiz == 0 || Ysiz == 0 || XTsiz == 0 || YTsiz == 0)
+      fail(0x00040001, "Image extent and/or tile size cannot be zero");
+    if (XTOsiz > XOsiz || YTOsiz > YOsiz)
+      fail(0x00040002, "Tile offset has to be smaller than the image offset");
+    if (XTsiz + XTOsiz <= XOsiz || YTsiz + YTOsiz <= YOsiz)
+      fail(0x00040003, "The top left tile must intersect with the image");
+    if (Xsiz <= XOsiz || Ysiz <= YOsiz)
+      fail(0x00040004, "The image extent must be larger than the image offset");
+    if (Rsiz & 0x00A0)
+      fail(0x000B0002, "codestreams that need ATK/DFS (Part 2 wavelet structures) are not "
+           "supported by the GPU path");
+  }
+  int received = 0;
+  qcc.clear();
+  for (;;) {
+    // scan to the next 0xFF xx marker of interest (the reference skips unknown bytes too)
+    if (r.pos + 1 >= r.n) fail(0x00030051, "File ended before finding a tile segment");
+    if (r.d[r.pos] != 0xFF) { ++r.pos; continue; }
+    uint16_t m = (uint16_t)(0xFF00 | r.d[r.pos + 1]);
+    bool known = m == M_CAP || m == M_PRF || m == M_CPF || m == M_COD || m == M_COC || m == M_QCD ||
+                 m == M_QCC || m == M_RGN || m == M_POC || m == M_PPM || m == M_TLM || m == M_PLM ||
+                 m == M_CRG || m == M_COM || m == M_DFS || m == M_ATK || m == M_NLT || m == M_SOT;
+    if (!known) { ++r.pos; continue; }
+    if (m == M_SOT) break;
+    r.pos += 2;
+    if (m == M_CAP) {
+      uint32_t L = r.u16();
+      Pcap = r.u32();
+      if (Pcap & 0xFFFDFFFF) fail(0x00050063, "error Pcap in CAP has options that are not supported");
+      if ((Pcap & 0x00020000) == 0)
+        fail(0x00050064, "error Pcap should have its 15th MSB set, Pcap^15.  This is not a JPH file");
+      Ccap0 = (uint16_t)r.u16();
+      if (L != 8) fail(0x00050066, "error in CAP marker length");
+    } else if (m == M_COD) {
+      uint32_t L = r.u16();
+      Scod = (uint8_t)r.u8(); prog_order = (uint8_t)r.u8(); num_layers = (uint16_t)r.u16();
+      mc_trans = (uint8_t)r.u8(); num_decomps = (uint8_t)r.u8(); cb_w_exp = (uint8_t)r.u8();
+      cb_h_exp = (uint8_t)r.u8(); block_style = (uint8_t)r.u8(); wavelet = (uint8_t)r.u8();
+      if (num_decomps > 32 || cb_w_exp > 8 || cb_h_exp > 8 || cb_w_exp + cb_h_exp > 8 ||
+          (block_style & 0x40) != 0x40 || (block_style & 0xB7) != 0x00)
+        fail(0x0005007D, "wrong settings in a COD-SPcod parameter");
+      if (wavelet > 1)
+        fail(0x000B0003, "arbitrary transformation kernels (ATK) are not supported by the GPU path");
+      if (Scod & 1)
+        for (int i = 0; i <= num_decomps; ++i) {
+          precinct_size[i] = (uint8_t)r.u8();
+          if (i && ((precinct_size[i] & 0xF) == 0 || (precinct_size[i] >> 4) == 0))
+            fail(0x0005007F, "Precinct width or height for resolutions other than the coarsest "
+                 "must be larger than 1");
+        }
+      if (L != 12u + ((Scod & 1) ? 1u + num_decomps : 0u)) fail(0x0005007C, "error in COD segment length");
+      if (num_layers != 1)
+        fail(0x00030053, "The current implementation supports 1 quality layer only.  This "
+             "codestream has %d quality layers", num_layers);
+      if (prog_order > 4) fail(0x0005007D, "wrong settings in a COD-SPcod parameter");
+      received |= 1;
+    } else if (m == M_QCD) {
+      read_quant(r, qcd, false, num_comps());
+      received |= 2;
+    } else if (m == M_QCC) {
+      QuantSet q;
+      read_quant(r, q, true, num_comps());
+      if (q.comp_idx >= num_comps())
+        fail(0x00030054, "The codestream carries a QCC marker segment for a component indexed "
+             "by %d, which is more than the allowed index number, since the codestream has %d "
+             "components", q.comp_idx, num_comps());
+      if (find_qcc(q.comp_idx))
+        fail(0x00030055, "The codestream has two QCC marker segments for one component of "
+             "index %d", q.comp_idx);
+      qcc.push_back(q);
+    } else if (m == M_COC)
+      fail(0x000B0004, "COC marker segments (per-component coding styles) are not supported by "
+           "the GPU path yet");
+    else if (m == M_DFS || m == M_ATK || m == M_NLT)
+      fail(0x000B0005, "DFS/ATK/NLT marker segments are not supported by the GPU path");
+    else {  // PRF CPF RGN POC PPM TLM PLM CRG COM: skipped
+      uint32_t L = r.u16();
+      if (L < 2 || !r.has(L - 2)) fail(0x00030041, "error reading marker");
+      r.pos += L - 2;
+    }
+  }
+  if (received != 3) fail(0x00030052, "markers error, COD and QCD are required");
+  return r.pos;
+}
+
+} // namespace ojb

@@ -1,0 +1,126 @@
+// ojb_params.h -- codestream parameters (SIZ / CAP / COD / QCD / QCC / SOT / TLM) for the
+// B200 HTJ2K path: the host-side metadata that wraps the GPU kernels in a valid codestream.
+//
+// Mirrors the behaviour of the reference's parameter classes so that main headers are
+// byte-identical for the same settings:
+//   SIZ  src/core/codestream/ojph_params.cpp:805-851   (write)  :854-933 (read)
+//   CAP  :968-989, check ojph_params_local.h:982-998
+//   COD  :1035-1078 (write) :1146-1204 (read)
+//   QCD  :1359-1481 (validity / step derivation) :1495-1612 (steps) :1778-1887 (write)
+//   SOT  :2343-2388   TLM :2470-2520
+#pragma once
+#include "ojb_common.h"
+
+namespace ojb {
+
+enum ProgOrder : uint8_t { PO_LRCP = 0, PO_RLCP = 1, PO_RPCL = 2, PO_PCRL = 3, PO_CPRL = 4 };
+enum Wavelet : uint8_t { DWT_IRV97 = 0, DWT_REV53 = 1 };
+enum TilepartDiv : uint32_t { TP_NONE = 0, TP_RES = 1, TP_COMP = 2 };
+
+struct CompInfo {
+  uint8_t bit_depth = 8;
+  bool is_signed = false;
+  uint8_t dx = 1, dy = 1;
+};
+
+// One QCD or QCC marker segment plus the inputs its step sizes are generated from
+struct QuantSet {
+  bool is_qcc = false;
+  bool enabled = true;
+  bool is_init = false;
+  uint16_t comp_idx = 0xFFFF;
+  uint8_t Sqcd = 0;
+  uint32_t num_subbands = 0;
+  uint16_t SP[97] = {0};        // 8-bit entries (reversible) or 16-bit (scalar expounded)
+  float base_delta = -1.0f;
+  uint8_t qfactor = 0;          // 0 = unset
+  int ctype = 0;                // 0 Y, 1 Cb, 2 Cr
+  uint32_t num_decomps = 0, bit_depth = 0;
+  bool is_signed = false, is_color_trans = false;
+  uint32_t wavelet = 0;
+  uint32_t sx = 1, sy = 1;
+
+  uint32_t guard_bits() const { return (uint32_t)(Sqcd >> 5); }
+  uint32_t kmax(uint32_t res, uint32_t band) const;          // get_Kmax, ojph_params.cpp:1715
+  uint32_t largest_kmax() const;                             // :1751
+  float irrev_delta(uint32_t res, uint32_t band) const;      // get_irrev_delta, :1650
+  void set_rev_quant(uint32_t num_decomps, uint32_t bit_depth, bool color);   // :1495
+  void set_irrev_quant(uint32_t num_decomps);                                // :1542
+};
+
+struct Params {
+  // ---- SIZ
+  uint16_t Rsiz = 0x4000;
+  uint32_t Xsiz = 0, Ysiz = 0, XOsiz = 0, YOsiz = 0;
+  uint32_t XTsiz = 0, YTsiz = 0, XTOsiz = 0, YTOsiz = 0;
+  std::vector<CompInfo> comps;
+  // ---- COD
+  uint8_t Scod = 0;
+  uint8_t prog_order = PO_RPCL;
+  uint16_t num_layers = 1;
+  uint8_t mc_trans = 0;
+  uint8_t num_decomps = 5;
+  uint8_t cb_w_exp = 4, cb_h_exp = 4;       // log2(dim) - 2
+  uint8_t block_style = 0x40;               // HT
+  uint8_t wavelet = DWT_IRV97;
+  uint8_t precinct_size[33] = {0};          // PPx | PPy << 4 per resolution (Scod & 1)
+  // ---- QCD / QCC
+  QuantSet qcd;
+  std::vector<QuantSet> qcc;                // in creation order
+  // ---- CAP
+  uint32_t Pcap = 0x00020000;
+  uint16_t Ccap0 = 0;
+  // ---- encoder options
+  bool need_tlm = false;
+  uint32_t tilepart_div = TP_NONE;
+  int planar = -1;
+
+  // helpers
+  uint32_t num_comps() const { return (uint32_t)comps.size(); }
+  bool reversible() const { return wavelet == DWT_REV53; }
+  bool color_transform() const { return mc_trans == 1; }
+  uint32_t log_cb_w() const { return cb_w_exp + 2u; }
+  uint32_t log_cb_h() const { return cb_h_exp + 2u; }
+  uint32_t log_pp_w(uint32_t r) const { return (Scod & 1) ? (precinct_size[r] & 0xF) : 15u; }
+  uint32_t log_pp_h(uint32_t r) const { return (Scod & 1) ? (precinct_size[r] >> 4) : 15u; }
+  bool stripe_causal() const { return (block_style & 0x8) != 0; }
+  bool uses_sop() const { return (Scod & 2) != 0; }
+  bool uses_eph() const { return (Scod & 4) != 0; }
+  uint32_t comp_width(uint32_t c) const
+  { return div_ceil(Xsiz, comps[c].dx) - div_ceil(XOsiz, comps[c].dx); }
+  uint32_t comp_height(uint32_t c) const
+  { return div_ceil(Ysiz, comps[c].dy) - div_ceil(YOsiz, comps[c].dy); }
+  const QuantSet& quant_for(uint32_t c) const;
+  QuantSet* find_qcc(uint32_t c);
+  QuantSet& add_qcc(uint32_t c);
+  uint32_t precision(uint32_t c) const;     // propose_precision, ojph_params.cpp:1684
+
+  // setters used by the C-ABI (same argument checks as ojph::param_cod / param_qcd setters)
+  void set_block_dims(uint32_t w, uint32_t h);                      // ojph_params.cpp:170-181
+  void set_precincts(int n, const uint32_t* w, const uint32_t* h);  // :184-209
+
+  // finalisation before writing headers (write_headers, ojph_codestream_local.cpp:556-636)
+  void finalize_for_encode();
+  void write_main_header(std::vector<uint8_t>& out, const char* const* comments,
+                         const uint32_t* comment_lens, uint32_t n_comments) const;
+  // decoder: parse from SOC up to (not including) the first SOT; returns offset of that SOT
+  size_t read_main_header(const uint8_t* data, size_t len);
+};
+
+// marker codes
+enum Marker : uint16_t {
+  M_SOC = 0xFF4F, M_CAP = 0xFF50, M_SIZ = 0xFF51, M_COD = 0xFF52, M_COC = 0xFF53,
+  M_TLM = 0xFF55, M_PRF = 0xFF56, M_PLM = 0xFF57, M_PLT = 0xFF58, M_CPF = 0xFF59,
+  M_QCD = 0xFF5C, M_QCC = 0xFF5D, M_RGN = 0xFF5E, M_POC = 0xFF5F, M_PPM = 0xFF60,
+  M_PPT = 0xFF61, M_CRG = 0xFF63, M_COM = 0xFF64, M_DFS = 0xFF72, M_ADS = 0xFF73,
+  M_NLT = 0xFF76, M_ATK = 0xFF79, M_SOT = 0xFF90, M_SOP = 0xFF91, M_EPH = 0xFF92,
+  M_SOD = 0xFF93, M_EOC = 0xFFD9
+};
+
+inline void put_u8(std::vector<uint8_t>& o, uint32_t v) { o.push_back((uint8_t)v); }
+inline void put_u16(std::vector<uint8_t>& o, uint32_t v)
+{ o.push_back((uint8_t)(v >> 8)); o.push_back((uint8_t)v); }
+inline void put_u32(std::vector<uint8_t>& o, uint32_t v)
+{ put_u16(o, v >> 16); put_u16(o, v & 0xFFFF); }
+
+} // namespace ojb

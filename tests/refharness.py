@@ -1,0 +1,110 @@
+"""ctypes wrapper over oracle/_ref/libojph_oracle.so (the UNMODIFIED reference behind a C harness;
+oracle/ref_harness.cpp).  Test infrastructure only."""
+import ctypes as C
+import os
+import numpy as np
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PATH = os.path.join(_ROOT, "oracle", "_ref", "libojph_oracle.so")
+
+
+class RParams(C.Structure):
+    _fields_ = [
+        ("width", C.c_uint32), ("height", C.c_uint32), ("off_x", C.c_uint32), ("off_y", C.c_uint32),
+        ("tile_w", C.c_uint32), ("tile_h", C.c_uint32), ("tile_off_x", C.c_uint32), ("tile_off_y", C.c_uint32),
+        ("num_comps", C.c_uint32), ("bit_depth", C.c_uint32 * 16), ("is_signed", C.c_uint32 * 16),
+        ("dx", C.c_uint32 * 16), ("dy", C.c_uint32 * 16),
+        ("num_decomps", C.c_uint32), ("block_w", C.c_uint32), ("block_h", C.c_uint32),
+        ("num_precincts", C.c_uint32), ("precinct_w", C.c_uint32 * 33), ("precinct_h", C.c_uint32 * 33),
+        ("reversible", C.c_uint32), ("color_transform", C.c_uint32), ("prog_order", C.c_uint32),
+        ("qstep", C.c_float), ("qfactor", C.c_uint32), ("tlm", C.c_uint32), ("tilepart_div", C.c_uint32),
+        ("planar", C.c_int32),
+    ]
+
+
+class RInfo(C.Structure):
+    _fields_ = [
+        ("width", C.c_uint32), ("height", C.c_uint32), ("off_x", C.c_uint32), ("off_y", C.c_uint32),
+        ("num_comps", C.c_uint32), ("bit_depth", C.c_uint32 * 16), ("is_signed", C.c_uint32 * 16),
+        ("dx", C.c_uint32 * 16), ("dy", C.c_uint32 * 16), ("comp_w", C.c_uint32 * 16), ("comp_h", C.c_uint32 * 16),
+        ("num_decomps", C.c_uint32), ("reversible", C.c_uint32), ("color_transform", C.c_uint32),
+    ]
+
+
+_lib = None
+
+
+def available():
+    return os.path.exists(PATH)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(PATH)
+        _lib.ojr_last_error.restype = C.c_char_p
+        _lib.ojr_irv_K.restype = C.c_float
+        _lib.ojr_irv_step.restype = C.c_float
+    return _lib
+
+
+def to_rparams(p):
+    """copy an openjph_b200 Params (same field layout by construction) into RParams"""
+    r = RParams()
+    C.memmove(C.byref(r), C.byref(p), C.sizeof(RParams))
+    return r
+
+
+def encode(p, planes):
+    L = lib()
+    r = to_rparams(p)
+    arrs = [np.ascontiguousarray(a, np.int32) for a in planes]
+    ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+    cap = sum(a.size for a in arrs) * 5 + (1 << 20)
+    out = np.zeros(cap, np.uint8)
+    n = C.c_uint64()
+    rc = L.ojr_encode(C.byref(r), ptrs, out.ctypes.data_as(C.c_void_p), C.c_uint64(cap), C.byref(n))
+    if rc != 0:
+        raise RuntimeError("reference encode failed: " + L.ojr_last_error().decode())
+    return out[:n.value].tobytes()
+
+
+def decode(j2c, resilient=False):
+    L = lib()
+    buf = np.frombuffer(j2c, np.uint8)
+    info = RInfo()
+    rc = L.ojr_read_info(buf.ctypes.data_as(C.c_void_p), C.c_uint64(buf.size), C.byref(info))
+    if rc != 0:
+        raise RuntimeError("reference read_headers failed: " + L.ojr_last_error().decode())
+    planes = [np.zeros((info.comp_h[c], info.comp_w[c]), np.int32) for c in range(info.num_comps)]
+    ptrs = (C.c_void_p * info.num_comps)(*[a.ctypes.data for a in planes])
+    rc = L.ojr_decode(buf.ctypes.data_as(C.c_void_p), C.c_uint64(buf.size), ptrs, 1 if resilient else 0)
+    if rc != 0:
+        raise RuntimeError("reference decode failed: " + L.ojr_last_error().decode())
+    return planes, info
+
+
+def encode_block(block, missing_msbs, variant=0):
+    """block: (h, w) uint32 sign-magnitude; returns bytes"""
+    L = lib()
+    h, w = block.shape
+    stride = (w + 15) & ~15
+    buf = np.zeros((h + 1, stride), np.uint32)
+    buf[:h, :w] = block
+    out = np.zeros(65536, np.uint8)
+    n = C.c_uint32()
+    rc = L.ojr_encode_block32(buf.ctypes.data_as(C.c_void_p), missing_msbs, w, h, stride,
+                              out.ctypes.data_as(C.c_void_p), out.size, C.byref(n), variant)
+    if rc != 0:
+        raise RuntimeError("reference block encode failed")
+    return out[:n.value].tobytes()
+
+
+def decode_block(data, w, h, missing_msbs, num_passes, len1, len2, causal=False, variant=0):
+    L = lib()
+    stride = (w + 15) & ~15
+    out = np.zeros((h + 2, stride), np.uint32)
+    src = np.frombuffer(bytes(data) + b"\0" * 64, np.uint8).copy()
+    rc = L.ojr_decode_block32(src.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), missing_msbs,
+                              num_passes, len1, len2, w, h, stride, 1 if causal else 0, variant)
+    return out[:h, :w].copy(), rc == 0
