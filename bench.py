@@ -1,0 +1,278 @@
+#!/usr/bin/env python3
+"""bench.py -- Mpixels/s encode+decode of the HTJ2K hot path.
+
+A step = one pass of the hot path over one frame: encode it to a codestream, then decode that
+codestream back (the metric BASELINE.json names is "Mpixels/s encode+decode").  Workload at every
+N: synthetic 8192x8192 3-component 12-bit frames, reversible 5/3 + RCT, 5 levels, 64x64 blocks
+(the headline configuration), one frame per GPU per step (weak scaling; frames are independent, so
+there is no data-path collective -- only the final gather of the codestream sizes to rank 0).
+
+  value : frame already resident in HBM when the timed region starts (encoder's device image
+          buffer), codestream left on the device, decoded image left on the device
+  e2e   : the reference-facing C-ABI frame calls with HOST buffers (pinned): H2D of the planes,
+          D2H of the codestream, H2D of the codestream, D2H of the decoded planes, all timed
+  --impl reference : the unmodified reference (oracle/_ref, compiled from /root/reference by
+          oracle/Makefile) on the host cores, one process per core, in-memory files
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+W = H = 8192
+NC, BD, LEVELS = 3, 12, 5
+CPU_TILE = 4096            # the CPU arms process a bounded sample: one 4096x4096 quarter frame
+
+
+def workload_params(w=W, h=H):
+    import openjph_b200 as ob
+    return ob.make_params(w, h, NC, BD, num_decomps=LEVELS, reversible=True, color_transform=True)
+
+
+def make_frame(w, h, seed):
+    import images
+    return [p.astype("uint16") for p in images.synth_frame(w, h, NC, BD, seed)]
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.maxc = index, [], set(), False, None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.samples.append(float(f[0])); self.maxc = float(f[1])
+                for n, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.maxc, "reasons": sorted(self.reasons)}
+
+
+def cpu_worker(args):
+    """one reference encode+decode of a CPU_TILE^2 frame; returns seconds (enc, dec)"""
+    seed, reps = args
+    import numpy as np
+    import refharness as R
+    p = workload_params(CPU_TILE, CPU_TILE)
+    frame = [f.astype(np.int32) for f in make_frame(CPU_TILE, CPU_TILE, seed)]
+    te = td = 0.0
+    for _ in range(reps):
+        t0 = time.perf_counter(); cs = R.encode(p, frame); t1 = time.perf_counter()
+        out, _ = R.decode(cs); t2 = time.perf_counter()
+        te += t1 - t0; td += t2 - t1
+    assert all(np.array_equal(a, b) for a, b in zip(out, frame))
+    return te, td, len(cs)
+
+
+def run_cpu_reference(procs, steps, warmup):
+    """all host threads: `procs` processes, each one encodes+decodes one quarter frame per step"""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(procs) as pool:
+        for _ in range(warmup):
+            pool.map(cpu_worker, [(1234 + i, 1) for i in range(procs)])
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            pool.map(cpu_worker, [(1234 + i, 1) for i in range(procs)])
+        dt = time.perf_counter() - t0
+    pix = procs * steps * CPU_TILE * CPU_TILE
+    return pix / dt / 1e6, dt / steps * 1e3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cfg = {"workload": "8192x8192x3 12-bit, reversible 5/3 + RCT, 5 levels, 64x64 code-blocks, RPCL, one frame "
+                       "per GPU per step (encode then decode)", "frames_per_step": max(1, a.gpus),
+           "l2_policy": "inputs larger than L2 (402 MB frame, 805 MB coefficients)"}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        import refharness as R
+        if not R.available():
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref was not built (needs /root/reference at build time)"}))
+            return
+        procs = max(1, cores)
+        v, ms = run_cpu_reference(procs, max(1, a.steps), max(0, min(a.warmup, 1)))
+        sample = "%d processes x one %dx%dx3 12-bit quarter frame per step, in-memory files, ISA level %d" % (
+            procs, CPU_TILE, CPU_TILE, R.lib().ojr_cpu_ext_level())
+        print(json.dumps({"impl": "reference", "metric": "Mpixels/s encode+decode", "value": v, "unit": "Mpixels/s",
+                          "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+                          "data": "synthetic", "config": cfg,
+                          "cpu_baseline": {"value": v, "unit": "Mpixels/s", "cores": procs, "kind": "reference", "sample": sample},
+                          "e2e": {"value": v, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import numpy as np
+    import torch
+    import openjph_b200 as ob
+    from openjph_b200 import _lib
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L = _lib.lib()
+    assert L.ojb_set_device(local) == 0, L.ojb_last_error()
+    torch.cuda.set_device(local)
+
+    p = workload_params()
+    frame = make_frame(W, H, 1234 + rank)
+    # pinned host buffers
+    pin = [torch.empty((H, W), dtype=torch.uint16, pin_memory=True) for _ in range(NC)]
+    for t, f in zip(pin, frame):
+        t.numpy()[:] = f
+    out_pin = [torch.empty((H, W), dtype=torch.uint16, pin_memory=True) for _ in range(NC)]
+    cs_cap = W * H * NC * 2 + (1 << 20)
+    cs_pin = torch.empty(cs_cap, dtype=torch.uint8, pin_memory=True)
+    cs_dev = torch.empty(cs_cap, dtype=torch.uint8, device="cuda")
+    enc = L.ojb_enc_create(); dec = L.ojb_dec_create()
+
+    def ck(rc):
+        if rc != 0:
+            raise RuntimeError(L.ojb_last_error().decode())
+    ck(L.ojb_enc_configure(enc, C.byref(p), ob.U16))
+    planes = (C.c_void_p * NC)(*[t.data_ptr() for t in pin])
+    outs = (C.c_void_p * NC)(*[t.data_ptr() for t in out_pin])
+    n = C.c_uint64()
+    fi = _lib.FrameInfo()
+
+    def step_e2e():
+        ck(L.ojb_enc_encode_frame(enc, planes, None, cs_pin.data_ptr(), cs_cap, C.byref(n)))
+        ck(L.ojb_dec_read_headers(dec, cs_pin.data_ptr(), n.value, ob.U16, C.byref(fi)))
+        ck(L.ojb_dec_decode_frame(dec, outs, None))
+
+    def step_resident():
+        ck(L.ojb_enc_encode_resident(enc, cs_dev.data_ptr(), cs_cap, C.byref(n), 1))
+        ck(L.ojb_dec_read_headers(dec, cs_pin.data_ptr(), cs_len, ob.U16, C.byref(fi)))
+        ck(L.ojb_dec_use_device_codestream(dec, cs_dev.data_ptr()))
+        ck(L.ojb_dec_decode_resident(dec))
+
+    def timed(fn, steps):
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
+        return dt
+
+    # correctness of what is being timed: lossless round trip through the e2e path
+    step_e2e()
+    cs_len = n.value
+    for a_, b_ in zip(out_pin, frame):
+        assert np.array_equal(a_.numpy(), b_), "round trip is not lossless"
+    ck(L.ojb_enc_upload_frame(enc, planes, None))
+    for _ in range(max(3, a.warmup)):
+        step_resident()
+    sampler = ClockSampler(local); sampler.start()
+    # device-side stage timing of the resident path (CUDA events on the codec stream)
+    t_enc = t_dec = 0.0
+    stage_e, stage_d = {}, {}
+    te = (C.c_float * 8)(); td = (C.c_float * 8)()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    dt_res = timed(step_resident, a.steps)
+    L.ojb_enc_timings(enc, te); L.ojb_dec_timings(dec, td)
+    for _ in range(max(1, min(a.warmup, 2))):
+        step_e2e()
+    dt_e2e = timed(step_e2e, a.steps)
+    sampler.stop_flag = True; sampler.join(timeout=2)
+    # final gather of the per-rank codestream sizes (the only collective on the path)
+    sizes = [cs_len]
+    if dist is not None:
+        t = torch.tensor([cs_len], device="cuda", dtype=torch.int64)
+        g = [torch.zeros_like(t) for _ in range(world)] if rank == 0 else None
+        dist.gather(t, g, dst=0)
+        if rank == 0:
+            sizes = [int(x.item()) for x in g]
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    pix = W * H * a.gpus
+    value = pix * a.steps / dt_res / 1e6
+    e2e = pix * a.steps / dt_e2e / 1e6
+    import json as _j
+    peaks = {}
+    try:
+        peaks = _j.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650 GB/s"
+    names_e = ("h2d", "dwt", "ht_encode", "d2h_lengths", "host_wait", "assemble", "d2h_out", "host_ms")
+    names_d = ("h2d", "host_parse", "ht_decode", "dwt_inv", "d2h_image", "_5", "_6", "host_ms")
+    stage_e = {k: round(float(v), 4) for k, v in zip(names_e, te)}
+    stage_d = {k: round(float(v), 4) for k, v in zip(names_d, td) if not k.startswith("_")}
+    # dominant kernel = the slowest device stage of the resident step
+    samples = W * H * NC
+    cand = {"ht_encode": (stage_e["ht_encode"], 4 * samples + cs_len), "ht_decode": (stage_d["ht_decode"], 4 * samples + cs_len),
+            "dwt_fwd": (stage_e["dwt"], 2 * samples + 4 * samples * 4 // 3 + 4 * samples // 3),
+            "dwt_inv": (stage_d["dwt_inv"], 2 * samples + 4 * samples * 4 // 3 + 4 * samples // 3)}
+    dom = max(cand, key=lambda k: cand[k][0])
+    ach = cand[dom][1] / (cand[dom][0] * 1e-3) / 1e9 if cand[dom][0] > 0 else 0.0
+    roof = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+            "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": cand[dom][1], "ms_per_launch": cand[dom][0]}
+    cfg.update({"stages_encode_ms": stage_e, "stages_decode_ms": stage_d, "codestream_bytes": sizes,
+                "pipeline_hbm_frac": round(((2 * samples + cs_len) * 2 * a.gpus) / (dt_res / a.steps) / 1e9 / peak, 4)})
+    res = {"metric": "Mpixels/s encode+decode", "value": value, "unit": "Mpixels/s", "n_gpus": a.gpus, "steps": a.steps,
+           "warmup": a.warmup, "ms_per_step": dt_res / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": cfg,
+           "clocks": sampler.summary(),
+           "e2e": {"value": e2e, "unit": "Mpixels/s", "h2d_bytes_per_step": (W * H * NC * 2 + cs_len) * a.gpus,
+                   "d2h_bytes_per_step": (W * H * NC * 2 + cs_len) * a.gpus, "ms_per_step": dt_e2e / a.steps * 1e3},
+           "gpu_launches": int(L.ojb_enc_kernel_launches(enc) + L.ojb_dec_kernel_launches(dec)) * a.steps,
+           "roofline": roof}
+    if not a.no_cpu_baseline and world == 1 or (rank == 0 and not a.no_cpu_baseline):
+        import refharness as R
+        if R.available():
+            t0 = time.perf_counter()
+            te_, td_, _ = cpu_worker((1234, 2))
+            v1 = 2 * CPU_TILE * CPU_TILE / (te_ + td_) / 1e6
+            res["cpu_baseline"] = {"value": v1, "unit": "Mpixels/s", "cores": 1, "kind": "reference",
+                                   "sample": "2 x one %dx%dx3 12-bit quarter frame, 1 thread (the library's native mode), "
+                                             "in-memory; encode %.1f Mpix/s decode %.1f Mpix/s; ISA level %d" % (
+                                                 CPU_TILE, CPU_TILE, 2 * CPU_TILE * CPU_TILE / te_ / 1e6,
+                                                 2 * CPU_TILE * CPU_TILE / td_ / 1e6, R.lib().ojr_cpu_ext_level())}
+    print(json.dumps(res))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -82,6 +82,13 @@ int ojb_enc_upload_frame(ojb_encoder* e, const void* const* planes, const uint32
 int ojb_enc_encode_resident(ojb_encoder* e, uint8_t* out, uint64_t out_cap, uint64_t* out_len,
                             int out_on_device);
 uint32_t ojb_enc_kernel_launches(ojb_encoder* e);
+/* stage times of the last encode, CUDA events on the codec's stream, milliseconds:
+ * [0] H2D image  [1] DWT levels  [2] HT block encoder  [3] D2H block lengths  [4] wait + host packet
+ * headers (device idle)  [5] H2D headers + assembly kernels  [6] D2H codestream  [7] host ms */
+void ojb_enc_timings(ojb_encoder* e, float* ms8);
+/* last decode: [0] H2D codestream  [1] host packet parse (device idle)  [2] HT block decoder
+ * [3] inverse DWT levels  [4] D2H image  [7] host ms */
+void ojb_dec_timings(ojb_decoder* d, float* ms8);
 uint32_t ojb_enc_num_blocks(ojb_encoder* e);
 /* parity hook: copy one sub-band's quantised sign-magnitude plane (what the block coder reads)
  * after an encode; out has band_w * band_h words */
@@ -99,6 +106,9 @@ int ojb_dec_read_headers(ojb_decoder* d, const uint8_t* j2c, uint64_t len, uint3
 int ojb_dec_decode_frame(ojb_decoder* d, void* const* planes, const uint32_t* strides);
 int ojb_dec_decode_resident(ojb_decoder* d);             /* result stays in the device image buffer */
 void* ojb_dec_device_plane(ojb_decoder* d, uint32_t comp);
+/* after read_headers: the same codestream bytes are already in device memory (with >= 32 readable
+ * bytes after the end); the next decode reads them there instead of uploading j2c */
+int ojb_dec_use_device_codestream(ojb_decoder* d, const void* dev_bytes);
 uint32_t ojb_dec_failed_blocks(ojb_decoder* d);
 uint32_t ojb_dec_kernel_launches(ojb_decoder* d);
 int ojb_dec_read_band(ojb_decoder* d, uint32_t tile, uint32_t comp, uint32_t res, uint32_t band,

@@ -64,6 +64,8 @@ SYMBOLS = {
     "ojb_enc_encode_resident": (_I, [_VP, _VP, _U64, C.POINTER(_U64), _I]),
     "ojb_enc_kernel_launches": (_U32, [_VP]),
     "ojb_enc_num_blocks": (_U32, [_VP]),
+    "ojb_enc_timings": (None, [_VP, C.POINTER(C.c_float)]),
+    "ojb_dec_timings": (None, [_VP, C.POINTER(C.c_float)]),
     "ojb_enc_read_band": (_I, [_VP, _U32, _U32, _U32, _U32, _VP, C.POINTER(_U32), C.POINTER(_U32)]),
     "ojb_dec_create": (_VP, []),
     "ojb_dec_destroy": (None, [_VP]),
@@ -72,6 +74,7 @@ SYMBOLS = {
     "ojb_dec_decode_frame": (_I, [_VP, C.POINTER(_VP), C.POINTER(_U32)]),
     "ojb_dec_decode_resident": (_I, [_VP]),
     "ojb_dec_device_plane": (_VP, [_VP, _U32]),
+    "ojb_dec_use_device_codestream": (_I, [_VP, _VP]),
     "ojb_dec_failed_blocks": (_U32, [_VP]),
     "ojb_dec_kernel_launches": (_U32, [_VP]),
     "ojb_dec_read_band": (_I, [_VP, _U32, _U32, _U32, _U32, _VP, C.POINTER(_U32), C.POINTER(_U32)]),

@@ -146,6 +146,11 @@ class Encoder(_Base):
     def kernel_launches(self):
         return self.L.ojb_enc_kernel_launches(self.h)
 
+    def timings(self):
+        t = (C.c_float * 8)()
+        self.L.ojb_enc_timings(self.h, t)
+        return dict(zip(("h2d", "dwt", "ht_encode", "d2h_lengths", "host_wait", "assemble", "d2h_out", "host_ms"), list(t)))
+
 
 class Decoder(_Base):
     def __init__(self, resilient=False, lib=None):
@@ -200,6 +205,11 @@ class Decoder(_Base):
     @property
     def kernel_launches(self):
         return self.L.ojb_dec_kernel_launches(self.h)
+
+    def timings(self):
+        t = (C.c_float * 8)()
+        self.L.ojb_dec_timings(self.h, t)
+        return dict(zip(("h2d", "host_parse", "ht_decode", "dwt_inv", "d2h_image", "_5", "_6", "host_ms"), list(t)))
 
 
 def encode_blocks(samples, descs, lib=None):

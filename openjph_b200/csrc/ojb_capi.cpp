@@ -172,6 +172,14 @@ int ojb_enc_encode_resident(ojb_encoder* e, uint8_t* out, uint64_t out_cap, uint
   });
 }
 uint32_t ojb_enc_kernel_launches(ojb_encoder* e) { return e->enc.last_launches; }
+void ojb_enc_timings(ojb_encoder* e, float* ms8) {
+  for (int i = 0; i < 7; ++i) ms8[i] = e->enc.stage_ms[i];
+  ms8[7] = (float)e->enc.host_ms;
+}
+void ojb_dec_timings(ojb_decoder* d, float* ms8) {
+  for (int i = 0; i < 5; ++i) ms8[i] = d->dec.stage_ms[i];
+  ms8[5] = ms8[6] = 0; ms8[7] = (float)d->dec.host_ms;
+}
 uint32_t ojb_enc_num_blocks(ojb_encoder* e) { return e->configured ? e->enc.layout.num_blocks : 0; }
 int ojb_enc_read_band(ojb_encoder* e, uint32_t tile, uint32_t comp, uint32_t res, uint32_t band,
                       uint32_t* out, uint32_t* band_w, uint32_t* band_h) {
@@ -218,6 +226,7 @@ void* ojb_dec_device_plane(ojb_decoder* d, uint32_t comp) {
   if (!d->have_headers || comp >= d->dec.params.num_comps()) return nullptr;
   return img_plane(d->dec, comp);
 }
+int ojb_dec_use_device_codestream(ojb_decoder* d, const void* dev_bytes) { d->dec.dev_cs = (const uint8_t*)dev_bytes; return 0; }
 uint32_t ojb_dec_failed_blocks(ojb_decoder* d) { return d->dec.failed_blocks; }
 uint32_t ojb_dec_kernel_launches(ojb_decoder* d) { return d->dec.last_launches; }
 int ojb_dec_read_band(ojb_decoder* d, uint32_t tile, uint32_t comp, uint32_t res, uint32_t band,

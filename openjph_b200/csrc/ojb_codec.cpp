@@ -3,6 +3,7 @@
 #include "ht_tables.h"
 #include <algorithm>
 #include <cstring>
+#include <chrono>
 
 namespace ojb {
 
@@ -28,8 +29,14 @@ void PinnedBuf::reserve(size_t n) {
   cap = want;
 }
 
-CodecBase::CodecBase() { CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)); }
-CodecBase::~CodecBase() { if (stream) cudaStreamDestroy(stream); }
+CodecBase::CodecBase() {
+  CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  for (int i = 0; i < EV_MAX; ++i) CK(cudaEventCreate(&ev[i]));
+}
+CodecBase::~CodecBase() {
+  for (int i = 0; i < EV_MAX; ++i) if (ev[i]) cudaEventDestroy(ev[i]);
+  if (stream) cudaStreamDestroy(stream);
+}
 
 void CodecBase::upload_tables() {
   const HtTables& t = ht_tables();
@@ -238,6 +245,7 @@ size_t Encoder::encode(const void* const* planes, const uint32_t* strides, bool 
   const Params& P = params;
   uint32_t nc = P.num_comps(), es = esize_of(img_type);
   last_launches = 0;
+  mark(0);
   // 1. image planes -> device
   if (planes) {
     for (uint32_t c = 0; c < nc; ++c) {
@@ -252,6 +260,7 @@ size_t Encoder::encode(const void* const* planes, const uint32_t* strides, bool 
                              (size_t)img_w[c] * es, kind, stream));
     }
   }
+  mark(1);
   // 2. transform + block coding
   CK(cudaMemsetAsync(d_status.p, 0, 16, stream));
   for (size_t li = 0; li < jobs.size(); ++li) {
@@ -260,13 +269,17 @@ size_t Encoder::encode(const void* const* planes, const uint32_t* strides, bool 
                    job_maxc[li], d_image.p, d_coef.as<uint32_t>(), stream);
     ++last_launches;
   }
+  mark(2);
   uint32_t nb = (uint32_t)h_blocks.size();
   launch_ht_encode(d_blocks.as<EncBlock>(), nb, d_coef.as<uint32_t>(), d_slots.as<uint8_t>(),
                    d_results.as<EncResult>(), d_tables_enc.as<uint16_t>(), d_status.as<uint32_t>(), stream);
   ++last_launches;
+  mark(3);
   if (nb) CK(cudaMemcpyAsync(h_results.p, d_results.p, (size_t)nb * sizeof(EncResult), cudaMemcpyDeviceToHost, stream));
   CK(cudaMemcpyAsync(h_status.p, d_status.p, 16, cudaMemcpyDeviceToHost, stream));
+  mark(4);
   CK(cudaStreamSynchronize(stream));
+  auto host_t0 = std::chrono::steady_clock::now();
   CK(cudaGetLastError());
   status_flags = h_status.as<uint32_t>()[0];
   if (status_flags & 2u) fail(0x00020001, "mel encoder's buffer is full");
@@ -359,6 +372,8 @@ size_t Encoder::encode(const void* const* planes, const uint32_t* strides, bool 
   uint8_t* dev_out;
   if (out_on_device) dev_out = out; else { d_out.reserve(total + 64); dev_out = d_out.as<uint8_t>(); }
   h_hdr.reserve(blob.size() + 64); memcpy(h_hdr.p, blob.data(), blob.size());
+  host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
+  mark(5);
   d_hdr.reserve(blob.size() + 64);
   CK(cudaMemcpyAsync(d_hdr.p, h_hdr.p, blob.size(), cudaMemcpyHostToDevice, stream));
   h_pieces.reserve(pieces.size() * sizeof(CopyPiece)); d_pieces.reserve(pieces.size() * sizeof(CopyPiece));
@@ -370,8 +385,11 @@ size_t Encoder::encode(const void* const* planes, const uint32_t* strides, bool 
                        d_slots.as<uint8_t>(), dev_out, stream);
   launch_assemble(d_pieces.as<CopyPiece>(), (uint32_t)pieces.size(), d_slots.as<uint8_t>(), d_hdr.as<uint8_t>(), dev_out, stream);
   last_launches += 2;
+  mark(6);
   if (!out_on_device) CK(cudaMemcpyAsync(out, dev_out, total, cudaMemcpyDeviceToHost, stream));
+  mark(7);
   CK(cudaStreamSynchronize(stream));
+  collect(8);
   CK(cudaGetLastError());
   // reset the line front end for the next frame
   std::fill(line_cur.begin(), line_cur.end(), 0u); cur_comp = 0; lines_done = false;
@@ -384,7 +402,7 @@ size_t Encoder::encode(const void* const* planes, const uint32_t* strides, bool 
 void Decoder::read_headers(const uint8_t* data, size_t len, uint32_t sample_type) {
   Params np;
   size_t sot = np.read_main_header(data, len);
-  j2c = data; j2c_len = len; first_sot = sot;
+  j2c = data; j2c_len = len; first_sot = sot; dev_cs = nullptr;
   // geometry depends on SIZ/COD/QCD/QCC only; rebuild when any of those bytes changed
   std::vector<uint8_t> sig;
   {
@@ -528,9 +546,16 @@ uint32_t Decoder::decode(void* const* planes, const uint32_t* strides, bool plan
   uint32_t nc = P.num_comps(), es = esize_of(img_type), D = P.num_decomps;
   last_launches = 0;
   // codestream to the device while the host parses packet headers
-  d_cs.reserve(j2c_len + 64);
-  CK(cudaMemcpyAsync(d_cs.p, j2c, j2c_len, cudaMemcpyHostToDevice, stream));
-  CK(cudaMemsetAsync(d_cs.as<uint8_t>() + j2c_len, 0, 32, stream));
+  mark(0);
+  const uint8_t* cs_dev = dev_cs;
+  if (cs_dev == nullptr) {
+    d_cs.reserve(j2c_len + 64);
+    CK(cudaMemcpyAsync(d_cs.p, j2c, j2c_len, cudaMemcpyHostToDevice, stream));
+    CK(cudaMemsetAsync(d_cs.as<uint8_t>() + j2c_len, 0, 32, stream));
+    cs_dev = d_cs.as<uint8_t>();
+  }
+  mark(1);
+  auto host_t0 = std::chrono::steady_clock::now();
   parse_tiles();
   uint32_t nb = (uint32_t)h_dec_proto.size();
   DecBlock* hd = h_dec.as<DecBlock>();
@@ -552,11 +577,14 @@ uint32_t Decoder::decode(void* const* planes, const uint32_t* strides, bool plan
     hd[b] = d;
   }
   d_scratch.reserve((scratch + 64) * 4);
+  host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
+  mark(2);
   if (nb) CK(cudaMemcpyAsync(d_dec.p, h_dec.p, (size_t)nb * sizeof(DecBlock), cudaMemcpyHostToDevice, stream));
-  launch_ht_decode(d_dec.as<DecBlock>(), nb, d_cs.as<uint8_t>(), d_coef.as<uint32_t>(), d_scratch.as<uint32_t>(),
+  launch_ht_decode(d_dec.as<DecBlock>(), nb, cs_dev, d_coef.as<uint32_t>(), d_scratch.as<uint32_t>(),
                    d_tables_dec.as<uint16_t>(), P.reversible() ? (uint32_t)DEC_OUT_INT : (uint32_t)DEC_OUT_FLOAT,
                    d_bstatus.as<uint32_t>(), stream);
   last_launches += 2;
+  mark(3);
   if (nb) CK(cudaMemcpyAsync(h_bstatus.p, d_bstatus.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, stream));
   // synthesis, coarsest level first
   for (size_t li = jobs.size(); li-- > 0; ) {
@@ -566,6 +594,7 @@ uint32_t Decoder::decode(void* const* planes, const uint32_t* strides, bool plan
     ++last_launches;
   }
   (void)D;
+  mark(4);
   if (planes) {
     for (uint32_t c = 0; c < nc; ++c) {
       const uint8_t* s = d_image.as<uint8_t>() + img_off[c];
@@ -579,8 +608,10 @@ uint32_t Decoder::decode(void* const* planes, const uint32_t* strides, bool plan
                              (size_t)img_w[c] * es, kind, stream));
     }
   }
+  mark(5);
   CK(cudaStreamSynchronize(stream));
   CK(cudaGetLastError());
+  collect(6);
   failed_blocks = 0;
   const uint32_t* bs = h_bstatus.as<uint32_t>();
   for (uint32_t b = 0; b < nb; ++b) if (bs[b] & 1u) ++failed_blocks;

@@ -37,6 +37,13 @@ public:
   Layout layout;
   cudaStream_t stream = nullptr;
   uint32_t last_launches = 0;          // kernels launched by the last frame call
+  // stage timing of the last frame call (CUDA events on `stream`, ms)
+  enum { EV_MAX = 12 };
+  cudaEvent_t ev[EV_MAX] = {nullptr};
+  float stage_ms[EV_MAX] = {0};
+  double host_ms = 0;                  // host time between the two device phases
+  void mark(int i) { cudaEventRecord(ev[i], stream); }
+  void collect(int n) { for (int i = 0; i + 1 < n; ++i) cudaEventElapsedTime(&stage_ms[i], ev[i], ev[i + 1]); }
   void upload_tables();
   DeviceBuf d_tables_enc, d_tables_dec;
   // image planes on the device: component c at byte offset img_off[c], tight rows
@@ -96,6 +103,7 @@ public:
   uint32_t decode(void* const* planes, const uint32_t* strides, bool planes_on_device);
   uint32_t failed_blocks = 0;
   const uint8_t* j2c = nullptr; size_t j2c_len = 0; size_t first_sot = 0;
+  const uint8_t* dev_cs = nullptr;     // optional: the same bytes already resident in HBM (+32 bytes slack)
   std::vector<uint8_t> header_sig;     // bytes of the main header the geometry was built for
   std::vector<CodedBlock> coded;
   std::vector<DecBlock> h_dec_proto;   // geometry part of DecBlock, per block

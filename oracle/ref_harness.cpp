@@ -218,7 +218,8 @@ int ojr_decode(const uint8_t* j2c, uint64_t len, int32_t* const* planes,
     if (resilient) cs.enable_resilience();
     cs.read_headers(&f);
     ojr_info info; fill_info(cs, &info);
-    cs.set_planar(false);
+    // keep the library's own choice (read_headers: planar = !colour_transform,
+    // ojph_codestream_local.cpp:879): interleaved pulls stall on sub-sampled components
     cs.create();
     ui32 nc = info.num_comps;
     std::vector<ui32> row(nc, 0);
