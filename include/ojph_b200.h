@@ -95,6 +95,12 @@ uint32_t ojb_enc_num_blocks(ojb_encoder* e);
 int ojb_enc_read_band(ojb_encoder* e, uint32_t tile, uint32_t comp, uint32_t res, uint32_t band,
                       uint32_t* out, uint32_t* band_w, uint32_t* band_h);
 
+/* parity hook: geometry and quantisation of one sub-band as the reference derives them
+ * (subband::finalize_alloc, src/core/codestream/ojph_subband.cpp:133-203): info8 = band x0, y0, w, h,
+ * K_max, resolution x0, y0, number of code-blocks; delta2 = step, 1/step (irreversible) */
+int ojb_enc_band_info(ojb_encoder* e, uint32_t tile, uint32_t comp, uint32_t res, uint32_t band,
+                      uint32_t* info8, float* delta2);
+
 /* ---- decode: ojph::codestream read side ------------------------------------------------- */
 ojb_decoder* ojb_dec_create(void);
 void ojb_dec_destroy(ojb_decoder* d);
@@ -110,6 +116,11 @@ void* ojb_dec_device_plane(ojb_decoder* d, uint32_t comp);
  * bytes after the end); the next decode reads them there instead of uploading j2c */
 int ojb_dec_use_device_codestream(ojb_decoder* d, const void* dev_bytes);
 uint32_t ojb_dec_failed_blocks(ojb_decoder* d);
+/* parity hook: parse the packet headers of the codestream given to read_headers and list every
+ * code-block (precinct::parse, src/core/codestream/ojph_precinct.cpp:328-573): geometry, missing msbs,
+ * passes, lengths and the byte offset of its data in j2c */
+struct ojb_block_desc;
+int ojb_dec_list_blocks(ojb_decoder* d, struct ojb_block_desc* out, uint32_t cap, uint32_t* n);
 uint32_t ojb_dec_kernel_launches(ojb_decoder* d);
 int ojb_dec_read_band(ojb_decoder* d, uint32_t tile, uint32_t comp, uint32_t res, uint32_t band,
                       uint32_t* out, uint32_t* band_w, uint32_t* band_h);

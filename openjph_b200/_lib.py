@@ -67,6 +67,7 @@ SYMBOLS = {
     "ojb_enc_timings": (None, [_VP, C.POINTER(C.c_float)]),
     "ojb_dec_timings": (None, [_VP, C.POINTER(C.c_float)]),
     "ojb_enc_read_band": (_I, [_VP, _U32, _U32, _U32, _U32, _VP, C.POINTER(_U32), C.POINTER(_U32)]),
+    "ojb_enc_band_info": (_I, [_VP, _U32, _U32, _U32, _U32, C.POINTER(_U32), C.POINTER(C.c_float)]),
     "ojb_dec_create": (_VP, []),
     "ojb_dec_destroy": (None, [_VP]),
     "ojb_dec_enable_resilience": (_I, [_VP]),
@@ -76,6 +77,7 @@ SYMBOLS = {
     "ojb_dec_device_plane": (_VP, [_VP, _U32]),
     "ojb_dec_use_device_codestream": (_I, [_VP, _VP]),
     "ojb_dec_failed_blocks": (_U32, [_VP]),
+    "ojb_dec_list_blocks": (_I, [_VP, C.POINTER(BlockDesc), _U32, C.POINTER(_U32)]),
     "ojb_dec_kernel_launches": (_U32, [_VP]),
     "ojb_dec_read_band": (_I, [_VP, _U32, _U32, _U32, _U32, _VP, C.POINTER(_U32), C.POINTER(_U32)]),
     "ojb_encode_blocks": (_I, [_VP, _U64, C.POINTER(BlockDesc), _U32, _VP, _U64, C.POINTER(_U64)]),

@@ -146,6 +146,12 @@ class Encoder(_Base):
     def kernel_launches(self):
         return self.L.ojb_enc_kernel_launches(self.h)
 
+    def band_info(self, tile, comp, res, band):
+        i8 = (C.c_uint32 * 8)(); d2 = (C.c_float * 2)()
+        self._check(self.L.ojb_enc_band_info(self.h, tile, comp, res, band, i8, d2))
+        return dict(x0=i8[0], y0=i8[1], w=i8[2], h=i8[3], K_max=i8[4], res_x0=i8[5], res_y0=i8[6], nblocks=i8[7],
+                    delta=d2[0], delta_inv=d2[1])
+
     def timings(self):
         t = (C.c_float * 8)()
         self.L.ojb_enc_timings(self.h, t)
@@ -197,6 +203,13 @@ class Decoder(_Base):
         if out.size:
             self._check(self.L.ojb_dec_read_band(self.h, tile, comp, res, band, out.ctypes.data, C.byref(bw), C.byref(bh)))
         return out
+
+    def list_blocks(self):
+        n = C.c_uint32()
+        self._check(self.L.ojb_dec_list_blocks(self.h, None, 0, C.byref(n)))
+        arr = (_lib.BlockDesc * max(1, n.value))()
+        self._check(self.L.ojb_dec_list_blocks(self.h, arr, n.value, C.byref(n)))
+        return [arr[i] for i in range(n.value)]
 
     @property
     def failed_blocks(self):

@@ -189,6 +189,20 @@ int ojb_enc_read_band(ojb_encoder* e, uint32_t tile, uint32_t comp, uint32_t res
   });
 }
 
+int ojb_enc_band_info(ojb_encoder* e, uint32_t tile, uint32_t comp, uint32_t res, uint32_t band, uint32_t* info8, float* delta) {
+  return guarded([&] {
+    if (!e->configured) fail(0x000B0013, "encoder is not configured");
+    CodecBase& cb = e->enc;
+    if (tile >= cb.layout.tiles.size() || comp >= cb.params.num_comps() || res > cb.params.num_decomps || band > 3)
+      fail(0x000B0014, "no such sub-band");
+    const ResGeom& rg = cb.layout.tiles[tile].comps[comp].res[res];
+    const BandGeom& bg = rg.bands[band];
+    info8[0] = bg.rect.x0; info8[1] = bg.rect.y0; info8[2] = bg.rect.w; info8[3] = bg.rect.h;
+    info8[4] = bg.K_max; info8[5] = rg.rect.x0; info8[6] = rg.rect.y0; info8[7] = bg.empty ? 0u : bg.nbw * bg.nbh;
+    delta[0] = bg.delta; delta[1] = bg.delta_inv;
+  });
+}
+
 ojb_decoder* ojb_dec_create(void) {
   ojb_decoder* d = nullptr;
   guarded([&] { d = new ojb_decoder(); });
@@ -228,6 +242,23 @@ void* ojb_dec_device_plane(ojb_decoder* d, uint32_t comp) {
 }
 int ojb_dec_use_device_codestream(ojb_decoder* d, const void* dev_bytes) { d->dec.dev_cs = (const uint8_t*)dev_bytes; return 0; }
 uint32_t ojb_dec_failed_blocks(ojb_decoder* d) { return d->dec.failed_blocks; }
+int ojb_dec_list_blocks(ojb_decoder* d, ojb_block_desc* out, uint32_t cap, uint32_t* n) {
+  return guarded([&] {
+    if (!d->have_headers) fail(0x000B0015, "read_headers has not been called");
+    d->dec.parse_tiles();
+    uint32_t nb = (uint32_t)d->dec.h_dec_proto.size();
+    *n = nb;
+    for (uint32_t i = 0; i < nb && i < cap; ++i) {
+      const DecBlock& g = d->dec.h_dec_proto[i];
+      const CodedBlock& cb = d->dec.coded[i];
+      memset(&out[i], 0, sizeof(out[i]));
+      out[i].w = g.w; out[i].h = g.h; out[i].stride = g.stride; out[i].sample_off = g.dst_off;
+      out[i].missing_msbs = cb.missing_msbs; out[i].num_passes = cb.num_passes;
+      out[i].len1 = cb.pass_len[0]; out[i].len2 = cb.pass_len[1]; out[i].byte_off = cb.data_off;
+      out[i].causal = g.flags & 1;
+    }
+  });
+}
 uint32_t ojb_dec_kernel_launches(ojb_decoder* d) { return d->dec.last_launches; }
 int ojb_dec_read_band(ojb_decoder* d, uint32_t tile, uint32_t comp, uint32_t res, uint32_t band,
                       uint32_t* out, uint32_t* band_w, uint32_t* band_h) {
