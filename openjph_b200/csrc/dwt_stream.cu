@@ -1,0 +1,531 @@
+// dwt_stream.cu -- register-streaming lifting kernels (the fast path for every resolution that is
+// at least 2x2; dwt_fwd.cu / dwt_inv.cu remain the general shared-memory path for degenerate sizes).
+//
+// Same arithmetic, same order as the reference (forward: vertical lifting then horizontal on each
+// produced line, src/core/codestream/ojph_resolution.cpp:572-600 / :649-682; inverse: horizontal
+// synthesis then vertical, :738-781 / :841-898; step formulas src/core/transform/ojph_transform.cpp:
+// 209-257, 336-411, 514-590, 691-849), but organised for the GPU instead of line buffers:
+//   * one WARP owns a strip of 64 columns and streams down a chunk of rows; lane l holds the
+//     column pair (even, odd) = (low, high) positions 2l, 2l+1 of the strip;
+//   * VERTICAL lifting is a software pipeline in registers (state: 2 values per column for 5/3,
+//     4 for 9/7); every iteration consumes two input rows and emits one (low, high) output pair;
+//   * HORIZONTAL lifting of an emitted row is done with __shfl_up / __shfl_down between neighbouring
+//     lanes -- no shared memory, no block barrier anywhere in the kernel;
+//   * one or two lanes per side are halo (recomputed by the neighbouring strip), a few rows per
+//     chunk are pipeline priming; borders use mirrored coordinates (whole-sample symmetric
+//     extension, ojph_transform.cpp:372-374).
+// Level 1 fuses sample fetch, level shift / int->float and RCT / ICT on load (forward) and the
+// inverse of those on store (inverse); quantisation to MSB-aligned sign-magnitude is fused into
+// the sub-band store (forward).
+#include "dwt_common.cuh"
+#include "ojb_kernels.h"
+
+namespace ojb {
+
+#define DS_WARPS 4
+#define DS_ROWS 64            // output rows per warp chunk
+#define FULL 0xFFFFFFFFu
+
+namespace {
+
+template <bool REV> struct Tp;
+template <> struct Tp<true>  { typedef int T; };
+template <> struct Tp<false> { typedef float T; };
+
+template <bool REV> __device__ __forceinline__ constexpr int halo_lanes() { return REV ? 1 : 2; }
+
+__device__ __forceinline__ float lift(float d, float a, float b, float c) {     // d + c*(a+b), no FMA
+  return __fadd_rn(d, __fmul_rn(c, __fadd_rn(a, b)));
+}
+
+// horizontal analysis of one line held as (a0 = even column, a1 = odd column) per lane
+template <bool REV, typename T>
+__device__ __forceinline__ void horz_ana(T& a0, T& a1) {
+  if (REV) {
+    int r = __shfl_down_sync(FULL, (int)a0, 1);
+    a1 = (T)((int)a1 - (((int)a0 + r) >> 1));
+    int l = __shfl_up_sync(FULL, (int)a1, 1);
+    a0 = (T)((int)a0 + ((l + (int)a1 + 2) >> 2));
+  } else {
+    float r = __shfl_down_sync(FULL, (float)a0, 1);
+    a1 = (T)lift((float)a1, (float)a0, r, IRV_ALPHA);
+    float l = __shfl_up_sync(FULL, (float)a1, 1);
+    a0 = (T)lift((float)a0, l, (float)a1, IRV_BETA);
+    r = __shfl_down_sync(FULL, (float)a0, 1);
+    a1 = (T)lift((float)a1, (float)a0, r, IRV_GAMMA);
+    l = __shfl_up_sync(FULL, (float)a1, 1);
+    a0 = (T)lift((float)a0, l, (float)a1, IRV_DELTA);
+    a0 = (T)__fmul_rn((float)a0, 1.0f / IRV_K);
+    a1 = (T)__fmul_rn((float)a1, IRV_K);
+  }
+}
+
+// horizontal synthesis
+template <bool REV, typename T>
+__device__ __forceinline__ void horz_syn(T& a0, T& a1) {
+  if (REV) {
+    int l = __shfl_up_sync(FULL, (int)a1, 1);
+    a0 = (T)((int)a0 - ((l + (int)a1 + 2) >> 2));
+    int r = __shfl_down_sync(FULL, (int)a0, 1);
+    a1 = (T)((int)a1 + (((int)a0 + r) >> 1));
+  } else {
+    a0 = (T)__fmul_rn((float)a0, IRV_K);
+    a1 = (T)__fmul_rn((float)a1, 1.0f / IRV_K);
+    float l = __shfl_up_sync(FULL, (float)a1, 1);
+    a0 = (T)lift((float)a0, l, (float)a1, -IRV_DELTA);
+    float r = __shfl_down_sync(FULL, (float)a0, 1);
+    a1 = (T)lift((float)a1, (float)a0, r, -IRV_GAMMA);
+    l = __shfl_up_sync(FULL, (float)a1, 1);
+    a0 = (T)lift((float)a0, l, (float)a1, -IRV_BETA);
+    r = __shfl_down_sync(FULL, (float)a0, 1);
+    a1 = (T)lift((float)a1, (float)a0, r, -IRV_ALPHA);
+  }
+}
+
+__device__ __forceinline__ uint32_t to_signmag_rev(int v, uint32_t shift) {
+  return (v < 0 ? 0x80000000u : 0u) | ((uint32_t)(v < 0 ? -v : v) << shift);
+}
+__device__ __forceinline__ uint32_t to_signmag_irv(float v, float scale) {
+  const int q = __float2int_rn(__fmul_rn(v, scale));
+  return (q < 0 ? 0x80000000u : 0u) | (uint32_t)(q < 0 ? -q : q);
+}
+
+struct StripGeom {
+  int x0, y0, x1, y1;       // resolution rectangle
+  int u0;                   // absolute (even) column of this lane's pair
+  int c0, c1;               // source column indices (mirrored, relative to x0) of the pair
+  bool lane_valid;          // lane produces outputs (not halo) and its columns exist
+  bool has0, has1;          // column u0 / u0+1 inside [x0, x1)
+  int R0, R1;               // output rows of this chunk [R0, R1), R0 even (absolute)
+};
+
+template <bool REV>
+__device__ __forceinline__ bool strip_setup(const DwtJob& J, uint32_t local, uint32_t lane, StripGeom& g) {
+  const int V = 32 - 2 * halo_lanes<REV>();
+  const uint32_t strip = local % J.tiles_x, chunk = local / J.tiles_x;
+  g.x0 = (int)J.x0; g.y0 = (int)J.y0; g.x1 = g.x0 + (int)J.w; g.y1 = g.y0 + (int)J.h;
+  const int ue = g.x0 & ~1;
+  g.u0 = ue + (int)strip * 2 * V + 2 * ((int)lane - halo_lanes<REV>());
+  g.c0 = reflect_coord(g.u0, g.x0, g.x1 - 1) - g.x0;
+  g.c1 = reflect_coord(g.u0 + 1, g.x0, g.x1 - 1) - g.x0;
+  const bool inner = (int)lane >= halo_lanes<REV>() && (int)lane < 32 - halo_lanes<REV>();
+  g.has0 = inner && g.u0 >= g.x0 && g.u0 < g.x1;
+  g.has1 = inner && g.u0 + 1 >= g.x0 && g.u0 + 1 < g.x1;
+  g.lane_valid = g.has0 || g.has1;
+  const int ye = g.y0 & ~1;
+  g.R0 = ye + (int)chunk * DS_ROWS;
+  g.R1 = min(g.R0 + DS_ROWS, g.y1);
+  return g.R0 < g.y1;
+}
+
+// ---- forward ---------------------------------------------------------------------------------
+template <bool REV, int NC, bool FIRST>
+__device__ __forceinline__ void fwd_load_row(const DwtJob& J, const StripGeom& g, const void* image,
+                                             const uint32_t* coef, int v, typename Tp<REV>::T (&a)[NC][2])
+{
+  typedef typename Tp<REV>::T T;
+  const int vr = reflect_coord(v, g.y0, g.y1 - 1) - g.y0;
+  if (FIRST) {
+    int iv[NC][2];
+    #pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const size_t row = (size_t)vr * J.full_stride[k];
+      const unsigned char* base = reinterpret_cast<const unsigned char*>(image) + J.full_off[k];
+      if (J.src_type == SRC_U16) {
+        const unsigned short* p = reinterpret_cast<const unsigned short*>(base) + row;
+        iv[k][0] = p[g.c0]; iv[k][1] = p[g.c1];
+      } else if (J.src_type == SRC_U8) {
+        const unsigned char* p = base + row;
+        iv[k][0] = p[g.c0]; iv[k][1] = p[g.c1];
+      } else {
+        const int* p = reinterpret_cast<const int*>(base) + row;
+        iv[k][0] = p[g.c0]; iv[k][1] = p[g.c1];
+      }
+    }
+    if (REV) {
+      const int shift = J.is_signed ? 0 : (1 << (J.bit_depth - 1));
+      #pragma unroll
+      for (int k = 0; k < NC; ++k) { iv[k][0] -= shift; iv[k][1] -= shift; }
+      if (NC == 3) {
+        #pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int rr = iv[0][i], gg = iv[1][i], bb = iv[2][i];
+          iv[0][i] = (rr + (gg << 1) + bb) >> 2; iv[1][i] = bb - gg; iv[2][i] = rr - gg;
+        }
+      }
+      #pragma unroll
+      for (int k = 0; k < NC; ++k) { a[k][0] = (T)iv[k][0]; a[k][1] = (T)iv[k][1]; }
+    } else {
+      const float mul = (float)(1.0 / (double)(1ull << J.bit_depth));
+      const int half = J.is_signed ? 0 : (1 << (J.bit_depth - 1));
+      float f[NC][2];
+      #pragma unroll
+      for (int k = 0; k < NC; ++k) { f[k][0] = __fmul_rn((float)(iv[k][0] - half), mul); f[k][1] = __fmul_rn((float)(iv[k][1] - half), mul); }
+      if (NC == 3) {
+        #pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const float rr = f[0][i], gg = f[1][i], bb = f[2][i];
+          const float yy = __fadd_rn(__fadd_rn(__fmul_rn(ICT_ALPHA_RF, rr), __fmul_rn(ICT_ALPHA_GF, gg)), __fmul_rn(ICT_ALPHA_BF, bb));
+          f[0][i] = yy; f[1][i] = __fmul_rn(ICT_BETA_CBF, __fsub_rn(bb, yy)); f[2][i] = __fmul_rn(ICT_BETA_CRF, __fsub_rn(rr, yy));
+        }
+      }
+      #pragma unroll
+      for (int k = 0; k < NC; ++k) { a[k][0] = (T)f[k][0]; a[k][1] = (T)f[k][1]; }
+    }
+  } else {
+    const T* p = reinterpret_cast<const T*>(coef) + J.full_off[0] + (size_t)vr * J.full_stride[0];
+    a[0][0] = p[g.c0]; a[0][1] = p[g.c1];
+  }
+}
+
+// store one emitted (vertically low, vertically high) row pair after horizontal analysis
+template <bool REV, int NC>
+__device__ __forceinline__ void fwd_store_pair(const DwtJob& J, const StripGeom& g, uint32_t* coef, int vlow,
+                                               typename Tp<REV>::T (&lo)[NC][2], typename Tp<REV>::T (&hi)[NC][2])
+{
+  typedef typename Tp<REV>::T T;
+  #pragma unroll
+  for (int k = 0; k < NC; ++k) {
+    horz_ana<REV, T>(lo[k][0], lo[k][1]);
+    horz_ana<REV, T>(hi[k][0], hi[k][1]);
+  }
+  if (!g.lane_valid) return;
+  const int bxl = (g.u0 >> 1) - ((g.x0 + 1) >> 1);      // index in horizontally-low bands
+  const int bxh = (g.u0 >> 1) - (g.x0 >> 1);            // index in horizontally-high bands
+  #pragma unroll
+  for (int vpar = 0; vpar < 2; ++vpar) {
+    const int v = vlow + vpar;
+    if (v < g.y0 || v >= g.y1 || v < g.R0 || v >= g.R1) continue;
+    const int by = (v >> 1) - (vpar ? (g.y0 >> 1) : ((g.y0 + 1) >> 1));
+    #pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const T e = vpar ? hi[k][0] : lo[k][0], o = vpar ? hi[k][1] : lo[k][1];
+      const int bl = vpar ? 2 : 0, bh = vpar ? 3 : 1;
+      if (g.has0) {
+        if (bl == 0 && !J.last) reinterpret_cast<T*>(coef)[J.ll_off[k] + (size_t)by * J.ll_stride[k] + bxl] = e;
+        else coef[J.band_off[k][bl] + (size_t)by * J.band_stride[k][bl] + bxl] =
+               REV ? to_signmag_rev((int)e, J.band_shift[k][bl]) : to_signmag_irv((float)e, J.band_scale[k][bl]);
+      }
+      if (g.has1)
+        coef[J.band_off[k][bh] + (size_t)by * J.band_stride[k][bh] + bxh] =
+          REV ? to_signmag_rev((int)o, J.band_shift[k][bh]) : to_signmag_irv((float)o, J.band_scale[k][bh]);
+    }
+  }
+}
+
+template <bool REV, int NC, bool FIRST>
+__global__ void __launch_bounds__(DS_WARPS * 32)
+dwt_fwd_stream_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, const void* __restrict__ image,
+                      uint32_t* __restrict__ coef)
+{
+  typedef typename Tp<REV>::T T;
+  __shared__ DwtJob sj;
+  {
+    uint32_t ji = find_job(jobs, njobs, blockIdx.x);
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(&jobs[ji]);
+    uint32_t* d = reinterpret_cast<uint32_t*>(&sj);
+    for (uint32_t i = threadIdx.x; i < sizeof(DwtJob) / 4; i += blockDim.x) d[i] = s[i];
+  }
+  __syncthreads();
+  const DwtJob& J = sj;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // CTA = DS_WARPS adjacent strips of one row chunk
+  const uint32_t cta = blockIdx.x - J.cta_base;
+  const uint32_t strips_per_row = (J.tiles_x + DS_WARPS - 1) / DS_WARPS;
+  const uint32_t strip = (cta % strips_per_row) * DS_WARPS + warp, chunk = cta / strips_per_row;
+  if (strip >= J.tiles_x) return;
+  StripGeom g;
+  if (!strip_setup<REV>(J, chunk * J.tiles_x + strip, lane, g)) return;
+
+  if (REV) {
+    // 5/3: iteration k consumes rows (2k-1, 2k) and emits the pair (2k-2, 2k-1)
+    T xe[NC][2], hp[NC][2];           // x[2k-2], H[k-2]
+    const int k0 = g.R0 / 2;
+    fwd_load_row<REV, NC, FIRST>(J, g, image, coef, 2 * k0 - 2, xe);
+    #pragma unroll
+    for (int c = 0; c < NC; ++c) { hp[c][0] = 0; hp[c][1] = 0; }
+    const int k1 = (g.R1 + 1) / 2;    // last emitted pair index k1-1 covers rows up to R1-1
+    for (int k = k0; k <= k1; ++k) {
+      T xo[NC][2], xn[NC][2], lo[NC][2], hi[NC][2];
+      fwd_load_row<REV, NC, FIRST>(J, g, image, coef, 2 * k - 1, xo);
+      fwd_load_row<REV, NC, FIRST>(J, g, image, coef, 2 * k, xn);
+      #pragma unroll
+      for (int c = 0; c < NC; ++c)
+        #pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int h = (int)xo[c][i] - (((int)xe[c][i] + (int)xn[c][i]) >> 1);       // H[k-1]
+          const int l = (int)xe[c][i] + (((int)hp[c][i] + h + 2) >> 2);               // L[k-1]
+          lo[c][i] = (T)l; hi[c][i] = (T)h;
+          hp[c][i] = (T)h; xe[c][i] = xn[c][i];
+        }
+      fwd_store_pair<REV, NC>(J, g, coef, 2 * k - 2, lo, hi);      // rows 2k-2 (low), 2k-1 (high)
+    }
+  } else {
+    // 9/7: iteration k consumes rows (2k-1, 2k) and emits the pair (2k-4, 2k-3)
+    T xe[NC][2], d1[NC][2], s1[NC][2], d2[NC][2];   // x[2k-2], d1[k-2], s1[k-2], d2[k-3]
+    const int k0 = g.R0 / 2 - 1;
+    fwd_load_row<REV, NC, FIRST>(J, g, image, coef, 2 * k0 - 2, xe);
+    #pragma unroll
+    for (int c = 0; c < NC; ++c)
+      #pragma unroll
+      for (int i = 0; i < 2; ++i) { d1[c][i] = 0; s1[c][i] = 0; d2[c][i] = 0; }
+    const int k1 = (g.R1 + 1) / 2 + 1;
+    const float Kinv = 1.0f / IRV_K;
+    for (int k = k0; k <= k1; ++k) {
+      T xo[NC][2], xn[NC][2], lo[NC][2], hi[NC][2];
+      fwd_load_row<REV, NC, FIRST>(J, g, image, coef, 2 * k - 1, xo);
+      fwd_load_row<REV, NC, FIRST>(J, g, image, coef, 2 * k, xn);
+      #pragma unroll
+      for (int c = 0; c < NC; ++c)
+        #pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const float nd1 = lift((float)xo[c][i], (float)xe[c][i], (float)xn[c][i], IRV_ALPHA);     // d1[k-1]
+          const float ns1 = lift((float)xe[c][i], (float)d1[c][i], nd1, IRV_BETA);                  // s1[k-1]
+          const float nd2 = lift((float)d1[c][i], (float)s1[c][i], ns1, IRV_GAMMA);                 // d2[k-2]
+          const float ns2 = lift((float)s1[c][i], (float)d2[c][i], nd2, IRV_DELTA);                 // s2[k-2]
+          lo[c][i] = (T)__fmul_rn(ns2, Kinv); hi[c][i] = (T)__fmul_rn(nd2, IRV_K);
+          xe[c][i] = xn[c][i]; d1[c][i] = (T)nd1; s1[c][i] = (T)ns1; d2[c][i] = (T)nd2;
+        }
+      fwd_store_pair<REV, NC>(J, g, coef, 2 * k - 4, lo, hi);      // rows 2k-4 (low), 2k-3 (high)
+    }
+  }
+}
+
+// ---- inverse ---------------------------------------------------------------------------------
+// load the four sub-band samples that interleave into rows (2j, 2j+1), columns (u0, u0+1) and undo
+// the horizontal transform: L[..] = vertically-low row, H[..] = vertically-high row
+template <bool REV, int NC>
+__device__ __forceinline__ void inv_load_pair(const DwtJob& J, const StripGeom& g, const uint32_t* coef, int j,
+                                              typename Tp<REV>::T (&L)[NC][2], typename Tp<REV>::T (&H)[NC][2])
+{
+  typedef typename Tp<REV>::T T;
+  const T* cf = reinterpret_cast<const T*>(coef);
+  // mirrored absolute coordinates keep their parity, so each sample maps to a definite band
+  const int ua = reflect_coord(g.u0, g.x0, g.x1 - 1), ub = reflect_coord(g.u0 + 1, g.x0, g.x1 - 1);
+  const int bxl = (ua >> 1) - ((g.x0 + 1) >> 1), bxh = (ub >> 1) - (g.x0 >> 1);
+  const int va = reflect_coord(2 * j, g.y0, g.y1 - 1), vb = reflect_coord(2 * j + 1, g.y0, g.y1 - 1);
+  const int byl = (va >> 1) - ((g.y0 + 1) >> 1), byh = (vb >> 1) - (g.y0 >> 1);
+  #pragma unroll
+  for (int k = 0; k < NC; ++k) {
+    L[k][0] = J.last ? cf[J.band_off[k][0] + (size_t)byl * J.band_stride[k][0] + bxl]
+                     : cf[J.ll_off[k] + (size_t)byl * J.ll_stride[k] + bxl];
+    L[k][1] = cf[J.band_off[k][1] + (size_t)byl * J.band_stride[k][1] + bxh];
+    H[k][0] = cf[J.band_off[k][2] + (size_t)byh * J.band_stride[k][2] + bxl];
+    H[k][1] = cf[J.band_off[k][3] + (size_t)byh * J.band_stride[k][3] + bxh];
+    horz_syn<REV, T>(L[k][0], L[k][1]);
+    horz_syn<REV, T>(H[k][0], H[k][1]);
+  }
+}
+
+__device__ __forceinline__ int round_haz(float t) { return (int)(t + (t >= 0.0f ? 0.5f : -0.5f)); }
+
+template <bool REV, int NC, bool FIRST>
+__device__ __forceinline__ void inv_store_row(const DwtJob& J, const StripGeom& g, void* image, uint32_t* coef,
+                                              int v, typename Tp<REV>::T (&x)[NC][2])
+{
+  typedef typename Tp<REV>::T T;
+  if (!g.lane_valid || v < g.y0 || v >= g.y1 || v < g.R0 || v >= g.R1) return;
+  const int cx = g.u0 - g.x0;
+  if (!FIRST) {
+    T* p = reinterpret_cast<T*>(coef) + J.full_off[0] + (size_t)(v - g.y0) * J.full_stride[0];
+    if (g.has0) p[cx] = x[0][0];
+    if (g.has1) p[cx + 1] = x[0][1];
+    return;
+  }
+  int out[NC][2];
+  if (REV) {
+    int a[NC][2];
+    #pragma unroll
+    for (int k = 0; k < NC; ++k) { a[k][0] = (int)x[k][0]; a[k][1] = (int)x[k][1]; }
+    if (NC == 3) {
+      #pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int yy = a[0][i], cb = a[1][i], cr = a[2][i], gg = yy - ((cb + cr) >> 2);
+        a[0][i] = cr + gg; a[1][i] = gg; a[2][i] = cb + gg;
+      }
+    }
+    const int shift = J.is_signed ? 0 : (1 << (J.bit_depth - 1));
+    #pragma unroll
+    for (int k = 0; k < NC; ++k) { out[k][0] = a[k][0] + shift; out[k][1] = a[k][1] + shift; }
+  } else {
+    float f[NC][2];
+    #pragma unroll
+    for (int k = 0; k < NC; ++k) { f[k][0] = (float)x[k][0]; f[k][1] = (float)x[k][1]; }
+    if (NC == 3) {
+      #pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float yy = f[0][i], cb = f[1][i], cr = f[2][i];
+        f[1][i] = __fsub_rn(__fsub_rn(yy, __fmul_rn(ICT_GAMMA_CR2G, cr)), __fmul_rn(ICT_GAMMA_CB2G, cb));
+        f[0][i] = __fadd_rn(yy, __fmul_rn(ICT_GAMMA_CR2R, cr));
+        f[2][i] = __fadd_rn(yy, __fmul_rn(ICT_GAMMA_CB2B, cb));
+      }
+    }
+    const int B = (int)J.bit_depth;
+    const float mul = (float)(1ull << B);
+    const int lo = -(1 << (B - 1)), hi = (1 << (B - 1)) - 1;
+    const float flo = (float)lo, fhi = -(float)lo;
+    const int half = J.is_signed ? 0 : (1 << (B - 1));
+    #pragma unroll
+    for (int k = 0; k < NC; ++k)
+      #pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float t = __fmul_rn(f[k][i], mul);
+        int q = round_haz(t);
+        q = t >= flo ? q : lo; q = t < fhi ? q : hi;
+        out[k][i] = q + half;
+      }
+  }
+  #pragma unroll
+  for (int k = 0; k < NC; ++k) {
+    const size_t row = (size_t)(v - g.y0) * J.full_stride[k];
+    unsigned char* base = reinterpret_cast<unsigned char*>(image) + J.full_off[k];
+    if (J.src_type == SRC_U16) {
+      unsigned short* p = reinterpret_cast<unsigned short*>(base) + row;
+      if (g.has0) p[cx] = (unsigned short)min(max(out[k][0], 0), 65535);
+      if (g.has1) p[cx + 1] = (unsigned short)min(max(out[k][1], 0), 65535);
+    } else if (J.src_type == SRC_U8) {
+      unsigned char* p = base + row;
+      if (g.has0) p[cx] = (unsigned char)min(max(out[k][0], 0), 255);
+      if (g.has1) p[cx + 1] = (unsigned char)min(max(out[k][1], 0), 255);
+    } else {
+      int* p = reinterpret_cast<int*>(base) + row;
+      if (g.has0) p[cx] = out[k][0];
+      if (g.has1) p[cx + 1] = out[k][1];
+    }
+  }
+}
+
+template <bool REV, int NC, bool FIRST>
+__global__ void __launch_bounds__(DS_WARPS * 32)
+dwt_inv_stream_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, void* __restrict__ image,
+                      uint32_t* __restrict__ coef)
+{
+  typedef typename Tp<REV>::T T;
+  __shared__ DwtJob sj;
+  {
+    uint32_t ji = find_job(jobs, njobs, blockIdx.x);
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(&jobs[ji]);
+    uint32_t* d = reinterpret_cast<uint32_t*>(&sj);
+    for (uint32_t i = threadIdx.x; i < sizeof(DwtJob) / 4; i += blockDim.x) d[i] = s[i];
+  }
+  __syncthreads();
+  const DwtJob& J = sj;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t cta = blockIdx.x - J.cta_base;
+  const uint32_t strips_per_row = (J.tiles_x + DS_WARPS - 1) / DS_WARPS;
+  const uint32_t strip = (cta % strips_per_row) * DS_WARPS + warp, chunk = cta / strips_per_row;
+  if (strip >= J.tiles_x) return;
+  StripGeom g;
+  if (!strip_setup<REV>(J, chunk * J.tiles_x + strip, lane, g)) return;
+
+  if (REV) {
+    // 5/3: iteration j consumes the band-row pair j and emits rows (2j-1, 2j)
+    T hp[NC][2], xe[NC][2];          // H[j-1], x[2j-2]
+    const int j0 = g.R0 / 2;
+    {
+      T L[NC][2];
+      inv_load_pair<REV, NC>(J, g, coef, j0 - 1, L, hp);       // only H[j0-1] is needed
+      #pragma unroll
+      for (int c = 0; c < NC; ++c) { xe[c][0] = 0; xe[c][1] = 0; }
+    }
+    const int j1 = (g.R1 + 1) / 2;
+    for (int j = j0; j <= j1; ++j) {
+      T L[NC][2], H[NC][2], xo[NC][2], xn[NC][2];
+      inv_load_pair<REV, NC>(J, g, coef, j, L, H);
+      #pragma unroll
+      for (int c = 0; c < NC; ++c)
+        #pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int e = (int)L[c][i] - (((int)hp[c][i] + (int)H[c][i] + 2) >> 2);     // x[2j]
+          const int o = (int)hp[c][i] + (((int)xe[c][i] + e) >> 1);                   // x[2j-1]
+          xn[c][i] = (T)e; xo[c][i] = (T)o;
+          hp[c][i] = H[c][i]; xe[c][i] = (T)e;
+        }
+      inv_store_row<REV, NC, FIRST>(J, g, image, coef, 2 * j - 1, xo);
+      inv_store_row<REV, NC, FIRST>(J, g, image, coef, 2 * j, xn);
+    }
+  } else {
+    // 9/7: iteration j consumes the band-row pair j and emits rows (2j-3, 2j-2)
+    T hp[NC][2], s1[NC][2], d1[NC][2], xe[NC][2];      // Hr[j-1], s1[j-1], d1[j-2], x_e[j-2]
+    const int j0 = g.R0 / 2 - 1;
+    {
+      T L[NC][2];
+      inv_load_pair<REV, NC>(J, g, coef, j0 - 1, L, hp);
+      #pragma unroll
+      for (int c = 0; c < NC; ++c)
+        #pragma unroll
+        for (int i = 0; i < 2; ++i) { hp[c][i] = (T)__fmul_rn((float)hp[c][i], 1.0f / IRV_K); s1[c][i] = 0; d1[c][i] = 0; xe[c][i] = 0; }
+    }
+    const int j1 = (g.R1 + 1) / 2 + 1;
+    for (int j = j0; j <= j1; ++j) {
+      T L[NC][2], H[NC][2], xo[NC][2], xn[NC][2];
+      inv_load_pair<REV, NC>(J, g, coef, j, L, H);
+      #pragma unroll
+      for (int c = 0; c < NC; ++c)
+        #pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const float lr = __fmul_rn((float)L[c][i], IRV_K), hr = __fmul_rn((float)H[c][i], 1.0f / IRV_K);
+          const float ns1 = lift(lr, (float)hp[c][i], hr, -IRV_DELTA);                          // s1[j]
+          const float nd1 = lift((float)hp[c][i], (float)s1[c][i], ns1, -IRV_GAMMA);            // d1[j-1]
+          const float nxe = lift((float)s1[c][i], (float)d1[c][i], nd1, -IRV_BETA);             // x_e[j-1]
+          const float nxo = lift((float)d1[c][i], (float)xe[c][i], nxe, -IRV_ALPHA);            // x_o[j-2]
+          xo[c][i] = (T)nxo; xn[c][i] = (T)nxe;
+          hp[c][i] = (T)hr; s1[c][i] = (T)ns1; d1[c][i] = (T)nd1; xe[c][i] = (T)nxe;
+        }
+      inv_store_row<REV, NC, FIRST>(J, g, image, coef, 2 * j - 3, xo);
+      inv_store_row<REV, NC, FIRST>(J, g, image, coef, 2 * j - 2, xn);
+    }
+  }
+}
+
+template <bool REV, int NC, bool FIRST>
+void launch_fwd(const DwtJob* jobs, uint32_t njobs, uint32_t ctas, const void* image, uint32_t* coef, cudaStream_t st) {
+  auto k = dwt_fwd_stream_kernel<REV, NC, FIRST>;
+  OJB_LAUNCH(k, dim3(ctas), dim3(DS_WARPS * 32), 0, st, jobs, njobs, image, coef);
+}
+template <bool REV, int NC, bool FIRST>
+void launch_inv(const DwtJob* jobs, uint32_t njobs, uint32_t ctas, void* image, uint32_t* coef, cudaStream_t st) {
+  auto k = dwt_inv_stream_kernel<REV, NC, FIRST>;
+  OJB_LAUNCH(k, dim3(ctas), dim3(DS_WARPS * 32), 0, st, jobs, njobs, image, coef);
+}
+
+} // namespace
+
+// strips across / row chunks down; the launch uses ceil(strips / DS_WARPS) * chunks CTAs
+void dwt_stream_tiling(uint32_t x0, uint32_t y0, uint32_t w, uint32_t h, bool reversible,
+                       uint32_t& strips, uint32_t& chunks, uint32_t& ctas)
+{
+  const uint32_t V = 32 - 2 * (reversible ? 1u : 2u);
+  const uint32_t ue = x0 & ~1u, ye = y0 & ~1u;
+  strips = (x0 + w - ue + 2 * V - 1) / (2 * V);
+  chunks = (y0 + h - ye + DS_ROWS - 1) / DS_ROWS;
+  ctas = ((strips + DS_WARPS - 1) / DS_WARPS) * chunks;
+}
+
+void launch_dwt_fwd_stream(const DwtJob* jobs, uint32_t njobs, uint32_t total_ctas, bool reversible,
+                           uint32_t ncomp, bool first, const void* image, uint32_t* coef, cudaStream_t st)
+{
+  if (total_ctas == 0) return;
+  if (reversible) {
+    if (first) { if (ncomp == 3) launch_fwd<true, 3, true>(jobs, njobs, total_ctas, image, coef, st); else launch_fwd<true, 1, true>(jobs, njobs, total_ctas, image, coef, st); }
+    else launch_fwd<true, 1, false>(jobs, njobs, total_ctas, image, coef, st);
+  } else {
+    if (first) { if (ncomp == 3) launch_fwd<false, 3, true>(jobs, njobs, total_ctas, image, coef, st); else launch_fwd<false, 1, true>(jobs, njobs, total_ctas, image, coef, st); }
+    else launch_fwd<false, 1, false>(jobs, njobs, total_ctas, image, coef, st);
+  }
+}
+
+void launch_dwt_inv_stream(const DwtJob* jobs, uint32_t njobs, uint32_t total_ctas, bool reversible,
+                           uint32_t ncomp, bool first, void* image, uint32_t* coef, cudaStream_t st)
+{
+  if (total_ctas == 0) return;
+  if (reversible) {
+    if (first) { if (ncomp == 3) launch_inv<true, 3, true>(jobs, njobs, total_ctas, image, coef, st); else launch_inv<true, 1, true>(jobs, njobs, total_ctas, image, coef, st); }
+    else launch_inv<true, 1, false>(jobs, njobs, total_ctas, image, coef, st);
+  } else {
+    if (first) { if (ncomp == 3) launch_inv<false, 3, true>(jobs, njobs, total_ctas, image, coef, st); else launch_inv<false, 1, true>(jobs, njobs, total_ctas, image, coef, st); }
+    else launch_inv<false, 1, false>(jobs, njobs, total_ctas, image, coef, st);
+  }
+}
+
+} // namespace ojb

@@ -80,12 +80,14 @@ void CodecBase::build_dwt_jobs(bool forward) {
   const Params& P = params;
   uint32_t D = P.num_decomps, nc = P.num_comps();
   uint32_t nlev = D == 0 ? 1 : D;
-  jobs.assign(nlev, std::vector<DwtJob>());
-  job_ctas.assign(nlev, 0); job_maxc.assign(nlev, 1);
+  jobs.assign(nlev, std::vector<JobGroup>());
   uint32_t es = esize_of(img_type);
   for (uint32_t li = 0; li < nlev; ++li) {
     uint32_t r = D == 0 ? 0 : D - li;          // resolution being split (or rebuilt)
-    uint32_t cta = 0;
+    // groups: [0] streaming 3-comp first, [1] streaming 1-comp first, [2] streaming inner levels, [3] general
+    std::vector<JobGroup> grp(4);
+    grp[0].stream = grp[1].stream = grp[2].stream = true;
+    grp[0].ncomp = 3; grp[0].first = grp[1].first = true;
     for (const TileGeom& t : layout.tiles) {
       for (uint32_t c = 0; c < nc; ) {
         bool fused = (r == D) && P.color_transform() && c == 0;
@@ -125,23 +127,29 @@ void CodecBase::build_dwt_jobs(bool forward) {
             j.band_scale[i][0] = forward ? bg.delta_inv : bg.delta;
           }
         }
-        dwt_tiling(j.x0, j.y0, j.w, j.h, j.tiles_x, j.tiles_y);
-        j.cta_base = cta;
-        uint32_t n = j.tiles_x * j.tiles_y;
-        if (n) { cta += n; jobs[li].push_back(j); job_maxc[li] = std::max(job_maxc[li], k); }
+        const bool stream = !j.nodwt && j.w >= 2 && j.h >= 2 && !no_stream_dwt;
+        uint32_t gi, n;
+        if (stream) {
+          gi = j.first ? (k == 3 ? 0u : 1u) : 2u;
+          dwt_stream_tiling(j.x0, j.y0, j.w, j.h, P.reversible(), j.tiles_x, j.tiles_y, n);
+        } else {
+          gi = 3;
+          dwt_tiling(j.x0, j.y0, j.w, j.h, j.tiles_x, j.tiles_y);
+          n = j.tiles_x * j.tiles_y;
+          grp[3].ncomp = std::max(grp[3].ncomp, k);
+        }
+        j.cta_base = grp[gi].ctas;
+        if (n) { grp[gi].ctas += n; grp[gi].jobs.push_back(j); }
         c += k;
       }
     }
-    job_ctas[li] = cta;
+    for (JobGroup& g : grp) if (!g.jobs.empty()) jobs[li].push_back(g);
   }
   size_t total = 0;
-  job_dev_off.assign(nlev, 0);
-  for (uint32_t li = 0; li < nlev; ++li) { job_dev_off[li] = total; total += jobs[li].size(); }
+  for (auto& lv : jobs) for (JobGroup& g : lv) { g.dev_off = total; total += g.jobs.size(); }
   d_jobs.reserve(std::max<size_t>(1, total) * sizeof(DwtJob));
-  for (uint32_t li = 0; li < nlev; ++li)
-    if (!jobs[li].empty())
-      CK(cudaMemcpy(d_jobs.as<DwtJob>() + job_dev_off[li], jobs[li].data(), jobs[li].size() * sizeof(DwtJob),
-                    cudaMemcpyHostToDevice));
+  for (auto& lv : jobs) for (JobGroup& g : lv)
+    CK(cudaMemcpy(d_jobs.as<DwtJob>() + g.dev_off, g.jobs.data(), g.jobs.size() * sizeof(DwtJob), cudaMemcpyHostToDevice));
 }
 
 static void check_block_widths(const Layout& L) {
@@ -263,12 +271,16 @@ size_t Encoder::encode(const void* const* planes, const uint32_t* strides, bool 
   mark(1);
   // 2. transform + block coding
   CK(cudaMemsetAsync(d_status.p, 0, 16, stream));
-  for (size_t li = 0; li < jobs.size(); ++li) {
-    if (job_ctas[li] == 0) continue;
-    launch_dwt_fwd(d_jobs.as<DwtJob>() + job_dev_off[li], (uint32_t)jobs[li].size(), job_ctas[li], P.reversible(),
-                   job_maxc[li], d_image.p, d_coef.as<uint32_t>(), stream);
-    ++last_launches;
-  }
+  for (size_t li = 0; li < jobs.size(); ++li)
+    for (const JobGroup& g : jobs[li]) {
+      if (g.stream)
+        launch_dwt_fwd_stream(d_jobs.as<DwtJob>() + g.dev_off, (uint32_t)g.jobs.size(), g.ctas, P.reversible(), g.ncomp,
+                              g.first, d_image.p, d_coef.as<uint32_t>(), stream);
+      else
+        launch_dwt_fwd(d_jobs.as<DwtJob>() + g.dev_off, (uint32_t)g.jobs.size(), g.ctas, P.reversible(), g.ncomp,
+                       d_image.p, d_coef.as<uint32_t>(), stream);
+      ++last_launches;
+    }
   mark(2);
   uint32_t nb = (uint32_t)h_blocks.size();
   launch_ht_encode(d_blocks.as<EncBlock>(), nb, d_coef.as<uint32_t>(), d_slots.as<uint8_t>(),
@@ -587,12 +599,16 @@ uint32_t Decoder::decode(void* const* planes, const uint32_t* strides, bool plan
   mark(3);
   if (nb) CK(cudaMemcpyAsync(h_bstatus.p, d_bstatus.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, stream));
   // synthesis, coarsest level first
-  for (size_t li = jobs.size(); li-- > 0; ) {
-    if (job_ctas[li] == 0) continue;
-    launch_dwt_inv(d_jobs.as<DwtJob>() + job_dev_off[li], (uint32_t)jobs[li].size(), job_ctas[li], P.reversible(),
-                   job_maxc[li], d_image.p, d_coef.as<uint32_t>(), stream);
-    ++last_launches;
-  }
+  for (size_t li = jobs.size(); li-- > 0; )
+    for (const JobGroup& g : jobs[li]) {
+      if (g.stream)
+        launch_dwt_inv_stream(d_jobs.as<DwtJob>() + g.dev_off, (uint32_t)g.jobs.size(), g.ctas, P.reversible(), g.ncomp,
+                              g.first, d_image.p, d_coef.as<uint32_t>(), stream);
+      else
+        launch_dwt_inv(d_jobs.as<DwtJob>() + g.dev_off, (uint32_t)g.jobs.size(), g.ctas, P.reversible(), g.ncomp,
+                       d_image.p, d_coef.as<uint32_t>(), stream);
+      ++last_launches;
+    }
   (void)D;
   mark(4);
   if (planes) {

@@ -55,11 +55,12 @@ public:
   void plan_image(uint32_t sample_type);
   DeviceBuf d_coef;                    // coefficient arena (32-bit words)
   // DWT jobs per level (index 0: full resolution level D, ...), uploaded once
-  std::vector<std::vector<DwtJob>> jobs;
-  std::vector<uint32_t> job_ctas, job_maxc;
+  // jobs of one level are grouped by the kernel variant that runs them
+  struct JobGroup { std::vector<DwtJob> jobs; uint32_t ctas = 0, ncomp = 1; bool first = false, stream = false; size_t dev_off = 0; };
+  std::vector<std::vector<JobGroup>> jobs;
   DeviceBuf d_jobs;
-  std::vector<size_t> job_dev_off;
   void build_dwt_jobs(bool forward);
+  bool no_stream_dwt = false;          // force the general shared-memory DWT kernels (tests)
 };
 
 class Encoder : public CodecBase {
