@@ -1,11 +1,13 @@
 #!/usr/bin/env python3
 """bench.py -- Mpixels/s encode+decode of the HTJ2K hot path.
 
-A step = one pass of the hot path over one frame: encode it to a codestream, then decode that
-codestream back (the metric BASELINE.json names is "Mpixels/s encode+decode").  Workload at every
-N: synthetic 8192x8192 3-component 12-bit frames, reversible 5/3 + RCT, 5 levels, 64x64 blocks
-(the headline configuration), one frame per GPU per step (weak scaling; frames are independent, so
-there is no data-path collective -- only the final gather of the codestream sizes to rank 0).
+A step = one pass of the hot path over one batch of frames: each frame is encoded to a codestream,
+then that codestream is decoded back (the metric BASELINE.json names is "Mpixels/s encode+decode").
+Workload at every N: synthetic 8192x8192 3-component 12-bit frames, reversible 5/3 + RCT, 5 levels,
+64x64 blocks (the headline configuration), OJB_BENCH_WORKERS (4) frames per GPU per step, each on its
+own codec object / CUDA stream so that the host phases (packet headers) and copies of one frame
+overlap the kernels of another (weak scaling; frames are independent, so there is no data-path
+collective -- only the final gather of the codestream sizes to rank 0).
 
   value : frame already resident in HBM when the timed region starts (encoder's device image
           buffer), codestream left on the device, decoded image left on the device
@@ -111,8 +113,8 @@ def main():
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    cfg = {"workload": "8192x8192x3 12-bit, reversible 5/3 + RCT, 5 levels, 64x64 code-blocks, RPCL, one frame "
-                       "per GPU per step (encode then decode)", "frames_per_step": max(1, a.gpus),
+    cfg = {"workload": "8192x8192x3 12-bit, reversible 5/3 + RCT, 5 levels, 64x64 code-blocks, RPCL; a step = a batch of "
+                       "independent frames per GPU, each encoded then decoded", "frames_per_step": max(1, a.gpus),
            "l2_policy": "inputs larger than L2 (402 MB frame, 805 MB coefficients)"}
 
     if a.impl == "reference":
@@ -149,68 +151,80 @@ def main():
 
     p = workload_params()
     frame = make_frame(W, H, 1234 + rank)
-    # pinned host buffers
+    NW = int(os.environ.get("OJB_BENCH_WORKERS", "4"))      # frames in flight per GPU (one codec pair each)
+    # pinned host buffers: one input frame (shared, read-only), per-worker outputs
     pin = [torch.empty((H, W), dtype=torch.uint16, pin_memory=True) for _ in range(NC)]
     for t, f in zip(pin, frame):
         t.numpy()[:] = f
-    out_pin = [torch.empty((H, W), dtype=torch.uint16, pin_memory=True) for _ in range(NC)]
+    planes = (C.c_void_p * NC)(*[t.data_ptr() for t in pin])
     cs_cap = W * H * NC * 2 + (1 << 20)
-    cs_pin = torch.empty(cs_cap, dtype=torch.uint8, pin_memory=True)
-    cs_dev = torch.empty(cs_cap, dtype=torch.uint8, device="cuda")
-    enc = L.ojb_enc_create(); dec = L.ojb_dec_create()
 
     def ck(rc):
         if rc != 0:
             raise RuntimeError(L.ojb_last_error().decode())
-    ck(L.ojb_enc_configure(enc, C.byref(p), ob.U16))
-    planes = (C.c_void_p * NC)(*[t.data_ptr() for t in pin])
-    outs = (C.c_void_p * NC)(*[t.data_ptr() for t in out_pin])
-    n = C.c_uint64()
-    fi = _lib.FrameInfo()
 
-    def step_e2e():
-        ck(L.ojb_enc_encode_frame(enc, planes, None, cs_pin.data_ptr(), cs_cap, C.byref(n)))
-        ck(L.ojb_dec_read_headers(dec, cs_pin.data_ptr(), n.value, ob.U16, C.byref(fi)))
-        ck(L.ojb_dec_decode_frame(dec, outs, None))
+    class Worker:
+        def __init__(self):
+            self.enc = L.ojb_enc_create(); self.dec = L.ojb_dec_create()
+            ck(L.ojb_enc_configure(self.enc, C.byref(p), ob.U16))
+            self.out_pin = [torch.empty((H, W), dtype=torch.uint16, pin_memory=True) for _ in range(NC)]
+            self.outs = (C.c_void_p * NC)(*[t.data_ptr() for t in self.out_pin])
+            self.cs_pin = torch.empty(cs_cap, dtype=torch.uint8, pin_memory=True)
+            self.cs_dev = torch.empty(cs_cap, dtype=torch.uint8, device="cuda")
+            self.n = C.c_uint64(); self.fi = _lib.FrameInfo(); self.cs_len = 0
 
-    def step_resident():
-        ck(L.ojb_enc_encode_resident(enc, cs_dev.data_ptr(), cs_cap, C.byref(n), 1))
-        ck(L.ojb_dec_read_headers(dec, cs_pin.data_ptr(), cs_len, ob.U16, C.byref(fi)))
-        ck(L.ojb_dec_use_device_codestream(dec, cs_dev.data_ptr()))
-        ck(L.ojb_dec_decode_resident(dec))
+        def e2e(self):
+            ck(L.ojb_enc_encode_frame(self.enc, planes, None, self.cs_pin.data_ptr(), cs_cap, C.byref(self.n)))
+            ck(L.ojb_dec_read_headers(self.dec, self.cs_pin.data_ptr(), self.n.value, ob.U16, C.byref(self.fi)))
+            ck(L.ojb_dec_decode_frame(self.dec, self.outs, None))
 
-    def timed(fn, steps):
+        def resident(self):
+            ck(L.ojb_enc_encode_resident(self.enc, self.cs_dev.data_ptr(), cs_cap, C.byref(self.n), 1))
+            ck(L.ojb_dec_read_headers(self.dec, self.cs_pin.data_ptr(), self.cs_len, ob.U16, C.byref(self.fi)))
+            ck(L.ojb_dec_use_device_codestream(self.dec, self.cs_dev.data_ptr()))
+            ck(L.ojb_dec_decode_resident(self.dec))
+
+    workers = [Worker() for _ in range(NW)]
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(NW)
+
+    def timed(fn_name, steps, nworkers):
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(steps):
-            fn()
+            if nworkers == 1:
+                getattr(workers[0], fn_name)()
+            else:
+                list(pool.map(lambda w: getattr(w, fn_name)(), workers[:nworkers]))
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if dist is not None:
             t = torch.tensor([dt], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
         return dt
 
-    # correctness of what is being timed: lossless round trip through the e2e path
-    step_e2e()
-    cs_len = n.value
-    for a_, b_ in zip(out_pin, frame):
-        assert np.array_equal(a_.numpy(), b_), "round trip is not lossless"
-    ck(L.ojb_enc_upload_frame(enc, planes, None))
+    # correctness of what is being timed: lossless round trip through the e2e path, every worker
+    for w in workers:
+        w.e2e()
+        w.cs_len = w.n.value
+        for a_, b_ in zip(w.out_pin, frame):
+            assert np.array_equal(a_.numpy(), b_), "round trip is not lossless"
+        ck(L.ojb_enc_upload_frame(w.enc, planes, None))
+    cs_len = workers[0].cs_len
+    enc, dec = workers[0].enc, workers[0].dec
     for _ in range(max(3, a.warmup)):
-        step_resident()
+        list(pool.map(lambda w: w.resident(), workers))
     sampler = ClockSampler(local); sampler.start()
-    # device-side stage timing of the resident path (CUDA events on the codec stream)
-    t_enc = t_dec = 0.0
-    stage_e, stage_d = {}, {}
     te = (C.c_float * 8)(); td = (C.c_float * 8)()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    dt_res = timed(step_resident, a.steps)
+    # (1) serial pass: one frame at a time -> per-stage CUDA-event times of the kernels
+    dt_serial = timed("resident", a.steps, 1)
     L.ojb_enc_timings(enc, te); L.ojb_dec_timings(dec, td)
+    # (2) NW frames in flight: host phases and copies of one frame overlap the kernels of another
+    dt_res = timed("resident", a.steps, NW)
     for _ in range(max(1, min(a.warmup, 2))):
-        step_e2e()
-    dt_e2e = timed(step_e2e, a.steps)
+        list(pool.map(lambda w: w.e2e(), workers))
+    dt_e2e = timed("e2e", a.steps, NW)
     sampler.stop_flag = True; sampler.join(timeout=2)
     # final gather of the per-rank codestream sizes (the only collective on the path)
     sizes = [cs_len]
@@ -224,7 +238,7 @@ def main():
         if dist is not None:
             dist.destroy_process_group()
         return
-    pix = W * H * a.gpus
+    pix = W * H * a.gpus * NW
     value = pix * a.steps / dt_res / 1e6
     e2e = pix * a.steps / dt_e2e / 1e6
     import json as _j
@@ -248,15 +262,18 @@ def main():
     roof = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
             "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": cand[dom][1], "ms_per_launch": cand[dom][0]}
-    cfg.update({"stages_encode_ms": stage_e, "stages_decode_ms": stage_d, "codestream_bytes": sizes,
-                "pipeline_hbm_frac": round(((2 * samples + cs_len) * 2 * a.gpus) / (dt_res / a.steps) / 1e9 / peak, 4)})
+    cfg.update({"frames_per_step": NW * a.gpus, "frames_in_flight_per_gpu": NW,
+                "serial_ms_per_frame": round(dt_serial / a.steps * 1e3, 3),
+                "serial_Mpixels_per_s": round(W * H * a.steps / dt_serial / 1e6, 1),
+                "stages_encode_ms": stage_e, "stages_decode_ms": stage_d, "codestream_bytes": sizes,
+                "pipeline_hbm_frac": round(((2 * samples + cs_len) * 2 * NW) / (dt_res / a.steps) / 1e9 / peak, 4)})
     res = {"metric": "Mpixels/s encode+decode", "value": value, "unit": "Mpixels/s", "n_gpus": a.gpus, "steps": a.steps,
            "warmup": a.warmup, "ms_per_step": dt_res / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": cfg,
            "clocks": sampler.summary(),
-           "e2e": {"value": e2e, "unit": "Mpixels/s", "h2d_bytes_per_step": (W * H * NC * 2 + cs_len) * a.gpus,
-                   "d2h_bytes_per_step": (W * H * NC * 2 + cs_len) * a.gpus, "ms_per_step": dt_e2e / a.steps * 1e3},
-           "gpu_launches": int(L.ojb_enc_kernel_launches(enc) + L.ojb_dec_kernel_launches(dec)) * a.steps,
+           "e2e": {"value": e2e, "unit": "Mpixels/s", "h2d_bytes_per_step": (W * H * NC * 2 + cs_len) * a.gpus * NW,
+                   "d2h_bytes_per_step": (W * H * NC * 2 + cs_len) * a.gpus * NW, "ms_per_step": dt_e2e / a.steps * 1e3},
+           "gpu_launches": int(L.ojb_enc_kernel_launches(enc) + L.ojb_dec_kernel_launches(dec)) * a.steps * NW,
            "roofline": roof}
     if not a.no_cpu_baseline and world == 1 or (rank == 0 and not a.no_cpu_baseline):
         import refharness as R

@@ -4,6 +4,8 @@
 #include <algorithm>
 #include <cstring>
 #include <chrono>
+#include <atomic>
+#include <thread>
 
 namespace ojb {
 
@@ -31,6 +33,8 @@ void PinnedBuf::reserve(size_t n) {
 
 CodecBase::CodecBase() {
   CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  unsigned hc = std::thread::hardware_concurrency();
+  host_threads = hc == 0 ? 4u : std::min(8u, hc);
   for (int i = 0; i < EV_MAX; ++i) CK(cudaEventCreate(&ev[i]));
 }
 CodecBase::~CodecBase() {
@@ -306,31 +310,59 @@ size_t Encoder::encode(const void* const* planes, const uint32_t* strides, bool 
     cb.num_passes = len ? 1 : 0;
     cb.missing_msbs = len ? (uint8_t)(30u - h_blocks[b].p) : 0;
   }
-  struct Pkt { PacketRef ref; size_t hdr_off; uint32_t hdr_len, body; };
+  struct Pkt { PacketRef ref; std::vector<uint8_t> hdr; uint32_t hdr_len, body; };
   struct TilePart { uint32_t tile, first, count, tp_idx, tp_cnt; uint64_t bytes; };
-  std::vector<uint8_t> hdr;                // packet headers, in codestream order
   std::vector<Pkt> pkts;
   std::vector<TilePart> tps;
-  std::vector<PacketRef> seq; std::vector<uint32_t> tp_first;
-  for (uint32_t t = 0; t < (uint32_t)layout.tiles.size(); ++t) {
-    layout.packet_sequence(t, seq, tp_first);
-    size_t base = pkts.size();
-    for (const PacketRef& pr : seq) {
-      const ResGeom& rg = layout.res_of(pr);
-      Pkt k; k.ref = pr; k.hdr_off = hdr.size();
-      k.body = write_packet_header(rg, rg.precincts[pr.precinct], coded.data(), hdr);
-      k.hdr_len = (uint32_t)(hdr.size() - k.hdr_off);
-      pkts.push_back(k);
-    }
-    for (size_t i = 0; i < tp_first.size(); ++i) {
-      TilePart tp; tp.tile = t; tp.first = (uint32_t)(base + tp_first[i]);
-      uint32_t end = (i + 1 < tp_first.size()) ? tp_first[i + 1] : (uint32_t)seq.size();
-      tp.count = end - tp_first[i]; tp.tp_idx = (uint32_t)i; tp.tp_cnt = (uint32_t)tp_first.size();
-      tp.bytes = 0;
-      for (uint32_t q = 0; q < tp.count; ++q) tp.bytes += pkts[tp.first + q].hdr_len + pkts[tp.first + q].body;
-      tps.push_back(tp);
+  {
+    std::vector<PacketRef> seq; std::vector<uint32_t> tp_first;
+    for (uint32_t t = 0; t < (uint32_t)layout.tiles.size(); ++t) {
+      layout.packet_sequence(t, seq, tp_first);
+      size_t base = pkts.size();
+      for (const PacketRef& pr : seq) { pkts.emplace_back(); pkts.back().ref = pr; pkts.back().hdr_len = pkts.back().body = 0; }
+      for (size_t i = 0; i < tp_first.size(); ++i) {
+        TilePart tp; tp.tile = t; tp.first = (uint32_t)(base + tp_first[i]);
+        uint32_t end = (i + 1 < tp_first.size()) ? tp_first[i + 1] : (uint32_t)seq.size();
+        tp.count = end - tp_first[i]; tp.tp_idx = (uint32_t)i; tp.tp_cnt = (uint32_t)tp_first.size();
+        tp.bytes = 0;
+        tps.push_back(tp);
+      }
     }
   }
+  {
+    // packet headers are independent of each other: a few host threads share them (largest first)
+    std::vector<uint32_t> order(pkts.size());
+    for (uint32_t i = 0; i < order.size(); ++i) order[i] = i;
+    auto weight = [&](uint32_t i) {
+      const ResGeom& rg = layout.res_of(pkts[i].ref); const PrecinctGeom& pc = rg.precincts[pkts[i].ref.precinct];
+      uint32_t n = 0; for (int b = 0; b < 4; ++b) n += pc.cb_idx[b].w * pc.cb_idx[b].h; return n;
+    };
+    std::vector<uint32_t> wt(pkts.size());
+    for (uint32_t i = 0; i < wt.size(); ++i) wt[i] = weight(i);
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return wt[a] > wt[b]; });
+    std::atomic<uint32_t> next(0);
+    auto work = [&]() {
+      for (;;) {
+        uint32_t k = next.fetch_add(1);
+        if (k >= order.size()) break;
+        Pkt& pk = pkts[order[k]];
+        const ResGeom& rg = layout.res_of(pk.ref);
+        pk.hdr.reserve(64 + wt[order[k]] * 4);
+        pk.body = write_packet_header(rg, rg.precincts[pk.ref.precinct], coded.data(), pk.hdr);
+        pk.hdr_len = (uint32_t)pk.hdr.size();
+      }
+    };
+    uint32_t nthreads = (uint32_t)std::min<size_t>(std::min<size_t>(host_threads, pkts.size()), 16);
+    if (nb < 2048 || nthreads <= 1) work();
+    else {
+      std::vector<std::thread> th;
+      for (uint32_t i = 1; i < nthreads; ++i) th.emplace_back(work);
+      work();
+      for (auto& t : th) t.join();
+    }
+  }
+  for (TilePart& tp : tps)
+    for (uint32_t q = 0; q < tp.count; ++q) tp.bytes += pkts[tp.first + q].hdr_len + pkts[tp.first + q].body;
   // marker bytes: main header [+ TLM], SOT+SOD per tile-part, EOC
   std::vector<uint8_t> blob;               // everything that is not code-block data, in order
   struct Piece { size_t src, dst; uint32_t len; };
@@ -359,7 +391,7 @@ size_t Encoder::encode(const void* const* planes, const uint32_t* strides, bool 
     for (uint32_t q = 0; q < tp.count; ++q) {
       const Pkt& k = pkts[tp.first + q];
       size_t hs = blob.size();
-      blob.insert(blob.end(), hdr.begin() + (long)k.hdr_off, hdr.begin() + (long)(k.hdr_off + k.hdr_len));
+      blob.insert(blob.end(), k.hdr.begin(), k.hdr.end());
       add_piece(hs, k.hdr_len);
       if (k.body == 0) continue;
       const ResGeom& rg = layout.res_of(k.ref);

@@ -251,40 +251,49 @@ inline uint32_t log2ceil(uint32_t x) {
 // x + y * ceil(w / 2^i).  When a level's width is odd, the "right child" of the last
 // column aliases the first entry of the next row -- the reference computes its minima
 // that way (ojph_precinct.cpp:57-87,142-165), so byte-identical headers need the same.
+// Flat storage, reused across bands (one instance per thread).
 struct TagTree {
-  uint32_t w, h, nl;
-  std::vector<std::vector<uint8_t>> lev;
+  uint32_t w = 0, h = 0, nl = 0;
+  uint32_t off[18], wl[18];
+  std::vector<uint8_t> buf;
   void init(uint32_t nlev, uint32_t ww, uint32_t hh, uint8_t v) {
     w = ww; h = hh; nl = nlev;
-    lev.resize(nl + 1);
-    for (uint32_t i = 0; i < nl; ++i) lev[i].assign((size_t)1 << ((nl - 1 - i) << 1), v);
-    lev[nl].assign(1, 0);
+    uint32_t o = 0;
+    for (uint32_t i = 0; i < nl; ++i) { off[i] = o; wl[i] = (w + (1u << i) - 1) >> i; o += 1u << ((nl - 1 - i) << 1); }
+    off[nl] = o; wl[nl] = 1; o += 1;
+    if (buf.size() < o) buf.resize(o);
+    memset(buf.data(), v, o - 1);
+    buf[o - 1] = 0;
   }
-  uint8_t& at(uint32_t x, uint32_t y, uint32_t l) {
-    return lev[l][x + (size_t)y * ((w + (1u << l) - 1) >> l)];
-  }
+  uint8_t& at(uint32_t x, uint32_t y, uint32_t l) { return buf[off[l] + x + (size_t)y * wl[l]]; }
 };
 
 struct BitWriter {   // MSB first; a byte after 0xFF carries 7 bits (ojph_bitbuffer_write.h:85-143)
   std::vector<uint8_t>& o; int avail = 8; uint32_t tmp = 0;
   explicit BitWriter(std::vector<uint8_t>& out) : o(out) {}
-  void bit(uint32_t b) {
-    --avail; tmp |= (b & 1u) << avail;
-    if (avail <= 0) { o.push_back((uint8_t)tmp); avail = 8 - (tmp != 0xFF ? 0 : 1); tmp = 0; }
+  inline void bits(uint32_t v, int n) {      // the n low bits of v, MSB first
+    while (n > 0) {
+      int k = n < avail ? n : avail;
+      uint32_t chunk = (n >= 32 && k == 32) ? v : ((v >> (n - k)) & ((1u << k) - 1u));
+      avail -= k; n -= k;
+      tmp |= chunk << avail;
+      if (avail == 0) { o.push_back((uint8_t)tmp); avail = (tmp != 0xFF) ? 8 : 7; tmp = 0; }
+    }
   }
-  void bits(uint32_t v, int n) { for (int i = n - 1; i >= 0; --i) bit(v >> i); }
+  inline void bit(uint32_t b) { bits(b & 1u, 1); }
+  inline void zeros(int n) { while (n > 0) { int k = n < 24 ? n : 24; bits(0, k); n -= k; } }
   void finish() { if (avail < 8) o.push_back((uint8_t)tmp); }
 };
 
 struct BitReader {   // ojph_bitbuffer_read.h:73-130
   const uint8_t* d; size_t& pos; uint32_t& left; uint32_t tmp = 0; int avail = 0; bool unstuff = false;
   BitReader(const uint8_t* data, size_t& p, uint32_t& l) : d(data), pos(p), left(l) {}
-  bool fill() {
+  inline bool fill() {
     if (left > 0) { uint8_t t = d[pos++]; tmp = t; avail = 8 - (unstuff ? 1 : 0); unstuff = (t == 0xFF); --left; return true; }
     tmp = 0; avail = 8 - (unstuff ? 1 : 0); unstuff = false; return false;
   }
-  bool bit(uint32_t& b) { bool r = true; if (avail == 0) r = fill(); b = (tmp >> --avail) & 1u; return r; }
-  bool bits(int n, uint32_t& v) {
+  inline bool bit(uint32_t& b) { bool r = true; if (avail == 0) r = fill(); b = (tmp >> --avail) & 1u; return r; }
+  inline bool bits(int n, uint32_t& v) {
     v = 0; bool r = true;
     while (n) {
       if (avail == 0) r = fill();
@@ -296,6 +305,9 @@ struct BitReader {   // ojph_bitbuffer_read.h:73-130
   }
   bool finish() { bool r = true; if (unstuff) r = fill(); tmp = 0; avail = 0; return r; }
 };
+
+struct Trees { TagTree inc, incf, mm, mmf; };
+static thread_local Trees t_trees;
 
 } // namespace
 
@@ -312,7 +324,7 @@ uint32_t write_packet_header(const ResGeom& res, const PrecinctGeom& pc,
     const Rect& ci = pc.cb_idx[s];
     if (ci.w == 0 || ci.h == 0) continue;
     uint32_t nl = 1 + std::max(log2ceil(ci.w), log2ceil(ci.h));
-    TagTree inc, incf, mm, mmf;
+    TagTree &inc = t_trees.inc, &incf = t_trees.incf, &mm = t_trees.mm, &mmf = t_trees.mmf;
     inc.init(nl, ci.w, ci.h, 255); incf.init(nl, ci.w, ci.h, 0);
     mm.init(nl, ci.w, ci.h, 255); mmf.init(nl, ci.w, ci.h, 0);
     const CodedBlock* base = blocks + bg.block_base;
@@ -347,23 +359,28 @@ uint32_t write_packet_header(const ResGeom& res, const PrecinctGeom& pc,
     for (uint32_t y = 0; y < ci.h; ++y)
       for (uint32_t x = 0; x < ci.w; ++x) {
         const CodedBlock& cb = base[(size_t)(ci.y0 + y) * bg.nbw + ci.x0 + x];
-        for (uint32_t cl = nl; cl > 0; --cl) {   // inclusion
-          uint32_t lm = cl - 1;
-          if (incf.at(x >> lm, y >> lm, lm) == 0) {
-            uint32_t skipped = inc.at(x >> lm, y >> lm, lm);
-            skipped -= inc.at(x >> cl, y >> cl, cl);
-            bw.bit(1 - skipped);
-            incf.at(x >> lm, y >> lm, lm) = 1;
-          }
-          if (inc.at(x >> lm, y >> lm, lm) > 0) break;
+        // inclusion: levels along the leaf-to-root path are sent top-down, so the unsent ones are
+        // a prefix [0, u); a sent ancestor with a positive value means "nothing included below"
+        {
+          uint32_t u = 0;
+          while (u < nl && incf.at(x >> u, y >> u, u) == 0) ++u;
+          if (!(u < nl && inc.at(x >> u, y >> u, u) > 0))
+            for (uint32_t cl = u; cl > 0; --cl) {
+              uint32_t lm = cl - 1;
+              uint32_t v = inc.at(x >> lm, y >> lm, lm);
+              bw.bit(1 - (v - inc.at(x >> cl, y >> cl, cl)));
+              incf.at(x >> lm, y >> lm, lm) = 1;
+              if (v > 0) break;
+            }
         }
         if (cb.num_passes == 0) continue;
-        for (uint32_t cl = nl; cl > 0; --cl) {   // missing msbs
-          uint32_t lm = cl - 1;
-          if (mmf.at(x >> lm, y >> lm, lm) == 0) {
-            int nz = mm.at(x >> lm, y >> lm, lm);
-            nz -= mm.at(x >> cl, y >> cl, cl);
-            for (int i = 0; i < nz; ++i) bw.bit(0);
+        {   // missing msbs
+          uint32_t u = 0;
+          while (u < nl && mmf.at(x >> u, y >> u, u) == 0) ++u;
+          for (uint32_t cl = u; cl > 0; --cl) {
+            uint32_t lm = cl - 1;
+            int nz = (int)mm.at(x >> lm, y >> lm, lm) - (int)mm.at(x >> cl, y >> cl, cl);
+            bw.zeros(nz);
             bw.bit(1);
             mmf.at(x >> lm, y >> lm, lm) = 1;
           }
@@ -416,7 +433,7 @@ void parse_packet(const Params& P, const ResGeom& res, const PrecinctGeom& pc,
       empty_packet = false;
     }
     uint32_t nl = 1 + std::max(log2ceil(ci.w), log2ceil(ci.h));
-    TagTree inc, incf, mm, mmf;
+    TagTree &inc = t_trees.inc, &incf = t_trees.incf, &mm = t_trees.mm, &mmf = t_trees.mmf;
     inc.init(nl, ci.w, ci.h, 0); incf.init(nl, ci.w, ci.h, 0);
     mm.init(nl, ci.w, ci.h, 0); mmf.init(nl, ci.w, ci.h, 0);
     CodedBlock* base = blocks + bg.block_base;
@@ -424,24 +441,27 @@ void parse_packet(const Params& P, const ResGeom& res, const PrecinctGeom& pc,
       for (uint32_t x = 0; x < ci.w; ++x) {
         CodedBlock& cb = base[(size_t)(ci.y0 + y) * bg.nbw + ci.x0 + x];
         bool empty_cb = false;
-        for (uint32_t cl = nl; cl > 0; --cl) {
-          uint32_t l = cl - 1;
-          empty_cb = inc.at(x >> l, y >> l, l) == 1;
-          if (empty_cb) break;
-          if (incf.at(x >> l, y >> l, l) == 0) {
+        {
+          // received levels form a suffix of the leaf-to-root path; start at the lowest received one
+          uint32_t u = 0;
+          while (u < nl && incf.at(x >> u, y >> u, u) == 0) ++u;
+          if (u < nl && inc.at(x >> u, y >> u, u) == 1) empty_cb = true;
+          for (uint32_t cl = u; cl > 0 && !empty_cb; --cl) {
+            uint32_t l = cl - 1;
             if (!br.bit(bit)) { data_left = 0; throw Error(0x00030092, "error reading from file p1"); }
             empty_cb = (bit == 0);
             inc.at(x >> l, y >> l, l) = (uint8_t)(1 - bit);
             incf.at(x >> l, y >> l, l) = 1;
           }
-          if (empty_cb) break;
         }
         if (empty_cb) continue;
         uint32_t mmsbs = 0;
-        for (uint32_t lp = nl; lp > 0; --lp) {
-          uint32_t l = lp - 1;
-          mmsbs = mm.at(x >> lp, y >> lp, lp);
-          if (mmf.at(x >> l, y >> l, l) == 0) {
+        {
+          uint32_t u = 0;
+          while (u < nl && mmf.at(x >> u, y >> u, u) == 0) ++u;
+          mmsbs = mm.at(x >> u, y >> u, u);       // lowest received level (or the root's 0)
+          for (uint32_t lp = u; lp > 0; --lp) {
+            uint32_t l = lp - 1;
             bit = 0;
             while (bit == 0) {
               if (!br.bit(bit)) { data_left = 0; throw Error(0x00030092, "error reading from file p2"); }
