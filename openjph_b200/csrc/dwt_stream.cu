@@ -5,14 +5,16 @@
 // produced line, src/core/codestream/ojph_resolution.cpp:572-600 / :649-682; inverse: horizontal
 // synthesis then vertical, :738-781 / :841-898; step formulas src/core/transform/ojph_transform.cpp:
 // 209-257, 336-411, 514-590, 691-849), but organised for the GPU instead of line buffers:
-//   * one WARP owns a strip of 64 columns and streams down a chunk of rows; lane l holds the
-//     column pair (even, odd) = (low, high) positions 2l, 2l+1 of the strip;
+//   * one WARP owns a strip of 128 columns (120 produced + a halo lane each side) and streams down a
+//     chunk of rows; lane l holds four consecutive columns (even, odd, even, odd) = (low, high, low, high);
 //   * VERTICAL lifting is a software pipeline in registers (state: 2 values per column for 5/3,
 //     4 for 9/7); every iteration consumes two input rows and emits one (low, high) output pair;
 //   * HORIZONTAL lifting of an emitted row is done with __shfl_up / __shfl_down between neighbouring
 //     lanes -- no shared memory, no block barrier anywhere in the kernel;
-//   * one or two lanes per side are halo (recomputed by the neighbouring strip), a few rows per
-//     chunk are pipeline priming; borders use mirrored coordinates (whole-sample symmetric
+//   * loads and stores are 8/16-byte vectors wherever the four columns are contiguous and aligned,
+//     and the next iteration's rows are requested before the current pair is finished;
+//   * one lane per side is halo (recomputed by the neighbouring strip), a few rows per chunk are
+//     pipeline priming; borders use mirrored coordinates (whole-sample symmetric
 //     extension, ojph_transform.cpp:372-374).
 // Level 1 fuses sample fetch, level shift / int->float and RCT / ICT on load (forward) and the
 // inverse of those on store (inverse); quantisation to MSB-aligned sign-magnitude is fused into
@@ -24,6 +26,8 @@ namespace ojb {
 
 #define DS_WARPS 4
 #define DS_ROWS 64            // output rows per warp chunk
+#define DS_COLS 4             // columns per lane: (even, odd, even, odd) = (low, high, low, high)
+#define DS_VALID 30           // lanes that produce output; lanes 0 and 31 are halo (4 columns reach)
 #define FULL 0xFFFFFFFFu
 
 namespace {
@@ -32,53 +36,67 @@ template <bool REV> struct Tp;
 template <> struct Tp<true>  { typedef int T; };
 template <> struct Tp<false> { typedef float T; };
 
-template <bool REV> __device__ __forceinline__ constexpr int halo_lanes() { return REV ? 1 : 2; }
-
 __device__ __forceinline__ float lift(float d, float a, float b, float c) {     // d + c*(a+b), no FMA
   return __fadd_rn(d, __fmul_rn(c, __fadd_rn(a, b)));
 }
 
-// horizontal analysis of one line held as (a0 = even column, a1 = odd column) per lane
+// horizontal analysis of one line; a lane holds columns (a[0], a[1], a[2], a[3]) = (even, odd, even, odd)
 template <bool REV, typename T>
-__device__ __forceinline__ void horz_ana(T& a0, T& a1) {
+__device__ __forceinline__ void horz_ana(T (&a)[4]) {
   if (REV) {
-    int r = __shfl_down_sync(FULL, (int)a0, 1);
-    a1 = (T)((int)a1 - (((int)a0 + r) >> 1));
-    int l = __shfl_up_sync(FULL, (int)a1, 1);
-    a0 = (T)((int)a0 + ((l + (int)a1 + 2) >> 2));
+    const int r = __shfl_down_sync(FULL, (int)a[0], 1);
+    a[1] = (T)((int)a[1] - (((int)a[0] + (int)a[2]) >> 1));
+    a[3] = (T)((int)a[3] - (((int)a[2] + r) >> 1));
+    const int l = __shfl_up_sync(FULL, (int)a[3], 1);
+    a[0] = (T)((int)a[0] + ((l + (int)a[1] + 2) >> 2));
+    a[2] = (T)((int)a[2] + (((int)a[1] + (int)a[3] + 2) >> 2));
   } else {
-    float r = __shfl_down_sync(FULL, (float)a0, 1);
-    a1 = (T)lift((float)a1, (float)a0, r, IRV_ALPHA);
-    float l = __shfl_up_sync(FULL, (float)a1, 1);
-    a0 = (T)lift((float)a0, l, (float)a1, IRV_BETA);
-    r = __shfl_down_sync(FULL, (float)a0, 1);
-    a1 = (T)lift((float)a1, (float)a0, r, IRV_GAMMA);
-    l = __shfl_up_sync(FULL, (float)a1, 1);
-    a0 = (T)lift((float)a0, l, (float)a1, IRV_DELTA);
-    a0 = (T)__fmul_rn((float)a0, 1.0f / IRV_K);
-    a1 = (T)__fmul_rn((float)a1, IRV_K);
+    float r = __shfl_down_sync(FULL, (float)a[0], 1);
+    a[1] = (T)lift((float)a[1], (float)a[0], (float)a[2], IRV_ALPHA);
+    a[3] = (T)lift((float)a[3], (float)a[2], r, IRV_ALPHA);
+    float l = __shfl_up_sync(FULL, (float)a[3], 1);
+    a[0] = (T)lift((float)a[0], l, (float)a[1], IRV_BETA);
+    a[2] = (T)lift((float)a[2], (float)a[1], (float)a[3], IRV_BETA);
+    r = __shfl_down_sync(FULL, (float)a[0], 1);
+    a[1] = (T)lift((float)a[1], (float)a[0], (float)a[2], IRV_GAMMA);
+    a[3] = (T)lift((float)a[3], (float)a[2], r, IRV_GAMMA);
+    l = __shfl_up_sync(FULL, (float)a[3], 1);
+    a[0] = (T)lift((float)a[0], l, (float)a[1], IRV_DELTA);
+    a[2] = (T)lift((float)a[2], (float)a[1], (float)a[3], IRV_DELTA);
+    a[0] = (T)__fmul_rn((float)a[0], 1.0f / IRV_K);
+    a[2] = (T)__fmul_rn((float)a[2], 1.0f / IRV_K);
+    a[1] = (T)__fmul_rn((float)a[1], IRV_K);
+    a[3] = (T)__fmul_rn((float)a[3], IRV_K);
   }
 }
 
 // horizontal synthesis
 template <bool REV, typename T>
-__device__ __forceinline__ void horz_syn(T& a0, T& a1) {
+__device__ __forceinline__ void horz_syn(T (&a)[4]) {
   if (REV) {
-    int l = __shfl_up_sync(FULL, (int)a1, 1);
-    a0 = (T)((int)a0 - ((l + (int)a1 + 2) >> 2));
-    int r = __shfl_down_sync(FULL, (int)a0, 1);
-    a1 = (T)((int)a1 + (((int)a0 + r) >> 1));
+    const int l = __shfl_up_sync(FULL, (int)a[3], 1);
+    a[0] = (T)((int)a[0] - ((l + (int)a[1] + 2) >> 2));
+    a[2] = (T)((int)a[2] - (((int)a[1] + (int)a[3] + 2) >> 2));
+    const int r = __shfl_down_sync(FULL, (int)a[0], 1);
+    a[1] = (T)((int)a[1] + (((int)a[0] + (int)a[2]) >> 1));
+    a[3] = (T)((int)a[3] + (((int)a[2] + r) >> 1));
   } else {
-    a0 = (T)__fmul_rn((float)a0, IRV_K);
-    a1 = (T)__fmul_rn((float)a1, 1.0f / IRV_K);
-    float l = __shfl_up_sync(FULL, (float)a1, 1);
-    a0 = (T)lift((float)a0, l, (float)a1, -IRV_DELTA);
-    float r = __shfl_down_sync(FULL, (float)a0, 1);
-    a1 = (T)lift((float)a1, (float)a0, r, -IRV_GAMMA);
-    l = __shfl_up_sync(FULL, (float)a1, 1);
-    a0 = (T)lift((float)a0, l, (float)a1, -IRV_BETA);
-    r = __shfl_down_sync(FULL, (float)a0, 1);
-    a1 = (T)lift((float)a1, (float)a0, r, -IRV_ALPHA);
+    a[0] = (T)__fmul_rn((float)a[0], IRV_K);
+    a[2] = (T)__fmul_rn((float)a[2], IRV_K);
+    a[1] = (T)__fmul_rn((float)a[1], 1.0f / IRV_K);
+    a[3] = (T)__fmul_rn((float)a[3], 1.0f / IRV_K);
+    float l = __shfl_up_sync(FULL, (float)a[3], 1);
+    a[0] = (T)lift((float)a[0], l, (float)a[1], -IRV_DELTA);
+    a[2] = (T)lift((float)a[2], (float)a[1], (float)a[3], -IRV_DELTA);
+    float r = __shfl_down_sync(FULL, (float)a[0], 1);
+    a[1] = (T)lift((float)a[1], (float)a[0], (float)a[2], -IRV_GAMMA);
+    a[3] = (T)lift((float)a[3], (float)a[2], r, -IRV_GAMMA);
+    l = __shfl_up_sync(FULL, (float)a[3], 1);
+    a[0] = (T)lift((float)a[0], l, (float)a[1], -IRV_BETA);
+    a[2] = (T)lift((float)a[2], (float)a[1], (float)a[3], -IRV_BETA);
+    r = __shfl_down_sync(FULL, (float)a[0], 1);
+    a[1] = (T)lift((float)a[1], (float)a[0], (float)a[2], -IRV_ALPHA);
+    a[3] = (T)lift((float)a[3], (float)a[2], r, -IRV_ALPHA);
   }
 }
 
@@ -92,103 +110,149 @@ __device__ __forceinline__ uint32_t to_signmag_irv(float v, float scale) {
 
 struct StripGeom {
   int x0, y0, x1, y1;       // resolution rectangle
-  int u0;                   // absolute (even) column of this lane's pair
-  int c0, c1;               // source column indices (mirrored, relative to x0) of the pair
-  bool lane_valid;          // lane produces outputs (not halo) and its columns exist
-  bool has0, has1;          // column u0 / u0+1 inside [x0, x1)
+  int u0;                   // absolute (even) column of this lane's first column
+  int c[4];                 // source column indices (mirrored, relative to x0)
+  bool has[4];              // output lane and column u0+i inside [x0, x1)
+  bool lane_valid;          // any has[]
+  bool interior;            // all four columns exist unmirrored (any lane, halo included)
   int R0, R1;               // output rows of this chunk [R0, R1), R0 even (absolute)
 };
 
-template <bool REV>
-__device__ __forceinline__ bool strip_setup(const DwtJob& J, uint32_t local, uint32_t lane, StripGeom& g) {
-  const int V = 32 - 2 * halo_lanes<REV>();
-  const uint32_t strip = local % J.tiles_x, chunk = local / J.tiles_x;
+__device__ __forceinline__ bool strip_setup(const DwtJob& J, uint32_t strip, uint32_t chunk, uint32_t lane, StripGeom& g) {
   g.x0 = (int)J.x0; g.y0 = (int)J.y0; g.x1 = g.x0 + (int)J.w; g.y1 = g.y0 + (int)J.h;
   const int ue = g.x0 & ~1;
-  g.u0 = ue + (int)strip * 2 * V + 2 * ((int)lane - halo_lanes<REV>());
-  g.c0 = reflect_coord(g.u0, g.x0, g.x1 - 1) - g.x0;
-  g.c1 = reflect_coord(g.u0 + 1, g.x0, g.x1 - 1) - g.x0;
-  const bool inner = (int)lane >= halo_lanes<REV>() && (int)lane < 32 - halo_lanes<REV>();
-  g.has0 = inner && g.u0 >= g.x0 && g.u0 < g.x1;
-  g.has1 = inner && g.u0 + 1 >= g.x0 && g.u0 + 1 < g.x1;
-  g.lane_valid = g.has0 || g.has1;
+  g.u0 = ue + (int)strip * DS_COLS * DS_VALID + DS_COLS * ((int)lane - 1);
+  const bool inner = lane >= 1 && lane <= DS_VALID;
+  g.lane_valid = false;
+  #pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    g.c[i] = reflect_coord(g.u0 + i, g.x0, g.x1 - 1) - g.x0;
+    g.has[i] = inner && g.u0 + i >= g.x0 && g.u0 + i < g.x1;
+    g.lane_valid = g.lane_valid || g.has[i];
+  }
+  g.interior = g.u0 >= g.x0 && g.u0 + 3 < g.x1;
   const int ye = g.y0 & ~1;
   g.R0 = ye + (int)chunk * DS_ROWS;
   g.R1 = min(g.R0 + DS_ROWS, g.y1);
   return g.R0 < g.y1;
 }
 
+// four consecutive elements starting at p[i0] (one vector access when aligned) or four gathered ones
+__device__ __forceinline__ void load4_u16(const unsigned short* p, const StripGeom& g, int (&v)[4]) {
+  const unsigned short* q = p + g.c[0];
+  if (g.interior && (reinterpret_cast<size_t>(q) & 7) == 0) {
+    const uint2 t = *reinterpret_cast<const uint2*>(q);
+    v[0] = (int)(t.x & 0xFFFF); v[1] = (int)(t.x >> 16); v[2] = (int)(t.y & 0xFFFF); v[3] = (int)(t.y >> 16);
+  } else {
+    #pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = p[g.c[i]];
+  }
+}
+__device__ __forceinline__ void load4_u8(const unsigned char* p, const StripGeom& g, int (&v)[4]) {
+  const unsigned char* q = p + g.c[0];
+  if (g.interior && (reinterpret_cast<size_t>(q) & 3) == 0) {
+    const uint32_t t = *reinterpret_cast<const uint32_t*>(q);
+    v[0] = (int)(t & 0xFF); v[1] = (int)((t >> 8) & 0xFF); v[2] = (int)((t >> 16) & 0xFF); v[3] = (int)(t >> 24);
+  } else {
+    #pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = p[g.c[i]];
+  }
+}
+template <typename T>
+__device__ __forceinline__ void load4_w(const T* p, const StripGeom& g, T (&v)[4]) {     // 32-bit elements
+  const T* q = p + g.c[0];
+  if (g.interior && (reinterpret_cast<size_t>(q) & 15) == 0) {
+    const uint4 t = *reinterpret_cast<const uint4*>(q);
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+    #pragma unroll
+    for (int i = 0; i < 4; ++i) { T e; memcpy(&e, &w[i], 4); v[i] = e; }
+  } else {
+    #pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = p[g.c[i]];
+  }
+}
+// two consecutive 32-bit words
+__device__ __forceinline__ void store2_w(uint32_t* q, uint32_t a, uint32_t b, bool ha, bool hb) {
+  if (ha && hb && (reinterpret_cast<size_t>(q) & 7) == 0) *reinterpret_cast<uint2*>(q) = make_uint2(a, b);
+  else { if (ha) q[0] = a; if (hb) q[1] = b; }
+}
+__device__ __forceinline__ void load2_w(const uint32_t* q, bool vec, int i0, int i1, uint32_t& a, uint32_t& b) {
+  // q = row base; i0, i1 element indices (i1 == i0 + 1 when vec)
+  if (vec && (reinterpret_cast<size_t>(q + i0) & 7) == 0) { const uint2 t = *reinterpret_cast<const uint2*>(q + i0); a = t.x; b = t.y; }
+  else { a = q[i0]; b = q[i1]; }
+}
+template <typename T> __device__ __forceinline__ uint32_t as_bits(T v) { uint32_t r; memcpy(&r, &v, 4); return r; }
+template <typename T> __device__ __forceinline__ T from_bits(uint32_t v) { T r; memcpy(&r, &v, 4); return r; }
+
 // ---- forward ---------------------------------------------------------------------------------
 template <bool REV, int NC, bool FIRST>
 __device__ __forceinline__ void fwd_load_row(const DwtJob& J, const StripGeom& g, const void* image,
-                                             const uint32_t* coef, int v, typename Tp<REV>::T (&a)[NC][2])
+                                             const uint32_t* coef, int v, typename Tp<REV>::T (&a)[NC][4])
 {
   typedef typename Tp<REV>::T T;
   const int vr = reflect_coord(v, g.y0, g.y1 - 1) - g.y0;
   if (FIRST) {
-    int iv[NC][2];
+    int iv[NC][4];
     #pragma unroll
     for (int k = 0; k < NC; ++k) {
       const size_t row = (size_t)vr * J.full_stride[k];
       const unsigned char* base = reinterpret_cast<const unsigned char*>(image) + J.full_off[k];
-      if (J.src_type == SRC_U16) {
-        const unsigned short* p = reinterpret_cast<const unsigned short*>(base) + row;
-        iv[k][0] = p[g.c0]; iv[k][1] = p[g.c1];
-      } else if (J.src_type == SRC_U8) {
-        const unsigned char* p = base + row;
-        iv[k][0] = p[g.c0]; iv[k][1] = p[g.c1];
-      } else {
-        const int* p = reinterpret_cast<const int*>(base) + row;
-        iv[k][0] = p[g.c0]; iv[k][1] = p[g.c1];
-      }
+      if (J.src_type == SRC_U16) load4_u16(reinterpret_cast<const unsigned short*>(base) + row, g, iv[k]);
+      else if (J.src_type == SRC_U8) load4_u8(base + row, g, iv[k]);
+      else load4_w<int>(reinterpret_cast<const int*>(base) + row, g, iv[k]);
     }
     if (REV) {
       const int shift = J.is_signed ? 0 : (1 << (J.bit_depth - 1));
       #pragma unroll
-      for (int k = 0; k < NC; ++k) { iv[k][0] -= shift; iv[k][1] -= shift; }
+      for (int k = 0; k < NC; ++k)
+        #pragma unroll
+        for (int i = 0; i < 4; ++i) iv[k][i] -= shift;
       if (NC == 3) {
         #pragma unroll
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < 4; ++i) {
           const int rr = iv[0][i], gg = iv[1][i], bb = iv[2][i];
           iv[0][i] = (rr + (gg << 1) + bb) >> 2; iv[1][i] = bb - gg; iv[2][i] = rr - gg;
         }
       }
       #pragma unroll
-      for (int k = 0; k < NC; ++k) { a[k][0] = (T)iv[k][0]; a[k][1] = (T)iv[k][1]; }
+      for (int k = 0; k < NC; ++k)
+        #pragma unroll
+        for (int i = 0; i < 4; ++i) a[k][i] = (T)iv[k][i];
     } else {
       const float mul = (float)(1.0 / (double)(1ull << J.bit_depth));
       const int half = J.is_signed ? 0 : (1 << (J.bit_depth - 1));
-      float f[NC][2];
+      float f[NC][4];
       #pragma unroll
-      for (int k = 0; k < NC; ++k) { f[k][0] = __fmul_rn((float)(iv[k][0] - half), mul); f[k][1] = __fmul_rn((float)(iv[k][1] - half), mul); }
+      for (int k = 0; k < NC; ++k)
+        #pragma unroll
+        for (int i = 0; i < 4; ++i) f[k][i] = __fmul_rn((float)(iv[k][i] - half), mul);
       if (NC == 3) {
         #pragma unroll
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < 4; ++i) {
           const float rr = f[0][i], gg = f[1][i], bb = f[2][i];
           const float yy = __fadd_rn(__fadd_rn(__fmul_rn(ICT_ALPHA_RF, rr), __fmul_rn(ICT_ALPHA_GF, gg)), __fmul_rn(ICT_ALPHA_BF, bb));
           f[0][i] = yy; f[1][i] = __fmul_rn(ICT_BETA_CBF, __fsub_rn(bb, yy)); f[2][i] = __fmul_rn(ICT_BETA_CRF, __fsub_rn(rr, yy));
         }
       }
       #pragma unroll
-      for (int k = 0; k < NC; ++k) { a[k][0] = (T)f[k][0]; a[k][1] = (T)f[k][1]; }
+      for (int k = 0; k < NC; ++k)
+        #pragma unroll
+        for (int i = 0; i < 4; ++i) a[k][i] = (T)f[k][i];
     }
   } else {
     const T* p = reinterpret_cast<const T*>(coef) + J.full_off[0] + (size_t)vr * J.full_stride[0];
-    a[0][0] = p[g.c0]; a[0][1] = p[g.c1];
+    load4_w<T>(p, g, a[0]);
   }
 }
 
 // store one emitted (vertically low, vertically high) row pair after horizontal analysis
 template <bool REV, int NC>
 __device__ __forceinline__ void fwd_store_pair(const DwtJob& J, const StripGeom& g, uint32_t* coef, int vlow,
-                                               typename Tp<REV>::T (&lo)[NC][2], typename Tp<REV>::T (&hi)[NC][2])
+                                               typename Tp<REV>::T (&lo)[NC][4], typename Tp<REV>::T (&hi)[NC][4])
 {
   typedef typename Tp<REV>::T T;
   #pragma unroll
-  for (int k = 0; k < NC; ++k) {
-    horz_ana<REV, T>(lo[k][0], lo[k][1]);
-    horz_ana<REV, T>(hi[k][0], hi[k][1]);
-  }
+  for (int k = 0; k < NC; ++k) { horz_ana<REV, T>(lo[k]); horz_ana<REV, T>(hi[k]); }
   if (!g.lane_valid) return;
   const int bxl = (g.u0 >> 1) - ((g.x0 + 1) >> 1);      // index in horizontally-low bands
   const int bxh = (g.u0 >> 1) - (g.x0 >> 1);            // index in horizontally-high bands
@@ -199,16 +263,22 @@ __device__ __forceinline__ void fwd_store_pair(const DwtJob& J, const StripGeom&
     const int by = (v >> 1) - (vpar ? (g.y0 >> 1) : ((g.y0 + 1) >> 1));
     #pragma unroll
     for (int k = 0; k < NC; ++k) {
-      const T e = vpar ? hi[k][0] : lo[k][0], o = vpar ? hi[k][1] : lo[k][1];
+      const T (&r)[4] = vpar ? hi[k] : lo[k];
       const int bl = vpar ? 2 : 0, bh = vpar ? 3 : 1;
-      if (g.has0) {
-        if (bl == 0 && !J.last) reinterpret_cast<T*>(coef)[J.ll_off[k] + (size_t)by * J.ll_stride[k] + bxl] = e;
-        else coef[J.band_off[k][bl] + (size_t)by * J.band_stride[k][bl] + bxl] =
-               REV ? to_signmag_rev((int)e, J.band_shift[k][bl]) : to_signmag_irv((float)e, J.band_scale[k][bl]);
-      }
-      if (g.has1)
-        coef[J.band_off[k][bh] + (size_t)by * J.band_stride[k][bh] + bxh] =
-          REV ? to_signmag_rev((int)o, J.band_shift[k][bh]) : to_signmag_irv((float)o, J.band_scale[k][bh]);
+      if (bl == 0 && !J.last)
+        store2_w(coef + J.ll_off[k] + (size_t)by * J.ll_stride[k] + bxl, as_bits(r[0]), as_bits(r[2]), g.has[0], g.has[2]);
+      else if (REV)
+        store2_w(coef + J.band_off[k][bl] + (size_t)by * J.band_stride[k][bl] + bxl,
+                 to_signmag_rev((int)r[0], J.band_shift[k][bl]), to_signmag_rev((int)r[2], J.band_shift[k][bl]), g.has[0], g.has[2]);
+      else
+        store2_w(coef + J.band_off[k][bl] + (size_t)by * J.band_stride[k][bl] + bxl,
+                 to_signmag_irv((float)r[0], J.band_scale[k][bl]), to_signmag_irv((float)r[2], J.band_scale[k][bl]), g.has[0], g.has[2]);
+      if (REV)
+        store2_w(coef + J.band_off[k][bh] + (size_t)by * J.band_stride[k][bh] + bxh,
+                 to_signmag_rev((int)r[1], J.band_shift[k][bh]), to_signmag_rev((int)r[3], J.band_shift[k][bh]), g.has[1], g.has[3]);
+      else
+        store2_w(coef + J.band_off[k][bh] + (size_t)by * J.band_stride[k][bh] + bxh,
+                 to_signmag_irv((float)r[1], J.band_scale[k][bh]), to_signmag_irv((float)r[3], J.band_scale[k][bh]), g.has[1], g.has[3]);
     }
   }
 }
@@ -235,50 +305,58 @@ dwt_fwd_stream_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, const voi
   const uint32_t strip = (cta % strips_per_row) * DS_WARPS + warp, chunk = cta / strips_per_row;
   if (strip >= J.tiles_x) return;
   StripGeom g;
-  if (!strip_setup<REV>(J, chunk * J.tiles_x + strip, lane, g)) return;
+  if (!strip_setup(J, strip, chunk, lane, g)) return;
 
   if (REV) {
     // 5/3: iteration k consumes rows (2k-1, 2k) and emits the pair (2k-2, 2k-1)
-    T xe[NC][2], hp[NC][2];           // x[2k-2], H[k-2]
+    T xe[NC][4], hp[NC][4];           // x[2k-2], H[k-2]
     const int k0 = g.R0 / 2;
     fwd_load_row<REV, NC, FIRST>(J, g, image, coef, 2 * k0 - 2, xe);
     #pragma unroll
-    for (int c = 0; c < NC; ++c) { hp[c][0] = 0; hp[c][1] = 0; }
+    for (int c = 0; c < NC; ++c)
+      #pragma unroll
+      for (int i = 0; i < 4; ++i) hp[c][i] = 0;
     const int k1 = (g.R1 + 1) / 2;    // last emitted pair index k1-1 covers rows up to R1-1
+    T xo[NC][4], xn[NC][4];
+    fwd_load_row<REV, NC, FIRST>(J, g, image, coef, 2 * k0 - 1, xo);
+    fwd_load_row<REV, NC, FIRST>(J, g, image, coef, 2 * k0, xn);
     for (int k = k0; k <= k1; ++k) {
-      T xo[NC][2], xn[NC][2], lo[NC][2], hi[NC][2];
-      fwd_load_row<REV, NC, FIRST>(J, g, image, coef, 2 * k - 1, xo);
-      fwd_load_row<REV, NC, FIRST>(J, g, image, coef, 2 * k, xn);
+      T lo[NC][4], hi[NC][4];
       #pragma unroll
       for (int c = 0; c < NC; ++c)
         #pragma unroll
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < 4; ++i) {
           const int h = (int)xo[c][i] - (((int)xe[c][i] + (int)xn[c][i]) >> 1);       // H[k-1]
           const int l = (int)xe[c][i] + (((int)hp[c][i] + h + 2) >> 2);               // L[k-1]
           lo[c][i] = (T)l; hi[c][i] = (T)h;
           hp[c][i] = (T)h; xe[c][i] = xn[c][i];
         }
+      if (k < k1) {                   // next iteration's rows are in flight while this pair is finished
+        fwd_load_row<REV, NC, FIRST>(J, g, image, coef, 2 * k + 1, xo);
+        fwd_load_row<REV, NC, FIRST>(J, g, image, coef, 2 * k + 2, xn);
+      }
       fwd_store_pair<REV, NC>(J, g, coef, 2 * k - 2, lo, hi);      // rows 2k-2 (low), 2k-1 (high)
     }
   } else {
     // 9/7: iteration k consumes rows (2k-1, 2k) and emits the pair (2k-4, 2k-3)
-    T xe[NC][2], d1[NC][2], s1[NC][2], d2[NC][2];   // x[2k-2], d1[k-2], s1[k-2], d2[k-3]
+    T xe[NC][4], d1[NC][4], s1[NC][4], d2[NC][4];   // x[2k-2], d1[k-2], s1[k-2], d2[k-3]
     const int k0 = g.R0 / 2 - 1;
     fwd_load_row<REV, NC, FIRST>(J, g, image, coef, 2 * k0 - 2, xe);
     #pragma unroll
     for (int c = 0; c < NC; ++c)
       #pragma unroll
-      for (int i = 0; i < 2; ++i) { d1[c][i] = 0; s1[c][i] = 0; d2[c][i] = 0; }
+      for (int i = 0; i < 4; ++i) { d1[c][i] = 0; s1[c][i] = 0; d2[c][i] = 0; }
     const int k1 = (g.R1 + 1) / 2 + 1;
     const float Kinv = 1.0f / IRV_K;
+    T xo[NC][4], xn[NC][4];
+    fwd_load_row<REV, NC, FIRST>(J, g, image, coef, 2 * k0 - 1, xo);
+    fwd_load_row<REV, NC, FIRST>(J, g, image, coef, 2 * k0, xn);
     for (int k = k0; k <= k1; ++k) {
-      T xo[NC][2], xn[NC][2], lo[NC][2], hi[NC][2];
-      fwd_load_row<REV, NC, FIRST>(J, g, image, coef, 2 * k - 1, xo);
-      fwd_load_row<REV, NC, FIRST>(J, g, image, coef, 2 * k, xn);
+      T lo[NC][4], hi[NC][4];
       #pragma unroll
       for (int c = 0; c < NC; ++c)
         #pragma unroll
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < 4; ++i) {
           const float nd1 = lift((float)xo[c][i], (float)xe[c][i], (float)xn[c][i], IRV_ALPHA);     // d1[k-1]
           const float ns1 = lift((float)xe[c][i], (float)d1[c][i], nd1, IRV_BETA);                  // s1[k-1]
           const float nd2 = lift((float)d1[c][i], (float)s1[c][i], ns1, IRV_GAMMA);                 // d2[k-2]
@@ -286,34 +364,45 @@ dwt_fwd_stream_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, const voi
           lo[c][i] = (T)__fmul_rn(ns2, Kinv); hi[c][i] = (T)__fmul_rn(nd2, IRV_K);
           xe[c][i] = xn[c][i]; d1[c][i] = (T)nd1; s1[c][i] = (T)ns1; d2[c][i] = (T)nd2;
         }
+      if (k < k1) {
+        fwd_load_row<REV, NC, FIRST>(J, g, image, coef, 2 * k + 1, xo);
+        fwd_load_row<REV, NC, FIRST>(J, g, image, coef, 2 * k + 2, xn);
+      }
       fwd_store_pair<REV, NC>(J, g, coef, 2 * k - 4, lo, hi);      // rows 2k-4 (low), 2k-3 (high)
     }
   }
 }
 
 // ---- inverse ---------------------------------------------------------------------------------
-// load the four sub-band samples that interleave into rows (2j, 2j+1), columns (u0, u0+1) and undo
-// the horizontal transform: L[..] = vertically-low row, H[..] = vertically-high row
+// load the sub-band samples that interleave into rows (2j, 2j+1), columns u0..u0+3 and undo the
+// horizontal transform: L[..] = vertically-low row, H[..] = vertically-high row
 template <bool REV, int NC>
 __device__ __forceinline__ void inv_load_pair(const DwtJob& J, const StripGeom& g, const uint32_t* coef, int j,
-                                              typename Tp<REV>::T (&L)[NC][2], typename Tp<REV>::T (&H)[NC][2])
+                                              typename Tp<REV>::T (&L)[NC][4], typename Tp<REV>::T (&H)[NC][4])
 {
   typedef typename Tp<REV>::T T;
-  const T* cf = reinterpret_cast<const T*>(coef);
   // mirrored absolute coordinates keep their parity, so each sample maps to a definite band
-  const int ua = reflect_coord(g.u0, g.x0, g.x1 - 1), ub = reflect_coord(g.u0 + 1, g.x0, g.x1 - 1);
-  const int bxl = (ua >> 1) - ((g.x0 + 1) >> 1), bxh = (ub >> 1) - (g.x0 >> 1);
+  int bx[4];
+  #pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ua = g.c[i] + g.x0;
+    bx[i] = (ua >> 1) - ((i & 1) ? (g.x0 >> 1) : ((g.x0 + 1) >> 1));
+  }
   const int va = reflect_coord(2 * j, g.y0, g.y1 - 1), vb = reflect_coord(2 * j + 1, g.y0, g.y1 - 1);
   const int byl = (va >> 1) - ((g.y0 + 1) >> 1), byh = (vb >> 1) - (g.y0 >> 1);
   #pragma unroll
   for (int k = 0; k < NC; ++k) {
-    L[k][0] = J.last ? cf[J.band_off[k][0] + (size_t)byl * J.band_stride[k][0] + bxl]
-                     : cf[J.ll_off[k] + (size_t)byl * J.ll_stride[k] + bxl];
-    L[k][1] = cf[J.band_off[k][1] + (size_t)byl * J.band_stride[k][1] + bxh];
-    H[k][0] = cf[J.band_off[k][2] + (size_t)byh * J.band_stride[k][2] + bxl];
-    H[k][1] = cf[J.band_off[k][3] + (size_t)byh * J.band_stride[k][3] + bxh];
-    horz_syn<REV, T>(L[k][0], L[k][1]);
-    horz_syn<REV, T>(H[k][0], H[k][1]);
+    uint32_t w[2][4];
+    const uint32_t* r0 = J.last ? coef + J.band_off[k][0] + (size_t)byl * J.band_stride[k][0]
+                                : coef + J.ll_off[k] + (size_t)byl * J.ll_stride[k];
+    load2_w(r0, g.interior, bx[0], bx[2], w[0][0], w[0][2]);
+    load2_w(coef + J.band_off[k][1] + (size_t)byl * J.band_stride[k][1], g.interior, bx[1], bx[3], w[0][1], w[0][3]);
+    load2_w(coef + J.band_off[k][2] + (size_t)byh * J.band_stride[k][2], g.interior, bx[0], bx[2], w[1][0], w[1][2]);
+    load2_w(coef + J.band_off[k][3] + (size_t)byh * J.band_stride[k][3], g.interior, bx[1], bx[3], w[1][1], w[1][3]);
+    #pragma unroll
+    for (int i = 0; i < 4; ++i) { L[k][i] = from_bits<T>(w[0][i]); H[k][i] = from_bits<T>(w[1][i]); }
+    horz_syn<REV, T>(L[k]);
+    horz_syn<REV, T>(H[k]);
   }
 }
 
@@ -321,39 +410,50 @@ __device__ __forceinline__ int round_haz(float t) { return (int)(t + (t >= 0.0f 
 
 template <bool REV, int NC, bool FIRST>
 __device__ __forceinline__ void inv_store_row(const DwtJob& J, const StripGeom& g, void* image, uint32_t* coef,
-                                              int v, typename Tp<REV>::T (&x)[NC][2])
+                                              int v, typename Tp<REV>::T (&x)[NC][4])
 {
   typedef typename Tp<REV>::T T;
   if (!g.lane_valid || v < g.y0 || v >= g.y1 || v < g.R0 || v >= g.R1) return;
   const int cx = g.u0 - g.x0;
+  const bool all4 = g.has[0] && g.has[3];
   if (!FIRST) {
-    T* p = reinterpret_cast<T*>(coef) + J.full_off[0] + (size_t)(v - g.y0) * J.full_stride[0];
-    if (g.has0) p[cx] = x[0][0];
-    if (g.has1) p[cx + 1] = x[0][1];
+    uint32_t* p = coef + J.full_off[0] + (size_t)(v - g.y0) * J.full_stride[0] + cx;
+    if (all4 && (reinterpret_cast<size_t>(p) & 15) == 0)
+      *reinterpret_cast<uint4*>(p) = make_uint4(as_bits(x[0][0]), as_bits(x[0][1]), as_bits(x[0][2]), as_bits(x[0][3]));
+    else {
+      #pragma unroll
+      for (int i = 0; i < 4; ++i) if (g.has[i]) p[i] = as_bits(x[0][i]);
+    }
     return;
   }
-  int out[NC][2];
+  int out[NC][4];
   if (REV) {
-    int a[NC][2];
+    int a[NC][4];
     #pragma unroll
-    for (int k = 0; k < NC; ++k) { a[k][0] = (int)x[k][0]; a[k][1] = (int)x[k][1]; }
+    for (int k = 0; k < NC; ++k)
+      #pragma unroll
+      for (int i = 0; i < 4; ++i) a[k][i] = (int)x[k][i];
     if (NC == 3) {
       #pragma unroll
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < 4; ++i) {
         const int yy = a[0][i], cb = a[1][i], cr = a[2][i], gg = yy - ((cb + cr) >> 2);
         a[0][i] = cr + gg; a[1][i] = gg; a[2][i] = cb + gg;
       }
     }
     const int shift = J.is_signed ? 0 : (1 << (J.bit_depth - 1));
     #pragma unroll
-    for (int k = 0; k < NC; ++k) { out[k][0] = a[k][0] + shift; out[k][1] = a[k][1] + shift; }
+    for (int k = 0; k < NC; ++k)
+      #pragma unroll
+      for (int i = 0; i < 4; ++i) out[k][i] = a[k][i] + shift;
   } else {
-    float f[NC][2];
+    float f[NC][4];
     #pragma unroll
-    for (int k = 0; k < NC; ++k) { f[k][0] = (float)x[k][0]; f[k][1] = (float)x[k][1]; }
+    for (int k = 0; k < NC; ++k)
+      #pragma unroll
+      for (int i = 0; i < 4; ++i) f[k][i] = (float)x[k][i];
     if (NC == 3) {
       #pragma unroll
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < 4; ++i) {
         const float yy = f[0][i], cb = f[1][i], cr = f[2][i];
         f[1][i] = __fsub_rn(__fsub_rn(yy, __fmul_rn(ICT_GAMMA_CR2G, cr)), __fmul_rn(ICT_GAMMA_CB2G, cb));
         f[0][i] = __fadd_rn(yy, __fmul_rn(ICT_GAMMA_CR2R, cr));
@@ -368,7 +468,7 @@ __device__ __forceinline__ void inv_store_row(const DwtJob& J, const StripGeom& 
     #pragma unroll
     for (int k = 0; k < NC; ++k)
       #pragma unroll
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < 4; ++i) {
         const float t = __fmul_rn(f[k][i], mul);
         int q = round_haz(t);
         q = t >= flo ? q : lo; q = t < fhi ? q : hi;
@@ -380,17 +480,33 @@ __device__ __forceinline__ void inv_store_row(const DwtJob& J, const StripGeom& 
     const size_t row = (size_t)(v - g.y0) * J.full_stride[k];
     unsigned char* base = reinterpret_cast<unsigned char*>(image) + J.full_off[k];
     if (J.src_type == SRC_U16) {
-      unsigned short* p = reinterpret_cast<unsigned short*>(base) + row;
-      if (g.has0) p[cx] = (unsigned short)min(max(out[k][0], 0), 65535);
-      if (g.has1) p[cx + 1] = (unsigned short)min(max(out[k][1], 0), 65535);
+      unsigned short* p = reinterpret_cast<unsigned short*>(base) + row + cx;
+      uint32_t q[4];
+      #pragma unroll
+      for (int i = 0; i < 4; ++i) q[i] = (uint32_t)min(max(out[k][i], 0), 65535);
+      if (all4 && (reinterpret_cast<size_t>(p) & 7) == 0) *reinterpret_cast<uint2*>(p) = make_uint2(q[0] | (q[1] << 16), q[2] | (q[3] << 16));
+      else {
+        #pragma unroll
+        for (int i = 0; i < 4; ++i) if (g.has[i]) p[i] = (unsigned short)q[i];
+      }
     } else if (J.src_type == SRC_U8) {
-      unsigned char* p = base + row;
-      if (g.has0) p[cx] = (unsigned char)min(max(out[k][0], 0), 255);
-      if (g.has1) p[cx + 1] = (unsigned char)min(max(out[k][1], 0), 255);
+      unsigned char* p = base + row + cx;
+      uint32_t q[4];
+      #pragma unroll
+      for (int i = 0; i < 4; ++i) q[i] = (uint32_t)min(max(out[k][i], 0), 255);
+      if (all4 && (reinterpret_cast<size_t>(p) & 3) == 0) *reinterpret_cast<uint32_t*>(p) = q[0] | (q[1] << 8) | (q[2] << 16) | (q[3] << 24);
+      else {
+        #pragma unroll
+        for (int i = 0; i < 4; ++i) if (g.has[i]) p[i] = (unsigned char)q[i];
+      }
     } else {
-      int* p = reinterpret_cast<int*>(base) + row;
-      if (g.has0) p[cx] = out[k][0];
-      if (g.has1) p[cx + 1] = out[k][1];
+      int* p = reinterpret_cast<int*>(base) + row + cx;
+      if (all4 && (reinterpret_cast<size_t>(p) & 15) == 0)
+        *reinterpret_cast<uint4*>(p) = make_uint4((uint32_t)out[k][0], (uint32_t)out[k][1], (uint32_t)out[k][2], (uint32_t)out[k][3]);
+      else {
+        #pragma unroll
+        for (int i = 0; i < 4; ++i) if (g.has[i]) p[i] = out[k][i];
+      }
     }
   }
 }
@@ -416,54 +532,53 @@ dwt_inv_stream_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, void* __r
   const uint32_t strip = (cta % strips_per_row) * DS_WARPS + warp, chunk = cta / strips_per_row;
   if (strip >= J.tiles_x) return;
   StripGeom g;
-  if (!strip_setup<REV>(J, chunk * J.tiles_x + strip, lane, g)) return;
+  if (!strip_setup(J, strip, chunk, lane, g)) return;
 
   if (REV) {
     // 5/3: iteration j consumes the band-row pair j and emits rows (2j-1, 2j)
-    T hp[NC][2], xe[NC][2];          // H[j-1], x[2j-2]
+    T hp[NC][4], xe[NC][4];          // H[j-1], x[2j-2]
     const int j0 = g.R0 / 2;
-    {
-      T L[NC][2];
-      inv_load_pair<REV, NC>(J, g, coef, j0 - 1, L, hp);       // only H[j0-1] is needed
+    T L[NC][4], H[NC][4];
+    inv_load_pair<REV, NC>(J, g, coef, j0 - 1, L, hp);       // only H[j0-1] is needed
+    #pragma unroll
+    for (int c = 0; c < NC; ++c)
       #pragma unroll
-      for (int c = 0; c < NC; ++c) { xe[c][0] = 0; xe[c][1] = 0; }
-    }
+      for (int i = 0; i < 4; ++i) xe[c][i] = 0;
     const int j1 = (g.R1 + 1) / 2;
+    inv_load_pair<REV, NC>(J, g, coef, j0, L, H);
     for (int j = j0; j <= j1; ++j) {
-      T L[NC][2], H[NC][2], xo[NC][2], xn[NC][2];
-      inv_load_pair<REV, NC>(J, g, coef, j, L, H);
+      T xo[NC][4], xn[NC][4];
       #pragma unroll
       for (int c = 0; c < NC; ++c)
         #pragma unroll
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < 4; ++i) {
           const int e = (int)L[c][i] - (((int)hp[c][i] + (int)H[c][i] + 2) >> 2);     // x[2j]
           const int o = (int)hp[c][i] + (((int)xe[c][i] + e) >> 1);                   // x[2j-1]
           xn[c][i] = (T)e; xo[c][i] = (T)o;
           hp[c][i] = H[c][i]; xe[c][i] = (T)e;
         }
+      if (j < j1) inv_load_pair<REV, NC>(J, g, coef, j + 1, L, H);
       inv_store_row<REV, NC, FIRST>(J, g, image, coef, 2 * j - 1, xo);
       inv_store_row<REV, NC, FIRST>(J, g, image, coef, 2 * j, xn);
     }
   } else {
     // 9/7: iteration j consumes the band-row pair j and emits rows (2j-3, 2j-2)
-    T hp[NC][2], s1[NC][2], d1[NC][2], xe[NC][2];      // Hr[j-1], s1[j-1], d1[j-2], x_e[j-2]
+    T hp[NC][4], s1[NC][4], d1[NC][4], xe[NC][4];      // Hr[j-1], s1[j-1], d1[j-2], x_e[j-2]
     const int j0 = g.R0 / 2 - 1;
-    {
-      T L[NC][2];
-      inv_load_pair<REV, NC>(J, g, coef, j0 - 1, L, hp);
+    T L[NC][4], H[NC][4];
+    inv_load_pair<REV, NC>(J, g, coef, j0 - 1, L, hp);
+    #pragma unroll
+    for (int c = 0; c < NC; ++c)
       #pragma unroll
-      for (int c = 0; c < NC; ++c)
-        #pragma unroll
-        for (int i = 0; i < 2; ++i) { hp[c][i] = (T)__fmul_rn((float)hp[c][i], 1.0f / IRV_K); s1[c][i] = 0; d1[c][i] = 0; xe[c][i] = 0; }
-    }
+      for (int i = 0; i < 4; ++i) { hp[c][i] = (T)__fmul_rn((float)hp[c][i], 1.0f / IRV_K); s1[c][i] = 0; d1[c][i] = 0; xe[c][i] = 0; }
     const int j1 = (g.R1 + 1) / 2 + 1;
+    inv_load_pair<REV, NC>(J, g, coef, j0, L, H);
     for (int j = j0; j <= j1; ++j) {
-      T L[NC][2], H[NC][2], xo[NC][2], xn[NC][2];
-      inv_load_pair<REV, NC>(J, g, coef, j, L, H);
+      T xo[NC][4], xn[NC][4];
       #pragma unroll
       for (int c = 0; c < NC; ++c)
         #pragma unroll
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < 4; ++i) {
           const float lr = __fmul_rn((float)L[c][i], IRV_K), hr = __fmul_rn((float)H[c][i], 1.0f / IRV_K);
           const float ns1 = lift(lr, (float)hp[c][i], hr, -IRV_DELTA);                          // s1[j]
           const float nd1 = lift((float)hp[c][i], (float)s1[c][i], ns1, -IRV_GAMMA);            // d1[j-1]
@@ -472,6 +587,7 @@ dwt_inv_stream_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, void* __r
           xo[c][i] = (T)nxo; xn[c][i] = (T)nxe;
           hp[c][i] = (T)hr; s1[c][i] = (T)ns1; d1[c][i] = (T)nd1; xe[c][i] = (T)nxe;
         }
+      if (j < j1) inv_load_pair<REV, NC>(J, g, coef, j + 1, L, H);
       inv_store_row<REV, NC, FIRST>(J, g, image, coef, 2 * j - 3, xo);
       inv_store_row<REV, NC, FIRST>(J, g, image, coef, 2 * j - 2, xn);
     }
@@ -495,9 +611,10 @@ void launch_inv(const DwtJob* jobs, uint32_t njobs, uint32_t ctas, void* image, 
 void dwt_stream_tiling(uint32_t x0, uint32_t y0, uint32_t w, uint32_t h, bool reversible,
                        uint32_t& strips, uint32_t& chunks, uint32_t& ctas)
 {
-  const uint32_t V = 32 - 2 * (reversible ? 1u : 2u);
+  (void)reversible;
+  const uint32_t SW = DS_COLS * DS_VALID;          // output columns per strip
   const uint32_t ue = x0 & ~1u, ye = y0 & ~1u;
-  strips = (x0 + w - ue + 2 * V - 1) / (2 * V);
+  strips = (x0 + w - ue + SW - 1) / SW;
   chunks = (y0 + h - ye + DS_ROWS - 1) / DS_ROWS;
   ctas = ((strips + DS_WARPS - 1) / DS_WARPS) * chunks;
 }

@@ -33,23 +33,47 @@ struct DecTables {            // shared-memory copy
   uint16_t vlc0[1024], vlc1[1024], uvlc0[320], uvlc1[256];
 };
 
-// ---- step 1 readers (thread-private) ------------------------------------------------------
+// ---- step 1 readers (thread-private): 32 bits per refill, as the reference's mel_read /
+// rev_read do (ojph_block_decoder32.cpp:92-152, :307-357), built from two aligned word loads
+__device__ __forceinline__ uint32_t load_le32_any(const uint8_t* p) {
+  const uint32_t* a = reinterpret_cast<const uint32_t*>((size_t)p & ~(size_t)3);
+  const uint32_t sh = (uint32_t)((size_t)p & 3) * 8;
+  const uint32_t lo = a[0], hi = a[1];
+  return sh ? __funnelshift_r(lo, hi, sh) : lo;
+}
+
 struct MelDec {
   const uint8_t* p; int size; unsigned long long tmp; int bits; bool unstuff; int k;
 };
-__device__ __forceinline__ void mel_fill(MelDec& m) {       // keep >= 6 bits, MSB first
-  while (m.bits <= 56) {
-    uint32_t d = 0xFF;
-    if (m.size > 0) { d = *m.p++; if (m.size == 1) d |= 0xF; --m.size; }
-    int nb = 8 - (m.unstuff ? 1 : 0);
-    m.unstuff = (d == 0xFF);
-    d &= (1u << nb) - 1u;
-    m.tmp |= (unsigned long long)d << (64 - nb - m.bits);
-    m.bits += nb;
+__device__ __forceinline__ void mel_fill(MelDec& m) {       // MSB first; needs bits <= 32 on entry
+  if (m.bits > 32) return;
+  uint32_t val;
+  if (m.size > 4) { val = load_le32_any(m.p); m.p += 4; m.size -= 4; }
+  else {
+    val = 0xFFFFFFFFu;                                        // 0xFF fed past the end
+    int i = 0;
+    while (m.size > 0) {
+      uint32_t v = *m.p++;
+      if (m.size == 1) v |= 0xF;                              // MEL and VLC may share the last byte
+      val = (val & ~(0xFFu << i)) | (v << i);
+      --m.size; i += 8;
+    }
   }
+  uint32_t t = 0; int nb = 0;
+  bool us = m.unstuff;
+  #pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t d = (val >> (8 * i)) & 0xFFu;
+    const int n = 8 - (us ? 1 : 0);
+    t = (t << n) | (d & ((1u << n) - 1u));
+    nb += n;
+    us = (d == 0xFF);
+  }
+  m.unstuff = us;
+  m.tmp |= (unsigned long long)t << (64 - nb - m.bits);
+  m.bits += nb;
 }
-// one run: value 2*z+1 = z zero events then a one event; 2*z' (even) = z'+... see mel_decode
-// (:170-208): returns the reference's run code
+// one run code (mel_decode, :170-208): 2*z+1 = z zero events then a one; 2*(2^E - 1) = 2^E zeros
 __device__ __forceinline__ int mel_next_run(MelDec& m) {
   if (m.bits < 6) mel_fill(m);
   const int eval = (int)((0x5433222111000ull >> (4 * m.k)) & 7ull);
@@ -67,10 +91,11 @@ __device__ __forceinline__ int mel_next_run(MelDec& m) {
   return run;
 }
 
-struct RevDec {               // backward-growing stream (VLC)
+struct RevDec {               // backward-growing stream (VLC, MRP)
   const uint8_t* p; int size; unsigned long long tmp; uint32_t bits; bool unstuff;
 };
-__device__ __forceinline__ void rev_fill(RevDec& v) {       // keep >= 32 bits, LSB first
+// byte-wise refill (refinement passes, lane 0 only)
+__device__ __forceinline__ void rev_fill(RevDec& v) {       // LSB first
   while (v.bits <= 56) {
     uint32_t d = 0;
     if (v.size > 0) { d = *v.p--; --v.size; }
@@ -80,6 +105,29 @@ __device__ __forceinline__ void rev_fill(RevDec& v) {       // keep >= 32 bits, 
     v.tmp |= (unsigned long long)d << v.bits;
     v.bits += nb;
   }
+}
+// 32 bits per refill; needs bits <= 32 on entry
+__device__ __forceinline__ void rev_fill32(RevDec& v) {
+  if (v.bits > 32) return;
+  uint32_t val = 0;                                           // bytes p-3 .. p, byte p in the MSB
+  if (v.size > 3) { val = load_le32_any(v.p - 3); v.p -= 4; v.size -= 4; }
+  else {
+    int i = 24;
+    while (v.size > 0) { val |= (uint32_t)(*v.p--) << i; --v.size; i -= 8; }
+  }
+  uint32_t t = 0, nb = 0;
+  bool us = v.unstuff;
+  #pragma unroll
+  for (int i = 3; i >= 0; --i) {
+    const uint32_t d = (val >> (8 * i)) & 0xFFu;
+    const uint32_t n = 8 - ((us && (d & 0x7F) == 0x7F) ? 1u : 0u);
+    t |= (d & ((1u << n) - 1u)) << nb;
+    nb += n;
+    us = d > 0x8F;
+  }
+  v.unstuff = us;
+  v.tmp |= (unsigned long long)t << v.bits;
+  v.bits += nb;
 }
 
 __global__ void __launch_bounds__(128)
@@ -145,7 +193,7 @@ ht_dec_step1_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
             const uint32_t r = ((prev_br >> qq) | (qq < 31 ? (prev_bl >> (qq + 1)) : 0u)) & 1u;
             c = a | (l << 1) | (r << 2);
           }
-          rev_fill(vlc);
+          rev_fill32(vlc);
           uint32_t e = vtab[(c << 7) | ((uint32_t)vlc.tmp & 0x7F)];
           if (c == 0) {               // significance of an all-zero context comes from MEL
             run -= 2;
@@ -162,7 +210,7 @@ ht_dec_step1_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
       // U-VLC of the pair (:940-974 initial row, :1066-1085 others)
       uint32_t mode = ((t[0] >> 3) & 1u) | (((t[1] >> 3) & 1u) << 1);
       uint32_t ent;
-      rev_fill(vlc);
+      rev_fill32(vlc);
       if (y == 0) {
         if (mode == 3) {
           run -= 2;
@@ -332,9 +380,10 @@ __global__ void __launch_bounds__(DEC_WARPS * 32)
 ht_dec_step2_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
                     const uint8_t* __restrict__ cs, uint32_t* __restrict__ coef,
                     uint32_t* __restrict__ scratch, uint32_t out_mode,
-                    uint32_t* __restrict__ block_status)
+                    uint32_t* __restrict__ block_status, uint32_t ms_cap_words)
 {
   __shared__ uint32_t s_stage[DEC_WARPS][40];
+  OJB_DYN_SMEM(uint32_t, s_ms);          // DEC_WARPS x ms_cap_words: de-stuffed MagSgn when it fits
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t b = blockIdx.x * DEC_WARPS + warp;
   if (b >= nblocks) return;
@@ -352,6 +401,7 @@ ht_dec_step2_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
   const uint32_t* rec = scratch + blk.scratch_off;
   const uint32_t nqrows = (height + 1) >> 1;
   uint32_t* msbuf = scratch + blk.scratch_off + (size_t)qstride * nqrows;   // de-stuffed MagSgn words
+  if ((blk.len1 >> 2) + 4 <= ms_cap_words) msbuf = s_ms + (size_t)warp * ms_cap_words;
   const uint32_t x = 2 * lane;
   const bool has0 = x < width, has1 = x + 1 < width;
   const uint32_t mmsbp2 = blk.missing_msbs + 2u;
@@ -503,16 +553,23 @@ ht_dec_step2_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
 
 void launch_ht_decode(const DecBlock* blocks, uint32_t nblocks, const uint8_t* codestream,
                       uint32_t* coef, uint32_t* scratch, const uint16_t* tables, uint32_t out_mode,
-                      uint32_t* block_status, cudaStream_t st)
+                      uint32_t* block_status, uint32_t max_len1, cudaStream_t st)
 {
   if (nblocks == 0) return;
+  // shared-memory budget for the de-stuffed MagSgn bits of one block (<= 8 KB per warp); larger
+  // blocks use their global scratch
+  uint32_t ms_cap_words = ((max_len1 >> 2) + 4 + 31) & ~31u;
+  if (ms_cap_words > 2048) ms_cap_words = 2048;
   {
     dim3 grid((nblocks + 127) / 128), block(128);
     OJB_LAUNCH(ht_dec_step1_kernel, grid, block, 0, st, blocks, nblocks, codestream, scratch, tables, block_status);
   }
   {
     dim3 grid((nblocks + DEC_WARPS - 1) / DEC_WARPS), block(DEC_WARPS * 32);
-    OJB_LAUNCH(ht_dec_step2_kernel, grid, block, 0, st, blocks, nblocks, codestream, coef, scratch, out_mode, block_status);
+    size_t smem = (size_t)DEC_WARPS * ms_cap_words * 4;
+    cudaFuncSetAttribute(ht_dec_step2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    OJB_LAUNCH(ht_dec_step2_kernel, grid, block, smem, st, blocks, nblocks, codestream, coef, scratch, out_mode, block_status,
+               ms_cap_words);
   }
 }
 

@@ -4,11 +4,15 @@
 #include "ht_tables.h"
 #include <cstring>
 #include <new>
+#include <algorithm>
 
 using namespace ojb;
 
-struct ojb_encoder { Encoder enc; bool configured = false; };
-struct ojb_decoder { Decoder dec; bool have_headers = false; };
+// an object belongs to the device that was current when it was created; every entry point makes
+// that device current again, so objects may be driven from any host thread
+static int current_device() { int d = 0; cudaGetDevice(&d); return d; }
+struct ojb_encoder { int device = current_device(); Encoder enc; bool configured = false; };
+struct ojb_decoder { int device = current_device(); Decoder dec; bool have_headers = false; };
 
 static thread_local char g_err[1024] = "";
 
@@ -52,6 +56,10 @@ static void to_params(const ojb_params* s, Params& P) {
   P.planar = s->planar;
 }
 
+template <typename F> static int guarded_on(int device, F&& f) {
+  return guarded([&] { cuda_check(cudaSetDevice(device), "cudaSetDevice"); f(); });
+}
+
 extern "C" {
 
 const char* ojb_last_error(void) { return g_err; }
@@ -76,10 +84,10 @@ ojb_encoder* ojb_enc_create(void) {
   guarded([&] { e = new ojb_encoder(); });
   return e;
 }
-void ojb_enc_destroy(ojb_encoder* e) { delete e; }
+void ojb_enc_destroy(ojb_encoder* e) { if (e) { cudaSetDevice(e->device); delete e; } }
 
 int ojb_enc_configure(ojb_encoder* e, const ojb_params* p, uint32_t sample_type) {
-  return guarded([&] {
+  return guarded_on(e->device, [&] {
     if (sample_type > 2) fail(0x000B0012, "unknown sample container");
     Params P; to_params(p, P);
     e->enc.configure(P, sample_type);
@@ -89,7 +97,7 @@ int ojb_enc_configure(ojb_encoder* e, const ojb_params* p, uint32_t sample_type)
 
 int32_t* ojb_enc_exchange(ojb_encoder* e, int32_t* line, uint32_t* next_comp) {
   int32_t* r = nullptr;
-  guarded([&] {
+  guarded_on(e->device, [&] {
     if (!e->configured) fail(0x000B0013, "encoder is not configured");
     uint32_t nc = 0; r = e->enc.exchange(line, nc); if (next_comp) *next_comp = nc;
   });
@@ -97,7 +105,7 @@ int32_t* ojb_enc_exchange(ojb_encoder* e, int32_t* line, uint32_t* next_comp) {
 }
 
 int ojb_enc_flush(ojb_encoder* e, uint8_t* out, uint64_t out_cap, uint64_t* out_len) {
-  return guarded([&] {
+  return guarded_on(e->device, [&] {
     if (!e->configured) fail(0x000B0013, "encoder is not configured");
     Encoder& E = e->enc;
     uint32_t nc = E.params.num_comps();
@@ -114,7 +122,7 @@ int ojb_enc_flush(ojb_encoder* e, uint8_t* out, uint64_t out_cap, uint64_t* out_
 
 int ojb_enc_encode_frame(ojb_encoder* e, const void* const* planes, const uint32_t* strides,
                          uint8_t* out, uint64_t out_cap, uint64_t* out_len) {
-  return guarded([&] {
+  return guarded_on(e->device, [&] {
     if (!e->configured) fail(0x000B0013, "encoder is not configured");
     *out_len = e->enc.encode(planes, strides, false, out, (size_t)out_cap, false);
   });
@@ -160,13 +168,13 @@ void* ojb_enc_device_plane(ojb_encoder* e, uint32_t comp) {
   return img_plane(e->enc, comp);
 }
 int ojb_enc_upload_frame(ojb_encoder* e, const void* const* planes, const uint32_t* strides) {
-  return guarded([&] {
+  return guarded_on(e->device, [&] {
     if (!e->configured) fail(0x000B0013, "encoder is not configured");
     upload_frame(e->enc, planes, strides);
   });
 }
 int ojb_enc_encode_resident(ojb_encoder* e, uint8_t* out, uint64_t out_cap, uint64_t* out_len, int out_on_device) {
-  return guarded([&] {
+  return guarded_on(e->device, [&] {
     if (!e->configured) fail(0x000B0013, "encoder is not configured");
     *out_len = e->enc.encode(nullptr, nullptr, true, out, (size_t)out_cap, out_on_device != 0);
   });
@@ -183,14 +191,14 @@ void ojb_dec_timings(ojb_decoder* d, float* ms8) {
 uint32_t ojb_enc_num_blocks(ojb_encoder* e) { return e->configured ? e->enc.layout.num_blocks : 0; }
 int ojb_enc_read_band(ojb_encoder* e, uint32_t tile, uint32_t comp, uint32_t res, uint32_t band,
                       uint32_t* out, uint32_t* band_w, uint32_t* band_h) {
-  return guarded([&] {
+  return guarded_on(e->device, [&] {
     if (!e->configured) fail(0x000B0013, "encoder is not configured");
     read_band(e->enc, tile, comp, res, band, out, band_w, band_h);
   });
 }
 
 int ojb_enc_band_info(ojb_encoder* e, uint32_t tile, uint32_t comp, uint32_t res, uint32_t band, uint32_t* info8, float* delta) {
-  return guarded([&] {
+  return guarded_on(e->device, [&] {
     if (!e->configured) fail(0x000B0013, "encoder is not configured");
     CodecBase& cb = e->enc;
     if (tile >= cb.layout.tiles.size() || comp >= cb.params.num_comps() || res > cb.params.num_decomps || band > 3)
@@ -208,12 +216,12 @@ ojb_decoder* ojb_dec_create(void) {
   guarded([&] { d = new ojb_decoder(); });
   return d;
 }
-void ojb_dec_destroy(ojb_decoder* d) { delete d; }
+void ojb_dec_destroy(ojb_decoder* d) { if (d) { cudaSetDevice(d->device); delete d; } }
 int ojb_dec_enable_resilience(ojb_decoder* d) { d->dec.resilient = true; return 0; }
 
 int ojb_dec_read_headers(ojb_decoder* d, const uint8_t* j2c, uint64_t len, uint32_t sample_type,
                          ojb_frame_info* info) {
-  return guarded([&] {
+  return guarded_on(d->device, [&] {
     if (sample_type > 2) fail(0x000B0012, "unknown sample container");
     d->dec.read_headers(j2c, (size_t)len, sample_type);
     d->have_headers = true;
@@ -225,13 +233,13 @@ int ojb_dec_read_headers(ojb_decoder* d, const uint8_t* j2c, uint64_t len, uint3
   });
 }
 int ojb_dec_decode_frame(ojb_decoder* d, void* const* planes, const uint32_t* strides) {
-  return guarded([&] {
+  return guarded_on(d->device, [&] {
     if (!d->have_headers) fail(0x000B0015, "read_headers has not been called");
     d->dec.decode(planes, strides, false);
   });
 }
 int ojb_dec_decode_resident(ojb_decoder* d) {
-  return guarded([&] {
+  return guarded_on(d->device, [&] {
     if (!d->have_headers) fail(0x000B0015, "read_headers has not been called");
     d->dec.decode(nullptr, nullptr, true);
   });
@@ -243,7 +251,7 @@ void* ojb_dec_device_plane(ojb_decoder* d, uint32_t comp) {
 int ojb_dec_use_device_codestream(ojb_decoder* d, const void* dev_bytes) { d->dec.dev_cs = (const uint8_t*)dev_bytes; return 0; }
 uint32_t ojb_dec_failed_blocks(ojb_decoder* d) { return d->dec.failed_blocks; }
 int ojb_dec_list_blocks(ojb_decoder* d, ojb_block_desc* out, uint32_t cap, uint32_t* n) {
-  return guarded([&] {
+  return guarded_on(d->device, [&] {
     if (!d->have_headers) fail(0x000B0015, "read_headers has not been called");
     d->dec.parse_tiles();
     uint32_t nb = (uint32_t)d->dec.h_dec_proto.size();
@@ -262,7 +270,7 @@ int ojb_dec_list_blocks(ojb_decoder* d, ojb_block_desc* out, uint32_t cap, uint3
 uint32_t ojb_dec_kernel_launches(ojb_decoder* d) { return d->dec.last_launches; }
 int ojb_dec_read_band(ojb_decoder* d, uint32_t tile, uint32_t comp, uint32_t res, uint32_t band,
                       uint32_t* out, uint32_t* band_w, uint32_t* band_h) {
-  return guarded([&] {
+  return guarded_on(d->device, [&] {
     if (!d->have_headers) fail(0x000B0015, "read_headers has not been called");
     read_band(d->dec, tile, comp, res, band, out, band_w, band_h);
   });
@@ -335,6 +343,7 @@ int ojb_decode_blocks(const uint8_t* bytes, uint64_t n_bytes, ojb_block_desc* de
     cuda_check(cudaMemcpy(d_t.p, tb.data(), tb.size() * 2, cudaMemcpyHostToDevice), "tables");
     std::vector<DecBlock> db(n);
     size_t scratch = 0;
+    uint32_t max_len1 = 0;
     for (uint32_t i = 0; i < n; ++i) {
       DecBlock& d = db[i]; memset(&d, 0, sizeof(d));
       d.data_off = desc[i].byte_off; d.dst_off = desc[i].sample_off; d.stride = desc[i].stride;
@@ -343,12 +352,13 @@ int ojb_decode_blocks(const uint8_t* bytes, uint64_t n_bytes, ojb_block_desc* de
       d.K_max = (uint8_t)(desc[i].missing_msbs + 1); d.flags = desc[i].causal ? 1 : 0;
       uint32_t nq = (d.w + 1u) / 2, qs = (nq + 1) & ~1u, nqr = (d.h + 1u) / 2;
       d.scratch_off = scratch; scratch += (size_t)qs * nqr + (d.len1 + 3) / 4 + 4;
+      max_len1 = std::max(max_len1, d.len1);
     }
     d_b.reserve(n * sizeof(DecBlock)); d_o.reserve((n_words + 64) * 4); d_sc.reserve((scratch + 64) * 4); d_st.reserve(n * 4 + 16);
     cuda_check(cudaMemcpy(d_b.p, db.data(), n * sizeof(DecBlock), cudaMemcpyHostToDevice), "blocks");
     cuda_check(cudaMemcpy(d_o.p, samples, n_words * 4, cudaMemcpyHostToDevice), "out init");
     launch_ht_decode(d_b.as<DecBlock>(), n, d_cs.as<uint8_t>(), d_o.as<uint32_t>(), d_sc.as<uint32_t>(),
-                     d_t.as<uint16_t>(), DEC_OUT_SIGNMAG, d_st.as<uint32_t>(), 0);
+                     d_t.as<uint16_t>(), DEC_OUT_SIGNMAG, d_st.as<uint32_t>(), max_len1, 0);
     cuda_check(cudaDeviceSynchronize(), "ht_decode");
     cuda_check(cudaGetLastError(), "ht_decode");
     cuda_check(cudaMemcpy(samples, d_o.p, n_words * 4, cudaMemcpyDeviceToHost), "samples");

@@ -606,6 +606,7 @@ uint32_t Decoder::decode(void* const* planes, const uint32_t* strides, bool plan
   size_t scratch_fixed = 0;
   if (nb) { const DecBlock& l = h_dec_proto[nb - 1]; uint32_t nq = (l.w + 1u) / 2, qs = (nq + 1) & ~1u; scratch_fixed = l.scratch_off + (size_t)qs * ((l.h + 1u) / 2); }
   size_t scratch = scratch_fixed;
+  uint32_t max_len1 = 0;
   // per-block scratch = quad records (fixed part, laid out per block) ... MagSgn words appended
   // right after each block's records would move the records; keep records at proto offsets and put
   // the MagSgn buffers in a second region addressed through scratch_off + records size.
@@ -618,6 +619,7 @@ uint32_t Decoder::decode(void* const* planes, const uint32_t* strides, bool plan
     uint32_t nq = (d.w + 1u) / 2, qs = (nq + 1) & ~1u, nqr = (d.h + 1u) / 2;
     d.scratch_off = scratch;
     scratch += (size_t)qs * nqr + (d.len1 + 3) / 4 + 4;
+    max_len1 = std::max(max_len1, d.len1);
     hd[b] = d;
   }
   d_scratch.reserve((scratch + 64) * 4);
@@ -626,7 +628,7 @@ uint32_t Decoder::decode(void* const* planes, const uint32_t* strides, bool plan
   if (nb) CK(cudaMemcpyAsync(d_dec.p, h_dec.p, (size_t)nb * sizeof(DecBlock), cudaMemcpyHostToDevice, stream));
   launch_ht_decode(d_dec.as<DecBlock>(), nb, cs_dev, d_coef.as<uint32_t>(), d_scratch.as<uint32_t>(),
                    d_tables_dec.as<uint16_t>(), P.reversible() ? (uint32_t)DEC_OUT_INT : (uint32_t)DEC_OUT_FLOAT,
-                   d_bstatus.as<uint32_t>(), stream);
+                   d_bstatus.as<uint32_t>(), max_len1, stream);
   last_launches += 2;
   mark(3);
   if (nb) CK(cudaMemcpyAsync(h_bstatus.p, d_bstatus.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, stream));

@@ -14,7 +14,7 @@ void launch_ht_encode(const EncBlock* blocks, uint32_t nblocks, const uint32_t* 
 // tables: uint16 dec_vlc[2][1024], dec_uvlc0[320], dec_uvlc1[256]
 void launch_ht_decode(const DecBlock* blocks, uint32_t nblocks, const uint8_t* codestream,
                       uint32_t* coef, uint32_t* scratch, const uint16_t* tables, uint32_t out_mode,
-                      uint32_t* block_status, cudaStream_t st);
+                      uint32_t* block_status, uint32_t max_len1, cudaStream_t st);
 
 // forward / inverse DWT levels (dwt_fwd.cu / dwt_inv.cu).  jobs live in device memory.
 void launch_dwt_fwd(const DwtJob* jobs, uint32_t njobs, uint32_t total_ctas, bool reversible,

@@ -37,7 +37,7 @@ SMALL_IRV = [
 # a quick subset for the CPU (emulator) tier
 EMU_REV = ["cfg1_256_gray_L1", "gray_L0", "odd_rgb_L5", "offsets", "rgb16_noise", "block_4x4", "tilepart_RC_lrcp",
            "tiny_1x1", "thin_off", "signed10", "po_PCRL_precincts", "sub420_planar"]
-EMU_IRV = ["irv_rgb_qstep"]
+EMU_IRV = ["irv_rgb_qstep", "irv_tiles"]
 
 
 def make(case_kwargs):
