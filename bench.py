@@ -113,6 +113,27 @@ def run_cpu_reference(procs, steps, warmup):
     return pix / dt / 1e6, dt / steps * 1e3
 
 
+def bind_to_gpu_numa_node(torch, local):
+    """run this rank's host threads (and first-touch its pinned buffers) on the CPUs next to its GPU:
+    pinned memory on the far socket halves the PCIe rate.  Returns a note for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(local)
+        bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {w * 64 + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "%d CPUs local to GPU %s" % (len(cpus), bus)
+    except Exception as e:          # no NVML / no topology information: run unbound
+        return "unbound (%s)" % type(e).__name__
+    return "unbound"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -159,6 +180,7 @@ def main():
     L = _lib.lib()
     assert L.ojb_set_device(local) == 0, L.ojb_last_error()
     torch.cuda.set_device(local)
+    affinity = bind_to_gpu_numa_node(torch, local)      # before any pinned allocation (first touch)
 
     p = workload_params()
     frame = make_frame(W, H, 1234 + rank)
@@ -273,7 +295,7 @@ def main():
     roof = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
             "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": cand[dom][1], "ms_per_launch": cand[dom][0]}
-    cfg.update({"frames_per_step": NW * a.gpus, "frames_in_flight_per_gpu": NW,
+    cfg.update({"frames_per_step": NW * a.gpus, "frames_in_flight_per_gpu": NW, "host_affinity": affinity,
                 "serial_ms_per_frame": round(dt_serial / a.steps * 1e3, 3),
                 "serial_Mpixels_per_s": round(W * H * a.steps / dt_serial / 1e6, 1),
                 "stages_encode_ms": stage_e, "stages_decode_ms": stage_d, "codestream_bytes": sizes,

@@ -12,6 +12,8 @@
 
 namespace ojb {
 
+#define ASM_CHUNK 4096u
+
 namespace {
 
 // warp-cooperative byte copy with 4-byte stores where the destination allows it
@@ -58,11 +60,16 @@ __global__ void __launch_bounds__(128)
 assemble_kernel(const CopyPiece* __restrict__ pieces, uint32_t npieces, const uint8_t* __restrict__ slots,
                 const uint8_t* __restrict__ headers, uint8_t* __restrict__ out)
 {
+  // blockIdx.y walks a long piece in ASM_CHUNK-byte chunks so that a few large header runs do not
+  // serialise on a handful of warps
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= npieces) return;
   const CopyPiece p = pieces[warp];
-  const uint8_t* src = (p.src_sel ? headers : slots) + p.src_off;
-  warp_copy(out + p.dst_off, src, p.len, lane);
+  const uint64_t c0 = (uint64_t)blockIdx.y * ASM_CHUNK;
+  if (c0 >= p.len) return;
+  const uint32_t n = (uint32_t)min((uint64_t)ASM_CHUNK, (uint64_t)p.len - c0);
+  const uint8_t* src = (p.src_sel ? headers : slots) + p.src_off + c0;
+  warp_copy(out + p.dst_off + c0, src, n, lane);
 }
 
 } // namespace
@@ -75,11 +82,11 @@ void launch_gather_blocks(const EncBlock* blocks, const EncResult* results, cons
   OJB_LAUNCH(gather_blocks_kernel, grid, block, 0, st, blocks, results, dst_off, nblocks, slots, out);
 }
 
-void launch_assemble(const CopyPiece* pieces, uint32_t npieces, const uint8_t* slots,
+void launch_assemble(const CopyPiece* pieces, uint32_t npieces, uint32_t max_len, const uint8_t* slots,
                      const uint8_t* headers, uint8_t* out, cudaStream_t st)
 {
   if (npieces == 0) return;
-  dim3 grid((npieces + 3) / 4), block(128);
+  dim3 grid((npieces + 3) / 4, (max_len + ASM_CHUNK - 1) / ASM_CHUNK > 0 ? (max_len + ASM_CHUNK - 1) / ASM_CHUNK : 1), block(128);
   OJB_LAUNCH(assemble_kernel, grid, block, 0, st, pieces, npieces, slots, headers, out);
 }
 

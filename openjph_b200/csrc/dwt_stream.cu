@@ -25,8 +25,9 @@
 namespace ojb {
 
 #define DS_WARPS 4
-#define DS_ROWS 64            // output rows per warp chunk
+#define DS_ROWS 64            // output rows per warp chunk (large resolutions; small ones use fewer)
 #define DS_COLS 4             // columns per lane: (even, odd, even, odd) = (low, high, low, high)
+#define DS_STAGES 4           // row-pair stages of a lane's cp.async FIFO (3 in flight)
 #define DS_VALID 30           // lanes that produce output; lanes 0 and 31 are halo (4 columns reach)
 #define FULL 0xFFFFFFFFu
 
@@ -132,43 +133,54 @@ __device__ __forceinline__ bool strip_setup(const DwtJob& J, uint32_t strip, uin
   }
   g.interior = g.u0 >= g.x0 && g.u0 + 3 < g.x1;
   const int ye = g.y0 & ~1;
-  g.R0 = ye + (int)chunk * DS_ROWS;
-  g.R1 = min(g.R0 + DS_ROWS, g.y1);
+  g.R0 = ye + (int)chunk * (int)J.chunk_rows;
+  g.R1 = min(g.R0 + (int)J.chunk_rows, g.y1);
   return g.R0 < g.y1;
 }
 
-// four consecutive elements starting at p[i0] (one vector access when aligned) or four gathered ones
-__device__ __forceinline__ void load4_u16(const unsigned short* p, const StripGeom& g, int (&v)[4]) {
+// ---- asynchronous global -> shared copies.  Every lane owns a private FIFO of shared-memory slots:
+// it requests the rows of the next iterations with cp.async (no registers are held while the data is
+// in flight) and later reads back exactly the bytes it requested, so no cross-lane synchronisation
+// is needed -- cp.async.wait_group orders a lane's own copies.
+#ifdef OJB_EMU_BUILD
+template <int N> __device__ __forceinline__ void cp_async(void* dst, const void* src) { memcpy(dst, src, N); }
+__device__ __forceinline__ void cp_commit() {}
+template <int N> __device__ __forceinline__ void cp_wait() {}
+#else
+template <int N> __device__ __forceinline__ void cp_async(void* dst, const void* src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" :: "r"(d), "l"(src), "n"(N) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+#endif
+
+// request four 32-bit elements p[c[0..3]] into a 16-byte slot
+__device__ __forceinline__ void issue4_w(unsigned char* d, const uint32_t* p, const StripGeom& g) {
+  const uint32_t* q = p + g.c[0];
+  if (g.interior && (reinterpret_cast<size_t>(q) & 15) == 0) cp_async<16>(d, q);
+  else {
+    #pragma unroll
+    for (int i = 0; i < 4; ++i) cp_async<4>(d + 4 * i, p + g.c[i]);
+  }
+}
+__device__ __forceinline__ void issue4_u16(unsigned char* d, const unsigned short* p, const StripGeom& g) {
   const unsigned short* q = p + g.c[0];
-  if (g.interior && (reinterpret_cast<size_t>(q) & 7) == 0) {
-    const uint2 t = *reinterpret_cast<const uint2*>(q);
-    v[0] = (int)(t.x & 0xFFFF); v[1] = (int)(t.x >> 16); v[2] = (int)(t.y & 0xFFFF); v[3] = (int)(t.y >> 16);
-  } else {
+  const size_t a = reinterpret_cast<size_t>(q);
+  if (g.interior && (a & 7) == 0) cp_async<8>(d, q);
+  else if (g.interior && (a & 3) == 0) { cp_async<4>(d, q); cp_async<4>(d + 4, q + 2); }
+  else {                                   // mirrored or odd-aligned columns: plain loads (edge lanes)
+    unsigned short* ds = reinterpret_cast<unsigned short*>(d);
     #pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = p[g.c[i]];
+    for (int i = 0; i < 4; ++i) ds[i] = p[g.c[i]];
   }
 }
-__device__ __forceinline__ void load4_u8(const unsigned char* p, const StripGeom& g, int (&v)[4]) {
+__device__ __forceinline__ void issue4_u8(unsigned char* d, const unsigned char* p, const StripGeom& g) {
   const unsigned char* q = p + g.c[0];
-  if (g.interior && (reinterpret_cast<size_t>(q) & 3) == 0) {
-    const uint32_t t = *reinterpret_cast<const uint32_t*>(q);
-    v[0] = (int)(t & 0xFF); v[1] = (int)((t >> 8) & 0xFF); v[2] = (int)((t >> 16) & 0xFF); v[3] = (int)(t >> 24);
-  } else {
+  if (g.interior && (reinterpret_cast<size_t>(q) & 3) == 0) cp_async<4>(d, q);
+  else {
     #pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = p[g.c[i]];
-  }
-}
-template <typename T>
-__device__ __forceinline__ void load4_w(const T* p, const StripGeom& g, T (&v)[4]) {     // 32-bit elements
-  const T* q = p + g.c[0];
-  if (g.interior && (reinterpret_cast<size_t>(q) & 15) == 0) {
-    const uint4 t = *reinterpret_cast<const uint4*>(q);
-    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
-    #pragma unroll
-    for (int i = 0; i < 4; ++i) { T e; memcpy(&e, &w[i], 4); v[i] = e; }
-  } else {
-    #pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = p[g.c[i]];
+    for (int i = 0; i < 4; ++i) d[i] = p[g.c[i]];
   }
 }
 // two consecutive 32-bit words
@@ -176,30 +188,57 @@ __device__ __forceinline__ void store2_w(uint32_t* q, uint32_t a, uint32_t b, bo
   if (ha && hb && (reinterpret_cast<size_t>(q) & 7) == 0) *reinterpret_cast<uint2*>(q) = make_uint2(a, b);
   else { if (ha) q[0] = a; if (hb) q[1] = b; }
 }
-__device__ __forceinline__ void load2_w(const uint32_t* q, bool vec, int i0, int i1, uint32_t& a, uint32_t& b) {
-  // q = row base; i0, i1 element indices (i1 == i0 + 1 when vec)
-  if (vec && (reinterpret_cast<size_t>(q + i0) & 7) == 0) { const uint2 t = *reinterpret_cast<const uint2*>(q + i0); a = t.x; b = t.y; }
-  else { a = q[i0]; b = q[i1]; }
-}
 template <typename T> __device__ __forceinline__ uint32_t as_bits(T v) { uint32_t r; memcpy(&r, &v, 4); return r; }
 template <typename T> __device__ __forceinline__ T from_bits(uint32_t v) { T r; memcpy(&r, &v, 4); return r; }
 
 // ---- forward ---------------------------------------------------------------------------------
-template <bool REV, int NC, bool FIRST>
-__device__ __forceinline__ void fwd_load_row(const DwtJob& J, const StripGeom& g, const void* image,
-                                             const uint32_t* coef, int v, typename Tp<REV>::T (&a)[NC][4])
+// slot bytes of one lane for one (row, component): 4 samples in their source container
+__device__ __forceinline__ uint32_t fwd_slot_bytes(bool first, uint32_t src_type) {
+  return (first && src_type != SRC_I32) ? 8u : 16u;
+}
+
+// request source row v (mirrored into the resolution) into the row slot `st` (lane offset included)
+template <int NC, bool FIRST>
+__device__ __forceinline__ void fwd_issue_row(const DwtJob& J, const StripGeom& g, const void* image,
+                                              const uint32_t* coef, int v, unsigned char* st, uint32_t slot)
 {
-  typedef typename Tp<REV>::T T;
   const int vr = reflect_coord(v, g.y0, g.y1 - 1) - g.y0;
   if (FIRST) {
-    int iv[NC][4];
     #pragma unroll
     for (int k = 0; k < NC; ++k) {
       const size_t row = (size_t)vr * J.full_stride[k];
       const unsigned char* base = reinterpret_cast<const unsigned char*>(image) + J.full_off[k];
-      if (J.src_type == SRC_U16) load4_u16(reinterpret_cast<const unsigned short*>(base) + row, g, iv[k]);
-      else if (J.src_type == SRC_U8) load4_u8(base + row, g, iv[k]);
-      else load4_w<int>(reinterpret_cast<const int*>(base) + row, g, iv[k]);
+      unsigned char* d = st + (size_t)k * 32 * slot;
+      if (J.src_type == SRC_U16) issue4_u16(d, reinterpret_cast<const unsigned short*>(base) + row, g);
+      else if (J.src_type == SRC_U8) issue4_u8(d, base + row, g);
+      else issue4_w(d, reinterpret_cast<const uint32_t*>(base) + row, g);
+    }
+  } else {
+    issue4_w(st, coef + J.full_off[0] + (size_t)vr * J.full_stride[0], g);
+  }
+}
+
+// read a row slot back: level shift / int->float and RCT / ICT at level 1
+template <bool REV, int NC, bool FIRST>
+__device__ __forceinline__ void fwd_read_row(const DwtJob& J, const unsigned char* st, uint32_t slot,
+                                             typename Tp<REV>::T (&a)[NC][4])
+{
+  typedef typename Tp<REV>::T T;
+  if (FIRST) {
+    int iv[NC][4];
+    #pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const unsigned char* d = st + (size_t)k * 32 * slot;
+      if (J.src_type == SRC_U16) {
+        const uint2 t = *reinterpret_cast<const uint2*>(d);
+        iv[k][0] = (int)(t.x & 0xFFFF); iv[k][1] = (int)(t.x >> 16); iv[k][2] = (int)(t.y & 0xFFFF); iv[k][3] = (int)(t.y >> 16);
+      } else if (J.src_type == SRC_U8) {
+        const uint32_t t = *reinterpret_cast<const uint32_t*>(d);
+        iv[k][0] = (int)(t & 0xFF); iv[k][1] = (int)((t >> 8) & 0xFF); iv[k][2] = (int)((t >> 16) & 0xFF); iv[k][3] = (int)(t >> 24);
+      } else {
+        const uint4 t = *reinterpret_cast<const uint4*>(d);
+        iv[k][0] = (int)t.x; iv[k][1] = (int)t.y; iv[k][2] = (int)t.z; iv[k][3] = (int)t.w;
+      }
     }
     if (REV) {
       const int shift = J.is_signed ? 0 : (1 << (J.bit_depth - 1));
@@ -240,8 +279,8 @@ __device__ __forceinline__ void fwd_load_row(const DwtJob& J, const StripGeom& g
         for (int i = 0; i < 4; ++i) a[k][i] = (T)f[k][i];
     }
   } else {
-    const T* p = reinterpret_cast<const T*>(coef) + J.full_off[0] + (size_t)vr * J.full_stride[0];
-    load4_w<T>(p, g, a[0]);
+    const uint4 t = *reinterpret_cast<const uint4*>(st);
+    a[0][0] = from_bits<T>(t.x); a[0][1] = from_bits<T>(t.y); a[0][2] = from_bits<T>(t.z); a[0][3] = from_bits<T>(t.w);
   }
 }
 
@@ -307,21 +346,45 @@ dwt_fwd_stream_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, const voi
   StripGeom g;
   if (!strip_setup(J, strip, chunk, lane, g)) return;
 
+  // the lane's FIFO: DS_STAGES stages of one row pair each
+  OJB_DYN_SMEM(unsigned char, s_ring);
+  const uint32_t slot = fwd_slot_bytes(FIRST, J.src_type);
+  const uint32_t row_bytes = NC * 32 * slot, stage_bytes = 2 * row_bytes;
+  unsigned char* ring = s_ring + (size_t)warp * DS_STAGES * stage_bytes + (size_t)lane * slot;
+
+  // iteration k consumes rows (2k-1, 2k); 5/3 emits the pair (2k-2, 2k-1), 9/7 the pair (2k-4, 2k-3)
+  const int k0 = REV ? g.R0 / 2 : g.R0 / 2 - 1;
+  const int k1 = REV ? (g.R1 + 1) / 2 : (g.R1 + 1) / 2 + 1;     // last pair covers rows up to R1-1
+  T xe[NC][4];                                                // x[2k-2]
+  {                                                           // priming row through the last stage
+    unsigned char* sp = ring + (size_t)(DS_STAGES - 1) * stage_bytes;
+    fwd_issue_row<NC, FIRST>(J, g, image, coef, 2 * k0 - 2, sp, slot);
+    cp_commit(); cp_wait<0>();
+    fwd_read_row<REV, NC, FIRST>(J, sp, slot, xe);
+  }
+  int issued = k0;
+  #pragma unroll
+  for (int s = 0; s < DS_STAGES - 1; ++s) {
+    if (issued <= k1) {
+      unsigned char* st = ring + (size_t)((issued - k0) % DS_STAGES) * stage_bytes;
+      fwd_issue_row<NC, FIRST>(J, g, image, coef, 2 * issued - 1, st, slot);
+      fwd_issue_row<NC, FIRST>(J, g, image, coef, 2 * issued, st + row_bytes, slot);
+    }
+    cp_commit(); ++issued;
+  }
+
   if (REV) {
-    // 5/3: iteration k consumes rows (2k-1, 2k) and emits the pair (2k-2, 2k-1)
-    T xe[NC][4], hp[NC][4];           // x[2k-2], H[k-2]
-    const int k0 = g.R0 / 2;
-    fwd_load_row<REV, NC, FIRST>(J, g, image, coef, 2 * k0 - 2, xe);
+    T hp[NC][4];                      // H[k-2]
     #pragma unroll
     for (int c = 0; c < NC; ++c)
       #pragma unroll
       for (int i = 0; i < 4; ++i) hp[c][i] = 0;
-    const int k1 = (g.R1 + 1) / 2;    // last emitted pair index k1-1 covers rows up to R1-1
-    T xo[NC][4], xn[NC][4];
-    fwd_load_row<REV, NC, FIRST>(J, g, image, coef, 2 * k0 - 1, xo);
-    fwd_load_row<REV, NC, FIRST>(J, g, image, coef, 2 * k0, xn);
     for (int k = k0; k <= k1; ++k) {
-      T lo[NC][4], hi[NC][4];
+      T xo[NC][4], xn[NC][4], lo[NC][4], hi[NC][4];
+      cp_wait<DS_STAGES - 2>();
+      const unsigned char* st = ring + (size_t)((k - k0) % DS_STAGES) * stage_bytes;
+      fwd_read_row<REV, NC, FIRST>(J, st, slot, xo);
+      fwd_read_row<REV, NC, FIRST>(J, st + row_bytes, slot, xn);
       #pragma unroll
       for (int c = 0; c < NC; ++c)
         #pragma unroll
@@ -331,28 +394,27 @@ dwt_fwd_stream_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, const voi
           lo[c][i] = (T)l; hi[c][i] = (T)h;
           hp[c][i] = (T)h; xe[c][i] = xn[c][i];
         }
-      if (k < k1) {                   // next iteration's rows are in flight while this pair is finished
-        fwd_load_row<REV, NC, FIRST>(J, g, image, coef, 2 * k + 1, xo);
-        fwd_load_row<REV, NC, FIRST>(J, g, image, coef, 2 * k + 2, xn);
+      if (issued <= k1) {             // refill the stage consumed one iteration ago
+        unsigned char* sn = ring + (size_t)((issued - k0) % DS_STAGES) * stage_bytes;
+        fwd_issue_row<NC, FIRST>(J, g, image, coef, 2 * issued - 1, sn, slot);
+        fwd_issue_row<NC, FIRST>(J, g, image, coef, 2 * issued, sn + row_bytes, slot);
       }
+      cp_commit(); ++issued;
       fwd_store_pair<REV, NC>(J, g, coef, 2 * k - 2, lo, hi);      // rows 2k-2 (low), 2k-1 (high)
     }
   } else {
-    // 9/7: iteration k consumes rows (2k-1, 2k) and emits the pair (2k-4, 2k-3)
-    T xe[NC][4], d1[NC][4], s1[NC][4], d2[NC][4];   // x[2k-2], d1[k-2], s1[k-2], d2[k-3]
-    const int k0 = g.R0 / 2 - 1;
-    fwd_load_row<REV, NC, FIRST>(J, g, image, coef, 2 * k0 - 2, xe);
+    T d1[NC][4], s1[NC][4], d2[NC][4];   // d1[k-2], s1[k-2], d2[k-3]
     #pragma unroll
     for (int c = 0; c < NC; ++c)
       #pragma unroll
       for (int i = 0; i < 4; ++i) { d1[c][i] = 0; s1[c][i] = 0; d2[c][i] = 0; }
-    const int k1 = (g.R1 + 1) / 2 + 1;
     const float Kinv = 1.0f / IRV_K;
-    T xo[NC][4], xn[NC][4];
-    fwd_load_row<REV, NC, FIRST>(J, g, image, coef, 2 * k0 - 1, xo);
-    fwd_load_row<REV, NC, FIRST>(J, g, image, coef, 2 * k0, xn);
     for (int k = k0; k <= k1; ++k) {
-      T lo[NC][4], hi[NC][4];
+      T xo[NC][4], xn[NC][4], lo[NC][4], hi[NC][4];
+      cp_wait<DS_STAGES - 2>();
+      const unsigned char* st = ring + (size_t)((k - k0) % DS_STAGES) * stage_bytes;
+      fwd_read_row<REV, NC, FIRST>(J, st, slot, xo);
+      fwd_read_row<REV, NC, FIRST>(J, st + row_bytes, slot, xn);
       #pragma unroll
       for (int c = 0; c < NC; ++c)
         #pragma unroll
@@ -364,23 +426,24 @@ dwt_fwd_stream_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, const voi
           lo[c][i] = (T)__fmul_rn(ns2, Kinv); hi[c][i] = (T)__fmul_rn(nd2, IRV_K);
           xe[c][i] = xn[c][i]; d1[c][i] = (T)nd1; s1[c][i] = (T)ns1; d2[c][i] = (T)nd2;
         }
-      if (k < k1) {
-        fwd_load_row<REV, NC, FIRST>(J, g, image, coef, 2 * k + 1, xo);
-        fwd_load_row<REV, NC, FIRST>(J, g, image, coef, 2 * k + 2, xn);
+      if (issued <= k1) {
+        unsigned char* sn = ring + (size_t)((issued - k0) % DS_STAGES) * stage_bytes;
+        fwd_issue_row<NC, FIRST>(J, g, image, coef, 2 * issued - 1, sn, slot);
+        fwd_issue_row<NC, FIRST>(J, g, image, coef, 2 * issued, sn + row_bytes, slot);
       }
+      cp_commit(); ++issued;
       fwd_store_pair<REV, NC>(J, g, coef, 2 * k - 4, lo, hi);      // rows 2k-4 (low), 2k-3 (high)
     }
   }
 }
 
 // ---- inverse ---------------------------------------------------------------------------------
-// load the sub-band samples that interleave into rows (2j, 2j+1), columns u0..u0+3 and undo the
-// horizontal transform: L[..] = vertically-low row, H[..] = vertically-high row
-template <bool REV, int NC>
-__device__ __forceinline__ void inv_load_pair(const DwtJob& J, const StripGeom& g, const uint32_t* coef, int j,
-                                              typename Tp<REV>::T (&L)[NC][4], typename Tp<REV>::T (&H)[NC][4])
+// request the sub-band samples that interleave into rows (2j, 2j+1), columns u0..u0+3: per component
+// four 8-byte slots (LL|HL of the vertically-low row, LH|HH of the vertically-high row)
+template <int NC>
+__device__ __forceinline__ void inv_issue_pair(const DwtJob& J, const StripGeom& g, const uint32_t* coef, int j,
+                                               unsigned char* st)
 {
-  typedef typename Tp<REV>::T T;
   // mirrored absolute coordinates keep their parity, so each sample maps to a definite band
   int bx[4];
   #pragma unroll
@@ -392,15 +455,33 @@ __device__ __forceinline__ void inv_load_pair(const DwtJob& J, const StripGeom& 
   const int byl = (va >> 1) - ((g.y0 + 1) >> 1), byh = (vb >> 1) - (g.y0 >> 1);
   #pragma unroll
   for (int k = 0; k < NC; ++k) {
-    uint32_t w[2][4];
-    const uint32_t* r0 = J.last ? coef + J.band_off[k][0] + (size_t)byl * J.band_stride[k][0]
-                                : coef + J.ll_off[k] + (size_t)byl * J.ll_stride[k];
-    load2_w(r0, g.interior, bx[0], bx[2], w[0][0], w[0][2]);
-    load2_w(coef + J.band_off[k][1] + (size_t)byl * J.band_stride[k][1], g.interior, bx[1], bx[3], w[0][1], w[0][3]);
-    load2_w(coef + J.band_off[k][2] + (size_t)byh * J.band_stride[k][2], g.interior, bx[0], bx[2], w[1][0], w[1][2]);
-    load2_w(coef + J.band_off[k][3] + (size_t)byh * J.band_stride[k][3], g.interior, bx[1], bx[3], w[1][1], w[1][3]);
     #pragma unroll
-    for (int i = 0; i < 4; ++i) { L[k][i] = from_bits<T>(w[0][i]); H[k][i] = from_bits<T>(w[1][i]); }
+    for (int b = 0; b < 4; ++b) {
+      const uint32_t* r = (b == 0 && !J.last) ? coef + J.ll_off[k] + (size_t)byl * J.ll_stride[k]
+                                              : coef + J.band_off[k][b] + (size_t)(b < 2 ? byl : byh) * J.band_stride[k][b];
+      const int i0 = bx[b & 1], i1 = bx[(b & 1) + 2];
+      unsigned char* d = st + (size_t)(k * 4 + b) * 32 * 8;
+      if (g.interior && (reinterpret_cast<size_t>(r + i0) & 7) == 0) cp_async<8>(d, r + i0);
+      else { cp_async<4>(d, r + i0); cp_async<4>(d + 4, r + i1); }
+    }
+  }
+}
+
+// read a requested pair back and undo the horizontal transform: L[..] = vertically-low row,
+// H[..] = vertically-high row
+template <bool REV, int NC>
+__device__ __forceinline__ void inv_read_pair(const unsigned char* st, typename Tp<REV>::T (&L)[NC][4],
+                                              typename Tp<REV>::T (&H)[NC][4])
+{
+  typedef typename Tp<REV>::T T;
+  #pragma unroll
+  for (int k = 0; k < NC; ++k) {
+    const uint2 ll = *reinterpret_cast<const uint2*>(st + (size_t)(k * 4 + 0) * 32 * 8);
+    const uint2 hl = *reinterpret_cast<const uint2*>(st + (size_t)(k * 4 + 1) * 32 * 8);
+    const uint2 lh = *reinterpret_cast<const uint2*>(st + (size_t)(k * 4 + 2) * 32 * 8);
+    const uint2 hh = *reinterpret_cast<const uint2*>(st + (size_t)(k * 4 + 3) * 32 * 8);
+    L[k][0] = from_bits<T>(ll.x); L[k][1] = from_bits<T>(hl.x); L[k][2] = from_bits<T>(ll.y); L[k][3] = from_bits<T>(hl.y);
+    H[k][0] = from_bits<T>(lh.x); H[k][1] = from_bits<T>(hh.x); H[k][2] = from_bits<T>(lh.y); H[k][3] = from_bits<T>(hh.y);
     horz_syn<REV, T>(L[k]);
     horz_syn<REV, T>(H[k]);
   }
@@ -534,20 +615,39 @@ dwt_inv_stream_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, void* __r
   StripGeom g;
   if (!strip_setup(J, strip, chunk, lane, g)) return;
 
+  OJB_DYN_SMEM(unsigned char, s_ring);
+  constexpr int NS = (NC == 3) ? DS_STAGES - 1 : DS_STAGES;       // three components: 3 KB per stage
+  const uint32_t stage_bytes = NC * 4 * 32 * 8;
+  unsigned char* ring = s_ring + (size_t)warp * NS * stage_bytes + (size_t)lane * 8;
+
+  // iteration j consumes the band-row pair j; 5/3 emits rows (2j-1, 2j), 9/7 rows (2j-3, 2j-2)
+  const int j0 = REV ? g.R0 / 2 : g.R0 / 2 - 1;
+  const int j1 = REV ? (g.R1 + 1) / 2 : (g.R1 + 1) / 2 + 1;
+  T hp[NC][4];                                                // H[j-1] (9/7: scaled)
+  {
+    T L[NC][4];
+    unsigned char* sp = ring + (size_t)(NS - 1) * stage_bytes;   // priming pair through the last stage
+    inv_issue_pair<NC>(J, g, coef, j0 - 1, sp);               // only H[j0-1] is needed
+    cp_commit(); cp_wait<0>();
+    inv_read_pair<REV, NC>(sp, L, hp);
+  }
+  int issued = j0;
+  #pragma unroll
+  for (int s = 0; s < NS - 1; ++s) {
+    if (issued <= j1) inv_issue_pair<NC>(J, g, coef, issued, ring + (size_t)((issued - j0) % NS) * stage_bytes);
+    cp_commit(); ++issued;
+  }
+
   if (REV) {
-    // 5/3: iteration j consumes the band-row pair j and emits rows (2j-1, 2j)
-    T hp[NC][4], xe[NC][4];          // H[j-1], x[2j-2]
-    const int j0 = g.R0 / 2;
-    T L[NC][4], H[NC][4];
-    inv_load_pair<REV, NC>(J, g, coef, j0 - 1, L, hp);       // only H[j0-1] is needed
+    T xe[NC][4];                     // x[2j-2]
     #pragma unroll
     for (int c = 0; c < NC; ++c)
       #pragma unroll
       for (int i = 0; i < 4; ++i) xe[c][i] = 0;
-    const int j1 = (g.R1 + 1) / 2;
-    inv_load_pair<REV, NC>(J, g, coef, j0, L, H);
     for (int j = j0; j <= j1; ++j) {
-      T xo[NC][4], xn[NC][4];
+      T L[NC][4], H[NC][4], xo[NC][4], xn[NC][4];
+      cp_wait<NS - 2>();
+      inv_read_pair<REV, NC>(ring + (size_t)((j - j0) % NS) * stage_bytes, L, H);
       #pragma unroll
       for (int c = 0; c < NC; ++c)
         #pragma unroll
@@ -557,24 +657,21 @@ dwt_inv_stream_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, void* __r
           xn[c][i] = (T)e; xo[c][i] = (T)o;
           hp[c][i] = H[c][i]; xe[c][i] = (T)e;
         }
-      if (j < j1) inv_load_pair<REV, NC>(J, g, coef, j + 1, L, H);
+      if (issued <= j1) inv_issue_pair<NC>(J, g, coef, issued, ring + (size_t)((issued - j0) % NS) * stage_bytes);
+      cp_commit(); ++issued;
       inv_store_row<REV, NC, FIRST>(J, g, image, coef, 2 * j - 1, xo);
       inv_store_row<REV, NC, FIRST>(J, g, image, coef, 2 * j, xn);
     }
   } else {
-    // 9/7: iteration j consumes the band-row pair j and emits rows (2j-3, 2j-2)
-    T hp[NC][4], s1[NC][4], d1[NC][4], xe[NC][4];      // Hr[j-1], s1[j-1], d1[j-2], x_e[j-2]
-    const int j0 = g.R0 / 2 - 1;
-    T L[NC][4], H[NC][4];
-    inv_load_pair<REV, NC>(J, g, coef, j0 - 1, L, hp);
+    T s1[NC][4], d1[NC][4], xe[NC][4];      // s1[j-1], d1[j-2], x_e[j-2]
     #pragma unroll
     for (int c = 0; c < NC; ++c)
       #pragma unroll
       for (int i = 0; i < 4; ++i) { hp[c][i] = (T)__fmul_rn((float)hp[c][i], 1.0f / IRV_K); s1[c][i] = 0; d1[c][i] = 0; xe[c][i] = 0; }
-    const int j1 = (g.R1 + 1) / 2 + 1;
-    inv_load_pair<REV, NC>(J, g, coef, j0, L, H);
     for (int j = j0; j <= j1; ++j) {
-      T xo[NC][4], xn[NC][4];
+      T L[NC][4], H[NC][4], xo[NC][4], xn[NC][4];
+      cp_wait<NS - 2>();
+      inv_read_pair<REV, NC>(ring + (size_t)((j - j0) % NS) * stage_bytes, L, H);
       #pragma unroll
       for (int c = 0; c < NC; ++c)
         #pragma unroll
@@ -587,7 +684,8 @@ dwt_inv_stream_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, void* __r
           xo[c][i] = (T)nxo; xn[c][i] = (T)nxe;
           hp[c][i] = (T)hr; s1[c][i] = (T)ns1; d1[c][i] = (T)nd1; xe[c][i] = (T)nxe;
         }
-      if (j < j1) inv_load_pair<REV, NC>(J, g, coef, j + 1, L, H);
+      if (issued <= j1) inv_issue_pair<NC>(J, g, coef, issued, ring + (size_t)((issued - j0) % NS) * stage_bytes);
+      cp_commit(); ++issued;
       inv_store_row<REV, NC, FIRST>(J, g, image, coef, 2 * j - 3, xo);
       inv_store_row<REV, NC, FIRST>(J, g, image, coef, 2 * j - 2, xn);
     }
@@ -595,40 +693,49 @@ dwt_inv_stream_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, void* __r
 }
 
 template <bool REV, int NC, bool FIRST>
-void launch_fwd(const DwtJob* jobs, uint32_t njobs, uint32_t ctas, const void* image, uint32_t* coef, cudaStream_t st) {
+void launch_fwd(const DwtJob* jobs, uint32_t njobs, uint32_t ctas, uint32_t src_type, const void* image, uint32_t* coef, cudaStream_t st) {
   auto k = dwt_fwd_stream_kernel<REV, NC, FIRST>;
-  OJB_LAUNCH(k, dim3(ctas), dim3(DS_WARPS * 32), 0, st, jobs, njobs, image, coef);
+  const size_t slot = (FIRST && src_type != SRC_I32) ? 8 : 16;
+  const size_t smem = (size_t)DS_WARPS * DS_STAGES * 2 * NC * 32 * slot;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  OJB_LAUNCH(k, dim3(ctas), dim3(DS_WARPS * 32), smem, st, jobs, njobs, image, coef);
 }
 template <bool REV, int NC, bool FIRST>
 void launch_inv(const DwtJob* jobs, uint32_t njobs, uint32_t ctas, void* image, uint32_t* coef, cudaStream_t st) {
   auto k = dwt_inv_stream_kernel<REV, NC, FIRST>;
-  OJB_LAUNCH(k, dim3(ctas), dim3(DS_WARPS * 32), 0, st, jobs, njobs, image, coef);
+  const size_t smem = (size_t)DS_WARPS * ((NC == 3) ? DS_STAGES - 1 : DS_STAGES) * NC * 4 * 32 * 8;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  OJB_LAUNCH(k, dim3(ctas), dim3(DS_WARPS * 32), smem, st, jobs, njobs, image, coef);
 }
 
 } // namespace
 
 // strips across / row chunks down; the launch uses ceil(strips / DS_WARPS) * chunks CTAs
 void dwt_stream_tiling(uint32_t x0, uint32_t y0, uint32_t w, uint32_t h, bool reversible,
-                       uint32_t& strips, uint32_t& chunks, uint32_t& ctas)
+                       uint32_t& strips, uint32_t& chunks, uint32_t& chunk_rows, uint32_t& ctas)
 {
   (void)reversible;
   const uint32_t SW = DS_COLS * DS_VALID;          // output columns per strip
   const uint32_t ue = x0 & ~1u, ye = y0 & ~1u;
   strips = (x0 + w - ue + SW - 1) / SW;
-  chunks = (y0 + h - ye + DS_ROWS - 1) / DS_ROWS;
+  // a warp walks its chunk serially (one dependent memory round trip per row pair): small
+  // resolutions get shorter chunks so the launch still fills the machine
+  chunk_rows = DS_ROWS;
+  while (chunk_rows > 8 && strips * ((y0 + h - ye + chunk_rows - 1) / chunk_rows) < 148u * 8u) chunk_rows >>= 1;
+  chunks = (y0 + h - ye + chunk_rows - 1) / chunk_rows;
   ctas = ((strips + DS_WARPS - 1) / DS_WARPS) * chunks;
 }
 
 void launch_dwt_fwd_stream(const DwtJob* jobs, uint32_t njobs, uint32_t total_ctas, bool reversible,
-                           uint32_t ncomp, bool first, const void* image, uint32_t* coef, cudaStream_t st)
+                           uint32_t ncomp, bool first, uint32_t src_type, const void* image, uint32_t* coef, cudaStream_t st)
 {
   if (total_ctas == 0) return;
   if (reversible) {
-    if (first) { if (ncomp == 3) launch_fwd<true, 3, true>(jobs, njobs, total_ctas, image, coef, st); else launch_fwd<true, 1, true>(jobs, njobs, total_ctas, image, coef, st); }
-    else launch_fwd<true, 1, false>(jobs, njobs, total_ctas, image, coef, st);
+    if (first) { if (ncomp == 3) launch_fwd<true, 3, true>(jobs, njobs, total_ctas, src_type, image, coef, st); else launch_fwd<true, 1, true>(jobs, njobs, total_ctas, src_type, image, coef, st); }
+    else launch_fwd<true, 1, false>(jobs, njobs, total_ctas, src_type, image, coef, st);
   } else {
-    if (first) { if (ncomp == 3) launch_fwd<false, 3, true>(jobs, njobs, total_ctas, image, coef, st); else launch_fwd<false, 1, true>(jobs, njobs, total_ctas, image, coef, st); }
-    else launch_fwd<false, 1, false>(jobs, njobs, total_ctas, image, coef, st);
+    if (first) { if (ncomp == 3) launch_fwd<false, 3, true>(jobs, njobs, total_ctas, src_type, image, coef, st); else launch_fwd<false, 1, true>(jobs, njobs, total_ctas, src_type, image, coef, st); }
+    else launch_fwd<false, 1, false>(jobs, njobs, total_ctas, src_type, image, coef, st);
   }
 }
 

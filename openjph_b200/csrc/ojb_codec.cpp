@@ -135,7 +135,7 @@ void CodecBase::build_dwt_jobs(bool forward) {
         uint32_t gi, n;
         if (stream) {
           gi = j.first ? (k == 3 ? 0u : 1u) : 2u;
-          dwt_stream_tiling(j.x0, j.y0, j.w, j.h, P.reversible(), j.tiles_x, j.tiles_y, n);
+          dwt_stream_tiling(j.x0, j.y0, j.w, j.h, P.reversible(), j.tiles_x, j.tiles_y, j.chunk_rows, n);
         } else {
           gi = 3;
           dwt_tiling(j.x0, j.y0, j.w, j.h, j.tiles_x, j.tiles_y);
@@ -279,7 +279,7 @@ size_t Encoder::encode(const void* const* planes, const uint32_t* strides, bool 
     for (const JobGroup& g : jobs[li]) {
       if (g.stream)
         launch_dwt_fwd_stream(d_jobs.as<DwtJob>() + g.dev_off, (uint32_t)g.jobs.size(), g.ctas, P.reversible(), g.ncomp,
-                              g.first, d_image.p, d_coef.as<uint32_t>(), stream);
+                              g.first, img_type, d_image.p, d_coef.as<uint32_t>(), stream);
       else
         launch_dwt_fwd(d_jobs.as<DwtJob>() + g.dev_off, (uint32_t)g.jobs.size(), g.ctas, P.reversible(), g.ncomp,
                        d_image.p, d_coef.as<uint32_t>(), stream);
@@ -422,12 +422,16 @@ size_t Encoder::encode(const void* const* planes, const uint32_t* strides, bool 
   CK(cudaMemcpyAsync(d_hdr.p, h_hdr.p, blob.size(), cudaMemcpyHostToDevice, stream));
   h_pieces.reserve(pieces.size() * sizeof(CopyPiece)); d_pieces.reserve(pieces.size() * sizeof(CopyPiece));
   CopyPiece* cp = h_pieces.as<CopyPiece>();
-  for (size_t i = 0; i < pieces.size(); ++i) { cp[i].src_off = pieces[i].src; cp[i].dst_off = pieces[i].dst; cp[i].len = pieces[i].len; cp[i].src_sel = 1; }
+  uint32_t max_piece = 0;
+  for (size_t i = 0; i < pieces.size(); ++i) {
+    cp[i].src_off = pieces[i].src; cp[i].dst_off = pieces[i].dst; cp[i].len = pieces[i].len; cp[i].src_sel = 1;
+    max_piece = std::max(max_piece, cp[i].len);
+  }
   CK(cudaMemcpyAsync(d_pieces.p, h_pieces.p, pieces.size() * sizeof(CopyPiece), cudaMemcpyHostToDevice, stream));
   if (nb) CK(cudaMemcpyAsync(d_dst.p, h_dst.p, (size_t)nb * 8, cudaMemcpyHostToDevice, stream));
   launch_gather_blocks(d_blocks.as<EncBlock>(), d_results.as<EncResult>(), d_dst.as<uint64_t>(), nb,
                        d_slots.as<uint8_t>(), dev_out, stream);
-  launch_assemble(d_pieces.as<CopyPiece>(), (uint32_t)pieces.size(), d_slots.as<uint8_t>(), d_hdr.as<uint8_t>(), dev_out, stream);
+  launch_assemble(d_pieces.as<CopyPiece>(), (uint32_t)pieces.size(), max_piece, d_slots.as<uint8_t>(), d_hdr.as<uint8_t>(), dev_out, stream);
   last_launches += 2;
   mark(6);
   if (!out_on_device) CK(cudaMemcpyAsync(out, dev_out, total, cudaMemcpyDeviceToHost, stream));

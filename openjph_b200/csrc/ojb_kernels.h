@@ -23,9 +23,10 @@ void launch_dwt_inv(const DwtJob* jobs, uint32_t njobs, uint32_t total_ctas, boo
                     uint32_t max_ncomp, void* image, uint32_t* coef, cudaStream_t st);
 // register-streaming fast path (dwt_stream.cu) for resolutions of at least 2x2
 void dwt_stream_tiling(uint32_t x0, uint32_t y0, uint32_t w, uint32_t h, bool reversible,
-                       uint32_t& strips, uint32_t& chunks, uint32_t& ctas);
+                       uint32_t& strips, uint32_t& chunks, uint32_t& chunk_rows, uint32_t& ctas);
 void launch_dwt_fwd_stream(const DwtJob* jobs, uint32_t njobs, uint32_t total_ctas, bool reversible,
-                           uint32_t ncomp, bool first, const void* image, uint32_t* coef, cudaStream_t st);
+                           uint32_t ncomp, bool first, uint32_t src_type, const void* image, uint32_t* coef,
+                           cudaStream_t st);
 void launch_dwt_inv_stream(const DwtJob* jobs, uint32_t njobs, uint32_t total_ctas, bool reversible,
                            uint32_t ncomp, bool first, void* image, uint32_t* coef, cudaStream_t st);
 // CTA tiling of a w x h resolution at origin (x0,y0): number of tiles across / down
@@ -34,7 +35,7 @@ void dwt_tiling(uint32_t x0, uint32_t y0, uint32_t w, uint32_t h, uint32_t& tx, 
 // codestream assembly (assemble.cu): copy pieces (block heads/tails, header bytes) to their
 // final offsets
 struct CopyPiece { uint64_t src_off; uint64_t dst_off; uint32_t len; uint32_t src_sel; };  // src_sel 0: slots, 1: headers
-void launch_assemble(const CopyPiece* pieces, uint32_t npieces, const uint8_t* slots,
+void launch_assemble(const CopyPiece* pieces, uint32_t npieces, uint32_t max_len, const uint8_t* slots,
                      const uint8_t* headers, uint8_t* out, cudaStream_t st);
 // block pieces computed on the device from per-block results + destination offsets
 void launch_gather_blocks(const EncBlock* blocks, const EncResult* results, const uint64_t* dst_off,
