@@ -222,15 +222,22 @@ def main():
     pool = ThreadPoolExecutor(NW)
 
     def timed(fn_name, steps, nworkers):
+        """`steps` steps of `nworkers` frames each; with several workers every worker streams its own
+        `steps` frames back to back (no per-step barrier: frames of one worker overlap the other
+        workers' copies and host phases, as in a continuous stream)"""
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for _ in range(steps):
-            if nworkers == 1:
+        if nworkers == 1:
+            for _ in range(steps):
                 getattr(workers[0], fn_name)()
-            else:
-                list(pool.map(lambda w: getattr(w, fn_name)(), workers[:nworkers]))
+        else:
+            def loop(w):
+                f = getattr(w, fn_name)
+                for _ in range(steps):
+                    f()
+            list(pool.map(loop, workers[:nworkers]))
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if dist is not None:
@@ -258,6 +265,8 @@ def main():
     for _ in range(max(1, min(a.warmup, 2))):
         list(pool.map(lambda w: w.e2e(), workers))
     dt_e2e = timed("e2e", a.steps, NW)
+    te2 = (C.c_float * 8)(); td2 = (C.c_float * 8)()
+    L.ojb_enc_timings(enc, te2); L.ojb_dec_timings(dec, td2)
     sampler.stop_flag = True; sampler.join(timeout=2)
     # final gather of the per-rank codestream sizes (the only collective on the path)
     sizes = [cs_len]
@@ -285,6 +294,8 @@ def main():
     names_d = ("h2d", "host_parse", "ht_decode", "dwt_inv", "d2h_image", "_5", "_6", "host_ms")
     stage_e = {k: round(float(v), 4) for k, v in zip(names_e, te)}
     stage_d = {k: round(float(v), 4) for k, v in zip(names_d, td) if not k.startswith("_")}
+    e2e_e = {k: round(float(v), 3) for k, v in zip(names_e, te2)}
+    e2e_d = {k: round(float(v), 3) for k, v in zip(names_d, td2) if not k.startswith("_")}
     # dominant kernel = the slowest device stage of the resident step
     samples = W * H * NC
     cand = {"ht_encode": (stage_e["ht_encode"], 4 * samples + cs_len), "ht_decode": (stage_d["ht_decode"], 4 * samples + cs_len),
@@ -295,7 +306,7 @@ def main():
     roof = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
             "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": cand[dom][1], "ms_per_launch": cand[dom][0]}
-    cfg.update({"frames_per_step": NW * a.gpus, "frames_in_flight_per_gpu": NW, "host_affinity": affinity,
+    cfg.update({"frames_per_step": NW * a.gpus, "frames_in_flight_per_gpu": NW, "host_affinity": affinity, "e2e_stages_encode_ms": e2e_e, "e2e_stages_decode_ms": e2e_d,
                 "serial_ms_per_frame": round(dt_serial / a.steps * 1e3, 3),
                 "serial_Mpixels_per_s": round(W * H * a.steps / dt_serial / 1e6, 1),
                 "stages_encode_ms": stage_e, "stages_decode_ms": stage_d, "codestream_bytes": sizes,

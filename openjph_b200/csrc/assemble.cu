@@ -72,7 +72,30 @@ assemble_kernel(const CopyPiece* __restrict__ pieces, uint32_t npieces, const ui
   warp_copy(out + p.dst_off + c0, src, n, lane);
 }
 
+// small control-plane transfers (block lengths, offsets, header bytes, block descriptors) between
+// pinned host memory and the device, done by the SMs over the mapped host pointer: they never queue
+// on a copy engine behind another frame's image-sized transfer
+__global__ void __launch_bounds__(256)
+ctrl_copy_kernel(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, size_t bytes)
+{
+  const size_t n16 = bytes >> 4;
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+  const uint4* s = reinterpret_cast<const uint4*>(src);
+  uint4* d = reinterpret_cast<uint4*>(dst);
+  for (size_t i = tid; i < n16; i += nth) d[i] = s[i];
+  for (size_t i = (n16 << 4) + tid; i < bytes; i += nth) dst[i] = src[i];
+}
+
 } // namespace
+
+void launch_ctrl_copy(void* dst, const void* src, size_t bytes, cudaStream_t st)
+{
+  if (bytes == 0) return;
+  size_t ctas = (bytes / 16 + 255) / 256;
+  if (ctas < 1) ctas = 1;
+  if (ctas > 592) ctas = 592;
+  OJB_LAUNCH(ctrl_copy_kernel, dim3((unsigned)ctas), dim3(256), 0, st, (uint8_t*)dst, (const uint8_t*)src, bytes);
+}
 
 void launch_gather_blocks(const EncBlock* blocks, const EncResult* results, const uint64_t* dst_off,
                           uint32_t nblocks, const uint8_t* slots, uint8_t* out, cudaStream_t st)

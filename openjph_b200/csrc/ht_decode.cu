@@ -61,13 +61,18 @@ __device__ __forceinline__ void mel_fill(MelDec& m) {       // MSB first; needs 
   }
   uint32_t t = 0; int nb = 0;
   bool us = m.unstuff;
-  #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const uint32_t d = (val >> (8 * i)) & 0xFFu;
-    const int n = 8 - (us ? 1 : 0);
-    t = (t << n) | (d & ((1u << n) - 1u));
-    nb += n;
-    us = (d == 0xFF);
+  uint32_t ff = val & (val >> 1); ff &= ff >> 2; ff &= ff >> 4;      // bit 8i set <=> byte i == 0xFF
+  if (!us && (ff & 0x00010101u) == 0) {                              // no stuffed byte among the four
+    t = __byte_perm(val, 0, 0x0123); nb = 32; us = (ff >> 24) & 1u;
+  } else {
+    #pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t d = (val >> (8 * i)) & 0xFFu;
+      const int n = 8 - (us ? 1 : 0);
+      t = (t << n) | (d & ((1u << n) - 1u));
+      nb += n;
+      us = (d == 0xFF);
+    }
   }
   m.unstuff = us;
   m.tmp |= (unsigned long long)t << (64 - nb - m.bits);
@@ -93,6 +98,7 @@ __device__ __forceinline__ int mel_next_run(MelDec& m) {
 
 struct RevDec {               // backward-growing stream (VLC, MRP)
   const uint8_t* p; int size; unsigned long long tmp; uint32_t bits; bool unstuff;
+  uint32_t nxt;               // step 1: the next four bytes, requested one refill ahead
 };
 // byte-wise refill (refinement passes, lane 0 only)
 __device__ __forceinline__ void rev_fill(RevDec& v) {       // LSB first
@@ -110,20 +116,29 @@ __device__ __forceinline__ void rev_fill(RevDec& v) {       // LSB first
 __device__ __forceinline__ void rev_fill32(RevDec& v) {
   if (v.bits > 32) return;
   uint32_t val = 0;                                           // bytes p-3 .. p, byte p in the MSB
-  if (v.size > 3) { val = load_le32_any(v.p - 3); v.p -= 4; v.size -= 4; }
-  else {
+  if (v.size > 3) {
+    val = v.nxt; v.p -= 4; v.size -= 4;
+    if (v.size > 3) v.nxt = load_le32_any(v.p - 3);           // lands while these 32 bits are decoded
+  } else {
     int i = 24;
     while (v.size > 0) { val |= (uint32_t)(*v.p--) << i; --v.size; i -= 8; }
   }
   uint32_t t = 0, nb = 0;
   bool us = v.unstuff;
-  #pragma unroll
-  for (int i = 3; i >= 0; --i) {
-    const uint32_t d = (val >> (8 * i)) & 0xFFu;
-    const uint32_t n = 8 - ((us && (d & 0x7F) == 0x7F) ? 1u : 0u);
-    t |= (d & ((1u << n) - 1u)) << nb;
-    nb += n;
-    us = d > 0x8F;
+  // a byte whose low 7 bits are 0x7F and whose predecessor (the byte consumed before it) is > 0x8F
+  // carries 7 bits; all four bytes are tested at once and the byte loop runs only when one does
+  const uint32_t pv = (val >> 8) | (us ? 0x90000000u : 0u);
+  if (((((val & 0x7F7F7F7Fu) + 0x01010101u) & pv & ((pv & 0x70707070u) + 0x70707070u)) & 0x80808080u) == 0) {
+    t = __byte_perm(val, 0, 0x0123); nb = 32; us = (val & 0xFFu) > 0x8Fu;
+  } else {
+    #pragma unroll
+    for (int i = 3; i >= 0; --i) {
+      const uint32_t d = (val >> (8 * i)) & 0xFFu;
+      const uint32_t n = 8 - ((us && (d & 0x7F) == 0x7F) ? 1u : 0u);
+      t |= (d & ((1u << n) - 1u)) << nb;
+      nb += n;
+      us = d > 0x8F;
+    }
   }
   v.unstuff = us;
   v.tmp |= (unsigned long long)t << v.bits;
@@ -168,6 +183,8 @@ ht_dec_step1_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
     vlc.bits = 4 - (((vlc.tmp & 7) == 7) ? 1u : 0u);
     vlc.unstuff = (d | 0xF) > 0x8F;
   }
+  vlc.nxt = 0;
+  if (vlc.size > 3) vlc.nxt = load_le32_any(vlc.p - 3);
   int run = mel_next_run(mel);
 
   const uint32_t width = blk.w, height = blk.h;
@@ -230,8 +247,8 @@ ht_dec_step1_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
       const uint32_t kap = (y == 0) ? 1u : 0u;
       uint32_t u0 = kap + (ent & 7) + (suf & ~(0xFFu << len));
       uint32_t u1 = kap + (ent >> 3) + (suf >> len);
-      rrow[q] = (t[0] & 0xFFFF) | (u0 << 16);
-      if (q + 1 < qstride) rrow[q + 1] = (t[1] & 0xFFFF) | (u1 << 16);
+      // qstride is even and the scratch offset a multiple of 4 words: one 8-byte store per pair
+      *reinterpret_cast<uint2*>(rrow + q) = make_uint2((t[0] & 0xFFFF) | (u0 << 16), (t[1] & 0xFFFF) | (u1 << 16));
     }
     prev_bl = cur_bl; prev_br = cur_br;
   }
@@ -247,12 +264,11 @@ __device__ __forceinline__ uint32_t load_u32_unaligned(const uint8_t* p) {
   return __funnelshift_r(lo, a[1], sh);
 }
 
-// fetch 32 bits at bit position pos from a word buffer (words beyond nwords read as all ones)
+// fetch 32 bits at bit position pos from a word buffer of nwords words followed by two words of
+// ones (an exhausted MagSgn stream reads as 0xFF bytes)
 __device__ __forceinline__ uint32_t fetch_bits(const uint32_t* buf, uint32_t pos, uint32_t nwords) {
-  uint32_t wi = pos >> 5, sh = pos & 31;
-  uint32_t lo = wi < nwords ? buf[wi] : 0xFFFFFFFFu;
-  uint32_t hi = wi + 1 < nwords ? buf[wi + 1] : 0xFFFFFFFFu;
-  return __funnelshift_r(lo, hi, sh);
+  const uint32_t wi = min(pos >> 5, nwords);
+  return __funnelshift_r(buf[wi], buf[wi + 1], pos & 31);
 }
 
 __device__ __forceinline__ uint32_t to_output(uint32_t sm, uint32_t mode, uint32_t shift, float delta) {
@@ -268,6 +284,7 @@ __device__ __forceinline__ uint32_t to_output(uint32_t sm, uint32_t mode, uint32
 // simple byte-wise readers for the refinement passes (lane 0 only)
 struct FwdBits {              // SPP: forward, 0 fed when exhausted, 7-bit byte after 0xFF
   const uint8_t* p; int size; unsigned long long tmp; uint32_t bits; bool unstuff;
+  uint32_t nxt;               // step 1: the next four bytes, requested one refill ahead
 };
 __device__ __forceinline__ void fwd_fill(FwdBits& f) {
   while (f.bits <= 56) {
@@ -471,13 +488,16 @@ ht_dec_step2_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
     // tail: remaining bits + ones (an exhausted MagSgn stream reads as 0xFF bytes)
     const uint32_t ms_words = (nbits_total >> 5) + 1;
     if (lane == 0) msbuf[nbits_total >> 5] = carry_word | ((nbits_total & 31) ? (0xFFFFFFFFu << (nbits_total & 31)) : 0xFFFFFFFFu);
+    if (lane < 2) msbuf[ms_words + lane] = 0xFFFFFFFFu;
     __syncwarp();
 
     // ---- quad rows
     uint32_t pos = 0;                       // MagSgn bit position
     uint32_t pv1 = 0, pv3 = 0;              // v_n of bottom-left / bottom-right sample of the row above
+    uint32_t r_next = (lane < nq) ? rec[lane] : 0;
     for (uint32_t y = 0; y < height; y += 2) {
-      const uint32_t r = (lane < nq) ? rec[(size_t)(y >> 1) * qstride + lane] : 0;
+      const uint32_t r = r_next;            // the next row's records are requested a row ahead
+      if (y + 2 < height) r_next = (lane < nq) ? rec[(size_t)((y >> 1) + 1) * qstride + lane] : 0;
       const uint32_t inf = r & 0xFFFF, uq = r >> 16;
       const uint32_t rho = (inf >> 4) & 15u;
       uint32_t Uq;
@@ -499,14 +519,17 @@ ht_dec_step2_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
       #pragma unroll
       for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(FULL, incl, d); if ((int)lane >= d) incl += o; }
       const uint32_t tot = __shfl_sync(FULL, incl, 31);
-      uint32_t bp = pos + incl - mine;
-      uint32_t out[4], vn[4];
+      const uint32_t bp = pos + incl - mine;
+      uint32_t out[4], vn[4], msw[4];
+      msw[0] = fetch_bits(msbuf, bp, ms_words);                      // four independent fetches
+      msw[1] = fetch_bits(msbuf, bp + m[0], ms_words);
+      msw[2] = fetch_bits(msbuf, bp + m[0] + m[1], ms_words);
+      msw[3] = fetch_bits(msbuf, bp + m[0] + m[1] + m[2], ms_words);
       #pragma unroll
       for (int i = 0; i < 4; ++i) {
         out[i] = 0; vn[i] = 0;
         if ((rho >> i) & 1u) {
-          const uint32_t ms = fetch_bits(msbuf, bp, ms_words);
-          bp += m[i];
+          const uint32_t ms = msw[i];
           uint32_t v = ms & ((1u << m[i]) - 1u);
           v |= ((e1 >> i) & 1u) << m[i];
           v |= 1u;

@@ -27,8 +27,7 @@
 namespace ojb {
 
 #define ENC_WARPS 4
-#define ENC_MS_WORDS 160      // MagSgn row buffer: 32 quads x 4 x 31 bits + carry, 5 words / lane
-#define ENC_MS_PER_LANE 5
+#define ENC_MS_WORDS 160      // MagSgn row buffer: 32 quads x 4 x 31 bits + carry
 #define ENC_VLC_WORDS 32      // VLC row buffer: 16 pairs x 30 bits + carry
 #define ENC_MEL_BYTES 256
 
@@ -93,25 +92,21 @@ __device__ __forceinline__ uint32_t ff_bytes(uint32_t w) {
   uint32_t t = w & (w >> 1); t &= t >> 2; t &= t >> 4; return t & 0x01010101u;
 }
 
-// Insert a zero bit at bit position P of the row buffer (all lanes cooperate; lane owns
-// `per` consecutive words).  Bits at positions >= P move up by one.
-__device__ __forceinline__ void insert_zero_bit(uint32_t* buf, uint32_t P, uint32_t nwords,
-                                                uint32_t lane, uint32_t per) {
-  uint32_t base = lane * per;
-  uint32_t old[ENC_MS_PER_LANE];
-  uint32_t below = (base > 0 && base - 1 < nwords) ? buf[base - 1] : 0;
-  #pragma unroll
-  for (uint32_t i = 0; i < ENC_MS_PER_LANE; ++i)
-    old[i] = (i < per && base + i < nwords) ? buf[base + i] : 0;
-  __syncwarp();
-  uint32_t pw = P >> 5, pb = P & 31;
-  #pragma unroll
-  for (uint32_t i = 0; i < ENC_MS_PER_LANE; ++i) {
-    uint32_t wi = base + i;
-    if (i < per && wi < nwords && wi >= pw) {
-      uint32_t w = old[i], prev = (i == 0) ? below : old[i - 1], nw;
+// Insert a zero bit at bit position P of the row buffer (all lanes cooperate; in step k lane l
+// handles word 32k + l).  Bits at positions >= P move up by one.
+__device__ __forceinline__ void insert_zero_bit(uint32_t* buf, uint32_t P, uint32_t nwords, uint32_t lane) {
+  const uint32_t pw = P >> 5, pb = P & 31;
+  uint32_t carry = 0;                                  // word that precedes this step's 32 words
+  for (uint32_t wb = pw & ~31u; wb < nwords; wb += 32) {
+    const uint32_t wi = wb + lane;
+    const uint32_t w = (wi < nwords) ? buf[wi] : 0u;
+    uint32_t prev = __shfl_up_sync(FULL, w, 1);
+    if (lane == 0) prev = carry;
+    carry = __shfl_sync(FULL, w, 31);
+    if (wi < nwords && wi >= pw) {
+      uint32_t nw;
       if (wi > pw) nw = (w << 1) | (prev >> 31);
-      else { uint32_t lowmask = (1u << pb) - 1u; nw = (w & lowmask) | ((w & ~lowmask) << 1); }
+      else { const uint32_t lowmask = (1u << pb) - 1u; nw = (w & lowmask) | ((w & ~lowmask) << 1); }
       buf[wi] = nw;
     }
   }
@@ -127,33 +122,30 @@ __device__ __forceinline__ uint32_t ms_stuff(uint32_t* buf, uint32_t nbits, int&
   if (start < 0) {
     if (!prev_ff) start = 0;
     else if (nbits >= 7) {
-      insert_zero_bit(buf, 7, (nbits >> 5) + 2, lane, ENC_MS_PER_LANE);
+      insert_zero_bit(buf, 7, (nbits >> 5) + 2, lane);
       nbits++; start = 1;
     } else return nbits;                   // still pending
   }
   for (;;) {
     if (nbits < 15) break;
-    uint32_t jlim = (nbits - 7) / 8 - 1;   // last byte index whose successor has its 7 bits
-    uint32_t nwords = (nbits + 31) >> 5;
-    uint32_t base = lane * ENC_MS_PER_LANE;
-    uint32_t found = 0xFFFFFFFFu;
-    #pragma unroll
-    for (uint32_t i = 0; i < ENC_MS_PER_LANE; ++i) {
-      uint32_t wi = base + i;
-      if (wi < nwords && found == 0xFFFFFFFFu) {
-        uint32_t f = ff_bytes(buf[wi]);
-        while (f) {
-          uint32_t b = (uint32_t)(__ffs((int)f) - 1) >> 3;
-          uint32_t j = wi * 4 + b;
-          if (j >= (uint32_t)start && j <= jlim) { found = j; break; }
-          f &= f - 1;
-        }
+    const uint32_t jlim = (nbits - 7) / 8 - 1;   // last byte index whose successor has its 7 bits
+    // first 0xFF byte j with start <= j <= jlim: 32 words per step, lowest lane wins
+    uint32_t j = 0xFFFFFFFFu;
+    for (uint32_t wb = ((uint32_t)start >> 2) & ~31u; wb * 4 <= jlim; wb += 32) {
+      const uint32_t wi = wb + lane, lo = wi * 4;
+      uint32_t f = (lo <= jlim) ? ff_bytes(buf[wi]) : 0u;
+      if ((uint32_t)start > lo) f &= ((uint32_t)start - lo >= 4) ? 0u : (0xFFFFFFFFu << (8 * ((uint32_t)start - lo)));
+      if (jlim < lo + 3 && lo <= jlim) f &= 0xFFFFFFFFu >> (8 * (lo + 3 - jlim));
+      const uint32_t vote = __ballot_sync(FULL, f != 0);
+      if (vote) {
+        const uint32_t srcl = (uint32_t)__ffs((int)vote) - 1u;
+        const uint32_t fw = __shfl_sync(FULL, f, srcl);
+        j = (wb + srcl) * 4 + (((uint32_t)__ffs((int)fw) - 1u) >> 3);
+        break;
       }
     }
-    uint32_t vote = __ballot_sync(FULL, found != 0xFFFFFFFFu);
-    if (vote == 0) break;
-    uint32_t j = __shfl_sync(FULL, found, __ffs((int)vote) - 1);
-    insert_zero_bit(buf, 8 * (j + 1) + 7, nwords + 1, lane, ENC_MS_PER_LANE);
+    if (j == 0xFFFFFFFFu) break;
+    insert_zero_bit(buf, 8 * (j + 1) + 7, ((nbits + 31) >> 5) + 1, lane);
     nbits++; start = (int)j + 2;
   }
   if (nbits >= 7) start = max(start, (int)((nbits - 7) / 8));   // bytes <= jlim are settled
@@ -167,22 +159,23 @@ __device__ __forceinline__ uint32_t vlc_stuff(uint32_t* buf, uint32_t nbits, int
                                               uint32_t lane) {
   for (;;) {
     if (nbits < 7) break;
-    uint32_t jlim = (nbits - 7) / 8;       // last byte index that has 7 bits
-    uint32_t w = buf[lane];
-    uint32_t below = lane ? buf[lane - 1] : (prev << 24);
-    uint32_t found = 0xFFFFFFFFu;
-    #pragma unroll
-    for (uint32_t b = 0; b < 4; ++b) {
-      uint32_t j = lane * 4 + b;
-      uint32_t cur = (w >> (8 * b)) & 0xFFu;
-      uint32_t pv = b ? ((w >> (8 * b - 8)) & 0xFFu) : (below >> 24);
-      if (found == 0xFFFFFFFFu && j >= (uint32_t)start && j <= jlim && pv > 0x8F && (cur & 0x7F) == 0x7F)
-        found = j;
-    }
-    uint32_t vote = __ballot_sync(FULL, found != 0xFFFFFFFFu);
+    const uint32_t jlim = (nbits - 7) / 8;       // last byte index that has 7 bits
+    const uint32_t w = buf[lane];
+    uint32_t below = __shfl_up_sync(FULL, w, 1);
+    if (lane == 0) below = prev << 24;
+    // all four bytes at once: flag (bit 7 of the byte) where the low 7 bits are 0x7F and the
+    // preceding byte is > 0x8F (bit 7 set and any of bits 6..4 set)
+    const uint32_t pv = (w << 8) | (below >> 24);
+    uint32_t f = (((w & 0x7F7F7F7Fu) + 0x01010101u) & pv & (((pv & 0x70707070u) + 0x70707070u))) & 0x80808080u;
+    const uint32_t lo = lane * 4;
+    if ((uint32_t)start > lo) f &= ((uint32_t)start - lo >= 4) ? 0u : (0xFFFFFFFFu << (8 * ((uint32_t)start - lo)));
+    if (jlim < lo + 3) f &= (jlim < lo) ? 0u : (0xFFFFFFFFu >> (8 * (lo + 3 - jlim)));
+    const uint32_t vote = __ballot_sync(FULL, f != 0);
     if (vote == 0) break;
-    uint32_t j = __shfl_sync(FULL, found, __ffs((int)vote) - 1);
-    insert_zero_bit(buf, 8 * j + 7, ENC_VLC_WORDS, lane, 1);
+    const uint32_t srcl = (uint32_t)__ffs((int)vote) - 1u;
+    const uint32_t fw = __shfl_sync(FULL, f, srcl);
+    const uint32_t j = srcl * 4 + (((uint32_t)__ffs((int)fw) - 1u) >> 3);
+    insert_zero_bit(buf, 8 * j + 7, ENC_VLC_WORDS, lane);
     nbits++; start = (int)j + 1;
   }
   if (nbits >= 7) start = max(start, (int)((nbits - 7) / 8) + 1);
@@ -371,20 +364,21 @@ ht_encode_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
       uint32_t nw = nbits >> 5;
       if (ms_words + nw + vl_words + 24 >= slot_words) { overflow = true; break; }
       uint32_t* dst = reinterpret_cast<uint32_t*>(slot) + ms_words;
-      for (uint32_t i = lane; i < nw; i += 32) dst[i] = ms_buf[i];
-      uint32_t carry = ms_buf[nw];
-      uint32_t lastw = nw ? ms_buf[nw - 1] : 0;
+      const uint32_t carry = ms_buf[nw];
+      const uint32_t lastw = nw ? ms_buf[nw - 1] : 0;
       __syncwarp();
-      uint32_t used = (nbits + 31) >> 5;
-      for (uint32_t i = lane; i <= used + 1 && i < ENC_MS_WORDS; i += 32) ms_buf[i] = 0;
-      __syncwarp();
+      const uint32_t used = (nbits + 31) >> 5;
+      ms_cbits = nbits & 31;
+      // flush the complete words and clear the buffer in one sweep; word 0 restarts with the carry
+      for (uint32_t i = lane; i <= used + 1 && i < ENC_MS_WORDS; i += 32) {
+        if (i < nw) dst[i] = ms_buf[i];
+        ms_buf[i] = (i == 0) ? (carry & ((ms_cbits ? (1u << ms_cbits) : 1u) - 1u)) : 0u;
+      }
       if (nw) {
         ms_last = lastw >> 24; ms_words += nw;
         ms_start -= (int)(4 * nw);
         if (ms_start < 0) { ms_start = -1; ms_prev_ff = (ms_last == 0xFF); }
       }
-      ms_cbits = nbits & 31;
-      if (lane == 0) ms_buf[0] = carry & ((ms_cbits ? (1u << ms_cbits) : 1u) - 1u);
       __syncwarp();
     }
     // ---- VLC: same, written backward from the end of the slot
@@ -393,15 +387,13 @@ ht_encode_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
       uint32_t nw = nbits >> 5;
       if (ms_words + vl_words + nw + 24 >= slot_words) { overflow = true; break; }
       uint32_t* end = reinterpret_cast<uint32_t*>(slot) + slot_words;
-      if (lane < nw) end[-(int)(vl_words + lane) - 1] = bytes_rev(vl_buf[lane]);
-      uint32_t carry = vl_buf[nw];
-      uint32_t lastw = nw ? vl_buf[nw - 1] : 0;
-      __syncwarp();
-      vl_buf[lane] = 0;
-      __syncwarp();
-      if (nw) { vl_prev = lastw >> 24; vl_words += nw; vl_start -= (int)(4 * nw); }
+      const uint32_t mine = vl_buf[lane];
+      const uint32_t carry = __shfl_sync(FULL, mine, nw & 31);             // nw <= 31 here
+      const uint32_t lastw = __shfl_sync(FULL, mine, (nw ? nw - 1 : 0) & 31);
+      if (lane < nw) end[-(int)(vl_words + lane) - 1] = bytes_rev(mine);
       vl_cbits = nbits & 31;
-      if (lane == 0) vl_buf[0] = carry & ((vl_cbits ? (1u << vl_cbits) : 1u) - 1u);
+      vl_buf[lane] = (lane == 0) ? (carry & ((vl_cbits ? (1u << vl_cbits) : 1u) - 1u)) : 0u;
+      if (nw) { vl_prev = lastw >> 24; vl_words += nw; vl_start -= (int)(4 * nw); }
       __syncwarp();
     }
 

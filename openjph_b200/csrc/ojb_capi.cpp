@@ -351,7 +351,8 @@ int ojb_decode_blocks(const uint8_t* bytes, uint64_t n_bytes, ojb_block_desc* de
       d.missing_msbs = (uint8_t)desc[i].missing_msbs; d.num_passes = (uint8_t)desc[i].num_passes;
       d.K_max = (uint8_t)(desc[i].missing_msbs + 1); d.flags = desc[i].causal ? 1 : 0;
       uint32_t nq = (d.w + 1u) / 2, qs = (nq + 1) & ~1u, nqr = (d.h + 1u) / 2;
-      d.scratch_off = scratch; scratch += (size_t)qs * nqr + (d.len1 + 3) / 4 + 4;
+      scratch = (scratch + 3) & ~(size_t)3;
+      d.scratch_off = scratch; scratch += (size_t)qs * nqr + (((d.len1 + 3) / 4 + 4 + 3) & ~3u);
       max_len1 = std::max(max_len1, d.len1);
     }
     d_b.reserve(n * sizeof(DecBlock)); d_o.reserve((n_words + 64) * 4); d_sc.reserve((scratch + 64) * 4); d_st.reserve(n * 4 + 16);

@@ -291,8 +291,9 @@ size_t Encoder::encode(const void* const* planes, const uint32_t* strides, bool 
                    d_results.as<EncResult>(), d_tables_enc.as<uint16_t>(), d_status.as<uint32_t>(), stream);
   ++last_launches;
   mark(3);
-  if (nb) CK(cudaMemcpyAsync(h_results.p, d_results.p, (size_t)nb * sizeof(EncResult), cudaMemcpyDeviceToHost, stream));
-  CK(cudaMemcpyAsync(h_status.p, d_status.p, 16, cudaMemcpyDeviceToHost, stream));
+  if (nb) launch_ctrl_copy(h_results.p, d_results.p, (size_t)nb * sizeof(EncResult), stream);
+  launch_ctrl_copy(h_status.p, d_status.p, 16, stream);
+  last_launches += nb ? 2 : 1;
   mark(4);
   CK(cudaStreamSynchronize(stream));
   auto host_t0 = std::chrono::steady_clock::now();
@@ -419,7 +420,7 @@ size_t Encoder::encode(const void* const* planes, const uint32_t* strides, bool 
   host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
   mark(5);
   d_hdr.reserve(blob.size() + 64);
-  CK(cudaMemcpyAsync(d_hdr.p, h_hdr.p, blob.size(), cudaMemcpyHostToDevice, stream));
+  launch_ctrl_copy(d_hdr.p, h_hdr.p, blob.size(), stream);
   h_pieces.reserve(pieces.size() * sizeof(CopyPiece)); d_pieces.reserve(pieces.size() * sizeof(CopyPiece));
   CopyPiece* cp = h_pieces.as<CopyPiece>();
   uint32_t max_piece = 0;
@@ -427,8 +428,9 @@ size_t Encoder::encode(const void* const* planes, const uint32_t* strides, bool 
     cp[i].src_off = pieces[i].src; cp[i].dst_off = pieces[i].dst; cp[i].len = pieces[i].len; cp[i].src_sel = 1;
     max_piece = std::max(max_piece, cp[i].len);
   }
-  CK(cudaMemcpyAsync(d_pieces.p, h_pieces.p, pieces.size() * sizeof(CopyPiece), cudaMemcpyHostToDevice, stream));
-  if (nb) CK(cudaMemcpyAsync(d_dst.p, h_dst.p, (size_t)nb * 8, cudaMemcpyHostToDevice, stream));
+  launch_ctrl_copy(d_pieces.p, h_pieces.p, pieces.size() * sizeof(CopyPiece), stream);
+  if (nb) launch_ctrl_copy(d_dst.p, h_dst.p, (size_t)nb * 8, stream);
+  last_launches += (blob.size() ? 1 : 0) + (pieces.empty() ? 0 : 1) + (nb ? 1 : 0);
   launch_gather_blocks(d_blocks.as<EncBlock>(), d_results.as<EncResult>(), d_dst.as<uint64_t>(), nb,
                        d_slots.as<uint8_t>(), dev_out, stream);
   launch_assemble(d_pieces.as<CopyPiece>(), (uint32_t)pieces.size(), max_piece, d_slots.as<uint8_t>(), d_hdr.as<uint8_t>(), dev_out, stream);
@@ -621,21 +623,22 @@ uint32_t Decoder::decode(void* const* planes, const uint32_t* strides, bool plan
     d.len1 = cb.pass_len[0]; d.len2 = cb.pass_len[1];
     d.num_passes = cb.num_passes; d.missing_msbs = cb.missing_msbs; d.data_off = cb.data_off;
     uint32_t nq = (d.w + 1u) / 2, qs = (nq + 1) & ~1u, nqr = (d.h + 1u) / 2;
+    scratch = (scratch + 3) & ~(size_t)3;
     d.scratch_off = scratch;
-    scratch += (size_t)qs * nqr + (d.len1 + 3) / 4 + 4;
+    scratch += (size_t)qs * nqr + (((d.len1 + 3) / 4 + 4 + 3) & ~3u);
     max_len1 = std::max(max_len1, d.len1);
     hd[b] = d;
   }
   d_scratch.reserve((scratch + 64) * 4);
   host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
   mark(2);
-  if (nb) CK(cudaMemcpyAsync(d_dec.p, h_dec.p, (size_t)nb * sizeof(DecBlock), cudaMemcpyHostToDevice, stream));
+  if (nb) { launch_ctrl_copy(d_dec.p, h_dec.p, (size_t)nb * sizeof(DecBlock), stream); ++last_launches; }
   launch_ht_decode(d_dec.as<DecBlock>(), nb, cs_dev, d_coef.as<uint32_t>(), d_scratch.as<uint32_t>(),
                    d_tables_dec.as<uint16_t>(), P.reversible() ? (uint32_t)DEC_OUT_INT : (uint32_t)DEC_OUT_FLOAT,
                    d_bstatus.as<uint32_t>(), max_len1, stream);
   last_launches += 2;
   mark(3);
-  if (nb) CK(cudaMemcpyAsync(h_bstatus.p, d_bstatus.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, stream));
+  if (nb) { launch_ctrl_copy(h_bstatus.p, d_bstatus.p, (size_t)nb * 4, stream); ++last_launches; }
   // synthesis, coarsest level first
   for (size_t li = jobs.size(); li-- > 0; )
     for (const JobGroup& g : jobs[li]) {

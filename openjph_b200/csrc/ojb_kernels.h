@@ -37,6 +37,9 @@ void dwt_tiling(uint32_t x0, uint32_t y0, uint32_t w, uint32_t h, uint32_t& tx, 
 struct CopyPiece { uint64_t src_off; uint64_t dst_off; uint32_t len; uint32_t src_sel; };  // src_sel 0: slots, 1: headers
 void launch_assemble(const CopyPiece* pieces, uint32_t npieces, uint32_t max_len, const uint8_t* slots,
                      const uint8_t* headers, uint8_t* out, cudaStream_t st);
+// small host<->device control transfers done by a kernel over mapped pinned memory (both pointers
+// 16-byte aligned)
+void launch_ctrl_copy(void* dst, const void* src, size_t bytes, cudaStream_t st);
 // block pieces computed on the device from per-block results + destination offsets
 void launch_gather_blocks(const EncBlock* blocks, const EncResult* results, const uint64_t* dst_off,
                           uint32_t nblocks, const uint8_t* slots, uint8_t* out, cudaStream_t st);
