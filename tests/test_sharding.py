@@ -1,0 +1,96 @@
+"""Tile sharding across ranks.  CPU tier: host logic + the N>1 path over gloo with
+world_size 2, kernels under the SIMT emulator; GPU tier: the same over NCCL in tools/gpu_multi.sh
+(tests/test_gpu_parity.py covers the single-process form on a real device)."""
+import os
+import sys
+import numpy as np
+import pytest
+import cases
+import openjph_b200 as ob
+from openjph_b200 import sharding
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+TILED = dict(width=300, height=200, num_comps=3, bit_depth=8, num_decomps=3, reversible=True, color_transform=True,
+             tile=(128, 128), tlm=True)
+TILED_OFF = dict(width=300, height=200, num_comps=1, bit_depth=8, num_decomps=3, reversible=True, tile=(128, 100),
+                 offset=(7, 5), tile_offset=(3, 2), tilepart_div=1)
+TILED_SUB = dict(width=200, height=150, num_comps=3, bit_depth=8, num_decomps=2, reversible=True, tile=(96, 64),
+                 subsampling=[(1, 1), (2, 2), (2, 2)], planar=1)
+
+
+def test_tile_grid_and_split_roundtrip(ref):
+    p = cases.make(TILED)
+    grid = sharding.tile_grid(p)
+    assert len(grid) == 6 and grid[5]["x0"] == 256 and grid[5]["x1"] == 300 and grid[5]["y1"] == 200
+    frame = cases.frame_for(p)
+    cs = ref.encode(p, frame)
+    header, parts = sharding.split_codestream(cs)
+    assert [t for t, _ in parts] == list(range(6))
+    assert header + b"".join(b for _, b in parts) + b"\xff\xd9" == cs
+    geo = sharding.siz_params(header)
+    assert (geo.width, geo.height, geo.tile_w, geo.tile_h, geo.num_comps) == (300, 200, 128, 128, 3)
+
+
+@pytest.mark.parametrize("kw", [TILED, TILED_OFF, TILED_SUB], ids=["rgb_tlm", "offsets_tileparts", "sub420"])
+def test_sharded_encode_is_the_reference_codestream(kw, emu_lib, ref):
+    """tiles encoded one by one as one-tile images and re-assembled == the reference's codestream"""
+    p = cases.make(kw)
+    frame = cases.frame_for(p)
+    want = ref.encode(p, frame)
+    grid = sharding.tile_grid(p)
+    parts = {}
+    for r in range(2):          # two "ranks", sequentially
+        parts.update(sharding.encode_tiles(p, frame, [grid[t] for t in sharding.my_tiles(len(grid), r, 2)], ob.I32, emu_lib))
+    got = sharding.assemble(p, parts, lib=emu_lib)
+    assert got == want
+    geo, grid2, tiles = sharding.decode_tiles(want, range(len(grid)), ob.I32, emu_lib)
+    out = sharding.paste_tiles(geo, grid2, tiles)
+    for a, b in zip(out, frame):
+        assert np.array_equal(a, b)
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OJB_EMU_THREADS="2")
+    import torch.distributed as dist
+    import emu, refharness
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        L = emu.emu_lib(build=False)
+        p = cases.make(TILED)
+        frame = cases.frame_for(p)
+        cs = sharding.encode_sharded(p, frame, ob.I32, lib=L)
+        ok = True
+        if rank == 0:
+            ok = cs == refharness.encode(p, frame)
+        # decode side: every rank holds the stream, planes gathered on rank 0
+        blob = [cs]
+        dist.broadcast_object_list(blob, src=0)
+        planes = sharding.decode_sharded(blob[0], ob.I32, lib=L)
+        if rank == 0:
+            ok = ok and all(np.array_equal(a, b) for a, b in zip(planes, frame))
+        else:
+            ok = ok and cs is None and planes is None
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_sharded_encode_decode(emu_lib, ref):
+    import multiprocessing as mp
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = {}
+    for _ in range(2):
+        r, ok = q.get(timeout=240)
+        res[r] = ok
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    assert res == {0: True, 1: True}
