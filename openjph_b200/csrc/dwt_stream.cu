@@ -192,16 +192,12 @@ template <typename T> __device__ __forceinline__ uint32_t as_bits(T v) { uint32_
 template <typename T> __device__ __forceinline__ T from_bits(uint32_t v) { T r; memcpy(&r, &v, 4); return r; }
 
 // ---- forward ---------------------------------------------------------------------------------
-// slot bytes of one lane for one (row, component): 4 samples in their source container
-__device__ __forceinline__ uint32_t fwd_slot_bytes(bool first, uint32_t src_type) {
-  return (first && src_type != SRC_I32) ? 8u : 16u;
-}
-
 // request source row v (mirrored into the resolution) into the row slot `st` (lane offset included)
-template <int NC, bool FIRST>
+template <int NC, int SRC>
 __device__ __forceinline__ void fwd_issue_row(const DwtJob& J, const StripGeom& g, const void* image,
                                               const uint32_t* coef, int v, unsigned char* st, uint32_t slot)
 {
+  constexpr bool FIRST = SRC != SRC_COEF;     // the full-resolution side is the image
   const int vr = reflect_coord(v, g.y0, g.y1 - 1) - g.y0;
   if (FIRST) {
     #pragma unroll
@@ -209,8 +205,8 @@ __device__ __forceinline__ void fwd_issue_row(const DwtJob& J, const StripGeom& 
       const size_t row = (size_t)vr * J.full_stride[k];
       const unsigned char* base = reinterpret_cast<const unsigned char*>(image) + J.full_off[k];
       unsigned char* d = st + (size_t)k * 32 * slot;
-      if (J.src_type == SRC_U16) issue4_u16(d, reinterpret_cast<const unsigned short*>(base) + row, g);
-      else if (J.src_type == SRC_U8) issue4_u8(d, base + row, g);
+      if (SRC == SRC_U16) issue4_u16(d, reinterpret_cast<const unsigned short*>(base) + row, g);
+      else if (SRC == SRC_U8) issue4_u8(d, base + row, g);
       else issue4_w(d, reinterpret_cast<const uint32_t*>(base) + row, g);
     }
   } else {
@@ -219,20 +215,21 @@ __device__ __forceinline__ void fwd_issue_row(const DwtJob& J, const StripGeom& 
 }
 
 // read a row slot back: level shift / int->float and RCT / ICT at level 1
-template <bool REV, int NC, bool FIRST>
+template <bool REV, int NC, int SRC>
 __device__ __forceinline__ void fwd_read_row(const DwtJob& J, const unsigned char* st, uint32_t slot,
                                              typename Tp<REV>::T (&a)[NC][4])
 {
+  constexpr bool FIRST = SRC != SRC_COEF;     // the full-resolution side is the image
   typedef typename Tp<REV>::T T;
   if (FIRST) {
     int iv[NC][4];
     #pragma unroll
     for (int k = 0; k < NC; ++k) {
       const unsigned char* d = st + (size_t)k * 32 * slot;
-      if (J.src_type == SRC_U16) {
+      if (SRC == SRC_U16) {
         const uint2 t = *reinterpret_cast<const uint2*>(d);
         iv[k][0] = (int)(t.x & 0xFFFF); iv[k][1] = (int)(t.x >> 16); iv[k][2] = (int)(t.y & 0xFFFF); iv[k][3] = (int)(t.y >> 16);
-      } else if (J.src_type == SRC_U8) {
+      } else if (SRC == SRC_U8) {
         const uint32_t t = *reinterpret_cast<const uint32_t*>(d);
         iv[k][0] = (int)(t & 0xFF); iv[k][1] = (int)((t >> 8) & 0xFF); iv[k][2] = (int)((t >> 16) & 0xFF); iv[k][3] = (int)(t >> 24);
       } else {
@@ -322,7 +319,7 @@ __device__ __forceinline__ void fwd_store_pair(const DwtJob& J, const StripGeom&
   }
 }
 
-template <bool REV, int NC, bool FIRST>
+template <bool REV, int NC, int SRC>
 __global__ void __launch_bounds__(DS_WARPS * 32)
 dwt_fwd_stream_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, const void* __restrict__ image,
                       uint32_t* __restrict__ coef)
@@ -348,7 +345,7 @@ dwt_fwd_stream_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, const voi
 
   // the lane's FIFO: DS_STAGES stages of one row pair each
   OJB_DYN_SMEM(unsigned char, s_ring);
-  const uint32_t slot = fwd_slot_bytes(FIRST, J.src_type);
+  const uint32_t slot = (SRC == SRC_U8 || SRC == SRC_U16) ? 8u : 16u;   // 4 samples in their container
   const uint32_t row_bytes = NC * 32 * slot, stage_bytes = 2 * row_bytes;
   unsigned char* ring = s_ring + (size_t)warp * DS_STAGES * stage_bytes + (size_t)lane * slot;
 
@@ -358,17 +355,17 @@ dwt_fwd_stream_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, const voi
   T xe[NC][4];                                                // x[2k-2]
   {                                                           // priming row through the last stage
     unsigned char* sp = ring + (size_t)(DS_STAGES - 1) * stage_bytes;
-    fwd_issue_row<NC, FIRST>(J, g, image, coef, 2 * k0 - 2, sp, slot);
+    fwd_issue_row<NC, SRC>(J, g, image, coef, 2 * k0 - 2, sp, slot);
     cp_commit(); cp_wait<0>();
-    fwd_read_row<REV, NC, FIRST>(J, sp, slot, xe);
+    fwd_read_row<REV, NC, SRC>(J, sp, slot, xe);
   }
   int issued = k0;
   #pragma unroll
   for (int s = 0; s < DS_STAGES - 1; ++s) {
     if (issued <= k1) {
       unsigned char* st = ring + (size_t)((issued - k0) % DS_STAGES) * stage_bytes;
-      fwd_issue_row<NC, FIRST>(J, g, image, coef, 2 * issued - 1, st, slot);
-      fwd_issue_row<NC, FIRST>(J, g, image, coef, 2 * issued, st + row_bytes, slot);
+      fwd_issue_row<NC, SRC>(J, g, image, coef, 2 * issued - 1, st, slot);
+      fwd_issue_row<NC, SRC>(J, g, image, coef, 2 * issued, st + row_bytes, slot);
     }
     cp_commit(); ++issued;
   }
@@ -383,8 +380,8 @@ dwt_fwd_stream_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, const voi
       T xo[NC][4], xn[NC][4], lo[NC][4], hi[NC][4];
       cp_wait<DS_STAGES - 2>();
       const unsigned char* st = ring + (size_t)((k - k0) % DS_STAGES) * stage_bytes;
-      fwd_read_row<REV, NC, FIRST>(J, st, slot, xo);
-      fwd_read_row<REV, NC, FIRST>(J, st + row_bytes, slot, xn);
+      fwd_read_row<REV, NC, SRC>(J, st, slot, xo);
+      fwd_read_row<REV, NC, SRC>(J, st + row_bytes, slot, xn);
       #pragma unroll
       for (int c = 0; c < NC; ++c)
         #pragma unroll
@@ -396,8 +393,8 @@ dwt_fwd_stream_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, const voi
         }
       if (issued <= k1) {             // refill the stage consumed one iteration ago
         unsigned char* sn = ring + (size_t)((issued - k0) % DS_STAGES) * stage_bytes;
-        fwd_issue_row<NC, FIRST>(J, g, image, coef, 2 * issued - 1, sn, slot);
-        fwd_issue_row<NC, FIRST>(J, g, image, coef, 2 * issued, sn + row_bytes, slot);
+        fwd_issue_row<NC, SRC>(J, g, image, coef, 2 * issued - 1, sn, slot);
+        fwd_issue_row<NC, SRC>(J, g, image, coef, 2 * issued, sn + row_bytes, slot);
       }
       cp_commit(); ++issued;
       fwd_store_pair<REV, NC>(J, g, coef, 2 * k - 2, lo, hi);      // rows 2k-2 (low), 2k-1 (high)
@@ -413,8 +410,8 @@ dwt_fwd_stream_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, const voi
       T xo[NC][4], xn[NC][4], lo[NC][4], hi[NC][4];
       cp_wait<DS_STAGES - 2>();
       const unsigned char* st = ring + (size_t)((k - k0) % DS_STAGES) * stage_bytes;
-      fwd_read_row<REV, NC, FIRST>(J, st, slot, xo);
-      fwd_read_row<REV, NC, FIRST>(J, st + row_bytes, slot, xn);
+      fwd_read_row<REV, NC, SRC>(J, st, slot, xo);
+      fwd_read_row<REV, NC, SRC>(J, st + row_bytes, slot, xn);
       #pragma unroll
       for (int c = 0; c < NC; ++c)
         #pragma unroll
@@ -428,8 +425,8 @@ dwt_fwd_stream_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, const voi
         }
       if (issued <= k1) {
         unsigned char* sn = ring + (size_t)((issued - k0) % DS_STAGES) * stage_bytes;
-        fwd_issue_row<NC, FIRST>(J, g, image, coef, 2 * issued - 1, sn, slot);
-        fwd_issue_row<NC, FIRST>(J, g, image, coef, 2 * issued, sn + row_bytes, slot);
+        fwd_issue_row<NC, SRC>(J, g, image, coef, 2 * issued - 1, sn, slot);
+        fwd_issue_row<NC, SRC>(J, g, image, coef, 2 * issued, sn + row_bytes, slot);
       }
       cp_commit(); ++issued;
       fwd_store_pair<REV, NC>(J, g, coef, 2 * k - 4, lo, hi);      // rows 2k-4 (low), 2k-3 (high)
@@ -489,10 +486,11 @@ __device__ __forceinline__ void inv_read_pair(const unsigned char* st, typename 
 
 __device__ __forceinline__ int round_haz(float t) { return (int)(t + (t >= 0.0f ? 0.5f : -0.5f)); }
 
-template <bool REV, int NC, bool FIRST>
+template <bool REV, int NC, int SRC>
 __device__ __forceinline__ void inv_store_row(const DwtJob& J, const StripGeom& g, void* image, uint32_t* coef,
                                               int v, typename Tp<REV>::T (&x)[NC][4])
 {
+  constexpr bool FIRST = SRC != SRC_COEF;     // the full-resolution side is the image
   typedef typename Tp<REV>::T T;
   if (!g.lane_valid || v < g.y0 || v >= g.y1 || v < g.R0 || v >= g.R1) return;
   const int cx = g.u0 - g.x0;
@@ -560,7 +558,7 @@ __device__ __forceinline__ void inv_store_row(const DwtJob& J, const StripGeom& 
   for (int k = 0; k < NC; ++k) {
     const size_t row = (size_t)(v - g.y0) * J.full_stride[k];
     unsigned char* base = reinterpret_cast<unsigned char*>(image) + J.full_off[k];
-    if (J.src_type == SRC_U16) {
+    if (SRC == SRC_U16) {
       unsigned short* p = reinterpret_cast<unsigned short*>(base) + row + cx;
       uint32_t q[4];
       #pragma unroll
@@ -570,7 +568,7 @@ __device__ __forceinline__ void inv_store_row(const DwtJob& J, const StripGeom& 
         #pragma unroll
         for (int i = 0; i < 4; ++i) if (g.has[i]) p[i] = (unsigned short)q[i];
       }
-    } else if (J.src_type == SRC_U8) {
+    } else if (SRC == SRC_U8) {
       unsigned char* p = base + row + cx;
       uint32_t q[4];
       #pragma unroll
@@ -592,7 +590,7 @@ __device__ __forceinline__ void inv_store_row(const DwtJob& J, const StripGeom& 
   }
 }
 
-template <bool REV, int NC, bool FIRST>
+template <bool REV, int NC, int SRC>
 __global__ void __launch_bounds__(DS_WARPS * 32)
 dwt_inv_stream_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, void* __restrict__ image,
                       uint32_t* __restrict__ coef)
@@ -659,8 +657,8 @@ dwt_inv_stream_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, void* __r
         }
       if (issued <= j1) inv_issue_pair<NC>(J, g, coef, issued, ring + (size_t)((issued - j0) % NS) * stage_bytes);
       cp_commit(); ++issued;
-      inv_store_row<REV, NC, FIRST>(J, g, image, coef, 2 * j - 1, xo);
-      inv_store_row<REV, NC, FIRST>(J, g, image, coef, 2 * j, xn);
+      inv_store_row<REV, NC, SRC>(J, g, image, coef, 2 * j - 1, xo);
+      inv_store_row<REV, NC, SRC>(J, g, image, coef, 2 * j, xn);
     }
   } else {
     T s1[NC][4], d1[NC][4], xe[NC][4];      // s1[j-1], d1[j-2], x_e[j-2]
@@ -686,23 +684,23 @@ dwt_inv_stream_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, void* __r
         }
       if (issued <= j1) inv_issue_pair<NC>(J, g, coef, issued, ring + (size_t)((issued - j0) % NS) * stage_bytes);
       cp_commit(); ++issued;
-      inv_store_row<REV, NC, FIRST>(J, g, image, coef, 2 * j - 3, xo);
-      inv_store_row<REV, NC, FIRST>(J, g, image, coef, 2 * j - 2, xn);
+      inv_store_row<REV, NC, SRC>(J, g, image, coef, 2 * j - 3, xo);
+      inv_store_row<REV, NC, SRC>(J, g, image, coef, 2 * j - 2, xn);
     }
   }
 }
 
-template <bool REV, int NC, bool FIRST>
-void launch_fwd(const DwtJob* jobs, uint32_t njobs, uint32_t ctas, uint32_t src_type, const void* image, uint32_t* coef, cudaStream_t st) {
-  auto k = dwt_fwd_stream_kernel<REV, NC, FIRST>;
-  const size_t slot = (FIRST && src_type != SRC_I32) ? 8 : 16;
+template <bool REV, int NC, int SRC>
+void launch_fwd(const DwtJob* jobs, uint32_t njobs, uint32_t ctas, const void* image, uint32_t* coef, cudaStream_t st) {
+  auto k = dwt_fwd_stream_kernel<REV, NC, SRC>;
+  const size_t slot = (SRC == SRC_U8 || SRC == SRC_U16) ? 8 : 16;
   const size_t smem = (size_t)DS_WARPS * DS_STAGES * 2 * NC * 32 * slot;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   OJB_LAUNCH(k, dim3(ctas), dim3(DS_WARPS * 32), smem, st, jobs, njobs, image, coef);
 }
-template <bool REV, int NC, bool FIRST>
+template <bool REV, int NC, int SRC>
 void launch_inv(const DwtJob* jobs, uint32_t njobs, uint32_t ctas, void* image, uint32_t* coef, cudaStream_t st) {
-  auto k = dwt_inv_stream_kernel<REV, NC, FIRST>;
+  auto k = dwt_inv_stream_kernel<REV, NC, SRC>;
   const size_t smem = (size_t)DS_WARPS * ((NC == 3) ? DS_STAGES - 1 : DS_STAGES) * NC * 4 * 32 * 8;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   OJB_LAUNCH(k, dim3(ctas), dim3(DS_WARPS * 32), smem, st, jobs, njobs, image, coef);
@@ -730,26 +728,36 @@ void launch_dwt_fwd_stream(const DwtJob* jobs, uint32_t njobs, uint32_t total_ct
                            uint32_t ncomp, bool first, uint32_t src_type, const void* image, uint32_t* coef, cudaStream_t st)
 {
   if (total_ctas == 0) return;
+#define OJB_FWD(REV, NC, SRC) launch_fwd<REV, NC, SRC>(jobs, njobs, total_ctas, image, coef, st)
+#define OJB_FWD_SRC(REV, NC) do { if (src_type == SRC_U8) OJB_FWD(REV, NC, SRC_U8); else if (src_type == SRC_U16) OJB_FWD(REV, NC, SRC_U16); \
+                                  else OJB_FWD(REV, NC, SRC_I32); } while (0)
   if (reversible) {
-    if (first) { if (ncomp == 3) launch_fwd<true, 3, true>(jobs, njobs, total_ctas, src_type, image, coef, st); else launch_fwd<true, 1, true>(jobs, njobs, total_ctas, src_type, image, coef, st); }
-    else launch_fwd<true, 1, false>(jobs, njobs, total_ctas, src_type, image, coef, st);
+    if (!first) OJB_FWD(true, 1, SRC_COEF);
+    else if (ncomp == 3) OJB_FWD_SRC(true, 3); else OJB_FWD_SRC(true, 1);
   } else {
-    if (first) { if (ncomp == 3) launch_fwd<false, 3, true>(jobs, njobs, total_ctas, src_type, image, coef, st); else launch_fwd<false, 1, true>(jobs, njobs, total_ctas, src_type, image, coef, st); }
-    else launch_fwd<false, 1, false>(jobs, njobs, total_ctas, src_type, image, coef, st);
+    if (!first) OJB_FWD(false, 1, SRC_COEF);
+    else if (ncomp == 3) OJB_FWD_SRC(false, 3); else OJB_FWD_SRC(false, 1);
   }
+#undef OJB_FWD_SRC
+#undef OJB_FWD
 }
 
 void launch_dwt_inv_stream(const DwtJob* jobs, uint32_t njobs, uint32_t total_ctas, bool reversible,
-                           uint32_t ncomp, bool first, void* image, uint32_t* coef, cudaStream_t st)
+                           uint32_t ncomp, bool first, uint32_t src_type, void* image, uint32_t* coef, cudaStream_t st)
 {
   if (total_ctas == 0) return;
+#define OJB_INV(REV, NC, SRC) launch_inv<REV, NC, SRC>(jobs, njobs, total_ctas, image, coef, st)
+#define OJB_INV_SRC(REV, NC) do { if (src_type == SRC_U8) OJB_INV(REV, NC, SRC_U8); else if (src_type == SRC_U16) OJB_INV(REV, NC, SRC_U16); \
+                                  else OJB_INV(REV, NC, SRC_I32); } while (0)
   if (reversible) {
-    if (first) { if (ncomp == 3) launch_inv<true, 3, true>(jobs, njobs, total_ctas, image, coef, st); else launch_inv<true, 1, true>(jobs, njobs, total_ctas, image, coef, st); }
-    else launch_inv<true, 1, false>(jobs, njobs, total_ctas, image, coef, st);
+    if (!first) OJB_INV(true, 1, SRC_COEF);
+    else if (ncomp == 3) OJB_INV_SRC(true, 3); else OJB_INV_SRC(true, 1);
   } else {
-    if (first) { if (ncomp == 3) launch_inv<false, 3, true>(jobs, njobs, total_ctas, image, coef, st); else launch_inv<false, 1, true>(jobs, njobs, total_ctas, image, coef, st); }
-    else launch_inv<false, 1, false>(jobs, njobs, total_ctas, image, coef, st);
+    if (!first) OJB_INV(false, 1, SRC_COEF);
+    else if (ncomp == 3) OJB_INV_SRC(false, 3); else OJB_INV_SRC(false, 1);
   }
+#undef OJB_INV_SRC
+#undef OJB_INV
 }
 
 } // namespace ojb

@@ -98,7 +98,7 @@ __device__ __forceinline__ int mel_next_run(MelDec& m) {
 
 struct RevDec {               // backward-growing stream (VLC, MRP)
   const uint8_t* p; int size; unsigned long long tmp; uint32_t bits; bool unstuff;
-  uint32_t nxt;               // step 1: the next four bytes, requested one refill ahead
+  uint32_t nxt[3];            // step 1: the next twelve bytes, requested three refills ahead
 };
 // byte-wise refill (refinement passes, lane 0 only)
 __device__ __forceinline__ void rev_fill(RevDec& v) {       // LSB first
@@ -117,8 +117,9 @@ __device__ __forceinline__ void rev_fill32(RevDec& v) {
   if (v.bits > 32) return;
   uint32_t val = 0;                                           // bytes p-3 .. p, byte p in the MSB
   if (v.size > 3) {
-    val = v.nxt; v.p -= 4; v.size -= 4;
-    if (v.size > 3) v.nxt = load_le32_any(v.p - 3);           // lands while these 32 bits are decoded
+    val = v.nxt[0]; v.nxt[0] = v.nxt[1]; v.nxt[1] = v.nxt[2];
+    v.p -= 4; v.size -= 4;
+    if (v.size > 11) v.nxt[2] = load_le32_any(v.p - 11);      // lands while the next 96 bits are decoded
   } else {
     int i = 24;
     while (v.size > 0) { val |= (uint32_t)(*v.p--) << i; --v.size; i -= 8; }
@@ -183,8 +184,8 @@ ht_dec_step1_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
     vlc.bits = 4 - (((vlc.tmp & 7) == 7) ? 1u : 0u);
     vlc.unstuff = (d | 0xF) > 0x8F;
   }
-  vlc.nxt = 0;
-  if (vlc.size > 3) vlc.nxt = load_le32_any(vlc.p - 3);
+  #pragma unroll
+  for (int i = 0; i < 3; ++i) vlc.nxt[i] = (vlc.size > 3 + 4 * i) ? load_le32_any(vlc.p - 3 - 4 * i) : 0u;
   int run = mel_next_run(mel);
 
   const uint32_t width = blk.w, height = blk.h;
@@ -284,7 +285,7 @@ __device__ __forceinline__ uint32_t to_output(uint32_t sm, uint32_t mode, uint32
 // simple byte-wise readers for the refinement passes (lane 0 only)
 struct FwdBits {              // SPP: forward, 0 fed when exhausted, 7-bit byte after 0xFF
   const uint8_t* p; int size; unsigned long long tmp; uint32_t bits; bool unstuff;
-  uint32_t nxt;               // step 1: the next four bytes, requested one refill ahead
+  uint32_t nxt[3];            // step 1: the next twelve bytes, requested three refills ahead
 };
 __device__ __forceinline__ void fwd_fill(FwdBits& f) {
   while (f.bits <= 56) {
@@ -434,13 +435,13 @@ ht_dec_step2_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
     uint32_t carry_word = 0;            // partial last word (bits nbits_total & 31)
     bool prev_ff = false;
     uint32_t* stage = s_stage[warp];
+    uint32_t w_next = (4 * lane < mslen) ? load_u32_unaligned(data + 4 * lane) : 0xFFFFFFFFu;
     for (uint32_t base = 0; base < mslen; base += 128) {
       const uint32_t off = base + 4 * lane;
-      uint32_t w = 0xFFFFFFFFu;
-      if (off < mslen) {
-        w = load_u32_unaligned(data + off);
-        if (off + 4 > mslen) w |= 0xFFFFFFFFu << (8 * (mslen - off));    // beyond the segment: 0xFF
-      }
+      uint32_t w = w_next;                  // the next 128 bytes are requested while these are unpacked
+      if (off + 128 < mslen) w_next = load_u32_unaligned(data + off + 128);
+      else w_next = 0xFFFFFFFFu;
+      if (off < mslen && off + 4 > mslen) w |= 0xFFFFFFFFu << (8 * (mslen - off));    // beyond the segment: 0xFF
       const uint32_t lastb = w >> 24;
       uint32_t pv = __shfl_up_sync(FULL, lastb, 1);
       const bool pff = lane ? (pv == 0xFF) : prev_ff;

@@ -644,7 +644,7 @@ uint32_t Decoder::decode(void* const* planes, const uint32_t* strides, bool plan
     for (const JobGroup& g : jobs[li]) {
       if (g.stream)
         launch_dwt_inv_stream(d_jobs.as<DwtJob>() + g.dev_off, (uint32_t)g.jobs.size(), g.ctas, P.reversible(), g.ncomp,
-                              g.first, d_image.p, d_coef.as<uint32_t>(), stream);
+                              g.first, img_type, d_image.p, d_coef.as<uint32_t>(), stream);
       else
         launch_dwt_inv(d_jobs.as<DwtJob>() + g.dev_off, (uint32_t)g.jobs.size(), g.ctas, P.reversible(), g.ncomp,
                        d_image.p, d_coef.as<uint32_t>(), stream);

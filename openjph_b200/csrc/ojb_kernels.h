@@ -28,7 +28,7 @@ void launch_dwt_fwd_stream(const DwtJob* jobs, uint32_t njobs, uint32_t total_ct
                            uint32_t ncomp, bool first, uint32_t src_type, const void* image, uint32_t* coef,
                            cudaStream_t st);
 void launch_dwt_inv_stream(const DwtJob* jobs, uint32_t njobs, uint32_t total_ctas, bool reversible,
-                           uint32_t ncomp, bool first, void* image, uint32_t* coef, cudaStream_t st);
+                           uint32_t ncomp, bool first, uint32_t src_type, void* image, uint32_t* coef, cudaStream_t st);
 // CTA tiling of a w x h resolution at origin (x0,y0): number of tiles across / down
 void dwt_tiling(uint32_t x0, uint32_t y0, uint32_t w, uint32_t h, uint32_t& tx, uint32_t& ty);
 
