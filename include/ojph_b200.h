@@ -119,6 +119,16 @@ int ojb_dec_read_headers(ojb_decoder* d, const uint8_t* j2c, uint64_t len, uint3
 /* codestream::create() + the pull() loop: decodes every component into planes */
 int ojb_dec_decode_frame(ojb_decoder* d, void* const* planes, const uint32_t* strides);
 int ojb_dec_decode_resident(ojb_decoder* d);             /* result stays in the device image buffer */
+/* The reference's line interface on the read side (needs the OJB_I32 container):
+ *   ojb_dec_set_planar = codestream::set_planar (default after read_headers: colour transform ? 0 : 1,
+ *                        ojph_codestream_local.cpp:879);
+ *   ojb_dec_begin_pull = codestream::create() (:912-1115): runs the GPU decode into a library-owned frame;
+ *   ojb_dec_pull       = codestream::pull(ui32& comp_num) (:1227-1272): the next line, library owned and
+ *                        valid until the next call; planar => all rows of component 0 first, else row by
+ *                        row, component by component; NULL (and *comp_num = 0) after the last line. */
+int ojb_dec_set_planar(ojb_decoder* d, int planar);
+int ojb_dec_begin_pull(ojb_decoder* d);
+const int32_t* ojb_dec_pull(ojb_decoder* d, uint32_t* comp_num);
 void* ojb_dec_device_plane(ojb_decoder* d, uint32_t comp);
 /* after read_headers: the same codestream bytes are already in device memory (with >= 32 readable
  * bytes after the end); the next decode reads them there instead of uploading j2c */

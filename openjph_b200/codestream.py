@@ -196,6 +196,26 @@ class Decoder(_Base):
         self._check(self.L.ojb_dec_decode_frame(self.h, ptrs, None))
         return planes
 
+    def pull_lines(self, j2c, planar=None):
+        """the reference's read_headers() -> [set_planar] -> create() -> pull() loop; returns the planes
+        rebuilt from the pulled lines and the order the components came in"""
+        fi = self.read_headers(j2c, I32)
+        if planar is not None:
+            self._check(self.L.ojb_dec_set_planar(self.h, 1 if planar else 0))
+        self._check(self.L.ojb_dec_begin_pull(self.h))
+        planes = [np.zeros((fi.comp_h[c], fi.comp_w[c]), np.int32) for c in range(fi.num_comps)]
+        rows = [0] * fi.num_comps
+        order = []
+        nc = C.c_uint32()
+        line = self.L.ojb_dec_pull(self.h, C.byref(nc))
+        while line:
+            c = nc.value
+            order.append(c)
+            planes[c][rows[c]] = np.ctypeslib.as_array(C.cast(line, C.POINTER(C.c_int32)), shape=(fi.comp_w[c],))
+            rows[c] += 1
+            line = self.L.ojb_dec_pull(self.h, C.byref(nc))
+        return planes, order
+
     def read_band(self, tile, comp, res, band):
         bw, bh = C.c_uint32(), C.c_uint32()
         self._check(self.L.ojb_dec_read_band(self.h, tile, comp, res, band, None, C.byref(bw), C.byref(bh)))

@@ -12,7 +12,12 @@ using namespace ojb;
 // that device current again, so objects may be driven from any host thread
 static int current_device() { int d = 0; cudaGetDevice(&d); return d; }
 struct ojb_encoder { int device = current_device(); Encoder enc; bool configured = false; };
-struct ojb_decoder { int device = current_device(); Decoder dec; bool have_headers = false; };
+struct ojb_decoder {
+  int device = current_device(); Decoder dec; bool have_headers = false;
+  // line interface (pull): library-owned frame, cursor in the reference's line order
+  PinnedBuf frame; std::vector<size_t> plane_off; std::vector<uint32_t> line_cur;
+  uint32_t cur_comp = 0; int planar = -1; bool pulling = false;
+};
 
 static thread_local char g_err[1024] = "";
 
@@ -256,6 +261,51 @@ int ojb_dec_decode_frame(ojb_decoder* d, void* const* planes, const uint32_t* st
     d->dec.decode(planes, strides, false);
   });
 }
+int ojb_dec_set_planar(ojb_decoder* d, int planar) { d->planar = planar ? 1 : 0; return 0; }
+
+int ojb_dec_begin_pull(ojb_decoder* d) {
+  return guarded_on(d->device, [&] {
+    if (!d->have_headers) fail(0x000B0015, "read_headers has not been called");
+    Decoder& D = d->dec;
+    if (D.img_type != ST_I32) fail(0x000B0016, "the line interface needs the 32-bit sample container (OJB_I32)");
+    const uint32_t nc = D.params.num_comps();
+    d->plane_off.assign(nc, 0);
+    size_t tot = 0;
+    for (uint32_t c = 0; c < nc; ++c) { d->plane_off[c] = tot; tot += (size_t)D.img_w[c] * D.img_h[c]; }
+    d->frame.reserve(std::max<size_t>(tot, 1) * 4);
+    std::vector<void*> pl(nc);
+    for (uint32_t c = 0; c < nc; ++c) pl[c] = d->frame.as<int32_t>() + d->plane_off[c];
+    D.decode(pl.data(), nullptr, false);
+    d->line_cur.assign(nc, 0); d->cur_comp = 0; d->pulling = true;
+    if (d->planar < 0) d->planar = D.params.mc_trans ? 0 : 1;
+    // skip components without rows
+    while (d->cur_comp < nc && D.img_h[d->cur_comp] == 0) ++d->cur_comp;
+  });
+}
+
+const int32_t* ojb_dec_pull(ojb_decoder* d, uint32_t* comp_num) {
+  const int32_t* line = nullptr;
+  if (comp_num) *comp_num = 0;
+  guarded([&] {
+    if (!d->pulling) fail(0x000B0017, "ojb_dec_begin_pull has not been called");
+    Decoder& D = d->dec;
+    const uint32_t nc = D.params.num_comps();
+    if (d->cur_comp >= nc) { d->pulling = false; return; }        // past the last line
+    const uint32_t c = d->cur_comp;
+    line = d->frame.as<int32_t>() + d->plane_off[c] + (size_t)d->line_cur[c] * D.img_w[c];
+    if (comp_num) *comp_num = c;
+    d->line_cur[c]++;
+    if (d->planar == 1) {
+      while (d->cur_comp < nc && d->line_cur[d->cur_comp] >= D.img_h[d->cur_comp]) ++d->cur_comp;
+    } else {
+      uint32_t tries = 0, k = c;
+      do { k = (k + 1) % nc; ++tries; } while (d->line_cur[k] >= D.img_h[k] && tries <= nc);
+      d->cur_comp = tries > nc ? nc : k;
+    }
+  });
+  return line;
+}
+
 int ojb_dec_decode_resident(ojb_decoder* d) {
   return guarded_on(d->device, [&] {
     if (!d->have_headers) fail(0x000B0015, "read_headers has not been called");

@@ -81,3 +81,21 @@ def test_block_decoder_matches_reference(emu_lib, ref):
     got = ob.decode_blocks(coded, geoms, lib=emu_lib)
     for i, ((a, ok), b) in enumerate(zip(got, want)):
         assert ok and np.array_equal(a, b), "block %d %s" % (i, geoms[i])
+
+
+@pytest.mark.parametrize("name,planar", [("odd_rgb_L5", None), ("odd_rgb_L5", True), ("sub420_planar", True)])
+def test_line_interface_exchange_and_pull(name, planar, emu_lib, ref):
+    """exchange()/flush() on the write side and create()/pull() on the read side give the frame-at-once
+    results, in the reference's line order (ojph_codestream_local.cpp:1176-1224, :1227-1272)"""
+    p = cases.make(REV[name])
+    frame = cases.frame_for(p)
+    want = ref.encode(p, frame)
+    assert ob.Encoder(p, ob.I32, lib=emu_lib).encode_lines(frame) == want
+    planes, order = ob.Decoder(lib=emu_lib).pull_lines(want, planar=planar)
+    for a, b in zip(planes, frame):
+        assert np.array_equal(a, b)
+    nc = p.num_comps
+    if planar or (planar is None and not p.color_transform):
+        assert order == sorted(order)                     # component by component
+    else:
+        assert order[:2 * nc] == list(range(nc)) * 2      # row by row, component by component
