@@ -44,12 +44,23 @@ __device__ __forceinline__ uint32_t load_le32_any(const uint8_t* p) {
 
 struct MelDec {
   const uint8_t* p; int size; unsigned long long tmp; int bits; bool unstuff; int k;
+  // the aligned words that hold the next four bytes, requested one refill ahead (the funnel shift
+  // that needs them runs at the next refill, so the load latency is off the critical chain)
+  const uint32_t* wp; uint32_t lo, hi, sh;
 };
+__device__ __forceinline__ void mel_prime(MelDec& m) {
+  m.wp = reinterpret_cast<const uint32_t*>((size_t)m.p & ~(size_t)3);
+  m.sh = (uint32_t)((size_t)m.p & 3) * 8;
+  m.lo = m.wp[0]; m.hi = m.wp[1];
+}
 __device__ __forceinline__ void mel_fill(MelDec& m) {       // MSB first; needs bits <= 32 on entry
   if (m.bits > 32) return;
   uint32_t val;
-  if (m.size > 4) { val = load_le32_any(m.p); m.p += 4; m.size -= 4; }
-  else {
+  if (m.size > 4) {
+    val = m.sh ? __funnelshift_r(m.lo, m.hi, m.sh) : m.lo;
+    m.p += 4; m.size -= 4;
+    m.lo = m.hi; m.wp += 1; m.hi = m.wp[1];
+  } else {
     val = 0xFFFFFFFFu;                                        // 0xFF fed past the end
     int i = 0;
     while (m.size > 0) {
@@ -98,8 +109,17 @@ __device__ __forceinline__ int mel_next_run(MelDec& m) {
 
 struct RevDec {               // backward-growing stream (VLC, MRP)
   const uint8_t* p; int size; unsigned long long tmp; uint32_t bits; bool unstuff;
-  uint32_t nxt[3];            // step 1: the next twelve bytes, requested three refills ahead
+  // step 1: the aligned words that hold the next four bytes (p-3 .. p), requested one refill ahead
+  const uint32_t* wp; const uint32_t* wbase; uint32_t lo, hi, sh;
 };
+__device__ __forceinline__ void rev_prime(RevDec& v, const uint8_t* buffer_start) {
+  const uint8_t* q = v.p - 3;
+  v.wp = reinterpret_cast<const uint32_t*>((size_t)q & ~(size_t)3);
+  v.wbase = reinterpret_cast<const uint32_t*>((size_t)buffer_start & ~(size_t)3);
+  v.sh = (uint32_t)((size_t)q & 3) * 8;
+  v.lo = (v.wp >= v.wbase) ? v.wp[0] : 0u;
+  v.hi = (v.wp + 1 >= v.wbase) ? v.wp[1] : 0u;
+}
 // byte-wise refill (refinement passes, lane 0 only)
 __device__ __forceinline__ void rev_fill(RevDec& v) {       // LSB first
   while (v.bits <= 56) {
@@ -117,9 +137,10 @@ __device__ __forceinline__ void rev_fill32(RevDec& v) {
   if (v.bits > 32) return;
   uint32_t val = 0;                                           // bytes p-3 .. p, byte p in the MSB
   if (v.size > 3) {
-    val = v.nxt[0]; v.nxt[0] = v.nxt[1]; v.nxt[1] = v.nxt[2];
+    val = v.sh ? __funnelshift_r(v.lo, v.hi, v.sh) : v.lo;
     v.p -= 4; v.size -= 4;
-    if (v.size > 11) v.nxt[2] = load_le32_any(v.p - 11);      // lands while the next 96 bits are decoded
+    v.hi = v.lo; v.wp -= 1;
+    v.lo = (v.wp >= v.wbase) ? v.wp[0] : 0u;                  // lands while these 32 bits are decoded
   } else {
     int i = 24;
     while (v.size > 0) { val |= (uint32_t)(*v.p--) << i; --v.size; i -= 8; }
@@ -184,8 +205,8 @@ ht_dec_step1_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
     vlc.bits = 4 - (((vlc.tmp & 7) == 7) ? 1u : 0u);
     vlc.unstuff = (d | 0xF) > 0x8F;
   }
-  #pragma unroll
-  for (int i = 0; i < 3; ++i) vlc.nxt[i] = (vlc.size > 3 + 4 * i) ? load_le32_any(vlc.p - 3 - 4 * i) : 0u;
+  rev_prime(vlc, cs);
+  mel_prime(mel);
   int run = mel_next_run(mel);
 
   const uint32_t width = blk.w, height = blk.h;
@@ -285,7 +306,6 @@ __device__ __forceinline__ uint32_t to_output(uint32_t sm, uint32_t mode, uint32
 // simple byte-wise readers for the refinement passes (lane 0 only)
 struct FwdBits {              // SPP: forward, 0 fed when exhausted, 7-bit byte after 0xFF
   const uint8_t* p; int size; unsigned long long tmp; uint32_t bits; bool unstuff;
-  uint32_t nxt[3];            // step 1: the next twelve bytes, requested three refills ahead
 };
 __device__ __forceinline__ void fwd_fill(FwdBits& f) {
   while (f.bits <= 56) {
