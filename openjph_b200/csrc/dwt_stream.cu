@@ -20,6 +20,7 @@
 // inverse of those on store (inverse); quantisation to MSB-aligned sign-magnitude is fused into
 // the sub-band store (forward).
 #include "dwt_common.cuh"
+#include "ojb_async.cuh"
 #include "ojb_kernels.h"
 
 namespace ojb {
@@ -142,18 +143,6 @@ __device__ __forceinline__ bool strip_setup(const DwtJob& J, uint32_t strip, uin
 // it requests the rows of the next iterations with cp.async (no registers are held while the data is
 // in flight) and later reads back exactly the bytes it requested, so no cross-lane synchronisation
 // is needed -- cp.async.wait_group orders a lane's own copies.
-#ifdef OJB_EMU_BUILD
-template <int N> __device__ __forceinline__ void cp_async(void* dst, const void* src) { memcpy(dst, src, N); }
-__device__ __forceinline__ void cp_commit() {}
-template <int N> __device__ __forceinline__ void cp_wait() {}
-#else
-template <int N> __device__ __forceinline__ void cp_async(void* dst, const void* src) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" :: "r"(d), "l"(src), "n"(N) : "memory");
-}
-__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
-#endif
 
 // request four 32-bit elements p[c[0..3]] into a 16-byte slot
 __device__ __forceinline__ void issue4_w(unsigned char* d, const uint32_t* p, const StripGeom& g) {
@@ -320,7 +309,7 @@ __device__ __forceinline__ void fwd_store_pair(const DwtJob& J, const StripGeom&
 }
 
 template <bool REV, int NC, int SRC>
-__global__ void __launch_bounds__(DS_WARPS * 32)
+__global__ void __launch_bounds__(DS_WARPS * 32, (REV || NC == 1) ? 5 : 3)
 dwt_fwd_stream_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, const void* __restrict__ image,
                       uint32_t* __restrict__ coef)
 {
@@ -591,7 +580,7 @@ __device__ __forceinline__ void inv_store_row(const DwtJob& J, const StripGeom& 
 }
 
 template <bool REV, int NC, int SRC>
-__global__ void __launch_bounds__(DS_WARPS * 32)
+__global__ void __launch_bounds__(DS_WARPS * 32, (REV || NC == 1) ? 5 : 3)
 dwt_inv_stream_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, void* __restrict__ image,
                       uint32_t* __restrict__ coef)
 {

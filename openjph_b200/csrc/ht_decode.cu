@@ -18,6 +18,7 @@
 // src/core/codestream/ojph_codestream_gen.cpp:124-168) is fused into the final store.
 #include "ojb_device.h"
 #include "ojb_kernels.h"
+#include "ojb_async.cuh"
 
 namespace ojb {
 
@@ -26,6 +27,7 @@ namespace ojb {
 
 // block status bits
 #define DST_FAIL 1u
+#define DEC1_THREADS 128        // step 1: one thread per code-block
 
 namespace {
 
@@ -109,16 +111,30 @@ __device__ __forceinline__ int mel_next_run(MelDec& m) {
 
 struct RevDec {               // backward-growing stream (VLC, MRP)
   const uint8_t* p; int size; unsigned long long tmp; uint32_t bits; bool unstuff;
-  // step 1: the aligned words that hold the next four bytes (p-3 .. p), requested one refill ahead
-  const uint32_t* wp; const uint32_t* wbase; uint32_t lo, hi, sh;
+  // step 1: the stream is read backward one aligned word per refill.  The words are requested
+  // VLC_RING-1 refills ahead with cp.async into a per-thread ring in shared memory (global/L2
+  // latency is several refill periods for one serial chain per thread); `lo`/`hi` hold the two
+  // words the next refill's funnel shift needs.
+  const uint32_t* wnext; const uint32_t* wbase; uint32_t* ring; uint32_t ridx, lo, hi, sh;
 };
-__device__ __forceinline__ void rev_prime(RevDec& v, const uint8_t* buffer_start) {
+#define VLC_RING 8
+__device__ __forceinline__ void rev_ring_issue(RevDec& v) {
+  uint32_t* slot = v.ring + v.ridx * DEC1_THREADS;
+  if (v.wnext >= v.wbase) cp_async<4>(slot, v.wnext); else *slot = 0u;
+  cp_commit();
+  --v.wnext; v.ridx = (v.ridx + 1) & (VLC_RING - 1);
+}
+__device__ __forceinline__ void rev_prime(RevDec& v, const uint8_t* buffer_start, uint32_t* ring) {
   const uint8_t* q = v.p - 3;
-  v.wp = reinterpret_cast<const uint32_t*>((size_t)q & ~(size_t)3);
+  const uint32_t* wp = reinterpret_cast<const uint32_t*>((size_t)q & ~(size_t)3);
   v.wbase = reinterpret_cast<const uint32_t*>((size_t)buffer_start & ~(size_t)3);
   v.sh = (uint32_t)((size_t)q & 3) * 8;
-  v.lo = (v.wp >= v.wbase) ? v.wp[0] : 0u;
-  v.hi = (v.wp + 1 >= v.wbase) ? v.wp[1] : 0u;
+  v.lo = (wp >= v.wbase) ? wp[0] : 0u;
+  v.hi = (wp + 1 >= v.wbase) ? wp[1] : 0u;
+  v.ring = ring; v.ridx = 0; v.wnext = wp - 1;
+  #pragma unroll
+  for (int i = 0; i < VLC_RING - 1; ++i) rev_ring_issue(v);
+  v.ridx = 0;                                  // oldest request sits in slot 0
 }
 // byte-wise refill (refinement passes, lane 0 only)
 __device__ __forceinline__ void rev_fill(RevDec& v) {       // LSB first
@@ -139,8 +155,14 @@ __device__ __forceinline__ void rev_fill32(RevDec& v) {
   if (v.size > 3) {
     val = v.sh ? __funnelshift_r(v.lo, v.hi, v.sh) : v.lo;
     v.p -= 4; v.size -= 4;
-    v.hi = v.lo; v.wp -= 1;
-    v.lo = (v.wp >= v.wbase) ? v.wp[0] : 0u;                  // lands while these 32 bits are decoded
+    v.hi = v.lo;
+    cp_wait<VLC_RING - 2>();                                  // the oldest request has landed
+    const uint32_t take = v.ridx;
+    v.lo = v.ring[take * DEC1_THREADS];
+    // the freed slot takes the request VLC_RING-1 words further down the stream
+    v.ridx = (take + VLC_RING - 1) & (VLC_RING - 1);
+    rev_ring_issue(v);
+    v.ridx = (take + 1) & (VLC_RING - 1);
   } else {
     int i = 24;
     while (v.size > 0) { val |= (uint32_t)(*v.p--) << i; --v.size; i -= 8; }
@@ -167,12 +189,13 @@ __device__ __forceinline__ void rev_fill32(RevDec& v) {
   v.bits += nb;
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(DEC1_THREADS)
 ht_dec_step1_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
                     const uint8_t* __restrict__ cs, uint32_t* __restrict__ scratch,
                     const uint16_t* __restrict__ tables, uint32_t* __restrict__ block_status)
 {
   __shared__ DecTables T;
+  __shared__ uint32_t s_ring[VLC_RING * DEC1_THREADS];     // per-thread FIFO of VLC words (slot-major)
   {
     uint16_t* d = reinterpret_cast<uint16_t*>(&T);
     for (uint32_t i = threadIdx.x; i < sizeof(DecTables) / 2; i += blockDim.x) d[i] = tables[i];
@@ -205,7 +228,7 @@ ht_dec_step1_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
     vlc.bits = 4 - (((vlc.tmp & 7) == 7) ? 1u : 0u);
     vlc.unstuff = (d | 0xF) > 0x8F;
   }
-  rev_prime(vlc, cs);
+  rev_prime(vlc, cs, s_ring + threadIdx.x);
   mel_prime(mel);
   int run = mel_next_run(mel);
 
@@ -465,6 +488,22 @@ ht_dec_step2_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
       const uint32_t lastb = w >> 24;
       uint32_t pv = __shfl_up_sync(FULL, lastb, 1);
       const bool pff = lane ? (pv == 0xFF) : prev_ff;
+      // common case: a full chunk without any 0xFF byte ahead of another byte -> every byte carries
+      // 8 bits and the chunk is a plain 1024-bit shift by the carry length
+      {
+        uint32_t ff = w & (w >> 1); ff &= ff >> 2; ff &= ff >> 4;        // bit 8i set <=> byte i == 0xFF
+        if (base + 128 <= mslen && !__any_sync(FULL, pff || (ff & 0x00010101u))) {
+          const uint32_t cb = nbits_total & 31;
+          uint32_t lo = __shfl_up_sync(FULL, w, 1);
+          uint32_t o = lane ? __funnelshift_l(lo, w, cb) : (carry_word | (w << cb));
+          msbuf[(nbits_total >> 5) + lane] = o;
+          const uint32_t w31 = __shfl_sync(FULL, w, 31);
+          carry_word = cb ? (w31 >> (32 - cb)) : 0u;
+          prev_ff = (w31 >> 24) == 0xFF;
+          nbits_total += 1024;
+          continue;
+        }
+      }
       const uint32_t b0 = w & 0xFF, b1 = (w >> 8) & 0xFF, b2 = (w >> 16) & 0xFF, b3 = w >> 24;
       const uint32_t n0 = 8 - (pff ? 1u : 0u), n1 = 8 - (b0 == 0xFF ? 1u : 0u),
                      n2 = 8 - (b1 == 0xFF ? 1u : 0u), n3 = 8 - (b2 == 0xFF ? 1u : 0u);
@@ -605,7 +644,7 @@ void launch_ht_decode(const DecBlock* blocks, uint32_t nblocks, const uint8_t* c
   uint32_t ms_cap_words = ((max_len1 >> 2) + 4 + 31) & ~31u;
   if (ms_cap_words > 2048) ms_cap_words = 2048;
   {
-    dim3 grid((nblocks + 127) / 128), block(128);
+    dim3 grid((nblocks + DEC1_THREADS - 1) / DEC1_THREADS), block(DEC1_THREADS);
     OJB_LAUNCH(ht_dec_step1_kernel, grid, block, 0, st, blocks, nblocks, codestream, scratch, tables, block_status);
   }
   {
