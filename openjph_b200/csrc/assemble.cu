@@ -16,27 +16,30 @@ namespace ojb {
 
 namespace {
 
-// warp-cooperative byte copy with 4-byte stores where the destination allows it
+// warp-cooperative byte copy: 16-byte stores once the destination is aligned, the source read as
+// aligned words and funnel-shifted into place (source and destination alignments are independent)
 __device__ __forceinline__ void warp_copy(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src,
                                           uint32_t n, uint32_t lane) {
-  // head: bring dst to 4-byte alignment
-  uint32_t head = (uint32_t)((4 - ((size_t)dst & 3)) & 3);
+  uint32_t head = (uint32_t)((16 - ((size_t)dst & 15)) & 15);
   if (head > n) head = n;
   if (lane < head) dst[lane] = src[lane];
   dst += head; src += head; n -= head;
-  uint32_t nw = n >> 2;
+  const uint32_t n16 = n >> 4;
   const uint32_t sh = (uint32_t)((size_t)src & 3) * 8;
-  if (sh == 0) {
-    const uint32_t* s4 = reinterpret_cast<const uint32_t*>(src);
-    uint32_t* d4 = reinterpret_cast<uint32_t*>(dst);
-    for (uint32_t i = lane; i < nw; i += 32) d4[i] = s4[i];
-  } else {
-    const uint32_t* s4 = reinterpret_cast<const uint32_t*>(src - (sh >> 3));
-    uint32_t* d4 = reinterpret_cast<uint32_t*>(dst);
-    for (uint32_t i = lane; i < nw; i += 32) d4[i] = __funnelshift_r(s4[i], s4[i + 1], sh);
+  const uint32_t* s4 = reinterpret_cast<const uint32_t*>((size_t)src & ~(size_t)3);
+  uint4* d16 = reinterpret_cast<uint4*>(dst);
+  #pragma unroll 2
+  for (uint32_t i = lane; i < n16; i += 32) {
+    const uint32_t* p = s4 + 4 * (size_t)i;
+    uint32_t w0 = p[0], w1 = p[1], w2 = p[2], w3 = p[3];
+    if (sh) {
+      const uint32_t w4 = p[4];
+      w0 = __funnelshift_r(w0, w1, sh); w1 = __funnelshift_r(w1, w2, sh);
+      w2 = __funnelshift_r(w2, w3, sh); w3 = __funnelshift_r(w3, w4, sh);
+    }
+    d16[i] = make_uint4(w0, w1, w2, w3);
   }
-  uint32_t done = nw << 2;
-  uint32_t tail = n - done;
+  const uint32_t done = n16 << 4, tail = n - done;
   if (lane < tail) dst[done + lane] = src[done + lane];
 }
 

@@ -465,6 +465,7 @@ ht_dec_step2_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
   if ((blk.len1 >> 2) + 4 <= ms_cap_words) msbuf = s_ms + (size_t)warp * ms_cap_words;
   const uint32_t x = 2 * lane;
   const bool has0 = x < width, has1 = x + 1 < width;
+  const bool vec2 = ((blk.dst_off | stride) & 1u) == 0;      // block rows 8-byte aligned
   const uint32_t mmsbp2 = blk.missing_msbs + 2u;
   const uint32_t p = 30u - blk.missing_msbs;
 
@@ -601,12 +602,14 @@ ht_dec_step2_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
       pv1 = vn[1]; pv3 = vn[3];
       const uint32_t om = (np > 1) ? (uint32_t)DEC_OUT_SIGNMAG : out_mode;
       uint32_t* r0 = dst + (size_t)y * stride;
-      if (has0) r0[x] = to_output(out[0], om, shift, delta);
-      if (has1) r0[x + 1] = to_output(out[2], om, shift, delta);
+      const uint32_t o0 = to_output(out[0], om, shift, delta), o2 = to_output(out[2], om, shift, delta);
+      if (vec2 && has1) *reinterpret_cast<uint2*>(r0 + x) = make_uint2(o0, o2);      // 8-byte aligned rows
+      else { if (has0) r0[x] = o0; if (has1) r0[x + 1] = o2; }
       if (y + 1 < height) {
         uint32_t* r1 = r0 + stride;
-        if (has0) r1[x] = to_output(out[1], om, shift, delta);
-        if (has1) r1[x + 1] = to_output(out[3], om, shift, delta);
+        const uint32_t o1 = to_output(out[1], om, shift, delta), o3 = to_output(out[3], om, shift, delta);
+        if (vec2 && has1) *reinterpret_cast<uint2*>(r1 + x) = make_uint2(o1, o3);
+        else { if (has0) r1[x] = o1; if (has1) r1[x + 1] = o3; }
       }
     }
 

@@ -237,11 +237,16 @@ ht_encode_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
 
   // software prefetch of the first quad-row
   uint32_t n00 = 0, n01 = 0, n10 = 0, n11 = 0;
+  // a lane's two samples of a row are one 8-byte load when the block rows are 8-byte aligned (always
+  // so inside the codec: band planes are 16-byte aligned per block row)
+  const bool vec2 = ((blk.src_off | stride) & 1u) == 0;
+  auto load_pair = [&](const uint32_t* row, uint32_t& a, uint32_t& b) {
+    if (vec2) { if (has0) { const uint2 t = *reinterpret_cast<const uint2*>(row + x); a = t.x; b = has1 ? t.y : 0u; } }
+    else { if (has0) a = row[x]; if (has1) b = row[x + 1]; }
+  };
   {
-    const uint32_t* r0 = src;
-    if (has0) n00 = r0[x];
-    if (has1) n01 = r0[x + 1];
-    if (height > 1) { const uint32_t* r1 = src + stride; if (has0) n10 = r1[x]; if (has1) n11 = r1[x + 1]; }
+    load_pair(src, n00, n01);
+    if (height > 1) load_pair(src + stride, n10, n11);
   }
 
   for (uint32_t y = 0; y < height; y += 2) {
@@ -249,9 +254,8 @@ ht_encode_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
     n00 = n01 = n10 = n11 = 0;
     if (y + 2 < height) {
       const uint32_t* r0 = src + (size_t)(y + 2) * stride;
-      if (has0) n00 = r0[x];
-      if (has1) n01 = r0[x + 1];
-      if (y + 3 < height) { const uint32_t* r1 = r0 + stride; if (has0) n10 = r1[x]; if (has1) n11 = r1[x + 1]; }
+      load_pair(r0, n00, n01);
+      if (y + 3 < height) load_pair(r0 + stride, n10, n11);
     }
 
     // ---- per-sample quantities (ojph_block_encoder.cpp:591-643)
@@ -264,6 +268,12 @@ ht_encode_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
       v = ((t3 + t3) >> p) & ~1u; if (v) { rho |= 8; --v; e3 = 32 - __clz((int)v); s3 = --v + (t3 >> 31); }
     }
     any_sig |= rho;
+    // nothing significant in this quad-row nor in the one above: every context is 0, every quad is one
+    // MEL "0" event and no VLC / MagSgn bits (quantised high bands are mostly such rows)
+    if (!__any_sync(FULL, (rho | prev_rho) != 0)) {
+      mel_encode_events(mel, 0ull, nquads, mel_buf, lane);
+      continue;
+    }
     const uint32_t emax = max(max(e0, e1), max(e2, e3));
 
     // ---- neighbourhood: left quad of this row, the four samples above

@@ -1,0 +1,330 @@
+// ht_encode_serial.cu -- HTJ2K cleanup-pass block encoder, one THREAD per code-block.
+//
+// Computes what ojph_encode_codeblock32 computes (src/core/coding/ojph_block_encoder.cpp:542-1016),
+// byte for byte, like ht_encode.cu.  The three bit-streams of a block are inherently sequential
+// (byte stuffing and the adaptive MEL coder make every bit position depend on all earlier data), so
+// the warp-per-block kernel spends most of its instructions on warp-wide scans, shared-memory bit
+// scatter and stuffing fix-ups that keep 32 lanes in lock step.  Here every lane walks its own block
+// quad by quad with the three writers in registers -- about a third of the instructions per sample --
+// and a warp advances 32 independent blocks.  Latency (one serial chain per thread) is covered by
+// software prefetch of the next quad pair and by the other frames in flight on the device.
+//   * MagSgn and VLC are written as aligned 4-byte groups straight to the block's slot (MagSgn forward
+//     from the slot start, VLC backward from the slot end, as the gather kernel expects); the stuffing
+//     rules (7-bit byte after 0xFF, :483-488; 7-bit byte 0x7F after a byte > 0x8F, :393-404) are tested
+//     on four bytes at once and the byte-wise path runs only when one applies;
+//   * MEL bytes (<= 192, the reference's limit) stay in shared memory until termination;
+//   * the previous quad-row's significance / exponents live in a per-thread shared-memory row.
+#include "ojb_device.h"
+#include "ojb_kernels.h"
+
+namespace ojb {
+
+#define ES_THREADS 128
+#define ES_MEL_BYTES 200
+#define MEL_EXP(k) ((uint32_t)((0x5433222111000ull >> (4 * (k))) & 7ull))
+
+namespace {
+
+struct MsWriter {            // forward, LSB first
+  unsigned long long acc; uint32_t nbits, words; bool last_ff;
+};
+struct VlcWriter {           // backward, LSB first
+  unsigned long long acc; uint32_t nbits, words, prev;
+};
+struct MelWriter {
+  uint32_t k, run, tmp, rem, pos;
+};
+
+// emit four MagSgn bytes (needs nbits >= 32)
+__device__ __forceinline__ void ms_flush4(MsWriter& s, uint32_t* dst) {
+  const uint32_t lo = (uint32_t)s.acc;
+  uint32_t ff = lo & (lo >> 1); ff &= ff >> 2; ff &= ff >> 4;       // bit 8i <=> byte i == 0xFF
+  uint32_t w, used;
+  if (!s.last_ff && (ff & 0x00010101u) == 0) { w = lo; used = 32; s.last_ff = (ff >> 24) & 1u; }
+  else {
+    unsigned long long a = s.acc;
+    bool lf = s.last_ff;
+    w = 0; used = 0;
+    #pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t n = lf ? 7u : 8u;
+      const uint32_t b = (uint32_t)a & ((1u << n) - 1u);
+      w |= b << (8 * i); a >>= n; used += n; lf = (b == 0xFF);
+    }
+    s.last_ff = lf;
+  }
+  dst[s.words++] = w;
+  s.acc >>= used; s.nbits -= used;
+}
+__device__ __forceinline__ void ms_put(MsWriter& s, uint32_t cwd, uint32_t len, uint32_t* dst) {
+  s.acc |= (unsigned long long)cwd << s.nbits; s.nbits += len;
+  while (s.nbits >= 32) ms_flush4(s, dst);
+}
+
+// emit four VLC bytes (needs nbits >= 32); `end` = one past the slot, words grow downward
+__device__ __forceinline__ void vlc_flush4(VlcWriter& v, uint32_t* end) {
+  const uint32_t lo = (uint32_t)v.acc;
+  const uint32_t pv = (lo << 8) | v.prev;
+  uint32_t w, used;
+  if (((((lo & 0x7F7F7F7Fu) + 0x01010101u) & pv & ((pv & 0x70707070u) + 0x70707070u)) & 0x80808080u) == 0) {
+    w = lo; used = 32;
+  } else {
+    unsigned long long a = v.acc;
+    uint32_t p = v.prev;
+    w = 0; used = 0;
+    #pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint32_t b = (uint32_t)a & 0xFFu, n = 8;
+      if (p > 0x8F && (b & 0x7F) == 0x7F) { b = 0x7F; n = 7; }
+      w |= b << (8 * i); a >>= n; used += n; p = b;
+    }
+  }
+  v.prev = w >> 24;
+  ++v.words;
+  end[-(int)v.words] = __byte_perm(w, 0, 0x0123);
+  v.acc >>= used; v.nbits -= used;
+}
+__device__ __forceinline__ void vlc_put(VlcWriter& v, uint32_t cwd, uint32_t len, uint32_t* end) {
+  v.acc |= (unsigned long long)cwd << v.nbits; v.nbits += len;
+  while (v.nbits >= 32) vlc_flush4(v, end);
+}
+
+__device__ __forceinline__ void mel_bit(MelWriter& m, uint32_t v, uint8_t* buf) {
+  m.tmp = (m.tmp << 1) | v;
+  if (--m.rem == 0) {
+    if (m.pos < ES_MEL_BYTES) buf[m.pos * ES_THREADS] = (uint8_t)m.tmp;
+    m.pos++;
+    m.rem = (m.tmp == 0xFF) ? 7 : 8;
+    m.tmp = 0;
+  }
+}
+__device__ __forceinline__ void mel_event(MelWriter& m, bool one, uint8_t* buf) {     // mel_encode :321-348
+  if (!one) {
+    if (++m.run >= (1u << MEL_EXP(m.k))) { mel_bit(m, 1, buf); m.run = 0; m.k = m.k < 12 ? m.k + 1 : 12; }
+  } else {
+    mel_bit(m, 0, buf);
+    for (uint32_t t = MEL_EXP(m.k); t > 0; ) { --t; mel_bit(m, (m.run >> t) & 1u, buf); }
+    m.run = 0; m.k = m.k > 0 ? m.k - 1 : 0;
+  }
+}
+
+__global__ void __launch_bounds__(ES_THREADS)
+ht_encode_serial_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
+                        const uint32_t* __restrict__ coef, uint8_t* __restrict__ slots,
+                        EncResult* __restrict__ results, const uint16_t* __restrict__ tables,
+                        uint32_t* __restrict__ status, uint32_t prev_quads)
+{
+  __shared__ uint16_t s_vlc[2 * 2048];
+  __shared__ uint16_t s_uvlc[36];
+  __shared__ uint8_t s_mel[ES_MEL_BYTES * ES_THREADS];
+  OJB_DYN_SMEM(uint16_t, s_prev);          // prev_quads x ES_THREADS: rho | e1 << 4 | e3 << 9 of the row above
+
+  for (uint32_t i = threadIdx.x; i < 2 * 2048; i += blockDim.x) s_vlc[i] = tables[i];
+  if (threadIdx.x < 33) s_uvlc[threadIdx.x] = tables[2 * 2048 + threadIdx.x];
+  __syncthreads();
+
+  const uint32_t bidx = blockIdx.x * ES_THREADS + threadIdx.x;
+  if (bidx >= nblocks) return;
+  const EncBlock blk = blocks[bidx];
+  const uint32_t width = blk.w, height = blk.h, stride = blk.stride, p = blk.p;
+  const uint32_t* __restrict__ src = coef + blk.src_off;
+  uint8_t* slot = slots + blk.slot_off;
+  uint32_t* ms_dst = reinterpret_cast<uint32_t*>(slot);
+  uint32_t* vl_end = reinterpret_cast<uint32_t*>(slot + blk.slot_cap);
+  uint8_t* mel_buf = s_mel + threadIdx.x;
+  uint16_t* prev = s_prev + threadIdx.x;
+  const uint32_t nq = (width + 1) >> 1;
+  const uint32_t slot_words = blk.slot_cap >> 2;
+
+  MsWriter ms; ms.acc = 0; ms.nbits = 0; ms.words = 0; ms.last_ff = false;
+  // VLC starts as byte 0xFF (later the Scup byte) followed by the four bits 0xF (vlc_init, :365-375)
+  VlcWriter vlc; vlc.acc = 0xFFFull; vlc.nbits = 12; vlc.words = 0; vlc.prev = 0;
+  MelWriter mel; mel.k = 0; mel.run = 0; mel.tmp = 0; mel.rem = 8; mel.pos = 0;
+  uint32_t any_sig = 0;
+  bool overflow = false;
+  // aligned block rows: a quad pair of one row is one 16-byte load
+  const bool vec4 = ((blk.src_off | stride) & 3u) == 0;
+
+  for (uint32_t q = 0; q <= nq; ++q) prev[q * ES_THREADS] = 0;
+
+  for (uint32_t y = 0; y < height; y += 2) {
+    const uint32_t* r0 = src + (size_t)y * stride;
+    const uint32_t* r1 = r0 + stride;
+    const bool has_r1 = y + 1 < height;
+    const uint16_t* vtab = s_vlc + (y ? 2048u : 0u);
+    uint32_t rho_left = 0;
+    uint32_t pl = 0, pc = prev[0];               // row above: quad q-1, quad q (before being overwritten)
+
+    auto load_pair = [&](uint32_t q, uint32_t (&a)[4], uint32_t (&b)[4]) {
+      // samples 2q .. 2q+3 of the two rows (zero outside the block)
+      if (vec4 && 2 * q + 3 < width) {
+        const uint4 t = *reinterpret_cast<const uint4*>(r0 + 2 * q);
+        a[0] = t.x; a[1] = t.y; a[2] = t.z; a[3] = t.w;
+        if (has_r1) { const uint4 u = *reinterpret_cast<const uint4*>(r1 + 2 * q); b[0] = u.x; b[1] = u.y; b[2] = u.z; b[3] = u.w; }
+        else { b[0] = b[1] = b[2] = b[3] = 0; }
+      } else {
+        #pragma unroll
+        for (uint32_t i = 0; i < 4; ++i) {
+          const bool in = 2 * q + i < width;
+          a[i] = in ? r0[2 * q + i] : 0u;
+          b[i] = (in && has_r1) ? r1[2 * q + i] : 0u;
+        }
+      }
+    };
+
+    uint32_t na[4], nb[4];
+    load_pair(0, na, nb);
+    for (uint32_t q = 0; q < nq; q += 2) {
+      uint32_t ca[4], cb[4];
+      #pragma unroll
+      for (int i = 0; i < 4; ++i) { ca[i] = na[i]; cb[i] = nb[i]; }
+      if (q + 2 < nq) load_pair(q + 2, na, nb);          // next pair in flight while this one is coded
+
+      uint32_t uq[2] = {0, 0};
+      #pragma unroll
+      for (uint32_t h = 0; h < 2; ++h) {
+        const uint32_t qq = q + h;
+        if (qq >= nq) break;
+        // ---- per-sample quantities (:591-643); quad order TL, BL, TR, BR
+        const uint32_t t[4] = { ca[2 * h], cb[2 * h], ca[2 * h + 1], cb[2 * h + 1] };
+        uint32_t rho = 0, e[4] = {0, 0, 0, 0}, s[4] = {0, 0, 0, 0};
+        #pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint32_t v = ((t[i] + t[i]) >> p) & ~1u;
+          if (v) { rho |= 1u << i; --v; e[i] = 32 - __clz((int)v); s[i] = --v + (t[i] >> 31); }
+        }
+        any_sig |= rho;
+        const uint32_t emax = max(max(e[0], e[1]), max(e[2], e[3]));
+        // ---- context and exponent predictor from the row above
+        const uint32_t pr = prev[(qq + 1) * ES_THREADS];      // quad qq+1 of the row above
+        uint32_t kappa = 1, cq;
+        if (y == 0) cq = (rho_left >> 1) | (rho_left & 1);
+        else {
+          // max exponent of the four samples above (:862,:950): e3 of NW quad, e1/e3 of N quad, e1 of NE quad
+          const uint32_t me = max(max((pl >> 9) & 31u, (pc >> 4) & 31u), max((pc >> 9) & 31u, (pr >> 4) & 31u));
+          if (rho & (rho - 1)) kappa = max(1u, me > 0 ? me - 1 : 0u);
+          const uint32_t a = ((pl >> 3) | (pc >> 1)) & 1u;
+          const uint32_t b = ((rho_left >> 2) | (rho_left >> 3)) & 1u;
+          const uint32_t c = ((pc >> 3) | (pr >> 1)) & 1u;
+          cq = a | (b << 1) | (c << 2);
+        }
+        prev[qq * ES_THREADS] = (uint16_t)(rho | (e[1] << 4) | (e[3] << 9));
+        pl = pc; pc = pr;
+        const uint32_t Uq = max(emax, kappa);
+        const uint32_t u = Uq - kappa;
+        uq[h] = u;
+        uint32_t eps = 0;
+        if (u > 0) eps = (e[0] == emax ? 1u : 0u) | (e[1] == emax ? 2u : 0u) | (e[2] == emax ? 4u : 0u) | (e[3] == emax ? 8u : 0u);
+        const uint32_t tuple = vtab[(cq << 8) + (rho << 4) + eps];
+        vlc_put(vlc, tuple >> 8, (tuple >> 4) & 7u, vl_end);                     // :661-662
+        if (cq == 0) mel_event(mel, rho != 0, mel_buf);                          // :664-665
+        #pragma unroll
+        for (int i = 0; i < 4; ++i) {                                            // :667-674
+          if ((rho >> i) & 1u) {
+            const uint32_t m = Uq - ((tuple >> i) & 1u);
+            ms_put(ms, s[i] & ((1u << m) - 1u), m, ms_dst);
+          }
+        }
+        rho_left = rho;
+      }
+      // ---- U-VLC of the pair (:763-785, :985-988)
+      {
+        const uint32_t u0 = uq[0], u1 = uq[1];
+        uint32_t c0, c1;
+        if (y == 0) {
+          if (u0 > 0 && u1 > 0) mel_event(mel, min(u0, u1) > 2, mel_buf);
+          if (u0 > 2 && u1 > 2) { c0 = s_uvlc[u0 - 2]; c1 = s_uvlc[u1 - 2]; }
+          else if (u0 > 2 && u1 > 0) { c0 = s_uvlc[u0]; c1 = (u1 - 1) | (1u << 3); }     // one-bit u1
+          else { c0 = s_uvlc[u0]; c1 = s_uvlc[u1]; }
+        } else { c0 = s_uvlc[u0]; c1 = s_uvlc[u1]; }
+        // prefixes of both quads, then both suffixes, as one field of at most 3+3+5+5 bits
+        uint32_t bits = c0 & 7u, len = (c0 >> 3) & 7u;
+        bits |= (c1 & 7u) << len; len += (c1 >> 3) & 7u;
+        bits |= ((c0 >> 6) & 31u) << len; len += (c0 >> 11) & 31u;
+        bits |= ((c1 >> 6) & 31u) << len; len += (c1 >> 11) & 31u;
+        vlc_put(vlc, bits, len, vl_end);
+      }
+    }
+    if (ms.words + vlc.words + 24 >= slot_words) { overflow = true; break; }
+  }
+
+  if (overflow) { atomicOr(status, 1u); results[bidx].len_head = 0; results[bidx].len_tail = 0; return; }
+  if (any_sig == 0) { results[bidx].len_head = 0; results[bidx].len_tail = 0; return; }   // block not included
+
+  // ---- termination (terminate_mel_vlc :413-441, ms_terminate :517-533)
+  uint32_t ms_pos = ms.words * 4;
+  {
+    uint32_t acc = (uint32_t)ms.acc, nb = ms.nbits;        // < 32 raw bits: cut them into bytes
+    bool lf = ms.last_ff;
+    for (;;) {
+      const uint32_t n = lf ? 7u : 8u;
+      if (nb < n) break;
+      const uint32_t b = acc & ((1u << n) - 1u);
+      slot[ms_pos++] = (uint8_t)b; acc >>= n; nb -= n; lf = (b == 0xFF);
+    }
+    const uint32_t cap = lf ? 7u : 8u;
+    if (nb) {
+      const uint32_t t = cap - nb;
+      const uint32_t byte = acc | ((0xFFu & ((1u << t) - 1u)) << nb);
+      if (byte != 0xFF) slot[ms_pos++] = (uint8_t)byte;
+    } else if (cap == 7) ms_pos--;
+  }
+  if (mel.run > 0) mel_bit(mel, 1, mel_buf);
+  const uint32_t mel_tmp = (mel.tmp << mel.rem) & 0xFFu;
+  const uint32_t mel_mask = (0xFFu << mel.rem) & 0xFFu;
+  uint32_t vl_pos = vlc.words * 4;
+  uint8_t* vend = slot + blk.slot_cap;
+  uint32_t vl_tmp, vl_mask;
+  {
+    unsigned long long acc = vlc.acc;
+    uint32_t nb = vlc.nbits, pv = vlc.prev;
+    for (;;) {                           // complete bytes of the pending bits, with their stuffing
+      uint32_t b = (uint32_t)acc & 0xFFu, n = 8;
+      if (pv > 0x8F && nb >= 7 && (b & 0x7F) == 0x7F) { b = 0x7F; n = 7; }
+      if (nb < n) break;
+      vend[-(int)(++vl_pos)] = (uint8_t)b; acc >>= n; nb -= n; pv = b;
+    }
+    // the unfinished byte: after a byte > 0x8F only 7 bits are available at first (vlc_encode :379-405)
+    vl_tmp = (uint32_t)acc & 0xFFu;
+    vl_mask = 0xFFu >> (8 - nb);
+  }
+  if ((mel_mask | vl_mask) != 0) {
+    const uint32_t fuse = mel_tmp | vl_tmp;
+    if ((((fuse ^ mel_tmp) & mel_mask) | ((fuse ^ vl_tmp) & vl_mask)) == 0 && fuse != 0xFF && vl_pos > 1) {
+      if (mel.pos < ES_MEL_BYTES) mel_buf[mel.pos * ES_THREADS] = (uint8_t)fuse;
+      mel.pos++;
+    } else {
+      if (mel.pos < ES_MEL_BYTES) mel_buf[mel.pos * ES_THREADS] = (uint8_t)mel_tmp;
+      mel.pos++;
+      vend[-(int)(++vl_pos)] = (uint8_t)vl_tmp;
+    }
+  }
+  if (mel.pos > 192 || ms_pos + mel.pos + vl_pos + 8 > blk.slot_cap) {
+    atomicOr(status, mel.pos > 192 ? 2u : 1u);          // the reference errors out on MEL > 192 bytes
+    results[bidx].len_head = 0; results[bidx].len_tail = 0;
+    return;
+  }
+  for (uint32_t i = 0; i < mel.pos; ++i) slot[ms_pos + i] = mel_buf[i * ES_THREADS];
+  const uint32_t scup = mel.pos + vl_pos;
+  vend[-1] = (uint8_t)(scup >> 4);
+  vend[-2] = (uint8_t)((vend[-2] & 0xF0) | (scup & 0xF));
+  results[bidx].len_head = ms_pos + mel.pos;
+  results[bidx].len_tail = vl_pos;
+}
+
+} // namespace
+
+void launch_ht_encode_serial(const EncBlock* blocks, uint32_t nblocks, uint32_t max_width, const uint32_t* coef,
+                             uint8_t* slots, EncResult* results, const uint16_t* tables, uint32_t* status,
+                             cudaStream_t st)
+{
+  if (nblocks == 0) return;
+  const uint32_t prev_quads = (max_width + 1) / 2 + 2;
+  const size_t smem = (size_t)prev_quads * ES_THREADS * sizeof(uint16_t);
+  cudaFuncSetAttribute(ht_encode_serial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dim3 grid((nblocks + ES_THREADS - 1) / ES_THREADS), block(ES_THREADS);
+  OJB_LAUNCH(ht_encode_serial_kernel, grid, block, smem, st, blocks, nblocks, coef, slots, results, tables, status,
+             prev_quads);
+}
+
+} // namespace ojb

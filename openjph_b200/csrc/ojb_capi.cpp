@@ -374,7 +374,11 @@ int ojb_encode_blocks(const uint32_t* samples, uint64_t n_words, ojb_block_desc*
     d_b.reserve(n * sizeof(EncBlock)); d_r.reserve(n * sizeof(EncResult)); d_sl.reserve(slot + 64); d_st.reserve(64);
     cuda_check(cudaMemcpy(d_b.p, eb.data(), n * sizeof(EncBlock), cudaMemcpyHostToDevice), "blocks");
     cuda_check(cudaMemset(d_st.p, 0, 16), "status");
-    launch_ht_encode(d_b.as<EncBlock>(), n, d_s.as<uint32_t>(), d_sl.as<uint8_t>(), d_r.as<EncResult>(),
+    if (serial_block_coder())
+      launch_ht_encode_serial(d_b.as<EncBlock>(), n, 64, d_s.as<uint32_t>(), d_sl.as<uint8_t>(), d_r.as<EncResult>(),
+                     d_t.as<uint16_t>(), d_st.as<uint32_t>(), 0);
+    else
+      launch_ht_encode(d_b.as<EncBlock>(), n, d_s.as<uint32_t>(), d_sl.as<uint8_t>(), d_r.as<EncResult>(),
                      d_t.as<uint16_t>(), d_st.as<uint32_t>(), 0);
     cuda_check(cudaDeviceSynchronize(), "ht_encode");
     cuda_check(cudaGetLastError(), "ht_encode");

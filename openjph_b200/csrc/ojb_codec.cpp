@@ -31,6 +31,11 @@ void PinnedBuf::reserve(size_t n) {
   cap = want;
 }
 
+bool serial_block_coder() {
+  static const bool v = [] { const char* e = getenv("OJB_BLOCK_CODER"); return !(e && strcmp(e, "warp") == 0); }();
+  return v;
+}
+
 CodecBase::CodecBase() {
   CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   unsigned hc = std::thread::hardware_concurrency();
@@ -287,8 +292,12 @@ size_t Encoder::encode(const void* const* planes, const uint32_t* strides, bool 
     }
   mark(2);
   uint32_t nb = (uint32_t)h_blocks.size();
-  launch_ht_encode(d_blocks.as<EncBlock>(), nb, d_coef.as<uint32_t>(), d_slots.as<uint8_t>(),
-                   d_results.as<EncResult>(), d_tables_enc.as<uint16_t>(), d_status.as<uint32_t>(), stream);
+  if (serial_block_coder())
+    launch_ht_encode_serial(d_blocks.as<EncBlock>(), nb, 64, d_coef.as<uint32_t>(), d_slots.as<uint8_t>(),
+                            d_results.as<EncResult>(), d_tables_enc.as<uint16_t>(), d_status.as<uint32_t>(), stream);
+  else
+    launch_ht_encode(d_blocks.as<EncBlock>(), nb, d_coef.as<uint32_t>(), d_slots.as<uint8_t>(),
+                     d_results.as<EncResult>(), d_tables_enc.as<uint16_t>(), d_status.as<uint32_t>(), stream);
   ++last_launches;
   mark(3);
   if (nb) launch_ctrl_copy(h_results.p, d_results.p, (size_t)nb * sizeof(EncResult), stream);

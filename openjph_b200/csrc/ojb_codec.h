@@ -95,6 +95,10 @@ struct FrameInfo {
   uint32_t num_decomps, reversible, color_transform, num_tiles;
 };
 
+// block-coder variant: one thread per code-block (default) or one warp per code-block
+// (OJB_BLOCK_CODER=warp); both produce identical bytes
+bool serial_block_coder();
+
 class Decoder : public CodecBase {
 public:
   bool resilient = false;

@@ -9,6 +9,11 @@ namespace ojb {
 void launch_ht_encode(const EncBlock* blocks, uint32_t nblocks, const uint32_t* coef, uint8_t* slots,
                       EncResult* results, const uint16_t* tables, uint32_t* status, cudaStream_t st);
 
+// the same encoder with one THREAD per code-block (ht_encode_serial.cu); max_width = widest block
+void launch_ht_encode_serial(const EncBlock* blocks, uint32_t nblocks, uint32_t max_width, const uint32_t* coef,
+                             uint8_t* slots, EncResult* results, const uint16_t* tables, uint32_t* status,
+                             cudaStream_t st);
+
 // HT decoder (ht_decode.cu): step 1 = MEL/VLC chain, one THREAD per code-block; step 2 =
 // MagSgn (+SPP +MRP) one WARP per code-block.
 // tables: uint16 dec_vlc[2][1024], dec_uvlc0[320], dec_uvlc1[256]
