@@ -27,6 +27,7 @@ namespace ojb {
 
 // block status bits
 #define DST_FAIL 1u
+#define DST_EMPTY 2u              // serial decoder: block not included, to be zero-filled
 #define DEC1_THREADS 128        // step 1: one thread per code-block
 
 namespace {
@@ -635,6 +636,276 @@ ht_dec_step2_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
   } else if (lane == 0) block_status[b] = 0;
 }
 
+// ---- whole cleanup pass, one thread per code-block ---------------------------------------------
+// The serial form of the decoder (what ojph_decode_codeblock32 does, :742-1316, minus its two-step
+// split): the thread that decodes a quad pair's VLC / U-VLC codewords reads the pair's MagSgn bits
+// right away, so no quad records travel through memory and no warp-wide scan or shared bit buffer
+// is needed -- about a third of the instructions of step 1 + step 2.  Blocks that carry SPP / MRP
+// passes still write their quad records (refine_passes needs the CUP significance).
+struct MsDec {                // MagSgn: forward, LSB first, bytes past the segment read as 0xFF
+  const uint32_t* wnext; const uint8_t* seg_end; uint32_t* ring; uint32_t ridx, lo, hi, sh;
+  int left; unsigned long long tmp; uint32_t bits; bool unstuff;
+};
+__device__ __forceinline__ void ms_ring_issue(MsDec& m) {
+  uint32_t* slot = m.ring + m.ridx * DEC1_THREADS;
+  if (reinterpret_cast<const uint8_t*>(m.wnext) < m.seg_end) cp_async<4>(slot, m.wnext); else *slot = 0xFFFFFFFFu;
+  cp_commit();
+  ++m.wnext; m.ridx = (m.ridx + 1) & (VLC_RING - 1);
+}
+__device__ __forceinline__ void ms_prime(MsDec& m, const uint8_t* p, int len, const uint8_t* seg_end, uint32_t* ring) {
+  const uint32_t* wp = reinterpret_cast<const uint32_t*>((size_t)p & ~(size_t)3);
+  m.sh = (uint32_t)((size_t)p & 3) * 8;
+  m.seg_end = seg_end; m.left = len; m.tmp = 0; m.bits = 0; m.unstuff = false;
+  m.lo = wp[0]; m.hi = wp[1];
+  m.ring = ring; m.ridx = 0; m.wnext = wp + 2;
+  #pragma unroll
+  for (int i = 0; i < VLC_RING - 1; ++i) ms_ring_issue(m);
+  m.ridx = 0;
+}
+__device__ __forceinline__ void ms_fill(MsDec& m) {            // adds 28..32 bits; needs bits < 32
+  uint32_t val = m.sh ? __funnelshift_r(m.lo, m.hi, m.sh) : m.lo;
+  m.lo = m.hi;
+  cp_wait<VLC_RING - 2>();
+  const uint32_t take = m.ridx;
+  m.hi = m.ring[take * DEC1_THREADS];
+  m.ridx = (take + VLC_RING - 1) & (VLC_RING - 1);
+  ms_ring_issue(m);
+  m.ridx = (take + 1) & (VLC_RING - 1);
+  if (m.left < 4) val |= (m.left <= 0) ? 0xFFFFFFFFu : (0xFFFFFFFFu << (8 * m.left));
+  m.left -= 4;
+  uint32_t t, nb;
+  bool us = m.unstuff;
+  uint32_t ff = val & (val >> 1); ff &= ff >> 2; ff &= ff >> 4;      // bit 8i <=> byte i == 0xFF
+  if (!us && (ff & 0x00010101u) == 0) { t = val; nb = 32; us = (ff >> 24) & 1u; }
+  else {
+    t = 0; nb = 0;
+    #pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t d = (val >> (8 * i)) & 0xFFu;
+      const uint32_t n = us ? 7u : 8u;
+      t |= (d & ((1u << n) - 1u)) << nb;
+      nb += n; us = (d == 0xFF);
+    }
+  }
+  m.unstuff = us;
+  m.tmp |= (unsigned long long)t << m.bits;
+  m.bits += nb;
+}
+
+__global__ void __launch_bounds__(DEC1_THREADS)
+ht_decode_serial_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
+                        const uint8_t* __restrict__ cs, uint32_t* __restrict__ coef,
+                        uint32_t* __restrict__ scratch, const uint16_t* __restrict__ tables,
+                        uint32_t out_mode, uint32_t* __restrict__ block_status, uint32_t prev_quads)
+{
+  __shared__ DecTables T;
+  __shared__ uint32_t s_ring[VLC_RING * DEC1_THREADS];     // per-thread FIFO of VLC words (slot-major)
+  __shared__ uint32_t s_mring[VLC_RING * DEC1_THREADS];    // per-thread FIFO of MagSgn words
+  OJB_DYN_SMEM(uint16_t, s_prev);       // prev_quads x threads: msb(v_n) of the bottom samples of the row above
+  {
+    uint16_t* d = reinterpret_cast<uint16_t*>(&T);
+    for (uint32_t i = threadIdx.x; i < sizeof(DecTables) / 2; i += blockDim.x) d[i] = tables[i];
+  }
+  __syncthreads();
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nblocks) return;
+  const DecBlock blk = blocks[b];
+  uint32_t np = blk.num_passes;
+  if (np == 0 || blk.len1 == 0) { block_status[b] = DST_EMPTY; return; }     // zero-filled by the fill kernel
+  // validity gates (:752-820)
+  if (np > 1 && blk.len2 == 0) np = 1;
+  bool ok = true;
+  if (np > 3 || blk.missing_msbs >= 30 || blk.len1 < 2) ok = false;
+  if (blk.missing_msbs == 29 && np > 1) np = 1;      // p == 1: refinement passes are skipped
+  const uint8_t* data = cs + blk.data_off;
+  int lcup = (int)blk.len1, scup = 0;
+  if (ok) {
+    scup = ((int)data[lcup - 1] << 4) + (data[lcup - 2] & 0xF);
+    if (scup < 2 || scup > lcup || scup > 4079) ok = false;
+  }
+  if (!ok || (blk.w + 1u) / 2 + 2 > prev_quads) { block_status[b] = DST_FAIL; return; }
+
+  MelDec mel; mel.p = data + lcup - scup; mel.size = scup - 1; mel.tmp = 0; mel.bits = 0;
+  mel.unstuff = false; mel.k = 0;
+  RevDec vlc; vlc.p = data + lcup - 2; vlc.size = scup - 2;
+  {
+    uint32_t d = *vlc.p--;
+    vlc.tmp = d >> 4;
+    vlc.bits = 4 - (((vlc.tmp & 7) == 7) ? 1u : 0u);
+    vlc.unstuff = (d | 0xF) > 0x8F;
+  }
+  rev_prime(vlc, cs, s_ring + threadIdx.x);
+  mel_prime(mel);
+  MsDec ms;
+  ms_prime(ms, data, lcup - scup, data + lcup, s_mring + threadIdx.x);
+  int run = mel_next_run(mel);
+
+  const uint32_t width = blk.w, height = blk.h, stride = blk.stride;
+  const uint32_t nq = (width + 1) >> 1, qstride = (nq + 1) & ~1u;   // quads per row (even stride)
+  uint32_t* rec = scratch + blk.scratch_off;
+  uint32_t* dst = coef + blk.dst_off;
+  uint16_t* prev = s_prev + threadIdx.x;
+  const uint32_t mmsbp2 = blk.missing_msbs + 2u;
+  const uint32_t p = 30u - blk.missing_msbs;
+  const uint32_t shift = 31u - blk.K_max;
+  const float delta = blk.delta;
+  const uint32_t om = (np > 1) ? (uint32_t)DEC_OUT_SIGNMAG : out_mode;
+  const bool vec4 = ((blk.dst_off | stride) & 3u) == 0;
+  bool fail = false;
+  // significance of the row above as bit masks over up to 32 quads per word is not enough for wide
+  // blocks: the row-above state (sigma of the two bottom samples, msb of their v_n) lives in s_prev
+  for (uint32_t q = 0; q <= nq; ++q) prev[q * DEC1_THREADS] = 0;
+
+  for (uint32_t y = 0; y < height && !fail; y += 2) {
+    const uint16_t* vtab = y ? T.vlc1 : T.vlc0;
+    uint32_t rho_left = 0;
+    uint32_t* rrow = rec + (size_t)(y >> 1) * qstride;
+    uint32_t pl = 0, pc = prev[0];             // row above: quad q-1, quad q (read before being overwritten)
+    uint32_t* r0 = dst + (size_t)y * stride;
+    uint32_t* r1 = r0 + stride;
+    const bool has_r1 = y + 1 < height;
+    for (uint32_t q = 0; q < nq; q += 2) {
+      uint32_t t[2] = {0, 0}, pq[3];
+      pq[0] = pl; pq[1] = pc;
+      pq[2] = prev[(q + 1) * DEC1_THREADS];
+      const uint32_t pq3 = (q + 2 <= nq) ? prev[(q + 2) * DEC1_THREADS] : 0u;
+      #pragma unroll
+      for (uint32_t i = 0; i < 2; ++i) {
+        const uint32_t qq = q + i;
+        if (qq < nq) {
+          uint32_t c;
+          if (y == 0) c = (rho_left & 1) | (rho_left >> 1);
+          else {
+            // sigma bits of the row above: bit 10 = bottom-left, bit 11 = bottom-right of a quad
+            const uint32_t pw = i ? pq[1] : pq[0], pn = i ? pq[2] : pq[1], pe = i ? pq3 : pq[2];
+            const uint32_t a = ((pw >> 11) | (pn >> 10)) & 1u;
+            const uint32_t l = ((rho_left >> 2) | (rho_left >> 3)) & 1u;
+            const uint32_t r = ((pn >> 11) | (pe >> 10)) & 1u;
+            c = a | (l << 1) | (r << 2);
+          }
+          rev_fill32(vlc);
+          uint32_t e = vtab[(c << 7) | ((uint32_t)vlc.tmp & 0x7F)];
+          if (c == 0) {               // significance of an all-zero context comes from MEL
+            run -= 2;
+            if (run != -1) e = 0;
+            if (run < 0) run = mel_next_run(mel);
+          }
+          vlc.tmp >>= (e & 7); vlc.bits -= (e & 7);
+          t[i] = e;
+          rho_left = (e >> 4) & 15u;
+        }
+      }
+      // U-VLC of the pair (:940-974 initial row, :1066-1085 others)
+      uint32_t mode = ((t[0] >> 3) & 1u) | (((t[1] >> 3) & 1u) << 1);
+      uint32_t ent;
+      rev_fill32(vlc);
+      if (y == 0) {
+        if (mode == 3) {
+          run -= 2;
+          if (run == -1) mode = 4;
+          if (run < 0) run = mel_next_run(mel);
+        }
+        ent = T.uvlc0[(mode << 6) | ((uint32_t)vlc.tmp & 0x3F)];
+      } else
+        ent = T.uvlc1[(mode << 6) | ((uint32_t)vlc.tmp & 0x3F)];
+      vlc.tmp >>= (ent & 7); vlc.bits -= (ent & 7);
+      ent >>= 3;
+      uint32_t len = ent & 0xF;
+      uint32_t suf = (uint32_t)vlc.tmp & ((1u << len) - 1u);
+      vlc.tmp >>= len; vlc.bits -= len;
+      ent >>= 4;
+      len = ent & 7; ent >>= 3;
+      const uint32_t kap = (y == 0) ? 1u : 0u;
+      const uint32_t uu[2] = { kap + (ent & 7) + (suf & ~(0xFFu << len)), kap + (ent >> 3) + (suf >> len) };
+      if (np > 1)                       // the refinement passes look the CUP significance up
+        *reinterpret_cast<uint2*>(rrow + q) = make_uint2((t[0] & 0xFFFF) | (uu[0] << 16), (t[1] & 0xFFFF) | (uu[1] << 16));
+
+      // ---- MagSgn of the two quads (:1087-1316)
+      uint32_t o[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+      #pragma unroll
+      for (uint32_t i = 0; i < 2; ++i) {
+        const uint32_t qq = q + i;
+        if (qq >= nq) break;
+        const uint32_t inf = t[i] & 0xFFFF;
+        const uint32_t rho = (inf >> 4) & 15u, ek = inf >> 12, e1 = (inf >> 8) & 15u;
+        uint32_t Uq = uu[i];
+        if (y != 0) {
+          // exponent predictor: msb of v_n of the four samples above (stored as 31 - clz(v | 2))
+          const uint32_t pw = i ? pq[1] : pq[0], pn = i ? pq[2] : pq[1], pe = i ? pq3 : pq[2];
+          const uint32_t emax = max(max((pw >> 5) & 31u, pn & 31u), max((pn >> 5) & 31u, pe & 31u));
+          Uq += (rho & (rho - 1)) ? max(emax, 1u) : 1u;
+        }
+        if (Uq > mmsbp2) { fail = true; break; }
+        uint32_t vbl = 0, vbr = 0;
+        #pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if ((rho >> k) & 1u) {
+            const uint32_t m = Uq - ((ek >> k) & 1u);
+            while (ms.bits < 32) ms_fill(ms);
+            const uint32_t bits = (uint32_t)ms.tmp;
+            ms.tmp >>= m; ms.bits -= m;
+            uint32_t v = bits & ((1u << m) - 1u);
+            v |= ((e1 >> k) & 1u) << m;
+            v |= 1u;
+            if (k == 1) vbl = v;
+            if (k == 3) vbr = v;
+            o[i][k] = to_output((bits << 31) | ((v + 2u) << (p - 1)), om, shift, delta);
+          }
+        }
+        // row-above record of this quad for the next quad-row
+        prev[qq * DEC1_THREADS] = (uint16_t)((31u - (uint32_t)__clz((int)(vbl | 2u))) | ((31u - (uint32_t)__clz((int)(vbr | 2u))) << 5)
+                                             | (((rho >> 1) & 1u) << 10) | (((rho >> 3) & 1u) << 11));
+      }
+      pl = pq[2]; pc = pq3;
+      if (fail) break;
+      // ---- store the pair: samples 2q .. 2q+3 of the two rows
+      if (vec4 && 2 * q + 3 < width) {
+        *reinterpret_cast<uint4*>(r0 + 2 * q) = make_uint4(o[0][0], o[0][2], o[1][0], o[1][2]);
+        if (has_r1) *reinterpret_cast<uint4*>(r1 + 2 * q) = make_uint4(o[0][1], o[0][3], o[1][1], o[1][3]);
+      } else {
+        #pragma unroll
+        for (uint32_t k = 0; k < 4; ++k) {
+          const uint32_t x = 2 * q + k;
+          if (x < width) {
+            r0[x] = o[k >> 1][(k & 1) * 2];
+            if (has_r1) r1[x] = o[k >> 1][(k & 1) * 2 + 1];
+          }
+        }
+      }
+    }
+  }
+  if (fail) { block_status[b] = DST_FAIL; return; }
+
+  if (np > 1) {
+    refine_passes(blk, np, data, dst, rec, qstride, p);
+    if (out_mode != DEC_OUT_SIGNMAG)
+      for (uint32_t yy = 0; yy < height; ++yy)
+        for (uint32_t xx = 0; xx < width; ++xx) {
+          uint32_t* qp = dst + (size_t)yy * stride + xx;
+          *qp = to_output(*qp, out_mode, shift, delta);
+        }
+  }
+  block_status[b] = 0;
+}
+
+// zero-fill of blocks that are not included or failed to decode (one warp per block)
+__global__ void __launch_bounds__(DEC_WARPS * 32)
+ht_dec_fill_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks, uint32_t* __restrict__ coef,
+                   uint32_t* __restrict__ block_status)
+{
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t b = blockIdx.x * DEC_WARPS + warp;
+  if (b >= nblocks) return;
+  const uint32_t st = block_status[b];
+  if (st == 0) return;
+  const DecBlock blk = blocks[b];
+  uint32_t* dst = coef + blk.dst_off;
+  for (uint32_t yy = 0; yy < blk.h; ++yy)
+    for (uint32_t xx = lane; xx < blk.w; xx += 32) dst[(size_t)yy * blk.stride + xx] = 0;
+  __syncwarp();                          // every lane has read the status before it is rewritten
+  if (lane == 0) block_status[b] = (st & DST_FAIL) ? DST_FAIL : 0u;
+}
+
 } // namespace
 
 void launch_ht_decode(const DecBlock* blocks, uint32_t nblocks, const uint8_t* codestream,
@@ -656,6 +927,25 @@ void launch_ht_decode(const DecBlock* blocks, uint32_t nblocks, const uint8_t* c
     cudaFuncSetAttribute(ht_dec_step2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     OJB_LAUNCH(ht_dec_step2_kernel, grid, block, smem, st, blocks, nblocks, codestream, coef, scratch, out_mode, block_status,
                ms_cap_words);
+  }
+}
+
+void launch_ht_decode_serial(const DecBlock* blocks, uint32_t nblocks, uint32_t max_width, const uint8_t* codestream,
+                             uint32_t* coef, uint32_t* scratch, const uint16_t* tables, uint32_t out_mode,
+                             uint32_t* block_status, cudaStream_t st)
+{
+  if (nblocks == 0) return;
+  const uint32_t prev_quads = (max_width + 1) / 2 + 2;
+  const size_t smem = (size_t)prev_quads * DEC1_THREADS * sizeof(uint16_t);
+  cudaFuncSetAttribute(ht_decode_serial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  {
+    dim3 grid((nblocks + DEC1_THREADS - 1) / DEC1_THREADS), block(DEC1_THREADS);
+    OJB_LAUNCH(ht_decode_serial_kernel, grid, block, smem, st, blocks, nblocks, codestream, coef, scratch, tables, out_mode,
+               block_status, prev_quads);
+  }
+  {
+    dim3 grid((nblocks + DEC_WARPS - 1) / DEC_WARPS), block(DEC_WARPS * 32);
+    OJB_LAUNCH(ht_dec_fill_kernel, grid, block, 0, st, blocks, nblocks, coef, block_status);
   }
 }
 

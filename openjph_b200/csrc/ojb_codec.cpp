@@ -642,9 +642,14 @@ uint32_t Decoder::decode(void* const* planes, const uint32_t* strides, bool plan
   host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
   mark(2);
   if (nb) { launch_ctrl_copy(d_dec.p, h_dec.p, (size_t)nb * sizeof(DecBlock), stream); ++last_launches; }
-  launch_ht_decode(d_dec.as<DecBlock>(), nb, cs_dev, d_coef.as<uint32_t>(), d_scratch.as<uint32_t>(),
-                   d_tables_dec.as<uint16_t>(), P.reversible() ? (uint32_t)DEC_OUT_INT : (uint32_t)DEC_OUT_FLOAT,
-                   d_bstatus.as<uint32_t>(), max_len1, stream);
+  if (serial_block_coder())
+    launch_ht_decode_serial(d_dec.as<DecBlock>(), nb, 64, cs_dev, d_coef.as<uint32_t>(), d_scratch.as<uint32_t>(),
+                            d_tables_dec.as<uint16_t>(), P.reversible() ? (uint32_t)DEC_OUT_INT : (uint32_t)DEC_OUT_FLOAT,
+                            d_bstatus.as<uint32_t>(), stream);
+  else
+    launch_ht_decode(d_dec.as<DecBlock>(), nb, cs_dev, d_coef.as<uint32_t>(), d_scratch.as<uint32_t>(),
+                     d_tables_dec.as<uint16_t>(), P.reversible() ? (uint32_t)DEC_OUT_INT : (uint32_t)DEC_OUT_FLOAT,
+                     d_bstatus.as<uint32_t>(), max_len1, stream);
   last_launches += 2;
   mark(3);
   if (nb) { launch_ctrl_copy(h_bstatus.p, d_bstatus.p, (size_t)nb * 4, stream); ++last_launches; }

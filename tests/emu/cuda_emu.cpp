@@ -180,7 +180,14 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
 // ---- runtime API subset (device memory == host memory; everything is synchronous) --------
 struct emuStream_st { int dummy; };
 struct emuEvent_st { std::chrono::steady_clock::time_point t; };
-cudaError_t cudaMalloc(void** p, size_t n) { *p = aligned_alloc(256, (n + 255) & ~(size_t)255); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+// fresh device memory is filled with a poison pattern: a kernel that reads what nobody wrote shows up
+// as a test failure here instead of passing by luck on a zeroed heap
+cudaError_t cudaMalloc(void** p, size_t n) {
+  const size_t sz = (n + 255) & ~(size_t)255;
+  *p = aligned_alloc(256, sz);
+  if (*p) { static const int pat = [] { const char* e = getenv("OJB_EMU_POISON"); return e ? (int)strtol(e, nullptr, 0) : 0xA5; }(); memset(*p, pat, sz); }
+  return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+}
 cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
 cudaError_t cudaMallocHost(void** p, size_t n) { return cudaMalloc(p, n); }
 cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
