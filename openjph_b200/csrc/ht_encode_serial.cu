@@ -56,9 +56,16 @@ __device__ __forceinline__ void ms_flush4(MsWriter& s, uint32_t* dst) {
   dst[s.words++] = w;
   s.acc >>= used; s.nbits -= used;
 }
-__device__ __forceinline__ void ms_put(MsWriter& s, uint32_t cwd, uint32_t len, uint32_t* dst) {
-  s.acc |= (unsigned long long)cwd << s.nbits; s.nbits += len;
-  while (s.nbits >= 32) ms_flush4(s, dst);
+// append up to 62 bits (two samples); fewer than 32 bits are pending on entry and on exit
+__device__ __forceinline__ void ms_put(MsWriter& s, unsigned long long cwd, uint32_t len, uint32_t* dst) {
+  unsigned long long hi = s.nbits ? (cwd >> (64 - s.nbits)) : 0ull;      // bits that do not fit the low word
+  s.acc |= cwd << s.nbits; s.nbits += len;
+  while (s.nbits >= 32) {
+    const uint32_t before = s.nbits;
+    ms_flush4(s, dst);                                                    // shifts acc right by `used`
+    const uint32_t used = before - s.nbits;
+    s.acc |= hi << (64 - used); hi >>= used;
+  }
 }
 
 // emit four VLC bytes (needs nbits >= 32); `end` = one past the slot, words grow downward
@@ -181,6 +188,7 @@ ht_encode_serial_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
       if (q + 2 < nq) load_pair(q + 2, na, nb);          // next pair in flight while this one is coded
 
       uint32_t uq[2] = {0, 0};
+      uint32_t pair_bits = 0, pair_len = 0;      // CxtVLC codewords of the pair, then its U-VLC bits (<= 30)
       #pragma unroll
       for (uint32_t h = 0; h < 2; ++h) {
         const uint32_t qq = q + h;
@@ -216,14 +224,18 @@ ht_encode_serial_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
         uint32_t eps = 0;
         if (u > 0) eps = (e[0] == emax ? 1u : 0u) | (e[1] == emax ? 2u : 0u) | (e[2] == emax ? 4u : 0u) | (e[3] == emax ? 8u : 0u);
         const uint32_t tuple = vtab[(cq << 8) + (rho << 4) + eps];
-        vlc_put(vlc, tuple >> 8, (tuple >> 4) & 7u, vl_end);                     // :661-662
+        pair_bits |= (tuple >> 8) << pair_len; pair_len += (tuple >> 4) & 7u;      // :661-662
         if (cq == 0) mel_event(mel, rho != 0, mel_buf);                          // :664-665
-        #pragma unroll
-        for (int i = 0; i < 4; ++i) {                                            // :667-674
-          if ((rho >> i) & 1u) {
-            const uint32_t m = Uq - ((tuple >> i) & 1u);
-            ms_put(ms, s[i] & ((1u << m) - 1u), m, ms_dst);
-          }
+        {                                                                         // :667-674
+          uint32_t m[4];
+          #pragma unroll
+          for (int i = 0; i < 4; ++i) m[i] = ((rho >> i) & 1u) ? Uq - ((tuple >> i) & 1u) : 0u;
+          const unsigned long long A = (unsigned long long)(s[0] & ((1u << m[0]) - 1u)) |
+                                       ((unsigned long long)(s[1] & ((1u << m[1]) - 1u)) << m[0]);
+          const unsigned long long B = (unsigned long long)(s[2] & ((1u << m[2]) - 1u)) |
+                                       ((unsigned long long)(s[3] & ((1u << m[3]) - 1u)) << m[2]);
+          if (m[0] + m[1]) ms_put(ms, A, m[0] + m[1], ms_dst);
+          if (m[2] + m[3]) ms_put(ms, B, m[2] + m[3], ms_dst);
         }
         rho_left = rho;
       }
@@ -238,7 +250,8 @@ ht_encode_serial_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
           else { c0 = s_uvlc[u0]; c1 = s_uvlc[u1]; }
         } else { c0 = s_uvlc[u0]; c1 = s_uvlc[u1]; }
         // prefixes of both quads, then both suffixes, as one field of at most 3+3+5+5 bits
-        uint32_t bits = c0 & 7u, len = (c0 >> 3) & 7u;
+        uint32_t bits = pair_bits, len = pair_len;
+        bits |= (c0 & 7u) << len; len += (c0 >> 3) & 7u;
         bits |= (c1 & 7u) << len; len += (c1 >> 3) & 7u;
         bits |= ((c0 >> 6) & 31u) << len; len += (c0 >> 11) & 31u;
         bits |= ((c1 >> 6) & 31u) << len; len += (c1 >> 11) & 31u;

@@ -374,7 +374,7 @@ int ojb_encode_blocks(const uint32_t* samples, uint64_t n_words, ojb_block_desc*
     d_b.reserve(n * sizeof(EncBlock)); d_r.reserve(n * sizeof(EncResult)); d_sl.reserve(slot + 64); d_st.reserve(64);
     cuda_check(cudaMemcpy(d_b.p, eb.data(), n * sizeof(EncBlock), cudaMemcpyHostToDevice), "blocks");
     cuda_check(cudaMemset(d_st.p, 0, 16), "status");
-    if (serial_block_coder())
+    if (serial_block_encoder())
       launch_ht_encode_serial(d_b.as<EncBlock>(), n, 64, d_s.as<uint32_t>(), d_sl.as<uint8_t>(), d_r.as<EncResult>(),
                      d_t.as<uint16_t>(), d_st.as<uint32_t>(), 0);
     else
@@ -430,7 +430,7 @@ int ojb_decode_blocks(const uint8_t* bytes, uint64_t n_bytes, ojb_block_desc* de
     d_b.reserve(n * sizeof(DecBlock)); d_o.reserve((n_words + 64) * 4); d_sc.reserve((scratch + 64) * 4); d_st.reserve(n * 4 + 16);
     cuda_check(cudaMemcpy(d_b.p, db.data(), n * sizeof(DecBlock), cudaMemcpyHostToDevice), "blocks");
     cuda_check(cudaMemcpy(d_o.p, samples, n_words * 4, cudaMemcpyHostToDevice), "out init");
-    if (serial_block_coder())
+    if (serial_block_decoder())
       launch_ht_decode_serial(d_b.as<DecBlock>(), n, 64, d_cs.as<uint8_t>(), d_o.as<uint32_t>(), d_sc.as<uint32_t>(),
                               d_t.as<uint16_t>(), DEC_OUT_SIGNMAG, d_st.as<uint32_t>(), 0);
     else

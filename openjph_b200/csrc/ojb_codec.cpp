@@ -31,8 +31,12 @@ void PinnedBuf::reserve(size_t n) {
   cap = want;
 }
 
-bool serial_block_coder() {
-  static const bool v = [] { const char* e = getenv("OJB_BLOCK_CODER"); return !(e && strcmp(e, "warp") == 0); }();
+bool serial_block_encoder() {
+  static const bool v = [] { const char* e = getenv("OJB_BLOCK_ENCODER"); return !(e && strcmp(e, "warp") == 0); }();
+  return v;
+}
+bool serial_block_decoder() {
+  static const bool v = [] { const char* e = getenv("OJB_BLOCK_DECODER"); return e && strcmp(e, "serial") == 0; }();
   return v;
 }
 
@@ -292,7 +296,7 @@ size_t Encoder::encode(const void* const* planes, const uint32_t* strides, bool 
     }
   mark(2);
   uint32_t nb = (uint32_t)h_blocks.size();
-  if (serial_block_coder())
+  if (serial_block_encoder())
     launch_ht_encode_serial(d_blocks.as<EncBlock>(), nb, 64, d_coef.as<uint32_t>(), d_slots.as<uint8_t>(),
                             d_results.as<EncResult>(), d_tables_enc.as<uint16_t>(), d_status.as<uint32_t>(), stream);
   else
@@ -642,7 +646,7 @@ uint32_t Decoder::decode(void* const* planes, const uint32_t* strides, bool plan
   host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
   mark(2);
   if (nb) { launch_ctrl_copy(d_dec.p, h_dec.p, (size_t)nb * sizeof(DecBlock), stream); ++last_launches; }
-  if (serial_block_coder())
+  if (serial_block_decoder())
     launch_ht_decode_serial(d_dec.as<DecBlock>(), nb, 64, cs_dev, d_coef.as<uint32_t>(), d_scratch.as<uint32_t>(),
                             d_tables_dec.as<uint16_t>(), P.reversible() ? (uint32_t)DEC_OUT_INT : (uint32_t)DEC_OUT_FLOAT,
                             d_bstatus.as<uint32_t>(), stream);

@@ -95,9 +95,12 @@ struct FrameInfo {
   uint32_t num_decomps, reversible, color_transform, num_tiles;
 };
 
-// block-coder variant: one thread per code-block (default) or one warp per code-block
-// (OJB_BLOCK_CODER=warp); both produce identical bytes
-bool serial_block_coder();
+// block-coder variants, identical results.  Encoder: one thread per code-block by default (fewest
+// instructions, best with several frames in flight), OJB_BLOCK_ENCODER=warp selects one warp per
+// block.  Decoder: step 1 (thread per block) + step 2 (warp per block) by default,
+// OJB_BLOCK_DECODER=serial selects the single-pass thread-per-block kernel.
+bool serial_block_encoder();
+bool serial_block_decoder();
 
 class Decoder : public CodecBase {
 public:

@@ -189,3 +189,16 @@ def test_errors_are_reported_not_swallowed(gpu_lib):
         ob.Encoder(ob.make_params(64, 64, 2, 8, color_transform=True, reversible=True), ob.I32)   # < 3 comps
     with pytest.raises(ob.OjphError):
         ob.Decoder().decode(b"\xff\x4f\xff\x51" + b"\0" * 64)
+
+
+@pytest.mark.gpu
+def test_alternate_block_coder_variants_gpu(gpu_lib, ref):
+    """warp-per-block encoder and single-pass thread-per-block decoder (non-default) on the device"""
+    import os, subprocess, sys
+    if os.environ.get("OJB_VARIANT_CHILD"):
+        pytest.skip("already inside the child run")
+    env = dict(os.environ, OJB_BLOCK_ENCODER="warp", OJB_BLOCK_DECODER="serial", OJB_VARIANT_CHILD="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "--timeout", "600",
+                        "-k", "block_encoder or block_decoder or cfg2 or cfg3 or odd_rgb_L5 or offsets"],
+                       env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
