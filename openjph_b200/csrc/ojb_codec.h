@@ -97,10 +97,11 @@ struct FrameInfo {
 
 // block-coder variants, identical results.  Encoder: one thread per code-block by default (fewest
 // instructions, best with several frames in flight), OJB_BLOCK_ENCODER=warp selects one warp per
-// block.  Decoder: step 1 (thread per block) + step 2 (warp per block) by default,
-// OJB_BLOCK_DECODER=serial selects the single-pass thread-per-block kernel.
+// block.  Decoder: 0 = step 1 (thread per block) + step 2 (warp per block), the default;
+// OJB_BLOCK_DECODER=serial (1) = single-pass thread-per-block kernel; =destuff (2) = warp-parallel
+// de-stuffing of the MagSgn segments, then the thread-per-block kernel with branch-free bit fetches.
 bool serial_block_encoder();
-bool serial_block_decoder();
+int block_decoder_variant();
 
 class Decoder : public CodecBase {
 public:
