@@ -692,10 +692,6 @@ __device__ __forceinline__ void ms_fill(MsDec& m) {            // adds 28..32 bi
   m.bits += nb;
 }
 
-// DESTUFFED: the MagSgn bits were unpacked beforehand by ht_dec_destuff_kernel (one warp per block, in
-// parallel) into the block's scratch; every sample is then one branch-free 32-bit fetch at a bit
-// position, so the lanes of a warp do not diverge on refills
-template <bool DESTUFFED>
 __global__ void __launch_bounds__(DEC1_THREADS)
 ht_decode_serial_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
                         const uint8_t* __restrict__ cs, uint32_t* __restrict__ coef,
@@ -741,12 +737,7 @@ ht_decode_serial_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
   rev_prime(vlc, cs, s_ring + threadIdx.x);
   mel_prime(mel);
   MsDec ms;
-  if (!DESTUFFED) ms_prime(ms, data, lcup - scup, data + lcup, s_mring + threadIdx.x);
-  // destuffed form: bit buffer behind the quad-record region of the block's scratch, padded with ones
-  const uint32_t nqr_all = (blk.h + 1u) >> 1, qs_all = (((blk.w + 1u) >> 1) + 1u) & ~1u;
-  const uint32_t* msbuf = scratch + blk.scratch_off + (size_t)qs_all * nqr_all;
-  const uint32_t ms_words_max = ((uint32_t)(lcup - scup) >> 2) + 1u;
-  uint32_t ms_pos = 0;
+  ms_prime(ms, data, lcup - scup, data + lcup, s_mring + threadIdx.x);
   int run = mel_next_run(mel);
 
   const uint32_t width = blk.w, height = blk.h, stride = blk.stride;
@@ -850,13 +841,9 @@ ht_decode_serial_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
         for (int k = 0; k < 4; ++k) {
           if ((rho >> k) & 1u) {
             const uint32_t m = Uq - ((ek >> k) & 1u);
-            uint32_t bits;
-            if (DESTUFFED) { bits = fetch_bits(msbuf, ms_pos, ms_words_max); ms_pos += m; }
-            else {
-              while (ms.bits < 32) ms_fill(ms);
-              bits = (uint32_t)ms.tmp;
-              ms.tmp >>= m; ms.bits -= m;
-            }
+            while (ms.bits < 32) ms_fill(ms);
+            const uint32_t bits = (uint32_t)ms.tmp;
+            ms.tmp >>= m; ms.bits -= m;
             uint32_t v = bits & ((1u << m) - 1u);
             v |= ((e1 >> k) & 1u) << m;
             v |= 1u;
@@ -899,97 +886,6 @@ ht_decode_serial_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
         }
   }
   block_status[b] = 0;
-}
-
-// parallel de-stuffing of every block's MagSgn segment (one warp per block) into the block's scratch:
-// the same unpacking as the first phase of step 2, as a kernel of its own for the thread-per-block decoder
-__global__ void __launch_bounds__(DEC_WARPS * 32)
-ht_dec_destuff_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks, const uint8_t* __restrict__ cs,
-                      uint32_t* __restrict__ scratch)
-{
-  __shared__ uint32_t s_stage[DEC_WARPS][40];
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t b = blockIdx.x * DEC_WARPS + warp;
-  if (b >= nblocks) return;
-  const DecBlock blk = blocks[b];
-  if (blk.num_passes == 0 || blk.len1 < 2) return;
-  const uint8_t* data = cs + blk.data_off;
-  const int lcup = (int)blk.len1;
-  const int scup = ((int)data[lcup - 1] << 4) + (data[lcup - 2] & 0xF);
-  if (scup < 2 || scup > lcup || scup > 4079) return;          // the decode kernel reports the failure
-  const uint32_t mslen = (uint32_t)(lcup - scup);
-  const uint32_t nqrows = (blk.h + 1u) >> 1, qstride = (((blk.w + 1u) >> 1) + 1u) & ~1u;
-  uint32_t* msbuf = scratch + blk.scratch_off + (size_t)qstride * nqrows;
-  uint32_t* stage = s_stage[warp];
-  uint32_t nbits_total = 0, carry_word = 0;
-  bool prev_ff = false;
-  uint32_t w_next = (4 * lane < mslen) ? load_u32_unaligned(data + 4 * lane) : 0xFFFFFFFFu;
-  for (uint32_t base = 0; base < mslen; base += 128) {
-    const uint32_t off = base + 4 * lane;
-    uint32_t w = w_next;
-    if (off + 128 < mslen) w_next = load_u32_unaligned(data + off + 128);
-    else w_next = 0xFFFFFFFFu;
-    if (off < mslen && off + 4 > mslen) w |= 0xFFFFFFFFu << (8 * (mslen - off));
-    const uint32_t lastb = w >> 24;
-    uint32_t pv = __shfl_up_sync(FULL, lastb, 1);
-    const bool pff = lane ? (pv == 0xFF) : prev_ff;
-    {
-      uint32_t ff = w & (w >> 1); ff &= ff >> 2; ff &= ff >> 4;
-      if (base + 128 <= mslen && !__any_sync(FULL, pff || (ff & 0x00010101u))) {
-        const uint32_t cb = nbits_total & 31;
-        uint32_t lo = __shfl_up_sync(FULL, w, 1);
-        uint32_t o = lane ? __funnelshift_l(lo, w, cb) : (carry_word | (w << cb));
-        msbuf[(nbits_total >> 5) + lane] = o;
-        const uint32_t w31 = __shfl_sync(FULL, w, 31);
-        carry_word = cb ? (w31 >> (32 - cb)) : 0u;
-        prev_ff = (w31 >> 24) == 0xFF;
-        nbits_total += 1024;
-        continue;
-      }
-    }
-    const uint32_t b0 = w & 0xFF, b1 = (w >> 8) & 0xFF, b2 = (w >> 16) & 0xFF, b3 = w >> 24;
-    const uint32_t n0 = 8 - (pff ? 1u : 0u), n1 = 8 - (b0 == 0xFF ? 1u : 0u),
-                   n2 = 8 - (b1 == 0xFF ? 1u : 0u), n3 = 8 - (b2 == 0xFF ? 1u : 0u);
-    uint32_t t = b0 & ((1u << n0) - 1u);
-    t |= (b1 & ((1u << n1) - 1u)) << n0;
-    t |= (b2 & ((1u << n2) - 1u)) << (n0 + n1);
-    t |= (b3 & ((1u << n3) - 1u)) << (n0 + n1 + n2);
-    uint32_t n = (off < mslen) ? (n0 + n1 + n2 + n3) : 0u;
-    if (off < mslen && off + 4 > mslen) {
-      const uint32_t k = mslen - off;
-      n = n0 + (k > 1 ? n1 : 0) + (k > 2 ? n2 : 0);
-      t &= (n < 32) ? ((1u << n) - 1u) : 0xFFFFFFFFu;
-    }
-    uint32_t incl = n;
-    #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(FULL, incl, d); if ((int)lane >= d) incl += o; }
-    const uint32_t tot = __shfl_sync(FULL, incl, 31);
-    const uint32_t cb = nbits_total & 31;
-    for (uint32_t i = lane; i < 36; i += 32) stage[i] = 0;
-    __syncwarp();
-    if (lane == 0) stage[0] = carry_word;
-    __syncwarp();
-    if (n) {
-      const uint32_t o = cb + incl - n;
-      const unsigned long long v = (unsigned long long)t << (o & 31);
-      atomicOr(&stage[o >> 5], (uint32_t)v);
-      if ((uint32_t)(v >> 32)) atomicOr(&stage[(o >> 5) + 1], (uint32_t)(v >> 32));
-    }
-    __syncwarp();
-    const uint32_t nb = cb + tot, nw = nb >> 5;
-    uint32_t* o32 = msbuf + (nbits_total >> 5);
-    for (uint32_t i = lane; i < nw; i += 32) o32[i] = stage[i];
-    carry_word = stage[nw];
-    __syncwarp();
-    nbits_total += tot;
-    const uint32_t last_off = min(mslen, base + 128) - 1 - base;
-    const uint32_t wsrc = __shfl_sync(FULL, w, last_off >> 2);
-    prev_ff = ((wsrc >> (8 * (last_off & 3))) & 0xFF) == 0xFF;
-  }
-  // tail: remaining bits, then ones up to the fetch clamp of the decode kernel (mslen / 4 + 1 words) + 2
-  const uint32_t first_pad = nbits_total >> 5;
-  if (lane == 0) msbuf[first_pad] = carry_word | ((nbits_total & 31) ? (0xFFFFFFFFu << (nbits_total & 31)) : 0xFFFFFFFFu);
-  for (uint32_t i = first_pad + 1 + lane; i <= (mslen >> 2) + 3; i += 32) msbuf[i] = 0xFFFFFFFFu;
 }
 
 // zero-fill of blocks that are not included or failed to decode (one warp per block)
@@ -1036,26 +932,16 @@ void launch_ht_decode(const DecBlock* blocks, uint32_t nblocks, const uint8_t* c
 
 void launch_ht_decode_serial(const DecBlock* blocks, uint32_t nblocks, uint32_t max_width, const uint8_t* codestream,
                              uint32_t* coef, uint32_t* scratch, const uint16_t* tables, uint32_t out_mode,
-                             uint32_t* block_status, bool destuff_first, cudaStream_t st)
+                             uint32_t* block_status, cudaStream_t st)
 {
   if (nblocks == 0) return;
   const uint32_t prev_quads = (max_width + 1) / 2 + 2;
   const size_t smem = (size_t)prev_quads * DEC1_THREADS * sizeof(uint16_t);
-  if (destuff_first) {
-    dim3 grid((nblocks + DEC_WARPS - 1) / DEC_WARPS), block(DEC_WARPS * 32);
-    OJB_LAUNCH(ht_dec_destuff_kernel, grid, block, 0, st, blocks, nblocks, codestream, scratch);
-  }
+  cudaFuncSetAttribute(ht_decode_serial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   {
     dim3 grid((nblocks + DEC1_THREADS - 1) / DEC1_THREADS), block(DEC1_THREADS);
-    if (destuff_first) {
-      auto k = ht_decode_serial_kernel<true>;
-      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      OJB_LAUNCH(k, grid, block, smem, st, blocks, nblocks, codestream, coef, scratch, tables, out_mode, block_status, prev_quads);
-    } else {
-      auto k = ht_decode_serial_kernel<false>;
-      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      OJB_LAUNCH(k, grid, block, smem, st, blocks, nblocks, codestream, coef, scratch, tables, out_mode, block_status, prev_quads);
-    }
+    OJB_LAUNCH(ht_decode_serial_kernel, grid, block, smem, st, blocks, nblocks, codestream, coef, scratch, tables, out_mode,
+               block_status, prev_quads);
   }
   {
     dim3 grid((nblocks + DEC_WARPS - 1) / DEC_WARPS), block(DEC_WARPS * 32);

@@ -430,9 +430,9 @@ int ojb_decode_blocks(const uint8_t* bytes, uint64_t n_bytes, ojb_block_desc* de
     d_b.reserve(n * sizeof(DecBlock)); d_o.reserve((n_words + 64) * 4); d_sc.reserve((scratch + 64) * 4); d_st.reserve(n * 4 + 16);
     cuda_check(cudaMemcpy(d_b.p, db.data(), n * sizeof(DecBlock), cudaMemcpyHostToDevice), "blocks");
     cuda_check(cudaMemcpy(d_o.p, samples, n_words * 4, cudaMemcpyHostToDevice), "out init");
-    if (block_decoder_variant() != 0)
+    if (serial_block_decoder())
       launch_ht_decode_serial(d_b.as<DecBlock>(), n, 64, d_cs.as<uint8_t>(), d_o.as<uint32_t>(), d_sc.as<uint32_t>(),
-                              d_t.as<uint16_t>(), DEC_OUT_SIGNMAG, d_st.as<uint32_t>(), block_decoder_variant() == 2, 0);
+                              d_t.as<uint16_t>(), DEC_OUT_SIGNMAG, d_st.as<uint32_t>(), 0);
     else
       launch_ht_decode(d_b.as<DecBlock>(), n, d_cs.as<uint8_t>(), d_o.as<uint32_t>(), d_sc.as<uint32_t>(),
                        d_t.as<uint16_t>(), DEC_OUT_SIGNMAG, d_st.as<uint32_t>(), max_len1, 0);

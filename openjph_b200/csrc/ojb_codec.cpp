@@ -35,13 +35,8 @@ bool serial_block_encoder() {
   static const bool v = [] { const char* e = getenv("OJB_BLOCK_ENCODER"); return !(e && strcmp(e, "warp") == 0); }();
   return v;
 }
-int block_decoder_variant() {
-  static const int v = [] {
-    const char* e = getenv("OJB_BLOCK_DECODER");
-    if (e && strcmp(e, "serial") == 0) return 1;
-    if (e && strcmp(e, "destuff") == 0) return 2;
-    return 0;
-  }();
+bool serial_block_decoder() {
+  static const bool v = [] { const char* e = getenv("OJB_BLOCK_DECODER"); return e && strcmp(e, "serial") == 0; }();
   return v;
 }
 
@@ -651,10 +646,10 @@ uint32_t Decoder::decode(void* const* planes, const uint32_t* strides, bool plan
   host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
   mark(2);
   if (nb) { launch_ctrl_copy(d_dec.p, h_dec.p, (size_t)nb * sizeof(DecBlock), stream); ++last_launches; }
-  if (block_decoder_variant() != 0)
+  if (serial_block_decoder())
     launch_ht_decode_serial(d_dec.as<DecBlock>(), nb, 64, cs_dev, d_coef.as<uint32_t>(), d_scratch.as<uint32_t>(),
                             d_tables_dec.as<uint16_t>(), P.reversible() ? (uint32_t)DEC_OUT_INT : (uint32_t)DEC_OUT_FLOAT,
-                            d_bstatus.as<uint32_t>(), block_decoder_variant() == 2, stream);
+                            d_bstatus.as<uint32_t>(), stream);
   else
     launch_ht_decode(d_dec.as<DecBlock>(), nb, cs_dev, d_coef.as<uint32_t>(), d_scratch.as<uint32_t>(),
                      d_tables_dec.as<uint16_t>(), P.reversible() ? (uint32_t)DEC_OUT_INT : (uint32_t)DEC_OUT_FLOAT,

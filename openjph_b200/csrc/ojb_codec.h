@@ -97,11 +97,10 @@ struct FrameInfo {
 
 // block-coder variants, identical results.  Encoder: one thread per code-block by default (fewest
 // instructions, best with several frames in flight), OJB_BLOCK_ENCODER=warp selects one warp per
-// block.  Decoder: 0 = step 1 (thread per block) + step 2 (warp per block), the default;
-// OJB_BLOCK_DECODER=serial (1) = single-pass thread-per-block kernel; =destuff (2) = warp-parallel
-// de-stuffing of the MagSgn segments, then the thread-per-block kernel with branch-free bit fetches.
+// block.  Decoder: step 1 (thread per block) + step 2 (warp per block) by default,
+// OJB_BLOCK_DECODER=serial selects the single-pass thread-per-block kernel.
 bool serial_block_encoder();
-int block_decoder_variant();
+bool serial_block_decoder();
 
 class Decoder : public CodecBase {
 public:
