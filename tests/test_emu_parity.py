@@ -101,8 +101,7 @@ def test_line_interface_exchange_and_pull(name, planar, emu_lib, ref):
         assert order[:2 * nc] == list(range(nc)) * 2      # row by row, component by component
 
 
-@pytest.mark.parametrize("decoder", ["serial"])
-def test_alternate_block_coder_variants(decoder, emu_lib, ref):
+def test_alternate_block_coder_variants(emu_lib, ref):
     """the non-default kernels (warp-per-block encoder, single-pass thread-per-block decoder) are selected
     by environment variables read once per process: run a subset of this file in a child process"""
     import os, subprocess, sys

@@ -192,8 +192,7 @@ def test_errors_are_reported_not_swallowed(gpu_lib):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("decoder", ["serial"])
-def test_alternate_block_coder_variants_gpu(decoder, gpu_lib, ref):
+def test_alternate_block_coder_variants_gpu(gpu_lib, ref):
     """warp-per-block encoder and single-pass thread-per-block decoder (non-default) on the device"""
     import os, subprocess, sys
     if os.environ.get("OJB_VARIANT_CHILD"):
