@@ -1,0 +1,187 @@
+// ojph_b200_codestream.hpp -- header-only C++ facade over the C-ABI (ojph_b200.h) with the class and
+// method names of OpenJPH's public interface, so that code written against ojph::codestream
+// (src/core/openjph/ojph_codestream.h:88-383), ojph::param_siz / param_cod / param_qcd
+// (src/core/openjph/ojph_params.h) -- e.g. ojph_compress.cpp:1165-1203, ojph_expand.cpp:224-421 --
+// switches to the B200 path by replacing `ojph::codestream` with `ojph::b200::codestream`.
+//
+// The including translation unit provides OpenJPH's own public headers first (they are not part of
+// this repository):  ojph_base.h (ui8/ui32/si32, point, size), ojph_mem.h (line_buf), ojph_file.h
+// (outfile_base, infile_base).  Only what the reference's apps call is mirrored; Part-2 items the
+// hot path does not cover (NLT, COC per-component styles, DFS/ATK, resolution restriction) raise the
+// same kind of std::runtime_error the reference raises for invalid settings.
+#pragma once
+#include "ojph_b200.h"
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace ojph { namespace b200 {
+
+inline void raise(const char* what) {           // OJPH_ERROR: message on stderr + std::runtime_error
+  fprintf(stderr, "%s\n", what);
+  throw std::runtime_error("ojph error");
+}
+inline void check(int rc) { if (rc != 0) raise(ojb_last_error()); }
+
+struct state {                                   // what write_headers / read_headers consume
+  ojb_params p;
+  ojb_frame_info info;                           // decode side, after read_headers
+  bool reading = false;
+  int planar = -1;
+  state() { ojb_params_default(&p); memset(&info, 0, sizeof(info)); }
+};
+
+class param_siz {                                // ojph_params.h:55-101
+  state* s;
+public:
+  explicit param_siz(state* st) : s(st) {}
+  void set_image_extent(point extent) { s->p.width = extent.x; s->p.height = extent.y; }
+  void set_tile_size(size ts) { s->p.tile_w = ts.w; s->p.tile_h = ts.h; }
+  void set_image_offset(point o) { s->p.off_x = o.x; s->p.off_y = o.y; }
+  void set_tile_offset(point o) { s->p.tile_off_x = o.x; s->p.tile_off_y = o.y; }
+  void set_num_components(ui32 n) {
+    if (n == 0 || n > 16) raise("ojph error 0x00040005: this build supports 1..16 components");
+    s->p.num_comps = n;
+  }
+  void set_component(ui32 c, const point& downsampling, ui32 bit_depth, bool is_signed) {
+    if (c >= s->p.num_comps) raise("ojph error 0x00040002: component number is larger than the number of components");
+    s->p.dx[c] = downsampling.x; s->p.dy[c] = downsampling.y;
+    s->p.bit_depth[c] = bit_depth; s->p.is_signed[c] = is_signed ? 1u : 0u;
+  }
+  point get_image_extent() const { return s->reading ? point(s->info.width, s->info.height) : point(s->p.width, s->p.height); }
+  point get_image_offset() const { return s->reading ? point(s->info.off_x, s->info.off_y) : point(s->p.off_x, s->p.off_y); }
+  ui32 get_num_components() const { return s->reading ? s->info.num_comps : s->p.num_comps; }
+  ui32 get_bit_depth(ui32 c) const { return s->reading ? s->info.bit_depth[c] : s->p.bit_depth[c]; }
+  bool is_signed(ui32 c) const { return (s->reading ? s->info.is_signed[c] : s->p.is_signed[c]) != 0; }
+  point get_downsampling(ui32 c) const { return s->reading ? point(s->info.dx[c], s->info.dy[c]) : point(s->p.dx[c], s->p.dy[c]); }
+  ui32 get_recon_width(ui32 c) const { return s->info.comp_w[c]; }
+  ui32 get_recon_height(ui32 c) const { return s->info.comp_h[c]; }
+};
+
+class param_cod {                                // ojph_params.h:103-160
+  state* s;
+public:
+  explicit param_cod(state* st) : s(st) {}
+  void set_num_decomposition(ui32 n) { s->p.num_decomps = n; }
+  void set_block_dims(ui32 w, ui32 h) { s->p.block_w = w; s->p.block_h = h; }
+  void set_precinct_size(int num_levels, size* precinct_size) {
+    if (num_levels < 0 || num_levels > 33) raise("ojph error: too many precinct sizes");
+    s->p.num_precincts = (uint32_t)num_levels;
+    for (int i = 0; i < num_levels; ++i) { s->p.precinct_w[i] = precinct_size[i].w; s->p.precinct_h[i] = precinct_size[i].h; }
+  }
+  void set_progression_order(const char* name) {
+    static const char* names[5] = { "LRCP", "RLCP", "RPCL", "PCRL", "CPRL" };
+    for (uint32_t i = 0; i < 5; ++i) if (strcmp(name, names[i]) == 0) { s->p.prog_order = i; return; }
+    raise("ojph error 0x00050031: unknown progression order");
+  }
+  void set_color_transform(bool on) { s->p.color_transform = on ? 1u : 0u; }
+  void set_reversible(bool on) { s->p.reversible = on ? 1u : 0u; }
+  ui32 get_num_decompositions() const { return s->reading ? s->info.num_decomps : s->p.num_decomps; }
+  bool is_reversible() const { return (s->reading ? s->info.reversible : s->p.reversible) != 0; }
+  bool is_using_color_transform() const { return (s->reading ? s->info.color_transform : s->p.color_transform) != 0; }
+};
+
+class param_qcd {                                // ojph_params.h:186-250
+  state* s;
+public:
+  explicit param_qcd(state* st) : s(st) {}
+  void set_irrev_quant(float delta) { s->p.qstep = delta; }
+  void set_qfactor(ui8 qfactor) { s->p.qfactor = qfactor; }
+};
+
+class codestream {                               // ojph_codestream.h:88-383
+  state st;
+  ojb_encoder* enc = nullptr;
+  ojb_decoder* dec = nullptr;
+  outfile_base* out = nullptr;
+  std::vector<ui8> j2c;                          // decode: the whole stream (the GPU path is frame based)
+  line_buf line;
+  bool resilient = false;
+public:
+  codestream() {}
+  ~codestream() { close(); }
+  codestream(const codestream&) = delete;
+  codestream& operator=(const codestream&) = delete;
+
+  param_siz access_siz() { return param_siz(&st); }
+  param_cod access_cod() { return param_cod(&st); }
+  param_qcd access_qcd() { return param_qcd(&st); }
+
+  // ---- write side
+  void set_planar(bool planar) { st.planar = planar ? 1 : 0; }
+  void set_profile(const char* name) {           // profiles only constrain parameters (ojph_codestream_local.cpp:172-262)
+    if (name == nullptr || (strcmp(name, "IMF") != 0 && strcmp(name, "BROADCAST") != 0))
+      raise("ojph error 0x000300A1: unknown or unsupported profile");
+  }
+  void set_tilepart_divisions(bool at_resolutions, bool at_components) {
+    st.p.tilepart_div = (at_resolutions ? 1u : 0u) | (at_components ? 2u : 0u);
+  }
+  void request_tlm_marker(bool needed) { st.p.tlm = needed ? 1u : 0u; }
+  void write_headers(outfile_base* file, const void* comments = nullptr, ui32 num_comments = 0) {
+    if (comments != nullptr || num_comments != 0) raise("ojph error: extra COM segments are not supported by the B200 path");
+    st.p.planar = st.planar;
+    if (enc == nullptr) enc = ojb_enc_create();
+    if (enc == nullptr) raise(ojb_last_error());
+    check(ojb_enc_configure(enc, &st.p, OJB_I32));
+    out = file;
+  }
+  // first call with NULL; returns the line to fill and the component it belongs to; NULL after the last line
+  line_buf* exchange(line_buf* filled, ui32& next_component) {
+    si32* p = ojb_enc_exchange(enc, filled ? filled->i32 : nullptr, &next_component);
+    if (p == nullptr) return nullptr;
+    line.i32 = p; line.size = comp_width(next_component); line.pre_size = 0;
+    line.flags = line_buf::LFT_32BIT | line_buf::LFT_INTEGER;
+    return &line;
+  }
+  void flush() {
+    uint64_t cap = 1u << 20;
+    for (ui32 c = 0; c < st.p.num_comps; ++c) cap += (uint64_t)comp_width(c) * comp_height(c) * 4;
+    std::vector<ui8> buf(cap);
+    uint64_t n = 0;
+    check(ojb_enc_flush(enc, buf.data(), buf.size(), &n));
+    if (out->write(buf.data(), (size_t)n) != (size_t)n) raise("ojph error: could not write the codestream");
+  }
+
+  // ---- read side
+  void enable_resilience() { resilient = true; }
+  void read_headers(infile_base* file) {
+    ui8 tmp[1 << 16];
+    size_t k;
+    j2c.clear();
+    while ((k = file->read(tmp, sizeof(tmp))) > 0) j2c.insert(j2c.end(), tmp, tmp + k);
+    if (dec == nullptr) dec = ojb_dec_create();
+    if (dec == nullptr) raise(ojb_last_error());
+    if (resilient) ojb_dec_enable_resilience(dec);
+    check(ojb_dec_read_headers(dec, j2c.data(), j2c.size(), OJB_I32, &st.info));
+    st.reading = true;
+  }
+  void restrict_input_resolution(ui32 skipped_res_for_data, ui32 skipped_res_for_recon) {
+    if (skipped_res_for_data || skipped_res_for_recon) raise("ojph error: resolution restriction is not supported by the B200 path");
+  }
+  void create() {
+    if (st.planar >= 0) ojb_dec_set_planar(dec, st.planar);
+    check(ojb_dec_begin_pull(dec));
+  }
+  line_buf* pull(ui32& comp_num) {
+    const si32* p = ojb_dec_pull(dec, &comp_num);
+    if (p == nullptr) return nullptr;
+    line.i32 = const_cast<si32*>(p); line.size = st.info.comp_w[comp_num]; line.pre_size = 0;
+    line.flags = line_buf::LFT_32BIT | line_buf::LFT_INTEGER;
+    return &line;
+  }
+
+  void close() {
+    if (enc) { ojb_enc_destroy(enc); enc = nullptr; }
+    if (dec) { ojb_dec_destroy(dec); dec = nullptr; }
+    if (out) { out->close(); out = nullptr; }
+  }
+
+private:
+  static ui32 cdiv(ui32 a, ui32 b) { return (a + b - 1) / b; }
+  ui32 comp_width(ui32 c) const { return cdiv(st.p.width, st.p.dx[c]) - cdiv(st.p.off_x, st.p.dx[c]); }
+  ui32 comp_height(ui32 c) const { return cdiv(st.p.height, st.p.dy[c]) - cdiv(st.p.off_y, st.p.dy[c]); }
+};
+
+}} // namespace ojph::b200
