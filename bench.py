@@ -190,7 +190,7 @@ def main():
 
     p = workload_params()
     frame = make_frame(W, H, 1234 + rank)
-    NW = int(os.environ.get("OJB_BENCH_WORKERS", "6"))      # frames in flight per GPU (one codec pair each)
+    NW = int(os.environ.get("OJB_BENCH_WORKERS", "8"))      # frames in flight per GPU (one codec pair each)
     # pinned host buffers: one input frame (shared, read-only), per-worker outputs
     pin = [torch.empty((H, W), dtype=torch.uint16, pin_memory=True) for _ in range(NC)]
     for t, f in zip(pin, frame):
