@@ -4,7 +4,7 @@
 A step = one pass of the hot path over one batch of frames: each frame is encoded to a codestream,
 then that codestream is decoded back (the metric BASELINE.json names is "Mpixels/s encode+decode").
 Workload at every N: synthetic 8192x8192 3-component 12-bit frames, reversible 5/3 + RCT, 5 levels,
-64x64 blocks (the headline configuration), OJB_BENCH_WORKERS (4) frames per GPU per step, each on its
+64x64 blocks (the headline configuration), OJB_BENCH_WORKERS (default 8) frames per GPU per step, each on its
 own codec object / CUDA stream so that the host phases (packet headers) and copies of one frame
 overlap the kernels of another (weak scaling; frames are independent, so there is no data-path
 collective -- only the final gather of the codestream sizes to rank 0).
