@@ -587,15 +587,14 @@ void Decoder::parse_tiles() {
     }
     ++next_tp[Isot];
     uint32_t payload = Psot ? Psot - 12 : (uint32_t)(j2c_len - tile_start);
-    uint32_t data_left = payload - (uint32_t)(q - tile_start);
-    if (q + data_left > j2c_len) data_left = (uint32_t)(j2c_len - q);
+    uint32_t data_left = payload - (uint32_t)(q - tile_start);     // what Psot promises, not what the buffer holds
     if (!have_seq[Isot]) { std::vector<uint32_t> tpf; layout.packet_sequence(Isot, seqs[Isot], tpf); have_seq[Isot] = true; }
     try {
       std::vector<PacketRef>& seq = seqs[Isot];
       while (data_left > 0 && next_pkt[Isot] < seq.size()) {
         const PacketRef& pr = seq[next_pkt[Isot]++];
         const ResGeom& rg = layout.res_of(pr);
-        parse_packet(params, rg, rg.precincts[pr.precinct], coded.data(), d, q, data_left);
+        parse_packet(params, rg, rg.precincts[pr.precinct], coded.data(), d, q, data_left, j2c_len);
       }
     } catch (const Error& e) {
       if (!resilient) throw;

@@ -286,10 +286,15 @@ struct BitWriter {   // MSB first; a byte after 0xFF carries 7 bits (ojph_bitbuf
 };
 
 struct BitReader {   // ojph_bitbuffer_read.h:73-130
-  const uint8_t* d; size_t& pos; uint32_t& left; uint32_t tmp = 0; int avail = 0; bool unstuff = false;
-  BitReader(const uint8_t* data, size_t& p, uint32_t& l) : d(data), pos(p), left(l) {}
+  // `left` counts the bytes the tile-part SAYS it still has (Psot); `end` is where the buffer really
+  // ends: running out of buffer while `left` > 0 is the reference's failed file read (bb_read, :80-86)
+  const uint8_t* d; size_t& pos; uint32_t& left; size_t end; uint32_t tmp = 0; int avail = 0; bool unstuff = false;
+  BitReader(const uint8_t* data, size_t& p, uint32_t& l, size_t e) : d(data), pos(p), left(l), end(e) {}
   inline bool fill() {
-    if (left > 0) { uint8_t t = d[pos++]; tmp = t; avail = 8 - (unstuff ? 1 : 0); unstuff = (t == 0xFF); --left; return true; }
+    if (left > 0) {
+      if (pos >= end) throw Error(0x00030092, "error reading from file");
+      uint8_t t = d[pos++]; tmp = t; avail = 8 - (unstuff ? 1 : 0); unstuff = (t == 0xFF); --left; return true;
+    }
     tmp = 0; avail = 8 - (unstuff ? 1 : 0); unstuff = false; return false;
   }
   inline bool bit(uint32_t& b) { bool r = true; if (avail == 0) r = fill(); b = (tmp >> --avail) & 1u; return r; }
@@ -405,12 +410,14 @@ uint32_t write_packet_header(const ResGeom& res, const PrecinctGeom& pc,
 }
 
 void parse_packet(const Params& P, const ResGeom& res, const PrecinctGeom& pc,
-                  CodedBlock* blocks, const uint8_t* data, size_t& pos, uint32_t& data_left) {
-  BitReader br(data, pos, data_left);
+                  CodedBlock* blocks, const uint8_t* data, size_t& pos, uint32_t& data_left, size_t data_end) {
+  BitReader br(data, pos, data_left, data_end);
   if (P.uses_sop() && data_left >= 2) {            // optional SOP marker segment
+    if (pos + 2 > data_end) throw Error(0x00030092, "error reading from file");
     if (data[pos] == 0xFF && data[pos + 1] == 0x91) {
       pos += 2; data_left -= 2;
       if (data_left < 4) throw Error(0x00030092, "precinct truncated early");
+      if (pos + 4 > data_end) throw Error(0x00030092, "error reading from file");
       uint32_t L = ((uint32_t)data[pos] << 8) | data[pos + 1];
       if (L != 4) throw Error(0x00030092, "something is wrong with SOP length");
       pos += 4; data_left -= 4;
@@ -427,7 +434,10 @@ void parse_packet(const Params& P, const ResGeom& res, const PrecinctGeom& pc,
       br.bit(bit);
       if (bit == 0) {                              // empty packet
         br.finish();
-        if (P.uses_eph() && data_left >= 2) { pos += 2; data_left -= 2; }
+        if (P.uses_eph() && data_left >= 2) {
+          if (pos + 2 > data_end) throw Error(0x00030092, "error reading from file");
+          pos += 2; data_left -= 2;
+        }
         return;
       }
       empty_packet = false;
@@ -525,11 +535,16 @@ void parse_packet(const Params& P, const ResGeom& res, const PrecinctGeom& pc,
   if (empty_packet) { uint32_t bit = 0; br.bit(bit); }
   br.finish();
   if (P.uses_eph() && data_left >= 2) {
+    if (pos + 2 > data_end) throw Error(0x00030092, "error reading from file");
     if (!(data[pos] == 0xFF && data[pos + 1] == 0x92))
       throw Error(0x00030092, "should find EPH, but found something else");
     pos += 2; data_left -= 2;
   }
-  // code-block bodies follow in band / raster order
+  // code-block bodies follow in band / raster order.  A body the buffer cannot deliver is dropped and
+  // the rest of this packet with it (bb_read_chunk, ojph_bitbuffer_read.h:134-150; ojph_precinct.cpp:
+  // 536-573), but the tile-part's byte budget stays what Psot says: the next packet header then fails
+  // to read, which is how a truncation is detected outside resilient mode.
+  bool body_ok = true;
   for (uint32_t s = 0; s < 4; ++s) {
     const BandGeom& bg = res.bands[s];
     if (bg.empty) continue;
@@ -539,14 +554,14 @@ void parse_packet(const Params& P, const ResGeom& res, const PrecinctGeom& pc,
       for (uint32_t x = 0; x < ci.w; ++x) {
         CodedBlock& cb = base[(size_t)(ci.y0 + y) * bg.nbw + ci.x0 + x];
         uint32_t nbytes = cb.pass_len[0] + cb.pass_len[1];
-        if (data_left) {
+        if (data_left && body_ok) {
           if (nbytes) {
-            if (nbytes > data_left) {              // truncated block: do not decode it
-              cb.pass_len[0] = cb.pass_len[1] = 0;
-              pos += data_left; data_left = 0;
-            } else {
-              cb.data_off = pos; pos += nbytes; data_left -= nbytes;
-            }
+            const uint32_t want = std::min(nbytes, data_left);
+            const size_t have = pos < data_end ? data_end - pos : 0;
+            const uint32_t got = (uint32_t)std::min<size_t>(want, have);
+            if (got == nbytes) cb.data_off = pos;
+            else { cb.pass_len[0] = cb.pass_len[1] = 0; body_ok = false; }       // truncated block: not decoded
+            pos += got; data_left -= got;
           }
         } else
           cb.pass_len[0] = cb.pass_len[1] = 0;

@@ -98,8 +98,9 @@ uint32_t write_packet_header(const ResGeom& res, const PrecinctGeom& pc,
 
 // Parses one packet header starting at data[pos]; fills blocks[] (lengths, passes, missing
 // msbs, data_off) and advances pos past header and body.  data_left is the number of bytes
-// left in the tile-part.  Throws Error on malformed input.
+// left in the tile-part according to its SOT (Psot), data_end the size of the buffer: running out of
+// buffer with data_left > 0 throws like the reference's failed file read.  Throws Error on malformed input.
 void parse_packet(const Params& p, const ResGeom& res, const PrecinctGeom& pc,
-                  CodedBlock* blocks, const uint8_t* data, size_t& pos, uint32_t& data_left);
+                  CodedBlock* blocks, const uint8_t* data, size_t& pos, uint32_t& data_left, size_t data_end);
 
 } // namespace ojb

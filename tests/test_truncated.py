@@ -1,0 +1,53 @@
+"""The reference's tests/test_truncated_decode.cpp, restated for the B200 path: a codestream cut to k/16 of
+its length must decode (to something) in resilient mode for every k, and a truncation that the
+non-resilient parser detects must raise instead -- the flag, and only the flag, decides."""
+import numpy as np
+import pytest
+import openjph_b200 as ob
+
+W = H = 256
+NUM_CUTS = 16
+
+
+def _codestream(lib):
+    y, x = np.mgrid[0:H, 0:W]
+    img = ((x * 7 + y * 13 + ((x * y) >> 3)) & 0xFF).astype(np.int32)        # test_truncated_decode.cpp:78-81
+    p = ob.make_params(W, H, 1, 8, num_decomps=5, block=(64, 64), reversible=True)
+    return ob.Encoder(p, ob.I32, lib=lib).encode([img]), img
+
+
+def _check(lib, ref=None):
+    full, img = _codestream(lib)
+    assert len(full) > NUM_CUTS * 64
+    for resilient in (False, True):
+        out = ob.Decoder(resilient=resilient, lib=lib).decode(full)
+        assert np.array_equal(out[0], img)
+    detected = 0
+    for cut in range(1, NUM_CUTS):
+        part = full[:len(full) * cut // NUM_CUTS]
+        out = ob.Decoder(resilient=True, lib=lib).decode(part)               # must not raise
+        assert out[0].shape == (H, W)
+        raised = False
+        try:
+            ob.Decoder(resilient=False, lib=lib).decode(part)
+        except ob.OjphError:
+            raised = True
+            detected += 1
+        if ref is not None:                   # the same cuts are detected as by the reference's parser
+            ref_raised = False
+            try:
+                ref.decode(part, resilient=False)
+            except Exception:
+                ref_raised = True
+            assert raised == ref_raised, "cut %d/%d" % (cut, NUM_CUTS)
+    assert detected > 0, "no truncation was detected by the parser"
+    return detected
+
+
+def test_truncated_codestreams_emulator(emu_lib, ref):
+    _check(emu_lib, ref)
+
+
+@pytest.mark.gpu
+def test_truncated_codestreams_gpu(gpu_lib, ref):
+    _check(None, ref)
