@@ -360,7 +360,7 @@ int ojb_encode_blocks(const uint32_t* samples, uint64_t n_words, ojb_block_desc*
     std::vector<EncBlock> eb(n);
     uint64_t slot = 0;
     for (uint32_t i = 0; i < n; ++i) {
-      if (desc[i].w == 0 || desc[i].h == 0 || desc[i].w > 64 || desc[i].w * desc[i].h > 4096 || desc[i].missing_msbs > 29)
+      if (desc[i].w == 0 || desc[i].h == 0 || desc[i].w > 1024 || desc[i].w * desc[i].h > 4096 || desc[i].missing_msbs > 29)
         fail(0x000B0021, "unsupported code-block geometry");
       eb[i].src_off = desc[i].sample_off; eb[i].stride = desc[i].stride; eb[i].w = (uint16_t)desc[i].w; eb[i].h = (uint16_t)desc[i].h;
       eb[i].p = (uint16_t)(30u - desc[i].missing_msbs);
@@ -374,8 +374,10 @@ int ojb_encode_blocks(const uint32_t* samples, uint64_t n_words, ojb_block_desc*
     d_b.reserve(n * sizeof(EncBlock)); d_r.reserve(n * sizeof(EncResult)); d_sl.reserve(slot + 64); d_st.reserve(64);
     cuda_check(cudaMemcpy(d_b.p, eb.data(), n * sizeof(EncBlock), cudaMemcpyHostToDevice), "blocks");
     cuda_check(cudaMemset(d_st.p, 0, 16), "status");
-    if (serial_block_encoder())
-      launch_ht_encode_serial(d_b.as<EncBlock>(), n, 64, d_s.as<uint32_t>(), d_sl.as<uint8_t>(), d_r.as<EncResult>(),
+    uint32_t maxw = 4;
+    for (uint32_t i = 0; i < n; ++i) maxw = std::max(maxw, desc[i].w);
+    if (serial_block_encoder() || maxw > 64)
+      launch_ht_encode_serial(d_b.as<EncBlock>(), n, maxw, d_s.as<uint32_t>(), d_sl.as<uint8_t>(), d_r.as<EncResult>(),
                      d_t.as<uint16_t>(), d_st.as<uint32_t>(), 0);
     else
       launch_ht_encode(d_b.as<EncBlock>(), n, d_s.as<uint32_t>(), d_sl.as<uint8_t>(), d_r.as<EncResult>(),
@@ -430,8 +432,10 @@ int ojb_decode_blocks(const uint8_t* bytes, uint64_t n_bytes, ojb_block_desc* de
     d_b.reserve(n * sizeof(DecBlock)); d_o.reserve((n_words + 64) * 4); d_sc.reserve((scratch + 64) * 4); d_st.reserve(n * 4 + 16);
     cuda_check(cudaMemcpy(d_b.p, db.data(), n * sizeof(DecBlock), cudaMemcpyHostToDevice), "blocks");
     cuda_check(cudaMemcpy(d_o.p, samples, n_words * 4, cudaMemcpyHostToDevice), "out init");
-    if (serial_block_decoder())
-      launch_ht_decode_serial(d_b.as<DecBlock>(), n, 64, d_cs.as<uint8_t>(), d_o.as<uint32_t>(), d_sc.as<uint32_t>(),
+    uint32_t maxw = 4;
+    for (uint32_t i = 0; i < n; ++i) maxw = std::max(maxw, desc[i].w);
+    if (serial_block_decoder() || maxw > 64)
+      launch_ht_decode_serial(d_b.as<DecBlock>(), n, maxw, d_cs.as<uint8_t>(), d_o.as<uint32_t>(), d_sc.as<uint32_t>(),
                               d_t.as<uint16_t>(), DEC_OUT_SIGNMAG, d_st.as<uint32_t>(), 0);
     else
       launch_ht_decode(d_b.as<DecBlock>(), n, d_cs.as<uint8_t>(), d_o.as<uint32_t>(), d_sc.as<uint32_t>(),

@@ -165,14 +165,16 @@ void CodecBase::build_dwt_jobs(bool forward) {
     CK(cudaMemcpy(d_jobs.as<DwtJob>() + g.dev_off, g.jobs.data(), g.jobs.size() * sizeof(DwtJob), cudaMemcpyHostToDevice));
 }
 
-static void check_block_widths(const Layout& L) {
+// widest nominal code-block; blocks wider than 64 samples go through the thread-per-block kernels
+// (the warp-per-block kernels keep one quad column per lane)
+static uint32_t widest_block(const Layout& L) {
+  uint32_t w = 4;
   for (const TileGeom& t : L.tiles)
     for (const TileCompGeom& tc : t.comps)
       for (const ResGeom& rg : tc.res)
         for (uint32_t b = 0; b < 4; ++b)
-          if (!rg.bands[b].empty && (1u << rg.bands[b].xcb) > 64)
-            fail(0x000B0020, "code-block width %u: widths above 64 are not supported by the GPU "
-                 "block coder yet", 1u << rg.bands[b].xcb);
+          if (!rg.bands[b].empty) w = std::max(w, 1u << rg.bands[b].xcb);
+  return w;
 }
 
 //------------------------------------------------------------------------------------------
@@ -182,7 +184,7 @@ void Encoder::configure(const Params& p, uint32_t sample_type) {
   params = p;
   params.finalize_for_encode();
   layout.build(params);
-  check_block_widths(layout);
+  max_block_w = widest_block(layout);
   plan_image(sample_type);
   upload_tables();
   d_coef.reserve((layout.coef_words + 64) * 4);
@@ -296,8 +298,8 @@ size_t Encoder::encode(const void* const* planes, const uint32_t* strides, bool 
     }
   mark(2);
   uint32_t nb = (uint32_t)h_blocks.size();
-  if (serial_block_encoder())
-    launch_ht_encode_serial(d_blocks.as<EncBlock>(), nb, 64, d_coef.as<uint32_t>(), d_slots.as<uint8_t>(),
+  if (serial_block_encoder() || max_block_w > 64)
+    launch_ht_encode_serial(d_blocks.as<EncBlock>(), nb, max_block_w, d_coef.as<uint32_t>(), d_slots.as<uint8_t>(),
                             d_results.as<EncResult>(), d_tables_enc.as<uint16_t>(), d_status.as<uint32_t>(), stream);
   else
     launch_ht_encode(d_blocks.as<EncBlock>(), nb, d_coef.as<uint32_t>(), d_slots.as<uint8_t>(),
@@ -484,7 +486,7 @@ void Decoder::read_headers(const uint8_t* data, size_t len, uint32_t sample_type
                       "implemented on the GPU", c, pr);
   }
   layout.build(params);
-  check_block_widths(layout);
+  max_block_w = widest_block(layout);
   plan_image(sample_type);
   upload_tables();
   d_coef.reserve((layout.coef_words + 64) * 4);
@@ -645,8 +647,8 @@ uint32_t Decoder::decode(void* const* planes, const uint32_t* strides, bool plan
   host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
   mark(2);
   if (nb) { launch_ctrl_copy(d_dec.p, h_dec.p, (size_t)nb * sizeof(DecBlock), stream); ++last_launches; }
-  if (serial_block_decoder())
-    launch_ht_decode_serial(d_dec.as<DecBlock>(), nb, 64, cs_dev, d_coef.as<uint32_t>(), d_scratch.as<uint32_t>(),
+  if (serial_block_decoder() || max_block_w > 64)
+    launch_ht_decode_serial(d_dec.as<DecBlock>(), nb, max_block_w, cs_dev, d_coef.as<uint32_t>(), d_scratch.as<uint32_t>(),
                             d_tables_dec.as<uint16_t>(), P.reversible() ? (uint32_t)DEC_OUT_INT : (uint32_t)DEC_OUT_FLOAT,
                             d_bstatus.as<uint32_t>(), stream);
   else

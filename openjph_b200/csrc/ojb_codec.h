@@ -52,6 +52,7 @@ public:
   std::vector<uint64_t> img_off;
   std::vector<uint32_t> img_w, img_h;
   uint32_t img_type = ST_I32;
+  uint32_t max_block_w = 64;            // widest nominal code-block of the current geometry
   size_t img_bytes = 0;
   void plan_image(uint32_t sample_type);
   DeviceBuf d_coef;                    // coefficient arena (32-bit words)

@@ -12,6 +12,10 @@ SMALL_REV = [
     ("block_32x32", dict(width=200, height=150, num_comps=1, bit_depth=8, num_decomps=2, reversible=True, block=(32, 32))),
     ("block_64x16", dict(width=200, height=150, num_comps=1, bit_depth=8, num_decomps=2, reversible=True, block=(64, 16))),
     ("block_4x4", dict(width=40, height=30, num_comps=1, bit_depth=8, num_decomps=1, reversible=True, block=(4, 4))),
+    # wider than 64 samples: handled by the thread-per-block kernels
+    ("block_128x32", dict(width=700, height=300, num_comps=3, bit_depth=10, num_decomps=3, reversible=True, color_transform=True, block=(128, 32))),
+    ("block_1024x4", dict(width=1500, height=64, num_comps=1, bit_depth=8, num_decomps=2, reversible=True, block=(1024, 4))),
+    ("block_256x16", dict(width=600, height=200, num_comps=1, bit_depth=12, num_decomps=2, reversible=True, block=(256, 16))),
     ("tlm_tiles", dict(width=300, height=200, num_comps=3, bit_depth=8, num_decomps=2, reversible=True, color_transform=True, tile=(128, 128), tlm=True)),
     ("sub420_planar", dict(width=200, height=150, num_comps=3, bit_depth=8, num_decomps=3, reversible=True, subsampling=[(1, 1), (2, 2), (2, 2)], planar=1)),
     ("tilepart_R", dict(width=200, height=150, num_comps=3, bit_depth=8, num_decomps=3, reversible=True, color_transform=True, tilepart_div=1, tlm=True)),
@@ -35,7 +39,7 @@ SMALL_IRV = [
     ("irv_tiles", dict(width=300, height=200, num_comps=3, bit_depth=10, num_decomps=3, reversible=False, color_transform=True, tile=(128, 128), qfactor=75)),
 ]
 # a quick subset for the CPU (emulator) tier
-EMU_REV = ["cfg1_256_gray_L1", "gray_L0", "odd_rgb_L5", "offsets", "rgb16_noise", "block_4x4", "tilepart_RC_lrcp",
+EMU_REV = ["cfg1_256_gray_L1", "gray_L0", "odd_rgb_L5", "offsets", "rgb16_noise", "block_4x4", "block_128x32", "block_1024x4", "tilepart_RC_lrcp",
            "tiny_1x1", "thin_off", "signed10", "po_PCRL_precincts", "sub420_planar"]
 EMU_IRV = ["irv_rgb_qstep", "irv_tiles"]
 
