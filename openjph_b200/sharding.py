@@ -151,17 +151,35 @@ def my_tiles(ntiles, rank, world):
     return [t for t in range(ntiles) if t % world == rank]
 
 
+class TileEncoders:
+    """the encoders of one rank's tiles, configured once and reused frame after frame (device arenas,
+    descriptor tables and pinned buffers are per geometry, as with codestream::restart)"""
+
+    def __init__(self, p, tiles, sample_type=cs_mod.I32, lib=None):
+        self.p, self.tiles, self.sample_type = p, list(tiles), sample_type
+        self.encs = [cs_mod.Encoder(tile_params(p, t), sample_type, lib=lib) for t in self.tiles]
+
+    def encode(self, planes):
+        """-> {tile index: [tile-part bytes ...]} for this rank's tiles of the frame"""
+        out = {}
+        for tile, enc in zip(self.tiles, self.encs):
+            _, parts = split_codestream(enc.encode(crop_planes(self.p, planes, tile)))
+            out[tile["index"]] = [_with_isot(b, tile["index"]) for _, b in parts]
+        return out
+
+    def close(self):
+        for e in self.encs:
+            e.close()
+        self.encs = []
+
+
 def encode_tiles(p, planes, tiles, sample_type=cs_mod.I32, lib=None):
     """encode the given tiles of the image -> {tile index: [tile-part bytes ...]}"""
-    out = {}
-    for tile in tiles:
-        enc = cs_mod.Encoder(tile_params(p, tile), sample_type, lib=lib)
-        try:
-            _, parts = split_codestream(enc.encode(crop_planes(p, planes, tile)))
-        finally:
-            enc.close()
-        out[tile["index"]] = [_with_isot(b, tile["index"]) for _, b in parts]
-    return out
+    te = TileEncoders(p, tiles, sample_type, lib)
+    try:
+        return te.encode(planes)
+    finally:
+        te.close()
 
 
 def assemble(p, parts_by_tile, lib=None):
@@ -191,7 +209,7 @@ def _gather_bytes(payload, dst=0, group=None):
     cap = max(1, max(lens))
     buf = torch.zeros(cap, dtype=torch.uint8, device=dev)
     if payload:
-        buf[:len(payload)] = torch.frombuffer(bytearray(payload), dtype=torch.uint8).to(dev)
+        buf[:len(payload)] = torch.from_numpy(np.frombuffer(payload, np.uint8).copy()).to(dev, non_blocking=True)
     if rank == dst:
         got = [torch.empty(cap, dtype=torch.uint8, device=dev) for _ in range(world)]
         dist.gather(buf, got, dst=dst, group=group)
@@ -215,6 +233,29 @@ def _unpack(blob):
         out.setdefault(t, []).append(blob[pos:pos + l])
         pos += l
     return out
+
+
+class ShardedEncoder:
+    """one per rank: keeps the rank's tile encoders across frames; encode() is the per-frame call"""
+
+    def __init__(self, p, sample_type=cs_mod.I32, dst=0, group=None, lib=None):
+        dist = _dist()
+        self.p, self.dst, self.group, self.lib = p, dst, group, lib
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        grid = tile_grid(p)
+        self.tiles = TileEncoders(p, [grid[t] for t in my_tiles(len(grid), rank, world)], sample_type, lib)
+
+    def encode(self, planes):
+        got = _gather_bytes(_pack(self.tiles.encode(planes)), self.dst, self.group)
+        if got is None:
+            return None
+        allp = {}
+        for blob in got:
+            allp.update(_unpack(blob))
+        return assemble(self.p, allp, lib=self.lib)
+
+    def close(self):
+        self.tiles.close()
 
 
 def encode_sharded(p, planes, sample_type=cs_mod.I32, dst=0, group=None, lib=None):
