@@ -588,16 +588,12 @@ ht_dec_step2_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
       msw[2] = fetch_bits(msbuf, bp + m[0] + m[1], ms_words);
       msw[3] = fetch_bits(msbuf, bp + m[0] + m[1] + m[2], ms_words);
       #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        out[i] = 0; vn[i] = 0;
-        if ((rho >> i) & 1u) {
-          const uint32_t ms = msw[i];
-          uint32_t v = ms & ((1u << m[i]) - 1u);
-          v |= ((e1 >> i) & 1u) << m[i];
-          v |= 1u;
-          vn[i] = v;
-          out[i] = (ms << 31) | ((v + 2u) << (p - 1));
-        }
+      for (int i = 0; i < 4; ++i) {               // branch-free: insignificant samples are selected away
+        const bool sig = (rho >> i) & 1u;
+        const uint32_t ms = msw[i];
+        const uint32_t v = (ms & ((1u << m[i]) - 1u)) | (((e1 >> i) & 1u) << m[i]) | 1u;
+        vn[i] = sig ? v : 0u;
+        out[i] = sig ? ((ms << 31) | ((v + 2u) << (p - 1))) : 0u;
       }
       pos += tot;
       pv1 = vn[1]; pv3 = vn[3];
