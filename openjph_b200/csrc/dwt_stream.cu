@@ -144,38 +144,44 @@ __device__ __forceinline__ bool strip_setup(const DwtJob& J, uint32_t strip, uin
 // in flight) and later reads back exactly the bytes it requested, so no cross-lane synchronisation
 // is needed -- cp.async.wait_group orders a lane's own copies.
 
-// request four 32-bit elements p[c[0..3]] into a 16-byte slot
-__device__ __forceinline__ void issue4_w(unsigned char* d, const uint32_t* p, const StripGeom& g) {
-  const uint32_t* q = p + g.c[0];
-  if (g.interior && (reinterpret_cast<size_t>(q) & 15) == 0) cp_async<16>(d, q);
+// The image buffer and the coefficient arena are addressed with 32-bit byte offsets from their
+// (256-byte aligned) base; alignment is tested on the offset.
+// request four 32-bit elements base[row + c[0..3]] into a 16-byte slot (offsets in bytes)
+__device__ __forceinline__ void issue4_w(unsigned char* d, const unsigned char* base, uint32_t row_off, const StripGeom& g) {
+  const uint32_t o = row_off + 4u * (uint32_t)g.c[0];
+  if (g.interior && (o & 15u) == 0) cp_async<16>(d, base + o);
   else {
     #pragma unroll
-    for (int i = 0; i < 4; ++i) cp_async<4>(d + 4 * i, p + g.c[i]);
+    for (int i = 0; i < 4; ++i) cp_async<4>(d + 4 * i, base + row_off + 4u * (uint32_t)g.c[i]);
   }
 }
-__device__ __forceinline__ void issue4_u16(unsigned char* d, const unsigned short* p, const StripGeom& g) {
-  const unsigned short* q = p + g.c[0];
-  const size_t a = reinterpret_cast<size_t>(q);
-  if (g.interior && (a & 7) == 0) cp_async<8>(d, q);
-  else if (g.interior && (a & 3) == 0) { cp_async<4>(d, q); cp_async<4>(d + 4, q + 2); }
+__device__ __forceinline__ void issue4_u16(unsigned char* d, const unsigned char* base, uint32_t row_off, const StripGeom& g) {
+  const uint32_t o = row_off + 2u * (uint32_t)g.c[0];
+  if (g.interior && (o & 7u) == 0) cp_async<8>(d, base + o);
+  else if (g.interior && (o & 3u) == 0) { cp_async<4>(d, base + o); cp_async<4>(d + 4, base + o + 4); }
   else {                                   // mirrored or odd-aligned columns: plain loads (edge lanes)
     unsigned short* ds = reinterpret_cast<unsigned short*>(d);
+    const unsigned short* p = reinterpret_cast<const unsigned short*>(base + row_off);
     #pragma unroll
     for (int i = 0; i < 4; ++i) ds[i] = p[g.c[i]];
   }
 }
-__device__ __forceinline__ void issue4_u8(unsigned char* d, const unsigned char* p, const StripGeom& g) {
-  const unsigned char* q = p + g.c[0];
-  if (g.interior && (reinterpret_cast<size_t>(q) & 3) == 0) cp_async<4>(d, q);
+__device__ __forceinline__ void issue4_u8(unsigned char* d, const unsigned char* base, uint32_t row_off, const StripGeom& g) {
+  const uint32_t o = row_off + (uint32_t)g.c[0];
+  if (g.interior && (o & 3u) == 0) cp_async<4>(d, base + o);
   else {
     #pragma unroll
-    for (int i = 0; i < 4; ++i) d[i] = p[g.c[i]];
+    for (int i = 0; i < 4; ++i) d[i] = base[row_off + (uint32_t)g.c[i]];
   }
 }
 // two consecutive 32-bit words
-__device__ __forceinline__ void store2_w(uint32_t* q, uint32_t a, uint32_t b, bool ha, bool hb) {
-  if (ha && hb && (reinterpret_cast<size_t>(q) & 7) == 0) *reinterpret_cast<uint2*>(q) = make_uint2(a, b);
-  else { if (ha) q[0] = a; if (hb) q[1] = b; }
+// the arena (256-byte aligned) is addressed with 32-bit word indices here: the host selects these kernels
+// only when the coefficient arena has fewer than 2^32 words
+__device__ __forceinline__ void store2_w(uint32_t* base, uint32_t idx, uint32_t a, uint32_t b, bool ha, bool hb) {
+  // idx may have wrapped below zero for a lane whose first column is outside the band (ha false):
+  // element indices are formed in 32 bits before they meet the 64-bit base
+  if (ha && hb && (idx & 1u) == 0) *reinterpret_cast<uint2*>(base + idx) = make_uint2(a, b);
+  else { if (ha) base[idx] = a; if (hb) base[idx + 1u] = b; }
 }
 template <typename T> __device__ __forceinline__ uint32_t as_bits(T v) { uint32_t r; memcpy(&r, &v, 4); return r; }
 template <typename T> __device__ __forceinline__ T from_bits(uint32_t v) { T r; memcpy(&r, &v, 4); return r; }
@@ -189,17 +195,19 @@ __device__ __forceinline__ void fwd_issue_row(const DwtJob& J, const StripGeom& 
   constexpr bool FIRST = SRC != SRC_COEF;     // the full-resolution side is the image
   const int vr = reflect_coord(v, g.y0, g.y1 - 1) - g.y0;
   if (FIRST) {
+    const unsigned char* base = reinterpret_cast<const unsigned char*>(image);
     #pragma unroll
     for (int k = 0; k < NC; ++k) {
-      const size_t row = (size_t)vr * J.full_stride[k];
-      const unsigned char* base = reinterpret_cast<const unsigned char*>(image) + J.full_off[k];
+      constexpr uint32_t ES = (SRC == SRC_U16) ? 2u : (SRC == SRC_U8 ? 1u : 4u);
+      const uint32_t row_off = (uint32_t)J.full_off[k] + (uint32_t)vr * J.full_stride[k] * ES;     // bytes
       unsigned char* d = st + (size_t)k * 32 * slot;
-      if (SRC == SRC_U16) issue4_u16(d, reinterpret_cast<const unsigned short*>(base) + row, g);
-      else if (SRC == SRC_U8) issue4_u8(d, base + row, g);
-      else issue4_w(d, reinterpret_cast<const uint32_t*>(base) + row, g);
+      if (SRC == SRC_U16) issue4_u16(d, base, row_off, g);
+      else if (SRC == SRC_U8) issue4_u8(d, base, row_off, g);
+      else issue4_w(d, base, row_off, g);
     }
   } else {
-    issue4_w(st, coef + J.full_off[0] + (size_t)vr * J.full_stride[0], g);
+    issue4_w(st, reinterpret_cast<const unsigned char*>(coef),
+             ((uint32_t)J.full_off[0] + (uint32_t)vr * J.full_stride[0]) * 4u, g);
   }
 }
 
@@ -291,18 +299,18 @@ __device__ __forceinline__ void fwd_store_pair(const DwtJob& J, const StripGeom&
       const T (&r)[4] = vpar ? hi[k] : lo[k];
       const int bl = vpar ? 2 : 0, bh = vpar ? 3 : 1;
       if (bl == 0 && !J.last)
-        store2_w(coef + J.ll_off[k] + (size_t)by * J.ll_stride[k] + bxl, as_bits(r[0]), as_bits(r[2]), g.has[0], g.has[2]);
+        store2_w(coef, (uint32_t)J.ll_off[k] + (uint32_t)by * J.ll_stride[k] + (uint32_t)bxl, as_bits(r[0]), as_bits(r[2]), g.has[0], g.has[2]);
       else if (REV)
-        store2_w(coef + J.band_off[k][bl] + (size_t)by * J.band_stride[k][bl] + bxl,
+        store2_w(coef, (uint32_t)J.band_off[k][bl] + (uint32_t)by * J.band_stride[k][bl] + (uint32_t)bxl,
                  to_signmag_rev((int)r[0], J.band_shift[k][bl]), to_signmag_rev((int)r[2], J.band_shift[k][bl]), g.has[0], g.has[2]);
       else
-        store2_w(coef + J.band_off[k][bl] + (size_t)by * J.band_stride[k][bl] + bxl,
+        store2_w(coef, (uint32_t)J.band_off[k][bl] + (uint32_t)by * J.band_stride[k][bl] + (uint32_t)bxl,
                  to_signmag_irv((float)r[0], J.band_scale[k][bl]), to_signmag_irv((float)r[2], J.band_scale[k][bl]), g.has[0], g.has[2]);
       if (REV)
-        store2_w(coef + J.band_off[k][bh] + (size_t)by * J.band_stride[k][bh] + bxh,
+        store2_w(coef, (uint32_t)J.band_off[k][bh] + (uint32_t)by * J.band_stride[k][bh] + (uint32_t)bxh,
                  to_signmag_rev((int)r[1], J.band_shift[k][bh]), to_signmag_rev((int)r[3], J.band_shift[k][bh]), g.has[1], g.has[3]);
       else
-        store2_w(coef + J.band_off[k][bh] + (size_t)by * J.band_stride[k][bh] + bxh,
+        store2_w(coef, (uint32_t)J.band_off[k][bh] + (uint32_t)by * J.band_stride[k][bh] + (uint32_t)bxh,
                  to_signmag_irv((float)r[1], J.band_scale[k][bh]), to_signmag_irv((float)r[3], J.band_scale[k][bh]), g.has[1], g.has[3]);
     }
   }
@@ -443,12 +451,13 @@ __device__ __forceinline__ void inv_issue_pair(const DwtJob& J, const StripGeom&
   for (int k = 0; k < NC; ++k) {
     #pragma unroll
     for (int b = 0; b < 4; ++b) {
-      const uint32_t* r = (b == 0 && !J.last) ? coef + J.ll_off[k] + (size_t)byl * J.ll_stride[k]
-                                              : coef + J.band_off[k][b] + (size_t)(b < 2 ? byl : byh) * J.band_stride[k][b];
-      const int i0 = bx[b & 1], i1 = bx[(b & 1) + 2];
+      // 32-bit word indices into the arena (fewer than 2^32 words when these kernels are selected)
+      const uint32_t row = (b == 0 && !J.last) ? (uint32_t)J.ll_off[k] + (uint32_t)byl * J.ll_stride[k]
+                                               : (uint32_t)J.band_off[k][b] + (uint32_t)(b < 2 ? byl : byh) * J.band_stride[k][b];
+      const uint32_t i0 = row + (uint32_t)bx[b & 1], i1 = row + (uint32_t)bx[(b & 1) + 2];
       unsigned char* d = st + (size_t)(k * 4 + b) * 32 * 8;
-      if (g.interior && (reinterpret_cast<size_t>(r + i0) & 7) == 0) cp_async<8>(d, r + i0);
-      else { cp_async<4>(d, r + i0); cp_async<4>(d + 4, r + i1); }
+      if (g.interior && (i0 & 1u) == 0) cp_async<8>(d, coef + i0);
+      else { cp_async<4>(d, coef + i0); cp_async<4>(d + 4, coef + i1); }
     }
   }
 }
@@ -485,12 +494,13 @@ __device__ __forceinline__ void inv_store_row(const DwtJob& J, const StripGeom& 
   const int cx = g.u0 - g.x0;
   const bool all4 = g.has[0] && g.has[3];
   if (!FIRST) {
-    uint32_t* p = coef + J.full_off[0] + (size_t)(v - g.y0) * J.full_stride[0] + cx;
-    if (all4 && (reinterpret_cast<size_t>(p) & 15) == 0)
-      *reinterpret_cast<uint4*>(p) = make_uint4(as_bits(x[0][0]), as_bits(x[0][1]), as_bits(x[0][2]), as_bits(x[0][3]));
+    const uint32_t idx = (uint32_t)J.full_off[0] + (uint32_t)(v - g.y0) * J.full_stride[0] + (uint32_t)cx;
+    // (idx wraps below zero when the lane's first column lies left of the resolution: 32-bit sums)
+    if (all4 && (idx & 3u) == 0)
+      *reinterpret_cast<uint4*>(coef + idx) = make_uint4(as_bits(x[0][0]), as_bits(x[0][1]), as_bits(x[0][2]), as_bits(x[0][3]));
     else {
       #pragma unroll
-      for (int i = 0; i < 4; ++i) if (g.has[i]) p[i] = as_bits(x[0][i]);
+      for (int i = 0; i < 4; ++i) if (g.has[i]) coef[idx + (uint32_t)i] = as_bits(x[0][i]);
     }
     return;
   }
@@ -545,35 +555,37 @@ __device__ __forceinline__ void inv_store_row(const DwtJob& J, const StripGeom& 
   }
   #pragma unroll
   for (int k = 0; k < NC; ++k) {
-    const size_t row = (size_t)(v - g.y0) * J.full_stride[k];
-    unsigned char* base = reinterpret_cast<unsigned char*>(image) + J.full_off[k];
+    // 32-bit byte offset into the (256-byte aligned) image buffer
+    const uint32_t eidx = (uint32_t)(v - g.y0) * J.full_stride[k] + (uint32_t)cx;
+    unsigned char* base = reinterpret_cast<unsigned char*>(image);
     if (SRC == SRC_U16) {
-      unsigned short* p = reinterpret_cast<unsigned short*>(base) + row + cx;
+      const uint32_t o = (uint32_t)J.full_off[k] + 2u * eidx;
+
       uint32_t q[4];
       #pragma unroll
       for (int i = 0; i < 4; ++i) q[i] = (uint32_t)min(max(out[k][i], 0), 65535);
-      if (all4 && (reinterpret_cast<size_t>(p) & 7) == 0) *reinterpret_cast<uint2*>(p) = make_uint2(q[0] | (q[1] << 16), q[2] | (q[3] << 16));
+      if (all4 && (o & 7u) == 0) *reinterpret_cast<uint2*>(base + o) = make_uint2(q[0] | (q[1] << 16), q[2] | (q[3] << 16));
       else {
         #pragma unroll
-        for (int i = 0; i < 4; ++i) if (g.has[i]) p[i] = (unsigned short)q[i];
+        for (int i = 0; i < 4; ++i) if (g.has[i]) *reinterpret_cast<unsigned short*>(base + (o + 2u * (uint32_t)i)) = (unsigned short)q[i];
       }
     } else if (SRC == SRC_U8) {
-      unsigned char* p = base + row + cx;
+      const uint32_t o = (uint32_t)J.full_off[k] + eidx;
       uint32_t q[4];
       #pragma unroll
       for (int i = 0; i < 4; ++i) q[i] = (uint32_t)min(max(out[k][i], 0), 255);
-      if (all4 && (reinterpret_cast<size_t>(p) & 3) == 0) *reinterpret_cast<uint32_t*>(p) = q[0] | (q[1] << 8) | (q[2] << 16) | (q[3] << 24);
+      if (all4 && (o & 3u) == 0) *reinterpret_cast<uint32_t*>(base + o) = q[0] | (q[1] << 8) | (q[2] << 16) | (q[3] << 24);
       else {
         #pragma unroll
-        for (int i = 0; i < 4; ++i) if (g.has[i]) p[i] = (unsigned char)q[i];
+        for (int i = 0; i < 4; ++i) if (g.has[i]) base[o + (uint32_t)i] = (unsigned char)q[i];
       }
     } else {
-      int* p = reinterpret_cast<int*>(base) + row + cx;
-      if (all4 && (reinterpret_cast<size_t>(p) & 15) == 0)
-        *reinterpret_cast<uint4*>(p) = make_uint4((uint32_t)out[k][0], (uint32_t)out[k][1], (uint32_t)out[k][2], (uint32_t)out[k][3]);
+      const uint32_t o = (uint32_t)J.full_off[k] + 4u * eidx;
+      if (all4 && (o & 15u) == 0)
+        *reinterpret_cast<uint4*>(base + o) = make_uint4((uint32_t)out[k][0], (uint32_t)out[k][1], (uint32_t)out[k][2], (uint32_t)out[k][3]);
       else {
         #pragma unroll
-        for (int i = 0; i < 4; ++i) if (g.has[i]) p[i] = out[k][i];
+        for (int i = 0; i < 4; ++i) if (g.has[i]) *reinterpret_cast<int*>(base + (o + 4u * (uint32_t)i)) = out[k][i];
       }
     }
   }

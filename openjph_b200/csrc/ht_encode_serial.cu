@@ -198,8 +198,13 @@ ht_encode_serial_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
         uint32_t rho = 0, e[4] = {0, 0, 0, 0}, s[4] = {0, 0, 0, 0};
         #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          uint32_t v = ((t[i] + t[i]) >> p) & ~1u;
-          if (v) { rho |= 1u << i; --v; e[i] = 32 - __clz((int)v); s[i] = --v + (t[i] >> 31); }
+          // branch-free: v = 2 * magnitude (0 when insignificant); exponent of 2*mag - 1, MagSgn value
+          // 2*(mag - 1) + sign (only read when the sample is significant)
+          const uint32_t v = ((t[i] + t[i]) >> p) & ~1u;
+          const uint32_t sig = v ? 1u : 0u;
+          rho |= sig << i;
+          e[i] = sig ? 32u - (uint32_t)__clz((int)(v - 1u)) : 0u;
+          s[i] = v - 2u + (t[i] >> 31);
         }
         any_sig |= rho;
         const uint32_t emax = max(max(e[0], e[1]), max(e[2], e[3]));

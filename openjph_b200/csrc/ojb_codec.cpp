@@ -140,7 +140,7 @@ void CodecBase::build_dwt_jobs(bool forward) {
             j.band_scale[i][0] = forward ? bg.delta_inv : bg.delta;
           }
         }
-        const bool stream = !j.nodwt && j.w >= 2 && j.h >= 2 && !no_stream_dwt;
+        const bool stream = !j.nodwt && j.w >= 2 && j.h >= 2 && !no_stream_dwt && layout.coef_words < (1ull << 30) && img_bytes < (1ull << 32);   // 32-bit byte offsets in the stream kernels
         uint32_t gi, n;
         if (stream) {
           gi = j.first ? (k == 3 ? 0u : 1u) : 2u;
