@@ -180,17 +180,38 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
 // ---- runtime API subset (device memory == host memory; everything is synchronous) --------
 struct emuStream_st { int dummy; };
 struct emuEvent_st { std::chrono::steady_clock::time_point t; };
-// fresh device memory is filled with a poison pattern: a kernel that reads what nobody wrote shows up
-// as a test failure here instead of passing by luck on a zeroed heap
+// Fresh device memory is filled with a poison pattern (a kernel that reads what nobody wrote shows up
+// as a test failure instead of passing by luck on a zeroed heap) and sits between two guard zones that
+// are checked when it is freed (a kernel that writes just outside its buffer aborts the test run).
+static const size_t kGuard = 4096;
+struct AllocHeader { size_t size; unsigned long long magic; };
 cudaError_t cudaMalloc(void** p, size_t n) {
   const size_t sz = (n + 255) & ~(size_t)255;
-  *p = aligned_alloc(256, sz);
-  if (*p) { static const int pat = [] { const char* e = getenv("OJB_EMU_POISON"); return e ? (int)strtol(e, nullptr, 0) : 0xA5; }(); memset(*p, pat, sz); }
-  return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+  unsigned char* raw = (unsigned char*)aligned_alloc(4096, sz + 2 * kGuard);
+  if (!raw) { *p = nullptr; return cudaErrorMemoryAllocation; }
+  static const int pat = [] { const char* e = getenv("OJB_EMU_POISON"); return e ? (int)strtol(e, nullptr, 0) : 0xA5; }();
+  memset(raw, 0xEE, kGuard);
+  memset(raw + kGuard, pat, sz);
+  memset(raw + kGuard + sz, 0xEE, kGuard);
+  AllocHeader* h = (AllocHeader*)raw; h->size = sz; h->magic = 0x0A110CA7EDull;
+  *p = raw + kGuard;
+  return cudaSuccess;
 }
-cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+cudaError_t cudaFree(void* p) {
+  if (!p) return cudaSuccess;
+  unsigned char* raw = (unsigned char*)p - kGuard;
+  AllocHeader* h = (AllocHeader*)raw;
+  if (h->magic != 0x0A110CA7EDull) { fprintf(stderr, "[cuda_emu] free of a pointer cudaMalloc did not return, or its header was overwritten\n"); abort(); }
+  const size_t sz = h->size;
+  for (size_t i = sizeof(AllocHeader); i < kGuard; ++i)
+    if (raw[i] != 0xEE) { fprintf(stderr, "[cuda_emu] write BEFORE a device buffer of %zu bytes (guard offset -%zu)\n", sz, kGuard - i); abort(); }
+  for (size_t i = 0; i < kGuard; ++i)
+    if (raw[kGuard + sz + i] != 0xEE) { fprintf(stderr, "[cuda_emu] write PAST a device buffer of %zu bytes (+%zu)\n", sz, i); abort(); }
+  free(raw);
+  return cudaSuccess;
+}
 cudaError_t cudaMallocHost(void** p, size_t n) { return cudaMalloc(p, n); }
-cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
+cudaError_t cudaFreeHost(void* p) { return cudaFree(p); }
 cudaError_t cudaHostRegister(void*, size_t, unsigned) { return cudaSuccess; }
 cudaError_t cudaHostUnregister(void*) { return cudaSuccess; }
 cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
