@@ -37,13 +37,7 @@ struct DecTables {            // shared-memory copy
 };
 
 // ---- step 1 readers (thread-private): 32 bits per refill, as the reference's mel_read /
-// rev_read do (ojph_block_decoder32.cpp:92-152, :307-357), built from two aligned word loads
-__device__ __forceinline__ uint32_t load_le32_any(const uint8_t* p) {
-  const uint32_t* a = reinterpret_cast<const uint32_t*>((size_t)p & ~(size_t)3);
-  const uint32_t sh = (uint32_t)((size_t)p & 3) * 8;
-  const uint32_t lo = a[0], hi = a[1];
-  return sh ? __funnelshift_r(lo, hi, sh) : lo;
-}
+// rev_read do (ojph_block_decoder32.cpp:92-152, :307-357), built from aligned word loads
 
 struct MelDec {
   const uint8_t* p; int size; unsigned long long tmp; int bits; bool unstuff; int k;
