@@ -38,6 +38,14 @@ typedef struct ojb_params {
   uint32_t tlm;                    /* codestream::request_tlm_marker */
   uint32_t tilepart_div;           /* codestream::set_tilepart_divisions: bit0 resolutions, bit1 components */
   int32_t  planar;                 /* codestream::set_planar; -1 = not called */
+  /* per-component coding styles (COC): param_cod::set_reversible / set_num_decomposition /
+   * set_block_dims with a component index (ojph_params.cpp:255-281).  As in the reference a component's
+   * COC starts from the library defaults (5 levels, 64x64, irreversible), not from the COD values, so all
+   * four fields are read when coc_present[c] != 0. */
+  uint32_t coc_present[16];
+  uint32_t coc_reversible[16];
+  uint32_t coc_num_decomps[16];
+  uint32_t coc_block_w[16], coc_block_h[16];
 } ojb_params;
 
 typedef struct ojb_frame_info {

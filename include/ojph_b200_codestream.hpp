@@ -7,7 +7,7 @@
 // The including translation unit provides OpenJPH's own public headers first (they are not part of
 // this repository):  ojph_base.h (ui8/ui32/si32, point, size), ojph_mem.h (line_buf), ojph_file.h
 // (outfile_base, infile_base).  Only what the reference's apps call is mirrored; Part-2 items the
-// hot path does not cover (NLT, COC per-component styles, DFS/ATK, resolution restriction) raise the
+// hot path does not cover (NLT, DFS/ATK, resolution restriction) raise the
 // same kind of std::runtime_error the reference raises for invalid settings.
 #pragma once
 #include "ojph_b200.h"
@@ -62,6 +62,7 @@ public:
 
 class param_cod {                                // ojph_params.h:103-160
   state* s;
+  void coc(ui32 c) { if (c >= 16) raise("ojph error: per-component coding styles are limited to 16 components"); s->p.coc_present[c] = 1; }
 public:
   explicit param_cod(state* st) : s(st) {}
   void set_num_decomposition(ui32 n) { s->p.num_decomps = n; }
@@ -78,6 +79,11 @@ public:
   }
   void set_color_transform(bool on) { s->p.color_transform = on ? 1u : 0u; }
   void set_reversible(bool on) { s->p.reversible = on ? 1u : 0u; }
+  // per-component coding styles (COC; ojph_params.cpp:255-281): the component's style starts from the
+  // library defaults, as in the reference
+  void set_num_decomposition(ui32 comp_idx, ui32 n) { coc(comp_idx); s->p.coc_num_decomps[comp_idx] = n; }
+  void set_block_dims(ui32 comp_idx, ui32 w, ui32 h) { coc(comp_idx); s->p.coc_block_w[comp_idx] = w; s->p.coc_block_h[comp_idx] = h; }
+  void set_reversible(ui32 comp_idx, bool on) { coc(comp_idx); s->p.coc_reversible[comp_idx] = on ? 1u : 0u; }
   ui32 get_num_decompositions() const { return s->reading ? s->info.num_decomps : s->p.num_decomps; }
   bool is_reversible() const { return (s->reading ? s->info.reversible : s->p.reversible) != 0; }
   bool is_using_color_transform() const { return (s->reading ? s->info.color_transform : s->p.color_transform) != 0; }

@@ -22,7 +22,7 @@ class OjphError(RuntimeError):
 def make_params(width, height, num_comps=1, bit_depth=8, is_signed=False, num_decomps=5, block=(64, 64),
                 reversible=True, color_transform=False, prog_order="RPCL", qstep=-1.0, qfactor=0,
                 tile=(0, 0), offset=(0, 0), tile_offset=(0, 0), precincts=None, subsampling=None,
-                tlm=False, tilepart_div=0, planar=-1):
+                tlm=False, tilepart_div=0, planar=-1, coc=None):
     p = _lib.Params()
     p.width, p.height = width, height
     p.off_x, p.off_y = offset
@@ -49,6 +49,15 @@ def make_params(width, height, num_comps=1, bit_depth=8, is_signed=False, num_de
     p.tlm = 1 if tlm else 0
     p.tilepart_div = tilepart_div
     p.planar = planar
+    # per-component coding styles: {comp: dict(reversible=, num_decomps=, block=)}; as in the reference a
+    # component's COC starts from the library defaults (5 levels, 64x64, irreversible)
+    for c in range(16):
+        p.coc_num_decomps[c], p.coc_block_w[c], p.coc_block_h[c] = 5, 64, 64
+    for c, st in (coc or {}).items():
+        p.coc_present[c] = 1
+        p.coc_reversible[c] = 1 if st.get("reversible", False) else 0
+        p.coc_num_decomps[c] = st.get("num_decomps", 5)
+        p.coc_block_w[c], p.coc_block_h[c] = st.get("block", (64, 64))
     return p
 
 

@@ -450,6 +450,7 @@ ht_dec_step2_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
   const uint32_t np = st >> 8;
   const uint32_t shift = 31u - blk.K_max;
   const float delta = blk.delta;
+  if (out_mode == DEC_OUT_PER_BLOCK) out_mode = (blk.flags & 2) ? (uint32_t)DEC_OUT_FLOAT : (uint32_t)DEC_OUT_INT;
 
   bool fail = (st & DST_FAIL) != 0;
   const bool empty = (np == 0) && !fail;
@@ -739,6 +740,7 @@ ht_decode_serial_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
   const uint32_t p = 30u - blk.missing_msbs;
   const uint32_t shift = 31u - blk.K_max;
   const float delta = blk.delta;
+  if (out_mode == DEC_OUT_PER_BLOCK) out_mode = (blk.flags & 2) ? (uint32_t)DEC_OUT_FLOAT : (uint32_t)DEC_OUT_INT;
   const uint32_t om = (np > 1) ? (uint32_t)DEC_OUT_SIGNMAG : out_mode;
   const bool vec4 = ((blk.dst_off | stride) & 3u) == 0;
   bool fail = false;

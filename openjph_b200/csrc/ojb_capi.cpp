@@ -56,6 +56,15 @@ static void to_params(const ojb_params* s, Params& P) {
       P.qcd.qfactor = (uint8_t)s->qfactor;
     }
   }
+  for (uint32_t c = 0; c < s->num_comps; ++c) {
+    if (!s->coc_present[c]) continue;
+    CodStyle& cs = P.get_or_add_coc(c);
+    if (s->coc_num_decomps[c] > 32) fail(0x00050001, "maximum number of decompositions cannot exceed 32");
+    cs.num_decomps = (uint8_t)s->coc_num_decomps[c];
+    Params tmp; tmp.set_block_dims(s->coc_block_w[c], s->coc_block_h[c]);      // same argument checks
+    cs.cb_w_exp = tmp.cb_w_exp; cs.cb_h_exp = tmp.cb_h_exp;
+    cs.wavelet = s->coc_reversible[c] ? DWT_REV53 : DWT_IRV97;
+  }
   P.need_tlm = s->tlm != 0;
   P.tilepart_div = s->tilepart_div & 3u;
   P.planar = s->planar;
@@ -78,6 +87,7 @@ void ojb_params_default(ojb_params* p) {
   p->num_comps = 1; p->bit_depth[0] = 8;
   for (int c = 0; c < 16; ++c) { p->dx[c] = 1; p->dy[c] = 1; p->bit_depth[c] = 8; }
   p->num_decomps = 5; p->block_w = 64; p->block_h = 64; p->prog_order = 2; p->planar = -1;
+  for (int c = 0; c < 16; ++c) { p->coc_num_decomps[c] = 5; p->coc_block_w[c] = 64; p->coc_block_h[c] = 64; }
   p->qstep = -1.0f;
 }
 
@@ -172,7 +182,7 @@ static void upload_frame(Encoder& E, const void* const* planes, const uint32_t* 
 }
 static void read_band(CodecBase& cb, uint32_t tile, uint32_t comp, uint32_t res, uint32_t band, uint32_t* out,
                       uint32_t* bw, uint32_t* bh) {
-  if (tile >= cb.layout.tiles.size() || comp >= cb.params.num_comps() || res > cb.params.num_decomps || band > 3)
+  if (tile >= cb.layout.tiles.size() || comp >= cb.params.num_comps() || res > cb.params.decomps(comp) || band > 3)
     fail(0x000B0014, "no such sub-band");
   const BandGeom& bg = cb.layout.tiles[tile].comps[comp].res[res].bands[band];
   *bw = bg.rect.w; *bh = bg.rect.h;
@@ -224,7 +234,7 @@ int ojb_enc_band_info(ojb_encoder* e, uint32_t tile, uint32_t comp, uint32_t res
   return guarded_on(e->device, [&] {
     if (!e->configured) fail(0x000B0013, "encoder is not configured");
     CodecBase& cb = e->enc;
-    if (tile >= cb.layout.tiles.size() || comp >= cb.params.num_comps() || res > cb.params.num_decomps || band > 3)
+    if (tile >= cb.layout.tiles.size() || comp >= cb.params.num_comps() || res > cb.params.decomps(comp) || band > 3)
       fail(0x000B0014, "no such sub-band");
     const ResGeom& rg = cb.layout.tiles[tile].comps[comp].res[res];
     const BandGeom& bg = rg.bands[band];

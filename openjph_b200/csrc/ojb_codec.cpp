@@ -91,20 +91,35 @@ void CodecBase::plan_image(uint32_t sample_type) {
 
 void CodecBase::build_dwt_jobs(bool forward) {
   const Params& P = params;
-  uint32_t D = P.num_decomps, nc = P.num_comps();
-  uint32_t nlev = D == 0 ? 1 : D;
+  const uint32_t nc = P.num_comps();
+  // level li counts decompositions from the full resolution down; every component follows its own
+  // coding style (COC): component c takes part in levels li < max(1, D_c) with resolution D_c - li
+  uint32_t nlev = 1;
+  for (uint32_t c = 0; c < nc; ++c) nlev = std::max(nlev, P.decomps(c));
+  if (P.color_transform())
+    for (uint32_t c = 1; c < 3; ++c)
+      if (P.decomps(c) != P.decomps(0) || P.wavelet_of(c) != P.wavelet_of(0))
+        fail(0x000B0006, "the colour transform needs one coding style for the first three components");
   jobs.assign(nlev, std::vector<JobGroup>());
   uint32_t es = esize_of(img_type);
   for (uint32_t li = 0; li < nlev; ++li) {
-    uint32_t r = D == 0 ? 0 : D - li;          // resolution being split (or rebuilt)
-    // groups: [0] streaming 3-comp first, [1] streaming 1-comp first, [2] streaming inner levels, [3] general
-    std::vector<JobGroup> grp(4);
-    grp[0].stream = grp[1].stream = grp[2].stream = true;
-    grp[0].ncomp = 3; grp[0].first = grp[1].first = true;
+    // groups per wavelet w (0: 5/3, 1: 9/7): [4w+0] streaming 3-comp first, [4w+1] streaming 1-comp first,
+    // [4w+2] streaming inner levels, [4w+3] general
+    std::vector<JobGroup> grp(8);
+    for (uint32_t w = 0; w < 2; ++w) {
+      grp[4 * w].stream = grp[4 * w + 1].stream = grp[4 * w + 2].stream = true;
+      grp[4 * w].ncomp = 3; grp[4 * w].first = grp[4 * w + 1].first = true;
+      for (uint32_t i = 0; i < 4; ++i) grp[4 * w + i].reversible = (w == 0);
+    }
     for (const TileGeom& t : layout.tiles) {
       for (uint32_t c = 0; c < nc; ) {
-        bool fused = (r == D) && P.color_transform() && c == 0;
+        const uint32_t D = P.decomps(c);
+        bool fused = (li == 0) && P.color_transform() && c == 0;
         uint32_t k = fused ? 3 : 1;
+        if (li >= std::max(1u, D)) { c += k; continue; }       // this component has no such level
+        const uint32_t r = D == 0 ? 0 : D - li;                 // resolution being split (or rebuilt)
+        const bool rev = P.reversible(c);
+        const uint32_t gw = rev ? 0u : 4u;
         DwtJob j; memset(&j, 0, sizeof(j));
         const ResGeom& rg = t.comps[c].res[r];
         j.w = rg.rect.w; j.h = rg.rect.h; j.x0 = rg.rect.x0; j.y0 = rg.rect.y0;
@@ -143,13 +158,13 @@ void CodecBase::build_dwt_jobs(bool forward) {
         const bool stream = !j.nodwt && j.w >= 2 && j.h >= 2 && !no_stream_dwt && layout.coef_words < (1ull << 30) && img_bytes < (1ull << 32);   // 32-bit byte offsets in the stream kernels
         uint32_t gi, n;
         if (stream) {
-          gi = j.first ? (k == 3 ? 0u : 1u) : 2u;
-          dwt_stream_tiling(j.x0, j.y0, j.w, j.h, P.reversible(), j.tiles_x, j.tiles_y, j.chunk_rows, n);
+          gi = gw + (j.first ? (k == 3 ? 0u : 1u) : 2u);
+          dwt_stream_tiling(j.x0, j.y0, j.w, j.h, rev, j.tiles_x, j.tiles_y, j.chunk_rows, n);
         } else {
-          gi = 3;
+          gi = gw + 3;
           dwt_tiling(j.x0, j.y0, j.w, j.h, j.tiles_x, j.tiles_y);
           n = j.tiles_x * j.tiles_y;
-          grp[3].ncomp = std::max(grp[3].ncomp, k);
+          grp[gi].ncomp = std::max(grp[gi].ncomp, k);
         }
         j.cta_base = grp[gi].ctas;
         if (n) { grp[gi].ctas += n; grp[gi].jobs.push_back(j); }
@@ -289,10 +304,10 @@ size_t Encoder::encode(const void* const* planes, const uint32_t* strides, bool 
   for (size_t li = 0; li < jobs.size(); ++li)
     for (const JobGroup& g : jobs[li]) {
       if (g.stream)
-        launch_dwt_fwd_stream(d_jobs.as<DwtJob>() + g.dev_off, (uint32_t)g.jobs.size(), g.ctas, P.reversible(), g.ncomp,
+        launch_dwt_fwd_stream(d_jobs.as<DwtJob>() + g.dev_off, (uint32_t)g.jobs.size(), g.ctas, g.reversible, g.ncomp,
                               g.first, img_type, d_image.p, d_coef.as<uint32_t>(), stream);
       else
-        launch_dwt_fwd(d_jobs.as<DwtJob>() + g.dev_off, (uint32_t)g.jobs.size(), g.ctas, P.reversible(), g.ncomp,
+        launch_dwt_fwd(d_jobs.as<DwtJob>() + g.dev_off, (uint32_t)g.jobs.size(), g.ctas, g.reversible, g.ncomp,
                        d_image.p, d_coef.as<uint32_t>(), stream);
       ++last_launches;
     }
@@ -508,7 +523,7 @@ void Decoder::read_headers(const uint8_t* data, size_t len, uint32_t sample_type
               d.dst_off = bg.plane_off + bg.plane_pad_x + (uint64_t)(r.y0 - bg.rect.y0) * bg.plane_stride + (r.x0 - bg.rect.x0);
               d.stride = bg.plane_stride; d.w = (uint16_t)r.w; d.h = (uint16_t)r.h;
               d.K_max = (uint8_t)bg.K_max; d.delta = bg.delta;
-              d.flags = params.stripe_causal() ? 1 : 0;
+              d.flags = (params.stripe_causal(tc.comp) ? 1u : 0u) | (params.reversible(tc.comp) ? 0u : 2u);
               // quad records + de-stuffed MagSgn (a cleanup segment is < 65535 bytes; sized per frame)
               uint32_t nq = (r.w + 1) / 2, qs = (nq + 1) & ~1u, nqr = (r.h + 1) / 2;
               d.scratch_off = scratch;
@@ -531,7 +546,7 @@ void Decoder::info(FrameInfo& fi) const {
     fi.dx[c] = params.comps[c].dx; fi.dy[c] = params.comps[c].dy;
     fi.comp_w[c] = params.comp_width(c); fi.comp_h[c] = params.comp_height(c);
   }
-  fi.num_decomps = params.num_decomps; fi.reversible = params.reversible(); fi.color_transform = params.color_transform();
+  fi.num_decomps = params.num_decomps; fi.reversible = params.reversible();      // COD values (components may differ: COC) fi.color_transform = params.color_transform();
   fi.num_tiles = (uint32_t)layout.tiles.size();
 }
 
@@ -649,11 +664,11 @@ uint32_t Decoder::decode(void* const* planes, const uint32_t* strides, bool plan
   if (nb) { launch_ctrl_copy(d_dec.p, h_dec.p, (size_t)nb * sizeof(DecBlock), stream); ++last_launches; }
   if (serial_block_decoder() || max_block_w > 64)
     launch_ht_decode_serial(d_dec.as<DecBlock>(), nb, max_block_w, cs_dev, d_coef.as<uint32_t>(), d_scratch.as<uint32_t>(),
-                            d_tables_dec.as<uint16_t>(), P.reversible() ? (uint32_t)DEC_OUT_INT : (uint32_t)DEC_OUT_FLOAT,
+                            d_tables_dec.as<uint16_t>(), (uint32_t)DEC_OUT_PER_BLOCK,
                             d_bstatus.as<uint32_t>(), stream);
   else
     launch_ht_decode(d_dec.as<DecBlock>(), nb, cs_dev, d_coef.as<uint32_t>(), d_scratch.as<uint32_t>(),
-                     d_tables_dec.as<uint16_t>(), P.reversible() ? (uint32_t)DEC_OUT_INT : (uint32_t)DEC_OUT_FLOAT,
+                     d_tables_dec.as<uint16_t>(), (uint32_t)DEC_OUT_PER_BLOCK,
                      d_bstatus.as<uint32_t>(), max_len1, stream);
   last_launches += 2;
   mark(3);
@@ -662,10 +677,10 @@ uint32_t Decoder::decode(void* const* planes, const uint32_t* strides, bool plan
   for (size_t li = jobs.size(); li-- > 0; )
     for (const JobGroup& g : jobs[li]) {
       if (g.stream)
-        launch_dwt_inv_stream(d_jobs.as<DwtJob>() + g.dev_off, (uint32_t)g.jobs.size(), g.ctas, P.reversible(), g.ncomp,
+        launch_dwt_inv_stream(d_jobs.as<DwtJob>() + g.dev_off, (uint32_t)g.jobs.size(), g.ctas, g.reversible, g.ncomp,
                               g.first, img_type, d_image.p, d_coef.as<uint32_t>(), stream);
       else
-        launch_dwt_inv(d_jobs.as<DwtJob>() + g.dev_off, (uint32_t)g.jobs.size(), g.ctas, P.reversible(), g.ncomp,
+        launch_dwt_inv(d_jobs.as<DwtJob>() + g.dev_off, (uint32_t)g.jobs.size(), g.ctas, g.reversible, g.ncomp,
                        d_image.p, d_coef.as<uint32_t>(), stream);
       ++last_launches;
     }

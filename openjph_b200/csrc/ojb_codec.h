@@ -58,7 +58,7 @@ public:
   DeviceBuf d_coef;                    // coefficient arena (32-bit words)
   // DWT jobs per level (index 0: full resolution level D, ...), uploaded once
   // jobs of one level are grouped by the kernel variant that runs them
-  struct JobGroup { std::vector<DwtJob> jobs; uint32_t ctas = 0, ncomp = 1; bool first = false, stream = false; size_t dev_off = 0; };
+  struct JobGroup { std::vector<DwtJob> jobs; uint32_t ctas = 0, ncomp = 1; bool first = false, stream = false, reversible = true; size_t dev_off = 0; };
   std::vector<std::vector<JobGroup>> jobs;
   DeviceBuf d_jobs;
   void build_dwt_jobs(bool forward);

@@ -44,13 +44,14 @@ struct DecBlock {
   uint32_t len1, len2;  // cleanup bytes, SPP+MRP bytes
   uint32_t stride;      // words between rows of dst
   uint16_t w, h;
-  uint8_t missing_msbs, num_passes, K_max, flags;   // flags bit0: stripe-causal
+  uint8_t missing_msbs, num_passes, K_max, flags;   // flags bit0: stripe-causal, bit1: irreversible (float output)
   float delta;          // irreversible: step (already / 2^(31-K_max)); reversible: unused
 };
 enum : uint32_t {       // DecBlock output modes
   DEC_OUT_SIGNMAG = 0,  // raw sign-magnitude (kernel-level parity with ojph_decode_codeblock32)
   DEC_OUT_INT = 1,      // reversible: signed integers (tx_from_cb32 fused)
-  DEC_OUT_FLOAT = 2     // irreversible: float coefficient (tx_from_cb32 fused)
+  DEC_OUT_FLOAT = 2,    // irreversible: float coefficient (tx_from_cb32 fused)
+  DEC_OUT_PER_BLOCK = 3 // INT or FLOAT by the block's flags (components may differ: COC)
 };
 
 // ---- DWT --------------------------------------------------------------------------------

@@ -26,7 +26,7 @@ static void build_band(const Params& p, uint32_t comp, ResGeom& rg, uint32_t b, 
   bg.rect = br; bg.band_num = b;
   const QuantSet& q = p.quant_for(comp);
   bg.K_max = q.kmax(rg.res_num, b);
-  if (!p.reversible()) {
+  if (!p.reversible(comp)) {
     float d = q.irrev_delta(rg.res_num, b);
     d /= (float)(1u << (31 - bg.K_max));
     bg.delta = d; bg.delta_inv = 1.0f / d;
@@ -34,8 +34,8 @@ static void build_band(const Params& p, uint32_t comp, ResGeom& rg, uint32_t b, 
   bg.empty = br.empty();
   if (bg.empty) return;
   uint32_t off = rg.res_num > 0 ? 1u : 0u;
-  bg.xcb = std::min(p.log_cb_w(), rg.log_ppx - off);
-  bg.ycb = std::min(p.log_cb_h(), rg.log_ppy - off);
+  bg.xcb = std::min(p.log_cb_w(comp), rg.log_ppx - off);
+  bg.ycb = std::min(p.log_cb_h(comp), rg.log_ppy - off);
   bg.nbw = ((br.x1() + (1u << bg.xcb) - 1) >> bg.xcb) - (br.x0 >> bg.xcb);
   bg.nbh = ((br.y1() + (1u << bg.ycb) - 1) >> bg.ycb) - (br.y0 >> bg.ycb);
   bg.block_base = block_counter;
@@ -52,7 +52,7 @@ static void build_precincts(const Params& p, const TileGeom& tile, const TileCom
   const Rect& rr = rg.rect;
   rg.npw = rg.nph = 0;
   if (rr.empty()) return;
-  uint32_t D = p.num_decomps;
+  uint32_t D = p.decomps(tc.comp);
   rg.npw = ((rr.x1() + (1u << rg.log_ppx) - 1) >> rg.log_ppx) - (rr.x0 >> rg.log_ppx);
   rg.nph = ((rr.y1() + (1u << rg.log_ppy) - 1) >> rg.log_ppy) - (rr.y0 >> rg.log_ppy);
   rg.precincts.assign((size_t)rg.npw * rg.nph, PrecinctGeom());
@@ -100,7 +100,7 @@ static void build_precincts(const Params& p, const TileGeom& tile, const TileCom
 void Layout::build(const Params& params) {
   p = &params;
   const Params& P = params;
-  uint32_t nc = P.num_comps(), D = P.num_decomps;
+  uint32_t nc = P.num_comps();
   ntw = div_ceil(P.Xsiz - P.XTOsiz, P.XTsiz);
   nth = div_ceil(P.Ysiz - P.YTOsiz, P.YTsiz);
   if ((uint64_t)ntw * nth > 65535) fail(0x00030011, "the number of tiles cannot exceed 65535");
@@ -123,12 +123,13 @@ void Layout::build(const Params& params) {
         uint32_t dx = P.comps[c].dx, dy = P.comps[c].dy;
         tc.rect.x0 = div_ceil(t.rect.x0, dx); tc.rect.w = div_ceil(t.rect.x1(), dx) - tc.rect.x0;
         tc.rect.y0 = div_ceil(t.rect.y0, dy); tc.rect.h = div_ceil(t.rect.y1(), dy) - tc.rect.y0;
+        const uint32_t D = P.decomps(c);           // the component's own coding style (COC) if it has one
         tc.res.assign(D + 1, ResGeom());
         Rect rr = tc.rect;
         for (int r = (int)D; r >= 0; --r) {
           ResGeom& rg = tc.res[r];
           rg.rect = rr; rg.res_num = (uint32_t)r;
-          rg.log_ppx = P.log_pp_w((uint32_t)r); rg.log_ppy = P.log_pp_h((uint32_t)r);
+          rg.log_ppx = P.log_pp_w(c, (uint32_t)r); rg.log_ppy = P.log_pp_h(c, (uint32_t)r);
           // sample plane of this resolution (input of the level-r analysis / output of synthesis)
           rg.plane_stride = (rr.w + 15u) & ~15u;
           rg.plane_off = arena;
@@ -164,11 +165,13 @@ void Layout::packet_sequence(uint32_t tile, std::vector<PacketRef>& seq,
                              std::vector<uint32_t>& tp_first) const {
   const TileGeom& t = tiles[tile];
   const Params& P = *p;
-  uint32_t nc = P.num_comps(), D = P.num_decomps;
+  uint32_t nc = P.num_comps(), D = P.max_decomps();
   seq.clear(); tp_first.clear();
-  // per (comp,res) cursor over precincts in raster order
+  // per (comp,res) cursor over precincts in raster order; a component with fewer decompositions
+  // simply has no precincts at the higher resolution numbers (tile_comp::get_top_left_precinct,
+  // ojph_tile_comp.cpp:132-145)
   std::vector<uint32_t> cur((size_t)nc * (D + 1), 0);
-  auto npre = [&](uint32_t c, uint32_t r) { return (uint32_t)t.comps[c].res[r].precincts.size(); };
+  auto npre = [&](uint32_t c, uint32_t r) { return r < t.comps[c].res.size() ? (uint32_t)t.comps[c].res[r].precincts.size() : 0u; };
   auto emit_all = [&](uint32_t c, uint32_t r) {
     for (uint32_t i = 0; i < npre(c, r); ++i) seq.push_back(PacketRef{ tile, c, r, i });
   };

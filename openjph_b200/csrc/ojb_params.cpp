@@ -208,11 +208,11 @@ void Params::set_precincts(int n, const uint32_t* w, const uint32_t* h) {
 static void make_quant_steps(QuantSet& q, uint32_t comp, const Params& p) {
   if (q.is_init) fail(0x00040001, "Quantization step sizes already initialized.");
   q.is_init = true;
-  q.num_decomps = p.num_decomps;
+  q.num_decomps = p.decomps(comp);              // the component's COC when it has one (:1432-1460)
   q.bit_depth = p.comps[comp].bit_depth;
   q.is_signed = p.comps[comp].is_signed;
   q.is_color_trans = p.color_transform();
-  q.wavelet = p.wavelet;
+  q.wavelet = p.wavelet_of(comp);
   q.sx = p.comps[comp].dx; q.sy = p.comps[comp].dy;
   q.num_subbands = 1 + 3 * q.num_decomps;
   if (q.wavelet == DWT_REV53)
@@ -266,7 +266,8 @@ void Params::finalize_for_encode() {
   // QCD / QCC (param_qcd::check_validity, ojph_params.cpp:1359-1431)
   for (QuantSet& q : qcc) q.enabled = q.comp_idx < nc;
   uint32_t qcd_comp = 0;
-  for (uint32_t c = 0; c < nc; ++c) if (find_qcc(c) == nullptr) { qcd_comp = c; break; }
+  // the first component that uses COD (no COC) and has no QCC (ojph_params.cpp:1367-1377)
+  for (uint32_t c = 0; c < nc; ++c) if (find_coc(c) == nullptr && find_qcc(c) == nullptr) { qcd_comp = c; break; }
   if (qcd.qfactor != 0) {
     for (uint32_t i = 0; i < nc; ++i) {
       if (find_qcc(i) == nullptr) {
@@ -280,9 +281,9 @@ void Params::finalize_for_encode() {
   for (uint32_t c = 0; c < nc; ++c) {
     QuantSet* q = find_qcc(c);
     if (q == nullptr) {
-      bool needed = qcd.num_decomps != num_decomps || qcd.bit_depth != comps[c].bit_depth ||
+      bool needed = qcd.num_decomps != decomps(c) || qcd.bit_depth != comps[c].bit_depth ||
                     qcd.is_signed != comps[c].is_signed ||
-                    qcd.is_color_trans != color_transform() || qcd.wavelet != wavelet;
+                    qcd.is_color_trans != color_transform() || qcd.wavelet != wavelet_of(c);
       if (!needed) continue;
       QuantSet& nq = add_qcc(c);
       nq.base_delta = qcd.base_delta;
@@ -365,6 +366,16 @@ void Params::write_main_header(std::vector<uint8_t>& o, const char* const* comme
   put_u8(o, num_decomps); put_u8(o, cb_w_exp); put_u8(o, cb_h_exp); put_u8(o, block_style);
   put_u8(o, wavelet);
   if (Scod & 1) for (int i = 0; i <= num_decomps; ++i) put_u8(o, precinct_size[i]);
+  // COC, in creation order (param_cod::write_coc / internal_write_coc, ojph_params.cpp:1081-1143)
+  for (const CodStyle& c : coc) {
+    if (c.comp_idx >= nc) continue;
+    put_u16(o, M_COC);
+    put_u16(o, (nc < 257 ? 9u : 10u) + ((c.Scoc & 1) ? 1u + c.num_decomps : 0u));
+    if (nc < 257) put_u8(o, c.comp_idx); else put_u16(o, c.comp_idx);
+    put_u8(o, c.Scoc); put_u8(o, c.num_decomps); put_u8(o, c.cb_w_exp); put_u8(o, c.cb_h_exp);
+    put_u8(o, c.block_style); put_u8(o, c.wavelet);
+    if (c.Scoc & 1) for (int i = 0; i <= c.num_decomps; ++i) put_u8(o, c.precinct_size[i]);
+  }
   // QCD, QCC
   write_quant(o, qcd, nc);
   for (const QuantSet& q : qcc) if (q.enabled) write_quant(o, q, nc);
@@ -465,7 +476,7 @@ size_t Params::read_main_header(const uint8_t* data, size_t len) {
            "supported by the GPU path");
   }
   int received = 0;
-  qcc.clear();
+  qcc.clear(); coc.clear();
   for (;;) {
     // scan to the next 0xFF xx marker of interest (the reference skips unknown bytes too)
     if (r.pos + 1 >= r.n) fail(0x00030051, "File ended before finding a tile segment");
@@ -522,10 +533,33 @@ size_t Params::read_main_header(const uint8_t* data, size_t len) {
         fail(0x00030055, "The codestream has two QCC marker segments for one component of "
              "index %d", q.comp_idx);
       qcc.push_back(q);
-    } else if (m == M_COC)
-      fail(0x000B0004, "COC marker segments (per-component coding styles) are not supported by "
-           "the GPU path yet");
-    else if (m == M_DFS || m == M_ATK || m == M_NLT)
+    } else if (m == M_COC) {                    // param_cod::read_coc, ojph_params.cpp:1207-1290
+      uint32_t L = r.u16();
+      const uint32_t nc = num_comps();
+      CodStyle c;
+      c.comp_idx = (uint16_t)(nc < 257 ? r.u8() : r.u16());
+      c.Scoc = (uint8_t)r.u8(); c.num_decomps = (uint8_t)r.u8(); c.cb_w_exp = (uint8_t)r.u8();
+      c.cb_h_exp = (uint8_t)r.u8(); c.block_style = (uint8_t)r.u8(); c.wavelet = (uint8_t)r.u8();
+      if (c.comp_idx >= nc)
+        fail(0x00030056, "The codestream carries a COC marker segment for a component indexed by %d, which is "
+             "more than the allowed index number, since the codestream has %d components", c.comp_idx, nc);
+      if (find_coc(c.comp_idx))
+        fail(0x00030057, "The codestream has two COC marker segments for one component of index %d", c.comp_idx);
+      if (c.num_decomps > 32 || c.cb_w_exp > 8 || c.cb_h_exp > 8 || c.cb_w_exp + c.cb_h_exp > 8 ||
+          (c.block_style & 0x40) != 0x40 || (c.block_style & 0xB7) != 0x00)
+        fail(0x0005012D, "wrong settings in a COC-SPcoc parameter");
+      if (c.wavelet > 1)
+        fail(0x000B0003, "arbitrary transformation kernels (ATK) are not supported by the GPU path");
+      if (c.Scoc & 1)
+        for (int i = 0; i <= c.num_decomps; ++i) {
+          c.precinct_size[i] = (uint8_t)r.u8();
+          if (i && ((c.precinct_size[i] & 0xF) == 0 || (c.precinct_size[i] >> 4) == 0))
+            fail(0x0005012E, "Precinct width or height for resolutions other than the coarsest must be larger than 1");
+        }
+      if (L != (nc < 257 ? 9u : 10u) + ((c.Scoc & 1) ? 1u + c.num_decomps : 0u))
+        fail(0x0005012F, "error in COC segment length");
+      coc.push_back(c);
+    } else if (m == M_DFS || m == M_ATK || m == M_NLT)
       fail(0x000B0005, "DFS/ATK/NLT marker segments are not supported by the GPU path");
     else {  // PRF CPF RGN POC PPM TLM PLM CRG COM: skipped
       uint32_t L = r.u16();

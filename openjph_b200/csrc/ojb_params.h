@@ -48,6 +48,16 @@ struct QuantSet {
   void set_irrev_quant(uint32_t num_decomps);                                // :1542
 };
 
+// per-component coding style (COC marker segment; param_cod with type COC_MAIN,
+// ojph_params_local.h:330-440).  A new object starts from the library defaults -- not from the COD
+// values -- exactly as param_cod::init does (:630-646)
+struct CodStyle {
+  uint16_t comp_idx = 0xFFFF;
+  uint8_t Scoc = 0;                         // bit 0: user precinct sizes follow
+  uint8_t num_decomps = 5, cb_w_exp = 4, cb_h_exp = 4, block_style = 0x40, wavelet = DWT_IRV97;
+  uint8_t precinct_size[33] = {0};
+};
+
 struct Params {
   // ---- SIZ
   uint16_t Rsiz = 0x4000;
@@ -64,6 +74,7 @@ struct Params {
   uint8_t block_style = 0x40;               // HT
   uint8_t wavelet = DWT_IRV97;
   uint8_t precinct_size[33] = {0};          // PPx | PPy << 4 per resolution (Scod & 1)
+  std::vector<CodStyle> coc;                // per-component overrides, in creation order
   // ---- QCD / QCC
   QuantSet qcd;
   std::vector<QuantSet> qcc;                // in creation order
@@ -84,6 +95,30 @@ struct Params {
   uint32_t log_pp_w(uint32_t r) const { return (Scod & 1) ? (precinct_size[r] & 0xF) : 15u; }
   uint32_t log_pp_h(uint32_t r) const { return (Scod & 1) ? (precinct_size[r] >> 4) : 15u; }
   bool stripe_causal() const { return (block_style & 0x8) != 0; }
+  // per-component views: the component's COC when it has one, else the COD values
+  const CodStyle* find_coc(uint32_t c) const { for (const CodStyle& s : coc) if (s.comp_idx == c) return &s; return nullptr; }
+  CodStyle& get_or_add_coc(uint32_t c) {                           // param_cod::get_or_add_coc, ojph_params.cpp:1341
+    for (CodStyle& s : coc) if (s.comp_idx == c) return s;
+    coc.push_back(CodStyle()); coc.back().comp_idx = (uint16_t)c; return coc.back();
+  }
+  uint32_t decomps(uint32_t c) const { const CodStyle* s = find_coc(c); return s ? s->num_decomps : num_decomps; }
+  uint32_t max_decomps() const { uint32_t d = 0; for (uint32_t c = 0; c < num_comps(); ++c) d = std::max(d, decomps(c)); return d; }
+  uint32_t wavelet_of(uint32_t c) const { const CodStyle* s = find_coc(c); return s ? s->wavelet : wavelet; }
+  bool reversible(uint32_t c) const { return wavelet_of(c) == DWT_REV53; }
+  uint32_t log_cb_w(uint32_t c) const { const CodStyle* s = find_coc(c); return (s ? s->cb_w_exp : cb_w_exp) + 2u; }
+  uint32_t log_cb_h(uint32_t c) const { const CodStyle* s = find_coc(c); return (s ? s->cb_h_exp : cb_h_exp) + 2u; }
+  uint32_t log_pp_w(uint32_t c, uint32_t r) const {
+    const CodStyle* s = find_coc(c);
+    if (s) return (s->Scoc & 1) ? (s->precinct_size[r] & 0xF) : 15u;
+    return log_pp_w(r);
+  }
+  uint32_t log_pp_h(uint32_t c, uint32_t r) const {
+    const CodStyle* s = find_coc(c);
+    if (s) return (s->Scoc & 1) ? (s->precinct_size[r] >> 4) : 15u;
+    return log_pp_h(r);
+  }
+  bool stripe_causal(uint32_t c) const { const CodStyle* s = find_coc(c); return ((s ? s->block_style : block_style) & 0x8) != 0; }
+  bool mixed_wavelets() const { for (uint32_t c = 0; c < num_comps(); ++c) if (wavelet_of(c) != wavelet_of(0)) return true; return false; }
   bool uses_sop() const { return (Scod & 2) != 0; }
   bool uses_eph() const { return (Scod & 4) != 0; }
   uint32_t comp_width(uint32_t c) const

@@ -93,6 +93,8 @@ struct ojr_params {
   uint32_t tlm;                    // request TLM marker
   uint32_t tilepart_div;           // 0 none, 1 resolutions, 2 components, 3 both
   int32_t  planar;                 // -1 => library default
+  // per-component coding styles (COC), same meaning as in include/ojph_b200.h
+  uint32_t coc_present[16], coc_reversible[16], coc_num_decomps[16], coc_block_w[16], coc_block_h[16];
 };
 
 static char g_err[512] = "";
@@ -132,6 +134,12 @@ int ojr_encode(const ojr_params* p, const int32_t* const* planes,
     cod.set_progression_order(po_name(p->prog_order));
     cod.set_color_transform(p->color_transform != 0);
     cod.set_reversible(p->reversible != 0);
+    for (uint32_t c = 0; c < p->num_comps; ++c)
+      if (p->coc_present[c]) {
+        cod.set_num_decomposition(c, p->coc_num_decomps[c]);
+        cod.set_block_dims(c, p->coc_block_w[c], p->coc_block_h[c]);
+        cod.set_reversible(c, p->coc_reversible[c] != 0);
+      }
     if (!p->reversible) {
       if (p->qstep > 0.0f) cs.access_qcd().set_irrev_quant(p->qstep);
       if (p->qfactor) cs.access_qcd().set_qfactor((ui8)p->qfactor);

@@ -19,6 +19,8 @@ class RParams(C.Structure):
         ("reversible", C.c_uint32), ("color_transform", C.c_uint32), ("prog_order", C.c_uint32),
         ("qstep", C.c_float), ("qfactor", C.c_uint32), ("tlm", C.c_uint32), ("tilepart_div", C.c_uint32),
         ("planar", C.c_int32),
+        ("coc_present", C.c_uint32 * 16), ("coc_reversible", C.c_uint32 * 16), ("coc_num_decomps", C.c_uint32 * 16),
+        ("coc_block_w", C.c_uint32 * 16), ("coc_block_h", C.c_uint32 * 16),
     ]
 
 

@@ -1,0 +1,73 @@
+"""The reference's tests/test_mixed_coc.cpp (TestMixedCOC.FourCompMixedReversibility), restated: four
+components, three coded with the irreversible 9/7 wavelet through COD and one with the reversible 5/3
+through its own COC (+ QCC).  The reversible component must decode exactly; the per-component settings
+must survive the codestream.  Also: components with their own number of decompositions / block size."""
+import numpy as np
+import pytest
+import cases
+import openjph_b200 as ob
+
+W = H = 64
+
+
+def _frame():
+    y, x = np.mgrid[0:H, 0:W]
+    ramp = ((x + y * W) % 256).astype(np.int32)                 # test_mixed_coc.cpp:100-106
+    return [np.zeros((H, W), np.int32)] * 3 + [ramp]
+
+
+def _params():
+    return ob.make_params(W, H, 4, 8, num_decomps=5, block=(64, 64), reversible=False, color_transform=False,
+                          qstep=0.01, planar=1, coc={3: dict(reversible=True)})
+
+
+def _check_mixed(lib, ref):
+    p, frame = _params(), _frame()
+    want = ref.encode(p, frame)
+    got = ob.Encoder(p, ob.I32, lib=lib).encode(frame)
+    assert got == want                                          # all-zero 9/7 components: nothing rounding-dependent
+    assert b"\xff\x53" in got[:200]                             # a COC segment is there
+    for cs in (want, got):
+        out = ob.Decoder(lib=lib).decode(cs)
+        assert np.array_equal(out[3], frame[3])                 # the reversible component is exact
+        refout, _ = ref.decode(cs)
+        for a, b in zip(out, refout):
+            assert np.array_equal(a, b)
+
+
+def _check_varied(lib, ref):
+    """natural content; component 1 has 2 levels and 32x32 blocks, component 2 is reversible with 3 levels"""
+    p = ob.make_params(200, 150, 3, 8, num_decomps=4, reversible=False, qstep=0.02, planar=1,
+                       coc={1: dict(reversible=False, num_decomps=2, block=(32, 32)), 2: dict(reversible=True, num_decomps=3)})
+    frame = cases.frame_for(p)
+    want = ref.encode(p, frame)
+    refout, _ = ref.decode(want)
+    out = ob.Decoder(lib=lib).decode(want)
+    assert np.array_equal(out[2], frame[2]) and np.array_equal(refout[2], frame[2])
+    got = ob.Encoder(p, ob.I32, lib=lib).encode(frame)
+    assert len(got) == len(want)
+    cross, _ = ref.decode(got)
+    assert np.array_equal(cross[2], frame[2])
+    for c in (0, 1):
+        m_ref, p_ref = cases.mse_pae(refout[c], frame[c])
+        for planes in (out, cross):
+            m, pa = cases.mse_pae(planes[c], frame[c])
+            assert abs(m - m_ref) / (m_ref + 0.01) < 0.01 and abs(pa - p_ref) <= 1
+
+
+def test_mixed_reversibility_emulator(emu_lib, ref):
+    _check_mixed(emu_lib, ref)
+
+
+def test_per_component_styles_emulator(emu_lib, ref):
+    _check_varied(emu_lib, ref)
+
+
+@pytest.mark.gpu
+def test_mixed_reversibility_gpu(gpu_lib, ref):
+    _check_mixed(None, ref)
+
+
+@pytest.mark.gpu
+def test_per_component_styles_gpu(gpu_lib, ref):
+    _check_varied(None, ref)
