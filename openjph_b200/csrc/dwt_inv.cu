@@ -27,8 +27,10 @@ __device__ __forceinline__ void store_sample(void* img, uint32_t type, uint64_t 
   else reinterpret_cast<int*>(base)[idx] = v;
 }
 
-// round half away from zero by truncation, as ojph_round does (ojph_arch.h:317-326)
-__device__ __forceinline__ int round_haz(float t) { return (int)(t + (t >= 0.0f ? 0.5f : -0.5f)); }
+// float -> integer as the reference's SIMD builds do it (cvtps: round to nearest, ties to even;
+// ojph_colour_avx2.cpp:303).  The generic C path rounds ties away from zero (ojph_arch.h:317-326); the two
+// differ only on exact halves, which zero-decomposition 9/7 components produce systematically.
+__device__ __forceinline__ int round_haz(float t) { return __float2int_rn(t); }
 
 template <bool REV>
 __global__ void __launch_bounds__(DW_THREADS)

@@ -482,7 +482,10 @@ __device__ __forceinline__ void inv_read_pair(const unsigned char* st, typename 
   }
 }
 
-__device__ __forceinline__ int round_haz(float t) { return (int)(t + (t >= 0.0f ? 0.5f : -0.5f)); }
+// float -> integer as the reference's SIMD builds do it (cvtps: round to nearest, ties to even;
+// ojph_colour_avx2.cpp:303).  The generic C path rounds ties away from zero (ojph_arch.h:317-326); the two
+// differ only on exact halves, which zero-decomposition 9/7 components produce systematically.
+__device__ __forceinline__ int round_haz(float t) { return __float2int_rn(t); }
 
 template <bool REV, int NC, int SRC>
 __device__ __forceinline__ void inv_store_row(const DwtJob& J, const StripGeom& g, void* image, uint32_t* coef,

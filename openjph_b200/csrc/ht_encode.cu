@@ -226,7 +226,7 @@ ht_encode_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
   __syncwarp();
   // bytes available: MagSgn grows up from 0, VLC grows down from slot_cap
   const uint32_t slot_words = blk.slot_cap >> 2;
-  uint32_t any_sig = 0;
+  uint32_t any_sig = 0, negzero = 0;
   bool overflow = false;
 
   const uint32_t x = 2 * lane;
@@ -268,6 +268,8 @@ ht_encode_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
       v = ((t3 + t3) >> p) & ~1u; if (v) { rho |= 8; --v; e3 = 32 - __clz((int)v); s3 = --v + (t3 >> 31); }
     }
     any_sig |= rho;
+    if (blk.flags & ENC_CHECK_NEGZERO)              // magnitude-overflow words keep the block coded (ojb_device.h)
+      negzero |= (t0 == 0x80000000u) | (t1 == 0x80000000u) | (t2 == 0x80000000u) | (t3 == 0x80000000u);
     // nothing significant in this quad-row nor in the one above: every context is 0, every quad is one
     // MEL "0" event and no VLC / MagSgn bits (quantised high bands are mostly such rows)
     if (!__any_sync(FULL, (rho | prev_rho) != 0)) {
@@ -410,7 +412,7 @@ ht_encode_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
     prev_rho = rho; prev_e1 = e1; prev_e3 = e3;
   }
 
-  any_sig = __reduce_or_sync(FULL, any_sig);
+  any_sig = __reduce_or_sync(FULL, any_sig | negzero);
   if (overflow) {
     if (lane == 0) { atomicOr(status, 1u); results[bidx].len_head = 0; results[bidx].len_tail = 0; }
     return;

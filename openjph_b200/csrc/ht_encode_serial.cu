@@ -147,7 +147,7 @@ ht_encode_serial_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
   // VLC starts as byte 0xFF (later the Scup byte) followed by the four bits 0xF (vlc_init, :365-375)
   VlcWriter vlc; vlc.acc = 0xFFFull; vlc.nbits = 12; vlc.words = 0; vlc.prev = 0;
   MelWriter mel; mel.k = 0; mel.run = 0; mel.tmp = 0; mel.rem = 8; mel.pos = 0;
-  uint32_t any_sig = 0;
+  uint32_t any_sig = 0, negzero = 0;
   bool overflow = false;
   // aligned block rows: a quad pair of one row is one 16-byte load
   const bool vec4 = ((blk.src_off | stride) & 3u) == 0;
@@ -207,6 +207,8 @@ ht_encode_serial_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
           s[i] = v - 2u + (t[i] >> 31);
         }
         any_sig |= rho;
+        if (blk.flags & ENC_CHECK_NEGZERO)            // magnitude-overflow words keep the block coded
+          negzero |= (t[0] == 0x80000000u) | (t[1] == 0x80000000u) | (t[2] == 0x80000000u) | (t[3] == 0x80000000u);
         const uint32_t emax = max(max(e[0], e[1]), max(e[2], e[3]));
         // ---- context and exponent predictor from the row above
         const uint32_t pr = prev[(qq + 1) * ES_THREADS];      // quad qq+1 of the row above
@@ -267,7 +269,7 @@ ht_encode_serial_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
   }
 
   if (overflow) { atomicOr(status, 1u); results[bidx].len_head = 0; results[bidx].len_tail = 0; return; }
-  if (any_sig == 0) { results[bidx].len_head = 0; results[bidx].len_tail = 0; return; }   // block not included
+  if (any_sig == 0 && negzero == 0) { results[bidx].len_head = 0; results[bidx].len_tail = 0; return; }   // block not included
 
   // ---- termination (terminate_mel_vlc :413-441, ms_terminate :517-533)
   uint32_t ms_pos = ms.words * 4;

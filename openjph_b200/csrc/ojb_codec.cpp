@@ -221,6 +221,7 @@ void Encoder::configure(const Params& p, uint32_t sample_type) {
               e.src_off = bg.plane_off + bg.plane_pad_x + (uint64_t)(r.y0 - bg.rect.y0) * bg.plane_stride + (r.x0 - bg.rect.x0);
               e.stride = bg.plane_stride; e.w = (uint16_t)r.w; e.h = (uint16_t)r.h;
               e.p = (uint16_t)(31u - bg.K_max);
+              e.flags = (tc.res.size() == 1 && params.reversible(tc.comp)) ? (uint16_t)ENC_CHECK_NEGZERO : (uint16_t)0;
               // worst case: (K_max+1) MagSgn bits / sample (+1/15 stuffing), 30 VLC bits / quad pair
               // (+1/7), 192 MEL bytes, working margin of the kernel
               uint64_t ms = ((uint64_t)r.w * r.h * (bg.K_max + 1) + 7) / 8; ms += ms / 15 + 8;
@@ -346,15 +347,16 @@ size_t Encoder::encode(const void* const* planes, const uint32_t* strides, bool 
   std::vector<Pkt> pkts;
   std::vector<TilePart> tps;
   {
-    std::vector<PacketRef> seq; std::vector<uint32_t> tp_first;
+    std::vector<PacketRef> seq; std::vector<uint32_t> tp_first, tp_index;
+    uint32_t tp_total = 0;
     for (uint32_t t = 0; t < (uint32_t)layout.tiles.size(); ++t) {
-      layout.packet_sequence(t, seq, tp_first);
+      layout.packet_sequence(t, seq, tp_first, &tp_index, &tp_total);
       size_t base = pkts.size();
       for (const PacketRef& pr : seq) { pkts.emplace_back(); pkts.back().ref = pr; pkts.back().hdr_len = pkts.back().body = 0; }
       for (size_t i = 0; i < tp_first.size(); ++i) {
         TilePart tp; tp.tile = t; tp.first = (uint32_t)(base + tp_first[i]);
         uint32_t end = (i + 1 < tp_first.size()) ? tp_first[i + 1] : (uint32_t)seq.size();
-        tp.count = end - tp_first[i]; tp.tp_idx = (uint32_t)i; tp.tp_cnt = (uint32_t)tp_first.size();
+        tp.count = end - tp_first[i]; tp.tp_idx = tp_index[i]; tp.tp_cnt = tp_total;
         tp.bytes = 0;
         tps.push_back(tp);
       }

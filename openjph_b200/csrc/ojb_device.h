@@ -30,8 +30,14 @@ struct EncBlock {
   uint32_t slot_cap;    // slot size in bytes (multiple of 16)
   uint16_t w, h;
   uint16_t p;           // 30 - missing_msbs = 31 - K_max
-  uint16_t pad;
+  uint16_t flags;       // bit 0: look for magnitude-overflow words (0x80000000), see ENC_CHECK_NEGZERO
 };
+// A sample whose magnitude is exactly 2^K_max shifts out of the 31 magnitude bits and is stored as
+// 0x80000000: the reference still counts it in its max_val test (ojph_codeblock.cpp:143-147,
+// ojph_codestream_gen.cpp:59-78), so a block made only of such samples is coded (3 bytes, nothing
+// significant) instead of being skipped.  It happens with zero decompositions and no colour transform
+// (K_max = B - 1 + guard for the single band) for the most negative sample value.
+#define ENC_CHECK_NEGZERO 1u
 // result per block: [0] bytes at slot start (MagSgn + MEL), [1] bytes at slot end (VLC);
 // both 0 for a block with no significant sample (not included in the packet).
 struct EncResult { uint32_t len_head, len_tail; };

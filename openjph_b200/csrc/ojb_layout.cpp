@@ -162,7 +162,8 @@ void Layout::build(const Params& params) {
 // packet sequencing
 //------------------------------------------------------------------------------------------
 void Layout::packet_sequence(uint32_t tile, std::vector<PacketRef>& seq,
-                             std::vector<uint32_t>& tp_first) const {
+                             std::vector<uint32_t>& tp_first, std::vector<uint32_t>* tp_index,
+                             uint32_t* tp_total) const {
   const TileGeom& t = tiles[tile];
   const Params& P = *p;
   uint32_t nc = P.num_comps(), D = P.max_decomps();
@@ -186,11 +187,20 @@ void Layout::packet_sequence(uint32_t tile, std::vector<PacketRef>& seq,
   };
   uint32_t div = P.tilepart_div;
   if (div == TP_NONE) tp_first.push_back(0);
+  std::vector<uint32_t> idx;                 // TPsot of every tile-part when it is not simply its rank
+  uint32_t total = 0;
   if (P.prog_order == PO_LRCP || P.prog_order == PO_RLCP) {
     for (uint32_t r = 0; r <= D; ++r) {
       if (div == TP_RES) tp_first.push_back((uint32_t)seq.size());
       for (uint32_t c = 0; c < nc; ++c) {
-        if (div & TP_COMP) tp_first.push_back((uint32_t)seq.size());
+        if (div & TP_COMP) {
+          // one tile-part per EXISTING (resolution, component), numbered c + r * nc out of nc * (D + 1)
+          // -- the numbering has gaps when components have different decomposition counts (tile::flush,
+          // ojph_tile.cpp:634-652)
+          if (r >= t.comps[c].res.size()) continue;
+          tp_first.push_back((uint32_t)seq.size());
+          idx.push_back(c + r * nc); total = nc * (D + 1);
+        }
         emit_all(c, r);
       }
     }
@@ -237,6 +247,11 @@ void Layout::packet_sequence(uint32_t tile, std::vector<PacketRef>& seq,
     }
   }
   if (tp_first.empty()) tp_first.push_back(0);
+  if (tp_index) {
+    tp_index->clear();
+    for (uint32_t i = 0; i < tp_first.size(); ++i) tp_index->push_back(idx.size() == tp_first.size() ? idx[i] : i);
+  }
+  if (tp_total) *tp_total = (idx.size() == tp_first.size() && total) ? total : (uint32_t)tp_first.size();
 }
 
 //------------------------------------------------------------------------------------------

@@ -84,8 +84,8 @@ struct Layout {
   void build(const Params& params);
   // packets of one tile in progression order; tile-part boundaries in tp_first
   // (index into the sequence where each tile-part starts)
-  void packet_sequence(uint32_t tile, std::vector<PacketRef>& seq,
-                       std::vector<uint32_t>& tp_first) const;
+  void packet_sequence(uint32_t tile, std::vector<PacketRef>& seq, std::vector<uint32_t>& tp_first,
+                       std::vector<uint32_t>* tp_index = nullptr, uint32_t* tp_total = nullptr) const;
   const ResGeom& res_of(const PacketRef& pk) const
   { return tiles[pk.tile].comps[pk.comp].res[pk.res]; }
 };
