@@ -124,6 +124,12 @@ int ojb_dec_enable_resilience(ojb_decoder* d);           /* codestream::enable_r
 /* codestream::read_headers(infile_base*): j2c must stay valid until the decode call returns */
 int ojb_dec_read_headers(ojb_decoder* d, const uint8_t* j2c, uint64_t len, uint32_t sample_type,
                          ojb_frame_info* info);
+/* codestream::restrict_input_resolution(skipped_res_for_read, skipped_res_for_recon)
+ * (ojph_codestream_local.cpp:883-900), after read_headers: the top skipped_res_for_recon resolutions are
+ * not reconstructed (every component comes out 2^n times smaller; *info receives the new comp_w / comp_h),
+ * the top skipped_res_for_read (>= skipped_res_for_recon) are not decoded and read as zero. */
+int ojb_dec_restrict_input_resolution(ojb_decoder* d, uint32_t skipped_res_for_read, uint32_t skipped_res_for_recon,
+                                      ojb_frame_info* info);
 /* codestream::create() + the pull() loop: decodes every component into planes */
 int ojb_dec_decode_frame(ojb_decoder* d, void* const* planes, const uint32_t* strides);
 int ojb_dec_decode_resident(ojb_decoder* d);             /* result stays in the device image buffer */

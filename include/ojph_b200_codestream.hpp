@@ -7,7 +7,7 @@
 // The including translation unit provides OpenJPH's own public headers first (they are not part of
 // this repository):  ojph_base.h (ui8/ui32/si32, point, size), ojph_mem.h (line_buf), ojph_file.h
 // (outfile_base, infile_base).  Only what the reference's apps call is mirrored; Part-2 items the
-// hot path does not cover (NLT, DFS/ATK, resolution restriction) raise the
+// hot path does not cover (NLT, DFS/ATK) raise the
 // same kind of std::runtime_error the reference raises for invalid settings.
 #pragma once
 #include "ojph_b200.h"
@@ -164,7 +164,7 @@ public:
     st.reading = true;
   }
   void restrict_input_resolution(ui32 skipped_res_for_data, ui32 skipped_res_for_recon) {
-    if (skipped_res_for_data || skipped_res_for_recon) raise("ojph error: resolution restriction is not supported by the B200 path");
+    check(ojb_dec_restrict_input_resolution(dec, skipped_res_for_data, skipped_res_for_recon, &st.info));
   }
   void create() {
     if (st.planar >= 0) ojb_dec_set_planar(dec, st.planar);

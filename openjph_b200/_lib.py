@@ -77,6 +77,7 @@ SYMBOLS = {
     "ojb_dec_read_headers": (_I, [_VP, _VP, _U64, _U32, C.POINTER(FrameInfo)]),
     "ojb_dec_decode_frame": (_I, [_VP, C.POINTER(_VP), C.POINTER(_U32)]),
     "ojb_dec_decode_resident": (_I, [_VP]),
+    "ojb_dec_restrict_input_resolution": (_I, [_VP, _U32, _U32, C.POINTER(FrameInfo)]),
     "ojb_dec_set_planar": (_I, [_VP, _I]),
     "ojb_dec_begin_pull": (_I, [_VP]),
     "ojb_dec_pull": (_VP, [_VP, C.POINTER(_U32)]),

@@ -196,9 +196,17 @@ class Decoder(_Base):
         self.info = fi
         return fi
 
-    def decode(self, j2c=None, sample_type=I32):
+    def restrict_input_resolution(self, skipped_res_for_read, skipped_res_for_recon):
+        """codestream::restrict_input_resolution: after read_headers, before decode"""
+        self._check(self.L.ojb_dec_restrict_input_resolution(self.h, skipped_res_for_read, skipped_res_for_recon,
+                                                             C.byref(self.info)))
+        return self.info
+
+    def decode(self, j2c=None, sample_type=I32, skip=None):
         if j2c is not None:
             self.read_headers(j2c, sample_type)
+        if skip is not None:
+            self.restrict_input_resolution(*skip)
         fi = self.info
         planes = [np.zeros((fi.comp_h[c], fi.comp_w[c]), _NP[self.sample_type]) for c in range(fi.num_comps)]
         ptrs = (C.c_void_p * fi.num_comps)(*[a.ctypes.data for a in planes])

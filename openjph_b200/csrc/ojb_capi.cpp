@@ -265,6 +265,14 @@ int ojb_dec_read_headers(ojb_decoder* d, const uint8_t* j2c, uint64_t len, uint3
     }
   });
 }
+int ojb_dec_restrict_input_resolution(ojb_decoder* d, uint32_t skip_read, uint32_t skip_recon, ojb_frame_info* info) {
+  return guarded_on(d->device, [&] {
+    if (!d->have_headers) fail(0x000B0015, "read_headers has not been called");
+    d->dec.restrict_resolution(skip_read, skip_recon);
+    d->pulling = false;
+    if (info) { FrameInfo fi; d->dec.info(fi); memcpy(info, &fi, sizeof(fi)); }
+  });
+}
 int ojb_dec_decode_frame(ojb_decoder* d, void* const* planes, const uint32_t* strides) {
   return guarded_on(d->device, [&] {
     if (!d->have_headers) fail(0x000B0015, "read_headers has not been called");

@@ -80,7 +80,10 @@ void CodecBase::plan_image(uint32_t sample_type) {
       fail(0x000B0010, "16-bit sample container with %d-bit component", params.comps[c].bit_depth);
     if (sample_type != ST_I32 && params.comps[c].is_signed)
       fail(0x000B0011, "signed components need the 32-bit sample container");
-    img_w[c] = params.comp_width(c); img_h[c] = params.comp_height(c);
+    // reconstruction size: sub-sampling times 2^skip_recon (param_siz::get_recon_width, ojph_params.cpp)
+    const uint32_t rdx = params.comps[c].dx << skip_recon, rdy = params.comps[c].dy << skip_recon;
+    img_w[c] = div_ceil(params.Xsiz, rdx) - div_ceil(params.XOsiz, rdx);
+    img_h[c] = div_ceil(params.Ysiz, rdy) - div_ceil(params.YOsiz, rdy);
     img_off[c] = off;
     off += (size_t)img_w[c] * img_h[c] * esize_of(sample_type);
     off = (off + 255) & ~(size_t)255;
@@ -94,7 +97,7 @@ void CodecBase::build_dwt_jobs(bool forward) {
   const uint32_t nc = P.num_comps();
   // level li counts decompositions from the full resolution down; every component follows its own
   // coding style (COC): component c takes part in levels li < max(1, D_c) with resolution D_c - li
-  uint32_t nlev = 1;
+  uint32_t nlev = forward ? 1u : skip_recon + 1;
   for (uint32_t c = 0; c < nc; ++c) nlev = std::max(nlev, P.decomps(c));
   if (P.color_transform())
     for (uint32_t c = 1; c < 3; ++c)
@@ -114,23 +117,31 @@ void CodecBase::build_dwt_jobs(bool forward) {
     for (const TileGeom& t : layout.tiles) {
       for (uint32_t c = 0; c < nc; ) {
         const uint32_t D = P.decomps(c);
-        bool fused = (li == 0) && P.color_transform() && c == 0;
+        // levels above `top` are not run (decoder with restrict_resolution: reduced output); a component
+        // with nothing to split / rebuild (D == 0, or its whole pyramid skipped) is a plain conversion of LL
+        const uint32_t top = forward ? 0u : skip_recon;
+        const bool conv_only = D <= top;
+        const bool here = conv_only ? (li == top) : (li >= top && li < D);
+        const bool is_top = li == top;
+        bool fused = P.color_transform() && c == 0 && is_top;
         uint32_t k = fused ? 3 : 1;
-        if (li >= std::max(1u, D)) { c += k; continue; }       // this component has no such level
-        const uint32_t r = D == 0 ? 0 : D - li;                 // resolution being split (or rebuilt)
+        if (!here) { ++c; continue; }
+        const uint32_t r = conv_only ? 0 : D - li;               // resolution being split (or rebuilt)
         const bool rev = P.reversible(c);
         const uint32_t gw = rev ? 0u : 4u;
         DwtJob j; memset(&j, 0, sizeof(j));
         const ResGeom& rg = t.comps[c].res[r];
         j.w = rg.rect.w; j.h = rg.rect.h; j.x0 = rg.rect.x0; j.y0 = rg.rect.y0;
-        j.ncomp = k; j.first = (r == D) ? 1u : 0u; j.last = (r <= 1) ? 1u : 0u; j.nodwt = (D == 0) ? 1u : 0u;
+        j.ncomp = k; j.first = is_top ? 1u : 0u; j.last = (r <= 1) ? 1u : 0u; j.nodwt = conv_only ? 1u : 0u;
         j.src_type = img_type; j.bit_depth = P.comps[c].bit_depth; j.is_signed = P.comps[c].is_signed ? 1u : 0u;
         for (uint32_t i = 0; i < k; ++i) {
           const TileCompGeom& tc = t.comps[c + i];
           const ResGeom& rr = tc.res[r];
-          if (r == D) {
-            uint32_t cx0 = div_ceil(P.XOsiz, P.comps[c + i].dx), cy0 = div_ceil(P.YOsiz, P.comps[c + i].dy);
-            j.full_off[i] = img_off[c + i] + ((uint64_t)(tc.rect.y0 - cy0) * img_w[c + i] + (tc.rect.x0 - cx0)) * es;
+          if (is_top) {
+            // the resolution's rectangle sits at (ceil(x0 / 2^s) - ceil(XO / (dx 2^s))) in the output plane
+            const uint32_t sh = top;
+            uint32_t cx0 = div_ceil(P.XOsiz, P.comps[c + i].dx << sh), cy0 = div_ceil(P.YOsiz, P.comps[c + i].dy << sh);
+            j.full_off[i] = img_off[c + i] + ((uint64_t)(rr.rect.y0 - cy0) * img_w[c + i] + (rr.rect.x0 - cx0)) * es;
             j.full_stride[i] = img_w[c + i];
           } else { j.full_off[i] = rr.plane_off; j.full_stride[i] = rr.plane_stride; }
           if (r > 0) {
@@ -502,14 +513,15 @@ void Decoder::read_headers(const uint8_t* data, size_t len, uint32_t sample_type
     if (pr > 32) fail(0x000B0001, "component %u needs %u-bit coefficients; only the 32-bit path is "
                       "implemented on the GPU", c, pr);
   }
+  skip_read = skip_recon = 0;
   layout.build(params);
   max_block_w = widest_block(layout);
-  plan_image(sample_type);
   upload_tables();
   d_coef.reserve((layout.coef_words + 64) * 4);
-  build_dwt_jobs(false);
+  setup_geometry(sample_type);
   // geometry part of the block records
   h_dec_proto.assign(layout.num_blocks, DecBlock());
+  block_res.assign(layout.num_blocks, 0);
   size_t scratch = 0;
   for (const TileGeom& t : layout.tiles)
     for (const TileCompGeom& tc : t.comps)
@@ -521,6 +533,7 @@ void Decoder::read_headers(const uint8_t* data, size_t len, uint32_t sample_type
             for (uint32_t bx = 0; bx < bg.nbw; ++bx) {
               Rect r = bg.block_rect(bx, by);
               DecBlock& d = h_dec_proto[bg.block_base + by * bg.nbw + bx];
+              block_res[bg.block_base + by * bg.nbw + bx] = (uint8_t)(tc.res.size() - 1 - rg.res_num);
               memset(&d, 0, sizeof(d));
               d.dst_off = bg.plane_off + bg.plane_pad_x + (uint64_t)(r.y0 - bg.rect.y0) * bg.plane_stride + (r.x0 - bg.rect.x0);
               d.stride = bg.plane_stride; d.w = (uint16_t)r.w; d.h = (uint16_t)r.h;
@@ -539,6 +552,30 @@ void Decoder::read_headers(const uint8_t* data, size_t len, uint32_t sample_type
   h_bstatus.reserve(std::max<size_t>(1, h_dec_proto.size()) * 4);
 }
 
+void Decoder::setup_geometry(uint32_t sample_type) {
+  plan_image(sample_type);
+  build_dwt_jobs(false);
+}
+
+void Decoder::restrict_resolution(uint32_t skipped_res_for_read, uint32_t skipped_res_for_recon) {
+  // codestream::restrict_input_resolution (ojph_codestream_local.cpp:883-900)
+  if (skipped_res_for_read < skipped_res_for_recon)
+    fail(0x000300A1, "skipped_resolution for data %d must be equal or smaller than  skipped_resolution for "
+         "reconstruction %d", skipped_res_for_read, skipped_res_for_recon);
+  if (skipped_res_for_read > params.num_decomps)
+    fail(0x000300A2, "skipped_resolution for data %d must be smaller than  the number of decomposition levels %d",
+         skipped_res_for_read, params.num_decomps);
+  // a component with its own (COC) decomposition count below the request: the reference's arithmetic wraps
+  // (ojph_resolution.cpp:252-255) and what it then reads depends on the progression order; refused here
+  for (uint32_t c = 0; c < params.num_comps(); ++c)
+    if (skipped_res_for_read > params.decomps(c))
+      fail(0x000B0007, "component %u has %u decomposition levels; %u cannot be skipped", c, params.decomps(c),
+           skipped_res_for_read);
+  if (skipped_res_for_read == skip_read && skipped_res_for_recon == skip_recon) return;
+  skip_read = skipped_res_for_read; skip_recon = skipped_res_for_recon;
+  setup_geometry(img_type);
+}
+
 void Decoder::info(FrameInfo& fi) const {
   memset(&fi, 0, sizeof(fi));
   fi.width = params.Xsiz; fi.height = params.Ysiz; fi.off_x = params.XOsiz; fi.off_y = params.YOsiz;
@@ -546,7 +583,7 @@ void Decoder::info(FrameInfo& fi) const {
   for (uint32_t c = 0; c < fi.num_comps && c < 16; ++c) {
     fi.bit_depth[c] = params.comps[c].bit_depth; fi.is_signed[c] = params.comps[c].is_signed;
     fi.dx[c] = params.comps[c].dx; fi.dy[c] = params.comps[c].dy;
-    fi.comp_w[c] = params.comp_width(c); fi.comp_h[c] = params.comp_height(c);
+    fi.comp_w[c] = img_w[c]; fi.comp_h[c] = img_h[c];            // reconstruction size (restrict_resolution)
   }
   fi.num_decomps = params.num_decomps; fi.reversible = params.reversible();      // COD values (components may differ: COC) fi.color_transform = params.color_transform();
   fi.num_tiles = (uint32_t)layout.tiles.size();
@@ -653,6 +690,10 @@ uint32_t Decoder::decode(void* const* planes, const uint32_t* strides, bool plan
     const CodedBlock& cb = coded[b];
     d.len1 = cb.pass_len[0]; d.len2 = cb.pass_len[1];
     d.num_passes = cb.num_passes; d.missing_msbs = cb.missing_msbs; d.data_off = cb.data_off;
+    if (block_res[b] < skip_read) {            // resolution not read: its bands are zero ...
+      d.num_passes = 0; d.len1 = d.len2 = 0;
+      if (block_res[b] < skip_recon) d.w = d.h = 0;      // ... and not even needed: nothing to fill
+    }
     uint32_t nq = (d.w + 1u) / 2, qs = (nq + 1) & ~1u, nqr = (d.h + 1u) / 2;
     scratch = (scratch + 3) & ~(size_t)3;
     d.scratch_off = scratch;

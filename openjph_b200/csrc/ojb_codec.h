@@ -53,6 +53,10 @@ public:
   std::vector<uint32_t> img_w, img_h;
   uint32_t img_type = ST_I32;
   uint32_t max_block_w = 64;            // widest nominal code-block of the current geometry
+  // decoder: resolutions dropped from the top (codestream::restrict_input_resolution,
+  // ojph_codestream_local.cpp:883-900): skip_recon levels are not reconstructed (smaller output),
+  // skip_read >= skip_recon levels are not decoded (their bands read as zero)
+  uint32_t skip_read = 0, skip_recon = 0;
   size_t img_bytes = 0;
   void plan_image(uint32_t sample_type);
   DeviceBuf d_coef;                    // coefficient arena (32-bit words)
@@ -108,6 +112,10 @@ public:
   bool resilient = false;
   // parse main header; (re)builds geometry when parameters changed
   void read_headers(const uint8_t* j2c, size_t len, uint32_t sample_type);
+  // after read_headers, before decode: rebuilds the output planes and the synthesis schedule
+  void restrict_resolution(uint32_t skipped_res_for_read, uint32_t skipped_res_for_recon);
+  void setup_geometry(uint32_t sample_type);
+  std::vector<uint8_t> block_res;       // per block: how many resolutions lie above its own (D_c - r)
   void info(FrameInfo& fi) const;
   // decode into planes (host or device); returns number of code-blocks that failed to decode
   uint32_t decode(void* const* planes, const uint32_t* strides, bool planes_on_device);

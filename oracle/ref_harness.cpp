@@ -218,14 +218,28 @@ int ojr_read_info(const uint8_t* j2c, uint64_t len, ojr_info* info)
 }
 
 // planes[c] : caller-allocated int32[comp_w*comp_h]
-int ojr_decode(const uint8_t* j2c, uint64_t len, int32_t* const* planes,
-               int resilient)
+static int decode_impl(const uint8_t* j2c, uint64_t len, int32_t* const* planes, int resilient,
+                       uint32_t skip_read, uint32_t skip_recon, ojr_info* info_out);
+
+int ojr_decode(const uint8_t* j2c, uint64_t len, int32_t* const* planes, int resilient)
+{ return decode_impl(j2c, len, planes, resilient, 0, 0, NULL); }
+
+// restrict_input_resolution(skip_read, skip_recon); planes == NULL: only report the reconstruction sizes
+int ojr_decode_restricted(const uint8_t* j2c, uint64_t len, int32_t* const* planes, int resilient,
+                          uint32_t skip_read, uint32_t skip_recon, ojr_info* info)
+{ return decode_impl(j2c, len, planes, resilient, skip_read, skip_recon, info); }
+
+static int decode_impl(const uint8_t* j2c, uint64_t len, int32_t* const* planes, int resilient,
+                       uint32_t skip_read, uint32_t skip_recon, ojr_info* info_out)
 {
   try {
     ojph::codestream cs; mem_infile f; f.open(j2c, (size_t)len);
     if (resilient) cs.enable_resilience();
     cs.read_headers(&f);
+    if (skip_read || skip_recon) cs.restrict_input_resolution(skip_read, skip_recon);
     ojr_info info; fill_info(cs, &info);
+    if (info_out) *info_out = info;
+    if (planes == NULL) { cs.close(); return 0; }
     // keep the library's own choice (read_headers: planar = !colour_transform,
     // ojph_codestream_local.cpp:879): interleaved pulls stall on sub-sampled components
     cs.create();

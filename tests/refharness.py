@@ -86,6 +86,24 @@ def decode(j2c, resilient=False):
     return planes, info
 
 
+def decode_restricted(j2c, skip_read, skip_recon, resilient=False):
+    """codestream::restrict_input_resolution(skip_read, skip_recon) then decode"""
+    L = lib()
+    buf = np.frombuffer(j2c, np.uint8)
+    info = RInfo()
+    rc = L.ojr_decode_restricted(buf.ctypes.data_as(C.c_void_p), C.c_uint64(buf.size), None, 0,
+                                 C.c_uint32(skip_read), C.c_uint32(skip_recon), C.byref(info))
+    if rc != 0:
+        raise RuntimeError("reference read_headers/restrict failed: " + L.ojr_last_error().decode())
+    planes = [np.zeros((info.comp_h[c], info.comp_w[c]), np.int32) for c in range(info.num_comps)]
+    ptrs = (C.c_void_p * info.num_comps)(*[a.ctypes.data for a in planes])
+    rc = L.ojr_decode_restricted(buf.ctypes.data_as(C.c_void_p), C.c_uint64(buf.size), ptrs, 1 if resilient else 0,
+                                 C.c_uint32(skip_read), C.c_uint32(skip_recon), None)
+    if rc != 0:
+        raise RuntimeError("reference decode failed: " + L.ojr_last_error().decode())
+    return planes, info
+
+
 def encode_block(block, missing_msbs, variant=0):
     """block: (h, w) uint32 sign-magnitude; returns bytes"""
     L = lib()
