@@ -46,13 +46,27 @@ typedef struct ojb_params {
   uint32_t coc_reversible[16];
   uint32_t coc_num_decomps[16];
   uint32_t coc_block_w[16], coc_block_h[16];
+  /* non-linearity point transform (NLT marker; param_nlt::set_nonlinear_transform(comp, type),
+   * ojph_params.cpp:441, :2176): 0 = not called, else 1 + type (1: type 0 "none", 4: type 3 = two's
+   * complement <-> sign-magnitude mapping of signed samples, the only one the reference implements).
+   * nlt_all is the ALL_COMPS (65535) entry; nlt_seq[c] orders the per-component calls (marker order). */
+  uint32_t nlt_all;
+  uint32_t nlt_comp[16];
+  uint32_t nlt_seq[16];
 } ojb_params;
 
 typedef struct ojb_frame_info {
   uint32_t width, height, off_x, off_y, num_comps;
   uint32_t bit_depth[16], is_signed[16], dx[16], dy[16], comp_w[16], comp_h[16];
   uint32_t num_decomps, reversible, color_transform, num_tiles;
+  uint32_t nlt_type[16];           /* param_nlt::get_nonlinear_transform: 0 none, 3 type 3 */
 } ojb_frame_info;
+
+typedef struct ojb_comment {       /* ojph::comment_exchange (ojph_params.h): one extra COM segment */
+  const void* data;
+  uint16_t len;
+  uint16_t rcom;                   /* 0 binary, 1 Latin text */
+} ojb_comment;
 
 /* sample container of frame buffers */
 enum { OJB_U8 = 0, OJB_U16 = 1, OJB_I32 = 2 };
@@ -83,6 +97,9 @@ ojb_encoder* ojb_enc_create(void);                       /* codestream::codestre
 void ojb_enc_destroy(ojb_encoder* e);                    /* ~codestream / close() */
 /* access_siz/cod/qcd setters + write_headers(): validates, builds geometry and device arenas */
 int ojb_enc_configure(ojb_encoder* e, const ojb_params* p, uint32_t sample_type);
+/* the comments argument of write_headers(file, comments, num_comments) (ojph_codestream_local.cpp:688-706):
+ * extra COM segments after the library's own; copied, applies to the configure calls that follow */
+int ojb_enc_set_comments(ojb_encoder* e, const ojb_comment* comments, uint32_t num_comments);
 /* codestream::exchange(line_buf*, ui32& next_comp): first call with line == NULL; returns the
  * line to fill next (library owned, si32 samples), NULL after the last line */
 int32_t* ojb_enc_exchange(ojb_encoder* e, int32_t* line, uint32_t* next_comp);

@@ -7,7 +7,7 @@
 // The including translation unit provides OpenJPH's own public headers first (they are not part of
 // this repository):  ojph_base.h (ui8/ui32/si32, point, size), ojph_mem.h (line_buf), ojph_file.h
 // (outfile_base, infile_base).  Only what the reference's apps call is mirrored; Part-2 items the
-// hot path does not cover (NLT, DFS/ATK) raise the
+// hot path does not cover (DFS/ATK) raise the
 // same kind of std::runtime_error the reference raises for invalid settings.
 #pragma once
 #include "ojph_b200.h"
@@ -30,6 +30,7 @@ struct state {                                   // what write_headers / read_he
   ojb_frame_info info;                           // decode side, after read_headers
   bool reading = false;
   int planar = -1;
+  uint32_t nlt_calls = 0;
   state() { ojb_params_default(&p); memset(&info, 0, sizeof(info)); }
 };
 
@@ -97,6 +98,47 @@ public:
   void set_qfactor(ui8 qfactor) { s->p.qfactor = qfactor; }
 };
 
+class param_nlt {                                // ojph_params.h:299-342
+  state* s;
+public:
+  enum special_comp_num : ui16 { ALL_COMPS = 65535 };
+  enum nonlinearity : ui8 { OJPH_NLT_NO_NLT = 0, OJPH_NLT_GAMMA_STYLE_NLT = 1, OJPH_NLT_LUT_STYLE_NLT = 2,
+                            OJPH_NLT_BINARY_COMPLEMENT_NLT = 3, OJPH_NLT_UNDEFINED = 255 };
+  explicit param_nlt(state* st) : s(st) {}
+  void set_nonlinear_transform(ui32 comp_num, ui8 nl_type) {
+    if (nl_type != OJPH_NLT_NO_NLT && nl_type != OJPH_NLT_BINARY_COMPLEMENT_NLT)
+      raise("ojph error 0x00050171: Nonliearities other than type 0 (No Nonlinearity) or type  3 (Binary Binary "
+            "Complement to Sign Magnitude Conversion) are not supported yet");
+    if (comp_num == ALL_COMPS) { s->p.nlt_all = 1u + nl_type; return; }
+    if (comp_num >= 16) return;                  // entries for non-existing components are dropped anyway
+    if (s->p.nlt_comp[comp_num] == 0) s->p.nlt_seq[comp_num] = s->nlt_calls++;
+    s->p.nlt_comp[comp_num] = 1u + nl_type;
+  }
+  // decode side, after read_headers: the transform in force for the component
+  bool get_nonlinear_transform(ui32 comp_num, ui8& bit_depth, bool& is_signed, ui8& nl_type) const {
+    if (!s->reading || comp_num >= s->info.num_comps) return false;
+    bit_depth = (ui8)s->info.bit_depth[comp_num]; is_signed = s->info.is_signed[comp_num] != 0;
+    nl_type = (ui8)s->info.nlt_type[comp_num];
+    return nl_type != 0;
+  }
+};
+
+class comment_exchange {                         // ojph_params.h:345-358
+  friend class codestream;
+  const char* data = nullptr;
+  ui16 len = 0, Rcom = 0;
+public:
+  void set_string(const char* str) {
+    size_t t = strlen(str);
+    if (t > 65531) raise("ojph error 0x000500C1: COM marker string length cannot be larger than 65531");
+    data = str; len = (ui16)t; Rcom = 1;
+  }
+  void set_data(const char* d, ui16 l) {
+    if (l > 65531) raise("ojph error 0x000500C2: COM marker string length cannot be larger than 65531");
+    data = d; len = l; Rcom = 0;
+  }
+};
+
 class codestream {                               // ojph_codestream.h:88-383
   state st;
   ojb_encoder* enc = nullptr;
@@ -114,6 +156,7 @@ public:
   param_siz access_siz() { return param_siz(&st); }
   param_cod access_cod() { return param_cod(&st); }
   param_qcd access_qcd() { return param_qcd(&st); }
+  param_nlt access_nlt() { return param_nlt(&st); }
 
   // ---- write side
   void set_planar(bool planar) { st.planar = planar ? 1 : 0; }
@@ -125,11 +168,13 @@ public:
     st.p.tilepart_div = (at_resolutions ? 1u : 0u) | (at_components ? 2u : 0u);
   }
   void request_tlm_marker(bool needed) { st.p.tlm = needed ? 1u : 0u; }
-  void write_headers(outfile_base* file, const void* comments = nullptr, ui32 num_comments = 0) {
-    if (comments != nullptr || num_comments != 0) raise("ojph error: extra COM segments are not supported by the B200 path");
+  void write_headers(outfile_base* file, const comment_exchange* comments = nullptr, ui32 num_comments = 0) {
     st.p.planar = st.planar;
     if (enc == nullptr) enc = ojb_enc_create();
     if (enc == nullptr) raise(ojb_last_error());
+    std::vector<ojb_comment> com(num_comments);
+    for (ui32 i = 0; i < num_comments; ++i) { com[i].data = comments[i].data; com[i].len = comments[i].len; com[i].rcom = comments[i].Rcom; }
+    check(ojb_enc_set_comments(enc, com.data(), num_comments));
     check(ojb_enc_configure(enc, &st.p, OJB_I32));
     out = file;
   }

@@ -24,6 +24,7 @@ class Params(C.Structure):
         ("planar", C.c_int32),
         ("coc_present", C.c_uint32 * 16), ("coc_reversible", C.c_uint32 * 16), ("coc_num_decomps", C.c_uint32 * 16),
         ("coc_block_w", C.c_uint32 * 16), ("coc_block_h", C.c_uint32 * 16),
+        ("nlt_all", C.c_uint32), ("nlt_comp", C.c_uint32 * 16), ("nlt_seq", C.c_uint32 * 16),
     ]
 
 
@@ -33,8 +34,12 @@ class FrameInfo(C.Structure):
         ("num_comps", C.c_uint32), ("bit_depth", C.c_uint32 * 16), ("is_signed", C.c_uint32 * 16),
         ("dx", C.c_uint32 * 16), ("dy", C.c_uint32 * 16), ("comp_w", C.c_uint32 * 16), ("comp_h", C.c_uint32 * 16),
         ("num_decomps", C.c_uint32), ("reversible", C.c_uint32), ("color_transform", C.c_uint32),
-        ("num_tiles", C.c_uint32),
+        ("num_tiles", C.c_uint32), ("nlt_type", C.c_uint32 * 16),
     ]
+
+
+class Comment(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("len", C.c_uint16), ("rcom", C.c_uint16)]
 
 
 class BlockDesc(C.Structure):
@@ -59,6 +64,7 @@ SYMBOLS = {
     "ojb_enc_create": (_VP, []),
     "ojb_enc_destroy": (None, [_VP]),
     "ojb_enc_configure": (_I, [_VP, C.POINTER(Params), _U32]),
+    "ojb_enc_set_comments": (_I, [_VP, C.POINTER(Comment), _U32]),
     "ojb_enc_exchange": (_VP, [_VP, _VP, C.POINTER(_U32)]),
     "ojb_enc_flush": (_I, [_VP, _VP, _U64, C.POINTER(_U64)]),
     "ojb_enc_encode_frame": (_I, [_VP, C.POINTER(_VP), C.POINTER(_U32), _VP, _U64, C.POINTER(_U64)]),

@@ -22,7 +22,7 @@ class OjphError(RuntimeError):
 def make_params(width, height, num_comps=1, bit_depth=8, is_signed=False, num_decomps=5, block=(64, 64),
                 reversible=True, color_transform=False, prog_order="RPCL", qstep=-1.0, qfactor=0,
                 tile=(0, 0), offset=(0, 0), tile_offset=(0, 0), precincts=None, subsampling=None,
-                tlm=False, tilepart_div=0, planar=-1, coc=None):
+                tlm=False, tilepart_div=0, planar=-1, coc=None, nlt=None):
     p = _lib.Params()
     p.width, p.height = width, height
     p.off_x, p.off_y = offset
@@ -58,6 +58,12 @@ def make_params(width, height, num_comps=1, bit_depth=8, is_signed=False, num_de
         p.coc_reversible[c] = 1 if st.get("reversible", False) else 0
         p.coc_num_decomps[c] = st.get("num_decomps", 5)
         p.coc_block_w[c], p.coc_block_h[c] = st.get("block", (64, 64))
+    # param_nlt::set_nonlinear_transform calls, in order: {"all": 3, 1: 0, ...} (types 0 and 3)
+    for seq, (c, t) in enumerate((nlt or {}).items()):
+        if c == "all":
+            p.nlt_all = 1 + t
+        else:
+            p.nlt_comp[c], p.nlt_seq[c] = 1 + t, seq
     return p
 
 
@@ -78,13 +84,21 @@ class _Base:
 
 
 class Encoder(_Base):
-    def __init__(self, params, sample_type=I32, lib=None):
+    def __init__(self, params, sample_type=I32, lib=None, comments=None):
+        """comments: the extra COM segments of write_headers(file, comments, n): bytes (binary) or str (text)"""
         super().__init__(lib)
         self.h = self.L.ojb_enc_create()
         if not self.h:
             raise OjphError(self.L.ojb_last_error().decode(errors="replace"))
         self.params = params
         self.sample_type = sample_type
+        if comments:
+            keep = [c.encode("latin-1") if isinstance(c, str) else bytes(c) for c in comments]
+            arr = (_lib.Comment * len(keep))()
+            bufs = [C.create_string_buffer(k, len(k)) for k in keep]
+            for i, c in enumerate(comments):
+                arr[i].data, arr[i].len, arr[i].rcom = C.addressof(bufs[i]), len(keep[i]), 1 if isinstance(c, str) else 0
+            self._check(self.L.ojb_enc_set_comments(self.h, arr, len(keep)))
         self._check(self.L.ojb_enc_configure(self.h, C.byref(params), sample_type))
         self.dims = comp_dims(params)
         cap = sum(w * h for w, h in self.dims) * 4 + (1 << 20)

@@ -44,6 +44,11 @@ __device__ __forceinline__ int reflect_coord(int u, int lo, int hi) {
   return lo + t;
 }
 
+// NLT type 3, both directions (gen_rev_convert_nlt_type3, ojph_colour.cpp:273-310; the irreversible
+// conversions apply the same map, :343-351 and :405-411): two's complement <-> a sign-magnitude ordering of
+// the negative values, bias = 2^(B-1) + 1; an involution
+__device__ __forceinline__ int nlt_type3(int v, int bias) { return v >= 0 ? v : -v - bias; }
+
 // locate the job a CTA belongs to (jobs sorted by cta_base)
 __device__ __forceinline__ uint32_t find_job(const DwtJob* jobs, uint32_t njobs, uint32_t cta) {
   uint32_t lo = 0, hi = njobs;

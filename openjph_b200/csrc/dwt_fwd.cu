@@ -75,6 +75,10 @@ dwt_fwd_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, const void* __re
       for (uint32_t k = 0; k < nc; ++k)
         iv[k] = load_sample(image, J.src_type, J.full_off[k],
                             (size_t)(v - y0) * J.full_stride[k] + (size_t)(u - x0));
+      if (J.nlt_mask) {
+        const int bias = (1 << (J.bit_depth - 1)) + 1;
+        for (uint32_t k = 0; k < nc; ++k) if ((J.nlt_mask >> k) & 1u) iv[k] = nlt_type3(iv[k], bias);
+      }
       if (REV) {
         const int shift = J.is_signed ? 0 : (1 << (J.bit_depth - 1));
         for (uint32_t k = 0; k < nc; ++k) iv[k] -= shift;

@@ -221,6 +221,10 @@ dwt_inv_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, void* __restrict
         out[k] = q + half;
       }
     }
+    if (J.nlt_mask) {
+      const int bias = (1 << (J.bit_depth - 1)) + 1;
+      for (uint32_t k = 0; k < nc; ++k) if ((J.nlt_mask >> k) & 1u) out[k] = nlt_type3(out[k], bias);
+    }
     for (uint32_t k = 0; k < nc; ++k)
       store_sample(image, J.src_type, J.full_off[k], (size_t)(v - y0) * J.full_stride[k] + (size_t)(u - x0), out[k]);
   }

@@ -234,6 +234,15 @@ __device__ __forceinline__ void fwd_read_row(const DwtJob& J, const unsigned cha
         iv[k][0] = (int)t.x; iv[k][1] = (int)t.y; iv[k][2] = (int)t.z; iv[k][3] = (int)t.w;
       }
     }
+    if (J.nlt_mask) {
+      const int bias = (1 << (J.bit_depth - 1)) + 1;
+      #pragma unroll
+      for (int k = 0; k < NC; ++k)
+        if ((J.nlt_mask >> k) & 1u) {
+          #pragma unroll
+          for (int i = 0; i < 4; ++i) iv[k][i] = nlt_type3(iv[k][i], bias);
+        }
+    }
     if (REV) {
       const int shift = J.is_signed ? 0 : (1 << (J.bit_depth - 1));
       #pragma unroll
@@ -554,6 +563,15 @@ __device__ __forceinline__ void inv_store_row(const DwtJob& J, const StripGeom& 
         int q = round_haz(t);
         q = t >= flo ? q : lo; q = t < fhi ? q : hi;
         out[k][i] = q + half;
+      }
+  }
+  if (J.nlt_mask) {
+    const int bias = (1 << (J.bit_depth - 1)) + 1;
+    #pragma unroll
+    for (int k = 0; k < NC; ++k)
+      if ((J.nlt_mask >> k) & 1u) {
+        #pragma unroll
+        for (int i = 0; i < 4; ++i) out[k][i] = nlt_type3(out[k][i], bias);
       }
   }
   #pragma unroll

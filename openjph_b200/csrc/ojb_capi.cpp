@@ -11,7 +11,7 @@ using namespace ojb;
 // an object belongs to the device that was current when it was created; every entry point makes
 // that device current again, so objects may be driven from any host thread
 static int current_device() { int d = 0; cudaGetDevice(&d); return d; }
-struct ojb_encoder { int device = current_device(); Encoder enc; bool configured = false; };
+struct ojb_encoder { int device = current_device(); Encoder enc; bool configured = false; std::vector<Comment> comments; };
 struct ojb_decoder {
   int device = current_device(); Decoder dec; bool have_headers = false;
   // line interface (pull): library-owned frame, cursor in the reference's line order
@@ -64,6 +64,14 @@ static void to_params(const ojb_params* s, Params& P) {
     Params tmp; tmp.set_block_dims(s->coc_block_w[c], s->coc_block_h[c]);      // same argument checks
     cs.cb_w_exp = tmp.cb_w_exp; cs.cb_h_exp = tmp.cb_h_exp;
     cs.wavelet = s->coc_reversible[c] ? DWT_REV53 : DWT_IRV97;
+  }
+  // NLT: the default entry, then the per-component calls in the order they were made
+  if (s->nlt_all) P.set_nonlinear_transform(0xFFFF, s->nlt_all - 1);
+  {
+    uint32_t order[16], n = 0;
+    for (uint32_t c = 0; c < 16; ++c) if (s->nlt_comp[c]) order[n++] = c;
+    std::stable_sort(order, order + n, [&](uint32_t a, uint32_t b) { return s->nlt_seq[a] < s->nlt_seq[b]; });
+    for (uint32_t i = 0; i < n; ++i) P.set_nonlinear_transform(order[i], s->nlt_comp[order[i]] - 1);
   }
   P.need_tlm = s->tlm != 0;
   P.tilepart_div = s->tilepart_div & 3u;
@@ -123,8 +131,21 @@ int ojb_enc_configure(ojb_encoder* e, const ojb_params* p, uint32_t sample_type)
   return guarded_on(e->device, [&] {
     if (sample_type > 2) fail(0x000B0012, "unknown sample container");
     Params P; to_params(p, P);
+    P.comments = e->comments;
     e->enc.configure(P, sample_type);
     e->configured = true;
+  });
+}
+
+int ojb_enc_set_comments(ojb_encoder* e, const ojb_comment* comments, uint32_t num_comments) {
+  return guarded([&] {
+    std::vector<Comment> v(num_comments);
+    for (uint32_t i = 0; i < num_comments; ++i) {
+      if (comments[i].len > 65531) fail(0x000500C1, "COM marker string length cannot be larger than 65531");
+      const uint8_t* d = static_cast<const uint8_t*>(comments[i].data);
+      v[i].data.assign(d, d + comments[i].len); v[i].Rcom = comments[i].rcom;
+    }
+    e->comments.swap(v);
   });
 }
 

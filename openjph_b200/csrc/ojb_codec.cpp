@@ -134,6 +134,9 @@ void CodecBase::build_dwt_jobs(bool forward) {
         j.w = rg.rect.w; j.h = rg.rect.h; j.x0 = rg.rect.x0; j.y0 = rg.rect.y0;
         j.ncomp = k; j.first = is_top ? 1u : 0u; j.last = (r <= 1) ? 1u : 0u; j.nodwt = conv_only ? 1u : 0u;
         j.src_type = img_type; j.bit_depth = P.comps[c].bit_depth; j.is_signed = P.comps[c].is_signed ? 1u : 0u;
+        if (is_top && P.nlt_any())             // the type-3 map only touches signed samples (ojph_tile.cpp:352, 446)
+          for (uint32_t i = 0; i < k; ++i)
+            if (P.comps[c + i].is_signed && P.nlt_type(c + i) == 3) j.nlt_mask |= 1u << i;
         for (uint32_t i = 0; i < k; ++i) {
           const TileCompGeom& tc = t.comps[c + i];
           const ResGeom& rr = tc.res[r];
@@ -584,6 +587,7 @@ void Decoder::info(FrameInfo& fi) const {
     fi.bit_depth[c] = params.comps[c].bit_depth; fi.is_signed[c] = params.comps[c].is_signed;
     fi.dx[c] = params.comps[c].dx; fi.dy[c] = params.comps[c].dy;
     fi.comp_w[c] = img_w[c]; fi.comp_h[c] = img_h[c];            // reconstruction size (restrict_resolution)
+    fi.nlt_type[c] = params.nlt_type(c);
   }
   fi.num_decomps = params.num_decomps; fi.reversible = params.reversible();      // COD values (components may differ: COC) fi.color_transform = params.color_transform();
   fi.num_tiles = (uint32_t)layout.tiles.size();

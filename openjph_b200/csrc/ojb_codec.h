@@ -98,6 +98,7 @@ struct FrameInfo {
   uint32_t width, height, off_x, off_y, num_comps;
   uint32_t bit_depth[16], is_signed[16], dx[16], dy[16], comp_w[16], comp_h[16];
   uint32_t num_decomps, reversible, color_transform, num_tiles;
+  uint32_t nlt_type[16];
 };
 
 // block-coder variants, identical results.  Encoder: one thread per code-block by default (fewest

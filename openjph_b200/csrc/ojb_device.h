@@ -87,6 +87,7 @@ struct DwtJob {
   uint32_t src_type;      // SRC_* of the image buffer when first
   uint32_t bit_depth;     // for level shift / float conversion when first
   uint32_t is_signed;
+  uint32_t nlt_mask;      // bit i: NLT type 3 on (signed) component i of the job: v < 0 -> -v - (2^(B-1) + 1)
   uint32_t tiles_x, tiles_y;   // CTA tiling of this job
   uint32_t chunk_rows;         // streaming kernels: output rows per warp chunk (even)
   uint32_t cta_base;      // first CTA index of this job in the launch

@@ -320,6 +320,8 @@ void Params::finalize_for_encode() {
            "implemented on the GPU", c, pr);
   }
 
+  nlt_check_validity();
+
   // tile-part division rules (ojph_codestream_local.cpp:583-621)
   if ((prog_order == PO_LRCP || prog_order == PO_RLCP) && tilepart_div == TP_COMP)
     tilepart_div |= TP_RES;
@@ -330,6 +332,71 @@ void Params::finalize_for_encode() {
   else if (planar == 1 && color_transform())
     fail(0x00030021, "the planar interface option cannot be used when colour transform is "
          "employed");
+}
+
+//------------------------------------------------------------------------------------------
+// NLT: type 3 (two's complement <-> sign-magnitude mapping of signed samples) is the only
+// non-linearity the reference implements (ojph_params.cpp:2176-2190)
+//------------------------------------------------------------------------------------------
+void Params::set_nonlinear_transform(uint32_t comp, uint32_t type) {
+  if (type != 0 && type != 3)
+    fail(0x00050171, "Nonliearities other than type 0 (No Nonlinearity) or type  3 (Binary Binary Complement to "
+         "Sign Magnitude Conversion) are not supported yet");
+  NltEntry* e = nullptr;
+  if (comp == 0xFFFF) e = &nlt_all;
+  else {
+    for (NltEntry& x : nlt) if (x.comp_idx == comp) e = &x;
+    if (e == nullptr) { nlt.push_back(NltEntry()); e = &nlt.back(); e->comp_idx = (uint16_t)comp; }
+  }
+  e->Tnlt = (uint8_t)type; e->enabled = true;
+}
+
+void Params::nlt_check_validity() {          // param_nlt::check_validity, ojph_params.cpp:2087-2173
+  if (!nlt_any()) return;
+  const uint32_t nc = num_comps();
+  auto own = [&](uint32_t c) -> NltEntry* { for (NltEntry& x : nlt) if (x.comp_idx == c) return &x; return nullptr; };
+  auto bd_of = [&](uint32_t c) { return (uint8_t)((comps[c].bit_depth - 1) | (comps[c].is_signed ? 0x80 : 0)); };
+  if (nlt_all.enabled && nlt_all.Tnlt == 0) nlt_all.enabled = false;
+  if (nlt_all.enabled && nlt_all.Tnlt == 3) {
+    bool all_same = true;
+    uint32_t bit_depth = 0; bool is_signed = false;
+    for (uint32_t c = 0; c < nc; ++c) {
+      NltEntry* e = own(c);
+      if (e == nullptr || !e->enabled) {
+        if (bit_depth != 0) all_same = all_same && bit_depth == comps[c].bit_depth && is_signed == comps[c].is_signed;
+        else { bit_depth = comps[c].bit_depth; is_signed = comps[c].is_signed; }
+      } else e->BDnlt = bd_of(c);
+    }
+    if (all_same && bit_depth != 0) nlt_all.BDnlt = (uint8_t)((bit_depth - 1) | (is_signed ? 0x80 : 0));
+    else if (!all_same) {
+      nlt_all.enabled = false;
+      for (uint32_t c = 0; c < nc; ++c) {
+        NltEntry* e = own(c);
+        if (e == nullptr || !e->enabled) {
+          if (e == nullptr) { nlt.push_back(NltEntry()); e = &nlt.back(); e->comp_idx = (uint16_t)c; }
+          e->enabled = true; e->Tnlt = 3; e->BDnlt = bd_of(c);
+        }
+      }
+    }
+  } else {
+    for (uint32_t c = 0; c < nc; ++c) { NltEntry* e = own(c); if (e && e->enabled) e->BDnlt = bd_of(c); }
+  }
+  for (NltEntry& e : nlt) if (e.enabled && e.comp_idx >= nc) e.enabled = false;   // trim_non_existing_components
+  if (nlt_any()) Rsiz |= 0x8000 | 0x0200;    // RSIZ_EXT_FLAG | RSIZ_NLT_FLAG
+}
+
+uint32_t Params::nlt_type(uint32_t c) const {  // get_nonlinear_transform + the check of ojph_tile.cpp:292-300
+  const NltEntry* e = nullptr;
+  for (const NltEntry& x : nlt) if (x.comp_idx == c && x.enabled) e = &x;
+  if (e == nullptr && nlt_all.enabled) e = &nlt_all;
+  if (e == nullptr) return 0;
+  uint32_t bd = (uint32_t)(e->BDnlt & 0x7F) + 1; if (bd > 38) bd = 38;
+  const bool is = (e->BDnlt & 0x80) != 0;
+  if (bd != comps[c].bit_depth || is != comps[c].is_signed)
+    fail(0x000300A1, "Mismatch between Ssiz (bit_depth = %d, is_signed = %s) from SIZ marker segment, and BDnlt "
+         "(bit_depth = %d, is_signed = %s) from NLT marker segment, for component %d", comps[c].bit_depth,
+         comps[c].is_signed ? "True" : "False", bd, is ? "True" : "False", c);
+  return e->Tnlt == 3 ? 3u : 0u;
 }
 
 static void write_quant(std::vector<uint8_t>& o, const QuantSet& q, uint32_t nc) {
@@ -379,6 +446,13 @@ void Params::write_main_header(std::vector<uint8_t>& o, const char* const* comme
   // QCD, QCC
   write_quant(o, qcd, nc);
   for (const QuantSet& q : qcc) if (q.enabled) write_quant(o, q, nc);
+  // NLT: the default entry, then the per-component ones in creation order (param_nlt::write, :2210-2235)
+  auto put_nlt = [&](const NltEntry& e) {
+    if (!e.enabled) return;
+    put_u16(o, M_NLT); put_u16(o, 6); put_u16(o, e.comp_idx); put_u8(o, e.BDnlt); put_u8(o, e.Tnlt);
+  };
+  put_nlt(nlt_all);
+  for (const NltEntry& e : nlt) put_nlt(e);
   // COM: library signature, needed for byte-identical output
   // (ojph_codestream_local.cpp:668-686)
   static const char sig[] = "OpenJPH Ver 0.31.0.";
@@ -387,6 +461,10 @@ void Params::write_main_header(std::vector<uint8_t>& o, const char* const* comme
   for (uint32_t i = 0; i < n_comments; ++i) {
     put_u16(o, M_COM); put_u16(o, comment_lens[i] + 4); put_u16(o, 1);
     o.insert(o.end(), comments[i], comments[i] + comment_lens[i]);
+  }
+  for (const Comment& c : this->comments) {  // write_headers(file, comments, num_comments), :688-706
+    put_u16(o, M_COM); put_u16(o, (uint32_t)c.data.size() + 4); put_u16(o, c.Rcom);
+    o.insert(o.end(), c.data.begin(), c.data.end());
   }
 }
 
@@ -476,7 +554,7 @@ size_t Params::read_main_header(const uint8_t* data, size_t len) {
            "supported by the GPU path");
   }
   int received = 0;
-  qcc.clear(); coc.clear();
+  qcc.clear(); coc.clear(); nlt.clear(); nlt_all = NltEntry();
   for (;;) {
     // scan to the next 0xFF xx marker of interest (the reference skips unknown bytes too)
     if (r.pos + 1 >= r.n) fail(0x00030051, "File ended before finding a tile segment");
@@ -559,8 +637,19 @@ size_t Params::read_main_header(const uint8_t* data, size_t len) {
       if (L != (nc < 257 ? 9u : 10u) + ((c.Scoc & 1) ? 1u + c.num_decomps : 0u))
         fail(0x0005012F, "error in COC segment length");
       coc.push_back(c);
-    } else if (m == M_DFS || m == M_ATK || m == M_NLT)
-      fail(0x000B0005, "DFS/ATK/NLT marker segments are not supported by the GPU path");
+    } else if (m == M_NLT) {                // param_nlt::read, ojph_params.cpp:2238-2266
+      if (!r.has(6)) fail(0x00050141, "error reading NLT marker segment");
+      uint32_t L = r.u16(), comp = r.u16(), bd = r.u8(), t = r.u8();
+      if (L != 6 || (t != 3 && t != 0)) fail(0x00050145, "Unsupported NLT type %d\n", t);
+      NltEntry* e = nullptr;
+      if (comp == 0xFFFF) e = &nlt_all;
+      else {
+        for (NltEntry& x : nlt) if (x.comp_idx == comp) e = &x;
+        if (e == nullptr) { nlt.push_back(NltEntry()); e = &nlt.back(); }
+      }
+      e->enabled = true; e->comp_idx = (uint16_t)comp; e->BDnlt = (uint8_t)bd; e->Tnlt = (uint8_t)t;
+    } else if (m == M_DFS || m == M_ATK)
+      fail(0x000B0005, "DFS/ATK marker segments are not supported by the GPU path");
     else {  // PRF CPF RGN POC PPM TLM PLM CRG COM: skipped
       uint32_t L = r.u16();
       if (L < 2 || !r.has(L - 2)) fail(0x00030041, "error reading marker");

@@ -58,6 +58,20 @@ struct CodStyle {
   uint8_t precinct_size[33] = {0};
 };
 
+// one NLT marker segment (param_nlt, ojph_params_local.h:840-910): Cnlt = 0xFFFF is the default entry
+// for all components
+struct NltEntry {
+  uint16_t comp_idx = 0xFFFF;
+  uint8_t BDnlt = 0;
+  uint8_t Tnlt = 0xFF;                      // 0 none, 3 binary complement <-> sign magnitude; 0xFF undefined
+  bool enabled = false;
+};
+
+struct Comment {                            // comment_exchange, ojph_codestream.h / ojph_params.h
+  std::vector<uint8_t> data;
+  uint16_t Rcom = 1;                        // 0 binary, 1 Latin text
+};
+
 struct Params {
   // ---- SIZ
   uint16_t Rsiz = 0x4000;
@@ -78,6 +92,11 @@ struct Params {
   // ---- QCD / QCC
   QuantSet qcd;
   std::vector<QuantSet> qcc;                // in creation order
+  // ---- NLT
+  NltEntry nlt_all;                         // the ALL_COMPS entry
+  std::vector<NltEntry> nlt;                // per-component entries, in creation order
+  // ---- COM (after the library's own signature comment)
+  std::vector<Comment> comments;
   // ---- CAP
   uint32_t Pcap = 0x00020000;
   uint16_t Ccap0 = 0;
@@ -129,6 +148,13 @@ struct Params {
   QuantSet* find_qcc(uint32_t c);
   QuantSet& add_qcc(uint32_t c);
   uint32_t precision(uint32_t c) const;     // propose_precision, ojph_params.cpp:1684
+
+  // NLT (param_nlt, ojph_params.cpp:2087-2330)
+  void set_nonlinear_transform(uint32_t comp, uint32_t type);      // comp 65535 = all components
+  void nlt_check_validity();
+  // the transform in force for component c (0 or 3); raises on a BDnlt / SIZ mismatch as tile setup does
+  uint32_t nlt_type(uint32_t c) const;
+  bool nlt_any() const { if (nlt_all.enabled) return true; for (const NltEntry& e : nlt) if (e.enabled) return true; return false; }
 
   // setters used by the C-ABI (same argument checks as ojph::param_cod / param_qcd setters)
   void set_block_dims(uint32_t w, uint32_t h);                      // ojph_params.cpp:170-181

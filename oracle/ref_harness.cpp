@@ -18,6 +18,7 @@
 #include <cstring>
 #include <cstdint>
 #include <vector>
+#include <string>
 #include <stdexcept>
 
 #include "ojph_params.h"
@@ -95,6 +96,8 @@ struct ojr_params {
   int32_t  planar;                 // -1 => library default
   // per-component coding styles (COC), same meaning as in include/ojph_b200.h
   uint32_t coc_present[16], coc_reversible[16], coc_num_decomps[16], coc_block_w[16], coc_block_h[16];
+  // NLT: 0 = not set, else 1 + type; nlt_seq = order of the per-component calls
+  uint32_t nlt_all, nlt_comp[16], nlt_seq[16];
 };
 
 static char g_err[512] = "";
@@ -108,6 +111,14 @@ static const char* po_name(uint32_t po) {
 
 // planes[c] : int32 samples, row stride = comp width, as the caller would hand to
 // ojph::codestream::exchange (unsigned samples un-shifted).
+// extra COM segments for the next ojr_encode calls (write_headers(file, comments, num_comments))
+static std::vector<std::string> g_comment_data;
+static std::vector<int> g_comment_text;
+void ojr_set_comments(const char* const* data, const uint16_t* lens, const uint16_t* is_text, uint32_t n) {
+  g_comment_data.clear(); g_comment_text.clear();
+  for (uint32_t i = 0; i < n; ++i) { g_comment_data.emplace_back(data[i], data[i] + lens[i]); g_comment_text.push_back(is_text[i]); }
+}
+
 int ojr_encode(const ojr_params* p, const int32_t* const* planes,
                uint8_t* out, uint64_t out_cap, uint64_t* out_len)
 {
@@ -140,6 +151,10 @@ int ojr_encode(const ojr_params* p, const int32_t* const* planes,
         cod.set_block_dims(c, p->coc_block_w[c], p->coc_block_h[c]);
         cod.set_reversible(c, p->coc_reversible[c] != 0);
       }
+    if (p->nlt_all) cs.access_nlt().set_nonlinear_transform(param_nlt::ALL_COMPS, (ui8)(p->nlt_all - 1));
+    for (uint32_t k = 0; k < 16; ++k)            // per-component calls in their recorded order
+      for (uint32_t c = 0; c < 16; ++c)
+        if (p->nlt_comp[c] && p->nlt_seq[c] == k) cs.access_nlt().set_nonlinear_transform(c, (ui8)(p->nlt_comp[c] - 1));
     if (!p->reversible) {
       if (p->qstep > 0.0f) cs.access_qcd().set_irrev_quant(p->qstep);
       if (p->qfactor) cs.access_qcd().set_qfactor((ui8)p->qfactor);
@@ -153,7 +168,12 @@ int ojr_encode(const ojr_params* p, const int32_t* const* planes,
 
     mem_outfile f;
     f.open(1 << 20);
-    cs.write_headers(&f);
+    std::vector<comment_exchange> com(g_comment_data.size());
+    for (size_t i = 0; i < com.size(); ++i) {
+      if (g_comment_text[i]) com[i].set_string(g_comment_data[i].c_str());
+      else com[i].set_data(g_comment_data[i].data(), (ui16)g_comment_data[i].size());
+    }
+    cs.write_headers(&f, com.empty() ? NULL : com.data(), (ui32)com.size());
 
     ui32 nc = p->num_comps;
     std::vector<ui32> cw(nc), ch(nc), row(nc, 0);

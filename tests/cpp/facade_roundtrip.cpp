@@ -15,14 +15,16 @@
 
 using namespace ojph;
 
-template <typename CS>
-static std::vector<ui8> compress(const std::vector<std::vector<si32>>& planes, ui32 w, ui32 h, ui32 depth, bool planar)
+// extras: signed samples with NLT type 3 for all components (ojph_compress.cpp:859-866) and two COM segments
+template <typename CS, typename COM, typename NLT>
+static std::vector<ui8> compress(const std::vector<std::vector<si32>>& planes, ui32 w, ui32 h, ui32 depth, bool planar,
+                                 bool extras = false)
 {
   CS cs;
   auto siz = cs.access_siz();
   siz.set_image_extent(point(w, h));
   siz.set_num_components((ui32)planes.size());
-  for (ui32 c = 0; c < planes.size(); ++c) siz.set_component(c, point(1, 1), depth, false);
+  for (ui32 c = 0; c < planes.size(); ++c) siz.set_component(c, point(1, 1), depth, extras);
   siz.set_image_offset(point(0, 0));
   siz.set_tile_size(size(0, 0));
   siz.set_tile_offset(point(0, 0));
@@ -36,7 +38,15 @@ static std::vector<ui8> compress(const std::vector<std::vector<si32>>& planes, u
   cs.request_tlm_marker(true);
   mem_outfile f;
   f.open();
-  cs.write_headers(&f);
+  COM com[2];
+  if (extras) {
+    cs.access_nlt().set_nonlinear_transform(NLT::ALL_COMPS, NLT::OJPH_NLT_BINARY_COMPLEMENT_NLT);
+    com[0].set_string("facade round trip");
+    static const char raw[5] = { 1, 0, 2, (char)0xFF, 3 };
+    com[1].set_data(raw, 5);
+    cs.write_headers(&f, com, 2);
+  } else
+    cs.write_headers(&f);
   ui32 next = 0;
   std::vector<ui32> row(planes.size(), 0);
   line_buf* line = cs.exchange(NULL, next);
@@ -53,12 +63,13 @@ static std::vector<ui8> compress(const std::vector<std::vector<si32>>& planes, u
 }
 
 template <typename CS>
-static std::vector<std::vector<si32>> expand(const std::vector<ui8>& j2c)
+static std::vector<std::vector<si32>> expand(const std::vector<ui8>& j2c, ui32 skip = 0)
 {
   CS cs;
   mem_infile f;
   f.open(j2c.data(), j2c.size());
   cs.read_headers(&f);
+  if (skip) cs.restrict_input_resolution(skip, skip);          // ojph_expand -skip_res
   auto siz = cs.access_siz();
   const ui32 nc = siz.get_num_components();
   std::vector<std::vector<si32>> planes(nc);
@@ -87,14 +98,30 @@ int main()
     unsigned s = 12345u + (unsigned)planar;
     for (auto& p : planes)
       for (size_t i = 0; i < p.size(); ++i) { s = s * 1664525u + 1013904223u; p[i] = (si32)(((i % w) * 3 + (i / w) * 5 + (s >> 27)) & ((1u << depth) - 1)); }
-    std::vector<ui8> a = compress<ojph::codestream>(planes, w, h, depth, planar != 0);
-    std::vector<ui8> b = compress<ojph::b200::codestream>(planes, w, h, depth, planar != 0);
+    std::vector<ui8> a = compress<ojph::codestream, ojph::comment_exchange, ojph::param_nlt>(planes, w, h, depth, planar != 0);
+    std::vector<ui8> b = compress<ojph::b200::codestream, ojph::b200::comment_exchange, ojph::b200::param_nlt>(planes, w, h, depth, planar != 0);
     const bool same = a == b;
     std::vector<std::vector<si32>> ra = expand<ojph::codestream>(a);
     std::vector<std::vector<si32>> rb = expand<ojph::b200::codestream>(a);
     const bool lossless = ra == planes && rb == planes;
     printf("planar=%d codestream %zu bytes identical=%d lossless=%d\n", planar, a.size(), (int)same, (int)lossless);
     if (!same || !lossless) ++fails;
+  }
+  {   // signed samples + NLT type 3 + comments; then a reduced-resolution expand
+    std::vector<std::vector<si32>> planes(3, std::vector<si32>((size_t)w * h));
+    unsigned s = 777u;
+    for (auto& p : planes)
+      for (size_t i = 0; i < p.size(); ++i) {
+        s = s * 1664525u + 1013904223u;
+        p[i] = (si32)(((i % w) * 3 + (i / w) * 5 + (s >> 27)) & ((1u << depth) - 1)) - (si32)(1u << (depth - 1));
+      }
+    std::vector<ui8> a = compress<ojph::codestream, ojph::comment_exchange, ojph::param_nlt>(planes, w, h, depth, false, true);
+    std::vector<ui8> b = compress<ojph::b200::codestream, ojph::b200::comment_exchange, ojph::b200::param_nlt>(planes, w, h, depth, false, true);
+    const bool same = a == b;
+    const bool lossless = expand<ojph::codestream>(a) == planes && expand<ojph::b200::codestream>(a) == planes;
+    const bool reduced = expand<ojph::codestream>(a, 2) == expand<ojph::b200::codestream>(a, 2);
+    printf("nlt+comments codestream %zu bytes identical=%d lossless=%d reduced=%d\n", a.size(), (int)same, (int)lossless, (int)reduced);
+    if (!same || !lossless || !reduced) ++fails;
   }
   return fails ? 1 : 0;
 }

@@ -21,6 +21,7 @@ class RParams(C.Structure):
         ("planar", C.c_int32),
         ("coc_present", C.c_uint32 * 16), ("coc_reversible", C.c_uint32 * 16), ("coc_num_decomps", C.c_uint32 * 16),
         ("coc_block_w", C.c_uint32 * 16), ("coc_block_h", C.c_uint32 * 16),
+        ("nlt_all", C.c_uint32), ("nlt_comp", C.c_uint32 * 16), ("nlt_seq", C.c_uint32 * 16),
     ]
 
 
@@ -57,8 +58,19 @@ def to_rparams(p):
     return r
 
 
-def encode(p, planes):
+def _set_comments(L, comments):
+    comments = comments or []
+    keep = [c.encode("latin-1") if isinstance(c, str) else bytes(c) for c in comments]
+    n = len(keep)
+    data = (C.c_char_p * max(n, 1))(*keep)
+    lens = (C.c_uint16 * max(n, 1))(*[len(k) for k in keep])
+    text = (C.c_uint16 * max(n, 1))(*[1 if isinstance(c, str) else 0 for c in comments])
+    L.ojr_set_comments(data, lens, text, C.c_uint32(n))
+
+
+def encode(p, planes, comments=None):
     L = lib()
+    _set_comments(L, comments)
     r = to_rparams(p)
     arrs = [np.ascontiguousarray(a, np.int32) for a in planes]
     ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])

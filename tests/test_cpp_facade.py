@@ -22,4 +22,4 @@ def test_facade_matches_reference_application_code(emu_lib, ref, tmp_path):
     subprocess.check_call(cmd)
     r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert r.stdout.count("identical=1 lossless=1") == 2, r.stdout
+    assert r.stdout.count("identical=1 lossless=1") == 3 and "reduced=1" in r.stdout, r.stdout
