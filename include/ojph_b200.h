@@ -109,6 +109,17 @@ int ojb_enc_flush(ojb_encoder* e, uint8_t* out, uint64_t out_cap, uint64_t* out_
  * (NULL = tight); host pointers (pinned or pageable) */
 int ojb_enc_encode_frame(ojb_encoder* e, const void* const* planes, const uint32_t* strides,
                          uint8_t* out, uint64_t out_cap, uint64_t* out_len);
+/* File sample layouts of the reference's apps (src/apps/others/ojph_img_io.cpp), converted on the GPU:
+ *   OJB_RASTER_PNM  .pgm / .ppm payload (after the header): interleaved components, 8-bit or 16-bit
+ *                   big-endian samples (ppm_in::read :338-374, ppm_out::write :539-556); 1 or 3 components
+ *   OJB_RASTER_YUV  .yuv / .raw payload: component planes one after the other, 8-bit or 16-bit
+ *                   little-endian (yuv_in::read :1350-1378, yuv_out::write :1477-1516, raw_in / raw_out)
+ * Samples take 1 byte when the bit depth is <= 8, else 2; the codec must be configured / opened with the
+ * matching container (OJB_U8 / OJB_U16).  Decoded samples are clamped to [0, 2^depth - 1] as the
+ * reference's writers do. */
+enum { OJB_RASTER_PNM = 0, OJB_RASTER_YUV = 1 };
+int ojb_enc_encode_raster(ojb_encoder* e, uint32_t layout, const void* payload, uint64_t payload_bytes,
+                          uint8_t* out, uint64_t out_cap, uint64_t* out_len);
 /* device-resident variants: the frame lives in the encoder's image buffer */
 void* ojb_enc_device_plane(ojb_encoder* e, uint32_t comp);
 int ojb_enc_upload_frame(ojb_encoder* e, const void* const* planes, const uint32_t* strides);
@@ -150,6 +161,8 @@ int ojb_dec_restrict_input_resolution(ojb_decoder* d, uint32_t skipped_res_for_r
 /* codestream::create() + the pull() loop: decodes every component into planes */
 int ojb_dec_decode_frame(ojb_decoder* d, void* const* planes, const uint32_t* strides);
 int ojb_dec_decode_resident(ojb_decoder* d);             /* result stays in the device image buffer */
+/* decode into a file payload (see ojb_enc_encode_raster); *payload_bytes receives the size */
+int ojb_dec_decode_raster(ojb_decoder* d, uint32_t layout, void* payload, uint64_t payload_cap, uint64_t* payload_bytes);
 /* The reference's line interface on the read side (needs the OJB_I32 container):
  *   ojb_dec_set_planar = codestream::set_planar (default after read_headers: colour transform ? 0 : 1,
  *                        ojph_codestream_local.cpp:879);

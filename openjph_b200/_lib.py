@@ -65,6 +65,8 @@ SYMBOLS = {
     "ojb_enc_destroy": (None, [_VP]),
     "ojb_enc_configure": (_I, [_VP, C.POINTER(Params), _U32]),
     "ojb_enc_set_comments": (_I, [_VP, C.POINTER(Comment), _U32]),
+    "ojb_enc_encode_raster": (_I, [_VP, _U32, _VP, C.c_uint64, _VP, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "ojb_dec_decode_raster": (_I, [_VP, _U32, _VP, C.c_uint64, C.POINTER(C.c_uint64)]),
     "ojb_enc_exchange": (_VP, [_VP, _VP, C.POINTER(_U32)]),
     "ojb_enc_flush": (_I, [_VP, _VP, _U64, C.POINTER(_U64)]),
     "ojb_enc_encode_frame": (_I, [_VP, C.POINTER(_VP), C.POINTER(_U32), _VP, _U64, C.POINTER(_U64)]),

@@ -15,6 +15,9 @@ _NP = {U8: np.uint8, U16: np.uint16, I32: np.int32}
 PROG = {"LRCP": 0, "RLCP": 1, "RPCL": 2, "PCRL": 3, "CPRL": 4}
 
 
+RASTER = {"pnm": 0, "yuv": 1}
+
+
 class OjphError(RuntimeError):
     pass
 
@@ -132,6 +135,15 @@ class Encoder(_Base):
         self._check(self.L.ojb_enc_encode_frame(self.h, ptrs, None, self._out.ctypes.data, self._out.size, C.byref(n)))
         return self._out[:n.value].tobytes()
 
+    def encode_raster(self, payload, layout="pnm"):
+        """a file payload as the reference's apps read it: 'pnm' = interleaved, big-endian 16-bit / 8-bit
+        (.pgm / .ppm after the header); 'yuv' = planes one after the other, little-endian (.yuv / .raw)"""
+        buf = np.frombuffer(payload, np.uint8)
+        n = C.c_uint64()
+        self._check(self.L.ojb_enc_encode_raster(self.h, RASTER[layout], buf.ctypes.data, buf.size,
+                                                 self._out.ctypes.data, self._out.size, C.byref(n)))
+        return self._out[:n.value].tobytes()
+
     def upload(self, planes):
         arrs, ptrs = self._planes(planes)
         self._check(self.L.ojb_enc_upload_frame(self.h, ptrs, None))
@@ -226,6 +238,23 @@ class Decoder(_Base):
         ptrs = (C.c_void_p * fi.num_comps)(*[a.ctypes.data for a in planes])
         self._check(self.L.ojb_dec_decode_frame(self.h, ptrs, None))
         return planes
+
+    def decode_raster(self, j2c=None, layout="pnm", sample_type=None, skip=None):
+        """decode into a file payload (see Encoder.encode_raster); returns bytes"""
+        if j2c is not None:
+            if sample_type is None:                      # the container the file format implies
+                fi = self.read_headers(j2c, I32)
+                sample_type = U16 if max(fi.bit_depth[c] for c in range(fi.num_comps)) > 8 else U8
+            self.read_headers(j2c, sample_type)
+        if skip is not None:
+            self.restrict_input_resolution(*skip)
+        fi = self.info
+        es = 2 if self.sample_type == U16 else 1
+        cap = sum(fi.comp_w[c] * fi.comp_h[c] for c in range(fi.num_comps)) * es
+        out = np.zeros(max(cap, 1), np.uint8)
+        n = C.c_uint64()
+        self._check(self.L.ojb_dec_decode_raster(self.h, RASTER[layout], out.ctypes.data, cap, C.byref(n)))
+        return out[:n.value].tobytes()
 
     def pull_lines(self, j2c, planar=None):
         """the reference's read_headers() -> [set_planar] -> create() -> pull() loop; returns the planes

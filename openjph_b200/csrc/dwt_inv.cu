@@ -20,10 +20,11 @@ template <bool REV> struct PxI;
 template <> struct PxI<true>  { typedef int T; };
 template <> struct PxI<false> { typedef float T; };
 
-__device__ __forceinline__ void store_sample(void* img, uint32_t type, uint64_t byte_off, size_t idx, int v) {
+// 8 / 16-bit containers clamp to the component's range [0, smax] as the reference's file writers do
+__device__ __forceinline__ void store_sample(void* img, uint32_t type, uint64_t byte_off, size_t idx, int v, int smax) {
   unsigned char* base = reinterpret_cast<unsigned char*>(img) + byte_off;
-  if (type == SRC_U8) base[idx] = (unsigned char)min(max(v, 0), 255);
-  else if (type == SRC_U16) reinterpret_cast<unsigned short*>(base)[idx] = (unsigned short)min(max(v, 0), 65535);
+  if (type == SRC_U8) base[idx] = (unsigned char)min(max(v, 0), smax);
+  else if (type == SRC_U16) reinterpret_cast<unsigned short*>(base)[idx] = (unsigned short)min(max(v, 0), smax);
   else reinterpret_cast<int*>(base)[idx] = v;
 }
 
@@ -226,7 +227,7 @@ dwt_inv_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, void* __restrict
       for (uint32_t k = 0; k < nc; ++k) if ((J.nlt_mask >> k) & 1u) out[k] = nlt_type3(out[k], bias);
     }
     for (uint32_t k = 0; k < nc; ++k)
-      store_sample(image, J.src_type, J.full_off[k], (size_t)(v - y0) * J.full_stride[k] + (size_t)(u - x0), out[k]);
+      store_sample(image, J.src_type, J.full_off[k], (size_t)(v - y0) * J.full_stride[k] + (size_t)(u - x0), out[k], (1 << J.bit_depth) - 1);
   }
 }
 

@@ -574,6 +574,9 @@ __device__ __forceinline__ void inv_store_row(const DwtJob& J, const StripGeom& 
         for (int i = 0; i < 4; ++i) out[k][i] = nlt_type3(out[k][i], bias);
       }
   }
+  // 8 / 16-bit containers: clamp to the component's range as the reference's file writers do
+  // (gen_cvrt_32b*_to_*, yuv_out::write: src/apps/others/ojph_img_io.cpp:99-235, :1477-1516)
+  const int smax = (1 << J.bit_depth) - 1;
   #pragma unroll
   for (int k = 0; k < NC; ++k) {
     // 32-bit byte offset into the (256-byte aligned) image buffer
@@ -584,7 +587,7 @@ __device__ __forceinline__ void inv_store_row(const DwtJob& J, const StripGeom& 
 
       uint32_t q[4];
       #pragma unroll
-      for (int i = 0; i < 4; ++i) q[i] = (uint32_t)min(max(out[k][i], 0), 65535);
+      for (int i = 0; i < 4; ++i) q[i] = (uint32_t)min(max(out[k][i], 0), smax);
       if (all4 && (o & 7u) == 0) *reinterpret_cast<uint2*>(base + o) = make_uint2(q[0] | (q[1] << 16), q[2] | (q[3] << 16));
       else {
         #pragma unroll
@@ -594,7 +597,7 @@ __device__ __forceinline__ void inv_store_row(const DwtJob& J, const StripGeom& 
       const uint32_t o = (uint32_t)J.full_off[k] + eidx;
       uint32_t q[4];
       #pragma unroll
-      for (int i = 0; i < 4; ++i) q[i] = (uint32_t)min(max(out[k][i], 0), 255);
+      for (int i = 0; i < 4; ++i) q[i] = (uint32_t)min(max(out[k][i], 0), smax);
       if (all4 && (o & 3u) == 0) *reinterpret_cast<uint32_t*>(base + o) = q[0] | (q[1] << 8) | (q[2] << 16) | (q[3] << 24);
       else {
         #pragma unroll

@@ -11,12 +11,13 @@ using namespace ojb;
 // an object belongs to the device that was current when it was created; every entry point makes
 // that device current again, so objects may be driven from any host thread
 static int current_device() { int d = 0; cudaGetDevice(&d); return d; }
-struct ojb_encoder { int device = current_device(); Encoder enc; bool configured = false; std::vector<Comment> comments; };
+struct ojb_encoder { int device = current_device(); Encoder enc; bool configured = false; std::vector<Comment> comments; DeviceBuf d_raster; };
 struct ojb_decoder {
   int device = current_device(); Decoder dec; bool have_headers = false;
   // line interface (pull): library-owned frame, cursor in the reference's line order
   PinnedBuf frame; std::vector<size_t> plane_off; std::vector<uint32_t> line_cur;
   uint32_t cur_comp = 0; int planar = -1; bool pulling = false;
+  DeviceBuf d_raster;
 };
 
 static thread_local char g_err[1024] = "";
@@ -179,6 +180,87 @@ int ojb_enc_encode_frame(ojb_encoder* e, const void* const* planes, const uint32
   return guarded_on(e->device, [&] {
     if (!e->configured) fail(0x000B0013, "encoder is not configured");
     *out_len = e->enc.encode(planes, strides, false, out, (size_t)out_cap, false);
+  });
+}
+
+} // extern "C"
+
+// file sample layouts (raster.cu)
+namespace ojb {
+static uint64_t raster_geometry(CodecBase& cb, uint32_t layout, uint32_t& es, RasterPlanes& pl) {
+  const Params& P = cb.params;
+  const uint32_t nc = P.num_comps();
+  if (layout > 1) fail(0x000B0030, "unknown raster layout");
+  if (cb.img_type == ST_I32) fail(0x000B0031, "file payloads need the 8-bit or 16-bit sample container");
+  es = cb.img_type == ST_U8 ? 1u : 2u;
+  uint64_t total = 0;
+  for (uint32_t c = 0; c < nc; ++c) {
+    if ((P.comps[c].bit_depth > 8) != (es == 2))
+      fail(0x000B0032, "component %u: %u-bit samples take %u byte(s) in the file; open the codec with the matching container",
+           c, P.comps[c].bit_depth, P.comps[c].bit_depth > 8 ? 2u : 1u);
+    total += (uint64_t)cb.img_w[c] * cb.img_h[c] * es;
+  }
+  if (layout == OJB_RASTER_PNM) {
+    if (nc != 1 && nc != 3) fail(0x000B0033, "a .pgm / .ppm payload has 1 or 3 components");
+    for (uint32_t c = 0; c < nc; ++c) {
+      if (cb.img_w[c] != cb.img_w[0] || cb.img_h[c] != cb.img_h[0])
+        fail(0x000B0034, "a .ppm payload cannot hold sub-sampled components");
+      pl.off[c] = cb.img_off[c]; pl.stride[c] = cb.img_w[c];
+    }
+  }
+  return total;
+}
+} // namespace ojb
+
+extern "C" {
+
+int ojb_enc_encode_raster(ojb_encoder* e, uint32_t layout, const void* payload, uint64_t payload_bytes,
+                          uint8_t* out, uint64_t out_cap, uint64_t* out_len) {
+  return guarded_on(e->device, [&] {
+    if (!e->configured) fail(0x000B0013, "encoder is not configured");
+    Encoder& E = e->enc;
+    uint32_t es = 0; RasterPlanes pl; memset(&pl, 0, sizeof(pl));
+    const uint64_t need = raster_geometry(E, layout, es, pl);
+    if (payload_bytes != need) fail(0x03000011, "not enough data: the frame takes %llu bytes, got %llu",
+                                    (unsigned long long)need, (unsigned long long)payload_bytes);
+    const uint32_t nc = E.params.num_comps();
+    if (layout == OJB_RASTER_YUV) {
+      std::vector<const void*> planes(nc);
+      const uint8_t* p = static_cast<const uint8_t*>(payload);
+      for (uint32_t c = 0; c < nc; ++c) { planes[c] = p; p += (size_t)E.img_w[c] * E.img_h[c] * es; }
+      *out_len = E.encode(planes.data(), nullptr, false, out, (size_t)out_cap, false);
+      return;
+    }
+    e->d_raster.reserve(std::max<uint64_t>(need, 16));
+    cuda_check(cudaMemcpyAsync(e->d_raster.p, payload, need, cudaMemcpyHostToDevice, E.stream), "upload");
+    launch_raster_unpack(e->d_raster.p, E.d_image.p, pl, nc, es, E.img_w[0], E.img_h[0], E.stream);
+    *out_len = E.encode(nullptr, nullptr, false, out, (size_t)out_cap, false);
+    E.last_launches += 1;
+  });
+}
+
+int ojb_dec_decode_raster(ojb_decoder* d, uint32_t layout, void* payload, uint64_t payload_cap, uint64_t* payload_bytes) {
+  return guarded_on(d->device, [&] {
+    if (!d->have_headers) fail(0x000B0015, "read_headers has not been called");
+    Decoder& D = d->dec;
+    uint32_t es = 0; RasterPlanes pl; memset(&pl, 0, sizeof(pl));
+    const uint64_t need = raster_geometry(D, layout, es, pl);
+    if (payload_cap < need) fail(0x000B0035, "payload buffer too small: %llu bytes needed", (unsigned long long)need);
+    const uint32_t nc = D.params.num_comps();
+    if (layout == OJB_RASTER_YUV) {
+      std::vector<void*> planes(nc);
+      uint8_t* p = static_cast<uint8_t*>(payload);
+      for (uint32_t c = 0; c < nc; ++c) { planes[c] = p; p += (size_t)D.img_w[c] * D.img_h[c] * es; }
+      D.decode(planes.data(), nullptr, false);
+    } else {
+      D.decode(nullptr, nullptr, true);
+      d->d_raster.reserve(std::max<uint64_t>(need, 16));
+      launch_raster_pack(d->d_raster.p, D.d_image.p, pl, nc, es, D.img_w[0], D.img_h[0], D.stream);
+      cuda_check(cudaMemcpyAsync(payload, d->d_raster.p, need, cudaMemcpyDeviceToHost, D.stream), "download");
+      cuda_check(cudaStreamSynchronize(D.stream), "raster pack");
+      D.last_launches += 1;
+    }
+    *payload_bytes = need;
   });
 }
 

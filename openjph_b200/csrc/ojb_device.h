@@ -93,4 +93,10 @@ struct DwtJob {
   uint32_t cta_base;      // first CTA index of this job in the launch
 };
 
+// ---- raster layouts ------------------------------------------------------------------------
+struct RasterPlanes {        // where the component planes of the image buffer are (bytes / samples)
+  uint64_t off[3];
+  uint32_t stride[3];
+};
+
 } // namespace ojb

@@ -50,6 +50,11 @@ void launch_assemble(const CopyPiece* pieces, uint32_t npieces, uint32_t max_len
 // small host<->device control transfers done by a kernel over mapped pinned memory (both pointers
 // 16-byte aligned)
 void launch_ctrl_copy(void* dst, const void* src, size_t bytes, cudaStream_t st);
+// interleaved big-endian pixels (.pgm / .ppm payload) <-> the component planes of the image buffer
+void launch_raster_unpack(const void* src, void* image, const RasterPlanes& pl, uint32_t ncomp, uint32_t bytes_per_sample,
+                          uint32_t width, uint32_t height, cudaStream_t st);
+void launch_raster_pack(void* dst, const void* image, const RasterPlanes& pl, uint32_t ncomp, uint32_t bytes_per_sample,
+                        uint32_t width, uint32_t height, cudaStream_t st);
 // block pieces computed on the device from per-block results + destination offsets
 void launch_gather_blocks(const EncBlock* blocks, const EncResult* results, const uint64_t* dst_off,
                           uint32_t nblocks, const uint8_t* slots, uint8_t* out, cudaStream_t st);

@@ -37,6 +37,7 @@
 #include "ojph_codeblock_fun.h"
 #include "ojph_transform.h"
 #include "ojph_colour.h"
+#include "ojph_img_io.h"       // src/apps/common: the apps' file readers / writers (N2 oracle)
 
 using namespace ojph;
 
@@ -466,3 +467,68 @@ void ojr_irv_tx_from_cb32(const uint32_t* sp, float* dp, float delta, uint32_t n
 { local::gen_irv_tx_from_cb32(sp, dp, 0, delta, n); }
 
 } // extern "C"
+
+
+// ---- the apps' image readers / writers (src/apps/others/ojph_img_io.cpp) ---------------------------
+// kind 0: .pgm/.ppm through ppm_in / ppm_out (rows, components interleaved, as ojph_compress / ojph_expand
+// call them); kind 1: .yuv through yuv_in / yuv_out (one component after the other).
+extern "C" int ojr_read_image(const char* path, int kind, uint32_t w, uint32_t h, uint32_t nc, uint32_t bit_depth,
+                              const uint32_t* dx, const uint32_t* dy, int32_t* const* planes)
+{
+  try {
+    std::vector<si32> row(w + 64);
+    line_buf line; line.wrap(row.data(), w, 0);
+    if (kind == 0) {
+      ppm_in in; in.open(path);
+      if (in.get_width() != w || in.get_height() != h || in.get_num_components() != nc) throw std::runtime_error("pnm header mismatch");
+      for (uint32_t y = 0; y < h; ++y)
+        for (uint32_t c = 0; c < nc; ++c) { in.read(&line, c); memcpy(planes[c] + (size_t)y * w, line.i32, (size_t)w * 4); }
+      in.close();
+    } else {
+      yuv_in in;
+      ui32 bd = bit_depth; in.set_bit_depth(1, &bd);
+      std::vector<point> sub(nc);
+      for (uint32_t c = 0; c < nc; ++c) sub[c] = point(dx[c], dy[c]);
+      in.set_img_props(size(w, h), nc, nc, sub.data());
+      in.open(path);
+      for (uint32_t c = 0; c < nc; ++c) {
+        const uint32_t cw = (w + dx[c] - 1) / dx[c], ch = (h + dy[c] - 1) / dy[c];
+        for (uint32_t y = 0; y < ch; ++y) { in.read(&line, c); memcpy(planes[c] + (size_t)y * cw, line.i32, (size_t)cw * 4); }
+      }
+      in.close();
+    }
+    return 0;
+  } catch (const std::exception& e) { snprintf(g_err, sizeof(g_err), "%s", e.what()); return 1; }
+}
+
+extern "C" int ojr_write_image(const char* path, int kind, uint32_t nc, uint32_t bit_depth, const uint32_t* comp_w,
+                               const uint32_t* comp_h, const int32_t* const* planes)
+{
+  try {
+    uint32_t wmax = 0;
+    for (uint32_t c = 0; c < nc; ++c) wmax = comp_w[c] > wmax ? comp_w[c] : wmax;
+    std::vector<std::vector<si32>> rows(nc, std::vector<si32>(wmax + 64));
+    std::vector<line_buf> lines(nc);
+    for (uint32_t c = 0; c < nc; ++c) lines[c].wrap(rows[c].data(), comp_w[c], 0);
+    std::string name(path);
+    if (kind == 0) {
+      ppm_out out; out.configure(comp_w[0], comp_h[0], nc, bit_depth); out.open(&name[0]);
+      for (uint32_t y = 0; y < comp_h[0]; ++y)
+        for (uint32_t c = 0; c < nc; ++c) {
+          memcpy(rows[c].data(), planes[c] + (size_t)y * comp_w[c], (size_t)comp_w[c] * 4);
+          out.write(&lines[c], c);
+        }
+      out.close();
+    } else {
+      yuv_out out; std::vector<ui32> cw(comp_w, comp_w + nc);
+      out.configure(bit_depth, nc, cw.data()); out.open(&name[0]);
+      for (uint32_t c = 0; c < nc; ++c)
+        for (uint32_t y = 0; y < comp_h[c]; ++y) {
+          memcpy(rows[c].data(), planes[c] + (size_t)y * comp_w[c], (size_t)comp_w[c] * 4);
+          out.write(&lines[c], c);
+        }
+      out.close();
+    }
+    return 0;
+  } catch (const std::exception& e) { snprintf(g_err, sizeof(g_err), "%s", e.what()); return 1; }
+}

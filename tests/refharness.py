@@ -116,6 +116,34 @@ def decode_restricted(j2c, skip_read, skip_recon, resilient=False):
     return planes, info
 
 
+def read_image(path, kind, w, h, nc, bit_depth, subsampling=None):
+    """the apps' file readers (ppm_in: kind 0, yuv_in: kind 1) -> si32 component planes"""
+    L = lib()
+    sub = subsampling or [(1, 1)] * nc
+    dims = [((w + dx - 1) // dx, (h + dy - 1) // dy) for dx, dy in sub]
+    planes = [np.zeros((ch, cw), np.int32) for cw, ch in dims]
+    ptrs = (C.c_void_p * nc)(*[a.ctypes.data for a in planes])
+    dx = (C.c_uint32 * nc)(*[s[0] for s in sub])
+    dy = (C.c_uint32 * nc)(*[s[1] for s in sub])
+    rc = L.ojr_read_image(path.encode(), kind, C.c_uint32(w), C.c_uint32(h), C.c_uint32(nc), C.c_uint32(bit_depth), dx, dy, ptrs)
+    if rc != 0:
+        raise RuntimeError("reference image read failed: " + L.ojr_last_error().decode())
+    return planes
+
+
+def write_image(path, kind, bit_depth, planes):
+    """the apps' file writers (ppm_out: kind 0, yuv_out: kind 1)"""
+    L = lib()
+    nc = len(planes)
+    arrs = [np.ascontiguousarray(a, np.int32) for a in planes]
+    ptrs = (C.c_void_p * nc)(*[a.ctypes.data for a in arrs])
+    cw = (C.c_uint32 * nc)(*[a.shape[1] for a in arrs])
+    ch = (C.c_uint32 * nc)(*[a.shape[0] for a in arrs])
+    rc = L.ojr_write_image(path.encode(), kind, C.c_uint32(nc), C.c_uint32(bit_depth), cw, ch, ptrs)
+    if rc != 0:
+        raise RuntimeError("reference image write failed: " + L.ojr_last_error().decode())
+
+
 def encode_block(block, missing_msbs, variant=0):
     """block: (h, w) uint32 sign-magnitude; returns bytes"""
     L = lib()
