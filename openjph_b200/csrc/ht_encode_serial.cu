@@ -25,8 +25,8 @@ namespace ojb {
 
 namespace {
 
-struct MsWriter {            // forward, LSB first
-  unsigned long long acc; uint32_t nbits, words; bool last_ff;
+struct MsWriter {            // forward, LSB first: a 128-bit window (w1:w0), fewer than 64 bits pending between puts
+  unsigned long long w0, w1; uint32_t nbits, words; uint32_t last_ff;
 };
 struct VlcWriter {           // backward, LSB first
   unsigned long long acc; uint32_t nbits, words, prev;
@@ -35,37 +35,37 @@ struct MelWriter {
   uint32_t k, run, tmp, rem, pos;
 };
 
-// emit four MagSgn bytes (needs nbits >= 32)
-__device__ __forceinline__ void ms_flush4(MsWriter& s, uint32_t* dst) {
-  const uint32_t lo = (uint32_t)s.acc;
-  uint32_t ff = lo & (lo >> 1); ff &= ff >> 2; ff &= ff >> 4;       // bit 8i <=> byte i == 0xFF
-  uint32_t w, used;
-  if (!s.last_ff && (ff & 0x00010101u) == 0) { w = lo; used = 32; s.last_ff = (ff >> 24) & 1u; }
-  else {
-    unsigned long long a = s.acc;
-    bool lf = s.last_ff;
-    w = 0; used = 0;
-    #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint32_t n = lf ? 7u : 8u;
-      const uint32_t b = (uint32_t)a & ((1u << n) - 1u);
-      w |= b << (8 * i); a >>= n; used += n; lf = (b == 0xFF);
-    }
-    s.last_ff = lf;
+// Emit eight MagSgn bytes (needs nbits >= 64).  Byte stuffing (a byte after 0xFF carries 7 bits, :483-488)
+// is done on the whole 64-bit group: the 0xFF bytes are located with SWAR tests and a zero bit is opened
+// above each of them, lowest first -- no byte loop, and groups without 0xFF (the usual case) take the
+// straight path.  One 8-byte store per group.
+__device__ __forceinline__ void ms_flush8(MsWriter& s, uint2* dst) {
+  const unsigned long long M = 0x0001010101010101ull;         // bytes 0..6: a 0xFF in byte 7 shortens the NEXT group
+  const uint32_t lf = s.last_ff;
+  unsigned long long x = (s.w0 & 0x7Full) | ((s.w0 >> 7) << (7 + lf));   // 7-bit first byte after a 0xFF
+  uint32_t c = 64u - lf;                                                  // data bits this group takes
+  unsigned long long ff = x & (x >> 1); ff &= ff >> 2; ff &= ff >> 4; ff &= M;
+  while (ff) {
+    const uint32_t pos = (uint32_t)__ffsll((long long)ff) + 14u;          // top bit of the byte after the 0xFF
+    x = (x & ((1ull << pos) - 1ull)) | (((x >> pos) << pos) << 1);
+    --c;
+    ff = x & (x >> 1); ff &= ff >> 2; ff &= ff >> 4; ff &= M & (~0ull << pos);
   }
-  dst[s.words++] = w;
-  s.acc >>= used; s.nbits -= used;
+  dst[s.words >> 1] = make_uint2((uint32_t)x, (uint32_t)(x >> 32));
+  s.words += 2;
+  s.last_ff = ((uint32_t)(x >> 56) == 0xFFu) ? 1u : 0u;
+  // drop c (56..64) bits from the window
+  const uint32_t a1 = (uint32_t)(s.w0 >> 32), a2 = (uint32_t)s.w1, a3 = (uint32_t)(s.w1 >> 32), r = c - 32u;
+  const uint32_t n0 = __funnelshift_rc(a1, a2, r), n1 = __funnelshift_rc(a2, a3, r), n2 = __funnelshift_rc(a3, 0u, r);
+  s.w0 = (unsigned long long)n0 | ((unsigned long long)n1 << 32);
+  s.w1 = (unsigned long long)n2;
+  s.nbits -= c;
 }
-// append up to 62 bits (two samples); fewer than 32 bits are pending on entry and on exit
-__device__ __forceinline__ void ms_put(MsWriter& s, unsigned long long cwd, uint32_t len, uint32_t* dst) {
-  unsigned long long hi = s.nbits ? (cwd >> (64 - s.nbits)) : 0ull;      // bits that do not fit the low word
-  s.acc |= cwd << s.nbits; s.nbits += len;
-  while (s.nbits >= 32) {
-    const uint32_t before = s.nbits;
-    ms_flush4(s, dst);                                                    // shifts acc right by `used`
-    const uint32_t used = before - s.nbits;
-    s.acc |= hi << (64 - used); hi >>= used;
-  }
+// append up to 64 bits; fewer than 64 bits are pending on entry and on exit
+__device__ __forceinline__ void ms_put(MsWriter& s, unsigned long long cwd, uint32_t len, uint2* dst) {
+  s.w1 = (cwd >> 1) >> (63u - s.nbits);                     // the part that does not fit the low word
+  s.w0 |= cwd << s.nbits; s.nbits += len;
+  while (s.nbits >= 64) ms_flush8(s, dst);
 }
 
 // emit four VLC bytes (needs nbits >= 32); `end` = one past the slot, words grow downward
@@ -136,14 +136,14 @@ ht_encode_serial_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
   const uint32_t width = blk.w, height = blk.h, stride = blk.stride, p = blk.p;
   const uint32_t* __restrict__ src = coef + blk.src_off;
   uint8_t* slot = slots + blk.slot_off;
-  uint32_t* ms_dst = reinterpret_cast<uint32_t*>(slot);
+  uint2* ms_dst = reinterpret_cast<uint2*>(slot);          // slots are 16-byte aligned
   uint32_t* vl_end = reinterpret_cast<uint32_t*>(slot + blk.slot_cap);
   uint8_t* mel_buf = s_mel + threadIdx.x;
   uint16_t* prev = s_prev + threadIdx.x;
   const uint32_t nq = (width + 1) >> 1;
   const uint32_t slot_words = blk.slot_cap >> 2;
 
-  MsWriter ms; ms.acc = 0; ms.nbits = 0; ms.words = 0; ms.last_ff = false;
+  MsWriter ms; ms.w0 = 0; ms.w1 = 0; ms.nbits = 0; ms.words = 0; ms.last_ff = 0;
   // VLC starts as byte 0xFF (later the Scup byte) followed by the four bits 0xF (vlc_init, :365-375)
   VlcWriter vlc; vlc.acc = 0xFFFull; vlc.nbits = 12; vlc.words = 0; vlc.prev = 0;
   MelWriter mel; mel.k = 0; mel.run = 0; mel.tmp = 0; mel.rem = 8; mel.pos = 0;
@@ -151,6 +151,7 @@ ht_encode_serial_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
   bool overflow = false;
   // aligned block rows: a quad pair of one row is one 16-byte load
   const bool vec4 = ((blk.src_off | stride) & 3u) == 0;
+  const bool narrow = p >= 16;             // m_n <= K_max + 1 = 32 - p: four fields of a quad fit 64 bits
 
   for (uint32_t q = 0; q <= nq; ++q) prev[q * ES_THREADS] = 0;
 
@@ -241,8 +242,10 @@ ht_encode_serial_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
                                        ((unsigned long long)(s[1] & ((1u << m[1]) - 1u)) << m[0]);
           const unsigned long long B = (unsigned long long)(s[2] & ((1u << m[2]) - 1u)) |
                                        ((unsigned long long)(s[3] & ((1u << m[3]) - 1u)) << m[2]);
-          if (m[0] + m[1]) ms_put(ms, A, m[0] + m[1], ms_dst);
-          if (m[2] + m[3]) ms_put(ms, B, m[2] + m[3], ms_dst);
+          // one append per quad while its four fields fit 64 bits (K_max <= 15), else one per column
+          const uint32_t la = m[0] + m[1], lb = m[2] + m[3];
+          if (narrow) ms_put(ms, A | (B << la), la + lb, ms_dst);
+          else { ms_put(ms, A, la, ms_dst); ms_put(ms, B, lb, ms_dst); }
         }
         rho_left = rho;
       }
@@ -274,18 +277,18 @@ ht_encode_serial_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
   // ---- termination (terminate_mel_vlc :413-441, ms_terminate :517-533)
   uint32_t ms_pos = ms.words * 4;
   {
-    uint32_t acc = (uint32_t)ms.acc, nb = ms.nbits;        // < 32 raw bits: cut them into bytes
-    bool lf = ms.last_ff;
+    unsigned long long acc = ms.w0; uint32_t nb = ms.nbits;        // < 64 raw bits: cut them into bytes
+    bool lf = ms.last_ff != 0;
     for (;;) {
       const uint32_t n = lf ? 7u : 8u;
       if (nb < n) break;
-      const uint32_t b = acc & ((1u << n) - 1u);
+      const uint32_t b = (uint32_t)acc & ((1u << n) - 1u);
       slot[ms_pos++] = (uint8_t)b; acc >>= n; nb -= n; lf = (b == 0xFF);
     }
     const uint32_t cap = lf ? 7u : 8u;
     if (nb) {
       const uint32_t t = cap - nb;
-      const uint32_t byte = acc | ((0xFFu & ((1u << t) - 1u)) << nb);
+      const uint32_t byte = (uint32_t)acc | ((0xFFu & ((1u << t) - 1u)) << nb);
       if (byte != 0xFF) slot[ms_pos++] = (uint8_t)byte;
     } else if (cap == 7) ms_pos--;
   }

@@ -45,15 +45,16 @@ def test_irv_within_tolerance(name, emu_lib, ref):
 def test_block_encoder_random_blocks(emu_lib, ref):
     rng = np.random.default_rng(3)
     bufs, descs, want, off = [], [], [], 0
-    for it in range(60):
+    for it in range(100):
         w = int(rng.integers(1, 65)); h = int(rng.integers(1, min(64, 4096 // w) + 1))
         kmax = int(rng.integers(1, 28))
-        mode = it % 4
+        mode = it % 5
         if mode == 0: mag = rng.integers(0, 1 << kmax, (h, w), dtype=np.uint64)
         elif mode == 1: mag = np.full((h, w), (1 << kmax) - 1, dtype=np.uint64)       # 0xFF-heavy: exercises stuffing
         elif mode == 2: mag = (rng.random((h, w)) < 0.03) * rng.integers(0, 1 << kmax, (h, w), dtype=np.uint64)
-        else: mag = np.minimum(np.abs(rng.laplace(0, 2 ** (kmax / 3), (h, w))).astype(np.uint64), (1 << kmax) - 1)
-        sign = rng.integers(0, 2, (h, w), dtype=np.uint64)
+        elif mode == 3: mag = np.minimum(np.abs(rng.laplace(0, 2 ** (kmax / 3), (h, w))).astype(np.uint64), (1 << kmax) - 1)
+        else: mag = np.uint64(1) << rng.integers(0, kmax, (h, w), dtype=np.uint64)    # negative powers of two: MagSgn fields of ones
+        sign = rng.integers(0, 2, (h, w), dtype=np.uint64) if mode != 4 else np.ones((h, w), np.uint64)
         blk = ((sign << 31) | (mag << (31 - kmax))).astype(np.uint32)
         stride = (w + 15) & ~15
         buf = np.zeros((h, stride), np.uint32); buf[:, :w] = blk
