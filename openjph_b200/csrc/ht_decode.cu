@@ -633,56 +633,139 @@ ht_dec_step2_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
 // right away, so no quad records travel through memory and no warp-wide scan or shared bit buffer
 // is needed -- about a third of the instructions of step 1 + step 2.  Blocks that carry SPP / MRP
 // passes still write their quad records (refine_passes needs the CUP significance).
-struct MsDec {                // MagSgn: forward, LSB first, bytes past the segment read as 0xFF
-  const uint32_t* wnext; const uint8_t* seg_end; uint32_t* ring; uint32_t ridx, lo, hi, sh;
-  int left; unsigned long long tmp; uint32_t bits; bool unstuff;
+// ---- bit readers of the thread-per-block decoder ------------------------------------------------
+// Both streams are read as aligned 8-byte groups through per-thread cp.async rings; a group is un-stuffed
+// as a whole (the positions to delete come from one SWAR test, the usual group has none) and appended to a
+// 128-bit window (w1:w0).  The caller tops a window up to >= 64 bits at ONE point per quad (MagSgn) or
+// quad pair (VLC) -- the same point for every lane of the warp, so the refill is a piece of straight-line
+// code the whole warp runs together instead of a branch a few lanes take at a time -- and then reads its
+// fields from w0 without further checks.
+struct Win128 { unsigned long long w0, w1; uint32_t bits; };
+// append the low c bits of val (upper bits zero); needs bits < 64
+__device__ __forceinline__ void win_append(Win128& w, unsigned long long val, uint32_t c) {
+  w.w1 = (val >> 1) >> (63u - w.bits);
+  w.w0 |= val << w.bits;
+  w.bits += c;
+}
+// drop n (0..64) bits
+__device__ __forceinline__ void win_drop(Win128& w, uint32_t n) {
+  uint32_t a0 = (uint32_t)w.w0, a1 = (uint32_t)(w.w0 >> 32), a2 = (uint32_t)w.w1, a3 = (uint32_t)(w.w1 >> 32);
+  const bool big = n >= 32;
+  a0 = big ? a1 : a0; a1 = big ? a2 : a1; a2 = big ? a3 : a2; a3 = big ? 0u : a3;
+  const uint32_t rr = (n == 64) ? 32u : (n & 31u);
+  const uint32_t b0 = __funnelshift_rc(a0, a1, rr), b1 = __funnelshift_rc(a1, a2, rr), b2 = __funnelshift_rc(a2, a3, rr),
+                 b3 = __funnelshift_rc(a3, 0u, rr);
+  w.w0 = (unsigned long long)b0 | ((unsigned long long)b1 << 32);
+  w.w1 = (unsigned long long)b2 | ((unsigned long long)b3 << 32);
+  w.bits -= n;
+}
+// delete the bits of val marked in del (highest first, so lower positions stay valid); returns how many
+__device__ __forceinline__ uint32_t delete_bits(unsigned long long& val, unsigned long long del) {
+  uint32_t n = 0;
+  while (del) {
+    const uint32_t pos = 63u - (uint32_t)__clzll((long long)del);
+    val = (val & ((1ull << pos) - 1ull)) | (((val >> pos) >> 1) << pos);
+    del &= ~(1ull << pos);
+    ++n;
+  }
+  return n;
+}
+__device__ __forceinline__ unsigned long long u64_of(uint2 v) { return (unsigned long long)v.x | ((unsigned long long)v.y << 32); }
+
+// MagSgn: forward, LSB first, bytes past the segment read as 0xFF; the bit after every 0xFF byte is a
+// stuffing bit (frwd_read / frwd_init<0xFF>, :340-421)
+struct MsDec {
+  const uint2* wnext; const uint8_t* seg_end; uint2* ring; uint32_t ridx;
+  int left; Win128 w; uint32_t unstuff;
 };
 __device__ __forceinline__ void ms_ring_issue(MsDec& m) {
-  uint32_t* slot = m.ring + m.ridx * DEC1_THREADS;
-  if (reinterpret_cast<const uint8_t*>(m.wnext) < m.seg_end) cp_async<4>(slot, m.wnext); else *slot = 0xFFFFFFFFu;
+  uint2* slot = m.ring + m.ridx * DEC1_THREADS;
+  if (reinterpret_cast<const uint8_t*>(m.wnext) < m.seg_end) cp_async<8>(slot, m.wnext); else *slot = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
   cp_commit();
   ++m.wnext; m.ridx = (m.ridx + 1) & (VLC_RING - 1);
 }
-__device__ __forceinline__ void ms_prime(MsDec& m, const uint8_t* p, int len, const uint8_t* seg_end, uint32_t* ring) {
-  const uint32_t* wp = reinterpret_cast<const uint32_t*>((size_t)p & ~(size_t)3);
-  m.sh = (uint32_t)((size_t)p & 3) * 8;
-  m.seg_end = seg_end; m.left = len; m.tmp = 0; m.bits = 0; m.unstuff = false;
-  m.lo = wp[0]; m.hi = wp[1];
-  m.ring = ring; m.ridx = 0; m.wnext = wp + 2;
+// take a group of nv (1..8) bytes, first byte in the low byte of val
+__device__ __forceinline__ void ms_ingest(MsDec& m, unsigned long long val, uint32_t nv) {
+  if (m.left < (int)nv) val |= (m.left <= 0) ? ~0ull : (~0ull << (8 * m.left));
+  if (nv < 8) val &= (1ull << (8 * nv)) - 1ull;
+  m.left -= (int)nv;
+  unsigned long long ff = val & (val >> 1); ff &= ff >> 2; ff &= ff >> 4; ff &= 0x0101010101010101ull;   // bit 8i <=> byte i == 0xFF
+  // bits to delete: the top bit of the byte after each 0xFF (of byte 0 when the previous group ended in 0xFF)
+  unsigned long long del = ((ff << 15) | ((unsigned long long)m.unstuff << 7)) & ((nv < 8) ? ((1ull << (8 * nv)) - 1ull) : ~0ull);
+  m.unstuff = (uint32_t)(ff >> (8 * (nv - 1))) & 1u;
+  const uint32_t c = 8 * nv - delete_bits(val, del);
+  win_append(m.w, val, c);
+}
+__device__ __forceinline__ void ms_prime(MsDec& m, const uint8_t* p, int len, const uint8_t* seg_end, uint2* ring) {
+  const uint2* wp = reinterpret_cast<const uint2*>((size_t)p & ~(size_t)7);
+  const uint32_t a = (uint32_t)((size_t)p & 7);
+  m.seg_end = seg_end; m.left = len; m.w.w0 = 0; m.w.w1 = 0; m.w.bits = 0; m.unstuff = 0;
+  m.ring = ring; m.ridx = 0; m.wnext = wp + 1;
   #pragma unroll
   for (int i = 0; i < VLC_RING - 1; ++i) ms_ring_issue(m);
   m.ridx = 0;
+  ms_ingest(m, u64_of(wp[0]) >> (8 * a), 8 - a);           // the bytes up to the next 8-byte boundary: groups are aligned from here on
 }
-__device__ __forceinline__ void ms_fill(MsDec& m) {            // adds 28..32 bits; needs bits < 32
-  uint32_t val = m.sh ? __funnelshift_r(m.lo, m.hi, m.sh) : m.lo;
-  m.lo = m.hi;
+__device__ __forceinline__ void ms_fill(MsDec& m) {            // adds 56..64 bits; needs bits < 64
   cp_wait<VLC_RING - 2>();
   const uint32_t take = m.ridx;
-  m.hi = m.ring[take * DEC1_THREADS];
+  const unsigned long long val = u64_of(m.ring[take * DEC1_THREADS]);
   m.ridx = (take + VLC_RING - 1) & (VLC_RING - 1);
   ms_ring_issue(m);
   m.ridx = (take + 1) & (VLC_RING - 1);
-  if (m.left < 4) val |= (m.left <= 0) ? 0xFFFFFFFFu : (0xFFFFFFFFu << (8 * m.left));
-  m.left -= 4;
-  uint32_t t, nb;
-  bool us = m.unstuff;
-  uint32_t ff = val & (val >> 1); ff &= ff >> 2; ff &= ff >> 4;      // bit 8i <=> byte i == 0xFF
-  if (!us && (ff & 0x00010101u) == 0) { t = val; nb = 32; us = (ff >> 24) & 1u; }
-  else {
-    t = 0; nb = 0;
-    #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint32_t d = (val >> (8 * i)) & 0xFFu;
-      const uint32_t n = us ? 7u : 8u;
-      t |= (d & ((1u << n) - 1u)) << nb;
-      nb += n; us = (d == 0xFF);
-    }
-  }
-  m.unstuff = us;
-  m.tmp |= (unsigned long long)t << m.bits;
-  m.bits += nb;
+  ms_ingest(m, val, 8);
 }
 
+// VLC: backward from the end of the segment, LSB first, zeros once the segment is exhausted; a byte whose
+// low seven bits are ones and whose predecessor in reading order is > 0x8F carries seven bits (rev_read,
+// :220-302).  A group holds eight bytes in READING order (byte-reversed memory word).
+struct VlcDec {
+  const uint2* wnext; const uint2* wbase; uint2* ring; uint32_t ridx;
+  int left; Win128 w; uint32_t unstuff;
+};
+__device__ __forceinline__ void vlc_ring_issue(VlcDec& v) {
+  uint2* slot = v.ring + v.ridx * DEC1_THREADS;
+  if (v.wnext >= v.wbase) cp_async<8>(slot, v.wnext); else *slot = make_uint2(0u, 0u);
+  cp_commit();
+  --v.wnext; v.ridx = (v.ridx + 1) & (VLC_RING - 1);
+}
+__device__ __forceinline__ unsigned long long bswap64(unsigned long long x) {
+  return ((unsigned long long)__byte_perm((uint32_t)x, 0, 0x0123) << 32) | (unsigned long long)__byte_perm((uint32_t)(x >> 32), 0, 0x0123);
+}
+__device__ __forceinline__ void vlc_ingest(VlcDec& v, unsigned long long val, uint32_t nv) {
+  if (v.left < (int)nv) val &= (v.left <= 0) ? 0ull : ((1ull << (8 * v.left)) - 1ull);
+  v.left -= (int)nv;
+  const unsigned long long pv = (val << 8) | (v.unstuff ? 0x90ull : 0ull);        // predecessor of every byte
+  const unsigned long long del = ((val & 0x7F7F7F7F7F7F7F7Full) + 0x0101010101010101ull) & pv &
+                                 ((pv & 0x7070707070707070ull) + 0x7070707070707070ull) & 0x8080808080808080ull;
+  v.unstuff = ((uint32_t)(val >> (8 * (nv - 1))) & 0xFFu) > 0x8Fu ? 1u : 0u;
+  const uint32_t c = 8 * nv - delete_bits(val, del);
+  win_append(v.w, val, c);
+}
+// p = the first byte to read (then downward), size = bytes available from p down; the window already
+// holds the bits of the Scup nibble byte
+__device__ __forceinline__ void vlc_prime(VlcDec& v, const uint8_t* p, int size, const uint8_t* buffer_start, uint2* ring) {
+  const uint2* wp = reinterpret_cast<const uint2*>((size_t)p & ~(size_t)7);
+  const uint32_t a = (uint32_t)((size_t)p & 7);
+  v.wbase = reinterpret_cast<const uint2*>((size_t)buffer_start & ~(size_t)7);
+  v.left = size;
+  v.ring = ring; v.ridx = 0; v.wnext = wp - 1;
+  #pragma unroll
+  for (int i = 0; i < VLC_RING - 1; ++i) vlc_ring_issue(v);
+  v.ridx = 0;
+  vlc_ingest(v, bswap64(u64_of(wp[0])) >> (8 * (7 - a)), a + 1);   // down to the 8-byte boundary: groups are aligned from here on
+}
+__device__ __forceinline__ void vlc_fill(VlcDec& v) {         // adds 56..64 bits; needs bits < 64
+  cp_wait<VLC_RING - 2>();
+  const uint32_t take = v.ridx;
+  const unsigned long long val = bswap64(u64_of(v.ring[take * DEC1_THREADS]));
+  v.ridx = (take + VLC_RING - 1) & (VLC_RING - 1);
+  vlc_ring_issue(v);
+  v.ridx = (take + 1) & (VLC_RING - 1);
+  vlc_ingest(v, val, 8);
+}
+
+template <int MODE>       // 0: integer output, 1: float output, 2: per-block mode / blocks with refinement passes
 __global__ void __launch_bounds__(DEC1_THREADS)
 ht_decode_serial_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
                         const uint8_t* __restrict__ cs, uint32_t* __restrict__ coef,
@@ -690,8 +773,8 @@ ht_decode_serial_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
                         uint32_t out_mode, uint32_t* __restrict__ block_status, uint32_t prev_quads)
 {
   __shared__ DecTables T;
-  __shared__ uint32_t s_ring[VLC_RING * DEC1_THREADS];     // per-thread FIFO of VLC words (slot-major)
-  __shared__ uint32_t s_mring[VLC_RING * DEC1_THREADS];    // per-thread FIFO of MagSgn words
+  __shared__ uint2 s_ring[VLC_RING * DEC1_THREADS];        // per-thread FIFO of VLC 8-byte groups (slot-major)
+  __shared__ uint2 s_mring[VLC_RING * DEC1_THREADS];       // per-thread FIFO of MagSgn 8-byte groups
   OJB_DYN_SMEM(uint16_t, s_prev);       // prev_quads x threads: msb(v_n) of the bottom samples of the row above
   {
     uint16_t* d = reinterpret_cast<uint16_t*>(&T);
@@ -718,14 +801,14 @@ ht_decode_serial_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
 
   MelDec mel; mel.p = data + lcup - scup; mel.size = scup - 1; mel.tmp = 0; mel.bits = 0;
   mel.unstuff = false; mel.k = 0;
-  RevDec vlc; vlc.p = data + lcup - 2; vlc.size = scup - 2;
+  VlcDec vlc;
   {
-    uint32_t d = *vlc.p--;
-    vlc.tmp = d >> 4;
-    vlc.bits = 4 - (((vlc.tmp & 7) == 7) ? 1u : 0u);
-    vlc.unstuff = (d | 0xF) > 0x8F;
+    const uint32_t d = data[lcup - 2];                     // the byte that shares the Scup nibble (rev_init, :270-302)
+    vlc.w.w0 = d >> 4; vlc.w.w1 = 0;
+    vlc.w.bits = 4 - (((vlc.w.w0 & 7) == 7) ? 1u : 0u);
+    vlc.unstuff = (d | 0xF) > 0x8F ? 1u : 0u;
   }
-  rev_prime(vlc, cs, s_ring + threadIdx.x);
+  vlc_prime(vlc, data + lcup - 3, scup - 2, cs, s_ring + threadIdx.x);
   mel_prime(mel);
   MsDec ms;
   ms_prime(ms, data, lcup - scup, data + lcup, s_mring + threadIdx.x);
@@ -741,8 +824,11 @@ ht_decode_serial_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
   const uint32_t shift = 31u - blk.K_max;
   const float delta = blk.delta;
   if (out_mode == DEC_OUT_PER_BLOCK) out_mode = (blk.flags & 2) ? (uint32_t)DEC_OUT_FLOAT : (uint32_t)DEC_OUT_INT;
-  const uint32_t om = (np > 1) ? (uint32_t)DEC_OUT_SIGNMAG : out_mode;
+  // MODE 0 / 1: the launch has cleanup passes only and one output type, known at compile time
+  const uint32_t om = MODE == 0 ? (uint32_t)DEC_OUT_INT : MODE == 1 ? (uint32_t)DEC_OUT_FLOAT
+                                : ((np > 1) ? (uint32_t)DEC_OUT_SIGNMAG : out_mode);
   const bool vec4 = ((blk.dst_off | stride) & 3u) == 0;
+  const bool narrow = mmsbp2 <= 16;          // m_n <= missing_msbs + 2: the four fields of a quad fit 64 bits
   bool fail = false;
   // significance of the row above as bit masks over up to 32 quads per word is not enough for wide
   // blocks: the row-above state (sigma of the two bottom samples, msb of their v_n) lives in s_prev
@@ -758,6 +844,10 @@ ht_decode_serial_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
     const bool has_r1 = y + 1 < height;
     for (uint32_t q = 0; q < nq; q += 2) {
       uint32_t t[2] = {0, 0}, pq[3];
+      // one top-up per quad pair: the pair reads at most 2 x 7 + 6 + 10 bits
+      while (vlc.w.bits < 64) vlc_fill(vlc);
+      unsigned long long vt = vlc.w.w0;
+      uint32_t vused = 0;
       pq[0] = pl; pq[1] = pc;
       pq[2] = prev[(q + 1) * DEC1_THREADS];
       const uint32_t pq3 = (q + 2 <= nq) ? prev[(q + 2) * DEC1_THREADS] : 0u;
@@ -775,14 +865,13 @@ ht_decode_serial_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
             const uint32_t r = ((pn >> 11) | (pe >> 10)) & 1u;
             c = a | (l << 1) | (r << 2);
           }
-          rev_fill32(vlc);
-          uint32_t e = vtab[(c << 7) | ((uint32_t)vlc.tmp & 0x7F)];
+          uint32_t e = vtab[(c << 7) | ((uint32_t)vt & 0x7F)];
           if (c == 0) {               // significance of an all-zero context comes from MEL
             run -= 2;
             if (run != -1) e = 0;
             if (run < 0) run = mel_next_run(mel);
           }
-          vlc.tmp >>= (e & 7); vlc.bits -= (e & 7);
+          vt >>= (e & 7); vused += (e & 7);
           t[i] = e;
           rho_left = (e >> 4) & 15u;
         }
@@ -790,21 +879,21 @@ ht_decode_serial_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
       // U-VLC of the pair (:940-974 initial row, :1066-1085 others)
       uint32_t mode = ((t[0] >> 3) & 1u) | (((t[1] >> 3) & 1u) << 1);
       uint32_t ent;
-      rev_fill32(vlc);
       if (y == 0) {
         if (mode == 3) {
           run -= 2;
           if (run == -1) mode = 4;
           if (run < 0) run = mel_next_run(mel);
         }
-        ent = T.uvlc0[(mode << 6) | ((uint32_t)vlc.tmp & 0x3F)];
+        ent = T.uvlc0[(mode << 6) | ((uint32_t)vt & 0x3F)];
       } else
-        ent = T.uvlc1[(mode << 6) | ((uint32_t)vlc.tmp & 0x3F)];
-      vlc.tmp >>= (ent & 7); vlc.bits -= (ent & 7);
+        ent = T.uvlc1[(mode << 6) | ((uint32_t)vt & 0x3F)];
+      vt >>= (ent & 7); vused += (ent & 7);
       ent >>= 3;
       uint32_t len = ent & 0xF;
-      uint32_t suf = (uint32_t)vlc.tmp & ((1u << len) - 1u);
-      vlc.tmp >>= len; vlc.bits -= len;
+      uint32_t suf = (uint32_t)vt & ((1u << len) - 1u);
+      vused += len;
+      win_drop(vlc.w, vused);
       ent >>= 4;
       len = ent & 7; ent >>= 3;
       const uint32_t kap = (y == 0) ? 1u : 0u;
@@ -829,20 +918,41 @@ ht_decode_serial_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
         }
         if (Uq > mmsbp2) { fail = true; break; }
         uint32_t vbl = 0, vbr = 0;
+        // m_n = sigma_n * (U_q - ek_n) for the four samples at once, one byte each
+        uint32_t mk[4];
+        {
+          const uint32_t rb = (rho * 0x00204081u) & 0x01010101u, eb = (ek * 0x00204081u) & 0x01010101u;
+          const uint32_t mb = (Uq * 0x01010101u - eb) & (rb * 0xFFu);
+          mk[0] = mb & 0xFFu; mk[1] = (mb >> 8) & 0xFFu; mk[2] = (mb >> 16) & 0xFFu; mk[3] = mb >> 24;
+        }
+        // the window is topped up at the same two points of the quad in every lane; a quad whose four
+        // fields fit 64 bits (K_max <= 15) needs the first one only
         #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if ((rho >> k) & 1u) {
-            const uint32_t m = Uq - ((ek >> k) & 1u);
-            while (ms.bits < 32) ms_fill(ms);
-            const uint32_t bits = (uint32_t)ms.tmp;
-            ms.tmp >>= m; ms.bits -= m;
+        for (int half = 0; half < 2; ++half) {
+          if (half == 0 || !narrow) { while (ms.w.bits < 64) ms_fill(ms); }
+          uint32_t off = (half == 1 && narrow) ? mk[0] + mk[1] : 0u;
+          #pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            const int k = 2 * half + kk;
+            const uint32_t m = mk[k];
+            const uint32_t bits = (uint32_t)(ms.w.w0 >> off);
+            off += m;
             uint32_t v = bits & ((1u << m) - 1u);
             v |= ((e1 >> k) & 1u) << m;
             v |= 1u;
+            const bool sig = (rho >> k) & 1u;
+            v = sig ? v : 0u;
             if (k == 1) vbl = v;
             if (k == 3) vbr = v;
-            o[i][k] = to_output((bits << 31) | ((v + 2u) << (p - 1)), om, shift, delta);
+            const uint32_t mag = (v + 2u) << (p - 1);                 // magnitude with the half-LSB bin centre, bit 30 down
+            uint32_t val;
+            if (MODE == 0) { const uint32_t a = mag >> shift, sg = 0u - (bits & 1u); val = (a ^ sg) - sg; }   // two's complement
+            else if (MODE == 1) val = __float_as_uint(__fmul_rn((float)mag, delta)) | (bits << 31);
+            else val = to_output((bits << 31) | mag, om, shift, delta);
+            o[i][k] = sig ? val : 0u;
           }
+          if (!narrow) win_drop(ms.w, mk[2 * half] + mk[2 * half + 1]);
+          else if (half == 1) win_drop(ms.w, off);
         }
         // row-above record of this quad for the next quad-row
         prev[qq * DEC1_THREADS] = (uint16_t)((31u - (uint32_t)__clz((int)(vbl | 2u))) | ((31u - (uint32_t)__clz((int)(vbr | 2u))) << 5)
@@ -924,15 +1034,18 @@ void launch_ht_decode(const DecBlock* blocks, uint32_t nblocks, const uint8_t* c
 
 void launch_ht_decode_serial(const DecBlock* blocks, uint32_t nblocks, uint32_t max_width, const uint8_t* codestream,
                              uint32_t* coef, uint32_t* scratch, const uint16_t* tables, uint32_t out_mode,
-                             uint32_t* block_status, cudaStream_t st)
+                             bool cleanup_only, uint32_t* block_status, cudaStream_t st)
 {
   if (nblocks == 0) return;
   const uint32_t prev_quads = (max_width + 1) / 2 + 2;
   const size_t smem = (size_t)prev_quads * DEC1_THREADS * sizeof(uint16_t);
-  cudaFuncSetAttribute(ht_decode_serial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // specialised on the output type when no block carries SigProp / MagRef passes
+  auto k = (cleanup_only && out_mode == DEC_OUT_INT) ? ht_decode_serial_kernel<0>
+         : (cleanup_only && out_mode == DEC_OUT_FLOAT) ? ht_decode_serial_kernel<1> : ht_decode_serial_kernel<2>;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   {
     dim3 grid((nblocks + DEC1_THREADS - 1) / DEC1_THREADS), block(DEC1_THREADS);
-    OJB_LAUNCH(ht_decode_serial_kernel, grid, block, smem, st, blocks, nblocks, codestream, coef, scratch, tables, out_mode,
+    OJB_LAUNCH(k, grid, block, smem, st, blocks, nblocks, codestream, coef, scratch, tables, out_mode,
                block_status, prev_quads);
   }
   {

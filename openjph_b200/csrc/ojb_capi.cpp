@@ -557,7 +557,7 @@ int ojb_decode_blocks(const uint8_t* bytes, uint64_t n_bytes, ojb_block_desc* de
     for (uint32_t i = 0; i < n; ++i) maxw = std::max(maxw, desc[i].w);
     if (serial_block_decoder() || maxw > 64)
       launch_ht_decode_serial(d_b.as<DecBlock>(), n, maxw, d_cs.as<uint8_t>(), d_o.as<uint32_t>(), d_sc.as<uint32_t>(),
-                              d_t.as<uint16_t>(), DEC_OUT_SIGNMAG, d_st.as<uint32_t>(), 0);
+                              d_t.as<uint16_t>(), DEC_OUT_SIGNMAG, false, d_st.as<uint32_t>(), 0);
     else
       launch_ht_decode(d_b.as<DecBlock>(), n, d_cs.as<uint8_t>(), d_o.as<uint32_t>(), d_sc.as<uint32_t>(),
                        d_t.as<uint16_t>(), DEC_OUT_SIGNMAG, d_st.as<uint32_t>(), max_len1, 0);

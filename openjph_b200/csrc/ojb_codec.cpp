@@ -36,7 +36,7 @@ bool serial_block_encoder() {
   return v;
 }
 bool serial_block_decoder() {
-  static const bool v = [] { const char* e = getenv("OJB_BLOCK_DECODER"); return e && strcmp(e, "serial") == 0; }();
+  static const bool v = [] { const char* e = getenv("OJB_BLOCK_DECODER"); return !(e && strcmp(e, "twostep") == 0); }();
   return v;
 }
 
@@ -685,6 +685,7 @@ uint32_t Decoder::decode(void* const* planes, const uint32_t* strides, bool plan
   if (nb) { const DecBlock& l = h_dec_proto[nb - 1]; uint32_t nq = (l.w + 1u) / 2, qs = (nq + 1) & ~1u; scratch_fixed = l.scratch_off + (size_t)qs * ((l.h + 1u) / 2); }
   size_t scratch = scratch_fixed;
   uint32_t max_len1 = 0;
+  bool cleanup_only = true, any_rev = false, any_irv = false;    // lets the block decoder be specialised
   // per-block scratch = quad records (fixed part, laid out per block) ... MagSgn words appended
   // right after each block's records would move the records; keep records at proto offsets and put
   // the MagSgn buffers in a second region addressed through scratch_off + records size.
@@ -703,15 +704,18 @@ uint32_t Decoder::decode(void* const* planes, const uint32_t* strides, bool plan
     d.scratch_off = scratch;
     scratch += (size_t)qs * nqr + (((d.len1 + 3) / 4 + 4 + 3) & ~3u);
     max_len1 = std::max(max_len1, d.len1);
+    if (d.num_passes > 1) cleanup_only = false;
+    if (d.flags & 2) any_irv = true; else any_rev = true;
     hd[b] = d;
   }
+  const uint32_t dec_out = (any_rev && any_irv) ? (uint32_t)DEC_OUT_PER_BLOCK : any_irv ? (uint32_t)DEC_OUT_FLOAT : (uint32_t)DEC_OUT_INT;
   d_scratch.reserve((scratch + 64) * 4);
   host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
   mark(2);
   if (nb) { launch_ctrl_copy(d_dec.p, h_dec.p, (size_t)nb * sizeof(DecBlock), stream); ++last_launches; }
   if (serial_block_decoder() || max_block_w > 64)
     launch_ht_decode_serial(d_dec.as<DecBlock>(), nb, max_block_w, cs_dev, d_coef.as<uint32_t>(), d_scratch.as<uint32_t>(),
-                            d_tables_dec.as<uint16_t>(), (uint32_t)DEC_OUT_PER_BLOCK,
+                            d_tables_dec.as<uint16_t>(), dec_out, cleanup_only,
                             d_bstatus.as<uint32_t>(), stream);
   else
     launch_ht_decode(d_dec.as<DecBlock>(), nb, cs_dev, d_coef.as<uint32_t>(), d_scratch.as<uint32_t>(),

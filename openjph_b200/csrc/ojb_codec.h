@@ -103,8 +103,8 @@ struct FrameInfo {
 
 // block-coder variants, identical results.  Encoder: one thread per code-block by default (fewest
 // instructions, best with several frames in flight), OJB_BLOCK_ENCODER=warp selects one warp per
-// block.  Decoder: step 1 (thread per block) + step 2 (warp per block) by default,
-// OJB_BLOCK_DECODER=serial selects the single-pass thread-per-block kernel.
+// block.  Decoder: the single-pass thread-per-block kernel by default, OJB_BLOCK_DECODER=twostep selects
+// step 1 (thread per block) + step 2 (warp per block).
 bool serial_block_encoder();
 bool serial_block_decoder();
 

@@ -24,7 +24,7 @@ void launch_ht_decode(const DecBlock* blocks, uint32_t nblocks, const uint8_t* c
 // the same decoder with one THREAD per code-block for the whole cleanup pass (+ a zero-fill kernel)
 void launch_ht_decode_serial(const DecBlock* blocks, uint32_t nblocks, uint32_t max_width, const uint8_t* codestream,
                              uint32_t* coef, uint32_t* scratch, const uint16_t* tables, uint32_t out_mode,
-                             uint32_t* block_status, cudaStream_t st);
+                             bool cleanup_only, uint32_t* block_status, cudaStream_t st);
 
 // forward / inverse DWT levels (dwt_fwd.cu / dwt_inv.cu).  jobs live in device memory.
 void launch_dwt_fwd(const DwtJob* jobs, uint32_t njobs, uint32_t total_ctas, bool reversible,

@@ -197,7 +197,7 @@ def test_alternate_block_coder_variants_gpu(gpu_lib, ref):
     import os, subprocess, sys
     if os.environ.get("OJB_VARIANT_CHILD"):
         pytest.skip("already inside the child run")
-    env = dict(os.environ, OJB_BLOCK_ENCODER="warp", OJB_BLOCK_DECODER="serial", OJB_VARIANT_CHILD="1")
+    env = dict(os.environ, OJB_BLOCK_ENCODER="warp", OJB_BLOCK_DECODER="twostep", OJB_VARIANT_CHILD="1")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "--timeout", "600",
                         "-k", "block_encoder or block_decoder or cfg2 or cfg3 or odd_rgb_L5 or offsets"],
                        env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

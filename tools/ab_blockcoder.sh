@@ -3,8 +3,8 @@
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q --timeout 600 -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 tail -3 gpurun_out/pytest_gpu.log
-for v in serial warp serialdec; do
-  if [ $v = serialdec ]; then export OJB_BLOCK_ENCODER=serial OJB_BLOCK_DECODER=serial; else export OJB_BLOCK_ENCODER=$v; unset OJB_BLOCK_DECODER; fi
+for v in serial warp twostepdec; do
+  if [ $v = twostepdec ]; then export OJB_BLOCK_ENCODER=serial OJB_BLOCK_DECODER=twostep; else export OJB_BLOCK_ENCODER=$v; unset OJB_BLOCK_DECODER; fi
   OJB_BENCH_EXTRAS=${EXTRAS:-0} timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_$v.json 2> gpurun_out/bench_$v.err
   python - <<PY
 import json
