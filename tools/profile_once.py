@@ -8,7 +8,9 @@ import openjph_b200 as ob
 import images
 W = int(os.environ.get("PW", "8192")); H = int(os.environ.get("PH", "8192"))
 rev = os.environ.get("PREV", "1") == "1"
-p = ob.make_params(W, H, 3, 12, num_decomps=5, reversible=rev, color_transform=True, qfactor=0 if rev else 90)
+TH = int(os.environ.get("PTILE", "0"))       # tile height: PH = k * PTILE stacks k frames as tiles
+p = ob.make_params(W, H, 3, 12, num_decomps=5, reversible=rev, color_transform=True, qfactor=0 if rev else 90,
+                   tile=(W, TH) if TH else (0, 0))
 frame = [f.astype(np.uint16) for f in images.synth_frame(W, H, 3, 12, 1234)]
 enc = ob.Encoder(p, ob.U16)
 n = int(os.environ.get("PN", "1"))
