@@ -941,9 +941,8 @@ ht_decode_serial_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
             v |= ((e1 >> k) & 1u) << m;
             v |= 1u;
             const bool sig = (rho >> k) & 1u;
-            v = sig ? v : 0u;
-            if (k == 1) vbl = v;
-            if (k == 3) vbr = v;
+            if (k == 1) vbl = sig ? v : 0u;
+            if (k == 3) vbr = sig ? v : 0u;
             const uint32_t mag = (v + 2u) << (p - 1);                 // magnitude with the half-LSB bin centre, bit 30 down
             uint32_t val;
             if (MODE == 0) { const uint32_t a = mag >> shift, sg = 0u - (bits & 1u); val = (a ^ sg) - sg; }   // two's complement

@@ -202,9 +202,9 @@ ht_encode_serial_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
           // branch-free: v = 2 * magnitude (0 when insignificant); exponent of 2*mag - 1, MagSgn value
           // 2*(mag - 1) + sign (only read when the sample is significant)
           const uint32_t v = ((t[i] + t[i]) >> p) & ~1u;
-          const uint32_t sig = v ? 1u : 0u;
+          const uint32_t sig = min(v, 1u);
           rho |= sig << i;
-          e[i] = sig ? 32u - (uint32_t)__clz((int)(v - 1u)) : 0u;
+          e[i] = 32u - (uint32_t)__clz((int)(v - sig));          // v = 0: clz(0) = 32 -> 0
           s[i] = v - 2u + (t[i] >> 31);
         }
         any_sig |= rho;
@@ -229,15 +229,20 @@ ht_encode_serial_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
         const uint32_t Uq = max(emax, kappa);
         const uint32_t u = Uq - kappa;
         uq[h] = u;
-        uint32_t eps = 0;
-        if (u > 0) eps = (e[0] == emax ? 1u : 0u) | (e[1] == emax ? 2u : 0u) | (e[2] == emax ? 4u : 0u) | (e[3] == emax ? 8u : 0u);
+        // which samples reach the maximum exponent (only coded when u > 0); branch-free
+        const uint32_t eps = ((e[0] == emax ? 1u : 0u) | (e[1] == emax ? 2u : 0u) | (e[2] == emax ? 4u : 0u) | (e[3] == emax ? 8u : 0u))
+                             & (0u - min(u, 1u));
         const uint32_t tuple = vtab[(cq << 8) + (rho << 4) + eps];
         pair_bits |= (tuple >> 8) << pair_len; pair_len += (tuple >> 4) & 7u;      // :661-662
         if (cq == 0) mel_event(mel, rho != 0, mel_buf);                          // :664-665
         {                                                                         // :667-674
+          // m_n = sigma_n * (U_q - emb_n) for the four samples at once, one byte each (U_q >= 1, emb_n <= 1)
           uint32_t m[4];
-          #pragma unroll
-          for (int i = 0; i < 4; ++i) m[i] = ((rho >> i) & 1u) ? Uq - ((tuple >> i) & 1u) : 0u;
+          {
+            const uint32_t rb = (rho * 0x00204081u) & 0x01010101u, eb = ((tuple & 15u) * 0x00204081u) & 0x01010101u;
+            const uint32_t mb = (Uq * 0x01010101u - eb) & (rb * 0xFFu);
+            m[0] = mb & 0xFFu; m[1] = (mb >> 8) & 0xFFu; m[2] = (mb >> 16) & 0xFFu; m[3] = mb >> 24;
+          }
           const unsigned long long A = (unsigned long long)(s[0] & ((1u << m[0]) - 1u)) |
                                        ((unsigned long long)(s[1] & ((1u << m[1]) - 1u)) << m[0]);
           const unsigned long long B = (unsigned long long)(s[2] & ((1u << m[2]) - 1u)) |

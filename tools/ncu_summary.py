@@ -12,9 +12,16 @@ ki = h.index("Kernel Name")
 stall = [i for i, c in enumerate(h) if c.startswith("smsp__pcsamp_warps_issue_stalled_") and not c.endswith("_not_issued")]
 
 
+units = rows[1]
+SCALE = {"ns": 1e-6, "us": 1e-3, "usecond": 1e-3, "ms": 1.0, "msecond": 1.0, "s": 1e3, "second": 1e3,           # -> ms
+         "byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}                                               # -> MB
+
+
 def g(r, n):
+    """metric value; times come back in ms and byte counts in MB whatever unit ncu chose for the report"""
     try:
-        return float(r[h.index(n)])
+        i = h.index(n)
+        return float(r[i]) * SCALE.get(units[i], 1.0)
     except Exception:
         return 0.0
 
