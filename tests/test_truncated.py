@@ -4,6 +4,7 @@ non-resilient parser detects must raise instead -- the flag, and only the flag, 
 import numpy as np
 import pytest
 import openjph_b200 as ob
+import cases
 
 W = H = 256
 NUM_CUTS = 16
@@ -51,3 +52,21 @@ def test_truncated_codestreams_emulator(emu_lib, ref):
 @pytest.mark.gpu
 def test_truncated_codestreams_gpu(gpu_lib, ref):
     _check(None, ref)
+
+
+def test_corrupted_tile_data_is_survived(emu_lib, ref):
+    """random byte errors inside the tile data: a resilient decode must come back (failed blocks are zero-filled)
+    without touching memory outside its buffers (the emulator's guard zones abort on that)"""
+    rng = np.random.default_rng(11)
+    for kw in (dict(width=200, height=150, num_comps=3, bit_depth=8, num_decomps=3, reversible=True, color_transform=True),
+               dict(width=700, height=100, num_comps=1, bit_depth=10, num_decomps=2, reversible=True, block=(256, 16)),
+               dict(width=128, height=96, num_comps=3, bit_depth=12, num_decomps=4, reversible=False, color_transform=True, qfactor=90)):
+        p = cases.make(kw)
+        cs = bytearray(ref.encode(p, cases.frame_for(p)))
+        sod = cs.index(b"\xff\x93") + 2
+        for _ in range(12):
+            bad = bytearray(cs)
+            for _ in range(int(rng.integers(1, 30))):
+                bad[int(rng.integers(sod, len(bad) - 2))] = int(rng.integers(0, 256))
+            out = ob.Decoder(resilient=True, lib=emu_lib).decode(bytes(bad))
+            assert len(out) == p.num_comps and out[0].shape == (kw["height"], kw["width"])
