@@ -53,6 +53,9 @@ typedef struct ojb_params {
   uint32_t nlt_all;
   uint32_t nlt_comp[16];
   uint32_t nlt_seq[16];
+  /* codestream::set_profile (ojph_codestream_local.cpp:1124-1133): 0 none, 1 "IMF", 2 "BROADCAST".  A profile
+   * checks the parameters (:292-535) and forces TLM + tile-part division by components. */
+  uint32_t profile;
 } ojb_params;
 
 typedef struct ojb_frame_info {

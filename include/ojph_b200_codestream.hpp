@@ -160,9 +160,10 @@ public:
 
   // ---- write side
   void set_planar(bool planar) { st.planar = planar ? 1 : 0; }
-  void set_profile(const char* name) {           // profiles only constrain parameters (ojph_codestream_local.cpp:172-262)
-    if (name == nullptr || (strcmp(name, "IMF") != 0 && strcmp(name, "BROADCAST") != 0))
-      raise("ojph error 0x000300A1: unknown or unsupported profile");
+  void set_profile(const char* name) {           // ojph_codestream_local.cpp:1124-1133; rules applied at write_headers
+    if (name != nullptr && strcmp(name, "IMF") == 0) st.p.profile = 1;
+    else if (name != nullptr && strcmp(name, "BROADCAST") == 0) st.p.profile = 2;
+    else raise("ojph error 0x000300A1: unkownn or unsupported profile");
   }
   void set_tilepart_divisions(bool at_resolutions, bool at_components) {
     st.p.tilepart_div = (at_resolutions ? 1u : 0u) | (at_components ? 2u : 0u);

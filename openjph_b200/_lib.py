@@ -25,6 +25,7 @@ class Params(C.Structure):
         ("coc_present", C.c_uint32 * 16), ("coc_reversible", C.c_uint32 * 16), ("coc_num_decomps", C.c_uint32 * 16),
         ("coc_block_w", C.c_uint32 * 16), ("coc_block_h", C.c_uint32 * 16),
         ("nlt_all", C.c_uint32), ("nlt_comp", C.c_uint32 * 16), ("nlt_seq", C.c_uint32 * 16),
+        ("profile", C.c_uint32),
     ]
 
 

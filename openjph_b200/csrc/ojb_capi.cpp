@@ -74,6 +74,8 @@ static void to_params(const ojb_params* s, Params& P) {
     std::stable_sort(order, order + n, [&](uint32_t a, uint32_t b) { return s->nlt_seq[a] < s->nlt_seq[b]; });
     for (uint32_t i = 0; i < n; ++i) P.set_nonlinear_transform(order[i], s->nlt_comp[order[i]] - 1);
   }
+  if (s->profile > 2) fail(0x000300A1, "unkownn or unsupported profile");
+  P.profile = s->profile;
   P.need_tlm = s->tlm != 0;
   P.tilepart_div = s->tilepart_div & 3u;
   P.planar = s->planar;

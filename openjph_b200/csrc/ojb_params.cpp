@@ -321,6 +321,7 @@ void Params::finalize_for_encode() {
   }
 
   nlt_check_validity();
+  if (profile) check_profile();
 
   // tile-part division rules (ojph_codestream_local.cpp:583-621)
   if ((prog_order == PO_LRCP || prog_order == PO_RLCP) && tilepart_div == TP_COMP)
@@ -397,6 +398,84 @@ uint32_t Params::nlt_type(uint32_t c) const {  // get_nonlinear_transform + the 
          "(bit_depth = %d, is_signed = %s) from NLT marker segment, for component %d", comps[c].bit_depth,
          comps[c].is_signed ? "True" : "False", bd, is ? "True" : "False", c);
   return e->Tnlt == 3 ? 3u : 0u;
+}
+
+//------------------------------------------------------------------------------------------
+// IMF / BROADCAST profiles: parameter rules only -- but they also switch TLM on and force tile-part
+// division by components, so they change the bytes (check_imf_validity :292-455,
+// check_broadcast_validity :458-535)
+//------------------------------------------------------------------------------------------
+void Params::check_profile() {
+  const bool imf = profile == 1;
+  const char* nm = imf ? "IMF" : "broadcast";
+  const uint32_t base = imf ? 0x000300C0u : 0x000300B0u;       // the reference's error code blocks
+  const uint32_t nc = num_comps();
+  const bool rev = reversible();
+  // (the reference's frame-size tests for the 2K / 4K / 8K IMF levels are written `flag &= true` and never
+  // reject anything, :302-330; the levels only differ in the decomposition ceilings below)
+  bool lvl[3] = { true, true, true };
+  if (XOsiz || YOsiz) fail(base + (imf ? 3 : 1), "For %s profile, image offset (XOsiz, YOsiz) has to be 0.", nm);
+  if (XTOsiz || YTOsiz) fail(base + (imf ? 4 : 2), "For %s profile, tile offset (XTOsiz, YTOsiz) has to be 0.", nm);
+  if (nc > (imf ? 3u : 4u))
+    fail(base + (imf ? 5 : 3), "For %s profile, the number of components has to be less  or equal to %d", nm, imf ? 3 : 4);
+  bool plain = true, x422 = true;                                // 4:4:4, or 4:2:2 on components 1 and 2
+  for (uint32_t c = 0; c < nc; ++c) {
+    if (comps[c].dy != 1) plain = x422 = false;
+    if (comps[c].dx != 1) plain = false;
+    if (comps[c].dx != ((c == 1 || c == 2) ? 2u : 1u)) x422 = false;
+  }
+  if (!plain && !x422)
+    fail(base + (imf ? 6 : 4), "For %s profile, either no component downsampling is used, or the x-dimension of the 2nd "
+         "and 3rd components is downsampled by 2.", nm);
+  for (uint32_t c = 0; c < nc; ++c)
+    if (comps[c].bit_depth < 8 || comps[c].bit_depth > (imf ? 16u : 12u) || comps[c].is_signed)
+      fail(base + (imf ? 7 : 5), "For %s profile, compnent bit_depth has to be between 8 and %d bits inclusively, and the "
+           "samples must be unsigned", nm, imf ? 16 : 12);
+  if (imf) {
+    if (log_cb_w() != 5 || log_cb_h() != 5)
+      fail(0x000300C8, "For IMF profile, codeblock dimensions are restricted. Use \"-block_size {32,32}\" at the commandline");
+  } else {
+    if (num_decomps == 0 || num_decomps > 5)
+      fail(0x000300B6, "For broadcast profile, number of decompositions has to be between1 and 5 inclusively.");
+    if (log_cb_w() < 5 || log_cb_w() > 7)
+      fail(0x000300B7, "For broadcast profile, codeblock dimensions are restricted such that codeblock width has to be "
+           "either 32, 64, or 128.");
+    if (log_cb_h() < 5 || log_cb_h() > 7)
+      fail(0x000300B8, "For broadcast profile, codeblock dimensions are restricted such that codeblock height has to be "
+           "either 32, 64, or 128.");
+  }
+  // precincts: 128x128 at the coarsest resolution, 256x256 above (the reference's loop keeps only the test of
+  // the LAST resolution when there is more than one -- reproduced)
+  bool pz = log_pp_w(0) == 7 && log_pp_h(0) == 7;
+  for (uint32_t r = 1; r <= num_decomps; ++r) pz = log_pp_w(r) == 8 && log_pp_h(r) == 8;
+  if (!pz) fail(base + 9, "For %s profile, precinct sizes are restricted. Use \"-precincts {128,128},{256,256}\" at the commandline", nm);
+  if (prog_order != PO_CPRL)
+    fail(base + 10, "For %s profile, the CPRL progression order must be used. Use \"-prog_order CPRL\".", nm);
+  const uint32_t ntiles = div_ceil(Xsiz, XTsiz) * div_ceil(Ysiz, YTsiz);
+  if (imf) {
+    for (int i = 0; i < 3; ++i) lvl[i] = num_decomps <= 5u + (uint32_t)i;
+    if (num_decomps == 0 || !(lvl[0] || lvl[1] || lvl[2]))
+      fail(0x000300CB, "Number of decompositions does not match the IMF profile dictated by wavelet reversibility and "
+           "image dimensions.");
+    if (ntiles > 1) {
+      if (!rev) fail(0x000300CC, "Lossy IMF profile must have one tile.");
+      // square tiles of 1024 / 2048 / 4096, and enough tile width for the decomposition count
+      const uint32_t tw = XTsiz, th = YTsiz;
+      auto deep = [&](int top) {        // top: how many (width, levels) pairs the level allows
+        static const uint32_t w[4] = { 1024, 2048, 4096, 8192 };
+        for (int i = 0; i <= top; ++i) if (tw >= w[i] && num_decomps <= 4u + (uint32_t)i) return true;
+        return false;
+      };
+      auto square = [&](int top) { for (int i = 0; i <= top; ++i) if (tw == (1024u << i) && th == (1024u << i)) return true; return false; };
+      const bool ok2 = lvl[0] && square(0) && deep(1), ok4 = lvl[1] && square(1) && deep(2), ok8 = lvl[2] && square(2) && deep(3);
+      if (!ok2 && !ok4 && !ok8)
+        fail(0x000300CD, "Number of decompositions does not match the IMF profile dictated by wavelet reversibility and "
+             "image dimensions and tiles.");
+    }
+  } else if (ntiles != 1 && ntiles != 4)
+    fail(0x000300BB, "The broadcast profile can only have 1 or 4 tiles");
+  need_tlm = true;
+  tilepart_div = TP_COMP;                   // (the reference warns when it has to correct this)
 }
 
 static void write_quant(std::vector<uint8_t>& o, const QuantSet& q, uint32_t nc) {

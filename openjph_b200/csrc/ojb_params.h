@@ -101,6 +101,7 @@ struct Params {
   uint32_t Pcap = 0x00020000;
   uint16_t Ccap0 = 0;
   // ---- encoder options
+  uint32_t profile = 0;                     // codestream::set_profile: 0 none, 1 IMF, 2 BROADCAST
   bool need_tlm = false;
   uint32_t tilepart_div = TP_NONE;
   int planar = -1;
@@ -155,6 +156,9 @@ struct Params {
   // the transform in force for component c (0 or 3); raises on a BDnlt / SIZ mismatch as tile setup does
   uint32_t nlt_type(uint32_t c) const;
   bool nlt_any() const { if (nlt_all.enabled) return true; for (const NltEntry& e : nlt) if (e.enabled) return true; return false; }
+
+  // profile rules (check_imf_validity / check_broadcast_validity, ojph_codestream_local.cpp:292-535)
+  void check_profile();
 
   // setters used by the C-ABI (same argument checks as ojph::param_cod / param_qcd setters)
   void set_block_dims(uint32_t w, uint32_t h);                      // ojph_params.cpp:170-181

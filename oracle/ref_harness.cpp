@@ -99,6 +99,7 @@ struct ojr_params {
   uint32_t coc_present[16], coc_reversible[16], coc_num_decomps[16], coc_block_w[16], coc_block_h[16];
   // NLT: 0 = not set, else 1 + type; nlt_seq = order of the per-component calls
   uint32_t nlt_all, nlt_comp[16], nlt_seq[16];
+  uint32_t profile;                // 0 none, 1 IMF, 2 BROADCAST
 };
 
 static char g_err[512] = "";
@@ -163,6 +164,7 @@ int ojr_encode(const ojr_params* p, const int32_t* const* planes,
     // the apps always set planar explicitly (ojph_compress.cpp:763,868,1021); the
     // library default (planar = colour_transform, ojph_codestream_local.cpp:623) is unusable
     cs.set_planar(p->planar > 0);
+    if (p->profile) cs.set_profile(p->profile == 1 ? "IMF" : "BROADCAST");
     if (p->tlm) cs.request_tlm_marker(true);
     if (p->tilepart_div) cs.set_tilepart_divisions((p->tilepart_div & 1) != 0,
                                                    (p->tilepart_div & 2) != 0);
