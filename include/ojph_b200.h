@@ -56,6 +56,16 @@ typedef struct ojb_params {
   /* codestream::set_profile (ojph_codestream_local.cpp:1124-1133): 0 none, 1 "IMF", 2 "BROADCAST".  A profile
    * checks the parameters (:292-535) and forces TLM + tile-part division by components. */
   uint32_t profile;
+  /* per-component quantisation (QCC): param_qcd::set_irrev_quant(comp, delta) and set_qfactor(comp, ctype,
+   * qfactor) (ojph_params.cpp:2011-2035).  qcc_calls[c] bit 0: the delta call was made, bit 1: the qfactor
+   * call; *_seq give the order of ALL quantisation calls (the global qstep / qfactor above count as made
+   * first): the reference's per-component delta call lands on the component's QCC only if one already exists
+   * (made by an earlier per-component qfactor call) and on the global QCD otherwise, so order matters. */
+  uint32_t qcc_calls[16];
+  float    qcc_qstep[16];
+  uint32_t qcc_qstep_seq[16];
+  uint32_t qcc_qfactor[16], qcc_ctype[16];     /* ctype: 0 Y, 1 Cb, 2 Cr */
+  uint32_t qcc_qfactor_seq[16];
 } ojb_params;
 
 typedef struct ojb_frame_info {

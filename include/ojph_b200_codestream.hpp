@@ -30,7 +30,7 @@ struct state {                                   // what write_headers / read_he
   ojb_frame_info info;                           // decode side, after read_headers
   bool reading = false;
   int planar = -1;
-  uint32_t nlt_calls = 0;
+  uint32_t nlt_calls = 0, q_calls = 0;
   state() { ojb_params_default(&p); memset(&info, 0, sizeof(info)); }
 };
 
@@ -94,8 +94,19 @@ class param_qcd {                                // ojph_params.h:186-250
   state* s;
 public:
   explicit param_qcd(state* st) : s(st) {}
+  enum comp_type : ui8 { OJPH_COMP_Y = 0, OJPH_COMP_CB = 1, OJPH_COMP_CR = 2 };
   void set_irrev_quant(float delta) { s->p.qstep = delta; }
   void set_qfactor(ui8 qfactor) { s->p.qfactor = qfactor; }
+  // per-component (QCC) forms, ojph_params.h:229-243; the call order is recorded (see ojb_params)
+  void set_irrev_quant(ui32 comp_idx, float delta) {
+    if (comp_idx >= 16) return;
+    s->p.qcc_calls[comp_idx] |= 1u; s->p.qcc_qstep[comp_idx] = delta; s->p.qcc_qstep_seq[comp_idx] = ++s->q_calls;
+  }
+  void set_qfactor(ui32 comp_idx, comp_type ctype, ui8 qfactor) {
+    if (comp_idx >= 16) return;
+    s->p.qcc_calls[comp_idx] |= 2u; s->p.qcc_ctype[comp_idx] = ctype; s->p.qcc_qfactor[comp_idx] = qfactor;
+    s->p.qcc_qfactor_seq[comp_idx] = ++s->q_calls;
+  }
 };
 
 class param_nlt {                                // ojph_params.h:299-342

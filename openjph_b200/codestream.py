@@ -25,7 +25,7 @@ class OjphError(RuntimeError):
 def make_params(width, height, num_comps=1, bit_depth=8, is_signed=False, num_decomps=5, block=(64, 64),
                 reversible=True, color_transform=False, prog_order="RPCL", qstep=-1.0, qfactor=0,
                 tile=(0, 0), offset=(0, 0), tile_offset=(0, 0), precincts=None, subsampling=None,
-                tlm=False, tilepart_div=0, planar=-1, coc=None, nlt=None, profile=None):
+                tlm=False, tilepart_div=0, planar=-1, coc=None, nlt=None, profile=None, qcc=None):
     p = _lib.Params()
     p.width, p.height = width, height
     p.off_x, p.off_y = offset
@@ -62,6 +62,13 @@ def make_params(width, height, num_comps=1, bit_depth=8, is_signed=False, num_de
         p.coc_num_decomps[c] = st.get("num_decomps", 5)
         p.coc_block_w[c], p.coc_block_h[c] = st.get("block", (64, 64))
     p.profile = {None: 0, "IMF": 1, "BROADCAST": 2}[profile]          # codestream::set_profile
+    # per-component quantisation calls in order: [("qstep", comp, delta) | ("qfactor", comp, ctype, q), ...]
+    for seq, call in enumerate(qcc or [], start=1):
+        c = call[1]
+        if call[0] == "qstep":
+            p.qcc_calls[c] |= 1; p.qcc_qstep[c] = call[2]; p.qcc_qstep_seq[c] = seq
+        else:
+            p.qcc_calls[c] |= 2; p.qcc_ctype[c], p.qcc_qfactor[c] = call[2], call[3]; p.qcc_qfactor_seq[c] = seq
     # param_nlt::set_nonlinear_transform calls, in order: {"all": 3, 1: 0, ...} (types 0 and 3)
     for seq, (c, t) in enumerate((nlt or {}).items()):
         if c == "all":

@@ -57,6 +57,25 @@ static void to_params(const ojb_params* s, Params& P) {
       P.qcd.qfactor = (uint8_t)s->qfactor;
     }
   }
+  {   // per-component quantisation calls, replayed in the order they were made (after the global ones)
+    struct Call { uint32_t seq, comp, kind; };
+    std::vector<Call> calls;
+    for (uint32_t c = 0; c < 16; ++c) {
+      if (s->qcc_calls[c] & 1u) calls.push_back(Call{ s->qcc_qstep_seq[c], c, 0 });
+      if (s->qcc_calls[c] & 2u) calls.push_back(Call{ s->qcc_qfactor_seq[c], c, 1 });
+    }
+    std::stable_sort(calls.begin(), calls.end(), [](const Call& a, const Call& b) { return a.seq < b.seq; });
+    for (const Call& k : calls) {
+      QuantSet* q = P.find_qcc(k.comp);
+      if (k.kind == 0) (q ? *q : P.qcd).base_delta = s->qcc_qstep[k.comp];        // set_delta(comp_idx, delta), :2011-2018
+      else {
+        if (s->qcc_qfactor[k.comp] < 1 || s->qcc_qfactor[k.comp] > 100)
+          fail(0x00050191, "Qfactor must be between 1 and 100, but was set to %i.", s->qcc_qfactor[k.comp]);
+        if (q == nullptr) q = &P.add_qcc(k.comp);
+        q->qfactor = (uint8_t)s->qcc_qfactor[k.comp]; q->ctype = (int)std::min(s->qcc_ctype[k.comp], 2u);
+      }
+    }
+  }
   for (uint32_t c = 0; c < s->num_comps; ++c) {
     if (!s->coc_present[c]) continue;
     CodStyle& cs = P.get_or_add_coc(c);

@@ -100,6 +100,9 @@ struct ojr_params {
   // NLT: 0 = not set, else 1 + type; nlt_seq = order of the per-component calls
   uint32_t nlt_all, nlt_comp[16], nlt_seq[16];
   uint32_t profile;                // 0 none, 1 IMF, 2 BROADCAST
+  // per-component quantisation calls (see include/ojph_b200.h)
+  uint32_t qcc_calls[16]; float qcc_qstep[16]; uint32_t qcc_qstep_seq[16];
+  uint32_t qcc_qfactor[16], qcc_ctype[16], qcc_qfactor_seq[16];
 };
 
 static char g_err[512] = "";
@@ -161,6 +164,12 @@ int ojr_encode(const ojr_params* p, const int32_t* const* planes,
       if (p->qstep > 0.0f) cs.access_qcd().set_irrev_quant(p->qstep);
       if (p->qfactor) cs.access_qcd().set_qfactor((ui8)p->qfactor);
     }
+    for (uint32_t k = 1; k <= 32; ++k)              // the per-component calls in their recorded order
+      for (uint32_t c = 0; c < 16; ++c) {
+        if ((p->qcc_calls[c] & 1) && p->qcc_qstep_seq[c] == k) cs.access_qcd().set_irrev_quant(c, p->qcc_qstep[c]);
+        if ((p->qcc_calls[c] & 2) && p->qcc_qfactor_seq[c] == k)
+          cs.access_qcd().set_qfactor(c, ojph::param_qcd::ui8_2_comp_type((ui8)p->qcc_ctype[c]), (ui8)p->qcc_qfactor[c]);
+      }
     // the apps always set planar explicitly (ojph_compress.cpp:763,868,1021); the
     // library default (planar = colour_transform, ojph_codestream_local.cpp:623) is unusable
     cs.set_planar(p->planar > 0);
