@@ -171,6 +171,18 @@ int ojb_dec_read_headers(ojb_decoder* d, const uint8_t* j2c, uint64_t len, uint3
  * the top skipped_res_for_read (>= skipped_res_for_recon) are not decoded and read as zero. */
 int ojb_dec_restrict_input_resolution(ojb_decoder* d, uint32_t skipped_res_for_read, uint32_t skipped_res_for_recon,
                                       ojb_frame_info* info);
+/* the getters of ojph::param_cod on the read side (ojph_params.h:132-158), for one component (its COC when
+ * it has one, else the COD), and of param_siz that ojb_frame_info does not carry */
+typedef struct ojb_coding_style {
+  uint32_t num_decomps, reversible, color_transform;
+  uint32_t block_w, block_h;                 /* get_block_dims; log2 = get_log_block_dims */
+  uint32_t precinct_w[33], precinct_h[33];   /* get_precinct_size(level), 0 .. num_decomps */
+  uint32_t prog_order;                       /* get_progression_order: 0 LRCP 1 RLCP 2 RPCL 3 PCRL 4 CPRL */
+  uint32_t num_layers;
+  uint32_t may_use_sop, use_eph, vertical_causality;
+  uint32_t tile_w, tile_h, tile_off_x, tile_off_y;   /* param_siz::get_tile_size / get_tile_offset */
+} ojb_coding_style;
+int ojb_dec_get_coding_style(ojb_decoder* d, uint32_t comp, ojb_coding_style* out);
 /* codestream::create() + the pull() loop: decodes every component into planes */
 int ojb_dec_decode_frame(ojb_decoder* d, void* const* planes, const uint32_t* strides);
 int ojb_dec_decode_resident(ojb_decoder* d);             /* result stays in the device image buffer */

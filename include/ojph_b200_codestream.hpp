@@ -28,11 +28,19 @@ inline void check(int rc) { if (rc != 0) raise(ojb_last_error()); }
 struct state {                                   // what write_headers / read_headers consume
   ojb_params p;
   ojb_frame_info info;                           // decode side, after read_headers
+  ojb_decoder* dec = nullptr;                    // read side: for the per-component getters
   bool reading = false;
   int planar = -1;
   uint32_t nlt_calls = 0, q_calls = 0;
   state() { ojb_params_default(&p); memset(&info, 0, sizeof(info)); }
 };
+
+inline ojb_coding_style state_style(const state* s, ui32 c) {
+  ojb_coding_style cs; memset(&cs, 0, sizeof(cs));
+  if (s->dec == nullptr) raise("ojph error: coding-style getters need read_headers first");
+  check(ojb_dec_get_coding_style(s->dec, c, &cs));
+  return cs;
+}
 
 class param_siz {                                // ojph_params.h:55-101
   state* s;
@@ -51,18 +59,22 @@ public:
     s->p.dx[c] = downsampling.x; s->p.dy[c] = downsampling.y;
     s->p.bit_depth[c] = bit_depth; s->p.is_signed[c] = is_signed ? 1u : 0u;
   }
+  ojb_coding_style style(ui32 c) const { return state_style(s, c); }
   point get_image_extent() const { return s->reading ? point(s->info.width, s->info.height) : point(s->p.width, s->p.height); }
   point get_image_offset() const { return s->reading ? point(s->info.off_x, s->info.off_y) : point(s->p.off_x, s->p.off_y); }
   ui32 get_num_components() const { return s->reading ? s->info.num_comps : s->p.num_comps; }
   ui32 get_bit_depth(ui32 c) const { return s->reading ? s->info.bit_depth[c] : s->p.bit_depth[c]; }
   bool is_signed(ui32 c) const { return (s->reading ? s->info.is_signed[c] : s->p.is_signed[c]) != 0; }
   point get_downsampling(ui32 c) const { return s->reading ? point(s->info.dx[c], s->info.dy[c]) : point(s->p.dx[c], s->p.dy[c]); }
+  size get_tile_size() const { if (!s->reading) return size(s->p.tile_w, s->p.tile_h); ojb_coding_style cs = style(0); return size(cs.tile_w, cs.tile_h); }
+  point get_tile_offset() const { if (!s->reading) return point(s->p.tile_off_x, s->p.tile_off_y); ojb_coding_style cs = style(0); return point(cs.tile_off_x, cs.tile_off_y); }
   ui32 get_recon_width(ui32 c) const { return s->info.comp_w[c]; }
   ui32 get_recon_height(ui32 c) const { return s->info.comp_h[c]; }
 };
 
 class param_cod {                                // ojph_params.h:103-160
   state* s;
+  static ui32 lg(ui32 v) { ui32 n = 0; while ((1u << n) < v) ++n; return n; }
   void coc(ui32 c) { if (c >= 16) raise("ojph error: per-component coding styles are limited to 16 components"); s->p.coc_present[c] = 1; }
 public:
   explicit param_cod(state* st) : s(st) {}
@@ -85,6 +97,24 @@ public:
   void set_num_decomposition(ui32 comp_idx, ui32 n) { coc(comp_idx); s->p.coc_num_decomps[comp_idx] = n; }
   void set_block_dims(ui32 comp_idx, ui32 w, ui32 h) { coc(comp_idx); s->p.coc_block_w[comp_idx] = w; s->p.coc_block_h[comp_idx] = h; }
   void set_reversible(ui32 comp_idx, bool on) { coc(comp_idx); s->p.coc_reversible[comp_idx] = on ? 1u : 0u; }
+  // read-side getters (after read_headers): the component's COC when it has one, else the COD
+  size get_block_dims(ui32 c = 0) const { ojb_coding_style t = state_style(s, c); return size(t.block_w, t.block_h); }
+  size get_log_block_dims(ui32 c = 0) const { ojb_coding_style t = state_style(s, c); return size(lg(t.block_w), lg(t.block_h)); }
+  size get_precinct_size(ui32 level_num) const { ojb_coding_style t = state_style(s, 0); return size(t.precinct_w[level_num], t.precinct_h[level_num]); }
+  size get_precinct_size(ui32 c, ui32 level_num) const { ojb_coding_style t = state_style(s, c); return size(t.precinct_w[level_num], t.precinct_h[level_num]); }
+  size get_log_precinct_size(ui32 level_num) const { size p = get_precinct_size(level_num); return size(lg(p.w), lg(p.h)); }
+  size get_log_precinct_size(ui32 c, ui32 level_num) const { size p = get_precinct_size(c, level_num); return size(lg(p.w), lg(p.h)); }
+  int get_progression_order() const { return s->reading ? (int)state_style(s, 0).prog_order : (int)s->p.prog_order; }
+  const char* get_progression_order_as_string() const {
+    static const char* names[5] = { "LRCP", "RLCP", "RPCL", "PCRL", "CPRL" };
+    return names[get_progression_order() % 5];
+  }
+  int get_num_layers() const { return s->reading ? (int)state_style(s, 0).num_layers : 1; }
+  bool packets_may_use_sop() const { return s->reading && state_style(s, 0).may_use_sop != 0; }
+  bool packets_use_eph() const { return s->reading && state_style(s, 0).use_eph != 0; }
+  bool get_block_vertical_causality(ui32 c = 0) const { return s->reading && state_style(s, c).vertical_causality != 0; }
+  ui32 get_num_decompositions(ui32 c) const { return s->reading ? state_style(s, c).num_decomps : (s->p.coc_present[c] ? s->p.coc_num_decomps[c] : s->p.num_decomps); }
+  bool is_reversible(ui32 c) const { return s->reading ? state_style(s, c).reversible != 0 : (s->p.coc_present[c] ? s->p.coc_reversible[c] != 0 : s->p.reversible != 0); }
   ui32 get_num_decompositions() const { return s->reading ? s->info.num_decomps : s->p.num_decomps; }
   bool is_reversible() const { return (s->reading ? s->info.reversible : s->p.reversible) != 0; }
   bool is_using_color_transform() const { return (s->reading ? s->info.color_transform : s->p.color_transform) != 0; }
@@ -179,7 +209,16 @@ public:
   void set_tilepart_divisions(bool at_resolutions, bool at_components) {
     st.p.tilepart_div = (at_resolutions ? 1u : 0u) | (at_components ? 2u : 0u);
   }
+  bool is_tilepart_division_at_resolutions() { return (st.p.tilepart_div & 1u) != 0; }
+  bool is_tilepart_division_at_components() { return (st.p.tilepart_div & 2u) != 0; }
   void request_tlm_marker(bool needed) { st.p.tlm = needed ? 1u : 0u; }
+  bool is_tlm_requested() { return st.p.tlm != 0; }
+  // codestream::restart(): back to a freshly constructed object, device buffers kept for the next frame
+  void restart() {
+    if (out) { out->close(); out = nullptr; }
+    ojb_encoder* e = enc; ojb_decoder* d = dec;
+    st = state(); enc = e; dec = d; j2c.clear(); resilient = false;
+  }
   void write_headers(outfile_base* file, const comment_exchange* comments = nullptr, ui32 num_comments = 0) {
     st.p.planar = st.planar;
     if (enc == nullptr) enc = ojb_enc_create();
@@ -218,7 +257,7 @@ public:
     if (dec == nullptr) raise(ojb_last_error());
     if (resilient) ojb_dec_enable_resilience(dec);
     check(ojb_dec_read_headers(dec, j2c.data(), j2c.size(), OJB_I32, &st.info));
-    st.reading = true;
+    st.reading = true; st.dec = dec;
   }
   void restrict_input_resolution(ui32 skipped_res_for_data, ui32 skipped_res_for_recon) {
     check(ojb_dec_restrict_input_resolution(dec, skipped_res_for_data, skipped_res_for_recon, &st.info));
@@ -237,7 +276,7 @@ public:
 
   void close() {
     if (enc) { ojb_enc_destroy(enc); enc = nullptr; }
-    if (dec) { ojb_dec_destroy(dec); dec = nullptr; }
+    if (dec) { ojb_dec_destroy(dec); dec = nullptr; st.dec = nullptr; }
     if (out) { out->close(); out = nullptr; }
   }
 

@@ -41,6 +41,16 @@ class FrameInfo(C.Structure):
     ]
 
 
+class CodingStyle(C.Structure):
+    _fields_ = [
+        ("num_decomps", C.c_uint32), ("reversible", C.c_uint32), ("color_transform", C.c_uint32),
+        ("block_w", C.c_uint32), ("block_h", C.c_uint32), ("precinct_w", C.c_uint32 * 33), ("precinct_h", C.c_uint32 * 33),
+        ("prog_order", C.c_uint32), ("num_layers", C.c_uint32), ("may_use_sop", C.c_uint32), ("use_eph", C.c_uint32),
+        ("vertical_causality", C.c_uint32), ("tile_w", C.c_uint32), ("tile_h", C.c_uint32), ("tile_off_x", C.c_uint32),
+        ("tile_off_y", C.c_uint32),
+    ]
+
+
 class Comment(C.Structure):
     _fields_ = [("data", C.c_void_p), ("len", C.c_uint16), ("rcom", C.c_uint16)]
 
@@ -89,6 +99,7 @@ SYMBOLS = {
     "ojb_dec_decode_frame": (_I, [_VP, C.POINTER(_VP), C.POINTER(_U32)]),
     "ojb_dec_decode_resident": (_I, [_VP]),
     "ojb_dec_restrict_input_resolution": (_I, [_VP, _U32, _U32, C.POINTER(FrameInfo)]),
+    "ojb_dec_get_coding_style": (_I, [_VP, _U32, C.POINTER(CodingStyle)]),
     "ojb_dec_set_planar": (_I, [_VP, _I]),
     "ojb_dec_begin_pull": (_I, [_VP]),
     "ojb_dec_pull": (_VP, [_VP, C.POINTER(_U32)]),

@@ -230,6 +230,12 @@ class Decoder(_Base):
         self.info = fi
         return fi
 
+    def coding_style(self, comp=0):
+        """the read-side getters of ojph::param_cod / param_siz for one component (after read_headers)"""
+        cs = _lib.CodingStyle()
+        self._check(self.L.ojb_dec_get_coding_style(self.h, comp, C.byref(cs)))
+        return cs
+
     def restrict_input_resolution(self, skipped_res_for_read, skipped_res_for_recon):
         """codestream::restrict_input_resolution: after read_headers, before decode"""
         self._check(self.L.ojb_dec_restrict_input_resolution(self.h, skipped_res_for_read, skipped_res_for_recon,

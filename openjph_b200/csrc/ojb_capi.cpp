@@ -403,6 +403,25 @@ int ojb_dec_decode_frame(ojb_decoder* d, void* const* planes, const uint32_t* st
     d->dec.decode(planes, strides, false);
   });
 }
+int ojb_dec_get_coding_style(ojb_decoder* d, uint32_t comp, ojb_coding_style* out) {
+  return guarded([&] {
+    if (!d->have_headers) fail(0x000B0015, "read_headers has not been called");
+    const Params& P = d->dec.params;
+    if (comp >= P.num_comps()) fail(0x000B0036, "component %u does not exist", comp);
+    memset(out, 0, sizeof(*out));
+    out->num_decomps = P.decomps(comp); out->reversible = P.reversible(comp) ? 1u : 0u;
+    out->color_transform = P.color_transform() ? 1u : 0u;
+    out->block_w = 1u << P.log_cb_w(comp); out->block_h = 1u << P.log_cb_h(comp);
+    for (uint32_t r = 0; r <= P.decomps(comp) && r < 33; ++r) {
+      out->precinct_w[r] = 1u << P.log_pp_w(comp, r); out->precinct_h[r] = 1u << P.log_pp_h(comp, r);
+    }
+    out->prog_order = P.prog_order; out->num_layers = P.num_layers;
+    out->may_use_sop = P.uses_sop() ? 1u : 0u; out->use_eph = P.uses_eph() ? 1u : 0u;
+    out->vertical_causality = P.stripe_causal(comp) ? 1u : 0u;
+    out->tile_w = P.XTsiz; out->tile_h = P.YTsiz; out->tile_off_x = P.XTOsiz; out->tile_off_y = P.YTOsiz;
+  });
+}
+
 int ojb_dec_set_planar(ojb_decoder* d, int planar) { d->planar = planar ? 1 : 0; return 0; }
 
 int ojb_dec_begin_pull(ojb_decoder* d) {

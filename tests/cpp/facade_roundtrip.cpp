@@ -70,6 +70,15 @@ static std::vector<std::vector<si32>> expand(const std::vector<ui8>& j2c, ui32 s
   f.open(j2c.data(), j2c.size());
   cs.read_headers(&f);
   if (skip) cs.restrict_input_resolution(skip, skip);          // ojph_expand -skip_res
+  {   // the read-side getters an application may print (ojph_expand.cpp); both classes must agree
+    auto cod = cs.access_cod();
+    auto sz = cs.access_siz();
+    printf("  cod: %u levels, blocks %ux%u, precinct(0) %ux%u, order %s, layers %d, sop %d eph %d causal %d, tile %ux%u\n",
+           cod.get_num_decompositions(), cod.get_block_dims().w, cod.get_block_dims().h,
+           cod.get_precinct_size(0).w, cod.get_precinct_size(0).h, cod.get_progression_order_as_string(),
+           cod.get_num_layers(), (int)cod.packets_may_use_sop(), (int)cod.packets_use_eph(),
+           (int)cod.get_block_vertical_causality(), sz.get_tile_size().w, sz.get_tile_size().h);
+  }
   auto siz = cs.access_siz();
   const ui32 nc = siz.get_num_components();
   std::vector<std::vector<si32>> planes(nc);

@@ -71,3 +71,18 @@ def test_mixed_reversibility_gpu(gpu_lib, ref):
 @pytest.mark.gpu
 def test_per_component_styles_gpu(gpu_lib, ref):
     _check_varied(None, ref)
+
+
+def test_read_side_getters(emu_lib, ref):
+    """param_cod / param_siz getters after read_headers, per component (COC aware)"""
+    p = ob.make_params(300, 200, 3, 8, num_decomps=4, reversible=False, qstep=0.02, planar=1, tile=(256, 128),
+                       precincts=[(64, 64), (128, 128)], prog_order="PCRL", block=(32, 16),
+                       coc={1: dict(reversible=True, num_decomps=2, block=(64, 64))})
+    cs = ref.encode(p, cases.frame_for(p))
+    dec = ob.Decoder(lib=emu_lib)
+    dec.read_headers(cs)
+    a, b = dec.coding_style(0), dec.coding_style(1)
+    assert (a.num_decomps, a.reversible, a.block_w, a.block_h, a.prog_order) == (4, 0, 32, 16, 3)
+    assert (a.precinct_w[0], a.precinct_w[1], a.precinct_w[4]) == (64, 128, 128) and a.num_layers == 1
+    assert (b.num_decomps, b.reversible, b.block_w, b.block_h) == (2, 1, 64, 64) and b.precinct_w[0] == 32768
+    assert (a.tile_w, a.tile_h, a.tile_off_x) == (256, 128, 0)
