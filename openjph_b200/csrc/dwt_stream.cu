@@ -117,6 +117,7 @@ struct StripGeom {
   bool has[4];              // output lane and column u0+i inside [x0, x1)
   bool lane_valid;          // any has[]
   bool interior;            // all four columns exist unmirrored (any lane, halo included)
+  bool fast;                // warp-uniform: every lane's requests are whole aligned vectors (set by strip_fast_*)
   int R0, R1;               // output rows of this chunk [R0, R1), R0 even (absolute)
 };
 
@@ -133,6 +134,7 @@ __device__ __forceinline__ bool strip_setup(const DwtJob& J, uint32_t strip, uin
     g.lane_valid = g.lane_valid || g.has[i];
   }
   g.interior = g.u0 >= g.x0 && g.u0 + 3 < g.x1;
+  g.fast = false;
   const int ye = g.y0 & ~1;
   g.R0 = ye + (int)chunk * (int)J.chunk_rows;
   g.R1 = min(g.R0 + (int)J.chunk_rows, g.y1);
@@ -186,6 +188,45 @@ __device__ __forceinline__ void store2_w(uint32_t* base, uint32_t idx, uint32_t 
 template <typename T> __device__ __forceinline__ uint32_t as_bits(T v) { uint32_t r; memcpy(&r, &v, 4); return r; }
 template <typename T> __device__ __forceinline__ T from_bits(uint32_t v) { T r; memcpy(&r, &v, 4); return r; }
 
+// Warp-uniform decision, once per strip: are all requests of all lanes whole aligned vectors?  (True for every
+// strip that does not touch the left / right edge when offsets and strides are even enough, i.e. almost
+// always; the per-request tests above otherwise get if-converted and both variants are issued every time.)
+template <int NC, int SRC>
+__device__ __forceinline__ bool strip_fast_fwd(const DwtJob& J, const StripGeom& g) {
+  constexpr bool FIRST = SRC != SRC_COEF;
+  constexpr uint32_t ES = (SRC == SRC_U16) ? 2u : (SRC == SRC_U8 ? 1u : 4u);
+  bool ok = g.interior;
+  #pragma unroll
+  for (int k = 0; k < (FIRST ? NC : 1); ++k) {
+    const uint32_t off = FIRST ? (uint32_t)J.full_off[k] : (uint32_t)J.full_off[0] * 4u;
+    ok = ok && ((off + (uint32_t)g.c[0] * ES) % (4u * ES)) == 0 && ((J.full_stride[k] * ES) % (4u * ES)) == 0;
+  }
+  return __all_sync(0xFFFFFFFFu, ok);
+}
+template <int NC>
+__device__ __forceinline__ bool strip_fast_inv(const DwtJob& J, const StripGeom& g) {
+  bool ok = g.interior;
+  #pragma unroll
+  for (int i = 0; i < 2; ++i) {               // first column of the low (i = 0) and of the high (i = 1) band
+    const int ua = g.c[i] + g.x0;
+    const int bx = (ua >> 1) - ((i & 1) ? (g.x0 >> 1) : ((g.x0 + 1) >> 1));
+    // ... and the second column of the pair must be its neighbour
+    const int ub = g.c[i + 2] + g.x0;
+    const int bx2 = (ub >> 1) - ((i & 1) ? (g.x0 >> 1) : ((g.x0 + 1) >> 1));
+    ok = ok && bx2 == bx + 1;
+    #pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      #pragma unroll
+      for (int b = i; b < 4; b += 2) {
+        const uint32_t off = (b == 0 && !J.last) ? (uint32_t)J.ll_off[k] : (uint32_t)J.band_off[k][b];
+        const uint32_t str = (b == 0 && !J.last) ? J.ll_stride[k] : J.band_stride[k][b];
+        ok = ok && (((off + (uint32_t)bx) | str) & 1u) == 0;
+      }
+    }
+  }
+  return __all_sync(0xFFFFFFFFu, ok);
+}
+
 // ---- forward ---------------------------------------------------------------------------------
 // request source row v (mirrored into the resolution) into the row slot `st` (lane offset included)
 template <int NC, int SRC>
@@ -194,6 +235,17 @@ __device__ __forceinline__ void fwd_issue_row(const DwtJob& J, const StripGeom& 
 {
   constexpr bool FIRST = SRC != SRC_COEF;     // the full-resolution side is the image
   const int vr = reflect_coord(v, g.y0, g.y1 - 1) - g.y0;
+  if (g.fast) {                               // one aligned vector per component, no per-request tests
+    constexpr uint32_t ES = (SRC == SRC_U16) ? 2u : (SRC == SRC_U8 ? 1u : 4u);
+    const unsigned char* base = FIRST ? reinterpret_cast<const unsigned char*>(image) : reinterpret_cast<const unsigned char*>(coef);
+    #pragma unroll
+    for (int k = 0; k < (FIRST ? NC : 1); ++k) {
+      const uint32_t o = (FIRST ? (uint32_t)J.full_off[k] : (uint32_t)J.full_off[0] * 4u) +
+                         ((uint32_t)vr * J.full_stride[k] + (uint32_t)g.c[0]) * ES;
+      cp_async<4 * ES>(st + (size_t)k * 32 * slot, base + o);
+    }
+    return;
+  }
   if (FIRST) {
     const unsigned char* base = reinterpret_cast<const unsigned char*>(image);
     #pragma unroll
@@ -348,6 +400,7 @@ dwt_fwd_stream_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, const voi
   if (strip >= J.tiles_x) return;
   StripGeom g;
   if (!strip_setup(J, strip, chunk, lane, g)) return;
+  g.fast = strip_fast_fwd<NC, SRC>(J, g);
 
   // the lane's FIFO: DS_STAGES stages of one row pair each
   OJB_DYN_SMEM(unsigned char, s_ring);
@@ -456,6 +509,18 @@ __device__ __forceinline__ void inv_issue_pair(const DwtJob& J, const StripGeom&
   }
   const int va = reflect_coord(2 * j, g.y0, g.y1 - 1), vb = reflect_coord(2 * j + 1, g.y0, g.y1 - 1);
   const int byl = (va >> 1) - ((g.y0 + 1) >> 1), byh = (vb >> 1) - (g.y0 >> 1);
+  if (g.fast) {                               // every pair is one aligned 8-byte request
+    #pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      #pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const uint32_t row = (b == 0 && !J.last) ? (uint32_t)J.ll_off[k] + (uint32_t)byl * J.ll_stride[k]
+                                                 : (uint32_t)J.band_off[k][b] + (uint32_t)(b < 2 ? byl : byh) * J.band_stride[k][b];
+        cp_async<8>(st + (size_t)(k * 4 + b) * 32 * 8, coef + (row + (uint32_t)bx[b & 1]));
+      }
+    }
+    return;
+  }
   #pragma unroll
   for (int k = 0; k < NC; ++k) {
     #pragma unroll
@@ -637,6 +702,7 @@ dwt_inv_stream_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, void* __r
   if (strip >= J.tiles_x) return;
   StripGeom g;
   if (!strip_setup(J, strip, chunk, lane, g)) return;
+  g.fast = strip_fast_inv<NC>(J, g);
 
   OJB_DYN_SMEM(unsigned char, s_ring);
   constexpr int NS = (NC == 3) ? DS_STAGES - 1 : DS_STAGES;       // three components: 3 KB per stage
