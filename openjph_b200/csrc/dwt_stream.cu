@@ -19,6 +19,7 @@
 // Level 1 fuses sample fetch, level shift / int->float and RCT / ICT on load (forward) and the
 // inverse of those on store (inverse); quantisation to MSB-aligned sign-magnitude is fused into
 // the sub-band store (forward).
+#include <cstdlib>
 #include "dwt_common.cuh"
 #include "ojb_async.cuh"
 #include "ojb_kernels.h"
@@ -800,16 +801,21 @@ void launch_inv(const DwtJob* jobs, uint32_t njobs, uint32_t ctas, void* image, 
 } // namespace
 
 // strips across / row chunks down; the launch uses ceil(strips / DS_WARPS) * chunks CTAs
-void dwt_stream_tiling(uint32_t x0, uint32_t y0, uint32_t w, uint32_t h, bool reversible,
+void dwt_stream_tiling(uint32_t x0, uint32_t y0, uint32_t w, uint32_t h, bool reversible, bool forward,
                        uint32_t& strips, uint32_t& chunks, uint32_t& chunk_rows, uint32_t& ctas)
 {
-  (void)reversible;
   const uint32_t SW = DS_COLS * DS_VALID;          // output columns per strip
   const uint32_t ue = x0 & ~1u, ye = y0 & ~1u;
   strips = (x0 + w - ue + SW - 1) / SW;
-  // a warp walks its chunk serially (one dependent memory round trip per row pair): small
-  // resolutions get shorter chunks so the launch still fills the machine
-  chunk_rows = DS_ROWS;
+  // Rows per warp chunk.  A warp walks its chunk serially and re-reads the 2 (5/3) or 4 (9/7) rows above it;
+  // measured on the 8K frame (tools/chunk_probe.sh): the forward kernels like short chunks (many small CTAs
+  // even out the waves: 0.43 ms at 16 rows vs 0.49 at 64 for 5/3, 0.68 at 32 vs 0.70 for 9/7), the inverse
+  // ones are flat (5/3) or want the long ones (9/7: 0.58 at 64 vs 0.67 at 16)
+  chunk_rows = forward ? (reversible ? 16u : 32u) : (uint32_t)DS_ROWS;
+  {   // tuning knob: rows per warp chunk of the large resolutions (even)
+    static const uint32_t knob = [] { const char* e = getenv("OJB_DWT_CHUNK_ROWS"); return e ? (uint32_t)atoi(e) & ~1u : 0u; }();
+    if (knob >= 8) chunk_rows = knob;
+  }
   while (chunk_rows > 8 && strips * ((y0 + h - ye + chunk_rows - 1) / chunk_rows) < 148u * 8u) chunk_rows >>= 1;
   chunks = (y0 + h - ye + chunk_rows - 1) / chunk_rows;
   ctas = ((strips + DS_WARPS - 1) / DS_WARPS) * chunks;

@@ -173,7 +173,7 @@ void CodecBase::build_dwt_jobs(bool forward) {
         uint32_t gi, n;
         if (stream) {
           gi = gw + (j.first ? (k == 3 ? 0u : 1u) : 2u);
-          dwt_stream_tiling(j.x0, j.y0, j.w, j.h, rev, j.tiles_x, j.tiles_y, j.chunk_rows, n);
+          dwt_stream_tiling(j.x0, j.y0, j.w, j.h, rev, forward, j.tiles_x, j.tiles_y, j.chunk_rows, n);
         } else {
           gi = gw + 3;
           dwt_tiling(j.x0, j.y0, j.w, j.h, j.tiles_x, j.tiles_y);

@@ -32,7 +32,7 @@ void launch_dwt_fwd(const DwtJob* jobs, uint32_t njobs, uint32_t total_ctas, boo
 void launch_dwt_inv(const DwtJob* jobs, uint32_t njobs, uint32_t total_ctas, bool reversible,
                     uint32_t max_ncomp, void* image, uint32_t* coef, cudaStream_t st);
 // register-streaming fast path (dwt_stream.cu) for resolutions of at least 2x2
-void dwt_stream_tiling(uint32_t x0, uint32_t y0, uint32_t w, uint32_t h, bool reversible,
+void dwt_stream_tiling(uint32_t x0, uint32_t y0, uint32_t w, uint32_t h, bool reversible, bool forward,
                        uint32_t& strips, uint32_t& chunks, uint32_t& chunk_rows, uint32_t& ctas);
 void launch_dwt_fwd_stream(const DwtJob* jobs, uint32_t njobs, uint32_t total_ctas, bool reversible,
                            uint32_t ncomp, bool first, uint32_t src_type, const void* image, uint32_t* coef,
