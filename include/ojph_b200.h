@@ -146,6 +146,10 @@ void ojb_enc_timings(ojb_encoder* e, float* ms8);
 /* last decode: [0] H2D codestream  [1] host packet parse (device idle)  [2] HT block decoder
  * [3] inverse DWT levels  [4] D2H image  [7] host ms */
 void ojb_dec_timings(ojb_decoder* d, float* ms8);
+/* diagnostics: absolute stage marks of the last call (ms since ojb_marks_reference()), for timeline tools */
+int ojb_marks_reference(void);
+void ojb_enc_marks(ojb_encoder* e, float* ms8);
+void ojb_dec_marks(ojb_decoder* d, float* ms8);
 uint32_t ojb_enc_num_blocks(ojb_encoder* e);
 /* parity hook: copy one sub-band's quantised sign-magnitude plane (what the block coder reads)
  * after an encode; out has band_w * band_h words */

@@ -78,6 +78,9 @@ SYMBOLS = {
     "ojb_enc_destroy": (None, [_VP]),
     "ojb_enc_configure": (_I, [_VP, C.POINTER(Params), _U32]),
     "ojb_enc_set_comments": (_I, [_VP, C.POINTER(Comment), _U32]),
+    "ojb_marks_reference": (_I, []),
+    "ojb_enc_marks": (None, [_VP, C.POINTER(C.c_float)]),
+    "ojb_dec_marks": (None, [_VP, C.POINTER(C.c_float)]),
     "ojb_enc_encode_raster": (_I, [_VP, _U32, _VP, C.c_uint64, _VP, C.c_uint64, C.POINTER(C.c_uint64)]),
     "ojb_dec_decode_raster": (_I, [_VP, _U32, _VP, C.c_uint64, C.POINTER(C.c_uint64)]),
     "ojb_enc_exchange": (_VP, [_VP, _VP, C.POINTER(_U32)]),

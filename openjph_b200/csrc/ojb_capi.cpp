@@ -345,6 +345,20 @@ void ojb_dec_timings(ojb_decoder* d, float* ms8) {
   for (int i = 0; i < 5; ++i) ms8[i] = d->dec.stage_ms[i];
   ms8[5] = ms8[6] = 0; ms8[7] = (float)d->dec.host_ms;
 }
+// absolute positions of the stage marks of the last call on a device-wide time axis (ms since the first
+// call of this function family): lets a tool see which kernels of different codec objects ran concurrently
+static cudaEvent_t g_ref_event = nullptr;
+static void marks_of(CodecBase& cb, int n, float* out) {
+  for (int i = 0; i < n; ++i) { out[i] = -1.0f; if (g_ref_event) cudaEventElapsedTime(&out[i], g_ref_event, cb.ev[i]); }
+}
+int ojb_marks_reference(void) {
+  return guarded([&] {
+    if (g_ref_event == nullptr) { cuda_check(cudaEventCreate(&g_ref_event), "event"); }
+    cuda_check(cudaEventRecord(g_ref_event, 0), "record"); cuda_check(cudaEventSynchronize(g_ref_event), "sync");
+  });
+}
+void ojb_enc_marks(ojb_encoder* e, float* ms8) { marks_of(e->enc, 8, ms8); }
+void ojb_dec_marks(ojb_decoder* d, float* ms8) { marks_of(d->dec, 6, ms8); ms8[6] = ms8[7] = -1.0f; }
 uint32_t ojb_enc_num_blocks(ojb_encoder* e) { return e->configured ? e->enc.layout.num_blocks : 0; }
 int ojb_enc_read_band(ojb_encoder* e, uint32_t tile, uint32_t comp, uint32_t res, uint32_t band,
                       uint32_t* out, uint32_t* band_w, uint32_t* band_h) {
