@@ -111,3 +111,21 @@ def test_raster_errors(emu_lib):
     p2 = ob.make_params(32, 32, 3, 8, reversible=True, subsampling=[(1, 1), (2, 2), (2, 2)], planar=1)
     with pytest.raises(ob.OjphError):
         ob.Encoder(p2, ob.U8, lib=emu_lib).encode_raster(b"\0" * (32 * 32 * 3), "pnm")   # sub-sampled ppm
+
+
+@pytest.mark.gpu
+def test_raster_full_size_matches_planar_path_gpu(gpu_lib):
+    """BASELINE size (8192 x 8192 x 3, 12-bit): the .ppm payload path must give the codestream of the planar
+    path on the same samples, and decode back to the same payload (size-independent property, no oracle)"""
+    w = h = 8192
+    rng = np.random.default_rng(9)
+    base = (rng.integers(0, 4096, (h // 8, w // 8, 3), dtype=np.uint16)).repeat(8, axis=0).repeat(8, axis=1)
+    base[::7, ::5, :] ^= 0x155                                   # some texture
+    p = ob.make_params(w, h, 3, 12, num_decomps=5, reversible=True, color_transform=True)
+    payload = base.astype(">u2").tobytes()
+    enc = ob.Encoder(p, ob.U16)
+    a = enc.encode_raster(payload, "pnm")
+    b = enc.encode([np.ascontiguousarray(base[:, :, c]) for c in range(3)])
+    assert a == b
+    back = ob.Decoder().decode_raster(a, "pnm")
+    assert back == payload
