@@ -46,6 +46,8 @@ typedef struct ojb_params {
   uint32_t coc_reversible[16];
   uint32_t coc_num_decomps[16];
   uint32_t coc_block_w[16], coc_block_h[16];
+  uint32_t coc_num_precincts[16];             /* param_cod::set_precinct_size(comp_idx, n, sizes); 0 = default */
+  uint32_t coc_precinct_w[16][33], coc_precinct_h[16][33];
   /* non-linearity point transform (NLT marker; param_nlt::set_nonlinear_transform(comp, type),
    * ojph_params.cpp:441, :2176): 0 = not called, else 1 + type (1: type 0 "none", 4: type 3 = two's
    * complement <-> sign-magnitude mapping of signed samples, the only one the reference implements).

@@ -97,6 +97,12 @@ public:
   void set_num_decomposition(ui32 comp_idx, ui32 n) { coc(comp_idx); s->p.coc_num_decomps[comp_idx] = n; }
   void set_block_dims(ui32 comp_idx, ui32 w, ui32 h) { coc(comp_idx); s->p.coc_block_w[comp_idx] = w; s->p.coc_block_h[comp_idx] = h; }
   void set_reversible(ui32 comp_idx, bool on) { coc(comp_idx); s->p.coc_reversible[comp_idx] = on ? 1u : 0u; }
+  void set_precinct_size(ui32 comp_idx, int num_levels, size* precinct_size) {
+    coc(comp_idx);
+    if (num_levels < 0 || num_levels > 33) raise("ojph error: too many precinct sizes");
+    s->p.coc_num_precincts[comp_idx] = (uint32_t)num_levels;
+    for (int i = 0; i < num_levels; ++i) { s->p.coc_precinct_w[comp_idx][i] = precinct_size[i].w; s->p.coc_precinct_h[comp_idx][i] = precinct_size[i].h; }
+  }
   // read-side getters (after read_headers): the component's COC when it has one, else the COD
   size get_block_dims(ui32 c = 0) const { ojb_coding_style t = state_style(s, c); return size(t.block_w, t.block_h); }
   size get_log_block_dims(ui32 c = 0) const { ojb_coding_style t = state_style(s, c); return size(lg(t.block_w), lg(t.block_h)); }

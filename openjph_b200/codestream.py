@@ -61,6 +61,9 @@ def make_params(width, height, num_comps=1, bit_depth=8, is_signed=False, num_de
         p.coc_reversible[c] = 1 if st.get("reversible", False) else 0
         p.coc_num_decomps[c] = st.get("num_decomps", 5)
         p.coc_block_w[c], p.coc_block_h[c] = st.get("block", (64, 64))
+        for i, (pw, ph) in enumerate(st.get("precincts", [])):
+            p.coc_precinct_w[c][i], p.coc_precinct_h[c][i] = pw, ph
+        p.coc_num_precincts[c] = len(st.get("precincts", []))
     p.profile = {None: 0, "IMF": 1, "BROADCAST": 2}[profile]          # codestream::set_profile
     # per-component quantisation calls in order: [("qstep", comp, delta) | ("qfactor", comp, ctype, q), ...]
     for seq, call in enumerate(qcc or [], start=1):

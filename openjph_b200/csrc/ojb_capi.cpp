@@ -84,6 +84,12 @@ static void to_params(const ojb_params* s, Params& P) {
     Params tmp; tmp.set_block_dims(s->coc_block_w[c], s->coc_block_h[c]);      // same argument checks
     cs.cb_w_exp = tmp.cb_w_exp; cs.cb_h_exp = tmp.cb_h_exp;
     cs.wavelet = s->coc_reversible[c] ? DWT_REV53 : DWT_IRV97;
+    if (s->coc_num_precincts[c]) {            // same argument checks as the COD form (ojph_params.cpp:188-213)
+      Params t; t.num_decomps = cs.num_decomps;
+      t.set_precincts((int)std::min(s->coc_num_precincts[c], 33u), s->coc_precinct_w[c], s->coc_precinct_h[c]);
+      cs.Scoc |= 1;
+      for (uint32_t i = 0; i <= cs.num_decomps; ++i) cs.precinct_size[i] = t.precinct_size[i];
+    }
   }
   // NLT: the default entry, then the per-component calls in the order they were made
   if (s->nlt_all) P.set_nonlinear_transform(0xFFFF, s->nlt_all - 1);

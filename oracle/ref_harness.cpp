@@ -97,6 +97,7 @@ struct ojr_params {
   int32_t  planar;                 // -1 => library default
   // per-component coding styles (COC), same meaning as in include/ojph_b200.h
   uint32_t coc_present[16], coc_reversible[16], coc_num_decomps[16], coc_block_w[16], coc_block_h[16];
+  uint32_t coc_num_precincts[16], coc_precinct_w[16][33], coc_precinct_h[16][33];
   // NLT: 0 = not set, else 1 + type; nlt_seq = order of the per-component calls
   uint32_t nlt_all, nlt_comp[16], nlt_seq[16];
   uint32_t profile;                // 0 none, 1 IMF, 2 BROADCAST
@@ -155,6 +156,11 @@ int ojr_encode(const ojr_params* p, const int32_t* const* planes,
         cod.set_num_decomposition(c, p->coc_num_decomps[c]);
         cod.set_block_dims(c, p->coc_block_w[c], p->coc_block_h[c]);
         cod.set_reversible(c, p->coc_reversible[c] != 0);
+        if (p->coc_num_precincts[c]) {
+          size ps[33];
+          for (uint32_t i = 0; i < p->coc_num_precincts[c] && i < 33; ++i) ps[i] = size(p->coc_precinct_w[c][i], p->coc_precinct_h[c][i]);
+          cod.set_precinct_size(c, (int)p->coc_num_precincts[c], ps);
+        }
       }
     if (p->nlt_all) cs.access_nlt().set_nonlinear_transform(param_nlt::ALL_COMPS, (ui8)(p->nlt_all - 1));
     for (uint32_t k = 0; k < 16; ++k)            // per-component calls in their recorded order

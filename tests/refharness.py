@@ -21,6 +21,7 @@ class RParams(C.Structure):
         ("planar", C.c_int32),
         ("coc_present", C.c_uint32 * 16), ("coc_reversible", C.c_uint32 * 16), ("coc_num_decomps", C.c_uint32 * 16),
         ("coc_block_w", C.c_uint32 * 16), ("coc_block_h", C.c_uint32 * 16),
+        ("coc_num_precincts", C.c_uint32 * 16), ("coc_precinct_w", (C.c_uint32 * 33) * 16), ("coc_precinct_h", (C.c_uint32 * 33) * 16),
         ("nlt_all", C.c_uint32), ("nlt_comp", C.c_uint32 * 16), ("nlt_seq", C.c_uint32 * 16), ("profile", C.c_uint32),
         ("qcc_calls", C.c_uint32 * 16), ("qcc_qstep", C.c_float * 16), ("qcc_qstep_seq", C.c_uint32 * 16),
         ("qcc_qfactor", C.c_uint32 * 16), ("qcc_ctype", C.c_uint32 * 16), ("qcc_qfactor_seq", C.c_uint32 * 16),

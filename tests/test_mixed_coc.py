@@ -86,3 +86,18 @@ def test_read_side_getters(emu_lib, ref):
     assert (a.precinct_w[0], a.precinct_w[1], a.precinct_w[4]) == (64, 128, 128) and a.num_layers == 1
     assert (b.num_decomps, b.reversible, b.block_w, b.block_h) == (2, 1, 64, 64) and b.precinct_w[0] == 32768
     assert (a.tile_w, a.tile_h, a.tile_off_x) == (256, 128, 0)
+
+
+def test_per_component_precincts(emu_lib, ref):
+    """param_cod::set_precinct_size(comp_idx, ...): the component's COC carries its own precinct sizes"""
+    for po in ("RPCL", "CPRL", "LRCP"):
+        p = ob.make_params(300, 260, 3, 8, num_decomps=3, reversible=True, planar=1, prog_order=po, precincts=[(128, 128)],
+                           coc={1: dict(reversible=True, num_decomps=3, precincts=[(64, 64), (128, 64)]),
+                                2: dict(reversible=True, num_decomps=2, block=(32, 32), precincts=[(256, 256)])})
+        frame = cases.frame_for(p)
+        want = ref.encode(p, frame)
+        got = ob.Encoder(p, ob.I32, lib=emu_lib).encode(frame)
+        assert got == want, po
+        out = ob.Decoder(lib=emu_lib).decode(want)
+        for a, b in zip(out, frame):
+            assert np.array_equal(a, b)
