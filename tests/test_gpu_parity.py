@@ -202,3 +202,22 @@ def test_alternate_block_coder_variants_gpu(gpu_lib, ref):
                         "-k", "block_encoder or block_decoder or cfg2 or cfg3 or odd_rgb_L5 or offsets"],
                        env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_frame_beyond_32bit_offsets_gpu(gpu_lib):
+    """20480 x 20480 x 3: the coefficient arena has more than 2^30 words, so the streaming DWT kernels (32-bit
+    offsets) are not eligible and the general kernels take over; lossless round trip (no oracle at this size)"""
+    w = h = 20480
+    rng = np.random.default_rng(3)
+    small = rng.integers(0, 256, (h // 16, w // 16), dtype=np.uint8)
+    planes = []
+    for c in range(3):
+        a = small.repeat(16, axis=0).repeat(16, axis=1)
+        a[::3, ::5] += np.uint8(c + 1)
+        planes.append(a)
+    p = ob.make_params(w, h, 3, 8, num_decomps=5, reversible=True, color_transform=True)
+    cs = ob.Encoder(p, ob.U8).encode(planes)
+    out = ob.Decoder().decode(cs, ob.U8)
+    for a, b in zip(out, planes):
+        assert np.array_equal(a, b)
