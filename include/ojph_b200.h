@@ -132,7 +132,10 @@ int ojb_enc_encode_frame(ojb_encoder* e, const void* const* planes, const uint32
  * Samples take 1 byte when the bit depth is <= 8, else 2; the codec must be configured / opened with the
  * matching container (OJB_U8 / OJB_U16).  Decoded samples are clamped to [0, 2^depth - 1] as the
  * reference's writers do. */
-enum { OJB_RASTER_PNM = 0, OJB_RASTER_YUV = 1 };
+/*   OJB_RASTER_DPX_BE / _LE  image data of a .dpx file (encode only, like dpx_in :1800-2150): 10-bit RGB packed one
+ *                   32-bit word per pixel, or 16-bit RGB with rows padded to 32-bit words, chosen by the
+ *                   configured bit depth (10 or 16); _BE / _LE = byte order of the file (magic SDPX / XPDS) */
+enum { OJB_RASTER_PNM = 0, OJB_RASTER_YUV = 1, OJB_RASTER_DPX_BE = 2, OJB_RASTER_DPX_LE = 3 };
 int ojb_enc_encode_raster(ojb_encoder* e, uint32_t layout, const void* payload, uint64_t payload_bytes,
                           uint8_t* out, uint64_t out_cap, uint64_t* out_len);
 /* device-resident variants: the frame lives in the encoder's image buffer */

@@ -15,7 +15,7 @@ _NP = {U8: np.uint8, U16: np.uint16, I32: np.int32}
 PROG = {"LRCP": 0, "RLCP": 1, "RPCL": 2, "PCRL": 3, "CPRL": 4}
 
 
-RASTER = {"pnm": 0, "yuv": 1}
+RASTER = {"pnm": 0, "yuv": 1, "dpx_be": 2, "dpx_le": 3}
 
 
 class OjphError(RuntimeError):

@@ -217,7 +217,7 @@ namespace ojb {
 static uint64_t raster_geometry(CodecBase& cb, uint32_t layout, uint32_t& es, RasterPlanes& pl) {
   const Params& P = cb.params;
   const uint32_t nc = P.num_comps();
-  if (layout > 1) fail(0x000B0030, "unknown raster layout");
+  if (layout > 3) fail(0x000B0030, "unknown raster layout");
   if (cb.img_type == ST_I32) fail(0x000B0031, "file payloads need the 8-bit or 16-bit sample container");
   es = cb.img_type == ST_U8 ? 1u : 2u;
   uint64_t total = 0;
@@ -226,6 +226,18 @@ static uint64_t raster_geometry(CodecBase& cb, uint32_t layout, uint32_t& es, Ra
       fail(0x000B0032, "component %u: %u-bit samples take %u byte(s) in the file; open the codec with the matching container",
            c, P.comps[c].bit_depth, P.comps[c].bit_depth > 8 ? 2u : 1u);
     total += (uint64_t)cb.img_w[c] * cb.img_h[c] * es;
+  }
+  if (layout == OJB_RASTER_DPX_BE || layout == OJB_RASTER_DPX_LE) {
+    const uint32_t bd = P.comps[0].bit_depth;
+    if (nc != 3 || (bd != 10 && bd != 16))
+      fail(0x03000182, "DPX image formats other than 10-bit packed RGB and 16-bit RGB are not supported (as in the reference)");
+    for (uint32_t c = 0; c < nc; ++c) {
+      if (cb.img_w[c] != cb.img_w[0] || cb.img_h[c] != cb.img_h[0] || P.comps[c].bit_depth != bd)
+        fail(0x000B0034, "a .dpx payload holds three equal components");
+      pl.off[c] = cb.img_off[c]; pl.stride[c] = cb.img_w[c];
+    }
+    const uint64_t row = bd == 10 ? 4ull * cb.img_w[0] : 2ull * ((3ull * cb.img_w[0] + 1) & ~1ull);
+    return row * cb.img_h[0];
   }
   if (layout == OJB_RASTER_PNM) {
     if (nc != 1 && nc != 3) fail(0x000B0033, "a .pgm / .ppm payload has 1 or 3 components");
@@ -260,7 +272,11 @@ int ojb_enc_encode_raster(ojb_encoder* e, uint32_t layout, const void* payload, 
     }
     e->d_raster.reserve(std::max<uint64_t>(need, 16));
     cuda_check(cudaMemcpyAsync(e->d_raster.p, payload, need, cudaMemcpyHostToDevice, E.stream), "upload");
-    launch_raster_unpack(e->d_raster.p, E.d_image.p, pl, nc, es, E.img_w[0], E.img_h[0], E.stream);
+    if (layout == OJB_RASTER_PNM) launch_raster_unpack(e->d_raster.p, E.d_image.p, pl, nc, es, E.img_w[0], E.img_h[0], E.stream);
+    else {                                      // words / samples are extracted in the GPU's (little-endian) order
+      launch_raster_unpack_dpx(e->d_raster.p, E.d_image.p, pl, E.params.comps[0].bit_depth, layout == OJB_RASTER_DPX_BE,
+                               E.img_w[0], E.img_h[0], E.stream);
+    }
     *out_len = E.encode(nullptr, nullptr, false, out, (size_t)out_cap, false);
     E.last_launches += 1;
   });
@@ -274,6 +290,7 @@ int ojb_dec_decode_raster(ojb_decoder* d, uint32_t layout, void* payload, uint64
     const uint64_t need = raster_geometry(D, layout, es, pl);
     if (payload_cap < need) fail(0x000B0035, "payload buffer too small: %llu bytes needed", (unsigned long long)need);
     const uint32_t nc = D.params.num_comps();
+    if (layout > OJB_RASTER_YUV) fail(0x000B0037, "the .dpx layout is read-only, as in the reference");
     if (layout == OJB_RASTER_YUV) {
       std::vector<void*> planes(nc);
       uint8_t* p = static_cast<uint8_t*>(payload);

@@ -53,6 +53,9 @@ void launch_ctrl_copy(void* dst, const void* src, size_t bytes, cudaStream_t st)
 // interleaved big-endian pixels (.pgm / .ppm payload) <-> the component planes of the image buffer
 void launch_raster_unpack(const void* src, void* image, const RasterPlanes& pl, uint32_t ncomp, uint32_t bytes_per_sample,
                           uint32_t width, uint32_t height, cudaStream_t st);
+// .dpx image data: 10-bit packed RGB words or 16-bit RGB samples, either byte order
+void launch_raster_unpack_dpx(const void* src, void* image, const RasterPlanes& pl, uint32_t bit_depth, bool swap,
+                              uint32_t width, uint32_t height, cudaStream_t st);
 void launch_raster_pack(void* dst, const void* image, const RasterPlanes& pl, uint32_t ncomp, uint32_t bytes_per_sample,
                         uint32_t width, uint32_t height, cudaStream_t st);
 // block pieces computed on the device from per-block results + destination offsets

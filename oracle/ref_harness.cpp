@@ -501,6 +501,13 @@ extern "C" int ojr_read_image(const char* path, int kind, uint32_t w, uint32_t h
       for (uint32_t y = 0; y < h; ++y)
         for (uint32_t c = 0; c < nc; ++c) { in.read(&line, c); memcpy(planes[c] + (size_t)y * w, line.i32, (size_t)w * 4); }
       in.close();
+    } else if (kind == 2) {
+      dpx_in in; in.open(path);
+      if (in.get_size().w != w || in.get_size().h != h || in.get_num_components() != nc || in.get_bit_depth(0) != bit_depth)
+        throw std::runtime_error("dpx header mismatch");
+      for (uint32_t y = 0; y < h; ++y)
+        for (uint32_t c = 0; c < nc; ++c) { in.read(&line, c); memcpy(planes[c] + (size_t)y * w, line.i32, (size_t)w * 4); }
+      in.close();
     } else {
       yuv_in in;
       ui32 bd = bit_depth; in.set_bit_depth(1, &bd);

@@ -129,3 +129,45 @@ def test_raster_full_size_matches_planar_path_gpu(gpu_lib):
     assert a == b
     back = ob.Decoder().decode_raster(a, "pnm")
     assert back == payload
+
+
+def _dpx_file(path, w, h, bd, big_endian, payload):
+    """a minimal .dpx file around an image-data payload (the fields dpx_in::open reads, :1823-2030)"""
+    import struct
+    e = ">" if big_endian else "<"
+    hdr = bytearray(2048)
+    hdr[0:4] = struct.pack(e + "I", 0x53445058)
+    hdr[4:8] = struct.pack(e + "I", 2048)
+    hdr[8:16] = b"V2.0\0\0\0\0"
+    hdr[16:20] = struct.pack(e + "I", 2048 + len(payload))
+    hdr[768:772] = struct.pack(e + "HH", 0, 1)
+    hdr[772:780] = struct.pack(e + "II", w, h)
+    hdr[780:784] = struct.pack(e + "I", 0)
+    hdr[800:804] = bytes([50, 2, 2, bd])
+    hdr[804:808] = struct.pack(e + "HH", 1 if bd == 10 else 0, 0)
+    hdr[808:812] = struct.pack(e + "I", 2048)
+    path.write_bytes(bytes(hdr) + payload)
+
+
+@pytest.mark.parametrize("bd,big_endian,w,h", [(10, True, 131, 70), (10, False, 64, 33), (16, True, 77, 40), (16, False, 50, 31)])
+def test_dpx_payload_emulator(bd, big_endian, w, h, emu_lib, ref, tmp_path):
+    rng = np.random.default_rng(bd + w)
+    pix = rng.integers(0, 1 << bd, (h, w, 3), dtype=np.uint32)
+    if bd == 10:
+        words = (pix[:, :, 0] << 22) | (pix[:, :, 1] << 12) | (pix[:, :, 2] << 2)
+        payload = words.astype(">u4" if big_endian else "<u4").tobytes()
+    else:
+        row = np.zeros((h, (3 * w + 1) & ~1), np.uint16)
+        row[:, :3 * w] = pix.reshape(h, 3 * w)
+        payload = row.astype(">u2" if big_endian else "<u2").tobytes()
+    f = tmp_path / "in.dpx"
+    _dpx_file(f, w, h, bd, big_endian, payload)
+    planes = ref.read_image(str(f), 2, w, h, 3, bd)
+    for c in range(3):
+        assert np.array_equal(planes[c], pix[:, :, c])            # the test's idea of the format is the reference's
+    p = ob.make_params(w, h, 3, bd, num_decomps=3, reversible=True, color_transform=True)
+    want = ref.encode(p, planes)
+    got = ob.Encoder(p, ob.U16, lib=emu_lib).encode_raster(payload, "dpx_be" if big_endian else "dpx_le")
+    assert got == want
+    with pytest.raises(ob.OjphError):
+        ob.Decoder(lib=emu_lib).decode_raster(got, "dpx_be")      # read-only format
