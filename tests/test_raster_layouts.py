@@ -149,8 +149,21 @@ def _dpx_file(path, w, h, bd, big_endian, payload):
     path.write_bytes(bytes(hdr) + payload)
 
 
-@pytest.mark.parametrize("bd,big_endian,w,h", [(10, True, 131, 70), (10, False, 64, 33), (16, True, 77, 40), (16, False, 50, 31)])
+DPX_CASES = [(10, True, 131, 70), (10, False, 64, 33), (16, True, 77, 40), (16, False, 50, 31)]
+
+
+@pytest.mark.parametrize("bd,big_endian,w,h", DPX_CASES)
 def test_dpx_payload_emulator(bd, big_endian, w, h, emu_lib, ref, tmp_path):
+    _check_dpx(emu_lib, ref, tmp_path, bd, big_endian, w, h)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bd,big_endian,w,h", DPX_CASES)
+def test_dpx_payload_gpu(bd, big_endian, w, h, gpu_lib, ref, tmp_path):
+    _check_dpx(None, ref, tmp_path, bd, big_endian, w, h)
+
+
+def _check_dpx(emu_lib, ref, tmp_path, bd, big_endian, w, h):
     rng = np.random.default_rng(bd + w)
     pix = rng.integers(0, 1 << bd, (h, w, 3), dtype=np.uint32)
     if bd == 10:
