@@ -26,7 +26,7 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-PROFILE_JSON = "r01i_kernels.json"      # the committed ncu --set full summary the roofline's `traffic` comes from
+PROFILE_JSON = "r01k_kernels.json"      # the committed ncu --set full summary the roofline's `traffic` comes from
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
