@@ -37,6 +37,7 @@
 #include "ojph_codeblock_fun.h"
 #include "ojph_transform.h"
 #include "ojph_colour.h"
+#include "ojph_colour_local.h"
 #include "ojph_img_io.h"       // src/apps/common: the apps' file readers / writers (N2 oracle)
 
 using namespace ojph;
@@ -471,6 +472,22 @@ void ojr_irv_convert_to_integer(const float* src, int32_t* dst, uint32_t bit_dep
 {
   line_buf s, d; wrap_f32(s, (float*)src, n); wrap_i32(d, dst, n);
   local::gen_irv_convert_to_integer(&s, &d, 0, bit_depth, is_signed != 0, n);
+}
+// NLT type 3 variants (pin the oracle's restatement)
+void ojr_rev_convert_nlt_type3(const int32_t* src, int32_t* dst, int64_t shift, uint32_t n)
+{
+  line_buf s, d; wrap_i32(s, (int32_t*)src, n); wrap_i32(d, dst, n);
+  local::gen_rev_convert_nlt_type3(&s, 0, &d, 0, shift, n);
+}
+void ojr_irv_convert_to_float_nlt_type3(const int32_t* src, float* dst, uint32_t bit_depth, int is_signed, uint32_t n)
+{
+  line_buf s, d; wrap_i32(s, (int32_t*)src, n); wrap_f32(d, dst, n);
+  local::gen_irv_convert_to_float_nlt_type3(&s, 0, &d, bit_depth, is_signed != 0, n);
+}
+void ojr_irv_convert_to_integer_nlt_type3(const float* src, int32_t* dst, uint32_t bit_depth, int is_signed, uint32_t n)
+{
+  line_buf s, d; wrap_f32(s, (float*)src, n); wrap_i32(d, dst, n);
+  local::gen_irv_convert_to_integer_nlt_type3(&s, &d, 0, bit_depth, is_signed != 0, n);
 }
 void ojr_rev_tx_to_cb32(const int32_t* sp, uint32_t* dp, uint32_t K_max, uint32_t n,
                         uint32_t* max_val)

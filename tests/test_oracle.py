@@ -117,3 +117,30 @@ def test_port_matches_reference_live_on_random_blocks(ref):
         a, ok = O.decode_block(want, w, h, kmax - 1, 1, len(want), 0)
         b, ok2 = ref.decode_block(want, w, h, kmax - 1, 1, len(want), 0)
         assert ok == ok2 and np.array_equal(a, b)
+
+
+def test_nlt_type3_restatement_matches_reference_live(ref):
+    """a1's NLT type 3 variants: the plain-C restatement against the reference's generic line kernels"""
+    L, R = O.lib(), ref.lib()
+    rng = np.random.default_rng(21)
+    for bd in (8, 12, 16, 24):
+        lo, hi = -(1 << (bd - 1)), (1 << (bd - 1)) - 1
+        v = rng.integers(lo, hi + 1, 4099).astype(np.int32)
+        v[:4] = (lo, hi, -1, 0)
+        a, b = np.zeros_like(v), np.zeros_like(v)
+        L.oj_rev_convert_nlt3(O.ip(v), O.ip(a), bd, v.size)
+        R.ojr_rev_convert_nlt_type3(O.ip(v), O.ip(b), C.c_int64((1 << (bd - 1)) + 1), v.size)
+        assert np.array_equal(a, b)
+        back = np.zeros_like(v); L.oj_rev_convert_nlt3(O.ip(a), O.ip(back), bd, v.size)
+        assert np.array_equal(back, v)                               # an involution
+        for sg in (1, 0):
+            src = v if sg else (v - lo).astype(np.int32)
+            fa, fb = np.zeros(v.size, np.float32), np.zeros(v.size, np.float32)
+            L.oj_irv_to_float_nlt3(O.ip(src), O.fp(fa), bd, sg, v.size)
+            R.ojr_irv_convert_to_float_nlt_type3(O.ip(src), O.fp(fb), bd, sg, v.size)
+            assert np.array_equal(fa, fb)
+            f = (rng.random(v.size, dtype=np.float32) - 0.5) * 1.2       # overshoots the range on both sides
+            ia, ib = np.zeros(v.size, np.int32), np.zeros(v.size, np.int32)
+            L.oj_irv_to_int_nlt3(O.fp(f), O.ip(ia), bd, sg, v.size)
+            R.ojr_irv_convert_to_integer_nlt_type3(O.fp(f), O.ip(ib), bd, sg, v.size)
+            assert np.array_equal(ia, ib)
