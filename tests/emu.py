@@ -12,6 +12,10 @@ def emu_lib(build=True):
     global _emu
     if _emu is None:
         if build:
-            subprocess.check_call(["make", "-s", "-C", os.path.join(_ROOT, "openjph_b200", "csrc"), "emu", "-j8"])
+            import fcntl
+            # one builder at a time (pytest-xdist workers all arrive here)
+            with open(os.path.join(_ROOT, "tests", "emu", ".build.lock"), "w") as lock:
+                fcntl.flock(lock, fcntl.LOCK_EX)
+                subprocess.check_call(["make", "-s", "-C", os.path.join(_ROOT, "openjph_b200", "csrc"), "emu", "-j8"])
         _emu = _lib.bind(EMU_PATH)
     return _emu

@@ -14,8 +14,10 @@ I32P, F32P, U32P, U8P = C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(C.
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(PATH):
-            subprocess.check_call(["make", "-s", "-C", os.path.join(_ROOT, "oracle"), "-f", "Makefile.port"])
+        import fcntl
+        with open(os.path.join(_ROOT, "oracle", ".port.lock"), "w") as lock:       # one builder at a time (xdist)
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            subprocess.check_call(["make", "-s", "-C", os.path.join(_ROOT, "oracle"), "-f", "Makefile.port"])   # no-op when fresh
         _lib = C.CDLL(PATH)
         _lib.oj_ht_encode_block.restype = C.c_uint32
     return _lib

@@ -55,6 +55,12 @@ def random_case(seed):
         kw["nlt"] = {"all": 3} if rng2.random() < 0.5 else {int(rng2.integers(0, nc)): 3}
         if rng2.random() < 0.7:
             kw["is_signed"] = True
+    if "coc" in kw and rng2.random() < 0.4:          # the component's own precinct sizes
+        for st in kw["coc"].values():
+            st["precincts"] = [(int(2 ** rng2.integers(5, 9)), int(2 ** rng2.integers(5, 9))) for _ in range(int(rng2.integers(1, 3)))]
+    if not kw["reversible"] and rng2.random() < 0.25:  # per-component quantisation calls
+        c = int(rng2.integers(0, nc))
+        kw["qcc"] = [("qfactor", c, int(rng2.integers(0, 3)), int(rng2.integers(20, 100)))] if rng2.random() < 0.5 else [("qstep", c, float(rng2.choice([0.004, 0.03])))]
     return kw
 
 
