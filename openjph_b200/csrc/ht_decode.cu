@@ -1,8 +1,11 @@
 // ht_decode.cu -- HTJ2K block decoder for sm_100a: cleanup pass (+ SigProp + MagRef).
 //
 // Results are those of the reference's ojph_decode_codeblock32
-// (src/core/coding/ojph_block_decoder32.cpp:742-1612).  The work is split by its dependency
-// structure rather than by the reference's loop nest:
+// (src/core/coding/ojph_block_decoder32.cpp:742-1612).  Two variants, same results:
+//   * ht_decode_serial_kernel (default): the whole cleanup pass by ONE THREAD per code-block, see the
+//     comment above it (lock-step 64-bit refills of 128-bit bit windows);
+//   * step 1 + step 2 (OJB_BLOCK_DECODER=twostep), where the work is split by its dependency structure
+//     rather than by the reference's loop nest:
 //   step 1  MEL + VLC/U-VLC decoding is a strictly serial chain per code-block (each codeword's
 //           position and context depend on the previous one, :869-1089).  A warp cannot speed
 //           one chain up, so ONE THREAD decodes one code-block and a warp runs 32 chains at
@@ -631,7 +634,7 @@ ht_dec_step2_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
 // The serial form of the decoder (what ojph_decode_codeblock32 does, :742-1316, minus its two-step
 // split): the thread that decodes a quad pair's VLC / U-VLC codewords reads the pair's MagSgn bits
 // right away, so no quad records travel through memory and no warp-wide scan or shared bit buffer
-// is needed -- about a third of the instructions of step 1 + step 2.  Blocks that carry SPP / MRP
+// is needed -- 586 M warp instructions per 8K frame against 960 M for step 1 + step 2.  Blocks that carry SPP / MRP
 // passes still write their quad records (refine_passes needs the CUP significance).
 // ---- bit readers of the thread-per-block decoder ------------------------------------------------
 // Both streams are read as aligned 8-byte groups through per-thread cp.async rings; a group is un-stuffed

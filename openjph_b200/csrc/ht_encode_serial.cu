@@ -8,10 +8,12 @@
 // quad by quad with the three writers in registers -- about a third of the instructions per sample --
 // and a warp advances 32 independent blocks.  Latency (one serial chain per thread) is covered by
 // software prefetch of the next quad pair and by the other frames in flight on the device.
-//   * MagSgn and VLC are written as aligned 4-byte groups straight to the block's slot (MagSgn forward
-//     from the slot start, VLC backward from the slot end, as the gather kernel expects); the stuffing
-//     rules (7-bit byte after 0xFF, :483-488; 7-bit byte 0x7F after a byte > 0x8F, :393-404) are tested
-//     on four bytes at once and the byte-wise path runs only when one applies;
+//   * MagSgn goes through a 128-bit window: one append per quad (its four fields fit 64 bits when K_max <= 15),
+//     flushed straight to the block's slot as aligned 8-byte groups whose stuffing (7-bit byte after 0xFF,
+//     :483-488) is done on the whole group by SWAR -- the flush is the same straight-line code for every lane
+//     of the warp, not a byte loop a few lanes take at a time;
+//   * VLC is written backward from the slot end as aligned 4-byte groups (7-bit byte 0x7F after a byte > 0x8F,
+//     :393-404, tested on four bytes at once; the byte-wise path runs only when it applies);
 //   * MEL bytes (<= 192, the reference's limit) stay in shared memory until termination;
 //   * the previous quad-row's significance / exponents live in a per-thread shared-memory row.
 #include "ojb_device.h"
