@@ -832,6 +832,7 @@ ht_decode_serial_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
                                 : ((np > 1) ? (uint32_t)DEC_OUT_SIGNMAG : out_mode);
   const bool vec4 = ((blk.dst_off | stride) & 3u) == 0;
   const bool narrow = mmsbp2 <= 16;          // m_n <= missing_msbs + 2: the four fields of a quad fit 64 bits
+  const uint32_t pscale = 1u << (p - 1);
   bool fail = false;
   // significance of the row above as bit masks over up to 32 quads per word is not enough for wide
   // blocks: the row-above state (sigma of the two bottom samples, msb of their v_n) lives in s_prev
@@ -940,15 +941,17 @@ ht_decode_serial_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
             const uint32_t m = mk[k];
             const uint32_t bits = (uint32_t)(ms.w.w0 >> off);
             off += m;
-            uint32_t v = bits & ((1u << m) - 1u);
-            v |= ((e1 >> k) & 1u) << m;
-            v |= 1u;
+            // (multiplications by powers of two on purpose: this kernel is bound by the integer ALU pipe --
+            // shifts, logic, adds -- while the FMA pipe that executes IMAD is a fifth as busy)
+            const uint32_t pow = 1u << m;
+            uint32_t v = (bits & (pow - 1u)) | 1u;
+            v = ((e1 >> k) & 1u) * pow + v;                           // bit m is clear: + is |
             const bool sig = (rho >> k) & 1u;
             if (k == 1) vbl = sig ? v : 0u;
             if (k == 3) vbr = sig ? v : 0u;
-            const uint32_t mag = (v + 2u) << (p - 1);                 // magnitude with the half-LSB bin centre, bit 30 down
+            const uint32_t mag = v * pscale + 2u * pscale;            // (v + 2) << (p - 1): magnitude with the half-LSB bin centre, bit 30 down
             uint32_t val;
-            if (MODE == 0) { const uint32_t a = mag >> shift, sg = 0u - (bits & 1u); val = (a ^ sg) - sg; }   // two's complement
+            if (MODE == 0) { const uint32_t a = mag >> shift; val = a * (1u - 2u * (bits & 1u)); }   // two's complement: +a or -a
             else if (MODE == 1) val = __float_as_uint(__fmul_rn((float)mag, delta)) | (bits << 31);
             else val = to_output((bits << 31) | mag, om, shift, delta);
             o[i][k] = sig ? val : 0u;
