@@ -589,15 +589,18 @@ void read_quant(Reader& r, QuantSet& q, bool is_qcc, uint32_t nc) {
 
 size_t Params::read_main_header(const uint8_t* data, size_t len) {
   Reader r{ data, len, 0 };
-  // find SOC then SIZ (find_marker, ojph_codestream_local.cpp:717-741)
+  // find SOC then SIZ (find_marker, ojph_codestream_local.cpp:706-730: after a 0xFF the next byte is consumed
+  // whether it matches or not; read_headers ignores a failed search, so a stream without SOC / SIZ ends up
+  // in param_siz::read at the end of the data, :855-857)
   auto find = [&](uint16_t m) {
-    while (r.pos + 1 < r.n) {
-      if (r.d[r.pos] == 0xFF && r.d[r.pos + 1] == (m & 0xFF)) { r.pos += 2; return true; }
-      ++r.pos;
+    while (r.pos < r.n) {
+      if (r.d[r.pos++] != 0xFF) continue;
+      if (r.pos >= r.n) return false;
+      if (r.d[r.pos++] == (m & 0xFF)) return true;
     }
     return false;
   };
-  if (!find(M_SOC) || !find(M_SIZ)) fail(0x00030051, "File ended before finding a tile segment");
+  if (!find(M_SOC) || !find(M_SIZ) || !r.has(2)) fail(0x00050041, "error reading SIZ marker");
   // SIZ
   {
     uint32_t L = r.u16();

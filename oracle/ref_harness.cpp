@@ -15,6 +15,7 @@
 //     ojph_codestream_gen.cpp:59-168).
 // Every entry point catches the reference's exceptions and returns a negative int.
 #include <cstdio>
+#include <cstdarg>
 #include <cstring>
 #include <cstdint>
 #include <vector>
@@ -109,6 +110,24 @@ struct ojr_params {
 
 static char g_err[512] = "";
 const char* ojr_last_error() { return g_err; }
+// the reference reports errors through a message object (code, file, line, text) and then throws
+// std::runtime_error("ojph error"): keep the code and the text of the last one for the error-parity tests
+static uint32_t g_err_code = 0;
+static char g_err_text[512] = "";
+class capture_error : public ojph::message_error {
+public:
+  virtual void operator()(int error_code, const char* file_name, int line_num, const char* fmt, ...) {
+    (void)file_name; (void)line_num;
+    g_err_code = (uint32_t)error_code;
+    va_list args; va_start(args, fmt); vsnprintf(g_err_text, sizeof(g_err_text), fmt, args); va_end(args);
+    throw std::runtime_error("ojph error");
+  }
+};
+static capture_error g_capture;
+static ojph::message_error g_plain;          // the library's own behaviour (prints, then throws)
+extern "C" void ojr_capture_errors(int on) { ojph::configure_error(on ? (ojph::message_error*)&g_capture : &g_plain); g_err_code = 0; g_err_text[0] = 0; }
+extern "C" uint32_t ojr_last_error_code() { return g_err_code; }
+extern "C" const char* ojr_last_error_text() { return g_err_text; }
 int ojr_cpu_ext_level() { return ojph::get_cpu_ext_level(); }
 
 static const char* po_name(uint32_t po) {
