@@ -192,7 +192,16 @@ class codestream {                               // ojph_codestream.h:88-383
   ojb_decoder* dec = nullptr;
   outfile_base* out = nullptr;
   std::vector<ui8> j2c;                          // decode: the whole stream (the GPU path is frame based)
-  line_buf line;
+  line_buf lines[16];                            // one per component: callers keep the pointers of a row's components
+  std::vector<si32> stage[16];                   // pulled rows are handed out from 64-byte aligned, padded storage, like
+                                                 // the reference's own line buffers (its file writers use SIMD loads)
+  si32* staged(ui32 c, const si32* row, ui32 w) {
+    std::vector<si32>& v = stage[c & 15];
+    if (v.size() < (size_t)w + 48) v.assign((size_t)w + 48, 0);
+    si32* a = reinterpret_cast<si32*>((reinterpret_cast<size_t>(v.data()) + 63) & ~(size_t)63);
+    memcpy(a, row, (size_t)w * sizeof(si32));
+    return a;
+  }
   bool resilient = false;
 public:
   codestream() {}
@@ -207,6 +216,12 @@ public:
 
   // ---- write side
   void set_planar(bool planar) { st.planar = planar ? 1 : 0; }
+  // (the library defaults when set_planar was not called: ojph_codestream_local.cpp:623 on the write side,
+  // :879 on the read side)
+  bool is_planar() const {
+    if (st.planar >= 0) return st.planar != 0;
+    return st.reading ? st.info.color_transform == 0 : st.p.color_transform != 0;
+  }
   void set_profile(const char* name) {           // ojph_codestream_local.cpp:1124-1133; rules applied at write_headers
     if (name != nullptr && strcmp(name, "IMF") == 0) st.p.profile = 1;
     else if (name != nullptr && strcmp(name, "BROADCAST") == 0) st.p.profile = 2;
@@ -239,6 +254,7 @@ public:
   line_buf* exchange(line_buf* filled, ui32& next_component) {
     si32* p = ojb_enc_exchange(enc, filled ? filled->i32 : nullptr, &next_component);
     if (p == nullptr) return nullptr;
+    line_buf& line = lines[next_component & 15];
     line.i32 = p; line.size = comp_width(next_component); line.pre_size = 0;
     line.flags = line_buf::LFT_32BIT | line_buf::LFT_INTEGER;
     return &line;
@@ -275,7 +291,8 @@ public:
   line_buf* pull(ui32& comp_num) {
     const si32* p = ojb_dec_pull(dec, &comp_num);
     if (p == nullptr) return nullptr;
-    line.i32 = const_cast<si32*>(p); line.size = st.info.comp_w[comp_num]; line.pre_size = 0;
+    line_buf& line = lines[comp_num & 15];                      // (ppm_out keeps the three pointers until the row is complete)
+    line.i32 = staged(comp_num, p, st.info.comp_w[comp_num]); line.size = st.info.comp_w[comp_num]; line.pre_size = 0;
     line.flags = line_buf::LFT_32BIT | line_buf::LFT_INTEGER;
     return &line;
   }
