@@ -52,7 +52,29 @@ CASES = {
     "rev_12bit_tiles_tlm": (12, ["-reversible", "true", "-tile_size", "{96,64}", "-tlm_marker", "true", "-prog_order", "CPRL",
                                  "-tileparts", "C", "-block_size", "{32,32}", "-precincts", "{128,128},{64,64}"]),
     "irv_q": (10, ["-qstep", "0.01", "-num_decomps", "3", "-com", "made by the facade test"]),
+    "irv_qfactor": (8, ["-qfactor", "85", "-num_decomps", "4"]),
+    "rev_offsets_no_rct": (8, ["-reversible", "true", "-colour_trans", "false", "-image_offset", "{5,3}", "-tile_size", "{128,128}",
+                               "-tile_offset", "{1,2}", "-prog_order", "PCRL"]),
+    "broadcast_profile": (10, ["-reversible", "true", "-profile", "BROADCAST", "-prog_order", "CPRL", "-precincts", "{128,128},{256,256}"]),
 }
+
+
+def test_yuv420_through_the_apps(apps, tmp_path):
+    """a sub-sampled .yuv in and out (-dims / -num_comps / -downsamp / -bit_depth / -signed)"""
+    w, h = 128, 96
+    rng = np.random.default_rng(8)
+    src = tmp_path / "in.yuv"
+    src.write_bytes(b"".join(rng.integers(0, 256, n, dtype=np.uint8).tobytes() for n in (w * h, w * h // 4, w * h // 4)))
+    opts = ["-dims", "{%d,%d}" % (w, h), "-num_comps", "3", "-downsamp", "{1,1},{2,2}", "-bit_depth", "8", "-signed", "false",
+            "-reversible", "true", "-num_decomps", "3"]
+    res = {}
+    for fl in ("ref", "b200"):
+        j = tmp_path / ("o_%s.j2c" % fl)
+        subprocess.check_call([apps[("compress", fl)], "-i", str(src), "-o", str(j)] + opts, stdout=subprocess.DEVNULL)
+        o = tmp_path / ("b_%s.yuv" % fl)
+        subprocess.check_call([apps[("expand", fl)], "-i", str(j), "-o", str(o)], stdout=subprocess.DEVNULL)
+        res[fl] = (j.read_bytes(), o.read_bytes())
+    assert res["ref"] == res["b200"] and res["ref"][1] == src.read_bytes()
 
 
 @pytest.mark.parametrize("name", list(CASES))
