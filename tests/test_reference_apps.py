@@ -109,3 +109,78 @@ def test_unmodified_reference_apps_on_the_facade(name, apps, tmp_path):
         outs[fl] = o.read_bytes()
     if "-reversible" in opts:
         assert outs["ref"] == outs["b200"]
+
+
+# the encode half of the reference's own test matrix (tests/test_executables.cpp:1033-1690: SimpleEncIrv97*,
+# SimpleEncRev53*, tiles, 16-bit, gray, tall-narrow, qfactor), on synthetic images of the same kind
+MATRIX = [
+    ("irv97_64x64", "ppm8", ["-qstep", "0.1"]),
+    ("irv97_32x32", "ppm8", ["-qstep", "0.01", "-block_size", "{32,32}"]),
+    ("irv97_16x16", "ppm8", ["-qstep", "0.01", "-block_size", "{16,16}"]),
+    ("irv97_4x4", "ppm8", ["-qstep", "0.01", "-block_size", "{4,4}"]),
+    ("irv97_1024x4", "ppm8", ["-qstep", "0.01", "-block_size", "{4,1024}"]),
+    ("irv97_4x1024", "ppm8", ["-qstep", "0.01", "-block_size", "{1024,4}"]),
+    ("irv97_512x8", "ppm8", ["-qstep", "0.01", "-block_size", "{8,512}"]),
+    ("irv97_8x512", "ppm8", ["-qstep", "0.01", "-block_size", "{512,8}"]),
+    ("irv97_256x16", "ppm8", ["-qstep", "0.01", "-block_size", "{16,256}"]),
+    ("irv97_16x256", "ppm8", ["-qstep", "0.01", "-block_size", "{256,16}"]),
+    ("irv97_128x32", "ppm8", ["-qstep", "0.01", "-block_size", "{32,128}"]),
+    ("irv97_32x128", "ppm8", ["-qstep", "0.01", "-block_size", "{128,32}"]),
+    ("irv97_tiles_33x33_d5", "ppm8", ["-qstep", "0.01", "-tile_size", "{33,33}", "-num_decomps", "5"]),
+    ("irv97_tiles_33x33_d6", "ppm8", ["-qstep", "0.01", "-tile_size", "{33,33}", "-num_decomps", "6"]),
+    ("irv97_16bit", "ppm16", ["-qstep", "0.01"]),
+    ("irv97_16bit_gray", "pgm16", ["-qstep", "0.01"]),
+    ("rev53_16bit", "ppm16", ["-reversible", "true"]),
+    ("rev53_16bit_gray", "pgm16", ["-reversible", "true"]),
+    ("rev53_64x64", "ppm8", ["-reversible", "true"]),
+    ("rev53_32x32", "ppm8", ["-reversible", "true", "-block_size", "{32,32}"]),
+    ("rev53_4x4", "ppm8", ["-reversible", "true", "-block_size", "{4,4}"]),
+    ("rev53_1024x4", "ppm8", ["-reversible", "true", "-block_size", "{4,1024}"]),
+    ("rev53_4x1024", "ppm8", ["-reversible", "true", "-block_size", "{1024,4}"]),
+    ("rev53_tiles_32x32_d5", "ppm8", ["-reversible", "true", "-tile_size", "{32,32}", "-num_decomps", "5"]),
+    ("rev53_tiles_32x32_d6", "ppm8", ["-reversible", "true", "-tile_size", "{32,32}", "-num_decomps", "6"]),
+    ("irv97_tall_narrow", "tall", ["-qstep", "0.1"]),
+    ("irv97_tall_narrow1", "tall", ["-image_offset", "{1,0}", "-qstep", "0.1"]),
+    ("rev53_tall_narrow", "tall", ["-reversible", "true"]),
+    ("rev53_tall_narrow1", "tall", ["-image_offset", "{1,0}", "-reversible", "true"]),
+    ("irv97_qfactor50", "ppm8", ["-qfactor", "50"]),
+    ("irv97_qfactor50_gray", "pgm8", ["-qfactor", "50"]),
+]
+
+
+def _image(path_dir, kind):
+    w, h, nc, depth = {"ppm8": (300, 200, 3, 8), "ppm16": (200, 150, 3, 16), "pgm16": (200, 150, 1, 16),
+                       "pgm8": (300, 200, 1, 8), "tall": (7, 400, 3, 8)}[kind]
+    rng = np.random.default_rng(len(kind) + w)
+    y, x = np.mgrid[0:h, 0:w]
+    pix = np.stack([(np.sin(x / 9.0 + c) * np.cos(y / 6.0) * 0.45 + 0.5) * ((1 << depth) - 1) + rng.normal(0, (1 << depth) / 100.0, (h, w))
+                    for c in range(nc)], axis=-1)
+    pix = np.clip(np.rint(pix), 0, (1 << depth) - 1)
+    body = pix.astype(">u2").tobytes() if depth > 8 else pix.astype(np.uint8).tobytes()
+    p = path_dir / ("in." + ("ppm" if nc == 3 else "pgm"))
+    p.write_bytes((b"P6" if nc == 3 else b"P5") + b"\n%d %d\n%d\n" % (w, h, (1 << depth) - 1) + body)
+    return p, w * h * nc, depth
+
+
+@pytest.mark.parametrize("name,kind,opts", MATRIX, ids=[m[0] for m in MATRIX])
+def test_reference_encode_matrix_on_the_facade(name, kind, opts, apps, tmp_path):
+    src, nsamp, depth = _image(tmp_path, kind)
+    j, back = {}, {}
+    for fl in ("ref", "b200"):
+        j[fl] = tmp_path / ("o_%s.j2c" % fl)
+        subprocess.check_call([apps[("compress", fl)], "-i", str(src), "-o", str(j[fl])] + opts, stdout=subprocess.DEVNULL)
+        o = tmp_path / ("b_%s%s" % (fl, src.suffix))
+        subprocess.check_call([apps[("expand", fl)], "-i", str(j[fl]), "-o", str(o)], stdout=subprocess.DEVNULL)
+        back[fl] = o.read_bytes()
+    a, b = j["ref"].read_bytes(), j["b200"].read_bytes()
+    if "-reversible" in opts:
+        assert a == b and back["ref"] == back["b200"] == src.read_bytes()
+    else:
+        assert abs(len(a) - len(b)) <= max(4, len(a) // 1000) and a[:a.index(b"\xff\x90")] == b[:b.index(b"\xff\x90")]
+        dt = ">u2" if depth > 8 else np.uint8
+        es = 2 if depth > 8 else 1
+        orig = np.frombuffer(src.read_bytes()[-nsamp * es:], dt).astype(np.float64)
+        x, y = (np.frombuffer(back[f][-nsamp * es:], dt).astype(np.float64) for f in ("ref", "b200"))
+        m_ref, m_new = ((x - orig) ** 2).mean(), ((y - orig) ** 2).mean()
+        # the reference tests' own tolerance: MSE within 1 %, peak error within 1 (tests/test_executables.cpp:132-133)
+        assert abs(m_new - m_ref) <= max(0.01 * m_ref, 0.01) and abs(np.abs(y - orig).max() - np.abs(x - orig).max()) <= max(1, 0.01 * np.abs(x - orig).max())
