@@ -184,3 +184,24 @@ def test_reference_encode_matrix_on_the_facade(name, kind, opts, apps, tmp_path)
         m_ref, m_new = ((x - orig) ** 2).mean(), ((y - orig) ** 2).mean()
         # the reference tests' own tolerance: MSE within 1 %, peak error within 1 (tests/test_executables.cpp:132-133)
         assert abs(m_new - m_ref) <= max(0.01 * m_ref, 0.01) and abs(np.abs(y - orig).max() - np.abs(x - orig).max()) <= max(1, 0.01 * np.abs(x - orig).max())
+
+
+@pytest.mark.parametrize("bd,big_endian", [(10, True), (10, False), (16, True), (16, False)])
+def test_dpx_input_through_the_apps(bd, big_endian, apps, tmp_path):
+    """the reference's dpx_enc_* tests (tests/test_executables.cpp:1543-1630): a .dpx in, reversible"""
+    from test_raster_layouts import _dpx_file
+    w, h = 160, 90
+    rng = np.random.default_rng(bd)
+    pix = rng.integers(0, 1 << bd, (h, w, 3), dtype=np.uint32)
+    if bd == 10:
+        payload = ((pix[:, :, 0] << 22) | (pix[:, :, 1] << 12) | (pix[:, :, 2] << 2)).astype(">u4" if big_endian else "<u4").tobytes()
+    else:
+        payload = pix.reshape(h, 3 * w).astype(">u2" if big_endian else "<u2").tobytes()
+    src = tmp_path / "in.dpx"
+    _dpx_file(src, w, h, bd, big_endian, payload)
+    out = {}
+    for fl in ("ref", "b200"):
+        j = tmp_path / ("o_%s.j2c" % fl)
+        subprocess.check_call([apps[("compress", fl)], "-i", str(src), "-o", str(j), "-reversible", "true"], stdout=subprocess.DEVNULL)
+        out[fl] = j.read_bytes()
+    assert out["ref"] == out["b200"]
