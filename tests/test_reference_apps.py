@@ -205,3 +205,26 @@ def test_dpx_input_through_the_apps(bd, big_endian, apps, tmp_path):
         subprocess.check_call([apps[("compress", fl)], "-i", str(src), "-o", str(j), "-reversible", "true"], stdout=subprocess.DEVNULL)
         out[fl] = j.read_bytes()
     assert out["ref"] == out["b200"]
+
+
+def test_truncated_stream_through_expand(apps, tmp_path):
+    """ojph_expand -resilient true on a codestream cut short: both builds must agree on what comes out (and a
+    non-resilient run must fail in both)"""
+    src, _, _ = _image(tmp_path, "ppm8")
+    j = tmp_path / "full.j2c"
+    subprocess.check_call([apps[("compress", "ref")], "-i", str(src), "-o", str(j), "-reversible", "true", "-tile_size", "{128,128}"],
+                          stdout=subprocess.DEVNULL)
+    data = j.read_bytes()
+    for frac in (0.55, 0.8):
+        cut = tmp_path / ("cut_%d.j2c" % int(frac * 100))
+        cut.write_bytes(data[:int(len(data) * frac)])
+        res = {}
+        for fl in ("ref", "b200"):
+            o = tmp_path / ("r_%s_%d.ppm" % (fl, int(frac * 100)))
+            rc = subprocess.call([apps[("expand", fl)], "-i", str(cut), "-o", str(o), "-resilient", "true"],
+                                 stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            res[fl] = (rc, o.read_bytes() if o.exists() and rc == 0 else None)
+            strict = subprocess.call([apps[("expand", fl)], "-i", str(cut), "-o", str(tmp_path / "x.ppm")],
+                                     stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            assert strict != 0
+        assert res["ref"] == res["b200"], frac
