@@ -113,3 +113,28 @@ def test_alternate_block_coder_variants(emu_lib, ref):
                         "-k", "cfg1_256 or odd_rgb_L5 or rgb16_noise or offsets or irv_tiles or block_"],
                        env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("bd,ct", [(20, True), (24, False), (26, True), (27, True), (28, False)])
+def test_high_bit_depths_on_the_32bit_path(bd, ct, emu_lib, ref):
+    """the 32-bit coefficient path reaches 27-bit RGB with RCT (28-bit without): byte-identical and lossless"""
+    rng = np.random.default_rng(bd)
+    p = ob.make_params(96, 64, 3, bd, num_decomps=3, reversible=True, color_transform=ct, planar=0 if ct else 1)
+    fr = [rng.integers(0, 1 << bd, (64, 96)).astype(np.int32) for _ in range(3)]
+    want = ref.encode(p, fr)
+    assert ob.Encoder(p, ob.I32, lib=emu_lib).encode(fr) == want
+    for a, b in zip(ob.Decoder(lib=emu_lib).decode(want), fr):
+        assert np.array_equal(a, b)
+
+
+def test_beyond_the_32bit_path_is_refused_loudly(emu_lib, ref):
+    """28-bit RGB with RCT needs 33-bit coefficients (the reference switches to its 64-bit path): both directions
+    refuse with a clear error rather than produce something else"""
+    rng = np.random.default_rng(1)
+    p = ob.make_params(64, 48, 3, 28, num_decomps=3, reversible=True, color_transform=True)
+    fr = [rng.integers(0, 1 << 28, (48, 64)).astype(np.int32) for _ in range(3)]
+    with pytest.raises(ob.OjphError, match="0x000B0001"):
+        ob.Encoder(p, ob.I32, lib=emu_lib)
+    cs = ref.encode(p, fr)
+    with pytest.raises(ob.OjphError, match="0x000B0001"):
+        ob.Decoder(lib=emu_lib).decode(cs)
