@@ -340,9 +340,10 @@ def encode_blocks(samples, descs, lib=None):
     return [out[arr[i].byte_off:arr[i].byte_off + arr[i].len1].tobytes() for i in range(n)]
 
 
-def decode_blocks(coded, geoms, lib=None):
+def decode_blocks(coded, geoms, lib=None, causal=False):
     """batch ojph_decode_codeblock32: coded = list of (bytes, len1, len2, missing_msbs, num_passes),
-    geoms = list of (w, h) -> list of ((h, w) uint32 sign-magnitude arrays, ok flag)."""
+    geoms = list of (w, h) -> list of ((h, w) uint32 sign-magnitude arrays, ok flag); causal = the
+    stripe_causal argument for every block."""
     L = lib if lib is not None else _lib.lib()
     n = len(coded)
     arr = (_lib.BlockDesc * n)()
@@ -353,6 +354,7 @@ def decode_blocks(coded, geoms, lib=None):
         arr[i].sample_off, arr[i].stride, arr[i].w, arr[i].h = soff, stride, w, h
         arr[i].missing_msbs, arr[i].num_passes, arr[i].len1, arr[i].len2 = mm, npass, l1, l2
         arr[i].byte_off = len(blob)
+        arr[i].causal = 1 if causal else 0
         blob += data
         soff += stride * h
     cs = np.frombuffer(bytes(blob) + b"\0" * 64, np.uint8).copy()

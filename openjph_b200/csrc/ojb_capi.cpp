@@ -160,6 +160,7 @@ int ojb_enc_configure(ojb_encoder* e, const ojb_params* p, uint32_t sample_type)
     if (sample_type > 2) fail(0x000B0012, "unknown sample container");
     Params P; to_params(p, P);
     P.comments = e->comments;
+    e->configured = false;               // a failing configure leaves no half-built encoder behind
     e->enc.configure(P, sample_type);
     e->configured = true;
   });
@@ -417,6 +418,7 @@ int ojb_dec_read_headers(ojb_decoder* d, const uint8_t* j2c, uint64_t len, uint3
                          ojb_frame_info* info) {
   return guarded_on(d->device, [&] {
     if (sample_type > 2) fail(0x000B0012, "unknown sample container");
+    d->have_headers = false;             // a failing read_headers leaves no half-built decoder behind
     d->dec.read_headers(j2c, (size_t)len, sample_type);
     d->have_headers = true;
     if (info) {

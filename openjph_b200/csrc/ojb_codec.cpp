@@ -507,7 +507,11 @@ void Decoder::read_headers(const uint8_t* data, size_t len, uint32_t sample_type
     sig.push_back((uint8_t)sample_type);
   }
   if (sig == header_sig && !layout.tiles.empty()) return;
-  header_sig = sig;
+  // everything below can throw (precision check, geometry, cudaMalloc, container check): the signature
+  // that lets the next call skip this rebuild is committed last, so a failed setup is redone
+  header_sig.clear();
+  if (np.num_comps() > 16)
+    fail(0x000B0008, "%u components: the frame interface carries at most 16", np.num_comps());
   params = np;
   // the decoder side derives the same planar default as the reference (read_headers :879)
   params.planar = params.color_transform() ? 0 : 1;
@@ -553,6 +557,7 @@ void Decoder::read_headers(const uint8_t* data, size_t len, uint32_t sample_type
   h_dec.reserve(std::max<size_t>(1, h_dec_proto.size()) * sizeof(DecBlock));
   d_bstatus.reserve(std::max<size_t>(1, h_dec_proto.size()) * 4);
   h_bstatus.reserve(std::max<size_t>(1, h_dec_proto.size()) * 4);
+  header_sig = sig;
 }
 
 void Decoder::setup_geometry(uint32_t sample_type) {
@@ -589,7 +594,9 @@ void Decoder::info(FrameInfo& fi) const {
     fi.comp_w[c] = img_w[c]; fi.comp_h[c] = img_h[c];            // reconstruction size (restrict_resolution)
     fi.nlt_type[c] = params.nlt_type(c);
   }
-  fi.num_decomps = params.num_decomps; fi.reversible = params.reversible();      // COD values (components may differ: COC) fi.color_transform = params.color_transform();
+  // COD values (components may differ: COC)
+  fi.num_decomps = params.num_decomps; fi.reversible = params.reversible();
+  fi.color_transform = params.color_transform();
   fi.num_tiles = (uint32_t)layout.tiles.size();
 }
 

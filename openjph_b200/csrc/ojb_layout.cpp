@@ -442,6 +442,25 @@ void parse_packet(const Params& P, const ResGeom& res, const PrecinctGeom& pc,
     }
   }
   bool empty_packet = true;
+  // A header that fails to parse delivers no body: the blocks of this packet whose lengths were already
+  // read must not reach the block decoder (the reference decodes a block only once its body has been
+  // attached, ojph_codeblock.cpp:192-193) -- resilient mode swallows the exception and carries on.
+  struct DropOnError {
+    const ResGeom& res; const PrecinctGeom& pc; CodedBlock* blocks; bool armed = true;
+    ~DropOnError() {
+      if (!armed) return;
+      for (uint32_t s = 0; s < 4; ++s) {
+        const BandGeom& bg = res.bands[s];
+        if (bg.empty) continue;
+        const Rect& ci = pc.cb_idx[s];
+        for (uint32_t y = 0; y < ci.h; ++y)
+          for (uint32_t x = 0; x < ci.w; ++x) {
+            CodedBlock& cb = blocks[bg.block_base + (size_t)(ci.y0 + y) * bg.nbw + ci.x0 + x];
+            if (cb.data_off == 0) { cb.pass_len[0] = cb.pass_len[1] = 0; cb.num_passes = 0; }
+          }
+      }
+    }
+  } drop{res, pc, blocks};
   for (uint32_t s = 0; s < 4; ++s) {
     const BandGeom& bg = res.bands[s];
     if (bg.empty) continue;
@@ -456,6 +475,7 @@ void parse_packet(const Params& P, const ResGeom& res, const PrecinctGeom& pc,
           if (pos + 2 > data_end) throw Error(0x00030092, "error reading from file");
           pos += 2; data_left -= 2;
         }
+        drop.armed = false;
         return;
       }
       empty_packet = false;
@@ -562,6 +582,7 @@ void parse_packet(const Params& P, const ResGeom& res, const PrecinctGeom& pc,
   // the rest of this packet with it (bb_read_chunk, ojph_bitbuffer_read.h:134-150; ojph_precinct.cpp:
   // 536-573), but the tile-part's byte budget stays what Psot says: the next packet header then fails
   // to read, which is how a truncation is detected outside resilient mode.
+  drop.armed = false;
   bool body_ok = true;
   for (uint32_t s = 0; s < 4; ++s) {
     const BandGeom& bg = res.bands[s];

@@ -62,6 +62,11 @@ static std::vector<ui8> compress(const std::vector<std::vector<si32>>& planes, u
   return out;
 }
 
+// what the last expand() saw without ever calling set_planar: is_planar(), is_using_color_transform(), then the
+// component index of every pulled line -- the reference's defaults (read_headers: planar = !colour transform,
+// ojph_codestream_local.cpp:879) decide the order a caller's `if (is_planar())` loop relies on
+static std::vector<si32> g_trace;
+
 template <typename CS>
 static std::vector<std::vector<si32>> expand(const std::vector<ui8>& j2c, ui32 skip = 0)
 {
@@ -84,12 +89,16 @@ static std::vector<std::vector<si32>> expand(const std::vector<ui8>& j2c, ui32 s
   std::vector<std::vector<si32>> planes(nc);
   std::vector<ui32> row(nc, 0);
   cs.create();
+  g_trace.clear();
+  g_trace.push_back(cs.is_planar() ? 1 : 0);
+  g_trace.push_back(cs.access_cod().is_using_color_transform() ? 1 : 0);
   ui32 total = 0;
   for (ui32 c = 0; c < nc; ++c) { planes[c].resize((size_t)siz.get_recon_width(c) * siz.get_recon_height(c)); total += siz.get_recon_height(c); }
   for (ui32 i = 0; i < total; ++i) {
     ui32 c;
     line_buf* line = cs.pull(c);
     if (!line) { fprintf(stderr, "pull ended early\n"); exit(2); }
+    g_trace.push_back((si32)c);
     const ui32 w = siz.get_recon_width(c);
     for (ui32 x = 0; x < w; ++x) planes[c][(size_t)row[c] * w + x] = line->i32[x];
     row[c]++;
@@ -111,7 +120,10 @@ int main()
     std::vector<ui8> b = compress<ojph::b200::codestream, ojph::b200::comment_exchange, ojph::b200::param_nlt>(planes, w, h, depth, planar != 0);
     const bool same = a == b;
     std::vector<std::vector<si32>> ra = expand<ojph::codestream>(a);
+    const std::vector<si32> ta = g_trace;
     std::vector<std::vector<si32>> rb = expand<ojph::b200::codestream>(a);
+    const bool defaults = ta == g_trace && ta[0] == planar && ta[1] == 1 - planar;
+    if (!defaults) { printf("read-side defaults differ: planar %d/%d colour transform %d/%d\n", ta[0], g_trace[0], ta[1], g_trace[1]); ++fails; }
     const bool lossless = ra == planes && rb == planes;
     printf("planar=%d codestream %zu bytes identical=%d lossless=%d\n", planar, a.size(), (int)same, (int)lossless);
     if (!same || !lossless) ++fails;

@@ -46,10 +46,39 @@ def multipass_blocks():
         out["data_%d" % i] = np.frombuffer(data, np.uint8)
         out["meta_%d" % i] = np.array([b.w, b.h, b.missing_msbs, b.num_passes, b.len1, b.len2, int(ok)], np.uint32)
         out["want_%d" % i] = want
+        # the same bytes decoded with the stripe-causal rule (SPP ignores the row below the stripe,
+        # ojph_block_decoder32.cpp:1411-1415): the reference cannot ENCODE such a stream, so the causal path of
+        # the decoder is pinned by what the reference decodes from these blocks when told they are causal
+        wantc, okc = R.decode_block(data, b.w, b.h, b.missing_msbs, b.num_passes, b.len1, b.len2, causal=True)
+        out["wantc_%d" % i] = wantc
+        out["okc_%d" % i] = np.array(int(okc))
         i += 1
     out["n"] = np.array(i)
     np.savez_compressed(os.path.join(HERE, "ht_multipass_blocks.npz"), **out)
     print("ht_multipass_blocks:", i, "blocks")
+
+
+def whole_multipass_stream():
+    """test_j2c.npz: the in-tree stream itself (32 KB, the only in-tree stream with SPP / MRP passes) and what the
+    reference's ojph::codestream decodes from it -- as is, and with the vertically-causal bit of its COD segment
+    (Scod style bit 3 of SPcod's code-block style byte) switched on"""
+    cs = open("/root/reference/subprojects/js/html/test.j2c", "rb").read()
+    planes, info = R.decode(cs)
+    out = {"cs": np.frombuffer(cs, np.uint8)}
+    for c, a in enumerate(planes):
+        assert np.abs(a).max() < 32768
+        out["dec%d" % c] = a.astype(np.int16)
+    k = cs.index(b"\xff\x52")                      # COD: marker, Lcod(2), Scod(1), SGcod(4), SPcod: levels, xcb, ycb, style
+    causal = bytearray(cs)
+    assert causal[k + 12] & 0x40, "not an HT stream?"
+    causal[k + 12] |= 0x08
+    planes_c, _ = R.decode(bytes(causal))
+    out["cs_causal"] = np.frombuffer(bytes(causal), np.uint8)
+    for c, a in enumerate(planes_c):
+        out["decc%d" % c] = a.astype(np.int16)
+    out["differs"] = np.array(int(any(not np.array_equal(a, b) for a, b in zip(planes, planes_c))))
+    np.savez_compressed(os.path.join(HERE, "test_j2c.npz"), **out)
+    print("test_j2c: %d bytes, %d comps, causal decode differs: %d" % (len(cs), len(planes), int(out["differs"])))
 
 
 def encode_blocks():
@@ -179,4 +208,4 @@ def kernels():
 
 if __name__ == "__main__":
     assert R.available(), "build oracle/_ref first (make -C oracle)"
-    encode_blocks(); codestreams(); kernels(); multipass_blocks()
+    encode_blocks(); codestreams(); kernels(); multipass_blocks(); whole_multipass_stream()

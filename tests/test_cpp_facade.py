@@ -23,3 +23,15 @@ def test_facade_matches_reference_application_code(emu_lib, ref, tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("identical=1 lossless=1") == 3 and "reduced=1" in r.stdout, r.stdout
+
+
+@pytest.mark.gpu
+def test_facade_matches_reference_application_code_gpu(gpu_lib):
+    """the same program linked against the nvcc-built product library (prebuilt by oracle/Makefile: the GPU box
+    has no reference headers), kernels on the real device"""
+    exe = os.path.join(ROOT, "oracle", "_ref", "apps", "facade_roundtrip_b200")
+    if not os.path.exists(exe) and not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libopenjph_ref.so")):
+        pytest.skip("oracle/_ref was not built (needs /root/reference at build time)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("identical=1 lossless=1") == 3 and "reduced=1" in r.stdout, r.stdout

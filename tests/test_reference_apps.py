@@ -1,7 +1,8 @@
-"""Drop-in proof at the application level (CPU tier, needs /root/reference): the reference's own
-ojph_compress.cpp and ojph_expand.cpp, UNMODIFIED, are compiled twice -- against ojph::codestream and, through a
-force-included header, against ojph::b200::codestream -- and run on the same files: same codestream bytes, same
-decoded image."""
+"""Drop-in proof at the application level: the reference's own ojph_compress.cpp and ojph_expand.cpp, UNMODIFIED,
+are compiled twice -- against ojph::codestream and, through a force-included header, against
+ojph::b200::codestream -- and run on the same files: same codestream bytes, same decoded image.  Every test runs
+in the CPU tier over the SIMT-emulator build (needs /root/reference) and, marked `gpu`, over the nvcc-built
+product library on a real B200 (executables prebuilt by oracle/Makefile into oracle/_ref/apps)."""
 import os
 import subprocess
 import numpy as np
@@ -12,8 +13,23 @@ REF = "/root/reference/src"
 REFLIB = os.path.join(ROOT, "oracle", "_ref")
 
 
-@pytest.fixture(scope="module")
-def apps(tmp_path_factory, emu_lib):
+PREBUILT = os.path.join(REFLIB, "apps")
+
+
+@pytest.fixture(scope="module", params=["emu", pytest.param("gpu", marks=pytest.mark.gpu)])
+def apps(request, tmp_path_factory):
+    """(app, flavour) -> executable.  `emu`: compiled here against the SIMT-emulator build (CPU tier, needs
+    /root/reference).  `gpu`: the executables oracle/Makefile built against the nvcc-built product library
+    (oracle/_ref/apps, travels with gpurun) -- the same unmodified sources running on a real B200."""
+    if request.param == "gpu":
+        request.getfixturevalue("gpu_lib")
+        out = {(a, f): os.path.join(PREBUILT, "ojph_%s_%s" % (a, f)) for a in ("compress", "expand") for f in ("ref", "b200")}
+        missing = [v for v in out.values() if not os.path.exists(v)]
+        if missing and not os.path.exists(os.path.join(REFLIB, "libopenjph_ref.so")):
+            pytest.skip("oracle/_ref was not built (needs /root/reference at build time)")
+        assert not missing, "oracle/_ref/apps is incomplete: %s" % missing
+        return out
+    request.getfixturevalue("emu_lib")
     if not os.path.isdir(REF) or not os.path.exists(os.path.join(REFLIB, "libopenjph_ref.so")):
         pytest.skip("needs the reference sources and oracle/_ref")
     d = tmp_path_factory.mktemp("apps")

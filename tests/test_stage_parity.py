@@ -85,16 +85,21 @@ def test_blocks_match_port_gpu(gpu_lib):
     _blocks_vs_port(None, 500, 22)
 
 
-def _multipass_golden(lib):
+def _multipass_golden(lib, causal=False):
     import os
     z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ht_multipass_blocks.npz"))
     coded, geoms, want = [], [], []
     for i in range(int(z["n"])):
         w, h, mm, npass, l1, l2, ok_ref = [int(v) for v in z["meta_%d" % i]]
-        coded.append((z["data_%d" % i].tobytes(), l1, l2, mm, npass)); geoms.append((w, h)); want.append(z["want_%d" % i])
-    got = ob.decode_blocks(coded, geoms, lib=lib)
+        coded.append((z["data_%d" % i].tobytes(), l1, l2, mm, npass)); geoms.append((w, h))
+        want.append(z["wantc_%d" % i] if causal else z["want_%d" % i])
+    got = ob.decode_blocks(coded, geoms, lib=lib, causal=causal)
+    ndiff = 0
     for i, ((a, ok), b) in enumerate(zip(got, want)):
         assert ok and np.array_equal(a, b), i
+        ndiff += int(causal and not np.array_equal(b, z["want_%d" % i]))
+    if causal:
+        assert ndiff > 0, "the causal goldens do not exercise the causal rule"
 
 
 def test_sigprop_magref_golden_emulated(emu_lib):
@@ -104,6 +109,42 @@ def test_sigprop_magref_golden_emulated(emu_lib):
 @pytest.mark.gpu
 def test_sigprop_magref_golden_gpu(gpu_lib):
     _multipass_golden(None)
+
+
+def test_sigprop_stripe_causal_golden_emulated(emu_lib):
+    """stripe_causal = true: the bytes of test.j2c's blocks decoded as the reference decodes them when told so"""
+    _multipass_golden(emu_lib, causal=True)
+
+
+@pytest.mark.gpu
+def test_sigprop_stripe_causal_golden_gpu(gpu_lib):
+    _multipass_golden(None, causal=True)
+
+
+def _whole_multipass_stream(lib):
+    """the reference's in-tree subprojects/js/html/test.j2c (9/7, 77 of 89 coded blocks with SPP / MRP passes) decoded
+    as a whole codestream, against what the reference's ojph::codestream (= ojph_expand) produces from it; then the
+    same stream with the vertically-causal COD bit set"""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "test_j2c.npz"))
+    for cs_key, dec_key in (("cs", "dec"), ("cs_causal", "decc")):
+        out = ob.Decoder(lib=lib).decode(z[cs_key].tobytes())
+        assert len(out) == 3
+        for c in range(3):
+            want = z["%s%d" % (dec_key, c)].astype(np.int32)
+            assert out[c].shape == want.shape
+            assert np.abs(out[c] - want).max() <= 1, (cs_key, c)          # 9/7: the reference tests' peak-error tolerance
+            assert np.mean(out[c] != want) < 0.01, (cs_key, c)
+    assert int(z["differs"]) == 1
+
+
+def test_whole_multipass_stream_emulated(emu_lib):
+    _whole_multipass_stream(emu_lib)
+
+
+@pytest.mark.gpu
+def test_whole_multipass_stream_gpu(gpu_lib):
+    _whole_multipass_stream(None)
 
 
 def _codestream_goldens(lib):

@@ -28,6 +28,9 @@ def _check(lib, ref=None):
         part = full[:len(full) * cut // NUM_CUTS]
         out = ob.Decoder(resilient=True, lib=lib).decode(part)               # must not raise
         assert out[0].shape == (H, W)
+        if ref is not None:                   # what survives is what the reference reconstructs from the same bytes
+            want, _ = ref.decode(part, resilient=True)
+            assert np.array_equal(out[0], want[0]), "resilient decode of cut %d/%d differs from the reference" % (cut, NUM_CUTS)
         raised = False
         try:
             ob.Decoder(resilient=False, lib=lib).decode(part)
@@ -70,3 +73,38 @@ def test_corrupted_tile_data_is_survived(emu_lib, ref):
                 bad[int(rng.integers(sod, len(bad) - 2))] = int(rng.integers(0, 256))
             out = ob.Decoder(resilient=True, lib=emu_lib).decode(bytes(bad))
             assert len(out) == p.num_comps and out[0].shape == (kw["height"], kw["width"])
+
+
+def _check_failed_setup_is_not_remembered(lib):
+    """a read_headers that fails after the header bytes were accepted (10-bit stream, 8-bit container) must fail
+    again when repeated, and must not poison the decoder for a valid call"""
+    img = (np.arange(64 * 64, dtype=np.int32).reshape(64, 64) * 5) & 1023
+    p = ob.make_params(64, 64, 1, 10, num_decomps=2, reversible=True)
+    cs = ob.Encoder(p, ob.I32, lib=lib).encode([img])
+    dec = ob.Decoder(lib=lib)
+    for _ in range(2):
+        with pytest.raises(ob.OjphError):
+            dec.decode(cs, sample_type=ob.U8)
+    out = dec.decode(cs, sample_type=ob.U16)
+    assert np.array_equal(out[0], img)
+
+
+def test_failed_setup_is_not_remembered_emulator(emu_lib):
+    _check_failed_setup_is_not_remembered(emu_lib)
+
+
+@pytest.mark.gpu
+def test_failed_setup_is_not_remembered_gpu(gpu_lib):
+    _check_failed_setup_is_not_remembered(None)
+
+
+def test_frame_info_reports_colour_transform(emu_lib):
+    """Decoder::info: an RCT stream says so (the facade's is_using_color_transform / is_planar default hang on it)"""
+    rng = np.random.default_rng(3)
+    planes = [rng.integers(0, 256, (40, 56)).astype(np.int32) for _ in range(3)]
+    for ct in (True, False):
+        p = ob.make_params(56, 40, 3, 8, num_decomps=2, reversible=True, color_transform=ct)
+        cs = ob.Encoder(p, ob.I32, lib=emu_lib).encode(planes)
+        dec = ob.Decoder(lib=emu_lib)
+        info = dec.read_headers(cs)
+        assert bool(info.color_transform) == ct
