@@ -10,11 +10,19 @@ overlap the kernels of another (weak scaling; frames are independent, so there i
 collective -- only the final gather of the codestream sizes to rank 0).
 
   value : frame already resident in HBM when the timed region starts (encoder's device image
-          buffer), codestream left on the device, decoded image left on the device
+          buffer); the codestream is written to device memory and decoded FROM device memory (the
+          decoder fetches only the marker segments / packet headers its host parser reads, a few
+          64 KB pages per frame: ojb_dec_read_headers_device); decoded image left on the device
   e2e   : the reference-facing C-ABI frame calls with HOST buffers (pinned): H2D of the planes,
           D2H of the codestream, H2D of the codestream, D2H of the decoded planes, all timed
   --impl reference : the unmodified reference (oracle/_ref, compiled from /root/reference by
-          oracle/Makefile) on the host cores, one process per core, in-memory files
+          oracle/Makefile) on the host cores the job may use (cgroup quota honoured), one process per
+          core, each encoding + decoding whole 8192x8192 frames in memory with preallocated buffers
+
+`config` is the same object in both arms (the workload); everything specific to an arm or a run is
+under `detail`.  Besides the headline the GPU arm reports, under detail.configs, the other BASELINE
+configurations (cfg2..cfg5), the headline through 9/7 + ICT q90 and the two extremes SURVEY 8(d) asks for
+(all-zero and uniform-random frames), each with its own kernel times and frame-level roofline.
 """
 import argparse
 import ctypes as C
@@ -26,13 +34,16 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-PROFILE_JSON = "r01k_kernels.json"      # the committed ncu --set full summary the roofline's `traffic` comes from
+PROFILE_JSON = "r02_kernels.json"       # the committed ncu --set full summary the roofline's `traffic` comes from
+PROFILE_FALLBACK = "r01k_kernels.json"
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 W = H = 8192
 NC, BD, LEVELS = 3, 12, 5
-CPU_TILE = 4096            # the CPU arms process a bounded sample: one 4096x4096 quarter frame
+WORKLOAD = ("8192x8192x3 12-bit, reversible 5/3 + RCT, 5 levels, 64x64 code-blocks, RPCL; a step = a batch of "
+            "independent frames, each encoded then decoded")
+CONFIG = {"workload": WORKLOAD, "l2_policy": "inputs larger than L2 (402 MB frame, 805 MB coefficients)"}
 
 
 def workload_params(w=W, h=H):
@@ -40,9 +51,48 @@ def workload_params(w=W, h=H):
     return ob.make_params(w, h, NC, BD, num_decomps=LEVELS, reversible=True, color_transform=True)
 
 
-def make_frame(w, h, seed):
+def make_frame(w, h, seed, nc=NC, bd=BD):
     import images
-    return [p.astype("uint16") for p in images.synth_frame(w, h, NC, BD, seed)]
+    return [p.astype("uint16" if bd > 8 else "uint8") for p in images.synth_frame(w, h, nc, bd, seed)]
+
+
+def usable_cpus():
+    """host threads this job may really use: the affinity mask, cut down to the cgroup CPU quota"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    src = "affinity"
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            c = max(1, int(float(q) / float(per) + 0.5))
+            if c < n:
+                n, src = c, "cgroup cpu.max"
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read()); per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0 and max(1, q // per) < n:
+                n, src = max(1, q // per), "cgroup cfs quota"
+        except Exception:
+            pass
+    return n, src
+
+
+def usable_memory_bytes():
+    avail = None
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable:"):
+                avail = int(ln.split()[1]) * 1024
+    except Exception:
+        pass
+    try:
+        m = open("/sys/fs/cgroup/memory.max").read().strip()
+        if m != "max":
+            cur = int(open("/sys/fs/cgroup/memory.current").read())
+            left = int(m) - cur
+            avail = left if avail is None else min(avail, left)
+    except Exception:
+        pass
+    return avail
 
 
 class ClockSampler(threading.Thread):
@@ -72,46 +122,65 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.maxc, "reasons": sorted(self.reasons)}
 
 
-_CPU_FRAME = None
+# ---------------------------------------------------------------------------------------------
+# CPU arms: the unmodified reference (oracle/_ref) in memory, whole frames, nothing allocated in the timed call
+# ---------------------------------------------------------------------------------------------
+_CPU = {}
 
 
-def cpu_worker_init(seed):
-    """per-process set-up (outside the timed region): load the reference build, synthesise the frame"""
-    global _CPU_FRAME
-    import numpy as np
-    import refharness  # noqa: F401  (dlopen of oracle/_ref)
-    _CPU_FRAME = [f.astype(np.int32) for f in make_frame(CPU_TILE, CPU_TILE, seed)]
-
-
-def cpu_worker(args):
-    """one reference encode+decode of a CPU_TILE^2 frame; returns seconds (enc, dec) and the size"""
-    seed, check = args
+def cpu_worker_init(frame_file):
+    """per-process set-up, outside the timed region: load the reference build, the frame (int32 lines as
+    ojph::codestream::exchange takes them), and pre-touch the output buffers"""
     import numpy as np
     import refharness as R
-    if _CPU_FRAME is None:
-        cpu_worker_init(seed)
-    p = workload_params(CPU_TILE, CPU_TILE)
-    t0 = time.perf_counter(); cs = R.encode(p, _CPU_FRAME); t1 = time.perf_counter()
-    out, _ = R.decode(cs); t2 = time.perf_counter()
+    R.lib()
+    z = np.load(frame_file)
+    frame = [np.ascontiguousarray(z["c%d" % c], np.int32) for c in range(NC)]
+    h, w = frame[0].shape
+    _CPU["frame"] = frame
+    _CPU["p"] = workload_params(w, h)
+    _CPU["cs"] = np.empty(w * h * NC * 2 + (1 << 20), np.uint8)
+    _CPU["out"] = [np.empty((h, w), np.int32) for _ in range(NC)]
+    _CPU["cs"].fill(0)                                      # every page touched before the timed region
+    for a in _CPU["out"]:
+        a.fill(0)
+
+
+def cpu_worker(check):
+    """one reference encode + decode of the frame; returns seconds (enc, dec) and the codestream size"""
+    import numpy as np
+    import refharness as R
+    t0 = time.perf_counter(); n = R.encode_into(_CPU["p"], _CPU["frame"], _CPU["cs"]); t1 = time.perf_counter()
+    R.decode_into(_CPU["cs"], n, _CPU["out"]); t2 = time.perf_counter()
     if check:
-        assert all(np.array_equal(a, b) for a, b in zip(out, _CPU_FRAME))
-    return t1 - t0, t2 - t1, len(cs)
+        assert all(np.array_equal(a, b) for a, b in zip(_CPU["out"], _CPU["frame"]))
+    return t1 - t0, t2 - t1, n
 
 
-def run_cpu_reference(procs, steps, warmup):
-    """all host threads: `procs` persistent processes, each one encodes+decodes one quarter frame
-    per step; frames are synthesised once per process before the timed region"""
+def write_frame_file(frame):
+    import numpy as np
+    import tempfile
+    f = tempfile.NamedTemporaryFile(prefix="ojb_bench_frame_", suffix=".npz", delete=False)
+    f.close()
+    np.savez(f.name, **{"c%d" % c: a for c, a in enumerate(frame)})
+    return f.name
+
+
+def run_cpu_reference(procs, steps, warmup, frame_file):
+    """`procs` persistent processes, each one encodes + decodes one whole frame per step"""
     import multiprocessing as mp
     ctx = mp.get_context("spawn")
-    with ctx.Pool(procs, initializer=cpu_worker_init, initargs=(1234,)) as pool:
-        for _ in range(max(1, warmup)):
-            pool.map(cpu_worker, [(1234, True)] * procs, chunksize=1)
+    with ctx.Pool(procs, initializer=cpu_worker_init, initargs=(frame_file,)) as pool:
+        for i in range(max(1, warmup)):
+            pool.map(cpu_worker, [i == 0] * procs, chunksize=1)
         t0 = time.perf_counter()
+        per = []
         for _ in range(steps):
-            pool.map(cpu_worker, [(1234, False)] * procs, chunksize=1)
+            per += pool.map(cpu_worker, [False] * procs, chunksize=1)
         dt = time.perf_counter() - t0
-    pix = procs * steps * CPU_TILE * CPU_TILE
-    return pix / dt / 1e6, dt / steps * 1e3
+    pix = procs * steps * W * H
+    te = sum(p[0] for p in per) / len(per); td = sum(p[1] for p in per) / len(per)
+    return pix / dt / 1e6, dt / steps * 1e3, te, td
 
 
 def bind_to_gpu_numa_node(torch, local):
@@ -135,6 +204,10 @@ def bind_to_gpu_numa_node(torch, local):
     return "unbound"
 
 
+ENC_STAGES = ("h2d", "dwt", "ht_encode", "d2h_lengths", "host_wait", "assemble", "d2h_out", "host_ms")
+DEC_STAGES = ("h2d", "host_parse", "ht_decode", "dwt_inv", "d2h_image", "_5", "_6", "host_ms")
+
+
 def main():
     # the contract is ONE JSON line on stdout: keep the real stdout for it and send everything libraries
     # print at C level (e.g. NCCL's version banner) to stderr
@@ -150,10 +223,7 @@ def main():
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    cfg = {"workload": "8192x8192x3 12-bit, reversible 5/3 + RCT, 5 levels, 64x64 code-blocks, RPCL; a step = a batch of "
-                       "independent frames per GPU, each encoded then decoded", "frames_per_step": max(1, a.gpus),
-           "l2_policy": "inputs larger than L2 (402 MB frame, 805 MB coefficients)"}
+    cfg = dict(CONFIG)
 
     if a.impl == "reference":
         if rank != 0:
@@ -162,14 +232,24 @@ def main():
         if not R.available():
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref was not built (needs /root/reference at build time)"}), file=out); out.flush()
             return
-        procs = max(1, cores)
-        v, ms = run_cpu_reference(procs, max(1, a.steps), max(0, min(a.warmup, 1)))
-        sample = "%d processes x one %dx%dx3 12-bit quarter frame per step, in-memory files, ISA level %d" % (
-            procs, CPU_TILE, CPU_TILE, R.lib().ojr_cpu_ext_level())
+        cores, src = usable_cpus()
+        procs = int(os.environ.get("OJB_BENCH_CPU_PROCS", "0")) or cores
+        mem = usable_memory_bytes()
+        per_proc = W * H * NC * (4 + 4 + 2) + (512 << 20)          # int32 frame + int32 output + codestream + slack
+        if mem is not None:
+            procs = max(1, min(procs, int(mem * 0.6) // per_proc))
+        frame_file = write_frame_file(make_frame(W, H, 1234))
+        try:
+            v, ms, te, td = run_cpu_reference(procs, max(1, a.steps), max(0, min(a.warmup, 1)), frame_file)
+        finally:
+            os.unlink(frame_file)
+        sample = ("%d processes (%s: %d usable CPUs of %d in the affinity mask) x one whole 8192x8192x3 12-bit frame per step, in-memory "
+                  "files, buffers preallocated; per process encode %.2f s decode %.2f s; ISA level %d" % (
+                      procs, src, cores, len(os.sched_getaffinity(0)), te, td, R.lib().ojr_cpu_ext_level()))
         print(json.dumps({"impl": "reference", "metric": "Mpixels/s encode+decode", "value": v, "unit": "Mpixels/s",
                           "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
-                          "data": "synthetic", "config": cfg,
+                          "data": "synthetic", "config": cfg, "detail": {"frames_per_step": procs},
                           "cpu_baseline": {"value": v, "unit": "Mpixels/s", "cores": procs, "kind": "reference", "sample": sample},
                           "e2e": {"value": v, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), file=out)
         out.flush()
@@ -188,55 +268,67 @@ def main():
     assert L.ojb_set_device(local) == 0, L.ojb_last_error()
     torch.cuda.set_device(local)
     affinity = bind_to_gpu_numa_node(torch, local)      # before any pinned allocation (first touch)
-
-    p = workload_params()
-    frame = make_frame(W, H, 1234 + rank)
     NW = int(os.environ.get("OJB_BENCH_WORKERS", "8"))      # frames in flight per GPU (one codec pair each)
-    # pinned host buffers: one input frame (shared, read-only), per-worker outputs
-    pin = [torch.empty((H, W), dtype=torch.uint16, pin_memory=True) for _ in range(NC)]
-    for t, f in zip(pin, frame):
-        t.numpy()[:] = f
-    planes = (C.c_void_p * NC)(*[t.data_ptr() for t in pin])
-    cs_cap = W * H * NC * 2 + (1 << 20)
 
     def ck(rc):
         if rc != 0:
             raise RuntimeError(L.ojb_last_error().decode())
 
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(max(NW, 8))
+
+    class Workload:
+        """one configuration: a frame (list of uint8/uint16 planes), parameters, `n` codec pairs"""
+        def __init__(self, params, frame, n):
+            self.p = params
+            self.frame = frame
+            self.st = ob.U8 if frame[0].dtype == np.uint8 else ob.U16
+            self.nc = len(frame)
+            self.pix = frame[0].shape[0] * frame[0].shape[1]
+            self.in_bytes = sum(f.nbytes for f in frame)
+            self.pin = [torch.empty(f.shape, dtype=torch.uint8 if f.dtype == np.uint8 else torch.uint16, pin_memory=True) for f in frame]
+            for t, f in zip(self.pin, frame):
+                t.numpy()[:] = f
+            self.planes = (C.c_void_p * self.nc)(*[t.data_ptr() for t in self.pin])
+            self.cs_cap = self.in_bytes * 2 + (1 << 20)
+            self.workers = [Worker(self) for _ in range(n)]
+
+        def close(self):
+            for w in self.workers:
+                L.ojb_enc_destroy(w.enc); L.ojb_dec_destroy(w.dec)
+            self.workers = []
+
     class Worker:
-        def __init__(self, params=None):
+        def __init__(self, wl):
+            self.wl = wl
             self.enc = L.ojb_enc_create(); self.dec = L.ojb_dec_create()
-            ck(L.ojb_enc_configure(self.enc, C.byref(params if params is not None else p), ob.U16))
-            self.out_pin = [torch.empty((H, W), dtype=torch.uint16, pin_memory=True) for _ in range(NC)]
-            self.outs = (C.c_void_p * NC)(*[t.data_ptr() for t in self.out_pin])
-            self.cs_pin = torch.empty(cs_cap, dtype=torch.uint8, pin_memory=True)
-            self.cs_dev = torch.empty(cs_cap, dtype=torch.uint8, device="cuda")
+            ck(L.ojb_enc_configure(self.enc, C.byref(wl.p), wl.st))
+            self.out_pin = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in wl.pin]
+            self.outs = (C.c_void_p * wl.nc)(*[t.data_ptr() for t in self.out_pin])
+            self.cs_pin = torch.empty(wl.cs_cap, dtype=torch.uint8, pin_memory=True)
+            self.cs_dev = torch.empty(wl.cs_cap, dtype=torch.uint8, device="cuda")
             self.n = C.c_uint64(); self.fi = _lib.FrameInfo(); self.cs_len = 0
 
         def e2e(self):
-            ck(L.ojb_enc_encode_frame(self.enc, planes, None, self.cs_pin.data_ptr(), cs_cap, C.byref(self.n)))
-            ck(L.ojb_dec_read_headers(self.dec, self.cs_pin.data_ptr(), self.n.value, ob.U16, C.byref(self.fi)))
+            wl = self.wl
+            ck(L.ojb_enc_encode_frame(self.enc, wl.planes, None, self.cs_pin.data_ptr(), wl.cs_cap, C.byref(self.n)))
+            ck(L.ojb_dec_read_headers(self.dec, self.cs_pin.data_ptr(), self.n.value, wl.st, C.byref(self.fi)))
             ck(L.ojb_dec_decode_frame(self.dec, self.outs, None))
 
         def resident(self):
-            ck(L.ojb_enc_encode_resident(self.enc, self.cs_dev.data_ptr(), cs_cap, C.byref(self.n), 1))
-            ck(L.ojb_dec_read_headers(self.dec, self.cs_pin.data_ptr(), self.cs_len, ob.U16, C.byref(self.fi)))
-            ck(L.ojb_dec_use_device_codestream(self.dec, self.cs_dev.data_ptr()))
+            ck(L.ojb_enc_encode_resident(self.enc, self.cs_dev.data_ptr(), self.wl.cs_cap, C.byref(self.n), 1))
+            ck(L.ojb_dec_read_headers_device(self.dec, self.cs_dev.data_ptr(), self.n.value, self.wl.st, C.byref(self.fi)))
             ck(L.ojb_dec_decode_resident(self.dec))
 
-    workers = [Worker() for _ in range(NW)]
-    from concurrent.futures import ThreadPoolExecutor
-    pool = ThreadPoolExecutor(NW)
-
-    def timed(fn_name, steps, nworkers):
-        """`steps` steps of `nworkers` frames each; with several workers every worker streams its own
+    def timed(workers, fn_name, steps):
+        """`steps` steps of len(workers) frames each; with several workers every worker streams its own
         `steps` frames back to back (no per-step barrier: frames of one worker overlap the other
         workers' copies and host phases, as in a continuous stream)"""
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        if nworkers == 1:
+        if len(workers) == 1:
             for _ in range(steps):
                 getattr(workers[0], fn_name)()
         else:
@@ -244,70 +336,127 @@ def main():
                 f = getattr(w, fn_name)
                 for _ in range(steps):
                     f()
-            list(pool.map(loop, workers[:nworkers]))
+            list(pool.map(loop, workers))
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if dist is not None:
             t = torch.tensor([dt], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
         return dt
 
-    # correctness of what is being timed: lossless round trip through the e2e path, every worker
-    for w in workers:
-        w.e2e()
-        w.cs_len = w.n.value
-        for a_, b_ in zip(w.out_pin, frame):
-            assert np.array_equal(a_.numpy(), b_), "round trip is not lossless"
-        ck(L.ojb_enc_upload_frame(w.enc, planes, None))
-    cs_len = workers[0].cs_len
-    enc, dec = workers[0].enc, workers[0].dec
-    for _ in range(max(3, a.warmup)):
-        list(pool.map(lambda w: w.resident(), workers))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650 GB/s"
+
+    def measure(wl, steps, warmup, lossless, e2e=True):
+        """correctness of what is timed, then: serial pass (per-stage CUDA-event times), all workers in flight
+        resident (`value`), all workers in flight through host buffers (`e2e`)"""
+        ws = wl.workers
+        for w in ws:
+            w.e2e()
+            w.cs_len = w.n.value
+            if lossless:
+                for a_, b_ in zip(w.out_pin, wl.frame):
+                    assert np.array_equal(a_.numpy(), b_), "round trip is not lossless"
+            ck(L.ojb_enc_upload_frame(w.enc, wl.planes, None))
+        for _ in range(max(3, warmup)):
+            list(pool.map(lambda w: w.resident(), ws))
+        if lossless:                        # the device-resident path decodes the same samples
+            pl = (C.c_void_p * wl.nc)(*[t.data_ptr() for t in ws[0].out_pin])
+            for t in ws[0].out_pin:
+                t.zero_()
+            ck(L.ojb_dec_decode_frame(ws[0].dec, pl, None))
+            for a_, b_ in zip(ws[0].out_pin, wl.frame):
+                assert np.array_equal(a_.numpy(), b_), "device-resident round trip is not lossless"
+        te = (C.c_float * 8)(); td = (C.c_float * 8)()
+        dt_serial = timed(ws[:1], "resident", steps)
+        L.ojb_enc_timings(ws[0].enc, te); L.ojb_dec_timings(ws[0].dec, td)
+        dt_res = timed(ws, "resident", steps)
+        r = {"dt_serial": dt_serial, "dt_res": dt_res, "dt_e2e": None, "te": list(te), "td": list(td), "te2": None, "td2": None,
+             "cs_len": int(ws[0].cs_len), "mirror_bytes": int(L.ojb_dec_mirror_bytes(ws[0].dec))}
+        if e2e:
+            for _ in range(max(1, min(warmup, 2))):
+                list(pool.map(lambda w: w.e2e(), ws))
+            r["dt_e2e"] = timed(ws, "e2e", steps)
+            te2 = (C.c_float * 8)(); td2 = (C.c_float * 8)()
+            L.ojb_enc_timings(ws[0].enc, te2); L.ojb_dec_timings(ws[0].dec, td2)
+            r["te2"], r["td2"] = list(te2), list(td2)
+        return r
+
+    def frame_roofline(wl, r):
+        """A = S_in + S_out per frame and direction; the two-pass budget A2 = A + 2 * 4 bytes per sample"""
+        se = dict(zip(ENC_STAGES, r["te"])); sd = dict(zip(DEC_STAGES, r["td"]))
+        samples = sum(f.size for f in wl.frame)
+        A = wl.in_bytes + r["cs_len"]; A2 = A + 8 * samples
+        t_enc = (se["dwt"] + se["ht_encode"] + se["assemble"]) * 1e-3
+        t_dec = (sd["ht_decode"] + sd["dwt_inv"]) * 1e-3
+        return {"A_bytes": A, "A2_bytes": A2, "encode_kernels_ms": round(t_enc * 1e3, 3), "decode_kernels_ms": round(t_dec * 1e3, 3),
+                "encode_frac_A": round(A / t_enc / 1e9 / peak, 4), "encode_frac_A2": round(A2 / t_enc / 1e9 / peak, 4),
+                "decode_frac_A": round(A / t_dec / 1e9 / peak, 4), "decode_frac_A2": round(A2 / t_dec / 1e9 / peak, 4),
+                "encode_Mpix_s_device": round(wl.pix / t_enc / 1e6, 1), "decode_Mpix_s_device": round(wl.pix / t_dec / 1e6, 1)}
+
+    def summarize(name, wl, r, steps, note=None):
+        n = len(wl.workers)
+        d = {"workload": name, "frames_in_flight": n,
+             "Mpixels_per_s": round(wl.pix * n * a.gpus * steps / r["dt_res"] / 1e6, 1),
+             "serial_ms_per_frame": round(r["dt_serial"] / steps * 1e3, 3), "codestream_bytes": r["cs_len"],
+             "bits_per_sample": round(8.0 * r["cs_len"] / sum(f.size for f in wl.frame), 3),
+             "stages_encode_ms": {k: round(float(v), 4) for k, v in zip(ENC_STAGES, r["te"])},
+             "stages_decode_ms": {k: round(float(v), 4) for k, v in zip(DEC_STAGES, r["td"]) if not k.startswith("_")},
+             "roofline_frame": frame_roofline(wl, r)}
+        if r["dt_e2e"]:
+            d["e2e_Mpixels_per_s"] = round(wl.pix * n * a.gpus * steps / r["dt_e2e"] / 1e6, 1)
+        if note:
+            d["note"] = note
+        return d
+
+    # ---- headline --------------------------------------------------------------------------
+    p = workload_params()
+    frame = make_frame(W, H, 1234 + rank)
+    head = Workload(p, frame, NW)
     sampler = ClockSampler(local); sampler.start()
-    te = (C.c_float * 8)(); td = (C.c_float * 8)()
-    # (1) serial pass: one frame at a time -> per-stage CUDA-event times of the kernels
-    dt_serial = timed("resident", a.steps, 1)
-    L.ojb_enc_timings(enc, te); L.ojb_dec_timings(dec, td)
-    # (2) NW frames in flight: host phases and copies of one frame overlap the kernels of another
-    dt_res = timed("resident", a.steps, NW)
-    for _ in range(max(1, min(a.warmup, 2))):
-        list(pool.map(lambda w: w.e2e(), workers))
-    dt_e2e = timed("e2e", a.steps, NW)
-    te2 = (C.c_float * 8)(); td2 = (C.c_float * 8)()
-    L.ojb_enc_timings(enc, te2); L.ojb_dec_timings(dec, td2)
-    # secondary workload: the same frame through 9/7 + ICT at Qfactor 90 -- reported in
-    # config, not part of `value`
-    extra = None
-    if os.environ.get("OJB_BENCH_EXTRAS", "1") != "0":
-        try:
-            pi = ob.make_params(W, H, NC, BD, num_decomps=LEVELS, reversible=False, color_transform=True, qfactor=90)
-            keep = workers
-            xw = [Worker(pi) for _ in range(min(NW, 4))]
-            for w in xw:
-                w.e2e(); w.cs_len = w.n.value
-                ck(L.ojb_enc_upload_frame(w.enc, planes, None))
-            workers = xw
-            for _ in range(3):
-                list(pool.map(lambda w: w.resident(), xw))
-            dtx1 = timed("resident", a.steps, 1)
-            tex = (C.c_float * 8)(); tdx = (C.c_float * 8)()
-            L.ojb_enc_timings(xw[0].enc, tex); L.ojb_dec_timings(xw[0].dec, tdx)
-            dtx = timed("resident", a.steps, len(xw))
-            dtxe = timed("e2e", a.steps, len(xw))
-            mse = float(np.mean((xw[0].out_pin[1].numpy().astype(np.float64) - frame[1]) ** 2))
-            extra = {"workload": "same frame, irreversible 9/7 + ICT, Qfactor 90", "frames_in_flight": len(xw),
-                     "Mpixels_per_s": round(W * H * len(xw) * a.gpus * a.steps / dtx / 1e6, 1),
-                     "e2e_Mpixels_per_s": round(W * H * len(xw) * a.gpus * a.steps / dtxe / 1e6, 1),
-                     "serial_ms_per_frame": round(dtx1 / a.steps * 1e3, 3), "codestream_bytes": int(xw[0].cs_len),
-                     "mse_comp1": round(mse, 3),
-                     "stages_encode_ms": {k: round(float(v), 4) for k, v in zip(("h2d", "dwt", "ht_encode", "d2h_lengths", "host_wait", "assemble", "d2h_out", "host_ms"), tex)},
-                     "stages_decode_ms": {k: round(float(v), 4) for k, v in zip(("h2d", "host_parse", "ht_decode", "dwt_inv", "d2h_image"), tdx)}}
-            workers = keep
-            for w in xw:
-                L.ojb_enc_destroy(w.enc); L.ojb_dec_destroy(w.dec)
-        except Exception as e:      # the headline numbers stand on their own
-            extra = {"error": str(e)[:200]}
+    r = measure(head, a.steps, a.warmup, True)
     sampler.stop_flag = True; sampler.join(timeout=2)
-    # final gather of the per-rank codestream sizes (the only collective on the path)
+    cs_len = r["cs_len"]
+    enc, dec = head.workers[0].enc, head.workers[0].dec
+    launches = int(L.ojb_enc_kernel_launches(enc) + L.ojb_dec_kernel_launches(dec))
+    head.close()
+
+    # ---- the other configurations and the extremes (reported under detail.configs; not part of `value`) ----
+    configs = []
+    if os.environ.get("OJB_BENCH_EXTRAS", "1") != "0":
+        xs = max(2, min(a.steps, 3))
+        rng = np.random.default_rng(99 + rank)
+
+        def run_cfg(name, params, frm, nworkers, lossless, note=None, e2e=True):
+            try:
+                wl = Workload(params, frm, nworkers)
+                try:
+                    configs.append(summarize(name, wl, measure(wl, xs, 3, lossless, e2e), xs, note))
+                finally:
+                    wl.close()
+            except Exception as e:      # the headline numbers stand on their own
+                configs.append({"workload": name, "error": str(e)[:300]})
+
+        run_cfg("headline frame, irreversible 9/7 + ICT, Qfactor 90",
+                ob.make_params(W, H, NC, BD, num_decomps=LEVELS, reversible=False, color_transform=True, qfactor=90), frame, 4, False)
+        run_cfg("extreme: all-zero 8192x8192x3 12-bit frame (best case for the block coders), 5/3 + RCT", p,
+                [np.zeros((H, W), np.uint16) for _ in range(NC)], 2, True, e2e=False)
+        run_cfg("extreme: uniform-random full-range 8192x8192x3 12-bit frame (worst case, ~12 bits/sample), 5/3 + RCT", p,
+                [rng.integers(0, 1 << BD, (H, W), dtype=np.uint16) for _ in range(NC)], 2, True, e2e=False)
+        run_cfg("cfg2: 1920x1080 RGB 8-bit, reversible 5/3 + RCT, 5 levels",
+                ob.make_params(1920, 1080, 3, 8, num_decomps=5, reversible=True, color_transform=True), make_frame(1920, 1080, 7, 3, 8), 8, True)
+        run_cfg("cfg3: 4096x4096x3 12-bit, irreversible 9/7 + ICT, Qfactor 90, 6 levels",
+                ob.make_params(4096, 4096, 3, 12, num_decomps=6, reversible=False, color_transform=True, qfactor=90), make_frame(4096, 4096, 8, 3, 12), 8, False)
+        run_cfg("cfg4 on one GPU: 8192x8192x3 16-bit, reversible 5/3 + RCT, 4 tiles of 4096x4096, 5 levels",
+                ob.make_params(W, H, 3, 16, num_decomps=5, reversible=True, color_transform=True, tile=(4096, 4096)), make_frame(W, H, 9, 3, 16), 4, True,
+                note="the 4-tiles-over-4-GPUs form of this configuration is the `sharded` entry of a --gpus 4 run")
+        run_cfg("cfg5: 3840x2160x3 10-bit frames, irreversible 9/7 + ICT (qstep default), 5 levels; batch of 64 / N GPUs, 8 in flight",
+                ob.make_params(3840, 2160, 3, 10, num_decomps=5, reversible=False, color_transform=True), make_frame(3840, 2160, 10, 3, 10), 8, False)
+
+    # final gather of the per-rank codestream sizes (the only collective on the frame-parallel path)
     sizes = [cs_len]
     if dist is not None:
         t = torch.tensor([cs_len], device="cuda", dtype=torch.int64)
@@ -320,21 +469,12 @@ def main():
             dist.destroy_process_group()
         return
     pix = W * H * a.gpus * NW
-    value = pix * a.steps / dt_res / 1e6
-    e2e = pix * a.steps / dt_e2e / 1e6
-    import json as _j
-    peaks = {}
-    try:
-        peaks = _j.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650 GB/s"
-    names_e = ("h2d", "dwt", "ht_encode", "d2h_lengths", "host_wait", "assemble", "d2h_out", "host_ms")
-    names_d = ("h2d", "host_parse", "ht_decode", "dwt_inv", "d2h_image", "_5", "_6", "host_ms")
-    stage_e = {k: round(float(v), 4) for k, v in zip(names_e, te)}
-    stage_d = {k: round(float(v), 4) for k, v in zip(names_d, td) if not k.startswith("_")}
-    e2e_e = {k: round(float(v), 3) for k, v in zip(names_e, te2)}
-    e2e_d = {k: round(float(v), 3) for k, v in zip(names_d, td2) if not k.startswith("_")}
+    value = pix * a.steps / r["dt_res"] / 1e6
+    e2e = pix * a.steps / r["dt_e2e"] / 1e6
+    stage_e = {k: round(float(v), 4) for k, v in zip(ENC_STAGES, r["te"])}
+    stage_d = {k: round(float(v), 4) for k, v in zip(DEC_STAGES, r["td"]) if not k.startswith("_")}
+    e2e_e = {k: round(float(v), 3) for k, v in zip(ENC_STAGES, r["te2"])}
+    e2e_d = {k: round(float(v), 3) for k, v in zip(DEC_STAGES, r["td2"]) if not k.startswith("_")}
     # dominant kernel = the slowest device stage of the resident step
     samples = W * H * NC
     cand = {"ht_encode": (stage_e["ht_encode"], 4 * samples + cs_len), "ht_decode": (stage_d["ht_decode"], 4 * samples + cs_len),
@@ -343,55 +483,58 @@ def main():
     dom = max(cand, key=lambda k: cand[k][0])
     ach = cand[dom][1] / (cand[dom][0] * 1e-3) / 1e9 if cand[dom][0] > 0 else 0.0
     # DRAM bytes of the same kernel(s) from the committed ncu --set full capture (profiles/)
-    traffic = None
-    try:
-        prof = _j.load(open(os.path.join(ROOT, "profiles", PROFILE_JSON)))
-        keys = {"ht_encode": ["ht_encode_serial", "ht_encode"], "ht_decode": ["ht_decode_serial", "ht_dec_fill", "ht_dec_step1", "ht_dec_step2"],
-                "dwt_fwd": ["dwt_fwd"], "dwt_inv": ["dwt_inv"]}[dom]
-        traffic = sum(int(prof[k]["traffic_bytes"]) for k in keys if k in prof)
-    except Exception:
-        pass
+    traffic = None; traffic_src = None
+    for pj in (PROFILE_JSON, PROFILE_FALLBACK):
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", pj)))
+            keys = {"ht_encode": ["ht_encode_serial", "ht_encode"], "ht_decode": ["ht_decode_serial", "ht_dec_fill", "ht_dec_step1", "ht_dec_step2"],
+                    "dwt_fwd": ["dwt_fwd"], "dwt_inv": ["dwt_inv"]}[dom]
+            traffic = sum(int(prof[k]["traffic_bytes"]) for k in keys if k in prof)
+            traffic_src = "profiles/" + pj
+            break
+        except Exception:
+            pass
     roof = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-            "frac": round(ach / peak, 4), "traffic": traffic, "peak_source": peak_src,
+            "frac": round(ach / peak, 4), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": cand[dom][1], "ms_per_launch": cand[dom][0],
-            "note": "entropy-coding kernels are instruction-issue / latency bound (thread-per-block, ncu: 52-56 % "
-                    "issue-active at 16 % occupancy, DRAM traffic ~= algorithmic bytes); see profiles/README.md"}
-    # A = S_in + S_out per frame (and the two-pass budget A2 = A + 2*4*W*H*C), per direction
-    A = 2 * samples + cs_len
-    A2 = A + 8 * samples
-    t_enc = (stage_e["dwt"] + stage_e["ht_encode"] + stage_e["assemble"]) * 1e-3
-    t_dec = (stage_d["ht_decode"] + stage_d["dwt_inv"]) * 1e-3
-    roof["frame"] = {"A_bytes": A, "A2_bytes": A2,
-                     "encode_kernels_ms": round(t_enc * 1e3, 3), "decode_kernels_ms": round(t_dec * 1e3, 3),
-                     "encode_frac_A": round(A / t_enc / 1e9 / peak, 4), "encode_frac_A2": round(A2 / t_enc / 1e9 / peak, 4),
-                     "decode_frac_A": round(A / t_dec / 1e9 / peak, 4), "decode_frac_A2": round(A2 / t_dec / 1e9 / peak, 4),
-                     "encode_Mpix_s_device": round(W * H / t_enc / 1e6, 1), "decode_Mpix_s_device": round(W * H / t_dec / 1e6, 1)}
-    cfg.update({"frames_per_step": NW * a.gpus, "frames_in_flight_per_gpu": NW, "host_affinity": affinity, "irv97_ict_q90": extra, "e2e_stages_encode_ms": e2e_e, "e2e_stages_decode_ms": e2e_d,
-                "serial_ms_per_frame": round(dt_serial / a.steps * 1e3, 3),
-                "serial_Mpixels_per_s": round(W * H * a.steps / dt_serial / 1e6, 1),
-                "stages_encode_ms": stage_e, "stages_decode_ms": stage_d, "codestream_bytes": sizes,
-                "pipeline_hbm_frac": round(((2 * samples + cs_len) * 2 * NW) / (dt_res / a.steps) / 1e9 / peak, 4)})
+            "note": "entropy-coding kernels are instruction-issue / ALU-pipe bound (DRAM traffic ~= algorithmic bytes); see profiles/README.md",
+            "frame": frame_roofline(head, r)}
+    detail = {"frames_per_step": NW * a.gpus, "frames_in_flight_per_gpu": NW, "host_affinity": affinity,
+              "serial_ms_per_frame": round(r["dt_serial"] / a.steps * 1e3, 3),
+              "serial_Mpixels_per_s": round(W * H * a.steps / r["dt_serial"] / 1e6, 1),
+              "stages_encode_ms": stage_e, "stages_decode_ms": stage_d,
+              "e2e_stages_encode_ms": e2e_e, "e2e_stages_decode_ms": e2e_d, "codestream_bytes": sizes,
+              "resident_decode_header_fetch_bytes": r["mirror_bytes"],
+              "pipeline_hbm_frac": round(((2 * samples + cs_len) * 2 * NW) / (r["dt_res"] / a.steps) / 1e9 / peak, 4),
+              "configs": configs}
     res = {"metric": "Mpixels/s encode+decode", "value": value, "unit": "Mpixels/s", "n_gpus": a.gpus, "steps": a.steps,
-           "warmup": a.warmup, "ms_per_step": dt_res / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": cfg,
+           "warmup": a.warmup, "ms_per_step": r["dt_res"] / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": cfg, "detail": detail,
+           "value_note": "device-resident: frame in HBM, codestream written to and decoded from HBM; the decoder's host parser "
+                         "fetches only marker segments / packet headers (%d bytes of the %d-byte codestream per frame, inside the "
+                         "timed region)" % (r["mirror_bytes"], cs_len),
            "clocks": sampler.summary(),
            "e2e": {"value": e2e, "unit": "Mpixels/s", "h2d_bytes_per_step": (W * H * NC * 2 + cs_len) * a.gpus * NW,
-                   "d2h_bytes_per_step": (W * H * NC * 2 + cs_len) * a.gpus * NW, "ms_per_step": dt_e2e / a.steps * 1e3},
-           "gpu_launches": int(L.ojb_enc_kernel_launches(enc) + L.ojb_dec_kernel_launches(dec)) * a.steps * NW,
+                   "d2h_bytes_per_step": (W * H * NC * 2 + cs_len) * a.gpus * NW, "ms_per_step": r["dt_e2e"] / a.steps * 1e3},
+           "gpu_launches": launches * a.steps * NW,
            "roofline": roof}
-    if not a.no_cpu_baseline and world == 1 or (rank == 0 and not a.no_cpu_baseline):
+    if not a.no_cpu_baseline:
         import refharness as R
         if R.available():
-            cpu_worker_init(1234)
+            ff = write_frame_file(frame)
+            try:
+                cpu_worker_init(ff)
+            finally:
+                os.unlink(ff)
             te_ = td_ = 0.0
-            for _ in range(2):
-                e_, d_, _n = cpu_worker((1234, False)); te_ += e_; td_ += d_
-            v1 = 2 * CPU_TILE * CPU_TILE / (te_ + td_) / 1e6
+            reps = 2
+            for _ in range(reps):
+                e_, d_, _n = cpu_worker(False); te_ += e_; td_ += d_
+            v1 = reps * W * H / (te_ + td_) / 1e6
             res["cpu_baseline"] = {"value": v1, "unit": "Mpixels/s", "cores": 1, "kind": "reference",
-                                   "sample": "2 x one %dx%dx3 12-bit quarter frame, 1 thread (the library's native mode), "
-                                             "in-memory; encode %.1f Mpix/s decode %.1f Mpix/s; ISA level %d" % (
-                                                 CPU_TILE, CPU_TILE, 2 * CPU_TILE * CPU_TILE / te_ / 1e6,
-                                                 2 * CPU_TILE * CPU_TILE / td_ / 1e6, R.lib().ojr_cpu_ext_level())}
+                                   "sample": "%d x one whole 8192x8192x3 12-bit frame, 1 thread (the library's native mode), in-memory, "
+                                             "buffers preallocated; encode %.1f Mpix/s decode %.1f Mpix/s; ISA level %d" % (
+                                                 reps, reps * W * H / te_ / 1e6, reps * W * H / td_ / 1e6, R.lib().ojr_cpu_ext_level())}
     print(json.dumps(res), file=out); out.flush()
     if dist is not None:
         dist.destroy_process_group()

@@ -211,6 +211,14 @@ void* ojb_dec_device_plane(ojb_decoder* d, uint32_t comp);
 /* after read_headers: the same codestream bytes are already in device memory (with >= 32 readable
  * bytes after the end); the next decode reads them there instead of uploading j2c */
 int ojb_dec_use_device_codestream(ojb_decoder* d, const void* dev_bytes);
+/* codestream::read_headers for a codestream that exists in DEVICE memory only (complete when the call is
+ * made, >= 32 readable bytes after its end, valid until the decode call returns): the marker segments and
+ * packet headers the host parsers read (ojph_codestream_local.cpp:734-880, ojph_precinct.cpp:328-573) are
+ * fetched in 64 KB pages; code-block bodies never leave the device.  ojb_dec_mirror_bytes = bytes fetched
+ * so far for the current codestream (headers + the packet headers parsed by the last decode). */
+int ojb_dec_read_headers_device(ojb_decoder* d, const void* dev_j2c, uint64_t len, uint32_t sample_type,
+                                ojb_frame_info* info);
+uint64_t ojb_dec_mirror_bytes(ojb_decoder* d);
 uint32_t ojb_dec_failed_blocks(ojb_decoder* d);
 /* parity hook: parse the packet headers of the codestream given to read_headers and list every
  * code-block (precinct::parse, src/core/codestream/ojph_precinct.cpp:328-573): geometry, missing msbs,

@@ -109,6 +109,8 @@ SYMBOLS = {
     "ojb_dec_pull": (_VP, [_VP, C.POINTER(_U32)]),
     "ojb_dec_device_plane": (_VP, [_VP, _U32]),
     "ojb_dec_use_device_codestream": (_I, [_VP, _VP]),
+    "ojb_dec_read_headers_device": (_I, [_VP, _VP, _U64, _U32, C.POINTER(FrameInfo)]),
+    "ojb_dec_mirror_bytes": (_U64, [_VP]),
     "ojb_dec_failed_blocks": (_U32, [_VP]),
     "ojb_dec_list_blocks": (_I, [_VP, C.POINTER(BlockDesc), _U32, C.POINTER(_U32)]),
     "ojb_dec_kernel_launches": (_U32, [_VP]),

@@ -164,6 +164,12 @@ class Encoder(_Base):
         self._check(self.L.ojb_enc_encode_resident(self.h, self._out.ctypes.data, self._out.size, C.byref(n), 0))
         return self._out[:n.value].tobytes()
 
+    def encode_resident_to_device(self, dev_ptr, cap):
+        """encode the uploaded frame; the codestream is written to device memory at dev_ptr; returns its length"""
+        n = C.c_uint64()
+        self._check(self.L.ojb_enc_encode_resident(self.h, dev_ptr, cap, C.byref(n), 1))
+        return int(n.value)
+
     def encode_lines(self, planes):
         """the reference's exchange() loop + flush()."""
         nc = C.c_uint32()
@@ -232,6 +238,18 @@ class Decoder(_Base):
         self._check(self.L.ojb_dec_read_headers(self.h, self._buf.ctypes.data, self._buf.size, sample_type, C.byref(fi)))
         self.info = fi
         return fi
+
+    def read_headers_device(self, dev_ptr, length, sample_type=I32):
+        """read_headers for a codestream that is in device memory only (address, byte count)"""
+        self.sample_type = sample_type
+        fi = _lib.FrameInfo()
+        self._check(self.L.ojb_dec_read_headers_device(self.h, dev_ptr, length, sample_type, C.byref(fi)))
+        self.info = fi
+        return fi
+
+    @property
+    def mirror_bytes(self):
+        return int(self.L.ojb_dec_mirror_bytes(self.h))
 
     def coding_style(self, comp=0):
         """the read-side getters of ojph::param_cod / param_siz for one component (after read_headers)"""

@@ -516,6 +516,17 @@ void* ojb_dec_device_plane(ojb_decoder* d, uint32_t comp) {
   if (!d->have_headers || comp >= d->dec.params.num_comps()) return nullptr;
   return img_plane(d->dec, comp);
 }
+int ojb_dec_read_headers_device(ojb_decoder* d, const void* dev_j2c, uint64_t len, uint32_t sample_type,
+                                ojb_frame_info* info) {
+  return guarded_on(d->device, [&] {
+    if (sample_type > 2) fail(0x000B0012, "unknown sample container");
+    d->have_headers = false;
+    d->dec.read_headers_device(static_cast<const uint8_t*>(dev_j2c), (size_t)len, sample_type);
+    d->have_headers = true;
+    if (info) { FrameInfo fi; d->dec.info(fi); memcpy(info, &fi, sizeof(fi)); }
+  });
+}
+uint64_t ojb_dec_mirror_bytes(ojb_decoder* d) { return d->dec.mirrored ? d->dec.mirror.fetched_bytes : 0; }
 int ojb_dec_use_device_codestream(ojb_decoder* d, const void* dev_bytes) { d->dec.dev_cs = (const uint8_t*)dev_bytes; return 0; }
 uint32_t ojb_dec_failed_blocks(ojb_decoder* d) { return d->dec.failed_blocks; }
 int ojb_dec_list_blocks(ojb_decoder* d, ojb_block_desc* out, uint32_t cap, uint32_t* n) {

@@ -495,10 +495,41 @@ size_t Encoder::encode(const void* const* planes, const uint32_t* strides, bool 
 //------------------------------------------------------------------------------------------
 // Decoder
 //------------------------------------------------------------------------------------------
+void Decoder::Mirror::fetch(size_t first_page, size_t npages) {
+  // one copy for the missing page and, when the request is a single page, the one after it (headers of large
+  // packets run on for tens of kilobytes; the round trip, not the bytes, is the cost)
+  const size_t total = (len + (1u << PAGE_SHIFT) - 1) >> PAGE_SHIFT;
+  size_t last = std::min(total, first_page + std::max<size_t>(npages, 2));
+  while (last > first_page + 1 && present[last - 1]) --last;
+  const size_t a = first_page << PAGE_SHIFT, b = std::min(len, last << PAGE_SHIFT);
+  cuda_check(cudaMemcpyAsync(host.as<uint8_t>() + a, dev + a, b - a, cudaMemcpyDeviceToHost, owner->stream), "codestream page fetch");
+  cuda_check(cudaStreamSynchronize(owner->stream), "codestream page fetch");
+  for (size_t pg = first_page; pg < last; ++pg) present[pg] = 1;
+  fetched_bytes += b - a;
+}
+
+void Decoder::read_headers_device(const uint8_t* dev, size_t len, uint32_t sample_type) {
+  mirror.owner = this; mirror.dev = dev; mirror.len = len; mirror.fetched_bytes = 0;
+  mirror.host.reserve(len + 64);
+  mirror.present.assign((len + (1u << HostMirror::PAGE_SHIFT) - 1) >> HostMirror::PAGE_SHIFT, 0);
+  // the main header: normally well inside the first page; a parse that runs out of fetched bytes is repeated
+  // with everything fetched
+  size_t have = std::min<size_t>(len, 1u << HostMirror::PAGE_SHIFT);
+  if (len) mirror.need(0, have);
+  for (;;) {
+    try { read_headers(mirror.host.as<uint8_t>(), have, sample_type); break; }
+    catch (const Error&) {
+      if (have == len) throw;
+      have = len; mirror.need(0, len);
+    }
+  }
+  j2c_len = len; dev_cs = dev; mirrored = true;
+}
+
 void Decoder::read_headers(const uint8_t* data, size_t len, uint32_t sample_type) {
   Params np;
   size_t sot = np.read_main_header(data, len);
-  j2c = data; j2c_len = len; first_sot = sot; dev_cs = nullptr;
+  j2c = data; j2c_len = len; first_sot = sot; dev_cs = nullptr; mirrored = false;
   // geometry depends on SIZ/COD/QCD/QCC only; rebuild when any of those bytes changed
   std::vector<uint8_t> sig;
   {
@@ -610,8 +641,10 @@ void Decoder::parse_tiles() {
   std::vector<bool> have_seq(ntiles, false);
   size_t pos = first_sot;
   const uint8_t* d = j2c;
+  HostMirror* hm = mirrored ? &mirror : nullptr;
   while (pos + 2 <= j2c_len) {
     // find SOT or EOC
+    if (hm) hm->need(pos, 12);
     if (!(d[pos] == 0xFF && (d[pos + 1] == 0x90 || d[pos + 1] == 0xD9))) { ++pos; continue; }
     if (d[pos + 1] == 0xD9) break;
     if (pos + 12 > j2c_len) {
@@ -634,6 +667,7 @@ void Decoder::parse_tiles() {
     // skip tile-part header segments up to SOD
     size_t q = tile_start; bool sod = false;
     while (q + 2 <= tp_end) {
+      if (hm) hm->need(q, 4);
       if (d[q] != 0xFF) { ++q; continue; }
       uint8_t m = d[q + 1];
       if (m == 0x93) { sod = true; q += 2; break; }
@@ -661,7 +695,7 @@ void Decoder::parse_tiles() {
       while (data_left > 0 && next_pkt[Isot] < seq.size()) {
         const PacketRef& pr = seq[next_pkt[Isot]++];
         const ResGeom& rg = layout.res_of(pr);
-        parse_packet(params, rg, rg.precincts[pr.precinct], coded.data(), d, q, data_left, j2c_len);
+        parse_packet(params, rg, rg.precincts[pr.precinct], coded.data(), d, q, data_left, j2c_len, hm);
       }
     } catch (const Error& e) {
       if (!resilient) throw;

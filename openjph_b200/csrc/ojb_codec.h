@@ -113,6 +113,14 @@ public:
   bool resilient = false;
   // parse main header; (re)builds geometry when parameters changed
   void read_headers(const uint8_t* j2c, size_t len, uint32_t sample_type);
+  // the same for a codestream that is in DEVICE memory only (complete, with >= 32 readable bytes after its end):
+  // the marker segments and packet headers the host parsers touch are fetched page by page into a pinned mirror
+  void read_headers_device(const uint8_t* dev_j2c, size_t len, uint32_t sample_type);
+  struct Mirror : HostMirror {
+    Decoder* owner = nullptr; const uint8_t* dev = nullptr; PinnedBuf host; size_t fetched_bytes = 0;
+    void fetch(size_t first_page, size_t npages) override;
+  } mirror;
+  bool mirrored = false;                // j2c points into mirror.host
   // after read_headers, before decode: rebuilds the output planes and the synthesis schedule
   void restrict_resolution(uint32_t skipped_res_for_read, uint32_t skipped_res_for_recon);
   void setup_geometry(uint32_t sample_type);

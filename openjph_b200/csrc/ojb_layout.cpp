@@ -306,11 +306,12 @@ struct BitWriter {   // MSB first; a byte after 0xFF carries 7 bits (ojph_bitbuf
 struct BitReader {   // ojph_bitbuffer_read.h:73-130
   // `left` counts the bytes the tile-part SAYS it still has (Psot); `end` is where the buffer really
   // ends: running out of buffer while `left` > 0 is the reference's failed file read (bb_read, :80-86)
-  const uint8_t* d; size_t& pos; uint32_t& left; size_t end; uint32_t tmp = 0; int avail = 0; bool unstuff = false;
-  BitReader(const uint8_t* data, size_t& p, uint32_t& l, size_t e) : d(data), pos(p), left(l), end(e) {}
+  const uint8_t* d; size_t& pos; uint32_t& left; size_t end; HostMirror* hm; uint32_t tmp = 0; int avail = 0; bool unstuff = false;
+  BitReader(const uint8_t* data, size_t& p, uint32_t& l, size_t e, HostMirror* m) : d(data), pos(p), left(l), end(e), hm(m) {}
   inline bool fill() {
     if (left > 0) {
       if (pos >= end) throw Error(0x00030092, "error reading from file");
+      if (hm && !hm->present[pos >> HostMirror::PAGE_SHIFT]) hm->need(pos);
       uint8_t t = d[pos++]; tmp = t; avail = 8 - (unstuff ? 1 : 0); unstuff = (t == 0xFF); --left; return true;
     }
     tmp = 0; avail = 8 - (unstuff ? 1 : 0); unstuff = false; return false;
@@ -428,10 +429,12 @@ uint32_t write_packet_header(const ResGeom& res, const PrecinctGeom& pc,
 }
 
 void parse_packet(const Params& P, const ResGeom& res, const PrecinctGeom& pc,
-                  CodedBlock* blocks, const uint8_t* data, size_t& pos, uint32_t& data_left, size_t data_end) {
-  BitReader br(data, pos, data_left, data_end);
+                  CodedBlock* blocks, const uint8_t* data, size_t& pos, uint32_t& data_left, size_t data_end,
+                  HostMirror* mirror) {
+  BitReader br(data, pos, data_left, data_end, mirror);
   if (P.uses_sop() && data_left >= 2) {            // optional SOP marker segment
     if (pos + 2 > data_end) throw Error(0x00030092, "error reading from file");
+    if (mirror) mirror->need(pos, 6);
     if (data[pos] == 0xFF && data[pos + 1] == 0x91) {
       pos += 2; data_left -= 2;
       if (data_left < 4) throw Error(0x00030092, "precinct truncated early");
@@ -574,6 +577,7 @@ void parse_packet(const Params& P, const ResGeom& res, const PrecinctGeom& pc,
   br.finish();
   if (P.uses_eph() && data_left >= 2) {
     if (pos + 2 > data_end) throw Error(0x00030092, "error reading from file");
+    if (mirror) mirror->need(pos, 2);
     if (!(data[pos] == 0xFF && data[pos + 1] == 0x92))
       throw Error(0x00030092, "should find EPH, but found something else");
     pos += 2; data_left -= 2;

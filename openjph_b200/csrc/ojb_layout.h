@@ -11,6 +11,7 @@
 //   packet header write       ojph_precinct.cpp:94-278, parse :328-573
 //   packet order              ojph_tile.cpp:584-772 (write), :777-936 (parse)
 #pragma once
+#include <algorithm>
 #include "ojb_params.h"
 
 namespace ojb {
@@ -100,7 +101,22 @@ uint32_t write_packet_header(const ResGeom& res, const PrecinctGeom& pc,
 // msbs, data_off) and advances pos past header and body.  data_left is the number of bytes
 // left in the tile-part according to its SOT (Psot), data_end the size of the buffer: running out of
 // buffer with data_left > 0 throws like the reference's failed file read.  Throws Error on malformed input.
+// Host view of a codestream that lives in device memory: `data` is a host buffer of the same size of which only
+// the 64 KB pages marked present have been fetched.  The parsers touch marker segments and packet HEADERS only
+// (never code-block bodies), so a device-resident decode moves kilobytes, not the codestream, to the host.
+struct HostMirror {
+  enum : unsigned { PAGE_SHIFT = 16 };
+  std::vector<uint8_t> present; size_t len = 0;
+  virtual void fetch(size_t first_page, size_t npages) = 0;
+  virtual ~HostMirror() {}
+  inline void need(size_t pos, size_t n = 1) {
+    if (pos >= len) return;
+    size_t a = pos >> PAGE_SHIFT, b = (std::min(pos + n, len) - 1) >> PAGE_SHIFT;
+    for (size_t pg = a; pg <= b; ++pg) if (!present[pg]) { fetch(pg, b - pg + 1); break; }
+  }
+};
 void parse_packet(const Params& p, const ResGeom& res, const PrecinctGeom& pc,
-                  CodedBlock* blocks, const uint8_t* data, size_t& pos, uint32_t& data_left, size_t data_end);
+                  CodedBlock* blocks, const uint8_t* data, size_t& pos, uint32_t& data_left, size_t data_end,
+                  HostMirror* mirror = nullptr);
 
 } // namespace ojb

@@ -86,6 +86,28 @@ def encode(p, planes, comments=None):
     return out[:n.value].tobytes()
 
 
+def encode_into(p, planes_i32, out):
+    """encode into a caller-owned (pre-touched) uint8 buffer: nothing is allocated inside the call, so a timed
+    loop measures the reference and not page faults.  planes_i32: contiguous int32 arrays.  Returns the length."""
+    L = lib()
+    r = to_rparams(p)
+    ptrs = (C.c_void_p * len(planes_i32))(*[a.ctypes.data for a in planes_i32])
+    n = C.c_uint64()
+    rc = L.ojr_encode(C.byref(r), ptrs, out.ctypes.data_as(C.c_void_p), C.c_uint64(out.size), C.byref(n))
+    if rc != 0:
+        raise RuntimeError("reference encode failed: " + L.ojr_last_error().decode())
+    return int(n.value)
+
+
+def decode_into(buf, length, planes_i32):
+    """decode `length` bytes of the uint8 array `buf` into caller-owned int32 planes (see encode_into)"""
+    L = lib()
+    ptrs = (C.c_void_p * len(planes_i32))(*[a.ctypes.data for a in planes_i32])
+    rc = L.ojr_decode(buf.ctypes.data_as(C.c_void_p), C.c_uint64(length), ptrs, 0)
+    if rc != 0:
+        raise RuntimeError("reference decode failed: " + L.ojr_last_error().decode())
+
+
 def decode(j2c, resilient=False):
     L = lib()
     buf = np.frombuffer(j2c, np.uint8)
