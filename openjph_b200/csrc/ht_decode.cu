@@ -692,10 +692,11 @@ __device__ __forceinline__ void ms_ingest(MsDec& m, unsigned long long val, uint
   if (m.left < (int)nv) val |= (m.left <= 0) ? ~0ull : (~0ull << (8 * m.left));
   if (nv < 8) val &= (1ull << (8 * nv)) - 1ull;
   m.left -= (int)nv;
-  unsigned long long ff = val & (val >> 1); ff &= ff >> 2; ff &= ff >> 4; ff &= 0x0101010101010101ull;   // bit 8i <=> byte i == 0xFF
+  // bit 8i+7 <=> byte i == 0xFF: the low seven bits are all ones (adding 1 carries into bit 7) and bit 7 is set
+  const unsigned long long ff = ((val & 0x7F7F7F7F7F7F7F7Full) + 0x0101010101010101ull) & val & 0x8080808080808080ull;
   // bits to delete: the top bit of the byte after each 0xFF (of byte 0 when the previous group ended in 0xFF)
-  unsigned long long del = ((ff << 15) | ((unsigned long long)m.unstuff << 7)) & ((nv < 8) ? ((1ull << (8 * nv)) - 1ull) : ~0ull);
-  m.unstuff = (uint32_t)(ff >> (8 * (nv - 1))) & 1u;
+  unsigned long long del = ((ff << 8) | ((unsigned long long)m.unstuff << 7)) & ((nv < 8) ? ((1ull << (8 * nv)) - 1ull) : ~0ull);
+  m.unstuff = (uint32_t)(ff >> (8 * (nv - 1) + 7)) & 1u;
   const uint32_t c = 8 * nv - delete_bits(val, del);
   win_append(m.w, val, c);
 }
@@ -787,6 +788,7 @@ ht_decode_serial_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nblocks) return;
   const DecBlock blk = blocks[b];
+  if (blk.flags & DEC_FLAG_FAST) return;                 // decoded by ht_decode_fast_kernel
   uint32_t np = blk.num_passes;
   if (np == 0 || blk.len1 == 0) { block_status[b] = DST_EMPTY; return; }     // zero-filled by the fill kernel
   // validity gates (:752-820)
@@ -995,6 +997,193 @@ ht_decode_serial_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
   block_status[b] = 0;
 }
 
+
+// ---- fast path of the thread-per-block decoder ------------------------------------------------------------
+// The same cleanup pass for the blocks the host marks DEC_FLAG_FAST: one coding pass, width a multiple of 4 and
+// at most 64, even height, 16-byte aligned rows, missing_msbs + 2 <= 16 (so the four MagSgn fields of a quad fit
+// 64 bits).  Knowing that at compile time removes the per-quad bounds / pass / width tests of the general kernel,
+// and the state of the row above shrinks to registers plus one word per quad pair:
+//   * significance of the bottom samples of the row above: a 64-bit register, two bits per quad, walked four bits
+//     per pair; the contexts of both quads of a pair come out of six consecutive bits;
+//   * exponent predictor: per quad boundary q the OR g[q] = h(br of quad q-1) | h(bl of quad q) with h = v_n >> 1
+//     (16 bits, v_n < 2^17); kappa of quad q is 32 - clz(g[q] | g[q+1] | 1): one word load, one word store and one
+//     CLZ per quad instead of per-sample exponents, two 16-bit records and a 4-way max;
+//   * VLC through a 64-bit window refilled 32 bits at a time (a pair reads at most 30 bits), MagSgn through the
+//     128-bit window in 8-byte groups as in the general kernel.
+// A U_q beyond missing_msbs + 2 (corrupt data) is clamped and flagged; the block is then zero-filled.
+template <int MODE>       // 0: integer output, 1: float output, 2: sign-magnitude (kernel-level parity entry point)
+__global__ void __launch_bounds__(DEC1_THREADS)
+ht_decode_fast_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
+                      const uint8_t* __restrict__ cs, uint32_t* __restrict__ coef,
+                      const uint16_t* __restrict__ tables, uint32_t* __restrict__ block_status)
+{
+  __shared__ DecTables T;
+  __shared__ uint32_t s_vring[VLC_RING * DEC1_THREADS];    // per-thread FIFO of VLC words (slot-major)
+  __shared__ uint2 s_mring[VLC_RING * DEC1_THREADS];       // per-thread FIFO of MagSgn 8-byte groups
+  __shared__ uint32_t s_g[17 * DEC1_THREADS];              // g[2j] | g[2j+1] << 16 of the row above, per pair j
+  {
+    uint16_t* d = reinterpret_cast<uint16_t*>(&T);
+    for (uint32_t i = threadIdx.x; i < sizeof(DecTables) / 2; i += blockDim.x) d[i] = tables[i];
+  }
+  __syncthreads();
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nblocks) return;
+  const DecBlock blk = blocks[b];
+  if (!(blk.flags & DEC_FLAG_FAST)) return;
+  const uint8_t* data = cs + blk.data_off;
+  const int lcup = (int)blk.len1;
+  const int scup = ((int)data[lcup - 1] << 4) + (data[lcup - 2] & 0xF);
+  if (scup < 2 || scup > lcup || scup > 4079) { block_status[b] = DST_FAIL; return; }
+
+  MelDec mel; mel.p = data + lcup - scup; mel.size = scup - 1; mel.tmp = 0; mel.bits = 0;
+  mel.unstuff = false; mel.k = 0;
+  RevDec vlc; vlc.p = data + lcup - 2; vlc.size = scup - 2;
+  {
+    const uint32_t d = *vlc.p--;                            // the byte that shares the Scup nibble (rev_init, :270-302)
+    vlc.tmp = d >> 4;
+    vlc.bits = 4 - (((vlc.tmp & 7) == 7) ? 1u : 0u);
+    vlc.unstuff = (d | 0xF) > 0x8F;
+  }
+  rev_prime(vlc, cs, s_vring + threadIdx.x);
+  mel_prime(mel);
+  MsDec ms;
+  ms_prime(ms, data, lcup - scup, data + lcup, s_mring + threadIdx.x);
+  int run = mel_next_run(mel);
+
+  const uint32_t npairs = blk.w >> 2, height = blk.h, stride = blk.stride;
+  uint32_t* dst = coef + blk.dst_off;
+  uint32_t* gw = s_g + threadIdx.x;
+  const uint32_t mmsbp2 = blk.missing_msbs + 2u;
+  const uint32_t p = 30u - blk.missing_msbs;
+  const uint32_t pscale = 1u << (p - 1);
+  // integer output: ((v + 2) << (p - 1)) >> (31 - K_max) = ((v + 2) * 2^(K_max - missing_msbs - 1)) >> 1
+  const uint32_t mul_a = 1u << (blk.K_max - blk.missing_msbs - 1u);
+  const float delta = blk.delta;
+  uint32_t fail = 0;
+  for (uint32_t j = 0; j <= 16; ++j) gw[j * DEC1_THREADS] = 0;
+  uint32_t sg_lo = 0, sg_hi = 0;              // bottom-sample significance of the row above: bit 2q = left, 2q+1 = right
+
+  for (uint32_t y = 0; y < height; y += 2) {
+    const bool first = (y == 0);
+    const uint16_t* vtab = first ? T.vlc0 : T.vlc1;
+    const uint16_t* utab = first ? T.uvlc0 : T.uvlc1;
+    uint32_t* r0 = dst + (size_t)y * stride;
+    uint32_t* r1 = r0 + stride;
+    uint32_t rho_left = 0;
+    uint32_t rs_lo = sg_lo, rs_hi = sg_hi, rs_carry = 0;      // row-above significance, walked 4 bits per pair
+    uint32_t cu_lo = 0, cu_hi = 0;                            // this row's, built from the top down
+    uint32_t wj = gw[0];                                      // row-above exponent words: pair j, then pair j + 1
+    uint32_t h_carry = 0;                                     // h of the bottom-right sample of the quad to the left
+    #pragma unroll 1
+    for (uint32_t j = 0; j < npairs; ++j) {
+      while (vlc.bits <= 32) rev_fill32(vlc);                 // the pair reads at most 2 x 7 + 6 + 10 bits
+      uint32_t vt = (uint32_t)vlc.tmp, vused = 0;
+      const uint32_t wj1 = gw[(j + 1) * DEC1_THREADS];
+      // bit 0: right of quad 2j-1, 1: left of 2j, 2: right of 2j, 3: left of 2j+1, 4: right of 2j+1, 5: left of 2j+2
+      const uint32_t y6 = rs_carry | ((rs_lo & 0x1Fu) << 1);
+      const uint32_t z = y6 | (y6 >> 1);                      // bit 0: above quad 2j, bit 2: between, bit 4: beyond 2j+1
+      rs_carry = (rs_lo >> 3) & 1u;
+      rs_lo = __funnelshift_r(rs_lo, rs_hi, 4); rs_hi >>= 4;
+      uint32_t t[2];
+      #pragma unroll
+      for (uint32_t i = 0; i < 2; ++i) {
+        uint32_t c;
+        if (first) c = (rho_left & 1u) | (rho_left >> 1);
+        else c = ((z >> (2 * i)) & 5u) | (rho_left > 3u ? 2u : 0u);
+        uint32_t e = vtab[(c << 7) | (vt & 0x7Fu)];
+        if (c == 0) {               // significance of an all-zero context comes from MEL
+          run -= 2;
+          if (run != -1) e = 0;
+          if (run < 0) run = mel_next_run(mel);
+        }
+        vt >>= (e & 7u); vused += (e & 7u);
+        t[i] = e;
+        rho_left = (e >> 4) & 15u;
+      }
+      // U-VLC of the pair (:940-974 initial row, :1066-1085 others)
+      uint32_t mode = ((t[0] >> 3) & 1u) | ((t[1] >> 2) & 2u);
+      if (first && mode == 3) {
+        run -= 2;
+        if (run == -1) mode = 4;
+        if (run < 0) run = mel_next_run(mel);
+      }
+      uint32_t ent = utab[(mode << 6) | (vt & 0x3Fu)];
+      vt >>= (ent & 7u); vused += (ent & 7u);
+      ent >>= 3;
+      uint32_t len = ent & 0xFu;
+      const uint32_t suf = vt & ((1u << len) - 1u);
+      vused += len;
+      vlc.tmp >>= vused; vlc.bits -= vused;
+      ent >>= 4;
+      len = ent & 7u; ent >>= 3;
+      const uint32_t kap = first ? 1u : 0u;
+      const uint32_t uu[2] = { kap + (ent & 7u) + (suf & ~(0xFFu << len)), kap + (ent >> 3) + (suf >> len) };
+      // this row's significance bits of the pair, pushed in at the top
+      {
+        const uint32_t ta = (t[0] >> 5) & 5u, tb = (t[1] >> 5) & 5u;       // bit 0: bottom-left, bit 2: bottom-right
+        const uint32_t nb = ((ta | (ta >> 1)) & 3u) | (((tb | (tb >> 1)) & 3u) << 2);
+        cu_lo = __funnelshift_r(cu_lo, cu_hi, 4); cu_hi = (cu_hi >> 4) | (nb << 28);
+      }
+      // exponent predictor inputs of the two quads: g[2j] | g[2j+1], g[2j+1] | g[2j+2]
+      const uint32_t gor[2] = { (wj | (wj >> 16)) & 0xFFFFu, (wj >> 16) | (wj1 & 0xFFFFu) };
+      wj = wj1;
+
+      // ---- MagSgn of the two quads (:1087-1316)
+      uint32_t o[2][4], hb[2][2];
+      #pragma unroll
+      for (uint32_t i = 0; i < 2; ++i) {
+        const uint32_t inf = t[i];
+        const uint32_t rho = (inf >> 4) & 15u, ek = inf >> 12, e1 = (inf >> 8) & 15u;
+        uint32_t Uq = uu[i];
+        if (!first) Uq += (rho & (rho - 1u)) ? 32u - (uint32_t)__clz((int)(gor[i] | 1u)) : 1u;
+        fail |= (Uq > mmsbp2) ? 1u : 0u;
+        Uq = min(Uq, mmsbp2);
+        // m_n = sigma_n * (U_q - ek_n) for the four samples at once, one byte each
+        const uint32_t rb = (rho * 0x00204081u) & 0x01010101u, eb = (ek * 0x00204081u) & 0x01010101u;
+        const uint32_t mb = (Uq * 0x01010101u - eb) & (rb * 0xFFu);
+        const uint32_t m0 = mb & 0xFFu, m1 = (mb >> 8) & 0xFFu, m2 = (mb >> 16) & 0xFFu, m3 = mb >> 24;
+        while (ms.w.bits < 64) ms_fill(ms);                     // the quad reads at most 64 bits
+        const uint32_t lo = (uint32_t)ms.w.w0, hi = (uint32_t)(ms.w.w0 >> 32);
+        const uint32_t s01 = m0 + m1;                           // <= 32
+        const uint32_t lo2 = __funnelshift_rc(lo, hi, s01), hi2 = __funnelshift_rc(hi, 0u, s01);
+        const uint32_t f[4] = { lo, __funnelshift_r(lo, hi, m0), lo2, __funnelshift_r(lo2, hi2, m2) };
+        const uint32_t mm[4] = { m0, m1, m2, m3 };
+        win_drop(ms.w, s01 + m2 + m3);
+        #pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t m = mm[k], bits = f[k];
+          const uint32_t pw = 1u << m;
+          uint32_t v = (bits & (pw - 1u)) | 1u;
+          v = ((e1 >> k) & 1u) * pw + v;                          // bit m is clear: + is |
+          const bool sig = (rho >> k) & 1u;
+          if (k & 1) hb[i][k >> 1] = sig ? (v >> 1) : 0u;
+          uint32_t val;
+          if (MODE == 0) { const uint32_t a = (v * mul_a + 2u * mul_a) >> 1; val = a * (1u - 2u * (bits & 1u)); }   // two's complement: +a or -a
+          else {
+            const uint32_t mag = v * pscale + 2u * pscale;        // (v + 2) << (p - 1): magnitude with the half-LSB bin centre
+            if (MODE == 1) val = __float_as_uint(__fmul_rn((float)mag, delta)) | (bits << 31);
+            else val = (bits << 31) | mag;
+          }
+          o[i][k] = sig ? val : 0u;
+        }
+      }
+      gw[j * DEC1_THREADS] = (h_carry | hb[0][0]) | ((hb[0][1] | hb[1][0]) << 16);
+      h_carry = hb[1][1];
+      *reinterpret_cast<uint4*>(r0 + 4 * j) = make_uint4(o[0][0], o[0][2], o[1][0], o[1][2]);
+      *reinterpret_cast<uint4*>(r1 + 4 * j) = make_uint4(o[0][1], o[0][3], o[1][1], o[1][3]);
+    }
+    gw[npairs * DEC1_THREADS] = h_carry;                      // g[nq]: nothing to the right
+    if (fail) break;
+    // align this row's significance bits (npairs x 4 bits sit at the top of the 64-bit register)
+    {
+      const uint32_t sh = 64u - 4u * npairs;                  // 0, 4, ..., 60
+      const uint32_t a0 = sh >= 32 ? cu_hi : cu_lo, a1 = sh >= 32 ? 0u : cu_hi;
+      sg_lo = __funnelshift_r(a0, a1, sh & 31u); sg_hi = a1 >> (sh & 31u);
+    }
+  }
+  block_status[b] = fail ? DST_FAIL : 0u;
+}
+
 // zero-fill of blocks that are not included or failed to decode (one warp per block)
 __global__ void __launch_bounds__(DEC_WARPS * 32)
 ht_dec_fill_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks, uint32_t* __restrict__ coef,
@@ -1037,7 +1226,7 @@ void launch_ht_decode(const DecBlock* blocks, uint32_t nblocks, const uint8_t* c
   }
 }
 
-void launch_ht_decode_serial(const DecBlock* blocks, uint32_t nblocks, uint32_t max_width, const uint8_t* codestream,
+void launch_ht_decode_serial(const DecBlock* blocks, uint32_t nblocks, uint32_t nfast, uint32_t max_width, const uint8_t* codestream,
                              uint32_t* coef, uint32_t* scratch, const uint16_t* tables, uint32_t out_mode,
                              bool cleanup_only, uint32_t* block_status, cudaStream_t st)
 {
@@ -1048,8 +1237,13 @@ void launch_ht_decode_serial(const DecBlock* blocks, uint32_t nblocks, uint32_t 
   auto k = (cleanup_only && out_mode == DEC_OUT_INT) ? ht_decode_serial_kernel<0>
          : (cleanup_only && out_mode == DEC_OUT_FLOAT) ? ht_decode_serial_kernel<1> : ht_decode_serial_kernel<2>;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  {
-    dim3 grid((nblocks + DEC1_THREADS - 1) / DEC1_THREADS), block(DEC1_THREADS);
+  dim3 grid((nblocks + DEC1_THREADS - 1) / DEC1_THREADS), block(DEC1_THREADS);
+  if (nfast) {           // blocks flagged DEC_FLAG_FAST (cleanup pass only, one output type)
+    auto kf = out_mode == DEC_OUT_INT ? ht_decode_fast_kernel<0> : out_mode == DEC_OUT_FLOAT ? ht_decode_fast_kernel<1>
+                                                                                            : ht_decode_fast_kernel<2>;
+    OJB_LAUNCH(kf, grid, block, 0, st, blocks, nblocks, codestream, coef, tables, block_status);
+  }
+  if (nfast < nblocks) {
     OJB_LAUNCH(k, grid, block, smem, st, blocks, nblocks, codestream, coef, scratch, tables, out_mode,
                block_status, prev_quads);
   }

@@ -42,16 +42,18 @@ struct MelWriter {
 // above each of them, lowest first -- no byte loop, and groups without 0xFF (the usual case) take the
 // straight path.  One 8-byte store per group.
 __device__ __forceinline__ void ms_flush8(MsWriter& s, uint2* dst) {
-  const unsigned long long M = 0x0001010101010101ull;         // bytes 0..6: a 0xFF in byte 7 shortens the NEXT group
+  const unsigned long long M = 0x0080808080808080ull;         // bytes 0..6: a 0xFF in byte 7 shortens the NEXT group
+  const unsigned long long M7 = 0x0101010101010101ull;
   const uint32_t lf = s.last_ff;
   unsigned long long x = (s.w0 & 0x7Full) | ((s.w0 >> 7) << (7 + lf));   // 7-bit first byte after a 0xFF
   uint32_t c = 64u - lf;                                                  // data bits this group takes
-  unsigned long long ff = x & (x >> 1); ff &= ff >> 2; ff &= ff >> 4; ff &= M;
+  // bit 8i+7 <=> byte i == 0xFF (low seven bits all ones: adding 1 carries into bit 7; and bit 7 set)
+  unsigned long long ff = ((x & 0x7F7F7F7F7F7F7F7Full) + M7) & x & M;
   while (ff) {
-    const uint32_t pos = (uint32_t)__ffsll((long long)ff) + 14u;          // top bit of the byte after the 0xFF
+    const uint32_t pos = (uint32_t)__ffsll((long long)ff) + 7u;           // top bit of the byte after the 0xFF
     x = (x & ((1ull << pos) - 1ull)) | (((x >> pos) << pos) << 1);
     --c;
-    ff = x & (x >> 1); ff &= ff >> 2; ff &= ff >> 4; ff &= M & (~0ull << pos);
+    ff = ((x & 0x7F7F7F7F7F7F7F7Full) + M7) & x & M & (~0ull << pos);
   }
   dst[s.words >> 1] = make_uint2((uint32_t)x, (uint32_t)(x >> 32));
   s.words += 2;
@@ -117,6 +119,72 @@ __device__ __forceinline__ void mel_event(MelWriter& m, bool one, uint8_t* buf) 
   }
 }
 
+// terminate_mel_vlc :413-441, ms_terminate :517-533: the pending bits of the three streams, the MEL / VLC byte
+// fusion, MEL bytes moved behind MagSgn, Scup
+__device__ __forceinline__ void terminate_block(MsWriter& ms, VlcWriter& vlc, MelWriter& mel, uint8_t* mel_buf, uint8_t* slot,
+                                                uint32_t slot_cap, uint32_t* status, EncResult& res)
+{
+  // ---- termination (terminate_mel_vlc :413-441, ms_terminate :517-533)
+  uint32_t ms_pos = ms.words * 4;
+  {
+    unsigned long long acc = ms.w0; uint32_t nb = ms.nbits;        // < 64 raw bits: cut them into bytes
+    bool lf = ms.last_ff != 0;
+    for (;;) {
+      const uint32_t n = lf ? 7u : 8u;
+      if (nb < n) break;
+      const uint32_t b = (uint32_t)acc & ((1u << n) - 1u);
+      slot[ms_pos++] = (uint8_t)b; acc >>= n; nb -= n; lf = (b == 0xFF);
+    }
+    const uint32_t cap = lf ? 7u : 8u;
+    if (nb) {
+      const uint32_t t = cap - nb;
+      const uint32_t byte = (uint32_t)acc | ((0xFFu & ((1u << t) - 1u)) << nb);
+      if (byte != 0xFF) slot[ms_pos++] = (uint8_t)byte;
+    } else if (cap == 7) ms_pos--;
+  }
+  if (mel.run > 0) mel_bit(mel, 1, mel_buf);
+  const uint32_t mel_tmp = (mel.tmp << mel.rem) & 0xFFu;
+  const uint32_t mel_mask = (0xFFu << mel.rem) & 0xFFu;
+  uint32_t vl_pos = vlc.words * 4;
+  uint8_t* vend = slot + slot_cap;
+  uint32_t vl_tmp, vl_mask;
+  {
+    unsigned long long acc = vlc.acc;
+    uint32_t nb = vlc.nbits, pv = vlc.prev;
+    for (;;) {                           // complete bytes of the pending bits, with their stuffing
+      uint32_t b = (uint32_t)acc & 0xFFu, n = 8;
+      if (pv > 0x8F && nb >= 7 && (b & 0x7F) == 0x7F) { b = 0x7F; n = 7; }
+      if (nb < n) break;
+      vend[-(int)(++vl_pos)] = (uint8_t)b; acc >>= n; nb -= n; pv = b;
+    }
+    // the unfinished byte: after a byte > 0x8F only 7 bits are available at first (vlc_encode :379-405)
+    vl_tmp = (uint32_t)acc & 0xFFu;
+    vl_mask = 0xFFu >> (8 - nb);
+  }
+  if ((mel_mask | vl_mask) != 0) {
+    const uint32_t fuse = mel_tmp | vl_tmp;
+    if ((((fuse ^ mel_tmp) & mel_mask) | ((fuse ^ vl_tmp) & vl_mask)) == 0 && fuse != 0xFF && vl_pos > 1) {
+      if (mel.pos < ES_MEL_BYTES) mel_buf[mel.pos * ES_THREADS] = (uint8_t)fuse;
+      mel.pos++;
+    } else {
+      if (mel.pos < ES_MEL_BYTES) mel_buf[mel.pos * ES_THREADS] = (uint8_t)mel_tmp;
+      mel.pos++;
+      vend[-(int)(++vl_pos)] = (uint8_t)vl_tmp;
+    }
+  }
+  if (mel.pos > 192 || ms_pos + mel.pos + vl_pos + 8 > slot_cap) {
+    atomicOr(status, mel.pos > 192 ? 2u : 1u);          // the reference errors out on MEL > 192 bytes
+    res.len_head = 0; res.len_tail = 0;
+    return;
+  }
+  for (uint32_t i = 0; i < mel.pos; ++i) slot[ms_pos + i] = mel_buf[i * ES_THREADS];
+  const uint32_t scup = mel.pos + vl_pos;
+  vend[-1] = (uint8_t)(scup >> 4);
+  vend[-2] = (uint8_t)((vend[-2] & 0xF0) | (scup & 0xF));
+  res.len_head = ms_pos + mel.pos;
+  res.len_tail = vl_pos;
+}
+
 __global__ void __launch_bounds__(ES_THREADS)
 ht_encode_serial_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
                         const uint32_t* __restrict__ coef, uint8_t* __restrict__ slots,
@@ -135,6 +203,7 @@ ht_encode_serial_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
   const uint32_t bidx = blockIdx.x * ES_THREADS + threadIdx.x;
   if (bidx >= nblocks) return;
   const EncBlock blk = blocks[bidx];
+  if (blk.flags & ENC_FLAG_FAST) return;                 // coded by ht_encode_fast_kernel
   const uint32_t width = blk.w, height = blk.h, stride = blk.stride, p = blk.p;
   const uint32_t* __restrict__ src = coef + blk.src_off;
   uint8_t* slot = slots + blk.slot_off;
@@ -281,70 +350,170 @@ ht_encode_serial_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
   if (overflow) { atomicOr(status, 1u); results[bidx].len_head = 0; results[bidx].len_tail = 0; return; }
   if (any_sig == 0 && negzero == 0) { results[bidx].len_head = 0; results[bidx].len_tail = 0; return; }   // block not included
 
-  // ---- termination (terminate_mel_vlc :413-441, ms_terminate :517-533)
-  uint32_t ms_pos = ms.words * 4;
-  {
-    unsigned long long acc = ms.w0; uint32_t nb = ms.nbits;        // < 64 raw bits: cut them into bytes
-    bool lf = ms.last_ff != 0;
-    for (;;) {
-      const uint32_t n = lf ? 7u : 8u;
-      if (nb < n) break;
-      const uint32_t b = (uint32_t)acc & ((1u << n) - 1u);
-      slot[ms_pos++] = (uint8_t)b; acc >>= n; nb -= n; lf = (b == 0xFF);
+  terminate_block(ms, vlc, mel, mel_buf, slot, blk.slot_cap, status, results[bidx]);
+}
+
+// ---- fast path -------------------------------------------------------------------------------------------
+// The same encoder for the blocks the host marks ENC_FLAG_FAST: width a multiple of 4 and at most 64, even
+// height, 16-byte aligned rows, K_max <= 15 (the four MagSgn fields of a quad fit 64 bits; 2 * magnitude - 1 fits
+// 16 bits), no magnitude-overflow check.  Without the per-quad bounds / width / precision tests, and with the
+// row above kept as
+//   * a 64-bit register of bottom-sample significance bits (two per quad, walked four bits per pair) and
+//   * one word per quad pair of g[q] = x(br of quad q-1) | x(bl of quad q), x = 2 * magnitude - 1: the largest
+//     exponent of the four samples above a quad is 32 - clz(g[q] | g[q+1]) -- one CLZ instead of a 4-way max of
+//     stored exponents; inside the quad the largest exponent is 32 - clz(x0 | x1 | x2 | x3) and a sample reaches it
+//     iff x_i >> (e_max - 1) is non-zero.
+__global__ void __launch_bounds__(ES_THREADS)
+ht_encode_fast_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
+                      const uint32_t* __restrict__ coef, uint8_t* __restrict__ slots,
+                      EncResult* __restrict__ results, const uint16_t* __restrict__ tables,
+                      uint32_t* __restrict__ status)
+{
+  __shared__ uint16_t s_vlc[2 * 2048];
+  __shared__ uint16_t s_uvlc[36];
+  __shared__ uint8_t s_mel[ES_MEL_BYTES * ES_THREADS];
+  __shared__ uint32_t s_g[17 * ES_THREADS];
+
+  for (uint32_t i = threadIdx.x; i < 2 * 2048; i += blockDim.x) s_vlc[i] = tables[i];
+  if (threadIdx.x < 33) s_uvlc[threadIdx.x] = tables[2 * 2048 + threadIdx.x];
+  __syncthreads();
+
+  const uint32_t bidx = blockIdx.x * ES_THREADS + threadIdx.x;
+  if (bidx >= nblocks) return;
+  const EncBlock blk = blocks[bidx];
+  if (!(blk.flags & ENC_FLAG_FAST)) return;
+  const uint32_t npairs = blk.w >> 2, height = blk.h, stride = blk.stride, p = blk.p;
+  const uint32_t* __restrict__ src = coef + blk.src_off;
+  uint8_t* slot = slots + blk.slot_off;
+  uint2* ms_dst = reinterpret_cast<uint2*>(slot);          // slots are 16-byte aligned
+  uint32_t* vl_end = reinterpret_cast<uint32_t*>(slot + blk.slot_cap);
+  uint8_t* mel_buf = s_mel + threadIdx.x;
+  uint32_t* gw = s_g + threadIdx.x;
+  const uint32_t slot_words = blk.slot_cap >> 2;
+
+  MsWriter ms; ms.w0 = 0; ms.w1 = 0; ms.nbits = 0; ms.words = 0; ms.last_ff = 0;
+  VlcWriter vlc; vlc.acc = 0xFFFull; vlc.nbits = 12; vlc.words = 0; vlc.prev = 0;
+  MelWriter mel; mel.k = 0; mel.run = 0; mel.tmp = 0; mel.rem = 8; mel.pos = 0;
+  uint32_t any_sig = 0;
+  bool overflow = false;
+  for (uint32_t j = 0; j <= 16; ++j) gw[j * ES_THREADS] = 0;
+  uint32_t sg_lo = 0, sg_hi = 0;
+
+  for (uint32_t y = 0; y < height; y += 2) {
+    const bool first = (y == 0);
+    const uint4* r0 = reinterpret_cast<const uint4*>(src + (size_t)y * stride);
+    const uint4* r1 = reinterpret_cast<const uint4*>(src + (size_t)(y + 1) * stride);
+    const uint16_t* vtab = s_vlc + (first ? 0u : 2048u);
+    uint32_t rho_left = 0;
+    uint32_t rs_lo = sg_lo, rs_hi = sg_hi, rs_carry = 0;
+    uint32_t cu_lo = 0, cu_hi = 0;
+    uint32_t wj = gw[0], x_carry = 0;
+    uint4 na = r0[0], nb = r1[0];
+    #pragma unroll 1
+    for (uint32_t j = 0; j < npairs; ++j) {
+      const uint4 ca = na, cb = nb;
+      if (j + 1 < npairs) { na = r0[j + 1]; nb = r1[j + 1]; }          // next pair in flight while this one is coded
+      const uint32_t wj1 = gw[(j + 1) * ES_THREADS];
+      const uint32_t y6 = rs_carry | ((rs_lo & 0x1Fu) << 1);
+      const uint32_t z = y6 | (y6 >> 1);
+      rs_carry = (rs_lo >> 3) & 1u;
+      rs_lo = __funnelshift_r(rs_lo, rs_hi, 4); rs_hi >>= 4;
+      const uint32_t gor[2] = { (wj | (wj >> 16)) & 0xFFFFu, (wj >> 16) | (wj1 & 0xFFFFu) };
+      wj = wj1;
+
+      uint32_t uq[2], xb[2][2], rr[2];
+      uint32_t pair_bits = 0, pair_len = 0;      // CxtVLC codewords of the pair, then its U-VLC bits (<= 30)
+      #pragma unroll
+      for (uint32_t h = 0; h < 2; ++h) {
+        // quad order TL, BL, TR, BR
+        const uint32_t t[4] = { h ? ca.z : ca.x, h ? cb.z : cb.x, h ? ca.w : ca.y, h ? cb.w : cb.y };
+        uint32_t rho = 0, x[4], s[4];
+        #pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t v = ((t[i] + t[i]) >> p) & ~1u;           // 2 * magnitude
+          const uint32_t sig = min(v, 1u);
+          rho |= sig << i;
+          x[i] = v - sig;                                          // 2 * magnitude - 1 (0 when insignificant)
+          s[i] = v - 2u + (t[i] >> 31);                            // MagSgn value 2 * (magnitude - 1) + sign
+        }
+        any_sig |= rho;
+        rr[h] = rho;
+        xb[h][0] = x[1]; xb[h][1] = x[3];
+        const uint32_t emax = 32u - (uint32_t)__clz((int)(x[0] | x[1] | x[2] | x[3]));
+        uint32_t kappa = 1, cq;
+        if (first) cq = (rho_left >> 1) | (rho_left & 1);
+        else {
+          const int me = 32 - __clz((int)gor[h]);                  // largest exponent of the four samples above
+          if (rho & (rho - 1)) kappa = (uint32_t)max(1, me - 1);
+          cq = ((z >> (2 * h)) & 5u) | (rho_left > 3u ? 2u : 0u);
+        }
+        const uint32_t Uq = max(emax, kappa);
+        const uint32_t u = Uq - kappa;
+        uq[h] = u;
+        // which samples reach the maximum exponent (only coded when u > 0)
+        uint32_t eps = 0;
+        if (u > 0) {
+          const uint32_t sh = emax - 1u;                           // u > 0 => emax >= 2
+          eps = (x[0] >> sh) | ((x[1] >> sh) << 1) | ((x[2] >> sh) << 2) | ((x[3] >> sh) << 3);
+        }
+        const uint32_t tuple = vtab[(cq << 8) + (rho << 4) + eps];
+        pair_bits |= (tuple >> 8) << pair_len; pair_len += (tuple >> 4) & 7u;      // :661-662
+        if (cq == 0) mel_event(mel, rho != 0, mel_buf);                          // :664-665
+        {                                                                         // :667-674
+          const uint32_t rb = (rho * 0x00204081u) & 0x01010101u, eb = ((tuple & 15u) * 0x00204081u) & 0x01010101u;
+          const uint32_t mb = (Uq * 0x01010101u - eb) & (rb * 0xFFu);
+          const uint32_t m0 = mb & 0xFFu, m1 = (mb >> 8) & 0xFFu, m2 = (mb >> 16) & 0xFFu, m3 = mb >> 24;
+          // fields of at most 16 bits: each column of the quad fits a word
+          const uint32_t A = (s[0] & ((1u << m0) - 1u)) | ((s[1] & ((1u << m1) - 1u)) << m0);
+          const uint32_t B = (s[2] & ((1u << m2) - 1u)) | ((s[3] & ((1u << m3) - 1u)) << m2);
+          const uint32_t la = m0 + m1, lb = m2 + m3;               // <= 32 each
+          ms_put(ms, (unsigned long long)A | ((unsigned long long)B << la), la + lb, ms_dst);
+        }
+        rho_left = rho;
+      }
+      // this row's state for the next one
+      {
+        const uint32_t ta = (rr[0] >> 1) & 5u, tb = (rr[1] >> 1) & 5u;       // bit 0: bottom-left, bit 2: bottom-right
+        const uint32_t nbits4 = ((ta | (ta >> 1)) & 3u) | (((tb | (tb >> 1)) & 3u) << 2);
+        cu_lo = __funnelshift_r(cu_lo, cu_hi, 4); cu_hi = (cu_hi >> 4) | (nbits4 << 28);
+        gw[j * ES_THREADS] = (x_carry | xb[0][0]) | ((xb[0][1] | xb[1][0]) << 16);
+        x_carry = xb[1][1];
+      }
+      // ---- U-VLC of the pair (:763-785, :985-988)
+      {
+        const uint32_t u0 = uq[0], u1 = uq[1];
+        uint32_t c0, c1;
+        if (first) {
+          if (u0 > 0 && u1 > 0) mel_event(mel, min(u0, u1) > 2, mel_buf);
+          if (u0 > 2 && u1 > 2) { c0 = s_uvlc[u0 - 2]; c1 = s_uvlc[u1 - 2]; }
+          else if (u0 > 2 && u1 > 0) { c0 = s_uvlc[u0]; c1 = (u1 - 1) | (1u << 3); }     // one-bit u1
+          else { c0 = s_uvlc[u0]; c1 = s_uvlc[u1]; }
+        } else { c0 = s_uvlc[u0]; c1 = s_uvlc[u1]; }
+        uint32_t bits = pair_bits, len = pair_len;
+        bits |= (c0 & 7u) << len; len += (c0 >> 3) & 7u;
+        bits |= (c1 & 7u) << len; len += (c1 >> 3) & 7u;
+        bits |= ((c0 >> 6) & 31u) << len; len += (c0 >> 11) & 31u;
+        bits |= ((c1 >> 6) & 31u) << len; len += (c1 >> 11) & 31u;
+        vlc_put(vlc, bits, len, vl_end);
+      }
     }
-    const uint32_t cap = lf ? 7u : 8u;
-    if (nb) {
-      const uint32_t t = cap - nb;
-      const uint32_t byte = (uint32_t)acc | ((0xFFu & ((1u << t) - 1u)) << nb);
-      if (byte != 0xFF) slot[ms_pos++] = (uint8_t)byte;
-    } else if (cap == 7) ms_pos--;
-  }
-  if (mel.run > 0) mel_bit(mel, 1, mel_buf);
-  const uint32_t mel_tmp = (mel.tmp << mel.rem) & 0xFFu;
-  const uint32_t mel_mask = (0xFFu << mel.rem) & 0xFFu;
-  uint32_t vl_pos = vlc.words * 4;
-  uint8_t* vend = slot + blk.slot_cap;
-  uint32_t vl_tmp, vl_mask;
-  {
-    unsigned long long acc = vlc.acc;
-    uint32_t nb = vlc.nbits, pv = vlc.prev;
-    for (;;) {                           // complete bytes of the pending bits, with their stuffing
-      uint32_t b = (uint32_t)acc & 0xFFu, n = 8;
-      if (pv > 0x8F && nb >= 7 && (b & 0x7F) == 0x7F) { b = 0x7F; n = 7; }
-      if (nb < n) break;
-      vend[-(int)(++vl_pos)] = (uint8_t)b; acc >>= n; nb -= n; pv = b;
+    gw[npairs * ES_THREADS] = x_carry;
+    {
+      const uint32_t sh = 64u - 4u * npairs;
+      const uint32_t a0 = sh >= 32 ? cu_hi : cu_lo, a1 = sh >= 32 ? 0u : cu_hi;
+      sg_lo = __funnelshift_r(a0, a1, sh & 31u); sg_hi = a1 >> (sh & 31u);
     }
-    // the unfinished byte: after a byte > 0x8F only 7 bits are available at first (vlc_encode :379-405)
-    vl_tmp = (uint32_t)acc & 0xFFu;
-    vl_mask = 0xFFu >> (8 - nb);
+    if (ms.words + vlc.words + 24 >= slot_words) { overflow = true; break; }
   }
-  if ((mel_mask | vl_mask) != 0) {
-    const uint32_t fuse = mel_tmp | vl_tmp;
-    if ((((fuse ^ mel_tmp) & mel_mask) | ((fuse ^ vl_tmp) & vl_mask)) == 0 && fuse != 0xFF && vl_pos > 1) {
-      if (mel.pos < ES_MEL_BYTES) mel_buf[mel.pos * ES_THREADS] = (uint8_t)fuse;
-      mel.pos++;
-    } else {
-      if (mel.pos < ES_MEL_BYTES) mel_buf[mel.pos * ES_THREADS] = (uint8_t)mel_tmp;
-      mel.pos++;
-      vend[-(int)(++vl_pos)] = (uint8_t)vl_tmp;
-    }
-  }
-  if (mel.pos > 192 || ms_pos + mel.pos + vl_pos + 8 > blk.slot_cap) {
-    atomicOr(status, mel.pos > 192 ? 2u : 1u);          // the reference errors out on MEL > 192 bytes
-    results[bidx].len_head = 0; results[bidx].len_tail = 0;
-    return;
-  }
-  for (uint32_t i = 0; i < mel.pos; ++i) slot[ms_pos + i] = mel_buf[i * ES_THREADS];
-  const uint32_t scup = mel.pos + vl_pos;
-  vend[-1] = (uint8_t)(scup >> 4);
-  vend[-2] = (uint8_t)((vend[-2] & 0xF0) | (scup & 0xF));
-  results[bidx].len_head = ms_pos + mel.pos;
-  results[bidx].len_tail = vl_pos;
+
+  if (overflow) { atomicOr(status, 1u); results[bidx].len_head = 0; results[bidx].len_tail = 0; return; }
+  if (any_sig == 0) { results[bidx].len_head = 0; results[bidx].len_tail = 0; return; }   // block not included
+  terminate_block(ms, vlc, mel, mel_buf, slot, blk.slot_cap, status, results[bidx]);
 }
 
 } // namespace
 
-void launch_ht_encode_serial(const EncBlock* blocks, uint32_t nblocks, uint32_t max_width, const uint32_t* coef,
+void launch_ht_encode_serial(const EncBlock* blocks, uint32_t nblocks, uint32_t nfast, uint32_t max_width, const uint32_t* coef,
                              uint8_t* slots, EncResult* results, const uint16_t* tables, uint32_t* status,
                              cudaStream_t st)
 {
@@ -353,8 +522,11 @@ void launch_ht_encode_serial(const EncBlock* blocks, uint32_t nblocks, uint32_t 
   const size_t smem = (size_t)prev_quads * ES_THREADS * sizeof(uint16_t);
   cudaFuncSetAttribute(ht_encode_serial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid((nblocks + ES_THREADS - 1) / ES_THREADS), block(ES_THREADS);
-  OJB_LAUNCH(ht_encode_serial_kernel, grid, block, smem, st, blocks, nblocks, coef, slots, results, tables, status,
-             prev_quads);
+  if (nfast)
+    OJB_LAUNCH(ht_encode_fast_kernel, grid, block, 0, st, blocks, nblocks, coef, slots, results, tables, status);
+  if (nfast < nblocks)
+    OJB_LAUNCH(ht_encode_serial_kernel, grid, block, smem, st, blocks, nblocks, coef, slots, results, tables, status,
+               prev_quads);
 }
 
 } // namespace ojb

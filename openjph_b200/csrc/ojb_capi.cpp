@@ -570,6 +570,7 @@ int ojb_encode_blocks(const uint32_t* samples, uint64_t n_words, ojb_block_desc*
     cuda_check(cudaMemcpy(d_t.p, tb.data(), tb.size() * 2, cudaMemcpyHostToDevice), "tables");
     std::vector<EncBlock> eb(n);
     uint64_t slot = 0;
+    uint32_t nfast = 0;
     for (uint32_t i = 0; i < n; ++i) {
       if (desc[i].w == 0 || desc[i].h == 0 || desc[i].w > 1024 || desc[i].w * desc[i].h > 4096 || desc[i].missing_msbs > 29)
         fail(0x000B0021, "unsupported code-block geometry");
@@ -581,6 +582,7 @@ int ojb_encode_blocks(const uint32_t* samples, uint64_t n_words, ojb_block_desc*
       uint64_t vl = ((nq + 1) / 2 * 30 + 12 + 7) / 8; vl += vl / 7 + 8;
       uint64_t cap = (ms + vl + 192 + 160 + 15) & ~(uint64_t)15;
       eb[i].slot_off = slot; eb[i].slot_cap = (uint32_t)cap; slot += cap;
+      if (!getenv("OJB_NO_FAST_BLOCKS") && enc_block_is_fast(eb[i])) { eb[i].flags |= ENC_FLAG_FAST; ++nfast; }
     }
     d_b.reserve(n * sizeof(EncBlock)); d_r.reserve(n * sizeof(EncResult)); d_sl.reserve(slot + 64); d_st.reserve(64);
     cuda_check(cudaMemcpy(d_b.p, eb.data(), n * sizeof(EncBlock), cudaMemcpyHostToDevice), "blocks");
@@ -588,7 +590,7 @@ int ojb_encode_blocks(const uint32_t* samples, uint64_t n_words, ojb_block_desc*
     uint32_t maxw = 4;
     for (uint32_t i = 0; i < n; ++i) maxw = std::max(maxw, desc[i].w);
     if (serial_block_encoder() || maxw > 64)
-      launch_ht_encode_serial(d_b.as<EncBlock>(), n, maxw, d_s.as<uint32_t>(), d_sl.as<uint8_t>(), d_r.as<EncResult>(),
+      launch_ht_encode_serial(d_b.as<EncBlock>(), n, nfast, maxw, d_s.as<uint32_t>(), d_sl.as<uint8_t>(), d_r.as<EncResult>(),
                      d_t.as<uint16_t>(), d_st.as<uint32_t>(), 0);
     else
       launch_ht_encode(d_b.as<EncBlock>(), n, d_s.as<uint32_t>(), d_sl.as<uint8_t>(), d_r.as<EncResult>(),
@@ -628,7 +630,7 @@ int ojb_decode_blocks(const uint8_t* bytes, uint64_t n_bytes, ojb_block_desc* de
     cuda_check(cudaMemcpy(d_t.p, tb.data(), tb.size() * 2, cudaMemcpyHostToDevice), "tables");
     std::vector<DecBlock> db(n);
     size_t scratch = 0;
-    uint32_t max_len1 = 0;
+    uint32_t max_len1 = 0, nfast = 0;
     for (uint32_t i = 0; i < n; ++i) {
       DecBlock& d = db[i]; memset(&d, 0, sizeof(d));
       d.data_off = desc[i].byte_off; d.dst_off = desc[i].sample_off; d.stride = desc[i].stride;
@@ -639,6 +641,7 @@ int ojb_decode_blocks(const uint8_t* bytes, uint64_t n_bytes, ojb_block_desc* de
       scratch = (scratch + 3) & ~(size_t)3;
       d.scratch_off = scratch; scratch += (size_t)qs * nqr + (((d.len1 + 3) / 4 + 4 + 3) & ~3u);
       max_len1 = std::max(max_len1, d.len1);
+      if (!getenv("OJB_NO_FAST_BLOCKS") && dec_block_is_fast(d)) { d.flags |= DEC_FLAG_FAST; ++nfast; }
     }
     d_b.reserve(n * sizeof(DecBlock)); d_o.reserve((n_words + 64) * 4); d_sc.reserve((scratch + 64) * 4); d_st.reserve(n * 4 + 16);
     cuda_check(cudaMemcpy(d_b.p, db.data(), n * sizeof(DecBlock), cudaMemcpyHostToDevice), "blocks");
@@ -646,7 +649,7 @@ int ojb_decode_blocks(const uint8_t* bytes, uint64_t n_bytes, ojb_block_desc* de
     uint32_t maxw = 4;
     for (uint32_t i = 0; i < n; ++i) maxw = std::max(maxw, desc[i].w);
     if (serial_block_decoder() || maxw > 64)
-      launch_ht_decode_serial(d_b.as<DecBlock>(), n, maxw, d_cs.as<uint8_t>(), d_o.as<uint32_t>(), d_sc.as<uint32_t>(),
+      launch_ht_decode_serial(d_b.as<DecBlock>(), n, nfast, maxw, d_cs.as<uint8_t>(), d_o.as<uint32_t>(), d_sc.as<uint32_t>(),
                               d_t.as<uint16_t>(), DEC_OUT_SIGNMAG, false, d_st.as<uint32_t>(), 0);
     else
       launch_ht_decode(d_b.as<DecBlock>(), n, d_cs.as<uint8_t>(), d_o.as<uint32_t>(), d_sc.as<uint32_t>(),

@@ -221,6 +221,7 @@ void Encoder::configure(const Params& p, uint32_t sample_type) {
   build_dwt_jobs(true);
   // block descriptors and slots
   h_blocks.assign(layout.num_blocks, EncBlock());
+  num_fast_blocks = 0;
   size_t slot = 0;
   for (const TileGeom& t : layout.tiles)
     for (const TileCompGeom& tc : t.comps)
@@ -245,6 +246,7 @@ void Encoder::configure(const Params& p, uint32_t sample_type) {
               cap = (cap + 15) & ~(uint64_t)15;
               e.slot_off = slot; e.slot_cap = (uint32_t)cap;
               slot += cap;
+              if (!no_fast_blocks && enc_block_is_fast(e)) { e.flags |= ENC_FLAG_FAST; ++num_fast_blocks; }
             }
         }
   slot_bytes = slot + 64;
@@ -329,12 +331,12 @@ size_t Encoder::encode(const void* const* planes, const uint32_t* strides, bool 
   mark(2);
   uint32_t nb = (uint32_t)h_blocks.size();
   if (serial_block_encoder() || max_block_w > 64)
-    launch_ht_encode_serial(d_blocks.as<EncBlock>(), nb, max_block_w, d_coef.as<uint32_t>(), d_slots.as<uint8_t>(),
+    launch_ht_encode_serial(d_blocks.as<EncBlock>(), nb, num_fast_blocks, max_block_w, d_coef.as<uint32_t>(), d_slots.as<uint8_t>(),
                             d_results.as<EncResult>(), d_tables_enc.as<uint16_t>(), d_status.as<uint32_t>(), stream);
   else
     launch_ht_encode(d_blocks.as<EncBlock>(), nb, d_coef.as<uint32_t>(), d_slots.as<uint8_t>(),
                      d_results.as<EncResult>(), d_tables_enc.as<uint16_t>(), d_status.as<uint32_t>(), stream);
-  ++last_launches;
+  last_launches += (serial_block_encoder() || max_block_w > 64) ? (num_fast_blocks ? 1 : 0) + (num_fast_blocks < nb ? 1 : 0) : 1;
   mark(3);
   if (nb) launch_ctrl_copy(h_results.p, d_results.p, (size_t)nb * sizeof(EncResult), stream);
   launch_ctrl_copy(h_status.p, d_status.p, 16, stream);
@@ -750,19 +752,24 @@ uint32_t Decoder::decode(void* const* planes, const uint32_t* strides, bool plan
     hd[b] = d;
   }
   const uint32_t dec_out = (any_rev && any_irv) ? (uint32_t)DEC_OUT_PER_BLOCK : any_irv ? (uint32_t)DEC_OUT_FLOAT : (uint32_t)DEC_OUT_INT;
+  // blocks of the common shape go through the specialised kernel (one output type per launch)
+  uint32_t nfast = 0;
+  if (dec_out != DEC_OUT_PER_BLOCK && !no_fast_blocks)
+    for (uint32_t b = 0; b < nb; ++b)
+      if (dec_block_is_fast(hd[b])) { hd[b].flags |= DEC_FLAG_FAST; ++nfast; }
   d_scratch.reserve((scratch + 64) * 4);
   host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
   mark(2);
   if (nb) { launch_ctrl_copy(d_dec.p, h_dec.p, (size_t)nb * sizeof(DecBlock), stream); ++last_launches; }
   if (serial_block_decoder() || max_block_w > 64)
-    launch_ht_decode_serial(d_dec.as<DecBlock>(), nb, max_block_w, cs_dev, d_coef.as<uint32_t>(), d_scratch.as<uint32_t>(),
+    launch_ht_decode_serial(d_dec.as<DecBlock>(), nb, nfast, max_block_w, cs_dev, d_coef.as<uint32_t>(), d_scratch.as<uint32_t>(),
                             d_tables_dec.as<uint16_t>(), dec_out, cleanup_only,
                             d_bstatus.as<uint32_t>(), stream);
   else
     launch_ht_decode(d_dec.as<DecBlock>(), nb, cs_dev, d_coef.as<uint32_t>(), d_scratch.as<uint32_t>(),
                      d_tables_dec.as<uint16_t>(), (uint32_t)DEC_OUT_PER_BLOCK,
                      d_bstatus.as<uint32_t>(), max_len1, stream);
-  last_launches += 2;
+  last_launches += (serial_block_decoder() || max_block_w > 64) ? 1 + (nfast ? 1 : 0) + (nfast < nb ? 1 : 0) : 2;
   mark(3);
   if (nb) { launch_ctrl_copy(h_bstatus.p, d_bstatus.p, (size_t)nb * 4, stream); ++last_launches; }
   // synthesis, coarsest level first

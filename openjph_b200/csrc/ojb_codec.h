@@ -6,6 +6,7 @@
 #include "ojb_layout.h"
 #include "ojb_kernels.h"
 #include <memory>
+#include <cstdlib>
 
 namespace ojb {
 
@@ -67,6 +68,7 @@ public:
   DeviceBuf d_jobs;
   void build_dwt_jobs(bool forward);
   bool no_stream_dwt = false;          // force the general shared-memory DWT kernels (tests)
+  bool no_fast_blocks = getenv("OJB_NO_FAST_BLOCKS") != nullptr;   // force the general block-coder kernels (tests, A/B)
 };
 
 class Encoder : public CodecBase {
@@ -91,6 +93,7 @@ public:
   PinnedBuf h_results, h_dst, h_hdr, h_pieces, h_status;
   std::vector<CodedBlock> coded;
   size_t slot_bytes = 0;
+  uint32_t num_fast_blocks = 0;        // blocks flagged ENC_FLAG_FAST
   size_t out_cap_dev = 0;
 };
 

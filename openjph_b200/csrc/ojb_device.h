@@ -38,6 +38,12 @@ struct EncBlock {
 // significant) instead of being skipped.  It happens with zero decompositions and no colour transform
 // (K_max = B - 1 + guard for the single band) for the most negative sample value.
 #define ENC_CHECK_NEGZERO 1u
+// EncBlock::flags bit 1: the block qualifies for ht_encode_fast_kernel
+#define ENC_FLAG_FAST 2u
+inline bool enc_block_is_fast(const EncBlock& e) {
+  return e.w >= 4 && e.w <= 64 && (e.w & 3) == 0 && e.h >= 2 && (e.h & 1) == 0 && ((e.src_off | e.stride) & 3u) == 0 &&
+         e.p >= 16 && e.p <= 30 && !(e.flags & ENC_CHECK_NEGZERO);
+}
 // result per block: [0] bytes at slot start (MagSgn + MEL), [1] bytes at slot end (VLC);
 // both 0 for a block with no significant sample (not included in the packet).
 struct EncResult { uint32_t len_head, len_tail; };
@@ -53,6 +59,12 @@ struct DecBlock {
   uint8_t missing_msbs, num_passes, K_max, flags;   // flags bit0: stripe-causal, bit1: irreversible (float output)
   float delta;          // irreversible: step (already / 2^(31-K_max)); reversible: unused
 };
+// DecBlock::flags bit 2, set by the host per frame: the block qualifies for ht_decode_fast_kernel
+#define DEC_FLAG_FAST 4u
+inline bool dec_block_is_fast(const DecBlock& d) {
+  return d.num_passes == 1 && d.len1 >= 2 && d.w >= 4 && d.w <= 64 && (d.w & 3) == 0 && d.h >= 2 && (d.h & 1) == 0 &&
+         ((d.dst_off | d.stride) & 3u) == 0 && d.missing_msbs + 2u <= 16u && d.K_max > d.missing_msbs;
+}
 enum : uint32_t {       // DecBlock output modes
   DEC_OUT_SIGNMAG = 0,  // raw sign-magnitude (kernel-level parity with ojph_decode_codeblock32)
   DEC_OUT_INT = 1,      // reversible: signed integers (tx_from_cb32 fused)

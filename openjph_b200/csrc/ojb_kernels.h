@@ -9,8 +9,9 @@ namespace ojb {
 void launch_ht_encode(const EncBlock* blocks, uint32_t nblocks, const uint32_t* coef, uint8_t* slots,
                       EncResult* results, const uint16_t* tables, uint32_t* status, cudaStream_t st);
 
-// the same encoder with one THREAD per code-block (ht_encode_serial.cu); max_width = widest block
-void launch_ht_encode_serial(const EncBlock* blocks, uint32_t nblocks, uint32_t max_width, const uint32_t* coef,
+// the same encoder with one THREAD per code-block (ht_encode_serial.cu); max_width = widest block; nfast of the
+// blocks carry ENC_FLAG_FAST (see enc_block_is_fast) and go through the specialised kernel
+void launch_ht_encode_serial(const EncBlock* blocks, uint32_t nblocks, uint32_t nfast, uint32_t max_width, const uint32_t* coef,
                              uint8_t* slots, EncResult* results, const uint16_t* tables, uint32_t* status,
                              cudaStream_t st);
 
@@ -21,8 +22,9 @@ void launch_ht_decode(const DecBlock* blocks, uint32_t nblocks, const uint8_t* c
                       uint32_t* coef, uint32_t* scratch, const uint16_t* tables, uint32_t out_mode,
                       uint32_t* block_status, uint32_t max_len1, cudaStream_t st);
 
-// the same decoder with one THREAD per code-block for the whole cleanup pass (+ a zero-fill kernel)
-void launch_ht_decode_serial(const DecBlock* blocks, uint32_t nblocks, uint32_t max_width, const uint8_t* codestream,
+// the same decoder with one THREAD per code-block for the whole cleanup pass (+ a zero-fill kernel); nfast of the
+// blocks carry DEC_FLAG_FAST (see dec_block_is_fast) and go through the specialised kernel
+void launch_ht_decode_serial(const DecBlock* blocks, uint32_t nblocks, uint32_t nfast, uint32_t max_width, const uint8_t* codestream,
                              uint32_t* coef, uint32_t* scratch, const uint16_t* tables, uint32_t out_mode,
                              bool cleanup_only, uint32_t* block_status, cudaStream_t st);
 
