@@ -249,6 +249,46 @@ int ojb_encode_blocks(const uint32_t* samples, uint64_t n_words, ojb_block_desc*
 int ojb_decode_blocks(const uint8_t* bytes, uint64_t n_bytes, ojb_block_desc* desc, uint32_t n,
                       uint32_t* samples, uint64_t n_words);
 
+/* ---- one image over the GPUs of a box -----------------------------------------------------
+ * One process per GPU.  Tiles are independent units of the codestream (the reference builds one component /
+ * resolution tree per tile, src/core/codestream/ojph_codestream_local.cpp:132-168, and concatenates the
+ * tile-parts in tile-index order at flush, :1148-1164): rank r codes the tiles t with t % world == r, and the
+ * only data-path exchange is the final gather to the writer rank -- tile-part bytes on encode, decoded tile
+ * samples on decode -- device to device over NCCL.  The codestream on the writer is byte-identical to the one a
+ * single encoder (or the reference) produces.  Every rank makes the same calls in the same order.
+ * Transport: NCCL (communicator from a unique id the caller hands to every rank, e.g. through the launcher's
+ * store), or caller-supplied callbacks. */
+typedef struct ojb_shard ojb_shard;
+typedef struct ojb_comm_callbacks {
+  void* ctx;
+  int (*allgather)(void* ctx, const void* send_host, void* recv_host, uint64_t bytes_per_rank);
+  int (*bcast)(void* ctx, void* dev_buf, uint64_t bytes, uint32_t root);
+  int (*send)(void* ctx, const void* dev_buf, uint64_t bytes, uint32_t peer);     /* blocking */
+  int (*recv)(void* ctx, void* dev_buf, uint64_t bytes, uint32_t peer);           /* blocking */
+} ojb_comm_callbacks;
+int ojb_shard_unique_id(uint8_t out[128]);                        /* ncclGetUniqueId, on one rank */
+ojb_shard* ojb_shard_create_nccl(uint32_t rank, uint32_t world, const uint8_t unique_id[128]);   /* current device */
+ojb_shard* ojb_shard_create(uint32_t rank, uint32_t world, const ojb_comm_callbacks* cb);
+void ojb_shard_destroy(ojb_shard* s);
+const char* ojb_shard_last_error(void);
+/* param setters + write_headers of the whole image; this rank prepares its tiles */
+int ojb_shard_enc_configure(ojb_shard* s, const ojb_params* p, uint32_t sample_type, uint32_t writer_rank);
+/* exchange() loop + flush(): planes = the whole image in host memory (a rank reads only its own tiles'
+ * rectangles); the codestream arrives in out on the writer rank (*out_len = 0 elsewhere) */
+int ojb_shard_enc_encode(ojb_shard* s, const void* const* planes, const uint32_t* strides,
+                         uint8_t* out, uint64_t out_cap, uint64_t* out_len);
+/* read_headers + create + pull loop: j2c is read on the writer rank only (broadcast device to device); the
+ * decoded components arrive in planes on the writer rank */
+int ojb_shard_dec_decode(ojb_shard* s, const uint8_t* j2c, uint64_t len, uint32_t sample_type, uint32_t writer_rank,
+                         void* const* planes, const uint32_t* strides, ojb_frame_info* info);
+/* frame-parallel batches: variable-length gather of device buffers (one codestream per rank) to the writer's
+ * device buffer, rank order; offsets[world + 1] */
+int ojb_shard_gatherv(ojb_shard* s, const void* dev, uint64_t bytes, uint32_t writer_rank, void* out_dev, uint64_t out_cap,
+                      uint64_t* offsets);
+void ojb_shard_timings(ojb_shard* s, float* ms2);                 /* last call: codec ms, gather ms (this rank) */
+uint32_t ojb_shard_rank(ojb_shard* s);
+uint32_t ojb_shard_world(ojb_shard* s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,6 +56,15 @@ class Comment(C.Structure):
     _fields_ = [("data", C.c_void_p), ("len", C.c_uint16), ("rcom", C.c_uint16)]
 
 
+CB_ALLGATHER = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64)
+CB_BCAST = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32)
+CB_SENDRECV = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32)
+
+
+class CommCallbacks(C.Structure):
+    _fields_ = [("ctx", C.c_void_p), ("allgather", CB_ALLGATHER), ("bcast", CB_BCAST), ("send", CB_SENDRECV), ("recv", CB_SENDRECV)]
+
+
 class BlockDesc(C.Structure):
     _fields_ = [
         ("sample_off", C.c_uint64), ("stride", C.c_uint32), ("w", C.c_uint32), ("h", C.c_uint32),
@@ -115,6 +124,18 @@ SYMBOLS = {
     "ojb_dec_list_blocks": (_I, [_VP, C.POINTER(BlockDesc), _U32, C.POINTER(_U32)]),
     "ojb_dec_kernel_launches": (_U32, [_VP]),
     "ojb_dec_read_band": (_I, [_VP, _U32, _U32, _U32, _U32, _VP, C.POINTER(_U32), C.POINTER(_U32)]),
+    "ojb_shard_unique_id": (_I, [_VP]),
+    "ojb_shard_create_nccl": (_VP, [_U32, _U32, _VP]),
+    "ojb_shard_create": (_VP, [_U32, _U32, C.POINTER(CommCallbacks)]),
+    "ojb_shard_destroy": (None, [_VP]),
+    "ojb_shard_last_error": (C.c_char_p, []),
+    "ojb_shard_enc_configure": (_I, [_VP, C.POINTER(Params), _U32, _U32]),
+    "ojb_shard_enc_encode": (_I, [_VP, C.POINTER(_VP), C.POINTER(_U32), _VP, _U64, C.POINTER(_U64)]),
+    "ojb_shard_dec_decode": (_I, [_VP, _VP, _U64, _U32, _U32, C.POINTER(_VP), C.POINTER(_U32), C.POINTER(FrameInfo)]),
+    "ojb_shard_gatherv": (_I, [_VP, _VP, _U64, _U32, _VP, _U64, C.POINTER(_U64)]),
+    "ojb_shard_timings": (None, [_VP, C.POINTER(C.c_float)]),
+    "ojb_shard_rank": (_U32, [_VP]),
+    "ojb_shard_world": (_U32, [_VP]),
     "ojb_encode_blocks": (_I, [_VP, _U64, C.POINTER(BlockDesc), _U32, _VP, _U64, C.POINTER(_U64)]),
     "ojb_decode_blocks": (_I, [_VP, _U64, C.POINTER(BlockDesc), _U32, _VP, _U64]),
 }

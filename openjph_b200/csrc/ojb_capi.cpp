@@ -127,6 +127,8 @@ void ojb_params_default(ojb_params* p) {
   p->qstep = -1.0f;
 }
 
+void ojb_params_to_internal(const ojb_params* s, Params& P) { to_params(s, P); }      // ojb_shard.cpp
+
 int ojb_write_main_header(const ojb_params* p, const uint32_t* tp_tile, const uint32_t* tp_psot, uint32_t n_tp,
                           uint8_t* out, uint64_t out_cap, uint64_t* out_len) {
   return guarded([&] {

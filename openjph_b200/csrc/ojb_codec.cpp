@@ -115,6 +115,7 @@ void CodecBase::build_dwt_jobs(bool forward) {
       for (uint32_t i = 0; i < 4; ++i) grp[4 * w + i].reversible = (w == 0);
     }
     for (const TileGeom& t : layout.tiles) {
+      if (!tile_wanted(t.idx)) continue;
       for (uint32_t c = 0; c < nc; ) {
         const uint32_t D = P.decomps(c);
         // levels above `top` are not run (decoder with restrict_resolution: reduced output); a component
@@ -246,6 +247,7 @@ void Encoder::configure(const Params& p, uint32_t sample_type) {
               cap = (cap + 15) & ~(uint64_t)15;
               e.slot_off = slot; e.slot_cap = (uint32_t)cap;
               slot += cap;
+              if (!tile_wanted(t.idx)) { e.w = e.h = 0; }                  // another rank's tile: nothing to code
               if (!no_fast_blocks && enc_block_is_fast(e)) { e.flags |= ENC_FLAG_FAST; ++num_fast_blocks; }
             }
         }
@@ -366,6 +368,7 @@ size_t Encoder::encode(const void* const* planes, const uint32_t* strides, bool 
     std::vector<PacketRef> seq; std::vector<uint32_t> tp_first, tp_index;
     uint32_t tp_total = 0;
     for (uint32_t t = 0; t < (uint32_t)layout.tiles.size(); ++t) {
+      if (!tile_wanted(t)) continue;
       layout.packet_sequence(t, seq, tp_first, &tp_index, &tp_total);
       size_t base = pkts.size();
       for (const PacketRef& pr : seq) { pkts.emplace_back(); pkts.back().ref = pr; pkts.back().hdr_len = pkts.back().body = 0; }
@@ -423,16 +426,19 @@ size_t Encoder::encode(const void* const* planes, const uint32_t* strides, bool 
     else pieces.push_back(Piece{ src, (size_t)pos, len });
     pos += len;
   };
-  blob = main_header;
-  if (P.need_tlm) {
+  const bool partial = !tile_mask.empty();       // tile-parts only: the writer rank adds main header, TLM and EOC
+  if (!partial) blob = main_header;
+  last_tileparts.clear();
+  if (P.need_tlm && !partial) {
     if (4 + 6 * tps.size() > 65535) fail(0x000500B1, "too many tile-parts for one TLM marker segment");
     put_u16(blob, M_TLM); put_u16(blob, (uint32_t)(4 + 6 * tps.size())); put_u8(blob, 0); put_u8(blob, 0x60);
     for (const TilePart& tp : tps) { put_u16(blob, tp.tile); put_u32(blob, (uint32_t)(tp.bytes + 14)); }
   }
-  add_piece(0, (uint32_t)blob.size());
+  if (!blob.empty()) add_piece(0, (uint32_t)blob.size());
   uint64_t* dst = h_dst.as<uint64_t>();
   for (const TilePart& tp : tps) {
     size_t s = blob.size();
+    last_tileparts.push_back(TilePartOut{ tp.tile, pos, (uint32_t)(tp.bytes + 14) });
     put_u16(blob, M_SOT); put_u16(blob, 10); put_u16(blob, tp.tile); put_u32(blob, (uint32_t)(tp.bytes + 14));
     put_u8(blob, tp.tp_idx); put_u8(blob, tp.tp_cnt);
     put_u16(blob, M_SOD);
@@ -457,7 +463,7 @@ size_t Encoder::encode(const void* const* planes, const uint32_t* strides, bool 
       }
     }
   }
-  { size_t s = blob.size(); put_u16(blob, M_EOC); add_piece(s, 2); }
+  if (!partial) { size_t s = blob.size(); put_u16(blob, M_EOC); add_piece(s, 2); }
   const size_t total = (size_t)pos;
   if (total > out_cap) fail(0x000B0030, "output buffer too small: need %zu bytes, have %zu", total, out_cap);
 
@@ -538,6 +544,7 @@ void Decoder::read_headers(const uint8_t* data, size_t len, uint32_t sample_type
     // strip COM/TLM-like segments is unnecessary: compare everything up to the first SOT
     sig.assign(data, data + sot);
     sig.push_back((uint8_t)sample_type);
+    sig.insert(sig.end(), tile_mask.begin(), tile_mask.end());
   }
   if (sig == header_sig && !layout.tiles.empty()) return;
   // everything below can throw (precision check, geometry, cudaMalloc, container check): the signature
@@ -562,6 +569,8 @@ void Decoder::read_headers(const uint8_t* data, size_t len, uint32_t sample_type
   // geometry part of the block records
   h_dec_proto.assign(layout.num_blocks, DecBlock());
   block_res.assign(layout.num_blocks, 0);
+  block_wanted.clear();
+  if (!tile_mask.empty()) block_wanted.assign(layout.num_blocks, 0);
   size_t scratch = 0;
   for (const TileGeom& t : layout.tiles)
     for (const TileCompGeom& tc : t.comps)
@@ -574,6 +583,7 @@ void Decoder::read_headers(const uint8_t* data, size_t len, uint32_t sample_type
               Rect r = bg.block_rect(bx, by);
               DecBlock& d = h_dec_proto[bg.block_base + by * bg.nbw + bx];
               block_res[bg.block_base + by * bg.nbw + bx] = (uint8_t)(tc.res.size() - 1 - rg.res_num);
+              if (!block_wanted.empty()) block_wanted[bg.block_base + by * bg.nbw + bx] = tile_wanted(t.idx) ? 1 : 0;
               memset(&d, 0, sizeof(d));
               d.dst_off = bg.plane_off + bg.plane_pad_x + (uint64_t)(r.y0 - bg.rect.y0) * bg.plane_stride + (r.x0 - bg.rect.x0);
               d.stride = bg.plane_stride; d.w = (uint16_t)r.w; d.h = (uint16_t)r.h;
@@ -666,6 +676,7 @@ void Decoder::parse_tiles() {
       if (!resilient) fail(0x00030061, "wrong tile index");
       pos = tp_end; continue;
     }
+    if (!tile_wanted(Isot)) { pos = tp_end; continue; }          // another rank's tile
     // skip tile-part header segments up to SOD
     size_t q = tile_start; bool sod = false;
     while (q + 2 <= tp_end) {
@@ -715,7 +726,21 @@ uint32_t Decoder::decode(void* const* planes, const uint32_t* strides, bool plan
   const uint8_t* cs_dev = dev_cs;
   if (cs_dev == nullptr) {
     d_cs.reserve(j2c_len + 64);
-    CK(cudaMemcpyAsync(d_cs.p, j2c, j2c_len, cudaMemcpyHostToDevice, stream));
+    if (tile_mask.empty())
+      CK(cudaMemcpyAsync(d_cs.p, j2c, j2c_len, cudaMemcpyHostToDevice, stream));
+    else {
+      // only the tile-parts of this object's tiles, at their own offsets (walk the SOT chain by Psot)
+      size_t pos = first_sot;
+      while (pos + 12 <= j2c_len && j2c[pos] == 0xFF && j2c[pos + 1] == 0x90) {
+        const uint32_t Isot = ((uint32_t)j2c[pos + 4] << 8) | j2c[pos + 5];
+        const uint32_t Psot = ((uint32_t)j2c[pos + 6] << 24) | ((uint32_t)j2c[pos + 7] << 16) | ((uint32_t)j2c[pos + 8] << 8) | j2c[pos + 9];
+        const size_t end = (Psot && pos + Psot <= j2c_len) ? pos + Psot : j2c_len;
+        if (tile_wanted(Isot))
+          CK(cudaMemcpyAsync(d_cs.as<uint8_t>() + pos, j2c + pos, end - pos, cudaMemcpyHostToDevice, stream));
+        if (!Psot) break;
+        pos = end;
+      }
+    }
     CK(cudaMemsetAsync(d_cs.as<uint8_t>() + j2c_len, 0, 32, stream));
     cs_dev = d_cs.as<uint8_t>();
   }
@@ -738,6 +763,7 @@ uint32_t Decoder::decode(void* const* planes, const uint32_t* strides, bool plan
     const CodedBlock& cb = coded[b];
     d.len1 = cb.pass_len[0]; d.len2 = cb.pass_len[1];
     d.num_passes = cb.num_passes; d.missing_msbs = cb.missing_msbs; d.data_off = cb.data_off;
+    if (!block_wanted.empty() && !block_wanted[b]) { d.num_passes = 0; d.len1 = d.len2 = 0; d.w = d.h = 0; }   // another rank's tile
     if (block_res[b] < skip_read) {            // resolution not read: its bands are zero ...
       d.num_passes = 0; d.len1 = d.len2 = 0;
       if (block_res[b] < skip_recon) d.w = d.h = 0;      // ... and not even needed: nothing to fill

@@ -67,6 +67,11 @@ public:
   std::vector<std::vector<JobGroup>> jobs;
   DeviceBuf d_jobs;
   void build_dwt_jobs(bool forward);
+  // one image over several GPUs (ojb_shard.cpp): this object works on the tiles whose mask byte is set (empty =
+  // all tiles).  The geometry, arenas and block tables stay those of the whole image, so Isot, canvas coordinates
+  // and byte offsets are the single-encoder ones; DWT jobs, code-blocks and packets of the other tiles are skipped.
+  std::vector<uint8_t> tile_mask;
+  bool tile_wanted(uint32_t t) const { return tile_mask.empty() || (t < tile_mask.size() && tile_mask[t] != 0); }
   bool no_stream_dwt = false;          // force the general shared-memory DWT kernels (tests)
   bool no_fast_blocks = getenv("OJB_NO_FAST_BLOCKS") != nullptr;   // force the general block-coder kernels (tests, A/B)
 };
@@ -92,6 +97,9 @@ public:
   DeviceBuf d_blocks, d_results, d_status, d_slots, d_dst, d_hdr, d_pieces, d_out;
   PinnedBuf h_results, h_dst, h_hdr, h_pieces, h_status;
   std::vector<CodedBlock> coded;
+  // with a tile mask the output is this object's tile-parts only (no main header, no EOC); where each one sits:
+  struct TilePartOut { uint32_t tile; uint64_t offset; uint32_t bytes; };
+  std::vector<TilePartOut> last_tileparts;
   size_t slot_bytes = 0;
   uint32_t num_fast_blocks = 0;        // blocks flagged ENC_FLAG_FAST
   size_t out_cap_dev = 0;
@@ -128,6 +136,7 @@ public:
   void restrict_resolution(uint32_t skipped_res_for_read, uint32_t skipped_res_for_recon);
   void setup_geometry(uint32_t sample_type);
   std::vector<uint8_t> block_res;       // per block: how many resolutions lie above its own (D_c - r)
+  std::vector<uint8_t> block_wanted;    // with a tile mask: the block belongs to one of this object's tiles
   void info(FrameInfo& fi) const;
   // decode into planes (host or device); returns number of code-blocks that failed to decode
   uint32_t decode(void* const* planes, const uint32_t* strides, bool planes_on_device);

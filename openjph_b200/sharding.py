@@ -331,3 +331,131 @@ def decode_sharded(cs, sample_type=cs_mod.I32, dst=0, group=None, lib=None, gath
                 tp.append(np.frombuffer(b, dt, h * w, pos).reshape(h, w)); pos += h * w * dt.itemsize
             tiles[t] = tp
     return paste_tiles(geo, grid, tiles, sample_type)
+
+
+# ---- the native path: tile sharding below the C-ABI (ojb_shard.cpp) -----------------------------------------
+class NativeShard:
+    """One per rank.  Wraps ojb_shard: every rank keeps one encoder / decoder with the geometry of the whole image
+    and a tile mask; tile-parts (encode) and decoded tile samples (decode) go device to device to the writer rank.
+    Transport: NCCL inside the library (product path: the unique id is handed out through torch.distributed), or --
+    when `lib` is the SIMT-emulator build of the CPU test tier, which has no NCCL -- callbacks over the process
+    group (gloo), where "device" memory is host memory."""
+
+    def __init__(self, group=None, lib=None):
+        import torch
+        dist = _dist()
+        self.L = lib if lib is not None else _lib.lib()
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self._keep = None
+        if lib is None:
+            uid = torch.zeros(128, dtype=torch.uint8)
+            if self.rank == 0:
+                buf = (C.c_uint8 * 128)()
+                if self.L.ojb_shard_unique_id(buf) != 0:
+                    raise cs_mod.OjphError(self.L.ojb_shard_last_error().decode(errors="replace"))
+                uid = torch.tensor(list(buf), dtype=torch.uint8)
+            dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+            uid = uid.to(dev)
+            dist.broadcast(uid, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            ub = (C.c_uint8 * 128)(*uid.cpu().tolist())
+            self.h = self.L.ojb_shard_create_nccl(self.rank, self.world, ub)
+        else:
+            self._keep = self._gloo_callbacks()
+            self.h = self.L.ojb_shard_create(self.rank, self.world, C.byref(self._keep[0]))
+        if not self.h:
+            raise cs_mod.OjphError(self.L.ojb_shard_last_error().decode(errors="replace"))
+        self.info = None
+
+    def _gloo_callbacks(self):
+        import torch
+        dist = _dist()
+        group = self.group
+
+        def view(ptr, n):
+            return torch.from_numpy(np.frombuffer((C.c_uint8 * n).from_address(ptr), np.uint8)) if n else torch.zeros(0, dtype=torch.uint8)
+
+        def grank(r):
+            return dist.get_global_rank(group, r) if group is not None else r
+
+        def allgather(ctx, send, recv, n):
+            try:
+                out = list(view(recv, n * self.world).split(n))
+                dist.all_gather(out, view(send, n).clone(), group=group)
+                return 0
+            except Exception:
+                return 1
+
+        def bcast(ctx, buf, n, root):
+            try:
+                dist.broadcast(view(buf, n), src=grank(root), group=group)
+                return 0
+            except Exception:
+                return 1
+
+        def send(ctx, buf, n, peer):
+            try:
+                dist.send(view(buf, n).clone(), dst=grank(peer), group=group)
+                return 0
+            except Exception:
+                return 1
+
+        def recv(ctx, buf, n, peer):
+            try:
+                dist.recv(view(buf, n), src=grank(peer), group=group)
+                return 0
+            except Exception:
+                return 1
+
+        fns = (_lib.CB_ALLGATHER(allgather), _lib.CB_BCAST(bcast), _lib.CB_SENDRECV(send), _lib.CB_SENDRECV(recv))
+        cb = _lib.CommCallbacks(None, *fns)
+        return cb, fns
+
+    def _check(self, rc):
+        if rc != 0:
+            raise cs_mod.OjphError(self.L.ojb_shard_last_error().decode(errors="replace"))
+
+    def close(self):
+        if self.h:
+            self.L.ojb_shard_destroy(self.h)
+            self.h = None
+
+    def configure(self, p, sample_type=cs_mod.I32, writer=0):
+        self.p, self.sample_type, self.writer = p, sample_type, writer
+        self._check(self.L.ojb_shard_enc_configure(self.h, C.byref(p), sample_type, writer))
+        dims = cs_mod.comp_dims(p)
+        self._out = np.empty(sum(w * h for w, h in dims) * 5 + (1 << 20), np.uint8) if self.rank == writer else np.empty(16, np.uint8)
+
+    def encode(self, planes):
+        """planes: the whole image (every rank); returns the codestream on the writer, None elsewhere"""
+        arrs = [np.ascontiguousarray(a, cs_mod._NP[self.sample_type]) for a in planes]
+        ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+        n = C.c_uint64()
+        self._check(self.L.ojb_shard_enc_encode(self.h, ptrs, None, self._out.ctypes.data, self._out.size, C.byref(n)))
+        return self._out[:n.value].tobytes() if self.rank == self.writer else None
+
+    def decode(self, cs, dims=None, sample_type=cs_mod.I32, writer=0):
+        """cs: the codestream (needed on the writer only); dims: [(w, h)] of the components when known, else read
+        from the headers by a first call; returns the planes on the writer, None elsewhere"""
+        fi = _lib.FrameInfo()
+        buf = np.frombuffer(cs, np.uint8) if (cs is not None and self.rank == writer) else np.zeros(1, np.uint8)
+        n = buf.size if self.rank == writer else 0
+        if dims is None:
+            # geometry first (every rank needs its plane sizes on the writer only; a header-only decode would do, the
+            # call is collective so all ranks take this path together)
+            hdr = [None]
+            if self.rank == writer:
+                hdr[0] = bytes(cs[:1 << 16])
+            _dist().broadcast_object_list(hdr, src=_dist().get_global_rank(self.group, writer) if self.group is not None else writer, group=self.group)
+            dims = cs_mod.comp_dims(siz_params(hdr[0]))
+        planes = [np.zeros((h, w), cs_mod._NP[sample_type]) for w, h in dims] if self.rank == writer else None
+        ptrs = (C.c_void_p * len(dims))(*[a.ctypes.data for a in planes]) if planes is not None else None
+        self._check(self.L.ojb_shard_dec_decode(self.h, buf.ctypes.data, n, sample_type, writer, ptrs, None, C.byref(fi)))
+        self.info = fi
+        return planes
+
+    @property
+    def timings(self):
+        t = (C.c_float * 2)()
+        self.L.ojb_shard_timings(self.h, t)
+        return {"codec_ms": t[0], "gather_ms": t[1]}

@@ -218,6 +218,10 @@ cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memmo
 cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memmove(d, s, n); return cudaSuccess; }
 cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
 cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { memset(d, v, n); return cudaSuccess; }
+cudaError_t cudaMemcpy2DAsync(void* d, size_t dpitch, const void* s, size_t spitch, size_t width, size_t height, cudaMemcpyKind, cudaStream_t) {
+  for (size_t y = 0; y < height; ++y) memmove((char*)d + y * dpitch, (const char*)s + y * spitch, width);
+  return cudaSuccess;
+}
 cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = new emuStream_st(); return cudaSuccess; }
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = new emuStream_st(); return cudaSuccess; }
 cudaError_t cudaStreamDestroy(cudaStream_t s) { delete s; return cudaSuccess; }

@@ -220,6 +220,7 @@ cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind k);
 cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind k, cudaStream_t st = 0);
 cudaError_t cudaMemset(void* d, int v, size_t n);
 cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t st = 0);
+cudaError_t cudaMemcpy2DAsync(void* d, size_t dpitch, const void* s, size_t spitch, size_t width, size_t height, cudaMemcpyKind k, cudaStream_t st = 0);
 cudaError_t cudaStreamCreate(cudaStream_t* s);
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned f);
 cudaError_t cudaStreamDestroy(cudaStream_t s);

@@ -94,3 +94,65 @@ def test_gloo_world2_sharded_encode_decode(emu_lib, ref):
         pr.join(timeout=60)
         assert pr.exitcode == 0
     assert res == {0: True, 1: True}
+
+
+# ---- the native path (ojb_shard.cpp): tile masks below the C-ABI, transport behind callbacks --------------------
+def _native_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OJB_EMU_THREADS="2")
+    import torch.distributed as dist
+    import emu, refharness
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        L = emu.emu_lib(build=False)
+        ok = True
+        for kw, writer in ((TILED, 0), (TILED_OFF, 1), (TILED_SUB, 0),
+                           (dict(width=256, height=192, num_comps=3, bit_depth=12, num_decomps=3, reversible=False, color_transform=True,
+                                 qstep=0.002, tile=(128, 96)), 0)):
+            p = cases.make(kw)
+            frame = cases.frame_for(p)
+            sh = sharding.NativeShard(lib=L)
+            sh.configure(p, ob.I32, writer=writer)
+            for rep in range(2):                   # a second frame through the same objects
+                fr = frame if rep == 0 else [np.ascontiguousarray(a[::-1]) for a in frame]
+                cs = sh.encode(fr)
+                want = refharness.encode(p, fr) if rank == writer else None
+                if rank == writer:
+                    if p.reversible:
+                        ok = ok and cs == want
+                    else:
+                        ok = ok and len(cs) == len(want) and cs[:cs.index(b"\xff\x90")] == want[:want.index(b"\xff\x90")]
+                else:
+                    ok = ok and cs is None
+                planes = sh.decode(want, sample_type=ob.I32, writer=writer)
+                if rank == writer:
+                    ref_planes, _ = refharness.decode(want)
+                    tol = 0 if p.reversible else 1
+                    ok = ok and all(np.abs(a.astype(np.int64) - b).max() <= tol for a, b in zip(planes, ref_planes))
+                else:
+                    ok = ok and planes is None
+            sh.close()
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_native_shard(emu_lib, ref):
+    """world_size 2 over gloo: the C++ sharded encoder / decoder (tile masks, size allgather, tile-part and sample
+    gathers through the transport callbacks) against the reference's codestream and decode"""
+    import multiprocessing as mp
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_native_worker, args=(r, 2, port, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = {}
+    for _ in range(2):
+        r, ok = q.get(timeout=300)
+        res[r] = ok
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    assert res == {0: True, 1: True}
