@@ -208,6 +208,169 @@ ENC_STAGES = ("h2d", "dwt", "ht_encode", "d2h_lengths", "host_wait", "assemble",
 DEC_STAGES = ("h2d", "host_parse", "ht_decode", "dwt_inv", "d2h_image", "_5", "_6", "host_ms")
 
 
+def sharded_block(a, rank, world, L, ob, np, torch, dist, C, _lib, peak):
+    """Strong scaling of ONE image over the ranks: every rank passes the whole image (host, pinned), codes its tiles,
+    tile-part bytes / decoded samples go device to device over NCCL to rank 0, which delivers the codestream / the
+    planes to host memory.  Timed: encode + decode per frame, barrier + synchronize on both sides, max over ranks,
+    the gathers inside the timed region.  Checked outside it: the codestream equals the one a single encoder on
+    rank 0 produces (itself byte-identical to the reference, tests/), and the round trip."""
+    from openjph_b200 import sharding
+    steps = max(2, min(a.steps, 5))
+    out = {"transport": "NCCL send/recv + allgather inside libojph_b200.so (ojb_shard.cpp), tile t on rank t % N", "entries": []}
+
+    def timed_loop(fn, n):
+        dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / n * 1e3
+
+    def one(name, params, frame, lossless):
+        st = ob.U8 if frame[0].dtype == np.uint8 else ob.U16
+        pin = [torch.empty(f.shape, dtype=torch.uint8 if f.dtype == np.uint8 else torch.uint16, pin_memory=True) for f in frame]
+        for t, f in zip(pin, frame):
+            t.numpy()[:] = f
+        nc = len(frame)
+        planes = (C.c_void_p * nc)(*[t.data_ptr() for t in pin])
+        in_bytes = sum(f.nbytes for f in frame)
+        cap = in_bytes * 2 + (1 << 20)
+        cs_pin = torch.empty(cap if rank == 0 else 16, dtype=torch.uint8, pin_memory=True)
+        out_pin = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in pin] if rank == 0 else None
+        outs = (C.c_void_p * nc)(*[t.data_ptr() for t in out_pin]) if rank == 0 else None
+        sh = sharding.NativeShard()
+        n = C.c_uint64(); fi = _lib.FrameInfo()
+
+        def ck(rc):
+            if rc != 0:
+                raise RuntimeError(L.ojb_shard_last_error().decode())
+
+        ck(L.ojb_shard_enc_configure(sh.h, C.byref(params), st, 0))
+
+        def enc():
+            ck(L.ojb_shard_enc_encode(sh.h, planes, None, cs_pin.data_ptr(), cs_pin.numel(), C.byref(n)))
+
+        def dec():
+            ck(L.ojb_shard_dec_decode(sh.h, cs_pin.data_ptr(), cs_len, st, 0, outs, None, C.byref(fi)))
+
+        enc()
+        cs_len = int(n.value)
+        dec()
+        e = {"workload": name, "ranks": world}
+        # the same image on one GPU (rank 0 alone): reference point of the strong scaling, and the byte-identity check
+        one_gpu_ms = None
+        if rank == 0:
+            enc1 = L.ojb_enc_create(); dec1 = L.ojb_dec_create()
+            try:
+                if L.ojb_enc_configure(enc1, C.byref(params), st) != 0:
+                    raise RuntimeError(L.ojb_last_error().decode())
+                cs1 = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+                o1 = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in pin]
+                o1p = (C.c_void_p * nc)(*[t.data_ptr() for t in o1])
+                n1 = C.c_uint64()
+
+                def single():
+                    assert L.ojb_enc_encode_frame(enc1, planes, None, cs1.data_ptr(), cap, C.byref(n1)) == 0, L.ojb_last_error()
+                    assert L.ojb_dec_read_headers(dec1, cs1.data_ptr(), n1.value, st, C.byref(fi)) == 0, L.ojb_last_error()
+                    assert L.ojb_dec_decode_frame(dec1, o1p, None) == 0, L.ojb_last_error()
+                single(); single()
+                torch.cuda.synchronize(); t0 = time.perf_counter()
+                for _ in range(steps):
+                    single()
+                torch.cuda.synchronize(); one_gpu_ms = (time.perf_counter() - t0) / steps * 1e3
+                e["codestream_identical_to_one_gpu"] = bool(n1.value == cs_len and torch.equal(cs1[:cs_len], cs_pin[:cs_len]))
+                if lossless:
+                    e["round_trip_lossless"] = bool(all(np.array_equal(o.numpy(), f) for o, f in zip(out_pin, frame)))
+                else:
+                    e["max_abs_diff_vs_one_gpu_decode"] = int(max(np.abs(o.numpy().astype(np.int64) - q.numpy().astype(np.int64)).max() for o, q in zip(out_pin, o1)))
+            finally:
+                L.ojb_enc_destroy(enc1); L.ojb_dec_destroy(dec1)
+        for _ in range(2):
+            enc(); dec()
+        ms_enc = timed_loop(enc, steps)
+        ms_dec = timed_loop(dec, steps)
+        ms_both = timed_loop(lambda: (enc(), dec()), steps)
+        if rank == 0:
+            pix = frame[0].shape[0] * frame[0].shape[1]
+            e.update({"ms_per_frame_encode": round(ms_enc, 3), "ms_per_frame_decode": round(ms_dec, 3), "ms_per_frame": round(ms_both, 3),
+                      "Mpixels_per_s": round(pix / ms_both / 1e3, 1), "one_gpu_ms_per_frame": round(one_gpu_ms, 3),
+                      "time_vs_one_gpu": round(ms_both / one_gpu_ms, 3), "codestream_bytes": cs_len,
+                      "note": "host buffers on rank 0 (pinned): every rank uploads its own tiles, rank 0 receives the whole codestream / image"})
+            out["entries"].append(e)
+        sh.close()
+
+    tile_w = {2: 4096, 4: 4096, 8: 2048}.get(world, 4096)
+    one("cfg4: 8192x8192x3 16-bit, reversible 5/3 + RCT, 4 tiles of 4096x4096, 5 levels",
+        ob.make_params(W, H, 3, 16, num_decomps=5, reversible=True, color_transform=True, tile=(4096, 4096)), make_frame(W, H, 9, 3, 16), True)
+    one("headline frame as %d tiles of %dx4096 (12-bit, 5/3 + RCT, 5 levels)" % ((W // tile_w) * 2, tile_w),
+        ob.make_params(W, H, NC, BD, num_decomps=LEVELS, reversible=True, color_transform=True, tile=(tile_w, 4096)), make_frame(W, H, 1234), True)
+
+    # cfg5: a batch of 64 independent 4K frames, frame f on rank f % N, codestreams gathered to rank 0 over NCCL
+    try:
+        nfr = 64
+        p5 = ob.make_params(3840, 2160, 3, 10, num_decomps=5, reversible=False, color_transform=True)
+        fr = make_frame(3840, 2160, 10, 3, 10)
+        pin = [torch.empty(f.shape, dtype=torch.uint16, pin_memory=True) for f in fr]
+        for t, f in zip(pin, fr):
+            t.numpy()[:] = f
+        planes = (C.c_void_p * 3)(*[t.data_ptr() for t in pin])
+        mine = [f for f in range(nfr) if f % world == rank]
+        NW5 = 4
+        encs = []
+        for _ in range(NW5):
+            e_ = L.ojb_enc_create()
+            assert L.ojb_enc_configure(e_, C.byref(p5), ob.U16) == 0, L.ojb_last_error()
+            encs.append(e_)
+        per = 3840 * 2160 * 3 * 2
+        dev = torch.empty(len(mine) * per // 4 + (1 << 20), dtype=torch.uint8, device="cuda")     # q ~ lossy: well under 25 % of raw
+        gat = torch.empty((nfr * per // 4 + (1 << 20)) if rank == 0 else 16, dtype=torch.uint8, device="cuda")
+        host = torch.empty(gat.numel(), dtype=torch.uint8, pin_memory=True)
+        sh = sharding.NativeShard()
+        offs = (C.c_uint64 * (world + 1))()
+        from concurrent.futures import ThreadPoolExecutor
+        tp = ThreadPoolExecutor(NW5)
+
+        def batch():
+            lens = [0] * len(mine)
+            slot = per // 4
+
+            def work(k):
+                n_ = C.c_uint64()
+                for i in range(k, len(mine), NW5):
+                    assert L.ojb_enc_upload_frame(encs[k], planes, None) == 0, L.ojb_last_error()
+                    assert L.ojb_enc_encode_resident(encs[k], dev.data_ptr() + i * slot, slot, C.byref(n_), 1) == 0, L.ojb_last_error()
+                    lens[i] = int(n_.value)
+            list(tp.map(work, range(NW5)))
+            # pack this rank's codestreams back to back, then one variable-length gather to rank 0 and one D2H
+            pos = 0
+            for i, ln_ in enumerate(lens):
+                if pos != i * slot:
+                    dev[pos:pos + ln_].copy_(dev[i * slot:i * slot + ln_].clone())
+                pos += ln_
+            torch.cuda.synchronize()
+            assert L.ojb_shard_gatherv(sh.h, dev.data_ptr(), pos, 0, gat.data_ptr(), gat.numel(), offs) == 0, L.ojb_shard_last_error()
+            if rank == 0:
+                host[:offs[world]].copy_(gat[:offs[world]], non_blocking=True)
+                torch.cuda.synchronize()
+            return pos
+        batch()
+        ms = timed_loop(batch, 2)
+        if rank == 0:
+            out["entries"].append({"workload": "cfg5: batch of 64 independent 3840x2160x3 10-bit frames, irreversible 9/7 + ICT, frame f on rank f % N, "
+                                               "codestreams gathered to rank 0 (NCCL) and copied to host; encode only", "ranks": world,
+                                   "ms_per_batch": round(ms, 2), "Mpixels_per_s_encode": round(nfr * 3840 * 2160 / ms / 1e3, 1),
+                                   "gathered_bytes": int(offs[world])})
+        for e_ in encs:
+            L.ojb_enc_destroy(e_)
+        sh.close()
+    except Exception as ex:
+        if rank == 0:
+            out["entries"].append({"workload": "cfg5", "error": str(ex)[:300]})
+    return out if rank == 0 else None
+
+
 def main():
     # the contract is ONE JSON line on stdout: keep the real stdout for it and send everything libraries
     # print at C level (e.g. NCCL's version banner) to stderr
@@ -456,6 +619,14 @@ def main():
         run_cfg("cfg5: 3840x2160x3 10-bit frames, irreversible 9/7 + ICT (qstep default), 5 levels; batch of 64 / N GPUs, 8 in flight",
                 ob.make_params(3840, 2160, 3, 10, num_decomps=5, reversible=False, color_transform=True), make_frame(3840, 2160, 10, 3, 10), 8, False)
 
+    # ---- one image over the N GPUs: tiles sharded over ranks below the C-ABI, NCCL gather to rank 0 ----
+    sharded = None
+    if dist is not None and os.environ.get("OJB_BENCH_SHARDED", "1") != "0":
+        try:
+            sharded = sharded_block(a, rank, world, L, ob, np, torch, dist, C, _lib, peak)
+        except Exception as e:
+            sharded = {"error": str(e)[:300]}
+
     # final gather of the per-rank codestream sizes (the only collective on the frame-parallel path)
     sizes = [cs_len]
     if dist is not None:
@@ -506,7 +677,7 @@ def main():
               "e2e_stages_encode_ms": e2e_e, "e2e_stages_decode_ms": e2e_d, "codestream_bytes": sizes,
               "resident_decode_header_fetch_bytes": r["mirror_bytes"],
               "pipeline_hbm_frac": round(((2 * samples + cs_len) * 2 * NW) / (r["dt_res"] / a.steps) / 1e9 / peak, 4),
-              "configs": configs}
+              "configs": configs, "sharded": sharded}
     res = {"metric": "Mpixels/s encode+decode", "value": value, "unit": "Mpixels/s", "n_gpus": a.gpus, "steps": a.steps,
            "warmup": a.warmup, "ms_per_step": r["dt_res"] / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": cfg, "detail": detail,

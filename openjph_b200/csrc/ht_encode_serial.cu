@@ -390,6 +390,7 @@ ht_encode_fast_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
   uint8_t* mel_buf = s_mel + threadIdx.x;
   uint32_t* gw = s_g + threadIdx.x;
   const uint32_t slot_words = blk.slot_cap >> 2;
+  const uint32_t pm1 = p - 1u, vmask = (2u << (31u - p)) - 2u;       // p >= 16
 
   MsWriter ms; ms.w0 = 0; ms.w1 = 0; ms.nbits = 0; ms.words = 0; ms.last_ff = 0;
   VlcWriter vlc; vlc.acc = 0xFFFull; vlc.nbits = 12; vlc.words = 0; vlc.prev = 0;
@@ -421,7 +422,8 @@ ht_encode_fast_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
       const uint32_t gor[2] = { (wj | (wj >> 16)) & 0xFFFFu, (wj >> 16) | (wj1 & 0xFFFFu) };
       wj = wj1;
 
-      uint32_t uq[2], xb[2][2], rr[2];
+      uint32_t uq[2], xb[2][2], rr[2], cwl[2];
+      unsigned long long cwd[2];
       uint32_t pair_bits = 0, pair_len = 0;      // CxtVLC codewords of the pair, then its U-VLC bits (<= 30)
       #pragma unroll
       for (uint32_t h = 0; h < 2; ++h) {
@@ -430,7 +432,7 @@ ht_encode_fast_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
         uint32_t rho = 0, x[4], s[4];
         #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const uint32_t v = ((t[i] + t[i]) >> p) & ~1u;           // 2 * magnitude
+          const uint32_t v = (t[i] >> pm1) & vmask;                // 2 * magnitude (sign and the bit below the LSB dropped)
           const uint32_t sig = min(v, 1u);
           rho |= sig << i;
           x[i] = v - sig;                                          // 2 * magnitude - 1 (0 when insignificant)
@@ -451,11 +453,9 @@ ht_encode_fast_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
         const uint32_t u = Uq - kappa;
         uq[h] = u;
         // which samples reach the maximum exponent (only coded when u > 0)
-        uint32_t eps = 0;
-        if (u > 0) {
-          const uint32_t sh = emax - 1u;                           // u > 0 => emax >= 2
-          eps = (x[0] >> sh) | ((x[1] >> sh) << 1) | ((x[2] >> sh) << 2) | ((x[3] >> sh) << 3);
-        }
+        // (branch-free: every x_i < 2^emax, so x_i >> (emax - 1) is 0 or 1; an empty quad has u == 0)
+        const uint32_t sh = max(emax, 1u) - 1u;
+        const uint32_t eps = ((x[0] >> sh) | ((x[1] >> sh) << 1) | ((x[2] >> sh) << 2) | ((x[3] >> sh) << 3)) & (0u - min(u, 1u));
         const uint32_t tuple = vtab[(cq << 8) + (rho << 4) + eps];
         pair_bits |= (tuple >> 8) << pair_len; pair_len += (tuple >> 4) & 7u;      // :661-662
         if (cq == 0) mel_event(mel, rho != 0, mel_buf);                          // :664-665
@@ -467,10 +467,14 @@ ht_encode_fast_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
           const uint32_t A = (s[0] & ((1u << m0) - 1u)) | ((s[1] & ((1u << m1) - 1u)) << m0);
           const uint32_t B = (s[2] & ((1u << m2) - 1u)) | ((s[3] & ((1u << m3) - 1u)) << m2);
           const uint32_t la = m0 + m1, lb = m2 + m3;               // <= 32 each
-          ms_put(ms, (unsigned long long)A | ((unsigned long long)B << la), la + lb, ms_dst);
+          cwd[h] = (unsigned long long)A | ((unsigned long long)B << la); cwl[h] = la + lb;
         }
         rho_left = rho;
       }
+      // the two appends come after both quads have been worked out: their arithmetic is independent and
+      // overlaps, only the packing is a chain
+      ms_put(ms, cwd[0], cwl[0], ms_dst);
+      ms_put(ms, cwd[1], cwl[1], ms_dst);
       // this row's state for the next one
       {
         const uint32_t ta = (rr[0] >> 1) & 5u, tb = (rr[1] >> 1) & 5u;       // bit 0: bottom-left, bit 2: bottom-right
