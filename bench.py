@@ -12,7 +12,7 @@ collective -- only the final gather of the codestream sizes to rank 0).
   value : frame already resident in HBM when the timed region starts (encoder's device image
           buffer); the codestream is written to device memory and decoded FROM device memory (the
           decoder fetches only the marker segments / packet headers its host parser reads, a few
-          64 KB pages per frame: ojb_dec_read_headers_device); decoded image left on the device
+          32 KB pages per frame: ojb_dec_read_headers_device); decoded image left on the device
   e2e   : the reference-facing C-ABI frame calls with HOST buffers (pinned): H2D of the planes,
           D2H of the codestream, H2D of the codestream, D2H of the decoded planes, all timed
   --impl reference : the unmodified reference (oracle/_ref, compiled from /root/reference by

@@ -214,7 +214,7 @@ int ojb_dec_use_device_codestream(ojb_decoder* d, const void* dev_bytes);
 /* codestream::read_headers for a codestream that exists in DEVICE memory only (complete when the call is
  * made, >= 32 readable bytes after its end, valid until the decode call returns): the marker segments and
  * packet headers the host parsers read (ojph_codestream_local.cpp:734-880, ojph_precinct.cpp:328-573) are
- * fetched in 64 KB pages; code-block bodies never leave the device.  ojb_dec_mirror_bytes = bytes fetched
+ * fetched in 32 KB pages; code-block bodies never leave the device.  ojb_dec_mirror_bytes = bytes fetched
  * so far for the current codestream (headers + the packet headers parsed by the last decode). */
 int ojb_dec_read_headers_device(ojb_decoder* d, const void* dev_j2c, uint64_t len, uint32_t sample_type,
                                 ojb_frame_info* info);

@@ -232,7 +232,7 @@ __device__ __forceinline__ bool strip_fast_inv(const DwtJob& J, const StripGeom&
 // request source row v (mirrored into the resolution) into the row slot `st` (lane offset included)
 template <int NC, int SRC>
 __device__ __forceinline__ void fwd_issue_row(const DwtJob& J, const StripGeom& g, const void* image,
-                                              const uint32_t* coef, int v, unsigned char* st, uint32_t slot)
+                                              const uint32_t* coef, int v, unsigned char* st, uint32_t cpitch)
 {
   constexpr bool FIRST = SRC != SRC_COEF;     // the full-resolution side is the image
   const int vr = reflect_coord(v, g.y0, g.y1 - 1) - g.y0;
@@ -243,7 +243,7 @@ __device__ __forceinline__ void fwd_issue_row(const DwtJob& J, const StripGeom& 
     for (int k = 0; k < (FIRST ? NC : 1); ++k) {
       const uint32_t o = (FIRST ? (uint32_t)J.full_off[k] : (uint32_t)J.full_off[0] * 4u) +
                          ((uint32_t)vr * J.full_stride[k] + (uint32_t)g.c[0]) * ES;
-      cp_async<4 * ES>(st + (size_t)k * 32 * slot, base + o);
+      cp_async<4 * ES>(st + (size_t)k * cpitch, base + o);
     }
     return;
   }
@@ -253,7 +253,7 @@ __device__ __forceinline__ void fwd_issue_row(const DwtJob& J, const StripGeom& 
     for (int k = 0; k < NC; ++k) {
       constexpr uint32_t ES = (SRC == SRC_U16) ? 2u : (SRC == SRC_U8 ? 1u : 4u);
       const uint32_t row_off = (uint32_t)J.full_off[k] + (uint32_t)vr * J.full_stride[k] * ES;     // bytes
-      unsigned char* d = st + (size_t)k * 32 * slot;
+      unsigned char* d = st + (size_t)k * cpitch;
       if (SRC == SRC_U16) issue4_u16(d, base, row_off, g);
       else if (SRC == SRC_U8) issue4_u8(d, base, row_off, g);
       else issue4_w(d, base, row_off, g);
@@ -266,7 +266,7 @@ __device__ __forceinline__ void fwd_issue_row(const DwtJob& J, const StripGeom& 
 
 // read a row slot back: level shift / int->float and RCT / ICT at level 1
 template <bool REV, int NC, int SRC>
-__device__ __forceinline__ void fwd_read_row(const DwtJob& J, const unsigned char* st, uint32_t slot,
+__device__ __forceinline__ void fwd_read_row(const DwtJob& J, const unsigned char* st, uint32_t cpitch,
                                              typename Tp<REV>::T (&a)[NC][4])
 {
   constexpr bool FIRST = SRC != SRC_COEF;     // the full-resolution side is the image
@@ -275,7 +275,7 @@ __device__ __forceinline__ void fwd_read_row(const DwtJob& J, const unsigned cha
     int iv[NC][4];
     #pragma unroll
     for (int k = 0; k < NC; ++k) {
-      const unsigned char* d = st + (size_t)k * 32 * slot;
+      const unsigned char* d = st + (size_t)k * cpitch;
       if (SRC == SRC_U16) {
         const uint2 t = *reinterpret_cast<const uint2*>(d);
         iv[k][0] = (int)(t.x & 0xFFFF); iv[k][1] = (int)(t.x >> 16); iv[k][2] = (int)(t.y & 0xFFFF); iv[k][3] = (int)(t.y >> 16);
@@ -378,13 +378,19 @@ __device__ __forceinline__ void fwd_store_pair(const DwtJob& J, const StripGeom&
   }
 }
 
-template <bool REV, int NC, int SRC>
+// TMA = true: the source rows of a strip whose 32 lanes read one contiguous, 16-byte-alignable run of bytes (every
+// interior strip of the usual geometries) are requested by ONE lane with cp.async.bulk (SASS UBLKCP) -- one copy per
+// component row into a row slot of 32 x slot + 16 bytes -- and awaited on an mbarrier per FIFO stage, instead of one
+// cp.async (LDGSTS) per lane; edge strips keep the per-lane requests.  Selected by the host (OJB_DWT_TMA), A/B in
+// profiles/.
+template <bool REV, int NC, int SRC, bool TMA>
 __global__ void __launch_bounds__(DS_WARPS * 32, (REV || NC == 1) ? 5 : 3)
 dwt_fwd_stream_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, const void* __restrict__ image,
                       uint32_t* __restrict__ coef)
 {
   typedef typename Tp<REV>::T T;
   __shared__ DwtJob sj;
+  __shared__ unsigned long long s_bar[TMA ? DS_WARPS * DS_STAGES : 1];
   {
     uint32_t ji = find_job(jobs, njobs, blockIdx.x);
     const uint32_t* s = reinterpret_cast<const uint32_t*>(&jobs[ji]);
@@ -406,8 +412,51 @@ dwt_fwd_stream_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, const voi
   // the lane's FIFO: DS_STAGES stages of one row pair each
   OJB_DYN_SMEM(unsigned char, s_ring);
   const uint32_t slot = (SRC == SRC_U8 || SRC == SRC_U16) ? 8u : 16u;   // 4 samples in their container
-  const uint32_t row_bytes = NC * 32 * slot, stage_bytes = 2 * row_bytes;
-  unsigned char* ring = s_ring + (size_t)warp * DS_STAGES * stage_bytes + (size_t)lane * slot;
+  constexpr bool FIRSTK = SRC != SRC_COEF;
+  constexpr uint32_t ESK = (SRC == SRC_U16) ? 2u : (SRC == SRC_U8 ? 1u : 4u);
+  // bulk-copy mode of this strip (warp-uniform): every row of every component starts at the same offset modulo 16
+  bool tma = false;
+  uint32_t skip = 0, c0l0 = 0;
+  if (TMA) {
+    c0l0 = __shfl_sync(0xFFFFFFFFu, (uint32_t)g.c[0], 0);
+    bool ok = g.fast;
+    #pragma unroll
+    for (int k = 0; k < (FIRSTK ? NC : 1); ++k) {
+      const uint32_t off = (FIRSTK ? (uint32_t)J.full_off[k] : (uint32_t)J.full_off[0] * 4u) + c0l0 * ESK;
+      if (k == 0) skip = off & 15u;
+      ok = ok && (off & 15u) == skip && ((J.full_stride[k] * ESK) & 15u) == 0;
+    }
+    tma = ok;
+  }
+  const uint32_t cpitch = TMA ? 32 * slot + 16 : 32 * slot;            // bytes between the components of a row slot
+  const uint32_t row_bytes = NC * cpitch, stage_bytes = 2 * row_bytes;
+  unsigned char* wring = s_ring + (size_t)warp * DS_STAGES * stage_bytes;
+  unsigned char* ring = wring + (size_t)lane * slot + (tma ? skip : 0u);
+  unsigned long long* bar = s_bar + (TMA ? warp * DS_STAGES : 0);
+  if (TMA && tma) {
+    if (lane == 0) { for (int i = 0; i < DS_STAGES; ++i) mbar_init(bar + i, 1); }
+    fence_proxy_async();
+    __syncwarp();
+  }
+  // rows (2 * kk - 1, 2 * kk) of every component into stage `stg`: one bulk copy per component row, lane 0
+  auto issue_tma = [&](int kk, uint32_t stg) {
+    __syncwarp();                                 // the stage's previous rows have been read by every lane
+    if (lane == 0) {
+      fence_proxy_async();
+      const uint32_t nbytes = 32 * slot + 16;
+      mbar_expect_tx(bar + stg, 2u * (FIRSTK ? NC : 1) * nbytes);
+      const unsigned char* base = FIRSTK ? reinterpret_cast<const unsigned char*>(image) : reinterpret_cast<const unsigned char*>(coef);
+      #pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int vr = reflect_coord(2 * kk - 1 + r, g.y0, g.y1 - 1) - g.y0;
+        #pragma unroll
+        for (int k = 0; k < (FIRSTK ? NC : 1); ++k) {
+          const uint32_t o = (FIRSTK ? (uint32_t)J.full_off[k] : (uint32_t)J.full_off[0] * 4u) + ((uint32_t)vr * J.full_stride[k] + c0l0) * ESK - skip;
+          bulk_g2s(wring + (size_t)stg * stage_bytes + (size_t)r * row_bytes + (size_t)k * cpitch, base + o, nbytes, bar + stg);
+        }
+      }
+    }
+  };
 
   // iteration k consumes rows (2k-1, 2k); 5/3 emits the pair (2k-2, 2k-1), 9/7 the pair (2k-4, 2k-3)
   const int k0 = REV ? g.R0 / 2 : g.R0 / 2 - 1;
@@ -415,17 +464,20 @@ dwt_fwd_stream_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, const voi
   T xe[NC][4];                                                // x[2k-2]
   {                                                           // priming row through the last stage
     unsigned char* sp = ring + (size_t)(DS_STAGES - 1) * stage_bytes;
-    fwd_issue_row<NC, SRC>(J, g, image, coef, 2 * k0 - 2, sp, slot);
+    fwd_issue_row<NC, SRC>(J, g, image, coef, 2 * k0 - 2, sp - (tma ? skip : 0u), cpitch);     // (per-lane request, old lane layout)
     cp_commit(); cp_wait<0>();
-    fwd_read_row<REV, NC, SRC>(J, sp, slot, xe);
+    fwd_read_row<REV, NC, SRC>(J, sp - (tma ? skip : 0u), cpitch, xe);
   }
   int issued = k0;
   #pragma unroll
   for (int s = 0; s < DS_STAGES - 1; ++s) {
     if (issued <= k1) {
-      unsigned char* st = ring + (size_t)((issued - k0) % DS_STAGES) * stage_bytes;
-      fwd_issue_row<NC, SRC>(J, g, image, coef, 2 * issued - 1, st, slot);
-      fwd_issue_row<NC, SRC>(J, g, image, coef, 2 * issued, st + row_bytes, slot);
+      if (TMA && tma) issue_tma(issued, (uint32_t)((issued - k0) % DS_STAGES));
+      else {
+        unsigned char* st = ring + (size_t)((issued - k0) % DS_STAGES) * stage_bytes;
+        fwd_issue_row<NC, SRC>(J, g, image, coef, 2 * issued - 1, st, cpitch);
+        fwd_issue_row<NC, SRC>(J, g, image, coef, 2 * issued, st + row_bytes, cpitch);
+      }
     }
     cp_commit(); ++issued;
   }
@@ -438,10 +490,11 @@ dwt_fwd_stream_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, const voi
       for (int i = 0; i < 4; ++i) hp[c][i] = 0;
     for (int k = k0; k <= k1; ++k) {
       T xo[NC][4], xn[NC][4], lo[NC][4], hi[NC][4];
-      cp_wait<DS_STAGES - 2>();
+      if (TMA && tma) mbar_wait(bar + (k - k0) % DS_STAGES, (uint32_t)(((k - k0) / DS_STAGES) & 1));
+      else cp_wait<DS_STAGES - 2>();
       const unsigned char* st = ring + (size_t)((k - k0) % DS_STAGES) * stage_bytes;
-      fwd_read_row<REV, NC, SRC>(J, st, slot, xo);
-      fwd_read_row<REV, NC, SRC>(J, st + row_bytes, slot, xn);
+      fwd_read_row<REV, NC, SRC>(J, st, cpitch, xo);
+      fwd_read_row<REV, NC, SRC>(J, st + row_bytes, cpitch, xn);
       #pragma unroll
       for (int c = 0; c < NC; ++c)
         #pragma unroll
@@ -452,9 +505,12 @@ dwt_fwd_stream_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, const voi
           hp[c][i] = (T)h; xe[c][i] = xn[c][i];
         }
       if (issued <= k1) {             // refill the stage consumed one iteration ago
-        unsigned char* sn = ring + (size_t)((issued - k0) % DS_STAGES) * stage_bytes;
-        fwd_issue_row<NC, SRC>(J, g, image, coef, 2 * issued - 1, sn, slot);
-        fwd_issue_row<NC, SRC>(J, g, image, coef, 2 * issued, sn + row_bytes, slot);
+        if (TMA && tma) issue_tma(issued, (uint32_t)((issued - k0) % DS_STAGES));
+        else {
+          unsigned char* sn = ring + (size_t)((issued - k0) % DS_STAGES) * stage_bytes;
+          fwd_issue_row<NC, SRC>(J, g, image, coef, 2 * issued - 1, sn, cpitch);
+          fwd_issue_row<NC, SRC>(J, g, image, coef, 2 * issued, sn + row_bytes, cpitch);
+        }
       }
       cp_commit(); ++issued;
       fwd_store_pair<REV, NC>(J, g, coef, 2 * k - 2, lo, hi);      // rows 2k-2 (low), 2k-1 (high)
@@ -468,10 +524,11 @@ dwt_fwd_stream_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, const voi
     const float Kinv = 1.0f / IRV_K;
     for (int k = k0; k <= k1; ++k) {
       T xo[NC][4], xn[NC][4], lo[NC][4], hi[NC][4];
-      cp_wait<DS_STAGES - 2>();
+      if (TMA && tma) mbar_wait(bar + (k - k0) % DS_STAGES, (uint32_t)(((k - k0) / DS_STAGES) & 1));
+      else cp_wait<DS_STAGES - 2>();
       const unsigned char* st = ring + (size_t)((k - k0) % DS_STAGES) * stage_bytes;
-      fwd_read_row<REV, NC, SRC>(J, st, slot, xo);
-      fwd_read_row<REV, NC, SRC>(J, st + row_bytes, slot, xn);
+      fwd_read_row<REV, NC, SRC>(J, st, cpitch, xo);
+      fwd_read_row<REV, NC, SRC>(J, st + row_bytes, cpitch, xn);
       #pragma unroll
       for (int c = 0; c < NC; ++c)
         #pragma unroll
@@ -484,9 +541,12 @@ dwt_fwd_stream_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, const voi
           xe[c][i] = xn[c][i]; d1[c][i] = (T)nd1; s1[c][i] = (T)ns1; d2[c][i] = (T)nd2;
         }
       if (issued <= k1) {
-        unsigned char* sn = ring + (size_t)((issued - k0) % DS_STAGES) * stage_bytes;
-        fwd_issue_row<NC, SRC>(J, g, image, coef, 2 * issued - 1, sn, slot);
-        fwd_issue_row<NC, SRC>(J, g, image, coef, 2 * issued, sn + row_bytes, slot);
+        if (TMA && tma) issue_tma(issued, (uint32_t)((issued - k0) % DS_STAGES));
+        else {
+          unsigned char* sn = ring + (size_t)((issued - k0) % DS_STAGES) * stage_bytes;
+          fwd_issue_row<NC, SRC>(J, g, image, coef, 2 * issued - 1, sn, cpitch);
+          fwd_issue_row<NC, SRC>(J, g, image, coef, 2 * issued, sn + row_bytes, cpitch);
+        }
       }
       cp_commit(); ++issued;
       fwd_store_pair<REV, NC>(J, g, coef, 2 * k - 4, lo, hi);      // rows 2k-4 (low), 2k-3 (high)
@@ -782,10 +842,21 @@ dwt_inv_stream_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, void* __r
   }
 }
 
+bool dwt_use_tma() {
+  static const bool v = [] { const char* e = getenv("OJB_DWT_TMA"); return e && atoi(e) != 0; }();
+  return v;
+}
 template <bool REV, int NC, int SRC>
 void launch_fwd(const DwtJob* jobs, uint32_t njobs, uint32_t ctas, const void* image, uint32_t* coef, cudaStream_t st) {
-  auto k = dwt_fwd_stream_kernel<REV, NC, SRC>;
   const size_t slot = (SRC == SRC_U8 || SRC == SRC_U16) ? 8 : 16;
+  if (dwt_use_tma() && (SRC == SRC_U16 || SRC == SRC_COEF)) {          // bulk-copy staging (A/B: profiles/)
+    auto k = dwt_fwd_stream_kernel<REV, NC, SRC, (SRC == SRC_U16 || SRC == SRC_COEF)>;
+    const size_t smem = (size_t)DS_WARPS * DS_STAGES * 2 * NC * (32 * slot + 16);
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    OJB_LAUNCH(k, dim3(ctas), dim3(DS_WARPS * 32), smem, st, jobs, njobs, image, coef);
+    return;
+  }
+  auto k = dwt_fwd_stream_kernel<REV, NC, SRC, false>;
   const size_t smem = (size_t)DS_WARPS * DS_STAGES * 2 * NC * 32 * slot;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   OJB_LAUNCH(k, dim3(ctas), dim3(DS_WARPS * 32), smem, st, jobs, njobs, image, coef);

@@ -507,7 +507,7 @@ void Decoder::Mirror::fetch(size_t first_page, size_t npages) {
   // one copy for the missing page and, when the request is a single page, the one after it (headers of large
   // packets run on for tens of kilobytes; the round trip, not the bytes, is the cost)
   const size_t total = (len + (1u << PAGE_SHIFT) - 1) >> PAGE_SHIFT;
-  size_t last = std::min(total, first_page + std::max<size_t>(npages, 2));
+  size_t last = std::min(total, first_page + std::max<size_t>(npages, 1));
   while (last > first_page + 1 && present[last - 1]) --last;
   const size_t a = first_page << PAGE_SHIFT, b = std::min(len, last << PAGE_SHIFT);
   cuda_check(cudaMemcpyAsync(host.as<uint8_t>() + a, dev + a, b - a, cudaMemcpyDeviceToHost, owner->stream), "codestream page fetch");
@@ -520,6 +520,20 @@ void Decoder::read_headers_device(const uint8_t* dev, size_t len, uint32_t sampl
   mirror.owner = this; mirror.dev = dev; mirror.len = len; mirror.fetched_bytes = 0;
   mirror.host.reserve(len + 64);
   mirror.present.assign((len + (1u << HostMirror::PAGE_SHIFT) - 1) >> HostMirror::PAGE_SHIFT, 0);
+  // a stream of frames of one geometry keeps its packet headers in about the same places: the pages the previous
+  // frame's parse touched are requested up front, back to back, and awaited once (a miss is fetched on demand)
+  if (!mirror.last_pages.empty()) {
+    size_t got = 0;
+    for (size_t pg : mirror.last_pages) {
+      if (pg >= mirror.present.size() || mirror.present[pg]) continue;
+      const size_t a = pg << HostMirror::PAGE_SHIFT, b = std::min(len, (pg + 1) << HostMirror::PAGE_SHIFT);
+      CK(cudaMemcpyAsync(mirror.host.as<uint8_t>() + a, dev + a, b - a, cudaMemcpyDeviceToHost, stream));
+      mirror.present[pg] = 1; got += b - a;
+    }
+    CK(cudaStreamSynchronize(stream));
+    mirror.fetched_bytes += got;
+  }
+  mirror.last_pages.clear();
   // the main header: normally well inside the first page; a parse that runs out of fetched bytes is repeated
   // with everything fetched
   size_t have = std::min<size_t>(len, 1u << HostMirror::PAGE_SHIFT);
@@ -747,6 +761,10 @@ uint32_t Decoder::decode(void* const* planes, const uint32_t* strides, bool plan
   mark(1);
   auto host_t0 = std::chrono::steady_clock::now();
   parse_tiles();
+  if (mirrored) {
+    mirror.last_pages.clear();
+    for (size_t pg = 0; pg < mirror.present.size(); ++pg) if (mirror.present[pg]) mirror.last_pages.push_back(pg);
+  }
   uint32_t nb = (uint32_t)h_dec_proto.size();
   DecBlock* hd = h_dec.as<DecBlock>();
   size_t scratch_fixed = 0;

@@ -129,6 +129,7 @@ public:
   void read_headers_device(const uint8_t* dev_j2c, size_t len, uint32_t sample_type);
   struct Mirror : HostMirror {
     Decoder* owner = nullptr; const uint8_t* dev = nullptr; PinnedBuf host; size_t fetched_bytes = 0;
+    std::vector<size_t> last_pages;     // pages the previous frame's parse needed
     void fetch(size_t first_page, size_t npages) override;
   } mirror;
   bool mirrored = false;                // j2c points into mirror.host

@@ -102,10 +102,10 @@ uint32_t write_packet_header(const ResGeom& res, const PrecinctGeom& pc,
 // left in the tile-part according to its SOT (Psot), data_end the size of the buffer: running out of
 // buffer with data_left > 0 throws like the reference's failed file read.  Throws Error on malformed input.
 // Host view of a codestream that lives in device memory: `data` is a host buffer of the same size of which only
-// the 64 KB pages marked present have been fetched.  The parsers touch marker segments and packet HEADERS only
+// the 32 KB pages marked present have been fetched.  The parsers touch marker segments and packet HEADERS only
 // (never code-block bodies), so a device-resident decode moves kilobytes, not the codestream, to the host.
 struct HostMirror {
-  enum : unsigned { PAGE_SHIFT = 16 };
+  enum : unsigned { PAGE_SHIFT = 15 };
   std::vector<uint8_t> present; size_t len = 0;
   virtual void fetch(size_t first_page, size_t npages) = 0;
   virtual ~HostMirror() {}
