@@ -22,6 +22,7 @@
 #include "ojb_device.h"
 #include "ojb_kernels.h"
 #include "ojb_async.cuh"
+#include <cstdlib>
 
 namespace ojb {
 
@@ -116,12 +117,14 @@ struct RevDec {               // backward-growing stream (VLC, MRP)
   const uint32_t* wnext; const uint32_t* wbase; uint32_t* ring; uint32_t ridx, lo, hi, sh;
 };
 #define VLC_RING 8
+template <int STRIDE = DEC1_THREADS>
 __device__ __forceinline__ void rev_ring_issue(RevDec& v) {
-  uint32_t* slot = v.ring + v.ridx * DEC1_THREADS;
+  uint32_t* slot = v.ring + v.ridx * STRIDE;
   if (v.wnext >= v.wbase) cp_async<4>(slot, v.wnext); else *slot = 0u;
   cp_commit();
   --v.wnext; v.ridx = (v.ridx + 1) & (VLC_RING - 1);
 }
+template <int STRIDE = DEC1_THREADS>
 __device__ __forceinline__ void rev_prime(RevDec& v, const uint8_t* buffer_start, uint32_t* ring) {
   const uint8_t* q = v.p - 3;
   const uint32_t* wp = reinterpret_cast<const uint32_t*>((size_t)q & ~(size_t)3);
@@ -131,7 +134,7 @@ __device__ __forceinline__ void rev_prime(RevDec& v, const uint8_t* buffer_start
   v.hi = (wp + 1 >= v.wbase) ? wp[1] : 0u;
   v.ring = ring; v.ridx = 0; v.wnext = wp - 1;
   #pragma unroll
-  for (int i = 0; i < VLC_RING - 1; ++i) rev_ring_issue(v);
+  for (int i = 0; i < VLC_RING - 1; ++i) rev_ring_issue<STRIDE>(v);
   v.ridx = 0;                                  // oldest request sits in slot 0
 }
 // byte-wise refill (refinement passes, lane 0 only)
@@ -147,6 +150,7 @@ __device__ __forceinline__ void rev_fill(RevDec& v) {       // LSB first
   }
 }
 // 32 bits per refill; needs bits <= 32 on entry
+template <int STRIDE = DEC1_THREADS>
 __device__ __forceinline__ void rev_fill32(RevDec& v) {
   if (v.bits > 32) return;
   uint32_t val = 0;                                           // bytes p-3 .. p, byte p in the MSB
@@ -156,10 +160,10 @@ __device__ __forceinline__ void rev_fill32(RevDec& v) {
     v.hi = v.lo;
     cp_wait<VLC_RING - 2>();                                  // the oldest request has landed
     const uint32_t take = v.ridx;
-    v.lo = v.ring[take * DEC1_THREADS];
+    v.lo = v.ring[take * STRIDE];
     // the freed slot takes the request VLC_RING-1 words further down the stream
     v.ridx = (take + VLC_RING - 1) & (VLC_RING - 1);
-    rev_ring_issue(v);
+    rev_ring_issue<STRIDE>(v);
     v.ridx = (take + 1) & (VLC_RING - 1);
   } else {
     int i = 24;
@@ -681,8 +685,9 @@ struct MsDec {
   const uint2* wnext; const uint8_t* seg_end; uint2* ring; uint32_t ridx;
   int left; Win128 w; uint32_t unstuff;
 };
+template <int STRIDE = DEC1_THREADS>
 __device__ __forceinline__ void ms_ring_issue(MsDec& m) {
-  uint2* slot = m.ring + m.ridx * DEC1_THREADS;
+  uint2* slot = m.ring + m.ridx * STRIDE;
   if (reinterpret_cast<const uint8_t*>(m.wnext) < m.seg_end) cp_async<8>(slot, m.wnext); else *slot = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
   cp_commit();
   ++m.wnext; m.ridx = (m.ridx + 1) & (VLC_RING - 1);
@@ -700,22 +705,24 @@ __device__ __forceinline__ void ms_ingest(MsDec& m, unsigned long long val, uint
   const uint32_t c = 8 * nv - delete_bits(val, del);
   win_append(m.w, val, c);
 }
+template <int STRIDE = DEC1_THREADS>
 __device__ __forceinline__ void ms_prime(MsDec& m, const uint8_t* p, int len, const uint8_t* seg_end, uint2* ring) {
   const uint2* wp = reinterpret_cast<const uint2*>((size_t)p & ~(size_t)7);
   const uint32_t a = (uint32_t)((size_t)p & 7);
   m.seg_end = seg_end; m.left = len; m.w.w0 = 0; m.w.w1 = 0; m.w.bits = 0; m.unstuff = 0;
   m.ring = ring; m.ridx = 0; m.wnext = wp + 1;
   #pragma unroll
-  for (int i = 0; i < VLC_RING - 1; ++i) ms_ring_issue(m);
+  for (int i = 0; i < VLC_RING - 1; ++i) ms_ring_issue<STRIDE>(m);
   m.ridx = 0;
   ms_ingest(m, u64_of(wp[0]) >> (8 * a), 8 - a);           // the bytes up to the next 8-byte boundary: groups are aligned from here on
 }
+template <int STRIDE = DEC1_THREADS>
 __device__ __forceinline__ void ms_fill(MsDec& m) {            // adds 56..64 bits; needs bits < 64
   cp_wait<VLC_RING - 2>();
   const uint32_t take = m.ridx;
-  const unsigned long long val = u64_of(m.ring[take * DEC1_THREADS]);
+  const unsigned long long val = u64_of(m.ring[take * STRIDE]);
   m.ridx = (take + VLC_RING - 1) & (VLC_RING - 1);
-  ms_ring_issue(m);
+  ms_ring_issue<STRIDE>(m);
   m.ridx = (take + 1) & (VLC_RING - 1);
   ms_ingest(m, val, 8);
 }
@@ -1184,6 +1191,214 @@ ht_decode_fast_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
   block_status[b] = fail ? DST_FAIL : 0u;
 }
 
+
+// ---- the fast path split over two threads per code-block ------------------------------------------------------
+// A code-block's cleanup pass is two chains: MEL + VLC + U-VLC decoding (each codeword's position and context depend
+// on the one before) and MagSgn extraction (positions depend on the row above through the exponent predictor).  The
+// second needs the first's results but not the other way round, so the pair runs as a producer and a consumer
+// thread in different warps of one CTA: warps 0-1 decode the quad records (rho, e_k, e_1, u) of 64 blocks one
+// quad-row ahead into a double-buffered shared-memory row, warps 2-3 read them and do what is left of the fast
+// kernel.  Hand-over per quad-row through named barriers (producers bar.arrive on FULL, consumers bar.sync; the
+// reverse on EMPTY), no polling.  Twice the threads per block: the serial chain of a block -- which bounds the
+// kernel's duration when 49 152 blocks are all that is in flight -- is cut to the longer of the two halves.
+#define SP_BLOCKS 64
+template <int MODE>       // 0: integer output, 1: float output, 2: sign-magnitude
+__global__ void __launch_bounds__(2 * SP_BLOCKS)
+ht_decode_split_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
+                       const uint8_t* __restrict__ cs, uint32_t* __restrict__ coef,
+                       const uint16_t* __restrict__ tables, uint32_t* __restrict__ block_status)
+{
+  __shared__ DecTables T;
+  __shared__ uint32_t s_vring[VLC_RING * SP_BLOCKS];
+  __shared__ uint2 s_mring[VLC_RING * SP_BLOCKS];
+  __shared__ uint32_t s_g[17 * SP_BLOCKS];
+  __shared__ uint2 s_rec[2 * 16 * SP_BLOCKS];               // [stage][pair][block]: the quad records of one quad-row
+  __shared__ uint32_t s_rows;
+  {
+    uint16_t* d = reinterpret_cast<uint16_t*>(&T);
+    for (uint32_t i = threadIdx.x; i < sizeof(DecTables) / 2; i += blockDim.x) d[i] = tables[i];
+  }
+  if (threadIdx.x == 0) s_rows = 0;
+  __syncthreads();
+  const bool producer = threadIdx.x < SP_BLOCKS;
+  const uint32_t tid = producer ? threadIdx.x : threadIdx.x - SP_BLOCKS;
+  const uint32_t b = blockIdx.x * SP_BLOCKS + tid;
+  DecBlock blk;
+  bool active = b < nblocks;
+  if (active) { blk = blocks[b]; active = (blk.flags & DEC_FLAG_FAST) != 0; }
+  const uint8_t* data = nullptr;
+  int lcup = 0, scup = 0;
+  if (active) {
+    data = cs + blk.data_off;
+    lcup = (int)blk.len1;
+    scup = ((int)data[lcup - 1] << 4) + (data[lcup - 2] & 0xF);
+    if (scup < 2 || scup > lcup || scup > 4079) { if (!producer) block_status[b] = DST_FAIL; active = false; }
+  }
+  const uint32_t npairs = active ? (uint32_t)(blk.w >> 2) : 0u, myrows = active ? (uint32_t)(blk.h >> 1) : 0u;
+  if (producer && myrows) atomicMax(&s_rows, myrows);
+  __syncthreads();
+  const uint32_t rows = s_rows;
+  enum { BAR_FULL = 1, BAR_EMPTY = 3 };
+
+  if (producer) {
+    MelDec mel; RevDec vlc; int run = 0;
+    if (active) {
+      mel.p = data + lcup - scup; mel.size = scup - 1; mel.tmp = 0; mel.bits = 0; mel.unstuff = false; mel.k = 0;
+      vlc.p = data + lcup - 2; vlc.size = scup - 2;
+      const uint32_t d = *vlc.p--;                            // the byte that shares the Scup nibble (rev_init, :270-302)
+      vlc.tmp = d >> 4;
+      vlc.bits = 4 - (((vlc.tmp & 7) == 7) ? 1u : 0u);
+      vlc.unstuff = (d | 0xF) > 0x8F;
+      rev_prime<SP_BLOCKS>(vlc, cs, s_vring + tid);
+      mel_prime(mel);
+      run = mel_next_run(mel);
+    }
+    uint32_t sg_lo = 0, sg_hi = 0;              // bottom-sample significance of the row above: bit 2q = left, 2q+1 = right
+    for (uint32_t r = 0; r < rows; ++r) {
+      if (r >= 2) named_bar_sync(BAR_EMPTY + (r & 1), 2 * SP_BLOCKS);
+      if (r < myrows) {
+        const bool first = (r == 0);
+        const uint16_t* vtab = first ? T.vlc0 : T.vlc1;
+        const uint16_t* utab = first ? T.uvlc0 : T.uvlc1;
+        uint2* out = s_rec + (size_t)(r & 1) * 16 * SP_BLOCKS + tid;
+        uint32_t rho_left = 0;
+        uint32_t rs_lo = sg_lo, rs_hi = sg_hi, rs_carry = 0;
+        uint32_t cu_lo = 0, cu_hi = 0;
+        #pragma unroll 1
+        for (uint32_t j = 0; j < npairs; ++j) {
+          while (vlc.bits <= 32) rev_fill32<SP_BLOCKS>(vlc);          // the pair reads at most 2 x 7 + 6 + 10 bits
+          uint32_t vt = (uint32_t)vlc.tmp, vused = 0;
+          const uint32_t y6 = rs_carry | ((rs_lo & 0x1Fu) << 1);
+          const uint32_t z = y6 | (y6 >> 1);
+          rs_carry = (rs_lo >> 3) & 1u;
+          rs_lo = __funnelshift_r(rs_lo, rs_hi, 4); rs_hi >>= 4;
+          uint32_t t[2];
+          #pragma unroll
+          for (uint32_t i = 0; i < 2; ++i) {
+            uint32_t c;
+            if (first) c = (rho_left & 1u) | (rho_left >> 1);
+            else c = ((z >> (2 * i)) & 5u) | (rho_left > 3u ? 2u : 0u);
+            uint32_t e = vtab[(c << 7) | (vt & 0x7Fu)];
+            if (c == 0) {               // significance of an all-zero context comes from MEL
+              run -= 2;
+              if (run != -1) e = 0;
+              if (run < 0) run = mel_next_run(mel);
+            }
+            vt >>= (e & 7u); vused += (e & 7u);
+            t[i] = e;
+            rho_left = (e >> 4) & 15u;
+          }
+          uint32_t mode = ((t[0] >> 3) & 1u) | ((t[1] >> 2) & 2u);
+          if (first && mode == 3) {
+            run -= 2;
+            if (run == -1) mode = 4;
+            if (run < 0) run = mel_next_run(mel);
+          }
+          uint32_t ent = utab[(mode << 6) | (vt & 0x3Fu)];
+          vt >>= (ent & 7u); vused += (ent & 7u);
+          ent >>= 3;
+          uint32_t len = ent & 0xFu;
+          const uint32_t suf = vt & ((1u << len) - 1u);
+          vused += len;
+          vlc.tmp >>= vused; vlc.bits -= vused;
+          ent >>= 4;
+          len = ent & 7u; ent >>= 3;
+          const uint32_t kap = first ? 1u : 0u;
+          const uint32_t u0 = kap + (ent & 7u) + (suf & ~(0xFFu << len)), u1 = kap + (ent >> 3) + (suf >> len);
+          {
+            const uint32_t ta = (t[0] >> 5) & 5u, tb = (t[1] >> 5) & 5u;
+            const uint32_t nb = ((ta | (ta >> 1)) & 3u) | (((tb | (tb >> 1)) & 3u) << 2);
+            cu_lo = __funnelshift_r(cu_lo, cu_hi, 4); cu_hi = (cu_hi >> 4) | (nb << 28);
+          }
+          out[j * SP_BLOCKS] = make_uint2(t[0] | (u0 << 16), t[1] | (u1 << 16));
+        }
+        const uint32_t sh = 64u - 4u * npairs;
+        const uint32_t a0 = sh >= 32 ? cu_hi : cu_lo, a1 = sh >= 32 ? 0u : cu_hi;
+        sg_lo = __funnelshift_r(a0, a1, sh & 31u); sg_hi = a1 >> (sh & 31u);
+      }
+      __threadfence_block();
+      named_bar_arrive(BAR_FULL + (r & 1), 2 * SP_BLOCKS);
+    }
+    return;
+  }
+
+  // ---- consumer: MagSgn extraction and output
+  MsDec ms;
+  uint32_t* dst = nullptr; uint32_t* gw = s_g + tid;
+  uint32_t mmsbp2 = 0, pscale = 0, mul_a = 0, stride = 0, fail = 0;
+  float delta = 0.f;
+  if (active) {
+    ms_prime<SP_BLOCKS>(ms, data, lcup - scup, data + lcup, s_mring + tid);
+    dst = coef + blk.dst_off; stride = blk.stride;
+    mmsbp2 = blk.missing_msbs + 2u;
+    pscale = 1u << (29u - blk.missing_msbs);
+    mul_a = 1u << (blk.K_max - blk.missing_msbs - 1u);
+    delta = blk.delta;
+    for (uint32_t j = 0; j <= 16; ++j) gw[j * SP_BLOCKS] = 0;
+  }
+  for (uint32_t r = 0; r < rows; ++r) {
+    named_bar_sync(BAR_FULL + (r & 1), 2 * SP_BLOCKS);
+    if (r < myrows && !fail) {
+      const bool first = (r == 0);
+      const uint2* in = s_rec + (size_t)(r & 1) * 16 * SP_BLOCKS + tid;
+      uint32_t* r0 = dst + (size_t)(2 * r) * stride;
+      uint32_t* r1 = r0 + stride;
+      uint32_t wj = gw[0], h_carry = 0;
+      #pragma unroll 1
+      for (uint32_t j = 0; j < npairs; ++j) {
+        const uint2 rec = in[j * SP_BLOCKS];
+        const uint32_t wj1 = gw[(j + 1) * SP_BLOCKS];
+        const uint32_t gor[2] = { (wj | (wj >> 16)) & 0xFFFFu, (wj >> 16) | (wj1 & 0xFFFFu) };
+        wj = wj1;
+        uint32_t o[2][4], hb[2][2];
+        #pragma unroll
+        for (uint32_t i = 0; i < 2; ++i) {
+          const uint32_t inf = (i ? rec.y : rec.x) & 0xFFFFu;
+          const uint32_t rho = (inf >> 4) & 15u, ek = inf >> 12, e1 = (inf >> 8) & 15u;
+          uint32_t Uq = (i ? rec.y : rec.x) >> 16;
+          if (!first) Uq += (rho & (rho - 1u)) ? 32u - (uint32_t)__clz((int)(gor[i] | 1u)) : 1u;
+          fail |= (Uq > mmsbp2) ? 1u : 0u;
+          Uq = min(Uq, mmsbp2);
+          const uint32_t rb = (rho * 0x00204081u) & 0x01010101u, eb = (ek * 0x00204081u) & 0x01010101u;
+          const uint32_t mb = (Uq * 0x01010101u - eb) & (rb * 0xFFu);
+          const uint32_t m0 = mb & 0xFFu, m1 = (mb >> 8) & 0xFFu, m2 = (mb >> 16) & 0xFFu, m3 = mb >> 24;
+          while (ms.w.bits < 64) ms_fill<SP_BLOCKS>(ms);              // the quad reads at most 64 bits
+          const uint32_t lo = (uint32_t)ms.w.w0, hi = (uint32_t)(ms.w.w0 >> 32);
+          const uint32_t s01 = m0 + m1;                           // <= 32
+          const uint32_t lo2 = __funnelshift_rc(lo, hi, s01), hi2 = __funnelshift_rc(hi, 0u, s01);
+          const uint32_t f[4] = { lo, __funnelshift_r(lo, hi, m0), lo2, __funnelshift_r(lo2, hi2, m2) };
+          const uint32_t mm[4] = { m0, m1, m2, m3 };
+          win_drop(ms.w, s01 + m2 + m3);
+          #pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t m = mm[k], bits = f[k];
+            const uint32_t pw = 1u << m;
+            uint32_t v = (bits & (pw - 1u)) | 1u;
+            v = ((e1 >> k) & 1u) * pw + v;                          // bit m is clear: + is |
+            const bool sig = (rho >> k) & 1u;
+            if (k & 1) hb[i][k >> 1] = sig ? (v >> 1) : 0u;
+            uint32_t val;
+            if (MODE == 0) { const uint32_t a = (v * mul_a + 2u * mul_a) >> 1; val = a * (1u - 2u * (bits & 1u)); }
+            else {
+              const uint32_t mag = v * pscale + 2u * pscale;
+              if (MODE == 1) val = __float_as_uint(__fmul_rn((float)mag, delta)) | (bits << 31);
+              else val = (bits << 31) | mag;
+            }
+            o[i][k] = sig ? val : 0u;
+          }
+        }
+        gw[j * SP_BLOCKS] = (h_carry | hb[0][0]) | ((hb[0][1] | hb[1][0]) << 16);
+        h_carry = hb[1][1];
+        *reinterpret_cast<uint4*>(r0 + 4 * j) = make_uint4(o[0][0], o[0][2], o[1][0], o[1][2]);
+        *reinterpret_cast<uint4*>(r1 + 4 * j) = make_uint4(o[0][1], o[0][3], o[1][1], o[1][3]);
+      }
+      gw[npairs * SP_BLOCKS] = h_carry;
+    }
+    if (r + 2 < rows) named_bar_arrive(BAR_EMPTY + (r & 1), 2 * SP_BLOCKS);
+  }
+  if (active) block_status[b] = fail ? DST_FAIL : 0u;
+}
+
 // zero-fill of blocks that are not included or failed to decode (one warp per block)
 __global__ void __launch_bounds__(DEC_WARPS * 32)
 ht_dec_fill_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks, uint32_t* __restrict__ coef,
@@ -1239,9 +1454,17 @@ void launch_ht_decode_serial(const DecBlock* blocks, uint32_t nblocks, uint32_t 
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid((nblocks + DEC1_THREADS - 1) / DEC1_THREADS), block(DEC1_THREADS);
   if (nfast) {           // blocks flagged DEC_FLAG_FAST (cleanup pass only, one output type)
-    auto kf = out_mode == DEC_OUT_INT ? ht_decode_fast_kernel<0> : out_mode == DEC_OUT_FLOAT ? ht_decode_fast_kernel<1>
-                                                                                            : ht_decode_fast_kernel<2>;
-    OJB_LAUNCH(kf, grid, block, 0, st, blocks, nblocks, codestream, coef, tables, block_status);
+    static const bool split = [] { const char* e = getenv("OJB_DEC_SPLIT"); return !(e && atoi(e) == 0); }();
+    if (split) {           // two threads per block (default); OJB_DEC_SPLIT=0: one
+      auto kf = out_mode == DEC_OUT_INT ? ht_decode_split_kernel<0> : out_mode == DEC_OUT_FLOAT ? ht_decode_split_kernel<1>
+                                                                                              : ht_decode_split_kernel<2>;
+      dim3 g2((nblocks + SP_BLOCKS - 1) / SP_BLOCKS), b2(2 * SP_BLOCKS);
+      OJB_LAUNCH(kf, g2, b2, 0, st, blocks, nblocks, codestream, coef, tables, block_status);
+    } else {
+      auto kf = out_mode == DEC_OUT_INT ? ht_decode_fast_kernel<0> : out_mode == DEC_OUT_FLOAT ? ht_decode_fast_kernel<1>
+                                                                                              : ht_decode_fast_kernel<2>;
+      OJB_LAUNCH(kf, grid, block, 0, st, blocks, nblocks, codestream, coef, tables, block_status);
+    }
   }
   if (nfast < nblocks) {
     OJB_LAUNCH(k, grid, block, smem, st, blocks, nblocks, codestream, coef, scratch, tables, out_mode,

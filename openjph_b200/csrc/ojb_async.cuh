@@ -20,6 +20,16 @@ __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_grou
 template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 #endif
 
+// ---- named barriers: producer warps `arrive`, consumer warps `sync` (or the reverse); `count` = all threads that
+// take part either way (a multiple of 32)
+#ifdef OJB_EMU_BUILD
+__device__ __forceinline__ void named_bar_sync(unsigned id, unsigned count) { ojb_emu::named_barrier(id, count, true); }
+__device__ __forceinline__ void named_bar_arrive(unsigned id, unsigned count) { ojb_emu::named_barrier(id, count, false); }
+#else
+__device__ __forceinline__ void named_bar_sync(unsigned id, unsigned count) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(unsigned id, unsigned count) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(count) : "memory"); }
+#endif
+
 // ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) + mbarrier: one elected lane requests a whole contiguous run of
 // global bytes into shared memory; the copy engine completes a transaction count on an mbarrier every reader waits
 // on.  Source, destination and size must be multiples of 16 bytes.

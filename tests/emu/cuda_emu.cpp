@@ -30,6 +30,7 @@ struct BlockRun {
   std::vector<Fiber> fibers;
   std::vector<WarpState> warps;
   unsigned bar_count = 0, bar_gen = 0;
+  unsigned nbar_count[16] = {0}, nbar_gen[16] = {0};      // named barriers (bar.sync / bar.arrive id, count)
   unsigned nthreads = 0;
   ucontext_t sched;
   Fiber* cur = nullptr;
@@ -82,6 +83,16 @@ void block_barrier() {
   r->progress++;
   if (++r->bar_count == r->nthreads) { r->bar_count = 0; r->bar_gen++; }
   else while (r->bar_gen == my_gen) yield_fiber();
+}
+
+// bar.sync id, count (wait = true) / bar.arrive id, count (wait = false): the barrier completes when `count`
+// threads have arrived or waited
+void named_barrier(unsigned id, unsigned count, bool wait) {
+  BlockRun* r = t_run;
+  unsigned my_gen = r->nbar_gen[id & 15];
+  r->progress++;
+  if (++r->nbar_count[id & 15] == count) { r->nbar_count[id & 15] = 0; r->nbar_gen[id & 15]++; }
+  else if (wait) while (r->nbar_gen[id & 15] == my_gen) yield_fiber();
 }
 
 static void fiber_entry() {

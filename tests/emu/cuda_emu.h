@@ -139,6 +139,7 @@ static inline unsigned __reduce_min_sync(unsigned mask, unsigned v) {
 }
 static inline unsigned __activemask() { return 0xFFFFFFFFu; }
 static inline void __syncthreads() { ojb_emu::block_barrier(); }
+namespace ojb_emu { void named_barrier(unsigned id, unsigned count, bool wait); }
 static inline void __threadfence() { __sync_synchronize(); }
 static inline void __threadfence_block() { __sync_synchronize(); }
 
