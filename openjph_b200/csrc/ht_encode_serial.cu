@@ -18,6 +18,8 @@
 //   * the previous quad-row's significance / exponents live in a per-thread shared-memory row.
 #include "ojb_device.h"
 #include "ojb_kernels.h"
+#include "ojb_async.cuh"
+#include <cstdlib>
 
 namespace ojb {
 
@@ -100,27 +102,30 @@ __device__ __forceinline__ void vlc_put(VlcWriter& v, uint32_t cwd, uint32_t len
   while (v.nbits >= 32) vlc_flush4(v, end);
 }
 
+template <int MS = ES_THREADS>
 __device__ __forceinline__ void mel_bit(MelWriter& m, uint32_t v, uint8_t* buf) {
   m.tmp = (m.tmp << 1) | v;
   if (--m.rem == 0) {
-    if (m.pos < ES_MEL_BYTES) buf[m.pos * ES_THREADS] = (uint8_t)m.tmp;
+    if (m.pos < ES_MEL_BYTES) buf[m.pos * MS] = (uint8_t)m.tmp;
     m.pos++;
     m.rem = (m.tmp == 0xFF) ? 7 : 8;
     m.tmp = 0;
   }
 }
+template <int MS = ES_THREADS>
 __device__ __forceinline__ void mel_event(MelWriter& m, bool one, uint8_t* buf) {     // mel_encode :321-348
   if (!one) {
-    if (++m.run >= (1u << MEL_EXP(m.k))) { mel_bit(m, 1, buf); m.run = 0; m.k = m.k < 12 ? m.k + 1 : 12; }
+    if (++m.run >= (1u << MEL_EXP(m.k))) { mel_bit<MS>(m, 1, buf); m.run = 0; m.k = m.k < 12 ? m.k + 1 : 12; }
   } else {
-    mel_bit(m, 0, buf);
-    for (uint32_t t = MEL_EXP(m.k); t > 0; ) { --t; mel_bit(m, (m.run >> t) & 1u, buf); }
+    mel_bit<MS>(m, 0, buf);
+    for (uint32_t t = MEL_EXP(m.k); t > 0; ) { --t; mel_bit<MS>(m, (m.run >> t) & 1u, buf); }
     m.run = 0; m.k = m.k > 0 ? m.k - 1 : 0;
   }
 }
 
 // terminate_mel_vlc :413-441, ms_terminate :517-533: the pending bits of the three streams, the MEL / VLC byte
 // fusion, MEL bytes moved behind MagSgn, Scup
+template <int MS = ES_THREADS>
 __device__ __forceinline__ void terminate_block(MsWriter& ms, VlcWriter& vlc, MelWriter& mel, uint8_t* mel_buf, uint8_t* slot,
                                                 uint32_t slot_cap, uint32_t* status, EncResult& res)
 {
@@ -142,7 +147,7 @@ __device__ __forceinline__ void terminate_block(MsWriter& ms, VlcWriter& vlc, Me
       if (byte != 0xFF) slot[ms_pos++] = (uint8_t)byte;
     } else if (cap == 7) ms_pos--;
   }
-  if (mel.run > 0) mel_bit(mel, 1, mel_buf);
+  if (mel.run > 0) mel_bit<MS>(mel, 1, mel_buf);
   const uint32_t mel_tmp = (mel.tmp << mel.rem) & 0xFFu;
   const uint32_t mel_mask = (0xFFu << mel.rem) & 0xFFu;
   uint32_t vl_pos = vlc.words * 4;
@@ -164,10 +169,10 @@ __device__ __forceinline__ void terminate_block(MsWriter& ms, VlcWriter& vlc, Me
   if ((mel_mask | vl_mask) != 0) {
     const uint32_t fuse = mel_tmp | vl_tmp;
     if ((((fuse ^ mel_tmp) & mel_mask) | ((fuse ^ vl_tmp) & vl_mask)) == 0 && fuse != 0xFF && vl_pos > 1) {
-      if (mel.pos < ES_MEL_BYTES) mel_buf[mel.pos * ES_THREADS] = (uint8_t)fuse;
+      if (mel.pos < ES_MEL_BYTES) mel_buf[mel.pos * MS] = (uint8_t)fuse;
       mel.pos++;
     } else {
-      if (mel.pos < ES_MEL_BYTES) mel_buf[mel.pos * ES_THREADS] = (uint8_t)mel_tmp;
+      if (mel.pos < ES_MEL_BYTES) mel_buf[mel.pos * MS] = (uint8_t)mel_tmp;
       mel.pos++;
       vend[-(int)(++vl_pos)] = (uint8_t)vl_tmp;
     }
@@ -177,7 +182,7 @@ __device__ __forceinline__ void terminate_block(MsWriter& ms, VlcWriter& vlc, Me
     res.len_head = 0; res.len_tail = 0;
     return;
   }
-  for (uint32_t i = 0; i < mel.pos; ++i) slot[ms_pos + i] = mel_buf[i * ES_THREADS];
+  for (uint32_t i = 0; i < mel.pos; ++i) slot[ms_pos + i] = mel_buf[i * MS];
   const uint32_t scup = mel.pos + vl_pos;
   vend[-1] = (uint8_t)(scup >> 4);
   vend[-2] = (uint8_t)((vend[-2] & 0xF0) | (scup & 0xF));
@@ -515,6 +520,214 @@ ht_encode_fast_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
   terminate_block(ms, vlc, mel, mel_buf, slot, blk.slot_cap, status, results[bidx]);
 }
 
+
+// ---- the fast path split over two threads per code-block ---------------------------------------------------
+// Thread A of a block (warps 0-1 of the CTA) does everything that touches the samples: magnitudes, exponents,
+// contexts, the CxtVLC table look-up, and the MagSgn stream; per quad pair it hands thread B (warps 2-3) one word
+// -- the pair's CxtVLC bits and length, the two u_q, and which MEL events the pair produces -- through a
+// double-buffered shared-memory row.  B runs the adaptive MEL coder, the U-VLC tables and the backward VLC writer,
+// and terminates the block.  One direction only (A never needs anything from B), hand-over per quad-row with named
+// barriers as in the decoder.  The serial chain per block -- what bounds this kernel when one frame's 49 152 blocks
+// are all that is in flight -- loses the VLC / MEL part, and a CTA holds twice the warps.
+#define SE_BLOCKS 64
+struct SplitTail { unsigned long long w0; uint32_t nbits, words, last_ff, any_sig, overflow, pad; };
+__global__ void __launch_bounds__(2 * SE_BLOCKS)
+ht_encode_split_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
+                       const uint32_t* __restrict__ coef, uint8_t* __restrict__ slots,
+                       EncResult* __restrict__ results, const uint16_t* __restrict__ tables,
+                       uint32_t* __restrict__ status)
+{
+  __shared__ uint16_t s_vlc[2 * 2048];
+  __shared__ uint16_t s_uvlc[36];
+  __shared__ uint8_t s_mel[ES_MEL_BYTES * SE_BLOCKS];
+  __shared__ uint32_t s_g[17 * SE_BLOCKS];
+  __shared__ uint32_t s_rec[2 * 16 * SE_BLOCKS];            // [stage][pair][block]
+  __shared__ SplitTail s_tail[SE_BLOCKS];
+  __shared__ uint32_t s_rows;
+
+  for (uint32_t i = threadIdx.x; i < 2 * 2048; i += blockDim.x) s_vlc[i] = tables[i];
+  if (threadIdx.x < 33) s_uvlc[threadIdx.x] = tables[2 * 2048 + threadIdx.x];
+  if (threadIdx.x == 0) s_rows = 0;
+  __syncthreads();
+
+  const bool side_a = threadIdx.x < SE_BLOCKS;
+  const uint32_t tid = side_a ? threadIdx.x : threadIdx.x - SE_BLOCKS;
+  const uint32_t bidx = blockIdx.x * SE_BLOCKS + tid;
+  EncBlock blk;
+  bool active = bidx < nblocks;
+  if (active) { blk = blocks[bidx]; active = (blk.flags & ENC_FLAG_FAST) != 0; }
+  const uint32_t npairs = active ? (uint32_t)(blk.w >> 2) : 0u, myrows = active ? (uint32_t)(blk.h >> 1) : 0u;
+  if (side_a && myrows) atomicMax(&s_rows, myrows);
+  __syncthreads();
+  const uint32_t rows = s_rows;
+  enum { BAR_FULL = 1, BAR_EMPTY = 3 };
+  uint8_t* slot = active ? slots + blk.slot_off : nullptr;
+  // the VLC segment's worst case (30 bits per quad pair, one stuffing bit in seven, margin), as the host sized it
+  uint32_t vl_worst = 0;
+  if (active) {
+    const uint32_t nqp = ((uint32_t)(blk.w >> 1) * (uint32_t)(blk.h >> 1) + 1u) / 2u;
+    vl_worst = (nqp * 30u + 12u + 7u) / 8u; vl_worst += vl_worst / 7u + 8u;
+  }
+
+  if (side_a) {
+    const uint32_t stride = active ? blk.stride : 0u, p = active ? (uint32_t)blk.p : 16u;
+    const uint32_t* __restrict__ src = active ? coef + blk.src_off : coef;
+    uint2* ms_dst = reinterpret_cast<uint2*>(slot);
+    uint32_t* gw = s_g + tid;
+    const uint32_t pm1 = p - 1u, vmask = (2u << (31u - p)) - 2u;
+    // MagSgn cannot exceed its worst case ((K_max + 1) bits per sample, a stuffing bit per 15, as the host sized the
+    // slot); the test below is a safety net that keeps a faulty run out of the VLC side's part of the slot
+    uint32_t ms_limit = 0;
+    if (active) {
+      uint32_t mw = ((uint32_t)blk.w * blk.h * (32u - p) + 7u) / 8u; mw += mw / 15u + 8u;
+      ms_limit = (mw + 48u) >> 2;
+    }
+    MsWriter ms; ms.w0 = 0; ms.w1 = 0; ms.nbits = 0; ms.words = 0; ms.last_ff = 0;
+    uint32_t any_sig = 0, overflow = 0;
+    if (active) for (uint32_t j = 0; j <= 16; ++j) gw[j * SE_BLOCKS] = 0;
+    uint32_t sg_lo = 0, sg_hi = 0;
+    for (uint32_t r = 0; r < rows; ++r) {
+      if (r >= 2) named_bar_sync(BAR_EMPTY + (r & 1), 2 * SE_BLOCKS);
+      if (r < myrows && !overflow) {
+        const bool first = (r == 0);
+        const uint4* r0 = reinterpret_cast<const uint4*>(src + (size_t)(2 * r) * stride);
+        const uint4* r1 = reinterpret_cast<const uint4*>(src + (size_t)(2 * r + 1) * stride);
+        const uint16_t* vtab = s_vlc + (first ? 0u : 2048u);
+        uint32_t* out = s_rec + (size_t)(r & 1) * 16 * SE_BLOCKS + tid;
+        uint32_t rho_left = 0;
+        uint32_t rs_lo = sg_lo, rs_hi = sg_hi, rs_carry = 0;
+        uint32_t cu_lo = 0, cu_hi = 0;
+        uint32_t wj = gw[0], x_carry = 0;
+        uint4 na = r0[0], nb = r1[0];
+        #pragma unroll 1
+        for (uint32_t j = 0; j < npairs; ++j) {
+          const uint4 ca = na, cb = nb;
+          if (j + 1 < npairs) { na = r0[j + 1]; nb = r1[j + 1]; }
+          const uint32_t wj1 = gw[(j + 1) * SE_BLOCKS];
+          const uint32_t y6 = rs_carry | ((rs_lo & 0x1Fu) << 1);
+          const uint32_t z = y6 | (y6 >> 1);
+          rs_carry = (rs_lo >> 3) & 1u;
+          rs_lo = __funnelshift_r(rs_lo, rs_hi, 4); rs_hi >>= 4;
+          const uint32_t gor[2] = { (wj | (wj >> 16)) & 0xFFFFu, (wj >> 16) | (wj1 & 0xFFFFu) };
+          wj = wj1;
+          uint32_t uq[2], xb[2][2], rr[2], cwl[2], melf = 0;
+          unsigned long long cwd[2];
+          uint32_t pair_bits = 0, pair_len = 0;
+          #pragma unroll
+          for (uint32_t h = 0; h < 2; ++h) {
+            const uint32_t t[4] = { h ? ca.z : ca.x, h ? cb.z : cb.x, h ? ca.w : ca.y, h ? cb.w : cb.y };
+            uint32_t rho = 0, x[4], s[4];
+            #pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint32_t v = (t[i] >> pm1) & vmask;
+              const uint32_t sig = min(v, 1u);
+              rho |= sig << i;
+              x[i] = v - sig;
+              s[i] = v - 2u + (t[i] >> 31);
+            }
+            any_sig |= rho;
+            rr[h] = rho;
+            xb[h][0] = x[1]; xb[h][1] = x[3];
+            const uint32_t emax = 32u - (uint32_t)__clz((int)(x[0] | x[1] | x[2] | x[3]));
+            uint32_t kappa = 1, cq;
+            if (first) cq = (rho_left >> 1) | (rho_left & 1);
+            else {
+              const int me = 32 - __clz((int)gor[h]);
+              if (rho & (rho - 1)) kappa = (uint32_t)max(1, me - 1);
+              cq = ((z >> (2 * h)) & 5u) | (rho_left > 3u ? 2u : 0u);
+            }
+            const uint32_t Uq = max(emax, kappa);
+            const uint32_t u = Uq - kappa;
+            uq[h] = u;
+            const uint32_t sh = max(emax, 1u) - 1u;
+            const uint32_t eps = ((x[0] >> sh) | ((x[1] >> sh) << 1) | ((x[2] >> sh) << 2) | ((x[3] >> sh) << 3)) & (0u - min(u, 1u));
+            const uint32_t tuple = vtab[(cq << 8) + (rho << 4) + eps];
+            pair_bits |= (tuple >> 8) << pair_len; pair_len += (tuple >> 4) & 7u;
+            melf |= ((cq == 0 ? 1u : 0u) | (rho != 0 ? 2u : 0u)) << (2 * h);       // MEL event of this quad, and its value
+            {
+              const uint32_t rb = (rho * 0x00204081u) & 0x01010101u, eb = ((tuple & 15u) * 0x00204081u) & 0x01010101u;
+              const uint32_t mb = (Uq * 0x01010101u - eb) & (rb * 0xFFu);
+              const uint32_t m0 = mb & 0xFFu, m1 = (mb >> 8) & 0xFFu, m2 = (mb >> 16) & 0xFFu, m3 = mb >> 24;
+              const uint32_t A = (s[0] & ((1u << m0) - 1u)) | ((s[1] & ((1u << m1) - 1u)) << m0);
+              const uint32_t B = (s[2] & ((1u << m2) - 1u)) | ((s[3] & ((1u << m3) - 1u)) << m2);
+              const uint32_t la = m0 + m1, lb = m2 + m3;
+              cwd[h] = (unsigned long long)A | ((unsigned long long)B << la); cwl[h] = la + lb;
+            }
+            rho_left = rho;
+          }
+          // the pair's hand-over word: CxtVLC bits (<= 14) | their length << 14 | MEL flags << 18 | u_q0 << 22 | u_q1 << 27
+          out[j * SE_BLOCKS] = pair_bits | (pair_len << 14) | (melf << 18) | (uq[0] << 22) | (uq[1] << 27);
+          ms_put(ms, cwd[0], cwl[0], ms_dst);
+          ms_put(ms, cwd[1], cwl[1], ms_dst);
+          {
+            const uint32_t ta = (rr[0] >> 1) & 5u, tb = (rr[1] >> 1) & 5u;
+            const uint32_t nbits4 = ((ta | (ta >> 1)) & 3u) | (((tb | (tb >> 1)) & 3u) << 2);
+            cu_lo = __funnelshift_r(cu_lo, cu_hi, 4); cu_hi = (cu_hi >> 4) | (nbits4 << 28);
+            gw[j * SE_BLOCKS] = (x_carry | xb[0][0]) | ((xb[0][1] | xb[1][0]) << 16);
+            x_carry = xb[1][1];
+          }
+        }
+        gw[npairs * SE_BLOCKS] = x_carry;
+        const uint32_t sh = 64u - 4u * npairs;
+        const uint32_t a0 = sh >= 32 ? cu_hi : cu_lo, a1 = sh >= 32 ? 0u : cu_hi;
+        sg_lo = __funnelshift_r(a0, a1, sh & 31u); sg_hi = a1 >> (sh & 31u);
+        if (ms.words > ms_limit) overflow = 1;
+      }
+      __threadfence_block();
+      named_bar_arrive(BAR_FULL + (r & 1), 2 * SE_BLOCKS);
+    }
+    if (active) {
+      SplitTail& t = s_tail[tid];
+      t.w0 = ms.w0; t.nbits = ms.nbits; t.words = ms.words; t.last_ff = ms.last_ff; t.any_sig = any_sig; t.overflow = overflow;
+    }
+    __syncthreads();
+    return;
+  }
+
+  // ---- side B: MEL, U-VLC, the VLC stream, termination
+  uint32_t* vl_end = active ? reinterpret_cast<uint32_t*>(slot + blk.slot_cap) : nullptr;
+  uint8_t* mel_buf = s_mel + tid;
+  VlcWriter vlc; vlc.acc = 0xFFFull; vlc.nbits = 12; vlc.words = 0; vlc.prev = 0;
+  MelWriter mel; mel.k = 0; mel.run = 0; mel.tmp = 0; mel.rem = 8; mel.pos = 0;
+  uint32_t overflow_b = 0;
+  for (uint32_t r = 0; r < rows; ++r) {
+    named_bar_sync(BAR_FULL + (r & 1), 2 * SE_BLOCKS);
+    if (r < myrows && !overflow_b) {
+      const bool first = (r == 0);
+      const uint32_t* in = s_rec + (size_t)(r & 1) * 16 * SE_BLOCKS + tid;
+      #pragma unroll 1
+      for (uint32_t j = 0; j < npairs; ++j) {
+        const uint32_t w = in[j * SE_BLOCKS];
+        const uint32_t melf = (w >> 18) & 15u, u0 = (w >> 22) & 31u, u1 = w >> 27;
+        if (melf & 1u) mel_event<SE_BLOCKS>(mel, (melf & 2u) != 0, mel_buf);                  // :664-665
+        if (melf & 4u) mel_event<SE_BLOCKS>(mel, (melf & 8u) != 0, mel_buf);
+        uint32_t c0, c1;
+        if (first) {
+          if (u0 > 0 && u1 > 0) mel_event<SE_BLOCKS>(mel, min(u0, u1) > 2, mel_buf);
+          if (u0 > 2 && u1 > 2) { c0 = s_uvlc[u0 - 2]; c1 = s_uvlc[u1 - 2]; }
+          else if (u0 > 2 && u1 > 0) { c0 = s_uvlc[u0]; c1 = (u1 - 1) | (1u << 3); }     // one-bit u1
+          else { c0 = s_uvlc[u0]; c1 = s_uvlc[u1]; }
+        } else { c0 = s_uvlc[u0]; c1 = s_uvlc[u1]; }
+        uint32_t bits = w & 0x3FFFu, len = (w >> 14) & 15u;
+        bits |= (c0 & 7u) << len; len += (c0 >> 3) & 7u;
+        bits |= (c1 & 7u) << len; len += (c1 >> 3) & 7u;
+        bits |= ((c0 >> 6) & 31u) << len; len += (c0 >> 11) & 31u;
+        bits |= ((c1 >> 6) & 31u) << len; len += (c1 >> 11) & 31u;
+        vlc_put(vlc, bits, len, vl_end);
+      }
+      if (vlc.words * 4u >= vl_worst + 48u) overflow_b = 1;      // (cannot happen: vl_worst bounds the segment; the reserve is vl_worst + 64)
+    }
+    if (r + 2 < rows) named_bar_arrive(BAR_EMPTY + (r & 1), 2 * SE_BLOCKS);
+  }
+  __syncthreads();
+  if (!active) return;
+  const SplitTail t = s_tail[tid];
+  if (t.overflow || overflow_b) { atomicOr(status, 1u); results[bidx].len_head = 0; results[bidx].len_tail = 0; return; }
+  if (t.any_sig == 0) { results[bidx].len_head = 0; results[bidx].len_tail = 0; return; }   // block not included
+  MsWriter ms; ms.w0 = t.w0; ms.w1 = 0; ms.nbits = t.nbits; ms.words = t.words; ms.last_ff = t.last_ff;
+  terminate_block<SE_BLOCKS>(ms, vlc, mel, mel_buf, slot, blk.slot_cap, status, results[bidx]);
+}
+
 } // namespace
 
 void launch_ht_encode_serial(const EncBlock* blocks, uint32_t nblocks, uint32_t nfast, uint32_t max_width, const uint32_t* coef,
@@ -526,8 +739,14 @@ void launch_ht_encode_serial(const EncBlock* blocks, uint32_t nblocks, uint32_t 
   const size_t smem = (size_t)prev_quads * ES_THREADS * sizeof(uint16_t);
   cudaFuncSetAttribute(ht_encode_serial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid((nblocks + ES_THREADS - 1) / ES_THREADS), block(ES_THREADS);
-  if (nfast)
-    OJB_LAUNCH(ht_encode_fast_kernel, grid, block, 0, st, blocks, nblocks, coef, slots, results, tables, status);
+  if (nfast) {
+    static const bool split = [] { const char* e = getenv("OJB_ENC_SPLIT"); return !(e && atoi(e) == 0); }();
+    if (split) {           // two threads per block (default); OJB_ENC_SPLIT=0: one
+      dim3 g2((nblocks + SE_BLOCKS - 1) / SE_BLOCKS), b2(2 * SE_BLOCKS);
+      OJB_LAUNCH(ht_encode_split_kernel, g2, b2, 0, st, blocks, nblocks, coef, slots, results, tables, status);
+    } else
+      OJB_LAUNCH(ht_encode_fast_kernel, grid, block, 0, st, blocks, nblocks, coef, slots, results, tables, status);
+  }
   if (nfast < nblocks)
     OJB_LAUNCH(ht_encode_serial_kernel, grid, block, smem, st, blocks, nblocks, coef, slots, results, tables, status,
                prev_quads);

@@ -26,8 +26,18 @@ template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.as
 __device__ __forceinline__ void named_bar_sync(unsigned id, unsigned count) { ojb_emu::named_barrier(id, count, true); }
 __device__ __forceinline__ void named_bar_arrive(unsigned id, unsigned count) { ojb_emu::named_barrier(id, count, false); }
 #else
-__device__ __forceinline__ void named_bar_sync(unsigned id, unsigned count) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ void named_bar_arrive(unsigned id, unsigned count) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(count) : "memory"); }
+// (the barrier number is an immediate so that ptxas reserves only the barriers that are used: a register operand
+// makes it reserve all 16, and the SM's barrier pool then caps the CTAs per SM)
+template <unsigned ID> __device__ __forceinline__ void named_bar_sync_i(unsigned count) { asm volatile("bar.sync %0, %1;" :: "n"(ID), "r"(count) : "memory"); }
+template <unsigned ID> __device__ __forceinline__ void named_bar_arrive_i(unsigned count) { asm volatile("bar.arrive %0, %1;" :: "n"(ID), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_bar_sync(unsigned id, unsigned count) {
+  switch (id) { case 1: named_bar_sync_i<1>(count); break; case 2: named_bar_sync_i<2>(count); break;
+                case 3: named_bar_sync_i<3>(count); break; default: named_bar_sync_i<4>(count); break; }
+}
+__device__ __forceinline__ void named_bar_arrive(unsigned id, unsigned count) {
+  switch (id) { case 1: named_bar_arrive_i<1>(count); break; case 2: named_bar_arrive_i<2>(count); break;
+                case 3: named_bar_arrive_i<3>(count); break; default: named_bar_arrive_i<4>(count); break; }
+}
 #endif
 
 // ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) + mbarrier: one elected lane requests a whole contiguous run of
