@@ -1454,8 +1454,10 @@ void launch_ht_decode_serial(const DecBlock* blocks, uint32_t nblocks, uint32_t 
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid((nblocks + DEC1_THREADS - 1) / DEC1_THREADS), block(DEC1_THREADS);
   if (nfast) {           // blocks flagged DEC_FLAG_FAST (cleanup pass only, one output type)
-    static const bool split = [] { const char* e = getenv("OJB_DEC_SPLIT"); return !(e && atoi(e) == 0); }();
-    if (split) {           // two threads per block (default); OJB_DEC_SPLIT=0: one
+    // one thread per block by default; OJB_DEC_SPLIT=1 selects the producer / consumer pair (measured slower on a
+    // B200: the per-row hand-over couples 64 blocks to their slowest lane, profiles/r02c_split_ab.md)
+    static const bool split = [] { const char* e = getenv("OJB_DEC_SPLIT"); return e && atoi(e) != 0; }();
+    if (split) {
       auto kf = out_mode == DEC_OUT_INT ? ht_decode_split_kernel<0> : out_mode == DEC_OUT_FLOAT ? ht_decode_split_kernel<1>
                                                                                               : ht_decode_split_kernel<2>;
       dim3 g2((nblocks + SP_BLOCKS - 1) / SP_BLOCKS), b2(2 * SP_BLOCKS);

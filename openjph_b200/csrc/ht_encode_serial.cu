@@ -740,8 +740,10 @@ void launch_ht_encode_serial(const EncBlock* blocks, uint32_t nblocks, uint32_t 
   cudaFuncSetAttribute(ht_encode_serial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid((nblocks + ES_THREADS - 1) / ES_THREADS), block(ES_THREADS);
   if (nfast) {
-    static const bool split = [] { const char* e = getenv("OJB_ENC_SPLIT"); return !(e && atoi(e) == 0); }();
-    if (split) {           // two threads per block (default); OJB_ENC_SPLIT=0: one
+    // one thread per block by default; OJB_ENC_SPLIT=1 selects the two-thread split (measured slower on a B200,
+    // profiles/r02c_split_ab.md)
+    static const bool split = [] { const char* e = getenv("OJB_ENC_SPLIT"); return e && atoi(e) != 0; }();
+    if (split) {
       dim3 g2((nblocks + SE_BLOCKS - 1) / SE_BLOCKS), b2(2 * SE_BLOCKS);
       OJB_LAUNCH(ht_encode_split_kernel, g2, b2, 0, st, blocks, nblocks, coef, slots, results, tables, status);
     } else
