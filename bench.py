@@ -4,7 +4,7 @@
 A step = one pass of the hot path over one batch of frames: each frame is encoded to a codestream,
 then that codestream is decoded back (the metric BASELINE.json names is "Mpixels/s encode+decode").
 Workload at every N: synthetic 8192x8192 3-component 12-bit frames, reversible 5/3 + RCT, 5 levels,
-64x64 blocks (the headline configuration), OJB_BENCH_WORKERS (default 8) frames per GPU per step, each on its
+64x64 blocks (the headline configuration), OJB_BENCH_WORKERS (default 12) frames per GPU per step, each on its
 own codec object / CUDA stream so that the host phases (packet headers) and copies of one frame
 overlap the kernels of another (weak scaling; frames are independent, so there is no data-path
 collective -- only the final gather of the codestream sizes to rank 0).
@@ -431,7 +431,7 @@ def main():
     assert L.ojb_set_device(local) == 0, L.ojb_last_error()
     torch.cuda.set_device(local)
     affinity = bind_to_gpu_numa_node(torch, local)      # before any pinned allocation (first touch)
-    NW = int(os.environ.get("OJB_BENCH_WORKERS", "8"))      # frames in flight per GPU (one codec pair each)
+    NW = int(os.environ.get("OJB_BENCH_WORKERS", "12"))     # frames in flight per GPU (one codec pair each; value saturates at ~12, profiles/r02b_value_vs_frames_in_flight.log)
 
     def ck(rc):
         if rc != 0:
