@@ -611,7 +611,13 @@ void Decoder::read_headers(const uint8_t* data, size_t len, uint32_t sample_type
         }
   coded.assign(layout.num_blocks, CodedBlock());
   d_dec.reserve(std::max<size_t>(1, h_dec_proto.size()) * sizeof(DecBlock));
-  h_dec.reserve(std::max<size_t>(1, h_dec_proto.size()) * sizeof(DecBlock));
+  d_proto.reserve(std::max<size_t>(1, h_dec_proto.size()) * sizeof(DecBlock));
+  if (!h_dec_proto.empty())
+    CK(cudaMemcpy(d_proto.p, h_dec_proto.data(), h_dec_proto.size() * sizeof(DecBlock), cudaMemcpyHostToDevice));
+  h_dyn.reserve(std::max<size_t>(1, h_dec_proto.size()) * sizeof(DecDyn));
+  h_scr.reserve(std::max<size_t>(1, h_dec_proto.size()) * sizeof(uint64_t));
+  any_rev_blocks = any_irv_blocks = false;
+  for (const DecBlock& d : h_dec_proto) { if (d.flags & 2) any_irv_blocks = true; else any_rev_blocks = true; }
   d_bstatus.reserve(std::max<size_t>(1, h_dec_proto.size()) * 4);
   h_bstatus.reserve(std::max<size_t>(1, h_dec_proto.size()) * 4);
   header_sig = sig;
@@ -766,45 +772,47 @@ uint32_t Decoder::decode(void* const* planes, const uint32_t* strides, bool plan
     for (size_t pg = 0; pg < mirror.present.size(); ++pg) if (mirror.present[pg]) mirror.last_pages.push_back(pg);
   }
   uint32_t nb = (uint32_t)h_dec_proto.size();
-  DecBlock* hd = h_dec.as<DecBlock>();
+  DecDyn* hy = h_dyn.as<DecDyn>();
+  uint64_t* hs = h_scr.as<uint64_t>();
   size_t scratch_fixed = 0;
   if (nb) { const DecBlock& l = h_dec_proto[nb - 1]; uint32_t nq = (l.w + 1u) / 2, qs = (nq + 1) & ~1u; scratch_fixed = l.scratch_off + (size_t)qs * ((l.h + 1u) / 2); }
   size_t scratch = scratch_fixed;
-  uint32_t max_len1 = 0;
-  bool cleanup_only = true, any_rev = false, any_irv = false;    // lets the block decoder be specialised
-  // per-block scratch = quad records (fixed part, laid out per block) ... MagSgn words appended
-  // right after each block's records would move the records; keep records at proto offsets and put
-  // the MagSgn buffers in a second region addressed through scratch_off + records size.
-  // To keep one offset per block the records region of block b is re-based here.
+  uint32_t max_len1 = 0, nfast = 0;
+  bool cleanup_only = true;                 // lets the block decoder be specialised
+  const uint32_t dec_out = (any_rev_blocks && any_irv_blocks) ? (uint32_t)DEC_OUT_PER_BLOCK : any_irv_blocks ? (uint32_t)DEC_OUT_FLOAT : (uint32_t)DEC_OUT_INT;
+  const bool fast_ok = dec_out != DEC_OUT_PER_BLOCK && !no_fast_blocks;
+  // the frame's part of every block record (the geometry part sits in d_proto): lengths, passes, missing msbs, where
+  // the bytes are, and whether the block goes through the specialised kernel (one output type per launch).  Scratch
+  // (quad records + de-stuffed MagSgn of the general / two-step kernels) is laid out per frame.
   for (uint32_t b = 0; b < nb; ++b) {
     DecBlock d = h_dec_proto[b];
     const CodedBlock& cb = coded[b];
     d.len1 = cb.pass_len[0]; d.len2 = cb.pass_len[1];
     d.num_passes = cb.num_passes; d.missing_msbs = cb.missing_msbs; d.data_off = cb.data_off;
-    if (!block_wanted.empty() && !block_wanted[b]) { d.num_passes = 0; d.len1 = d.len2 = 0; d.w = d.h = 0; }   // another rank's tile
+    bool skip = false;
+    if (!block_wanted.empty() && !block_wanted[b]) { d.num_passes = 0; d.len1 = d.len2 = 0; skip = true; }   // another rank's tile
     if (block_res[b] < skip_read) {            // resolution not read: its bands are zero ...
       d.num_passes = 0; d.len1 = d.len2 = 0;
-      if (block_res[b] < skip_recon) d.w = d.h = 0;      // ... and not even needed: nothing to fill
+      if (block_res[b] < skip_recon) skip = true;        // ... and not even needed: nothing to fill
     }
+    if (skip) d.w = d.h = 0;
     uint32_t nq = (d.w + 1u) / 2, qs = (nq + 1) & ~1u, nqr = (d.h + 1u) / 2;
     scratch = (scratch + 3) & ~(size_t)3;
-    d.scratch_off = scratch;
+    hs[b] = scratch;
     scratch += (size_t)qs * nqr + (((d.len1 + 3) / 4 + 4 + 3) & ~3u);
     max_len1 = std::max(max_len1, d.len1);
     if (d.num_passes > 1) cleanup_only = false;
-    if (d.flags & 2) any_irv = true; else any_rev = true;
-    hd[b] = d;
+    if (fast_ok && dec_block_is_fast(d)) { d.flags |= DEC_FLAG_FAST; ++nfast; }
+    DecDyn y; y.data_off = d.data_off; y.len1 = (uint16_t)d.len1; y.len2 = (uint16_t)d.len2;
+    y.num_passes = d.num_passes; y.missing_msbs = d.missing_msbs; y.flags = d.flags; y.skip = skip ? 1 : 0;
+    hy[b] = y;
   }
-  const uint32_t dec_out = (any_rev && any_irv) ? (uint32_t)DEC_OUT_PER_BLOCK : any_irv ? (uint32_t)DEC_OUT_FLOAT : (uint32_t)DEC_OUT_INT;
-  // blocks of the common shape go through the specialised kernel (one output type per launch)
-  uint32_t nfast = 0;
-  if (dec_out != DEC_OUT_PER_BLOCK && !no_fast_blocks)
-    for (uint32_t b = 0; b < nb; ++b)
-      if (dec_block_is_fast(hd[b])) { hd[b].flags |= DEC_FLAG_FAST; ++nfast; }
   d_scratch.reserve((scratch + 64) * 4);
+  // scratch offsets are only read by blocks outside the specialised kernel
+  const bool need_scratch = nfast < nb || !(serial_block_decoder() || max_block_w > 64);
   host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
   mark(2);
-  if (nb) { launch_ctrl_copy(d_dec.p, h_dec.p, (size_t)nb * sizeof(DecBlock), stream); ++last_launches; }
+  if (nb) { launch_dec_merge(d_dec.as<DecBlock>(), d_proto.as<DecBlock>(), hy, need_scratch ? hs : nullptr, nb, stream); ++last_launches; }
   if (serial_block_decoder() || max_block_w > 64)
     launch_ht_decode_serial(d_dec.as<DecBlock>(), nb, nfast, max_block_w, cs_dev, d_coef.as<uint32_t>(), d_scratch.as<uint32_t>(),
                             d_tables_dec.as<uint16_t>(), dec_out, cleanup_only,

@@ -147,8 +147,9 @@ public:
   std::vector<uint8_t> header_sig;     // bytes of the main header the geometry was built for
   std::vector<CodedBlock> coded;
   std::vector<DecBlock> h_dec_proto;   // geometry part of DecBlock, per block
-  DeviceBuf d_cs, d_dec, d_scratch, d_bstatus;
-  PinnedBuf h_dec, h_bstatus;
+  DeviceBuf d_cs, d_dec, d_proto, d_scratch, d_bstatus;
+  PinnedBuf h_dyn, h_scr, h_bstatus;
+  bool any_rev_blocks = false, any_irv_blocks = false;
   void parse_tiles();
 };
 

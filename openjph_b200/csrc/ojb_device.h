@@ -59,6 +59,13 @@ struct DecBlock {
   uint8_t missing_msbs, num_passes, K_max, flags;   // flags bit0: stripe-causal, bit1: irreversible (float output)
   float delta;          // irreversible: step (already / 2^(31-K_max)); reversible: unused
 };
+// what changes from frame to frame for a block (the rest of DecBlock is geometry, uploaded once per parameter set):
+// 16 bytes per block cross PCIe per frame instead of 48
+struct DecDyn {
+  uint64_t data_off;
+  uint16_t len1, len2;
+  uint8_t num_passes, missing_msbs, flags, skip;       // skip: the block is not needed at all (w = h = 0)
+};
 // DecBlock::flags bit 2, set by the host per frame: the block qualifies for ht_decode_fast_kernel
 #define DEC_FLAG_FAST 4u
 inline bool dec_block_is_fast(const DecBlock& d) {

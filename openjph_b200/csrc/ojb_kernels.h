@@ -28,6 +28,11 @@ void launch_ht_decode_serial(const DecBlock* blocks, uint32_t nblocks, uint32_t 
                              uint32_t* coef, uint32_t* scratch, const uint16_t* tables, uint32_t out_mode,
                              bool cleanup_only, uint32_t* block_status, cudaStream_t st);
 
+// per-frame block records: blocks[b] = proto[b] with the frame's fields (dyn, and scratch offsets when given) applied.
+// dyn / scratch_off may be mapped pinned host memory (read by the SMs, like launch_ctrl_copy)
+void launch_dec_merge(DecBlock* blocks, const DecBlock* proto, const DecDyn* dyn, const uint64_t* scratch_off,
+                      uint32_t nblocks, cudaStream_t st);
+
 // forward / inverse DWT levels (dwt_fwd.cu / dwt_inv.cu).  jobs live in device memory.
 void launch_dwt_fwd(const DwtJob* jobs, uint32_t njobs, uint32_t total_ctas, bool reversible,
                     uint32_t max_ncomp, const void* image, uint32_t* coef, cudaStream_t st);
