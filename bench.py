@@ -292,12 +292,51 @@ def sharded_block(a, rank, world, L, ob, np, torch, dist, C, _lib, peak):
         ms_enc = timed_loop(enc, steps)
         ms_dec = timed_loop(dec, steps)
         ms_both = timed_loop(lambda: (enc(), dec()), steps)
+        # device-resident form: tiles already in each rank's HBM, codestream gathered into rank 0's HBM and decoded from
+        # there, decoded image gathered into rank 0's HBM -- no PCIe traffic besides headers, so what is timed is the
+        # sharded compute + the NCCL exchange (the host-buffer form above is bound by rank 0's PCIe link either way)
+        ck(L.ojb_shard_enc_upload(sh.h, planes, None))
+        nres = C.c_uint64()
+        lens_t = torch.zeros(1, dtype=torch.int64, device="cuda")
+
+        def res():
+            ck(L.ojb_shard_enc_encode_resident(sh.h, C.byref(nres)))
+            ck(L.ojb_shard_dec_decode_resident(sh.h, L.ojb_shard_device_codestream(sh.h), cs_len, st, 0, C.byref(fi)))
+        res(); res()
+        ms_res = timed_loop(res, steps)
+        one_gpu_res_ms = None
+        if rank == 0:
+            enc1 = L.ojb_enc_create(); dec1 = L.ojb_dec_create()
+            try:
+                assert L.ojb_enc_configure(enc1, C.byref(params), st) == 0, L.ojb_last_error()
+                assert L.ojb_enc_upload_frame(enc1, planes, None) == 0, L.ojb_last_error()
+                csd = torch.empty(cap, dtype=torch.uint8, device="cuda")
+                n1 = C.c_uint64()
+
+                def single_res():
+                    assert L.ojb_enc_encode_resident(enc1, csd.data_ptr(), cap, C.byref(n1), 1) == 0, L.ojb_last_error()
+                    assert L.ojb_dec_read_headers_device(dec1, csd.data_ptr(), n1.value, st, C.byref(fi)) == 0, L.ojb_last_error()
+                    assert L.ojb_dec_decode_resident(dec1) == 0, L.ojb_last_error()
+                single_res(); single_res()
+                torch.cuda.synchronize(); t0 = time.perf_counter()
+                for _ in range(steps):
+                    single_res()
+                torch.cuda.synchronize(); one_gpu_res_ms = (time.perf_counter() - t0) / steps * 1e3
+            finally:
+                L.ojb_enc_destroy(enc1); L.ojb_dec_destroy(dec1)
+        dist.barrier()
         if rank == 0:
             pix = frame[0].shape[0] * frame[0].shape[1]
-            e.update({"ms_per_frame_encode": round(ms_enc, 3), "ms_per_frame_decode": round(ms_dec, 3), "ms_per_frame": round(ms_both, 3),
-                      "Mpixels_per_s": round(pix / ms_both / 1e3, 1), "one_gpu_ms_per_frame": round(one_gpu_ms, 3),
-                      "time_vs_one_gpu": round(ms_both / one_gpu_ms, 3), "codestream_bytes": cs_len,
-                      "note": "host buffers on rank 0 (pinned): every rank uploads its own tiles, rank 0 receives the whole codestream / image"})
+            e.update({"host_buffers": {"ms_per_frame_encode": round(ms_enc, 3), "ms_per_frame_decode": round(ms_dec, 3), "ms_per_frame": round(ms_both, 3),
+                                       "Mpixels_per_s": round(pix / ms_both / 1e3, 1), "one_gpu_ms_per_frame": round(one_gpu_ms, 3),
+                                       "time_vs_one_gpu": round(ms_both / one_gpu_ms, 3),
+                                       "note": "pinned host buffers on rank 0: every rank uploads its own tiles, rank 0's PCIe link carries the whole "
+                                               "codestream and the whole decoded image, so this form cannot scale"},
+                      "device_resident": {"ms_per_frame": round(ms_res, 3), "Mpixels_per_s": round(pix / ms_res / 1e3, 1),
+                                          "one_gpu_ms_per_frame": round(one_gpu_res_ms, 3), "time_vs_one_gpu": round(ms_res / one_gpu_res_ms, 3),
+                                          "note": "one frame at a time (latency, not a stream): encode + NCCL gather of tile-parts + NCCL broadcast + decode + "
+                                                  "NCCL gather of samples, against the same two calls on one GPU"},
+                      "codestream_bytes": cs_len})
             out["entries"].append(e)
         sh.close()
 
@@ -324,8 +363,9 @@ def sharded_block(a, rank, world, L, ob, np, torch, dist, C, _lib, peak):
             assert L.ojb_enc_configure(e_, C.byref(p5), ob.U16) == 0, L.ojb_last_error()
             encs.append(e_)
         per = 3840 * 2160 * 3 * 2
-        dev = torch.empty(len(mine) * per // 4 + (1 << 20), dtype=torch.uint8, device="cuda")     # q ~ lossy: well under 25 % of raw
-        gat = torch.empty((nfr * per // 4 + (1 << 20)) if rank == 0 else 16, dtype=torch.uint8, device="cuda")
+        slot = (per * 6 // 10 + 4095) & ~4095                   # the default step size gives ~6 bits / sample on this frame
+        dev = torch.empty(len(mine) * slot + (1 << 20), dtype=torch.uint8, device="cuda")
+        gat = torch.empty((nfr * slot + (1 << 20)) if rank == 0 else 16, dtype=torch.uint8, device="cuda")
         host = torch.empty(gat.numel(), dtype=torch.uint8, pin_memory=True)
         sh = sharding.NativeShard()
         offs = (C.c_uint64 * (world + 1))()
@@ -334,7 +374,6 @@ def sharded_block(a, rank, world, L, ob, np, torch, dist, C, _lib, peak):
 
         def batch():
             lens = [0] * len(mine)
-            slot = per // 4
 
             def work(k):
                 n_ = C.c_uint64()

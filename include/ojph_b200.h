@@ -281,6 +281,14 @@ int ojb_shard_enc_encode(ojb_shard* s, const void* const* planes, const uint32_t
  * decoded components arrive in planes on the writer rank */
 int ojb_shard_dec_decode(ojb_shard* s, const uint8_t* j2c, uint64_t len, uint32_t sample_type, uint32_t writer_rank,
                          void* const* planes, const uint32_t* strides, ojb_frame_info* info);
+/* device-resident forms: tiles uploaded once per rank, codestream left in / read from the writer's device memory, decoded
+ * image left in the writer's device image buffer */
+int ojb_shard_enc_upload(ojb_shard* s, const void* const* planes, const uint32_t* strides);
+int ojb_shard_enc_encode_resident(ojb_shard* s, uint64_t* out_len);
+const void* ojb_shard_device_codestream(ojb_shard* s);
+int ojb_shard_dec_decode_resident(ojb_shard* s, const void* dev_j2c, uint64_t len, uint32_t sample_type, uint32_t writer_rank,
+                                  ojb_frame_info* info);
+void* ojb_shard_device_plane(ojb_shard* s, uint32_t comp);
 /* frame-parallel batches: variable-length gather of device buffers (one codestream per rank) to the writer's
  * device buffer, rank order; offsets[world + 1] */
 int ojb_shard_gatherv(ojb_shard* s, const void* dev, uint64_t bytes, uint32_t writer_rank, void* out_dev, uint64_t out_cap,

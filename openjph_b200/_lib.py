@@ -132,6 +132,11 @@ SYMBOLS = {
     "ojb_shard_enc_configure": (_I, [_VP, C.POINTER(Params), _U32, _U32]),
     "ojb_shard_enc_encode": (_I, [_VP, C.POINTER(_VP), C.POINTER(_U32), _VP, _U64, C.POINTER(_U64)]),
     "ojb_shard_dec_decode": (_I, [_VP, _VP, _U64, _U32, _U32, C.POINTER(_VP), C.POINTER(_U32), C.POINTER(FrameInfo)]),
+    "ojb_shard_enc_upload": (_I, [_VP, C.POINTER(_VP), C.POINTER(_U32)]),
+    "ojb_shard_enc_encode_resident": (_I, [_VP, C.POINTER(_U64)]),
+    "ojb_shard_device_codestream": (_VP, [_VP]),
+    "ojb_shard_dec_decode_resident": (_I, [_VP, _VP, _U64, _U32, _U32, C.POINTER(FrameInfo)]),
+    "ojb_shard_device_plane": (_VP, [_VP, _U32]),
     "ojb_shard_gatherv": (_I, [_VP, _VP, _U64, _U32, _VP, _U64, C.POINTER(_U64)]),
     "ojb_shard_timings": (None, [_VP, C.POINTER(C.c_float)]),
     "ojb_shard_rank": (_U32, [_VP]),

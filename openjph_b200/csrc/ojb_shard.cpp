@@ -160,6 +160,7 @@ struct ojb_shard {
   DeviceBuf d_parts, d_final, d_stage, d_cs;
   PinnedBuf h_hdr;
   float ms_encode = 0, ms_gather = 0;       // last call: this rank's codec time, exchange + assembly + D2H
+  size_t final_len = 0;                     // writer: length of the codestream in d_final
 };
 
 static thread_local char g_serr[1024] = "";
@@ -235,8 +236,8 @@ int ojb_shard_enc_configure(ojb_shard* s, const ojb_params* p, uint32_t sample_t
 
 // planes: the WHOLE image on the host (every rank passes the same pointers or at least valid memory for its own
 // tiles); out / out_cap / out_len matter on the writer only.
-int ojb_shard_enc_encode(ojb_shard* s, const void* const* planes, const uint32_t* strides,
-                         uint8_t* out, uint64_t out_cap, uint64_t* out_len) {
+static int shard_encode(ojb_shard* s, const void* const* planes, const uint32_t* strides,
+                        uint8_t* out, uint64_t out_cap, uint64_t* out_len, bool encode_only_upload) {
   return sguarded(s, [&] {
     if (!s->enc_ready) fail(0x000B0013, "encoder is not configured");
     Encoder& E = s->enc; Comm& C = *s->comm;
@@ -245,22 +246,24 @@ int ojb_shard_enc_encode(ojb_shard* s, const void* const* planes, const uint32_t
     const uint32_t ntiles = (uint32_t)E.layout.tiles.size();
     cudaEvent_t e0 = E.ev[CodecBase::EV_MAX - 3], e1 = E.ev[CodecBase::EV_MAX - 2], e2 = E.ev[CodecBase::EV_MAX - 1];
     cudaEventRecord(e0, E.stream);
-    // 1. this rank's tile rectangles -> device image buffer
+    // 1. this rank's tile rectangles -> device image buffer (planes == NULL: they are there already)
     size_t my_in = 0;
     for (const TileGeom& t : E.layout.tiles) {
       if (!E.tile_wanted(t.idx)) continue;
       for (uint32_t c = 0; c < nc; ++c) {
         const Rect& r = t.comps[c].rect;
         if (r.w == 0 || r.h == 0) continue;
+        my_in += (size_t)r.w * r.h * es;
+        if (!planes) continue;
         const uint32_t cx0 = div_ceil(P.XOsiz, P.comps[c].dx), cy0 = div_ceil(P.YOsiz, P.comps[c].dy);
         const uint32_t st = strides ? strides[c] : E.img_w[c];
         const size_t so = ((size_t)(r.y0 - cy0) * st + (r.x0 - cx0)) * es, dof = ((size_t)(r.y0 - cy0) * E.img_w[c] + (r.x0 - cx0)) * es;
         cuda_check(cudaMemcpy2DAsync(E.d_image.as<uint8_t>() + E.img_off[c] + dof, (size_t)E.img_w[c] * es,
                                      (const uint8_t*)planes[c] + so, (size_t)st * es, (size_t)r.w * es, r.h,
                                      cudaMemcpyHostToDevice, E.stream), "tile upload");
-        my_in += (size_t)r.w * r.h * es;
       }
     }
+    if (encode_only_upload) { cuda_check(cudaStreamSynchronize(E.stream), "tile upload"); return; }
     // 2. code this rank's tiles: tile-parts, back to back, in device memory
     s->d_parts.reserve(my_in * 2 + (1u << 20));
     const size_t my_bytes = E.encode(nullptr, nullptr, true, s->d_parts.as<uint8_t>(), s->d_parts.cap, true);
@@ -307,7 +310,7 @@ int ojb_shard_enc_encode(ojb_shard* s, const void* const* planes, const uint32_t
       hdr_len = hdr.size();
       total = hdr_len; for (uint32_t t = 0; t < ntiles; ++t) total += tbytes[t];
       total += 2;
-      if (total > out_cap) fail(0x000B0030, "output buffer too small: need %zu bytes, have %zu", total, (size_t)out_cap);
+      if (out && total > out_cap) fail(0x000B0030, "output buffer too small: need %zu bytes, have %zu", total, (size_t)out_cap);
       s->d_final.reserve(total + 64);
       size_t pos = hdr_len;
       for (uint32_t t = 0; t < ntiles; ++t) {
@@ -331,8 +334,9 @@ int ojb_shard_enc_encode(ojb_shard* s, const void* const* planes, const uint32_t
     (void)my_bytes;
     C.exchange(sends, recvs, E.stream);
     if (C.rank == s->writer) {
-      cuda_check(cudaMemcpyAsync(out, s->d_final.p, total, cudaMemcpyDeviceToHost, E.stream), "codestream D2H");
+      if (out) cuda_check(cudaMemcpyAsync(out, s->d_final.p, total, cudaMemcpyDeviceToHost, E.stream), "codestream D2H");
       if (out_len) *out_len = total;
+      s->final_len = total;
     } else if (out_len) *out_len = 0;
     cudaEventRecord(e2, E.stream);
     cuda_check(cudaStreamSynchronize(E.stream), "shard encode");
@@ -340,10 +344,24 @@ int ojb_shard_enc_encode(ojb_shard* s, const void* const* planes, const uint32_t
   });
 }
 
+int ojb_shard_enc_encode(ojb_shard* s, const void* const* planes, const uint32_t* strides,
+                         uint8_t* out, uint64_t out_cap, uint64_t* out_len) {
+  return shard_encode(s, planes, strides, out, out_cap, out_len, false);
+}
+// device-resident form: every rank uploads its tiles once (ojb_shard_enc_upload), ojb_shard_enc_encode_resident leaves the
+// codestream in the writer's device memory (ojb_shard_device_codestream)
+int ojb_shard_enc_upload(ojb_shard* s, const void* const* planes, const uint32_t* strides) {
+  return shard_encode(s, planes, strides, nullptr, 0, nullptr, true);
+}
+int ojb_shard_enc_encode_resident(ojb_shard* s, uint64_t* out_len) {
+  return shard_encode(s, nullptr, nullptr, nullptr, 0, out_len, false);
+}
+const void* ojb_shard_device_codestream(ojb_shard* s) { return s->d_final.p; }
+
 // cs / len: the codestream on the writer's host (ignored elsewhere).  planes: where the writer wants the decoded
 // components (whole image, host); ignored on the other ranks.  info (may be NULL) is filled on every rank.
-int ojb_shard_dec_decode(ojb_shard* s, const uint8_t* cs, uint64_t len, uint32_t sample_type, uint32_t writer_rank,
-                         void* const* planes, const uint32_t* strides, ojb_frame_info* info) {
+static int shard_decode(ojb_shard* s, const uint8_t* cs, bool cs_on_device, uint64_t len, uint32_t sample_type, uint32_t writer_rank,
+                        void* const* planes, const uint32_t* strides, bool keep_on_device, ojb_frame_info* info) {
   return sguarded(s, [&] {
     Decoder& D = s->dec; Comm& C = *s->comm;
     if (sample_type > 2) fail(0x000B0012, "unknown sample container");
@@ -356,7 +374,8 @@ int ojb_shard_dec_decode(ojb_shard* s, const uint8_t* cs, uint64_t len, uint32_t
     if (n < 4) fail(0x00050041, "error reading SIZ marker");
     s->d_cs.reserve(n + 64);
     cudaEventRecord(e0, D.stream);
-    if (C.rank == writer_rank) cuda_check(cudaMemcpyAsync(s->d_cs.p, cs, n, cudaMemcpyHostToDevice, D.stream), "codestream H2D");
+    if (C.rank == writer_rank)
+      cuda_check(cudaMemcpyAsync(s->d_cs.p, cs, n, cs_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, D.stream), "codestream to the broadcast buffer");
     cuda_check(cudaMemsetAsync(s->d_cs.as<uint8_t>() + n, 0, 32, D.stream), "codestream slack");
     C.bcast(s->d_cs.p, n, writer_rank, D.stream);
     cuda_check(cudaStreamSynchronize(D.stream), "codestream broadcast");
@@ -408,6 +427,20 @@ int ojb_shard_dec_decode(ojb_shard* s, const uint8_t* cs, uint64_t len, uint32_t
           recvs.push_back(Xfer{ t % C.world, s->d_stage.as<uint8_t>() + toff[t], toff[t + 1] - toff[t] });
     }
     C.exchange(sends, recvs, D.stream);
+    if (C.rank == writer_rank && keep_on_device) {        // the other ranks' tiles into the writer's device image buffer
+      for (uint32_t t = 0; t < ntiles; ++t) {
+        if (t % C.world == C.rank) continue;
+        size_t o = toff[t];
+        for (uint32_t c = 0; c < nc; ++c) {
+          const Rect& r = D.layout.tiles[t].comps[c].rect;
+          if (r.w == 0 || r.h == 0) continue;
+          cuda_check(cudaMemcpy2DAsync(D.d_image.as<uint8_t>() + D.img_off[c] + plane_pos(r, c, D.img_w[c]), (size_t)D.img_w[c] * es,
+                                       s->d_stage.as<uint8_t>() + o, (size_t)r.w * es, (size_t)r.w * es, r.h,
+                                       cudaMemcpyDeviceToDevice, D.stream), "tile unpack");
+          o += (size_t)r.w * r.h * es;
+        }
+      }
+    }
     if (C.rank == writer_rank && planes) {
       for (uint32_t t = 0; t < ntiles; ++t) {
         size_t o = toff[t];
@@ -430,6 +463,21 @@ int ojb_shard_dec_decode(ojb_shard* s, const uint8_t* cs, uint64_t len, uint32_t
     cuda_check(cudaStreamSynchronize(D.stream), "shard decode");
     cudaEventElapsedTime(&s->ms_encode, e0, e1); cudaEventElapsedTime(&s->ms_gather, e1, e2);
   });
+}
+
+int ojb_shard_dec_decode(ojb_shard* s, const uint8_t* cs, uint64_t len, uint32_t sample_type, uint32_t writer_rank,
+                         void* const* planes, const uint32_t* strides, ojb_frame_info* info) {
+  return shard_decode(s, cs, false, len, sample_type, writer_rank, planes, strides, false, info);
+}
+// device-resident form: the codestream is in the writer's device memory, the decoded image stays in the writer's
+// device image buffer (ojb_shard_device_plane)
+int ojb_shard_dec_decode_resident(ojb_shard* s, const void* dev_cs, uint64_t len, uint32_t sample_type, uint32_t writer_rank,
+                                  ojb_frame_info* info) {
+  return shard_decode(s, static_cast<const uint8_t*>(dev_cs), true, len, sample_type, writer_rank, nullptr, nullptr, true, info);
+}
+void* ojb_shard_device_plane(ojb_shard* s, uint32_t comp) {
+  if (comp >= s->dec.img_off.size()) return nullptr;
+  return s->dec.d_image.as<uint8_t>() + s->dec.img_off[comp];
 }
 
 // variable-length gather of device buffers (whole codestreams of a frame-parallel batch, BASELINE configs[4]):

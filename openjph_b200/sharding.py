@@ -454,6 +454,29 @@ class NativeShard:
         self.info = fi
         return planes
 
+    # ---- device-resident forms (tiles uploaded once per rank; codestream and decoded image stay on the writer's device)
+    def upload(self, planes):
+        arrs = [np.ascontiguousarray(a, cs_mod._NP[self.sample_type]) for a in planes]
+        ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+        self._check(self.L.ojb_shard_enc_upload(self.h, ptrs, None))
+
+    def encode_resident(self):
+        """-> (device address of the codestream on the writer, length); (None, 0) elsewhere"""
+        n = C.c_uint64()
+        self._check(self.L.ojb_shard_enc_encode_resident(self.h, C.byref(n)))
+        return (self.L.ojb_shard_device_codestream(self.h), int(n.value)) if self.rank == self.writer else (None, 0)
+
+    def decode_resident(self, dev_ptr, length, sample_type=cs_mod.I32, writer=0):
+        """codestream at dev_ptr on the writer; decoded planes stay in the writer's device image buffer
+        (device_plane(c)); returns the frame info"""
+        fi = _lib.FrameInfo()
+        self._check(self.L.ojb_shard_dec_decode_resident(self.h, dev_ptr, length, sample_type, writer, C.byref(fi)))
+        self.info = fi
+        return fi
+
+    def device_plane(self, comp):
+        return self.L.ojb_shard_device_plane(self.h, comp)
+
     @property
     def timings(self):
         t = (C.c_float * 2)()

@@ -131,6 +131,21 @@ def _native_worker(rank, world, port, q):
                     ok = ok and all(np.abs(a.astype(np.int64) - b).max() <= tol for a, b in zip(planes, ref_planes))
                 else:
                     ok = ok and planes is None
+            # device-resident forms (under the emulator "device" memory is host memory: read it back directly)
+            import ctypes
+            sh.upload(frame)
+            addr, n = sh.encode_resident()
+            want = refharness.encode(p, frame) if rank == writer else None
+            if rank == writer and p.reversible:
+                ok = ok and ctypes.string_at(addr, n) == want
+            lens = [n]
+            dist.broadcast_object_list(lens, src=writer)
+            fi = sh.decode_resident(addr, lens[0], ob.I32, writer)
+            if rank == writer:
+                ref_planes, _ = refharness.decode(want if p.reversible else ctypes.string_at(addr, n))
+                for c, rp in enumerate(ref_planes):
+                    got = np.frombuffer(ctypes.string_at(sh.device_plane(c), rp.size * 4), np.int32).reshape(rp.shape)
+                    ok = ok and np.abs(got.astype(np.int64) - rp).max() <= (0 if p.reversible else 1)
             sh.close()
         q.put((rank, bool(ok)))
     finally:
