@@ -21,9 +21,12 @@ namespace ojb {
 
 namespace {
 
-template <bool REV> struct Px;
-template <> struct Px<true>  { typedef int T; };
-template <> struct Px<false> { typedef float T; };
+// sample type of the transform: int32 (5/3), fp32 (9/7), int64 (5/3 when the precision exceeds 32 bits: the reference's
+// 64-bit line buffers, rev_vert_step / rev_horz_ana on si64, ojph_transform.cpp:316-332, :497-509)
+template <bool REV, bool WIDE> struct Px;
+template <> struct Px<true, false>  { typedef int T; typedef int I; };
+template <> struct Px<false, false> { typedef float T; typedef int I; };
+template <> struct Px<true, true>   { typedef long long T; typedef long long I; };
 
 __device__ __forceinline__ int load_sample(const void* img, uint32_t type, uint64_t byte_off, size_t idx) {
   const unsigned char* base = reinterpret_cast<const unsigned char*>(img) + byte_off;
@@ -33,19 +36,20 @@ __device__ __forceinline__ int load_sample(const void* img, uint32_t type, uint6
 }
 
 // 5/3 lifting step on smem (predict: odd -= (a+b)>>1 ; update: even += (a+b+2)>>2)
-__device__ __forceinline__ int rev_pred(int d, int a, int b) { return d - ((a + b) >> 1); }
-__device__ __forceinline__ int rev_upd(int d, int a, int b) { return d + ((a + b + 2) >> 2); }
+template <typename I> __device__ __forceinline__ I rev_pred(I d, I a, I b) { return d - ((a + b) >> 1); }
+template <typename I> __device__ __forceinline__ I rev_upd(I d, I a, I b) { return d + ((a + b + 2) >> 2); }
 // 9/7: dst += coeff * (a + b), separate multiply and add (no FMA), ojph_transform.cpp:703
 __device__ __forceinline__ float irv_step(float d, float a, float b, float c) {
   return __fadd_rn(d, __fmul_rn(c, __fadd_rn(a, b)));
 }
 
-template <bool REV>
+template <bool REV, bool WIDE>
 __global__ void __launch_bounds__(DW_THREADS)
 dwt_fwd_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, const void* __restrict__ image,
                uint32_t* __restrict__ coef)
 {
-  typedef typename Px<REV>::T T;
+  typedef typename Px<REV, WIDE>::T T;
+  typedef typename Px<REV, WIDE>::I I;
   OJB_DYN_SMEM(T, smem);
   __shared__ DwtJob sj;
   {
@@ -71,19 +75,24 @@ dwt_fwd_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, const void* __re
     const int v = reflect_coord(V0 - DW_H + (int)r, y0, y1 - 1);
     T val[3];
     if (J.first) {
-      int iv[3];
+      I iv[3];
       for (uint32_t k = 0; k < nc; ++k)
-        iv[k] = load_sample(image, J.src_type, J.full_off[k],
-                            (size_t)(v - y0) * J.full_stride[k] + (size_t)(u - x0));
+        iv[k] = (I)load_sample(image, J.src_type, J.full_off[k],
+                               (size_t)(v - y0) * J.full_stride[k] + (size_t)(u - x0));
       if (J.nlt_mask) {
-        const int bias = (1 << (J.bit_depth - 1)) + 1;
-        for (uint32_t k = 0; k < nc; ++k) if ((J.nlt_mask >> k) & 1u) iv[k] = nlt_type3(iv[k], bias);
+        const I bias = ((I)1 << (J.bit_depth - 1)) + 1;
+        for (uint32_t k = 0; k < nc; ++k) if ((J.nlt_mask >> k) & 1u) iv[k] = iv[k] >= 0 ? iv[k] : -iv[k] - bias;
       }
       if (REV) {
-        const int shift = J.is_signed ? 0 : (1 << (J.bit_depth - 1));
+        const I shift = J.is_signed ? (I)0 : ((I)1 << (J.bit_depth - 1));
         for (uint32_t k = 0; k < nc; ++k) iv[k] -= shift;
+        // with the colour transform the reference converts into 32-bit temporary lines whatever the precision
+        // (tile::pre_alloc / finalize_alloc, ojph_tile.cpp:181-183, :312-317): the level-shifted samples wrap to
+        // si32 before the (64-bit) RCT -- byte-identical streams for 32-bit samples need the same
+        if (WIDE && nc == 3)
+          for (uint32_t k = 0; k < nc; ++k) iv[k] = (I)(int)iv[k];
         if (nc == 3) {   // RCT
-          int rr = iv[0], gg = iv[1], bb = iv[2];
+          I rr = iv[0], gg = iv[1], bb = iv[2];
           iv[0] = (rr + (gg << 1) + bb) >> 2; iv[1] = bb - gg; iv[2] = rr - gg;
         }
         for (uint32_t k = 0; k < nc; ++k) val[k] = (T)iv[k];
@@ -91,7 +100,7 @@ dwt_fwd_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, const void* __re
         const float mul = (float)(1.0 / (double)(1ull << J.bit_depth));
         const int half = J.is_signed ? 0 : (1 << (J.bit_depth - 1));
         float f[3];
-        for (uint32_t k = 0; k < nc; ++k) f[k] = __fmul_rn((float)(iv[k] - half), mul);
+        for (uint32_t k = 0; k < nc; ++k) f[k] = __fmul_rn((float)((int)iv[k] - half), mul);
         if (nc == 3) {   // ICT
           float rr = f[0], gg = f[1], bb = f[2];
           float yy = __fadd_rn(__fadd_rn(__fmul_rn(ICT_ALPHA_RF, rr), __fmul_rn(ICT_ALPHA_GF, gg)),
@@ -124,7 +133,7 @@ dwt_fwd_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, const void* __re
             const int rr = e / DW_COLS, c = e - rr * DW_COLS;
             const int r = rfirst + 2 * rr;
             T d = t[r * DW_PITCH + c], a = t[(r - 1) * DW_PITCH + c], b = t[(r + 1) * DW_PITCH + c];
-            if (REV) d = (T)((s == 1) ? rev_pred((int)d, (int)a, (int)b) : rev_upd((int)d, (int)a, (int)b));
+            if (REV) d = (T)((s == 1) ? rev_pred<I>((I)d, (I)a, (I)b) : rev_upd<I>((I)d, (I)a, (I)b));
             else {
               const float cf = (s == 1) ? IRV_ALPHA : (s == 2) ? IRV_BETA : (s == 3) ? IRV_GAMMA : IRV_DELTA;
               d = (T)irv_step((float)d, (float)a, (float)b, cf);
@@ -150,7 +159,7 @@ dwt_fwd_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, const void* __re
         T* t = smem + k * DW_TILE_WORDS;
         for (uint32_t e = tid; e < DW_ROWS * DW_COLS; e += DW_THREADS) {
           const uint32_t r = e / DW_COLS, c = e - r * DW_COLS;
-          t[r * DW_PITCH + c] = REV ? (T)((int)t[r * DW_PITCH + c] << 1) : (T)__fmul_rn((float)t[r * DW_PITCH + c], 2.0f);
+          t[r * DW_PITCH + c] = REV ? (T)((I)t[r * DW_PITCH + c] << 1) : (T)__fmul_rn((float)t[r * DW_PITCH + c], 2.0f);
         }
       }
       __syncthreads();
@@ -167,7 +176,7 @@ dwt_fwd_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, const void* __re
             const int rr = e / ncols, j = e - rr * ncols;
             const int r = DW_H + rr, c = cfirst + 2 * j;
             T d = t[r * DW_PITCH + c], a = t[r * DW_PITCH + c - 1], b = t[r * DW_PITCH + c + 1];
-            if (REV) d = (T)((s == 1) ? rev_pred((int)d, (int)a, (int)b) : rev_upd((int)d, (int)a, (int)b));
+            if (REV) d = (T)((s == 1) ? rev_pred<I>((I)d, (I)a, (I)b) : rev_upd<I>((I)d, (I)a, (I)b));
             else {
               const float cf = (s == 1) ? IRV_ALPHA : (s == 2) ? IRV_BETA : (s == 3) ? IRV_GAMMA : IRV_DELTA;
               d = (T)irv_step((float)d, (float)a, (float)b, cf);
@@ -202,11 +211,18 @@ dwt_fwd_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, const void* __re
           bx = (u >> 1) - (bh ? (x0 >> 1) : ((x0 + 1) >> 1));
           by = (v >> 1) - (bv ? (y0 >> 1) : ((y0 + 1) >> 1));
           if (hscale) val = (T)__fmul_rn((float)val, bh ? IRV_K : (1.0f / IRV_K));
-          if (wodd1) val = REV ? (T)((int)val << 1) : (T)__fmul_rn((float)val, 2.0f);
+          if (wodd1) val = REV ? (T)((I)val << 1) : (T)__fmul_rn((float)val, 2.0f);
         }
         if (band == 0 && !J.last) {
           reinterpret_cast<T*>(coef)[J.ll_off[k] + (size_t)by * J.ll_stride[k] + (size_t)bx] = val;
         } else {
+          if (WIDE) {          // 64-bit sign-magnitude words (gen_rev_tx_to_cb64, ojph_codestream_gen.cpp:81-100)
+            const long long iv = (long long)val;
+            const unsigned long long mag = (unsigned long long)(iv < 0 ? -iv : iv) << J.band_shift[k][band];
+            reinterpret_cast<unsigned long long*>(coef)[J.band_off[k][band] + (size_t)by * J.band_stride[k][band] + (size_t)bx] =
+              (iv < 0 ? 0x8000000000000000ull : 0ull) | mag;
+            continue;
+          }
           uint32_t sm;
           if (REV) {
             const int iv = (int)val;
@@ -232,16 +248,20 @@ void dwt_tiling(uint32_t x0, uint32_t y0, uint32_t w, uint32_t h, uint32_t& tx, 
 }
 
 void launch_dwt_fwd(const DwtJob* jobs, uint32_t njobs, uint32_t total_ctas, bool reversible,
-                    uint32_t max_ncomp, const void* image, uint32_t* coef, cudaStream_t st)
+                    uint32_t max_ncomp, const void* image, uint32_t* coef, cudaStream_t st, bool wide)
 {
   if (total_ctas == 0) return;
-  size_t smem = (size_t)max_ncomp * DW_TILE_WORDS * 4;
-  if (reversible) {
-    auto k = dwt_fwd_kernel<true>;
+  size_t smem = (size_t)max_ncomp * DW_TILE_WORDS * (wide ? 8 : 4);
+  if (reversible && wide) {
+    auto k = dwt_fwd_kernel<true, true>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    OJB_LAUNCH(k, dim3(total_ctas), dim3(DW_THREADS), smem, st, jobs, njobs, image, coef);
+  } else if (reversible) {
+    auto k = dwt_fwd_kernel<true, false>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     OJB_LAUNCH(k, dim3(total_ctas), dim3(DW_THREADS), smem, st, jobs, njobs, image, coef);
   } else {
-    auto k = dwt_fwd_kernel<false>;
+    auto k = dwt_fwd_kernel<false, false>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     OJB_LAUNCH(k, dim3(total_ctas), dim3(DW_THREADS), smem, st, jobs, njobs, image, coef);
   }

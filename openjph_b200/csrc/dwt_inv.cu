@@ -16,9 +16,10 @@ namespace ojb {
 
 namespace {
 
-template <bool REV> struct PxI;
-template <> struct PxI<true>  { typedef int T; };
-template <> struct PxI<false> { typedef float T; };
+template <bool REV, bool WIDE> struct PxI;
+template <> struct PxI<true, false>  { typedef int T; typedef int I; };
+template <> struct PxI<false, false> { typedef float T; typedef int I; };
+template <> struct PxI<true, true>   { typedef long long T; typedef long long I; };      // 64-bit lines (precision > 32 bits)
 
 // 8 / 16-bit containers clamp to the component's range [0, smax] as the reference's file writers do
 __device__ __forceinline__ void store_sample(void* img, uint32_t type, uint64_t byte_off, size_t idx, int v, int smax) {
@@ -33,12 +34,13 @@ __device__ __forceinline__ void store_sample(void* img, uint32_t type, uint64_t 
 // differ only on exact halves, which zero-decomposition 9/7 components produce systematically.
 __device__ __forceinline__ int round_haz(float t) { return __float2int_rn(t); }
 
-template <bool REV>
+template <bool REV, bool WIDE>
 __global__ void __launch_bounds__(DW_THREADS)
 dwt_inv_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, void* __restrict__ image,
                uint32_t* __restrict__ coef)
 {
-  typedef typename PxI<REV>::T T;
+  typedef typename PxI<REV, WIDE>::T T;
+  typedef typename PxI<REV, WIDE>::I I;
   OJB_DYN_SMEM(T, smem);
   __shared__ DwtJob sj;
   {
@@ -108,8 +110,8 @@ dwt_inv_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, void* __restrict
             const int c = cfirst + 2 * j;
             T d = t[r * DW_PITCH + c], a = t[r * DW_PITCH + c - 1], b = t[r * DW_PITCH + c + 1];
             if (REV) {
-              if (s == 1) d = (T)((int)d - (((int)a + (int)b + 2) >> 2));
-              else d = (T)((int)d + (((int)a + (int)b) >> 1));
+              if (s == 1) d = (T)((I)d - (((I)a + (I)b + 2) >> 2));
+              else d = (T)((I)d + (((I)a + (I)b) >> 1));
             } else {
               const float co = (s == 1) ? IRV_DELTA : (s == 2) ? IRV_GAMMA : (s == 3) ? IRV_BETA : IRV_ALPHA;
               d = (T)__fadd_rn((float)d, __fmul_rn(-co, __fadd_rn((float)a, (float)b)));
@@ -124,7 +126,7 @@ dwt_inv_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, void* __restrict
         T* t = smem + k * DW_TILE_WORDS;
         for (uint32_t e = tid; e < DW_ROWS * DW_COLS; e += DW_THREADS) {
           const uint32_t r = e / DW_COLS, c = e - r * DW_COLS;
-          t[r * DW_PITCH + c] = REV ? (T)((int)t[r * DW_PITCH + c] >> 1) : (T)__fmul_rn((float)t[r * DW_PITCH + c], 0.5f);
+          t[r * DW_PITCH + c] = REV ? (T)((I)t[r * DW_PITCH + c] >> 1) : (T)__fmul_rn((float)t[r * DW_PITCH + c], 0.5f);
         }
       }
       __syncthreads();
@@ -154,8 +156,8 @@ dwt_inv_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, void* __restrict
             const int r = rfirst + 2 * rr;
             T d = t[r * DW_PITCH + c], a = t[(r - 1) * DW_PITCH + c], b = t[(r + 1) * DW_PITCH + c];
             if (REV) {
-              if (s == 1) d = (T)((int)d - (((int)a + (int)b + 2) >> 2));
-              else d = (T)((int)d + (((int)a + (int)b) >> 1));
+              if (s == 1) d = (T)((I)d - (((I)a + (I)b + 2) >> 2));
+              else d = (T)((I)d + (((I)a + (I)b) >> 1));
             } else {
               const float co = (s == 1) ? IRV_DELTA : (s == 2) ? IRV_GAMMA : (s == 3) ? IRV_BETA : IRV_ALPHA;
               d = (T)__fadd_rn((float)d, __fmul_rn(-co, __fadd_rn((float)a, (float)b)));
@@ -170,7 +172,7 @@ dwt_inv_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, void* __restrict
         T* t = smem + k * DW_TILE_WORDS;
         for (uint32_t e = tid; e < DW_ROWS * DW_COLS; e += DW_THREADS) {
           const uint32_t r = e / DW_COLS, c = e - r * DW_COLS;
-          t[r * DW_PITCH + c] = REV ? (T)((int)t[r * DW_PITCH + c] >> 1) : (T)__fmul_rn((float)t[r * DW_PITCH + c], 0.5f);
+          t[r * DW_PITCH + c] = REV ? (T)((I)t[r * DW_PITCH + c] >> 1) : (T)__fmul_rn((float)t[r * DW_PITCH + c], 0.5f);
         }
       }
       __syncthreads();
@@ -190,15 +192,23 @@ dwt_inv_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, void* __restrict
     }
     int out[3];
     if (REV) {
-      int a[3];
-      for (uint32_t k = 0; k < nc; ++k) a[k] = (int)smem[k * DW_TILE_WORDS + r * DW_PITCH + c];
+      I a[3];
+      for (uint32_t k = 0; k < nc; ++k) a[k] = (I)smem[k * DW_TILE_WORDS + r * DW_PITCH + c];
       if (nc == 3) {
-        int yy = a[0], cb = a[1], cr = a[2];
-        int gg = yy - ((cb + cr) >> 2);
+        I yy = a[0], cb = a[1], cr = a[2];
+        I gg = yy - ((cb + cr) >> 2);
         a[0] = cr + gg; a[1] = gg; a[2] = cb + gg;
       }
-      const int shift = J.is_signed ? 0 : (1 << (J.bit_depth - 1));
-      for (uint32_t k = 0; k < nc; ++k) out[k] = a[k] + shift;
+      if (WIDE && J.nlt_mask) {           // rev_convert_nlt_type3 on 64-bit lines: the map, then the cast to si32
+        const I bias = ((I)1 << (J.bit_depth - 1)) + 1;
+        for (uint32_t k = 0; k < nc; ++k) {
+          if ((J.nlt_mask >> k) & 1u) out[k] = (int)(a[k] >= 0 ? a[k] : -a[k] - bias);
+          else out[k] = (int)(a[k] + (J.is_signed ? (I)0 : ((I)1 << (J.bit_depth - 1))));
+        }
+      } else {
+        const I shift = J.is_signed ? (I)0 : ((I)1 << (J.bit_depth - 1));
+        for (uint32_t k = 0; k < nc; ++k) out[k] = (int)(a[k] + shift);
+      }
     } else {
       float f[3];
       for (uint32_t k = 0; k < nc; ++k) f[k] = (float)smem[k * DW_TILE_WORDS + r * DW_PITCH + c];
@@ -222,28 +232,32 @@ dwt_inv_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, void* __restrict
         out[k] = q + half;
       }
     }
-    if (J.nlt_mask) {
+    if (J.nlt_mask && !WIDE) {
       const int bias = (1 << (J.bit_depth - 1)) + 1;
       for (uint32_t k = 0; k < nc; ++k) if ((J.nlt_mask >> k) & 1u) out[k] = nlt_type3(out[k], bias);
     }
     for (uint32_t k = 0; k < nc; ++k)
-      store_sample(image, J.src_type, J.full_off[k], (size_t)(v - y0) * J.full_stride[k] + (size_t)(u - x0), out[k], (1 << J.bit_depth) - 1);
+      store_sample(image, J.src_type, J.full_off[k], (size_t)(v - y0) * J.full_stride[k] + (size_t)(u - x0), out[k], (int)((1u << (J.bit_depth & 31u)) - 1u));
   }
 }
 
 } // namespace
 
 void launch_dwt_inv(const DwtJob* jobs, uint32_t njobs, uint32_t total_ctas, bool reversible,
-                    uint32_t max_ncomp, void* image, uint32_t* coef, cudaStream_t st)
+                    uint32_t max_ncomp, void* image, uint32_t* coef, cudaStream_t st, bool wide)
 {
   if (total_ctas == 0) return;
-  size_t smem = (size_t)max_ncomp * DW_TILE_WORDS * 4;
-  if (reversible) {
-    auto k = dwt_inv_kernel<true>;
+  size_t smem = (size_t)max_ncomp * DW_TILE_WORDS * (wide ? 8 : 4);
+  if (reversible && wide) {
+    auto k = dwt_inv_kernel<true, true>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    OJB_LAUNCH(k, dim3(total_ctas), dim3(DW_THREADS), smem, st, jobs, njobs, image, coef);
+  } else if (reversible) {
+    auto k = dwt_inv_kernel<true, false>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     OJB_LAUNCH(k, dim3(total_ctas), dim3(DW_THREADS), smem, st, jobs, njobs, image, coef);
   } else {
-    auto k = dwt_inv_kernel<false>;
+    auto k = dwt_inv_kernel<false, false>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     OJB_LAUNCH(k, dim3(total_ctas), dim3(DW_THREADS), smem, st, jobs, njobs, image, coef);
   }

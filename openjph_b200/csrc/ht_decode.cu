@@ -1399,6 +1399,188 @@ ht_decode_split_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
   if (active) block_status[b] = fail ? DST_FAIL : 0u;
 }
 
+
+// ---- 64-bit samples (precision beyond 32 bits) ------------------------------------------------------------------
+// ojph_decode_codeblock64 (src/core/coding/ojph_block_decoder64.cpp:766-1316), cleanup pass, one thread per block,
+// written for clarity rather than speed (the path serves 28..32-bit lossless content): p = 62 - missing_msbs, MagSgn
+// fields of up to 43 bits read one sample at a time, exponents kept in 6 bits, and the 4-bit U-VLC extension for
+// u_q > 32 (:1000-1010 initial row, with the bias of the table entry; :1122-1131 others).  Output: 64-bit two's
+// complement integers (gen_rev_tx_from_cb64, ojph_codestream_gen.cpp:140-155) or the raw sign-magnitude words.
+template <bool SIGNMAG>
+__global__ void __launch_bounds__(DEC1_THREADS)
+ht_decode_wide_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
+                      const uint8_t* __restrict__ cs, unsigned long long* __restrict__ coef,
+                      const uint16_t* __restrict__ tables, uint32_t* __restrict__ block_status, uint32_t prev_quads)
+{
+  __shared__ DecTables T;
+  __shared__ uint2 s_ring[VLC_RING * DEC1_THREADS];
+  __shared__ uint2 s_mring[VLC_RING * DEC1_THREADS];
+  OJB_DYN_SMEM(uint16_t, s_prev);       // prev_quads x threads: exp(bl) | exp(br) << 6 | sigma(bl) << 12 | sigma(br) << 13
+  {
+    uint16_t* d = reinterpret_cast<uint16_t*>(&T);
+    for (uint32_t i = threadIdx.x; i < sizeof(DecTables) / 2; i += blockDim.x) d[i] = tables[i];
+  }
+  __syncthreads();
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nblocks) return;
+  const DecBlock blk = blocks[b];
+  const uint32_t np = blk.num_passes;
+  if (np == 0 || blk.len1 == 0) { block_status[b] = DST_EMPTY; return; }
+  bool ok = np == 1 && blk.missing_msbs <= 60 && blk.len1 >= 2;       // (refinement passes are refused by the host)
+  const uint8_t* data = cs + blk.data_off;
+  const int lcup = (int)blk.len1;
+  int scup = 0;
+  if (ok) {
+    scup = ((int)data[lcup - 1] << 4) + (data[lcup - 2] & 0xF);
+    if (scup < 2 || scup > lcup || scup > 4079) ok = false;
+  }
+  if (!ok || (blk.w + 1u) / 2 + 2 > prev_quads) { block_status[b] = DST_FAIL; return; }
+
+  MelDec mel; mel.p = data + lcup - scup; mel.size = scup - 1; mel.tmp = 0; mel.bits = 0; mel.unstuff = false; mel.k = 0;
+  VlcDec vlc;
+  {
+    const uint32_t d = data[lcup - 2];
+    vlc.w.w0 = d >> 4; vlc.w.w1 = 0;
+    vlc.w.bits = 4 - (((vlc.w.w0 & 7) == 7) ? 1u : 0u);
+    vlc.unstuff = (d | 0xF) > 0x8F ? 1u : 0u;
+  }
+  vlc_prime(vlc, data + lcup - 3, scup - 2, cs, s_ring + threadIdx.x);
+  mel_prime(mel);
+  MsDec ms;
+  ms_prime(ms, data, lcup - scup, data + lcup, s_mring + threadIdx.x);
+  int run = mel_next_run(mel);
+
+  const uint32_t width = blk.w, height = blk.h, stride = blk.stride;
+  const uint32_t nq = (width + 1) >> 1;
+  unsigned long long* dst = coef + blk.dst_off;
+  uint16_t* prev = s_prev + threadIdx.x;
+  const uint32_t mmsbp2 = blk.missing_msbs + 2u;
+  const uint32_t p = 62u - blk.missing_msbs;
+  const uint32_t shift = 63u - blk.K_max;
+  bool fail = false;
+  for (uint32_t q = 0; q <= nq + 1 && q < prev_quads; ++q) prev[q * DEC1_THREADS] = 0;
+
+  for (uint32_t y = 0; y < height && !fail; y += 2) {
+    const bool first = y == 0;
+    const uint16_t* vtab = first ? T.vlc0 : T.vlc1;
+    uint32_t rho_left = 0;
+    uint32_t pl = 0, pc = prev[0];
+    unsigned long long* r0 = dst + (size_t)y * stride;
+    unsigned long long* r1 = r0 + stride;
+    const bool has_r1 = y + 1 < height;
+    for (uint32_t q = 0; q < nq && !fail; q += 2) {
+      uint32_t t[2] = {0, 0}, pq[3];
+      while (vlc.w.bits < 64) vlc_fill(vlc);                  // the pair reads at most 2 x 7 + 6 + 10 + 8 bits
+      unsigned long long vt = vlc.w.w0;
+      uint32_t vused = 0;
+      pq[0] = pl; pq[1] = pc;
+      pq[2] = prev[(q + 1) * DEC1_THREADS];
+      const uint32_t pq3 = (q + 2 <= nq) ? prev[(q + 2) * DEC1_THREADS] : 0u;
+      for (uint32_t i = 0; i < 2; ++i) {
+        if (q + i >= nq) break;
+        uint32_t c;
+        if (first) c = (rho_left & 1) | (rho_left >> 1);
+        else {
+          const uint32_t pw = i ? pq[1] : pq[0], pn = i ? pq[2] : pq[1], pe = i ? pq3 : pq[2];
+          const uint32_t a = ((pw >> 13) | (pn >> 12)) & 1u;
+          const uint32_t l = ((rho_left >> 2) | (rho_left >> 3)) & 1u;
+          const uint32_t r = ((pn >> 13) | (pe >> 12)) & 1u;
+          c = a | (l << 1) | (r << 2);
+        }
+        uint32_t e = vtab[(c << 7) | ((uint32_t)vt & 0x7F)];
+        if (c == 0) {
+          run -= 2;
+          if (run != -1) e = 0;
+          if (run < 0) run = mel_next_run(mel);
+        }
+        vt >>= (e & 7); vused += (e & 7);
+        t[i] = e;
+        rho_left = (e >> 4) & 15u;
+      }
+      uint32_t mode = ((t[0] >> 3) & 1u) | (((t[1] >> 3) & 1u) << 1);
+      uint32_t ent;
+      if (first) {
+        if (mode == 3) {
+          run -= 2;
+          if (run == -1) mode = 4;
+          if (run < 0) run = mel_next_run(mel);
+        }
+        ent = T.uvlc0[(mode << 6) | ((uint32_t)vt & 0x3F)];
+      } else
+        ent = T.uvlc1[(mode << 6) | ((uint32_t)vt & 0x3F)];
+      vt >>= (ent & 7); vused += (ent & 7);
+      ent >>= 3;
+      uint32_t len = ent & 0xF;
+      const uint32_t suf = (uint32_t)vt & ((1u << len) - 1u);
+      vt >>= len; vused += len;
+      ent >>= 4;
+      len = ent & 7; ent >>= 3;
+      uint32_t uq[2] = { (ent & 7) + (suf & ~(0xFFu << len)), (ent >> 3) + (suf >> len) };
+      // extensions: u_q > 32 once the initial row's "+2" of the both-large mode is taken off
+      const uint32_t bias = (first && mode == 4) ? 2u : 0u;
+      for (uint32_t i = 0; i < 2; ++i)
+        if (uq[i] - bias > 32u && uq[i] >= bias) {
+          uq[i] += ((uint32_t)vt & 0xFu) << 2;
+          vt >>= 4; vused += 4;
+        }
+      win_drop(vlc.w, vused);
+      const uint32_t kap = first ? 1u : 0u;
+
+      for (uint32_t i = 0; i < 2 && !fail; ++i) {
+        const uint32_t qq = q + i;
+        if (qq >= nq) break;
+        const uint32_t inf = t[i] & 0xFFFF;
+        const uint32_t rho = (inf >> 4) & 15u, ek = inf >> 12, e1 = (inf >> 8) & 15u;
+        uint32_t Uq = uq[i] + kap;
+        if (!first) {
+          const uint32_t pw = i ? pq[1] : pq[0], pn = i ? pq[2] : pq[1], pe = i ? pq3 : pq[2];
+          const uint32_t emax = max(max((pw >> 6) & 63u, pn & 63u), max((pn >> 6) & 63u, pe & 63u));
+          Uq += (rho & (rho - 1)) ? max(emax, 1u) : 1u;
+        }
+        if (Uq > mmsbp2) { fail = true; break; }
+        unsigned long long val[4] = {0, 0, 0, 0};
+        uint32_t ex[4] = {0, 0, 0, 0};
+        for (int k = 0; k < 4; ++k) {
+          if (!((rho >> k) & 1u)) continue;
+          const uint32_t m = Uq - ((ek >> k) & 1u);                   // <= 43
+          while (ms.w.bits < 64) ms_fill(ms);
+          const unsigned long long bits = ms.w.w0;
+          win_drop(ms.w, m);
+          unsigned long long v = (bits & ((1ull << m) - 1ull)) | ((unsigned long long)((e1 >> k) & 1u) << m) | 1ull;
+          ex[k] = 63u - (uint32_t)__clzll((long long)(v | 2ull));
+          const unsigned long long mag = (v + 2ull) << (p - 1);       // magnitude with the half-LSB bin centre, bit 62 down
+          if (SIGNMAG) val[k] = ((bits & 1ull) << 63) | mag;
+          else { const long long a = (long long)(mag >> shift); val[k] = (unsigned long long)((bits & 1ull) ? -a : a); }
+        }
+        prev[qq * DEC1_THREADS] = (uint16_t)(ex[1] | (ex[3] << 6) | (((rho >> 1) & 1u) << 12) | (((rho >> 3) & 1u) << 13));
+        const uint32_t x = 2 * qq;
+        r0[x] = val[0]; if (has_r1) r1[x] = val[1];
+        if (x + 1 < width) { r0[x + 1] = val[2]; if (has_r1) r1[x + 1] = val[3]; }
+      }
+      pl = pq[2]; pc = pq3;
+    }
+  }
+  block_status[b] = fail ? DST_FAIL : 0u;
+}
+
+// zero-fill of 64-bit blocks that are not included or failed to decode
+__global__ void __launch_bounds__(DEC_WARPS * 32)
+ht_dec_fill_wide_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks, unsigned long long* __restrict__ coef,
+                        uint32_t* __restrict__ block_status)
+{
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t b = blockIdx.x * DEC_WARPS + warp;
+  if (b >= nblocks) return;
+  const uint32_t st = block_status[b];
+  if (st == 0) return;
+  const DecBlock blk = blocks[b];
+  unsigned long long* dst = coef + blk.dst_off;
+  for (uint32_t yy = 0; yy < blk.h; ++yy)
+    for (uint32_t xx = lane; xx < blk.w; xx += 32) dst[(size_t)yy * blk.stride + xx] = 0;
+  __syncwarp();
+  if (lane == 0) block_status[b] = (st & DST_FAIL) ? DST_FAIL : 0u;
+}
+
 // zero-fill of blocks that are not included or failed to decode (one warp per block)
 __global__ void __launch_bounds__(DEC_WARPS * 32)
 ht_dec_fill_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks, uint32_t* __restrict__ coef,
@@ -1439,6 +1621,21 @@ void launch_ht_decode(const DecBlock* blocks, uint32_t nblocks, const uint8_t* c
     OJB_LAUNCH(ht_dec_step2_kernel, grid, block, smem, st, blocks, nblocks, codestream, coef, scratch, out_mode, block_status,
                ms_cap_words);
   }
+}
+
+void launch_ht_decode_wide(const DecBlock* blocks, uint32_t nblocks, uint32_t max_width, const uint8_t* codestream,
+                           uint32_t* coef, const uint16_t* tables, bool signmag, uint32_t* block_status, cudaStream_t st)
+{
+  if (nblocks == 0) return;
+  const uint32_t prev_quads = (max_width + 1) / 2 + 2;
+  const size_t smem = (size_t)prev_quads * DEC1_THREADS * sizeof(uint16_t);
+  auto k = signmag ? ht_decode_wide_kernel<true> : ht_decode_wide_kernel<false>;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dim3 grid((nblocks + DEC1_THREADS - 1) / DEC1_THREADS), block(DEC1_THREADS);
+  OJB_LAUNCH(k, grid, block, smem, st, blocks, nblocks, codestream, reinterpret_cast<unsigned long long*>(coef), tables, block_status,
+             prev_quads);
+  dim3 g2((nblocks + DEC_WARPS - 1) / DEC_WARPS), b2(DEC_WARPS * 32);
+  OJB_LAUNCH(ht_dec_fill_wide_kernel, g2, b2, 0, st, blocks, nblocks, reinterpret_cast<unsigned long long*>(coef), block_status);
 }
 
 void launch_ht_decode_serial(const DecBlock* blocks, uint32_t nblocks, uint32_t nfast, uint32_t max_width, const uint8_t* codestream,

@@ -29,6 +29,10 @@ namespace ojb {
 
 namespace {
 
+template <bool WIDE> struct WordOf;
+template <> struct WordOf<false> { typedef uint32_t W; };
+template <> struct WordOf<true> { typedef unsigned long long W; };
+
 struct MsWriter {            // forward, LSB first: a 128-bit window (w1:w0), fewer than 64 bits pending between puts
   unsigned long long w0, w1; uint32_t nbits, words; uint32_t last_ff;
 };
@@ -190,9 +194,13 @@ __device__ __forceinline__ void terminate_block(MsWriter& ms, VlcWriter& vlc, Me
   res.len_tail = vl_pos;
 }
 
+// WIDE: 64-bit sign-magnitude samples (ojph_encode_codeblock64, src/core/coding/ojph_block_encoder.cpp:1026-1523): the same
+// pass with p = 62 - missing_msbs, exponents up to 6 bits, MagSgn fields of up to 43 bits appended one sample at a time,
+// and the 4-bit U-VLC extension for u_q > 32 (uvlc_tbl entries 33.., :236-247) after the two suffixes (:1491-1492)
+template <bool WIDE>
 __global__ void __launch_bounds__(ES_THREADS)
 ht_encode_serial_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
-                        const uint32_t* __restrict__ coef, uint8_t* __restrict__ slots,
+                        const uint32_t* __restrict__ coef32, uint8_t* __restrict__ slots,
                         EncResult* __restrict__ results, const uint16_t* __restrict__ tables,
                         uint32_t* __restrict__ status, uint32_t prev_quads)
 {
@@ -209,8 +217,10 @@ ht_encode_serial_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
   if (bidx >= nblocks) return;
   const EncBlock blk = blocks[bidx];
   if (blk.flags & ENC_FLAG_FAST) return;                 // coded by ht_encode_fast_kernel
+  typedef typename WordOf<WIDE>::W W;
+  constexpr uint32_t WB = WIDE ? 64u : 32u, EB = WIDE ? 6u : 5u, EM = (1u << EB) - 1u;     // word bits; bits of a stored exponent
   const uint32_t width = blk.w, height = blk.h, stride = blk.stride, p = blk.p;
-  const uint32_t* __restrict__ src = coef + blk.src_off;
+  const W* __restrict__ src = reinterpret_cast<const W*>(coef32) + blk.src_off;
   uint8_t* slot = slots + blk.slot_off;
   uint2* ms_dst = reinterpret_cast<uint2*>(slot);          // slots are 16-byte aligned
   uint32_t* vl_end = reinterpret_cast<uint32_t*>(slot + blk.slot_cap);
@@ -226,22 +236,22 @@ ht_encode_serial_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
   uint32_t any_sig = 0, negzero = 0;
   bool overflow = false;
   // aligned block rows: a quad pair of one row is one 16-byte load
-  const bool vec4 = ((blk.src_off | stride) & 3u) == 0;
-  const bool narrow = p >= 16;             // m_n <= K_max + 1 = 32 - p: four fields of a quad fit 64 bits
+  const bool vec4 = !WIDE && ((blk.src_off | stride) & 3u) == 0;
+  const bool narrow = !WIDE && p >= 16;    // m_n <= K_max + 1 = 32 - p: four fields of a quad fit 64 bits
 
   for (uint32_t q = 0; q <= nq; ++q) prev[q * ES_THREADS] = 0;
 
   for (uint32_t y = 0; y < height; y += 2) {
-    const uint32_t* r0 = src + (size_t)y * stride;
-    const uint32_t* r1 = r0 + stride;
+    const W* r0 = src + (size_t)y * stride;
+    const W* r1 = r0 + stride;
     const bool has_r1 = y + 1 < height;
     const uint16_t* vtab = s_vlc + (y ? 2048u : 0u);
     uint32_t rho_left = 0;
     uint32_t pl = 0, pc = prev[0];               // row above: quad q-1, quad q (before being overwritten)
 
-    auto load_pair = [&](uint32_t q, uint32_t (&a)[4], uint32_t (&b)[4]) {
+    auto load_pair = [&](uint32_t q, W (&a)[4], W (&b)[4]) {
       // samples 2q .. 2q+3 of the two rows (zero outside the block)
-      if (vec4 && 2 * q + 3 < width) {
+      if (!WIDE && vec4 && 2 * q + 3 < width) {
         const uint4 t = *reinterpret_cast<const uint4*>(r0 + 2 * q);
         a[0] = t.x; a[1] = t.y; a[2] = t.z; a[3] = t.w;
         if (has_r1) { const uint4 u = *reinterpret_cast<const uint4*>(r1 + 2 * q); b[0] = u.x; b[1] = u.y; b[2] = u.z; b[3] = u.w; }
@@ -250,16 +260,16 @@ ht_encode_serial_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
         #pragma unroll
         for (uint32_t i = 0; i < 4; ++i) {
           const bool in = 2 * q + i < width;
-          a[i] = in ? r0[2 * q + i] : 0u;
-          b[i] = (in && has_r1) ? r1[2 * q + i] : 0u;
+          a[i] = in ? r0[2 * q + i] : (W)0;
+          b[i] = (in && has_r1) ? r1[2 * q + i] : (W)0;
         }
       }
     };
 
-    uint32_t na[4], nb[4];
+    W na[4], nb[4];
     load_pair(0, na, nb);
     for (uint32_t q = 0; q < nq; q += 2) {
-      uint32_t ca[4], cb[4];
+      W ca[4], cb[4];
       #pragma unroll
       for (int i = 0; i < 4; ++i) { ca[i] = na[i]; cb[i] = nb[i]; }
       if (q + 2 < nq) load_pair(q + 2, na, nb);          // next pair in flight while this one is coded
@@ -271,21 +281,24 @@ ht_encode_serial_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
         const uint32_t qq = q + h;
         if (qq >= nq) break;
         // ---- per-sample quantities (:591-643); quad order TL, BL, TR, BR
-        const uint32_t t[4] = { ca[2 * h], cb[2 * h], ca[2 * h + 1], cb[2 * h + 1] };
-        uint32_t rho = 0, e[4] = {0, 0, 0, 0}, s[4] = {0, 0, 0, 0};
+        const W t[4] = { ca[2 * h], cb[2 * h], ca[2 * h + 1], cb[2 * h + 1] };
+        uint32_t rho = 0, e[4] = {0, 0, 0, 0};
+        W s[4] = {0, 0, 0, 0};
         #pragma unroll
         for (int i = 0; i < 4; ++i) {
           // branch-free: v = 2 * magnitude (0 when insignificant); exponent of 2*mag - 1, MagSgn value
           // 2*(mag - 1) + sign (only read when the sample is significant)
-          const uint32_t v = ((t[i] + t[i]) >> p) & ~1u;
-          const uint32_t sig = min(v, 1u);
+          const W v = ((W)(t[i] + t[i]) >> p) & ~(W)1;
+          const uint32_t sig = v ? 1u : 0u;
           rho |= sig << i;
-          e[i] = 32u - (uint32_t)__clz((int)(v - sig));          // v = 0: clz(0) = 32 -> 0
-          s[i] = v - 2u + (t[i] >> 31);
+          e[i] = WIDE ? 64u - (uint32_t)__clzll((long long)(v - sig)) : 32u - (uint32_t)__clz((int)(uint32_t)(v - sig));   // v = 0 -> 0
+          s[i] = v - 2u + (t[i] >> (WB - 1));
         }
         any_sig |= rho;
-        if (blk.flags & ENC_CHECK_NEGZERO)            // magnitude-overflow words keep the block coded
-          negzero |= (t[0] == 0x80000000u) | (t[1] == 0x80000000u) | (t[2] == 0x80000000u) | (t[3] == 0x80000000u);
+        if (blk.flags & ENC_CHECK_NEGZERO) {          // magnitude-overflow words keep the block coded
+          const W nz = (W)1 << (WB - 1);
+          negzero |= (t[0] == nz) | (t[1] == nz) | (t[2] == nz) | (t[3] == nz);
+        }
         const uint32_t emax = max(max(e[0], e[1]), max(e[2], e[3]));
         // ---- context and exponent predictor from the row above
         const uint32_t pr = prev[(qq + 1) * ES_THREADS];      // quad qq+1 of the row above
@@ -293,14 +306,14 @@ ht_encode_serial_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
         if (y == 0) cq = (rho_left >> 1) | (rho_left & 1);
         else {
           // max exponent of the four samples above (:862,:950): e3 of NW quad, e1/e3 of N quad, e1 of NE quad
-          const uint32_t me = max(max((pl >> 9) & 31u, (pc >> 4) & 31u), max((pc >> 9) & 31u, (pr >> 4) & 31u));
+          const uint32_t me = max(max((pl >> (4 + EB)) & EM, (pc >> 4) & EM), max((pc >> (4 + EB)) & EM, (pr >> 4) & EM));
           if (rho & (rho - 1)) kappa = max(1u, me > 0 ? me - 1 : 0u);
           const uint32_t a = ((pl >> 3) | (pc >> 1)) & 1u;
           const uint32_t b = ((rho_left >> 2) | (rho_left >> 3)) & 1u;
           const uint32_t c = ((pc >> 3) | (pr >> 1)) & 1u;
           cq = a | (b << 1) | (c << 2);
         }
-        prev[qq * ES_THREADS] = (uint16_t)(rho | (e[1] << 4) | (e[3] << 9));
+        prev[qq * ES_THREADS] = (uint16_t)(rho | (e[1] << 4) | (e[3] << (4 + EB)));
         pl = pc; pc = pr;
         const uint32_t Uq = max(emax, kappa);
         const uint32_t u = Uq - kappa;
@@ -319,14 +332,20 @@ ht_encode_serial_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
             const uint32_t mb = (Uq * 0x01010101u - eb) & (rb * 0xFFu);
             m[0] = mb & 0xFFu; m[1] = (mb >> 8) & 0xFFu; m[2] = (mb >> 16) & 0xFFu; m[3] = mb >> 24;
           }
-          const unsigned long long A = (unsigned long long)(s[0] & ((1u << m[0]) - 1u)) |
-                                       ((unsigned long long)(s[1] & ((1u << m[1]) - 1u)) << m[0]);
-          const unsigned long long B = (unsigned long long)(s[2] & ((1u << m[2]) - 1u)) |
-                                       ((unsigned long long)(s[3] & ((1u << m[3]) - 1u)) << m[2]);
-          // one append per quad while its four fields fit 64 bits (K_max <= 15), else one per column
-          const uint32_t la = m[0] + m[1], lb = m[2] + m[3];
-          if (narrow) ms_put(ms, A | (B << la), la + lb, ms_dst);
-          else { ms_put(ms, A, la, ms_dst); ms_put(ms, B, lb, ms_dst); }
+          if (WIDE) {                         // fields of up to 43 bits: one append per sample (ms_encode64, :1477-1484)
+            #pragma unroll
+            for (int i = 0; i < 4; ++i)
+              ms_put(ms, (unsigned long long)s[i] & ((1ull << m[i]) - 1ull), m[i], ms_dst);
+          } else {
+            const unsigned long long A = (unsigned long long)((uint32_t)s[0] & ((1u << m[0]) - 1u)) |
+                                         ((unsigned long long)((uint32_t)s[1] & ((1u << m[1]) - 1u)) << m[0]);
+            const unsigned long long B = (unsigned long long)((uint32_t)s[2] & ((1u << m[2]) - 1u)) |
+                                         ((unsigned long long)((uint32_t)s[3] & ((1u << m[3]) - 1u)) << m[2]);
+            // one append per quad while its four fields fit 64 bits (K_max <= 15), else one per column
+            const uint32_t la = m[0] + m[1], lb = m[2] + m[3];
+            if (narrow) ms_put(ms, A | (B << la), la + lb, ms_dst);
+            else { ms_put(ms, A, la, ms_dst); ms_put(ms, B, lb, ms_dst); }
+          }
         }
         rho_left = rho;
       }
@@ -334,12 +353,20 @@ ht_encode_serial_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
       {
         const uint32_t u0 = uq[0], u1 = uq[1];
         uint32_t c0, c1;
+        // U-VLC code of u: table for u <= 32; beyond it (64-bit samples only) prefix "000", suffix 28 + (u - 33) % 4 and a
+        // 4-bit extension (u - 33) / 4
+        uint32_t x0 = 0, x1 = 0, xl0 = 0, xl1 = 0;
+        auto code = [&](uint32_t u, uint32_t& ext, uint32_t& extl) -> uint32_t {
+          if (!WIDE || u <= 32) return s_uvlc[u];
+          ext = (u - 33u) >> 2; extl = 4;
+          return (3u << 3) | ((28u + ((u - 33u) & 3u)) << 6) | (5u << 11);
+        };
         if (y == 0) {
           if (u0 > 0 && u1 > 0) mel_event(mel, min(u0, u1) > 2, mel_buf);
-          if (u0 > 2 && u1 > 2) { c0 = s_uvlc[u0 - 2]; c1 = s_uvlc[u1 - 2]; }
-          else if (u0 > 2 && u1 > 0) { c0 = s_uvlc[u0]; c1 = (u1 - 1) | (1u << 3); }     // one-bit u1
-          else { c0 = s_uvlc[u0]; c1 = s_uvlc[u1]; }
-        } else { c0 = s_uvlc[u0]; c1 = s_uvlc[u1]; }
+          if (u0 > 2 && u1 > 2) { c0 = code(u0 - 2, x0, xl0); c1 = code(u1 - 2, x1, xl1); }
+          else if (u0 > 2 && u1 > 0) { c0 = code(u0, x0, xl0); c1 = (u1 - 1) | (1u << 3); }     // one-bit u1
+          else { c0 = code(u0, x0, xl0); c1 = code(u1, x1, xl1); }
+        } else { c0 = code(u0, x0, xl0); c1 = code(u1, x1, xl1); }
         // prefixes of both quads, then both suffixes, as one field of at most 3+3+5+5 bits
         uint32_t bits = pair_bits, len = pair_len;
         bits |= (c0 & 7u) << len; len += (c0 >> 3) & 7u;
@@ -347,6 +374,7 @@ ht_encode_serial_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
         bits |= ((c0 >> 6) & 31u) << len; len += (c0 >> 11) & 31u;
         bits |= ((c1 >> 6) & 31u) << len; len += (c1 >> 11) & 31u;
         vlc_put(vlc, bits, len, vl_end);
+        if (WIDE && (xl0 | xl1)) vlc_put(vlc, x0 | (x1 << xl0), xl0 + xl1, vl_end);
       }
     }
     if (ms.words + vlc.words + 24 >= slot_words) { overflow = true; break; }
@@ -732,12 +760,14 @@ ht_encode_split_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
 
 void launch_ht_encode_serial(const EncBlock* blocks, uint32_t nblocks, uint32_t nfast, uint32_t max_width, const uint32_t* coef,
                              uint8_t* slots, EncResult* results, const uint16_t* tables, uint32_t* status,
-                             cudaStream_t st)
+                             cudaStream_t st, bool wide)
 {
   if (nblocks == 0) return;
+  if (wide) nfast = 0;
   const uint32_t prev_quads = (max_width + 1) / 2 + 2;
   const size_t smem = (size_t)prev_quads * ES_THREADS * sizeof(uint16_t);
-  cudaFuncSetAttribute(ht_encode_serial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(ht_encode_serial_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(ht_encode_serial_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid((nblocks + ES_THREADS - 1) / ES_THREADS), block(ES_THREADS);
   if (nfast) {
     // one thread per block by default; OJB_ENC_SPLIT=1 selects the two-thread split (measured slower on a B200,
@@ -749,8 +779,11 @@ void launch_ht_encode_serial(const EncBlock* blocks, uint32_t nblocks, uint32_t 
     } else
       OJB_LAUNCH(ht_encode_fast_kernel, grid, block, 0, st, blocks, nblocks, coef, slots, results, tables, status);
   }
-  if (nfast < nblocks)
-    OJB_LAUNCH(ht_encode_serial_kernel, grid, block, smem, st, blocks, nblocks, coef, slots, results, tables, status,
+  if (wide)
+    OJB_LAUNCH(ht_encode_serial_kernel<true>, grid, block, smem, st, blocks, nblocks, coef, slots, results, tables, status,
+               prev_quads);
+  else if (nfast < nblocks)
+    OJB_LAUNCH(ht_encode_serial_kernel<false>, grid, block, smem, st, blocks, nblocks, coef, slots, results, tables, status,
                prev_quads);
 }
 

@@ -337,6 +337,7 @@ static void read_band(CodecBase& cb, uint32_t tile, uint32_t comp, uint32_t res,
   const BandGeom& bg = cb.layout.tiles[tile].comps[comp].res[res].bands[band];
   *bw = bg.rect.w; *bh = bg.rect.h;
   if (bg.empty || out == nullptr) return;
+  if (cb.wide) fail(0x000B0016, "the band parity hook reads 32-bit planes only");
   for (uint32_t y = 0; y < bg.rect.h; ++y)
     cuda_check(cudaMemcpy(out + (size_t)y * bg.rect.w,
                           cb.d_coef.as<uint32_t>() + bg.plane_off + bg.plane_pad_x + (size_t)y * bg.plane_stride,

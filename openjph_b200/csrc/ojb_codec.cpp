@@ -154,23 +154,23 @@ void CodecBase::build_dwt_jobs(bool forward) {
             for (uint32_t b = 1; b < 4; ++b) {
               const BandGeom& bg = rr.bands[b];
               j.band_off[i][b] = bg.plane_off + bg.plane_pad_x; j.band_stride[i][b] = bg.plane_stride;
-              j.band_shift[i][b] = 31u - bg.K_max;
+              j.band_shift[i][b] = (wide ? 63u : 31u) - bg.K_max;
               j.band_scale[i][b] = forward ? bg.delta_inv : bg.delta;
             }
             if (r == 1) {
               const BandGeom& bg = lo.bands[0];
               j.band_off[i][0] = bg.plane_off + bg.plane_pad_x; j.band_stride[i][0] = bg.plane_stride;
-              j.band_shift[i][0] = 31u - bg.K_max;
+              j.band_shift[i][0] = (wide ? 63u : 31u) - bg.K_max;
               j.band_scale[i][0] = forward ? bg.delta_inv : bg.delta;
             }
           } else {   // zero decomposition levels
             const BandGeom& bg = rr.bands[0];
             j.band_off[i][0] = bg.plane_off + bg.plane_pad_x; j.band_stride[i][0] = bg.plane_stride;
-            j.band_shift[i][0] = 31u - bg.K_max;
+            j.band_shift[i][0] = (wide ? 63u : 31u) - bg.K_max;
             j.band_scale[i][0] = forward ? bg.delta_inv : bg.delta;
           }
         }
-        const bool stream = !j.nodwt && j.w >= 2 && j.h >= 2 && !no_stream_dwt && layout.coef_words < (1ull << 30) && img_bytes < (1ull << 32);   // 32-bit byte offsets in the stream kernels
+        const bool stream = !wide && !j.nodwt && j.w >= 2 && j.h >= 2 && !no_stream_dwt && layout.coef_words < (1ull << 30) && img_bytes < (1ull << 32);   // 32-bit byte offsets in the stream kernels
         uint32_t gi, n;
         if (stream) {
           gi = gw + (j.first ? (k == 3 ? 0u : 1u) : 2u);
@@ -213,11 +213,13 @@ static uint32_t widest_block(const Layout& L) {
 void Encoder::configure(const Params& p, uint32_t sample_type) {
   params = p;
   params.finalize_for_encode();
+  wide = params.needs_wide();
+  if (wide && sample_type != ST_I32) fail(0x000B0010, "samples beyond 16 bits need the 32-bit sample container");
   layout.build(params);
   max_block_w = widest_block(layout);
   plan_image(sample_type);
   upload_tables();
-  d_coef.reserve((layout.coef_words + 64) * 4);
+  d_coef.reserve((layout.coef_words + 64) * (wide ? 8 : 4));
   CK(cudaMemset(d_coef.p, 0, d_coef.cap));
   build_dwt_jobs(true);
   // block descriptors and slots
@@ -236,19 +238,19 @@ void Encoder::configure(const Params& p, uint32_t sample_type) {
               EncBlock& e = h_blocks[bg.block_base + by * bg.nbw + bx];
               e.src_off = bg.plane_off + bg.plane_pad_x + (uint64_t)(r.y0 - bg.rect.y0) * bg.plane_stride + (r.x0 - bg.rect.x0);
               e.stride = bg.plane_stride; e.w = (uint16_t)r.w; e.h = (uint16_t)r.h;
-              e.p = (uint16_t)(31u - bg.K_max);
+              e.p = (uint16_t)((wide ? 63u : 31u) - bg.K_max);
               e.flags = (tc.res.size() == 1 && params.reversible(tc.comp)) ? (uint16_t)ENC_CHECK_NEGZERO : (uint16_t)0;
               // worst case: (K_max+1) MagSgn bits / sample (+1/15 stuffing), 30 VLC bits / quad pair
               // (+1/7), 192 MEL bytes, working margin of the kernel
               uint64_t ms = ((uint64_t)r.w * r.h * (bg.K_max + 1) + 7) / 8; ms += ms / 15 + 8;
               uint64_t nq = (uint64_t)((r.w + 1) / 2) * ((r.h + 1) / 2);
-              uint64_t vl = ((nq + 1) / 2 * 30 + 12 + 7) / 8; vl += vl / 7 + 8;
+              uint64_t vl = ((nq + 1) / 2 * (wide ? 38 : 30) + 12 + 7) / 8; vl += vl / 7 + 8;      // (+ two 4-bit U-VLC extensions per pair)
               uint64_t cap = ms + vl + 192 + 160;
               cap = (cap + 15) & ~(uint64_t)15;
               e.slot_off = slot; e.slot_cap = (uint32_t)cap;
               slot += cap;
               if (!tile_wanted(t.idx)) { e.w = e.h = 0; }                  // another rank's tile: nothing to code
-              if (!no_fast_blocks && enc_block_is_fast(e)) { e.flags |= ENC_FLAG_FAST; ++num_fast_blocks; }
+              if (!no_fast_blocks && !wide && enc_block_is_fast(e)) { e.flags |= ENC_FLAG_FAST; ++num_fast_blocks; }
             }
         }
   slot_bytes = slot + 64;
@@ -327,14 +329,14 @@ size_t Encoder::encode(const void* const* planes, const uint32_t* strides, bool 
                               g.first, img_type, d_image.p, d_coef.as<uint32_t>(), stream);
       else
         launch_dwt_fwd(d_jobs.as<DwtJob>() + g.dev_off, (uint32_t)g.jobs.size(), g.ctas, g.reversible, g.ncomp,
-                       d_image.p, d_coef.as<uint32_t>(), stream);
+                       d_image.p, d_coef.as<uint32_t>(), stream, wide);
       ++last_launches;
     }
   mark(2);
   uint32_t nb = (uint32_t)h_blocks.size();
-  if (serial_block_encoder() || max_block_w > 64)
+  if (serial_block_encoder() || max_block_w > 64 || wide)
     launch_ht_encode_serial(d_blocks.as<EncBlock>(), nb, num_fast_blocks, max_block_w, d_coef.as<uint32_t>(), d_slots.as<uint8_t>(),
-                            d_results.as<EncResult>(), d_tables_enc.as<uint16_t>(), d_status.as<uint32_t>(), stream);
+                            d_results.as<EncResult>(), d_tables_enc.as<uint16_t>(), d_status.as<uint32_t>(), stream, wide);
   else
     launch_ht_encode(d_blocks.as<EncBlock>(), nb, d_coef.as<uint32_t>(), d_slots.as<uint8_t>(),
                      d_results.as<EncResult>(), d_tables_enc.as<uint16_t>(), d_status.as<uint32_t>(), stream);
@@ -358,7 +360,7 @@ size_t Encoder::encode(const void* const* planes, const uint32_t* strides, bool 
     uint32_t len = res[b].len_head + res[b].len_tail;
     cb.pass_len[0] = len; cb.pass_len[1] = 0;
     cb.num_passes = len ? 1 : 0;
-    cb.missing_msbs = len ? (uint8_t)(30u - h_blocks[b].p) : 0;
+    cb.missing_msbs = len ? (uint8_t)((wide ? 62u : 30u) - h_blocks[b].p) : 0;
   }
   struct Pkt { PacketRef ref; std::vector<uint8_t> hdr; uint32_t hdr_len, body; };
   struct TilePart { uint32_t tile, first, count, tp_idx, tp_cnt; uint64_t bytes; };
@@ -569,16 +571,13 @@ void Decoder::read_headers(const uint8_t* data, size_t len, uint32_t sample_type
   params = np;
   // the decoder side derives the same planar default as the reference (read_headers :879)
   params.planar = params.color_transform() ? 0 : 1;
-  for (uint32_t c = 0; c < params.num_comps(); ++c) {
-    uint32_t pr = params.precision(c);
-    if (pr > 32) fail(0x000B0001, "component %u needs %u-bit coefficients; only the 32-bit path is "
-                      "implemented on the GPU", c, pr);
-  }
+  wide = params.needs_wide();
+  if (wide && sample_type != ST_I32) fail(0x000B0010, "samples beyond 16 bits need the 32-bit sample container");
   skip_read = skip_recon = 0;
   layout.build(params);
   max_block_w = widest_block(layout);
   upload_tables();
-  d_coef.reserve((layout.coef_words + 64) * 4);
+  d_coef.reserve((layout.coef_words + 64) * (wide ? 8 : 4));
   setup_geometry(sample_type);
   // geometry part of the block records
   h_dec_proto.assign(layout.num_blocks, DecBlock());
@@ -780,7 +779,7 @@ uint32_t Decoder::decode(void* const* planes, const uint32_t* strides, bool plan
   uint32_t max_len1 = 0, nfast = 0;
   bool cleanup_only = true;                 // lets the block decoder be specialised
   const uint32_t dec_out = (any_rev_blocks && any_irv_blocks) ? (uint32_t)DEC_OUT_PER_BLOCK : any_irv_blocks ? (uint32_t)DEC_OUT_FLOAT : (uint32_t)DEC_OUT_INT;
-  const bool fast_ok = dec_out != DEC_OUT_PER_BLOCK && !no_fast_blocks;
+  const bool fast_ok = dec_out != DEC_OUT_PER_BLOCK && !no_fast_blocks && !wide;
   // the frame's part of every block record (the geometry part sits in d_proto): lengths, passes, missing msbs, where
   // the bytes are, and whether the block goes through the specialised kernel (one output type per launch).  Scratch
   // (quad records + de-stuffed MagSgn of the general / two-step kernels) is laid out per frame.
@@ -813,7 +812,11 @@ uint32_t Decoder::decode(void* const* planes, const uint32_t* strides, bool plan
   host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
   mark(2);
   if (nb) { launch_dec_merge(d_dec.as<DecBlock>(), d_proto.as<DecBlock>(), hy, need_scratch ? hs : nullptr, nb, stream); ++last_launches; }
-  if (serial_block_decoder() || max_block_w > 64)
+  if (wide) {
+    if (!cleanup_only) fail(0x000B0009, "SigProp / MagRef passes are not implemented on the 64-bit coefficient path");
+    launch_ht_decode_wide(d_dec.as<DecBlock>(), nb, max_block_w, cs_dev, d_coef.as<uint32_t>(), d_tables_dec.as<uint16_t>(), false,
+                          d_bstatus.as<uint32_t>(), stream);
+  } else if (serial_block_decoder() || max_block_w > 64)
     launch_ht_decode_serial(d_dec.as<DecBlock>(), nb, nfast, max_block_w, cs_dev, d_coef.as<uint32_t>(), d_scratch.as<uint32_t>(),
                             d_tables_dec.as<uint16_t>(), dec_out, cleanup_only,
                             d_bstatus.as<uint32_t>(), stream);
@@ -832,7 +835,7 @@ uint32_t Decoder::decode(void* const* planes, const uint32_t* strides, bool plan
                               g.first, img_type, d_image.p, d_coef.as<uint32_t>(), stream);
       else
         launch_dwt_inv(d_jobs.as<DwtJob>() + g.dev_off, (uint32_t)g.jobs.size(), g.ctas, g.reversible, g.ncomp,
-                       d_image.p, d_coef.as<uint32_t>(), stream);
+                       d_image.p, d_coef.as<uint32_t>(), stream, wide);
       ++last_launches;
     }
   (void)D;

@@ -60,7 +60,8 @@ public:
   uint32_t skip_read = 0, skip_recon = 0;
   size_t img_bytes = 0;
   void plan_image(uint32_t sample_type);
-  DeviceBuf d_coef;                    // coefficient arena (32-bit words)
+  DeviceBuf d_coef;                    // coefficient arena (32-bit words; 64-bit elements in wide mode)
+  bool wide = false;                   // some component needs more than 32 bits: every plane holds 64-bit elements, general kernels only
   // DWT jobs per level (index 0: full resolution level D, ...), uploaded once
   // jobs of one level are grouped by the kernel variant that runs them
   struct JobGroup { std::vector<DwtJob> jobs; uint32_t ctas = 0, ncomp = 1; bool first = false, stream = false, reversible = true; size_t dev_off = 0; };

@@ -13,7 +13,7 @@ void launch_ht_encode(const EncBlock* blocks, uint32_t nblocks, const uint32_t* 
 // blocks carry ENC_FLAG_FAST (see enc_block_is_fast) and go through the specialised kernel
 void launch_ht_encode_serial(const EncBlock* blocks, uint32_t nblocks, uint32_t nfast, uint32_t max_width, const uint32_t* coef,
                              uint8_t* slots, EncResult* results, const uint16_t* tables, uint32_t* status,
-                             cudaStream_t st);
+                             cudaStream_t st, bool wide = false);
 
 // HT decoder (ht_decode.cu): step 1 = MEL/VLC chain, one THREAD per code-block; step 2 =
 // MagSgn (+SPP +MRP) one WARP per code-block.
@@ -33,11 +33,16 @@ void launch_ht_decode_serial(const DecBlock* blocks, uint32_t nblocks, uint32_t 
 void launch_dec_merge(DecBlock* blocks, const DecBlock* proto, const DecDyn* dyn, const uint64_t* scratch_off,
                       uint32_t nblocks, cudaStream_t st);
 
+// 64-bit samples (precision beyond 32 bits): cleanup pass only, output int64 (or the raw sign-magnitude words)
+void launch_ht_decode_wide(const DecBlock* blocks, uint32_t nblocks, uint32_t max_width, const uint8_t* codestream,
+                           uint32_t* coef, const uint16_t* tables, bool signmag, uint32_t* block_status, cudaStream_t st);
+
 // forward / inverse DWT levels (dwt_fwd.cu / dwt_inv.cu).  jobs live in device memory.
+// wide: 64-bit samples and sign-magnitude words (reversible, precision > 32 bits); offsets and strides count elements
 void launch_dwt_fwd(const DwtJob* jobs, uint32_t njobs, uint32_t total_ctas, bool reversible,
-                    uint32_t max_ncomp, const void* image, uint32_t* coef, cudaStream_t st);
+                    uint32_t max_ncomp, const void* image, uint32_t* coef, cudaStream_t st, bool wide = false);
 void launch_dwt_inv(const DwtJob* jobs, uint32_t njobs, uint32_t total_ctas, bool reversible,
-                    uint32_t max_ncomp, void* image, uint32_t* coef, cudaStream_t st);
+                    uint32_t max_ncomp, void* image, uint32_t* coef, cudaStream_t st, bool wide = false);
 // register-streaming fast path (dwt_stream.cu) for resolutions of at least 2x2
 void dwt_stream_tiling(uint32_t x0, uint32_t y0, uint32_t w, uint32_t h, bool reversible, bool forward,
                        uint32_t& strips, uint32_t& chunks, uint32_t& chunk_rows, uint32_t& ctas);

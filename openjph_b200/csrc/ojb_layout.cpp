@@ -28,7 +28,7 @@ static void build_band(const Params& p, uint32_t comp, ResGeom& rg, uint32_t b, 
   bg.K_max = q.kmax(rg.res_num, b);
   if (!p.reversible(comp)) {
     float d = q.irrev_delta(rg.res_num, b);
-    d /= (float)(1u << (31 - bg.K_max));
+    d /= (float)(1u << (31 - std::min(bg.K_max, 31u)));
     bg.delta = d; bg.delta_inv = 1.0f / d;
   }
   bg.empty = br.empty();

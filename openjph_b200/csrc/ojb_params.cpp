@@ -183,6 +183,20 @@ uint32_t Params::precision(uint32_t c) const {
   return p + 2;   // + sign bit + one spare bit (ojph_params.cpp:1700-1706)
 }
 
+bool Params::needs_wide() const {
+  bool wide = false;
+  for (uint32_t c = 0; c < num_comps(); ++c)
+    if (precision(c) > 32) {
+      wide = true;
+      bool rev = reversible(c);
+      if (color_transform() && c < 3) rev = reversible(0) && reversible(1) && reversible(2);
+      if (!rev)
+        fail(0x000B0001, "component %u needs %u-bit coefficients and is irreversible; the 64-bit path is built for "
+             "reversible components only", c, precision(c));
+    }
+  return wide;
+}
+
 void Params::set_block_dims(uint32_t w, uint32_t h) {
   uint32_t lw = w ? ilog2(w) : 0, lh = h ? ilog2(h) : 0;
   if (w == 0 || w != (1u << lw) || h == 0 || h != (1u << lh) || lw < 2 || lh < 2 || lw + lh > 12)
@@ -310,15 +324,7 @@ void Params::finalize_for_encode() {
   uint32_t Bp = (B <= 8) ? 0 : (B < 28 ? B - 8 : 13 + (B >> 2));
   Ccap0 = (uint16_t)(Ccap0 | (uint16_t)Bp);
 
-  // 32-bit coefficient path only (64-bit path is out of scope)
-  for (uint32_t c = 0; c < nc; ++c) {
-    uint32_t pr = quant_for(c).largest_kmax() + 2;
-    if (color_transform() && c < 3)
-      for (uint32_t i = 0; i < 3; ++i) pr = std::max(pr, quant_for(i).largest_kmax() + 2);
-    if (pr > 32)
-      fail(0x000B0001, "component %u needs %u-bit coefficients; only the 32-bit path is "
-           "implemented on the GPU", c, pr);
-  }
+  (void)needs_wide();        // 64-bit coefficients: reversible components only (refuses the rest)
 
   nlt_check_validity();
   if (profile) check_profile();

@@ -149,6 +149,9 @@ struct Params {
   QuantSet* find_qcc(uint32_t c);
   QuantSet& add_qcc(uint32_t c);
   uint32_t precision(uint32_t c) const;     // propose_precision, ojph_params.cpp:1684
+  // true when some component needs more than 32 bits (the reference's 64-bit line buffers and code-block words,
+  // ojph_codeblock.cpp:85-91); fails when such a component is irreversible (not built here)
+  bool needs_wide() const;
 
   // NLT (param_nlt, ojph_params.cpp:2087-2330)
   void set_nonlinear_transform(uint32_t comp, uint32_t type);      // comp 65535 = all components

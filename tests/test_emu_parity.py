@@ -127,14 +127,13 @@ def test_high_bit_depths_on_the_32bit_path(bd, ct, emu_lib, ref):
         assert np.array_equal(a, b)
 
 
-def test_beyond_the_32bit_path_is_refused_loudly(emu_lib, ref):
-    """28-bit RGB with RCT needs 33-bit coefficients (the reference switches to its 64-bit path): both directions
-    refuse with a clear error rather than produce something else"""
+def test_beyond_the_32bit_path_runs_on_64bit_coefficients(emu_lib, ref):
+    """28-bit RGB with RCT needs 33-bit coefficients: the reference switches to its 64-bit line buffers and block
+    coders, and so does this build (byte-identical, lossless)"""
     rng = np.random.default_rng(1)
     p = ob.make_params(64, 48, 3, 28, num_decomps=3, reversible=True, color_transform=True)
     fr = [rng.integers(0, 1 << 28, (48, 64)).astype(np.int32) for _ in range(3)]
-    with pytest.raises(ob.OjphError, match="0x000B0001"):
-        ob.Encoder(p, ob.I32, lib=emu_lib)
     cs = ref.encode(p, fr)
-    with pytest.raises(ob.OjphError, match="0x000B0001"):
-        ob.Decoder(lib=emu_lib).decode(cs)
+    assert ob.Encoder(p, ob.I32, lib=emu_lib).encode(fr) == cs
+    for a, b in zip(ob.Decoder(lib=emu_lib).decode(cs), fr):
+        assert np.array_equal(a, b)

@@ -1,8 +1,8 @@
-"""The reference's self-contained known-answer tests SimpleEncRev53Raw{8,16}{Signed,Unsigned}
-(tests/test_executables.cpp:1698-1712; frame generator :297-310): a 256x256 one-component frame holding a
+"""The reference's self-contained known-answer tests SimpleEncRev53Raw{8,16,24,32}{Signed,Unsigned}
+(tests/test_executables.cpp:1698-1728; frame generator :297-344): a 256x256 one-component frame holding a
 ramp from the smallest to the largest value of the sample type, reversible 5/3, default parameters of
-ojph_compress -- lossless exact, and here also codestream-identical to the reference.  The 24/32-bit
-variants use the 64-bit coefficient path, which is out of scope."""
+ojph_compress -- lossless exact, and here also codestream-identical to the reference.  The 32-bit variants run
+on the 64-bit coefficient path (general DWT kernels on int64, 64-bit block coders)."""
 import numpy as np
 import pytest
 import openjph_b200 as ob
@@ -15,7 +15,8 @@ def ramp(bit_depth, is_signed):
     upper = (1 << (bit_depth - 1)) - 1 if is_signed else (1 << bit_depth) - 1
     lower = -(1 << (bit_depth - 1)) if is_signed else 0
     idx = np.arange(n, dtype=np.int64)
-    return (lower + idx * (upper - lower) // (n - 1)).astype(np.int32).reshape(H, W)
+    v = lower + idx * (upper - lower) // (n - 1)
+    return (v & 0xFFFFFFFF).astype(np.uint32).astype(np.int32).reshape(H, W)      # 32-bit unsigned: the bit pattern in an si32 line
 
 
 def _roundtrip(lib, ref, bit_depth, is_signed):
@@ -29,12 +30,12 @@ def _roundtrip(lib, ref, bit_depth, is_signed):
     assert np.array_equal(refout[0], img)
 
 
-@pytest.mark.parametrize("bit_depth,is_signed", [(8, True), (8, False), (16, True), (16, False)])
+@pytest.mark.parametrize("bit_depth,is_signed", [(8, True), (8, False), (16, True), (16, False), (24, True), (24, False), (32, True), (32, False)])
 def test_simple_enc_rev53_raw_emulator(bit_depth, is_signed, emu_lib, ref):
     _roundtrip(emu_lib, ref, bit_depth, is_signed)
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("bit_depth,is_signed", [(8, True), (8, False), (16, True), (16, False)])
+@pytest.mark.parametrize("bit_depth,is_signed", [(8, True), (8, False), (16, True), (16, False), (24, True), (24, False), (32, True), (32, False)])
 def test_simple_enc_rev53_raw_gpu(bit_depth, is_signed, gpu_lib, ref):
     _roundtrip(None, ref, bit_depth, is_signed)

@@ -246,10 +246,10 @@ def test_truncated_stream_through_expand(apps, tmp_path):
         assert res["ref"] == res["b200"], frac
 
 
-@pytest.mark.parametrize("bd,signed", [(8, True), (8, False), (16, True), (16, False), (24, True), (24, False)])
+@pytest.mark.parametrize("bd,signed", [(8, True), (8, False), (16, True), (16, False), (24, True), (24, False), (32, True), (32, False)])
 def test_raw_round_trip_through_the_apps(bd, signed, apps, tmp_path):
-    """the reference's SimpleEncRev53Raw{8,16,24}{Signed,Unsigned} (tests/test_executables.cpp:1698-1721): a .raw
-    file in, reversible, .raw out, bit exact; the 32-bit-sample ones need the 64-bit coefficient path (refused)"""
+    """the reference's SimpleEncRev53Raw{8,16,24,32}{Signed,Unsigned} (tests/test_executables.cpp:1698-1728): a .raw
+    file in, reversible, .raw out, bit exact; the 32-bit-sample ones run on the 64-bit coefficient path"""
     w = h = 96
     rng = np.random.default_rng(bd + signed)
     lo, hi = (-(1 << (bd - 1)), (1 << (bd - 1))) if signed else (0, 1 << bd)
@@ -269,14 +269,3 @@ def test_raw_round_trip_through_the_apps(bd, signed, apps, tmp_path):
         subprocess.check_call([apps[("expand", fl)], "-i", str(j), "-o", str(o)], stdout=subprocess.DEVNULL)
         res[fl] = (j.read_bytes(), o.read_bytes())
     assert res["ref"] == res["b200"] and res["ref"][1] == raw
-
-
-def test_raw32_is_refused_not_miscoded(apps, tmp_path):
-    w = h = 32
-    src = tmp_path / "in.raw"
-    src.write_bytes(np.random.default_rng(0).integers(0, 1 << 32, w * h, dtype=np.uint64).astype("<u4").tobytes())
-    opts = ["-reversible", "true", "-dims", "{%d,%d}" % (w, h), "-num_comps", "1", "-downsamp", "{1,1}", "-bit_depth", "32", "-signed", "false"]
-    assert subprocess.call([apps[("compress", "ref")], "-i", str(src), "-o", str(tmp_path / "r.j2c")] + opts, stdout=subprocess.DEVNULL) == 0
-    rc = subprocess.call([apps[("compress", "b200")], "-i", str(src), "-o", str(tmp_path / "b.j2c")] + opts,
-                         stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-    assert rc != 0
