@@ -269,3 +269,25 @@ def test_raw_round_trip_through_the_apps(bd, signed, apps, tmp_path):
         subprocess.check_call([apps[("expand", fl)], "-i", str(j), "-o", str(o)], stdout=subprocess.DEVNULL)
         res[fl] = (j.read_bytes(), o.read_bytes())
     assert res["ref"] == res["b200"] and res["ref"][1] == raw
+
+
+@pytest.mark.parametrize("nc", [1, 3])
+def test_pfm_float_through_the_apps(nc, apps, tmp_path):
+    """a .pfm (32-bit float) file in and out (ojph_compress.cpp:602-690, ojph_expand.cpp pfm_out): the applications treat
+    the floats as 32-bit signed integers with the type-3 non-linearity, reversible -- the 64-bit coefficient path"""
+    w, h = 96, 64
+    rng = np.random.default_rng(40 + nc)
+    y, x = np.mgrid[0:h, 0:w]
+    pix = np.stack([(np.sin(x / 7.0 + c) * np.cos(y / 5.0) * (3.0 + c) + rng.normal(0, 0.01, (h, w))).astype("<f4") for c in range(nc)], axis=-1)
+    src = tmp_path / "in.pfm"
+    src.write_bytes((b"PF" if nc == 3 else b"Pf") + b"\n%d %d\n-1.0\n" % (w, h) + pix.tobytes())
+    res = {}
+    for fl in ("ref", "b200"):
+        j = tmp_path / ("o_%s.j2c" % fl)
+        subprocess.check_call([apps[("compress", fl)], "-i", str(src), "-o", str(j), "-reversible", "true"], stdout=subprocess.DEVNULL)
+        o = tmp_path / ("b_%s.pfm" % fl)
+        subprocess.check_call([apps[("expand", fl)], "-i", str(j), "-o", str(o)], stdout=subprocess.DEVNULL)
+        res[fl] = (j.read_bytes(), o.read_bytes())
+    assert res["ref"][0] == res["b200"][0]
+    assert res["ref"][1] == res["b200"][1]
+    assert res["ref"][1][-pix.nbytes:] == pix.tobytes()
