@@ -1,6 +1,6 @@
 """A codestream that never leaves the device: the encoder writes it to device memory, the decoder reads its headers
 from there (ojb_dec_read_headers_device) -- only the marker segments and packet headers the host parsers touch are
-fetched (32 KB pages), code-block bodies stay in HBM.  Same decoded samples as the host-buffer path."""
+fetched (32 KB pages; a codestream under 8 MB is simply copied whole), code-block bodies stay in HBM.  Same decoded samples as the host-buffer path."""
 import numpy as np
 import pytest
 import openjph_b200 as ob
@@ -60,4 +60,4 @@ def test_device_resident_codestream_emulator(emu_lib):
 def test_device_resident_codestream_gpu(gpu_lib):
     _check(None, 640, 480, 3, 8, 1.0, num_decomps=4, reversible=True, color_transform=True)
     _check(None, 4096, 4096, 3, 12, 0.10, num_decomps=5, reversible=True, color_transform=True)
-    _check(None, 2048, 2048, 1, 10, 0.5, num_decomps=5, reversible=False, qstep=0.002, tile=(1024, 1024), tlm=True)
+    _check(None, 2048, 2048, 1, 10, 1.0, num_decomps=5, reversible=False, qstep=0.002, tile=(1024, 1024), tlm=True)
