@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libojph_b200.so")
+# OJB_LIB_PATH: another nvcc build of the same library (A/B of compile-time knobs); still no fallback of any kind
+LIB_PATH = os.environ.get("OJB_LIB_PATH") or os.path.join(_HERE, "libojph_b200.so")
 
 
 class Params(C.Structure):

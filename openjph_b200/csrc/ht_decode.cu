@@ -26,6 +26,11 @@
 
 namespace ojb {
 
+// minimum CTAs per SM asked of the fast coders (caps registers per thread: 6 -> 85, 7 -> 73, 8 -> 64); more frames'
+// kernels fit on an SM at once, at the price of spills beyond 7 (A/B: profiles/r02f_coder_occupancy.md)
+#ifndef OJB_CODER_MINB
+#define OJB_CODER_MINB 1
+#endif
 #define FULL 0xFFFFFFFFu
 #define DEC_WARPS 4
 
@@ -1019,7 +1024,7 @@ ht_decode_serial_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
 //     128-bit window in 8-byte groups as in the general kernel.
 // A U_q beyond missing_msbs + 2 (corrupt data) is clamped and flagged; the block is then zero-filled.
 template <int MODE>       // 0: integer output, 1: float output, 2: sign-magnitude (kernel-level parity entry point)
-__global__ void __launch_bounds__(DEC1_THREADS)
+__global__ void __launch_bounds__(DEC1_THREADS, OJB_CODER_MINB)
 ht_decode_fast_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
                       const uint8_t* __restrict__ cs, uint32_t* __restrict__ coef,
                       const uint16_t* __restrict__ tables, uint32_t* __restrict__ block_status)

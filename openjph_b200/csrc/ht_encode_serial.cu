@@ -23,6 +23,9 @@
 
 namespace ojb {
 
+#ifndef OJB_CODER_MINB
+#define OJB_CODER_MINB 1
+#endif
 #define ES_THREADS 128
 #define ES_MEL_BYTES 200
 #define MEL_EXP(k) ((uint32_t)((0x5433222111000ull >> (4 * (k))) & 7ull))
@@ -396,7 +399,7 @@ ht_encode_serial_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
 //     exponent of the four samples above a quad is 32 - clz(g[q] | g[q+1]) -- one CLZ instead of a 4-way max of
 //     stored exponents; inside the quad the largest exponent is 32 - clz(x0 | x1 | x2 | x3) and a sample reaches it
 //     iff x_i >> (e_max - 1) is non-zero.
-__global__ void __launch_bounds__(ES_THREADS)
+__global__ void __launch_bounds__(ES_THREADS, OJB_CODER_MINB)
 ht_encode_fast_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
                       const uint32_t* __restrict__ coef, uint8_t* __restrict__ slots,
                       EncResult* __restrict__ results, const uint16_t* __restrict__ tables,
