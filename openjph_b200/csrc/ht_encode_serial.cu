@@ -407,7 +407,6 @@ ht_encode_fast_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
 {
   __shared__ uint16_t s_vlc[2 * 2048];
   __shared__ uint16_t s_uvlc[36];
-  __shared__ uint8_t s_mel[ES_MEL_BYTES * ES_THREADS];
   __shared__ uint32_t s_g[17 * ES_THREADS];
 
   for (uint32_t i = threadIdx.x; i < 2 * 2048; i += blockDim.x) s_vlc[i] = tables[i];
@@ -423,9 +422,17 @@ ht_encode_fast_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
   uint8_t* slot = slots + blk.slot_off;
   uint2* ms_dst = reinterpret_cast<uint2*>(slot);          // slots are 16-byte aligned
   uint32_t* vl_end = reinterpret_cast<uint32_t*>(slot + blk.slot_cap);
-  uint8_t* mel_buf = s_mel + threadIdx.x;
   uint32_t* gw = s_g + threadIdx.x;
   const uint32_t slot_words = blk.slot_cap >> 2;
+  // MEL bytes (a few dozen per block, at most 192) are parked inside the block's own slot, in the gap the host's
+  // sizing leaves between the MagSgn worst case and the VLC worst case, instead of 200 bytes of shared memory per
+  // thread: the kernel's footprint drops from 42 KB to 17 KB per CTA and more frames' CTAs fit on an SM
+  uint8_t* mel_buf;
+  {
+    const uint32_t nqp = ((uint32_t)(blk.w >> 1) * (uint32_t)(blk.h >> 1) + 1u) / 2u;
+    uint32_t vl_worst = (nqp * 30u + 12u + 7u) / 8u; vl_worst += vl_worst / 7u + 8u;
+    mel_buf = slot + (blk.slot_cap - vl_worst - 216u);
+  }
   const uint32_t pm1 = p - 1u, vmask = (2u << (31u - p)) - 2u;       // p >= 16
 
   MsWriter ms; ms.w0 = 0; ms.w1 = 0; ms.nbits = 0; ms.words = 0; ms.last_ff = 0;
@@ -494,7 +501,7 @@ ht_encode_fast_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
         const uint32_t eps = ((x[0] >> sh) | ((x[1] >> sh) << 1) | ((x[2] >> sh) << 2) | ((x[3] >> sh) << 3)) & (0u - min(u, 1u));
         const uint32_t tuple = vtab[(cq << 8) + (rho << 4) + eps];
         pair_bits |= (tuple >> 8) << pair_len; pair_len += (tuple >> 4) & 7u;      // :661-662
-        if (cq == 0) mel_event(mel, rho != 0, mel_buf);                          // :664-665
+        if (cq == 0) mel_event<1>(mel, rho != 0, mel_buf);                          // :664-665
         {                                                                         // :667-674
           const uint32_t rb = (rho * 0x00204081u) & 0x01010101u, eb = ((tuple & 15u) * 0x00204081u) & 0x01010101u;
           const uint32_t mb = (Uq * 0x01010101u - eb) & (rb * 0xFFu);
@@ -524,7 +531,7 @@ ht_encode_fast_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
         const uint32_t u0 = uq[0], u1 = uq[1];
         uint32_t c0, c1;
         if (first) {
-          if (u0 > 0 && u1 > 0) mel_event(mel, min(u0, u1) > 2, mel_buf);
+          if (u0 > 0 && u1 > 0) mel_event<1>(mel, min(u0, u1) > 2, mel_buf);
           if (u0 > 2 && u1 > 2) { c0 = s_uvlc[u0 - 2]; c1 = s_uvlc[u1 - 2]; }
           else if (u0 > 2 && u1 > 0) { c0 = s_uvlc[u0]; c1 = (u1 - 1) | (1u << 3); }     // one-bit u1
           else { c0 = s_uvlc[u0]; c1 = s_uvlc[u1]; }
@@ -548,7 +555,7 @@ ht_encode_fast_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
 
   if (overflow) { atomicOr(status, 1u); results[bidx].len_head = 0; results[bidx].len_tail = 0; return; }
   if (any_sig == 0) { results[bidx].len_head = 0; results[bidx].len_tail = 0; return; }   // block not included
-  terminate_block(ms, vlc, mel, mel_buf, slot, blk.slot_cap, status, results[bidx]);
+  terminate_block<1>(ms, vlc, mel, mel_buf, slot, blk.slot_cap, status, results[bidx]);
 }
 
 
