@@ -121,7 +121,9 @@ struct RevDec {               // backward-growing stream (VLC, MRP)
   // words the next refill's funnel shift needs.
   const uint32_t* wnext; const uint32_t* wbase; uint32_t* ring; uint32_t ridx, lo, hi, sh;
 };
+#ifndef VLC_RING
 #define VLC_RING 8
+#endif
 template <int STRIDE = DEC1_THREADS>
 __device__ __forceinline__ void rev_ring_issue(RevDec& v) {
   uint32_t* slot = v.ring + v.ridx * STRIDE;
@@ -1029,15 +1031,21 @@ ht_decode_fast_kernel(const DecBlock* __restrict__ blocks, uint32_t nblocks,
                       const uint8_t* __restrict__ cs, uint32_t* __restrict__ coef,
                       const uint16_t* __restrict__ tables, uint32_t* __restrict__ block_status)
 {
+#ifdef OJB_DEC_TABLES_GLOBAL
+  const DecTables& T = *reinterpret_cast<const DecTables*>(tables);       // 5 KB, hot in L1
+#else
   __shared__ DecTables T;
+#endif
   __shared__ uint32_t s_vring[VLC_RING * DEC1_THREADS];    // per-thread FIFO of VLC words (slot-major)
   __shared__ uint2 s_mring[VLC_RING * DEC1_THREADS];       // per-thread FIFO of MagSgn 8-byte groups
   __shared__ uint32_t s_g[17 * DEC1_THREADS];              // g[2j] | g[2j+1] << 16 of the row above, per pair j
+#ifndef OJB_DEC_TABLES_GLOBAL
   {
     uint16_t* d = reinterpret_cast<uint16_t*>(&T);
     for (uint32_t i = threadIdx.x; i < sizeof(DecTables) / 2; i += blockDim.x) d[i] = tables[i];
   }
   __syncthreads();
+#endif
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nblocks) return;
   const DecBlock blk = blocks[b];
