@@ -697,7 +697,8 @@ def main():
     for pj in (PROFILE_JSON, PROFILE_FALLBACK):
         try:
             prof = json.load(open(os.path.join(ROOT, "profiles", pj)))
-            keys = {"ht_encode": ["ht_encode_serial", "ht_encode"], "ht_decode": ["ht_decode_serial", "ht_dec_fill", "ht_dec_step1", "ht_dec_step2"],
+            keys = {"ht_encode": ["ht_encode_fast", "ht_encode_serial", "ht_encode"],
+                    "ht_decode": ["ht_decode_fast", "ht_decode_serial", "ht_dec_fill", "ht_dec_step1", "ht_dec_step2"],
                     "dwt_fwd": ["dwt_fwd"], "dwt_inv": ["dwt_inv"]}[dom]
             traffic = sum(int(prof[k]["traffic_bytes"]) for k in keys if k in prof)
             traffic_src = "profiles/" + pj
