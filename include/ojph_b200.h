@@ -68,6 +68,24 @@ typedef struct ojb_params {
   uint32_t qcc_qstep_seq[16];
   uint32_t qcc_qfactor[16], qcc_ctype[16];     /* ctype: 0 Y, 1 Cb, 2 Cr */
   uint32_t qcc_qfactor_seq[16];
+  /* Part 2 wavelet structures.  The reference READS DFS and ATK marker segments (param_dfs::read,
+   * ojph_params.cpp:2596; param_atk::read, :2770; resolution::finalize_alloc, ojph_resolution.cpp:264-396) and has
+   * no writer for them; the decoder here reads what it reads, and the encoder fields below are this library's
+   * own addition so that such streams can be produced (and checked against the reference's decoder):
+   *   dfs_type[i], i < dfs_num_levels: how decomposition level i + 1 (1 = finest) splits -- 1 both ways,
+   *     2 horizontally only, 3 vertically only; levels past the list repeat the last entry; 0 levels = dyadic.
+   *   atk_*: a whole-sample symmetric lifting kernel with one tap pair per step, steps in SYNTHESIS order (step 0
+   *     acts on the even samples): irreversible x[n] -= A (x[n-1] + x[n+1]) with scaling K, or reversible
+   *     x[n] -= (b + a (x[n-1] + x[n+1])) >> e.  atk_num_steps = 0 keeps the COD's 5/3 or 9/7; at most 4 steps run
+   *     on the device. */
+  uint32_t dfs_num_levels;
+  uint32_t dfs_type[32];
+  uint32_t atk_num_steps;
+  uint32_t atk_reversible;
+  float    atk_K;
+  float    atk_A[8];
+  int32_t  atk_a[8], atk_b[8];
+  uint32_t atk_e[8];
 } ojb_params;
 
 typedef struct ojb_frame_info {

@@ -30,6 +30,9 @@ class Params(C.Structure):
         ("profile", C.c_uint32),
         ("qcc_calls", C.c_uint32 * 16), ("qcc_qstep", C.c_float * 16), ("qcc_qstep_seq", C.c_uint32 * 16),
         ("qcc_qfactor", C.c_uint32 * 16), ("qcc_ctype", C.c_uint32 * 16), ("qcc_qfactor_seq", C.c_uint32 * 16),
+        ("dfs_num_levels", C.c_uint32), ("dfs_type", C.c_uint32 * 32),
+        ("atk_num_steps", C.c_uint32), ("atk_reversible", C.c_uint32), ("atk_K", C.c_float), ("atk_A", C.c_float * 8),
+        ("atk_a", C.c_int32 * 8), ("atk_b", C.c_int32 * 8), ("atk_e", C.c_uint32 * 8),
     ]
 
 

@@ -25,7 +25,7 @@ class OjphError(RuntimeError):
 def make_params(width, height, num_comps=1, bit_depth=8, is_signed=False, num_decomps=5, block=(64, 64),
                 reversible=True, color_transform=False, prog_order="RPCL", qstep=-1.0, qfactor=0,
                 tile=(0, 0), offset=(0, 0), tile_offset=(0, 0), precincts=None, subsampling=None,
-                tlm=False, tilepart_div=0, planar=-1, coc=None, nlt=None, profile=None, qcc=None):
+                tlm=False, tilepart_div=0, planar=-1, coc=None, nlt=None, profile=None, qcc=None, decomp=None, atk=None):
     p = _lib.Params()
     p.width, p.height = width, height
     p.off_x, p.off_y = offset
@@ -72,6 +72,25 @@ def make_params(width, height, num_comps=1, bit_depth=8, is_signed=False, num_de
             p.qcc_calls[c] |= 1; p.qcc_qstep[c] = call[2]; p.qcc_qstep_seq[c] = seq
         else:
             p.qcc_calls[c] |= 2; p.qcc_ctype[c], p.qcc_qfactor[c] = call[2], call[3]; p.qcc_qfactor_seq[c] = seq
+    # Part 2 structures (encoder extension; the reference only reads them): decomp = "BHVHB" or [1, 2, 3, ...] per
+    # level, finest first (B both ways, H horizontal only, V vertical only); atk = dict(reversible=False, K=..., A=[...])
+    # or dict(reversible=True, steps=[(a, b, e), ...]), lifting steps in synthesis order
+    if decomp:
+        kinds = [{"X": 0, "B": 1, "H": 2, "V": 3}[d] if isinstance(d, str) else int(d) for d in decomp]
+        p.dfs_num_levels = len(kinds)
+        for i, k in enumerate(kinds):
+            p.dfs_type[i] = k
+    if atk:
+        if atk.get("reversible", False):
+            p.atk_reversible = 1
+            p.atk_num_steps = len(atk["steps"])
+            for i, (a, b, e) in enumerate(atk["steps"]):
+                p.atk_a[i], p.atk_b[i], p.atk_e[i] = a, b, e
+        else:
+            p.atk_num_steps = len(atk["A"])
+            p.atk_K = atk["K"]
+            for i, a in enumerate(atk["A"]):
+                p.atk_A[i] = a
     # param_nlt::set_nonlinear_transform calls, in order: {"all": 3, 1: 0, ...} (types 0 and 3)
     for seq, (c, t) in enumerate((nlt or {}).items()):
         if c == "all":

@@ -35,9 +35,6 @@ __device__ __forceinline__ int load_sample(const void* img, uint32_t type, uint6
   return reinterpret_cast<const int*>(base)[idx];
 }
 
-// 5/3 lifting step on smem (predict: odd -= (a+b)>>1 ; update: even += (a+b+2)>>2)
-template <typename I> __device__ __forceinline__ I rev_pred(I d, I a, I b) { return d - ((a + b) >> 1); }
-template <typename I> __device__ __forceinline__ I rev_upd(I d, I a, I b) { return d + ((a + b + 2) >> 2); }
 // 9/7: dst += coeff * (a + b), separate multiply and add (no FMA), ojph_transform.cpp:703
 __device__ __forceinline__ float irv_step(float d, float a, float b, float c) {
   return __fadd_rn(d, __fmul_rn(c, __fadd_rn(a, b)));
@@ -119,32 +116,35 @@ dwt_fwd_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, const void* __re
   }
   __syncthreads();
 
-  if (!J.nodwt) {
-    const int NSTEPS = REV ? 2 : 4;
-    // ---- vertical lifting on every column (halo columns too: they feed the horizontal pass)
+  // One lifting step of the kernel in analysis direction; steps are numbered in synthesis order (param_atk,
+  // ojph_params_local.h:1103-1232): step s touches the samples of parity s & 1 and analysis runs them last to first
+  // (gen_rev_vert_step / gen_irv_vert_step, ojph_transform.cpp:209-262, :691-704).  The built-in 5/3 and 9/7 are the
+  // same formula with their table values (init_rev53 / init_irv97, ojph_params.cpp:2870-2895).
+  auto lift = [&](T d, T a, T b, int s) -> T {
+    if (REV) return (T)((I)d + (((I)J.step_b[s] + (I)J.step_a[s] * ((I)a + (I)b)) >> J.step_e[s]));
+    return (T)irv_step((float)d, (float)a, (float)b, J.step_A[s]);
+  };
+  const int NS = (int)J.nsteps;
+  // ---- vertical lifting on every column (halo columns too: they feed the horizontal pass)
+  if (J.vsplit) {
     if (J.h > 1) {
-      for (int s = 1; s <= NSTEPS; ++s) {
-        const int rfirst = s;                       // parity of s: odd rows for odd steps
-        const int rlast = DW_ROWS - 1 - s;
+      for (int i = 0; i < NS; ++i) {
+        const int s = NS - 1 - i, par = s & 1;
+        int rfirst = i + 1; if ((rfirst & 1) != par) ++rfirst;
+        int rlast = DW_ROWS - 2 - i; if ((rlast & 1) != par) --rlast;
         const int count = ((rlast - rfirst) / 2 + 1) * DW_COLS;
         for (uint32_t k = 0; k < nc; ++k) {
           T* t = smem + k * DW_TILE_WORDS;
           for (int e = (int)tid; e < count; e += DW_THREADS) {
             const int rr = e / DW_COLS, c = e - rr * DW_COLS;
             const int r = rfirst + 2 * rr;
-            T d = t[r * DW_PITCH + c], a = t[(r - 1) * DW_PITCH + c], b = t[(r + 1) * DW_PITCH + c];
-            if (REV) d = (T)((s == 1) ? rev_pred<I>((I)d, (I)a, (I)b) : rev_upd<I>((I)d, (I)a, (I)b));
-            else {
-              const float cf = (s == 1) ? IRV_ALPHA : (s == 2) ? IRV_BETA : (s == 3) ? IRV_GAMMA : IRV_DELTA;
-              d = (T)irv_step((float)d, (float)a, (float)b, cf);
-            }
-            t[r * DW_PITCH + c] = d;
+            t[r * DW_PITCH + c] = lift(t[r * DW_PITCH + c], t[(r - 1) * DW_PITCH + c], t[(r + 1) * DW_PITCH + c], s);
           }
         }
         __syncthreads();
       }
       if (!REV) {      // low rows * 1/K, high rows * K (ojph_resolution.cpp:662-676)
-        const float K = IRV_K, Kinv = 1.0f / IRV_K;
+        const float K = J.K, Kinv = 1.0f / J.K;
         for (uint32_t k = 0; k < nc; ++k) {
           T* t = smem + k * DW_TILE_WORDS;
           for (uint32_t e = tid; e < DW_TH * DW_COLS; e += DW_THREADS) {
@@ -164,55 +164,49 @@ dwt_fwd_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, const void* __re
       }
       __syncthreads();
     }
-    // ---- horizontal lifting on the rows this tile outputs
-    if (J.w > 1) {
-      for (int s = 1; s <= NSTEPS; ++s) {
-        const int cfirst = s, clast = DW_COLS - 1 - s;
-        const int ncols = (clast - cfirst) / 2 + 1;
-        const int count = DW_TH * ncols;
-        for (uint32_t k = 0; k < nc; ++k) {
-          T* t = smem + k * DW_TILE_WORDS;
-          for (int e = (int)tid; e < count; e += DW_THREADS) {
-            const int rr = e / ncols, j = e - rr * ncols;
-            const int r = DW_H + rr, c = cfirst + 2 * j;
-            T d = t[r * DW_PITCH + c], a = t[r * DW_PITCH + c - 1], b = t[r * DW_PITCH + c + 1];
-            if (REV) d = (T)((s == 1) ? rev_pred<I>((I)d, (I)a, (I)b) : rev_upd<I>((I)d, (I)a, (I)b));
-            else {
-              const float cf = (s == 1) ? IRV_ALPHA : (s == 2) ? IRV_BETA : (s == 3) ? IRV_GAMMA : IRV_DELTA;
-              d = (T)irv_step((float)d, (float)a, (float)b, cf);
-            }
-            t[r * DW_PITCH + c] = d;
-          }
+  }
+  // ---- horizontal lifting on the rows this tile outputs
+  if (J.hsplit && J.w > 1) {
+    for (int i = 0; i < NS; ++i) {
+      const int s = NS - 1 - i, par = s & 1;
+      int cfirst = i + 1; if ((cfirst & 1) != par) ++cfirst;
+      int clast = DW_COLS - 2 - i; if ((clast & 1) != par) --clast;
+      const int ncols = (clast - cfirst) / 2 + 1;
+      const int count = DW_TH * ncols;
+      for (uint32_t k = 0; k < nc; ++k) {
+        T* t = smem + k * DW_TILE_WORDS;
+        for (int e = (int)tid; e < count; e += DW_THREADS) {
+          const int rr = e / ncols, j = e - rr * ncols;
+          const int r = DW_H + rr, c = cfirst + 2 * j;
+          t[r * DW_PITCH + c] = lift(t[r * DW_PITCH + c], t[r * DW_PITCH + c - 1], t[r * DW_PITCH + c + 1], s);
         }
-        __syncthreads();
       }
+      __syncthreads();
     }
   }
 
-  // ---- store: de-interleave into LL / HL / LH / HH
-  const bool hscale = !REV && !J.nodwt && J.w > 1;
-  const bool wodd1 = !J.nodwt && J.w == 1 && (x0 & 1);         // single odd column: x2
+  // ---- store: de-interleave into LL / HL / LH / HH (a level that splits one way only has LL and HL, or LL and LH)
+  const bool hs = J.hsplit != 0, vs = J.vsplit != 0;
+  const bool hscale = !REV && hs && J.w > 1;
+  const bool wodd1 = hs && J.w == 1 && (x0 & 1);         // single odd column: x2
+  const uint32_t nrows = vs ? DW_TH / 2 : DW_TH, ncols = hs ? DW_TW / 2 : DW_TW;
+  const float Kh = J.K, Kl = 1.0f / J.K;
   for (uint32_t k = 0; k < nc; ++k) {
     const T* t = smem + k * DW_TILE_WORDS;
     for (uint32_t band = 0; band < 4; ++band) {
       const int bh = (int)(band & 1), bv = (int)(band >> 1);
-      if (J.nodwt && band) break;
-      for (uint32_t e = tid; e < (DW_TH / 2) * (DW_TW / 2) * (J.nodwt ? 4u : 1u); e += DW_THREADS) {
-        int r, c;
-        if (J.nodwt) { r = DW_H + (int)(e / DW_TW); c = DW_H + (int)(e % DW_TW); }
-        else { r = DW_H + 2 * (int)(e / (DW_TW / 2)) + bv; c = DW_H + 2 * (int)(e % (DW_TW / 2)) + bh; }
+      if ((bh && !hs) || (bv && !vs)) continue;
+      for (uint32_t e = tid; e < nrows * ncols; e += DW_THREADS) {
+        const int rr = (int)(e / ncols), cc = (int)(e - (uint32_t)rr * ncols);
+        const int r = DW_H + (vs ? 2 * rr + bv : rr), c = DW_H + (hs ? 2 * cc + bh : cc);
         const int u = U0 + c - DW_H, v = V0 + r - DW_H;
         if (u < x0 || u >= x1 || v < y0 || v >= y1) continue;
         T val = t[r * DW_PITCH + c];
-        int bx, by;
-        if (J.nodwt) { bx = u - x0; by = v - y0; }
-        else {
-          // with a single row / column the lone sample keeps its parity class
-          bx = (u >> 1) - (bh ? (x0 >> 1) : ((x0 + 1) >> 1));
-          by = (v >> 1) - (bv ? (y0 >> 1) : ((y0 + 1) >> 1));
-          if (hscale) val = (T)__fmul_rn((float)val, bh ? IRV_K : (1.0f / IRV_K));
-          if (wodd1) val = REV ? (T)((I)val << 1) : (T)__fmul_rn((float)val, 2.0f);
-        }
+        // with a single row / column the lone sample keeps its parity class
+        const int bx = hs ? (u >> 1) - (bh ? (x0 >> 1) : ((x0 + 1) >> 1)) : u - x0;
+        const int by = vs ? (v >> 1) - (bv ? (y0 >> 1) : ((y0 + 1) >> 1)) : v - y0;
+        if (hscale) val = (T)__fmul_rn((float)val, bh ? Kh : Kl);
+        if (wodd1) val = REV ? (T)((I)val << 1) : (T)__fmul_rn((float)val, 2.0f);
         if (band == 0 && !J.last) {
           reinterpret_cast<T*>(coef)[J.ll_off[k] + (size_t)by * J.ll_stride[k] + (size_t)bx] = val;
         } else {

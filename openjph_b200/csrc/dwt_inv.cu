@@ -67,12 +67,11 @@ dwt_inv_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, void* __restrict
     const int v = reflect_coord(V0 - DW_H + (int)r, y0, y1 - 1);
     for (uint32_t k = 0; k < nc; ++k) {
       T val;
-      if (J.nodwt) {
-        val = cf[J.band_off[k][0] + (size_t)(v - y0) * J.band_stride[k][0] + (size_t)(u - x0)];
-      } else {
-        const int bh = u & 1, bv = v & 1, band = bh + 2 * bv;
-        const int bx = (u >> 1) - (bh ? (x0 >> 1) : ((x0 + 1) >> 1));
-        const int by = (v >> 1) - (bv ? (y0 >> 1) : ((y0 + 1) >> 1));
+      {
+        // a level that splits one way only (DFS) interleaves LL with HL along x, or LL with LH along y
+        const int bh = J.hsplit ? (u & 1) : 0, bv = J.vsplit ? (v & 1) : 0, band = bh + 2 * bv;
+        const int bx = J.hsplit ? (u >> 1) - (bh ? (x0 >> 1) : ((x0 + 1) >> 1)) : u - x0;
+        const int by = J.vsplit ? (v >> 1) - (bv ? (y0 >> 1) : ((y0 + 1) >> 1)) : v - y0;
         if (band == 0 && !J.last) val = cf[J.ll_off[k] + (size_t)by * J.ll_stride[k] + (size_t)bx];
         else val = cf[J.band_off[k][band] + (size_t)by * J.band_stride[k][band] + (size_t)bx];
       }
@@ -81,12 +80,18 @@ dwt_inv_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, void* __restrict
   }
   __syncthreads();
 
-  if (!J.nodwt) {
-    const int NSTEPS = REV ? 2 : 4;
-    // ---- horizontal synthesis on every row (halo rows feed the vertical pass)
+  // One lifting step in synthesis direction, steps in the kernel's own (synthesis) order: step s acts on the samples
+  // of parity s & 1 (gen_rev_horz_syn / gen_irv_horz_syn, ojph_transform.cpp:514-560, :785-849)
+  auto unlift = [&](T d, T a, T b, int s) -> T {
+    if (REV) return (T)((I)d - (((I)J.step_b[s] + (I)J.step_a[s] * ((I)a + (I)b)) >> J.step_e[s]));
+    return (T)__fadd_rn((float)d, __fmul_rn(-J.step_A[s], __fadd_rn((float)a, (float)b)));
+  };
+  const int NS = (int)J.nsteps;
+  // ---- horizontal synthesis on every row (halo rows feed the vertical pass)
+  if (J.hsplit) {
     if (J.w > 1) {
       if (!REV) {   // low * K, high * 1/K (irv_horz_syn, ojph_transform.cpp:797-809)
-        const float K = IRV_K, Kinv = 1.0f / IRV_K;
+        const float K = J.K, Kinv = 1.0f / J.K;
         for (uint32_t k = 0; k < nc; ++k) {
           T* t = smem + k * DW_TILE_WORDS;
           for (uint32_t e = tid; e < DW_ROWS * DW_COLS; e += DW_THREADS) {
@@ -96,11 +101,10 @@ dwt_inv_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, void* __restrict
         }
         __syncthreads();
       }
-      for (int s = 1; s <= NSTEPS; ++s) {
-        // synthesis step s updates even positions for odd s, odd positions for even s
-        const int par = (s & 1) ? 0 : 1;
-        int cfirst = s; if ((cfirst & 1) != par) ++cfirst;
-        int clast = DW_COLS - 1 - s; if ((clast & 1) != par) --clast;
+      for (int s = 0; s < NS; ++s) {
+        const int par = s & 1;
+        int cfirst = s + 1; if ((cfirst & 1) != par) ++cfirst;
+        int clast = DW_COLS - 2 - s; if ((clast & 1) != par) --clast;
         const int ncols = (clast - cfirst) / 2 + 1;
         const int count = DW_ROWS * ncols;
         for (uint32_t k = 0; k < nc; ++k) {
@@ -108,15 +112,7 @@ dwt_inv_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, void* __restrict
           for (int e = (int)tid; e < count; e += DW_THREADS) {
             const int r = e / ncols, j = e - r * ncols;
             const int c = cfirst + 2 * j;
-            T d = t[r * DW_PITCH + c], a = t[r * DW_PITCH + c - 1], b = t[r * DW_PITCH + c + 1];
-            if (REV) {
-              if (s == 1) d = (T)((I)d - (((I)a + (I)b + 2) >> 2));
-              else d = (T)((I)d + (((I)a + (I)b) >> 1));
-            } else {
-              const float co = (s == 1) ? IRV_DELTA : (s == 2) ? IRV_GAMMA : (s == 3) ? IRV_BETA : IRV_ALPHA;
-              d = (T)__fadd_rn((float)d, __fmul_rn(-co, __fadd_rn((float)a, (float)b)));
-            }
-            t[r * DW_PITCH + c] = d;
+            t[r * DW_PITCH + c] = unlift(t[r * DW_PITCH + c], t[r * DW_PITCH + c - 1], t[r * DW_PITCH + c + 1], s);
           }
         }
         __syncthreads();
@@ -131,10 +127,12 @@ dwt_inv_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, void* __restrict
       }
       __syncthreads();
     }
-    // ---- vertical synthesis on the columns this tile outputs
+  }
+  // ---- vertical synthesis on the columns this tile outputs
+  if (J.vsplit) {
     if (J.h > 1) {
       if (!REV) {   // even rows * K, odd rows * 1/K (ojph_resolution.cpp:855-872)
-        const float K = IRV_K, Kinv = 1.0f / IRV_K;
+        const float K = J.K, Kinv = 1.0f / J.K;
         for (uint32_t k = 0; k < nc; ++k) {
           T* t = smem + k * DW_TILE_WORDS;
           for (uint32_t e = tid; e < DW_ROWS * DW_TW; e += DW_THREADS) {
@@ -144,25 +142,17 @@ dwt_inv_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, void* __restrict
         }
         __syncthreads();
       }
-      for (int s = 1; s <= NSTEPS; ++s) {
-        const int par = (s & 1) ? 0 : 1;
-        int rfirst = s; if ((rfirst & 1) != par) ++rfirst;
-        int rlast = DW_ROWS - 1 - s; if ((rlast & 1) != par) --rlast;
+      for (int s = 0; s < NS; ++s) {
+        const int par = s & 1;
+        int rfirst = s + 1; if ((rfirst & 1) != par) ++rfirst;
+        int rlast = DW_ROWS - 2 - s; if ((rlast & 1) != par) --rlast;
         const int count = ((rlast - rfirst) / 2 + 1) * DW_TW;
         for (uint32_t k = 0; k < nc; ++k) {
           T* t = smem + k * DW_TILE_WORDS;
           for (int e = (int)tid; e < count; e += DW_THREADS) {
             const int rr = e / DW_TW, c = DW_H + (e - rr * DW_TW);
             const int r = rfirst + 2 * rr;
-            T d = t[r * DW_PITCH + c], a = t[(r - 1) * DW_PITCH + c], b = t[(r + 1) * DW_PITCH + c];
-            if (REV) {
-              if (s == 1) d = (T)((I)d - (((I)a + (I)b + 2) >> 2));
-              else d = (T)((I)d + (((I)a + (I)b) >> 1));
-            } else {
-              const float co = (s == 1) ? IRV_DELTA : (s == 2) ? IRV_GAMMA : (s == 3) ? IRV_BETA : IRV_ALPHA;
-              d = (T)__fadd_rn((float)d, __fmul_rn(-co, __fadd_rn((float)a, (float)b)));
-            }
-            t[r * DW_PITCH + c] = d;
+            t[r * DW_PITCH + c] = unlift(t[r * DW_PITCH + c], t[(r - 1) * DW_PITCH + c], t[(r + 1) * DW_PITCH + c], s);
           }
         }
         __syncthreads();

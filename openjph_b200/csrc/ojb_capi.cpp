@@ -99,6 +99,28 @@ static void to_params(const ojb_params* s, Params& P) {
     std::stable_sort(order, order + n, [&](uint32_t a, uint32_t b) { return s->nlt_seq[a] < s->nlt_seq[b]; });
     for (uint32_t i = 0; i < n; ++i) P.set_nonlinear_transform(order[i], s->nlt_comp[order[i]] - 1);
   }
+  // Part 2 structures (this library's encoder extension)
+  if (s->dfs_num_levels) {
+    if (s->dfs_num_levels > 32) fail(0x000B0022, "at most 32 decomposition levels can be described");
+    for (uint32_t i = 0; i < s->dfs_num_levels; ++i) P.enc_dfs.push_back((uint8_t)std::min(s->dfs_type[i], 255u));
+  }
+  if (s->atk_num_steps) {
+    if (s->atk_num_steps > 8) fail(0x000B0023, "at most 8 lifting steps go through this structure");
+    P.enc_atk_set = true;
+    P.enc_atk.Satk = s->atk_reversible ? 0x1000 : 0;
+    P.enc_atk.K = s->atk_reversible ? 1.0f : s->atk_K;
+    if (!s->atk_reversible && !(s->atk_K > 0.0f)) fail(0x000B0023, "the kernel's scaling factor K must be positive");
+    for (uint32_t i = 0; i < s->atk_num_steps; ++i) {
+      AtkStep t; t.A = s->atk_A[i];
+      if (s->atk_a[i] < -32768 || s->atk_a[i] > 32767 || s->atk_b[i] < -32768 || s->atk_b[i] > 32767 || s->atk_e[i] > 255)
+        fail(0x000B0023, "reversible lifting parameters out of range");
+      t.a = (int16_t)s->atk_a[i]; t.b = (int16_t)s->atk_b[i]; t.e = (uint8_t)s->atk_e[i];
+      P.enc_atk.steps.push_back(t);
+    }
+    // the kernel decides reversibility for every component
+    P.wavelet = s->atk_reversible ? DWT_REV53 : DWT_IRV97;
+    if (!s->atk_reversible && s->qstep > 0.0f) P.qcd.base_delta = s->qstep;
+  }
   if (s->profile > 2) fail(0x000300A1, "unkownn or unsupported profile");
   P.profile = s->profile;
   P.need_tlm = s->tlm != 0;

@@ -81,7 +81,8 @@ void CodecBase::plan_image(uint32_t sample_type) {
     if (sample_type != ST_I32 && params.comps[c].is_signed)
       fail(0x000B0011, "signed components need the 32-bit sample container");
     // reconstruction size: sub-sampling times 2^skip_recon (param_siz::get_recon_width, ojph_params.cpp)
-    const uint32_t rdx = params.comps[c].dx << skip_recon, rdy = params.comps[c].dy << skip_recon;
+    uint32_t fx, fy; params.res_downsamp(c, skip_recon, fx, fy);   // 2^skip_recon both ways unless a DFS says otherwise (get_recon_downsampling, :931-944)
+    const uint32_t rdx = params.comps[c].dx * fx, rdy = params.comps[c].dy * fy;
     img_w[c] = div_ceil(params.Xsiz, rdx) - div_ceil(params.XOsiz, rdx);
     img_h[c] = div_ceil(params.Ysiz, rdy) - div_ceil(params.YOsiz, rdy);
     img_off[c] = off;
@@ -101,7 +102,7 @@ void CodecBase::build_dwt_jobs(bool forward) {
   for (uint32_t c = 0; c < nc; ++c) nlev = std::max(nlev, P.decomps(c));
   if (P.color_transform())
     for (uint32_t c = 1; c < 3; ++c)
-      if (P.decomps(c) != P.decomps(0) || P.wavelet_of(c) != P.wavelet_of(0))
+      if (P.decomps(c) != P.decomps(0) || P.wavelet_of(c) != P.wavelet_of(0) || P.dfs_of(c) != P.dfs_of(0))
         fail(0x000B0006, "the colour transform needs one coding style for the first three components");
   jobs.assign(nlev, std::vector<JobGroup>());
   uint32_t es = esize_of(img_type);
@@ -133,7 +134,20 @@ void CodecBase::build_dwt_jobs(bool forward) {
         DwtJob j; memset(&j, 0, sizeof(j));
         const ResGeom& rg = t.comps[c].res[r];
         j.w = rg.rect.w; j.h = rg.rect.h; j.x0 = rg.rect.x0; j.y0 = rg.rect.y0;
-        j.ncomp = k; j.first = is_top ? 1u : 0u; j.last = (r <= 1) ? 1u : 0u; j.nodwt = conv_only ? 1u : 0u;
+        j.ncomp = k; j.first = is_top ? 1u : 0u; j.last = (r <= 1) ? 1u : 0u;
+        // which way this level lifts (one way only, or not at all, under a DFS marker segment) and with which kernel
+        j.hsplit = conv_only ? 0u : rg.hsplit; j.vsplit = conv_only ? 0u : rg.vsplit;
+        j.nodwt = (j.hsplit | j.vsplit) ? 0u : 1u;
+        {
+          const AtkSpec& kern = P.atk_of(c);
+          if (kern.steps.size() > DWT_MAX_STEPS)
+            fail(0x000B0025, "transformation kernels with more than %d lifting steps are not built (this one has %d)",
+                 DWT_MAX_STEPS, (int)kern.steps.size());
+          j.nsteps = (uint32_t)kern.steps.size(); j.K = kern.K;
+          for (uint32_t i = 0; i < j.nsteps; ++i) {
+            j.step_A[i] = kern.steps[i].A; j.step_a[i] = kern.steps[i].a; j.step_b[i] = kern.steps[i].b; j.step_e[i] = kern.steps[i].e;
+          }
+        }
         j.src_type = img_type; j.bit_depth = P.comps[c].bit_depth; j.is_signed = P.comps[c].is_signed ? 1u : 0u;
         if (is_top && P.nlt_any())             // the type-3 map only touches signed samples (ojph_tile.cpp:352, 446)
           for (uint32_t i = 0; i < k; ++i)
@@ -143,8 +157,8 @@ void CodecBase::build_dwt_jobs(bool forward) {
           const ResGeom& rr = tc.res[r];
           if (is_top) {
             // the resolution's rectangle sits at (ceil(x0 / 2^s) - ceil(XO / (dx 2^s))) in the output plane
-            const uint32_t sh = top;
-            uint32_t cx0 = div_ceil(P.XOsiz, P.comps[c + i].dx << sh), cy0 = div_ceil(P.YOsiz, P.comps[c + i].dy << sh);
+            uint32_t fx, fy; P.res_downsamp(c + i, top, fx, fy);
+            uint32_t cx0 = div_ceil(P.XOsiz, P.comps[c + i].dx * fx), cy0 = div_ceil(P.YOsiz, P.comps[c + i].dy * fy);
             j.full_off[i] = img_off[c + i] + ((uint64_t)(rr.rect.y0 - cy0) * img_w[c + i] + (rr.rect.x0 - cx0)) * es;
             j.full_stride[i] = img_w[c + i];
           } else { j.full_off[i] = rr.plane_off; j.full_stride[i] = rr.plane_stride; }
@@ -153,6 +167,7 @@ void CodecBase::build_dwt_jobs(bool forward) {
             j.ll_off[i] = lo.plane_off; j.ll_stride[i] = lo.plane_stride;
             for (uint32_t b = 1; b < 4; ++b) {
               const BandGeom& bg = rr.bands[b];
+              if (((b & 1) && !rr.hsplit) || ((b >> 1) && !rr.vsplit)) continue;       // no such band at this level
               j.band_off[i][b] = bg.plane_off + bg.plane_pad_x; j.band_stride[i][b] = bg.plane_stride;
               j.band_shift[i][b] = (wide ? 63u : 31u) - bg.K_max;
               j.band_scale[i][b] = forward ? bg.delta_inv : bg.delta;
@@ -170,7 +185,7 @@ void CodecBase::build_dwt_jobs(bool forward) {
             j.band_scale[i][0] = forward ? bg.delta_inv : bg.delta;
           }
         }
-        const bool stream = !wide && !j.nodwt && j.w >= 2 && j.h >= 2 && !no_stream_dwt && layout.coef_words < (1ull << 30) && img_bytes < (1ull << 32);   // 32-bit byte offsets in the stream kernels
+        const bool stream = !wide && !j.nodwt && j.hsplit && j.vsplit && P.wavelet_of(c) <= 1 && j.w >= 2 && j.h >= 2 && !no_stream_dwt && layout.coef_words < (1ull << 30) && img_bytes < (1ull << 32);   // 32-bit byte offsets in the stream kernels
         uint32_t gi, n;
         if (stream) {
           gi = gw + (j.first ? (k == 3 ? 0u : 1u) : 2u);
@@ -239,7 +254,10 @@ void Encoder::configure(const Params& p, uint32_t sample_type) {
               e.src_off = bg.plane_off + bg.plane_pad_x + (uint64_t)(r.y0 - bg.rect.y0) * bg.plane_stride + (r.x0 - bg.rect.x0);
               e.stride = bg.plane_stride; e.w = (uint16_t)r.w; e.h = (uint16_t)r.h;
               e.p = (uint16_t)((wide ? 63u : 31u) - bg.K_max);
-              e.flags = (tc.res.size() == 1 && params.reversible(tc.comp)) ? (uint16_t)ENC_CHECK_NEGZERO : (uint16_t)0;
+              // (a DFS whose levels all leave the resolution unsplit is the same single-band situation)
+              bool unsplit = true;
+              for (const ResGeom& q : tc.res) if (q.hsplit | q.vsplit) unsplit = false;
+              e.flags = (unsplit && params.reversible(tc.comp)) ? (uint16_t)ENC_CHECK_NEGZERO : (uint16_t)0;
               // worst case: (K_max+1) MagSgn bits / sample (+1/15 stuffing), 30 VLC bits / quad pair
               // (+1/7), 192 MEL bytes, working margin of the kernel
               uint64_t ms = ((uint64_t)r.w * r.h * (bg.K_max + 1) + 7) / 8; ms += ms / 15 + 8;

@@ -102,6 +102,7 @@ enum : uint32_t { SRC_U8 = 0, SRC_U16 = 1, SRC_I32 = 2, SRC_COEF = 3 };
 
 // one analysis (or synthesis) level of one tile-component (or of 3 colour components at once
 // for the first level when the colour transform is used)
+#define DWT_MAX_STEPS 4        // = the halo of the general kernels' tile (DW_H): one sample per lifting step
 struct DwtJob {
   // geometry of the resolution being split
   uint32_t w, h;          // size
@@ -120,7 +121,13 @@ struct DwtJob {
   uint32_t ncomp;         // 1, or 3 when the colour transform is fused (level 1 only)
   uint32_t first;         // 1: full-resolution side is the image (level shift / colour transform)
   uint32_t last;          // 1: LL is a final band (quantise it to band 0), else raw to ll_off
-  uint32_t nodwt;         // 1: zero decomposition levels: convert/quantise only
+  uint32_t nodwt;         // 1: nothing to lift at this level (zero decomposition levels, or a DFS level without transform): == !(hsplit | vsplit)
+  // general (shared-memory tile) kernels only -- the streaming kernels are built for the dyadic 5/3 and 9/7:
+  uint32_t hsplit, vsplit;     // the level lifts along x / along y (DFS: a level may split one way only)
+  uint32_t nsteps;             // lifting steps of the kernel, SYNTHESIS order: step s acts on samples of parity s & 1
+  float step_A[DWT_MAX_STEPS]; // irreversible: x[n] -= A (x[n-1] + x[n+1]) on synthesis, += on analysis
+  int step_a[DWT_MAX_STEPS], step_b[DWT_MAX_STEPS]; uint32_t step_e[DWT_MAX_STEPS];   // reversible: (b + a (x[n-1] + x[n+1])) >> e
+  float K;                     // irreversible: low-pass / K, high-pass * K after analysis
   uint32_t src_type;      // SRC_* of the image buffer when first
   uint32_t bit_depth;     // for level shift / float conversion when first
   uint32_t is_signed;

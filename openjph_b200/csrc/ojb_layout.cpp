@@ -24,18 +24,16 @@ static void build_band(const Params& p, uint32_t comp, ResGeom& rg, uint32_t b, 
                        uint32_t& block_counter, uint64_t& arena) {
   BandGeom& bg = rg.bands[b];
   bg.rect = br; bg.band_num = b;
-  const QuantSet& q = p.quant_for(comp);
-  bg.K_max = q.kmax(rg.res_num, b);
+  bg.K_max = p.band_kmax(comp, rg.res_num, b);
   if (!p.reversible(comp)) {
-    float d = q.irrev_delta(rg.res_num, b);
+    float d = p.band_delta(comp, rg.res_num, b);
     d /= (float)(1u << (31 - std::min(bg.K_max, 31u)));
     bg.delta = d; bg.delta_inv = 1.0f / d;
   }
   bg.empty = br.empty();
   if (bg.empty) return;
-  uint32_t off = rg.res_num > 0 ? 1u : 0u;
-  bg.xcb = std::min(p.log_cb_w(comp), rg.log_ppx - off);
-  bg.ycb = std::min(p.log_cb_h(comp), rg.log_ppy - off);
+  bg.xcb = std::min(p.log_cb_w(comp), rg.log_ppx - rg.hsplit);      // subband::finalize_alloc, ojph_subband.cpp:70-74
+  bg.ycb = std::min(p.log_cb_h(comp), rg.log_ppy - rg.vsplit);
   bg.nbw = ((br.x1() + (1u << bg.xcb) - 1) >> bg.xcb) - (br.x0 >> bg.xcb);
   bg.nbh = ((br.y1() + (1u << bg.ycb) - 1) >> bg.ycb) - (br.y0 >> bg.ycb);
   bg.block_base = block_counter;
@@ -52,15 +50,14 @@ static void build_precincts(const Params& p, const TileGeom& tile, const TileCom
   const Rect& rr = rg.rect;
   rg.npw = rg.nph = 0;
   if (rr.empty()) return;
-  uint32_t D = p.decomps(tc.comp);
   rg.npw = ((rr.x1() + (1u << rg.log_ppx) - 1) >> rg.log_ppx) - (rr.x0 >> rg.log_ppx);
   rg.nph = ((rr.y1() + (1u << rg.log_ppy) - 1) >> rg.log_ppy) - (rr.y0 >> rg.log_ppy);
   rg.precincts.assign((size_t)rg.npw * rg.nph, PrecinctGeom());
   uint32_t xlb = (rr.x0 >> rg.log_ppx) << rg.log_ppx, ylb = (rr.y0 >> rg.log_ppy) << rg.log_ppy;
   // resolution down-sampling relative to the canvas, including component sub-sampling
   // (tile_comp::finalize_alloc passes comp_downsamp as the initial res_downsamp)
-  uint64_t dsx = (uint64_t)p.comps[tc.comp].dx << (D - rg.res_num);
-  uint64_t dsy = (uint64_t)p.comps[tc.comp].dy << (D - rg.res_num);
+  uint64_t dsx = (uint64_t)p.comps[tc.comp].dx * rg.dsx;
+  uint64_t dsy = (uint64_t)p.comps[tc.comp].dy * rg.dsy;
   for (uint32_t y = 0; y < rg.nph; ++y)
     for (uint32_t x = 0; x < rg.npw; ++x) {
       PrecinctGeom& pc = rg.precincts[(size_t)y * rg.npw + x];
@@ -70,7 +67,7 @@ static void build_precincts(const Params& p, const TileGeom& tile, const TileCom
       pc.img_y = std::max(ty, tile.rect.y0);
     }
   // code-block index rectangles (subband::get_cb_indices)
-  uint32_t shift = rg.res_num > 0 ? 1u : 0u;
+  const uint32_t xshift = rg.hsplit, yshift = rg.vsplit;
   for (uint32_t b = (rg.res_num ? 1 : 0); b < (rg.res_num ? 4u : 1u); ++b) {
     const BandGeom& bg = rg.bands[b];
     if (bg.empty) continue;
@@ -78,15 +75,15 @@ static void build_precincts(const Params& p, const TileGeom& tile, const TileCom
     for (uint32_t y = 0; y < rg.nph; ++y) {
       uint32_t pcy0 = std::max(rr.y0, ylb + (y << rg.log_ppy));
       uint32_t pcy1 = std::min(rr.y1(), ylb + ((y + 1) << rg.log_ppy));
-      pcy0 = (pcy0 - (b >> 1) + (1u << shift) - 1) >> shift;
-      pcy1 = (pcy1 - (b >> 1) + (1u << shift) - 1) >> shift;
+      pcy0 = (pcy0 - (b >> 1) + (1u << yshift) - 1) >> yshift;
+      pcy1 = (pcy1 - (b >> 1) + (1u << yshift) - 1) >> yshift;
       uint32_t yb = ((pcy1 + (1u << bg.ycb) - 1) >> bg.ycb) - (pcy0 >> bg.ycb);
       uint32_t colx = 0;
       for (uint32_t x = 0; x < rg.npw; ++x) {
         uint32_t pcx0 = std::max(rr.x0, xlb + (x << rg.log_ppx));
         uint32_t pcx1 = std::min(rr.x1(), xlb + ((x + 1) << rg.log_ppx));
-        pcx0 = (pcx0 - (b & 1) + (1u << shift) - 1) >> shift;
-        pcx1 = (pcx1 - (b & 1) + (1u << shift) - 1) >> shift;
+        pcx0 = (pcx0 - (b & 1) + (1u << xshift) - 1) >> xshift;
+        pcx1 = (pcx1 - (b & 1) + (1u << xshift) - 1) >> xshift;
         uint32_t xb = ((pcx1 + (1u << bg.xcb) - 1) >> bg.xcb) - (pcx0 >> bg.xcb);
         Rect& r = rg.precincts[(size_t)y * rg.npw + x].cb_idx[b];
         r.x0 = colx; r.y0 = coly; r.w = xb; r.h = yb;
@@ -126,6 +123,7 @@ void Layout::build(const Params& params) {
         const uint32_t D = P.decomps(c);           // the component's own coding style (COC) if it has one
         tc.res.assign(D + 1, ResGeom());
         Rect rr = tc.rect;
+        uint32_t dsx = 1, dsy = 1;
         for (int r = (int)D; r >= 0; --r) {
           ResGeom& rg = tc.res[r];
           rg.rect = rr; rg.res_num = (uint32_t)r;
@@ -138,16 +136,23 @@ void Layout::build(const Params& params) {
             arena = (arena + 31) & ~(uint64_t)31;
           }
           uint32_t trx0 = rr.x0, trx1 = rr.x1(), try0 = rr.y0, try1 = rr.y1();
+          rg.dsx = dsx; rg.dsy = dsy;
           if (r > 0) {
+            // how level D - r + 1 splits this resolution: both ways, or -- with a DFS marker segment -- one way or not
+            // at all (resolution::finalize_alloc, ojph_resolution.cpp:264-396)
+            const DfsType ds = P.dwt_type(c, D - (uint32_t)r + 1);
+            rg.hsplit = (ds == DFS_BIDIR || ds == DFS_HORZ) ? 1u : 0u;
+            rg.vsplit = (ds == DFS_BIDIR || ds == DFS_VERT) ? 1u : 0u;
             for (uint32_t i = 1; i < 4; ++i) {
-              Rect br;
-              br.x0 = (trx0 - (i & 1) + 1) >> 1; br.w = ((trx1 - (i & 1) + 1) >> 1) - br.x0;
-              br.y0 = (try0 - (i >> 1) + 1) >> 1; br.h = ((try1 - (i >> 1) + 1) >> 1) - br.y0;
+              if (((i & 1) && !rg.hsplit) || ((i >> 1) && !rg.vsplit)) continue;
+              Rect br = rr;
+              if (rg.hsplit) { br.x0 = (trx0 - (i & 1) + 1) >> 1; br.w = ((trx1 - (i & 1) + 1) >> 1) - br.x0; }
+              if (rg.vsplit) { br.y0 = (try0 - (i >> 1) + 1) >> 1; br.h = ((try1 - (i >> 1) + 1) >> 1) - br.y0; }
               build_band(P, c, rg, i, br, num_blocks, arena);
             }
-            Rect ll;
-            ll.x0 = (trx0 + 1) >> 1; ll.w = ((trx1 + 1) >> 1) - ll.x0;
-            ll.y0 = (try0 + 1) >> 1; ll.h = ((try1 + 1) >> 1) - ll.y0;
+            Rect ll = rr;
+            if (rg.hsplit) { ll.x0 = (trx0 + 1) >> 1; ll.w = ((trx1 + 1) >> 1) - ll.x0; dsx *= 2; }
+            if (rg.vsplit) { ll.y0 = (try0 + 1) >> 1; ll.h = ((try1 + 1) >> 1) - ll.y0; dsy *= 2; }
             rr = ll;
           } else
             build_band(P, c, rg, 0, rr, num_blocks, arena);

@@ -51,7 +51,11 @@ struct PrecinctGeom {
 struct ResGeom {
   Rect rect;                       // resolution rectangle (tile-component coordinates / 2^(D-r))
   uint32_t res_num = 0;
-  BandGeom bands[4];               // r == 0: bands[0]; r > 0: bands[1..3]
+  BandGeom bands[4];               // r == 0: bands[0]; r > 0: bands[1..3] (HL only / LH only when the level splits one way)
+  uint32_t hsplit = 0, vsplit = 0; // 1: this resolution is split horizontally / vertically into resolution r - 1 and its bands
+                                   // (resolution::transform_flags, ojph_resolution.cpp:290-297); both 0 at r == 0 and for a
+                                   // DFS level without transform
+  uint32_t dsx = 1, dsy = 1;       // down-sampling of this resolution relative to the tile-component (res_downsamp / comp_downsamp)
   uint32_t log_ppx = 15, log_ppy = 15;
   uint32_t npw = 0, nph = 0;       // precincts across / down
   std::vector<PrecinctGeom> precincts;

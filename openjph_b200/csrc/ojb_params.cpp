@@ -123,8 +123,7 @@ void QuantSet::set_irrev_quant(uint32_t nd) {
   }
 }
 
-uint32_t QuantSet::kmax(uint32_t res, uint32_t band) const {
-  uint32_t idx = res ? (res - 1) * 3 + band : 0;
+uint32_t QuantSet::kmax_at(uint32_t idx) const {
   if (idx >= num_subbands) idx = num_subbands - 1;
   uint32_t bits = 0;
   if ((Sqcd & 0x1F) == 0) { bits = (uint32_t)(SP[idx] & 0xFF) >> 3; bits = bits ? bits - 1 : 0; }
@@ -143,11 +142,10 @@ uint32_t QuantSet::largest_kmax() const {
   return bits + guard_bits();
 }
 
-float QuantSet::irrev_delta(uint32_t res, uint32_t band) const {
+float QuantSet::irrev_delta_at(uint32_t idx, uint32_t band) const {
   static const float arr[4] = { 1.0f, 2.0f, 2.0f, 4.0f };
   if ((Sqcd & 0x1F) != 2)
     fail(0x00050101, "irreversible transform with reversible (no quantization) step sizes");
-  uint32_t idx = res ? (res - 1) * 3 + band : 0;
   if (idx >= num_subbands) idx = num_subbands - 1;
   int eps = SP[idx] >> 11;
   float mantissa = (float)((SP[idx] & 0x7FF) | 0x800) * arr[band];
@@ -155,6 +153,143 @@ float QuantSet::irrev_delta(uint32_t res, uint32_t band) const {
   mantissa /= (float)(1u << eps);
   return mantissa;
 }
+
+//------------------------------------------------------------------------------------------
+// DFS / ATK (Part 2 wavelet structures)
+//------------------------------------------------------------------------------------------
+DfsType DfsSpec::type(uint32_t decomp_level) const {
+  decomp_level = std::min<uint32_t>(decomp_level, Ids);      // levels past the list repeat its last entry
+  uint32_t d = decomp_level - 1;
+  return (DfsType)((Ddfs[d >> 2] >> (6 - 2 * (d & 3))) & 3);
+}
+
+uint32_t DfsSpec::subband_idx(const uint32_t num_decomps, uint32_t res, uint32_t band) const {
+  static const uint32_t ns[4] = { 0, 3, 1, 1 };
+  if (res == 0) return 0;
+  uint32_t idx = 0, i = 1;
+  for (; i < res; ++i) idx += ns[type(num_decomps - i + 1)];
+  idx += band;
+  if (type(num_decomps - i + 1) == DFS_VERT && band == 2) --idx;
+  return idx;
+}
+
+AtkSpec AtkSpec::irv97() {
+  AtkSpec a; a.Satk = 0x4a00; a.K = (float)1.230174104914001; a.steps.resize(4);
+  a.steps[0].A = (float)0.443506852043971; a.steps[1].A = (float)0.882911075530934;
+  a.steps[2].A = (float)-0.052980118572961; a.steps[3].A = (float)-1.586134342059924;
+  return a;
+}
+AtkSpec AtkSpec::rev53() {
+  AtkSpec a; a.Satk = 0x5801; a.steps.resize(2);
+  a.steps[0].a = 1; a.steps[0].b = 2; a.steps[0].e = 2;
+  a.steps[1].a = -1; a.steps[1].b = 1; a.steps[1].e = 1;
+  return a;
+}
+
+const AtkSpec& Params::atk_for(uint32_t w) const {
+  static const AtkSpec k97 = AtkSpec::irv97(), k53 = AtkSpec::rev53();
+  for (const AtkSpec& a : atk) if (a.index() == w) return a;
+  if (w == 0) return k97;
+  if (w == 1) return k53;
+  fail(0x00050131, "A COD/COC segment employs the DWT kernel atk = %d, but a corresponding ATK segment cannot be found.", w);
+}
+
+const DfsSpec* Params::dfs_of(uint32_t c) const {
+  const CodStyle* s = find_coc(c);
+  if (s == nullptr || s->dfs_idx < 0) return nullptr;
+  if (dfs.empty())
+    fail(0x00070001, "There is a problem with codestream marker segments. COD/COC specifies the use of a DFS marker "
+         "but there are no DFS markers within the main codestream headers");
+  for (const DfsSpec& d : dfs) if (d.Sdfs == (uint16_t)s->dfs_idx) return &d;
+  fail(0x00070002, "There is a problem with codestream marker segments. COD/COC specifies the use of a DFS marker "
+       "with index %d, but there are no such marker within the main codestream headers", s->dfs_idx);
+}
+
+void Params::res_downsamp(uint32_t c, uint32_t skipped, uint32_t& fx, uint32_t& fy) const {
+  fx = fy = 1;
+  for (uint32_t level = 1; level <= skipped; ++level) {
+    DfsType t = dwt_type(c, level);
+    if (t == DFS_BIDIR || t == DFS_HORZ) fx *= 2;
+    if (t == DFS_BIDIR || t == DFS_VERT) fy *= 2;
+  }
+}
+
+uint32_t Params::subband_index(uint32_t c, uint32_t res, uint32_t band) const {
+  const DfsSpec* d = dfs_of(c);
+  if (d) return d->subband_idx(decomps(c), res, band);
+  return res ? (res - 1) * 3 + band : 0;
+}
+
+namespace {
+// Step sizes for a decomposition structure / kernel the reference has no tables for (it only decodes them): the
+// same recipe as set_rev_quant / set_irrev_quant (ojph_params.cpp:1495-1599) with the gains measured on the
+// kernel itself.  1-D, linearised (a reversible step is a / 2^e without rounding), symmetric extension, even origin:
+//   bibo_l[n] / bibo_h[n]: worst-case amplification of n low-pass stages / of n - 1 low-pass stages and a high-pass one
+//   norm_l[n] / norm_h[n]: L2 norm of the synthesis waveform of one coefficient of those bands
+struct KernelGains {
+  enum { DEPTH = 6 };
+  double bibo_l[DEPTH + 1], bibo_h[DEPTH + 1], norm_l[DEPTH + 1], norm_h[DEPTH + 1];
+  static double coef(const AtkSpec& k, size_t s) { return k.reversible() ? (double)k.steps[s].a / (double)(1u << k.steps[s].e) : (double)k.steps[s].A; }
+  // one analysis stage on the first len entries of every column of m (rows = samples), even origin
+  static void analyse(std::vector<std::vector<double>>& m, size_t len, const AtkSpec& k) {
+    const size_t N = k.steps.size(), W = m[0].size();
+    auto row = [&](long i) -> std::vector<double>& { if (i < 0) i = -i; if (i >= (long)len) i = 2 * ((long)len - 1) - i; return m[(size_t)i]; };
+    for (size_t s = N; s-- > 0; ) {
+      const double a = coef(k, s);
+      for (size_t i = (s & 1); i < len; i += 2) {
+        const std::vector<double>& p = row((long)i - 1); const std::vector<double>& q = row((long)i + 1);
+        std::vector<double>& d = m[i];
+        for (size_t j = 0; j < W; ++j) d[j] += a * (p[j] + q[j]);
+      }
+    }
+    std::vector<std::vector<double>> t(len);
+    const double kl = k.reversible() ? 1.0 : 1.0 / (double)k.K, kh = k.reversible() ? 1.0 : (double)k.K;
+    const size_t nl = (len + 1) / 2;
+    for (size_t i = 0; i < len; ++i) {
+      std::vector<double>& d = t[(i & 1) ? nl + i / 2 : i / 2];
+      d.swap(m[i]);
+      for (double& v : d) v *= (i & 1) ? kh : kl;
+    }
+    for (size_t i = 0; i < len; ++i) m[i].swap(t[i]);
+  }
+  static void synthesise(std::vector<double>& x, size_t len, const AtkSpec& k) {
+    const size_t N = k.steps.size(), nl = (len + 1) / 2;
+    std::vector<double> t(len);
+    const double kl = k.reversible() ? 1.0 : (double)k.K, kh = k.reversible() ? 1.0 : 1.0 / (double)k.K;
+    for (size_t i = 0; i < len; ++i) t[i] = (i & 1) ? x[nl + i / 2] * kh : x[i / 2] * kl;
+    auto at = [&](long i) { if (i < 0) i = -i; if (i >= (long)len) i = 2 * ((long)len - 1) - i; return t[(size_t)i]; };
+    for (size_t s = 0; s < N; ++s) {
+      const double a = coef(k, s);
+      for (size_t i = (s & 1); i < len; i += 2) t[i] -= a * (at((long)i - 1) + at((long)i + 1));
+    }
+    for (size_t i = 0; i < len; ++i) x[i] = t[i];
+  }
+  explicit KernelGains(const AtkSpec& k) {
+    const size_t L = (size_t)16 << DEPTH;
+    bibo_l[0] = norm_l[0] = 1.0; bibo_h[0] = norm_h[0] = 1.0;
+    std::vector<std::vector<double>> m(L, std::vector<double>(L, 0.0));
+    for (size_t i = 0; i < L; ++i) m[i][i] = 1.0;
+    size_t len = L;
+    auto worst = [&](size_t a, size_t b) { double g = 0; for (size_t i = a; i < b; ++i) { double s = 0; for (double v : m[i]) s += std::fabs(v); g = std::max(g, s); } return g; };
+    for (int n = 1; n <= DEPTH; ++n) {
+      analyse(m, len, k);
+      bibo_l[n] = worst(0, len / 2); bibo_h[n] = worst(len / 2, len);
+      len /= 2;
+    }
+    for (int n = 1; n <= DEPTH; ++n) {
+      for (int hi = 0; hi < 2; ++hi) {
+        std::vector<double> x(L, 0.0);
+        size_t l = L >> n;                         // length of the low band after n stages
+        x[(hi ? l : 0) + l / 2] = 1.0;
+        for (int j = n; j >= 1; --j) synthesise(x, L >> (j - 1), k);
+        double e = 0; for (double v : x) e += v * v;
+        (hi ? norm_h : norm_l)[n] = std::sqrt(e);
+      }
+    }
+  }
+  static int clampd(uint32_t n) { return (int)std::min<uint32_t>(n, DEPTH); }
+};
+} // namespace
 
 //------------------------------------------------------------------------------------------
 // Params
@@ -219,6 +354,66 @@ void Params::set_precincts(int n, const uint32_t* w, const uint32_t* h) {
   }
 }
 
+// QCD / QCC of a component with a DFS structure and / or an ATK kernel (see KernelGains)
+static void make_part2_steps(QuantSet& q, uint32_t comp, const Params& p) {
+  const AtkSpec& k = p.atk_of(comp);
+  const KernelGains g(k);
+  const uint32_t D = q.num_decomps;
+  const bool rev = k.reversible();
+  if (q.qfactor != 0) fail(0x000B0020, "Qfactor needs the 9/7 kernel on a dyadic decomposition");
+  // bands in marker order: LL, then for every resolution 1..D the bands its level produces
+  struct B { double bibo, norm; uint32_t band; };
+  std::vector<B> bands;
+  auto count = [&](uint32_t upto, bool horz) {          // levels 1..upto that split in this direction
+    uint32_t n = 0;
+    for (uint32_t l = 1; l <= upto; ++l) { DfsType t = p.dwt_type(comp, l); if (t == DFS_BIDIR || t == (horz ? DFS_HORZ : DFS_VERT)) ++n; }
+    return n;
+  };
+  {
+    int nx = KernelGains::clampd(count(D, true)), ny = KernelGains::clampd(count(D, false));
+    bands.push_back(B{ g.bibo_l[nx] * g.bibo_l[ny], g.norm_l[nx] * g.norm_l[ny], 0 });
+  }
+  for (uint32_t r = 1; r <= D; ++r) {
+    const uint32_t level = D - r + 1;
+    const DfsType t = p.dwt_type(comp, level);
+    const bool hx = t == DFS_BIDIR || t == DFS_HORZ, vy = t == DFS_BIDIR || t == DFS_VERT;
+    const int nx = KernelGains::clampd(count(level - 1, true)), ny = KernelGains::clampd(count(level - 1, false));
+    const int nx1 = KernelGains::clampd((uint32_t)nx + 1), ny1 = KernelGains::clampd((uint32_t)ny + 1);
+    for (uint32_t b = 1; b < 4; ++b) {
+      const bool bh = (b & 1) != 0, bv = (b & 2) != 0;
+      if ((bh && !hx) || (bv && !vy)) continue;
+      const double bx = hx ? (bh ? g.bibo_h[nx1] : g.bibo_l[nx1]) : g.bibo_l[nx], by = vy ? (bv ? g.bibo_h[ny1] : g.bibo_l[ny1]) : g.bibo_l[ny];
+      const double ex = hx ? (bh ? g.norm_h[nx1] : g.norm_l[nx1]) : g.norm_l[nx], ey = vy ? (bv ? g.norm_h[ny1] : g.norm_l[ny1]) : g.norm_l[ny];
+      bands.push_back(B{ bx * by, ex * ey, b });
+    }
+  }
+  q.num_subbands = (uint32_t)bands.size();
+  if (rev) {
+    const uint32_t Bd = q.bit_depth + ((comp < 3 && q.is_color_trans) ? 1u : 0u);
+    uint32_t max_BX = 0; uint8_t tmp[97];
+    for (size_t i = 0; i < bands.size(); ++i) {
+      uint32_t X = (uint32_t)std::max(0.0, ceil(log(bands[i].bibo) / M_LN2 - 1e-9));
+      tmp[i] = (uint8_t)(Bd + X); max_BX = std::max(max_BX, Bd + X);
+    }
+    if (max_BX > 38)
+      fail(0x00050151, "The specified combination of bit_depth, colour transform, and type of "
+           "wavelet transform requires more than 38 bits; it requires %d bits.", max_BX);
+    int guard = std::max(1, (int)max_BX - 31);
+    q.Sqcd = (uint8_t)(guard << 5);
+    for (size_t i = 0; i < bands.size(); ++i) q.SP[i] = (uint16_t)(uint8_t)((uint8_t)(tmp[i] - guard) << 3);
+  } else {
+    static const double arr[4] = { 1.0, 2.0, 2.0, 4.0 };
+    if (q.base_delta == -1.0f) q.base_delta = 1.0f / (float)(1u << std::min(16u, q.bit_depth));
+    double worst = 1.0;
+    for (const B& b : bands) worst = std::max(worst, b.bibo / arr[b.band]);
+    int guard = std::max(1, (int)ceil(log(worst) / M_LN2 - 1e-9));
+    if (guard > 7) fail(0x000B0021, "the transformation kernel amplifies by more than 7 guard bits");
+    q.Sqcd = (uint8_t)((guard << 5) | 0x2);
+    for (size_t i = 0; i < bands.size(); ++i)
+      q.SP[i] = pack_step((float)((double)q.base_delta / (bands[i].norm * arr[bands[i].band])));
+  }
+}
+
 static void make_quant_steps(QuantSet& q, uint32_t comp, const Params& p) {
   if (q.is_init) fail(0x00040001, "Quantization step sizes already initialized.");
   q.is_init = true;
@@ -229,6 +424,7 @@ static void make_quant_steps(QuantSet& q, uint32_t comp, const Params& p) {
   q.wavelet = p.wavelet_of(comp);
   q.sx = p.comps[comp].dx; q.sy = p.comps[comp].dy;
   q.num_subbands = 1 + 3 * q.num_decomps;
+  if (p.is_part2(comp)) { make_part2_steps(q, comp, p); return; }
   if (q.wavelet == DWT_REV53)
     q.set_rev_quant(q.num_decomps, q.bit_depth, comp < 3 ? q.is_color_trans : false);
   else {
@@ -277,6 +473,45 @@ void Params::finalize_for_encode() {
         fail(0x00040013, "For RPCL and PCRL progression orders,component downsampling "
              "factors have to be powers of 2");
 
+  // Part 2 structures asked of the encoder: one DFS (index 1) and / or one ATK (index 2) shared by every component
+  // through its COC -- the only place a DFS index can go (param_cod::is_dfs_defined, ojph_params_local.h:613-618)
+  if (!enc_dfs.empty() || enc_atk_set) {
+    if (!enc_dfs.empty()) {
+      if (enc_dfs.size() > 32) fail(0x000B0022, "at most 32 decomposition levels can be described");
+      DfsSpec d; d.Sdfs = 1; d.Ids = (uint8_t)enc_dfs.size();
+      for (size_t i = 0; i < enc_dfs.size(); ++i) {
+        if (enc_dfs[i] > 3) fail(0x000B0022, "decomposition level type must be 0 (no split), 1 (both ways), 2 (horizontal) or 3 (vertical)");
+        d.Ddfs[i >> 2] = (uint8_t)(d.Ddfs[i >> 2] | (enc_dfs[i] << (6 - 2 * (i & 3))));
+      }
+      dfs.assign(1, d);
+      Rsiz |= 0x8080;
+    }
+    if (enc_atk_set) {
+      AtkSpec a = enc_atk;
+      const bool rev = a.reversible();
+      if (a.steps.empty() || a.steps.size() > 255) fail(0x000B0023, "a transformation kernel needs 1..255 lifting steps");
+      // whole-sample symmetric, even-indexed first step, symmetric extension; 16-bit integers or floats
+      a.Satk = (uint16_t)(2u | (rev ? 0x1100u : 0x0200u) | 0x0800u | 0x4000u);
+      if (rev) for (const AtkStep& t : a.steps) if (t.e > 30) fail(0x000B0023, "lifting step down-shift beyond 30 bits");
+      atk.assign(1, a);
+      Rsiz |= 0x8020;
+    }
+    for (uint32_t c = 0; c < nc; ++c) {
+      CodStyle* st = const_cast<CodStyle*>(find_coc(c));
+      if (st == nullptr) {
+        CodStyle n; n.comp_idx = (uint16_t)c; n.Scoc = (uint8_t)(Scod & 1); n.num_decomps = num_decomps; n.cb_w_exp = cb_w_exp;
+        n.cb_h_exp = cb_h_exp; n.block_style = block_style; n.wavelet = wavelet;
+        memcpy(n.precinct_size, precinct_size, sizeof(n.precinct_size));
+        coc.push_back(n); st = &coc.back();
+      }
+      if (!enc_dfs.empty()) {
+        if (st->num_decomps != num_decomps) fail(0x000B0024, "a decomposition structure needs the same number of levels in every component");
+        st->dfs_idx = 1;
+      }
+      if (enc_atk_set) st->wavelet = 2;
+    }
+  }
+
   // QCD / QCC (param_qcd::check_validity, ojph_params.cpp:1359-1431)
   for (QuantSet& q : qcc) q.enabled = q.comp_idx < nc;
   uint32_t qcd_comp = 0;
@@ -307,13 +542,15 @@ void Params::finalize_for_encode() {
   }
 
   // CAP (ojph_params_local.h:982-998); MAGB over QCD and every QCC (ojph_params.cpp:1615)
-  if (wavelet == DWT_REV53) Ccap0 &= 0xFFDF; else Ccap0 |= 0x0020;
+  if (reversible()) Ccap0 &= 0xFFDF; else Ccap0 |= 0x0020;
   Ccap0 &= 0xFFE0;
   uint32_t B = 0;
+  const bool part2 = any_part2();
   auto magb = [&](const QuantSet& q) {
     uint32_t nd = (q.num_subbands - 1) / 3;
     for (uint32_t i = 0; i < q.num_subbands; ++i) {
       uint32_t t;
+      if (part2) { B = std::max(B, q.kmax_at(i)); continue; }      // no dyadic level to take the band's gain from
       if ((q.Sqcd & 0x1F) == 0) t = ((uint32_t)(q.SP[i] & 0xFF) >> 3) + q.guard_bits() - 1u;
       else { uint32_t nb = nd - (i ? (i - 1) / 3 : 0); t = (uint32_t)(q.SP[i] >> 11) + q.guard_bits() - nb; }
       B = std::max(B, t);
@@ -522,15 +759,40 @@ void Params::write_main_header(std::vector<uint8_t>& o, const char* const* comme
   for (const CodStyle& c : coc) {
     if (c.comp_idx >= nc) continue;
     put_u16(o, M_COC);
-    put_u16(o, (nc < 257 ? 9u : 10u) + ((c.Scoc & 1) ? 1u + c.num_decomps : 0u));
+    const uint32_t nd = c.dfs_idx >= 0 ? num_decomps : c.num_decomps;
+    put_u16(o, (nc < 257 ? 9u : 10u) + ((c.Scoc & 1) ? 1u + nd : 0u));
     if (nc < 257) put_u8(o, c.comp_idx); else put_u16(o, c.comp_idx);
-    put_u8(o, c.Scoc); put_u8(o, c.num_decomps); put_u8(o, c.cb_w_exp); put_u8(o, c.cb_h_exp);
+    put_u8(o, c.Scoc); put_u8(o, c.dfs_idx >= 0 ? (0x80u | (uint32_t)c.dfs_idx) : c.num_decomps); put_u8(o, c.cb_w_exp); put_u8(o, c.cb_h_exp);
     put_u8(o, c.block_style); put_u8(o, c.wavelet);
-    if (c.Scoc & 1) for (int i = 0; i <= c.num_decomps; ++i) put_u8(o, c.precinct_size[i]);
+    if (c.Scoc & 1) for (uint32_t i = 0; i <= nd; ++i) put_u8(o, c.precinct_size[i]);
   }
   // QCD, QCC
   write_quant(o, qcd, nc);
   for (const QuantSet& q : qcc) if (q.enabled) write_quant(o, q, nc);
+  // DFS / ATK (T.801 A.3.? layouts as param_dfs::read / param_atk::read expect them, ojph_params.cpp:2596-2645, :2770-2867)
+  for (const DfsSpec& d : dfs) {
+    const uint32_t nb = (d.Ids + 3u) / 4u;
+    put_u16(o, M_DFS); put_u16(o, 5 + nb); put_u16(o, d.Sdfs); put_u8(o, d.Ids);
+    for (uint32_t i = 0; i < nb; ++i) put_u8(o, d.Ddfs[i]);
+  }
+  for (const AtkSpec& a : atk) {
+    const bool rev = a.reversible();
+    const uint32_t cs = a.coeff_type() == 0 ? 1u : a.coeff_type() == 1 ? 2u : 4u;
+    auto put_coef = [&](float f, int iv) {
+      if (rev) { if (cs == 1) put_u8(o, (uint32_t)(uint8_t)(int8_t)iv); else put_u16(o, (uint32_t)(uint16_t)(int16_t)iv); }
+      else { uint32_t u; memcpy(&u, &f, 4); put_u32(o, u); }
+    };
+    const uint32_t n = (uint32_t)a.steps.size();
+    put_u16(o, M_ATK);
+    put_u16(o, 5 + (rev ? n * (4 + cs) : cs + n * (1 + cs)));
+    put_u16(o, a.Satk);
+    if (!rev) put_coef(a.K, 0);
+    put_u8(o, n);
+    for (const AtkStep& t : a.steps) {
+      if (rev) { put_u8(o, t.e); put_u16(o, (uint32_t)(uint16_t)t.b); put_u8(o, 1); put_coef(0.f, t.a); }
+      else { put_u8(o, 1); put_coef(t.A, 0); }
+    }
+  }
   // NLT: the default entry, then the per-component ones in creation order (param_nlt::write, :2210-2235)
   auto put_nlt = [&](const NltEntry& e) {
     if (!e.enabled) return;
@@ -637,12 +899,9 @@ size_t Params::read_main_header(const uint8_t* data, size_t len) {
       fail(0x00040003, "The top left tile must intersect with the image");
     if (Xsiz <= XOsiz || Ysiz <= YOsiz)
       fail(0x00040004, "The image extent must be larger than the image offset");
-    if (Rsiz & 0x00A0)
-      fail(0x000B0002, "codestreams that need ATK/DFS (Part 2 wavelet structures) are not "
-           "supported by the GPU path");
   }
   int received = 0;
-  qcc.clear(); coc.clear(); nlt.clear(); nlt_all = NltEntry();
+  qcc.clear(); coc.clear(); nlt.clear(); nlt_all = NltEntry(); dfs.clear(); atk.clear();
   for (;;) {
     // scan to the next 0xFF xx marker of interest (the reference skips unknown bytes too)
     if (r.pos + 1 >= r.n) fail(0x00030051, "File ended before finding a tile segment");
@@ -670,8 +929,6 @@ size_t Params::read_main_header(const uint8_t* data, size_t len) {
       if (num_decomps > 32 || cb_w_exp > 8 || cb_h_exp > 8 || cb_w_exp + cb_h_exp > 8 ||
           (block_style & 0x40) != 0x40 || (block_style & 0xB7) != 0x00)
         fail(0x0005007D, "wrong settings in a COD-SPcod parameter");
-      if (wavelet > 1)
-        fail(0x000B0003, "arbitrary transformation kernels (ATK) are not supported by the GPU path");
       if (Scod & 1)
         for (int i = 0; i <= num_decomps; ++i) {
           precinct_size[i] = (uint8_t)r.u8();
@@ -711,11 +968,12 @@ size_t Params::read_main_header(const uint8_t* data, size_t len) {
              "more than the allowed index number, since the codestream has %d components", c.comp_idx, nc);
       if (find_coc(c.comp_idx))
         fail(0x00030057, "The codestream has two COC marker segments for one component of index %d", c.comp_idx);
+      // a decomposition byte with its top bit set names a DFS marker segment; the level count is then the COD's as
+      // read so far (is_dfs_defined / get_num_decompositions, ojph_params_local.h:503-518, :613-618)
+      if (c.num_decomps & 0x80) { c.dfs_idx = c.num_decomps & 0xF; c.num_decomps = num_decomps; }
       if (c.num_decomps > 32 || c.cb_w_exp > 8 || c.cb_h_exp > 8 || c.cb_w_exp + c.cb_h_exp > 8 ||
           (c.block_style & 0x40) != 0x40 || (c.block_style & 0xB7) != 0x00)
         fail(0x0005012D, "wrong settings in a COC-SPcoc parameter");
-      if (c.wavelet > 1)
-        fail(0x000B0003, "arbitrary transformation kernels (ATK) are not supported by the GPU path");
       if (c.Scoc & 1)
         for (int i = 0; i <= c.num_decomps; ++i) {
           c.precinct_size[i] = (uint8_t)r.u8();
@@ -736,14 +994,96 @@ size_t Params::read_main_header(const uint8_t* data, size_t len) {
         if (e == nullptr) { nlt.push_back(NltEntry()); e = &nlt.back(); }
       }
       e->enabled = true; e->comp_idx = (uint16_t)comp; e->BDnlt = (uint8_t)bd; e->Tnlt = (uint8_t)t;
-    } else if (m == M_DFS || m == M_ATK)
-      fail(0x000B0005, "DFS/ATK marker segments are not supported by the GPU path");
-    else {  // PRF CPF RGN POC PPM TLM PLM CRG COM: skipped
+    } else if (m == M_DFS) {                // param_dfs::read, ojph_params.cpp:2596-2645
+      if (!r.has(2)) fail(0x000500D1, "error reading DFS-Ldfs parameter");
+      (void)r.u16();
+      if (!r.has(2)) fail(0x000500D2, "error reading DFS-Sdfs parameter");
+      DfsSpec d; d.Sdfs = (uint16_t)r.u16();
+      if (d.Sdfs > 15) fail(0x000500D3, "The DFS-Sdfs parameter is %d, which is larger than the permissible 15", d.Sdfs);
+      if (!r.has(1)) fail(0x000500D4, "error reading DFS-Ids parameter");
+      const uint32_t ids = r.u8();
+      if (ids == 0) fail(0x000500D8, "The value of the Ids member in the DFS marker segment cannot be 0");
+      d.Ids = (uint8_t)std::min(ids, 32u);
+      for (uint32_t i = 0; i < d.Ids; i += 4) { if (!r.has(1)) fail(0x000500D6, "error reading DFS-Ddfs parameters"); d.Ddfs[i / 4] = (uint8_t)r.u8(); }
+      for (uint32_t i = d.Ids; i < ids; i += 4) { if (!r.has(1)) fail(0x000500D7, "error reading DFS-Ddfs parameters"); (void)r.u8(); }
+      dfs.push_back(d);
+    } else if (m == M_ATK) {                // param_atk::read, ojph_params.cpp:2770-2867
+      if (!r.has(2)) fail(0x000500E1, "error reading ATK-Latk parameter");
+      int bytes = (int)r.u16() - 2;
+      if (!r.has(2)) fail(0x000500E2, "error reading ATK-Satk parameter");
+      AtkSpec a; a.Satk = (uint16_t)r.u16(); bytes -= 2;
+      const uint32_t idx = a.index();
+      bool dup = idx == 0 || idx == 1;
+      for (const AtkSpec& o2 : atk) if (o2.index() == idx) dup = true;
+      if (dup) fail(0x000500F3, "ATK-Satk parameter sets ATK marker index to the illegal value of %d. ATK-Satk should be in "
+                    "(2-255) and must not be repeated", idx);
+      if (a.Satk & 0x2000) fail(0x000500E3, "ATK-Satk parameter sets m_init to 1, requiring odd-indexed subsequence in first "
+                                "reconstruction step, which is not supported yet.");
+      if (!(a.Satk & 0x800)) fail(0x000500E4, "ATK-Satk parameter specified ARB filter, which is not supported yet.");
+      if (a.reversible() && a.coeff_type() >= 2) fail(0x000500E5, "ATK-Satk parameter does not make sense. It employs floats with reversible filtering.");
+      if (!(a.Satk & 0x4000)) fail(0x000500E6, "ATK-Satk parameter requires constant boundary extension, which is not supported yet.");
+      // coefficient readers (read_coefficient, :2687-2767); a 128-bit float keeps sign, 8 exponent bits and 23 mantissa bits
+      auto read_float = [&](float& K) -> bool {
+        switch (a.coeff_type()) {
+          case 0: if (!r.has(1)) return false; K = (float)r.u8(); bytes -= 1; return true;
+          case 1: if (!r.has(2)) return false; K = (float)r.u16(); bytes -= 2; return true;
+          case 2: { if (!r.has(4)) return false; uint32_t u = r.u32(); memcpy(&K, &u, 4); bytes -= 4; return true; }
+          case 3: { if (!r.has(8)) return false; uint64_t u = ((uint64_t)r.u32() << 32); u |= r.u32(); double d; memcpy(&d, &u, 8); K = (float)d; bytes -= 8; return true; }
+          case 4: {
+            if (!r.has(16)) return false;
+            uint64_t v = ((uint64_t)r.u32() << 32); v |= r.u32(); (void)r.u32(); (void)r.u32(); bytes -= 16;
+            int e = (int)((v >> 48) & 0x7FFF); e -= 16383; e += 127; e &= 0xFF; e <<= 23;
+            uint32_t i = ((uint32_t)(v >> 32) & 0x80000000u) | (uint32_t)e | (uint32_t)((v >> 25) & 0x007FFFFF);
+            memcpy(&K, &i, 4); return true;
+          }
+          default: return true;               // types 5..7: nothing is read (the reference's fall-through)
+        }
+      };
+      auto read_int = [&](int16_t& K) -> bool {
+        if (a.coeff_type() == 0) { if (!r.has(1)) return false; K = (int16_t)(int8_t)r.u8(); bytes -= 1; return true; }
+        if (a.coeff_type() == 1) { if (!r.has(2)) return false; K = (int16_t)r.u16(); bytes -= 2; return true; }
+        return false;
+      };
+      if (!a.reversible() && !read_float(a.K)) fail(0x000500E7, "error reading ATK-Katk parameter");
+      if (!r.has(1)) fail(0x000500E8, "error reading ATK-Natk parameter");
+      const uint32_t n = r.u8(); bytes -= 1;
+      a.steps.resize(n);
+      for (uint32_t i = 0; i < n; ++i) {
+        AtkStep& t = a.steps[i];
+        if (a.reversible()) {
+          if (!r.has(1)) fail(0x000500E9, "error reading ATK-Eatk parameter");
+          t.e = (uint8_t)r.u8(); bytes -= 1;
+          if (!r.has(2)) fail(0x000500EA, "error reading ATK-Batk parameter");
+          t.b = (int16_t)r.u16(); bytes -= 2;
+          if (!r.has(1)) fail(0x000500EB, "error reading ATK-LCatk parameter");
+          const uint32_t lc = r.u8(); bytes -= 1;
+          if (lc == 0) fail(0x000500EC, "Encountered a ATK-LCatk value of zero; something is wrong.");
+          if (lc > 1) fail(0x000500ED, "ATK-LCatk value greater than 1; that is, a multitap filter is not supported");
+          if (!read_int(t.a)) fail(0x000500EE, "Error reding ATK-Aatk parameter");
+        } else {
+          if (!r.has(1)) fail(0x000500EF, "error reading ATK-LCatk parameter");
+          const uint32_t lc = r.u8(); bytes -= 1;
+          if (lc == 0) fail(0x000500F0, "Encountered a ATK-LCatk value of zero; something is wrong.");
+          if (lc > 1) fail(0x000500F1, "ATK-LCatk value greater than 1; that is, a multitap filter is not supported.");
+          if (!read_float(t.A)) fail(0x000500F2, "Error reding ATK-Aatk parameter");
+        }
+      }
+      if (bytes != 0) fail(0x000500F3, "The length of an ATK marker segment (ATK-Latk) is not correct");
+      atk.push_back(a);
+    } else {  // PRF CPF RGN POC PPM TLM PLM CRG COM: skipped
       uint32_t L = r.u16();
       if (L < 2 || !r.has(L - 2)) fail(0x00030041, "error reading marker");
       r.pos += L - 2;
     }
   }
+  // param_cod::update_atk (ojph_params.cpp:1279-1298): every kernel index must resolve
+  (void)atk_for(wavelet);
+  for (const CodStyle& c : coc)
+    if (c.wavelet > 1) {
+      bool found = false;
+      for (const AtkSpec& a : atk) if (a.index() == c.wavelet) found = true;
+      if (!found) fail(0x00050132, "A COC segment employs the DWT kernel atk = %d, but a corresponding ATK segment cannot be found", c.wavelet);
+    }
   if (received != 3) fail(0x00030052, "markers error, COD and QCD are required");
   return r.pos;
 }

@@ -41,11 +41,36 @@ struct QuantSet {
   uint32_t sx = 1, sy = 1;
 
   uint32_t guard_bits() const { return (uint32_t)(Sqcd >> 5); }
-  uint32_t kmax(uint32_t res, uint32_t band) const;          // get_Kmax, ojph_params.cpp:1715
+  uint32_t kmax(uint32_t res, uint32_t band) const { return kmax_at(res ? (res - 1) * 3 + band : 0); }   // get_Kmax, ojph_params.cpp:1715
+  uint32_t kmax_at(uint32_t idx) const;
   uint32_t largest_kmax() const;                             // :1751
-  float irrev_delta(uint32_t res, uint32_t band) const;      // get_irrev_delta, :1650
+  float irrev_delta(uint32_t res, uint32_t band) const { return irrev_delta_at(res ? (res - 1) * 3 + band : 0, band); }   // get_irrev_delta, :1650
+  float irrev_delta_at(uint32_t idx, uint32_t band) const;
   void set_rev_quant(uint32_t num_decomps, uint32_t bit_depth, bool color);   // :1495
   void set_irrev_quant(uint32_t num_decomps);                                // :1542
+};
+
+// Part 2 wavelet structures the reference DECODES (it never writes them): down-sampling factor styles (DFS marker,
+// param_dfs, ojph_params_local.h:1032-1094, ojph_params.cpp:2530-2645) and arbitrary transformation kernels
+// (ATK marker, param_atk, ojph_params_local.h:1103-1232, ojph_params.cpp:2654-2895)
+enum DfsType : uint8_t { DFS_NONE = 0, DFS_BIDIR = 1, DFS_HORZ = 2, DFS_VERT = 3 };
+struct DfsSpec {
+  uint16_t Sdfs = 0;             // index, <= 15
+  uint8_t Ids = 0;               // number of decomposition levels described, <= 32 kept
+  uint8_t Ddfs[8] = {0};         // 2 bits per level, finest level first
+  DfsType type(uint32_t decomp_level) const;                                        // get_dwt_type, :2539
+  uint32_t subband_idx(const uint32_t num_decomps, uint32_t res, uint32_t band) const;     // get_subband_idx, :2550
+};
+struct AtkStep { float A = 0.f; int16_t a = 0, b = 0; uint8_t e = 0; };   // irreversible: A; reversible: (b + a (x[-1] + x[+1])) >> e
+struct AtkSpec {
+  uint16_t Satk = 0;
+  float K = 1.0f;
+  std::vector<AtkStep> steps;    // in SYNTHESIS order: step 0 is undone first and acts on the even (low-pass) samples
+  uint32_t index() const { return Satk & 0xFFu; }
+  uint32_t coeff_type() const { return (Satk >> 8) & 7u; }
+  bool reversible() const { return (Satk & 0x1000) != 0; }
+  static AtkSpec irv97();        // init_irv97, :2870
+  static AtkSpec rev53();        // init_rev53, :2884
 };
 
 // per-component coding style (COC marker segment; param_cod with type COC_MAIN,
@@ -56,6 +81,9 @@ struct CodStyle {
   uint8_t Scoc = 0;                         // bit 0: user precinct sizes follow
   uint8_t num_decomps = 5, cb_w_exp = 4, cb_h_exp = 4, block_style = 0x40, wavelet = DWT_IRV97;
   uint8_t precinct_size[33] = {0};
+  int dfs_idx = -1;                         // >= 0: SPcoc's decomposition byte is 0x80 | index of a DFS marker segment,
+                                            // and the number of decompositions is the COD's (get_num_decompositions,
+                                            // ojph_params_local.h:503-518)
 };
 
 // one NLT marker segment (param_nlt, ojph_params_local.h:840-910): Cnlt = 0xFFFF is the default entry
@@ -89,6 +117,14 @@ struct Params {
   uint8_t wavelet = DWT_IRV97;
   uint8_t precinct_size[33] = {0};          // PPx | PPy << 4 per resolution (Scod & 1)
   std::vector<CodStyle> coc;                // per-component overrides, in creation order
+  // ---- DFS / ATK (Part 2), in marker order
+  std::vector<DfsSpec> dfs;
+  std::vector<AtkSpec> atk;
+  // encoder request (this library's own extension -- the reference has no writer for these): one decomposition
+  // structure and / or one kernel for every component.  enc_dfs lists DfsType per level, finest first.
+  std::vector<uint8_t> enc_dfs;
+  bool enc_atk_set = false;
+  AtkSpec enc_atk;
   // ---- QCD / QCC
   QuantSet qcd;
   std::vector<QuantSet> qcc;                // in creation order
@@ -108,7 +144,7 @@ struct Params {
 
   // helpers
   uint32_t num_comps() const { return (uint32_t)comps.size(); }
-  bool reversible() const { return wavelet == DWT_REV53; }
+  bool reversible() const { return wavelet <= 1 ? wavelet == DWT_REV53 : atk_for(wavelet).reversible(); }
   bool color_transform() const { return mc_trans == 1; }
   uint32_t log_cb_w() const { return cb_w_exp + 2u; }
   uint32_t log_cb_h() const { return cb_h_exp + 2u; }
@@ -121,10 +157,24 @@ struct Params {
     for (CodStyle& s : coc) if (s.comp_idx == c) return s;
     coc.push_back(CodStyle()); coc.back().comp_idx = (uint16_t)c; return coc.back();
   }
-  uint32_t decomps(uint32_t c) const { const CodStyle* s = find_coc(c); return s ? s->num_decomps : num_decomps; }
+  uint32_t decomps(uint32_t c) const { const CodStyle* s = find_coc(c); return (s && s->dfs_idx < 0) ? s->num_decomps : num_decomps; }
   uint32_t max_decomps() const { uint32_t d = 0; for (uint32_t c = 0; c < num_comps(); ++c) d = std::max(d, decomps(c)); return d; }
   uint32_t wavelet_of(uint32_t c) const { const CodStyle* s = find_coc(c); return s ? s->wavelet : wavelet; }
-  bool reversible(uint32_t c) const { return wavelet_of(c) == DWT_REV53; }
+  bool reversible(uint32_t c) const { uint32_t w = wavelet_of(c); return w <= 1 ? w == DWT_REV53 : atk_for(w).reversible(); }
+  // the kernel with index w: 0 and 1 are the built-in 9/7 and 5/3 (param_atk::get_atk, ojph_params.cpp:2654-2684)
+  const AtkSpec& atk_for(uint32_t w) const;
+  const AtkSpec& atk_of(uint32_t c) const { return atk_for(wavelet_of(c)); }
+  const DfsSpec* dfs_of(uint32_t c) const;                         // nullptr: dyadic (Mallat) decomposition
+  // how decomposition level `level` (1 = finest) of component c splits its resolution
+  DfsType dwt_type(uint32_t c, uint32_t level) const { const DfsSpec* d = dfs_of(c); return d ? d->type(level) : DFS_BIDIR; }
+  bool is_part2(uint32_t c) const { return dfs_of(c) != nullptr || wavelet_of(c) > 1; }
+  bool any_part2() const { for (uint32_t c = 0; c < num_comps(); ++c) if (is_part2(c)) return true; return false; }
+  // resolution down-sampling after `skipped` levels from the top (param_dfs::get_res_downsamp, :2575)
+  void res_downsamp(uint32_t c, uint32_t skipped, uint32_t& fx, uint32_t& fy) const;
+  // index of (resolution, band) in the component's QCD / QCC step list
+  uint32_t subband_index(uint32_t c, uint32_t res, uint32_t band) const;
+  uint32_t band_kmax(uint32_t c, uint32_t res, uint32_t band) const { return quant_for(c).kmax_at(subband_index(c, res, band)); }
+  float band_delta(uint32_t c, uint32_t res, uint32_t band) const { return quant_for(c).irrev_delta_at(subband_index(c, res, band), band); }
   uint32_t log_cb_w(uint32_t c) const { const CodStyle* s = find_coc(c); return (s ? s->cb_w_exp : cb_w_exp) + 2u; }
   uint32_t log_cb_h(uint32_t c) const { const CodStyle* s = find_coc(c); return (s ? s->cb_h_exp : cb_h_exp) + 2u; }
   uint32_t log_pp_w(uint32_t c, uint32_t r) const {

@@ -1,0 +1,236 @@
+"""Part 2 wavelet structures (second half): DFS marker segments -- decomposition levels that split
+horizontally only, vertically only or not at all (param_dfs, ojph_params.cpp:2530-2645; resolution::finalize_alloc,
+ojph_resolution.cpp:264-396) -- and ATK marker segments -- arbitrary whole-sample symmetric lifting kernels
+(param_atk, :2654-2895; gen_rev_vert_step / gen_irv_horz_syn, ojph_transform.cpp:209-262, :785-849).
+
+The reference only DECODES these (Kakadu writes them), so the oracle here is its decoder: streams produced by this
+library's encoder extension must decode in the unmodified reference to exactly what this library's decoder returns --
+bit for bit for reversible kernels (where both must also return the input), and for irreversible kernels too at these
+sizes (same operations in the same order); the test allows one level of difference there and checks the error against
+the input is what the step size predicts.  The reference's own test of this feature
+(tests/test_executables.cpp:1015-1026, simple_dec_irv53_bhvhb_low_latency) uses a Kakadu-made file that is not
+available offline; `test_reference_low_latency_configuration` reproduces its parameters on a synthetic image."""
+import struct
+import numpy as np
+import pytest
+import openjph_b200 as ob
+from openjph_b200.codestream import comp_dims
+
+IRV53 = dict(K=1.0, A=[0.25, -0.5])                               # Kakadu's I5X3: the 5/3 taps without rounding
+IRV97 = dict(K=1.230174104914001, A=[0.443506852043971, 0.882911075530934, -0.052980118572961, -1.586134342059924])
+REV53 = dict(reversible=True, steps=[(1, 2, 2), (-1, 1, 1)])
+REV3 = dict(reversible=True, steps=[(1, 4, 3), (-1, 1, 1), (1, 2, 2)])     # three steps: the first synthesis step is on the low band
+REV_GEN = dict(reversible=True, steps=[(3, 8, 4), (-5, 4, 3)])             # a, b, e all away from the 5/3 shortcuts
+
+
+def _smooth(rng, w, h, bd, signed):
+    y, x = np.mgrid[0:h, 0:w]
+    f = (np.sin(x / 7.0 + rng.random() * 6) + np.cos(y / 5.0 + rng.random() * 6) + 0.3 * rng.standard_normal((h, w))) / 2.6
+    # (-2^(B-1) is left out: with no splitting level its magnitude needs one bit more than K_max, exactly as with
+    # zero decompositions in the reference -- ojb_device.h, ENC_CHECK_NEGZERO)
+    lo, hi = (-(1 << (bd - 1)) + 1, (1 << (bd - 1)) - 1) if signed else (0, (1 << bd) - 1)
+    v = np.clip(np.round((f * 0.5 + 0.5) * (hi - lo) + lo), lo, hi)
+    if rng.random() < 0.25:
+        v = rng.integers(lo, hi + 1, (h, w))
+    return v.astype(np.int32)
+
+
+def _case(seed):
+    rng = np.random.default_rng(9000 + seed)
+    nc = int(rng.choice([1, 1, 3, 4]))
+    bd = int(rng.choice([8, 10, 12, 16]))
+    sg = bool(rng.random() < 0.2)
+    w, h = int(rng.integers(1, 140)), int(rng.integers(1, 110))
+    nd = int(rng.integers(1, 6))
+    rev = bool(rng.random() < 0.5)
+    kw = dict(num_decomps=nd, reversible=rev, color_transform=bool(nc >= 3 and rng.random() < 0.6),
+              prog_order=str(rng.choice(["LRCP", "RLCP", "RPCL", "PCRL", "CPRL"])))
+    bw = int(rng.choice([4, 8, 16, 32, 64, 128])); bh = int(rng.choice([b for b in (4, 8, 16, 32, 64, 256) if b * bw <= 4096]))
+    kw["block"] = (bw, bh)
+    what = rng.random()
+    if what < 0.75:
+        kw["decomp"] = "".join(rng.choice(list("BBHVX"), size=int(rng.integers(1, nd + 1))))
+    if what > 0.45:
+        kw["atk"] = [REV53, REV3, REV_GEN][int(rng.integers(0, 3))] if rev else [IRV53, IRV97][int(rng.integers(0, 2))]
+    if rng.random() < 0.3:
+        kw["tile"] = (int(rng.integers(24, 90)), int(rng.integers(24, 90)))
+    if rng.random() < 0.3:
+        ox, oy = int(rng.integers(0, 9)), int(rng.integers(0, 9))
+        kw["offset"] = (ox, oy); kw["tile_offset"] = (int(rng.integers(0, ox + 1)), int(rng.integers(0, oy + 1)))
+        w += ox; h += oy
+    if rng.random() < 0.4:
+        kw["precincts"] = [(int(rng.choice([32, 64, 128])), int(rng.choice([32, 64, 128])))] * (nd + 1)
+    if nc == 4 and rng.random() < 0.5 and not kw["color_transform"]:
+        kw["subsampling"] = [(1, 1), (2, 1), (2, 2), (1, 1)]
+    if rng.random() < 0.2:
+        kw["tilepart_div"] = int(rng.integers(1, 4)); kw["tlm"] = True
+    if not rev and rng.random() < 0.5:
+        kw["qstep"] = float(rng.choice([0.01, 0.002, 0.0005]))
+    p = ob.make_params(w, h, nc, bd, is_signed=sg, **kw)
+    planes = [_smooth(rng, cw, ch, bd, sg) for (cw, ch) in comp_dims(p)]
+    return p, planes, kw
+
+
+def _roundtrip(lib, ref, p, planes, kw, tag):
+    cs = ob.Encoder(p, ob.I32, lib=lib).encode(planes)
+    hdr = cs[:cs.index(b"\xff\x90")]
+    assert (b"\xff\x72" in hdr) == ("decomp" in kw) and (b"\xff\x79" in hdr) == ("atk" in kw), tag
+    mine = ob.Decoder(lib=lib).decode(cs)
+    theirs, _ = ref.decode(cs)
+    rev = kw["reversible"]
+    for c, (a, b, src) in enumerate(zip(mine, theirs, planes)):
+        assert a.shape == b.shape == src.shape, (tag, c)
+        d = int(np.abs(a.astype(np.int64) - b).max()) if a.size else 0
+        assert d <= (0 if rev else 1), (tag, c, d)                       # the reference decoder is the oracle
+        if rev:
+            assert np.array_equal(a, src), (tag, c)
+    return cs, mine
+
+
+def _check_random(lib, ref, seeds):
+    kinds = set()
+    for seed in seeds:
+        p, planes, kw = _case(seed)
+        cs, mine = _roundtrip(lib, ref, p, planes, kw, seed)
+        kinds.add(("decomp" in kw, "atk" in kw, kw["reversible"]))
+        if not kw["reversible"]:           # the step sizes derived from the kernel's own gains give a sane reconstruction
+            bd = p.bit_depth[0]
+            q = kw.get("qstep", 1.0 / (1 << min(bd, 16)))
+            for a, src in zip(mine, planes):
+                if a.size:
+                    rms = float(np.sqrt(np.mean((a.astype(np.float64) - src) ** 2)))
+                    assert rms <= max(1.0, 6.0 * q * (1 << bd)), (seed, rms, q)
+    assert len(kinds) >= 5
+
+
+def test_part2_random_configs_emulator(emu_lib, ref):
+    _check_random(emu_lib, ref, range(60))
+
+
+@pytest.mark.gpu
+def test_part2_random_configs_gpu(gpu_lib, ref):
+    _check_random(gpu_lib, ref, range(120))
+
+
+def _low_latency(lib, ref, w, h):
+    # ojph_compress' counterpart in Kakadu: Corder=PCRL Clevels=5 Cmodes=HT|CAUSAL Catk=2 Kkernels:I2=I5X3
+    # Cprecincts={16,8192},{8,8192},{4,8192} Cblk={8,256} Cdecomp=B(-:-:-),H(-),V(-),H(-),B(-:-:-) Qstep=0.0001
+    # (tests/test_executables.cpp:1015-1019); precinct sizes are (width, height) here, and the stripe-causal mode has
+    # no encoder-side effect with a single cleanup pass
+    rng = np.random.default_rng(5)
+    kw = dict(num_decomps=5, reversible=False, color_transform=True, prog_order="PCRL", decomp="BHVHB", atk=IRV53,
+              precincts=[(8192, 4), (8192, 4), (8192, 4), (8192, 4), (8192, 8), (8192, 16)], block=(256, 8), qstep=0.0001)
+    p = ob.make_params(w, h, 3, 8, **kw)
+    planes = [_smooth(rng, w, h, 8, False) for _ in range(3)]
+    cs, mine = _roundtrip(lib, ref, p, planes, kw, "low-latency")
+    for a, src in zip(mine, planes):
+        assert int(np.abs(a - src).max()) <= 2                              # Qstep 0.0001: near lossless
+    return cs
+
+
+def test_reference_low_latency_configuration_emulator(emu_lib, ref):
+    _low_latency(emu_lib, ref, 300, 200)
+
+
+@pytest.mark.gpu
+def test_reference_low_latency_configuration_gpu(gpu_lib, ref):
+    _low_latency(gpu_lib, ref, 2048, 1556)
+
+
+def _restricted(lib, ref):
+    # reduced-resolution output follows the DFS: a level that splits one way halves one dimension only
+    # (param_dfs::get_res_downsamp, ojph_params.cpp:2575-2593)
+    rng = np.random.default_rng(11)
+    for decomp, rev in (("HVB", True), ("VHH", True), ("BHV", False), ("XHB", True)):
+        kw = dict(num_decomps=3, reversible=rev, decomp=decomp, block=(32, 32))
+        p = ob.make_params(201, 155, 1, 8, **kw)
+        planes = [_smooth(rng, 201, 155, 8, False)]
+        cs = ob.Encoder(p, ob.I32, lib=lib).encode(planes)
+        for skip in ((1, 1), (2, 2), (3, 3), (2, 1), (3, 0)):
+            want, _ = ref.decode_restricted(cs, *skip)
+            got = ob.Decoder(lib=lib).decode(cs, skip=skip)
+            assert got[0].shape == want[0].shape, (decomp, skip, got[0].shape, want[0].shape)
+            assert int(np.abs(got[0].astype(np.int64) - want[0]).max()) <= (0 if rev else 1), (decomp, skip)
+
+
+def test_restricted_resolution_follows_dfs_emulator(emu_lib, ref):
+    _restricted(emu_lib, ref)
+
+
+@pytest.mark.gpu
+def test_restricted_resolution_follows_dfs_gpu(gpu_lib, ref):
+    _restricted(gpu_lib, ref)
+
+
+def _marker(cs, code):
+    i = cs.index(code)
+    return i, struct.unpack(">H", cs[i + 2:i + 4])[0]
+
+
+def test_header_errors_match_reference(emu_lib, ref, capfd):
+    """marker-segment faults are refused with the reference's error codes (param_dfs::read / param_atk::read /
+    param_cod::update_atk / resolution::pre_alloc); the reference prints its code on stderr"""
+    rng = np.random.default_rng(3)
+    p = ob.make_params(64, 64, 1, 8, num_decomps=3, reversible=False, decomp="BHV", atk=IRV53)
+    cs = bytearray(ob.Encoder(p, ob.I32, lib=emu_lib).encode([_smooth(rng, 64, 64, 8, False)]))
+    dfs, _ = _marker(cs, b"\xff\x72"); atk, latk = _marker(cs, b"\xff\x79")
+
+    def both(mut, code):
+        bad = bytearray(cs); mut(bad)
+        with pytest.raises(ob.OjphError) as e:
+            ob.Decoder(lib=emu_lib).decode(bytes(bad))
+        assert ("%08x" % code) in str(e.value).lower(), str(e.value)
+        capfd.readouterr()
+        with pytest.raises(RuntimeError):
+            ref.decode(bytes(bad))
+        err = capfd.readouterr().err.lower()
+        assert ("0x%08x" % code) in err, err
+
+    def sdfs(b): b[dfs + 5] = 2                         # the COCs name DFS 1; only DFS 2 is there
+    both(sdfs, 0x00070002)
+    def sdfs16(b): b[dfs + 5] = 16
+    both(sdfs16, 0x000500D3)
+    def ids0(b): b[dfs + 6] = 0
+    both(ids0, 0x000500D8)
+    def atk_index(b): b[atk + 5] = 3                    # the COCs name ATK 2
+    both(atk_index, 0x00050132)
+    def atk_arb(b): b[atk + 4] &= ~0x08 & 0xFF          # not whole-sample symmetric
+    both(atk_arb, 0x000500E4)
+    def atk_minit(b): b[atk + 4] |= 0x20
+    both(atk_minit, 0x000500E3)
+    def atk_ext(b): b[atk + 4] &= ~0x40 & 0xFF          # constant boundary extension
+    both(atk_ext, 0x000500E6)
+    def atk_len(b): b[atk + 3] += 1
+    both(atk_len, 0x000500F3)
+    def atk_taps(b): b[atk + 11] = 2                    # LCatk of the first step (Latk Satk Katk(4) Natk | LCatk)
+    both(atk_taps, 0x000500F1)
+
+
+def test_more_than_four_steps_is_refused(emu_lib):
+    p = ob.make_params(32, 32, 1, 8, num_decomps=1, reversible=True,
+                       atk=dict(reversible=True, steps=[(1, 2, 2), (-1, 1, 1)] * 3))
+    with pytest.raises(ob.OjphError) as e:
+        ob.Encoder(p, ob.I32, lib=emu_lib)
+    assert "000b0025" in str(e.value).lower()
+
+
+def test_kernel_gains_reproduce_the_reference_tables(emu_lib):
+    """the step sizes of a kernel given as an ATK come from gains measured on the kernel (KernelGains,
+    ojb_params.cpp); for the 9/7 and 5/3 taps they must land on what the reference's tables give the built-in
+    kernels (set_rev_quant / set_irrev_quant, ojph_params.cpp:1495-1599)"""
+    def qcd(cs):
+        i = cs.index(b"\xff\x5c"); n = struct.unpack(">H", cs[i + 2:i + 4])[0]
+        return cs[i + 4], cs[i + 5:i + 2 + n]
+    planes = [np.zeros((64, 64), np.int32)]
+    for rev, atk in ((False, IRV97), (True, REV53)):
+        a = ob.Encoder(ob.make_params(64, 64, 1, 8, num_decomps=5, reversible=rev), ob.I32, lib=emu_lib).encode(planes)
+        b = ob.Encoder(ob.make_params(64, 64, 1, 8, num_decomps=5, reversible=rev, atk=atk), ob.I32, lib=emu_lib).encode(planes)
+        (sa, qa), (sb, qb) = qcd(a), qcd(b)
+        assert sa == sb and len(qa) == len(qb)
+        if rev:
+            assert qa == qb
+        else:
+            ua = struct.unpack(">%dH" % (len(qa) // 2), qa); ub = struct.unpack(">%dH" % (len(qb) // 2), qb)
+            for x, y in zip(ua, ub):
+                dx = (1 + (x & 0x7FF) / 2048.0) / 2.0 ** (x >> 11); dy = (1 + (y & 0x7FF) / 2048.0) / 2.0 ** (y >> 11)
+                assert abs(dx - dy) <= 2e-3 * dx, (x, y)
