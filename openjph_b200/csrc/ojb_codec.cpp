@@ -254,10 +254,7 @@ void Encoder::configure(const Params& p, uint32_t sample_type) {
               e.src_off = bg.plane_off + bg.plane_pad_x + (uint64_t)(r.y0 - bg.rect.y0) * bg.plane_stride + (r.x0 - bg.rect.x0);
               e.stride = bg.plane_stride; e.w = (uint16_t)r.w; e.h = (uint16_t)r.h;
               e.p = (uint16_t)((wide ? 63u : 31u) - bg.K_max);
-              // (a DFS whose levels all leave the resolution unsplit is the same single-band situation)
-              bool unsplit = true;
-              for (const ResGeom& q : tc.res) if (q.hsplit | q.vsplit) unsplit = false;
-              e.flags = (unsplit && params.reversible(tc.comp)) ? (uint16_t)ENC_CHECK_NEGZERO : (uint16_t)0;
+              e.flags = (tc.res.size() == 1 && params.reversible(tc.comp)) ? (uint16_t)ENC_CHECK_NEGZERO : (uint16_t)0;
               // worst case: (K_max+1) MagSgn bits / sample (+1/15 stuffing), 30 VLC bits / quad pair
               // (+1/7), 192 MEL bytes, working margin of the kernel
               uint64_t ms = ((uint64_t)r.w * r.h * (bg.K_max + 1) + 7) / 8; ms += ms / 15 + 8;

@@ -38,21 +38,26 @@ inline float vw_gain(int ctype) {
   if (ctype == 1) return 1.8051f / 1.7321f;
   return 1.5734f / 1.7321f;
 }
-float vw_delta_ref(uint32_t qfactor, uint32_t bit_depth, float& power) {
-  constexpr uint8_t t0 = 65, t1 = 97;
-  constexpr float alpha_t0 = 0.04f, alpha_t1 = 0.10f;
-  constexpr float m_t0 = 2.0f * (1.0f - t0 / 100.0f);
-  constexpr float m_t1 = 2.0f * (1.0f - t1 / 100.0f);
-  float m_q = qfactor < 50 ? 50.0f / (float)qfactor : 2.0f * (1.0f - (float)qfactor / 100.0f);
-  float alpha_q;
-  if (qfactor <= t0) { power = 1.0f; alpha_q = alpha_t0; }
-  else if (qfactor < t1) {
-    power = std::log(m_q) - std::log(m_t1);
-    power /= std::log(m_t0) - std::log(m_t1);
-    alpha_q = alpha_t1 * std::pow(alpha_t0 / alpha_t1, power);
-  } else { power = 0.0f; alpha_q = alpha_t1; }
-  const float eps = std::sqrt(0.5f) * std::ldexp(1.0f, -(int)bit_depth);
-  return alpha_q * m_q + eps;
+// Reference step size of the Qfactor model (param_qcd::get_delta_ref, ojph_params.cpp:690-725): a JPEG-style quality
+// scale `slope(Q)` -- 50/Q below 50, 2 (1 - Q/100) above -- weighted by a colour / level factor that is 0.04 up to the
+// knee Q = 65, 0.10 from Q = 97 and geometrically interpolated in log-slope between them; `blend` (1 at the knee, 0 at
+// the top) is also the exponent the visual weights are raised to.  Every operation is in float in this order: the
+// packed QCD values must come out identical to the reference's.
+float vw_delta_ref(uint32_t qfactor, uint32_t bit_depth, float& blend) {
+  constexpr uint8_t knee = 65, top = 97;
+  constexpr float w_knee = 0.04f, w_top = 0.10f;
+  constexpr float slope_knee = 2.0f * (1.0f - knee / 100.0f);
+  constexpr float slope_top = 2.0f * (1.0f - top / 100.0f);
+  const float slope = qfactor < 50 ? 50.0f / (float)qfactor : 2.0f * (1.0f - (float)qfactor / 100.0f);
+  float weight;
+  if (qfactor <= knee) { blend = 1.0f; weight = w_knee; }
+  else if (qfactor < top) {
+    blend = std::log(slope) - std::log(slope_top);
+    blend /= std::log(slope_knee) - std::log(slope_top);
+    weight = w_top * std::pow(w_knee / w_top, blend);
+  } else { blend = 0.0f; weight = w_top; }
+  const float floor_step = std::sqrt(0.5f) * std::ldexp(1.0f, -(int)bit_depth);      // never below ~0.7 LSB
+  return weight * slope + floor_step;
 }
 
 // exponent/mantissa packing of an irreversible step (encode_SPqcd, ojph_params.cpp:1602)
@@ -393,6 +398,10 @@ static void make_part2_steps(QuantSet& q, uint32_t comp, const Params& p) {
     uint32_t max_BX = 0; uint8_t tmp[97];
     for (size_t i = 0; i < bands.size(); ++i) {
       uint32_t X = (uint32_t)std::max(0.0, ceil(log(bands[i].bibo) / M_LN2 - 1e-9));
+      // a band nothing has filtered (every level of the DFS leaves the resolution unsplit) still has to hold
+      // -2^(B-1), whose magnitude needs B bits: the reference's zero-decomposition streams lose exactly that value
+      // (K_max = B - 1 there, see ENC_CHECK_NEGZERO); a writer free to choose its exponents need not
+      if (bands[i].bibo <= 1.0) X = 1;
       tmp[i] = (uint8_t)(Bd + X); max_BX = std::max(max_BX, Bd + X);
     }
     if (max_BX > 38)
