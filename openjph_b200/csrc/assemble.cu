@@ -53,6 +53,7 @@ gather_blocks_kernel(const EncBlock* __restrict__ blocks, const EncResult* __res
   const EncResult r = results[warp];
   if (r.len_head + r.len_tail == 0) return;
   const EncBlock b = blocks[warp];
+  if (dst_off[warp] == ~0ull) return;                  // the codestream does not fit its buffer (hdr_layout_kernel)
   uint8_t* d = out + dst_off[warp];
   const uint8_t* slot = slots + b.slot_off;
   warp_copy(d, slot, r.len_head, lane);

@@ -281,8 +281,97 @@ void Encoder::configure(const Params& p, uint32_t sample_type) {
   coded.assign(layout.num_blocks, CodedBlock());
   main_header.clear();
   params.write_main_header(main_header, nullptr, nullptr, 0);
+  build_header_plan();
   // line-based front end state
   line_cur.assign(params.num_comps(), 0); cur_comp = 0; lines_done = false;
+}
+
+// The static side of pkt_headers.cu: packets in stream order, their bands with blocks (segments), blocks in header
+// order (items), groups of 32 items, tile-parts -- everything that depends on the geometry only.
+void Encoder::build_header_plan() {
+  device_headers = false;
+  memset(&hplan, 0, sizeof(hplan));
+  if (getenv("OJB_HOST_HEADERS") || !tile_mask.empty()) return;
+  std::vector<HdrSeg> segs; std::vector<HdrPkt> pkts; std::vector<HdrGroup> groups; std::vector<HdrTp> tps; std::vector<uint32_t> item_seg;
+  uint64_t nodes = 0, hoff = 0; uint32_t max_cap = 0;
+  auto log2ceil = [](uint32_t x) { uint32_t t = 31u - (uint32_t)__builtin_clz(x); return t + ((x & (x - 1)) ? 1u : 0u); };
+  fixed_blob = main_header;
+  std::vector<PacketRef> seq; std::vector<uint32_t> tp_first, tp_index; uint32_t tp_total = 0;
+  struct TpTmp { uint32_t tile, first, count, idx, cnt; };
+  std::vector<TpTmp> tpt;
+  for (uint32_t t = 0; t < (uint32_t)layout.tiles.size(); ++t) {
+    layout.packet_sequence(t, seq, tp_first, &tp_index, &tp_total);
+    const uint32_t base = (uint32_t)pkts.size();
+    for (const PacketRef& pr : seq) {
+      const ResGeom& rg = layout.res_of(pr); const PrecinctGeom& pc = rg.precincts[pr.precinct];
+      HdrPkt pk; memset(&pk, 0, sizeof(pk));
+      pk.first_seg = (uint32_t)segs.size(); pk.first_item = (uint32_t)item_seg.size(); pk.first_group = (uint32_t)groups.size();
+      for (uint32_t sb = 0; sb < 4; ++sb) {
+        const BandGeom& bg = rg.bands[sb];
+        if (bg.empty) continue;
+        const Rect& ci = pc.cb_idx[sb];
+        if (ci.w == 0 || ci.h == 0) continue;
+        HdrSeg sg; sg.pkt = (uint32_t)pkts.size(); sg.first_item = (uint32_t)item_seg.size();
+        sg.w = ci.w; sg.h = ci.h; sg.nl = 1 + std::max(log2ceil(ci.w), log2ceil(ci.h));
+        sg.block0 = bg.block_base + ci.y0 * bg.nbw + ci.x0; sg.nbw = bg.nbw; sg.tree_off = (uint32_t)nodes;
+        for (uint32_t l = 0, pw = ci.w, ph = ci.h; l < sg.nl; ++l) { nodes += (uint64_t)pw * ph; pw = (pw + 1) >> 1; ph = (ph + 1) >> 1; }
+        item_seg.insert(item_seg.end(), (size_t)ci.w * ci.h, (uint32_t)segs.size());
+        segs.push_back(sg);
+      }
+      pk.nsegs = (uint32_t)segs.size() - pk.first_seg; pk.nitems = (uint32_t)item_seg.size() - pk.first_item;
+      for (uint32_t i = 0; i < pk.nitems; i += 32) groups.push_back(HdrGroup{ pk.first_item + i, std::min(32u, pk.nitems - i) });
+      pk.ngroups = (uint32_t)groups.size() - pk.first_group;
+      // <= 160 bits per block, one stuffed bit per eight at worst
+      const uint64_t cap = (((uint64_t)pk.nitems * 23 + 16) + 3) & ~(uint64_t)3;
+      pk.hdr_off = (uint32_t)hoff; hoff += cap; max_cap = (uint32_t)std::max<uint64_t>(max_cap, cap);
+      pkts.push_back(pk);
+    }
+    for (size_t i = 0; i < tp_first.size(); ++i) {
+      const uint32_t end = (i + 1 < tp_first.size()) ? tp_first[i + 1] : (uint32_t)seq.size();
+      if (end == tp_first[i]) return;                 // a tile-part without packets: the host writer handles it
+      tpt.push_back(TpTmp{ t, base + tp_first[i], end - tp_first[i], tp_index[i], tp_total });
+      pkts[base + tp_first[i]].tp_first = 1;
+    }
+  }
+  if (nodes >= (1ull << 32) || hoff >= (1ull << 32) || item_seg.size() >= (1ull << 31)) return;
+  if (params.need_tlm) {
+    if (4 + 6 * tpt.size() > 65535) fail(0x000500B1, "too many tile-parts for one TLM marker segment");
+    put_u16(fixed_blob, M_TLM); put_u16(fixed_blob, (uint32_t)(4 + 6 * tpt.size())); put_u8(fixed_blob, 0); put_u8(fixed_blob, 0x60);
+    for (const TpTmp& tp : tpt) { put_u16(fixed_blob, tp.tile); put_u32(fixed_blob, 0); }
+  }
+  for (size_t i = 0; i < tpt.size(); ++i)
+    tps.push_back(HdrTp{ tpt[i].first, tpt[i].count, tpt[i].tile, tpt[i].idx, tpt[i].cnt,
+                         params.need_tlm ? (uint32_t)(main_header.size() + 6 + 6 * i + 2) : 0xFFFFFFFFu });
+  int nb = 0;
+  auto up = [&](const void* src, size_t bytes) -> void* {
+    DeviceBuf& b = d_hplan[nb++]; b.reserve(std::max<size_t>(16, bytes));
+    if (bytes) CK(cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice));
+    return b.p;
+  };
+  auto scratch = [&](size_t bytes) -> void* { DeviceBuf& b = d_hplan[nb++]; b.reserve(std::max<size_t>(16, bytes)); return b.p; };
+  hplan.nsegs = (uint32_t)segs.size(); hplan.npkts = (uint32_t)pkts.size(); hplan.nitems = (uint32_t)item_seg.size();
+  hplan.ngroups = (uint32_t)groups.size(); hplan.ntps = (uint32_t)tps.size(); hplan.max_hdr_cap = max_cap;
+  hplan.segs = (const HdrSeg*)up(segs.data(), segs.size() * sizeof(HdrSeg));
+  hplan.pkts = (const HdrPkt*)up(pkts.data(), pkts.size() * sizeof(HdrPkt));
+  hplan.groups = (const HdrGroup*)up(groups.data(), groups.size() * sizeof(HdrGroup));
+  hplan.tps = (const HdrTp*)up(tps.data(), tps.size() * sizeof(HdrTp));
+  hplan.item_seg = (const uint32_t*)up(item_seg.data(), item_seg.size() * 4);
+  const size_t ni = item_seg.size(), ng = groups.size(), np = pkts.size();
+  hplan.tinc = (uint8_t*)scratch(nodes); hplan.tmm = (uint8_t*)scratch(nodes); hplan.tfi = (uint32_t*)scratch(nodes * 4);
+  hplan.seg_root = (uint8_t*)scratch(segs.size());
+  hplan.ibits = (uint32_t*)scratch(ni * 20); hplan.inbits = (uint16_t*)scratch(ni * 2); hplan.itab = (uint16_t*)scratch(ni * 32);
+  hplan.ilen = (uint32_t*)scratch(ni * 4);
+  hplan.gcomp = (uint32_t*)scratch(ng * 64); hplan.gbits = (uint32_t*)scratch(ng * 4); hplan.glen = (uint32_t*)scratch(ng * 4);
+  hplan.gstate = (uint32_t*)scratch(ng * 4); hplan.gpos = (uint32_t*)scratch(ng * 4); hplan.gbody = (uint32_t*)scratch(ng * 4);
+  hplan.istate = (uint8_t*)scratch(ni); hplan.ipos = (uint32_t*)scratch(ni * 4); hplan.ibody = (uint32_t*)scratch(ni * 4);
+  hplan.phdr = (uint32_t*)scratch(np * 4); hplan.pbody = (uint32_t*)scratch(np * 4); hplan.ppos = (uint64_t*)scratch(np * 8);
+  hscr_bytes = (size_t)hoff + 16;
+  hplan.hscr = (uint32_t*)scratch(hscr_bytes);
+  hplan.total = (uint64_t*)scratch(16);
+  d_fixed.reserve(fixed_blob.size() + 16);
+  CK(cudaMemcpy(d_fixed.p, fixed_blob.data(), fixed_blob.size(), cudaMemcpyHostToDevice));
+  h_total.reserve(64);
+  device_headers = true;
 }
 
 int32_t* Encoder::exchange(const int32_t* line_written, uint32_t& next_comp) {
@@ -357,6 +446,49 @@ size_t Encoder::encode(const void* const* planes, const uint32_t* strides, bool 
                      d_results.as<EncResult>(), d_tables_enc.as<uint16_t>(), d_status.as<uint32_t>(), stream);
   last_launches += (serial_block_encoder() || max_block_w > 64) ? (num_fast_blocks ? 1 : 0) + (num_fast_blocks < nb ? 1 : 0) : 1;
   mark(3);
+  if (device_headers) {
+    // packet headers, markers and layout by kernels; the host only learns the length (and, for a host buffer, waits
+    // for it before asking for the copy)
+    launch_ctrl_copy(h_status.p, d_status.p, 16, stream);
+    mark(4); mark(5);
+    uint8_t* dev_out;
+    uint64_t cap = out_cap;
+    if (out_on_device) dev_out = out;
+    else {
+      if (d_out.cap < 1024) d_out.reserve(std::max<size_t>(1 << 20, fixed_blob.size() + 64));
+      dev_out = d_out.as<uint8_t>(); cap = std::min<uint64_t>(out_cap, d_out.cap);
+    }
+    uint64_t total = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      if (fixed_blob.size() <= cap) CK(cudaMemcpyAsync(dev_out, d_fixed.p, fixed_blob.size(), cudaMemcpyDeviceToDevice, stream));
+      CK(cudaMemsetAsync(hplan.hscr, 0, hscr_bytes, stream));
+      launch_packet_headers(hplan, d_blocks.as<EncBlock>(), d_results.as<EncResult>(), wide ? 62u : 30u, fixed_blob.size(), cap, true,
+                            dev_out, d_dst.as<uint64_t>(), stream);
+      launch_gather_blocks(d_blocks.as<EncBlock>(), d_results.as<EncResult>(), d_dst.as<uint64_t>(), nb, d_slots.as<uint8_t>(), dev_out, stream);
+      launch_ctrl_copy(h_total.p, hplan.total, 16, stream);
+      last_launches += packet_header_launches(hplan) + 3;
+      mark(6);
+      CK(cudaStreamSynchronize(stream));
+      CK(cudaGetLastError());
+      status_flags = h_status.as<uint32_t>()[0];
+      if (status_flags & 2u) fail(0x00020001, "mel encoder's buffer is full");
+      if (status_flags & 1u) fail(0x00020005, "block encoder's output slot is full");
+      total = h_total.as<uint64_t>()[0];
+      if (h_total.as<uint64_t>()[1] == 0) break;
+      // did not fit: the caller's buffer is too small, or (host output) the staging buffer has to grow once
+      if (total > out_cap || out_on_device || attempt == 1)
+        fail(0x000B0030, "output buffer too small: need %zu bytes, have %zu", (size_t)total, out_cap);
+      d_out.reserve(total + 64); dev_out = d_out.as<uint8_t>(); cap = std::min<uint64_t>(out_cap, d_out.cap);
+    }
+    host_ms = 0;
+    if (!out_on_device) CK(cudaMemcpyAsync(out, dev_out, total, cudaMemcpyDeviceToHost, stream));
+    mark(7);
+    CK(cudaStreamSynchronize(stream));
+    collect(8);
+    CK(cudaGetLastError());
+    std::fill(line_cur.begin(), line_cur.end(), 0u); cur_comp = 0; lines_done = false;
+    return (size_t)total;
+  }
   if (nb) launch_ctrl_copy(h_results.p, d_results.p, (size_t)nb * sizeof(EncResult), stream);
   launch_ctrl_copy(h_status.p, d_status.p, 16, stream);
   last_launches += nb ? 2 : 1;

@@ -137,6 +137,32 @@ struct DwtJob {
   uint32_t cta_base;      // first CTA index of this job in the launch
 };
 
+// ---- packet headers on the device (pkt_headers.cu) -----------------------------------------------------------------
+// static plan, built once per configuration; every "item" is one code-block in header order (packets in stream order,
+// inside a packet the bands that have blocks, inside a band the precinct's blocks in raster order)
+struct HdrSeg {          // one band of one precinct with code-blocks in it (the loop body of precinct::prepare_precinct)
+  uint32_t pkt;          // packet, in stream order
+  uint32_t first_item;
+  uint32_t w, h, nl;     // the precinct's code-block grid in this band; tag-tree levels = 1 + max(ceil log2 w, ceil log2 h)
+  uint32_t block0, nbw;  // block index of item (x, y) = block0 + y * nbw + x
+  uint32_t tree_off;     // first node of this segment's trees in the node arrays
+};
+struct HdrPkt { uint32_t first_seg, nsegs, first_item, nitems, first_group, ngroups, hdr_off /* bytes into the header scratch, x4 */, tp_first; };
+struct HdrGroup { uint32_t first_item, n; };       // <= 32 consecutive items of one packet
+struct HdrTp { uint32_t first_pkt, npkts, tile, tp_idx, tp_cnt, tlm_off /* byte offset of its Ptlm in the output, or ~0 */; };
+struct HdrPlanDev {
+  uint32_t nsegs, npkts, nitems, ngroups, ntps, max_hdr_cap;
+  const HdrSeg* segs; const HdrPkt* pkts; const HdrGroup* groups; const HdrTp* tps; const uint32_t* item_seg;
+  // per frame
+  uint8_t *tinc, *tmm; uint32_t* tfi; uint8_t* seg_root;
+  uint32_t* ibits; uint16_t* inbits; uint16_t* itab; uint32_t* ilen;
+  uint32_t *gcomp, *gbits, *glen, *gstate, *gpos, *gbody;
+  uint8_t* istate; uint32_t *ipos, *ibody;
+  uint32_t *phdr, *pbody; uint64_t* ppos;
+  uint32_t* hscr;        // packet header bytes, zeroed before every frame
+  uint64_t* total;       // [0] codestream length, [1] 1 when it exceeds the output capacity (nothing is written then)
+};
+
 // ---- raster layouts ------------------------------------------------------------------------
 struct RasterPlanes {        // where the component planes of the image buffer are (bytes / samples)
   uint64_t off[3];

@@ -70,6 +70,11 @@ void launch_raster_unpack_dpx(const void* src, void* image, const RasterPlanes& 
                               uint32_t width, uint32_t height, cudaStream_t st);
 void launch_raster_pack(void* dst, const void* image, const RasterPlanes& pl, uint32_t ncomp, uint32_t bytes_per_sample,
                         uint32_t width, uint32_t height, cudaStream_t st);
+// packet headers, SOT / TLM / EOC and the destination of every block body, all on the device (pkt_headers.cu);
+// `out` must already hold the fixed bytes (main header, TLM with blank lengths); dst[] feeds launch_gather_blocks
+void launch_packet_headers(const HdrPlanDev& plan, const EncBlock* blocks, const EncResult* results, uint32_t mmsb_base,
+                           uint64_t fixed_len, uint64_t cap, bool write_eoc, uint8_t* out, uint64_t* dst, cudaStream_t st);
+uint32_t packet_header_launches(const HdrPlanDev& plan);
 // block pieces computed on the device from per-block results + destination offsets
 void launch_gather_blocks(const EncBlock* blocks, const EncResult* results, const uint64_t* dst_off,
                           uint32_t nblocks, const uint8_t* slots, uint8_t* out, cudaStream_t st);
