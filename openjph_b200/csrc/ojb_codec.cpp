@@ -291,15 +291,18 @@ void Encoder::configure(const Params& p, uint32_t sample_type) {
 void Encoder::build_header_plan() {
   device_headers = false;
   memset(&hplan, 0, sizeof(hplan));
-  if (getenv("OJB_HOST_HEADERS") || !tile_mask.empty()) return;
+  if (getenv("OJB_HOST_HEADERS")) return;
+  const bool partial = !tile_mask.empty();        // this rank's tile-parts only: no main header, TLM or EOC (ojb_shard.cpp)
   std::vector<HdrSeg> segs; std::vector<HdrPkt> pkts; std::vector<HdrGroup> groups; std::vector<HdrTp> tps; std::vector<uint32_t> item_seg;
   uint64_t nodes = 0, hoff = 0; uint32_t max_cap = 0;
   auto log2ceil = [](uint32_t x) { uint32_t t = 31u - (uint32_t)__builtin_clz(x); return t + ((x & (x - 1)) ? 1u : 0u); };
-  fixed_blob = main_header;
+  fixed_blob.clear();
+  if (!partial) fixed_blob = main_header;
   std::vector<PacketRef> seq; std::vector<uint32_t> tp_first, tp_index; uint32_t tp_total = 0;
   struct TpTmp { uint32_t tile, first, count, idx, cnt; };
   std::vector<TpTmp> tpt;
   for (uint32_t t = 0; t < (uint32_t)layout.tiles.size(); ++t) {
+    if (!tile_wanted(t)) continue;
     layout.packet_sequence(t, seq, tp_first, &tp_index, &tp_total);
     const uint32_t base = (uint32_t)pkts.size();
     for (const PacketRef& pr : seq) {
@@ -334,14 +337,17 @@ void Encoder::build_header_plan() {
     }
   }
   if (nodes >= (1ull << 32) || hoff >= (1ull << 32) || item_seg.size() >= (1ull << 31)) return;
-  if (params.need_tlm) {
+  const bool tlm = params.need_tlm && !partial;
+  if (tlm) {
     if (4 + 6 * tpt.size() > 65535) fail(0x000500B1, "too many tile-parts for one TLM marker segment");
     put_u16(fixed_blob, M_TLM); put_u16(fixed_blob, (uint32_t)(4 + 6 * tpt.size())); put_u8(fixed_blob, 0); put_u8(fixed_blob, 0x60);
     for (const TpTmp& tp : tpt) { put_u16(fixed_blob, tp.tile); put_u32(fixed_blob, 0); }
   }
+  h_tp_tile.clear();
+  for (const TpTmp& tp : tpt) h_tp_tile.push_back(tp.tile);
   for (size_t i = 0; i < tpt.size(); ++i)
     tps.push_back(HdrTp{ tpt[i].first, tpt[i].count, tpt[i].tile, tpt[i].idx, tpt[i].cnt,
-                         params.need_tlm ? (uint32_t)(main_header.size() + 6 + 6 * i + 2) : 0xFFFFFFFFu });
+                         tlm ? (uint32_t)(main_header.size() + 6 + 6 * i + 2) : 0xFFFFFFFFu });
   int nb = 0;
   auto up = [&](const void* src, size_t bytes) -> void* {
     DeviceBuf& b = d_hplan[nb++]; b.reserve(std::max<size_t>(16, bytes));
@@ -368,6 +374,8 @@ void Encoder::build_header_plan() {
   hscr_bytes = (size_t)hoff + 16;
   hplan.hscr = (uint32_t*)scratch(hscr_bytes);
   hplan.total = (uint64_t*)scratch(16);
+  hplan.tp_out = (uint64_t*)scratch(tps.size() * 16);
+  h_tpout.reserve(std::max<size_t>(16, tps.size() * 16));
   d_fixed.reserve(fixed_blob.size() + 16);
   CK(cudaMemcpy(d_fixed.p, fixed_blob.data(), fixed_blob.size(), cudaMemcpyHostToDevice));
   h_total.reserve(64);
@@ -462,8 +470,9 @@ size_t Encoder::encode(const void* const* planes, const uint32_t* strides, bool 
     for (int attempt = 0; attempt < 2; ++attempt) {
       if (fixed_blob.size() <= cap) CK(cudaMemcpyAsync(dev_out, d_fixed.p, fixed_blob.size(), cudaMemcpyDeviceToDevice, stream));
       CK(cudaMemsetAsync(hplan.hscr, 0, hscr_bytes, stream));
-      launch_packet_headers(hplan, d_blocks.as<EncBlock>(), d_results.as<EncResult>(), wide ? 62u : 30u, fixed_blob.size(), cap, true,
-                            dev_out, d_dst.as<uint64_t>(), stream);
+      launch_packet_headers(hplan, d_blocks.as<EncBlock>(), d_results.as<EncResult>(), wide ? 62u : 30u, fixed_blob.size(), cap,
+                            tile_mask.empty(), dev_out, d_dst.as<uint64_t>(), stream);
+      if (!tile_mask.empty() && hplan.ntps) { launch_ctrl_copy(h_tpout.p, hplan.tp_out, (size_t)hplan.ntps * 16, stream); ++last_launches; }
       launch_gather_blocks(d_blocks.as<EncBlock>(), d_results.as<EncResult>(), d_dst.as<uint64_t>(), nb, d_slots.as<uint8_t>(), dev_out, stream);
       launch_ctrl_copy(h_total.p, hplan.total, 16, stream);
       last_launches += packet_header_launches(hplan) + 3;
@@ -481,6 +490,10 @@ size_t Encoder::encode(const void* const* planes, const uint32_t* strides, bool 
       d_out.reserve(total + 64); dev_out = d_out.as<uint8_t>(); cap = std::min<uint64_t>(out_cap, d_out.cap);
     }
     host_ms = 0;
+    last_tileparts.clear();
+    if (!tile_mask.empty())
+      for (uint32_t i = 0; i < hplan.ntps; ++i)
+        last_tileparts.push_back(TilePartOut{ h_tp_tile[i], h_tpout.as<uint64_t>()[2 * i], (uint32_t)h_tpout.as<uint64_t>()[2 * i + 1] });
     if (!out_on_device) CK(cudaMemcpyAsync(out, dev_out, total, cudaMemcpyDeviceToHost, stream));
     mark(7);
     CK(cudaStreamSynchronize(stream));

@@ -104,14 +104,15 @@ public:
   size_t slot_bytes = 0;
   uint32_t num_fast_blocks = 0;        // blocks flagged ENC_FLAG_FAST
   // packet headers, tile-part markers and the byte layout on the device (pkt_headers.cu): no host round trip between
-  // the block coder and the finished codestream.  OJB_HOST_HEADERS=1 keeps the host writer (ojb_layout.cpp) -- also
-  // used with a tile mask (the sharded encoder wants its tile-parts' positions on the host) and for the odd
-  // configuration with an empty tile-part
+  // the block coder and the finished codestream.  OJB_HOST_HEADERS=1 keeps the host writer (ojb_layout.cpp), which also
+  // serves the odd configuration with an empty tile-part.  With a tile mask (ojb_shard.cpp) the output is this rank's
+  // tile-parts only and their positions come back in a few bytes
   bool device_headers = false;
   HdrPlanDev hplan;
   std::vector<uint8_t> fixed_blob;     // main header [+ TLM with blank lengths]
   DeviceBuf d_fixed, d_hplan[32];
-  PinnedBuf h_total;
+  PinnedBuf h_total, h_tpout;
+  std::vector<uint32_t> h_tp_tile;
   size_t hscr_bytes = 0;
   void build_header_plan();
   size_t out_cap_dev = 0;

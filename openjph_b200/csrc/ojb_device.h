@@ -161,6 +161,7 @@ struct HdrPlanDev {
   uint32_t *phdr, *pbody; uint64_t* ppos;
   uint32_t* hscr;        // packet header bytes, zeroed before every frame
   uint64_t* total;       // [0] codestream length, [1] 1 when it exceeds the output capacity (nothing is written then)
+  uint64_t* tp_out;      // per tile-part: byte offset of its SOT in the output, Psot
 };
 
 // ---- raster layouts ------------------------------------------------------------------------

@@ -299,7 +299,8 @@ hdr_write_kernel(const HdrSeg* __restrict__ segs, const HdrPkt* __restrict__ pkt
 __global__ void __launch_bounds__(HL_THREADS)
 hdr_layout_kernel(const HdrPkt* __restrict__ pkts, uint32_t npkts, const HdrTp* __restrict__ tps, uint32_t ntps,
                   const uint32_t* __restrict__ phdr, const uint32_t* __restrict__ pbody, uint64_t fixed_len, uint64_t cap,
-                  uint32_t write_eoc, uint64_t* __restrict__ ppos, uint8_t* __restrict__ out, uint64_t* __restrict__ total)
+                  uint32_t write_eoc, uint64_t* __restrict__ ppos, uint8_t* __restrict__ out, uint64_t* __restrict__ total,
+                  uint64_t* __restrict__ tp_out)
 {
   __shared__ unsigned long long sscan[HL_THREADS];
   __shared__ unsigned long long carry;
@@ -337,6 +338,7 @@ hdr_layout_kernel(const HdrPkt* __restrict__ pkts, uint32_t npkts, const HdrTp* 
     s[0] = 0xFF; s[1] = 0x90; s[2] = 0; s[3] = 10; s[4] = (uint8_t)(tp.tile >> 8); s[5] = (uint8_t)tp.tile;
     s[6] = (uint8_t)(psot >> 24); s[7] = (uint8_t)(psot >> 16); s[8] = (uint8_t)(psot >> 8); s[9] = (uint8_t)psot;
     s[10] = (uint8_t)tp.tp_idx; s[11] = (uint8_t)tp.tp_cnt; s[12] = 0xFF; s[13] = 0x93;
+    tp_out[2 * t] = start; tp_out[2 * t + 1] = psot;
     if (tp.tlm_off != 0xFFFFFFFFu) {
       uint8_t* m = out + tp.tlm_off;
       m[0] = (uint8_t)(psot >> 24); m[1] = (uint8_t)(psot >> 16); m[2] = (uint8_t)(psot >> 8); m[3] = (uint8_t)psot;
@@ -398,7 +400,7 @@ void launch_packet_headers(const HdrPlanDev& pl, const EncBlock* blocks, const E
                pl.inbits, pl.istate, pl.ipos, pl.hscr);
   }
   OJB_LAUNCH(hdr_layout_kernel, dim3(1), dim3(HL_THREADS), 0, st, pl.pkts, pl.npkts, pl.tps, pl.ntps, pl.phdr, pl.pbody, fixed_len, cap,
-             write_eoc ? 1u : 0u, pl.ppos, out, pl.total);
+             write_eoc ? 1u : 0u, pl.ppos, out, pl.total, pl.tp_out);
   if (pl.nitems)
     OJB_LAUNCH(hdr_place_kernel, dim3((pl.nitems + 127) / 128), dim3(128), 0, st, pl.segs, pl.item_seg, pl.nitems, pl.ibody, pl.ppos,
                pl.phdr, pl.total, dst);
