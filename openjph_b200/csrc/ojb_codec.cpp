@@ -291,7 +291,7 @@ void Encoder::configure(const Params& p, uint32_t sample_type) {
 void Encoder::build_header_plan() {
   device_headers = false;
   memset(&hplan, 0, sizeof(hplan));
-  if (getenv("OJB_HOST_HEADERS")) return;
+  { const char* e = getenv("OJB_HOST_HEADERS"); if (e && *e && *e != '0') return; }
   const bool partial = !tile_mask.empty();        // this rank's tile-parts only: no main header, TLM or EOC (ojb_shard.cpp)
   std::vector<HdrSeg> segs; std::vector<HdrPkt> pkts; std::vector<HdrGroup> groups; std::vector<HdrTp> tps; std::vector<uint32_t> item_seg;
   uint64_t nodes = 0, hoff = 0; uint32_t max_cap = 0;

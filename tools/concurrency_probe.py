@@ -11,9 +11,9 @@ import openjph_b200 as ob
 from openjph_b200 import _lib
 import images
 L = _lib.lib()
-W = H = 8192
-p = ob.make_params(W, H, 3, 12, num_decomps=5, reversible=True, color_transform=True)
-frame = [f.astype(np.uint16) for f in images.synth_frame(W, H, 3, 12, 1234)]
+W = int(os.environ.get("PROBE_W", "8192")); H = int(os.environ.get("PROBE_H", "8192")); BD = int(os.environ.get("PROBE_BD", "12"))
+p = ob.make_params(W, H, 3, BD, num_decomps=5, reversible=True, color_transform=True)
+frame = [f.astype(np.uint16) for f in images.synth_frame(W, H, 3, BD, 1234)]
 pin = [torch.from_numpy(f).pin_memory() for f in frame]
 planes = (C.c_void_p * 3)(*[t.data_ptr() for t in pin])
 cap = W * H * 3 * 2 + (1 << 20)
@@ -39,7 +39,7 @@ class Wk:
         assert L.ojb_dec_decode_resident(self.dec) == 0
 
 
-def run(mode, nw, iters=12):
+def run(mode, nw, iters=int(os.environ.get("PROBE_ITERS", "12"))):
     ws = WS[:nw]
     for w in ws:
         w.te[:] = 0; w.td[:] = 0; w.k = 0
