@@ -4,7 +4,7 @@
 A step = one pass of the hot path over one batch of frames: each frame is encoded to a codestream,
 then that codestream is decoded back (the metric BASELINE.json names is "Mpixels/s encode+decode").
 Workload at every N: synthetic 8192x8192 3-component 12-bit frames, reversible 5/3 + RCT, 5 levels,
-64x64 blocks (the headline configuration), OJB_BENCH_WORKERS (default 12) frames per GPU per step, each on its
+64x64 blocks (the headline configuration), OJB_BENCH_WORKERS (default 16) frames per GPU per step, each on its
 own codec object / CUDA stream so that the host phases (packet headers) and copies of one frame
 overlap the kernels of another (weak scaling; frames are independent, so there is no data-path
 collective -- only the final gather of the codestream sizes to rank 0).
@@ -470,11 +470,15 @@ def main():
     assert L.ojb_set_device(local) == 0, L.ojb_last_error()
     torch.cuda.set_device(local)
     affinity = bind_to_gpu_numa_node(torch, local)      # before any pinned allocation (first touch)
-    NW = int(os.environ.get("OJB_BENCH_WORKERS", "12"))     # frames in flight per GPU (one codec pair each; value saturates at ~12, profiles/r02b_value_vs_frames_in_flight.log)
+    NW = int(os.environ.get("OJB_BENCH_WORKERS", "16"))     # frames in flight per GPU (one codec pair each; 12 -> 16 still buys ~3 %, gpurun_out value_probe; profiles/README.md)
 
     def ck(rc):
         if rc != 0:
             raise RuntimeError(L.ojb_last_error().decode())
+
+    # frames in flight through HOST buffers (`e2e`): the PCIe link saturates earlier than the SMs, and every such frame
+    # pins 0.8 GB of host memory -- fewer of them (value_probe: e2e peaks at 8)
+    NE = min(NW, int(os.environ.get("OJB_BENCH_E2E_WORKERS", "8")))
 
     from concurrent.futures import ThreadPoolExecutor
     pool = ThreadPoolExecutor(max(NW, 8))
@@ -493,7 +497,8 @@ def main():
                 t.numpy()[:] = f
             self.planes = (C.c_void_p * self.nc)(*[t.data_ptr() for t in self.pin])
             self.cs_cap = self.in_bytes * 2 + (1 << 20)
-            self.workers = [Worker(self) for _ in range(n)]
+            self.ne = min(n, NE)
+            self.workers = [Worker(self, i < self.ne) for i in range(n)]
 
         def close(self):
             for w in self.workers:
@@ -501,13 +506,15 @@ def main():
             self.workers = []
 
     class Worker:
-        def __init__(self, wl):
+        def __init__(self, wl, host=True):
             self.wl = wl
+            self.host = host             # has pinned host buffers: takes part in the e2e leg
             self.enc = L.ojb_enc_create(); self.dec = L.ojb_dec_create()
             ck(L.ojb_enc_configure(self.enc, C.byref(wl.p), wl.st))
-            self.out_pin = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in wl.pin]
-            self.outs = (C.c_void_p * wl.nc)(*[t.data_ptr() for t in self.out_pin])
-            self.cs_pin = torch.empty(wl.cs_cap, dtype=torch.uint8, pin_memory=True)
+            if host:
+                self.out_pin = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in wl.pin]
+                self.outs = (C.c_void_p * wl.nc)(*[t.data_ptr() for t in self.out_pin])
+                self.cs_pin = torch.empty(wl.cs_cap, dtype=torch.uint8, pin_memory=True)
             self.cs_dev = torch.empty(wl.cs_cap, dtype=torch.uint8, device="cuda")
             self.n = C.c_uint64(); self.fi = _lib.FrameInfo(); self.cs_len = 0
 
@@ -556,12 +563,14 @@ def main():
         """correctness of what is timed, then: serial pass (per-stage CUDA-event times), all workers in flight
         resident (`value`), all workers in flight through host buffers (`e2e`)"""
         ws = wl.workers
+        wh = [w for w in ws if w.host]
         for w in ws:
-            w.e2e()
-            w.cs_len = w.n.value
-            if lossless:
-                for a_, b_ in zip(w.out_pin, wl.frame):
-                    assert np.array_equal(a_.numpy(), b_), "round trip is not lossless"
+            if w.host:
+                w.e2e()
+                w.cs_len = w.n.value
+                if lossless:
+                    for a_, b_ in zip(w.out_pin, wl.frame):
+                        assert np.array_equal(a_.numpy(), b_), "round trip is not lossless"
             ck(L.ojb_enc_upload_frame(w.enc, wl.planes, None))
         for _ in range(max(3, warmup)):
             list(pool.map(lambda w: w.resident(), ws))
@@ -580,8 +589,8 @@ def main():
              "cs_len": int(ws[0].cs_len), "mirror_bytes": int(L.ojb_dec_mirror_bytes(ws[0].dec))}
         if e2e:
             for _ in range(max(1, min(warmup, 2))):
-                list(pool.map(lambda w: w.e2e(), ws))
-            r["dt_e2e"] = timed(ws, "e2e", steps)
+                list(pool.map(lambda w: w.e2e(), wh))
+            r["dt_e2e"] = timed(wh, "e2e", steps)
             te2 = (C.c_float * 8)(); td2 = (C.c_float * 8)()
             L.ojb_enc_timings(ws[0].enc, te2); L.ojb_dec_timings(ws[0].dec, td2)
             r["te2"], r["td2"] = list(te2), list(td2)
@@ -609,7 +618,8 @@ def main():
              "stages_decode_ms": {k: round(float(v), 4) for k, v in zip(DEC_STAGES, r["td"]) if not k.startswith("_")},
              "roofline_frame": frame_roofline(wl, r)}
         if r["dt_e2e"]:
-            d["e2e_Mpixels_per_s"] = round(wl.pix * n * a.gpus * steps / r["dt_e2e"] / 1e6, 1)
+            d["e2e_Mpixels_per_s"] = round(wl.pix * wl.ne * a.gpus * steps / r["dt_e2e"] / 1e6, 1)
+            d["e2e_frames_in_flight"] = wl.ne
         if note:
             d["note"] = note
         return d
@@ -640,7 +650,8 @@ def main():
                     # scheduler, not the kernels); the entry says how many
                     ws_ = wl.workers
                     for w in ws_:
-                        w.e2e()
+                        if w.host:
+                            w.e2e()
                         ck(L.ojb_enc_upload_frame(w.enc, wl.planes, None))
                     list(pool.map(lambda w: w.resident(), ws_))
                     dt1 = timed(ws_, "resident", 1)
@@ -691,7 +702,7 @@ def main():
         return
     pix = W * H * a.gpus * NW
     value = pix * a.steps / r["dt_res"] / 1e6
-    e2e = pix * a.steps / r["dt_e2e"] / 1e6
+    e2e = W * H * a.gpus * head.ne * a.steps / r["dt_e2e"] / 1e6
     stage_e = {k: round(float(v), 4) for k, v in zip(ENC_STAGES, r["te"])}
     stage_d = {k: round(float(v), 4) for k, v in zip(DEC_STAGES, r["td"]) if not k.startswith("_")}
     e2e_e = {k: round(float(v), 3) for k, v in zip(ENC_STAGES, r["te2"])}
@@ -721,7 +732,7 @@ def main():
             "algorithmic_bytes_per_launch": cand[dom][1], "ms_per_launch": cand[dom][0],
             "note": "entropy-coding kernels are instruction-issue / ALU-pipe bound (DRAM traffic ~= algorithmic bytes); see profiles/README.md",
             "frame": frame_roofline(head, r)}
-    detail = {"frames_per_step": NW * a.gpus, "frames_in_flight_per_gpu": NW, "host_affinity": affinity,
+    detail = {"frames_per_step": NW * a.gpus, "frames_in_flight_per_gpu": NW, "e2e_frames_in_flight_per_gpu": head.ne, "host_affinity": affinity,
               "serial_ms_per_frame": round(r["dt_serial"] / a.steps * 1e3, 3),
               "serial_Mpixels_per_s": round(W * H * a.steps / r["dt_serial"] / 1e6, 1),
               "stages_encode_ms": stage_e, "stages_decode_ms": stage_d,
@@ -736,8 +747,9 @@ def main():
                          "fetches only marker segments / packet headers (%d bytes of the %d-byte codestream per frame, inside the "
                          "timed region)" % (r["mirror_bytes"], cs_len),
            "clocks": sampler.summary(),
-           "e2e": {"value": e2e, "unit": "Mpixels/s", "h2d_bytes_per_step": (W * H * NC * 2 + cs_len) * a.gpus * NW,
-                   "d2h_bytes_per_step": (W * H * NC * 2 + cs_len) * a.gpus * NW, "ms_per_step": r["dt_e2e"] / a.steps * 1e3},
+           "e2e": {"value": e2e, "unit": "Mpixels/s", "h2d_bytes_per_step": (W * H * NC * 2 + cs_len) * a.gpus * head.ne,
+                   "d2h_bytes_per_step": (W * H * NC * 2 + cs_len) * a.gpus * head.ne, "ms_per_step": r["dt_e2e"] / a.steps * 1e3,
+                   "frames_per_step": head.ne * a.gpus},
            "gpu_launches": launches * a.steps * NW,
            "roofline": roof}
     if not a.no_cpu_baseline:
