@@ -433,6 +433,118 @@ uint32_t write_packet_header(const ResGeom& res, const PrecinctGeom& pc,
   return body;
 }
 
+namespace {
+// The same header grammar as the loop in parse_packet, read through a 64-bit window of de-stuffed bits instead of
+// one bit at a time (the host parse is the longest host phase of a decode: 49 152 blocks per headline frame).  It
+// is an optimistic pass: anything out of the ordinary -- an empty packet, the byte budget or the buffer running
+// out, a value the slow loop would refuse -- makes it return false WITHOUT having moved pos / data_left, and the
+// byte-at-a-time loop then re-reads the packet and reports whatever there is to report, exactly as before.
+struct BitWindow {
+  const uint8_t* d; size_t pos, start, limit; HostMirror* hm;
+  uint64_t acc = 0; int n = 0;             // n valid bits at the top of acc; the rest of acc is zero
+  BitWindow(const uint8_t* data, size_t p, size_t lim, HostMirror* m) : d(data), pos(p), start(p), limit(lim), hm(m) {}
+  inline int bits_of(size_t i) const { return (i > start && d[i - 1] == 0xFF) ? 7 : 8; }   // a byte after 0xFF carries 7
+  inline void refill() {
+    while (n <= 56 && pos < limit) {
+      if (hm && !hm->present[pos >> HostMirror::PAGE_SHIFT]) hm->need(pos);
+      const int k = bits_of(pos);
+      acc |= (uint64_t)(d[pos] & (k == 7 ? 0x7F : 0xFF)) << (64 - n - k);
+      n += k; ++pos;
+    }
+  }
+  inline bool need(int k) { if (n < k) refill(); return n >= k; }
+  inline uint32_t take(int k) { uint32_t v = (uint32_t)(acc >> (64 - k)); acc <<= k; n -= k; return v; }   // 1 <= k <= 32
+  // length of the run of `bit` ahead, consumed together with the bit that ends it; -1 when the data runs out
+  inline int run(uint32_t bit) {
+    int total = 0;
+    for (;;) {
+      if (n == 0 && !need(1)) return -1;
+      const uint64_t a = bit ? ~acc : acc;
+      int z = a ? __builtin_clzll(a) : 64;
+      if (z >= n) { total += n; acc = 0; n = 0; continue; }      // the whole window is the run: go on
+      total += z; acc <<= (z + 1); n -= z + 1;
+      return total;
+    }
+  }
+  // bytes whose bits were (at least partly) consumed: give back the look-ahead
+  inline size_t consumed_end() { size_t p = pos; int m = n; while (p > start && m >= bits_of(p - 1)) { m -= bits_of(p - 1); --p; } return p; }
+};
+
+bool parse_header_fast(const ResGeom& res, const PrecinctGeom& pc, CodedBlock* blocks, const uint8_t* data,
+                       size_t& pos, uint32_t& data_left, size_t data_end, HostMirror* mirror, bool& unstuff) {
+  if (data_left == 0 || pos >= data_end) return false;
+  BitWindow w(data, pos, std::min(data_end, pos + (size_t)data_left), mirror);
+  bool first_band = true;
+  for (uint32_t s = 0; s < 4; ++s) {
+    const BandGeom& bg = res.bands[s];
+    if (bg.empty) continue;
+    const Rect& ci = pc.cb_idx[s];
+    if (ci.w == 0 || ci.h == 0) continue;
+    if (first_band) {
+      if (!w.need(1) || w.take(1) == 0) return false;             // empty packets go the slow way
+      first_band = false;
+    }
+    const uint32_t nl = 1 + std::max(log2ceil(ci.w), log2ceil(ci.h));
+    TagTree &inc = t_trees.inc, &incf = t_trees.incf, &mm = t_trees.mm, &mmf = t_trees.mmf;
+    inc.init(nl, ci.w, ci.h, 0); incf.init(nl, ci.w, ci.h, 0);
+    mm.init(nl, ci.w, ci.h, 0); mmf.init(nl, ci.w, ci.h, 0);
+    CodedBlock* base = blocks + bg.block_base;
+    for (uint32_t y = 0; y < ci.h; ++y)
+      for (uint32_t x = 0; x < ci.w; ++x) {
+        CodedBlock& cb = base[(size_t)(ci.y0 + y) * bg.nbw + ci.x0 + x];
+        bool empty_cb = false;
+        {
+          uint32_t u = 0;
+          while (u < nl && incf.at(x >> u, y >> u, u) == 0) ++u;
+          if (u < nl && inc.at(x >> u, y >> u, u) == 1) empty_cb = true;
+          for (uint32_t cl = u; cl > 0 && !empty_cb; --cl) {
+            const uint32_t l = cl - 1;
+            if (!w.need(1)) return false;
+            const uint32_t bit = w.take(1);
+            empty_cb = (bit == 0);
+            inc.at(x >> l, y >> l, l) = (uint8_t)(1 - bit);
+            incf.at(x >> l, y >> l, l) = 1;
+          }
+        }
+        if (empty_cb) continue;
+        uint32_t mmsbs;
+        {
+          uint32_t u = 0;
+          while (u < nl && mmf.at(x >> u, y >> u, u) == 0) ++u;
+          mmsbs = mm.at(x >> u, y >> u, u);
+          for (uint32_t lp = u; lp > 0; --lp) {
+            const uint32_t l = lp - 1;
+            const int z = w.run(0);
+            if (z < 0 || z > 255) return false;
+            mmsbs += (uint32_t)z;
+            mm.at(x >> l, y >> l, l) = (uint8_t)mmsbs;
+            mmf.at(x >> l, y >> l, l) = 1;
+          }
+        }
+        if (mmsbs > bg.K_max) return false;
+        if (!w.need(1)) return false;
+        if (w.take(1)) return false;                               // more than one coding pass: the general loop
+        const int ones = w.run(1);
+        if (ones < 0 || ones > 28) return false;
+        const int nb = 3 + ones;                                   // Lblock; no placeholder passes here
+        if (!w.need(nb)) return false;
+        const uint32_t len = w.take(nb);
+        if (len < 2 || len >= 65535) return false;
+        cb.missing_msbs = (uint8_t)mmsbs;
+        cb.num_passes = 1;
+        cb.pass_len[0] = len; cb.pass_len[1] = 0;
+      }
+  }
+  if (first_band) return false;                                    // no band with blocks: one bit to read, slow way
+  const size_t end = w.consumed_end();
+  if (end == pos) return false;
+  data_left -= (uint32_t)(end - pos);
+  pos = end;
+  unstuff = data[end - 1] == 0xFF;
+  return true;
+}
+} // namespace
+
 void parse_packet(const Params& P, const ResGeom& res, const PrecinctGeom& pc,
                   CodedBlock* blocks, const uint8_t* data, size_t& pos, uint32_t& data_left, size_t data_end,
                   HostMirror* mirror) {
@@ -469,7 +581,10 @@ void parse_packet(const Params& P, const ResGeom& res, const PrecinctGeom& pc,
       }
     }
   } drop{res, pc, blocks};
-  for (uint32_t s = 0; s < 4; ++s) {
+  bool fast_unstuff = false;
+  const bool fast_done = parse_header_fast(res, pc, blocks, data, pos, data_left, data_end, mirror, fast_unstuff);
+  if (fast_done) { br.unstuff = fast_unstuff; empty_packet = false; }
+  for (uint32_t s = 0; s < 4 && !fast_done; ++s) {
     const BandGeom& bg = res.bands[s];
     if (bg.empty) continue;
     const Rect& ci = pc.cb_idx[s];

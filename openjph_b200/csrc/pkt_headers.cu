@@ -197,71 +197,112 @@ hdr_items_kernel(const HdrSeg* __restrict__ segs, const HdrPkt* __restrict__ pkt
   }
 }
 
+// 16 groups x 16 entry states per CTA; the groups' item tables are staged in shared memory first (the walk is a chain
+// of 32 dependent look-ups: at global-memory latency it would dominate the kernel)
+#define HG_GROUPS 16u
 __global__ void __launch_bounds__(256)
 hdr_groups_kernel(const HdrGroup* __restrict__ groups, uint32_t ngroups, const uint16_t* __restrict__ itab,
                   const uint16_t* __restrict__ inbits, const uint32_t* __restrict__ ilen,
                   uint32_t* __restrict__ gcomp, uint32_t* __restrict__ gbits, uint32_t* __restrict__ glen)
 {
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t g = t >> 4, s = t & 15u;
-  if (g >= ngroups) return;
-  const HdrGroup gr = groups[g];
-  uint32_t st = s, extra = 0, nbits = 0, len = 0;
-  for (uint32_t k = 0; k < gr.n; ++k) {
-    const uint32_t it = gr.first_item + k;
-    const uint32_t e = itab[(size_t)it * 16 + st];
-    extra += e >> 4; st = e & 15u;
-    if (s == 0) { nbits += inbits[it]; len += ilen[it]; }
+  __shared__ uint32_t stab[HG_GROUPS * 32 * 8];           // 32 items x 16 uint16 per group
+  const uint32_t tid = threadIdx.x, gl = tid >> 4, s = tid & 15u;
+  const uint32_t g0 = blockIdx.x * HG_GROUPS;
+  const uint32_t* itab32 = reinterpret_cast<const uint32_t*>(itab);
+  for (uint32_t k = 0; k < HG_GROUPS; ++k) {
+    const uint32_t g = g0 + k;
+    if (g >= ngroups) break;
+    const HdrGroup gr = groups[g];
+    if (tid < gr.n * 8) stab[k * 256 + tid] = itab32[(size_t)gr.first_item * 8 + tid];     // 8 words per item
   }
-  gcomp[(size_t)g * 16 + s] = st | (extra << 4);
-  if (s == 0) { gbits[g] = nbits; glen[g] = len; }
+  __syncthreads();
+  const uint32_t g = g0 + gl;
+  const bool live = g < ngroups;                           // every lane stays for the shuffles below
+  HdrGroup gr; gr.first_item = 0; gr.n = 0;
+  if (live) gr = groups[g];
+  const uint16_t* tab = reinterpret_cast<const uint16_t*>(stab + gl * 256);
+  uint32_t st = s, extra = 0;
+  for (uint32_t k = 0; k < gr.n; ++k) {
+    const uint32_t e = tab[k * 16 + st];
+    extra += e >> 4; st = e & 15u;
+  }
+  if (live) gcomp[(size_t)g * 16 + s] = st | (extra << 4);
+  // the group's bit and byte totals: the 16 lanes share the 32 items
+  uint32_t nbits = 0, len = 0;
+  for (uint32_t k = s; k < gr.n; k += 16) { nbits += inbits[gr.first_item + k]; len += ilen[gr.first_item + k]; }
+  #pragma unroll
+  for (uint32_t d = 8; d; d >>= 1) { nbits += __shfl_xor_sync(0xFFFFFFFFu, nbits, d, 16); len += __shfl_xor_sync(0xFFFFFFFFu, len, d, 16); }
+  if (live && s == 0) { gbits[g] = nbits; glen[g] = len; }
 }
 
-#define HC_CHUNK 64u
-__global__ void __launch_bounds__(32)
+#define HC_CHUNK 256u
+#define HC_THREADS 256u
+__global__ void __launch_bounds__(HC_THREADS)
 hdr_chain_kernel(const HdrPkt* __restrict__ pkts, const uint32_t* __restrict__ gcomp, const uint32_t* __restrict__ gbits,
                  const uint32_t* __restrict__ glen, uint32_t* __restrict__ gstate, uint32_t* __restrict__ gpos,
                  uint32_t* __restrict__ gbody, uint32_t* __restrict__ phdr, uint32_t* __restrict__ pbody)
 {
   __shared__ uint32_t sc[HC_CHUNK * 16], sb[HC_CHUNK], sl[HC_CHUNK];
+  __shared__ uint32_t carry[3];
   const HdrPkt pk = pkts[blockIdx.x];
-  const uint32_t lane = threadIdx.x;
-  uint32_t st = HS_START, pos = 0, body = 0;
+  const uint32_t tid = threadIdx.x;
+  if (tid == 0) { carry[0] = HS_START; carry[1] = 0; carry[2] = 0; }
   for (uint32_t g0 = 0; g0 < pk.ngroups; g0 += HC_CHUNK) {
     const uint32_t n = min(HC_CHUNK, pk.ngroups - g0);
-    for (uint32_t i = lane; i < n * 16; i += 32) sc[i] = gcomp[(size_t)(pk.first_group + g0) * 16 + i];
-    for (uint32_t i = lane; i < n; i += 32) { sb[i] = gbits[pk.first_group + g0 + i]; sl[i] = glen[pk.first_group + g0 + i]; }
-    __syncwarp();
-    if (lane == 0)
+    // the whole CTA fetches the chunk (every thread has its loads in flight at once), one thread walks it
+    for (uint32_t i = tid; i < n * 16; i += HC_THREADS) sc[i] = gcomp[(size_t)(pk.first_group + g0) * 16 + i];
+    for (uint32_t i = tid; i < n; i += HC_THREADS) { sb[i] = gbits[pk.first_group + g0 + i]; sl[i] = glen[pk.first_group + g0 + i]; }
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t st = carry[0], pos = carry[1], body = carry[2];
       for (uint32_t i = 0; i < n; ++i) {
         const uint32_t g = pk.first_group + g0 + i;
         gstate[g] = st; gpos[g] = pos; gbody[g] = body;
         const uint32_t e = sc[i * 16 + st];
         pos += sb[i] + (e >> 4); st = e & 15u; body += sl[i];
       }
-    __syncwarp();
+      carry[0] = st; carry[1] = pos; carry[2] = body;
+    }
+    __syncthreads();
   }
-  if (lane == 0) {
-    phdr[blockIdx.x] = pk.nitems ? (pos + 7u) >> 3 : 1u;      // a packet without bands is the single zero byte too
-    pbody[blockIdx.x] = body;
+  if (tid == 0) {
+    phdr[blockIdx.x] = pk.nitems ? (carry[1] + 7u) >> 3 : 1u;      // a packet without bands is the single zero byte too
+    pbody[blockIdx.x] = carry[2];
   }
 }
 
-__global__ void __launch_bounds__(128)
+#define HE_GROUPS 32u
+__global__ void __launch_bounds__(256)
 hdr_expand_kernel(const HdrGroup* __restrict__ groups, uint32_t ngroups, const uint16_t* __restrict__ itab,
                   const uint16_t* __restrict__ inbits, const uint32_t* __restrict__ ilen,
                   const uint32_t* __restrict__ gstate, const uint32_t* __restrict__ gpos, const uint32_t* __restrict__ gbody,
                   uint8_t* __restrict__ istate, uint32_t* __restrict__ ipos, uint32_t* __restrict__ ibody)
 {
-  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  // 32 groups per CTA: tables, bit counts and lengths staged by 256 threads, then one thread per group walks its 32 items
+  __shared__ uint32_t stab[HE_GROUPS * 256];
+  __shared__ uint16_t snb[HE_GROUPS * 32];
+  __shared__ uint32_t sln[HE_GROUPS * 32];
+  const uint32_t tid = threadIdx.x, g0 = blockIdx.x * HE_GROUPS;
+  const uint32_t* itab32 = reinterpret_cast<const uint32_t*>(itab);
+  for (uint32_t k = 0; k < HE_GROUPS; ++k) {
+    const uint32_t g = g0 + k;
+    if (g >= ngroups) break;
+    const HdrGroup gr = groups[g];
+    if (tid < gr.n * 8) stab[k * 256 + tid] = itab32[(size_t)gr.first_item * 8 + tid];
+    if (tid < gr.n) { snb[k * 32 + tid] = inbits[gr.first_item + tid]; sln[k * 32 + tid] = ilen[gr.first_item + tid]; }
+  }
+  __syncthreads();
+  if (tid >= HE_GROUPS) return;
+  const uint32_t g = g0 + tid;
   if (g >= ngroups) return;
   const HdrGroup gr = groups[g];
+  const uint16_t* tab = reinterpret_cast<const uint16_t*>(stab + tid * 256);
   uint32_t st = gstate[g], pos = gpos[g], body = gbody[g];
   for (uint32_t k = 0; k < gr.n; ++k) {
     const uint32_t it = gr.first_item + k;
     istate[it] = (uint8_t)st; ipos[it] = pos; ibody[it] = body;
-    const uint32_t e = itab[(size_t)it * 16 + st];
-    pos += inbits[it] + (e >> 4); st = e & 15u; body += ilen[it];
+    const uint32_t e = tab[k * 16 + st];
+    pos += snb[tid * 32 + k] + (e >> 4); st = e & 15u; body += sln[tid * 32 + k];
   }
 }
 
@@ -387,14 +428,14 @@ void launch_packet_headers(const HdrPlanDev& pl, const EncBlock* blocks, const E
   if (pl.nitems) {
     OJB_LAUNCH(hdr_items_kernel, dim3((pl.nitems + 127) / 128), dim3(128), 0, st, pl.segs, pl.pkts, pl.item_seg, pl.nitems, results,
                pl.tinc, pl.tmm, pl.tfi, pl.seg_root, pl.ibits, pl.inbits, pl.itab, pl.ilen);
-    OJB_LAUNCH(hdr_groups_kernel, dim3((pl.ngroups * 16 + 255) / 256), dim3(256), 0, st, pl.groups, pl.ngroups, pl.itab, pl.inbits, pl.ilen,
+    OJB_LAUNCH(hdr_groups_kernel, dim3((pl.ngroups + HG_GROUPS - 1) / HG_GROUPS), dim3(256), 0, st, pl.groups, pl.ngroups, pl.itab, pl.inbits, pl.ilen,
                pl.gcomp, pl.gbits, pl.glen);
   }
   if (pl.npkts)
-    OJB_LAUNCH(hdr_chain_kernel, dim3(pl.npkts), dim3(32), 0, st, pl.pkts, pl.gcomp, pl.gbits, pl.glen, pl.gstate, pl.gpos, pl.gbody,
+    OJB_LAUNCH(hdr_chain_kernel, dim3(pl.npkts), dim3(HC_THREADS), 0, st, pl.pkts, pl.gcomp, pl.gbits, pl.glen, pl.gstate, pl.gpos, pl.gbody,
                pl.phdr, pl.pbody);
   if (pl.nitems) {
-    OJB_LAUNCH(hdr_expand_kernel, dim3((pl.ngroups + 127) / 128), dim3(128), 0, st, pl.groups, pl.ngroups, pl.itab, pl.inbits, pl.ilen,
+    OJB_LAUNCH(hdr_expand_kernel, dim3((pl.ngroups + HE_GROUPS - 1) / HE_GROUPS), dim3(256), 0, st, pl.groups, pl.ngroups, pl.itab, pl.inbits, pl.ilen,
                pl.gstate, pl.gpos, pl.gbody, pl.istate, pl.ipos, pl.ibody);
     OJB_LAUNCH(hdr_write_kernel, dim3((pl.nitems + 127) / 128), dim3(128), 0, st, pl.segs, pl.pkts, pl.item_seg, pl.nitems, pl.ibits,
                pl.inbits, pl.istate, pl.ipos, pl.hscr);
