@@ -743,7 +743,8 @@ def main():
     res = {"metric": "Mpixels/s encode+decode", "value": value, "unit": "Mpixels/s", "n_gpus": a.gpus, "steps": a.steps,
            "warmup": a.warmup, "ms_per_step": r["dt_res"] / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": cfg, "detail": detail,
-           "value_note": "device-resident: frame in HBM, codestream written to and decoded from HBM; the decoder's host parser "
+           "value_note": "device-resident: frame in HBM, codestream written to and decoded from HBM; the encoder produces packet "
+                         "headers and markers on the device (only the length returns to the host); the decoder's host parser "
                          "fetches only marker segments / packet headers (%d bytes of the %d-byte codestream per frame, inside the "
                          "timed region)" % (r["mirror_bytes"], cs_len),
            "clocks": sampler.summary(),
