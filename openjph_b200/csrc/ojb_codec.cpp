@@ -941,6 +941,7 @@ uint32_t Decoder::decode(void* const* planes, const uint32_t* strides, bool plan
   mark(1);
   auto host_t0 = std::chrono::steady_clock::now();
   parse_tiles();
+  auto host_t1 = std::chrono::steady_clock::now();
   if (mirrored) {
     mirror.last_pages.clear();
     for (size_t pg = 0; pg < mirror.present.size(); ++pg) if (mirror.present[pg]) mirror.last_pages.push_back(pg);
@@ -985,6 +986,7 @@ uint32_t Decoder::decode(void* const* planes, const uint32_t* strides, bool plan
   // scratch offsets are only read by blocks outside the specialised kernel
   const bool need_scratch = nfast < nb || !(serial_block_decoder() || max_block_w > 64);
   host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
+  if (getenv("OJB_PARSE_PROF")) fprintf(stderr, "decode host: parse %.3f ms, records %.3f ms\n", std::chrono::duration<double, std::milli>(host_t1 - host_t0).count(), host_ms - std::chrono::duration<double, std::milli>(host_t1 - host_t0).count());
   mark(2);
   if (nb) { launch_dec_merge(d_dec.as<DecBlock>(), d_proto.as<DecBlock>(), hy, need_scratch ? hs : nullptr, nb, stream); ++last_launches; }
   if (wide) {
