@@ -1653,9 +1653,12 @@ void launch_ht_decode_wide(const DecBlock* blocks, uint32_t nblocks, uint32_t ma
 
 void launch_ht_decode_serial(const DecBlock* blocks, uint32_t nblocks, uint32_t nfast, uint32_t max_width, const uint8_t* codestream,
                              uint32_t* coef, uint32_t* scratch, const uint16_t* tables, uint32_t out_mode,
-                             bool cleanup_only, uint32_t* block_status, cudaStream_t st)
+                             bool cleanup_only, uint32_t* block_status, cudaStream_t st, const SideStream* side)
 {
   if (nblocks == 0) return;
+  const bool forked = side && side->st && nfast && nfast < nblocks;      // both kernels to run: the general one on the side stream
+  cudaStream_t sg = forked ? side->st : st;
+  if (forked) { cudaEventRecord(side->fork, st); cudaStreamWaitEvent(side->st, side->fork, 0); }
   const uint32_t prev_quads = (max_width + 1) / 2 + 2;
   const size_t smem = (size_t)prev_quads * DEC1_THREADS * sizeof(uint16_t);
   // specialised on the output type when no block carries SigProp / MagRef passes
@@ -1679,9 +1682,10 @@ void launch_ht_decode_serial(const DecBlock* blocks, uint32_t nblocks, uint32_t 
     }
   }
   if (nfast < nblocks) {
-    OJB_LAUNCH(k, grid, block, smem, st, blocks, nblocks, codestream, coef, scratch, tables, out_mode,
+    OJB_LAUNCH(k, grid, block, smem, sg, blocks, nblocks, codestream, coef, scratch, tables, out_mode,
                block_status, prev_quads);
   }
+  if (forked) { cudaEventRecord(side->join, side->st); cudaStreamWaitEvent(st, side->join, 0); }
   {
     dim3 grid((nblocks + DEC_WARPS - 1) / DEC_WARPS), block(DEC_WARPS * 32);
     OJB_LAUNCH(ht_dec_fill_kernel, grid, block, 0, st, blocks, nblocks, coef, block_status);

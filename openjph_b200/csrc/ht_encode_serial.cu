@@ -770,10 +770,14 @@ ht_encode_split_kernel(const EncBlock* __restrict__ blocks, uint32_t nblocks,
 
 void launch_ht_encode_serial(const EncBlock* blocks, uint32_t nblocks, uint32_t nfast, uint32_t max_width, const uint32_t* coef,
                              uint8_t* slots, EncResult* results, const uint16_t* tables, uint32_t* status,
-                             cudaStream_t st, bool wide)
+                             cudaStream_t st, bool wide, const SideStream* side)
 {
   if (nblocks == 0) return;
   if (wide) nfast = 0;
+  // both kernels to run: the general one goes to the side stream
+  const bool forked = side && side->st && nfast && nfast < nblocks && !wide;
+  cudaStream_t sg = forked ? side->st : st;
+  if (forked) { cudaEventRecord(side->fork, st); cudaStreamWaitEvent(side->st, side->fork, 0); }
   const uint32_t prev_quads = (max_width + 1) / 2 + 2;
   const size_t smem = (size_t)prev_quads * ES_THREADS * sizeof(uint16_t);
   cudaFuncSetAttribute(ht_encode_serial_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -793,8 +797,9 @@ void launch_ht_encode_serial(const EncBlock* blocks, uint32_t nblocks, uint32_t 
     OJB_LAUNCH(ht_encode_serial_kernel<true>, grid, block, smem, st, blocks, nblocks, coef, slots, results, tables, status,
                prev_quads);
   else if (nfast < nblocks)
-    OJB_LAUNCH(ht_encode_serial_kernel<false>, grid, block, smem, st, blocks, nblocks, coef, slots, results, tables, status,
+    OJB_LAUNCH(ht_encode_serial_kernel<false>, grid, block, smem, sg, blocks, nblocks, coef, slots, results, tables, status,
                prev_quads);
+  if (forked) { cudaEventRecord(side->join, side->st); cudaStreamWaitEvent(st, side->join, 0); }
 }
 
 } // namespace ojb

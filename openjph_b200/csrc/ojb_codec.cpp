@@ -42,12 +42,18 @@ bool serial_block_decoder() {
 
 CodecBase::CodecBase() {
   CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&side.st, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&side.fork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&side.join, cudaEventDisableTiming));
   unsigned hc = std::thread::hardware_concurrency();
   host_threads = hc == 0 ? 4u : std::min(8u, hc);
   for (int i = 0; i < EV_MAX; ++i) CK(cudaEventCreate(&ev[i]));
 }
 CodecBase::~CodecBase() {
   for (int i = 0; i < EV_MAX; ++i) if (ev[i]) cudaEventDestroy(ev[i]);
+  if (side.fork) cudaEventDestroy(side.fork);
+  if (side.join) cudaEventDestroy(side.join);
+  if (side.st) cudaStreamDestroy(side.st);
   if (stream) cudaStreamDestroy(stream);
 }
 
@@ -448,7 +454,7 @@ size_t Encoder::encode(const void* const* planes, const uint32_t* strides, bool 
   uint32_t nb = (uint32_t)h_blocks.size();
   if (serial_block_encoder() || max_block_w > 64 || wide)
     launch_ht_encode_serial(d_blocks.as<EncBlock>(), nb, num_fast_blocks, max_block_w, d_coef.as<uint32_t>(), d_slots.as<uint8_t>(),
-                            d_results.as<EncResult>(), d_tables_enc.as<uint16_t>(), d_status.as<uint32_t>(), stream, wide);
+                            d_results.as<EncResult>(), d_tables_enc.as<uint16_t>(), d_status.as<uint32_t>(), stream, wide, &side);
   else
     launch_ht_encode(d_blocks.as<EncBlock>(), nb, d_coef.as<uint32_t>(), d_slots.as<uint8_t>(),
                      d_results.as<EncResult>(), d_tables_enc.as<uint16_t>(), d_status.as<uint32_t>(), stream);
@@ -996,7 +1002,7 @@ uint32_t Decoder::decode(void* const* planes, const uint32_t* strides, bool plan
   } else if (serial_block_decoder() || max_block_w > 64)
     launch_ht_decode_serial(d_dec.as<DecBlock>(), nb, nfast, max_block_w, cs_dev, d_coef.as<uint32_t>(), d_scratch.as<uint32_t>(),
                             d_tables_dec.as<uint16_t>(), dec_out, cleanup_only,
-                            d_bstatus.as<uint32_t>(), stream);
+                            d_bstatus.as<uint32_t>(), stream, &side);
   else
     launch_ht_decode(d_dec.as<DecBlock>(), nb, cs_dev, d_coef.as<uint32_t>(), d_scratch.as<uint32_t>(),
                      d_tables_dec.as<uint16_t>(), (uint32_t)DEC_OUT_PER_BLOCK,

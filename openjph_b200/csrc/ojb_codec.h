@@ -37,6 +37,7 @@ public:
   Params params;
   Layout layout;
   cudaStream_t stream = nullptr;
+  SideStream side;                     // second stream + fork / join events (see ojb_kernels.h)
   uint32_t last_launches = 0;          // kernels launched by the last frame call
   uint32_t host_threads = 4;           // host threads used for packet headers
   // stage timing of the last frame call (CUDA events on `stream`, ms)

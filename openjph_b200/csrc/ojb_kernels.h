@@ -4,6 +4,11 @@
 
 namespace ojb {
 
+// a second stream of the same codec object: the specialised and the general block-coder kernels of one frame work
+// on disjoint blocks and each lasts as long as its longest block's serial chain, so they run side by side
+// (fork after the producer of their input, join before the consumer of their output)
+struct SideStream { cudaStream_t st = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+
 // HT cleanup encoder, one warp per code-block (ht_encode.cu)
 // tables: uint16 enc_vlc[2][2048] followed by enc_uvlc[33] in device memory
 void launch_ht_encode(const EncBlock* blocks, uint32_t nblocks, const uint32_t* coef, uint8_t* slots,
@@ -13,7 +18,7 @@ void launch_ht_encode(const EncBlock* blocks, uint32_t nblocks, const uint32_t* 
 // blocks carry ENC_FLAG_FAST (see enc_block_is_fast) and go through the specialised kernel
 void launch_ht_encode_serial(const EncBlock* blocks, uint32_t nblocks, uint32_t nfast, uint32_t max_width, const uint32_t* coef,
                              uint8_t* slots, EncResult* results, const uint16_t* tables, uint32_t* status,
-                             cudaStream_t st, bool wide = false);
+                             cudaStream_t st, bool wide = false, const SideStream* side = nullptr);
 
 // HT decoder (ht_decode.cu): step 1 = MEL/VLC chain, one THREAD per code-block; step 2 =
 // MagSgn (+SPP +MRP) one WARP per code-block.
@@ -26,7 +31,7 @@ void launch_ht_decode(const DecBlock* blocks, uint32_t nblocks, const uint8_t* c
 // blocks carry DEC_FLAG_FAST (see dec_block_is_fast) and go through the specialised kernel
 void launch_ht_decode_serial(const DecBlock* blocks, uint32_t nblocks, uint32_t nfast, uint32_t max_width, const uint8_t* codestream,
                              uint32_t* coef, uint32_t* scratch, const uint16_t* tables, uint32_t out_mode,
-                             bool cleanup_only, uint32_t* block_status, cudaStream_t st);
+                             bool cleanup_only, uint32_t* block_status, cudaStream_t st, const SideStream* side = nullptr);
 
 // per-frame block records: blocks[b] = proto[b] with the frame's fields (dyn, and scratch offsets when given) applied.
 // dyn / scratch_off may be mapped pinned host memory (read by the SMs, like launch_ctrl_copy)
