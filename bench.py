@@ -671,15 +671,15 @@ def main():
         run_cfg("extreme: uniform-random full-range 8192x8192x3 12-bit frame (worst case, ~12 bits/sample), 5/3 + RCT", p,
                 [rng.integers(0, 1 << BD, (H, W), dtype=np.uint16) for _ in range(NC)], 2, True, e2e=False)
         run_cfg("cfg2: 1920x1080 RGB 8-bit, reversible 5/3 + RCT, 5 levels",
-                ob.make_params(1920, 1080, 3, 8, num_decomps=5, reversible=True, color_transform=True), make_frame(1920, 1080, 7, 3, 8), 32, True,
-                note="small frames: one frame is 1 519 code-blocks = 48 warps, so the device fills only with many frames in flight")
+                ob.make_params(1920, 1080, 3, 8, num_decomps=5, reversible=True, color_transform=True), make_frame(1920, 1080, 7, 3, 8), 8, True,
+                note="small frames: one frame is 1 519 code-blocks = 48 warps; more than 8 frames in flight LOWER the rate (32: 4.4 Gpixel/s): about 45 launches per frame, the stream is bound by the launch rate of the process")
         run_cfg("cfg3: 4096x4096x3 12-bit, irreversible 9/7 + ICT, Qfactor 90, 6 levels",
-                ob.make_params(4096, 4096, 3, 12, num_decomps=6, reversible=False, color_transform=True, qfactor=90), make_frame(4096, 4096, 8, 3, 12), 16, False)
+                ob.make_params(4096, 4096, 3, 12, num_decomps=6, reversible=False, color_transform=True, qfactor=90), make_frame(4096, 4096, 8, 3, 12), 8, False)
         run_cfg("cfg4 on one GPU: 8192x8192x3 16-bit, reversible 5/3 + RCT, 4 tiles of 4096x4096, 5 levels",
                 ob.make_params(W, H, 3, 16, num_decomps=5, reversible=True, color_transform=True, tile=(4096, 4096)), make_frame(W, H, 9, 3, 16), 4, True,
                 note="the 4-tiles-over-4-GPUs form of this configuration is the `sharded` entry of a --gpus 4 run")
-        run_cfg("cfg5: 3840x2160x3 10-bit frames, irreversible 9/7 + ICT (qstep default), 5 levels; batch of 64 / N GPUs, 24 in flight",
-                ob.make_params(3840, 2160, 3, 10, num_decomps=5, reversible=False, color_transform=True), make_frame(3840, 2160, 10, 3, 10), 24, False)
+        run_cfg("cfg5: 3840x2160x3 10-bit frames, irreversible 9/7 + ICT (qstep default), 5 levels; batch of 64 / N GPUs, 8 in flight",
+                ob.make_params(3840, 2160, 3, 10, num_decomps=5, reversible=False, color_transform=True), make_frame(3840, 2160, 10, 3, 10), 8, False)
 
     # ---- one image over the N GPUs: tiles sharded over ranks below the C-ABI, NCCL gather to rank 0 ----
     sharded = None
