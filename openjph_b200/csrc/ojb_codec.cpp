@@ -49,7 +49,14 @@ CodecBase::CodecBase() {
   host_threads = hc == 0 ? 4u : std::min(8u, hc);
   for (int i = 0; i < EV_MAX; ++i) CK(cudaEventCreate(&ev[i]));
 }
+void CodecBase::drop_graph() {
+#ifndef OJB_EMU_BUILD
+  if (fgraph.exec) { cudaGraphExecDestroy(fgraph.exec); fgraph.exec = nullptr; }
+#endif
+  fgraph.key.clear();
+}
 CodecBase::~CodecBase() {
+  drop_graph();
   for (int i = 0; i < EV_MAX; ++i) if (ev[i]) cudaEventDestroy(ev[i]);
   if (side.fork) cudaEventDestroy(side.fork);
   if (side.join) cudaEventDestroy(side.join);
@@ -438,7 +445,9 @@ size_t Encoder::encode(const void* const* planes, const uint32_t* strides, bool 
     }
   }
   mark(1);
+  uint32_t nb = (uint32_t)h_blocks.size();
   // 2. transform + block coding
+  auto enqueue_front = [&] {
   CK(cudaMemsetAsync(d_status.p, 0, 16, stream));
   for (size_t li = 0; li < jobs.size(); ++li)
     for (const JobGroup& g : jobs[li]) {
@@ -451,7 +460,6 @@ size_t Encoder::encode(const void* const* planes, const uint32_t* strides, bool 
       ++last_launches;
     }
   mark(2);
-  uint32_t nb = (uint32_t)h_blocks.size();
   if (serial_block_encoder() || max_block_w > 64 || wide)
     launch_ht_encode_serial(d_blocks.as<EncBlock>(), nb, num_fast_blocks, max_block_w, d_coef.as<uint32_t>(), d_slots.as<uint8_t>(),
                             d_results.as<EncResult>(), d_tables_enc.as<uint16_t>(), d_status.as<uint32_t>(), stream, wide, &side);
@@ -460,11 +468,10 @@ size_t Encoder::encode(const void* const* planes, const uint32_t* strides, bool 
                      d_results.as<EncResult>(), d_tables_enc.as<uint16_t>(), d_status.as<uint32_t>(), stream);
   last_launches += (serial_block_encoder() || max_block_w > 64) ? (num_fast_blocks ? 1 : 0) + (num_fast_blocks < nb ? 1 : 0) : 1;
   mark(3);
+  };
   if (device_headers) {
     // packet headers, markers and layout by kernels; the host only learns the length (and, for a host buffer, waits
     // for it before asking for the copy)
-    launch_ctrl_copy(h_status.p, d_status.p, 16, stream);
-    mark(4); mark(5);
     uint8_t* dev_out;
     uint64_t cap = out_cap;
     if (out_on_device) dev_out = out;
@@ -474,6 +481,8 @@ size_t Encoder::encode(const void* const* planes, const uint32_t* strides, bool 
     }
     uint64_t total = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
+      auto enqueue_all = [&] {
+      if (attempt == 0) { enqueue_front(); launch_ctrl_copy(h_status.p, d_status.p, 16, stream); ++last_launches; mark(4); mark(5); }
       if (fixed_blob.size() <= cap) CK(cudaMemcpyAsync(dev_out, d_fixed.p, fixed_blob.size(), cudaMemcpyDeviceToDevice, stream));
       CK(cudaMemsetAsync(hplan.hscr, 0, hscr_bytes, stream));
       launch_packet_headers(hplan, d_blocks.as<EncBlock>(), d_results.as<EncResult>(), wide ? 62u : 30u, fixed_blob.size(), cap,
@@ -481,8 +490,14 @@ size_t Encoder::encode(const void* const* planes, const uint32_t* strides, bool 
       if (!tile_mask.empty() && hplan.ntps) { launch_ctrl_copy(h_tpout.p, hplan.tp_out, (size_t)hplan.ntps * 16, stream); ++last_launches; }
       launch_gather_blocks(d_blocks.as<EncBlock>(), d_results.as<EncResult>(), d_dst.as<uint64_t>(), nb, d_slots.as<uint8_t>(), dev_out, stream);
       launch_ctrl_copy(h_total.p, hplan.total, 16, stream);
-      last_launches += packet_header_launches(hplan) + 3;
+      last_launches += packet_header_launches(hplan) + 2;
       mark(6);
+      };
+      // resident form (frame already in HBM, codestream stays there): nothing in the call depends on host data, so
+      // the whole thing replays as a graph
+      if (planes == nullptr && out_on_device)
+        run_frame({ (uint64_t)(size_t)dev_out, cap, (uint64_t)nb, (uint64_t)num_fast_blocks, (uint64_t)(size_t)d_slots.p, (uint64_t)(size_t)d_coef.p }, enqueue_all);
+      else enqueue_all();
       CK(cudaStreamSynchronize(stream));
       CK(cudaGetLastError());
       status_flags = h_status.as<uint32_t>()[0];
@@ -508,6 +523,7 @@ size_t Encoder::encode(const void* const* planes, const uint32_t* strides, bool 
     std::fill(line_cur.begin(), line_cur.end(), 0u); cur_comp = 0; lines_done = false;
     return (size_t)total;
   }
+  enqueue_front();
   if (nb) launch_ctrl_copy(h_results.p, d_results.p, (size_t)nb * sizeof(EncResult), stream);
   launch_ctrl_copy(h_status.p, d_status.p, 16, stream);
   last_launches += nb ? 2 : 1;
@@ -993,6 +1009,7 @@ uint32_t Decoder::decode(void* const* planes, const uint32_t* strides, bool plan
   const bool need_scratch = nfast < nb || !(serial_block_decoder() || max_block_w > 64);
   host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
   if (getenv("OJB_PARSE_PROF")) fprintf(stderr, "decode host: parse %.3f ms, records %.3f ms\n", std::chrono::duration<double, std::milli>(host_t1 - host_t0).count(), host_ms - std::chrono::duration<double, std::milli>(host_t1 - host_t0).count());
+  auto enqueue = [&] {
   mark(2);
   if (nb) { launch_dec_merge(d_dec.as<DecBlock>(), d_proto.as<DecBlock>(), hy, need_scratch ? hs : nullptr, nb, stream); ++last_launches; }
   if (wide) {
@@ -1037,6 +1054,14 @@ uint32_t Decoder::decode(void* const* planes, const uint32_t* strides, bool plan
     }
   }
   mark(5);
+  };
+  // resident form (codestream in HBM, image stays there): what follows the host parse replays as a graph -- the
+  // frame's own data (block records, lengths, offsets) reaches the kernels through the pinned record buffer
+  if (planes == nullptr && dev_cs != nullptr)
+    run_frame({ (uint64_t)(size_t)cs_dev, (uint64_t)nb, (uint64_t)(nfast != 0), (uint64_t)(nfast < nb), (uint64_t)cleanup_only, (uint64_t)dec_out,
+                (uint64_t)need_scratch, (uint64_t)(size_t)d_scratch.p, (uint64_t)max_len1 * (serial_block_decoder() || max_block_w > 64 ? 0 : 1),
+                (uint64_t)skip_recon, (uint64_t)(size_t)hy, (uint64_t)(size_t)d_coef.p, (uint64_t)(size_t)d_image.p }, enqueue);
+  else enqueue();
   CK(cudaStreamSynchronize(stream));
   CK(cudaGetLastError());
   collect(6);

@@ -46,6 +46,14 @@ public:
   float stage_ms[EV_MAX] = {0};
   double host_ms = 0;                  // host time between the two device phases
   void mark(int i) { cudaEventRecord(ev[i], stream); }
+  // The device work of a frame call as a CUDA graph.  Small frames are bound by the launch rate of the process
+  // (about 45 launches per encode + decode), not by the SMs: the resident forms, whose launches and arguments repeat
+  // frame after frame, run eagerly the first time a given argument set is seen, are captured the second time and are
+  // one cudaGraphLaunch from then on.  `key` holds everything the enqueued work depends on.  OJB_NO_GRAPHS=1 disables it.
+  struct FrameGraph { std::vector<uint64_t> key, seen; cudaGraphExec_t exec = nullptr; uint32_t launches = 0; bool off = false; };
+  FrameGraph fgraph;
+  template <typename F> void run_frame(const std::vector<uint64_t>& key, F&& enqueue);
+  void drop_graph();
   void collect(int n) { for (int i = 0; i + 1 < n; ++i) cudaEventElapsedTime(&stage_ms[i], ev[i], ev[i + 1]); }
   void upload_tables();
   DeviceBuf d_tables_enc, d_tables_dec;
@@ -166,5 +174,35 @@ public:
   bool any_rev_blocks = false, any_irv_blocks = false;
   void parse_tiles();
 };
+
+
+template <typename F> void CodecBase::run_frame(const std::vector<uint64_t>& key, F&& enqueue) {
+#ifdef OJB_EMU_BUILD
+  (void)key; enqueue();
+#else
+  static const bool disabled = [] { const char* e = getenv("OJB_NO_GRAPHS"); return e && *e && *e != '0'; }();
+  FrameGraph& g = fgraph;
+  if (disabled || g.off) { enqueue(); return; }
+  if (g.exec && g.key == key) {
+    if (cudaGraphLaunch(g.exec, stream) == cudaSuccess) { last_launches += g.launches; return; }
+    cudaGetLastError(); drop_graph(); g.off = true; enqueue(); return;
+  }
+  if (g.seen != key) { g.seen = key; enqueue(); return; }       // first sight of this argument set: eager
+  drop_graph();
+  if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); g.off = true; enqueue(); return; }
+  const uint32_t l0 = last_launches;
+  cudaGraph_t graph = nullptr;
+  try { enqueue(); } catch (...) { cudaStreamEndCapture(stream, &graph); if (graph) cudaGraphDestroy(graph); cudaGetLastError(); g.off = true; throw; }
+  g.launches = last_launches - l0;
+  cudaError_t rc = cudaStreamEndCapture(stream, &graph);
+  if (rc == cudaSuccess) rc = cudaGraphInstantiate(&g.exec, graph, 0);
+  if (graph) cudaGraphDestroy(graph);
+  if (rc == cudaSuccess) rc = cudaGraphLaunch(g.exec, stream);
+  if (rc != cudaSuccess) {          // whatever the capture could not take: this object stays eager
+    cudaGetLastError(); drop_graph(); g.off = true; last_launches = l0; enqueue(); return;
+  }
+  g.key = key;
+#endif
+}
 
 } // namespace ojb

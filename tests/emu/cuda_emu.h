@@ -205,6 +205,7 @@ static inline unsigned atomicCAS(unsigned* a, unsigned c, unsigned v)
 typedef int cudaError_t;
 typedef struct emuStream_st* cudaStream_t;
 typedef struct emuEvent_st* cudaEvent_t;
+typedef struct emuGraphExec_st* cudaGraphExec_t;   // never instantiated: the emulator runs every frame eagerly
 enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1 };
 enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2,
                       cudaMemcpyDeviceToDevice = 3, cudaMemcpyDefault = 4 };
