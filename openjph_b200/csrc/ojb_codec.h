@@ -45,7 +45,12 @@ public:
   cudaEvent_t ev[EV_MAX] = {nullptr};
   float stage_ms[EV_MAX] = {0};
   double host_ms = 0;                  // host time between the two device phases
+  bool capturing = false;              // inside run_frame's stream capture: stage marks become event-record NODES
+#ifdef OJB_EMU_BUILD
   void mark(int i) { cudaEventRecord(ev[i], stream); }
+#else
+  void mark(int i) { if (capturing) cudaEventRecordWithFlags(ev[i], stream, cudaEventRecordExternal); else cudaEventRecord(ev[i], stream); }
+#endif
   // The device work of a frame call as a CUDA graph.  Small frames are bound by the launch rate of the process
   // (about 45 launches per encode + decode), not by the SMs: the resident forms, whose launches and arguments repeat
   // frame after frame, run eagerly the first time a given argument set is seen, are captured the second time and are
@@ -192,7 +197,9 @@ template <typename F> void CodecBase::run_frame(const std::vector<uint64_t>& key
   if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); g.off = true; enqueue(); return; }
   const uint32_t l0 = last_launches;
   cudaGraph_t graph = nullptr;
-  try { enqueue(); } catch (...) { cudaStreamEndCapture(stream, &graph); if (graph) cudaGraphDestroy(graph); cudaGetLastError(); g.off = true; throw; }
+  capturing = true;
+  try { enqueue(); } catch (...) { capturing = false; cudaStreamEndCapture(stream, &graph); if (graph) cudaGraphDestroy(graph); cudaGetLastError(); g.off = true; throw; }
+  capturing = false;
   g.launches = last_launches - l0;
   cudaError_t rc = cudaStreamEndCapture(stream, &graph);
   if (rc == cudaSuccess) rc = cudaGraphInstantiate(&g.exec, graph, 0);

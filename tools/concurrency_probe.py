@@ -65,7 +65,8 @@ def run(mode, nw, iters=int(os.environ.get("PROBE_ITERS", "12"))):
     print(s, flush=True)
 
 
-WS = [Wk() for _ in range(12)]
+_WL = [int(x) for x in os.environ.get("PROBE_WORKERS", "1,2,4,8,12").split(",")]
+WS = [Wk() for _ in range(max(_WL))]
 for mode in os.environ.get("PROBE_MODES", "enc,dec,both").split(","):
     for nw in [int(x) for x in os.environ.get("PROBE_WORKERS", "1,2,4,8,12").split(",")]:
         run(mode, nw)
