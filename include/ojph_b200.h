@@ -76,8 +76,8 @@ typedef struct ojb_params {
    *     2 horizontally only, 3 vertically only; levels past the list repeat the last entry; 0 levels = dyadic.
    *   atk_*: a whole-sample symmetric lifting kernel with one tap pair per step, steps in SYNTHESIS order (step 0
    *     acts on the even samples): irreversible x[n] -= A (x[n-1] + x[n+1]) with scaling K, or reversible
-   *     x[n] -= (b + a (x[n-1] + x[n+1])) >> e.  atk_num_steps = 0 keeps the COD's 5/3 or 9/7; at most 4 steps run
-   *     on the device. */
+   *     x[n] -= (b + a (x[n-1] + x[n+1])) >> e.  atk_num_steps = 0 keeps the COD's 5/3 or 9/7; at most 8 steps
+   *     (a longer kernel in a codestream is refused, 0x000B0025). */
   uint32_t dfs_num_levels;
   uint32_t dfs_type[32];
   uint32_t atk_num_steps;

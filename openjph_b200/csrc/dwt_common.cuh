@@ -6,7 +6,7 @@ namespace ojb {
 
 #define DW_TW 128            // tile width  (samples of the resolution being split/merged)
 #define DW_TH 32             // tile height
-#define DW_H 4               // halo on every side (9/7: 4 lifting steps reach +-4)
+#define DW_H 8               // halo on every side: one sample per lifting step (9/7 needs 4; ATK kernels up to 8)
 #define DW_COLS (DW_TW + 2 * DW_H)
 #define DW_ROWS (DW_TH + 2 * DW_H)
 #define DW_PITCH (DW_COLS + 1)

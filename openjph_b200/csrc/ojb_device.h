@@ -102,7 +102,7 @@ enum : uint32_t { SRC_U8 = 0, SRC_U16 = 1, SRC_I32 = 2, SRC_COEF = 3 };
 
 // one analysis (or synthesis) level of one tile-component (or of 3 colour components at once
 // for the first level when the colour transform is used)
-#define DWT_MAX_STEPS 4        // = the halo of the general kernels' tile (DW_H): one sample per lifting step
+#define DWT_MAX_STEPS 8        // = the halo of the general kernels' tile (DW_H): one sample per lifting step
 struct DwtJob {
   // geometry of the resolution being split
   uint32_t w, h;          // size

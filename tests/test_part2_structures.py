@@ -204,12 +204,25 @@ def test_header_errors_match_reference(emu_lib, ref, capfd):
     both(atk_taps, 0x000500F1)
 
 
-def test_more_than_four_steps_is_refused(emu_lib):
-    p = ob.make_params(32, 32, 1, 8, num_decomps=1, reversible=True,
-                       atk=dict(reversible=True, steps=[(1, 2, 2), (-1, 1, 1)] * 3))
+def test_long_kernels(emu_lib, ref):
+    """up to eight lifting steps run (the tile halo of the general kernels is one sample per step); more are refused"""
+    rng = np.random.default_rng(21)
+    for steps in ([(1, 2, 2), (-1, 1, 1)] * 3, [(1, 4, 3), (-1, 1, 1), (1, 2, 2), (-1, 2, 2), (1, 8, 4), (-1, 4, 3), (1, 2, 2), (-1, 1, 1)]):
+        kw = dict(num_decomps=3, reversible=True, atk=dict(reversible=True, steps=steps), decomp="BHB")
+        p = ob.make_params(150, 97, 1, 10, **kw)
+        _roundtrip(emu_lib, ref, p, [_smooth(rng, 150, 97, 10, False)], kw, len(steps))
+    kw = dict(num_decomps=2, reversible=False, atk=dict(K=1.1, A=[0.1, -0.2, 0.05, 0.3, -0.1, 0.2]))
+    p = ob.make_params(150, 97, 1, 10, **kw)
+    _roundtrip(emu_lib, ref, p, [_smooth(rng, 150, 97, 10, False)], kw, "irv6")
+
+
+def test_more_than_eight_steps_is_refused(emu_lib):
+    import ctypes as C
+    p = ob.make_params(32, 32, 1, 8, num_decomps=1, reversible=True, atk=dict(reversible=True, steps=[(1, 2, 2), (-1, 1, 1)] * 4))
+    p.atk_num_steps = 9
     with pytest.raises(ob.OjphError) as e:
         ob.Encoder(p, ob.I32, lib=emu_lib)
-    assert "000b0025" in str(e.value).lower()
+    assert "000b0023" in str(e.value).lower()
 
 
 def test_kernel_gains_reproduce_the_reference_tables(emu_lib):
