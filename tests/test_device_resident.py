@@ -61,3 +61,56 @@ def test_device_resident_codestream_gpu(gpu_lib):
     _check(None, 640, 480, 3, 8, 1.0, num_decomps=4, reversible=True, color_transform=True)
     _check(None, 4096, 4096, 3, 12, 0.10, num_decomps=5, reversible=True, color_transform=True)
     _check(None, 2048, 2048, 1, 10, 1.0, num_decomps=5, reversible=False, qstep=0.002, tile=(1024, 1024), tlm=True)
+
+
+def _stream_of_frames(lib, on_gpu):
+    """several DIFFERENT frames through the same resident encoder / decoder pair: from the third call on the device
+    work is one replayed CUDA graph (CodecBase::run_frame), so every frame must still come out as its own"""
+    import ctypes as C
+    w, h, nc, bd = 512, 320, 3, 10
+    p = ob.make_params(w, h, nc, bd, num_decomps=4, reversible=True, color_transform=True, block=(32, 32))
+    enc = ob.Encoder(p, ob.I32, lib=lib)
+    dec = ob.Decoder(lib=lib)
+    L = enc.L
+    cap = w * h * nc * 4 + (1 << 16)
+    keep, addr = _device_buffer(None if on_gpu else lib, cap)
+    rng = np.random.default_rng(31)
+    frames = [images.synth_frame(w, h, nc, bd, 40 + i) for i in range(5)]
+    frames.insert(2, [np.zeros((h, w), np.int32) for _ in range(nc)])                  # nothing to code at all
+    frames.insert(4, [rng.integers(0, 1 << bd, (h, w)).astype(np.int32) for _ in range(nc)])   # full-range noise
+    for k, fr in enumerate(frames):
+        want = ob.Encoder(p, ob.I32, lib=lib).encode(fr)
+        enc.upload(fr)
+        n = enc.encode_resident_to_device(addr, cap)
+        assert n == len(want), k
+        if on_gpu:
+            got = keep[:n].cpu().numpy().tobytes()
+        else:
+            got = keep[:n].tobytes()
+        assert got == want, k
+        dec.read_headers_device(addr, n)
+        assert L.ojb_dec_decode_resident(dec.h) == 0, L.ojb_last_error()
+        for c in range(nc):
+            ptr = L.ojb_dec_device_plane(dec.h, c)
+            if on_gpu:
+                host = np.empty((h, w), np.int32)
+                rt = None
+                for name in ("libcudart.so.12", "/usr/local/cuda/lib64/libcudart.so", "libcudart.so"):
+                    try:
+                        rt = C.CDLL(name); break
+                    except OSError:
+                        pass
+                assert rt is not None, "no CUDA runtime to read the device plane back with"
+                assert rt.cudaMemcpy(C.c_void_p(host.ctypes.data), C.c_void_p(ptr), C.c_size_t(host.nbytes), 2) == 0
+            else:
+                host = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_int32)), (h, w)).copy()
+            assert np.array_equal(host, fr[c]), (k, c)
+
+
+def test_resident_stream_of_different_frames_emulator(emu_lib):
+    _stream_of_frames(emu_lib, False)
+
+
+@pytest.mark.gpu
+def test_resident_stream_of_different_frames_gpu(gpu_lib):
+    _stream_of_frames(gpu_lib, True)
