@@ -311,6 +311,18 @@ void* ojb_shard_device_plane(ojb_shard* s, uint32_t comp);
  * device buffer, rank order; offsets[world + 1] */
 int ojb_shard_gatherv(ojb_shard* s, const void* dev, uint64_t bytes, uint32_t writer_rank, void* out_dev, uint64_t out_cap,
                       uint64_t* offsets);
+/* How the image is cut (before ojb_shard_enc_configure / the decode calls; every rank the same).  0 (default): tiles.
+ * 1: ROW REGIONS -- every tile-component is cut into `world` horizontal slabs; rank g codes the code-blocks that start
+ * in slab g from an input halo of 2 (2^D - 1) rows (5/3) / 4 (2^D - 1) rows (9/7) per side, the footprint of one
+ * lifting step reaching +-1 (src/core/transform/ojph_transform.cpp:376-390), so nothing is exchanged in mid-pipeline;
+ * the one exchange is the gather of code-block bytes + lengths to the writer, which then writes packet headers and
+ * markers as a single encoder does (precinct::write, src/core/codestream/ojph_precinct.cpp:281-324).  This also
+ * splits a SINGLE-TILE image; the codestream stays byte-identical.  Decode: each rank decodes the
+ * blocks its slab depends on and delivers its rows. */
+int ojb_shard_set_partition(ojb_shard* s, uint32_t kind);
+/* row regions, after ojb_shard_enc_configure: rows [*lo, *hi) of component comp (first tile) this rank's encoder reads;
+ * returns 0 when the partition is not row regions */
+uint32_t ojb_shard_region_rows(ojb_shard* s, uint32_t comp, uint32_t* lo, uint32_t* hi);
 void ojb_shard_timings(ojb_shard* s, float* ms2);                 /* last call: codec ms, gather ms (this rank) */
 uint32_t ojb_shard_rank(ojb_shard* s);
 uint32_t ojb_shard_world(ojb_shard* s);

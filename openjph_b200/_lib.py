@@ -142,6 +142,8 @@ SYMBOLS = {
     "ojb_shard_dec_decode_resident": (_I, [_VP, _VP, _U64, _U32, _U32, C.POINTER(FrameInfo)]),
     "ojb_shard_device_plane": (_VP, [_VP, _U32]),
     "ojb_shard_gatherv": (_I, [_VP, _VP, _U64, _U32, _VP, _U64, C.POINTER(_U64)]),
+    "ojb_shard_set_partition": (_I, [_VP, _U32]),
+    "ojb_shard_region_rows": (_U32, [_VP, _U32, C.POINTER(_U32), C.POINTER(_U32)]),
     "ojb_shard_timings": (None, [_VP, C.POINTER(C.c_float)]),
     "ojb_shard_rank": (_U32, [_VP]),
     "ojb_shard_world": (_U32, [_VP]),

@@ -60,6 +60,52 @@ gather_blocks_kernel(const EncBlock* __restrict__ blocks, const EncResult* __res
   warp_copy(d + r.len_head, slot + b.slot_cap - r.len_tail, r.len_tail, lane);
 }
 
+// ---- row regions (ojb_shard.cpp): code-block bytes change ranks between the block coder and the packet headers ----
+// where each block's bytes start when the blocks are packed back to back (head piece, then tail piece) in block order:
+// the exclusive prefix sum of len_head + len_tail, one CTA; total[0] = the sum.  gather_blocks_kernel with these
+// offsets is the packer.
+#define BO_THREADS 1024
+__global__ void __launch_bounds__(BO_THREADS)
+block_offsets_kernel(const EncResult* __restrict__ results, uint32_t n, uint64_t* __restrict__ off, uint64_t* __restrict__ total)
+{
+  __shared__ unsigned long long ssum[BO_THREADS];
+  const uint32_t tid = threadIdx.x, per = (n + BO_THREADS - 1) / BO_THREADS;
+  const uint32_t b0 = min(n, tid * per), b1 = min(n, b0 + per);
+  unsigned long long sum = 0;
+  for (uint32_t b = b0; b < b1; ++b) sum += (unsigned long long)results[b].len_head + results[b].len_tail;
+  ssum[tid] = sum;
+  __syncthreads();
+  for (uint32_t d = 1; d < BO_THREADS; d <<= 1) {
+    const unsigned long long t = tid >= d ? ssum[tid - d] : 0;
+    __syncthreads();
+    ssum[tid] += t;
+    __syncthreads();
+  }
+  unsigned long long run = ssum[tid] - sum;
+  for (uint32_t b = b0; b < b1; ++b) { off[b] = run; run += (unsigned long long)results[b].len_head + results[b].len_tail; }
+  if (tid == BO_THREADS - 1) total[0] = ssum[tid];
+}
+
+// the writer's side: the blocks `rank` coded go from its packed bytes into their slots (as if coded here) and their
+// lengths into the writer's result array; a warp per block
+__global__ void __launch_bounds__(128)
+scatter_blocks_kernel(const EncBlock* __restrict__ blocks, const uint8_t* __restrict__ owner, uint32_t rank,
+                      const EncResult* __restrict__ results_in, const uint64_t* __restrict__ off, uint32_t nblocks,
+                      const uint8_t* __restrict__ packed, uint8_t* __restrict__ slots, EncResult* __restrict__ results_out)
+{
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= nblocks || owner[warp] != rank) return;
+  const EncResult r = results_in[warp];
+  if (lane == 0) results_out[warp] = r;
+  if (r.len_head + r.len_tail == 0) return;
+  const EncBlock b = blocks[warp];
+  if (r.len_head + r.len_tail > b.slot_cap) return;        // cannot happen with a sane peer; never write outside the slot
+  const uint8_t* src = packed + off[warp];
+  uint8_t* slot = slots + b.slot_off;
+  warp_copy(slot, src, r.len_head, lane);
+  warp_copy(slot + b.slot_cap - r.len_tail, src + r.len_head, r.len_tail, lane);
+}
+
 __global__ void __launch_bounds__(128)
 assemble_kernel(const CopyPiece* __restrict__ pieces, uint32_t npieces, const uint8_t* __restrict__ slots,
                 const uint8_t* __restrict__ headers, uint8_t* __restrict__ out)
@@ -129,6 +175,20 @@ void launch_gather_blocks(const EncBlock* blocks, const EncResult* results, cons
   if (nblocks == 0) return;
   dim3 grid((nblocks + 3) / 4), block(128);
   OJB_LAUNCH(gather_blocks_kernel, grid, block, 0, st, blocks, results, dst_off, nblocks, slots, out);
+}
+
+void launch_block_offsets(const EncResult* results, uint32_t nblocks, uint64_t* off, uint64_t* total, cudaStream_t st)
+{
+  OJB_LAUNCH(block_offsets_kernel, dim3(1), dim3(BO_THREADS), 0, st, results, nblocks, off, total);
+}
+
+void launch_scatter_blocks(const EncBlock* blocks, const uint8_t* owner, uint32_t rank, const EncResult* results_in,
+                           const uint64_t* off, uint32_t nblocks, const uint8_t* packed, uint8_t* slots,
+                           EncResult* results_out, cudaStream_t st)
+{
+  if (nblocks == 0) return;
+  dim3 grid((nblocks + 3) / 4), block(128);
+  OJB_LAUNCH(scatter_blocks_kernel, grid, block, 0, st, blocks, owner, rank, results_in, off, nblocks, packed, slots, results_out);
 }
 
 void launch_assemble(const CopyPiece* pieces, uint32_t npieces, uint32_t max_len, const uint8_t* slots,

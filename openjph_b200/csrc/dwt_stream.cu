@@ -403,7 +403,7 @@ dwt_fwd_stream_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, const voi
   // CTA = DS_WARPS adjacent strips of one row chunk
   const uint32_t cta = blockIdx.x - J.cta_base;
   const uint32_t strips_per_row = (J.tiles_x + DS_WARPS - 1) / DS_WARPS;
-  const uint32_t strip = (cta % strips_per_row) * DS_WARPS + warp, chunk = cta / strips_per_row;
+  const uint32_t strip = (cta % strips_per_row) * DS_WARPS + warp, chunk = J.chunk0 + cta / strips_per_row;
   if (strip >= J.tiles_x) return;
   StripGeom g;
   if (!strip_setup(J, strip, chunk, lane, g)) return;
@@ -759,7 +759,7 @@ dwt_inv_stream_kernel(const DwtJob* __restrict__ jobs, uint32_t njobs, void* __r
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t cta = blockIdx.x - J.cta_base;
   const uint32_t strips_per_row = (J.tiles_x + DS_WARPS - 1) / DS_WARPS;
-  const uint32_t strip = (cta % strips_per_row) * DS_WARPS + warp, chunk = cta / strips_per_row;
+  const uint32_t strip = (cta % strips_per_row) * DS_WARPS + warp, chunk = J.chunk0 + cta / strips_per_row;
   if (strip >= J.tiles_x) return;
   StripGeom g;
   if (!strip_setup(J, strip, chunk, lane, g)) return;

@@ -106,8 +106,162 @@ void CodecBase::plan_image(uint32_t sample_type) {
   d_image.reserve(img_bytes);
 }
 
+// the register-streaming kernels take a level when it splits both ways with the built-in 5/3 or 9/7, the resolution is
+// at least 2 x 2 and byte / word offsets fit 32 bits (dwt_stream.cu)
+static bool level_streams(const CodecBase& C, const Params& P, uint32_t c, const ResGeom& rg) {
+  return !C.wide && rg.hsplit && rg.vsplit && P.wavelet_of(c) <= 1 && rg.rect.w >= 2 && rg.rect.h >= 2 && !C.no_stream_dwt &&
+         C.layout.coef_words < (1ull << 30) && C.img_bytes < (1ull << 32);
+}
+
+// slab g of `world` of a tile-component: rows [lo, hi) in absolute component coordinates; inner boundaries on multiples
+// of 128 rows (two code-block rows of the first level, whole row chunks of the kernels)
+CodecBase::RowSpan CodecBase::region_slab(const Rect& tc, uint32_t g, uint32_t world) {
+  auto bound = [&](uint32_t i) -> uint32_t {
+    if (i == 0) return tc.y0;
+    if (i >= world) return tc.y1();
+    const uint64_t y = (uint64_t)tc.y0 + (uint64_t)tc.h * i / world;
+    return std::min(std::max((uint32_t)(y & ~(uint64_t)127), tc.y0), tc.y1());
+  };
+  RowSpan s; s.lo = bound(g); s.hi = bound(g + 1);
+  return s;
+}
+
+// Row-region sharding (see ojb_codec.h): block ownership, the window of row chunks every level's job runs, the
+// blocks a decoder has to decode and the image rows read / delivered -- all from the geometry, identically on
+// every rank.  What a chunk [R0, R1) of the streaming kernels reads (dwt_stream.cu): analysis, source rows
+// [R0 - m, R1 + m); synthesis, interleaved band rows [R0 - m, R1 + m + 1) (even: a low-pass row, odd: a
+// high-pass row, index >> 1); m = 2 for 5/3, 4 for 9/7, mirrored at the resolution's own borders only.
+void CodecBase::plan_region(bool forward) {
+  const Params& P = params;
+  const uint32_t nc = P.num_comps(), W = region.world, me = region.rank;
+  region_win.assign(layout.tiles.size(), std::vector<std::vector<RegionWin>>());
+  region_rows.assign(layout.tiles.size(), std::vector<RowSpan>());
+  region_owner.assign(layout.num_blocks, 0);
+  region_blocks.assign(layout.num_blocks, 0);
+  struct Span { int64_t lo = INT64_MAX, hi = INT64_MIN; bool empty() const { return lo >= hi; }
+                void add(int64_t a, int64_t b) { if (a < b) { lo = std::min(lo, a); hi = std::max(hi, b); } } };
+  for (const TileGeom& t : layout.tiles) {
+    region_win[t.idx].assign(nc, std::vector<RegionWin>());
+    region_rows[t.idx].assign(nc, RowSpan());
+    for (uint32_t c = 0; c < nc; ++c) {
+      const TileCompGeom& tc = t.comps[c];
+      const uint32_t D = (uint32_t)tc.res.size() - 1;
+      region_win[t.idx][c].assign(D + 1, RegionWin());
+      bool streams = D >= 1;
+      for (uint32_t r = 1; r <= D && streams; ++r) streams = level_streams(*this, P, c, tc.res[r]);
+      // block ownership: by the slab the block's first row falls into, scaled up to the component's resolution
+      for (uint32_t r = 0; r <= D; ++r)
+        for (uint32_t b = 0; b < 4; ++b) {
+          const BandGeom& bg = tc.res[r].bands[b];
+          if (bg.empty) continue;
+          const uint32_t depth = r ? D - r + 1 : D;
+          for (uint32_t by = 0; by < bg.nbh; ++by) {
+            const Rect br = bg.block_rect(0, by);
+            const uint64_t yf = std::min<uint64_t>(std::max<uint64_t>((uint64_t)br.y0 << depth, tc.rect.y0), tc.rect.y1() ? tc.rect.y1() - 1 : 0);
+            uint32_t g = 0;
+            while (g + 1 < W && yf >= region_slab(tc.rect, g, W).hi) ++g;
+            for (uint32_t bx = 0; bx < bg.nbw; ++bx) {
+              region_owner[bg.block_base + by * bg.nbw + bx] = (uint8_t)g;
+              if (forward) region_blocks[bg.block_base + by * bg.nbw + bx] = g == me ? 1 : 0;
+            }
+          }
+        }
+      // rows of band b of resolution r spanned by the blocks this rank owns (encoder)
+      auto owned_rows = [&](uint32_t r, uint32_t b) {
+        Span s; const BandGeom& bg = tc.res[r].bands[b];
+        if (bg.empty) return s;
+        for (uint32_t by = 0; by < bg.nbh; ++by)
+          if (region_owner[bg.block_base + by * bg.nbw] == me) { const Rect br = bg.block_rect(0, by); s.add(br.y0, br.y1()); }
+        return s;
+      };
+      auto want_rows = [&](uint32_t r, uint32_t b, const Span& rows) {      // decoder: blocks of the band that meet the rows
+        const BandGeom& bg = tc.res[r].bands[b];
+        if (bg.empty || rows.empty()) return;
+        for (uint32_t by = 0; by < bg.nbh; ++by) {
+          const Rect br = bg.block_rect(0, by);
+          if ((int64_t)br.y0 < rows.hi && (int64_t)br.y1() > rows.lo)
+            for (uint32_t bx = 0; bx < bg.nbw; ++bx) region_blocks[bg.block_base + by * bg.nbw + bx] = 1;
+        }
+      };
+      const RowSpan slab = region_slab(tc.rect, me, W);
+      if (!streams) {
+        // whole-plane transforms on every rank; the decoder then needs every block of the component
+        if (forward) { region_rows[t.idx][c].lo = tc.rect.y0; region_rows[t.idx][c].hi = tc.rect.y1(); }
+        else {
+          region_rows[t.idx][c] = slab;
+          for (uint32_t r = 0; r <= D; ++r) for (uint32_t b = 0; b < 4; ++b) { Span all; all.add(0, INT64_MAX); want_rows(r, b, all); }
+        }
+        continue;
+      }
+      const uint32_t m = P.reversible(c) ? 2u : 4u;
+      // rows [lo, hi) of resolution r that have to be produced -> the chunks that do it and what they read
+      auto chunks_for = [&](uint32_t r, Span out, RegionWin& w, Span& read) {
+        const ResGeom& rg = tc.res[r];
+        const int64_t y0 = rg.rect.y0, y1 = rg.rect.y1(), ye = y0 & ~(int64_t)1;
+        out.lo = std::max(out.lo, y0); out.hi = std::min(out.hi, y1);
+        w.full = false; w.chunk0 = 0; w.nchunks = 0; read = Span();
+        if (out.empty()) return;
+        uint32_t strips, chunks, cr, ctas;
+        dwt_stream_tiling(rg.rect.x0, rg.rect.y0, rg.rect.w, rg.rect.h, P.reversible(c), forward, strips, chunks, cr, ctas);
+        const int64_t c_lo = (out.lo - ye) / cr, c_hi = (out.hi - 1 - ye) / cr;
+        w.chunk0 = (uint32_t)c_lo; w.nchunks = (uint32_t)(c_hi - c_lo + 1);
+        const int64_t R0 = ye + c_lo * cr, R1 = std::min<int64_t>(ye + (c_hi + 1) * cr, y1);
+        read.add(std::max(y0, R0 - (int64_t)m), std::min(y1, R1 + (int64_t)m + (forward ? 0 : 1)));
+      };
+      if (forward) {
+        Span low = owned_rows(0, 0);                          // rows of resolution r - 1 this rank needs
+        for (uint32_t r = 1; r <= D; ++r) {
+          Span out;
+          if (!low.empty()) out.add(2 * low.lo, 2 * (low.hi - 1) + 1);
+          { const Span s = owned_rows(r, 1); if (!s.empty()) out.add(2 * s.lo, 2 * (s.hi - 1) + 1); }
+          for (uint32_t b = 2; b < 4; ++b) { const Span s = owned_rows(r, b); if (!s.empty()) out.add(2 * s.lo + 1, 2 * (s.hi - 1) + 2); }
+          Span read;
+          chunks_for(r, out, region_win[t.idx][c][r], read);
+          low = read;
+        }
+        if (!low.empty()) { region_rows[t.idx][c].lo = (uint32_t)low.lo; region_rows[t.idx][c].hi = (uint32_t)low.hi; }
+      } else {
+        region_rows[t.idx][c] = slab;
+        Span out; out.add(slab.lo, slab.hi);
+        for (uint32_t r = D; r >= 1; --r) {
+          Span read;
+          chunks_for(r, out, region_win[t.idx][c][r], read);
+          Span bandrows;
+          if (!read.empty()) bandrows.add(read.lo >> 1, ((read.hi - 1) >> 1) + 1);
+          for (uint32_t b = 1; b < 4; ++b) want_rows(r, b, bandrows);
+          out = bandrows;
+        }
+        want_rows(0, 0, out);
+      }
+    }
+    // the colour transform fuses the first three components into one job at the top level: one window for the three
+    if (P.color_transform() && nc >= 3) {
+      const uint32_t D = (uint32_t)t.comps[0].res.size() - 1;
+      RegionWin& a = region_win[t.idx][0][D];
+      if (D >= 1 && !a.full) {
+        uint32_t lo = UINT32_MAX, hi = 0;
+        for (uint32_t c = 0; c < 3; ++c) {
+          const RegionWin& w = region_win[t.idx][c][D];
+          if (w.nchunks) { lo = std::min(lo, w.chunk0); hi = std::max(hi, w.chunk0 + w.nchunks); }
+        }
+        for (uint32_t c = 0; c < 3; ++c) { RegionWin& w = region_win[t.idx][c][D]; w.chunk0 = lo < hi ? lo : 0; w.nchunks = lo < hi ? hi - lo : 0; }
+        if (forward) {
+          uint32_t rl = UINT32_MAX, rh = 0;
+          for (uint32_t c = 0; c < 3; ++c) if (region_rows[t.idx][c].hi > region_rows[t.idx][c].lo) { rl = std::min(rl, region_rows[t.idx][c].lo); rh = std::max(rh, region_rows[t.idx][c].hi); }
+          for (uint32_t c = 0; c < 3; ++c) { region_rows[t.idx][c].lo = rl < rh ? rl : 0; region_rows[t.idx][c].hi = rl < rh ? rh : 0; }
+        }
+      }
+    }
+  }
+}
+
 void CodecBase::build_dwt_jobs(bool forward) {
   const Params& P = params;
+  if (region.on()) {
+    if (!tile_mask.empty()) fail(0x000B0045, "a tile mask and row regions cannot be combined");
+    if (skip_read || skip_recon) fail(0x000B0046, "reduced-resolution decoding is not available with row regions");
+    plan_region(forward);
+  } else { region_win.clear(); region_rows.clear(); region_owner.clear(); region_blocks.clear(); }
   const uint32_t nc = P.num_comps();
   // level li counts decompositions from the full resolution down; every component follows its own
   // coding style (COC): component c takes part in levels li < max(1, D_c) with resolution D_c - li
@@ -198,11 +352,16 @@ void CodecBase::build_dwt_jobs(bool forward) {
             j.band_scale[i][0] = forward ? bg.delta_inv : bg.delta;
           }
         }
-        const bool stream = !wide && !j.nodwt && j.hsplit && j.vsplit && P.wavelet_of(c) <= 1 && j.w >= 2 && j.h >= 2 && !no_stream_dwt && layout.coef_words < (1ull << 30) && img_bytes < (1ull << 32);   // 32-bit byte offsets in the stream kernels
+        const bool stream = !j.nodwt && level_streams(*this, P, c, rg);   // 32-bit byte offsets in the stream kernels
         uint32_t gi, n;
         if (stream) {
           gi = gw + (j.first ? (k == 3 ? 0u : 1u) : 2u);
           dwt_stream_tiling(j.x0, j.y0, j.w, j.h, rev, forward, j.tiles_x, j.tiles_y, j.chunk_rows, n);
+          if (region.on() && !conv_only && !region_win[t.idx][c][r].full) {      // this rank's window of row chunks
+            const RegionWin& rw = region_win[t.idx][c][r];
+            const uint32_t per_row = j.tiles_y ? n / j.tiles_y : 0;
+            j.chunk0 = rw.chunk0; j.tiles_y = rw.nchunks; n = per_row * rw.nchunks;
+          }
         } else {
           gi = gw + 3;
           dwt_tiling(j.x0, j.y0, j.w, j.h, j.tiles_x, j.tiles_y);
@@ -278,6 +437,7 @@ void Encoder::configure(const Params& p, uint32_t sample_type) {
               e.slot_off = slot; e.slot_cap = (uint32_t)cap;
               slot += cap;
               if (!tile_wanted(t.idx)) { e.w = e.h = 0; }                  // another rank's tile: nothing to code
+              if (region.on() && !region_blocks[bg.block_base + by * bg.nbw + bx]) { e.w = e.h = 0; }   // another rank's rows
               if (!no_fast_blocks && !wide && enc_block_is_fast(e)) { e.flags |= ENC_FLAG_FAST; ++num_fast_blocks; }
             }
         }
@@ -446,9 +606,11 @@ size_t Encoder::encode(const void* const* planes, const uint32_t* strides, bool 
   }
   mark(1);
   uint32_t nb = (uint32_t)h_blocks.size();
-  // 2. transform + block coding
+  // 2. transform + block coding (row regions, ojb_shard.cpp: PHASE_FRONT stops after it -- lengths and bytes of this
+  // rank's blocks then travel to the writer --, PHASE_BACK on the writer starts behind it)
   auto enqueue_front = [&] {
   CK(cudaMemsetAsync(d_status.p, 0, 16, stream));
+  if (phase != PHASE_BACK)
   for (size_t li = 0; li < jobs.size(); ++li)
     for (const JobGroup& g : jobs[li]) {
       if (g.stream)
@@ -460,6 +622,7 @@ size_t Encoder::encode(const void* const* planes, const uint32_t* strides, bool 
       ++last_launches;
     }
   mark(2);
+  if (phase == PHASE_BACK) { mark(3); return; }
   if (serial_block_encoder() || max_block_w > 64 || wide)
     launch_ht_encode_serial(d_blocks.as<EncBlock>(), nb, num_fast_blocks, max_block_w, d_coef.as<uint32_t>(), d_slots.as<uint8_t>(),
                             d_results.as<EncResult>(), d_tables_enc.as<uint16_t>(), d_status.as<uint32_t>(), stream, wide, &side);
@@ -469,6 +632,18 @@ size_t Encoder::encode(const void* const* planes, const uint32_t* strides, bool 
   last_launches += (serial_block_encoder() || max_block_w > 64) ? (num_fast_blocks ? 1 : 0) + (num_fast_blocks < nb ? 1 : 0) : 1;
   mark(3);
   };
+  if (phase == PHASE_FRONT) {
+    enqueue_front();
+    launch_ctrl_copy(h_status.p, d_status.p, 16, stream); ++last_launches;
+    mark(4);
+    CK(cudaStreamSynchronize(stream));
+    CK(cudaGetLastError());
+    collect(5);
+    status_flags = h_status.as<uint32_t>()[0];
+    if (status_flags & 2u) fail(0x00020001, "mel encoder's buffer is full");
+    if (status_flags & 1u) fail(0x00020005, "block encoder's output slot is full");
+    return 0;
+  }
   if (device_headers) {
     // packet headers, markers and layout by kernels; the host only learns the length (and, for a host buffer, waits
     // for it before asking for the copy)
@@ -495,7 +670,7 @@ size_t Encoder::encode(const void* const* planes, const uint32_t* strides, bool 
       };
       // resident form (frame already in HBM, codestream stays there): nothing in the call depends on host data, so
       // the whole thing replays as a graph
-      if (planes == nullptr && out_on_device)
+      if (planes == nullptr && out_on_device && phase == PHASE_ALL)
         run_frame({ (uint64_t)(size_t)dev_out, cap, (uint64_t)nb, (uint64_t)num_fast_blocks, (uint64_t)(size_t)d_slots.p, (uint64_t)(size_t)d_coef.p }, enqueue_all);
       else enqueue_all();
       CK(cudaStreamSynchronize(stream));
@@ -758,6 +933,7 @@ void Decoder::read_headers(const uint8_t* data, size_t len, uint32_t sample_type
     sig.assign(data, data + sot);
     sig.push_back((uint8_t)sample_type);
     sig.insert(sig.end(), tile_mask.begin(), tile_mask.end());
+    if (region.on()) { sig.push_back(0xA5); sig.push_back((uint8_t)region.rank); sig.push_back((uint8_t)region.world); }
   }
   if (sig == header_sig && !layout.tiles.empty()) return;
   // everything below can throw (precision check, geometry, cudaMalloc, container check): the signature
@@ -781,6 +957,7 @@ void Decoder::read_headers(const uint8_t* data, size_t len, uint32_t sample_type
   block_res.assign(layout.num_blocks, 0);
   block_wanted.clear();
   if (!tile_mask.empty()) block_wanted.assign(layout.num_blocks, 0);
+  if (region.on()) block_wanted = region_blocks;           // row regions: the blocks this rank's rows depend on (plan_region)
   size_t scratch = 0;
   for (const TileGeom& t : layout.tiles)
     for (const TileCompGeom& tc : t.comps)
@@ -793,7 +970,7 @@ void Decoder::read_headers(const uint8_t* data, size_t len, uint32_t sample_type
               Rect r = bg.block_rect(bx, by);
               DecBlock& d = h_dec_proto[bg.block_base + by * bg.nbw + bx];
               block_res[bg.block_base + by * bg.nbw + bx] = (uint8_t)(tc.res.size() - 1 - rg.res_num);
-              if (!block_wanted.empty()) block_wanted[bg.block_base + by * bg.nbw + bx] = tile_wanted(t.idx) ? 1 : 0;
+              if (!tile_mask.empty()) block_wanted[bg.block_base + by * bg.nbw + bx] = tile_wanted(t.idx) ? 1 : 0;
               memset(&d, 0, sizeof(d));
               d.dst_off = bg.plane_off + bg.plane_pad_x + (uint64_t)(r.y0 - bg.rect.y0) * bg.plane_stride + (r.x0 - bg.rect.x0);
               d.stride = bg.plane_stride; d.w = (uint16_t)r.w; d.h = (uint16_t)r.h;

@@ -87,6 +87,25 @@ public:
   // and byte offsets are the single-encoder ones; DWT jobs, code-blocks and packets of the other tiles are skipped.
   std::vector<uint8_t> tile_mask;
   bool tile_wanted(uint32_t t) const { return tile_mask.empty() || (t < tile_mask.size() && tile_mask[t] != 0); }
+  // one image over several GPUs by ROW REGIONS (ojb_shard.cpp, partition "regions"): a tile-component is
+  // cut into `world` horizontal slabs.  Encoder: rank g codes the code-blocks whose first row falls into slab g and runs,
+  // at every decomposition level, only the row chunks of the streaming DWT kernels those blocks depend on -- the input
+  // rows it needs are its slab plus a halo of about 2 (2^D - 1) rows (5/3) or 4 (2^D - 1) rows (9/7) each side, the
+  // exact footprint of one lifting step reaching +-1 (ojph_transform.cpp:376-390), so no coefficient crosses a rank
+  // boundary in mid-pipeline.  Decoder: rank g delivers the image rows of slab g, runs the synthesis chunks that
+  // produce them and decodes every code-block those chunks read (its own and a halo of its neighbours').  The
+  // geometry, arenas and block tables stay those of the whole image, as with a tile mask.  A tile-component whose
+  // levels do not all run on the streaming kernels (degenerate sizes, DFS / ATK, 64-bit path) keeps whole-plane
+  // transforms on every rank; only its block coding is shared.
+  struct RegionSpec { uint32_t rank = 0, world = 0; bool on() const { return world > 1; } } region;
+  struct RegionWin { uint32_t chunk0 = 0, nchunks = 0; bool full = true; };   // row chunks of one level's job; full: all of them
+  std::vector<std::vector<std::vector<RegionWin>>> region_win;   // [tile][comp][resolution being split / rebuilt]
+  std::vector<uint8_t> region_owner;   // encoder: the rank that codes block b
+  std::vector<uint8_t> region_blocks;  // the blocks this object works on (encoder: the ones it owns; decoder: all its rows depend on)
+  struct RowSpan { uint32_t lo = 0, hi = 0; };       // rows [lo, hi) in absolute tile-component coordinates
+  std::vector<std::vector<RowSpan>> region_rows;     // [tile][comp]: encoder: image rows this rank reads; decoder: rows it delivers
+  static RowSpan region_slab(const Rect& tc, uint32_t g, uint32_t world);
+  void plan_region(bool forward);
   bool no_stream_dwt = false;          // force the general shared-memory DWT kernels (tests)
   bool no_fast_blocks = getenv("OJB_NO_FAST_BLOCKS") != nullptr;   // force the general block-coder kernels (tests, A/B)
 };
@@ -100,6 +119,9 @@ public:
   size_t encode(const void* const* planes, const uint32_t* strides, bool planes_on_device,
                 uint8_t* out, size_t out_cap, bool out_on_device);
   uint32_t status_flags = 0;
+  // row regions (ojb_shard.cpp): the frame call split at the point where code-block bytes change hands
+  enum Phase : uint32_t { PHASE_ALL = 0, PHASE_FRONT = 1, PHASE_BACK = 2 };
+  uint32_t phase = PHASE_ALL;
   // line-based front end (ojph::codestream::exchange): lines go to a pinned frame
   PinnedBuf h_frame;
   std::vector<uint32_t> line_cur;

@@ -134,6 +134,8 @@ struct DwtJob {
   uint32_t nlt_mask;      // bit i: NLT type 3 on (signed) component i of the job: v < 0 -> -v - (2^(B-1) + 1)
   uint32_t tiles_x, tiles_y;   // CTA tiling of this job
   uint32_t chunk_rows;         // streaming kernels: output rows per warp chunk (even)
+  uint32_t chunk0;             // streaming kernels: first row chunk of the launch (row-region sharding runs a window of
+                               // tiles_y chunks starting here; 0 otherwise)
   uint32_t cta_base;      // first CTA index of this job in the launch
 };
 

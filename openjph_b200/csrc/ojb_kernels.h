@@ -84,4 +84,13 @@ uint32_t packet_header_launches(const HdrPlanDev& plan);
 void launch_gather_blocks(const EncBlock* blocks, const EncResult* results, const uint64_t* dst_off,
                           uint32_t nblocks, const uint8_t* slots, uint8_t* out, cudaStream_t st);
 
+// row regions (ojb_shard.cpp).  launch_block_offsets: off[b] = where block b's bytes start when all blocks are packed
+// back to back in block order (head piece, then tail piece), total[0] = their sum -- launch_gather_blocks with these
+// offsets packs.  launch_scatter_blocks: on the writer, the blocks owned by `rank` go from that rank's packed bytes
+// into their slots and their lengths into the writer's result array.
+void launch_block_offsets(const EncResult* results, uint32_t nblocks, uint64_t* off, uint64_t* total, cudaStream_t st);
+void launch_scatter_blocks(const EncBlock* blocks, const uint8_t* owner, uint32_t rank, const EncResult* results_in,
+                           const uint64_t* off, uint32_t nblocks, const uint8_t* packed, uint8_t* slots,
+                           EncResult* results_out, cudaStream_t st);
+
 } // namespace ojb

@@ -161,6 +161,10 @@ struct ojb_shard {
   PinnedBuf h_hdr;
   float ms_encode = 0, ms_gather = 0;       // last call: this rank's codec time, exchange + assembly + D2H
   size_t final_len = 0;                     // writer: length of the codestream in d_final
+  // partition: 0 = tiles (t % world), 1 = row regions of every tile-component (CodecBase::region, ojb_codec.h)
+  uint32_t partition = 0;
+  DeviceBuf d_pack, d_off, d_owner;         // regions: [lengths | packed block bytes] of this rank, block offsets, block owners
+  PinnedBuf h_tot;
 };
 
 static thread_local char g_serr[1024] = "";
@@ -227,11 +231,180 @@ int ojb_shard_enc_configure(ojb_shard* s, const ojb_params* p, uint32_t sample_t
     s->full = P; s->full.finalize_for_encode();
     Layout L; L.build(s->full);
     const uint32_t ntiles = (uint32_t)L.tiles.size();
-    s->enc.tile_mask.assign(ntiles, 0);
-    for (uint32_t t = 0; t < ntiles; ++t) s->enc.tile_mask[t] = (t % s->comm->world == s->comm->rank) ? 1 : 0;
+    s->enc.tile_mask.clear(); s->enc.region = CodecBase::RegionSpec();
+    if (s->partition == 1 && s->comm->world > 1) {
+      if (s->comm->world > 255) fail(0x000B0044, "row regions: at most 255 ranks");
+      s->enc.region.rank = s->comm->rank; s->enc.region.world = s->comm->world;
+    } else {
+      s->enc.tile_mask.assign(ntiles, 0);
+      for (uint32_t t = 0; t < ntiles; ++t) s->enc.tile_mask[t] = (t % s->comm->world == s->comm->rank) ? 1 : 0;
+    }
     s->enc.configure(P, sample_type);
+    if (s->enc.region.on()) {
+      s->d_owner.reserve(std::max<size_t>(1, s->enc.region_owner.size()));
+      if (!s->enc.region_owner.empty())
+        cuda_check(cudaMemcpy(s->d_owner.p, s->enc.region_owner.data(), s->enc.region_owner.size(), cudaMemcpyHostToDevice), "block owners");
+    }
     s->enc_ready = true;
   });
+}
+
+// ---- row regions --------------------------------------------------------------------------------------------------
+// Encode: every rank uploads the image rows its slab's coefficients depend on (slab + halo), runs its window of every
+// DWT level and codes its own code-blocks (Encoder::PHASE_FRONT).  Then the one exchange of the path: each rank packs
+// its blocks' bytes back to back behind the per-block lengths and sends them to the writer (sizes by one 8-byte
+// allgather), the writer drops them into its slot arena as if it had coded them (scatter_blocks_kernel) and finishes
+// as a single encoder does: packet headers, markers and layout on the device (Encoder::PHASE_BACK).  Byte-identical
+// to the one-GPU / reference codestream -- also for a single-tile image, which tile sharding cannot split.
+static void region_upload(ojb_shard* s, const void* const* planes, const uint32_t* strides) {
+  Encoder& E = s->enc; const Params& P = E.params;
+  const uint32_t nc = P.num_comps(), es = esize(s->sample_type);
+  for (const TileGeom& t : E.layout.tiles)
+    for (uint32_t c = 0; c < nc; ++c) {
+      const Rect& r = t.comps[c].rect;
+      const CodecBase::RowSpan rows = E.region_rows[t.idx][c];
+      if (r.w == 0 || rows.hi <= rows.lo) continue;
+      const uint32_t cx0 = div_ceil(P.XOsiz, P.comps[c].dx), cy0 = div_ceil(P.YOsiz, P.comps[c].dy);
+      const uint32_t st = strides ? strides[c] : E.img_w[c];
+      const size_t so = ((size_t)(rows.lo - cy0) * st + (r.x0 - cx0)) * es, dof = ((size_t)(rows.lo - cy0) * E.img_w[c] + (r.x0 - cx0)) * es;
+      cuda_check(cudaMemcpy2DAsync(E.d_image.as<uint8_t>() + E.img_off[c] + dof, (size_t)E.img_w[c] * es,
+                                   (const uint8_t*)planes[c] + so, (size_t)st * es, (size_t)r.w * es, rows.hi - rows.lo,
+                                   cudaMemcpyHostToDevice, E.stream), "region upload");
+    }
+}
+
+static void region_encode(ojb_shard* s, const void* const* planes, const uint32_t* strides,
+                          uint8_t* out, uint64_t out_cap, uint64_t* out_len, bool encode_only_upload) {
+  Encoder& E = s->enc; Comm& C = *s->comm;
+  const uint32_t nb = (uint32_t)E.h_blocks.size();
+  cudaEvent_t e0 = E.ev[CodecBase::EV_MAX - 3], e1 = E.ev[CodecBase::EV_MAX - 2], e2 = E.ev[CodecBase::EV_MAX - 1];
+  cudaEventRecord(e0, E.stream);
+  if (planes) region_upload(s, planes, strides);
+  if (encode_only_upload) { cuda_check(cudaStreamSynchronize(E.stream), "region upload"); return; }
+  // 1. this rank's share of the transform and of the block coding
+  E.phase = Encoder::PHASE_FRONT;
+  try { E.encode(nullptr, nullptr, true, nullptr, 0, true); } catch (...) { E.phase = Encoder::PHASE_ALL; throw; }
+  E.phase = Encoder::PHASE_ALL;
+  cudaEventRecord(e1, E.stream);
+  // 2. how many bytes that made; every rank learns every total
+  s->d_off.reserve(((size_t)nb + 4) * 8);
+  s->h_tot.reserve(64);
+  uint64_t* d_total = s->d_off.as<uint64_t>() + (((size_t)nb + 1) & ~(size_t)1);      // 16-byte aligned (ctrl copy)
+  launch_block_offsets(E.d_results.as<EncResult>(), nb, s->d_off.as<uint64_t>(), d_total, E.stream);
+  launch_ctrl_copy(s->h_tot.p, d_total, 16, E.stream);
+  cuda_check(cudaStreamSynchronize(E.stream), "block totals");
+  std::vector<uint64_t> mine(1, s->h_tot.as<uint64_t>()[0]), tot(C.world, 0);
+  C.allgather(mine.data(), tot.data(), 8);
+  const size_t meta = (size_t)nb * sizeof(EncResult);
+  std::vector<Xfer> sends, recvs;
+  std::vector<size_t> roff(C.world + 1, 0);
+  if (C.rank != s->writer) {
+    // 3. [lengths of all blocks | this rank's bytes, packed] -> writer
+    s->d_pack.reserve(meta + (size_t)mine[0] + 64);
+    if (nb) cuda_check(cudaMemcpyAsync(s->d_pack.p, E.d_results.p, meta, cudaMemcpyDeviceToDevice, E.stream), "lengths");
+    launch_gather_blocks(E.d_blocks.as<EncBlock>(), E.d_results.as<EncResult>(), s->d_off.as<uint64_t>(), nb, E.d_slots.as<uint8_t>(),
+                         s->d_pack.as<uint8_t>() + meta, E.stream);
+    sends.push_back(Xfer{ s->writer, s->d_pack.p, meta + (size_t)mine[0] });
+  } else {
+    for (uint32_t r = 0; r < C.world; ++r) roff[r + 1] = roff[r] + (r == C.rank ? 0 : ((meta + (size_t)tot[r] + 64 + 255) & ~(size_t)255));
+    s->d_stage.reserve(roff[C.world] + 64);
+    for (uint32_t r = 0; r < C.world; ++r)
+      if (r != C.rank) recvs.push_back(Xfer{ r, s->d_stage.as<uint8_t>() + roff[r], meta + (size_t)tot[r] });
+  }
+  C.exchange(sends, recvs, E.stream);
+  size_t total = 0;
+  if (C.rank == s->writer) {
+    // 4. the other ranks' blocks into the slot arena, then the back half of a single encoder's frame call
+    for (uint32_t r = 0; r < C.world; ++r) {
+      if (r == C.rank) continue;
+      const uint8_t* base = s->d_stage.as<uint8_t>() + roff[r];
+      launch_block_offsets(reinterpret_cast<const EncResult*>(base), nb, s->d_off.as<uint64_t>(), d_total, E.stream);
+      launch_scatter_blocks(E.d_blocks.as<EncBlock>(), s->d_owner.as<uint8_t>(), r, reinterpret_cast<const EncResult*>(base),
+                            s->d_off.as<uint64_t>(), nb, base + meta, E.d_slots.as<uint8_t>(), E.d_results.as<EncResult>(), E.stream);
+    }
+    uint64_t sum = 0; for (uint32_t r = 0; r < C.world; ++r) sum += tot[r];
+    const size_t cap = (size_t)sum + (size_t)nb * 24 + E.fixed_blob.size() + E.main_header.size() + (1u << 16);
+    s->d_final.reserve(cap + 64);
+    E.phase = Encoder::PHASE_BACK;
+    try { total = E.encode(nullptr, nullptr, true, s->d_final.as<uint8_t>(), cap, true); } catch (...) { E.phase = Encoder::PHASE_ALL; throw; }
+    E.phase = Encoder::PHASE_ALL;
+    if (out) {
+      if (total > out_cap) fail(0x000B0030, "output buffer too small: need %zu bytes, have %zu", total, (size_t)out_cap);
+      cuda_check(cudaMemcpyAsync(out, s->d_final.p, total, cudaMemcpyDeviceToHost, E.stream), "codestream D2H");
+    }
+    s->final_len = total;
+  }
+  if (out_len) *out_len = total;
+  cudaEventRecord(e2, E.stream);
+  cuda_check(cudaStreamSynchronize(E.stream), "region encode");
+  cudaEventElapsedTime(&s->ms_encode, e0, e1); cudaEventElapsedTime(&s->ms_gather, e1, e2);
+}
+
+// Decode: the codestream is broadcast, every rank parses the headers, decodes the blocks its slab's rows depend on,
+// runs its window of every synthesis level and sends the rows of its slab to the writer.
+static void region_decode(ojb_shard* s, uint32_t sample_type, uint32_t writer_rank, void* const* planes, const uint32_t* strides,
+                          bool keep_on_device, cudaEvent_t e1) {
+  Decoder& D = s->dec; Comm& C = *s->comm;
+  D.decode(nullptr, nullptr, true);
+  cudaEventRecord(e1, D.stream);
+  const Params& P = D.params;
+  const uint32_t nc = P.num_comps(), es = esize(sample_type);
+  // every rank's slab of every tile-component, packed tile after tile, component after component
+  std::vector<size_t> roff(C.world + 1, 0);
+  for (uint32_t r = 0; r < C.world; ++r) {
+    size_t b = 0;
+    for (const TileGeom& t : D.layout.tiles)
+      for (uint32_t c = 0; c < nc; ++c) {
+        const CodecBase::RowSpan sp = CodecBase::region_slab(t.comps[c].rect, r, C.world);
+        b += (size_t)t.comps[c].rect.w * (sp.hi - sp.lo) * es;
+      }
+    roff[r + 1] = roff[r] + ((b + 255) & ~(size_t)255);
+  }
+  auto plane_pos = [&](uint32_t x0, uint32_t y0, uint32_t c, uint32_t pitch) {
+    const uint32_t cx0 = div_ceil(P.XOsiz, P.comps[c].dx), cy0 = div_ceil(P.YOsiz, P.comps[c].dy);
+    return ((size_t)(y0 - cy0) * pitch + (x0 - cx0)) * es;
+  };
+  // walk the slab rectangles of rank r: f(tile-component rectangle, rows, offset in the rank's packed piece)
+  auto for_slabs = [&](uint32_t r, auto&& f) {
+    size_t o = 0;
+    for (const TileGeom& t : D.layout.tiles)
+      for (uint32_t c = 0; c < nc; ++c) {
+        const Rect& rc = t.comps[c].rect;
+        const CodecBase::RowSpan sp = CodecBase::region_slab(rc, r, C.world);
+        if (rc.w == 0 || sp.hi <= sp.lo) continue;
+        f(c, rc, sp, o);
+        o += (size_t)rc.w * (sp.hi - sp.lo) * es;
+      }
+  };
+  std::vector<Xfer> sends, recvs;
+  s->d_stage.reserve(roff[C.world] + 64);
+  if (C.rank != writer_rank) {
+    for_slabs(C.rank, [&](uint32_t c, const Rect& rc, const CodecBase::RowSpan& sp, size_t o) {
+      cuda_check(cudaMemcpy2DAsync(s->d_stage.as<uint8_t>() + roff[C.rank] + o, (size_t)rc.w * es,
+                                   D.d_image.as<uint8_t>() + D.img_off[c] + plane_pos(rc.x0, sp.lo, c, D.img_w[c]), (size_t)D.img_w[c] * es,
+                                   (size_t)rc.w * es, sp.hi - sp.lo, cudaMemcpyDeviceToDevice, D.stream), "slab pack");
+    });
+    if (roff[C.rank + 1] > roff[C.rank]) sends.push_back(Xfer{ writer_rank, s->d_stage.as<uint8_t>() + roff[C.rank], roff[C.rank + 1] - roff[C.rank] });
+  } else {
+    for (uint32_t r = 0; r < C.world; ++r)
+      if (r != C.rank && roff[r + 1] > roff[r]) recvs.push_back(Xfer{ r, s->d_stage.as<uint8_t>() + roff[r], roff[r + 1] - roff[r] });
+  }
+  C.exchange(sends, recvs, D.stream);
+  if (C.rank != writer_rank) return;
+  for (uint32_t r = 0; r < C.world; ++r)
+    for_slabs(r, [&](uint32_t c, const Rect& rc, const CodecBase::RowSpan& sp, size_t o) {
+      const uint8_t* src = (r == C.rank) ? D.d_image.as<uint8_t>() + D.img_off[c] + plane_pos(rc.x0, sp.lo, c, D.img_w[c])
+                                         : s->d_stage.as<uint8_t>() + roff[r] + o;
+      const size_t spitch = (r == C.rank) ? (size_t)D.img_w[c] * es : (size_t)rc.w * es;
+      if (keep_on_device && r != C.rank)
+        cuda_check(cudaMemcpy2DAsync(D.d_image.as<uint8_t>() + D.img_off[c] + plane_pos(rc.x0, sp.lo, c, D.img_w[c]), (size_t)D.img_w[c] * es,
+                                     src, spitch, (size_t)rc.w * es, sp.hi - sp.lo, cudaMemcpyDeviceToDevice, D.stream), "slab unpack");
+      if (planes) {
+        const uint32_t st = strides ? strides[c] : D.img_w[c];
+        cuda_check(cudaMemcpy2DAsync((uint8_t*)planes[c] + plane_pos(rc.x0, sp.lo, c, st), (size_t)st * es, src, spitch,
+                                     (size_t)rc.w * es, sp.hi - sp.lo, cudaMemcpyDeviceToHost, D.stream), "slab D2H");
+      }
+    });
 }
 
 // planes: the WHOLE image on the host (every rank passes the same pointers or at least valid memory for its own
@@ -240,6 +413,7 @@ static int shard_encode(ojb_shard* s, const void* const* planes, const uint32_t*
                         uint8_t* out, uint64_t out_cap, uint64_t* out_len, bool encode_only_upload) {
   return sguarded(s, [&] {
     if (!s->enc_ready) fail(0x000B0013, "encoder is not configured");
+    if (s->enc.region.on()) { region_encode(s, planes, strides, out, out_cap, out_len, encode_only_upload); return; }
     Encoder& E = s->enc; Comm& C = *s->comm;
     const Params& P = E.params;
     const uint32_t nc = P.num_comps(), es = esize(s->sample_type);
@@ -381,6 +555,18 @@ static int shard_decode(ojb_shard* s, const uint8_t* cs, bool cs_on_device, uint
     cuda_check(cudaStreamSynchronize(D.stream), "codestream broadcast");
     // 2. headers from device memory.  The tile mask follows from the tile count: a first frame (or a change of
     // geometry) is parsed once to learn it and then again with the mask; later frames hit the cached geometry.
+    if (s->partition == 1 && C.world > 1) {
+      if (C.world > 255) fail(0x000B0044, "row regions: at most 255 ranks");
+      D.tile_mask.clear(); D.region.rank = C.rank; D.region.world = C.world;
+      D.read_headers_device(s->d_cs.as<uint8_t>(), n, sample_type);
+      if (info) { FrameInfo fi; D.info(fi); memcpy(info, &fi, sizeof(fi)); }
+      region_decode(s, sample_type, writer_rank, planes, strides, keep_on_device, e1);
+      cudaEventRecord(e2, D.stream);
+      cuda_check(cudaStreamSynchronize(D.stream), "shard decode");
+      cudaEventElapsedTime(&s->ms_encode, e0, e1); cudaEventElapsedTime(&s->ms_gather, e1, e2);
+      return;
+    }
+    D.region = CodecBase::RegionSpec();
     D.read_headers_device(s->d_cs.as<uint8_t>(), n, sample_type);
     const uint32_t ntiles = (uint32_t)D.layout.tiles.size();
     if (D.tile_mask.size() != ntiles) {
@@ -507,6 +693,19 @@ int ojb_shard_gatherv(ojb_shard* s, const void* dev, uint64_t bytes, uint32_t wr
   });
 }
 
+int ojb_shard_set_partition(ojb_shard* s, uint32_t kind) {
+  return sguarded(s, [&] {
+    if (kind > 1) fail(0x000B0047, "unknown partition %u (0: tiles, 1: row regions)", kind);
+    if (kind != s->partition) { s->partition = kind; s->enc_ready = false; }
+  });
+}
+uint32_t ojb_shard_region_rows(ojb_shard* s, uint32_t comp, uint32_t* lo, uint32_t* hi) {
+  // image rows of component `comp` (tile 0) this rank's encoder reads: its slab plus the halo
+  if (!s->enc_ready || !s->enc.region.on() || s->enc.region_rows.empty() || comp >= s->enc.region_rows[0].size()) return 0;
+  if (lo) *lo = s->enc.region_rows[0][comp].lo;
+  if (hi) *hi = s->enc.region_rows[0][comp].hi;
+  return 1;
+}
 void ojb_shard_timings(ojb_shard* s, float* ms2) { ms2[0] = s->ms_encode; ms2[1] = s->ms_gather; }
 uint32_t ojb_shard_rank(ojb_shard* s) { return s->comm->rank; }
 uint32_t ojb_shard_world(ojb_shard* s) { return s->comm->world; }

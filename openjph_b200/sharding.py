@@ -420,6 +420,20 @@ class NativeShard:
             self.L.ojb_shard_destroy(self.h)
             self.h = None
 
+    def set_partition(self, kind):
+        """0 / "tiles": rank r codes the tiles t % world == r (default); 1 / "regions": every tile-component is cut into
+        `world` row slabs (input halo, no mid-pipeline exchange) -- this also splits a single-tile image.  Call it on
+        every rank before configure() / decode()."""
+        k = {"tiles": 0, "regions": 1}.get(kind, kind)
+        self._check(self.L.ojb_shard_set_partition(self.h, int(k)))
+
+    def region_rows(self, comp=0):
+        """row regions, after configure(): image rows [lo, hi) of component comp this rank's encoder reads"""
+        lo, hi = C.c_uint32(), C.c_uint32()
+        if not self.L.ojb_shard_region_rows(self.h, comp, C.byref(lo), C.byref(hi)):
+            return None
+        return int(lo.value), int(hi.value)
+
     def configure(self, p, sample_type=cs_mod.I32, writer=0):
         self.p, self.sample_type, self.writer = p, sample_type, writer
         self._check(self.L.ojb_shard_enc_configure(self.h, C.byref(p), sample_type, writer))

