@@ -216,7 +216,8 @@ def sharded_block(a, rank, world, L, ob, np, torch, dist, C, _lib, peak):
     rank 0 produces (itself byte-identical to the reference, tests/), and the round trip."""
     from openjph_b200 import sharding
     steps = max(2, min(a.steps, 5))
-    out = {"transport": "NCCL send/recv + allgather inside libojph_b200.so (ojb_shard.cpp), tile t on rank t % N", "entries": []}
+    out = {"transport": "NCCL send/recv + allgather inside libojph_b200.so (ojb_shard.cpp); tiles: tile t on rank t % N; row regions: "
+                        "slab g of every tile-component on rank g", "entries": []}
 
     def timed_loop(fn, n):
         dist.barrier(); torch.cuda.synchronize()
@@ -228,7 +229,7 @@ def sharded_block(a, rank, world, L, ob, np, torch, dist, C, _lib, peak):
         t = torch.tensor([dt], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()) / n * 1e3
 
-    def one(name, params, frame, lossless):
+    def one(name, params, frame, lossless, partition=0):
         st = ob.U8 if frame[0].dtype == np.uint8 else ob.U16
         pin = [torch.empty(f.shape, dtype=torch.uint8 if f.dtype == np.uint8 else torch.uint16, pin_memory=True) for f in frame]
         for t, f in zip(pin, frame):
@@ -247,6 +248,8 @@ def sharded_block(a, rank, world, L, ob, np, torch, dist, C, _lib, peak):
             if rc != 0:
                 raise RuntimeError(L.ojb_shard_last_error().decode())
 
+        if partition:
+            ck(L.ojb_shard_set_partition(sh.h, partition))
         ck(L.ojb_shard_enc_configure(sh.h, C.byref(params), st, 0))
 
         def enc():
@@ -258,7 +261,16 @@ def sharded_block(a, rank, world, L, ob, np, torch, dist, C, _lib, peak):
         enc()
         cs_len = int(n.value)
         dec()
-        e = {"workload": name, "ranks": world}
+        e = {"workload": name, "ranks": world, "partition": "row regions" if partition else "tiles"}
+        if partition:
+            lo, hi = C.c_uint32(), C.c_uint32()
+            rows = [0, 0]
+            if L.ojb_shard_region_rows(sh.h, 0, C.byref(lo), C.byref(hi)):
+                rows = [int(lo.value), int(hi.value)]
+            rt = torch.tensor(rows, dtype=torch.int64, device="cuda")
+            allr = [torch.zeros_like(rt) for _ in range(world)]
+            dist.all_gather(allr, rt)
+            e["input_rows_per_rank"] = [[int(x[0]), int(x[1])] for x in allr]      # slab + halo each rank reads
         # the same image on one GPU (rank 0 alone): reference point of the strong scaling, and the byte-identity check
         one_gpu_ms = None
         if rank == 0:
@@ -345,6 +357,12 @@ def sharded_block(a, rank, world, L, ob, np, torch, dist, C, _lib, peak):
         ob.make_params(W, H, 3, 16, num_decomps=5, reversible=True, color_transform=True, tile=(4096, 4096)), make_frame(W, H, 9, 3, 16), True)
     one("headline frame as %d tiles of %dx4096 (12-bit, 5/3 + RCT, 5 levels)" % ((W // tile_w) * 2, tile_w),
         ob.make_params(W, H, NC, BD, num_decomps=LEVELS, reversible=True, color_transform=True, tile=(tile_w, 4096)), make_frame(W, H, 1234), True)
+
+    # the headline frame as it is -- ONE tile -- cut into N row regions: input halo, no mid-pipeline exchange,
+    # code-block bytes gathered to rank 0 which writes the packet headers; byte-identical to the one-GPU codestream
+    if os.environ.get("OJB_BENCH_REGIONS", "1") != "0":
+        one("headline frame, single tile, as %d row regions (12-bit, 5/3 + RCT, 5 levels)" % world,
+            ob.make_params(W, H, NC, BD, num_decomps=LEVELS, reversible=True, color_transform=True), make_frame(W, H, 1234), True, partition=1)
 
     # cfg5: a batch of 64 independent 4K frames, frame f on rank f % N, codestreams gathered to rank 0 over NCCL
     try:

@@ -14,7 +14,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 # (parameters, writer rank).  Heights are a few slabs of 128 rows; five levels make the halo 62 (5/3) / 124 (9/7)
 # rows; odd offsets move the lifting parity; the tiled case cuts every tile; the last one is too small to cut
-# (ranks without rows) and the DFS one keeps whole-plane transforms (general kernels) and shares block coding only.
+# (ranks without rows); the tall one is for eight ranks; the DFS and the 30-bit (64-bit coefficient path) ones keep
+# whole-plane transforms on every rank (general kernels) and share the block coding only.
 REGION_CASES = [
     (dict(width=200, height=512, num_comps=3, bit_depth=8, num_decomps=5, reversible=True, color_transform=True), 0),
     (dict(width=333, height=700, num_comps=1, bit_depth=12, num_decomps=4, reversible=True, offset=(5, 3), block=(32, 32)), 1),
@@ -24,6 +25,9 @@ REGION_CASES = [
     (dict(width=300, height=600, num_comps=3, bit_depth=8, num_decomps=3, reversible=True, color_transform=True,
           tile=(160, 384), tilepart_div=1), 1),
     (dict(width=96, height=100, num_comps=1, bit_depth=8, num_decomps=2, reversible=True), 0),
+    (dict(width=80, height=1100, num_comps=1, bit_depth=8, num_decomps=4, reversible=True, block=(32, 32)), 0),
+    (dict(width=120, height=400, num_comps=1, bit_depth=8, num_decomps=3, reversible=True, decomp="BHB", block=(32, 32)), 1),
+    (dict(width=70, height=300, num_comps=1, bit_depth=30, num_decomps=3, reversible=True, block=(32, 32)), 0),
 ]
 
 
@@ -37,6 +41,18 @@ def _worker(rank, world, port, q, which):
     try:
         L = emu.emu_lib(build=False)
         ok, notes = True, []
+
+        def one_encoder(p, fr):
+            # the reference's codestream; it has no writer for DFS segments (this library's extension, checked against
+            # the reference's DECODER in test_part2_structures.py): there the single-process encoder is the yardstick
+            if p.dfs_num_levels == 0:
+                return refharness.encode(p, fr)
+            enc = ob.Encoder(p, ob.I32, lib=L)
+            try:
+                return enc.encode(fr)
+            finally:
+                enc.close()
+
         for ci in which:
             kw, writer = REGION_CASES[ci]
             writer = writer % world
@@ -56,7 +72,7 @@ def _worker(rank, world, port, q, which):
                         a[:max(0, rows[0] - oy)] = -12345
                         a[max(0, rows[1] - oy):] = -12345
                 cs = sh.encode(mine)
-                want = refharness.encode(p, fr) if rank == writer else None
+                want = one_encoder(p, fr) if rank == writer else None
                 if rank == writer:
                     if p.reversible:
                         good = cs == want
@@ -80,7 +96,7 @@ def _worker(rank, world, port, q, which):
             # device-resident forms (under the emulator "device" memory is host memory)
             sh.upload(frame)
             addr, n = sh.encode_resident()
-            want = refharness.encode(p, frame) if rank == writer else None
+            want = one_encoder(p, frame) if rank == writer else None
             if rank == writer and p.reversible:
                 good = ctypes.string_at(addr, n) == want
                 if not good:
@@ -131,4 +147,9 @@ def test_gloo_world2_row_regions(emu_lib, ref):
 
 def test_gloo_world3_row_regions(emu_lib, ref):
     """three ranks (uneven slabs, a middle rank with a halo on both sides)"""
-    _run(3, [0, 1, 2])
+    _run(3, [0, 1, 2, 7, 8])
+
+
+def test_gloo_world8_row_regions(emu_lib, ref):
+    """eight ranks on a tall image (slabs of 128 rows, ranks that own no deep-level block) and on the 9/7 case"""
+    _run(8, [6, 2])
