@@ -1,5 +1,6 @@
 // ojb_layout.cpp -- geometry, packet sequencing, packet headers (see ojb_layout.h).
 #include "ojb_layout.h"
+#include <cstdlib>
 #include <algorithm>
 #include <climits>
 #include <cstring>
@@ -445,6 +446,21 @@ struct BitWindow {
   BitWindow(const uint8_t* data, size_t p, size_t lim, HostMirror* m) : d(data), pos(p), start(p), limit(lim), hm(m) {}
   inline int bits_of(size_t i) const { return (i > start && d[i - 1] == 0xFF) ? 7 : 8; }   // a byte after 0xFF carries 7
   inline void refill() {
+    // the usual case in one step: the next eight bytes hold no 0xFF and neither does the byte before them, so each
+    // carries eight bits -- as many whole bytes as fit are appended at once (with a device-resident codestream only
+    // when their page has already been fetched: a page is never fetched for bytes that may not be read)
+    if (n <= 56 && pos + 8 <= limit && (!hm || (hm->present[pos >> HostMirror::PAGE_SHIFT] && hm->present[(pos + 7) >> HostMirror::PAGE_SHIFT]))) {
+      uint64_t v; memcpy(&v, d + pos, 8);
+      const bool prev_ff = pos > start && d[pos - 1] == 0xFF;
+      if (!prev_ff && ((((v & 0x7F7F7F7F7F7F7F7Full) + 0x0101010101010101ull) & v & 0x8080808080808080ull) == 0)) {
+        v = __builtin_bswap64(v);
+        const int take = (64 - n) >> 3;              // 1..8 whole bytes
+        const uint64_t top = take == 8 ? v : (v & (~0ull << (64 - 8 * take)));
+        acc |= n ? (top >> n) : top;
+        n += 8 * take; pos += (size_t)take;
+        return;
+      }
+    }
     while (n <= 56 && pos < limit) {
       if (hm && !hm->present[pos >> HostMirror::PAGE_SHIFT]) hm->need(pos);
       const int k = bits_of(pos);
@@ -470,6 +486,21 @@ struct BitWindow {
   inline size_t consumed_end() { size_t p = pos; int m = n; while (p > start && m >= bits_of(p - 1)) { m -= bits_of(p - 1); --p; } return p; }
 };
 
+// a tag tree of the fast parser: one byte per node, 0xFF = nothing received for it yet (the values it can hold are 0 / 1
+// for inclusion and at most K_max for missing MSBs).  Same node addressing as TagTree.
+struct FastTree {
+  uint32_t nl = 0, off[18], wl[18];
+  std::vector<uint8_t> buf;
+  void init(uint32_t nlev, uint32_t w) {
+    nl = nlev;
+    uint32_t o = 0;
+    for (uint32_t i = 0; i < nl; ++i) { off[i] = o; wl[i] = (w + (1u << i) - 1) >> i; o += 1u << ((nl - 1 - i) << 1); }
+    if (buf.size() < o) buf.resize(o);
+    memset(buf.data(), 0xFF, o);
+  }
+};
+static thread_local FastTree t_finc, t_fmm;
+
 bool parse_header_fast(const ResGeom& res, const PrecinctGeom& pc, CodedBlock* blocks, const uint8_t* data,
                        size_t& pos, uint32_t& data_left, size_t data_end, HostMirror* mirror, bool& unstuff) {
   if (data_left == 0 || pos >= data_end) return false;
@@ -485,43 +516,55 @@ bool parse_header_fast(const ResGeom& res, const PrecinctGeom& pc, CodedBlock* b
       first_band = false;
     }
     const uint32_t nl = 1 + std::max(log2ceil(ci.w), log2ceil(ci.h));
-    TagTree &inc = t_trees.inc, &incf = t_trees.incf, &mm = t_trees.mm, &mmf = t_trees.mmf;
-    inc.init(nl, ci.w, ci.h, 0); incf.init(nl, ci.w, ci.h, 0);
-    mm.init(nl, ci.w, ci.h, 0); mmf.init(nl, ci.w, ci.h, 0);
+    if (nl > 16) return false;
+    FastTree &ti = t_finc, &tm = t_fmm;
+    ti.init(nl, ci.w); tm.init(nl, ci.w);
+    uint8_t* I = ti.buf.data(); uint8_t* M = tm.buf.data();
     CodedBlock* base = blocks + bg.block_base;
-    for (uint32_t y = 0; y < ci.h; ++y)
+    const uint32_t kmax = bg.K_max;
+    for (uint32_t y = 0; y < ci.h; ++y) {
+      uint32_t rb[18];                                            // first node of this row's ancestors, per level
+      for (uint32_t l = 0; l < nl; ++l) rb[l] = ti.off[l] + (y >> l) * ti.wl[l];
+      // levels 0 .. u0-1 of a leaf's path cannot have been reached before it: the leaf is the raster-first one below
+      // those nodes (x and y are multiples of 2^l); the search for the lowest level already received starts there
+      const uint32_t uy = y ? (uint32_t)__builtin_ctz(y) : 31u;
+      CodedBlock* row = base + (size_t)(ci.y0 + y) * bg.nbw + ci.x0;
       for (uint32_t x = 0; x < ci.w; ++x) {
-        CodedBlock& cb = base[(size_t)(ci.y0 + y) * bg.nbw + ci.x0 + x];
-        bool empty_cb = false;
+        const uint32_t u0 = std::min(std::min(x ? (uint32_t)__builtin_ctz(x) : 31u, uy) + 1u, nl);
+        if (w.n < 40) w.refill();
+        // inclusion: the bits of the levels below the lowest one already received, top-down, up to the first 0
         {
-          uint32_t u = 0;
-          while (u < nl && incf.at(x >> u, y >> u, u) == 0) ++u;
-          if (u < nl && inc.at(x >> u, y >> u, u) == 1) empty_cb = true;
-          for (uint32_t cl = u; cl > 0 && !empty_cb; --cl) {
-            const uint32_t l = cl - 1;
-            if (!w.need(1)) return false;
-            const uint32_t bit = w.take(1);
-            empty_cb = (bit == 0);
-            inc.at(x >> l, y >> l, l) = (uint8_t)(1 - bit);
-            incf.at(x >> l, y >> l, l) = 1;
+          uint32_t u = u0;
+          while (u < nl && I[rb[u] + (x >> u)] == 0xFF) ++u;
+          if (u < nl && I[rb[u] + (x >> u)] == 1) continue;       // an ancestor said: nothing included below
+          if (w.n < (int)u) return false;                         // (u <= 16 bits; only at the very end of the data)
+          const uint32_t v = (uint32_t)(w.acc >> 48) | (0xFFFFu >> u);     // the u bits ahead, ones behind them
+          const uint32_t ones = (uint32_t)__builtin_clz(~(v << 16) | 1u);   // leading ones among them, 0 .. u
+          if (ones >= u) {
+            for (uint32_t l = 0; l < u; ++l) I[rb[l] + (x >> l)] = 0;
+            if (u) { w.acc <<= u; w.n -= (int)u; }
+          } else {
+            for (uint32_t l = u - ones; l < u; ++l) I[rb[l] + (x >> l)] = 0;
+            I[rb[u - ones - 1] + (x >> (u - ones - 1))] = 1;
+            w.acc <<= (ones + 1); w.n -= (int)(ones + 1);
+            continue;
           }
         }
-        if (empty_cb) continue;
         uint32_t mmsbs;
         {
-          uint32_t u = 0;
-          while (u < nl && mmf.at(x >> u, y >> u, u) == 0) ++u;
-          mmsbs = mm.at(x >> u, y >> u, u);
+          uint32_t u = u0;
+          while (u < nl && M[rb[u] + (x >> u)] == 0xFF) ++u;
+          mmsbs = u < nl ? M[rb[u] + (x >> u)] : 0u;
           for (uint32_t lp = u; lp > 0; --lp) {
             const uint32_t l = lp - 1;
             const int z = w.run(0);
-            if (z < 0 || z > 255) return false;
+            if (z < 0 || z > 254) return false;
             mmsbs += (uint32_t)z;
-            mm.at(x >> l, y >> l, l) = (uint8_t)mmsbs;
-            mmf.at(x >> l, y >> l, l) = 1;
+            if (mmsbs > 254) return false;
+            M[rb[l] + (x >> l)] = (uint8_t)mmsbs;
           }
         }
-        if (mmsbs > bg.K_max) return false;
+        if (mmsbs > kmax) return false;
         if (!w.need(1)) return false;
         if (w.take(1)) return false;                               // more than one coding pass: the general loop
         const int ones = w.run(1);
@@ -530,10 +573,12 @@ bool parse_header_fast(const ResGeom& res, const PrecinctGeom& pc, CodedBlock* b
         if (!w.need(nb)) return false;
         const uint32_t len = w.take(nb);
         if (len < 2 || len >= 65535) return false;
+        CodedBlock& cb = row[x];
         cb.missing_msbs = (uint8_t)mmsbs;
         cb.num_passes = 1;
         cb.pass_len[0] = len; cb.pass_len[1] = 0;
       }
+    }
   }
   if (first_band) return false;                                    // no band with blocks: one bit to read, slow way
   const size_t end = w.consumed_end();
@@ -582,7 +627,10 @@ void parse_packet(const Params& P, const ResGeom& res, const PrecinctGeom& pc,
     }
   } drop{res, pc, blocks};
   bool fast_unstuff = false;
-  const bool fast_done = parse_header_fast(res, pc, blocks, data, pos, data_left, data_end, mirror, fast_unstuff);
+  // OJB_PARSE_SLOW=1: the byte-wise loop only (tests compare the two readers)
+  const char* slow_only = getenv("OJB_PARSE_SLOW");
+  const bool fast_done = !(slow_only && *slow_only == '1') &&
+                         parse_header_fast(res, pc, blocks, data, pos, data_left, data_end, mirror, fast_unstuff);
   if (fast_done) { br.unstuff = fast_unstuff; empty_packet = false; }
   for (uint32_t s = 0; s < 4 && !fast_done; ++s) {
     const BandGeom& bg = res.bands[s];
