@@ -442,6 +442,17 @@ void Encoder::configure(const Params& p, uint32_t sample_type) {
             }
         }
   slot_bytes = slot + 64;
+  // One rank's share of a sharded image may be a few thousand blocks: one thread per block then leaves most of the
+  // device idle for as long as one block's serial chain lasts, and the warp-per-block kernel -- more instructions,
+  // a ten times shorter chain -- is faster.  Measured on a B200 (profiles/r02k_small_frames_ab.log): 6 144 blocks
+  // 0.40 -> 0.23 ms, 12 288 blocks 0.40 -> 0.39 ms, 24 576 blocks 0.48 -> 0.73 ms.  OJB_ENC_WARP_BELOW moves the limit.
+  {
+    uint32_t coded_blocks = 0;
+    for (const EncBlock& e : h_blocks) if (e.w && e.h) ++coded_blocks;
+    uint32_t limit = 8192;
+    if (const char* e = getenv("OJB_ENC_WARP_BELOW")) limit = (uint32_t)strtoul(e, nullptr, 10);
+    few_blocks_warp = (region.on() || !tile_mask.empty()) && coded_blocks > 0 && coded_blocks <= limit && max_block_w <= 64 && !wide;
+  }
   d_slots.reserve(slot_bytes);
   d_blocks.reserve(std::max<size_t>(1, h_blocks.size()) * sizeof(EncBlock));
   if (!h_blocks.empty())
@@ -623,13 +634,14 @@ size_t Encoder::encode(const void* const* planes, const uint32_t* strides, bool 
     }
   mark(2);
   if (phase == PHASE_BACK) { mark(3); return; }
-  if (serial_block_encoder() || max_block_w > 64 || wide)
+  const bool thread_per_block = (serial_block_encoder() && !few_blocks_warp) || max_block_w > 64 || wide;
+  if (thread_per_block)
     launch_ht_encode_serial(d_blocks.as<EncBlock>(), nb, num_fast_blocks, max_block_w, d_coef.as<uint32_t>(), d_slots.as<uint8_t>(),
                             d_results.as<EncResult>(), d_tables_enc.as<uint16_t>(), d_status.as<uint32_t>(), stream, wide, &side);
   else
     launch_ht_encode(d_blocks.as<EncBlock>(), nb, d_coef.as<uint32_t>(), d_slots.as<uint8_t>(),
                      d_results.as<EncResult>(), d_tables_enc.as<uint16_t>(), d_status.as<uint32_t>(), stream);
-  last_launches += (serial_block_encoder() || max_block_w > 64) ? (num_fast_blocks ? 1 : 0) + (num_fast_blocks < nb ? 1 : 0) : 1;
+  last_launches += thread_per_block ? (num_fast_blocks ? 1 : 0) + (num_fast_blocks < nb ? 1 : 0) : 1;
   mark(3);
   };
   if (phase == PHASE_FRONT) {

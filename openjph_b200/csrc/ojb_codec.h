@@ -139,6 +139,7 @@ public:
   std::vector<TilePartOut> last_tileparts;
   size_t slot_bytes = 0;
   uint32_t num_fast_blocks = 0;        // blocks flagged ENC_FLAG_FAST
+  bool few_blocks_warp = false;        // sharded image, few blocks on this rank: the warp-per-block encoder (see configure)
   // packet headers, tile-part markers and the byte layout on the device (pkt_headers.cu): no host round trip between
   // the block coder and the finished codestream.  OJB_HOST_HEADERS=1 keeps the host writer (ojb_layout.cpp), which also
   // serves the odd configuration with an empty tile-part.  With a tile mask (ojb_shard.cpp) the output is this rank's
