@@ -257,6 +257,7 @@ void CodecBase::plan_region(bool forward) {
 
 void CodecBase::build_dwt_jobs(bool forward) {
   const Params& P = params;
+  drop_graph(); fgraph.seen.clear();       // a new geometry: whatever was captured launched the old job lists
   if (region.on()) {
     if (!tile_mask.empty()) fail(0x000B0045, "a tile mask and row regions cannot be combined");
     if (skip_read || skip_recon) fail(0x000B0046, "reduced-resolution decoding is not available with row regions");
