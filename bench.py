@@ -316,6 +316,11 @@ def sharded_block(a, rank, world, L, ob, np, torch, dist, C, _lib, peak):
             ck(L.ojb_shard_dec_decode_resident(sh.h, L.ojb_shard_device_codestream(sh.h), cs_len, st, 0, C.byref(fi)))
         res(); res()
         ms_res = timed_loop(res, steps)
+        # where one frame's time goes on the writer (CUDA events inside the library; not part of the timed loops)
+        tm = (C.c_float * 2)()
+        ck(L.ojb_shard_enc_encode_resident(sh.h, C.byref(nres))); L.ojb_shard_timings(sh.h, tm); split_e = (float(tm[0]), float(tm[1]))
+        ck(L.ojb_shard_dec_decode_resident(sh.h, L.ojb_shard_device_codestream(sh.h), cs_len, st, 0, C.byref(fi))); L.ojb_shard_timings(sh.h, tm)
+        split_d = (float(tm[0]), float(tm[1]))
         one_gpu_res_ms = None
         if rank == 0:
             enc1 = L.ojb_enc_create(); dec1 = L.ojb_dec_create()
@@ -346,6 +351,8 @@ def sharded_block(a, rank, world, L, ob, np, torch, dist, C, _lib, peak):
                                                "codestream and the whole decoded image, so this form cannot scale"},
                       "device_resident": {"ms_per_frame": round(ms_res, 3), "Mpixels_per_s": round(pix / ms_res / 1e3, 1),
                                           "one_gpu_ms_per_frame": round(one_gpu_res_ms, 3), "time_vs_one_gpu": round(ms_res / one_gpu_res_ms, 3),
+                                          "writer_split_ms": {"encode_own_share": round(split_e[0], 3), "encode_exchange_headers_layout": round(split_e[1], 3),
+                                                              "decode_broadcast_parse_own_share": round(split_d[0], 3), "decode_gather": round(split_d[1], 3)},
                                           "note": "one frame at a time (latency, not a stream): encode + NCCL gather of tile-parts + NCCL broadcast + decode + "
                                                   "NCCL gather of samples, against the same two calls on one GPU"},
                       "codestream_bytes": cs_len})

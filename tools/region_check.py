@@ -35,18 +35,20 @@ for ci, kw in enumerate(CASES):
         t1 = time.perf_counter()
         want = None
         if rank == 0:
-            if p.dfs_num_levels == 0:
+            # reversible: the reference's codestream.  Irreversible 9/7 (the reference's own ISA variants differ in the last
+            # bit) and DFS (the reference has no writer): the one-GPU encoder is the yardstick -- the
+            # regions must reproduce it byte for byte -- and the reference is held to its tests' tolerance on decode
+            if p.reversible and p.dfs_num_levels == 0:
                 want = refharness.encode(p, fr)
-            else:                       # the reference has no DFS writer: the one-GPU encoder is the yardstick there
+            else:
                 e1 = ob.Encoder(p, ob.I32)
                 want = e1.encode(fr); e1.close()
-        if rank == 0:
-            if p.reversible:
-                ok = ok and cs == want
-            else:
-                ok = ok and len(cs) == len(want) and cs[:cs.index(b"\xff\x90")] == want[:want.index(b"\xff\x90")]
+            ok = ok and cs == want
         planes = sh.decode(want, sample_type=ob.I32, writer=0)
         if rank == 0:
+            d1 = ob.Decoder()
+            one_planes = d1.decode(want, ob.I32); d1.close()
+            ok = ok and all(np.array_equal(a, b) for a, b in zip(planes, one_planes))
             ref_planes, _ = refharness.decode(want)
             err = max(int(np.abs(a.astype(np.int64) - b).max()) for a, b in zip(planes, ref_planes))
             ok = ok and err <= (0 if p.reversible else 1)
