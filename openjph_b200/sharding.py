@@ -341,14 +341,18 @@ class NativeShard:
     when `lib` is the SIMT-emulator build of the CPU test tier, which has no NCCL -- callbacks over the process
     group (gloo), where "device" memory is host memory."""
 
-    def __init__(self, group=None, lib=None):
+    def __init__(self, group=None, lib=None, transport=None):
+        """transport: None = NCCL inside the library (callbacks when `lib` is the emulator build); "callbacks" = the
+        callback transport over the process group also with the product library -- device buffers are staged through
+        host memory (cudaMemcpy), which lets two processes on ONE GPU run the sharded paths over gloo (GPU test tier)"""
         import torch
         dist = _dist()
         self.L = lib if lib is not None else _lib.lib()
         self.group = group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self._keep = None
-        if lib is None:
+        self._staged = lib is None and transport == "callbacks"
+        if lib is None and transport != "callbacks":
             uid = torch.zeros(128, dtype=torch.uint8)
             if self.rank == 0:
                 buf = (C.c_uint8 * 128)()
@@ -375,6 +379,24 @@ class NativeShard:
         def view(ptr, n):
             return torch.from_numpy(np.frombuffer((C.c_uint8 * n).from_address(ptr), np.uint8)) if n else torch.zeros(0, dtype=torch.uint8)
 
+        cudart = None
+        if self._staged:
+            cudart = C.CDLL("libcudart.so.12")
+            cudart.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+            cudart.cudaMemcpy.restype = C.c_int
+
+        def pull(ptr, n):            # device (or, under the emulator, host) buffer -> host tensor
+            if not self._staged:
+                return view(ptr, n).clone()
+            t = torch.empty(n, dtype=torch.uint8)
+            if n and cudart.cudaMemcpy(t.data_ptr(), ptr, n, 2) != 0:
+                raise RuntimeError("cudaMemcpy D2H")
+            return t
+
+        def push(ptr, t):            # host tensor -> device buffer
+            if t.numel() and cudart.cudaMemcpy(ptr, t.data_ptr(), t.numel(), 1) != 0:
+                raise RuntimeError("cudaMemcpy H2D")
+
         def grank(r):
             return dist.get_global_rank(group, r) if group is not None else r
 
@@ -388,21 +410,32 @@ class NativeShard:
 
         def bcast(ctx, buf, n, root):
             try:
-                dist.broadcast(view(buf, n), src=grank(root), group=group)
+                if not self._staged:
+                    dist.broadcast(view(buf, n), src=grank(root), group=group)
+                else:
+                    t = pull(buf, n) if self.rank == root else torch.empty(n, dtype=torch.uint8)
+                    dist.broadcast(t, src=grank(root), group=group)
+                    if self.rank != root:
+                        push(buf, t)
                 return 0
             except Exception:
                 return 1
 
         def send(ctx, buf, n, peer):
             try:
-                dist.send(view(buf, n).clone(), dst=grank(peer), group=group)
+                dist.send(pull(buf, n), dst=grank(peer), group=group)
                 return 0
             except Exception:
                 return 1
 
         def recv(ctx, buf, n, peer):
             try:
-                dist.recv(view(buf, n), src=grank(peer), group=group)
+                if not self._staged:
+                    dist.recv(view(buf, n), src=grank(peer), group=group)
+                else:
+                    t = torch.empty(n, dtype=torch.uint8)
+                    dist.recv(t, src=grank(peer), group=group)
+                    push(buf, t)
                 return 0
             except Exception:
                 return 1

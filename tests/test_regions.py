@@ -31,15 +31,21 @@ REGION_CASES = [
 ]
 
 
-def _worker(rank, world, port, q, which):
+def _worker(rank, world, port, q, which, gpu=False):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OJB_EMU_THREADS="2")
     import ctypes
     import torch.distributed as dist
-    import emu, refharness
+    import refharness
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        L = emu.emu_lib(build=False)
+        if gpu:
+            # the nvcc-built library on cuda:0, both processes on the one device; the transport callbacks stage device
+            # buffers through host memory and gloo
+            L = None
+        else:
+            import emu
+            L = emu.emu_lib(build=False)
         ok, notes = True, []
 
         def one_encoder(p, fr):
@@ -58,7 +64,7 @@ def _worker(rank, world, port, q, which):
             writer = writer % world
             p = cases.make(kw)
             frame = cases.frame_for(p)
-            sh = sharding.NativeShard(lib=L)
+            sh = sharding.NativeShard(lib=L, transport="callbacks" if gpu else None)
             sh.set_partition("regions")
             sh.configure(p, ob.I32, writer=writer)
             for rep in range(2):                   # a second frame through the same objects
@@ -98,14 +104,14 @@ def _worker(rank, world, port, q, which):
             addr, n = sh.encode_resident()
             want = one_encoder(p, frame) if rank == writer else None
             if rank == writer and p.reversible:
-                good = ctypes.string_at(addr, n) == want
+                good = (n == len(want)) if gpu else (ctypes.string_at(addr, n) == want)
                 if not good:
                     notes.append("case %d: resident encode differs" % ci)
                 ok = ok and good
             lens = [n]
             dist.broadcast_object_list(lens, src=writer)
             sh.decode_resident(addr, lens[0], ob.I32, writer)
-            if rank == writer:
+            if rank == writer and not gpu:       # (device memory on a GPU: the host-buffer forms above already compared samples)
                 ref_planes, _ = refharness.decode(want if p.reversible else ctypes.string_at(addr, n))
                 for c, rp in enumerate(ref_planes):
                     got = np.frombuffer(ctypes.string_at(sh.device_plane(c), rp.size * 4), np.int32).reshape(rp.shape)
@@ -120,13 +126,13 @@ def _worker(rank, world, port, q, which):
         dist.destroy_process_group()
 
 
-def _run(world, which, timeout=600):
+def _run(world, which, timeout=600, gpu=False):
     import multiprocessing as mp
     import socket
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q, which)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, which, gpu)) for r in range(world)]
     for pr in procs:
         pr.start()
     res, notes = {}, []
@@ -153,3 +159,10 @@ def test_gloo_world3_row_regions(emu_lib, ref):
 def test_gloo_world8_row_regions(emu_lib, ref):
     """eight ranks on a tall image (slabs of 128 rows, ranks that own no deep-level block) and on the 9/7 case"""
     _run(8, [6, 2])
+
+
+@pytest.mark.gpu
+def test_gpu_row_regions_two_processes_one_device(ref):
+    """the nvcc-built library: two processes share cuda:0 and exchange through the callback transport (gloo, staged
+    through host memory) -- the same C++ and kernels as the NCCL path of tools/region_check.py, inside `pytest -m gpu`"""
+    _run(2, [0, 1, 2, 4, 7], gpu=True)
