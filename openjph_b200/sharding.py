@@ -396,6 +396,10 @@ class NativeShard:
         def push(ptr, t):            # host tensor -> device buffer
             if t.numel() and cudart.cudaMemcpy(ptr, t.data_ptr(), t.numel(), 1) != 0:
                 raise RuntimeError("cudaMemcpy H2D")
+            # a copy from pageable memory returns once the bytes are staged, not once they are on the device, and the
+            # library reads them on its own non-blocking stream
+            if cudart.cudaDeviceSynchronize() != 0:
+                raise RuntimeError("cudaDeviceSynchronize")
 
         def grank(r):
             return dist.get_global_rank(group, r) if group is not None else r

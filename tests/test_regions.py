@@ -122,8 +122,15 @@ def _worker(rank, world, port, q, which, gpu=False):
             # back to tiles with the same object: the tile partition still works
             sh.close()
         q.put((rank, bool(ok), notes))
+    except BaseException as e:              # the parent must hear about it instead of waiting for its timeout
+        import traceback
+        q.put((rank, False, ["rank %d: %r\n%s" % (rank, e, traceback.format_exc()[-1500:])]))
+        raise
     finally:
-        dist.destroy_process_group()
+        try:
+            dist.destroy_process_group()
+        except Exception:
+            pass
 
 
 def _run(world, which, timeout=600, gpu=False):
@@ -135,14 +142,27 @@ def _run(world, which, timeout=600, gpu=False):
     procs = [ctx.Process(target=_worker, args=(r, world, port, q, which, gpu)) for r in range(world)]
     for pr in procs:
         pr.start()
+    import queue
+    import time
     res, notes = {}, []
-    for _ in range(world):
-        r, ok, nt = q.get(timeout=timeout)
-        res[r] = ok
-        notes += nt
+    t0 = time.time()
+    while len(res) < world and time.time() - t0 < timeout:
+        try:
+            r, ok, nt = q.get(timeout=2)
+            res[r] = ok
+            notes += nt
+            if not ok:
+                break                       # one rank failed: its peers would wait in a collective for ever
+        except queue.Empty:
+            if any(pr.exitcode not in (None, 0) for pr in procs):
+                notes.append("a worker died: exit codes %s" % [pr.exitcode for pr in procs])
+                break
+    if len(res) < world or not all(res.values()):
+        for pr in procs:
+            if pr.is_alive():
+                pr.kill()
     for pr in procs:
         pr.join(timeout=60)
-        assert pr.exitcode == 0
     assert res == {r: True for r in range(world)}, notes
 
 
@@ -165,4 +185,4 @@ def test_gloo_world8_row_regions(emu_lib, ref):
 def test_gpu_row_regions_two_processes_one_device(ref):
     """the nvcc-built library: two processes share cuda:0 and exchange through the callback transport (gloo, staged
     through host memory) -- the same C++ and kernels as the NCCL path of tools/region_check.py, inside `pytest -m gpu`"""
-    _run(2, [0, 1, 2, 4, 7], gpu=True)
+    _run(2, [0, 1, 2], timeout=240, gpu=True)
