@@ -116,11 +116,17 @@ static bool level_streams(const CodecBase& C, const Params& P, uint32_t c, const
 // slab g of `world` of a tile-component: rows [lo, hi) in absolute component coordinates; inner boundaries on multiples
 // of 128 rows (two code-block rows of the first level, whole row chunks of the kernels)
 CodecBase::RowSpan CodecBase::region_slab(const Rect& tc, uint32_t g, uint32_t world) {
+  // OJB_REGION_ALIGN (a power of two; tests): finer slab boundaries, so that small images are cut as well
+  static const uint64_t align = [] {
+    const char* e = getenv("OJB_REGION_ALIGN");
+    uint64_t a = e ? strtoull(e, nullptr, 10) : 128;
+    return (a >= 2 && (a & (a - 1)) == 0) ? a : (uint64_t)128;
+  }();
   auto bound = [&](uint32_t i) -> uint32_t {
     if (i == 0) return tc.y0;
     if (i >= world) return tc.y1();
     const uint64_t y = (uint64_t)tc.y0 + (uint64_t)tc.h * i / world;
-    return std::min(std::max((uint32_t)(y & ~(uint64_t)127), tc.y0), tc.y1());
+    return std::min(std::max((uint32_t)(y & ~(align - 1)), tc.y0), tc.y1());
   };
   RowSpan s; s.lo = bound(g); s.hi = bound(g + 1);
   return s;

@@ -133,13 +133,14 @@ def _worker(rank, world, port, q, which, gpu=False):
             pass
 
 
-def _run(world, which, timeout=600, gpu=False):
+def _run(world, which, timeout=600, gpu=False, worker=None):
     import multiprocessing as mp
     import socket
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q, which, gpu)) for r in range(world)]
+    procs = [ctx.Process(target=worker, args=(r, world, port, q, which)) if worker is not None else
+             ctx.Process(target=_worker, args=(r, world, port, q, which, gpu)) for r in range(world)]
     for pr in procs:
         pr.start()
     import queue
@@ -186,3 +187,68 @@ def test_gpu_row_regions_two_processes_one_device(ref):
     """the nvcc-built library: two processes share cuda:0 and exchange through the callback transport (gloo, staged
     through host memory) -- the same C++ and kernels as the NCCL path of tools/region_check.py, inside `pytest -m gpu`"""
     _run(2, [0, 1, 2], timeout=240, gpu=True)
+
+
+# ---- seeded random geometry, cut fine (OJB_REGION_ALIGN=8 so that images of a hundred rows are split) -----------------
+def _random_worker(rank, world, port, q, seeds):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OJB_EMU_THREADS="2", OJB_REGION_ALIGN="8")
+    import torch.distributed as dist
+    import emu
+    import test_random_configs as trc
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        L = emu.emu_lib(build=False)
+        ok, notes, ran = True, [], 0
+        for seed in seeds:
+            kw = trc.random_case(seed)
+            rng = np.random.default_rng(9000 + seed)
+            oy = kw["offset"][1]
+            kw["height"] = (kw["height"] - oy) * int(rng.integers(1, 4)) + int(rng.integers(0, 40)) + oy     # something to cut
+            p = cases.make(kw)
+            frame = cases.frame_for(p)
+            # the single-process codec is the yardstick (itself held to the reference by test_random_configs.py); a
+            # configuration it refuses -- or whose stream the decoder refuses like the reference does -- is skipped
+            want, err = None, None
+            if rank == 0:
+                try:
+                    e1 = ob.Encoder(p, ob.I32, lib=L); want = e1.encode(frame); e1.close()
+                    d1 = ob.Decoder(lib=L); one = d1.decode(want, ob.I32); d1.close()
+                except Exception as e:
+                    err = str(e)
+            flag = [err]
+            dist.broadcast_object_list(flag, src=0)
+            if flag[0] is not None:
+                continue
+            ran += 1
+            sh = sharding.NativeShard(lib=L)
+            sh.set_partition("regions")
+            sh.configure(p, ob.I32, writer=0)
+            cs = sh.encode(frame)
+            planes = sh.decode(want, sample_type=ob.I32, writer=0)
+            if rank == 0:
+                if cs != want:
+                    ok = False; notes.append("seed %d: codestream differs %r" % (seed, kw))
+                elif not all(np.array_equal(a, b) for a, b in zip(planes, one)):
+                    ok = False; notes.append("seed %d: samples differ %r" % (seed, kw))
+            sh.close()
+        if ran < len(seeds) // 2:
+            ok = False; notes.append("only %d of %d configurations ran" % (ran, len(seeds)))
+        q.put((rank, bool(ok), notes))
+    except BaseException as e:
+        import traceback
+        q.put((rank, False, ["rank %d: %r\n%s" % (rank, e, traceback.format_exc()[-1500:])]))
+        raise
+    finally:
+        try:
+            dist.destroy_process_group()
+        except Exception:
+            pass
+
+
+@pytest.mark.parametrize("world,seeds", [(2, range(0, 30)), (3, range(100, 120))], ids=["world2", "world3"])
+def test_gloo_row_regions_random_geometry(world, seeds, emu_lib, ref):
+    """tiles, offsets, sub-sampling, per-component coding styles, precincts, zero to five levels, 4x4 to 128x32
+    code-blocks, every progression order: the regions reproduce the single encoder byte for byte and the single
+    decoder sample for sample"""
+    _run(world, list(seeds), worker=_random_worker)

@@ -10,3 +10,7 @@ if [ -z "$SKIP_SHARD" ]; then
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 tools/shard_check.py > gpurun_out/shard_n$N.json 2> gpurun_out/shard_n$N.err; echo "shard exit $?" >> gpurun_out/shard_n$N.err
 cat gpurun_out/shard_n$N.json; tail -3 gpurun_out/shard_n$N.err
 fi
+if [ -z "$SKIP_REGIONS" ]; then
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 tools/region_check.py > gpurun_out/region_n$N.json 2> gpurun_out/region_n$N.err; echo "region exit $?" >> gpurun_out/region_n$N.err
+cat gpurun_out/region_n$N.json; tail -3 gpurun_out/region_n$N.err
+fi
