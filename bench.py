@@ -208,6 +208,40 @@ ENC_STAGES = ("h2d", "dwt", "ht_encode", "d2h_lengths", "host_wait", "assemble",
 DEC_STAGES = ("h2d", "host_parse", "ht_decode", "dwt_inv", "d2h_image", "_5", "_6", "host_ms")
 
 
+def host_link_probe(torch, dist, world):
+    """H2D + D2H of 256 MB pinned buffers at the same time on this rank's GPU, all ranks at once (behind a barrier); GB/s
+    moved per rank, both directions summed.  Not part of any timed region."""
+    val = -1.0
+    if dist is not None:
+        dist.barrier()
+    try:
+        n = 256 << 20
+        h_in = torch.empty(n, dtype=torch.uint8, pin_memory=True); h_out = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        h_in.zero_()
+        d_a = torch.empty(n, dtype=torch.uint8, device="cuda"); d_b = torch.zeros(n, dtype=torch.uint8, device="cuda")
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def go():
+            with torch.cuda.stream(s1):
+                d_a.copy_(h_in, non_blocking=True)
+            with torch.cuda.stream(s2):
+                h_out.copy_(d_b, non_blocking=True)
+        go(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(6):
+            go()
+        torch.cuda.synchronize()
+        val = 2 * 6 * n / (time.perf_counter() - t0) / 1e9
+    except Exception:
+        val = -1.0
+    if dist is None:
+        return [round(val, 1)]
+    t = torch.tensor([val], device="cuda", dtype=torch.float64)
+    g = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(g, t)
+    return [round(float(x.item()), 1) for x in g]
+
+
 def sharded_block(a, rank, world, L, ob, np, torch, dist, C, _lib, peak):
     """Strong scaling of ONE image over the ranks: every rank passes the whole image (host, pinned), codes its tiles,
     tile-part bytes / decoded samples go device to device over NCCL to rank 0, which delivers the codestream / the
@@ -714,6 +748,10 @@ def main():
         except Exception as e:
             sharded = {"error": str(e)[:300]}
 
+    # what the host side of every GPU's link delivers while ALL ranks copy at once (pinned memory, H2D and D2H together):
+    # `e2e` moves 631 MB per frame and direction, and GPUs that share a socket share its memory / IO bandwidth
+    link = host_link_probe(torch, dist, world)
+
     # final gather of the per-rank codestream sizes (the only collective on the frame-parallel path)
     sizes = [cs_len]
     if dist is not None:
@@ -765,6 +803,7 @@ def main():
               "e2e_stages_encode_ms": e2e_e, "e2e_stages_decode_ms": e2e_d, "codestream_bytes": sizes,
               "resident_decode_header_fetch_bytes": r["mirror_bytes"],
               "pipeline_hbm_frac": round(((2 * samples + cs_len) * 2 * NW) / (r["dt_res"] / a.steps) / 1e9 / peak, 4),
+              "host_link_duplex_GBps_per_rank": link,
               "configs": configs, "sharded": sharded}
     res = {"metric": "Mpixels/s encode+decode", "value": value, "unit": "Mpixels/s", "n_gpus": a.gpus, "steps": a.steps,
            "warmup": a.warmup, "ms_per_step": r["dt_res"] / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
