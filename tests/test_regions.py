@@ -1,7 +1,9 @@
 """Row-region sharding of one image over ranks (the split that also cuts a single-tile image).
-CPU tier: the C++ of ojb_shard.cpp / CodecBase::plan_region with world_size 2 and 3 over gloo, kernels under the
-SIMT emulator, against the reference's codestream and decode.  GPU tier: tools/gpu_multi.sh runs the same
-configurations over NCCL."""
+CPU tier: the C++ of ojb_shard.cpp / CodecBase::plan_region with world_size 2, 3 and 8 over gloo, kernels under the
+SIMT emulator, against the reference's codestream and decode; seeded random geometry against the single codec.
+GPU tier: the nvcc-built library with two processes on one device (callback transport staged through host memory);
+tools/region_check.py runs the same configurations and two larger ones over NCCL under torchrun
+(profiles/r02k_region_check_n2.json)."""
 import os
 import sys
 import numpy as np
