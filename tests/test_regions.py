@@ -184,13 +184,6 @@ def test_gloo_world8_row_regions(emu_lib, ref):
     _run(8, [6, 2])
 
 
-@pytest.mark.gpu
-def test_gpu_row_regions_two_processes_one_device(ref):
-    """the nvcc-built library: two processes share cuda:0 and exchange through the callback transport (gloo, staged
-    through host memory) -- the same C++ and kernels as the NCCL path of tools/region_check.py, inside `pytest -m gpu`"""
-    _run(2, [0, 1, 2], timeout=240, gpu=True)
-
-
 # ---- seeded random geometry, cut fine (OJB_REGION_ALIGN=8 so that images of a hundred rows are split) -----------------
 def _random_worker(rank, world, port, q, seeds):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
