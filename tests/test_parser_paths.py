@@ -72,3 +72,52 @@ def test_window_reader_equals_bytewise_loop(ci, emu_lib, ref):
             assert any(b[1] for b in fast)
         if kind in ("holes", "flat"):
             assert any(b[1] == 0 for b in fast)          # blocks that are not included
+
+
+def _blocks_or_error(L, cs, slow, resilient):
+    buf = np.frombuffer(cs, np.uint8)
+    d = L.ojb_dec_create()
+    try:
+        if resilient:
+            L.ojb_dec_enable_resilience(d)
+        fi = _lib.FrameInfo()
+        if L.ojb_dec_read_headers(d, buf.ctypes.data, buf.size, ob.I32, C.byref(fi)) != 0:
+            return ("main header", L.ojb_last_error())
+        n = C.c_uint32()
+        if slow:
+            os.environ["OJB_PARSE_SLOW"] = "1"
+        try:
+            if L.ojb_dec_list_blocks(d, None, 0, C.byref(n)) != 0:
+                return ("error", L.ojb_last_error())
+            out = (_lib.BlockDesc * n.value)()
+            if L.ojb_dec_list_blocks(d, out, n.value, C.byref(n)) != 0:
+                return ("error", L.ojb_last_error())
+        finally:
+            os.environ.pop("OJB_PARSE_SLOW", None)
+        return [(b.missing_msbs, b.num_passes, b.len1, b.len2, b.byte_off) for b in out]
+    finally:
+        L.ojb_dec_destroy(d)
+
+
+def test_damaged_streams_read_alike(emu_lib, ref):
+    """corrupted and truncated packet headers: the window reader gives up where anything is out of the ordinary and the
+    byte-wise loop reports -- so both paths end with the same block records or the same error (code and text), with and
+    without resilience"""
+    rng = np.random.default_rng(5)
+    trials = 0
+    for ci in (0, 2, 5):
+        kw, kind = PARSER_CASES[ci]
+        p = cases.make(kw)
+        cs0 = ref.encode(p, _frames(p, kind, 1))
+        sod = cs0.index(b"\xff\x93") + 2
+        for _ in range(40):
+            b = bytearray(cs0)
+            for _k in range(int(rng.integers(1, 4))):
+                b[sod + int(rng.integers(0, min(len(b) - sod, 4000)))] = int(rng.integers(0, 256))
+            if rng.random() < 0.3:
+                b = b[:sod + int(rng.integers(1, len(b) - sod))]
+            cs = bytes(b)
+            for resilient in (False, True):
+                assert _blocks_or_error(emu_lib, cs, False, resilient) == _blocks_or_error(emu_lib, cs, True, resilient)
+                trials += 1
+    assert trials == 240
