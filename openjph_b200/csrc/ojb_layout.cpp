@@ -502,8 +502,9 @@ struct FastTree {
 static thread_local FastTree t_finc, t_fmm;
 
 bool parse_header_fast(const ResGeom& res, const PrecinctGeom& pc, CodedBlock* blocks, const uint8_t* data,
-                       size_t& pos, uint32_t& data_left, size_t data_end, HostMirror* mirror, bool& unstuff) {
+                       size_t& pos, uint32_t& data_left, size_t data_end, HostMirror* mirror, bool& unstuff, uint64_t& body_total) {
   if (data_left == 0 || pos >= data_end) return false;
+  uint64_t body = 0;                      // bytes of the bodies read so far: a block's data_off is set RELATIVE to the first body
   BitWindow w(data, pos, std::min(data_end, pos + (size_t)data_left), mirror);
   bool first_band = true;
   for (uint32_t s = 0; s < 4; ++s) {
@@ -577,9 +578,11 @@ bool parse_header_fast(const ResGeom& res, const PrecinctGeom& pc, CodedBlock* b
         cb.missing_msbs = (uint8_t)mmsbs;
         cb.num_passes = 1;
         cb.pass_len[0] = len; cb.pass_len[1] = 0;
+        cb.data_off = body; body += len;
       }
     }
   }
+  body_total = body;
   if (first_band) return false;                                    // no band with blocks: one bit to read, slow way
   const size_t end = w.consumed_end();
   if (end == pos) return false;
@@ -629,8 +632,17 @@ void parse_packet(const Params& P, const ResGeom& res, const PrecinctGeom& pc,
   bool fast_unstuff = false;
   // OJB_PARSE_SLOW=1: the byte-wise loop only (tests compare the two readers)
   const char* slow_only = getenv("OJB_PARSE_SLOW");
+  uint64_t fast_body = 0;
   const bool fast_done = !(slow_only && *slow_only == '1') &&
-                         parse_header_fast(res, pc, blocks, data, pos, data_left, data_end, mirror, fast_unstuff);
+                         parse_header_fast(res, pc, blocks, data, pos, data_left, data_end, mirror, fast_unstuff, fast_body);
+  if (!fast_done && !(slow_only && *slow_only == '1'))
+    for (uint32_t s = 0; s < 4; ++s) {            // the optimistic pass left relative offsets behind: not delivered
+      const BandGeom& bg = res.bands[s];
+      if (bg.empty) continue;
+      const Rect& ci = pc.cb_idx[s];
+      for (uint32_t y = 0; y < ci.h; ++y)
+        for (uint32_t x = 0; x < ci.w; ++x) blocks[bg.block_base + (size_t)(ci.y0 + y) * bg.nbw + ci.x0 + x].data_off = 0;
+    }
   if (fast_done) { br.unstuff = fast_unstuff; empty_packet = false; }
   for (uint32_t s = 0; s < 4 && !fast_done; ++s) {
     const BandGeom& bg = res.bands[s];
@@ -755,6 +767,28 @@ void parse_packet(const Params& P, const ResGeom& res, const PrecinctGeom& pc,
   // 536-573), but the tile-part's byte budget stays what Psot says: the next packet header then fails
   // to read, which is how a truncation is detected outside resilient mode.
   drop.armed = false;
+  if (fast_done && fast_body <= data_left && pos < data_end && fast_body <= data_end - pos) {
+    // every body is there: the offsets were laid out while the header was read, relative to the first body
+    for (uint32_t s = 0; s < 4; ++s) {
+      const BandGeom& bg = res.bands[s];
+      if (bg.empty) continue;
+      const Rect& ci = pc.cb_idx[s];
+      for (uint32_t y = 0; y < ci.h; ++y) {
+        CodedBlock* row = blocks + bg.block_base + (size_t)(ci.y0 + y) * bg.nbw + ci.x0;
+        for (uint32_t x = 0; x < ci.w; ++x) if (row[x].pass_len[0]) row[x].data_off += pos;
+      }
+    }
+    pos += (size_t)fast_body; data_left -= (uint32_t)fast_body;
+    return;
+  }
+  if (fast_done)            // a body the buffer cannot deliver: the general rule below decides block by block
+    for (uint32_t s = 0; s < 4; ++s) {
+      const BandGeom& bg = res.bands[s];
+      if (bg.empty) continue;
+      const Rect& ci = pc.cb_idx[s];
+      for (uint32_t y = 0; y < ci.h; ++y)
+        for (uint32_t x = 0; x < ci.w; ++x) blocks[bg.block_base + (size_t)(ci.y0 + y) * bg.nbw + ci.x0 + x].data_off = 0;
+    }
   bool body_ok = true;
   for (uint32_t s = 0; s < 4; ++s) {
     const BandGeom& bg = res.bands[s];
