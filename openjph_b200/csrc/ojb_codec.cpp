@@ -1002,6 +1002,15 @@ void Decoder::read_headers(const uint8_t* data, size_t len, uint32_t sample_type
             }
         }
   coded.assign(layout.num_blocks, CodedBlock());
+  block_static.assign(layout.num_blocks, DecStatic());
+  for (size_t b = 0; b < h_dec_proto.size(); ++b) {
+    const DecBlock& d = h_dec_proto[b];
+    DecStatic& g = block_static[b];
+    const uint32_t nq = (d.w + 1u) / 2, qs = (nq + 1) & ~1u, nqr = (d.h + 1u) / 2;
+    g.quad_words = qs * nqr; g.flags = d.flags; g.K_max = d.K_max;
+    DecBlock t = d; t.num_passes = 1; t.len1 = 2; t.missing_msbs = 0; t.K_max = 1;       // the frame's part of the test set to "yes"
+    g.fast_shape = dec_block_is_fast(t) ? 1 : 0;
+  }
   d_dec.reserve(std::max<size_t>(1, h_dec_proto.size()) * sizeof(DecBlock));
   d_proto.reserve(std::max<size_t>(1, h_dec_proto.size()) * sizeof(DecBlock));
   if (!h_dec_proto.empty())
@@ -1177,27 +1186,31 @@ uint32_t Decoder::decode(void* const* planes, const uint32_t* strides, bool plan
   // the frame's part of every block record (the geometry part sits in d_proto): lengths, passes, missing msbs, where
   // the bytes are, and whether the block goes through the specialised kernel (one output type per launch).  Scratch
   // (quad records + de-stuffed MagSgn of the general / two-step kernels) is laid out per frame.
+  // (the geometry a block's record needs here -- quad-record words, static flags, whether its shape suits the
+  // specialised kernel -- sits in 8 bytes per block, block_static, instead of the 48-byte DecBlock prototype)
+  const bool masked = !block_wanted.empty(), restricted = skip_read > 0;
+  const DecStatic* bst = block_static.data();
   for (uint32_t b = 0; b < nb; ++b) {
-    DecBlock d = h_dec_proto[b];
     const CodedBlock& cb = coded[b];
-    d.len1 = cb.pass_len[0]; d.len2 = cb.pass_len[1];
-    d.num_passes = cb.num_passes; d.missing_msbs = cb.missing_msbs; d.data_off = cb.data_off;
+    const DecStatic g = bst[b];
+    uint32_t len1 = cb.pass_len[0], len2 = cb.pass_len[1], np = cb.num_passes;
+    const uint32_t mm = cb.missing_msbs;
     bool skip = false;
-    if (!block_wanted.empty() && !block_wanted[b]) { d.num_passes = 0; d.len1 = d.len2 = 0; skip = true; }   // another rank's tile
-    if (block_res[b] < skip_read) {            // resolution not read: its bands are zero ...
-      d.num_passes = 0; d.len1 = d.len2 = 0;
-      if (block_res[b] < skip_recon) skip = true;        // ... and not even needed: nothing to fill
+    if (masked && !block_wanted[b]) { np = 0; len1 = len2 = 0; skip = true; }   // another rank's tile / rows
+    if (restricted && block_res[b] < skip_read) {            // resolution not read: its bands are zero ...
+      np = 0; len1 = len2 = 0;
+      if (block_res[b] < skip_recon) skip = true;            // ... and not even needed: nothing to fill
     }
-    if (skip) d.w = d.h = 0;
-    uint32_t nq = (d.w + 1u) / 2, qs = (nq + 1) & ~1u, nqr = (d.h + 1u) / 2;
     scratch = (scratch + 3) & ~(size_t)3;
     hs[b] = scratch;
-    scratch += (size_t)qs * nqr + (((d.len1 + 3) / 4 + 4 + 3) & ~3u);
-    max_len1 = std::max(max_len1, d.len1);
-    if (d.num_passes > 1) cleanup_only = false;
-    if (fast_ok && dec_block_is_fast(d)) { d.flags |= DEC_FLAG_FAST; ++nfast; }
-    DecDyn y; y.data_off = d.data_off; y.len1 = (uint16_t)d.len1; y.len2 = (uint16_t)d.len2;
-    y.num_passes = d.num_passes; y.missing_msbs = d.missing_msbs; y.flags = d.flags; y.skip = skip ? 1 : 0;
+    scratch += (size_t)(skip ? 0u : g.quad_words) + (((len1 + 3) / 4 + 4 + 3) & ~3u);
+    max_len1 = std::max(max_len1, len1);
+    if (np > 1) cleanup_only = false;
+    uint32_t flags = g.flags;
+    // dec_block_is_fast(): the shape part is g.fast_shape, the frame's part is checked here
+    if (fast_ok && g.fast_shape && !skip && np == 1 && len1 >= 2 && mm + 2u <= 16u && g.K_max > mm) { flags |= DEC_FLAG_FAST; ++nfast; }
+    DecDyn y; y.data_off = cb.data_off; y.len1 = (uint16_t)len1; y.len2 = (uint16_t)len2;
+    y.num_passes = (uint8_t)np; y.missing_msbs = (uint8_t)mm; y.flags = (uint8_t)flags; y.skip = skip ? 1 : 0;
     hy[b] = y;
   }
   d_scratch.reserve((scratch + 64) * 4);

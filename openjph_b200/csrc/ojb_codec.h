@@ -197,6 +197,10 @@ public:
   std::vector<uint8_t> header_sig;     // bytes of the main header the geometry was built for
   std::vector<CodedBlock> coded;
   std::vector<DecBlock> h_dec_proto;   // geometry part of DecBlock, per block
+  // what the per-frame record loop of decode() needs of it: quad-record words (scratch), static flags, K_max, and
+  // whether the block's shape qualifies for ht_decode_fast_kernel (dec_block_is_fast minus the frame's fields)
+  struct DecStatic { uint32_t quad_words = 0; uint8_t flags = 0, K_max = 0, fast_shape = 0, pad = 0; };
+  std::vector<DecStatic> block_static;
   DeviceBuf d_cs, d_dec, d_proto, d_scratch, d_bstatus;
   PinnedBuf h_dyn, h_scr, h_bstatus;
   bool any_rev_blocks = false, any_irv_blocks = false;
