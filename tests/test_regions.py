@@ -121,7 +121,9 @@ def _worker(rank, world, port, q, which, gpu=False):
                     if not good:
                         notes.append("case %d: resident decode differs in component %d" % (ci, c))
                     ok = ok and good
-            # back to tiles with the same object: the tile partition still works
+            # an unknown partition is refused (and the object keeps the one it had)
+            if (L if L is not None else sh.L).ojb_shard_set_partition(sh.h, 5) == 0:
+                ok = False; notes.append("case %d: partition 5 was accepted" % ci)
             sh.close()
         q.put((rank, bool(ok), notes))
     except BaseException as e:              # the parent must hear about it instead of waiting for its timeout
